@@ -1,0 +1,163 @@
+#!/usr/bin/env python3
+"""Generate the golden fixtures under tests/golden/ by running the UNMODIFIED
+reference (FreeFEM 4.15, built by `make -C oracle ref` into oracle/_ref/) on small
+cases of the hot path and dumping mesh, dof table, matrix (COO as stored by
+HashMatrix, i.e. insertion order), right-hand side, CG solution and iteration
+count with 17 significant digits (exact round trip of fp64).
+
+Only runs where /root/reference was available to build oracle/_ref (the dev
+container); the resulting *.npz files are committed and are what the tests read.
+
+    python tests/golden/make_golden.py [case ...]
+"""
+import os, re, subprocess, sys, tempfile
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+FF = os.path.join(ROOT, "oracle", "_ref", "FreeFem++-nw")
+
+LAP2 = "dx(u)*dx(v)+dy(u)*dy(v)"
+LAP3 = "dx(u)*dx(v)+dy(u)*dy(v)+dz(u)*dz(v)"
+LAME = ("lambda*(dx(u1)+dy(u2)+dz(u3))*(dx(v1)+dy(v2)+dz(v3))"
+        "+2.*mu*(dx(u1)*dx(v1)+dy(u2)*dy(v2)+dz(u3)*dz(v3)"
+        "+0.5*(dy(u1)+dx(u2))*(dy(v1)+dx(v2))+0.5*(dz(u1)+dx(u3))*(dz(v1)+dx(v3))"
+        "+0.5*(dz(u2)+dy(u3))*(dz(v2)+dy(v3)))")
+LAME_PRE = "real E=21.5e4, sigma=0.29; real mu=E/(2*(1+sigma)); real lambda=E*sigma/((1+sigma)*(1-2*sigma));"
+
+# name -> dict(dim, mesh, fe, unk, tst, bil, lin, bc, intopt, pre, solve)
+CASES = {
+    # config 1 shape: 2-D P1 Laplace, f=1, u=0 on the whole boundary
+    "lap2d_p1_sq4": dict(dim=2, mesh="square(4,4)", fe="P1", bil=LAP2, lin="1.*v", bc="on(1,2,3,4,u=0)"),
+    "lap2d_p1_sq12x9": dict(dim=2, mesh="square(12,9)", fe="P1", bil=LAP2, lin="1.*v", bc="on(1,2,3,4,u=0)"),
+    "lap2d_p1_warp": dict(dim=2, mesh="square(7,5,[x+0.2*y*y,y*(1+0.3*x)])", fe="P1", bil=LAP2, lin="3.*v",
+                          bc="on(1,u=1)+on(3,u=2)"),
+    "lap2d_p2_sq3": dict(dim=2, mesh="square(3,3)", fe="P2", bil=LAP2, lin="1.*v", bc="on(1,2,3,4,u=0)"),
+    "lap2d_p2_warp": dict(dim=2, mesh="square(4,3,[x+0.2*y*y,y*(1+0.3*x)])", fe="P2", bil=LAP2 + "+2.*u*v",
+                          lin="1.*v", bc="on(2,4,u=0)"),
+    # config 2 / 5 shape: 3-D P1 Poisson
+    "lap3d_p1_cube2": dict(dim=3, mesh="cube(2,2,2)", fe="P1", bil=LAP3, lin="1.*v", bc="on(1,2,3,4,5,6,u=0)"),
+    "lap3d_p1_cube5": dict(dim=3, mesh="cube(5,5,5)", fe="P1", bil=LAP3, lin="1.*v", bc="on(1,2,3,4,5,6,u=0)"),
+    "lap3d_p1_cube342": dict(dim=3, mesh="cube(3,4,2)", fe="P1", bil=LAP3, lin="1.*v", bc="on(1,2,3,4,5,6,u=0)"),
+    "lap3d_p1_warp": dict(dim=3, mesh="cube(3,3,3,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", fe="P1", bil=LAP3,
+                          lin="2.*v", bc="on(1,u=1)+on(6,u=-1)"),
+    "lap3d_p2_cube2": dict(dim=3, mesh="cube(2,2,2)", fe="P2", bil=LAP3, lin="1.*v", bc="on(1,2,3,4,5,6,u=0)"),
+    # config 4 shape: heat step matrix  u*v/dt + grad u . grad v  (Heat3d.idp)
+    "heat3d_p1_cube3": dict(dim=3, mesh="cube(3,3,3)", fe="P1", pre="real dt=0.01;", bil="u*v/dt+" + LAP3,
+                            lin="1.*v", bc="on(1,2,3,4,5,6,u=0)"),
+    # mass only, lumped quadrature
+    "mass3d_p1_lump": dict(dim=3, mesh="cube(2,2,2)", fe="P1", bil="u*v", lin="1.*v", bc="", intopt=",qfV=qfV1lump",
+                           solve=False),
+    "mass2d_p2_qf2": dict(dim=2, mesh="square(3,2)", fe="P2", bil="u*v", lin="1.*v", bc="", intopt=",qft=qf2pT",
+                          solve=False),
+    # non-symmetric form: checks row = test function, column = unknown
+    "nonsym3d_p1": dict(dim=3, mesh="cube(2,3,2)", fe="P1", bil="dx(u)*v+2.*u*dy(v)+0.5*dz(u)*dx(v)", lin="dx(v)+2.*v",
+                        bc="", solve=False),
+    "nonsym2d_p2": dict(dim=2, mesh="square(3,2)", fe="P2", bil="dx(u)*v+2.*u*dy(v)+0.5*dy(u)*dx(v)", lin="dy(v)+2.*v",
+                        bc="", solve=False),
+    # config 3 shape: 3-component Lame (beam-3d.md macros), gravity on the 3rd component, clamped on label 1
+    "lame3d_p2_cube2": dict(dim=3, mesh="cube(2,2,2)", fe="[P2,P2,P2]", unk="[u1,u2,u3]", tst="[v1,v2,v3]",
+                            pre=LAME_PRE, bil=LAME, lin="-0.05*v3", bc="on(1,u1=0,u2=0,u3=0)"),
+    "lame3d_p1_cube3": dict(dim=3, mesh="cube(3,2,3)", fe="[P1,P1,P1]", unk="[u1,u2,u3]", tst="[v1,v2,v3]",
+                            pre=LAME_PRE, bil=LAME, lin="-0.05*v3", bc="on(1,u1=0,u2=0,u3=0)"),
+    "lame3d_p2_warp": dict(dim=3, mesh="cube(2,1,2,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", fe="[P2,P2,P2]",
+                           unk="[u1,u2,u3]", tst="[v1,v2,v3]", pre=LAME_PRE, bil=LAME, lin="-0.05*v3",
+                           bc="on(1,u1=0,u2=0,u3=0)+on(3,u1=0.01,u2=0,u3=-0.02)"),
+}
+
+
+def script(c, out):
+    dim = c["dim"]
+    unk, tst = c.get("unk", "u"), c.get("tst", "v")
+    mtype, integ = ("mesh", "int2d") if dim == 2 else ("mesh3", "int3d")
+    opt = c.get("intopt", "")
+    bc = ("+" + c["bc"]) if c["bc"] else ""
+    nvk = dim + 1
+    s = []
+    s.append('load "msh3"')
+    s.append(c.get("pre", ""))
+    s.append(f"{mtype} Th = {c['mesh']};")
+    s.append(f"fespace Vh(Th,{c['fe']});")
+    s.append(f"varf va({unk},{tst}) = {integ}(Th{opt})({c['bil']}) + {integ}(Th{opt})({c['lin']}){bc};")
+    s.append("matrix A = va(Vh,Vh,solver=CG,eps=1e-6);")
+    s.append("real[int] b = va(0,Vh);")
+    # mesh dump
+    s.append(f'{{ ofstream f("{out}/mesh.txt"); f.precision(17);')
+    s.append('  f << Th.nv << " " << Th.nt << " " << Th.nbe << endl;')
+    if dim == 2:
+        s.append('  for(int i=0;i<Th.nv;++i) f << Th(i).x << " " << Th(i).y << " " << Th(i).label << endl;')
+    else:
+        s.append('  for(int i=0;i<Th.nv;++i) f << Th(i).x << " " << Th(i).y << " " << Th(i).z << " " << Th(i).label << endl;')
+    s.append("  for(int k=0;k<Th.nt;++k){ for(int i=0;i<%d;++i) f << Th[k][i] << \" \"; f << Th[k].label << endl; }" % nvk)
+    s.append("  for(int e=0;e<Th.nbe;++e){ for(int i=0;i<%d;++i) f << Th.be(e)[i] << \" \"; "
+             "f << Th.be(e).label << \" \" << Th.be(e).Element << \" \" << Th.be(e).whoinElement << endl; } }" % dim)
+    # dof table
+    s.append(f'{{ ofstream f("{out}/dof.txt"); f << Vh.ndof << " " << Vh.ndofK << endl;')
+    s.append('  for(int k=0;k<Th.nt;++k){ for(int i=0;i<Vh.ndofK;++i) f << Vh(k,i) << " "; f << endl; } }')
+    # matrix as stored (COO, insertion order), rhs
+    s.append("{ int[int] I(1),J(1); real[int] C(1); [I,J,C]=A;")
+    s.append(f'  ofstream f("{out}/A.txt"); f.precision(17); f << A.n << " " << A.m << " " << A.nnz << endl;')
+    s.append('  for(int k=0;k<I.n;++k) f << I[k] << " " << J[k] << " " << C[k] << endl; }')
+    s.append(f'{{ ofstream f("{out}/b.txt"); f.precision(17); for(int i=0;i<b.n;++i) f << b[i] << endl; }}')
+    if c.get("solve", True):
+        s.append("Vh %s; %s[] = 0; verbosity=1;" % (unk, unk.strip("[]").split(",")[0]))
+        u0 = unk.strip("[]").split(",")[0]
+        s.append(f"{u0}[] = A^-1*b; verbosity=0;")
+        s.append(f'{{ ofstream f("{out}/u.txt"); f.precision(17); for(int i=0;i<{u0}[].n;++i) f << {u0}[][i] << endl; }}')
+    return "\n".join(s) + "\n"
+
+
+def toks(path):
+    with open(path) as f:
+        return f.read().split()
+
+
+def run_case(name):
+    c = CASES[name]
+    dim = c["dim"]
+    with tempfile.TemporaryDirectory() as td:
+        edp = os.path.join(td, "case.edp")
+        src = script(c, td)
+        with open(edp, "w") as f:
+            f.write(src)
+        r = subprocess.run([FF, "-nw", "-v", "1", edp], capture_output=True, text=True, cwd=td)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout[-3000:] + r.stderr[-3000:])
+            raise SystemExit(f"reference failed on {name}")
+        t = toks(os.path.join(td, "mesh.txt"))
+        nv, nt, nbe = int(t[0]), int(t[1]), int(t[2])
+        p = 3
+        vt = np.array(t[p:p + nv * (dim + 1)], dtype=np.float64).reshape(nv, dim + 1); p += nv * (dim + 1)
+        et = np.array(t[p:p + nt * (dim + 2)], dtype=np.int64).reshape(nt, dim + 2); p += nt * (dim + 2)
+        bt = np.array(t[p:p + nbe * (dim + 3)], dtype=np.int64).reshape(nbe, dim + 3); p += nbe * (dim + 3)
+        assert p == len(t)
+        t = toks(os.path.join(td, "dof.txt"))
+        ndof, ndofK = int(t[0]), int(t[1])
+        dof = np.array(t[2:], dtype=np.int32).reshape(nt, ndofK)
+        t = toks(os.path.join(td, "A.txt"))
+        n, m, nnz = int(t[0]), int(t[1]), int(t[2])
+        a = np.array(t[3:], dtype=np.float64).reshape(-1, 3)
+        assert a.shape[0] == nnz and n == ndof
+        b = np.array(toks(os.path.join(td, "b.txt")), dtype=np.float64)
+        out = dict(dim=np.int32(dim), xyz=np.ascontiguousarray(vt[:, :dim]), vlab=vt[:, dim].astype(np.int32),
+                   conn=et[:, :dim + 1].astype(np.int32), elab=et[:, dim + 1].astype(np.int32),
+                   bconn=bt[:, :dim].astype(np.int32), blab=bt[:, dim].astype(np.int32),
+                   belem=bt[:, dim + 1].astype(np.int32), bface=bt[:, dim + 2].astype(np.int32),
+                   ndof=np.int32(ndof), dof=dof,
+                   coo_i=a[:, 0].astype(np.int32), coo_j=a[:, 1].astype(np.int32), coo_a=a[:, 2].copy(), b=b,
+                   edp=np.array(src))
+        if c.get("solve", True):
+            out["u"] = np.array(toks(os.path.join(td, "u.txt")), dtype=np.float64)
+            mm = re.search(r"GC:\s+converge after\s+(\d+)", r.stdout)
+            assert mm, r.stdout[-2000:]
+            out["cg_iters"] = np.int32(int(mm.group(1)))
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+        print(f"{name}: nv={nv} nt={nt} nbe={nbe} ndof={ndof} nnz={nnz}"
+              + (f" cg_iters={int(out['cg_iters'])}" if "cg_iters" in out else ""))
+
+
+if __name__ == "__main__":
+    if not os.path.exists(FF):
+        raise SystemExit("oracle/_ref/FreeFem++-nw missing: run `make -C oracle ref -j8` (needs /root/reference)")
+    for nm in (sys.argv[1:] or list(CASES)):
+        run_case(nm)
