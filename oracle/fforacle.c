@@ -1,0 +1,599 @@
+/* fforacle.c — CPU ORACLE (test infrastructure only; see fforacle.h for the contract and the
+ * reference file:line each routine restates).  Plain C99, single thread, like the reference path. */
+#include "fforacle.h"
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ------------------------------------------------------------------ quadrature ---------- */
+/* Published rules (Stroud 1971 p.314; Keast / Grundmann-Moeller 14-point degree 5), as tabulated in
+ * femlib/QuadratureFormular.cpp:127-188 (triangle) and :690-743 (tetrahedron; weights sum to 1). */
+static int q_set(int dim, int n, const double *P, const double *W, double *pts, double *w)
+{
+    for (int i = 0; i < n; ++i) {
+        w[i] = W[i];
+        for (int d = 0; d < dim; ++d) pts[i * dim + d] = P[i * dim + d];
+    }
+    return n;
+}
+
+int ffo_quadrature(int dim, const char *name, double *pts, double *w)
+{
+    if (dim == 2) {
+        if (!strcmp(name, "qf1pT")) {
+            const double P[] = {1. / 3., 1. / 3.}, W[] = {1.};
+            return q_set(2, 1, P, W, pts, w);
+        }
+        if (!strcmp(name, "qf1pTlump")) {
+            const double P[] = {0., 0., 1., 0., 0., 1.}, W[] = {1. / 3., 1. / 3., 1. / 3.};
+            return q_set(2, 3, P, W, pts, w);
+        }
+        if (!strcmp(name, "qf2pT")) {
+            const double P[] = {0.5, 0.5, 0.0, 0.5, 0.5, 0.0}, W[] = {1. / 3., 1. / 3., 1. / 3.};
+            return q_set(2, 3, P, W, pts, w);
+        }
+        if (!strcmp(name, "qf5pT")) {
+            const double sqrt15 = 3.87298334620741688517926539978;
+            const double t = 1.E0 / 3.E0, A = 0.225E0;
+            const double r = (6 - sqrt15) / 21, s = (9 + 2 * sqrt15) / 21, B = (155 - sqrt15) / 1200;
+            const double u = (6 + sqrt15) / 21, v = (9 - 2 * sqrt15) / 21, C = (155 + sqrt15) / 1200;
+            const double P[] = {t, t, r, r, r, s, s, r, u, u, u, v, v, u};
+            const double W[] = {A, B, B, B, C, C, C};
+            return q_set(2, 7, P, W, pts, w);
+        }
+        return -1;
+    }
+    if (dim == 3) {
+        if (!strcmp(name, "qfV1")) {
+            const double P[] = {0.25, 0.25, 0.25}, W[] = {1.};
+            return q_set(3, 1, P, W, pts, w);
+        }
+        if (!strcmp(name, "qfV1lump")) {
+            const double P[] = {0, 0, 0, 1., 0, 0, 0, 1., 0, 0, 0, 1.}, W[] = {0.25, 0.25, 0.25, 0.25};
+            return q_set(3, 4, P, W, pts, w);
+        }
+        if (!strcmp(name, "qfV2")) {
+            const double a = 0.58541019662496845446137605030968, b = 0.138196601125010515179541316563436;
+            const double P[] = {a, b, b, b, a, b, b, b, a, b, b, b}, W[] = {0.25, 0.25, 0.25, 0.25};
+            return q_set(3, 4, P, W, pts, w);
+        }
+        if (!strcmp(name, "qfV5")) {
+            const double a1 = 0.7217942490673263207930282587889082, b1 = 0.0927352503108912264023239137370306;
+            const double a2 = 0.067342242210098170607962798709629, b2 = 0.310885919263300609797345733763457;
+            const double a3 = 0.454496295874350350508119473720660, b3 = 0.045503704125649649491880526279339;
+            const double w1 = 0.0122488405193936582572850342477212 * 6.;
+            const double w2 = 0.0187813209530026417998642753888810 * 6.;
+            const double w3 = 7.09100346284691107301157135337624E-3 * 6.;
+            const double P[] = {a1, b1, b1, b1, a1, b1, b1, b1, a1, b1, b1, b1,
+                                a2, b2, b2, b2, a2, b2, b2, b2, a2, b2, b2, b2,
+                                a3, a3, b3, a3, b3, a3, b3, a3, a3, b3, b3, a3, b3, a3, b3, a3, b3, b3};
+            const double W[] = {w1, w1, w1, w1, w2, w2, w2, w2, w3, w3, w3, w3, w3, w3};
+            return q_set(3, 14, P, W, pts, w);
+        }
+        return -1;
+    }
+    return -1;
+}
+
+/* ------------------------------------------------------------------ meshes -------------- */
+static const int nvfaceTet[4][3] = {{3, 2, 1}, {0, 2, 3}, {3, 1, 0}, {0, 1, 2}};
+static const int nvedgeTet[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+static const int nvedgeTri[3][2] = {{1, 2}, {2, 0}, {0, 1}};
+
+/* the kind=6 split of BuildCube (the hex_decoupe row whose 6 boundary diagonals all have code 0):
+ * all six tets share the diagonal 0-7 of the cell; local corner id = a + 2b + 4c. */
+static const int cubeTets[6][4] = {{4, 0, 6, 7}, {0, 4, 5, 7}, {1, 0, 5, 7}, {0, 1, 3, 7}, {2, 0, 3, 7}, {0, 2, 6, 7}};
+
+void ffo_cube_sizes(int nx, int ny, int nz, int *nv, int *nt, int *nbe)
+{
+    *nv = (nx + 1) * (ny + 1) * (nz + 1);
+    *nt = 6 * nx * ny * nz;
+    *nbe = 4 * (nx * ny + nx * nz + ny * nz);
+}
+
+void ffo_cube(int nx, int ny, int nz, double *xyz, int32_t *conn, int32_t *elab,
+              int32_t *bconn, int32_t *blab, int32_t *belem, int32_t *bface)
+{
+    const int nj = nx + 1, nk = nj * (ny + 1);
+    const double xd = 1. / nx, yd = 1. / ny, zd = 1. / nz;
+    const int nff[6] = {3, 1, 0, 2, 4, 5}; /* plane bit -> label index; labels are 1..6 */
+    int nv = (nx + 1) * (ny + 1) * (nz + 1);
+    int *vlab = (int *)malloc(sizeof(int) * (size_t)nv);
+    int p = 0;
+    for (int k = 0; k <= nz; ++k)
+        for (int j = 0; j <= ny; ++j)
+            for (int i = 0; i <= nx; ++i, ++p) {
+                xyz[3 * p + 0] = 0 + xd * i;
+                xyz[3 * p + 1] = 0 + yd * j;
+                xyz[3 * p + 2] = 0 + zd * k;
+                vlab[p] = 1 * (i == 0) + 2 * (i == nx) + 4 * (j == 0) + 8 * (j == ny) + 16 * (k == 0) + 32 * (k == nz);
+            }
+    int t = 0, kf = 0;
+    for (int k = 0; k < nz; ++k)
+        for (int j = 0; j < ny; ++j)
+            for (int i = 0; i < nx; ++i) {
+                int n[8];
+                for (int c = 0; c < 2; ++c)
+                    for (int b = 0; b < 2; ++b)
+                        for (int a = 0; a < 2; ++a) n[a + 2 * b + 4 * c] = (i + a) + nj * (j + b) + nk * (k + c);
+                for (int d = 0; d < 6; ++d, ++t) {
+                    int nu[4];
+                    for (int q = 0; q < 4; ++q) nu[q] = conn[4 * t + q] = n[cubeTets[d][q]];
+                    elab[t] = 0;
+                    for (int f = 0; f < 4; ++f) {
+                        int nf[3] = {nu[nvfaceTet[f][0]], nu[nvfaceTet[f][1]], nu[nvfaceTet[f][2]]};
+                        int l = vlab[nf[0]] & vlab[nf[1]] & vlab[nf[2]];
+                        for (int kk = 0; kk < 6; ++kk)
+                            if (l == (1 << kk)) {
+                                if (bconn) {
+                                    bconn[3 * kf + 0] = nf[0];
+                                    bconn[3 * kf + 1] = nf[1];
+                                    bconn[3 * kf + 2] = nf[2];
+                                    blab[kf] = nff[kk] + 1;
+                                    belem[kf] = t;
+                                    bface[kf] = f;
+                                }
+                                kf++;
+                            }
+                    }
+                }
+            }
+    free(vlab);
+}
+
+void ffo_square_sizes(int nx, int ny, int *nv, int *nt, int *nbe)
+{
+    *nv = (nx + 1) * (ny + 1);
+    *nt = 2 * nx * ny;
+    *nbe = 2 * (nx + ny);
+}
+
+void ffo_square(int nx, int ny, double *xy, int32_t *conn, int32_t *elab,
+                int32_t *bconn, int32_t *blab, int32_t *belem, int32_t *bface)
+{
+    const int nx1 = nx + 1, ny1 = ny + 1;
+    int p = 0;
+    for (int j = 0; j < ny1; ++j)
+        for (int i = 0; i < nx1; ++i, ++p) {
+            xy[2 * p + 0] = (double)i / nx;
+            xy[2 * p + 1] = (double)j / ny;
+        }
+    int t = 0;
+    for (int j = 0; j < ny; ++j)
+        for (int i = 0; i < nx; ++i) { /* flags=0: diagonal i0-i2, direct orientation */
+            int i0 = i + j * nx1, i1 = i0 + 1, i2 = i1 + nx1, i3 = i2 - 1;
+            conn[3 * t + 0] = i0; conn[3 * t + 1] = i1; conn[3 * t + 2] = i2; elab[t++] = 0;
+            conn[3 * t + 0] = i0; conn[3 * t + 1] = i2; conn[3 * t + 2] = i3; elab[t++] = 0;
+        }
+    if (!bconn) return;
+    int e = 0;
+    for (int i = 0; i < nx; ++i, ++e) { /* bottom, label 1 */
+        bconn[2 * e] = i; bconn[2 * e + 1] = i + 1; blab[e] = 1;
+        belem[e] = 2 * i; bface[e] = 2;
+    }
+    for (int j = 0; j < ny; ++j, ++e) { /* right, label 2 */
+        int i1 = nx + j * nx1;
+        bconn[2 * e] = i1; bconn[2 * e + 1] = i1 + nx1; blab[e] = 2;
+        belem[e] = 2 * ((nx - 1) + j * nx); bface[e] = 0;
+    }
+    for (int i = 0; i < nx; ++i, ++e) { /* top, label 3 */
+        int i1 = i + ny * nx1;
+        bconn[2 * e] = i1; bconn[2 * e + 1] = i1 + 1; blab[e] = 3;
+        belem[e] = 2 * (i + (ny - 1) * nx) + 1; bface[e] = 0;
+    }
+    for (int j = 0; j < ny; ++j, ++e) { /* left, label 4 */
+        int i1 = j * nx1;
+        bconn[2 * e] = i1; bconn[2 * e + 1] = i1 + nx1; blab[e] = 4;
+        belem[e] = 2 * (j * nx) + 1; bface[e] = 1;
+    }
+}
+
+/* ------------------------------------------------------------------ dof numbering ------- */
+int ffo_nloc(int dim, int order)
+{
+    if (order == 1) return dim + 1;
+    return dim == 2 ? 6 : 10;
+}
+
+typedef struct { uint64_t key; int32_t val; } hent;
+
+static uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+
+/* insert-or-find; returns pointer to the slot value, *isnew set */
+static int32_t *hfind(hent *tab, uint64_t mask, uint64_t key, int *isnew)
+{
+    uint64_t h = mix64(key) & mask;
+    for (;;) {
+        if (tab[h].key == key) { *isnew = 0; return &tab[h].val; }
+        if (tab[h].key == UINT64_MAX) { tab[h].key = key; *isnew = 1; return &tab[h].val; }
+        h = (h + 1) & mask;
+    }
+}
+
+static hent *hnew(uint64_t want, uint64_t *mask)
+{
+    uint64_t sz = 16;
+    while (sz < 2 * want) sz <<= 1;
+    hent *t = (hent *)malloc(sizeof(hent) * sz);
+    for (uint64_t i = 0; i < sz; ++i) t[i].key = UINT64_MAX;
+    *mask = sz - 1;
+    return t;
+}
+
+int ffo_p2_nodes_3d(int nv, int nt, const int32_t *conn, int32_t *elem2node)
+{
+    /* keys: vertex (v,inf) and edge (min,max) in one table; numbered at first encounter walking
+     * elements in order, 4 vertices then the 6 edges {01,02,03,12,13,23} (GenericMesh.hpp:1878-1929). */
+    uint64_t mask;
+    hent *tab = hnew((uint64_t)nt * 3 + (uint64_t)nv + 16, &mask);
+    int nn = 0;
+    for (int k = 0; k < nt; ++k) {
+        const int32_t *K = conn + 4 * (size_t)k;
+        for (int a = 0; a < 10; ++a) {
+            uint64_t key;
+            if (a < 4) key = ((uint64_t)(uint32_t)K[a] << 32) | 0xffffffffu;
+            else {
+                uint32_t v0 = (uint32_t)K[nvedgeTet[a - 4][0]], v1 = (uint32_t)K[nvedgeTet[a - 4][1]];
+                if (v0 > v1) { uint32_t s = v0; v0 = v1; v1 = s; }
+                key = ((uint64_t)v0 << 32) | v1;
+            }
+            int isnew;
+            int32_t *pv = hfind(tab, mask, key, &isnew);
+            if (isnew) *pv = nn++;
+            elem2node[10 * (size_t)k + a] = *pv;
+        }
+    }
+    free(tab);
+    return nn;
+}
+
+/* ------------------------------------------------------------------ geometry + basis ---- */
+/* R3.hpp:90-104 — determinant by Gaussian elimination with partial pivoting on x */
+static double det3(const double *a, const double *b, const double *c)
+{
+    double A[3] = {a[0], a[1], a[2]}, B[3] = {b[0], b[1], b[2]}, C[3] = {c[0], c[1], c[2]}, T[3];
+    double s = 1.;
+    if (fabs(A[0]) < fabs(B[0])) { memcpy(T, A, 24); memcpy(A, B, 24); memcpy(B, T, 24); s = -s; }
+    if (fabs(A[0]) < fabs(C[0])) { memcpy(T, A, 24); memcpy(A, C, 24); memcpy(C, T, 24); s = -s; }
+    if (fabs(A[0]) > 1e-50) {
+        s *= A[0];
+        A[1] /= A[0]; A[2] /= A[0];
+        B[1] -= A[1] * B[0]; B[2] -= A[2] * B[0];
+        C[1] -= A[1] * C[0]; C[2] -= A[2] * C[0];
+        return s * (B[1] * C[2] - B[2] * C[1]);
+    }
+    return 0.;
+}
+
+static void cross3(const double *x, const double *p, double *r)
+{ /* R3::operator^ */
+    r[0] = x[1] * p[2] - x[2] * p[1];
+    r[1] = p[0] * x[2] - x[0] * p[2];
+    r[2] = x[0] * p[1] - x[1] * p[0];
+}
+
+/* element geometry: measure and grad(lambda_i). X: (dim+1) x dim vertex coords. */
+static double geom(int dim, const double *X, double (*G)[3])
+{
+    if (dim == 3) {
+        double V1[3], V2[3], V3[3], c[3];
+        for (int d = 0; d < 3; ++d) { V1[d] = X[3 + d] - X[d]; V2[d] = X[6 + d] - X[d]; V3[d] = X[9 + d] - X[d]; }
+        double mes = det3(V1, V2, V3) / 6.;
+        double det1 = 1. / (6. * mes);
+        cross3(V2, V3, c); for (int d = 0; d < 3; ++d) G[1][d] = c[d] * det1;
+        cross3(V3, V1, c); for (int d = 0; d < 3; ++d) G[2][d] = c[d] * det1;
+        cross3(V1, V2, c); for (int d = 0; d < 3; ++d) G[3][d] = c[d] * det1;
+        for (int d = 0; d < 3; ++d) G[0][d] = -G[1][d] - G[2][d] - G[3][d];
+        return mes;
+    }
+    /* triangle: area = ((B-A)^(C-A))*0.5 ; H(i) = (-E.y, E.x)/(2 area), E = v[(i+2)%3]-v[(i+1)%3] */
+    double bx = X[2] - X[0], by = X[3] - X[1], cx = X[4] - X[0], cy = X[5] - X[1];
+    double area = (bx * cy - by * cx) * 0.5;
+    for (int i = 0; i < 3; ++i) {
+        int i1 = (i + 1) % 3, i2 = (i + 2) % 3;
+        double ex = X[2 * i2] - X[2 * i1], ey = X[2 * i2 + 1] - X[2 * i1 + 1];
+        G[i][0] = -ey / (2 * area);
+        G[i][1] = ex / (2 * area);
+        G[i][2] = 0;
+    }
+    return area;
+}
+
+/* basis values at reference point P: val[a][s], s=0 value, s=1..dim gradient (FB of P1/P2) */
+static void basis(int dim, int order, const double *P, double (*G)[3], double (*val)[4])
+{
+    double l[4];
+    if (dim == 3) { l[0] = 1. - (P[0] + P[1] + P[2]); l[1] = P[0]; l[2] = P[1]; l[3] = P[2]; }
+    else { l[0] = 1 - P[0] - P[1]; l[1] = P[0]; l[2] = P[1]; l[3] = 0; }
+    const int nv = dim + 1;
+    if (order == 1) {
+        for (int a = 0; a < nv; ++a) {
+            val[a][0] = l[a];
+            for (int d = 0; d < dim; ++d) val[a][1 + d] = G[a][d];
+        }
+        return;
+    }
+    double l4[4];
+    for (int a = 0; a < nv; ++a) l4[a] = 4 * l[a] - 1;
+    for (int a = 0; a < nv; ++a) {
+        val[a][0] = l[a] * (2 * l[a] - 1.);
+        for (int d = 0; d < dim; ++d) val[a][1 + d] = G[a][d] * l4[a];
+    }
+    if (dim == 3) {
+        for (int e = 0; e < 6; ++e) {
+            int i0 = nvedgeTet[e][0], i1 = nvedgeTet[e][1];
+            val[4 + e][0] = 4. * l[i0] * l[i1];
+            for (int d = 0; d < 3; ++d) val[4 + e][1 + d] = 4 * (G[i1][d] * l[i0] + G[i0][d] * l[i1]);
+        }
+    } else {
+        /* FESpace.cpp:1219-1262: dof 3+e sits on the edge opposite vertex e */
+        val[3][0] = 4 * l[1] * l[2]; val[4][0] = 4 * l[0] * l[2]; val[5][0] = 4 * l[1] * l[0];
+        for (int d = 0; d < 2; ++d) {
+            val[3][1 + d] = 4 * (G[1][d] * l[2] + G[2][d] * l[1]);
+            val[4][1 + d] = 4 * (G[2][d] * l[0] + G[0][d] * l[2]);
+            val[5][1 + d] = 4 * (G[0][d] * l[1] + G[1][d] * l[0]);
+        }
+    }
+}
+
+static int opslot(int op)
+{ /* id,dx,dy,dz -> 0..3 */
+    switch (op) { case FFO_OP_ID: return 0; case FFO_OP_DX: return 1; case FFO_OP_DY: return 2; case FFO_OP_DZ: return 3; }
+    return -1;
+}
+
+static int in_labels(int lab, int nlab, const int32_t *labels)
+{
+    if (!labels) return 1;
+    for (int i = 0; i < nlab; ++i) if (labels[i] == lab) return 1;
+    return 0;
+}
+
+static void elem_coords(int dim, const double *xyz, const int32_t *K, double *X)
+{
+    for (int a = 0; a <= dim; ++a)
+        for (int d = 0; d < dim; ++d) X[a * dim + d] = xyz[(size_t)K[a] * dim + d];
+}
+
+/* ------------------------------------------------------------------ bilinear form ------- */
+int64_t ffo_assemble_coo(int dim, int nv, const double *xyz, int nt, const int32_t *conn, const int32_t *elab,
+                         int order, int ncomp, const int32_t *elem2node,
+                         int nterms, const ffo_bterm *terms, int nq, const double *qpts, const double *qw,
+                         int nlab, const int32_t *labels,
+                         int32_t *coo_i, int32_t *coo_j, double *coo_a)
+{
+    (void)nv;
+    const int nloc = ffo_nloc(dim, order), nd = nloc * ncomp;
+    const int nvk = dim + 1;
+    uint64_t mask;
+    hent *tab = hnew((uint64_t)nt * (uint64_t)(nd < 8 ? nd * 4 : nd * 8) + 64, &mask);
+    double *mat = (double *)malloc(sizeof(double) * (size_t)nd * nd);
+    int32_t *gd = (int32_t *)malloc(sizeof(int32_t) * (size_t)nd);
+    int64_t nnz = 0;
+    for (int k = 0; k < nt; ++k) {
+        if (!in_labels(elab ? elab[k] : 0, nlab, labels)) continue;
+        const int32_t *K = conn + (size_t)nvk * k;
+        const int32_t *N = elem2node ? elem2node + (size_t)nloc * k : K;
+        double X[12], G[4][3], val[10][4];
+        elem_coords(dim, xyz, K, X);
+        double mes = geom(dim, X, G);
+        for (int i = 0; i < nd * nd; ++i) mat[i] = 0.;
+        /* Element_Op: quadrature point outermost, then terms, then (i,j) */
+        for (int q = 0; q < nq; ++q) {
+            double coef = mes * qw[q];
+            basis(dim, order, qpts + (size_t)q * dim, G, val);
+            for (int t = 0; t < nterms; ++t) {
+                int so = opslot(terms[t].uop), to = opslot(terms[t].vop);
+                double ccc = terms[t].coef;
+                ccc *= coef;
+                int fi = terms[t].vcomp * nloc, fj = terms[t].ucomp * nloc;
+                for (int a = 0; a < nloc; ++a)
+                    for (int b = 0; b < nloc; ++b) {
+                        double w_i = val[a][to], w_j = val[b][so];
+                        mat[(fi + a) * nd + fj + b] += ccc * w_i * w_j;
+                    }
+            }
+        }
+        for (int c = 0; c < ncomp; ++c)
+            for (int a = 0; a < nloc; ++a) gd[c * nloc + a] = N[a] * ncomp + c;
+        /* HashMatrix::operator+=: every (il,jl) couple creates/accumulates an entry */
+        for (int il = 0; il < nd; ++il)
+            for (int jl = 0; jl < nd; ++jl) {
+                uint64_t key = ((uint64_t)(uint32_t)gd[il] << 32) | (uint32_t)gd[jl];
+                int isnew;
+                int32_t *pv = hfind(tab, mask, key, &isnew);
+                if (isnew) {
+                    *pv = (int32_t)nnz;
+                    coo_i[nnz] = gd[il]; coo_j[nnz] = gd[jl]; coo_a[nnz] = 0.;
+                    nnz++;
+                }
+                coo_a[*pv] += mat[il * nd + jl];
+            }
+    }
+    free(tab); free(mat); free(gd);
+    return nnz;
+}
+
+typedef struct { int32_t i, j; int64_t k; } ijk;
+static int cmp_ij(const void *a, const void *b)
+{
+    const ijk *x = (const ijk *)a, *y = (const ijk *)b;
+    if (x->i != y->i) return x->i < y->i ? -1 : 1;
+    if (x->j != y->j) return x->j < y->j ? -1 : 1;
+    return 0;
+}
+
+void ffo_coo_to_csr(int n, int64_t nnz, const int32_t *coo_i, const int32_t *coo_j, const double *coo_a,
+                    int32_t *rowptr, int32_t *colind, double *vals)
+{
+    ijk *s = (ijk *)malloc(sizeof(ijk) * (size_t)(nnz ? nnz : 1));
+    for (int64_t k = 0; k < nnz; ++k) { s[k].i = coo_i[k]; s[k].j = coo_j[k]; s[k].k = k; }
+    qsort(s, (size_t)nnz, sizeof(ijk), cmp_ij);
+    for (int i = 0; i <= n; ++i) rowptr[i] = 0;
+    for (int64_t k = 0; k < nnz; ++k) {
+        rowptr[s[k].i + 1]++;
+        colind[k] = s[k].j;
+        if (vals) vals[k] = coo_a[s[k].k];
+    }
+    for (int i = 0; i < n; ++i) rowptr[i + 1] += rowptr[i];
+    free(s);
+}
+
+/* ------------------------------------------------------------------ linear form --------- */
+void ffo_assemble_rhs(int dim, int nv, const double *xyz, int nt, const int32_t *conn, const int32_t *elab,
+                      int order, int ncomp, const int32_t *elem2node, int ndof,
+                      int nterms, const ffo_lterm *terms, int nq, const double *qpts, const double *qw,
+                      int nlab, const int32_t *labels, double *b)
+{
+    (void)nv;
+    const int nloc = ffo_nloc(dim, order), nvk = dim + 1;
+    for (int i = 0; i < ndof; ++i) b[i] = 0.;
+    for (int k = 0; k < nt; ++k) {
+        if (!in_labels(elab ? elab[k] : 0, nlab, labels)) continue;
+        const int32_t *K = conn + (size_t)nvk * k;
+        const int32_t *N = elem2node ? elem2node + (size_t)nloc * k : K;
+        double X[12], G[4][3], val[10][4];
+        elem_coords(dim, xyz, K, X);
+        double mes = geom(dim, X, G);
+        for (int q = 0; q < nq; ++q) {
+            double coef = mes * qw[q];
+            basis(dim, order, qpts + (size_t)q * dim, G, val);
+            for (int c = 0; c < ncomp; ++c)
+                for (int a = 0; a < nloc; ++a)
+                    for (int t = 0; t < nterms; ++t) {
+                        /* fu(i,comp,op) vanishes unless comp is the component of local dof i */
+                        double w_i = (terms[t].vcomp == c) ? val[a][opslot(terms[t].vop)] : 0.;
+                        double av = coef * terms[t].coef * w_i;
+                        b[N[a] * ncomp + c] += av;
+                    }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ Dirichlet ----------- */
+int ffo_bc_pairs(int dim, int nt, const int32_t *conn, int order, int ncomp, const int32_t *elem2node,
+                 int nbe, const int32_t *blab, const int32_t *belem, const int32_t *bface,
+                 int nlab, const int32_t *labels, int compmask, const double *values,
+                 int32_t *out_dof, double *out_val)
+{
+    (void)nt;
+    const int nloc = ffo_nloc(dim, order), nvk = dim + 1;
+    int n = 0;
+    for (int ib = 0; ib < nbe; ++ib) {
+        if (!in_labels(blab[ib], nlab, labels)) continue;
+        int it = belem[ib], ie = bface[ib];
+        const int32_t *N = elem2node ? elem2node + (size_t)nloc * it : conn + (size_t)nvk * it;
+        for (int c = 0; c < ncomp; ++c) {
+            if (!(compmask >> c & 1)) continue;
+            for (int a = 0; a < nloc; ++a) {
+                int on;
+                if (a < nvk) on = (a != ie); /* face ie is opposite vertex ie */
+                else if (dim == 2) on = (a - 3 == ie);
+                else on = (nvedgeTet[a - 4][0] != ie && nvedgeTet[a - 4][1] != ie);
+                if (!on) continue;
+                out_dof[n] = N[a] * ncomp + c;
+                out_val[n] = values ? values[c] : 0.;
+                n++;
+            }
+        }
+    }
+    (void)nvedgeTri;
+    return n;
+}
+
+void ffo_bc_matrix_coo(int64_t nnz, const int32_t *coo_i, const int32_t *coo_j, double *coo_a,
+                       int n, int nbc, const int32_t *dofs, double tgv)
+{
+    char *on = (char *)calloc((size_t)n, 1);
+    for (int k = 0; k < nbc; ++k) on[dofs[k]] = 1;
+    for (int64_t k = 0; k < nnz; ++k)
+        if (coo_i[k] == coo_j[k] && on[coo_i[k]]) coo_a[k] = tgv;
+    free(on);
+}
+
+void ffo_bc_rhs(double *b, int nbc, const int32_t *dofs, const double *vals, double tgv)
+{
+    for (int k = 0; k < nbc; ++k) b[dofs[k]] = tgv * vals[k];
+}
+
+/* ------------------------------------------------------------------ SpMV + CG ----------- */
+void ffo_spmv_coo(int n, int64_t nnz, const int32_t *ai, const int32_t *aj, const double *aa,
+                  const double *x, double *y)
+{
+    for (int i = 0; i < n; ++i) y[i] = 0.; /* CGMatVirt::matmul zeroes, then addMatMul */
+    for (int64_t k = 0; k < nnz; ++k) y[ai[k]] += aa[k] * x[aj[k]];
+}
+
+static double dotp(int n, const double *x, const double *y)
+{
+    double s = 0;
+    for (int i = 0; i < n; ++i) s += x[i] * y[i];
+    return s;
+}
+
+int ffo_cg(int n, int64_t nnz, const int32_t *ai, const int32_t *aj, const double *aa,
+           const double *b, double *x, double eps, int itmax, double tgv, int *iters, double *gcg_out)
+{
+    double *diag = (double *)calloc((size_t)n, sizeof(double));
+    char *has = (char *)calloc((size_t)n, 1);
+    for (int64_t k = 0; k < nnz; ++k)
+        if (ai[k] == aj[k]) { diag[ai[k]] = aa[k]; has[ai[k]] = 1; }
+    /* gettgv (HashMatrix.cpp:1341-1371), ratio 1e6 */
+    double ttgv = 0, max1 = 0; int ntgv = 0;
+    for (int i = 0; i < n; ++i)
+        if (has[i]) {
+            double a = diag[i];
+            if (a > ttgv) { max1 = ttgv; ttgv = a; ntgv = 1; }
+            else if (a == ttgv) ++ntgv;
+            else if (a > max1) max1 = a;
+        }
+    if (max1 * 1e6 > ttgv) { ttgv = 0; ntgv = 0; }
+    /* HMatVirtPrecon ctor: wcl, diag1 */
+    double *d1 = (double *)malloc(sizeof(double) * (size_t)n);
+    for (int i = 0; i < n; ++i) d1[i] = (diag[i] * diag[i] < 1e-60) ? 1. : 1. / diag[i];
+    if (ntgv) { /* SetInitWithBC */
+        double tgve = ttgv <= 0 ? 1e200 : ttgv;
+        for (int i = 0; i < n; ++i)
+            if (diag[i] == tgve) x[i] = b[i] / tgv;
+    }
+    if (itmax <= 0) itmax = n;
+    /* ConjugueGradient (CG.cpp:195-265); AH aliases CG */
+    double *G = (double *)malloc(sizeof(double) * (size_t)n);
+    double *CG = (double *)malloc(sizeof(double) * (size_t)n);
+    double *H = (double *)malloc(sizeof(double) * (size_t)n);
+    double *AH = CG;
+    double eps2 = eps * eps, gCg, gCgp, rho, gamma;
+    int ret = 0, it = 0;
+    ffo_spmv_coo(n, nnz, ai, aj, aa, x, G);
+    for (int i = 0; i < n; ++i) G[i] += -1. * b[i];
+    for (int i = 0; i < n; ++i) { CG[i] = 0.; CG[i] += d1[i] * G[i]; }
+    gCg = dotp(n, G, CG);
+    for (int i = 0; i < n; ++i) H[i] = CG[i];
+    for (int i = 0; i < n; ++i) H[i] *= -1.;
+    if (eps > 0) eps2 *= gCg;
+    if (gCg < 1e-30) { ret = 2; it = 0; }
+    else
+        for (int iter = 1; iter <= itmax; ++iter) {
+            gCgp = gCg;
+            double gh = dotp(n, G, H);
+            ffo_spmv_coo(n, nnz, ai, aj, aa, H, AH);
+            rho = -gh / dotp(n, H, AH);
+            for (int i = 0; i < n; ++i) x[i] += rho * H[i];
+            for (int i = 0; i < n; ++i) G[i] += rho * AH[i];
+            for (int i = 0; i < n; ++i) { CG[i] = 0.; CG[i] += d1[i] * G[i]; }
+            gCg = dotp(n, G, CG);
+            gamma = gCg / gCgp;
+            for (int i = 0; i < n; ++i) H[i] *= gamma;
+            for (int i = 0; i < n; ++i) H[i] += -1. * CG[i];
+            it = iter;
+            if (gCg < eps2) { ret = 1; break; }
+        }
+    if (iters) *iters = it;
+    if (gcg_out) *gcg_out = gCg;
+    free(G); free(CG); free(H); free(d1); free(diag); free(has);
+    return ret;
+}

@@ -1,0 +1,103 @@
+/* fforacle.h — CPU ORACLE for the ffcuda hot path.  TEST INFRASTRUCTURE ONLY.
+ *
+ * A plain-C restatement of FreeFEM 4.15's algorithm for
+ *   varf -> element loop -> MatriceMorse (COO/CSR) + right-hand side -> Jacobi-CG
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+ * legs may load this library, and only as the checker.  The product (libffcuda_core.so,
+ * ffcuda.so) never links or calls it.
+ *
+ * Parity status: PINNED — tests/test_oracle_golden.py checks every function here against
+ * the fixtures in tests/golden/ (npz files), which were dumped from the unmodified reference
+ * built by `make -C oracle ref` (tests/golden/make_golden.py).
+ *
+ * Reference files restated (paths under /root/reference/src):
+ *   fflib/msh3.cpp:7683-7742,7879-8132      BuildCube        -> ffo_cube
+ *   fflib/lgmesh.cpp:1229-1384              Carre_           -> ffo_square
+ *   femlib/GenericMesh.hpp:1711-1954        BuildDFNumbering -> ffo_p2_nodes_3d
+ *   femlib/QuadratureFormular.cpp           rule tables      -> ffo_quadrature
+ *   femlib/Mesh3dn.hpp:65-71,126-136, R3.hpp:90-104, fem.hpp:277,321-324   geometry
+ *   femlib/P012_3d.cpp:123-300, FESpace.cpp:1100-1136,1219-1262            P1/P2 basis
+ *   fflib/problem.cpp:6063-6160,6337-6437   Element_Op       -> ffo_assemble_coo
+ *   femlib/HashMatrix.cpp:1295-1332,671-682,993-1030   += / Sortij / Buildp -> COO order, CSR
+ *   fflib/problem.cpp:7839-7985             Element_rhs      -> ffo_assemble_rhs
+ *   fflib/problem.cpp:9881-10194, HashMatrix.cpp:1195-1238   AssembleBC/SetBC -> ffo_bc_*
+ *   femlib/VirtualSolverCG.hpp:13-192, CG.cpp:195-265, HashMatrix.cpp:1087-1154,1341-1371
+ *                                            SolverCG         -> ffo_cg
+ */
+#ifndef FFORACLE_H
+#define FFORACLE_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* operator codes = FreeFEM's (femlib/FESpacen.hpp:73-82) */
+enum { FFO_OP_ID = 0, FFO_OP_DX = 1, FFO_OP_DY = 2, FFO_OP_DZ = 6 };
+
+typedef struct { int32_t ucomp, uop, vcomp, vop; double coef; } ffo_bterm; /* unknown=column, test=row */
+typedef struct { int32_t vcomp, vop; double coef; } ffo_lterm;
+
+/* quadrature rules by FreeFEM name: 2-D "qf1pT" "qf1pTlump" "qf2pT" "qf5pT"(default);
+ * 3-D "qfV1" "qfV1lump" "qfV2" "qfV5"(default).  pts: npts*dim reference coords. Returns npts (<=16) or -1. */
+int ffo_quadrature(int dim, const char *name, double *pts, double *w);
+
+/* meshes.  belem/bface = Th.BoundaryElement(ib, ie). */
+void ffo_cube_sizes(int nx, int ny, int nz, int *nv, int *nt, int *nbe);
+void ffo_cube(int nx, int ny, int nz, double *xyz, int32_t *conn, int32_t *elab,
+              int32_t *bconn, int32_t *blab, int32_t *belem, int32_t *bface);
+void ffo_square_sizes(int nx, int ny, int *nv, int *nt, int *nbe);
+void ffo_square(int nx, int ny, double *xy, int32_t *conn, int32_t *elab,
+                int32_t *bconn, int32_t *blab, int32_t *belem, int32_t *bface);
+
+/* 3-D P2 node numbering (vertices and edges in first-encounter order). elem2node: nt*10. Returns nnodes. */
+int ffo_p2_nodes_3d(int nv, int nt, const int32_t *conn, int32_t *elem2node);
+
+/* number of nodes per element for (dim, order) */
+int ffo_nloc(int dim, int order);
+
+/* Bilinear form -> COO in HashMatrix insertion order (duplicates merged).  elem2node may be NULL for P1.
+ * dof(node,c) = node*ncomp + c ; local dof i = c*nloc + a.  labels==NULL: all regions.
+ * coo arrays must hold nt*(nloc*ncomp)^2 entries (upper bound).  Returns nnz. */
+int64_t ffo_assemble_coo(int dim, int nv, const double *xyz, int nt, const int32_t *conn, const int32_t *elab,
+                         int order, int ncomp, const int32_t *elem2node,
+                         int nterms, const ffo_bterm *terms, int nq, const double *qpts, const double *qw,
+                         int nlab, const int32_t *labels,
+                         int32_t *coo_i, int32_t *coo_j, double *coo_a);
+
+/* COO -> CSR sorted by (i,j) (Sortij/Buildp). */
+void ffo_coo_to_csr(int n, int64_t nnz, const int32_t *coo_i, const int32_t *coo_j, const double *coo_a,
+                    int32_t *rowptr, int32_t *colind, double *vals);
+
+/* Linear form: b zeroed then filled (OpArraytoLinearForm + Element_rhs). */
+void ffo_assemble_rhs(int dim, int nv, const double *xyz, int nt, const int32_t *conn, const int32_t *elab,
+                      int order, int ncomp, const int32_t *elem2node, int ndof,
+                      int nterms, const ffo_lterm *terms, int nq, const double *qpts, const double *qw,
+                      int nlab, const int32_t *labels, double *b);
+
+/* Dirichlet dofs as AssembleBC visits them: for each boundary element (in order) whose label is in
+ * labels[], for each component c with compmask bit c set, each dof lying on that face -> (dof, value[c]).
+ * Later pairs overwrite earlier ones.  out arrays sized nbe*ncomp*nlocface at most.  Returns count. */
+int ffo_bc_pairs(int dim, int nt, const int32_t *conn, int order, int ncomp, const int32_t *elem2node,
+                 int nbe, const int32_t *blab, const int32_t *belem, const int32_t *bface,
+                 int nlab, const int32_t *labels, int compmask, const double *values,
+                 int32_t *out_dof, double *out_val);
+
+/* matrix: diag(dof) = tgv (overwrite) on COO or CSR values (diag must exist). rhs: b[dof] = tgv*val. */
+void ffo_bc_matrix_coo(int64_t nnz, const int32_t *coo_i, const int32_t *coo_j, double *coo_a,
+                       int n, int nbc, const int32_t *dofs, double tgv);
+void ffo_bc_rhs(double *b, int nbc, const int32_t *dofs, const double *vals, double tgv);
+
+/* y = A x over entries in the order given (HashMatrix::addMatMul on COO storage order). */
+void ffo_spmv_coo(int n, int64_t nnz, const int32_t *ai, const int32_t *aj, const double *aa,
+                  const double *x, double *y);
+
+/* SolverCG::dosolver: Jacobi preconditioner, tgv rows via gettgv, SetInitWithBC, ConjugueGradient.
+ * x holds the initial guess on entry.  itmax<=0 -> n.  Returns ConjugueGradient's code
+ * (1 converged, 2 converged at start, 0 not converged); *iters = iterations done. */
+int ffo_cg(int n, int64_t nnz, const int32_t *ai, const int32_t *aj, const double *aa,
+           const double *b, double *x, double eps, int itmax, double tgv, int *iters, double *gcg_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,87 @@
+"""Case table shared by the oracle tests and the GPU parity tests: for every golden fixture, the
+variational form exactly as FreeFEM stores it (term lists after LinearComb merging),
+the quadrature rule the script selects, and the boundary conditions of the .edp that produced it
+(tests/golden/make_golden.py)."""
+import os
+import numpy as np
+
+ID, DX, DY, DZ = 0, 1, 2, 6
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+LAP2 = [(0, DX, 0, DX, 1.0), (0, DY, 0, DY, 1.0)]
+LAP3 = [(0, DX, 0, DX, 1.0), (0, DY, 0, DY, 1.0), (0, DZ, 0, DZ, 1.0)]
+
+_E, _SIG = 21.5e4, 0.29
+MU = _E / (2 * (1 + _SIG))
+LAMBDA = _E * _SIG / ((1 + _SIG) * (1 - 2 * _SIG))
+
+
+def lame_terms():
+    """21 terms (ucomp,uop,vcomp,vop,coef) in the order FreeFEM holds them."""
+    d = [DX, DY, DZ]
+    order = [((0, 1), (0, 1)), ((0, 1), (1, 2)), ((0, 1), (2, 6)), ((1, 2), (0, 1)), ((1, 2), (1, 2)), ((1, 2), (2, 6)),
+             ((2, 6), (0, 1)), ((2, 6), (1, 2)), ((2, 6), (2, 6)), ((1, 6), (1, 6)), ((1, 6), (2, 2)), ((2, 2), (1, 6)),
+             ((2, 2), (2, 2)), ((0, 6), (0, 6)), ((0, 6), (2, 1)), ((2, 1), (0, 6)), ((2, 1), (2, 1)), ((0, 2), (0, 2)),
+             ((0, 2), (1, 1)), ((1, 1), (0, 2)), ((1, 1), (1, 1))]
+    out = []
+    for (uc, uo), (vc, vo) in order:
+        if uo == d[uc] and vo == d[vc]:  # div-div (+ diagonal of 2 mu eps:eps)
+            c = LAMBDA + 2.0 * MU if uc == vc else LAMBDA
+        else:
+            c = MU
+        out.append((uc, uo, vc, vo, c))
+    return out
+
+
+# name -> (order, ncomp, bilinear terms, linear terms, quadrature name, [ (labels, compmask, values) ... ])
+ALL6 = [1, 2, 3, 4, 5, 6]
+CASES = {
+    "lap2d_p1_sq4": (1, 1, LAP2, [(0, ID, 1.0)], "qf5pT", [([1, 2, 3, 4], 1, [0.0])]),
+    "lap2d_p1_sq12x9": (1, 1, LAP2, [(0, ID, 1.0)], "qf5pT", [([1, 2, 3, 4], 1, [0.0])]),
+    "lap2d_p1_warp": (1, 1, LAP2, [(0, ID, 3.0)], "qf5pT", [([1], 1, [1.0]), ([3], 1, [2.0])]),
+    "lap2d_p2_sq3": (2, 1, LAP2, [(0, ID, 1.0)], "qf5pT", [([1, 2, 3, 4], 1, [0.0])]),
+    "lap2d_p2_warp": (2, 1, LAP2 + [(0, ID, 0, ID, 2.0)], [(0, ID, 1.0)], "qf5pT", [([2, 4], 1, [0.0])]),
+    "lap3d_p1_cube2": (1, 1, LAP3, [(0, ID, 1.0)], "qfV5", [(ALL6, 1, [0.0])]),
+    "lap3d_p1_cube5": (1, 1, LAP3, [(0, ID, 1.0)], "qfV5", [(ALL6, 1, [0.0])]),
+    "lap3d_p1_cube342": (1, 1, LAP3, [(0, ID, 1.0)], "qfV5", [(ALL6, 1, [0.0])]),
+    "lap3d_p1_warp": (1, 1, LAP3, [(0, ID, 2.0)], "qfV5", [([1], 1, [1.0]), ([6], 1, [-1.0])]),
+    "lap3d_p2_cube2": (2, 1, LAP3, [(0, ID, 1.0)], "qfV5", [(ALL6, 1, [0.0])]),
+    "heat3d_p1_cube3": (1, 1, [(0, ID, 0, ID, 1.0 / 0.01)] + LAP3, [(0, ID, 1.0)], "qfV5", [(ALL6, 1, [0.0])]),
+    "mass3d_p1_lump": (1, 1, [(0, ID, 0, ID, 1.0)], [(0, ID, 1.0)], "qfV1lump", []),
+    "mass2d_p2_qf2": (2, 1, [(0, ID, 0, ID, 1.0)], [(0, ID, 1.0)], "qf2pT", []),
+    "nonsym3d_p1": (1, 1, [(0, DX, 0, ID, 1.0), (0, ID, 0, DY, 2.0), (0, DZ, 0, DX, 0.5)],
+                    [(0, DX, 1.0), (0, ID, 2.0)], "qfV5", []),
+    "nonsym2d_p2": (2, 1, [(0, DX, 0, ID, 1.0), (0, ID, 0, DY, 2.0), (0, DY, 0, DX, 0.5)],
+                    [(0, DY, 1.0), (0, ID, 2.0)], "qf5pT", []),
+    "lame3d_p2_cube2": (2, 3, lame_terms(), [(2, ID, -0.05)], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
+    "lame3d_p1_cube3": (1, 3, lame_terms(), [(2, ID, -0.05)], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
+    "lame3d_p2_warp": (2, 3, lame_terms(), [(2, ID, -0.05)], "qfV5",
+                       [([1], 7, [0.0, 0.0, 0.0]), ([3], 7, [0.01, 0.0, -0.02])]),
+}
+
+
+def load(name):
+    g = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    g["dim"] = int(g["dim"])
+    g["ndof"] = int(g["ndof"])
+    return g
+
+
+def golden_csr(g):
+    """(rowptr, colind, vals) of the reference matrix = its COO sorted by (i,j) (HashMatrix::CSR())."""
+    n = g["ndof"]
+    key = g["coo_i"].astype(np.int64) * n + g["coo_j"]
+    o = np.argsort(key, kind="stable")
+    rp = np.zeros(n + 1, np.int32)
+    np.add.at(rp, g["coo_i"] + 1, 1)
+    return np.cumsum(rp).astype(np.int32), g["coo_j"][o].astype(np.int32), g["coo_a"][o]
+
+
+def elem2node(g, order, ncomp):
+    """node table (nt x nloc) recovered from the reference dof table: dof(k, c*nloc+a) = node*ncomp + c."""
+    dof = g["dof"]
+    nl = dof.shape[1] // ncomp
+    e2n = dof[:, :nl] // ncomp
+    for c in range(ncomp):
+        assert np.array_equal(dof[:, c * nl:(c + 1) * nl], e2n * ncomp + c)
+    return np.ascontiguousarray(e2n, dtype=np.int32)

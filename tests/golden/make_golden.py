@@ -95,6 +95,7 @@ def script(c, out):
     s.append(f'{{ ofstream f("{out}/dof.txt"); f << Vh.ndof << " " << Vh.ndofK << endl;')
     s.append('  for(int k=0;k<Th.nt;++k){ for(int i=0;i<Vh.ndofK;++i) f << Vh(k,i) << " "; f << endl; } }')
     # matrix as stored (COO, insertion order), rhs
+    s.append(f'{{ ofstream f("{out}/Ains.txt"); f.precision(17); f << A; }}  // HashMatrix storage (insertion) order')
     s.append("{ int[int] I(1),J(1); real[int] C(1); [I,J,C]=A;")
     s.append(f'  ofstream f("{out}/A.txt"); f.precision(17); f << A.n << " " << A.m << " " << A.nnz << endl;')
     s.append('  for(int k=0;k<I.n;++k) f << I[k] << " " << J[k] << " " << C[k] << endl; }')
@@ -139,11 +140,17 @@ def run_case(name):
         a = np.array(t[3:], dtype=np.float64).reshape(-1, 3)
         assert a.shape[0] == nnz and n == ndof
         b = np.array(toks(os.path.join(td, "b.txt")), dtype=np.float64)
+        with open(os.path.join(td, "Ains.txt")) as f:
+            lines = [ln for ln in f if not ln.startswith("#")]
+        assert "COO" in open(os.path.join(td, "Ains.txt")).readline()
+        ins = np.array(" ".join(lines[1:]).split(), dtype=np.float64).reshape(-1, 3)
+        assert ins.shape[0] == nnz
         out = dict(dim=np.int32(dim), xyz=np.ascontiguousarray(vt[:, :dim]), vlab=vt[:, dim].astype(np.int32),
                    conn=et[:, :dim + 1].astype(np.int32), elab=et[:, dim + 1].astype(np.int32),
                    bconn=bt[:, :dim].astype(np.int32), blab=bt[:, dim].astype(np.int32),
                    belem=bt[:, dim + 1].astype(np.int32), bface=bt[:, dim + 2].astype(np.int32),
                    ndof=np.int32(ndof), dof=dof,
+                   ins_i=ins[:, 0].astype(np.int32), ins_j=ins[:, 1].astype(np.int32),
                    coo_i=a[:, 0].astype(np.int32), coo_j=a[:, 1].astype(np.int32), coo_a=a[:, 2].copy(), b=b,
                    edp=np.array(src))
         if c.get("solve", True):

@@ -1,0 +1,128 @@
+"""CPU tests: pin the oracle (oracle/fforacle.c) against the fixtures dumped from the unmodified
+reference FreeFEM 4.15 (tests/golden/*.npz).  Tolerances: sparsity pattern and COO insertion order
+bit-exact; values/RHS/solution 1e-12 relative to the largest regular entry (north star), and the CG
+iteration count must match."""
+import numpy as np
+import pytest
+
+import ff_cases as fc
+import oracle_lib as ol
+
+TGV = 1e30
+RTOL = 1e-12
+
+
+def _mesh(g):
+    return {k: g[k] for k in ("dim", "xyz", "conn", "elab", "bconn", "blab", "belem", "bface")}
+
+
+def _scale(a):
+    a = np.abs(a[np.abs(a) < 1e29])
+    return a.max() if a.size else 1.0
+
+
+def _bc(g, order, ncomp, e2n, bcs):
+    dofs, vals = [], []
+    for labels, mask, values in bcs:
+        d, v = ol.bc_pairs(_mesh(g), order, ncomp, e2n, labels, mask, values)
+        dofs.append(d)
+        vals.append(v)
+    if not dofs:
+        return np.zeros(0, np.int32), np.zeros(0)
+    return np.concatenate(dofs), np.concatenate(vals)
+
+
+@pytest.mark.parametrize("name", sorted(fc.CASES))
+def test_matrix_rhs_solution(name):
+    order, ncomp, bt, lt, qname, bcs = fc.CASES[name]
+    g = fc.load(name)
+    dim, n = g["dim"], g["ndof"]
+    e2n = fc.elem2node(g, order, ncomp)
+    qp, qw = ol.quadrature(dim, qname)
+    ci, cj, ca = ol.assemble_coo(_mesh(g), order, ncomp, e2n, bt, qp, qw)
+    # HashMatrix insertion order (storage order before any CSR()/COO() call): bit-exact
+    assert np.array_equal(ci, g["ins_i"]) and np.array_equal(cj, g["ins_j"])
+    # the script's `[I,J,C]=A` sorted the reference storage by (i,j); do the same (Sortij)
+    o = np.argsort(ci.astype(np.int64) * n + cj, kind="stable")
+    ci, cj, ca = ci[o], cj[o], ca[o]
+    assert np.array_equal(ci, g["coo_i"]) and np.array_equal(cj, g["coo_j"])
+    dofs, vals = _bc(g, order, ncomp, e2n, bcs)
+    ca = ol.bc_matrix_coo(ci, cj, ca, n, dofs, TGV)
+    assert np.array_equal(np.abs(ca) > 1e29, np.abs(g["coo_a"]) > 1e29)
+    assert np.max(np.abs(ca - g["coo_a"])[np.abs(ca) < 1e29]) <= RTOL * _scale(g["coo_a"])
+    # sorted CSR pattern
+    rp, col, _ = ol.coo_to_csr(n, ci, cj, ca)
+    grp, gcol, _ = fc.golden_csr(g)
+    assert np.array_equal(rp, grp) and np.array_equal(col, gcol)
+    # right-hand side
+    b = ol.assemble_rhs(_mesh(g), order, ncomp, e2n, n, lt, qp, qw)
+    b = ol.bc_rhs(b, dofs, vals, TGV)
+    big = np.abs(g["b"]) > 1e20
+    assert np.array_equal(np.abs(b) > 1e20, big)
+    assert np.allclose(b[big], g["b"][big], rtol=1e-15, atol=0)
+    assert np.max(np.abs(b - g["b"])[~big], initial=0.0) <= RTOL * max(np.abs(g["b"][~big]).max(initial=0.0), 1e-300)
+    # CG on the oracle's own matrix/rhs.  Scalar cases are bit-identical to the reference all the way
+    # (same operation order).  The 3-component Lame cases differ from the reference in <=0.1% of the
+    # entries by 1 ulp (term summation order) and CG at eps=1e-6 is not converged to round-off, so that
+    # ulp is amplified by the iteration (observed: 1.5e-8, one iteration more); there the pin on ffo_cg is
+    # test_cg_on_reference_matrix below and here only the converged residual is checked.
+    if "u" in g:
+        x, it, ret, _ = ol.cg(n, ci, cj, ca, b, np.zeros(n), eps=1e-6, itmax=0, tgv=TGV)
+        assert ret in (1, 2)
+        if ncomp == 1:
+            assert it == int(g["cg_iters"])
+            assert np.max(np.abs(x - g["u"])) <= RTOL * np.abs(g["u"]).max()
+        else:
+            assert abs(it - int(g["cg_iters"])) <= 2
+            assert np.max(np.abs(x - g["u"])) <= 1e-6 * np.abs(g["u"]).max()
+
+
+@pytest.mark.parametrize("name", sorted(k for k in fc.CASES if fc.CASES[k][5]))
+def test_cg_on_reference_matrix(name):
+    """ffo_cg fed with the reference's own A and b must reproduce its iterate: same count, u to 1e-12."""
+    g = fc.load(name)
+    n = g["ndof"]
+    x, it, ret, _ = ol.cg(n, g["coo_i"], g["coo_j"], g["coo_a"], g["b"], np.zeros(n), eps=1e-6, itmax=0, tgv=TGV)
+    assert ret in (1, 2) and it == int(g["cg_iters"])
+    assert np.max(np.abs(x - g["u"])) <= RTOL * np.abs(g["u"]).max()
+
+
+@pytest.mark.parametrize("nxyz,name", [((2, 2, 2), "lap3d_p1_cube2"), ((5, 5, 5), "lap3d_p1_cube5"),
+                                       ((3, 4, 2), "lap3d_p1_cube342"), ((3, 3, 3), "heat3d_p1_cube3")])
+def test_cube_generator_bit_exact(nxyz, name):
+    g = fc.load(name)
+    m = ol.cube(*nxyz)
+    for k in ("xyz", "conn", "elab", "bconn", "blab", "belem", "bface"):
+        assert np.array_equal(m[k], g[k]), k
+
+
+@pytest.mark.parametrize("nxy,name", [((4, 4), "lap2d_p1_sq4"), ((12, 9), "lap2d_p1_sq12x9"), ((3, 3), "lap2d_p2_sq3")])
+def test_square_generator_bit_exact(nxy, name):
+    g = fc.load(name)
+    m = ol.square(*nxy)
+    for k in ("xyz", "conn", "elab", "bconn", "blab", "belem", "bface"):
+        assert np.array_equal(m[k], g[k]), k
+
+
+@pytest.mark.parametrize("name", ["lap3d_p2_cube2", "lame3d_p2_cube2", "lame3d_p2_warp"])
+def test_p2_numbering_3d_bit_exact(name):
+    order, ncomp = fc.CASES[name][:2]
+    g = fc.load(name)
+    e2n, nn = ol.p2_nodes_3d(g["xyz"].shape[0], g["conn"])
+    assert nn * ncomp == g["ndof"]
+    assert np.array_equal(e2n, fc.elem2node(g, order, ncomp))
+
+
+def test_known_answers_from_survey():
+    # cube(2,2,2) P1 -> n=27 nnz=223, rows (1,1)=tgv (1,2)=-1/6 (1,4)=-1/6 (1,5)=0; tet 0 = 9 0 12 13
+    g = fc.load("lap3d_p1_cube2")
+    rp, col, val = fc.golden_csr(g)
+    assert g["ndof"] == 27 and len(col) == 223
+    assert list(col[:4]) == [0, 1, 3, 4] and val[0] == 1e30
+    assert abs(val[1] + 1 / 6) < 1e-15 and abs(val[2] + 1 / 6) < 1e-15 and abs(val[3]) < 1e-15
+    assert list(ol.cube(2, 2, 2)["conn"][0]) == [9, 0, 12, 13]
+    assert list(map(list, ol.cube(1, 1, 1)["conn"])) == [[4, 0, 6, 7], [0, 4, 5, 7], [1, 0, 5, 7], [0, 1, 3, 7],
+                                                         [2, 0, 3, 7], [0, 2, 6, 7]]
+    assert list(map(list, ol.square(2, 1)["conn"])) == [[0, 1, 4], [0, 4, 3], [1, 2, 5], [1, 5, 4]]
+    g2 = fc.load("lap2d_p1_sq4")
+    assert g2["ndof"] == 25 and len(g2["coo_i"]) == 137
