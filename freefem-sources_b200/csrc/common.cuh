@@ -1,0 +1,205 @@
+// common.cuh — internal definitions shared by the CUDA translation units of libffcuda_core.so.
+// Nothing here is part of the public ABI (include/ffcuda.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "../../include/ffcuda.h"
+
+struct FFError : std::runtime_error {
+    explicit FFError(const std::string &s) : std::runtime_error(s) {}
+};
+
+#define FF_CUDA(call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            throw FFError(std::string("CUDA error: ") + cudaGetErrorString(e__) + " at " + __FILE__ +   \
+                          ":" + std::to_string(__LINE__) + " (" #call ")");                             \
+    } while (0)
+
+#define FF_REQUIRE(cond, msg)                                                                           \
+    do {                                                                                                \
+        if (!(cond)) throw FFError(std::string("ffcuda: ") + (msg));                                    \
+    } while (0)
+
+void ff_set_thread_error(const std::string &s);
+
+// every extern "C" entry point wraps its body with these: no exception crosses the ABI
+#define FF_API_BEGIN try {
+#define FF_API_END(ctxexpr)                                                                             \
+    }                                                                                                   \
+    catch (const std::exception &e)                                                                     \
+    {                                                                                                   \
+        ff_report_error((ctxexpr), e.what());                                                           \
+        return 1;                                                                                       \
+    }                                                                                                   \
+    catch (...)                                                                                         \
+    {                                                                                                   \
+        ff_report_error((ctxexpr), "unknown exception");                                                \
+        return 1;                                                                                       \
+    }                                                                                                   \
+    return 0;
+
+struct ProfEntry {
+    double ms = 0;
+    int64_t count = 0;
+};
+struct ProfPending {
+    std::string name;
+    cudaEvent_t e0, e1;
+};
+
+struct ffcuda_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    std::string err;
+    bool prof = false;
+    std::map<std::string, ProfEntry> prof_acc;
+    std::vector<ProfPending> prof_pending;
+    int64_t launches = 0;
+    int sm_count = 148;
+    // reduction scratch (device) + pinned host mirror
+    double *d_scal = nullptr;   // small array of device scalars
+    double *h_scal = nullptr;   // pinned
+    double *d_partial = nullptr;
+    size_t partial_cap = 0;
+    // multi-GPU
+    int rank = 0, nranks = 1;
+    void *nccl_comm = nullptr;
+};
+
+void ff_report_error(ffcuda_ctx *ctx, const char *msg);
+void ff_prof_flush(ffcuda_ctx *ctx);
+void ff_comm_release(ffcuda_ctx *ctx); // comm.cu
+
+// RAII device buffer
+template <class T>
+struct DBuf {
+    T *p = nullptr;
+    size_t n = 0;
+    DBuf() {}
+    DBuf(const DBuf &) = delete;
+    DBuf &operator=(const DBuf &) = delete;
+    ~DBuf() { release(); }
+    void alloc(size_t count)
+    {
+        release();
+        n = count;
+        if (count) FF_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    size_t bytes() const { return n * sizeof(T); }
+};
+
+// kernel launch wrapper: counts the launch, optionally brackets it with events on the launch stream
+template <class F>
+inline void ff_launch(ffcuda_ctx *ctx, const char *name, F &&f)
+{
+    ctx->launches++;
+    if (ctx->prof) {
+        ProfPending pp;
+        pp.name = name;
+        FF_CUDA(cudaEventCreate(&pp.e0));
+        FF_CUDA(cudaEventCreate(&pp.e1));
+        FF_CUDA(cudaEventRecord(pp.e0, ctx->stream));
+        f();
+        FF_CUDA(cudaEventRecord(pp.e1, ctx->stream));
+        ctx->prof_pending.push_back(pp);
+        if (ctx->prof_pending.size() > 4096) ff_prof_flush(ctx);
+    } else {
+        f();
+    }
+    FF_CUDA(cudaGetLastError());
+}
+
+static inline int ff_blocks(size_t n, int threads) { return (int)((n + threads - 1) / threads); }
+
+// ---- handle structs --------------------------------------------------------------------------------
+struct ffcuda_mesh {
+    ffcuda_ctx *ctx = nullptr;
+    int dim = 0, nv = 0, nt = 0, nbe = 0;
+    int vstride = 0;          // doubles per vertex on the device: 2 (2-D) or 4 (3-D, padded: one 32 B sector)
+    DBuf<double> xyz;         // nv*vstride
+    DBuf<int32_t> conn;       // nt*(dim+1)
+    DBuf<int32_t> elab;       // nt
+    DBuf<int32_t> bconn, blab, belem, bface;
+    // distributed (slab partition): local vertices [0,nv_owned) are owned, the rest are ghosts
+    int nv_owned = 0;
+    DBuf<int64_t> gid;        // global vertex id of each local vertex
+    int nbr[2] = {-1, -1};    // lower / upper neighbour rank
+    int send_off[2] = {0, 0}, send_cnt[2] = {0, 0};   // owned vertices to send (contiguous ranges)
+    int recv_off[2] = {0, 0}, recv_cnt[2] = {0, 0};   // ghost ranges to receive into
+    bool distributed = false;
+};
+
+struct ffcuda_space {
+    ffcuda_mesh *mesh = nullptr;
+    ffcuda_ctx *ctx = nullptr;
+    int order = 1, ncomp = 1, nloc = 0, nnodes = 0, nnodes_owned = 0;
+    DBuf<int32_t> e2n_own;    // nt*nloc when order 2
+    const int32_t *e2n = nullptr;   // = conn for P1
+    struct ffcuda_pattern *last_pattern = nullptr;   // most recent ffcuda_symbolic result (incidence lists for the rhs)
+};
+
+struct ffcuda_pattern {
+    ffcuda_space *space = nullptr;
+    ffcuda_ctx *ctx = nullptr;
+    int nrows_node = 0;       // owned nodes = block rows
+    int ncols_node = 0;       // local nodes (owned + ghost)
+    int ncomp = 1;
+    int n = 0;                // dof rows
+    int64_t nnz = 0;          // dof-level
+    int64_t nnz_node = 0;
+    int maxrow_node = 0;      // longest node row
+    DBuf<int32_t> nrowptr, ncol;          // node-level CSR
+    DBuf<int32_t> rowptr_own, colind_own; // dof-level CSR (only when ncomp > 1)
+    const int32_t *rowptr = nullptr, *colind = nullptr;
+    DBuf<int32_t> incptr;     // nrows_node+1
+    DBuf<uint32_t> inc;       // (element << 4) | local node
+    DBuf<uint8_t> pos8;       // per incidence, nlocp bytes: position of each element node in the node row
+    DBuf<uint16_t> pos16;     // used instead when maxrow_node > 255
+    int nlocp = 0;            // padded nloc in the pos table (4, 8 or 16... see symbolic.cu)
+    DBuf<int32_t> diagpos;    // n: index into vals of A(i,i)
+};
+
+struct ffcuda_matrix {
+    ffcuda_ctx *ctx = nullptr;
+    ffcuda_pattern *pattern = nullptr;    // null for from_csr matrices
+    int n = 0, ncols = 0;
+    int64_t nnz = 0;
+    DBuf<int32_t> rowptr_own, colind_own, diagpos_own;
+    const int32_t *rowptr = nullptr, *colind = nullptr, *diagpos = nullptr;
+    DBuf<double> vals;
+    // CG workspace (lazily allocated)
+    DBuf<double> wG, wH, wAH, wD1, wX;
+    DBuf<int32_t> wcl;
+};
+
+struct ffcuda_vec {
+    ffcuda_ctx *ctx = nullptr;
+    int n = 0;
+    DBuf<double> d;
+};
+
+struct ffcuda_bc {
+    ffcuda_ctx *ctx = nullptr;
+    int ndofs = 0;
+    DBuf<int32_t> dofs;
+    DBuf<double> vals;
+};
+
+// ---- shared device helpers ----------------------------------------------------------------------
+void ff_exclusive_scan_i32(ffcuda_ctx *ctx, const int32_t *in, int32_t *out, size_t n, int64_t *total);
+// out[n] receives the total as well when with_total
+int ff_nloc(int dim, int order);

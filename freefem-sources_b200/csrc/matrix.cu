@@ -1,0 +1,299 @@
+// matrix.cu — device-resident CSR matrices and Dirichlet (penalty) conditions.
+// AssembleBC (fflib/problem.cpp:9881-10194) + HashMatrix::SetBC (femlib/HashMatrix.cpp:1195-1238), tgv >= 0.
+#include "common.cuh"
+#include <algorithm>
+
+extern "C" int ffcuda_matrix_create(ffcuda_pattern *p, ffcuda_matrix **out)
+{
+    ffcuda_matrix *A = nullptr;
+    FF_API_BEGIN
+    FF_REQUIRE(p && out, "ffcuda_matrix_create: null argument");
+    ffcuda_ctx *ctx = p->ctx;
+    FF_CUDA(cudaSetDevice(ctx->device));
+    A = new ffcuda_matrix();
+    A->ctx = ctx;
+    A->pattern = p;
+    A->n = p->n;
+    A->ncols = p->ncols_node * p->ncomp;
+    A->nnz = p->nnz;
+    A->rowptr = p->rowptr;
+    A->colind = p->colind;
+    A->diagpos = p->diagpos.p;
+    A->vals.alloc((size_t)p->nnz);
+    FF_CUDA(cudaMemsetAsync(A->vals.p, 0, A->vals.bytes(), ctx->stream));
+    *out = A;
+    A = nullptr;
+    FF_API_END((delete A, p ? p->ctx : nullptr))
+}
+
+__global__ void k_find_diag(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind, int n, int32_t *__restrict__ diagpos)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int d = -1;
+    for (int j = rowptr[i]; j < rowptr[i + 1]; ++j)
+        if (colind[j] == i) d = j;
+    diagpos[i] = d;
+}
+
+extern "C" int ffcuda_matrix_from_csr(ffcuda_ctx *ctx, int n, int64_t nnz, const int32_t *rowptr, const int32_t *colind,
+                                      const double *vals, ffcuda_matrix **out)
+{
+    ffcuda_matrix *A = nullptr;
+    FF_API_BEGIN
+    FF_REQUIRE(ctx && out && rowptr && colind && n > 0 && nnz >= 0, "ffcuda_matrix_from_csr: bad arguments");
+    FF_REQUIRE(nnz < ((int64_t)1 << 31), "matrix exceeds 2^31 nonzeros");
+    FF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    A = new ffcuda_matrix();
+    A->ctx = ctx;
+    A->n = n;
+    A->ncols = n;
+    A->nnz = nnz;
+    A->rowptr_own.alloc((size_t)n + 1);
+    A->colind_own.alloc((size_t)nnz);
+    A->diagpos_own.alloc((size_t)n);
+    A->vals.alloc((size_t)nnz);
+    FF_CUDA(cudaMemcpyAsync(A->rowptr_own.p, rowptr, A->rowptr_own.bytes(), cudaMemcpyHostToDevice, st));
+    FF_CUDA(cudaMemcpyAsync(A->colind_own.p, colind, A->colind_own.bytes(), cudaMemcpyHostToDevice, st));
+    if (vals) FF_CUDA(cudaMemcpyAsync(A->vals.p, vals, A->vals.bytes(), cudaMemcpyHostToDevice, st));
+    else FF_CUDA(cudaMemsetAsync(A->vals.p, 0, A->vals.bytes(), st));
+    A->rowptr = A->rowptr_own.p;
+    A->colind = A->colind_own.p;
+    A->diagpos = A->diagpos_own.p;
+    ff_launch(ctx, "matrix_find_diag", [&] { k_find_diag<<<ff_blocks(n, 256), 256, 0, st>>>(A->rowptr, A->colind, n, A->diagpos_own.p); });
+    FF_CUDA(cudaStreamSynchronize(st));
+    *out = A;
+    A = nullptr;
+    FF_API_END((delete A, ctx))
+}
+
+extern "C" int ffcuda_matrix_info(ffcuda_matrix *A, int *n, int64_t *nnz)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A, "null matrix");
+    if (n) *n = A->n;
+    if (nnz) *nnz = A->nnz;
+    FF_API_END(A ? A->ctx : nullptr)
+}
+
+extern "C" int ffcuda_matrix_download(ffcuda_matrix *A, double *vals)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A && vals, "null argument");
+    FF_CUDA(cudaSetDevice(A->ctx->device));
+    FF_CUDA(cudaMemcpyAsync(vals, A->vals.p, A->vals.bytes(), cudaMemcpyDeviceToHost, A->ctx->stream));
+    FF_CUDA(cudaStreamSynchronize(A->ctx->stream));
+    FF_API_END(A ? A->ctx : nullptr)
+}
+
+extern "C" int ffcuda_matrix_upload(ffcuda_matrix *A, const double *vals)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A && vals, "null argument");
+    FF_CUDA(cudaSetDevice(A->ctx->device));
+    FF_CUDA(cudaMemcpyAsync(A->vals.p, vals, A->vals.bytes(), cudaMemcpyHostToDevice, A->ctx->stream));
+    FF_CUDA(cudaStreamSynchronize(A->ctx->stream));
+    FF_API_END(A ? A->ctx : nullptr)
+}
+
+extern "C" void ffcuda_matrix_destroy(ffcuda_matrix *A)
+{
+    if (!A) return;
+    cudaSetDevice(A->ctx->device);
+    delete A;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Dirichlet conditions
+// ---------------------------------------------------------------------------------------------------
+extern "C" int ffcuda_bc_from_pairs(ffcuda_space *s, int n, const int32_t *dofs, const double *vals, ffcuda_bc **out)
+{
+    ffcuda_bc *bc = nullptr;
+    FF_API_BEGIN
+    FF_REQUIRE(s && out && n >= 0 && (n == 0 || (dofs && vals)), "ffcuda_bc_from_pairs: bad arguments");
+    ffcuda_ctx *ctx = s->ctx;
+    FF_CUDA(cudaSetDevice(ctx->device));
+    const int ndof = s->nnodes_owned * s->ncomp;
+    // later pairs win (AssembleBC overwrites B[ddf] as it walks the boundary elements)
+    std::vector<std::pair<int32_t, int>> ord(n);
+    for (int i = 0; i < n; ++i) {
+        FF_REQUIRE(dofs[i] >= 0 && dofs[i] < ndof, "Dirichlet dof out of range");
+        ord[i] = {dofs[i], i};
+    }
+    std::sort(ord.begin(), ord.end());
+    std::vector<int32_t> ud;
+    std::vector<double> uv;
+    for (int i = 0; i < n; ++i)
+        if (i + 1 == n || ord[i + 1].first != ord[i].first) {
+            ud.push_back(ord[i].first);
+            uv.push_back(vals[ord[i].second]);
+        }
+    bc = new ffcuda_bc();
+    bc->ctx = ctx;
+    bc->ndofs = (int)ud.size();
+    bc->dofs.alloc(ud.size());
+    bc->vals.alloc(uv.size());
+    if (bc->ndofs) {
+        FF_CUDA(cudaMemcpy(bc->dofs.p, ud.data(), bc->dofs.bytes(), cudaMemcpyHostToDevice));
+        FF_CUDA(cudaMemcpy(bc->vals.p, uv.data(), bc->vals.bytes(), cudaMemcpyHostToDevice));
+    }
+    *out = bc;
+    bc = nullptr;
+    FF_API_END((delete bc, s ? s->ctx : nullptr))
+}
+
+struct LabSet {
+    int n;
+    int lab[32];
+};
+
+// mark the dofs lying on boundary elements whose label is selected (Element::onWhatBorder semantics:
+// a vertex is on face ie iff it is not the vertex opposite to it; an edge iff both its ends are)
+__global__ void k_bc_mark(int dim, int nbe, const int32_t *__restrict__ blab, const int32_t *__restrict__ belem,
+                          const int32_t *__restrict__ bface, const int32_t *__restrict__ e2n, int nloc, int ncomp, int compmask,
+                          int ndof, LabSet L, int32_t *__restrict__ flag)
+{
+    int ib = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ib >= nbe) return;
+    int l = blab[ib];
+    bool ok = false;
+    for (int i = 0; i < L.n; ++i) ok |= (L.lab[i] == l);
+    if (!ok) return;
+    const int it = belem[ib], ie = bface[ib], nvk = dim + 1;
+    const int e0[6] = {0, 0, 0, 1, 1, 2}, e1[6] = {1, 2, 3, 2, 3, 3};
+    for (int a = 0; a < nloc; ++a) {
+        bool on;
+        if (a < nvk) on = (a != ie);
+        else if (dim == 2) on = (a - 3 == ie);
+        else on = (e0[a - 4] != ie && e1[a - 4] != ie);
+        if (!on) continue;
+        int node = e2n[(size_t)it * nloc + a];
+        for (int c = 0; c < ncomp; ++c)
+            if (compmask >> c & 1) {
+                int d = node * ncomp + c;
+                if (d < ndof) flag[d] = 1;
+            }
+    }
+}
+
+__global__ void k_bc_compact(const int32_t *__restrict__ flag, const int32_t *__restrict__ off, int ndof, int ncomp,
+                             double v0, double v1, double v2, int32_t *__restrict__ dofs, double *__restrict__ vals)
+{
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= ndof || !flag[d]) return;
+    int c = d % ncomp;
+    dofs[off[d]] = d;
+    vals[off[d]] = c == 0 ? v0 : (c == 1 ? v1 : v2);
+}
+
+extern "C" int ffcuda_bc_from_labels(ffcuda_space *s, int nlab, const int32_t *labels, int compmask, const double *values,
+                                     ffcuda_bc **out)
+{
+    ffcuda_bc *bc = nullptr;
+    FF_API_BEGIN
+    FF_REQUIRE(s && out && nlab > 0 && labels, "ffcuda_bc_from_labels: bad arguments");
+    FF_REQUIRE(nlab <= 32, "at most 32 labels per on(...)");
+    ffcuda_ctx *ctx = s->ctx;
+    ffcuda_mesh *m = s->mesh;
+    FF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int ndof = s->nnodes_owned * s->ncomp;
+    LabSet L;
+    L.n = nlab;
+    for (int i = 0; i < nlab; ++i) L.lab[i] = labels[i];
+    DBuf<int32_t> flag, off;
+    flag.alloc((size_t)ndof + 1);
+    off.alloc((size_t)ndof + 1);
+    FF_CUDA(cudaMemsetAsync(flag.p, 0, flag.bytes(), st));
+    if (m->nbe)
+        ff_launch(ctx, "bc_mark", [&] {
+            k_bc_mark<<<ff_blocks(m->nbe, 128), 128, 0, st>>>(m->dim, m->nbe, m->blab.p, m->belem.p, m->bface.p, s->e2n, s->nloc,
+                                                              s->ncomp, compmask, ndof, L, flag.p);
+        });
+    int64_t cnt = 0;
+    ff_exclusive_scan_i32(ctx, flag.p, off.p, (size_t)ndof + 1, &cnt);
+    bc = new ffcuda_bc();
+    bc->ctx = ctx;
+    bc->ndofs = (int)cnt;
+    bc->dofs.alloc((size_t)cnt);
+    bc->vals.alloc((size_t)cnt);
+    double v[3] = {0, 0, 0};
+    if (values)
+        for (int c = 0; c < s->ncomp; ++c) v[c] = values[c];
+    if (cnt)
+        ff_launch(ctx, "bc_compact", [&] {
+            k_bc_compact<<<ff_blocks(ndof, 256), 256, 0, st>>>(flag.p, off.p, ndof, s->ncomp, v[0], v[1], v[2], bc->dofs.p, bc->vals.p);
+        });
+    FF_CUDA(cudaStreamSynchronize(st));
+    *out = bc;
+    bc = nullptr;
+    FF_API_END((delete bc, s ? s->ctx : nullptr))
+}
+
+extern "C" int ffcuda_bc_count(ffcuda_bc *bc, int *ndofs)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(bc && ndofs, "null argument");
+    *ndofs = bc->ndofs;
+    FF_API_END(bc ? bc->ctx : nullptr)
+}
+
+__global__ void k_bc_matrix(const int32_t *__restrict__ dofs, int n, const int32_t *__restrict__ diagpos, double *__restrict__ vals, double tgv)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) vals[diagpos[dofs[i]]] = tgv;
+}
+
+__global__ void k_bc_vec(const int32_t *__restrict__ dofs, const double *__restrict__ g, int n, double *__restrict__ b, double scale)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) b[dofs[i]] = scale * g[i];
+}
+
+extern "C" int ffcuda_matrix_apply_bc(ffcuda_matrix *A, ffcuda_bc *bc, double tgv)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A && bc, "null argument");
+    FF_REQUIRE(tgv >= 0, "only the penalty form of Dirichlet conditions (tgv >= 0) is on the ffcuda path");
+    ffcuda_ctx *ctx = A->ctx;
+    FF_CUDA(cudaSetDevice(ctx->device));
+    if (bc->ndofs)
+        ff_launch(ctx, "bc_matrix", [&] {
+            k_bc_matrix<<<ff_blocks(bc->ndofs, 256), 256, 0, ctx->stream>>>(bc->dofs.p, bc->ndofs, A->diagpos, A->vals.p, tgv);
+        });
+    FF_API_END(A ? A->ctx : nullptr)
+}
+
+extern "C" int ffcuda_vec_apply_bc(ffcuda_vec *b, ffcuda_bc *bc, double tgv)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(b && bc, "null argument");
+    ffcuda_ctx *ctx = b->ctx;
+    FF_CUDA(cudaSetDevice(ctx->device));
+    if (bc->ndofs)
+        ff_launch(ctx, "bc_vec", [&] {
+            k_bc_vec<<<ff_blocks(bc->ndofs, 256), 256, 0, ctx->stream>>>(bc->dofs.p, bc->vals.p, bc->ndofs, b->d.p, tgv);
+        });
+    FF_API_END(b ? b->ctx : nullptr)
+}
+
+extern "C" int ffcuda_vec_set_bc_values(ffcuda_vec *x, ffcuda_bc *bc)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(x && bc, "null argument");
+    ffcuda_ctx *ctx = x->ctx;
+    FF_CUDA(cudaSetDevice(ctx->device));
+    if (bc->ndofs)
+        ff_launch(ctx, "bc_vec", [&] {
+            k_bc_vec<<<ff_blocks(bc->ndofs, 256), 256, 0, ctx->stream>>>(bc->dofs.p, bc->vals.p, bc->ndofs, x->d.p, 1.0);
+        });
+    FF_API_END(x ? x->ctx : nullptr)
+}
+
+extern "C" void ffcuda_bc_destroy(ffcuda_bc *bc)
+{
+    if (!bc) return;
+    cudaSetDevice(bc->ctx->device);
+    delete bc;
+}

@@ -1,0 +1,441 @@
+// mesh.cu — mesh handles: upload of a host (FreeFEM) mesh, and device-side generation of the structured
+// cube / square meshes with FreeFEM's exact vertex, element and boundary-element ordering
+// (BuildCube fflib/msh3.cpp:7879-8132 with kind=6; Carre_ fflib/lgmesh.cpp:1229-1384 with flags=0).
+#include "common.cuh"
+#include <algorithm>
+#include <array>
+#include <memory>
+#include <unordered_map>
+
+// local vertex tables of the reference simplices (femlib/Mesh3dn.cpp:71-72)
+__constant__ int c_nvfaceTet[4][3] = {{3, 2, 1}, {0, 2, 3}, {3, 1, 0}, {0, 1, 2}};
+// kind=6 split of a cell into 6 tets around the diagonal 0-7 (corner id = a + 2b + 4c)
+__constant__ int c_cubeTets[6][4] = {{4, 0, 6, 7}, {0, 4, 5, 7}, {1, 0, 5, 7}, {0, 1, 3, 7}, {2, 0, 3, 7}, {0, 2, 6, 7}};
+static const int h_nvfaceTet[4][3] = {{3, 2, 1}, {0, 2, 3}, {3, 1, 0}, {0, 1, 2}};
+
+__global__ void k_pad_xyz3(const double *__restrict__ in, double *__restrict__ out, int nv)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv) return;
+    double4 v = make_double4(in[3 * (size_t)i], in[3 * (size_t)i + 1], in[3 * (size_t)i + 2], 0.0);
+    reinterpret_cast<double4 *>(out)[i] = v;
+}
+
+__global__ void k_unpad_xyz3(const double *__restrict__ in, double *__restrict__ out, int nv)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv) return;
+    double4 v = reinterpret_cast<const double4 *>(in)[i];
+    out[3 * (size_t)i] = v.x;
+    out[3 * (size_t)i + 1] = v.y;
+    out[3 * (size_t)i + 2] = v.z;
+}
+
+static void recover_boundary_elements(int dim, int nt, const int32_t *conn, int nbe, const int32_t *bconn,
+                                      std::vector<int32_t> &belem, std::vector<int32_t> &bface)
+{
+    // host-side input preparation: match every boundary element with the (element, local face) that has the
+    // same vertex set (what Mesh3::BoundaryElement returns).  First element in element order wins.
+    struct Key {
+        std::array<int32_t, 3> v;
+        bool operator==(const Key &o) const { return v == o.v; }
+    };
+    struct KeyHash {
+        size_t operator()(const Key &k) const
+        {
+            uint64_t h = 1469598103934665603ull;
+            for (int i = 0; i < 3; ++i) h = (h ^ (uint32_t)k.v[i]) * 1099511628211ull;
+            return (size_t)h;
+        }
+    };
+    std::unordered_map<Key, int32_t, KeyHash> want;
+    want.reserve((size_t)nbe * 2);
+    for (int ib = 0; ib < nbe; ++ib) {
+        Key k;
+        k.v = {-1, -1, -1};
+        for (int i = 0; i < dim; ++i) k.v[i] = bconn[(size_t)ib * dim + i];
+        std::sort(k.v.begin(), k.v.begin() + dim);
+        want.emplace(k, ib);
+    }
+    belem.assign(nbe, -1);
+    bface.assign(nbe, -1);
+    const int nvk = dim + 1;
+    for (int t = 0; t < nt; ++t)
+        for (int f = 0; f < nvk; ++f) {
+            Key k;
+            k.v = {-1, -1, -1};
+            int m = 0;
+            for (int a = 0; a < nvk; ++a)
+                if (a != f) k.v[m++] = conn[(size_t)t * nvk + a];
+            std::sort(k.v.begin(), k.v.begin() + dim);
+            auto it = want.find(k);
+            if (it != want.end() && belem[it->second] < 0) {
+                belem[it->second] = t;
+                bface[it->second] = f;
+            }
+        }
+    for (int ib = 0; ib < nbe; ++ib)
+        FF_REQUIRE(belem[ib] >= 0, "boundary element " + std::to_string(ib) + " is not a face of any element");
+}
+
+extern "C" int ffcuda_mesh_upload(ffcuda_ctx *ctx, int dim, int nv, const double *xyz, int nt, const int32_t *conn,
+                                  const int32_t *elab, int nbe, const int32_t *bconn, const int32_t *blab,
+                                  const int32_t *belem, const int32_t *bface, ffcuda_mesh **out)
+{
+    ffcuda_mesh *m = nullptr;
+    FF_API_BEGIN
+    FF_REQUIRE(ctx && out, "ffcuda_mesh_upload: null context/output");
+    FF_REQUIRE(dim == 2 || dim == 3, "dim must be 2 or 3");
+    FF_REQUIRE(nv > 0 && nt > 0 && xyz && conn, "empty mesh");
+    FF_REQUIRE(nbe == 0 || (bconn && blab), "boundary arrays missing");
+    FF_REQUIRE((int64_t)nt < (int64_t)1 << 27, "too many elements for one device (limit 2^27)");
+    FF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    m = new ffcuda_mesh();
+    m->ctx = ctx;
+    m->dim = dim; m->nv = nv; m->nt = nt; m->nbe = nbe;
+    m->nv_owned = nv;
+    const int nvk = dim + 1;
+    m->vstride = dim == 3 ? 4 : 2;
+    m->xyz.alloc((size_t)nv * m->vstride);
+    if (dim == 3) {
+        DBuf<double> tmp;
+        tmp.alloc((size_t)nv * 3);
+        FF_CUDA(cudaMemcpyAsync(tmp.p, xyz, tmp.bytes(), cudaMemcpyHostToDevice, st));
+        ff_launch(ctx, "mesh_pad_xyz", [&] { k_pad_xyz3<<<ff_blocks(nv, 256), 256, 0, st>>>(tmp.p, m->xyz.p, nv); });
+        FF_CUDA(cudaStreamSynchronize(st));
+    } else {
+        FF_CUDA(cudaMemcpyAsync(m->xyz.p, xyz, m->xyz.bytes(), cudaMemcpyHostToDevice, st));
+    }
+    m->conn.alloc((size_t)nt * nvk);
+    FF_CUDA(cudaMemcpyAsync(m->conn.p, conn, m->conn.bytes(), cudaMemcpyHostToDevice, st));
+    m->elab.alloc((size_t)nt);
+    if (elab) FF_CUDA(cudaMemcpyAsync(m->elab.p, elab, m->elab.bytes(), cudaMemcpyHostToDevice, st));
+    else FF_CUDA(cudaMemsetAsync(m->elab.p, 0, m->elab.bytes(), st));
+    if (nbe) {
+        std::vector<int32_t> be, bf;
+        if (!belem || !bface) {
+            recover_boundary_elements(dim, nt, conn, nbe, bconn, be, bf);
+            belem = be.data();
+            bface = bf.data();
+        }
+        m->bconn.alloc((size_t)nbe * dim);
+        m->blab.alloc(nbe); m->belem.alloc(nbe); m->bface.alloc(nbe);
+        FF_CUDA(cudaMemcpyAsync(m->bconn.p, bconn, m->bconn.bytes(), cudaMemcpyHostToDevice, st));
+        FF_CUDA(cudaMemcpyAsync(m->blab.p, blab, m->blab.bytes(), cudaMemcpyHostToDevice, st));
+        FF_CUDA(cudaMemcpyAsync(m->belem.p, belem, m->belem.bytes(), cudaMemcpyHostToDevice, st));
+        FF_CUDA(cudaMemcpyAsync(m->bface.p, bface, m->bface.bytes(), cudaMemcpyHostToDevice, st));
+        FF_CUDA(cudaStreamSynchronize(st));
+    }
+    FF_CUDA(cudaStreamSynchronize(st));
+    *out = m;
+    m = nullptr;
+    FF_API_END((delete m, ctx))
+}
+
+// ---------------------------------------------------------------------------------------------------
+// cube(nx,ny,nz) — whole, or the z-slab of one rank (owned vertex layers + one ghost layer each side)
+// ---------------------------------------------------------------------------------------------------
+struct CubeLayout {
+    int nx, ny, nz;
+    int c_lo, ncl;          // first local cell layer, number of local cell layers
+    int L0, nown;           // first owned vertex layer, number of owned vertex layers
+    int has_lower, has_upper;
+};
+
+// local id of the vertex (i,j,k): owned layers first, then the lower ghost layer, then the upper one
+__device__ __forceinline__ int cube_lv(const CubeLayout &C, int i, int j, int k)
+{
+    const int nj = C.nx + 1, nk = nj * (C.ny + 1), r = j * nj + i;
+    if (k >= C.L0 && k < C.L0 + C.nown) return (k - C.L0) * nk + r;
+    if (k < C.L0) return C.nown * nk + r;
+    return C.nown * nk + (C.has_lower ? nk : 0) + r;
+}
+
+__global__ void k_cube_vertices(double *__restrict__ xyz4, int64_t *__restrict__ gid, const CubeLayout C, int nvloc)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= nvloc) return;
+    const int nj = C.nx + 1, nk = nj * (C.ny + 1);
+    int kl = p / nk, r = p - kl * nk;
+    int k;
+    if (kl < C.nown) k = C.L0 + kl;
+    else if (C.has_lower && kl == C.nown) k = C.L0 - 1;
+    else k = C.L0 + C.nown;
+    int j = r / nj, i = r - j * nj;
+    double xd = 1. / C.nx, yd = 1. / C.ny, zd = 1. / C.nz;
+    reinterpret_cast<double4 *>(xyz4)[p] = make_double4(0 + xd * i, 0 + yd * j, 0 + zd * k, 0.0);
+    if (gid) gid[p] = (int64_t)k * nk + r;
+}
+
+__device__ __forceinline__ int cube_vlab(int i, int j, int k, int nx, int ny, int nz)
+{
+    return 1 * (i == 0) + 2 * (i == nx) + 4 * (j == 0) + 8 * (j == ny) + 16 * (k == 0) + 32 * (k == nz);
+}
+
+// one thread per cell: writes its 6 tets; counts (pass 0) or writes (pass 1) its boundary triangles in the
+// reference order (tet d, face f, plane kk).
+template <int PASS>
+__global__ void k_cube_cells(const CubeLayout C, int32_t *__restrict__ conn, int32_t *__restrict__ bcount,
+                             const int32_t *__restrict__ boff, int32_t *__restrict__ bconn, int32_t *__restrict__ blab,
+                             int32_t *__restrict__ belem, int32_t *__restrict__ bface)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int nx = C.nx, ny = C.ny, nz = C.nz;
+    int nc = nx * ny * C.ncl;
+    if (c >= nc) return;
+    int kc = c / (nx * ny), r = c - kc * nx * ny;
+    int j = r / nx, i = r - j * nx;
+    int k = C.c_lo + kc;
+    int n[8], lab[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        int a = q & 1, b = (q >> 1) & 1, cc = q >> 2;
+        n[q] = cube_lv(C, i + a, j + b, k + cc);
+        lab[q] = cube_vlab(i + a, j + b, k + cc, nx, ny, nz);
+    }
+    const int nff[6] = {3, 1, 0, 2, 4, 5};
+    int kf = PASS ? boff[c] : 0;
+    for (int d = 0; d < 6; ++d) {
+        int t = 6 * c + d;
+        int lc[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) lc[q] = c_cubeTets[d][q];
+        if (PASS == 0) reinterpret_cast<int4 *>(conn)[t] = make_int4(n[lc[0]], n[lc[1]], n[lc[2]], n[lc[3]]);
+        for (int f = 0; f < 4; ++f) {
+            int f0 = lc[c_nvfaceTet[f][0]], f1 = lc[c_nvfaceTet[f][1]], f2 = lc[c_nvfaceTet[f][2]];
+            int l = lab[f0] & lab[f1] & lab[f2];
+            if (l && (l & (l - 1)) == 0) { // exactly one boundary plane
+                if (PASS) {
+                    int kk = __ffs(l) - 1;
+                    bconn[3 * (size_t)kf] = n[f0];
+                    bconn[3 * (size_t)kf + 1] = n[f1];
+                    bconn[3 * (size_t)kf + 2] = n[f2];
+                    blab[kf] = nff[kk] + 1;
+                    belem[kf] = t;
+                    bface[kf] = f;
+                }
+                kf++;
+            }
+        }
+    }
+    if (PASS == 0) bcount[c] = kf;
+}
+
+static void build_cube(ffcuda_ctx *ctx, int nx, int ny, int nz, int rank, int nranks, ffcuda_mesh **out)
+{
+    FF_REQUIRE(nx > 0 && ny > 0 && nz > 0, "cube sizes must be positive");
+    FF_REQUIRE(nranks >= 1 && nz + 1 >= nranks, "cube has fewer vertex layers than ranks");
+    CubeLayout C;
+    C.nx = nx; C.ny = ny; C.nz = nz;
+    const int64_t L0 = (int64_t)rank * (nz + 1) / nranks, L1 = (int64_t)(rank + 1) * (nz + 1) / nranks;
+    C.L0 = (int)L0;
+    C.nown = (int)(L1 - L0);
+    C.has_lower = rank > 0;
+    C.has_upper = rank < nranks - 1;
+    C.c_lo = std::max(C.L0 - 1, 0);
+    const int c_hi = std::min(C.L0 + C.nown - 1, nz - 1); // inclusive
+    C.ncl = c_hi - C.c_lo + 1;
+    const int64_t nk = (int64_t)(nx + 1) * (ny + 1);
+    int64_t nc64 = (int64_t)nx * ny * C.ncl;
+    FF_REQUIRE(nc64 * 6 < ((int64_t)1 << 27), "cube (slab) too large for one device (limit 2^27 tets); use more ranks");
+    FF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::unique_ptr<ffcuda_mesh> m(new ffcuda_mesh());
+    m->ctx = ctx;
+    m->dim = 3; m->vstride = 4;
+    int nc = (int)nc64;
+    m->nv_owned = (int)(nk * C.nown);
+    m->nv = (int)(nk * (C.nown + C.has_lower + C.has_upper));
+    m->nt = 6 * nc;
+    m->xyz.alloc((size_t)m->nv * 4);
+    m->conn.alloc((size_t)m->nt * 4);
+    m->elab.alloc(m->nt);
+    FF_CUDA(cudaMemsetAsync(m->elab.p, 0, m->elab.bytes(), st));
+    if (nranks > 1) {
+        m->distributed = true;
+        m->gid.alloc(m->nv);
+        m->nbr[0] = C.has_lower ? rank - 1 : -1;
+        m->nbr[1] = C.has_upper ? rank + 1 : -1;
+        m->send_off[0] = 0; m->send_cnt[0] = (int)nk;
+        m->send_off[1] = (int)(nk * (C.nown - 1)); m->send_cnt[1] = (int)nk;
+        m->recv_off[0] = m->nv_owned; m->recv_cnt[0] = (int)nk;
+        m->recv_off[1] = m->nv_owned + (C.has_lower ? (int)nk : 0); m->recv_cnt[1] = (int)nk;
+    }
+    ff_launch(ctx, "mesh_cube_vertices", [&] { k_cube_vertices<<<ff_blocks(m->nv, 256), 256, 0, st>>>(m->xyz.p, m->gid.p, C, m->nv); });
+    DBuf<int32_t> bcount, boff;
+    bcount.alloc(nc); boff.alloc(nc);
+    ff_launch(ctx, "mesh_cube_cells", [&] {
+        k_cube_cells<0><<<ff_blocks(nc, 128), 128, 0, st>>>(C, m->conn.p, bcount.p, nullptr, nullptr, nullptr, nullptr, nullptr);
+    });
+    int64_t tot = 0;
+    ff_exclusive_scan_i32(ctx, bcount.p, boff.p, nc, &tot);
+    if (nranks == 1) FF_REQUIRE(tot == 4 * ((int64_t)nx * ny + (int64_t)nx * nz + (int64_t)ny * nz), "internal: boundary face count mismatch");
+    m->nbe = (int)tot;
+    m->bconn.alloc((size_t)m->nbe * 3);
+    m->blab.alloc(m->nbe); m->belem.alloc(m->nbe); m->bface.alloc(m->nbe);
+    ff_launch(ctx, "mesh_cube_bfaces", [&] {
+        k_cube_cells<1><<<ff_blocks(nc, 128), 128, 0, st>>>(C, nullptr, nullptr, boff.p, m->bconn.p, m->blab.p, m->belem.p, m->bface.p);
+    });
+    FF_CUDA(cudaStreamSynchronize(st));
+    *out = m.release();
+}
+
+extern "C" int ffcuda_mesh_cube(ffcuda_ctx *ctx, int nx, int ny, int nz, ffcuda_mesh **out)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(ctx && out, "ffcuda_mesh_cube: null context/output");
+    build_cube(ctx, nx, ny, nz, 0, 1, out);
+    FF_API_END(ctx)
+}
+
+extern "C" int ffcuda_mesh_cube_distributed(ffcuda_ctx *ctx, int nx, int ny, int nz, ffcuda_mesh **out)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(ctx && out, "ffcuda_mesh_cube_distributed: null context/output");
+    FF_REQUIRE(ctx->nranks == 1 || ctx->nccl_comm, "ffcuda_mesh_cube_distributed: call ffcuda_comm_init first");
+    build_cube(ctx, nx, ny, nz, ctx->rank, ctx->nranks, out);
+    FF_API_END(ctx)
+}
+
+extern "C" int ffcuda_mesh_local_to_global(ffcuda_mesh *m, int *nowned, int *nlocal, int64_t *gid)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(m, "null mesh");
+    if (nowned) *nowned = m->nv_owned;
+    if (nlocal) *nlocal = m->nv;
+    if (gid) {
+        FF_CUDA(cudaSetDevice(m->ctx->device));
+        if (m->gid.p) {
+            FF_CUDA(cudaMemcpy(gid, m->gid.p, m->gid.bytes(), cudaMemcpyDeviceToHost));
+        } else
+            for (int i = 0; i < m->nv; ++i) gid[i] = i;
+    }
+    FF_API_END(m ? m->ctx : nullptr)
+}
+
+// ---------------------------------------------------------------------------------------------------
+// square(nx,ny)
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_square_vertices(double *__restrict__ xy, int nx, int ny)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int nx1 = nx + 1;
+    if (p >= nx1 * (ny + 1)) return;
+    int j = p / nx1, i = p - j * nx1;
+    reinterpret_cast<double2 *>(xy)[p] = make_double2((double)i / nx, (double)j / ny);
+}
+
+__global__ void k_square_cells(int32_t *__restrict__ conn, int nx, int ny)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= nx * ny) return;
+    int j = c / nx, i = c - j * nx, nx1 = nx + 1;
+    int i0 = i + j * nx1, i1 = i0 + 1, i2 = i1 + nx1, i3 = i2 - 1;
+    int32_t *t = conn + 6 * (size_t)c;
+    t[0] = i0; t[1] = i1; t[2] = i2;
+    t[3] = i0; t[4] = i2; t[5] = i3;
+}
+
+__global__ void k_square_bedges(int32_t *__restrict__ bconn, int32_t *__restrict__ blab, int32_t *__restrict__ belem,
+                                int32_t *__restrict__ bface, int nx, int ny)
+{
+    int e = blockIdx.x * blockDim.x + threadIdx.x;
+    int nbe = 2 * (nx + ny), nx1 = nx + 1;
+    if (e >= nbe) return;
+    int v0, v1, lab, el, f;
+    if (e < nx) { // bottom
+        int i = e;
+        v0 = i; v1 = i + 1; lab = 1; el = 2 * i; f = 2;
+    } else if (e < nx + ny) { // right
+        int j = e - nx;
+        v0 = nx + j * nx1; v1 = v0 + nx1; lab = 2; el = 2 * ((nx - 1) + j * nx); f = 0;
+    } else if (e < 2 * nx + ny) { // top
+        int i = e - nx - ny;
+        v0 = i + ny * nx1; v1 = v0 + 1; lab = 3; el = 2 * (i + (ny - 1) * nx) + 1; f = 0;
+    } else { // left
+        int j = e - 2 * nx - ny;
+        v0 = j * nx1; v1 = v0 + nx1; lab = 4; el = 2 * (j * nx) + 1; f = 1;
+    }
+    bconn[2 * e] = v0; bconn[2 * e + 1] = v1;
+    blab[e] = lab; belem[e] = el; bface[e] = f;
+}
+
+extern "C" int ffcuda_mesh_square(ffcuda_ctx *ctx, int nx, int ny, ffcuda_mesh **out)
+{
+    ffcuda_mesh *m = nullptr;
+    FF_API_BEGIN
+    FF_REQUIRE(ctx && out, "ffcuda_mesh_square: null context/output");
+    FF_REQUIRE(nx > 0 && ny > 0, "square sizes must be positive");
+    FF_REQUIRE((int64_t)nx * ny * 2 < ((int64_t)1 << 27), "square too large");
+    FF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    m = new ffcuda_mesh();
+    m->ctx = ctx;
+    m->dim = 2; m->vstride = 2;
+    m->nv = (nx + 1) * (ny + 1);
+    m->nv_owned = m->nv;
+    m->nt = 2 * nx * ny;
+    m->nbe = 2 * (nx + ny);
+    m->xyz.alloc((size_t)m->nv * 2);
+    m->conn.alloc((size_t)m->nt * 3);
+    m->elab.alloc(m->nt);
+    m->bconn.alloc((size_t)m->nbe * 2);
+    m->blab.alloc(m->nbe); m->belem.alloc(m->nbe); m->bface.alloc(m->nbe);
+    FF_CUDA(cudaMemsetAsync(m->elab.p, 0, m->elab.bytes(), st));
+    ff_launch(ctx, "mesh_square_vertices", [&] { k_square_vertices<<<ff_blocks(m->nv, 256), 256, 0, st>>>(m->xyz.p, nx, ny); });
+    ff_launch(ctx, "mesh_square_cells", [&] { k_square_cells<<<ff_blocks((size_t)nx * ny, 256), 256, 0, st>>>(m->conn.p, nx, ny); });
+    ff_launch(ctx, "mesh_square_bedges", [&] {
+        k_square_bedges<<<ff_blocks(m->nbe, 256), 256, 0, st>>>(m->bconn.p, m->blab.p, m->belem.p, m->bface.p, nx, ny);
+    });
+    FF_CUDA(cudaStreamSynchronize(st));
+    *out = m;
+    m = nullptr;
+    FF_API_END((delete m, ctx))
+}
+
+extern "C" int ffcuda_mesh_info(ffcuda_mesh *m, int *dim, int *nv, int *nt, int *nbe)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(m, "null mesh");
+    if (dim) *dim = m->dim;
+    if (nv) *nv = m->nv;
+    if (nt) *nt = m->nt;
+    if (nbe) *nbe = m->nbe;
+    FF_API_END(m ? m->ctx : nullptr)
+}
+
+extern "C" int ffcuda_mesh_download(ffcuda_mesh *m, double *xyz, int32_t *conn, int32_t *elab, int32_t *bconn,
+                                    int32_t *blab, int32_t *belem, int32_t *bface)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(m, "null mesh");
+    ffcuda_ctx *ctx = m->ctx;
+    FF_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    if (xyz) {
+        if (m->dim == 3) {
+            DBuf<double> tmp;
+            tmp.alloc((size_t)m->nv * 3);
+            ff_launch(ctx, "mesh_unpad_xyz", [&] { k_unpad_xyz3<<<ff_blocks(m->nv, 256), 256, 0, st>>>(m->xyz.p, tmp.p, m->nv); });
+            FF_CUDA(cudaMemcpyAsync(xyz, tmp.p, tmp.bytes(), cudaMemcpyDeviceToHost, st));
+            FF_CUDA(cudaStreamSynchronize(st));
+        } else
+            FF_CUDA(cudaMemcpyAsync(xyz, m->xyz.p, m->xyz.bytes(), cudaMemcpyDeviceToHost, st));
+    }
+    if (conn) FF_CUDA(cudaMemcpyAsync(conn, m->conn.p, m->conn.bytes(), cudaMemcpyDeviceToHost, st));
+    if (elab) FF_CUDA(cudaMemcpyAsync(elab, m->elab.p, m->elab.bytes(), cudaMemcpyDeviceToHost, st));
+    if (bconn && m->nbe) FF_CUDA(cudaMemcpyAsync(bconn, m->bconn.p, m->bconn.bytes(), cudaMemcpyDeviceToHost, st));
+    if (blab && m->nbe) FF_CUDA(cudaMemcpyAsync(blab, m->blab.p, m->blab.bytes(), cudaMemcpyDeviceToHost, st));
+    if (belem && m->nbe) FF_CUDA(cudaMemcpyAsync(belem, m->belem.p, m->belem.bytes(), cudaMemcpyDeviceToHost, st));
+    if (bface && m->nbe) FF_CUDA(cudaMemcpyAsync(bface, m->bface.p, m->bface.bytes(), cudaMemcpyDeviceToHost, st));
+    FF_CUDA(cudaStreamSynchronize(st));
+    FF_API_END(m ? m->ctx : nullptr)
+}
+
+extern "C" void ffcuda_mesh_destroy(ffcuda_mesh *m)
+{
+    if (!m) return;
+    cudaSetDevice(m->ctx->device);
+    delete m;
+}

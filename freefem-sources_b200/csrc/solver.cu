@@ -1,0 +1,506 @@
+// solver.cu — KERNEL 4: CSR SpMV (a group of T lanes per row) and the Jacobi-preconditioned CG built on it.
+//
+// Replaces HashMatrix::addMatMul (femlib/HashMatrix.cpp:1087-1154), HMatVirtPrecon / SolverCG::dosolver
+// (femlib/VirtualSolverCG.hpp:13-192), gettgv (HashMatrix.cpp:1341-1371) and ConjugueGradient
+// (femlib/CG.cpp:195-265).  The recurrence, the initial guess handling (SetInitWithBC), the preconditioner and the
+// stopping rule are the reference's; what differs is the summation order of the SpMV rows and of the dot products
+// (fixed-shape trees: bit-reproducible from run to run, ~1e-16 relative away from the sequential CPU sums).
+//
+// One CG iteration = 3 kernels, every scalar stays on the device (no host round trip inside the loop):
+//   K1  AH = A*H           fused with the dot products <G,H> and <H,AH>        reads 12 B/nnz + H,G   writes AH
+//   K2  G += rho*AH        fused with <G, D1*G>  (rho = -<G,H>/<H,AH>)          reads G,AH,D1          writes G
+//   K3  x += rho*H ; H = gamma*H - D1*G  (gamma = gCg/gCg_prev) ; convergence   reads x,H,G,D1         writes x,H
+// Dot products: per-block partial sums in a fixed tree, finished by the last block to retire (fixed order over the
+// partials) -> deterministic, no fp64 atomics.  The host enqueues iterations in batches and polls a device flag;
+// kernels of iterations past the converged one are no-ops, so x is exactly the iterate of the stopping iteration.
+#include "common.cuh"
+#include <cmath>
+
+// d_scal layout (doubles)
+enum { S_GH = 0, S_HAH = 1, S_GCG0 = 2, S_GCG1 = 3, S_EPS2 = 4, S_TMP0 = 8, S_TMP1 = 9, S_TMP2 = 10 };
+// d_flag layout (ints)
+enum { F_CONV_ITER = 0, F_COUNTER = 2 };
+
+static constexpr int RED_THREADS = 256;
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// fixed-shape block sum (all threads must call); result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double *sh /* >= 32 doubles */)
+{
+    v = warp_sum(v);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (l == 0) sh[w] = v;
+    __syncthreads();
+    double r = 0;
+    if (w == 0) {
+        r = l < nw ? sh[l] : 0.0;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+// Every block deposits NV partial sums; the last block to retire adds the partials of all blocks in a fixed order
+// and stores the totals in out[0..NV).  counter must be 0 on entry and is reset to 0 on exit.
+template <int NV>
+__device__ __forceinline__ void grid_sum_finish(const double (&v)[NV], double *__restrict__ partial, int *counter,
+                                                double *__restrict__ out, double *sh)
+{
+    __shared__ bool last;
+    double r[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) r[k] = block_sum(v[k], sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) partial[(size_t)k * gridDim.x + blockIdx.x] = r[k];
+        __threadfence();
+        int t = atomicAdd(counter, 1);
+        last = (t == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double s = 0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += __ldcg(partial + (size_t)k * gridDim.x + i);
+        s = block_sum(s, sh);
+        if (threadIdx.x == 0) out[k] = s;
+    }
+    if (threadIdx.x == 0) *counter = 0;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// row product: T lanes per row, lane l takes entries l, l+T, ... ; xor tree over the T lanes
+// ---------------------------------------------------------------------------------------------------
+template <int T>
+__device__ __forceinline__ double row_product(const int32_t *__restrict__ colind, const double *__restrict__ vals,
+                                              const double *__restrict__ x, int rb, int re, int l)
+{
+    double s = 0;
+    for (int j = rb + l; j < re; j += T) s = fma(__ldcs(vals + j), __ldg(x + __ldcs(colind + j)), s);
+#pragma unroll
+    for (int o = T >> 1; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    return s;
+}
+
+// y = A x  (optionally y = A x - b)
+template <int T>
+__global__ void __launch_bounds__(RED_THREADS) k_spmv(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                                                      const double *__restrict__ vals, const double *__restrict__ x,
+                                                      const double *__restrict__ sub, double *__restrict__ y, int n)
+{
+    const int l = threadIdx.x & (T - 1);
+    const int ngroups = gridDim.x * (RED_THREADS / T);
+    const int nround = (n + ngroups - 1) / ngroups; // uniform trip count: shuffles stay convergent
+    for (int it = 0; it < nround; ++it) {
+        const int row = it * ngroups + blockIdx.x * (RED_THREADS / T) + threadIdx.x / T;
+        const bool ok = row < n;
+        const int rb = ok ? __ldg(rowptr + row) : 0, re = ok ? __ldg(rowptr + row + 1) : 0;
+        double s = row_product<T>(colind, vals, x, rb, re, l);
+        if (ok && l == 0) y[row] = sub ? s - sub[row] : s;
+    }
+}
+
+// CG start: G = A x - b ; partial <G, D1 G>
+template <int T>
+__global__ void __launch_bounds__(RED_THREADS) k_cg_init1(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                                                          const double *__restrict__ vals, const double *__restrict__ x,
+                                                          const double *__restrict__ b, const double *__restrict__ d1,
+                                                          double *__restrict__ G, int n, double *__restrict__ partial,
+                                                          int *__restrict__ flags, double *__restrict__ scal)
+{
+    __shared__ double sh[32];
+    const int l = threadIdx.x & (T - 1);
+    const int ngroups = gridDim.x * (RED_THREADS / T);
+    double acc[1] = {0.0};
+    const int nround = (n + ngroups - 1) / ngroups; // uniform trip count: shuffles stay convergent
+    for (int it = 0; it < nround; ++it) {
+        const int row = it * ngroups + blockIdx.x * (RED_THREADS / T) + threadIdx.x / T;
+        const bool ok = row < n;
+        const int rb = ok ? __ldg(rowptr + row) : 0, re = ok ? __ldg(rowptr + row + 1) : 0;
+        double s = row_product<T>(colind, vals, x, rb, re, l);
+        if (ok && l == 0) {
+            const double g = s - b[row];
+            G[row] = g;
+            acc[0] = fma(g, d1[row] * g, acc[0]);
+        }
+    }
+    grid_sum_finish<1>(acc, partial, flags + F_COUNTER, scal + S_GCG0, sh);
+}
+
+// CG start, second half: H = -D1 G ; eps2 ; "converged before the first iteration"
+__global__ void __launch_bounds__(RED_THREADS) k_cg_init2(const double *__restrict__ G, const double *__restrict__ d1,
+                                                          double *__restrict__ H, int n, double eps, int *__restrict__ flags,
+                                                          double *__restrict__ scal)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += stride) H[i] = -(d1[i] * G[i]);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const double gcg = scal[S_GCG0];
+        double eps2 = eps * eps;
+        if (eps > 0) eps2 *= gcg;
+        scal[S_EPS2] = eps2;
+        if (gcg != gcg) flags[F_CONV_ITER] = -2; // NaN: bad matrix (the reference asserts)
+        else if (gcg < 1e-30) flags[F_CONV_ITER] = -1;
+    }
+}
+
+// K1: AH = A H ; <G,H>, <H,AH>
+template <int T>
+__global__ void __launch_bounds__(RED_THREADS) k_cg_spmv(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                                                         const double *__restrict__ vals, const double *__restrict__ H,
+                                                         const double *__restrict__ G, double *__restrict__ AH, int n, int iter,
+                                                         double *__restrict__ partial, int *__restrict__ flags,
+                                                         double *__restrict__ scal)
+{
+    __shared__ double sh[32];
+    {
+        const int ci = flags[F_CONV_ITER]; // 0: running, -1/-2: stopped before the first iteration, k>0: converged at k
+        if (ci != 0 && iter > ci) return;
+    }
+    const int l = threadIdx.x & (T - 1);
+    const int ngroups = gridDim.x * (RED_THREADS / T);
+    double acc[2] = {0.0, 0.0};
+    const int nround = (n + ngroups - 1) / ngroups;
+    for (int it = 0; it < nround; ++it) {
+        const int row = it * ngroups + blockIdx.x * (RED_THREADS / T) + threadIdx.x / T;
+        const bool ok = row < n;
+        const int rb = ok ? __ldg(rowptr + row) : 0, re = ok ? __ldg(rowptr + row + 1) : 0;
+        double s = row_product<T>(colind, vals, H, rb, re, l);
+        if (ok && l == 0) {
+            const double h = H[row];
+            AH[row] = s;
+            acc[0] = fma(G[row], h, acc[0]);
+            acc[1] = fma(h, s, acc[1]);
+        }
+    }
+    grid_sum_finish<2>(acc, partial, flags + F_COUNTER, scal + S_GH, sh);
+}
+
+// K2: G += rho AH ; <G, D1 G> -> scal[S_GCG0 + (iter & 1)]
+__global__ void __launch_bounds__(RED_THREADS) k_cg_update_g(double *__restrict__ G, const double *__restrict__ AH,
+                                                             const double *__restrict__ d1, int n, int iter,
+                                                             double *__restrict__ partial, int *__restrict__ flags,
+                                                             double *__restrict__ scal)
+{
+    __shared__ double sh[32];
+    {
+        const int ci = flags[F_CONV_ITER]; // 0: running, -1/-2: stopped before the first iteration, k>0: converged at k
+        if (ci != 0 && iter > ci) return;
+    }
+    const double rho = -scal[S_GH] / scal[S_HAH];
+    double acc[1] = {0.0};
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += stride) {
+        const double g = fma(rho, AH[i], G[i]);
+        G[i] = g;
+        acc[0] = fma(g, d1[i] * g, acc[0]);
+    }
+    grid_sum_finish<1>(acc, partial, flags + F_COUNTER, scal + S_GCG0 + (iter & 1), sh);
+}
+
+// K3: x += rho H ; H = gamma H - D1 G ; convergence test
+__global__ void __launch_bounds__(RED_THREADS) k_cg_update_xh(double *__restrict__ x, double *__restrict__ H,
+                                                              const double *__restrict__ G, const double *__restrict__ d1, int n,
+                                                              int iter, int *__restrict__ flags, const double *__restrict__ scal)
+{
+    {
+        const int ci = flags[F_CONV_ITER]; // 0: running, -1/-2: stopped before the first iteration, k>0: converged at k
+        if (ci != 0 && iter > ci) return;
+    }
+    const double rho = -scal[S_GH] / scal[S_HAH];
+    const double gcg = scal[S_GCG0 + (iter & 1)], gcgp = scal[S_GCG0 + ((iter - 1) & 1)];
+    const double gamma = gcg / gcgp;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += stride) {
+        const double h = H[i];
+        x[i] = fma(rho, h, x[i]);
+        H[i] = gamma * h - d1[i] * G[i];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0 && gcg < scal[S_EPS2]) {
+        // other blocks of this launch test `iter > conv_iter`, which stays false for them
+        flags[F_CONV_ITER] = iter;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// preconditioner set-up: diag, gettgv statistics, D1, SetInitWithBC
+// ---------------------------------------------------------------------------------------------------
+// pass 0: max of the diagonal.  pass 1: largest diagonal value < ref, and number of entries == ref
+__global__ void __launch_bounds__(RED_THREADS) k_diag_stats(const int32_t *__restrict__ diagpos, const double *__restrict__ vals, int n,
+                                                            int pass, double ref, double *__restrict__ partial,
+                                                            int *__restrict__ flags, double *__restrict__ out)
+{
+    __shared__ double sh[32];
+    __shared__ bool last;
+    double m = -INFINITY, cnt = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += stride) {
+        const int p = diagpos[i];
+        if (p < 0) continue;
+        const double a = vals[p];
+        if (pass == 0) m = fmax(m, a);
+        else if (a == ref) cnt += 1;
+        else if (a < ref) m = fmax(m, a);
+    }
+    // block max
+    for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) sh[w] = m;
+    __syncthreads();
+    if (w == 0) {
+        m = l < (int)(blockDim.x >> 5) ? sh[l] : -INFINITY;
+        for (int o = 16; o; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    double c = block_sum(cnt, sh);
+    if (threadIdx.x == 0) {
+        partial[blockIdx.x] = m;
+        partial[gridDim.x + blockIdx.x] = c;
+        __threadfence();
+        last = (atomicAdd(flags + F_COUNTER, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    if (threadIdx.x == 0) {
+        double mm = -INFINITY, cc = 0;
+        for (int i = 0; i < (int)gridDim.x; ++i) {
+            mm = fmax(mm, __ldcg(partial + i));
+            cc += __ldcg(partial + gridDim.x + i);
+        }
+        out[0] = mm;
+        out[1] = cc;
+        flags[F_COUNTER] = 0;
+    }
+}
+
+__global__ void k_precond(const int32_t *__restrict__ diagpos, const double *__restrict__ vals, int n, double *__restrict__ d1,
+                          int has_tgv, double ttgv, double tgv, const double *__restrict__ b, double *__restrict__ x)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int p = diagpos[i];
+    const double a = p >= 0 ? vals[p] : 0.0;
+    d1[i] = (a * a < 1e-60) ? 1.0 : 1.0 / a;
+    if (has_tgv && a == ttgv) x[i] = b[i] / tgv; // SetInitWithBC
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+void ff_halo_exchange(ffcuda_matrix *A, double *v);                    // comm.cu (no-op on one GPU)
+void ff_allreduce(ffcuda_matrix *A, double *d, int count, int op_max); // comm.cu (no-op on one GPU)
+
+static int *ctx_flags(ffcuda_ctx *ctx) { return reinterpret_cast<int *>(ctx->d_scal + 32); }
+
+static void ensure_partial(ffcuda_ctx *ctx, size_t ndoubles)
+{
+    if (ctx->partial_cap >= ndoubles) return;
+    if (ctx->d_partial) cudaFree(ctx->d_partial);
+    ctx->d_partial = nullptr;
+    FF_CUDA(cudaMalloc((void **)&ctx->d_partial, ndoubles * sizeof(double)));
+    ctx->partial_cap = ndoubles;
+}
+
+static int pick_T(const ffcuda_matrix *A)
+{
+    const double avg = A->n ? (double)A->nnz / A->n : 1.0;
+    if (avg <= 6) return 4;
+    if (avg <= 12) return 8;
+    if (avg <= 40) return 16;
+    return 32;
+}
+
+static int grid_for(const ffcuda_ctx *ctx, size_t work_threads)
+{
+    size_t need = (work_threads + RED_THREADS - 1) / RED_THREADS;
+    size_t cap = (size_t)ctx->sm_count * 8;
+    return (int)std::max<size_t>(1, std::min(need, cap));
+}
+
+#define FF_DISPATCH_T(T, ...)                  \
+    switch (T) {                               \
+    case 4: { constexpr int TT = 4; __VA_ARGS__; } break;   \
+    case 8: { constexpr int TT = 8; __VA_ARGS__; } break;   \
+    case 16: { constexpr int TT = 16; __VA_ARGS__; } break; \
+    default: { constexpr int TT = 32; __VA_ARGS__; } break; \
+    }
+
+static void spmv_launch(ffcuda_matrix *A, const double *x, const double *sub, double *y)
+{
+    ffcuda_ctx *ctx = A->ctx;
+    const int T = pick_T(A);
+    const int grid = grid_for(ctx, (size_t)A->n * T);
+    FF_DISPATCH_T(T, ff_launch(ctx, "spmv", [&] {
+                      k_spmv<TT><<<grid, RED_THREADS, 0, ctx->stream>>>(A->rowptr, A->colind, A->vals.p, x, sub, y, A->n);
+                  }));
+}
+
+extern "C" int ffcuda_spmv(ffcuda_matrix *A, ffcuda_vec *x, ffcuda_vec *y)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A && x && y, "ffcuda_spmv: null argument");
+    FF_REQUIRE(x->n >= A->ncols, "ffcuda_spmv: x is shorter than the number of (owned + ghost) columns");
+    FF_REQUIRE(y->n >= A->n, "ffcuda_spmv: y is shorter than the number of rows");
+    FF_REQUIRE(x->d.p != y->d.p, "ffcuda_spmv: x and y must be different vectors");
+    FF_CUDA(cudaSetDevice(A->ctx->device));
+    ff_halo_exchange(A, x->d.p);
+    spmv_launch(A, x->d.p, nullptr, y->d.p);
+    FF_API_END(A ? A->ctx : nullptr)
+}
+
+static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, int itmax, double tgv, int *iters, int *converged,
+                      double *gcg_out)
+{
+    ffcuda_ctx *ctx = A->ctx;
+    cudaStream_t st = ctx->stream;
+    const int n = A->n, ncols = A->ncols;
+    FF_REQUIRE(A->diagpos, "matrix has no diagonal index");
+    if (itmax <= 0) itmax = n;
+    if (!A->wG.p) {
+        A->wG.alloc(n);
+        A->wAH.alloc(n);
+        A->wD1.alloc(n);
+        A->wH.alloc(ncols);
+        if (ncols > n) A->wX.alloc(ncols);
+    }
+    double *G = A->wG.p, *H = A->wH.p, *AH = A->wAH.p, *D1 = A->wD1.p;
+    double *scal = ctx->d_scal;
+    int *flags = ctx_flags(ctx);
+    const int T = pick_T(A);
+    const int grid_s = grid_for(ctx, (size_t)n * T), grid_v = grid_for(ctx, (size_t)n);
+    ensure_partial(ctx, 2 * (size_t)std::max(grid_s, grid_v) + 16);
+    double *partial = ctx->d_partial;
+    FF_CUDA(cudaMemsetAsync(scal, 0, 64 * sizeof(double), st));
+
+    // --- gettgv: largest diagonal value, its multiplicity, and the next one (ratio 1e6)
+    double *hs = ctx->h_scal;
+    ff_launch(ctx, "cg_diag_stats", [&] { k_diag_stats<<<grid_v, RED_THREADS, 0, st>>>(A->diagpos, A->vals.p, n, 0, 0.0, partial, flags, scal + S_TMP0); });
+    ff_allreduce(A, scal + S_TMP0, 1, 1);
+    FF_CUDA(cudaMemcpyAsync(hs, scal + S_TMP0, sizeof(double), cudaMemcpyDeviceToHost, st));
+    FF_CUDA(cudaStreamSynchronize(st));
+    double ttgv = hs[0];
+    ff_launch(ctx, "cg_diag_stats", [&] { k_diag_stats<<<grid_v, RED_THREADS, 0, st>>>(A->diagpos, A->vals.p, n, 1, ttgv, partial, flags, scal + S_TMP0); });
+    ff_allreduce(A, scal + S_TMP0, 1, 1);
+    ff_allreduce(A, scal + S_TMP1, 1, 0);
+    FF_CUDA(cudaMemcpyAsync(hs, scal + S_TMP0, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    FF_CUDA(cudaStreamSynchronize(st));
+    double max1 = hs[0];
+    long ntgv = (long)hs[1];
+    if (!(ttgv > 0)) { // the reference starts its scan from ttgv = max1 = 0
+        ttgv = 0;
+        ntgv = 0;
+    }
+    if (!(max1 > 0)) max1 = 0;
+    if (max1 * 1e6 > ttgv) {
+        ttgv = 0;
+        ntgv = 0;
+    }
+    ff_launch(ctx, "cg_precond", [&] {
+        k_precond<<<ff_blocks(n, 256), 256, 0, st>>>(A->diagpos, A->vals.p, n, D1, ntgv > 0, ttgv, tgv, b, x);
+    });
+
+    // --- G = A x - b, H = -D1 G
+    const double *xin = x;
+    if (ncols > n) {
+        FF_CUDA(cudaMemcpyAsync(A->wX.p, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        ff_halo_exchange(A, A->wX.p);
+        xin = A->wX.p;
+    }
+    FF_DISPATCH_T(T, ff_launch(ctx, "cg_init_spmv", [&] {
+                      k_cg_init1<TT><<<grid_s, RED_THREADS, 0, st>>>(A->rowptr, A->colind, A->vals.p, xin, b, D1, G, n, partial, flags, scal);
+                  }));
+    ff_allreduce(A, scal + S_GCG0, 1, 0);
+    ff_launch(ctx, "cg_init_h", [&] { k_cg_init2<<<grid_v, RED_THREADS, 0, st>>>(G, D1, H, n, eps, flags, scal); });
+
+    // --- iterations, enqueued in batches; the flag of batch k is inspected while batch k+1 runs
+    int *hflags = reinterpret_cast<int *>(ctx->h_scal + 32); // 2 slots of 4 ints
+    cudaEvent_t ev[2];
+    FF_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+    FF_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    int it = 0, slot = 0, batch = 4;
+    bool pending[2] = {false, false}, done = false;
+    try {
+        FF_CUDA(cudaMemcpyAsync(hflags, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+        FF_CUDA(cudaStreamSynchronize(st));
+        done = hflags[F_CONV_ITER] != 0;
+        while (!done && it < itmax) {
+            const int nb = std::min(batch, itmax - it);
+            for (int k = 0; k < nb; ++k) {
+                ++it;
+                ff_halo_exchange(A, H);
+                FF_DISPATCH_T(T, ff_launch(ctx, "cg_spmv_dots", [&] {
+                                  k_cg_spmv<TT><<<grid_s, RED_THREADS, 0, st>>>(A->rowptr, A->colind, A->vals.p, H, G, AH, n, it, partial, flags, scal);
+                              }));
+                ff_allreduce(A, scal + S_GH, 2, 0);
+                ff_launch(ctx, "cg_update_g", [&] { k_cg_update_g<<<grid_v, RED_THREADS, 0, st>>>(G, AH, D1, n, it, partial, flags, scal); });
+                ff_allreduce(A, scal + S_GCG0 + (it & 1), 1, 0);
+                ff_launch(ctx, "cg_update_xh", [&] { k_cg_update_xh<<<grid_v, RED_THREADS, 0, st>>>(x, H, G, D1, n, it, flags, scal); });
+            }
+            FF_CUDA(cudaMemcpyAsync(hflags + 4 * slot, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+            FF_CUDA(cudaEventRecord(ev[slot], st));
+            pending[slot] = true;
+            const int prev = slot ^ 1;
+            if (pending[prev]) {
+                FF_CUDA(cudaEventSynchronize(ev[prev]));
+                pending[prev] = false;
+                if (hflags[4 * prev + F_CONV_ITER] != 0) done = true;
+            }
+            slot ^= 1;
+            if (batch < 32) batch *= 2;
+        }
+        FF_CUDA(cudaStreamSynchronize(st));
+    } catch (...) {
+        cudaEventDestroy(ev[0]);
+        cudaEventDestroy(ev[1]);
+        throw;
+    }
+    cudaEventDestroy(ev[0]);
+    cudaEventDestroy(ev[1]);
+    FF_CUDA(cudaMemcpyAsync(hflags, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+    FF_CUDA(cudaMemcpyAsync(hs, scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    FF_CUDA(cudaStreamSynchronize(st));
+    const int ci = hflags[F_CONV_ITER];
+    FF_REQUIRE(ci != -2, "CG: <g,Cg> is NaN (bad matrix)");
+    const int ret = ci == -1 ? 2 : (ci > 0 ? 1 : 0);
+    const int nit = ret == 2 ? 0 : (ret == 1 ? ci : it);
+    if (iters) *iters = nit;
+    if (converged) *converged = ret;
+    if (gcg_out) *gcg_out = hs[S_GCG0 + (nit & 1)];
+}
+
+extern "C" int ffcuda_cg(ffcuda_matrix *A, ffcuda_vec *b, ffcuda_vec *x, double eps, int itmax, double tgv, int *iters,
+                         int *converged, double *gcg)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A && b && x, "ffcuda_cg: null argument");
+    FF_REQUIRE(b->n >= A->n && x->n >= A->n, "ffcuda_cg: vectors shorter than the matrix");
+    FF_CUDA(cudaSetDevice(A->ctx->device));
+    cg_device(A, b->d.p, x->d.p, eps, itmax, tgv, iters, converged, gcg);
+    FF_API_END(A ? A->ctx : nullptr)
+}
+
+extern "C" int ffcuda_cg_host(ffcuda_matrix *A, const double *b, double *x, double eps, int itmax, double tgv, int *iters,
+                              int *converged, double *gcg)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A && b && x, "ffcuda_cg_host: null argument");
+    ffcuda_ctx *ctx = A->ctx;
+    FF_CUDA(cudaSetDevice(ctx->device));
+    DBuf<double> db, dx;
+    db.alloc(A->n);
+    dx.alloc(A->n);
+    FF_CUDA(cudaMemcpyAsync(db.p, b, db.bytes(), cudaMemcpyHostToDevice, ctx->stream));
+    FF_CUDA(cudaMemcpyAsync(dx.p, x, dx.bytes(), cudaMemcpyHostToDevice, ctx->stream));
+    cg_device(A, db.p, dx.p, eps, itmax, tgv, iters, converged, gcg);
+    FF_CUDA(cudaMemcpyAsync(x, dx.p, dx.bytes(), cudaMemcpyDeviceToHost, ctx->stream));
+    FF_CUDA(cudaStreamSynchronize(ctx->stream));
+    FF_API_END(A ? A->ctx : nullptr)
+}

@@ -1,0 +1,378 @@
+"""ctypes harness over the C ABI of libffcuda_core.so (include/ffcuda.h).
+
+This is NOT the product's host side (that is the C++ FreeFEM plugin, plugin/ffcuda.cpp): it only lets tests/ and
+bench.py drive exactly the entry points the plugin calls.  No numpy/torch arithmetic happens here; every compute
+call goes to the CUDA library and fails loudly (FfcudaError) when the library or a CUDA device is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libffcuda_core.so")
+OP_ID, OP_DX, OP_DY, OP_DZ = 0, 1, 2, 6
+
+# every symbol include/ffcuda.h declares (checked against the header by tests/test_abi.py)
+SYMBOLS = """ffcuda_ctx_create ffcuda_ctx_destroy ffcuda_last_error ffcuda_ctx_sync ffcuda_ctx_set_stream ffcuda_ctx_get_stream
+ffcuda_prof_enable ffcuda_prof_reset ffcuda_prof_get ffcuda_launch_count ffcuda_mesh_upload ffcuda_mesh_cube ffcuda_mesh_square
+ffcuda_mesh_info ffcuda_mesh_download ffcuda_mesh_destroy ffcuda_space_create ffcuda_space_info ffcuda_space_download_dofs
+ffcuda_space_destroy ffcuda_symbolic ffcuda_pattern_info ffcuda_pattern_download ffcuda_pattern_destroy ffcuda_matrix_create
+ffcuda_matrix_from_csr ffcuda_matrix_info ffcuda_matrix_download ffcuda_matrix_upload ffcuda_matrix_destroy ffcuda_vec_create
+ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_destroy ffcuda_assemble_bilinear
+ffcuda_assemble_linear ffcuda_bc_from_pairs ffcuda_bc_from_labels ffcuda_bc_count ffcuda_matrix_apply_bc ffcuda_vec_apply_bc
+ffcuda_vec_set_bc_values ffcuda_bc_destroy ffcuda_spmv ffcuda_cg ffcuda_cg_host ffcuda_comm_unique_id ffcuda_comm_init
+ffcuda_comm_finalize ffcuda_mesh_cube_distributed ffcuda_mesh_local_to_global""".split()
+
+
+class FfcudaError(RuntimeError):
+    pass
+
+
+class BTerm(C.Structure):
+    _fields_ = [("ucomp", C.c_int32), ("uop", C.c_int32), ("vcomp", C.c_int32), ("vop", C.c_int32), ("coef", C.c_double)]
+
+
+class LTerm(C.Structure):
+    _fields_ = [("vcomp", C.c_int32), ("vop", C.c_int32), ("coef", C.c_double)]
+
+
+_lib = None
+
+
+def lib():
+    """Load the CUDA library; there is no fallback of any kind."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise FfcudaError(f"{LIB_PATH} is missing: build it with `make -C freefem-sources_b200` (no CPU fallback exists)")
+        L = C.CDLL(LIB_PATH)
+        L.ffcuda_last_error.restype = C.c_char_p
+        L.ffcuda_last_error.argtypes = [C.c_void_p]
+        L.ffcuda_launch_count.restype = C.c_int64
+        L.ffcuda_launch_count.argtypes = [C.c_void_p]
+        L.ffcuda_vec_ptr.restype = C.c_void_p
+        L.ffcuda_vec_ptr.argtypes = [C.c_void_p]
+        L.ffcuda_ctx_get_stream.restype = C.c_void_p
+        L.ffcuda_ctx_get_stream.argtypes = [C.c_void_p]
+        for name in SYMBOLS:
+            f = getattr(L, name)
+            if name.endswith("_destroy"):
+                f.restype = None
+                f.argtypes = [C.c_void_p]
+        _lib = L
+    return _lib
+
+
+def _ck(rc, ctx=None):
+    if rc != 0:
+        msg = lib().ffcuda_last_error(ctx)
+        if not msg:
+            msg = lib().ffcuda_last_error(None)
+        raise FfcudaError((msg or b"unknown error").decode())
+
+
+def _i32(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _h(obj):
+    return C.c_void_p(obj.h)
+
+
+class _Handle:
+    _destroy = None
+
+    def __init__(self, h, ctx):
+        self.h = h
+        self.ctx = ctx
+
+    def close(self):
+        if getattr(self, "h", None):
+            getattr(lib(), self._destroy)(C.c_void_p(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context(_Handle):
+    _destroy = "ffcuda_ctx_destroy"
+
+    def __init__(self, device=0):
+        out = C.c_void_p()
+        _ck(lib().ffcuda_ctx_create(int(device), C.byref(out)))
+        super().__init__(out.value, self)
+
+    def sync(self):
+        _ck(lib().ffcuda_ctx_sync(_h(self)), self.h)
+
+    def set_stream(self, cuda_stream):
+        _ck(lib().ffcuda_ctx_set_stream(_h(self), C.c_void_p(cuda_stream)), self.h)
+
+    def prof_enable(self, on=True):
+        _ck(lib().ffcuda_prof_enable(_h(self), int(on)), self.h)
+
+    def prof_reset(self):
+        _ck(lib().ffcuda_prof_reset(_h(self)), self.h)
+
+    def prof_get(self, prefix=""):
+        ms, n = C.c_double(), C.c_int64()
+        _ck(lib().ffcuda_prof_get(_h(self), prefix.encode(), C.byref(ms), C.byref(n)), self.h)
+        return ms.value, n.value
+
+    def launch_count(self):
+        return lib().ffcuda_launch_count(_h(self))
+
+    # ---- multi-GPU
+    @staticmethod
+    def comm_unique_id():
+        buf = (C.c_char * 128)()
+        _ck(lib().ffcuda_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_init(self, rank, nranks, id128):
+        _ck(lib().ffcuda_comm_init(_h(self), rank, nranks, id128), self.h)
+
+    def comm_finalize(self):
+        _ck(lib().ffcuda_comm_finalize(_h(self)), self.h)
+
+    # ---- factories
+    def mesh_upload(self, dim, xyz, conn, elab=None, bconn=None, blab=None, belem=None, bface=None):
+        xyz, conn, elab = _f64(xyz), _i32(conn), _i32(elab)
+        bconn, blab, belem, bface = _i32(bconn), _i32(blab), _i32(belem), _i32(bface)
+        nbe = 0 if blab is None else len(blab)
+        out = C.c_void_p()
+        _ck(lib().ffcuda_mesh_upload(_h(self), dim, xyz.shape[0], _p(xyz), conn.shape[0], _p(conn), _p(elab), nbe, _p(bconn),
+                                     _p(blab), _p(belem), _p(bface), C.byref(out)), self.h)
+        return Mesh(out.value, self)
+
+    def mesh_cube(self, nx, ny, nz, distributed=False):
+        out = C.c_void_p()
+        f = lib().ffcuda_mesh_cube_distributed if distributed else lib().ffcuda_mesh_cube
+        _ck(f(_h(self), nx, ny, nz, C.byref(out)), self.h)
+        return Mesh(out.value, self)
+
+    def mesh_square(self, nx, ny):
+        out = C.c_void_p()
+        _ck(lib().ffcuda_mesh_square(_h(self), nx, ny, C.byref(out)), self.h)
+        return Mesh(out.value, self)
+
+    def vec(self, n):
+        out = C.c_void_p()
+        _ck(lib().ffcuda_vec_create(_h(self), int(n), C.byref(out)), self.h)
+        return Vec(out.value, self, int(n))
+
+    def vec_from(self, host):
+        host = _f64(host)
+        v = self.vec(len(host))
+        v.upload(host)
+        return v
+
+    def matrix_from_csr(self, n, rowptr, colind, vals):
+        rowptr, colind, vals = _i32(rowptr), _i32(colind), _f64(vals)
+        out = C.c_void_p()
+        _ck(lib().ffcuda_matrix_from_csr(_h(self), int(n), C.c_int64(len(colind)), _p(rowptr), _p(colind), _p(vals), C.byref(out)),
+            self.h)
+        return Matrix(out.value, self, None)
+
+
+class Mesh(_Handle):
+    _destroy = "ffcuda_mesh_destroy"
+
+    def info(self):
+        d, nv, nt, nbe = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        _ck(lib().ffcuda_mesh_info(_h(self), C.byref(d), C.byref(nv), C.byref(nt), C.byref(nbe)), self.ctx.h)
+        return d.value, nv.value, nt.value, nbe.value
+
+    def download(self):
+        dim, nv, nt, nbe = self.info()
+        m = dict(dim=dim, xyz=np.zeros((nv, dim)), conn=np.zeros((nt, dim + 1), np.int32), elab=np.zeros(nt, np.int32),
+                 bconn=np.zeros((nbe, dim), np.int32), blab=np.zeros(nbe, np.int32), belem=np.zeros(nbe, np.int32),
+                 bface=np.zeros(nbe, np.int32))
+        _ck(lib().ffcuda_mesh_download(_h(self), _p(m["xyz"]), _p(m["conn"]), _p(m["elab"]), _p(m["bconn"]), _p(m["blab"]),
+                                       _p(m["belem"]), _p(m["bface"])), self.ctx.h)
+        return m
+
+    def local_to_global(self):
+        no, nl = C.c_int(), C.c_int()
+        _ck(lib().ffcuda_mesh_local_to_global(_h(self), C.byref(no), C.byref(nl), None), self.ctx.h)
+        gid = np.zeros(nl.value, np.int64)
+        _ck(lib().ffcuda_mesh_local_to_global(_h(self), C.byref(no), C.byref(nl), _p(gid)), self.ctx.h)
+        return no.value, gid
+
+    def space(self, order=1, ncomp=1, elem2node=None, nnodes=0):
+        e2n = _i32(elem2node)
+        out = C.c_void_p()
+        _ck(lib().ffcuda_space_create(_h(self), order, ncomp, _p(e2n), int(nnodes), C.byref(out)), self.ctx.h)
+        return Space(out.value, self.ctx, self)
+
+
+class Space(_Handle):
+    _destroy = "ffcuda_space_destroy"
+
+    def __init__(self, h, ctx, mesh):
+        super().__init__(h, ctx)
+        self.mesh = mesh
+
+    def info(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        _ck(lib().ffcuda_space_info(_h(self), C.byref(a), C.byref(b), C.byref(c)), self.ctx.h)
+        return a.value, b.value, c.value  # ndof, ndofK, nnodes
+
+    def dofs(self):
+        ndof, ndofK, _ = self.info()
+        nt = self.mesh.info()[2]
+        d = np.zeros((nt, ndofK), np.int32)
+        _ck(lib().ffcuda_space_download_dofs(_h(self), _p(d)), self.ctx.h)
+        return d
+
+    def symbolic(self):
+        out = C.c_void_p()
+        _ck(lib().ffcuda_symbolic(_h(self), C.byref(out)), self.ctx.h)
+        return Pattern(out.value, self.ctx, self)
+
+    def bc_from_labels(self, labels, compmask, values):
+        labels, values = _i32(labels), _f64(values)
+        out = C.c_void_p()
+        _ck(lib().ffcuda_bc_from_labels(_h(self), len(labels), _p(labels), int(compmask), _p(values), C.byref(out)), self.ctx.h)
+        return BC(out.value, self.ctx)
+
+    def bc_from_pairs(self, dofs, vals):
+        dofs, vals = _i32(dofs), _f64(vals)
+        out = C.c_void_p()
+        _ck(lib().ffcuda_bc_from_pairs(_h(self), len(dofs), _p(dofs), _p(vals), C.byref(out)), self.ctx.h)
+        return BC(out.value, self.ctx)
+
+    def assemble_linear(self, b, terms, qpts, qw, labels=None, accumulate=False):
+        arr = (LTerm * max(len(terms), 1))()
+        for k, (vc, vo, c) in enumerate(terms):
+            arr[k] = LTerm(vc, vo, c)
+        qpts, qw, lab = _f64(qpts), _f64(qw), _i32(labels)
+        _ck(lib().ffcuda_assemble_linear(_h(b), _h(self), len(terms), arr, len(qw), _p(qpts), _p(qw),
+                                         0 if lab is None else len(lab), _p(lab), int(accumulate)), self.ctx.h)
+
+
+class Pattern(_Handle):
+    _destroy = "ffcuda_pattern_destroy"
+
+    def __init__(self, h, ctx, space):
+        super().__init__(h, ctx)
+        self.space = space
+
+    def info(self):
+        n, nnz = C.c_int(), C.c_int64()
+        _ck(lib().ffcuda_pattern_info(_h(self), C.byref(n), C.byref(nnz)), self.ctx.h)
+        return n.value, nnz.value
+
+    def download(self):
+        n, nnz = self.info()
+        rp, ci = np.zeros(n + 1, np.int32), np.zeros(nnz, np.int32)
+        _ck(lib().ffcuda_pattern_download(_h(self), _p(rp), _p(ci)), self.ctx.h)
+        return rp, ci
+
+    def matrix(self):
+        out = C.c_void_p()
+        _ck(lib().ffcuda_matrix_create(_h(self), C.byref(out)), self.ctx.h)
+        return Matrix(out.value, self.ctx, self)
+
+
+class Matrix(_Handle):
+    _destroy = "ffcuda_matrix_destroy"
+
+    def __init__(self, h, ctx, pattern):
+        super().__init__(h, ctx)
+        self.pattern = pattern
+
+    def info(self):
+        n, nnz = C.c_int(), C.c_int64()
+        _ck(lib().ffcuda_matrix_info(_h(self), C.byref(n), C.byref(nnz)), self.ctx.h)
+        return n.value, nnz.value
+
+    def download(self, out=None):
+        _, nnz = self.info()
+        v = np.zeros(nnz) if out is None else out
+        _ck(lib().ffcuda_matrix_download(_h(self), _p(v)), self.ctx.h)
+        return v
+
+    def upload(self, vals):
+        vals = _f64(vals)
+        _ck(lib().ffcuda_matrix_upload(_h(self), _p(vals)), self.ctx.h)
+
+    def assemble(self, terms, qpts, qw, labels=None, accumulate=False):
+        arr = (BTerm * max(len(terms), 1))()
+        for k, (uc, uo, vc, vo, c) in enumerate(terms):
+            arr[k] = BTerm(uc, uo, vc, vo, c)
+        qpts, qw, lab = _f64(qpts), _f64(qw), _i32(labels)
+        _ck(lib().ffcuda_assemble_bilinear(_h(self), _h(self.pattern.space), len(terms), arr, len(qw), _p(qpts), _p(qw),
+                                           0 if lab is None else len(lab), _p(lab), int(accumulate)), self.ctx.h)
+
+    def apply_bc(self, bc, tgv=1e30):
+        _ck(lib().ffcuda_matrix_apply_bc(_h(self), _h(bc), C.c_double(tgv)), self.ctx.h)
+
+    def spmv(self, x, y):
+        _ck(lib().ffcuda_spmv(_h(self), _h(x), _h(y)), self.ctx.h)
+
+    def cg(self, b, x, eps=1e-6, itmax=0, tgv=1e30):
+        it, conv, g = C.c_int(), C.c_int(), C.c_double()
+        _ck(lib().ffcuda_cg(_h(self), _h(b), _h(x), C.c_double(eps), int(itmax), C.c_double(tgv), C.byref(it), C.byref(conv),
+                            C.byref(g)), self.ctx.h)
+        return it.value, conv.value, g.value
+
+    def cg_host(self, b, x, eps=1e-6, itmax=0, tgv=1e30):
+        """b, x: contiguous float64 numpy arrays (x: initial guess in, solution out)."""
+        assert b.dtype == np.float64 and x.dtype == np.float64 and b.flags.c_contiguous and x.flags.c_contiguous
+        it, conv, g = C.c_int(), C.c_int(), C.c_double()
+        _ck(lib().ffcuda_cg_host(_h(self), _p(b), _p(x), C.c_double(eps), int(itmax), C.c_double(tgv), C.byref(it),
+                                 C.byref(conv), C.byref(g)), self.ctx.h)
+        return it.value, conv.value, g.value
+
+
+class Vec(_Handle):
+    _destroy = "ffcuda_vec_destroy"
+
+    def __init__(self, h, ctx, n):
+        super().__init__(h, ctx)
+        self.n = n
+
+    def upload(self, host):
+        host = _f64(host)
+        assert len(host) == self.n
+        _ck(lib().ffcuda_vec_upload(_h(self), _p(host)), self.ctx.h)
+
+    def download(self, out=None):
+        v = np.zeros(self.n) if out is None else out
+        _ck(lib().ffcuda_vec_download(_h(self), _p(v)), self.ctx.h)
+        return v
+
+    def fill(self, value):
+        _ck(lib().ffcuda_vec_fill(_h(self), C.c_double(value)), self.ctx.h)
+
+    def ptr(self):
+        return lib().ffcuda_vec_ptr(_h(self))
+
+    def apply_bc(self, bc, tgv=1e30):
+        _ck(lib().ffcuda_vec_apply_bc(_h(self), _h(bc), C.c_double(tgv)), self.ctx.h)
+
+    def set_bc_values(self, bc):
+        _ck(lib().ffcuda_vec_set_bc_values(_h(self), _h(bc)), self.ctx.h)
+
+
+class BC(_Handle):
+    _destroy = "ffcuda_bc_destroy"
+
+    def count(self):
+        n = C.c_int()
+        _ck(lib().ffcuda_bc_count(_h(self), C.byref(n)), self.ctx.h)
+        return n.value

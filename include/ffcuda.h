@@ -1,0 +1,181 @@
+/* ffcuda.h — C ABI of libffcuda_core.so, the B200-native (sm_100a) implementation of FreeFEM's
+ * finite-element assembly + CG hot path.
+ *
+ * This is the drop-in boundary (SURVEY.md §8 b, layer B2): plain C, opaque handles, plain pointers and
+ * sizes, no C++/torch/FreeFEM types.  It is called by
+ *   - freefem-sources_b200/plugin/ffcuda.cpp  (the FreeFEM plugin, `load "ffcuda"`, layer B1), and
+ *   - the standalone harness (tests/, bench.py through ctypes).
+ * Every function returns 0 on success, non-zero on failure; ffcuda_last_error() gives the message.
+ * No exception crosses the boundary.  Host buffers belong to the caller, device memory to the library.
+ * One host thread per context.  There is NO CPU fallback: without a CUDA device every compute entry fails.
+ *
+ * Reference interfaces replaced (paths under FreeFEM 4.15 src/):
+ *   ffcuda_mesh_upload          <- reads Mesh/Mesh3 (femlib/fem.hpp, Mesh3dn.hpp, GenericMesh.hpp:315)
+ *   ffcuda_mesh_cube / _square  <- BuildCube fflib/msh3.cpp:7879-8132, Carre_ fflib/lgmesh.cpp:1229-1384
+ *   ffcuda_space_create         <- FESpace/FESpace3 dof numbering: GFElement::operator() femlib/FESpacen.hpp:444,656,
+ *                                  BuildDFNumbering femlib/GenericMesh.hpp:1711-1954
+ *   ffcuda_symbolic             <- HashMatrix::operator+=(MatriceElementaire&) femlib/HashMatrix.cpp:1295-1332
+ *                                  (entry creation) + Sortij/Buildp/CSR() :671-682,:993-1030,:859-876
+ *   ffcuda_assemble_bilinear    <- AssembleBilinearForm fflib/problem.cpp:803-1111 (2-D), :1117-1417 (3-D),
+ *                                  Element_Op :6063-6160, :6337-6437, MatriceElementairePleine::call
+ *                                  femlib/MatriceCreuse_tpl.hpp:233-258
+ *   ffcuda_assemble_linear      <- AssembleLinearForm fflib/problem.cpp:10555, :10878-11227, Element_rhs :7839-7985
+ *   ffcuda_bc_* / *_apply_bc    <- AssembleBC fflib/problem.cpp:9881-10034, :10039-10194, HashMatrix::SetBC
+ *                                  femlib/HashMatrix.cpp:1195-1238 (tgv >= 0 branch)
+ *   ffcuda_spmv                 <- HashMatrix::addMatMul femlib/HashMatrix.cpp:1087-1154
+ *   ffcuda_cg                   <- SolverCG::dosolver femlib/VirtualSolverCG.hpp:112-192, HMatVirtPrecon :13-111,
+ *                                  ConjugueGradient femlib/CG.cpp:195-265, gettgv HashMatrix.cpp:1341-1371
+ */
+#ifndef FFCUDA_H
+#define FFCUDA_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ffcuda_ctx ffcuda_ctx;
+typedef struct ffcuda_mesh ffcuda_mesh;
+typedef struct ffcuda_space ffcuda_space;
+typedef struct ffcuda_pattern ffcuda_pattern;
+typedef struct ffcuda_matrix ffcuda_matrix;
+typedef struct ffcuda_vec ffcuda_vec;
+typedef struct ffcuda_bc ffcuda_bc;
+
+/* differential operator codes = FreeFEM's (femlib/FESpacen.hpp:73-82) */
+enum { FFCUDA_OP_ID = 0, FFCUDA_OP_DX = 1, FFCUDA_OP_DY = 2, FFCUDA_OP_DZ = 6 };
+
+/* one term of a bilinear form: coef * d^uop(u_ucomp) * d^vop(v_vcomp); unknown -> column, test -> row
+ * (BilinearOperator = LinearComb<pair<MGauche,MDroit>,C_F0>, femlib/DOperator.hpp:279-319) */
+typedef struct { int32_t ucomp, uop, vcomp, vop; double coef; } ffcuda_bterm;
+/* one term of a linear form: coef * d^vop(v_vcomp) */
+typedef struct { int32_t vcomp, vop; double coef; } ffcuda_lterm;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int ffcuda_ctx_create(int device, ffcuda_ctx **out);
+void ffcuda_ctx_destroy(ffcuda_ctx *ctx);
+const char *ffcuda_last_error(ffcuda_ctx *ctx); /* ctx may be NULL: last error of the calling thread */
+int ffcuda_ctx_sync(ffcuda_ctx *ctx);
+/* run all library work on an externally owned cudaStream_t (e.g. torch's current stream); NULL restores
+ * the library-owned stream */
+int ffcuda_ctx_set_stream(ffcuda_ctx *ctx, void *cuda_stream);
+void *ffcuda_ctx_get_stream(ffcuda_ctx *ctx);
+/* built-in kernel profiler: when enabled every kernel launch is bracketed by CUDA events on the launch
+ * stream.  ffcuda_prof_get returns accumulated milliseconds and launch count of kernels whose name starts
+ * with `prefix` ("" = all). */
+int ffcuda_prof_enable(ffcuda_ctx *ctx, int on);
+int ffcuda_prof_reset(ffcuda_ctx *ctx);
+int ffcuda_prof_get(ffcuda_ctx *ctx, const char *prefix, double *ms, int64_t *launches);
+/* total number of kernels launched by this context since creation / last reset (always counted) */
+int64_t ffcuda_launch_count(ffcuda_ctx *ctx);
+
+/* ---- mesh ---------------------------------------------------------------------------------------- */
+/* dim 2: triangles, dim 3: tetrahedra.  xyz: nv*dim (x,y[,z] per vertex).  conn: nt*(dim+1) vertex ids.
+ * elab: nt region labels (NULL = 0).  Boundary elements: bconn nbe*dim vertex ids, blab labels,
+ * belem/bface = Th.BoundaryElement(ib, ie) (element and local face; face ie is opposite local vertex ie).
+ * belem/bface may be NULL (then they are recovered by matching faces on the device). */
+int ffcuda_mesh_upload(ffcuda_ctx *ctx, int dim, int nv, const double *xyz, int nt, const int32_t *conn,
+                       const int32_t *elab, int nbe, const int32_t *bconn, const int32_t *blab,
+                       const int32_t *belem, const int32_t *bface, ffcuda_mesh **out);
+/* structured meshes generated ON THE DEVICE with FreeFEM's vertex/element/boundary ordering and labels */
+int ffcuda_mesh_cube(ffcuda_ctx *ctx, int nx, int ny, int nz, ffcuda_mesh **out);
+int ffcuda_mesh_square(ffcuda_ctx *ctx, int nx, int ny, ffcuda_mesh **out);
+int ffcuda_mesh_info(ffcuda_mesh *m, int *dim, int *nv, int *nt, int *nbe);
+/* any output pointer may be NULL */
+int ffcuda_mesh_download(ffcuda_mesh *m, double *xyz, int32_t *conn, int32_t *elab, int32_t *bconn,
+                         int32_t *blab, int32_t *belem, int32_t *bface);
+void ffcuda_mesh_destroy(ffcuda_mesh *m);
+
+/* ---- finite-element space ------------------------------------------------------------------------ */
+/* order 1|2 Lagrange, ncomp identical components ([P2,P2,P2] -> order 2, ncomp 3).
+ * Numbering contract (FESpacen.cpp:196-235, probed): dof(node,c) = node*ncomp + c; local dof i of an
+ * element = c*nloc + a, nodes a = vertices then edges ({01,02,03,12,13,23} in 3-D; edge opposite vertex
+ * a-3 in 2-D).  elem2node: nt*nloc node ids as FreeFEM numbered them (Vh(k,a)/ncomp); NULL means
+ * "number them for me": P1 -> vertex ids; P2 3-D -> first-encounter order of BuildDFNumbering; P2 2-D is
+ * rejected (FreeFEM applies its Gibbs renumbering there, FESpace.cpp:991 — pass the table). */
+int ffcuda_space_create(ffcuda_mesh *m, int order, int ncomp, const int32_t *elem2node, int nnodes,
+                        ffcuda_space **out);
+int ffcuda_space_info(ffcuda_space *s, int *ndof, int *ndofK, int *nnodes);
+int ffcuda_space_download_dofs(ffcuda_space *s, int32_t *dof /* nt*ndofK, FreeFEM's Vh(k,i) */);
+void ffcuda_space_destroy(ffcuda_space *s);
+
+/* ---- symbolic sparsity (kernel 1) ----------------------------------------------------------------- */
+/* CSR pattern of the (Vh,Vh) matrix exactly as MatriceMorse would hold it after CSR(): one entry per couple
+ * of dofs sharing an element (structural zeros and uncoupled components included), rows and columns sorted
+ * ascending, int32, 0-based.  Also builds the node->element incidence used by the row-owner assembly. */
+int ffcuda_symbolic(ffcuda_space *s, ffcuda_pattern **out);
+int ffcuda_pattern_info(ffcuda_pattern *p, int *n, int64_t *nnz);
+int ffcuda_pattern_download(ffcuda_pattern *p, int32_t *rowptr /* n+1 */, int32_t *colind /* nnz */);
+void ffcuda_pattern_destroy(ffcuda_pattern *p);
+
+/* ---- matrices and vectors (device resident) ------------------------------------------------------- */
+int ffcuda_matrix_create(ffcuda_pattern *p, ffcuda_matrix **out); /* values zeroed */
+/* a matrix given by host CSR arrays (solver-only use: `set(A,solver=CG)` on an existing MatriceMorse) */
+int ffcuda_matrix_from_csr(ffcuda_ctx *ctx, int n, int64_t nnz, const int32_t *rowptr, const int32_t *colind,
+                           const double *vals, ffcuda_matrix **out);
+int ffcuda_matrix_info(ffcuda_matrix *A, int *n, int64_t *nnz);
+int ffcuda_matrix_download(ffcuda_matrix *A, double *vals /* nnz, CSR order */);
+int ffcuda_matrix_upload(ffcuda_matrix *A, const double *vals);
+void ffcuda_matrix_destroy(ffcuda_matrix *A);
+
+int ffcuda_vec_create(ffcuda_ctx *ctx, int n, ffcuda_vec **out); /* zeroed */
+int ffcuda_vec_upload(ffcuda_vec *v, const double *host);
+int ffcuda_vec_download(ffcuda_vec *v, double *host);
+int ffcuda_vec_fill(ffcuda_vec *v, double value);
+void *ffcuda_vec_ptr(ffcuda_vec *v); /* device pointer (double*) */
+void ffcuda_vec_destroy(ffcuda_vec *v);
+
+/* ---- numeric assembly (kernels 2+3 fused: row-owner gather with in-register element evaluation) ---- */
+/* A (+)= sum over elements whose region label is in labels[] (NULL = all) of the local matrices of the
+ * form.  Quadrature: nq points, qpts nq*dim reference coordinates, qw weights summing to 1 (the rule
+ * FreeFEM selected through qforder/qft/qfV; default 7-point (2-D) / 14-point (3-D)).  Coefficients are
+ * constants (MeshIndependent() terms).  accumulate=0 overwrites A. */
+int ffcuda_assemble_bilinear(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms,
+                             int nq, const double *qpts, const double *qw,
+                             int nlab, const int32_t *labels, int accumulate);
+int ffcuda_assemble_linear(ffcuda_vec *b, ffcuda_space *s, int nterms, const ffcuda_lterm *terms,
+                           int nq, const double *qpts, const double *qw,
+                           int nlab, const int32_t *labels, int accumulate);
+
+/* ---- Dirichlet conditions (penalty, tgv >= 0) ------------------------------------------------------ */
+/* explicit (dof, value) pairs as AssembleBC produced them on the host (later pairs win) */
+int ffcuda_bc_from_pairs(ffcuda_space *s, int n, const int32_t *dofs, const double *vals, ffcuda_bc **out);
+/* on(labels..., u_c = values[c]) for the components in compmask, evaluated on the device */
+int ffcuda_bc_from_labels(ffcuda_space *s, int nlab, const int32_t *labels, int compmask, const double *values,
+                          ffcuda_bc **out);
+/* several ffcuda_bc may be applied in sequence (one per on(...) item of the varf) */
+int ffcuda_bc_count(ffcuda_bc *bc, int *ndofs);
+int ffcuda_matrix_apply_bc(ffcuda_matrix *A, ffcuda_bc *bc, double tgv); /* A(d,d) = tgv      */
+int ffcuda_vec_apply_bc(ffcuda_vec *b, ffcuda_bc *bc, double tgv);       /* b[d] = tgv*g(d)    */
+int ffcuda_vec_set_bc_values(ffcuda_vec *x, ffcuda_bc *bc);              /* x[d] = g(d)        */
+void ffcuda_bc_destroy(ffcuda_bc *bc);
+
+/* ---- SpMV and CG (kernel 4) ------------------------------------------------------------------------ */
+int ffcuda_spmv(ffcuda_matrix *A, ffcuda_vec *x, ffcuda_vec *y); /* y = A x */
+/* Jacobi-preconditioned CG with FreeFEM's recurrence, tgv-row handling and stopping rule
+ * (gCg < eps^2 * gCg0 for eps > 0, absolute gCg < eps^2 for eps < 0).  x: initial guess in, solution out.
+ * itmax <= 0 -> n.  Returns 0 also when not converged; *converged = 1 converged, 2 converged before the
+ * first iteration, 0 itmax reached.  *gcg = final <g,Cg>. */
+int ffcuda_cg(ffcuda_matrix *A, ffcuda_vec *b, ffcuda_vec *x, double eps, int itmax, double tgv,
+              int *iters, int *converged, double *gcg);
+/* same with host vectors (the call the FreeFEM solver plugin makes) */
+int ffcuda_cg_host(ffcuda_matrix *A, const double *b, double *x, double eps, int itmax, double tgv,
+                   int *iters, int *converged, double *gcg);
+
+/* ---- multi-GPU (one process per GPU; the caller's launcher provides rank/size and moves the 128-byte
+ *      NCCL id between ranks, e.g. with torch.distributed) ------------------------------------------- */
+int ffcuda_comm_unique_id(void *id128);
+int ffcuda_comm_init(ffcuda_ctx *ctx, int rank, int nranks, const void *id128);
+int ffcuda_comm_finalize(ffcuda_ctx *ctx);
+/* slab partition of cube(nx,ny,nz) along z into nranks parts: builds this rank's local mesh (owned
+ * elements + one layer of halo elements), local numbering (owned vertices first, then ghosts) and the
+ * halo exchange lists.  The space/pattern/matrix/vector calls above then work on the local problem:
+ * rows = owned dofs, columns = owned + ghost dofs; ffcuda_spmv and ffcuda_cg exchange ghosts and
+ * all-reduce dot products over NCCL. */
+int ffcuda_mesh_cube_distributed(ffcuda_ctx *ctx, int nx, int ny, int nz, ffcuda_mesh **out);
+/* global ids of the local vertices (owned first): for gathering results / parity checks */
+int ffcuda_mesh_local_to_global(ffcuda_mesh *m, int *nowned, int *nlocal, int64_t *gid /* nlocal or NULL */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
