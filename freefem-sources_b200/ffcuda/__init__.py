@@ -22,11 +22,20 @@ ffcuda_matrix_from_csr ffcuda_matrix_info ffcuda_matrix_download ffcuda_matrix_u
 ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_destroy ffcuda_assemble_bilinear
 ffcuda_assemble_linear ffcuda_bc_from_pairs ffcuda_bc_from_labels ffcuda_bc_count ffcuda_matrix_apply_bc ffcuda_vec_apply_bc
 ffcuda_vec_set_bc_values ffcuda_bc_destroy ffcuda_spmv ffcuda_cg ffcuda_cg_host ffcuda_comm_unique_id ffcuda_comm_init
-ffcuda_comm_finalize ffcuda_mesh_cube_distributed ffcuda_mesh_local_to_global""".split()
+ffcuda_comm_finalize ffcuda_mesh_cube_distributed ffcuda_mesh_local_to_global ffcuda_quadrature""".split()
 
 
 class FfcudaError(RuntimeError):
     pass
+
+
+def quadrature(dim, qforder=6):
+    """FreeFEM's default rule for int2d/int3d(Th, qforder=...): (points nq x dim, weights nq)."""
+    n = C.c_int()
+    _ck(lib().ffcuda_quadrature(dim, qforder, C.byref(n), None, None))
+    pts, w = np.zeros((n.value, dim)), np.zeros(n.value)
+    _ck(lib().ffcuda_quadrature(dim, qforder, C.byref(n), _p(pts), _p(w)))
+    return pts, w
 
 
 class BTerm(C.Structure):

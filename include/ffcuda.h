@@ -22,6 +22,8 @@
  *   ffcuda_assemble_linear      <- AssembleLinearForm fflib/problem.cpp:10555, :10878-11227, Element_rhs :7839-7985
  *   ffcuda_bc_* / *_apply_bc    <- AssembleBC fflib/problem.cpp:9881-10034, :10039-10194, HashMatrix::SetBC
  *                                  femlib/HashMatrix.cpp:1195-1238 (tgv >= 0 branch)
+ *   ffcuda_quadrature           <- CDomainOfIntegration::FIT/FIV fflib/problem.cpp:14102-14145, QF_Simplex
+ *                                  femlib/QuadratureFormular.cpp:73-115 and the rule tables :138-188, :699-743
  *   ffcuda_spmv                 <- HashMatrix::addMatMul femlib/HashMatrix.cpp:1087-1154
  *   ffcuda_cg                   <- SolverCG::dosolver femlib/VirtualSolverCG.hpp:112-192, HMatVirtPrecon :13-111,
  *                                  ConjugueGradient femlib/CG.cpp:195-265, gettgv HashMatrix.cpp:1341-1371
@@ -123,6 +125,12 @@ int ffcuda_vec_download(ffcuda_vec *v, double *host);
 int ffcuda_vec_fill(ffcuda_vec *v, double value);
 void *ffcuda_vec_ptr(ffcuda_vec *v); /* device pointer (double*) */
 void ffcuda_vec_destroy(ffcuda_vec *v);
+
+/* ---- default quadrature ------------------------------------------------------------------------------ */
+/* The rule FreeFEM uses for int2d/int3d(Th, qforder=q) (default q = 6): fewest points exact for degree q-1.
+ * qpts: nq*dim reference coordinates, qw: weights summing to 1; either may be NULL to query *nq (<= 16).
+ * Host-only helper (no device needed); the FreeFEM plugin forwards FreeFEM's own tables instead. */
+int ffcuda_quadrature(int dim, int qforder, int *nq, double *qpts, double *qw);
 
 /* ---- numeric assembly (kernels 2+3 fused: row-owner gather with in-register element evaluation) ---- */
 /* A (+)= sum over elements whose region label is in labels[] (NULL = all) of the local matrices of the

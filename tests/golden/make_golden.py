@@ -105,6 +105,9 @@ def script(c, out):
         u0 = unk.strip("[]").split(",")[0]
         s.append(f"{u0}[] = A^-1*b; verbosity=0;")
         s.append(f'{{ ofstream f("{out}/u.txt"); f.precision(17); for(int i=0;i<{u0}[].n;++i) f << {u0}[][i] << endl; }}')
+        # second solve converged to round-off: the comparison point that does not depend on where eps=1e-6 stops
+        s.append(f"verbosity=1; set(A,solver=CG,eps=1e-14); {u0}[] = 0; {u0}[] = A^-1*b; verbosity=0;")
+        s.append(f'{{ ofstream f("{out}/u14.txt"); f.precision(17); for(int i=0;i<{u0}[].n;++i) f << {u0}[][i] << endl; }}')
     return "\n".join(s) + "\n"
 
 
@@ -155,9 +158,11 @@ def run_case(name):
                    edp=np.array(src))
         if c.get("solve", True):
             out["u"] = np.array(toks(os.path.join(td, "u.txt")), dtype=np.float64)
-            mm = re.search(r"GC:\s+converge after\s+(\d+)", r.stdout)
-            assert mm, r.stdout[-2000:]
-            out["cg_iters"] = np.int32(int(mm.group(1)))
+            mm = re.findall(r"GC:\s+converge after\s+(\d+)", r.stdout)
+            assert len(mm) == 2, r.stdout[-2000:]
+            out["cg_iters"] = np.int32(int(mm[0]))
+            out["u14"] = np.array(toks(os.path.join(td, "u14.txt")), dtype=np.float64)
+            out["cg_iters14"] = np.int32(int(mm[1]))
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(f"{name}: nv={nv} nt={nt} nbe={nbe} ndof={ndof} nnz={nnz}"
               + (f" cg_iters={int(out['cg_iters'])}" if "cg_iters" in out else ""))

@@ -75,6 +75,10 @@ def test_matrix_rhs_solution(name):
         else:
             assert abs(it - int(g["cg_iters"])) <= 2
             assert np.max(np.abs(x - g["u"])) <= 1e-6 * np.abs(g["u"]).max()
+        # both converged to round-off (eps=1e-14): 1e-12 for every case
+        x, it, ret, _ = ol.cg(n, ci, cj, ca, b, np.zeros(n), eps=1e-14, itmax=0, tgv=TGV)
+        assert ret in (1, 2) and abs(it - int(g["cg_iters14"])) <= 3
+        assert np.max(np.abs(x - g["u14"])) <= RTOL * np.abs(g["u14"]).max()
 
 
 @pytest.mark.parametrize("name", sorted(k for k in fc.CASES if fc.CASES[k][5]))
@@ -85,6 +89,9 @@ def test_cg_on_reference_matrix(name):
     x, it, ret, _ = ol.cg(n, g["coo_i"], g["coo_j"], g["coo_a"], g["b"], np.zeros(n), eps=1e-6, itmax=0, tgv=TGV)
     assert ret in (1, 2) and it == int(g["cg_iters"])
     assert np.max(np.abs(x - g["u"])) <= RTOL * np.abs(g["u"]).max()
+    x, it, ret, _ = ol.cg(n, g["coo_i"], g["coo_j"], g["coo_a"], g["b"], np.zeros(n), eps=1e-14, itmax=0, tgv=TGV)
+    assert ret in (1, 2) and it == int(g["cg_iters14"])
+    assert np.max(np.abs(x - g["u14"])) <= RTOL * np.abs(g["u14"]).max()
 
 
 @pytest.mark.parametrize("nxyz,name", [((2, 2, 2), "lap3d_p1_cube2"), ((5, 5, 5), "lap3d_p1_cube5"),
