@@ -106,12 +106,13 @@ struct Geom {
 // one padded vertex (x,y,z,0) = one 32-byte sector, through the read-only path
 __device__ __forceinline__ double4 ldg_vertex(const double *__restrict__ xyz4, int v)
 {
-    const double2 *X = reinterpret_cast<const double2 *>(xyz4) + 2 * (size_t)v;
-    const double2 a = __ldg(X), b = __ldg(X + 1);
-    return make_double4(a.x, a.y, b.x, b.y);
+    double4 r; // one 256-bit load (LDG.E.256 on sm_100a)
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.x), "=d"(r.y), "=d"(r.z), "=d"(r.w) : "l"(xyz4 + 4 * (size_t)v));
+    return r;
 }
 
-__device__ __forceinline__ void load_geom3(const double *__restrict__ xyz4, int v0, int v1, int v2, int v3, Geom<3> &G)
+__device__ __forceinline__ void load_geom3(const double *__restrict__ xyz4, int v0, int v1, int v2, int v3, Geom<3> &G,
+                                           int want_grad = 1)
 {
     const double4 p0 = ldg_vertex(xyz4, v0), p1 = ldg_vertex(xyz4, v1), p2 = ldg_vertex(xyz4, v2), p3 = ldg_vertex(xyz4, v3);
     const double ax = p1.x - p0.x, ay = p1.y - p0.y, az = p1.z - p0.z;
@@ -119,14 +120,15 @@ __device__ __forceinline__ void load_geom3(const double *__restrict__ xyz4, int 
     const double cx = p3.x - p0.x, cy = p3.y - p0.y, cz = p3.z - p0.z;
     // n1 = V2 x V3, n2 = V3 x V1, n3 = V1 x V2 ; det = V1 . n1 ; grad lambda_r = n_r / det (Mesh3dn.hpp:126-136)
     const double n1x = by * cz - bz * cy, n1y = bz * cx - bx * cz, n1z = bx * cy - by * cx;
+    const double det = ax * n1x + ay * n1y + az * n1z;
+    G.mes = det * (1.0 / 6.0);
+    if (!want_grad) return;
     const double n2x = cy * az - cz * ay, n2y = cz * ax - cx * az, n2z = cx * ay - cy * ax;
     const double n3x = ay * bz - az * by, n3y = az * bx - ax * bz, n3z = ax * by - ay * bx;
-    const double det = ax * n1x + ay * n1y + az * n1z;
     const double inv = 1.0 / det;
     G.g[0][0] = n1x * inv; G.g[0][1] = n1y * inv; G.g[0][2] = n1z * inv;
     G.g[1][0] = n2x * inv; G.g[1][1] = n2y * inv; G.g[1][2] = n2z * inv;
     G.g[2][0] = n3x * inv; G.g[2][1] = n3y * inv; G.g[2][2] = n3z * inv;
-    G.mes = det * (1.0 / 6.0);
 }
 
 __device__ __forceinline__ void load_geom2(const double *__restrict__ xy, int v0, int v1, int v2, Geom<2> &G)
@@ -151,39 +153,66 @@ __device__ __forceinline__ bool region_ok(int nlab, const int *labels, const int
     return ok;
 }
 
-template <typename PosT>
-struct PosLoad;
-template <>
-struct PosLoad<uint8_t> {
-    static __device__ __forceinline__ void load4(const uint8_t *p, size_t e, int out[4])
-    {
-        uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(p) + e);
-        out[0] = w & 255; out[1] = (w >> 8) & 255; out[2] = (w >> 16) & 255; out[3] = w >> 24;
-    }
-};
-template <>
-struct PosLoad<uint16_t> {
-    static __device__ __forceinline__ void load4(const uint16_t *p, size_t e, int out[4])
-    {
-        uint2 w = __ldg(reinterpret_cast<const uint2 *>(p) + e);
-        out[0] = w.x & 65535; out[1] = w.x >> 16; out[2] = w.y & 65535; out[3] = w.y >> 16;
-    }
-};
+// ----------------------------------------------------------------------------------------------------
+// P1: one thread per node row, incidence records in the ELL-32 layout (a warp reads 32 consecutive records)
+// ----------------------------------------------------------------------------------------------------
+// one padded vertex (x,y,z,0) with a single 256-bit load through the read-only path (LDG.E.256 on sm_100a)
+__device__ __forceinline__ void ld_vertex256(const double *__restrict__ xyz4, int v, double &x, double &y, double &z)
+{
+    double w;
+    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(xyz4 + 4 * (size_t)v));
+    (void)w;
+}
 
-// ----------------------------------------------------------------------------------------------------
-// P1: one thread per node row
-// ----------------------------------------------------------------------------------------------------
-template <int DIM, int NC, typename PosT>
+// Unscaled "normals" N[b][x] = det * d lambda_b / d x  and det = DIM! * |K| (signed).
+//   3-D: N1 = V2 x V3, N2 = V3 x V1, N3 = V1 x V2, det = V1 . N1 (Mesh3dn.hpp:126-136);  2-D: fem.hpp:321-324.
+template <int DIM>
+__device__ __forceinline__ void p1_normals(const double *__restrict__ xyz, const int32_t *__restrict__ conn, int k,
+                                           double (&N)[DIM + 1][DIM], double &det)
+{
+    if (DIM == 3) {
+        const int4 K = __ldg(reinterpret_cast<const int4 *>(conn) + k);
+        double x0, y0, z0, x1, y1, z1, x2, y2, z2, x3, y3, z3;
+        ld_vertex256(xyz, K.x, x0, y0, z0);
+        ld_vertex256(xyz, K.y, x1, y1, z1);
+        ld_vertex256(xyz, K.z, x2, y2, z2);
+        ld_vertex256(xyz, K.w, x3, y3, z3);
+        const double ax = x1 - x0, ay = y1 - y0, az = z1 - z0;
+        const double bx = x2 - x0, by = y2 - y0, bz = z2 - z0;
+        const double cx = x3 - x0, cy = y3 - y0, cz = z3 - z0;
+        N[1][0] = by * cz - bz * cy; N[1][1] = bz * cx - bx * cz; N[1][2] = bx * cy - by * cx;
+        N[2][0] = cy * az - cz * ay; N[2][1] = cz * ax - cx * az; N[2][2] = cx * ay - cy * ax;
+        N[3][0] = ay * bz - az * by; N[3][1] = az * bx - ax * bz; N[3][2] = ax * by - ay * bx;
+        det = ax * N[1][0] + ay * N[1][1] + az * N[1][2];
+    } else {
+        const int v0 = __ldg(conn + 3 * (size_t)k), v1 = __ldg(conn + 3 * (size_t)k + 1), v2 = __ldg(conn + 3 * (size_t)k + 2);
+        const double2 *X = reinterpret_cast<const double2 *>(xyz);
+        const double2 p0 = __ldg(X + v0), p1 = __ldg(X + v1), p2 = __ldg(X + v2);
+        const double bx = p1.x - p0.x, by = p1.y - p0.y, cx = p2.x - p0.x, cy = p2.y - p0.y;
+        det = bx * cy - by * cx;
+        N[1][0] = cy; N[1][1] = -cx;
+        N[2][0] = -by; N[2][1] = bx;
+    }
+#pragma unroll
+    for (int x = 0; x < DIM; ++x) {
+        double s = N[1][x];
+#pragma unroll
+        for (int r = 2; r <= DIM; ++r) s += N[r][x];
+        N[0][x] = -s;
+    }
+}
+
+template <int DIM, int NC>
 __global__ void __launch_bounds__(128) k_asm_p1(const double *__restrict__ xyz, const int32_t *__restrict__ conn,
                                                 const int32_t *__restrict__ elab, int nrows,
-                                                const int32_t *__restrict__ nrowptr, const int32_t *__restrict__ incptr,
-                                                const uint32_t *__restrict__ inc, const PosT *__restrict__ pos,
-                                                double *__restrict__ vals, int S, int accumulate,
+                                                const int32_t *__restrict__ nrowptr, const IncView V,
+                                                const uint32_t *__restrict__ pos, double *__restrict__ vals, int S, int accumulate,
                                                 const __grid_constant__ FormParams F)
 {
     extern __shared__ double sacc[];
     constexpr int NV = DIM + 1;
-    const int tid = threadIdx.x;
+    constexpr double RFAC = DIM == 3 ? 1.0 / 6.0 : 0.5; // |K| = det * RFAC
+    const int tid = threadIdx.x, lane = tid & 31;
     const int row = blockIdx.x * blockDim.x + tid;
     double *acc = sacc + (size_t)tid * S;
     int L = 0, rb = 0;
@@ -192,74 +221,71 @@ __global__ void __launch_bounds__(128) k_asm_p1(const double *__restrict__ xyz, 
         L = nrowptr[row + 1] - rb;
         const int nflat = NC * NC * L;
         for (int j = 0; j < nflat; ++j) acc[j] = 0.0;
-        const int ie = incptr[row + 1];
-        for (int e = incptr[row]; e < ie; ++e) {
-            const uint32_t ka = __ldg(inc + e);
+    }
+    const int blk = row >> 5, nblk = (nrows + 31) >> 5;
+    if (blk < nblk) {
+        const uint32_t base = V.blkoff[blk];
+        const int Lb = (int)((V.blkoff[blk + 1] - base) >> 5);
+        const uint32_t *rinc = V.inc + base + lane;
+        const uint32_t *rpos = pos + base + lane;
+        const bool gradgrad = (F.mask & 0xEEE0u) != 0, valgrad = (F.mask & 0x000Eu) != 0, gradval = (F.mask & 0x1110u) != 0,
+                   valval = (F.mask & 1u) != 0;
+        for (int e = 0; e < Lb; ++e) {
+            const uint32_t ka = __ldcs(rinc + (size_t)e * 32);
+            if (ka == FF_NOREC) continue;
+            const uint32_t pw = __ldcs(rpos + (size_t)e * 32);
             const int k = ka >> 4, a = ka & 15;
             if (!region_ok(F.nlab, F.labels, elab, k)) continue;
-            int p[4];
-            PosLoad<PosT>::load4(pos, (size_t)e, p);
-            Geom<DIM> G;
-            if (DIM == 3) {
-                const int4 K = __ldg(reinterpret_cast<const int4 *>(conn) + k);
-                load_geom3(xyz, K.x, K.y, K.z, K.w, reinterpret_cast<Geom<3> &>(G));
-            } else {
-                const int v0 = __ldg(conn + 3 * (size_t)k), v1 = __ldg(conn + 3 * (size_t)k + 1), v2 = __ldg(conn + 3 * (size_t)k + 2);
-                load_geom2(xyz, v0, v1, v2, reinterpret_cast<Geom<2> &>(G));
-            }
-            // gradients of the NV barycentric functions: gl[b][x]
-            double gl[NV][DIM];
+            double N[NV][DIM], det;
+            p1_normals<DIM>(xyz, conn, k, N, det);
+            double na[DIM];
 #pragma unroll
             for (int x = 0; x < DIM; ++x) {
-                double s = 0;
+                double v = N[0][x];
 #pragma unroll
-                for (int r = 0; r < DIM; ++r) {
-                    gl[r + 1][x] = G.g[r][x];
-                    s -= G.g[r][x];
-                }
-                gl[0][x] = s;
+                for (int b = 1; b < NV; ++b) v = (a == b) ? N[b][x] : v;
+                na[x] = v;
             }
-            double ga[DIM];
+            // |K| W g_a[sv] g_b[su] = (W RFAC / det) N_a[sv] N_b[su] ; |K| L_a g_b[su] = RFAC L_a N_b[su] ; |K| M = RFAC det M
+            const double sgg = gradgrad ? F.W * RFAC * __drcp_rn(det) : 0.0;
+            const double La = F.Lh[a] * RFAC;
 #pragma unroll
-            for (int x = 0; x < DIM; ++x) {
-                double v = gl[0][x];
+            for (int cv = 0; cv < NC; ++cv)
 #pragma unroll
-                for (int b = 1; b < NV; ++b) v = (a == b) ? gl[b][x] : v;
-                ga[x] = v;
-            }
-            const double La = F.Lh[a];
+                for (int cu = 0; cu < NC; ++cu) {
+                    // wa[su] = sgg * sum_sv C[sv][su] N_a[sv]  ;  ca0 = RFAC * sum_sv C[sv][0] N_a[sv]
+                    double wa[DIM], ca0 = 0.0, c0[DIM];
 #pragma unroll
-            for (int b = 0; b < NV; ++b) {
-                // M[sv][su] of the pair (a,b), slot 0 = value, 1..DIM = derivative
-                double M[DIM + 1][DIM + 1];
-                M[0][0] = (F.mask & 1u) ? F.Mh[a][b] : 0.0;
+                    for (int su = 0; su < DIM; ++su) {
+                        double t = 0.0;
 #pragma unroll
-                for (int su = 1; su <= DIM; ++su) M[0][su] = La * gl[b][su - 1];
+                        for (int sv = 0; sv < DIM; ++sv)
+                            if (F.mask >> ((sv + 1) * 4 + su + 1) & 1u) t = fma(F.C[cv][cu][sv + 1][su + 1], na[sv], t);
+                        wa[su] = t * sgg;
+                        c0[su] = valgrad ? F.C[cv][cu][0][su + 1] * La : 0.0;
+                    }
+                    if (gradval) {
 #pragma unroll
-                for (int sv = 1; sv <= DIM; ++sv) {
-                    M[sv][0] = ga[sv - 1] * F.Lh[b];
+                        for (int sv = 0; sv < DIM; ++sv) ca0 = fma(F.C[cv][cu][sv + 1][0], na[sv], ca0);
+                        ca0 *= RFAC;
+                    }
+                    const double cm = valval ? F.C[cv][cu][0][0] * RFAC * det : 0.0;
 #pragma unroll
-                    for (int su = 1; su <= DIM; ++su) M[sv][su] = F.W * ga[sv - 1] * gl[b][su - 1];
-                }
-                const int pb = p[b];
-#pragma unroll
-                for (int cv = 0; cv < NC; ++cv)
-#pragma unroll
-                    for (int cu = 0; cu < NC; ++cu) {
+                    for (int b = 0; b < NV; ++b) {
                         double v = 0.0;
 #pragma unroll
-                        for (int sv = 0; sv <= DIM; ++sv)
-#pragma unroll
-                            for (int su = 0; su <= DIM; ++su)
-                                if (F.mask >> (sv * 4 + su) & 1u) v = fma(F.C[cv][cu][sv][su], M[sv][su], v);
-                        acc[cv * (NC * L) + pb * NC + cu] += G.mes * v;
+                        for (int su = 0; su < DIM; ++su) v = fma(wa[su] + c0[su], N[b][su], v);
+                        if (gradval) v = fma(ca0, F.Lh[b], v);
+                        if (valval) v = fma(cm, F.Mh[a][b], v);
+                        const int pb = (pw >> (8 * b)) & 255;
+                        acc[cv * (NC * L) + pb * NC + cu] += v;
                     }
-            }
+                }
         }
     }
     __syncwarp();
     // coalesced write-out: the 32 rows of a warp are contiguous in vals; lanes sweep one row segment at a time
-    const int lane = tid & 31, wbase = tid & ~31;
+    const int wbase = tid & ~31;
     for (int r = 0; r < 32; ++r) {
         const int rrb = __shfl_sync(0xffffffffu, rb, r), rL = __shfl_sync(0xffffffffu, L, r);
         const int nflat = NC * NC * rL;
@@ -371,32 +397,46 @@ __global__ void __launch_bounds__(128) k_asm_p2(const double *__restrict__ xyz, 
 }
 
 // ----------------------------------------------------------------------------------------------------
-// right-hand side: one thread per node row (P1 and P2)
+// right-hand side: one thread per node row (P1: ELL-32 records, P2: CSR lists)
 // ----------------------------------------------------------------------------------------------------
 template <int DIM, int NC>
 __global__ void __launch_bounds__(128) k_rhs(const double *__restrict__ xyz, const int32_t *__restrict__ conn,
-                                             const int32_t *__restrict__ elab, int nrows, const int32_t *__restrict__ incptr,
-                                             const uint32_t *__restrict__ inc, const double *__restrict__ Fh /* nloc*(DIM+1) */,
-                                             int nloc, double *__restrict__ bvec, int accumulate,
-                                             const __grid_constant__ LinParams Lp)
+                                             const int32_t *__restrict__ elab, int nrows, const IncView V,
+                                             const double *__restrict__ Fh /* nloc*(DIM+1) */, int nloc, int hasgrad,
+                                             double *__restrict__ bvec, int accumulate, const __grid_constant__ LinParams Lp)
 {
     __shared__ double sF[10 * 4];
     for (int x = threadIdx.x; x < nloc * (DIM + 1); x += blockDim.x) sF[x] = Fh[x];
     __syncthreads();
     const int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= nrows) return;
+    const int lane = threadIdx.x & 31;
     double out[NC];
 #pragma unroll
     for (int c = 0; c < NC; ++c) out[c] = 0.0;
-    const int ie = incptr[row + 1];
-    for (int e = incptr[row]; e < ie; ++e) {
-        const uint32_t ka = __ldg(inc + e);
+    // record walk: ELL -> every lane of the warp runs the padded length of its block; CSR -> its own list
+    int ne = 0, stride = 1;
+    const uint32_t *rinc = V.inc;
+    if (V.ell) {
+        const int blk = row >> 5, nblk = (nrows + 31) >> 5;
+        if (blk < nblk) {
+            const uint32_t base = V.blkoff[blk];
+            ne = (int)((V.blkoff[blk + 1] - base) >> 5);
+            rinc = V.inc + base + lane;
+            stride = 32;
+        }
+    } else if (row < nrows) {
+        ne = V.cnt[row];
+        rinc = V.inc + V.incptr[row];
+    }
+    for (int e = 0; e < ne; ++e) {
+        const uint32_t ka = __ldcs(rinc + (size_t)e * stride);
+        if (ka == FF_NOREC) continue;
         const int k = ka >> 4, a = ka & 15;
         if (!region_ok(Lp.nlab, Lp.labels, elab, k)) continue;
         Geom<DIM> G;
         if (DIM == 3) {
             const int4 K = __ldg(reinterpret_cast<const int4 *>(conn) + k);
-            load_geom3(xyz, K.x, K.y, K.z, K.w, reinterpret_cast<Geom<3> &>(G));
+            load_geom3(xyz, K.x, K.y, K.z, K.w, reinterpret_cast<Geom<3> &>(G), hasgrad);
         } else {
             const int v0 = __ldg(conn + 3 * (size_t)k), v1 = __ldg(conn + 3 * (size_t)k + 1), v2 = __ldg(conn + 3 * (size_t)k + 2);
             load_geom2(xyz, v0, v1, v2, reinterpret_cast<Geom<2> &>(G));
@@ -406,8 +446,10 @@ __global__ void __launch_bounds__(128) k_rhs(const double *__restrict__ xyz, con
 #pragma unroll
         for (int x = 0; x < DIM; ++x) {
             double s = 0;
+            if (hasgrad) {
 #pragma unroll
-            for (int r = 0; r < DIM; ++r) s = fma(sF[a * (DIM + 1) + r + 1], G.g[r][x], s);
+                for (int r = 0; r < DIM; ++r) s = fma(sF[a * (DIM + 1) + r + 1], G.g[r][x], s);
+            }
             Fa[x + 1] = s;
         }
 #pragma unroll
@@ -418,33 +460,39 @@ __global__ void __launch_bounds__(128) k_rhs(const double *__restrict__ xyz, con
             out[c] += G.mes * v;
         }
     }
+    if (row < nrows) {
 #pragma unroll
-    for (int c = 0; c < NC; ++c) {
-        size_t d = (size_t)row * NC + c;
-        bvec[d] = accumulate ? bvec[d] + out[c] : out[c];
+        for (int c = 0; c < NC; ++c) {
+            size_t d = (size_t)row * NC + c;
+            bvec[d] = accumulate ? bvec[d] + out[c] : out[c];
+        }
     }
 }
 
 // ----------------------------------------------------------------------------------------------------
 // host drivers
 // ----------------------------------------------------------------------------------------------------
-template <int DIM, int NC, typename PosT>
-static void launch_p1(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const FormParams &F, const PosT *pos, int accumulate)
+template <int DIM, int NC>
+static void launch_p1(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const FormParams &F, int accumulate)
 {
     ffcuda_pattern *P = A->pattern;
     ffcuda_mesh *m = s->mesh;
+    FF_REQUIRE(P->pos8.p, "internal: P1 pattern without 8-bit positions");
     int S = NC * NC * P->maxrow_node;
     S |= 1; // odd stride: threads of a warp land in different banks
     int threads = 128;
     while (threads > 32 && (size_t)threads * S * 8 > 64 * 1024) threads >>= 1;
     size_t shmem = (size_t)threads * S * 8;
     FF_REQUIRE(shmem <= 200 * 1024, "matrix rows too long for the shared-memory row accumulators");
-    auto kern = k_asm_p1<DIM, NC, PosT>;
+    auto kern = k_asm_p1<DIM, NC>;
     FF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-    int blocks = ff_blocks((size_t)P->nrows_node, threads);
+    // rows are taken in whole ELL blocks of 32: the grid covers ceil(nrows/32) warps
+    const int nwarps = (P->nrows_node + 31) / 32;
+    int blocks = ff_blocks((size_t)nwarps * 32, threads);
+    const IncView V = ff_view(s->incidence);
     ff_launch(ctx, "asm_rows_p1", [&] {
-        kern<<<blocks, threads, shmem, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, P->nrows_node, P->nrowptr.p, P->incptr.p,
-                                                      P->inc.p, pos, A->vals.p, S, accumulate, F);
+        kern<<<blocks, threads, shmem, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, P->nrows_node, P->nrowptr.p, V,
+                                                      reinterpret_cast<const uint32_t *>(P->pos8.p), A->vals.p, S, accumulate, F);
     });
 }
 
@@ -466,26 +514,30 @@ static void launch_p2(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const 
     auto kern = k_asm_p2<DIM, NC, GL, PosT>;
     FF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     int blocks = ff_blocks((size_t)P->nrows_node, groups);
+    const Incidence &I = s->incidence;
     ff_launch(ctx, "asm_rows_p2", [&] {
-        kern<<<blocks, threads, shmem, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, P->nrows_node, P->nrowptr.p, P->incptr.p,
-                                                      P->inc.p, pos, Rg, A->vals.p, S, accumulate, F);
+        kern<<<blocks, threads, shmem, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, P->nrows_node, P->nrowptr.p, I.incptr.p,
+                                                      I.inc.p, pos, Rg, A->vals.p, S, accumulate, F);
     });
 }
 
+template <int DIM>
+static void dispatch_p1(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const FormParams &F, int accumulate)
+{
+    const int nc = s->ncomp;
+    if (nc == 1) launch_p1<DIM, 1>(ctx, A, s, F, accumulate);
+    else if (nc == 2) launch_p1<DIM, 2>(ctx, A, s, F, accumulate);
+    else launch_p1<DIM, 3>(ctx, A, s, F, accumulate);
+}
+
 template <int DIM, typename PosT>
-static void dispatch_nc(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const FormParams &F, const double *Rg, const PosT *pos,
+static void dispatch_p2(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const FormParams &F, const double *Rg, const PosT *pos,
                         int accumulate)
 {
     const int nc = s->ncomp;
-    if (s->order == 1) {
-        if (nc == 1) launch_p1<DIM, 1, PosT>(ctx, A, s, F, pos, accumulate);
-        else if (nc == 2) launch_p1<DIM, 2, PosT>(ctx, A, s, F, pos, accumulate);
-        else launch_p1<DIM, 3, PosT>(ctx, A, s, F, pos, accumulate);
-    } else {
-        if (nc == 1) launch_p2<DIM, 1, PosT>(ctx, A, s, F, Rg, pos, accumulate);
-        else if (nc == 2) launch_p2<DIM, 2, PosT>(ctx, A, s, F, Rg, pos, accumulate);
-        else launch_p2<DIM, 3, PosT>(ctx, A, s, F, Rg, pos, accumulate);
-    }
+    if (nc == 1) launch_p2<DIM, 1, PosT>(ctx, A, s, F, Rg, pos, accumulate);
+    else if (nc == 2) launch_p2<DIM, 2, PosT>(ctx, A, s, F, Rg, pos, accumulate);
+    else launch_p2<DIM, 3, PosT>(ctx, A, s, F, Rg, pos, accumulate);
 }
 
 extern "C" int ffcuda_assemble_bilinear(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms, int nq,
@@ -496,7 +548,7 @@ extern "C" int ffcuda_assemble_bilinear(ffcuda_matrix *A, ffcuda_space *s, int n
     FF_REQUIRE(nterms >= 0 && (nterms == 0 || terms), "bad term list");
     FF_REQUIRE(nq > 0 && qpts && qw, "quadrature rule missing");
     ffcuda_ctx *ctx = s->ctx;
-    FF_CUDA(cudaSetDevice(ctx->device));
+    ff_enter(ctx);
     const int dim = s->mesh->dim, nloc = s->nloc, nc = s->ncomp, ns = dim + 1;
     FormParams F;
     memset(&F, 0, sizeof(F));
@@ -530,41 +582,43 @@ extern "C" int ffcuda_assemble_bilinear(ffcuda_matrix *A, ffcuda_space *s, int n
         }
     }
     ffcuda_pattern *P = A->pattern;
+    if (accumulate) ff_matrix_touch(A);
+    A->vals_stale = false;
     DBuf<double> Rg;
     if (s->order == 2) {
         Rg.alloc(R.size());
         FF_CUDA(cudaMemcpyAsync(Rg.p, R.data(), Rg.bytes(), cudaMemcpyHostToDevice, ctx->stream));
     }
-    if (P->pos8.p) {
-        if (dim == 3) dispatch_nc<3, uint8_t>(ctx, A, s, F, Rg.p, P->pos8.p, accumulate);
-        else dispatch_nc<2, uint8_t>(ctx, A, s, F, Rg.p, P->pos8.p, accumulate);
+    if (s->order == 1) {
+        if (dim == 3) dispatch_p1<3>(ctx, A, s, F, accumulate);
+        else dispatch_p1<2>(ctx, A, s, F, accumulate);
+    } else if (P->pos8.p) {
+        if (dim == 3) dispatch_p2<3, uint8_t>(ctx, A, s, F, Rg.p, P->pos8.p, accumulate);
+        else dispatch_p2<2, uint8_t>(ctx, A, s, F, Rg.p, P->pos8.p, accumulate);
     } else {
-        if (dim == 3) dispatch_nc<3, uint16_t>(ctx, A, s, F, Rg.p, P->pos16.p, accumulate);
-        else dispatch_nc<2, uint16_t>(ctx, A, s, F, Rg.p, P->pos16.p, accumulate);
+        if (dim == 3) dispatch_p2<3, uint16_t>(ctx, A, s, F, Rg.p, P->pos16.p, accumulate);
+        else dispatch_p2<2, uint16_t>(ctx, A, s, F, Rg.p, P->pos16.p, accumulate);
     }
-    if (s->order == 2) FF_CUDA(cudaStreamSynchronize(ctx->stream)); // Rg is released on return
+    // Rg is released through the stream-ordered allocator: no synchronisation needed
     FF_API_END(s ? s->ctx : nullptr)
 }
 
 template <int DIM>
-static void launch_rhs(ffcuda_ctx *ctx, ffcuda_vec *b, ffcuda_space *s, ffcuda_pattern *P, const LinParams &Lp, const double *Fh,
-                       int accumulate)
+static void launch_rhs(ffcuda_ctx *ctx, ffcuda_vec *b, ffcuda_space *s, const LinParams &Lp, const double *Fh, int hasgrad, int accumulate)
 {
     ffcuda_mesh *m = s->mesh;
-    const int nrows = P->nrows_node;
-    int blocks = ff_blocks((size_t)nrows, 128);
+    const int nrows = s->incidence.nrows;
+    const IncView V = ff_view(s->incidence);
+    int blocks = ff_blocks((size_t)((nrows + 31) / 32) * 32, 128);
     ff_launch(ctx, "rhs_rows", [&] {
         if (s->ncomp == 1)
-            k_rhs<DIM, 1><<<blocks, 128, 0, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, nrows, P->incptr.p, P->inc.p, Fh, s->nloc, b->d.p, accumulate, Lp);
+            k_rhs<DIM, 1><<<blocks, 128, 0, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, nrows, V, Fh, s->nloc, hasgrad, b->d.p, accumulate, Lp);
         else if (s->ncomp == 2)
-            k_rhs<DIM, 2><<<blocks, 128, 0, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, nrows, P->incptr.p, P->inc.p, Fh, s->nloc, b->d.p, accumulate, Lp);
+            k_rhs<DIM, 2><<<blocks, 128, 0, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, nrows, V, Fh, s->nloc, hasgrad, b->d.p, accumulate, Lp);
         else
-            k_rhs<DIM, 3><<<blocks, 128, 0, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, nrows, P->incptr.p, P->inc.p, Fh, s->nloc, b->d.p, accumulate, Lp);
+            k_rhs<DIM, 3><<<blocks, 128, 0, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, nrows, V, Fh, s->nloc, hasgrad, b->d.p, accumulate, Lp);
     });
 }
-
-// the linear form needs the node->element incidence of a pattern; the space remembers the last pattern built on it
-extern ffcuda_pattern *ff_space_pattern(ffcuda_space *s);
 
 extern "C" int ffcuda_assemble_linear(ffcuda_vec *b, ffcuda_space *s, int nterms, const ffcuda_lterm *terms, int nq,
                                       const double *qpts, const double *qw, int nlab, const int32_t *labels, int accumulate)
@@ -573,17 +627,20 @@ extern "C" int ffcuda_assemble_linear(ffcuda_vec *b, ffcuda_space *s, int nterms
     FF_REQUIRE(b && s, "ffcuda_assemble_linear: null argument");
     FF_REQUIRE(nq > 0 && qpts && qw, "quadrature rule missing");
     ffcuda_ctx *ctx = s->ctx;
-    FF_CUDA(cudaSetDevice(ctx->device));
-    ffcuda_pattern *P = ff_space_pattern(s);
-    FF_REQUIRE(P, "ffcuda_assemble_linear: run ffcuda_symbolic on the space first (the row-owner gather needs its incidence lists)");
-    FF_REQUIRE(b->n >= P->n, "right-hand side vector too short");
+    ff_enter(ctx);
+    ff_build_incidence(s); // the row-owner gather walks the node -> element lists of the space
+    FF_REQUIRE(b->n >= s->nnodes_owned * s->ncomp, "right-hand side vector too short");
     const int dim = s->mesh->dim, nloc = s->nloc, nc = s->ncomp, ns = dim + 1;
     LinParams Lp;
     memset(&Lp, 0, sizeof(Lp));
+    int hasgrad = 0;
     for (int t = 0; t < nterms; ++t) {
         FF_REQUIRE(terms[t].vcomp >= 0 && terms[t].vcomp < nc, "term component out of range");
-        Lp.CL[terms[t].vcomp][op_slot(dim, terms[t].vop)] += terms[t].coef;
+        const int slot = op_slot(dim, terms[t].vop);
+        Lp.CL[terms[t].vcomp][slot] += terms[t].coef;
+        if (slot > 0 && terms[t].coef != 0.0) hasgrad = 1;
     }
+    if (dim == 2) hasgrad = 1; // the 2-D geometry helper always evaluates the gradients
     fill_labels(nlab, labels, Lp.nlab, Lp.labels);
     std::vector<double> Fh((size_t)nloc * ns, 0.0);
     for (int q = 0; q < nq; ++q) {
@@ -595,8 +652,8 @@ extern "C" int ffcuda_assemble_linear(ffcuda_vec *b, ffcuda_space *s, int nterms
     DBuf<double> dF;
     dF.alloc(Fh.size());
     FF_CUDA(cudaMemcpyAsync(dF.p, Fh.data(), dF.bytes(), cudaMemcpyHostToDevice, ctx->stream));
-    if (dim == 3) launch_rhs<3>(ctx, b, s, P, Lp, dF.p, accumulate);
-    else launch_rhs<2>(ctx, b, s, P, Lp, dF.p, accumulate);
-    FF_CUDA(cudaStreamSynchronize(ctx->stream));
+    // (a pageable source is staged before cudaMemcpyAsync returns: Fh may go out of scope)
+    if (dim == 3) launch_rhs<3>(ctx, b, s, Lp, dF.p, hasgrad, accumulate);
+    else launch_rhs<2>(ctx, b, s, Lp, dF.p, hasgrad, accumulate);
     FF_API_END(s ? s->ctx : nullptr)
 }

@@ -79,7 +79,7 @@ extern "C" int ffcuda_comm_init(ffcuda_ctx *ctx, int rank, int nranks, const voi
     FF_API_BEGIN
     FF_REQUIRE(ctx && nranks >= 1 && rank >= 0 && rank < nranks, "ffcuda_comm_init: bad arguments");
     FF_REQUIRE(!ctx->nccl_comm, "communicator already initialised");
-    FF_CUDA(cudaSetDevice(ctx->device));
+    ff_enter(ctx);
     if (nranks > 1) {
         FF_REQUIRE(id128, "ffcuda_comm_init: null NCCL id");
         ncclUniqueId id;
@@ -107,7 +107,7 @@ extern "C" int ffcuda_comm_finalize(ffcuda_ctx *ctx)
 {
     FF_API_BEGIN
     FF_REQUIRE(ctx, "null context");
-    FF_CUDA(cudaSetDevice(ctx->device));
+    ff_enter(ctx);
     FF_CUDA(cudaStreamSynchronize(ctx->stream));
     ff_comm_release(ctx);
     FF_API_END(ctx)

@@ -75,6 +75,10 @@ struct ffcuda_ctx {
 };
 
 void ff_report_error(ffcuda_ctx *ctx, const char *msg);
+// every entry point starts with this: selects the device and makes ctx the thread's current context, whose stream
+// orders the device allocations of DBuf (stream-ordered allocator; the pool keeps its memory between calls)
+void ff_enter(ffcuda_ctx *ctx);
+ffcuda_ctx *ff_current_ctx();
 void ff_prof_flush(ffcuda_ctx *ctx);
 void ff_comm_release(ffcuda_ctx *ctx); // comm.cu
 
@@ -87,15 +91,29 @@ struct DBuf {
     DBuf(const DBuf &) = delete;
     DBuf &operator=(const DBuf &) = delete;
     ~DBuf() { release(); }
+    cudaStream_t st = nullptr; // stream the block was allocated on (stream-ordered allocator)
+    bool pooled = false;
     void alloc(size_t count)
     {
         release();
         n = count;
-        if (count) FF_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+        if (!count) return;
+        ffcuda_ctx *c = ff_current_ctx();
+        if (c) {
+            st = c->stream;
+            pooled = true;
+            FF_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), st));
+        } else {
+            pooled = false;
+            FF_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+        }
     }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) {
+            if (pooled) cudaFreeAsync(p, st);
+            else cudaFree(p);
+        }
         p = nullptr;
         n = 0;
     }
@@ -143,14 +161,43 @@ struct ffcuda_mesh {
     bool distributed = false;
 };
 
+// node -> (element, local node) incidence lists = the transpose of the element -> node table.  A property of the FE
+// space: built on first use and kept with it (re-assemblies on the same fespace reuse it).
+//   order 1 (thread-per-row kernels): ELL-32 layout - rows are taken in blocks of 32 (one warp), record e of lane l of
+//     block b sits at blkoff[b] + e*32 + l, so a warp walking its 32 rows in lockstep reads 128 contiguous bytes;
+//     blocks are padded with FF_NOREC to the longest list of the block.
+//   order 2 (lane-group-per-row kernels): plain CSR lists, record e of row r at incptr[r] + e.
+static constexpr uint32_t FF_NOREC = 0xffffffffu;
+struct Incidence {
+    bool built = false;
+    int ell = 0;
+    int nrows = 0, maxinc = 0;
+    int64_t nrec = 0;         // records allocated (padding included)
+    DBuf<int32_t> cnt;        // nrows+1 list lengths (cnt[nrows] = 0)
+    DBuf<int32_t> incptr;     // nrows+1 (CSR layout only)
+    DBuf<uint32_t> blkoff;    // nblk+1  (ELL layout only)
+    DBuf<uint32_t> inc;       // nrec records: (element << 4) | local node, each list sorted by element
+};
+struct IncView {
+    const int32_t *cnt, *incptr;
+    const uint32_t *blkoff, *inc;
+    int ell;
+    __device__ __forceinline__ size_t idx(int row, int e) const
+    {
+        return ell ? (size_t)blkoff[row >> 5] + (size_t)e * 32 + (row & 31) : (size_t)incptr[row] + e;
+    }
+};
+static inline IncView ff_view(const Incidence &I) { return IncView{I.cnt.p, I.incptr.p, I.blkoff.p, I.inc.p, I.ell}; }
+
 struct ffcuda_space {
     ffcuda_mesh *mesh = nullptr;
     ffcuda_ctx *ctx = nullptr;
     int order = 1, ncomp = 1, nloc = 0, nnodes = 0, nnodes_owned = 0;
     DBuf<int32_t> e2n_own;    // nt*nloc when order 2
     const int32_t *e2n = nullptr;   // = conn for P1
-    struct ffcuda_pattern *last_pattern = nullptr;   // most recent ffcuda_symbolic result (incidence lists for the rhs)
+    Incidence incidence;
 };
+void ff_build_incidence(ffcuda_space *s); // symbolic.cu; no-op when already built
 
 struct ffcuda_pattern {
     ffcuda_space *space = nullptr;
@@ -165,11 +212,11 @@ struct ffcuda_pattern {
     DBuf<int32_t> nrowptr, ncol;          // node-level CSR
     DBuf<int32_t> rowptr_own, colind_own; // dof-level CSR (only when ncomp > 1)
     const int32_t *rowptr = nullptr, *colind = nullptr;
-    DBuf<int32_t> incptr;     // nrows_node+1
-    DBuf<uint32_t> inc;       // (element << 4) | local node
-    DBuf<uint8_t> pos8;       // per incidence, nlocp bytes: position of each element node in the node row
+    // per incidence record (same indexing as space->incidence.inc), nlocp entries: position of each node of that
+    // element inside the node row
+    DBuf<uint8_t> pos8;
     DBuf<uint16_t> pos16;     // used instead when maxrow_node > 255
-    int nlocp = 0;            // padded nloc in the pos table (4, 8 or 16... see symbolic.cu)
+    int nlocp = 0;            // padded nloc in the pos table (4 for P1, nloc for P2)
     DBuf<int32_t> diagpos;    // n: index into vals of A(i,i)
 };
 
@@ -181,6 +228,13 @@ struct ffcuda_matrix {
     DBuf<int32_t> rowptr_own, colind_own, diagpos_own;
     const int32_t *rowptr = nullptr, *colind = nullptr, *diagpos = nullptr;
     DBuf<double> vals;
+    bool vals_stale = false;  // allocated but not yet zeroed/written (ffcuda_matrix_create defers the memset)
+    int maxrow = 0;           // longest dof row
+    // CSR-stream SpMV set-up (lazily built, once per matrix): row-block table
+    int stream_state = 0;     // 0 not prepared, 1 ready, -1 not applicable
+    int stream_nblk = 0, stream_T = 1;
+    size_t stream_shmem = 0;
+    DBuf<int32_t> stream_rb;
     // CG workspace (lazily allocated)
     DBuf<double> wG, wH, wAH, wD1, wX;
     DBuf<int32_t> wcl;
@@ -198,6 +252,8 @@ struct ffcuda_bc {
     DBuf<int32_t> dofs;
     DBuf<double> vals;
 };
+
+void ff_matrix_touch(ffcuda_matrix *A); // matrix.cu: zero the values if nothing has written them yet
 
 // ---- shared device helpers ----------------------------------------------------------------------
 void ff_exclusive_scan_i32(ffcuda_ctx *ctx, const int32_t *in, int32_t *out, size_t n, int64_t *total);

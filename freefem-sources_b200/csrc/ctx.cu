@@ -11,6 +11,14 @@ void ff_report_error(ffcuda_ctx *ctx, const char *msg)
     if (ctx) ctx->err = g_thread_err;
 }
 
+static thread_local ffcuda_ctx *g_cur_ctx = nullptr;
+ffcuda_ctx *ff_current_ctx() { return g_cur_ctx; }
+void ff_enter(ffcuda_ctx *ctx)
+{
+    g_cur_ctx = ctx;
+    if (ctx) cudaSetDevice(ctx->device);
+}
+
 int ff_nloc(int dim, int order) { return order == 1 ? dim + 1 : (dim == 2 ? 6 : 10); }
 
 void ff_prof_flush(ffcuda_ctx *ctx)
@@ -43,6 +51,12 @@ extern "C" int ffcuda_ctx_create(int device, ffcuda_ctx **out)
     FF_CUDA(cudaSetDevice(device));
     ctx = new ffcuda_ctx();
     ctx->device = device;
+    {   // device allocations go through the stream-ordered allocator; keep freed blocks in the pool (no trimming)
+        cudaMemPool_t pool;
+        FF_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        uint64_t keep = UINT64_MAX;
+        FF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     FF_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     cudaDeviceProp prop;
@@ -58,13 +72,14 @@ extern "C" int ffcuda_ctx_create(int device, ffcuda_ctx **out)
 extern "C" void ffcuda_ctx_destroy(ffcuda_ctx *ctx)
 {
     if (!ctx) return;
-    cudaSetDevice(ctx->device);
+    ff_enter(ctx);
     try { ff_prof_flush(ctx); } catch (...) {}
     ff_comm_release(ctx);
     if (ctx->d_scal) cudaFree(ctx->d_scal);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->d_partial) cudaFree(ctx->d_partial);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    if (g_cur_ctx == ctx) g_cur_ctx = nullptr;
     delete ctx;
 }
 
@@ -259,7 +274,7 @@ extern "C" int ffcuda_vec_create(ffcuda_ctx *ctx, int n, ffcuda_vec **out)
 {
     FF_API_BEGIN
     FF_REQUIRE(ctx && out && n >= 0, "ffcuda_vec_create: bad arguments");
-    FF_CUDA(cudaSetDevice(ctx->device));
+    ff_enter(ctx);
     ffcuda_vec *v = new ffcuda_vec();
     v->ctx = ctx;
     v->n = n;
@@ -304,6 +319,6 @@ extern "C" void *ffcuda_vec_ptr(ffcuda_vec *v) { return v ? (void *)v->d.p : nul
 extern "C" void ffcuda_vec_destroy(ffcuda_vec *v)
 {
     if (!v) return;
-    cudaSetDevice(v->ctx->device);
+    ff_enter(v->ctx);
     delete v;
 }

@@ -9,7 +9,7 @@ extern "C" int ffcuda_matrix_create(ffcuda_pattern *p, ffcuda_matrix **out)
     FF_API_BEGIN
     FF_REQUIRE(p && out, "ffcuda_matrix_create: null argument");
     ffcuda_ctx *ctx = p->ctx;
-    FF_CUDA(cudaSetDevice(ctx->device));
+    ff_enter(ctx);
     A = new ffcuda_matrix();
     A->ctx = ctx;
     A->pattern = p;
@@ -19,11 +19,27 @@ extern "C" int ffcuda_matrix_create(ffcuda_pattern *p, ffcuda_matrix **out)
     A->rowptr = p->rowptr;
     A->colind = p->colind;
     A->diagpos = p->diagpos.p;
+    A->maxrow = p->maxrow_node * p->ncomp;
     A->vals.alloc((size_t)p->nnz);
-    FF_CUDA(cudaMemsetAsync(A->vals.p, 0, A->vals.bytes(), ctx->stream));
+    A->vals_stale = true; // zeroed on first read; an overwriting assembly never pays for the memset
     *out = A;
     A = nullptr;
     FF_API_END((delete A, p ? p->ctx : nullptr))
+}
+
+void ff_matrix_touch(ffcuda_matrix *A)
+{
+    if (!A->vals_stale) return;
+    FF_CUDA(cudaMemsetAsync(A->vals.p, 0, A->vals.bytes(), A->ctx->stream));
+    A->vals_stale = false;
+}
+
+__global__ void k_maxrow(const int32_t *__restrict__ rowptr, int n, int32_t *__restrict__ out)
+{
+    int m = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) m = max(m, rowptr[i + 1] - rowptr[i]);
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(out, m);
 }
 
 __global__ void k_find_diag(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind, int n, int32_t *__restrict__ diagpos)
@@ -43,7 +59,7 @@ extern "C" int ffcuda_matrix_from_csr(ffcuda_ctx *ctx, int n, int64_t nnz, const
     FF_API_BEGIN
     FF_REQUIRE(ctx && out && rowptr && colind && n > 0 && nnz >= 0, "ffcuda_matrix_from_csr: bad arguments");
     FF_REQUIRE(nnz < ((int64_t)1 << 31), "matrix exceeds 2^31 nonzeros");
-    FF_CUDA(cudaSetDevice(ctx->device));
+    ff_enter(ctx);
     cudaStream_t st = ctx->stream;
     A = new ffcuda_matrix();
     A->ctx = ctx;
@@ -62,7 +78,14 @@ extern "C" int ffcuda_matrix_from_csr(ffcuda_ctx *ctx, int n, int64_t nnz, const
     A->colind = A->colind_own.p;
     A->diagpos = A->diagpos_own.p;
     ff_launch(ctx, "matrix_find_diag", [&] { k_find_diag<<<ff_blocks(n, 256), 256, 0, st>>>(A->rowptr, A->colind, n, A->diagpos_own.p); });
+    DBuf<int32_t> d_max;
+    d_max.alloc(1);
+    FF_CUDA(cudaMemsetAsync(d_max.p, 0, sizeof(int32_t), st));
+    ff_launch(ctx, "matrix_maxrow", [&] { k_maxrow<<<ctx->sm_count * 4, 256, 0, st>>>(A->rowptr, n, d_max.p); });
+    int32_t h_max = 0;
+    FF_CUDA(cudaMemcpyAsync(&h_max, d_max.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     FF_CUDA(cudaStreamSynchronize(st));
+    A->maxrow = h_max;
     *out = A;
     A = nullptr;
     FF_API_END((delete A, ctx))
@@ -81,7 +104,8 @@ extern "C" int ffcuda_matrix_download(ffcuda_matrix *A, double *vals)
 {
     FF_API_BEGIN
     FF_REQUIRE(A && vals, "null argument");
-    FF_CUDA(cudaSetDevice(A->ctx->device));
+    ff_enter(A->ctx);
+    ff_matrix_touch(A);
     FF_CUDA(cudaMemcpyAsync(vals, A->vals.p, A->vals.bytes(), cudaMemcpyDeviceToHost, A->ctx->stream));
     FF_CUDA(cudaStreamSynchronize(A->ctx->stream));
     FF_API_END(A ? A->ctx : nullptr)
@@ -91,7 +115,8 @@ extern "C" int ffcuda_matrix_upload(ffcuda_matrix *A, const double *vals)
 {
     FF_API_BEGIN
     FF_REQUIRE(A && vals, "null argument");
-    FF_CUDA(cudaSetDevice(A->ctx->device));
+    ff_enter(A->ctx);
+    A->vals_stale = false;
     FF_CUDA(cudaMemcpyAsync(A->vals.p, vals, A->vals.bytes(), cudaMemcpyHostToDevice, A->ctx->stream));
     FF_CUDA(cudaStreamSynchronize(A->ctx->stream));
     FF_API_END(A ? A->ctx : nullptr)
@@ -100,7 +125,7 @@ extern "C" int ffcuda_matrix_upload(ffcuda_matrix *A, const double *vals)
 extern "C" void ffcuda_matrix_destroy(ffcuda_matrix *A)
 {
     if (!A) return;
-    cudaSetDevice(A->ctx->device);
+    ff_enter(A->ctx);
     delete A;
 }
 
@@ -113,7 +138,7 @@ extern "C" int ffcuda_bc_from_pairs(ffcuda_space *s, int n, const int32_t *dofs,
     FF_API_BEGIN
     FF_REQUIRE(s && out && n >= 0 && (n == 0 || (dofs && vals)), "ffcuda_bc_from_pairs: bad arguments");
     ffcuda_ctx *ctx = s->ctx;
-    FF_CUDA(cudaSetDevice(ctx->device));
+    ff_enter(ctx);
     const int ndof = s->nnodes_owned * s->ncomp;
     // later pairs win (AssembleBC overwrites B[ddf] as it walks the boundary elements)
     std::vector<std::pair<int32_t, int>> ord(n);
@@ -196,7 +221,7 @@ extern "C" int ffcuda_bc_from_labels(ffcuda_space *s, int nlab, const int32_t *l
     FF_REQUIRE(nlab <= 32, "at most 32 labels per on(...)");
     ffcuda_ctx *ctx = s->ctx;
     ffcuda_mesh *m = s->mesh;
-    FF_CUDA(cudaSetDevice(ctx->device));
+    ff_enter(ctx);
     cudaStream_t st = ctx->stream;
     const int ndof = s->nnodes_owned * s->ncomp;
     LabSet L;
@@ -257,7 +282,8 @@ extern "C" int ffcuda_matrix_apply_bc(ffcuda_matrix *A, ffcuda_bc *bc, double tg
     FF_REQUIRE(A && bc, "null argument");
     FF_REQUIRE(tgv >= 0, "only the penalty form of Dirichlet conditions (tgv >= 0) is on the ffcuda path");
     ffcuda_ctx *ctx = A->ctx;
-    FF_CUDA(cudaSetDevice(ctx->device));
+    ff_enter(ctx);
+    ff_matrix_touch(A);
     if (bc->ndofs)
         ff_launch(ctx, "bc_matrix", [&] {
             k_bc_matrix<<<ff_blocks(bc->ndofs, 256), 256, 0, ctx->stream>>>(bc->dofs.p, bc->ndofs, A->diagpos, A->vals.p, tgv);
@@ -270,7 +296,7 @@ extern "C" int ffcuda_vec_apply_bc(ffcuda_vec *b, ffcuda_bc *bc, double tgv)
     FF_API_BEGIN
     FF_REQUIRE(b && bc, "null argument");
     ffcuda_ctx *ctx = b->ctx;
-    FF_CUDA(cudaSetDevice(ctx->device));
+    ff_enter(ctx);
     if (bc->ndofs)
         ff_launch(ctx, "bc_vec", [&] {
             k_bc_vec<<<ff_blocks(bc->ndofs, 256), 256, 0, ctx->stream>>>(bc->dofs.p, bc->vals.p, bc->ndofs, b->d.p, tgv);
@@ -283,7 +309,7 @@ extern "C" int ffcuda_vec_set_bc_values(ffcuda_vec *x, ffcuda_bc *bc)
     FF_API_BEGIN
     FF_REQUIRE(x && bc, "null argument");
     ffcuda_ctx *ctx = x->ctx;
-    FF_CUDA(cudaSetDevice(ctx->device));
+    ff_enter(ctx);
     if (bc->ndofs)
         ff_launch(ctx, "bc_vec", [&] {
             k_bc_vec<<<ff_blocks(bc->ndofs, 256), 256, 0, ctx->stream>>>(bc->dofs.p, bc->vals.p, bc->ndofs, x->d.p, 1.0);
@@ -294,6 +320,6 @@ extern "C" int ffcuda_vec_set_bc_values(ffcuda_vec *x, ffcuda_bc *bc)
 extern "C" void ffcuda_bc_destroy(ffcuda_bc *bc)
 {
     if (!bc) return;
-    cudaSetDevice(bc->ctx->device);
+    ff_enter(bc->ctx);
     delete bc;
 }

@@ -11,7 +11,6 @@
 __constant__ int c_nvfaceTet[4][3] = {{3, 2, 1}, {0, 2, 3}, {3, 1, 0}, {0, 1, 2}};
 // kind=6 split of a cell into 6 tets around the diagonal 0-7 (corner id = a + 2b + 4c)
 __constant__ int c_cubeTets[6][4] = {{4, 0, 6, 7}, {0, 4, 5, 7}, {1, 0, 5, 7}, {0, 1, 3, 7}, {2, 0, 3, 7}, {0, 2, 6, 7}};
-static const int h_nvfaceTet[4][3] = {{3, 2, 1}, {0, 2, 3}, {3, 1, 0}, {0, 1, 2}};
 
 __global__ void k_pad_xyz3(const double *__restrict__ in, double *__restrict__ out, int nv)
 {
@@ -89,7 +88,7 @@ extern "C" int ffcuda_mesh_upload(ffcuda_ctx *ctx, int dim, int nv, const double
     FF_REQUIRE(nv > 0 && nt > 0 && xyz && conn, "empty mesh");
     FF_REQUIRE(nbe == 0 || (bconn && blab), "boundary arrays missing");
     FF_REQUIRE((int64_t)nt < (int64_t)1 << 27, "too many elements for one device (limit 2^27)");
-    FF_CUDA(cudaSetDevice(ctx->device));
+    ff_enter(ctx);
     cudaStream_t st = ctx->stream;
     m = new ffcuda_mesh();
     m->ctx = ctx;
@@ -239,7 +238,7 @@ static void build_cube(ffcuda_ctx *ctx, int nx, int ny, int nz, int rank, int nr
     const int64_t nk = (int64_t)(nx + 1) * (ny + 1);
     int64_t nc64 = (int64_t)nx * ny * C.ncl;
     FF_REQUIRE(nc64 * 6 < ((int64_t)1 << 27), "cube (slab) too large for one device (limit 2^27 tets); use more ranks");
-    FF_CUDA(cudaSetDevice(ctx->device));
+    ff_enter(ctx);
     cudaStream_t st = ctx->stream;
     std::unique_ptr<ffcuda_mesh> m(new ffcuda_mesh());
     m->ctx = ctx;
@@ -305,7 +304,7 @@ extern "C" int ffcuda_mesh_local_to_global(ffcuda_mesh *m, int *nowned, int *nlo
     if (nowned) *nowned = m->nv_owned;
     if (nlocal) *nlocal = m->nv;
     if (gid) {
-        FF_CUDA(cudaSetDevice(m->ctx->device));
+        ff_enter(m->ctx);
         if (m->gid.p) {
             FF_CUDA(cudaMemcpy(gid, m->gid.p, m->gid.bytes(), cudaMemcpyDeviceToHost));
         } else
@@ -368,7 +367,7 @@ extern "C" int ffcuda_mesh_square(ffcuda_ctx *ctx, int nx, int ny, ffcuda_mesh *
     FF_REQUIRE(ctx && out, "ffcuda_mesh_square: null context/output");
     FF_REQUIRE(nx > 0 && ny > 0, "square sizes must be positive");
     FF_REQUIRE((int64_t)nx * ny * 2 < ((int64_t)1 << 27), "square too large");
-    FF_CUDA(cudaSetDevice(ctx->device));
+    ff_enter(ctx);
     cudaStream_t st = ctx->stream;
     m = new ffcuda_mesh();
     m->ctx = ctx;
@@ -411,7 +410,7 @@ extern "C" int ffcuda_mesh_download(ffcuda_mesh *m, double *xyz, int32_t *conn, 
     FF_API_BEGIN
     FF_REQUIRE(m, "null mesh");
     ffcuda_ctx *ctx = m->ctx;
-    FF_CUDA(cudaSetDevice(ctx->device));
+    ff_enter(ctx);
     cudaStream_t st = ctx->stream;
     if (xyz) {
         if (m->dim == 3) {
@@ -436,6 +435,6 @@ extern "C" int ffcuda_mesh_download(ffcuda_mesh *m, double *xyz, int32_t *conn, 
 extern "C" void ffcuda_mesh_destroy(ffcuda_mesh *m)
 {
     if (!m) return;
-    cudaSetDevice(m->ctx->device);
+    ff_enter(m->ctx);
     delete m;
 }

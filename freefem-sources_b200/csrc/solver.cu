@@ -90,6 +90,111 @@ __device__ __forceinline__ double row_product(const int32_t *__restrict__ colind
     return s;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// CSR-stream SpMV (the default): a CTA owns a contiguous run of rows holding about TILE non-zeros (row-block table
+// built once per matrix).  Phase 1: the 256 threads sweep the run's (value, column) pairs in perfectly coalesced
+// order, STREAM_ITEMS independent loads per thread in flight, gather x and park the products in shared memory.
+// Phase 2: a group of T lanes per row adds the row's products (T = 1: left to right, the CPU's own order).
+// MODE 0: y = A x          MODE 1: y = A x - sub, partial <y, d1 y>          MODE 2: y = A x, partials <g,x>, <x,y>
+// ---------------------------------------------------------------------------------------------------
+static constexpr int STREAM_TILE = 2048;
+static constexpr int STREAM_ITEMS = STREAM_TILE / RED_THREADS;
+
+__global__ void k_stream_blocks(const int32_t *__restrict__ rowptr, int n, int nblk, int32_t *__restrict__ rb)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j > nblk) return;
+    if (j == nblk) {
+        rb[j] = n;
+        return;
+    }
+    // smallest row r with rowptr[r] >= j * TILE
+    const long long target = (long long)j * STREAM_TILE;
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (rowptr[mid] < target) lo = mid + 1;
+        else hi = mid;
+    }
+    rb[j] = lo;
+}
+
+template <int T, int MODE>
+__global__ void __launch_bounds__(RED_THREADS) k_spmv_stream(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                                                             const double *__restrict__ vals, const double *__restrict__ x,
+                                                             const int32_t *__restrict__ rb, const double *__restrict__ aux0,
+                                                             const double *__restrict__ aux1, double *__restrict__ y, int iter,
+                                                             double *__restrict__ partial, int *__restrict__ flags,
+                                                             double *__restrict__ out)
+{
+    extern __shared__ double sprod[];
+    __shared__ double sh[32];
+    if (MODE == 2) {
+        const int ci = flags[F_CONV_ITER]; // 0: running, -1/-2: stopped before the first iteration, k>0: converged at k
+        if (ci != 0 && iter > ci) return;
+    }
+    const int r0 = rb[blockIdx.x], r1 = rb[blockIdx.x + 1];
+    const int nz0 = __ldg(rowptr + r0), nz1 = __ldg(rowptr + r1);
+    const int cnt = nz1 - nz0;
+    // phase 1
+    for (int base = 0; base < cnt; base += STREAM_TILE) {
+        double v[STREAM_ITEMS];
+        int c[STREAM_ITEMS];
+#pragma unroll
+        for (int i = 0; i < STREAM_ITEMS; ++i) {
+            const int j = base + i * RED_THREADS + threadIdx.x;
+            const bool ok = j < cnt;
+            c[i] = ok ? __ldcs(colind + nz0 + j) : 0;
+            v[i] = ok ? __ldcs(vals + nz0 + j) : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < STREAM_ITEMS; ++i) {
+            const int j = base + i * RED_THREADS + threadIdx.x;
+            if (j < cnt) sprod[j] = v[i] * __ldg(x + c[i]);
+        }
+    }
+    __syncthreads();
+    // phase 2
+    double acc0 = 0.0, acc1 = 0.0;
+    const int l = threadIdx.x & (T - 1);
+    const int nrow = r1 - r0;
+    const int nround = (nrow + RED_THREADS / T - 1) / (RED_THREADS / T); // uniform trip count: shuffles stay convergent
+    for (int it = 0; it < nround; ++it) {
+        const int rl = it * (RED_THREADS / T) + threadIdx.x / T;
+        const bool ok = rl < nrow;
+        const int row = r0 + rl;
+        double s = 0.0;
+        if (ok) {
+            const int b = __ldg(rowptr + row) - nz0, e = __ldg(rowptr + row + 1) - nz0;
+            for (int j = b + l; j < e; j += T) s += sprod[j];
+        }
+#pragma unroll
+        for (int o = T >> 1; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (ok && l == 0) {
+            if (MODE == 0) y[row] = s;
+            if (MODE == 1) {
+                const double g = s - aux0[row];
+                y[row] = g;
+                acc0 = fma(g, aux1[row] * g, acc0);
+            }
+            if (MODE == 2) {
+                const double h = x[row];
+                y[row] = s;
+                acc0 = fma(aux0[row], h, acc0);
+                acc1 = fma(h, s, acc1);
+            }
+        }
+    }
+    if (MODE == 1) {
+        double a[1] = {acc0};
+        grid_sum_finish<1>(a, partial, flags + F_COUNTER, out, sh);
+    }
+    if (MODE == 2) {
+        double a[2] = {acc0, acc1};
+        grid_sum_finish<2>(a, partial, flags + F_COUNTER, out, sh);
+    }
+}
+
 // y = A x  (optionally y = A x - b)
 template <int T>
 __global__ void __launch_bounds__(RED_THREADS) k_spmv(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
@@ -333,9 +438,63 @@ static int grid_for(const ffcuda_ctx *ctx, size_t work_threads)
     default: { constexpr int TT = 32; __VA_ARGS__; } break; \
     }
 
+// ---- CSR-stream set-up (once per matrix): row-block table; T lanes per row in the reduction phase
+static bool stream_prepare(ffcuda_matrix *A)
+{
+    if (A->stream_state) return A->stream_state > 0;
+    ffcuda_ctx *ctx = A->ctx;
+    const size_t shmem = ((size_t)STREAM_TILE + (size_t)A->maxrow) * sizeof(double);
+    if (A->maxrow <= 0 || shmem > 160 * 1024 || A->nnz == 0) {
+        A->stream_state = -1; // rows too long for the shared-memory tile: lane-group kernel
+        return false;
+    }
+    A->stream_nblk = (int)((A->nnz + STREAM_TILE - 1) / STREAM_TILE);
+    A->stream_rb.alloc((size_t)A->stream_nblk + 1);
+    ff_launch(ctx, "spmv_row_blocks", [&] {
+        k_stream_blocks<<<ff_blocks((size_t)A->stream_nblk + 1, 256), 256, 0, ctx->stream>>>(A->rowptr, A->n, A->stream_nblk, A->stream_rb.p);
+    });
+    const double rows_per_blk = (double)A->n / A->stream_nblk;
+    int T = 1;
+    while (T < 32 && rows_per_blk * T * 2 <= RED_THREADS) T <<= 1;
+    A->stream_T = T;
+    A->stream_shmem = shmem;
+    A->stream_state = 1;
+    return true;
+}
+
+#define FF_DISPATCH_ST(T, ...)                                \
+    switch (T) {                                              \
+    case 1: { constexpr int TT = 1; __VA_ARGS__; } break;     \
+    case 2: { constexpr int TT = 2; __VA_ARGS__; } break;     \
+    case 4: { constexpr int TT = 4; __VA_ARGS__; } break;     \
+    case 8: { constexpr int TT = 8; __VA_ARGS__; } break;     \
+    case 16: { constexpr int TT = 16; __VA_ARGS__; } break;   \
+    default: { constexpr int TT = 32; __VA_ARGS__; } break;   \
+    }
+
+template <int MODE>
+static void stream_launch(ffcuda_matrix *A, const char *name, const double *x, const double *aux0, const double *aux1, double *y,
+                          int iter, double *partial, int *flags, double *out)
+{
+    ffcuda_ctx *ctx = A->ctx;
+    FF_DISPATCH_ST(A->stream_T, {
+        auto kern = k_spmv_stream<TT, MODE>;
+        if (A->stream_shmem > 48 * 1024)
+            FF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A->stream_shmem));
+        ff_launch(ctx, name, [&] {
+            kern<<<A->stream_nblk, RED_THREADS, A->stream_shmem, ctx->stream>>>(A->rowptr, A->colind, A->vals.p, x, A->stream_rb.p, aux0,
+                                                                                 aux1, y, iter, partial, flags, out);
+        });
+    });
+}
+
 static void spmv_launch(ffcuda_matrix *A, const double *x, const double *sub, double *y)
 {
     ffcuda_ctx *ctx = A->ctx;
+    if (!sub && stream_prepare(A)) {
+        stream_launch<0>(A, "spmv", x, nullptr, nullptr, y, 0, nullptr, nullptr, nullptr);
+        return;
+    }
     const int T = pick_T(A);
     const int grid = grid_for(ctx, (size_t)A->n * T);
     FF_DISPATCH_T(T, ff_launch(ctx, "spmv", [&] {
@@ -350,7 +509,8 @@ extern "C" int ffcuda_spmv(ffcuda_matrix *A, ffcuda_vec *x, ffcuda_vec *y)
     FF_REQUIRE(x->n >= A->ncols, "ffcuda_spmv: x is shorter than the number of (owned + ghost) columns");
     FF_REQUIRE(y->n >= A->n, "ffcuda_spmv: y is shorter than the number of rows");
     FF_REQUIRE(x->d.p != y->d.p, "ffcuda_spmv: x and y must be different vectors");
-    FF_CUDA(cudaSetDevice(A->ctx->device));
+    ff_enter(A->ctx);
+    ff_matrix_touch(A);
     ff_halo_exchange(A, x->d.p);
     spmv_launch(A, x->d.p, nullptr, y->d.p);
     FF_API_END(A ? A->ctx : nullptr)
@@ -363,6 +523,7 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
     cudaStream_t st = ctx->stream;
     const int n = A->n, ncols = A->ncols;
     FF_REQUIRE(A->diagpos, "matrix has no diagonal index");
+    ff_matrix_touch(A);
     if (itmax <= 0) itmax = n;
     if (!A->wG.p) {
         A->wG.alloc(n);
@@ -375,7 +536,8 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
     double *scal = ctx->d_scal;
     int *flags = ctx_flags(ctx);
     const int T = pick_T(A);
-    const int grid_s = grid_for(ctx, (size_t)n * T), grid_v = grid_for(ctx, (size_t)n);
+    const bool streamed = stream_prepare(A);
+    const int grid_s = streamed ? A->stream_nblk : grid_for(ctx, (size_t)n * T), grid_v = grid_for(ctx, (size_t)n);
     ensure_partial(ctx, 2 * (size_t)std::max(grid_s, grid_v) + 16);
     double *partial = ctx->d_partial;
     FF_CUDA(cudaMemsetAsync(scal, 0, 64 * sizeof(double), st));
@@ -414,9 +576,12 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
         ff_halo_exchange(A, A->wX.p);
         xin = A->wX.p;
     }
-    FF_DISPATCH_T(T, ff_launch(ctx, "cg_init_spmv", [&] {
-                      k_cg_init1<TT><<<grid_s, RED_THREADS, 0, st>>>(A->rowptr, A->colind, A->vals.p, xin, b, D1, G, n, partial, flags, scal);
-                  }));
+    if (streamed)
+        stream_launch<1>(A, "cg_init_spmv", xin, b, D1, G, 0, partial, flags, scal + S_GCG0);
+    else
+        FF_DISPATCH_T(T, ff_launch(ctx, "cg_init_spmv", [&] {
+                          k_cg_init1<TT><<<grid_s, RED_THREADS, 0, st>>>(A->rowptr, A->colind, A->vals.p, xin, b, D1, G, n, partial, flags, scal);
+                      }));
     ff_allreduce(A, scal + S_GCG0, 1, 0);
     ff_launch(ctx, "cg_init_h", [&] { k_cg_init2<<<grid_v, RED_THREADS, 0, st>>>(G, D1, H, n, eps, flags, scal); });
 
@@ -436,9 +601,12 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
             for (int k = 0; k < nb; ++k) {
                 ++it;
                 ff_halo_exchange(A, H);
-                FF_DISPATCH_T(T, ff_launch(ctx, "cg_spmv_dots", [&] {
-                                  k_cg_spmv<TT><<<grid_s, RED_THREADS, 0, st>>>(A->rowptr, A->colind, A->vals.p, H, G, AH, n, it, partial, flags, scal);
-                              }));
+                if (streamed)
+                    stream_launch<2>(A, "cg_spmv_dots", H, G, nullptr, AH, it, partial, flags, scal + S_GH);
+                else
+                    FF_DISPATCH_T(T, ff_launch(ctx, "cg_spmv_dots", [&] {
+                                      k_cg_spmv<TT><<<grid_s, RED_THREADS, 0, st>>>(A->rowptr, A->colind, A->vals.p, H, G, AH, n, it, partial, flags, scal);
+                                  }));
                 ff_allreduce(A, scal + S_GH, 2, 0);
                 ff_launch(ctx, "cg_update_g", [&] { k_cg_update_g<<<grid_v, RED_THREADS, 0, st>>>(G, AH, D1, n, it, partial, flags, scal); });
                 ff_allreduce(A, scal + S_GCG0 + (it & 1), 1, 0);
@@ -482,7 +650,7 @@ extern "C" int ffcuda_cg(ffcuda_matrix *A, ffcuda_vec *b, ffcuda_vec *x, double 
     FF_API_BEGIN
     FF_REQUIRE(A && b && x, "ffcuda_cg: null argument");
     FF_REQUIRE(b->n >= A->n && x->n >= A->n, "ffcuda_cg: vectors shorter than the matrix");
-    FF_CUDA(cudaSetDevice(A->ctx->device));
+    ff_enter(A->ctx);
     cg_device(A, b->d.p, x->d.p, eps, itmax, tgv, iters, converged, gcg);
     FF_API_END(A ? A->ctx : nullptr)
 }
@@ -493,7 +661,7 @@ extern "C" int ffcuda_cg_host(ffcuda_matrix *A, const double *b, double *x, doub
     FF_API_BEGIN
     FF_REQUIRE(A && b && x, "ffcuda_cg_host: null argument");
     ffcuda_ctx *ctx = A->ctx;
-    FF_CUDA(cudaSetDevice(ctx->device));
+    ff_enter(ctx);
     DBuf<double> db, dx;
     db.alloc(A->n);
     dx.alloc(A->n);

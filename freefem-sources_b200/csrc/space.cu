@@ -40,7 +40,7 @@ extern "C" int ffcuda_space_create(ffcuda_mesh *m, int order, int ncomp, const i
     ffcuda_ctx *ctx = m->ctx;
     FF_REQUIRE(order == 1 || order == 2, "only P1 and P2 Lagrange spaces are supported");
     FF_REQUIRE(ncomp >= 1 && ncomp <= 3, "1 to 3 components supported");
-    FF_CUDA(cudaSetDevice(ctx->device));
+    ff_enter(ctx);
     s = new ffcuda_space();
     s->mesh = m;
     s->ctx = ctx;
@@ -91,7 +91,7 @@ extern "C" int ffcuda_space_download_dofs(ffcuda_space *s, int32_t *dof)
     FF_REQUIRE(s && dof, "null argument");
     const int nt = s->mesh->nt, nloc = s->nloc, nc = s->ncomp;
     std::vector<int32_t> e2n((size_t)nt * nloc);
-    FF_CUDA(cudaSetDevice(s->ctx->device));
+    ff_enter(s->ctx);
     FF_CUDA(cudaMemcpy(e2n.data(), s->e2n, e2n.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
     for (int k = 0; k < nt; ++k)
         for (int c = 0; c < nc; ++c)
@@ -103,6 +103,6 @@ extern "C" int ffcuda_space_download_dofs(ffcuda_space *s, int32_t *dof)
 extern "C" void ffcuda_space_destroy(ffcuda_space *s)
 {
     if (!s) return;
-    cudaSetDevice(s->ctx->device);
+    ff_enter(s->ctx);
     delete s;
 }

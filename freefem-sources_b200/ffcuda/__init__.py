@@ -285,9 +285,11 @@ class Pattern(_Handle):
         _ck(lib().ffcuda_pattern_info(_h(self), C.byref(n), C.byref(nnz)), self.ctx.h)
         return n.value, nnz.value
 
-    def download(self):
+    def download(self, rp=None, ci=None):
         n, nnz = self.info()
-        rp, ci = np.zeros(n + 1, np.int32), np.zeros(nnz, np.int32)
+        rp = np.zeros(n + 1, np.int32) if rp is None else rp
+        ci = np.zeros(nnz, np.int32) if ci is None else ci
+        assert rp.dtype == np.int32 and ci.dtype == np.int32 and len(rp) == n + 1 and len(ci) == nnz
         _ck(lib().ffcuda_pattern_download(_h(self), _p(rp), _p(ci)), self.ctx.h)
         return rp, ci
 

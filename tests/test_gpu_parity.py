@@ -99,16 +99,28 @@ def test_golden_case(ctx, name):
 
 @pytest.mark.parametrize("name", sorted(k for k in fc.CASES if fc.CASES[k][5]))
 def test_cg_on_reference_matrix(ctx, name):
-    """the solver entry the FreeFEM plugin calls (host CSR in, host vectors in/out) fed with the reference's own A, b:
-    same iteration count, u within 1e-12."""
+    """the solver entry the FreeFEM plugin calls (host CSR in, host vectors in/out) fed with the reference's own A, b.
+    Only the summation order of the SpMV rows and of the dot products differs from the reference here."""
+    order, ncomp = fc.CASES[name][:2]
     g = fc.load(name)
     n = g["ndof"]
     rp, ci, val = fc.golden_csr(g)
     A = ctx.matrix_from_csr(n, rp, ci, val)
+    b = np.ascontiguousarray(g["b"])
     x = np.zeros(n)
-    it, conv, _ = A.cg_host(np.ascontiguousarray(g["b"]), x, eps=1e-6, itmax=0, tgv=TGV)
-    assert conv in (1, 2) and it == int(g["cg_iters"])
-    assert np.max(np.abs(x - g["u"])) <= RTOL * np.abs(g["u"]).max()
+    it, conv, _ = A.cg_host(b, x, eps=1e-6, itmax=0, tgv=TGV)
+    assert conv in (1, 2)
+    umax = np.abs(g["u"]).max()
+    if order == 1 and ncomp == 1:   # the reference's own stopping point: same count, 1e-12
+        assert it == int(g["cg_iters"])
+        assert np.max(np.abs(x - g["u"])) <= RTOL * umax
+    else:                           # longer, worse-conditioned runs: an eps=1e-6 iterate amplifies round-off (see above)
+        assert abs(it - int(g["cg_iters"])) <= 2
+        assert np.max(np.abs(x - g["u"])) <= 1e-6 * umax
+    x = np.zeros(n)                 # converged to round-off: 1e-12 for every case
+    it, conv, _ = A.cg_host(b, x, eps=1e-14, itmax=0, tgv=TGV)
+    assert conv in (1, 2) and abs(it - int(g["cg_iters14"])) <= 3
+    assert np.max(np.abs(x - g["u14"])) <= RTOL * np.abs(g["u14"]).max()
 
 
 @pytest.mark.parametrize("name", ["lap3d_p2_cube2", "lame3d_p2_cube2", "lame3d_p2_warp"])
