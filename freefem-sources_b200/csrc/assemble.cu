@@ -18,6 +18,7 @@
 // contracted per element with the inverse Jacobian.  Same mathematics as the reference loop, different
 // summation order (differences ~1e-16 relative).
 #include "common.cuh"
+#include <algorithm>
 #include <cmath>
 
 // ----------------------------------------------------------------------------------------------------
@@ -72,6 +73,7 @@ struct FormParams {
     double W;             // sum of weights
     double Lh[4];         // sum_q w_q lambda_a
     double Mh[4][4];      // sum_q w_q lambda_a lambda_b
+    double fast_cw, fast_md, fast_mo; // FAST P1 path: c*W*RFAC, m*M_diag*RFAC, m*M_offdiag*RFAC
     uint32_t mask;        // bit (sv*4+su) set when some C[.][.][sv][su] != 0
     int nlab;             // <0: all regions
     int labels[MAXLAB];
@@ -156,39 +158,21 @@ __device__ __forceinline__ bool region_ok(int nlab, const int *labels, const int
 // ----------------------------------------------------------------------------------------------------
 // P1: one thread per node row, incidence records in the ELL-32 layout (a warp reads 32 consecutive records)
 // ----------------------------------------------------------------------------------------------------
-// one padded vertex (x,y,z,0) with a single 256-bit load through the read-only path (LDG.E.256 on sm_100a)
-__device__ __forceinline__ void ld_vertex256(const double *__restrict__ xyz4, int v, double &x, double &y, double &z)
-{
-    double w;
-    asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(x), "=d"(y), "=d"(z), "=d"(w) : "l"(xyz4 + 4 * (size_t)v));
-    (void)w;
-}
-
-// Unscaled "normals" N[b][x] = det * d lambda_b / d x  and det = DIM! * |K| (signed).
+// Unscaled "normals" N[b][x] = det * d lambda_b / d x  and det = DIM! * |K| (signed), from the vertex coordinates.
 //   3-D: N1 = V2 x V3, N2 = V3 x V1, N3 = V1 x V2, det = V1 . N1 (Mesh3dn.hpp:126-136);  2-D: fem.hpp:321-324.
 template <int DIM>
-__device__ __forceinline__ void p1_normals(const double *__restrict__ xyz, const int32_t *__restrict__ conn, int k,
-                                           double (&N)[DIM + 1][DIM], double &det)
+__device__ __forceinline__ void p1_normals(const double (&X)[DIM + 1][DIM], double (&N)[DIM + 1][DIM], double &det)
 {
     if (DIM == 3) {
-        const int4 K = __ldg(reinterpret_cast<const int4 *>(conn) + k);
-        double x0, y0, z0, x1, y1, z1, x2, y2, z2, x3, y3, z3;
-        ld_vertex256(xyz, K.x, x0, y0, z0);
-        ld_vertex256(xyz, K.y, x1, y1, z1);
-        ld_vertex256(xyz, K.z, x2, y2, z2);
-        ld_vertex256(xyz, K.w, x3, y3, z3);
-        const double ax = x1 - x0, ay = y1 - y0, az = z1 - z0;
-        const double bx = x2 - x0, by = y2 - y0, bz = z2 - z0;
-        const double cx = x3 - x0, cy = y3 - y0, cz = z3 - z0;
-        N[1][0] = by * cz - bz * cy; N[1][1] = bz * cx - bx * cz; N[1][2] = bx * cy - by * cx;
-        N[2][0] = cy * az - cz * ay; N[2][1] = cz * ax - cx * az; N[2][2] = cx * ay - cy * ax;
-        N[3][0] = ay * bz - az * by; N[3][1] = az * bx - ax * bz; N[3][2] = ax * by - ay * bx;
-        det = ax * N[1][0] + ay * N[1][1] + az * N[1][2];
+        const double ax = X[1][0] - X[0][0], ay = X[1][1] - X[0][1], az = X[1][DIM - 1] - X[0][DIM - 1];
+        const double bx = X[2][0] - X[0][0], by = X[2][1] - X[0][1], bz = X[2][DIM - 1] - X[0][DIM - 1];
+        const double cx = X[DIM][0] - X[0][0], cy = X[DIM][1] - X[0][1], cz = X[DIM][DIM - 1] - X[0][DIM - 1];
+        N[1][0] = by * cz - bz * cy; N[1][1] = bz * cx - bx * cz; N[1][DIM - 1] = bx * cy - by * cx;
+        N[2][0] = cy * az - cz * ay; N[2][1] = cz * ax - cx * az; N[2][DIM - 1] = cx * ay - cy * ax;
+        N[DIM][0] = ay * bz - az * by; N[DIM][1] = az * bx - ax * bz; N[DIM][DIM - 1] = ax * by - ay * bx;
+        det = ax * N[1][0] + ay * N[1][1] + az * N[1][DIM - 1];
     } else {
-        const int v0 = __ldg(conn + 3 * (size_t)k), v1 = __ldg(conn + 3 * (size_t)k + 1), v2 = __ldg(conn + 3 * (size_t)k + 2);
-        const double2 *X = reinterpret_cast<const double2 *>(xyz);
-        const double2 p0 = __ldg(X + v0), p1 = __ldg(X + v1), p2 = __ldg(X + v2);
-        const double bx = p1.x - p0.x, by = p1.y - p0.y, cx = p2.x - p0.x, cy = p2.y - p0.y;
+        const double bx = X[1][0] - X[0][0], by = X[1][1] - X[0][1], cx = X[2][0] - X[0][0], cy = X[2][1] - X[0][1];
         det = bx * cy - by * cx;
         N[1][0] = cy; N[1][1] = -cx;
         N[2][0] = -by; N[2][1] = bx;
@@ -202,85 +186,174 @@ __device__ __forceinline__ void p1_normals(const double *__restrict__ xyz, const
     }
 }
 
-template <int DIM, int NC>
+// The warp's ELL block: stage the coordinates of its distinct vertices (blkvert) in shared memory, SoA, once.
+// Returns true when the block is staged.
+template <int DIM>
+__device__ __forceinline__ bool p1_stage(const double *__restrict__ xyz, const int32_t *__restrict__ blkvert,
+                                         const int32_t *__restrict__ blkvcnt, int blk, int lane, int SV, double *stage)
+{
+    const int vcnt = blkvcnt[blk];
+    if (vcnt < 0) return false;
+    for (int s = lane; s < vcnt; s += 32) {
+        const int v = __ldg(blkvert + (size_t)blk * FF_STAGE_MAX + s);
+        if (DIM == 3) {
+            const double4 p = ldg_vertex(xyz, v);
+            stage[s] = p.x; stage[SV + s] = p.y; stage[2 * SV + s] = p.z;
+        } else {
+            const double2 p = __ldg(reinterpret_cast<const double2 *>(xyz) + v);
+            stage[s] = p.x; stage[SV + s] = p.y;
+        }
+    }
+    __syncwarp();
+    return true;
+}
+
+// vertices 1..DIM of a record (owner-first order) from the staged coordinates; X[0] (the owner) is already set
+template <int DIM>
+__device__ __forceinline__ void p1_points_staged(const double *stage, int SV, uint32_t lw, double (&X)[DIM + 1][DIM])
+{
+#pragma unroll
+    for (int b = 1; b <= DIM; ++b) {
+        const int s = (lw >> (8 * b)) & 255;
+#pragma unroll
+        for (int x = 0; x < DIM; ++x) X[b][x] = stage[x * SV + s];
+    }
+}
+
+// vertices 1..DIM of element k in owner-first order (a = local index of the owner) straight from global memory
+template <int DIM>
+__device__ __forceinline__ void p1_points_global(const double *__restrict__ xyz, const int32_t *__restrict__ conn, int k, int a,
+                                                 double (&X)[DIM + 1][DIM])
+{
+#pragma unroll
+    for (int i = 1; i <= DIM; ++i) {
+        const int o = DIM == 3 ? (a ^ i) : (a + i) % 3;
+        const int v = __ldg(conn + (size_t)(DIM + 1) * k + o);
+        if (DIM == 3) {
+            const double4 p = ldg_vertex(xyz, v);
+            X[i][0] = p.x; X[i][1] = p.y; X[i][DIM - 1] = p.z;
+        } else {
+            const double2 p = __ldg(reinterpret_cast<const double2 *>(xyz) + v);
+            X[i][0] = p.x; X[i][1] = p.y;
+        }
+    }
+}
+
+// Thread per row.  Every record lists its element's vertices OWNER-FIRST (the row's vertex, then the others in an even
+// permutation of the element's order): the thread evaluates the simplex with its own vertex as origin, so the row of
+// the element matrix it needs is always "row 0": N[0] is its own normal, no selection by local index.
+// FAST: scalar space, form = c grad u . grad v (+ m u v) with a symmetric quadrature rule -> a handful of constants.
+template <int DIM, int NC, bool FAST>
 __global__ void __launch_bounds__(128) k_asm_p1(const double *__restrict__ xyz, const int32_t *__restrict__ conn,
                                                 const int32_t *__restrict__ elab, int nrows,
                                                 const int32_t *__restrict__ nrowptr, const IncView V,
-                                                const uint32_t *__restrict__ pos, double *__restrict__ vals, int S, int accumulate,
+                                                const uint32_t *__restrict__ loc, const int32_t *__restrict__ blkvert,
+                                                const int32_t *__restrict__ blkvcnt, const uint32_t *__restrict__ pos,
+                                                double *__restrict__ vals, int S, int SV, int accumulate,
                                                 const __grid_constant__ FormParams F)
 {
-    extern __shared__ double sacc[];
+    extern __shared__ double smem_d[];
     constexpr int NV = DIM + 1;
     constexpr double RFAC = DIM == 3 ? 1.0 / 6.0 : 0.5; // |K| = det * RFAC
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     const int row = blockIdx.x * blockDim.x + tid;
+    double *stage = smem_d + (size_t)warp * DIM * SV;                     // [DIM][SV] per warp
+    double *sacc = smem_d + (size_t)nwarp * DIM * SV;                     // [thread][S]
     double *acc = sacc + (size_t)tid * S;
-    int L = 0, rb = 0;
+    int L = 0, rb = 0, mycnt = 0;
+    double X[NV][DIM];
     if (row < nrows) {
         rb = nrowptr[row];
         L = nrowptr[row + 1] - rb;
+        mycnt = V.cnt[row];
         const int nflat = NC * NC * L;
         for (int j = 0; j < nflat; ++j) acc[j] = 0.0;
+        if (DIM == 3) { // P1: node id = vertex id
+            const double4 p = ldg_vertex(xyz, row);
+            X[0][0] = p.x; X[0][1] = p.y; X[0][DIM - 1] = p.z;
+        } else {
+            const double2 p = __ldg(reinterpret_cast<const double2 *>(xyz) + row);
+            X[0][0] = p.x; X[0][1] = p.y;
+        }
     }
     const int blk = row >> 5, nblk = (nrows + 31) >> 5;
     if (blk < nblk) {
+        const bool staged = p1_stage<DIM>(xyz, blkvert, blkvcnt, blk, lane, SV, stage);
         const uint32_t base = V.blkoff[blk];
         const int Lb = (int)((V.blkoff[blk + 1] - base) >> 5);
         const uint32_t *rinc = V.inc + base + lane;
         const uint32_t *rpos = pos + base + lane;
+        const uint32_t *rloc = loc + base + lane;
+        const bool need_inc = !FAST || !staged || F.nlab >= 0;
         const bool gradgrad = (F.mask & 0xEEE0u) != 0, valgrad = (F.mask & 0x000Eu) != 0, gradval = (F.mask & 0x1110u) != 0,
                    valval = (F.mask & 1u) != 0;
         for (int e = 0; e < Lb; ++e) {
-            const uint32_t ka = __ldcs(rinc + (size_t)e * 32);
-            if (ka == FF_NOREC) continue;
+            if (e >= mycnt) continue;
             const uint32_t pw = __ldcs(rpos + (size_t)e * 32);
-            const int k = ka >> 4, a = ka & 15;
-            if (!region_ok(F.nlab, F.labels, elab, k)) continue;
-            double N[NV][DIM], det;
-            p1_normals<DIM>(xyz, conn, k, N, det);
-            double na[DIM];
-#pragma unroll
-            for (int x = 0; x < DIM; ++x) {
-                double v = N[0][x];
-#pragma unroll
-                for (int b = 1; b < NV; ++b) v = (a == b) ? N[b][x] : v;
-                na[x] = v;
+            int k = 0, a = 0;
+            if (need_inc) {
+                const uint32_t ka = __ldcs(rinc + (size_t)e * 32);
+                k = ka >> 4;
+                a = ka & 15;
+                if (!region_ok(F.nlab, F.labels, elab, k)) continue;
             }
-            // |K| W g_a[sv] g_b[su] = (W RFAC / det) N_a[sv] N_b[su] ; |K| L_a g_b[su] = RFAC L_a N_b[su] ; |K| M = RFAC det M
-            const double sgg = gradgrad ? F.W * RFAC * __drcp_rn(det) : 0.0;
-            const double La = F.Lh[a] * RFAC;
+            double N[NV][DIM], det;
+            if (staged) p1_points_staged<DIM>(stage, SV, __ldcs(rloc + (size_t)e * 32), X);
+            else p1_points_global<DIM>(xyz, conn, k, a, X);
+            p1_normals<DIM>(X, N, det);
+            if (FAST) {
+                // |K| c W g_0 . g_i = (c W RFAC / det) N_0 . N_i ; |K| m M_0i = RFAC det m M_0i
+                const double sgg = F.fast_cw * __drcp_rn(det);
+                double w[DIM];
 #pragma unroll
-            for (int cv = 0; cv < NC; ++cv)
+                for (int x = 0; x < DIM; ++x) w[x] = sgg * N[0][x];
+                const double md = F.fast_md * det, mo = F.fast_mo * det;
 #pragma unroll
-                for (int cu = 0; cu < NC; ++cu) {
-                    // wa[su] = sgg * sum_sv C[sv][su] N_a[sv]  ;  ca0 = RFAC * sum_sv C[sv][0] N_a[sv]
-                    double wa[DIM], ca0 = 0.0, c0[DIM];
+                for (int i = 0; i < NV; ++i) {
+                    double v = i == 0 ? md : mo;
 #pragma unroll
-                    for (int su = 0; su < DIM; ++su) {
-                        double t = 0.0;
-#pragma unroll
-                        for (int sv = 0; sv < DIM; ++sv)
-                            if (F.mask >> ((sv + 1) * 4 + su + 1) & 1u) t = fma(F.C[cv][cu][sv + 1][su + 1], na[sv], t);
-                        wa[su] = t * sgg;
-                        c0[su] = valgrad ? F.C[cv][cu][0][su + 1] * La : 0.0;
-                    }
-                    if (gradval) {
-#pragma unroll
-                        for (int sv = 0; sv < DIM; ++sv) ca0 = fma(F.C[cv][cu][sv + 1][0], na[sv], ca0);
-                        ca0 *= RFAC;
-                    }
-                    const double cm = valval ? F.C[cv][cu][0][0] * RFAC * det : 0.0;
-#pragma unroll
-                    for (int b = 0; b < NV; ++b) {
-                        double v = 0.0;
-#pragma unroll
-                        for (int su = 0; su < DIM; ++su) v = fma(wa[su] + c0[su], N[b][su], v);
-                        if (gradval) v = fma(ca0, F.Lh[b], v);
-                        if (valval) v = fma(cm, F.Mh[a][b], v);
-                        const int pb = (pw >> (8 * b)) & 255;
-                        acc[cv * (NC * L) + pb * NC + cu] += v;
-                    }
+                    for (int x = 0; x < DIM; ++x) v = fma(w[x], N[i][x], v);
+                    const int pb = (pw >> (8 * i)) & 255;
+                    acc[pb] += v;
                 }
+            } else {
+                // |K| W g_0[sv] g_i[su] = (W RFAC / det) N_0[sv] N_i[su] ; |K| L g_i[su] = RFAC L N_i[su] ; |K| M = RFAC det M
+                const double sgg = gradgrad ? F.W * RFAC * __drcp_rn(det) : 0.0;
+                const double La = F.Lh[a] * RFAC;
+#pragma unroll
+                for (int cv = 0; cv < NC; ++cv)
+#pragma unroll
+                    for (int cu = 0; cu < NC; ++cu) {
+                        // wa[su] = sgg * sum_sv C[sv][su] N_0[sv] (+ C[0][su] L_a RFAC) ;  ca0 = RFAC * sum_sv C[sv][0] N_0[sv]
+                        double wa[DIM], ca0 = 0.0;
+#pragma unroll
+                        for (int su = 0; su < DIM; ++su) {
+                            double t = 0.0;
+#pragma unroll
+                            for (int sv = 0; sv < DIM; ++sv)
+                                if (F.mask >> ((sv + 1) * 4 + su + 1) & 1u) t = fma(F.C[cv][cu][sv + 1][su + 1], N[0][sv], t);
+                            wa[su] = t * sgg;
+                            if (valgrad) wa[su] = fma(F.C[cv][cu][0][su + 1], La, wa[su]);
+                        }
+                        if (gradval) {
+#pragma unroll
+                            for (int sv = 0; sv < DIM; ++sv) ca0 = fma(F.C[cv][cu][sv + 1][0], N[0][sv], ca0);
+                            ca0 *= RFAC;
+                        }
+                        const double cm = valval ? F.C[cv][cu][0][0] * RFAC * det : 0.0;
+#pragma unroll
+                        for (int i = 0; i < NV; ++i) {
+                            const int o = DIM == 3 ? (a ^ i) : (a + i) % 3; // the element's own local index of vertex i
+                            double v = wa[0] * N[i][0];
+#pragma unroll
+                            for (int su = 1; su < DIM; ++su) v = fma(wa[su], N[i][su], v);
+                            if (gradval) v = fma(ca0, F.Lh[o], v);
+                            if (valval) v = fma(cm, F.Mh[a][o], v);
+                            const int pb = (pw >> (8 * i)) & 255;
+                            acc[cv * (NC * L) + pb * NC + cu] += v;
+                        }
+                    }
+            }
         }
     }
     __syncwarp();
@@ -292,6 +365,98 @@ __global__ void __launch_bounds__(128) k_asm_p1(const double *__restrict__ xyz, 
         const double *src = sacc + (size_t)(wbase + r) * S;
         double *dst = vals + (size_t)NC * NC * rrb;
         for (int j = lane; j < nflat; j += 32) dst[j] = accumulate ? dst[j] + src[j] : src[j];
+    }
+}
+
+// reciprocal of a double to ~1 ulp without the slow path of a correctly rounded division: hardware seed + two Newton steps
+__device__ __forceinline__ double fast_rcp(double d)
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double t = fma(-d, r, 1.0);
+    r = fma(r, t, r);
+    t = fma(-d, r, 1.0);
+    return fma(r, t, r);
+}
+
+// The lean kernel behind the headline configurations: scalar P1, form = c grad u . grad v (+ m u v), no region filter,
+// every ELL block staged.  Per record it reads 8 bytes (position word + slot word), everything else is shared memory
+// and fp64 registers; records are prefetched one iteration ahead.
+template <int DIM>
+__global__ void __launch_bounds__(128) k_asm_p1_lean(const double *__restrict__ xyz, int nrows, const int32_t *__restrict__ nrowptr,
+                                                     const int32_t *__restrict__ cnt, const uint32_t *__restrict__ blkoff,
+                                                     const uint32_t *__restrict__ loc, const int32_t *__restrict__ blkvert,
+                                                     const int32_t *__restrict__ blkvcnt, const uint32_t *__restrict__ pos,
+                                                     double *__restrict__ vals, int S, int SV, int accumulate, double cw, double cmd,
+                                                     double cmo)
+{
+    extern __shared__ double smem_d[];
+    constexpr int NV = DIM + 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
+    const int row = blockIdx.x * blockDim.x + tid;
+    const double *stage = smem_d + (size_t)warp * DIM * SV;
+    double *sacc = smem_d + (size_t)nwarp * DIM * SV;
+    double *acc = sacc + (size_t)tid * S;
+    int L = 0, rb = 0, mycnt = 0;
+    double X[NV][DIM];
+    if (row < nrows) {
+        rb = nrowptr[row];
+        L = nrowptr[row + 1] - rb;
+        mycnt = cnt[row];
+        for (int j = 0; j < L; ++j) acc[j] = 0.0;
+        if (DIM == 3) {
+            const double4 p = ldg_vertex(xyz, row);
+            X[0][0] = p.x; X[0][1] = p.y; X[0][DIM - 1] = p.z;
+        } else {
+            const double2 p = __ldg(reinterpret_cast<const double2 *>(xyz) + row);
+            X[0][0] = p.x; X[0][1] = p.y;
+        }
+    }
+    const int blk = row >> 5, nblk = (nrows + 31) >> 5;
+    if (blk < nblk) {
+        p1_stage<DIM>(xyz, blkvert, blkvcnt, blk, lane, SV, const_cast<double *>(stage));
+        const uint32_t base = blkoff[blk];
+        const int Lb = (int)((blkoff[blk + 1] - base) >> 5);
+        const uint32_t *ppos = pos + base + lane, *ploc = loc + base + lane;
+        uint32_t pw = 0, lw = 0;
+        if (Lb > 0) {
+            pw = __ldcs(ppos);
+            lw = __ldcs(ploc);
+        }
+        for (int e = 0; e < Lb; ++e) {
+            const uint32_t pwc = pw, lwc = lw;
+            ppos += 32;
+            ploc += 32;
+            if (e + 1 < Lb) { // prefetch the next record (padding records hold unused words)
+                pw = __ldcs(ppos);
+                lw = __ldcs(ploc);
+            }
+            if (e < mycnt) {
+                double N[NV][DIM], det;
+                p1_points_staged<DIM>(stage, SV, lwc, X);
+                p1_normals<DIM>(X, N, det);
+                const double sgg = cw * fast_rcp(det);
+                double w[DIM];
+#pragma unroll
+                for (int x = 0; x < DIM; ++x) w[x] = sgg * N[0][x];
+                const double md = cmd * det, mo = cmo * det;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    double v = i == 0 ? md : mo;
+#pragma unroll
+                    for (int x = 0; x < DIM; ++x) v = fma(w[x], N[i][x], v);
+                    acc[(pwc >> (8 * i)) & 255] += v;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    const int wbase = tid & ~31;
+    for (int r = 0; r < 32; ++r) {
+        const int rrb = __shfl_sync(0xffffffffu, rb, r), rL = __shfl_sync(0xffffffffu, L, r);
+        const double *src = sacc + (size_t)(wbase + r) * S;
+        double *dst = vals + (size_t)rrb;
+        for (int j = lane; j < rL; j += 32) dst[j] = accumulate ? dst[j] + src[j] : src[j];
     }
 }
 
@@ -402,6 +567,8 @@ __global__ void __launch_bounds__(128) k_asm_p2(const double *__restrict__ xyz, 
 template <int DIM, int NC>
 __global__ void __launch_bounds__(128) k_rhs(const double *__restrict__ xyz, const int32_t *__restrict__ conn,
                                              const int32_t *__restrict__ elab, int nrows, const IncView V,
+                                             const uint32_t *__restrict__ loc, const int32_t *__restrict__ blkvert,
+                                             const int32_t *__restrict__ blkvcnt, int SV,
                                              const double *__restrict__ Fh /* nloc*(DIM+1) */, int nloc, int hasgrad,
                                              double *__restrict__ bvec, int accumulate, const __grid_constant__ LinParams Lp)
 {
@@ -428,36 +595,69 @@ __global__ void __launch_bounds__(128) k_rhs(const double *__restrict__ xyz, con
         ne = V.cnt[row];
         rinc = V.inc + V.incptr[row];
     }
+    extern __shared__ double stage_all[];
+    bool staged = false;
+    double *stage = stage_all + (size_t)(threadIdx.x >> 5) * DIM * SV;
+    const uint32_t *rloc = nullptr;
+    double X[DIM + 1][DIM];
+    if (V.ell && ne > 0) {
+        const int blk = row >> 5;
+        staged = p1_stage<DIM>(xyz, blkvert, blkvcnt, blk, lane, SV, stage);
+        rloc = loc + V.blkoff[blk] + lane;
+        if (row < nrows) { // P1: node id = vertex id
+            if (DIM == 3) {
+                const double4 p = ldg_vertex(xyz, row);
+                X[0][0] = p.x; X[0][1] = p.y; X[0][DIM - 1] = p.z;
+            } else {
+                const double2 p = __ldg(reinterpret_cast<const double2 *>(xyz) + row);
+                X[0][0] = p.x; X[0][1] = p.y;
+            }
+        }
+    }
+    constexpr double RFAC = DIM == 3 ? 1.0 / 6.0 : 0.5;
     for (int e = 0; e < ne; ++e) {
         const uint32_t ka = __ldcs(rinc + (size_t)e * stride);
         if (ka == FF_NOREC) continue;
         const int k = ka >> 4, a = ka & 15;
         if (!region_ok(Lp.nlab, Lp.labels, elab, k)) continue;
-        Geom<DIM> G;
-        if (DIM == 3) {
-            const int4 K = __ldg(reinterpret_cast<const int4 *>(conn) + k);
-            load_geom3(xyz, K.x, K.y, K.z, K.w, reinterpret_cast<Geom<3> &>(G), hasgrad);
-        } else {
-            const int v0 = __ldg(conn + 3 * (size_t)k), v1 = __ldg(conn + 3 * (size_t)k + 1), v2 = __ldg(conn + 3 * (size_t)k + 2);
-            load_geom2(xyz, v0, v1, v2, reinterpret_cast<Geom<2> &>(G));
-        }
-        double Fa[DIM + 1];
+        double Fa[DIM + 1], mes;
         Fa[0] = sF[a * (DIM + 1)];
+        if (staged) {
+            // P1 from the staged coordinates, owner-first: |K| = det RFAC, grad of the row's own basis function = N_0 / det,
+            // and sum_q w_q d(lambda_a)/d(xhat_r) g_r = W grad(lambda_a) with W = -Fh[0][1]
+            double N[DIM + 1][DIM], det;
+            p1_points_staged<DIM>(stage, SV, __ldcs(rloc + (size_t)e * 32), X);
+            p1_normals<DIM>(X, N, det);
+            mes = det * RFAC;
+            const double winv = hasgrad ? -sF[1] * __drcp_rn(det) : 0.0;
 #pragma unroll
-        for (int x = 0; x < DIM; ++x) {
-            double s = 0;
-            if (hasgrad) {
-#pragma unroll
-                for (int r = 0; r < DIM; ++r) s = fma(sF[a * (DIM + 1) + r + 1], G.g[r][x], s);
+            for (int x = 0; x < DIM; ++x) Fa[x + 1] = N[0][x] * winv;
+        } else {
+            Geom<DIM> G;
+            if (DIM == 3) {
+                const int4 K = __ldg(reinterpret_cast<const int4 *>(conn) + k);
+                load_geom3(xyz, K.x, K.y, K.z, K.w, reinterpret_cast<Geom<3> &>(G), hasgrad);
+            } else {
+                const int v0 = __ldg(conn + 3 * (size_t)k), v1 = __ldg(conn + 3 * (size_t)k + 1), v2 = __ldg(conn + 3 * (size_t)k + 2);
+                load_geom2(xyz, v0, v1, v2, reinterpret_cast<Geom<2> &>(G));
             }
-            Fa[x + 1] = s;
+            mes = G.mes;
+#pragma unroll
+            for (int x = 0; x < DIM; ++x) {
+                double s = 0;
+                if (hasgrad) {
+#pragma unroll
+                    for (int r = 0; r < DIM; ++r) s = fma(sF[a * (DIM + 1) + r + 1], G.g[r][x], s);
+                }
+                Fa[x + 1] = s;
+            }
         }
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             double v = 0;
 #pragma unroll
             for (int s = 0; s <= DIM; ++s) v = fma(Lp.CL[c][s], Fa[s], v);
-            out[c] += G.mes * v;
+            out[c] += mes * v;
         }
     }
     if (row < nrows) {
@@ -473,26 +673,40 @@ __global__ void __launch_bounds__(128) k_rhs(const double *__restrict__ xyz, con
 // host drivers
 // ----------------------------------------------------------------------------------------------------
 template <int DIM, int NC>
-static void launch_p1(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const FormParams &F, int accumulate)
+static void launch_p1(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const FormParams &F, int accumulate, bool fast)
 {
     ffcuda_pattern *P = A->pattern;
     ffcuda_mesh *m = s->mesh;
     FF_REQUIRE(P->pos8.p, "internal: P1 pattern without 8-bit positions");
+    const Incidence &I = s->incidence;
     int S = NC * NC * P->maxrow_node;
     S |= 1; // odd stride: threads of a warp land in different banks
+    const int SV = std::max(4, (I.maxstage + 3) & ~3); // staged vertices per warp (SoA, DIM planes)
     int threads = 128;
-    while (threads > 32 && (size_t)threads * S * 8 > 64 * 1024) threads >>= 1;
-    size_t shmem = (size_t)threads * S * 8;
+    while (threads > 32 && (size_t)threads * S * 8 + (size_t)(threads / 32) * DIM * SV * 8 > 48 * 1024) threads >>= 1;
+    size_t shmem = (size_t)threads * S * 8 + (size_t)(threads / 32) * DIM * SV * 8;
     FF_REQUIRE(shmem <= 200 * 1024, "matrix rows too long for the shared-memory row accumulators");
-    auto kern = k_asm_p1<DIM, NC>;
+    if (NC == 1 && fast && F.nlab < 0 && I.nunstaged == 0) {
+        auto lean = k_asm_p1_lean<DIM>;
+        FF_CUDA(cudaFuncSetAttribute(lean, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+        const int nw = (P->nrows_node + 31) / 32;
+        ff_launch(ctx, "asm_rows_p1", [&] {
+            lean<<<ff_blocks((size_t)nw * 32, threads), threads, shmem, ctx->stream>>>(
+                m->xyz.p, P->nrows_node, P->nrowptr.p, I.cnt.p, I.blkoff.p, I.loc.p, I.blkvert.p, I.blkvcnt.p,
+                reinterpret_cast<const uint32_t *>(P->pos8.p), A->vals.p, S, SV, accumulate, F.fast_cw, F.fast_md, F.fast_mo);
+        });
+        return;
+    }
+    auto kern = (NC == 1 && fast) ? k_asm_p1<DIM, NC, (NC == 1)> : k_asm_p1<DIM, NC, false>;
     FF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     // rows are taken in whole ELL blocks of 32: the grid covers ceil(nrows/32) warps
     const int nwarps = (P->nrows_node + 31) / 32;
     int blocks = ff_blocks((size_t)nwarps * 32, threads);
     const IncView V = ff_view(s->incidence);
     ff_launch(ctx, "asm_rows_p1", [&] {
-        kern<<<blocks, threads, shmem, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, P->nrows_node, P->nrowptr.p, V,
-                                                      reinterpret_cast<const uint32_t *>(P->pos8.p), A->vals.p, S, accumulate, F);
+        kern<<<blocks, threads, shmem, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, P->nrows_node, P->nrowptr.p, V, I.loc.p,
+                                                      I.blkvert.p, I.blkvcnt.p, reinterpret_cast<const uint32_t *>(P->pos8.p),
+                                                      A->vals.p, S, SV, accumulate, F);
     });
 }
 
@@ -522,12 +736,12 @@ static void launch_p2(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const 
 }
 
 template <int DIM>
-static void dispatch_p1(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const FormParams &F, int accumulate)
+static void dispatch_p1(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const FormParams &F, int accumulate, bool fast)
 {
     const int nc = s->ncomp;
-    if (nc == 1) launch_p1<DIM, 1>(ctx, A, s, F, accumulate);
-    else if (nc == 2) launch_p1<DIM, 2>(ctx, A, s, F, accumulate);
-    else launch_p1<DIM, 3>(ctx, A, s, F, accumulate);
+    if (nc == 1) launch_p1<DIM, 1>(ctx, A, s, F, accumulate, fast);
+    else if (nc == 2) launch_p1<DIM, 2>(ctx, A, s, F, accumulate, false);
+    else launch_p1<DIM, 3>(ctx, A, s, F, accumulate, false);
 }
 
 template <int DIM, typename PosT>
@@ -590,8 +804,25 @@ extern "C" int ffcuda_assemble_bilinear(ffcuda_matrix *A, ffcuda_space *s, int n
         FF_CUDA(cudaMemcpyAsync(Rg.p, R.data(), Rg.bytes(), cudaMemcpyHostToDevice, ctx->stream));
     }
     if (s->order == 1) {
-        if (dim == 3) dispatch_p1<3>(ctx, A, s, F, accumulate);
-        else dispatch_p1<2>(ctx, A, s, F, accumulate);
+        // FAST path: scalar space, c grad u . grad v (+ m u v), symmetric rule (M_aa all equal, M_ab all equal)
+        bool fast = nc == 1 && (F.mask & 0x111Eu) == 0;
+        const double c = F.C[0][0][1][1];
+        for (int sv = 1; sv <= dim && fast; ++sv)
+            for (int su = 1; su <= dim; ++su)
+                if (F.C[0][0][sv][su] != (sv == su ? c : 0.0)) fast = false;
+        for (int a = 0; a < nloc && fast && (F.mask & 1u); ++a)
+            for (int b = 0; b < nloc; ++b) {
+                const double ref = a == b ? F.Mh[0][0] : F.Mh[0][1];
+                if (fabs(F.Mh[a][b] - ref) > 1e-15 * fabs(F.Mh[0][0])) fast = false;
+            }
+        if (fast) {
+            const double rfac = dim == 3 ? 1.0 / 6.0 : 0.5;
+            F.fast_cw = c * F.W * rfac;
+            F.fast_md = F.C[0][0][0][0] * F.Mh[0][0] * rfac;
+            F.fast_mo = F.C[0][0][0][0] * F.Mh[0][1] * rfac;
+        }
+        if (dim == 3) dispatch_p1<3>(ctx, A, s, F, accumulate, fast);
+        else dispatch_p1<2>(ctx, A, s, F, accumulate, fast);
     } else if (P->pos8.p) {
         if (dim == 3) dispatch_p2<3, uint8_t>(ctx, A, s, F, Rg.p, P->pos8.p, accumulate);
         else dispatch_p2<2, uint8_t>(ctx, A, s, F, Rg.p, P->pos8.p, accumulate);
@@ -610,13 +841,16 @@ static void launch_rhs(ffcuda_ctx *ctx, ffcuda_vec *b, ffcuda_space *s, const Li
     const int nrows = s->incidence.nrows;
     const IncView V = ff_view(s->incidence);
     int blocks = ff_blocks((size_t)((nrows + 31) / 32) * 32, 128);
+    const Incidence &I = s->incidence;
+    const int SV = std::max(4, (I.maxstage + 3) & ~3);
+    const size_t shmem = I.ell ? (size_t)4 * DIM * SV * 8 : 0;
     ff_launch(ctx, "rhs_rows", [&] {
         if (s->ncomp == 1)
-            k_rhs<DIM, 1><<<blocks, 128, 0, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, nrows, V, Fh, s->nloc, hasgrad, b->d.p, accumulate, Lp);
+            k_rhs<DIM, 1><<<blocks, 128, shmem, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, nrows, V, I.loc.p, I.blkvert.p, I.blkvcnt.p, SV, Fh, s->nloc, hasgrad, b->d.p, accumulate, Lp);
         else if (s->ncomp == 2)
-            k_rhs<DIM, 2><<<blocks, 128, 0, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, nrows, V, Fh, s->nloc, hasgrad, b->d.p, accumulate, Lp);
+            k_rhs<DIM, 2><<<blocks, 128, shmem, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, nrows, V, I.loc.p, I.blkvert.p, I.blkvcnt.p, SV, Fh, s->nloc, hasgrad, b->d.p, accumulate, Lp);
         else
-            k_rhs<DIM, 3><<<blocks, 128, 0, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, nrows, V, Fh, s->nloc, hasgrad, b->d.p, accumulate, Lp);
+            k_rhs<DIM, 3><<<blocks, 128, shmem, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, nrows, V, I.loc.p, I.blkvert.p, I.blkvcnt.p, SV, Fh, s->nloc, hasgrad, b->d.p, accumulate, Lp);
     });
 }
 

@@ -72,6 +72,40 @@ struct ffcuda_ctx {
     // multi-GPU
     int rank = 0, nranks = 1;
     void *nccl_comm = nullptr;
+    // lifetime: every handle created on the context holds a reference; ffcuda_ctx_destroy only marks the context
+    // closed and the last handle to go tears it down
+    int refs = 0;
+    bool closed = false;
+    // caching device allocator (ctx.cu): freed blocks are kept and handed out again, cudaMalloc/cudaFree (which
+    // synchronise the device) are off the hot path.  Safe because all the work of a context is ordered on one stream.
+    std::multimap<size_t, void *> pool_free;
+    std::map<void *, size_t> pool_live;
+    size_t pool_cached = 0, pool_total = 0;
+};
+// a blocking copy ORDERED ON THE CONTEXT'S STREAM (plain cudaMemcpy runs on the legacy stream, which does not
+// synchronise with the non-blocking stream of the context: with the caching allocator a block can be handed out again
+// while earlier kernels that used it are still in flight on the context's stream)
+static inline cudaError_t ff_memcpy_sync(ffcuda_ctx *ctx, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind)
+{
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, ctx->stream);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize(ctx->stream);
+}
+void *ff_pool_alloc(ffcuda_ctx *ctx, size_t bytes);
+void ff_pool_free(ffcuda_ctx *ctx, void *p);
+void ff_pool_trim(ffcuda_ctx *ctx);
+void ff_ctx_unref(ffcuda_ctx *ctx);
+struct CtxRef { // first member of every handle struct: released after the handle's device buffers
+    ffcuda_ctx *c = nullptr;
+    void set(ffcuda_ctx *x)
+    {
+        c = x;
+        if (c) c->refs++;
+    }
+    ~CtxRef()
+    {
+        if (c) ff_ctx_unref(c);
+    }
 };
 
 void ff_report_error(ffcuda_ctx *ctx, const char *msg);
@@ -91,27 +125,20 @@ struct DBuf {
     DBuf(const DBuf &) = delete;
     DBuf &operator=(const DBuf &) = delete;
     ~DBuf() { release(); }
-    cudaStream_t st = nullptr; // stream the block was allocated on (stream-ordered allocator)
-    bool pooled = false;
+    ffcuda_ctx *owner = nullptr; // context whose caching allocator owns the block (nullptr: plain cudaMalloc)
     void alloc(size_t count)
     {
         release();
         n = count;
         if (!count) return;
-        ffcuda_ctx *c = ff_current_ctx();
-        if (c) {
-            st = c->stream;
-            pooled = true;
-            FF_CUDA(cudaMallocAsync((void **)&p, count * sizeof(T), st));
-        } else {
-            pooled = false;
-            FF_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
-        }
+        owner = ff_current_ctx();
+        if (owner) p = static_cast<T *>(ff_pool_alloc(owner, count * sizeof(T)));
+        else FF_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
     }
     void release()
     {
         if (p) {
-            if (pooled) cudaFreeAsync(p, st);
+            if (owner) ff_pool_free(owner, p);
             else cudaFree(p);
         }
         p = nullptr;
@@ -145,6 +172,7 @@ static inline int ff_blocks(size_t n, int threads) { return (int)((n + threads -
 
 // ---- handle structs --------------------------------------------------------------------------------
 struct ffcuda_mesh {
+    CtxRef ref; // keep first
     ffcuda_ctx *ctx = nullptr;
     int dim = 0, nv = 0, nt = 0, nbe = 0;
     int vstride = 0;          // doubles per vertex on the device: 2 (2-D) or 4 (3-D, padded: one 32 B sector)
@@ -177,7 +205,16 @@ struct Incidence {
     DBuf<int32_t> incptr;     // nrows+1 (CSR layout only)
     DBuf<uint32_t> blkoff;    // nblk+1  (ELL layout only)
     DBuf<uint32_t> inc;       // nrec records: (element << 4) | local node, each list sorted by element
+    // ELL layout only - vertex staging tables for the thread-per-row numeric kernels: the distinct vertices touched by
+    // the 32 rows of a block (at most FF_STAGE_MAX, else the block is marked unstaged and read through global
+    // memory), and for every record the 4 block-local slots of its element's vertices
+    DBuf<uint32_t> loc;       // nrec words, byte i = slot of the record's i-th vertex in OWNER-FIRST order (see blk_load)
+    DBuf<int32_t> blkvert;    // nblk * FF_STAGE_MAX global vertex ids
+    DBuf<int32_t> blkvcnt;    // nblk: number of distinct vertices, -1 = unstaged
+    int maxstage = 0;         // largest blkvcnt
+    int nunstaged = 0;        // number of blocks that could not be staged
 };
+static constexpr int FF_STAGE_MAX = 256;
 struct IncView {
     const int32_t *cnt, *incptr;
     const uint32_t *blkoff, *inc;
@@ -190,6 +227,7 @@ struct IncView {
 static inline IncView ff_view(const Incidence &I) { return IncView{I.cnt.p, I.incptr.p, I.blkoff.p, I.inc.p, I.ell}; }
 
 struct ffcuda_space {
+    CtxRef ref; // keep first
     ffcuda_mesh *mesh = nullptr;
     ffcuda_ctx *ctx = nullptr;
     int order = 1, ncomp = 1, nloc = 0, nnodes = 0, nnodes_owned = 0;
@@ -200,6 +238,7 @@ struct ffcuda_space {
 void ff_build_incidence(ffcuda_space *s); // symbolic.cu; no-op when already built
 
 struct ffcuda_pattern {
+    CtxRef ref; // keep first
     ffcuda_space *space = nullptr;
     ffcuda_ctx *ctx = nullptr;
     int nrows_node = 0;       // owned nodes = block rows
@@ -213,7 +252,7 @@ struct ffcuda_pattern {
     DBuf<int32_t> rowptr_own, colind_own; // dof-level CSR (only when ncomp > 1)
     const int32_t *rowptr = nullptr, *colind = nullptr;
     // per incidence record (same indexing as space->incidence.inc), nlocp entries: position of each node of that
-    // element inside the node row
+    // element inside the node row.  P1: in OWNER-FIRST order (entry 0 = the diagonal), see blk_load in symbolic.cu
     DBuf<uint8_t> pos8;
     DBuf<uint16_t> pos16;     // used instead when maxrow_node > 255
     int nlocp = 0;            // padded nloc in the pos table (4 for P1, nloc for P2)
@@ -221,6 +260,7 @@ struct ffcuda_pattern {
 };
 
 struct ffcuda_matrix {
+    CtxRef ref; // keep first
     ffcuda_ctx *ctx = nullptr;
     ffcuda_pattern *pattern = nullptr;    // null for from_csr matrices
     int n = 0, ncols = 0;
@@ -232,7 +272,7 @@ struct ffcuda_matrix {
     int maxrow = 0;           // longest dof row
     // CSR-stream SpMV set-up (lazily built, once per matrix): row-block table
     int stream_state = 0;     // 0 not prepared, 1 ready, -1 not applicable
-    int stream_nblk = 0, stream_T = 1;
+    int stream_nblk = 0, stream_T = 1, stream_grid = 1;
     size_t stream_shmem = 0;
     DBuf<int32_t> stream_rb;
     // CG workspace (lazily allocated)
@@ -241,12 +281,14 @@ struct ffcuda_matrix {
 };
 
 struct ffcuda_vec {
+    CtxRef ref; // keep first
     ffcuda_ctx *ctx = nullptr;
     int n = 0;
     DBuf<double> d;
 };
 
 struct ffcuda_bc {
+    CtxRef ref; // keep first
     ffcuda_ctx *ctx = nullptr;
     int ndofs = 0;
     DBuf<int32_t> dofs;

@@ -51,12 +51,6 @@ extern "C" int ffcuda_ctx_create(int device, ffcuda_ctx **out)
     FF_CUDA(cudaSetDevice(device));
     ctx = new ffcuda_ctx();
     ctx->device = device;
-    {   // device allocations go through the stream-ordered allocator; keep freed blocks in the pool (no trimming)
-        cudaMemPool_t pool;
-        FF_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
-        uint64_t keep = UINT64_MAX;
-        FF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    }
     FF_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
     ctx->stream = ctx->own_stream;
     cudaDeviceProp prop;
@@ -69,18 +63,83 @@ extern "C" int ffcuda_ctx_create(int device, ffcuda_ctx **out)
     FF_API_END(ctx)
 }
 
-extern "C" void ffcuda_ctx_destroy(ffcuda_ctx *ctx)
+// ---------------------------------------------------------------------------------------------------
+// caching device allocator
+// ---------------------------------------------------------------------------------------------------
+static size_t pool_round(size_t bytes) { return bytes < (1u << 20) ? (bytes + 511) & ~(size_t)511 : (bytes + ((1u << 20) - 1)) & ~(size_t)((1u << 20) - 1); }
+
+void ff_pool_trim(ffcuda_ctx *ctx)
 {
-    if (!ctx) return;
-    ff_enter(ctx);
+    if (ctx->pool_free.empty()) return;
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->pool_free) cudaFree(kv.second);
+    ctx->pool_total -= ctx->pool_cached;
+    ctx->pool_cached = 0;
+    ctx->pool_free.clear();
+}
+
+void *ff_pool_alloc(ffcuda_ctx *ctx, size_t bytes)
+{
+    const size_t want = pool_round(bytes);
+    // smallest cached block that fits without wasting more than a quarter of it
+    auto it = ctx->pool_free.lower_bound(want);
+    if (it != ctx->pool_free.end() && it->first <= want + want / 4 + (1u << 20)) {
+        void *p = it->second;
+        ctx->pool_cached -= it->first;
+        ctx->pool_live[p] = it->first;
+        ctx->pool_free.erase(it);
+        return p;
+    }
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { // give the cache back to the driver and retry once
+        cudaGetLastError();
+        ff_pool_trim(ctx);
+        e = cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess)
+        throw FFError(std::string("out of device memory allocating ") + std::to_string(want) + " bytes: " + cudaGetErrorString(e));
+    ctx->pool_live[p] = want;
+    ctx->pool_total += want;
+    return p;
+}
+
+void ff_pool_free(ffcuda_ctx *ctx, void *p)
+{
+    auto it = ctx->pool_live.find(p);
+    if (it == ctx->pool_live.end()) return;
+    const size_t sz = it->second;
+    ctx->pool_live.erase(it);
+    ctx->pool_free.emplace(sz, p);
+    ctx->pool_cached += sz;
+}
+
+static void ctx_teardown(ffcuda_ctx *ctx)
+{
+    cudaSetDevice(ctx->device);
     try { ff_prof_flush(ctx); } catch (...) {}
     ff_comm_release(ctx);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &kv : ctx->pool_free) cudaFree(kv.second);
+    for (auto &kv : ctx->pool_live) cudaFree(kv.first);
     if (ctx->d_scal) cudaFree(ctx->d_scal);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->d_partial) cudaFree(ctx->d_partial);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (g_cur_ctx == ctx) g_cur_ctx = nullptr;
     delete ctx;
+}
+
+void ff_ctx_unref(ffcuda_ctx *ctx)
+{
+    if (--ctx->refs <= 0 && ctx->closed) ctx_teardown(ctx);
+}
+
+extern "C" void ffcuda_ctx_destroy(ffcuda_ctx *ctx)
+{
+    if (!ctx || ctx->closed) return;
+    ctx->closed = true;
+    if (ctx->refs <= 0) ctx_teardown(ctx); // otherwise the last handle still alive tears it down
 }
 
 extern "C" const char *ffcuda_last_error(ffcuda_ctx *ctx)
@@ -277,6 +336,7 @@ extern "C" int ffcuda_vec_create(ffcuda_ctx *ctx, int n, ffcuda_vec **out)
     ff_enter(ctx);
     ffcuda_vec *v = new ffcuda_vec();
     v->ctx = ctx;
+    v->ref.set(ctx);
     v->n = n;
     v->d.alloc((size_t)n);
     if (n) FF_CUDA(cudaMemsetAsync(v->d.p, 0, v->d.bytes(), ctx->stream));

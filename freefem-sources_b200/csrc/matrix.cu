@@ -12,6 +12,7 @@ extern "C" int ffcuda_matrix_create(ffcuda_pattern *p, ffcuda_matrix **out)
     ff_enter(ctx);
     A = new ffcuda_matrix();
     A->ctx = ctx;
+    A->ref.set(ctx);
     A->pattern = p;
     A->n = p->n;
     A->ncols = p->ncols_node * p->ncomp;
@@ -63,6 +64,7 @@ extern "C" int ffcuda_matrix_from_csr(ffcuda_ctx *ctx, int n, int64_t nnz, const
     cudaStream_t st = ctx->stream;
     A = new ffcuda_matrix();
     A->ctx = ctx;
+    A->ref.set(ctx);
     A->n = n;
     A->ncols = n;
     A->nnz = nnz;
@@ -156,12 +158,13 @@ extern "C" int ffcuda_bc_from_pairs(ffcuda_space *s, int n, const int32_t *dofs,
         }
     bc = new ffcuda_bc();
     bc->ctx = ctx;
+    bc->ref.set(ctx);
     bc->ndofs = (int)ud.size();
     bc->dofs.alloc(ud.size());
     bc->vals.alloc(uv.size());
     if (bc->ndofs) {
-        FF_CUDA(cudaMemcpy(bc->dofs.p, ud.data(), bc->dofs.bytes(), cudaMemcpyHostToDevice));
-        FF_CUDA(cudaMemcpy(bc->vals.p, uv.data(), bc->vals.bytes(), cudaMemcpyHostToDevice));
+        FF_CUDA(ff_memcpy_sync(ctx, bc->dofs.p, ud.data(), bc->dofs.bytes(), cudaMemcpyHostToDevice));
+        FF_CUDA(ff_memcpy_sync(ctx, bc->vals.p, uv.data(), bc->vals.bytes(), cudaMemcpyHostToDevice));
     }
     *out = bc;
     bc = nullptr;
@@ -240,6 +243,7 @@ extern "C" int ffcuda_bc_from_labels(ffcuda_space *s, int nlab, const int32_t *l
     ff_exclusive_scan_i32(ctx, flag.p, off.p, (size_t)ndof + 1, &cnt);
     bc = new ffcuda_bc();
     bc->ctx = ctx;
+    bc->ref.set(ctx);
     bc->ndofs = (int)cnt;
     bc->dofs.alloc((size_t)cnt);
     bc->vals.alloc((size_t)cnt);

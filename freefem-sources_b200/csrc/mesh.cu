@@ -92,6 +92,7 @@ extern "C" int ffcuda_mesh_upload(ffcuda_ctx *ctx, int dim, int nv, const double
     cudaStream_t st = ctx->stream;
     m = new ffcuda_mesh();
     m->ctx = ctx;
+    m->ref.set(ctx);
     m->dim = dim; m->nv = nv; m->nt = nt; m->nbe = nbe;
     m->nv_owned = nv;
     const int nvk = dim + 1;
@@ -242,6 +243,7 @@ static void build_cube(ffcuda_ctx *ctx, int nx, int ny, int nz, int rank, int nr
     cudaStream_t st = ctx->stream;
     std::unique_ptr<ffcuda_mesh> m(new ffcuda_mesh());
     m->ctx = ctx;
+    m->ref.set(ctx);
     m->dim = 3; m->vstride = 4;
     int nc = (int)nc64;
     m->nv_owned = (int)(nk * C.nown);
@@ -306,7 +308,7 @@ extern "C" int ffcuda_mesh_local_to_global(ffcuda_mesh *m, int *nowned, int *nlo
     if (gid) {
         ff_enter(m->ctx);
         if (m->gid.p) {
-            FF_CUDA(cudaMemcpy(gid, m->gid.p, m->gid.bytes(), cudaMemcpyDeviceToHost));
+            FF_CUDA(ff_memcpy_sync(m->ctx, gid, m->gid.p, m->gid.bytes(), cudaMemcpyDeviceToHost));
         } else
             for (int i = 0; i < m->nv; ++i) gid[i] = i;
     }
@@ -371,6 +373,7 @@ extern "C" int ffcuda_mesh_square(ffcuda_ctx *ctx, int nx, int ny, ffcuda_mesh *
     cudaStream_t st = ctx->stream;
     m = new ffcuda_mesh();
     m->ctx = ctx;
+    m->ref.set(ctx);
     m->dim = 2; m->vstride = 2;
     m->nv = (nx + 1) * (ny + 1);
     m->nv_owned = m->nv;

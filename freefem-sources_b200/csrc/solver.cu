@@ -122,7 +122,7 @@ __global__ void k_stream_blocks(const int32_t *__restrict__ rowptr, int n, int n
 template <int T, int MODE>
 __global__ void __launch_bounds__(RED_THREADS) k_spmv_stream(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
                                                              const double *__restrict__ vals, const double *__restrict__ x,
-                                                             const int32_t *__restrict__ rb, const double *__restrict__ aux0,
+                                                             const int32_t *__restrict__ rb, int nblk, const double *__restrict__ aux0,
                                                              const double *__restrict__ aux1, double *__restrict__ y, int iter,
                                                              double *__restrict__ partial, int *__restrict__ flags,
                                                              double *__restrict__ out)
@@ -133,57 +133,62 @@ __global__ void __launch_bounds__(RED_THREADS) k_spmv_stream(const int32_t *__re
         const int ci = flags[F_CONV_ITER]; // 0: running, -1/-2: stopped before the first iteration, k>0: converged at k
         if (ci != 0 && iter > ci) return;
     }
-    const int r0 = rb[blockIdx.x], r1 = rb[blockIdx.x + 1];
-    const int nz0 = __ldg(rowptr + r0), nz1 = __ldg(rowptr + r1);
-    const int cnt = nz1 - nz0;
-    // phase 1
-    for (int base = 0; base < cnt; base += STREAM_TILE) {
-        double v[STREAM_ITEMS];
-        int c[STREAM_ITEMS];
-#pragma unroll
-        for (int i = 0; i < STREAM_ITEMS; ++i) {
-            const int j = base + i * RED_THREADS + threadIdx.x;
-            const bool ok = j < cnt;
-            c[i] = ok ? __ldcs(colind + nz0 + j) : 0;
-            v[i] = ok ? __ldcs(vals + nz0 + j) : 0.0;
-        }
-#pragma unroll
-        for (int i = 0; i < STREAM_ITEMS; ++i) {
-            const int j = base + i * RED_THREADS + threadIdx.x;
-            if (j < cnt) sprod[j] = v[i] * __ldg(x + c[i]);
-        }
-    }
-    __syncthreads();
-    // phase 2
     double acc0 = 0.0, acc1 = 0.0;
     const int l = threadIdx.x & (T - 1);
-    const int nrow = r1 - r0;
-    const int nround = (nrow + RED_THREADS / T - 1) / (RED_THREADS / T); // uniform trip count: shuffles stay convergent
-    for (int it = 0; it < nround; ++it) {
-        const int rl = it * (RED_THREADS / T) + threadIdx.x / T;
-        const bool ok = rl < nrow;
-        const int row = r0 + rl;
-        double s = 0.0;
-        if (ok) {
-            const int b = __ldg(rowptr + row) - nz0, e = __ldg(rowptr + row + 1) - nz0;
-            for (int j = b + l; j < e; j += T) s += sprod[j];
-        }
+    // each CTA takes a contiguous share of the row blocks (the grid is sized to the machine, not to the matrix)
+    const int t0 = (int)((long long)nblk * blockIdx.x / gridDim.x), t1 = (int)((long long)nblk * (blockIdx.x + 1) / gridDim.x);
+    for (int t = t0; t < t1; ++t) {
+        const int r0 = rb[t], r1 = rb[t + 1];
+        const int nz0 = __ldg(rowptr + r0), nz1 = __ldg(rowptr + r1);
+        const int cnt = nz1 - nz0;
+        // phase 1: products into shared memory
+        for (int base = 0; base < cnt; base += STREAM_TILE) {
+            double v[STREAM_ITEMS];
+            int c[STREAM_ITEMS];
 #pragma unroll
-        for (int o = T >> 1; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (ok && l == 0) {
-            if (MODE == 0) y[row] = s;
-            if (MODE == 1) {
-                const double g = s - aux0[row];
-                y[row] = g;
-                acc0 = fma(g, aux1[row] * g, acc0);
+            for (int i = 0; i < STREAM_ITEMS; ++i) {
+                const int j = base + i * RED_THREADS + threadIdx.x;
+                const bool ok = j < cnt;
+                c[i] = ok ? __ldcs(colind + nz0 + j) : 0;
+                v[i] = ok ? __ldcs(vals + nz0 + j) : 0.0;
             }
-            if (MODE == 2) {
-                const double h = x[row];
-                y[row] = s;
-                acc0 = fma(aux0[row], h, acc0);
-                acc1 = fma(h, s, acc1);
+#pragma unroll
+            for (int i = 0; i < STREAM_ITEMS; ++i) {
+                const int j = base + i * RED_THREADS + threadIdx.x;
+                if (j < cnt) sprod[j] = v[i] * __ldg(x + c[i]);
             }
         }
+        __syncthreads();
+        // phase 2: row sums
+        const int nrow = r1 - r0;
+        const int nround = (nrow + RED_THREADS / T - 1) / (RED_THREADS / T); // uniform trip count: shuffles stay convergent
+        for (int it = 0; it < nround; ++it) {
+            const int rl = it * (RED_THREADS / T) + threadIdx.x / T;
+            const bool ok = rl < nrow;
+            const int row = r0 + rl;
+            double s = 0.0;
+            if (ok) {
+                const int b = __ldg(rowptr + row) - nz0, e = __ldg(rowptr + row + 1) - nz0;
+                for (int j = b + l; j < e; j += T) s += sprod[j];
+            }
+#pragma unroll
+            for (int o = T >> 1; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if (ok && l == 0) {
+                if (MODE == 0) y[row] = s;
+                if (MODE == 1) {
+                    const double g = s - aux0[row];
+                    y[row] = g;
+                    acc0 = fma(g, aux1[row] * g, acc0);
+                }
+                if (MODE == 2) {
+                    const double h = x[row];
+                    y[row] = s;
+                    acc0 = fma(aux0[row], h, acc0);
+                    acc1 = fma(h, s, acc1);
+                }
+            }
+        }
+        __syncthreads(); // sprod is reused by the next row block
     }
     if (MODE == 1) {
         double a[1] = {acc0};
@@ -458,6 +463,12 @@ static bool stream_prepare(ffcuda_matrix *A)
     while (T < 32 && rows_per_blk * T * 2 <= RED_THREADS) T <<= 1;
     A->stream_T = T;
     A->stream_shmem = shmem;
+    {   // persistent grid: as many CTAs as the machine holds at once (threads and shared memory), at most one per block
+        int per_sm = 2048 / RED_THREADS;
+        const int by_smem = (int)((200 * 1024) / (shmem + 1024));
+        per_sm = std::max(1, std::min(per_sm, by_smem));
+        A->stream_grid = std::max(1, std::min(A->stream_nblk, ctx->sm_count * per_sm));
+    }
     A->stream_state = 1;
     return true;
 }
@@ -482,8 +493,8 @@ static void stream_launch(ffcuda_matrix *A, const char *name, const double *x, c
         if (A->stream_shmem > 48 * 1024)
             FF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A->stream_shmem));
         ff_launch(ctx, name, [&] {
-            kern<<<A->stream_nblk, RED_THREADS, A->stream_shmem, ctx->stream>>>(A->rowptr, A->colind, A->vals.p, x, A->stream_rb.p, aux0,
-                                                                                 aux1, y, iter, partial, flags, out);
+            kern<<<A->stream_grid, RED_THREADS, A->stream_shmem, ctx->stream>>>(A->rowptr, A->colind, A->vals.p, x, A->stream_rb.p,
+                                                                                 A->stream_nblk, aux0, aux1, y, iter, partial, flags, out);
         });
     });
 }
@@ -537,7 +548,7 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
     int *flags = ctx_flags(ctx);
     const int T = pick_T(A);
     const bool streamed = stream_prepare(A);
-    const int grid_s = streamed ? A->stream_nblk : grid_for(ctx, (size_t)n * T), grid_v = grid_for(ctx, (size_t)n);
+    const int grid_s = streamed ? A->stream_grid : grid_for(ctx, (size_t)n * T), grid_v = grid_for(ctx, (size_t)n);
     ensure_partial(ctx, 2 * (size_t)std::max(grid_s, grid_v) + 16);
     double *partial = ctx->d_partial;
     FF_CUDA(cudaMemsetAsync(scal, 0, 64 * sizeof(double), st));

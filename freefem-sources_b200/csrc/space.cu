@@ -44,6 +44,7 @@ extern "C" int ffcuda_space_create(ffcuda_mesh *m, int order, int ncomp, const i
     s = new ffcuda_space();
     s->mesh = m;
     s->ctx = ctx;
+    s->ref.set(ctx);
     s->order = order;
     s->ncomp = ncomp;
     s->nloc = ff_nloc(m->dim, order);
@@ -58,13 +59,13 @@ extern "C" int ffcuda_space_create(ffcuda_mesh *m, int order, int ncomp, const i
             FF_REQUIRE(m->dim == 3,
                        "2-D P2: FreeFEM renumbers the nodes (Gibbs, FESpace.cpp:991); pass the element->node table");
             std::vector<int32_t> conn((size_t)m->nt * 4);
-            FF_CUDA(cudaMemcpy(conn.data(), m->conn.p, m->conn.bytes(), cudaMemcpyDeviceToHost));
+            FF_CUDA(ff_memcpy_sync(ctx, conn.data(), m->conn.p, m->conn.bytes(), cudaMemcpyDeviceToHost));
             nnodes = number_p2_nodes_3d(m->nt, conn, tab);
             elem2node = tab.data();
         }
         FF_REQUIRE(nnodes > 0, "nnodes must be positive when an element->node table is given");
         s->e2n_own.alloc((size_t)m->nt * s->nloc);
-        FF_CUDA(cudaMemcpy(s->e2n_own.p, elem2node, s->e2n_own.bytes(), cudaMemcpyHostToDevice));
+        FF_CUDA(ff_memcpy_sync(ctx, s->e2n_own.p, elem2node, s->e2n_own.bytes(), cudaMemcpyHostToDevice));
         s->e2n = s->e2n_own.p;
         s->nnodes = nnodes;
         s->nnodes_owned = nnodes;
@@ -92,7 +93,7 @@ extern "C" int ffcuda_space_download_dofs(ffcuda_space *s, int32_t *dof)
     const int nt = s->mesh->nt, nloc = s->nloc, nc = s->ncomp;
     std::vector<int32_t> e2n((size_t)nt * nloc);
     ff_enter(s->ctx);
-    FF_CUDA(cudaMemcpy(e2n.data(), s->e2n, e2n.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    FF_CUDA(ff_memcpy_sync(s->ctx, e2n.data(), s->e2n, e2n.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
     for (int k = 0; k < nt; ++k)
         for (int c = 0; c < nc; ++c)
             for (int a = 0; a < nloc; ++a)

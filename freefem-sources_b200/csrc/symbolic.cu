@@ -83,6 +83,307 @@ __global__ void k_sort_inc(const IncView V, uint32_t *__restrict__ inc, int nrow
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// P1 (ELL layout): block-level kernels.  One warp owns the 32 rows of an ELL block; the block's records and the
+// vertex ids of their elements are first brought into shared memory with coalesced / fully independent loads, after
+// which all the set logic runs out of shared memory.
+// ---------------------------------------------------------------------------------------------------------------
+static constexpr uint32_t HT_EMPTY = 0xffffffffu;
+
+__device__ __forceinline__ uint32_t ht_hash(uint32_t v, int log) { return (v * 0x9E3779B1u) >> (32 - log); }
+
+// records of block b -> recs[e*32 + lane] ; vertex ids of every record's element -> cand[lane*cstride + e*4 + i]
+// in OWNER-FIRST order: i = 0 is the row's own vertex (local vertex a of the element), i = 1.. the others in an order
+// that is an even permutation of the element's own (a^i on tetrahedra, (a+i)%3 on triangles), so that the re-ordered
+// simplex has the same orientation.  -1 where there is no record / no 4th vertex.
+template <int NLOC>
+__device__ __forceinline__ void blk_load(const int32_t *__restrict__ conn, const IncView &V, uint32_t base, int Lb, int lane,
+                                         int cstride, uint32_t *recs, int32_t *cand)
+{
+    for (int e = 0; e < Lb; ++e) recs[e * 32 + lane] = __ldcs(V.inc + base + (size_t)e * 32 + lane);
+    int4 *crow = reinterpret_cast<int4 *>(cand + (size_t)lane * cstride);
+#pragma unroll 4
+    for (int e = 0; e < Lb; ++e) {
+        const uint32_t r = recs[e * 32 + lane];
+        int4 c = make_int4(-1, -1, -1, -1);
+        if (r != FF_NOREC) {
+            const size_t k = r >> 4;
+            const int a = r & 15;
+            if (NLOC == 4) {
+                const int4 q = __ldg(reinterpret_cast<const int4 *>(conn) + k);
+                // c[i] = q[a ^ i]
+                c.x = a == 0 ? q.x : a == 1 ? q.y : a == 2 ? q.z : q.w;
+                c.y = a == 0 ? q.y : a == 1 ? q.x : a == 2 ? q.w : q.z;
+                c.z = a == 0 ? q.z : a == 1 ? q.w : a == 2 ? q.x : q.y;
+                c.w = a == 0 ? q.w : a == 1 ? q.z : a == 2 ? q.y : q.x;
+            } else {
+                const int q0 = __ldg(conn + 3 * k), q1 = __ldg(conn + 3 * k + 1), q2 = __ldg(conn + 3 * k + 2);
+                // c[i] = q[(a + i) % 3]
+                c.x = a == 0 ? q0 : a == 1 ? q1 : q2;
+                c.y = a == 0 ? q1 : a == 1 ? q2 : q0;
+                c.z = a == 0 ? q2 : a == 1 ? q0 : q1;
+            }
+        }
+        crow[e] = c;
+    }
+    __syncwarp();
+}
+
+// stage tables of the incidence: distinct vertices of the block (slot numbering) and per-record slot bytes
+template <int NLOC>
+__global__ void __launch_bounds__(128) k_block_stage(const int32_t *__restrict__ conn, int nrows, const IncView V, int Lmax,
+                                                     uint32_t *__restrict__ loc, int32_t *__restrict__ blkvert,
+                                                     int32_t *__restrict__ blkvcnt, int32_t *__restrict__ maxstage)
+{
+    extern __shared__ uint32_t smem_u[];
+    constexpr int BT = 1024, BLOG = 10;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cstride = Lmax * 4 + 4;
+    const size_t per_warp = (size_t)Lmax * 32 + (size_t)32 * cstride + 2 * BT + FF_STAGE_MAX + 4;
+    uint32_t *recs = smem_u + (size_t)w * per_warp;
+    int32_t *cand = reinterpret_cast<int32_t *>(recs + (size_t)Lmax * 32);
+    uint32_t *bkey = reinterpret_cast<uint32_t *>(cand + (size_t)32 * cstride);
+    uint32_t *bslot = bkey + BT;
+    int32_t *vlist = reinterpret_cast<int32_t *>(bslot + BT);
+    int *bcnt = vlist + FF_STAGE_MAX;
+    const int blk = blockIdx.x * (blockDim.x >> 5) + w, nblk = (nrows + 31) >> 5;
+    if (blk >= nblk) return;
+    const uint32_t base = V.blkoff[blk];
+    const int Lb = (int)((V.blkoff[blk + 1] - base) >> 5);
+    for (int x = lane; x < BT; x += 32) bkey[x] = HT_EMPTY;
+    if (lane == 0) *bcnt = 0;
+    blk_load<NLOC>(conn, V, base, Lb, lane, cstride, recs, cand);
+    // insert: lane = row, walking its own records
+    for (int e = 0; e < Lb; ++e) {
+#pragma unroll
+        for (int b = 0; b < NLOC; ++b) {
+            const int vi = cand[(size_t)lane * cstride + e * 4 + b];
+            // more than FF_STAGE_MAX distinct vertices: the block will be marked unstaged, stop filling the table
+            // (at most 32 lanes overshoot by one insertion each: the 1024-slot table cannot fill up)
+            if (vi < 0 || *reinterpret_cast<volatile int *>(bcnt) > FF_STAGE_MAX) continue;
+            const uint32_t v = (uint32_t)vi;
+            uint32_t h = ht_hash(v, BLOG);
+            while (true) {
+                uint32_t k = bkey[h];
+                if (k == v) break;
+                if (k == HT_EMPTY) {
+                    k = atomicCAS(&bkey[h], HT_EMPTY, v);
+                    if (k == HT_EMPTY) {
+                        const int slot = atomicAdd(bcnt, 1);
+                        bslot[h] = (uint32_t)slot;
+                        if (slot < FF_STAGE_MAX) vlist[slot] = vi;
+                        break;
+                    }
+                    if (k == v) break;
+                }
+                h = (h + 1) & (BT - 1);
+            }
+        }
+    }
+    __syncwarp();
+    const int nv = *bcnt;
+    const bool staged = nv <= FF_STAGE_MAX;
+    for (int e = 0; e < Lb; ++e) {
+        if (recs[e * 32 + lane] == FF_NOREC) continue;
+        uint32_t word = 0;
+        if (staged) {
+#pragma unroll
+            for (int b = 0; b < NLOC; ++b) {
+                const uint32_t v = (uint32_t)cand[(size_t)lane * cstride + e * 4 + b];
+                uint32_t h = ht_hash(v, BLOG);
+                while (bkey[h] != v) h = (h + 1) & (BT - 1);
+                word |= bslot[h] << (8 * b);
+            }
+        }
+        loc[base + (size_t)e * 32 + lane] = word;
+    }
+    if (staged)
+        for (int x = lane; x < nv; x += 32) blkvert[(size_t)blk * FF_STAGE_MAX + x] = vlist[x];
+    if (lane == 0) {
+        blkvcnt[blk] = staged ? nv : -1;
+        if (staged) atomicMax(maxstage, nv);
+        else atomicAdd(maxstage + 1, 1);
+    }
+}
+
+__device__ __forceinline__ int warp_sort32(int v, int lane)
+{
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int o = __shfl_xor_sync(0xffffffffu, v, j);
+            const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+            v = (lower == up) ? min(v, o) : max(v, o);
+        }
+    return v;
+}
+
+// bitonic sort of u[0..m) (m a power of two >= 64) by one warp in shared memory
+__device__ __forceinline__ void warp_sort_smem(int32_t *u, int m, int lane)
+{
+    for (int k = 2; k <= m; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int x = lane; x < m; x += 32) {
+                const int y = x ^ j;
+                if (y > x) {
+                    const int a = u[x], b = u[y];
+                    const bool up = (x & k) == 0;
+                    if ((a > b) == up) {
+                        u[x] = b;
+                        u[y] = a;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+}
+
+// row patterns of the 32 rows of a block in ONE pass: sorted distinct columns into a fixed-stride scratch
+// (tmpcol[row*cap + x], compacted after the scan of the row lengths), positions of every record's vertices in the row
+template <int NLOC>
+__global__ void __launch_bounds__(128) k_block_pattern(const int32_t *__restrict__ conn, int nrows, const IncView V, int Lmax, int cap,
+                                                       int TSR, int RLOG, int32_t *__restrict__ tmpcol, int32_t *__restrict__ rowlen,
+                                                       int32_t *__restrict__ diagnode, uint32_t *__restrict__ pos,
+                                                       int32_t *__restrict__ maxrow)
+{
+    extern __shared__ uint32_t smem_u[];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cstride = Lmax * 4 + 4;
+    int UL = 64;
+    while (UL < cap) UL <<= 1; // room for the shared-memory bitonic sort
+    const int RW = (Lmax * 33 + 3) & ~3;
+    const size_t per_warp = (size_t)RW + (size_t)32 * cstride + 2 * (size_t)TSR + UL;
+    uint32_t *recs = smem_u + (size_t)w * per_warp; // records, later the position words [e*33 + row]
+    int32_t *cand = reinterpret_cast<int32_t *>(recs + RW);
+    uint32_t *rkey = reinterpret_cast<uint32_t *>(cand + (size_t)32 * cstride);
+    uint32_t *rrank = rkey + TSR;
+    int32_t *ulist = reinterpret_cast<int32_t *>(rrank + TSR);
+    const uint32_t lt = (1u << lane) - 1u, hmask = (uint32_t)TSR - 1u;
+    const int blk = blockIdx.x * (blockDim.x >> 5) + w, nblk = (nrows + 31) >> 5;
+    if (blk >= nblk) return;
+    const uint32_t base = V.blkoff[blk];
+    const int Lb = (int)((V.blkoff[blk + 1] - base) >> 5);
+    blk_load<NLOC>(conn, V, base, Lb, lane, cstride, recs, cand);
+    const int myrow = blk * 32 + lane;
+    const int mycnt = myrow < nrows ? V.cnt[myrow] : 0;
+    __syncwarp();
+    int localmax = 0;
+    for (int x = lane; x < TSR; x += 32) rkey[x] = HT_EMPTY; // cleared once; every row removes its own keys when done
+    __syncwarp();
+    for (int r = 0; r < 32; ++r) {
+        const int row = blk * 32 + r;
+        if (row >= nrows) break;
+        const int cnt = __shfl_sync(0xffffffffu, mycnt, r);
+        const int ncand = cnt * 4;
+        const int32_t *crow = cand + (size_t)r * cstride;
+        if (lane == 0) { // the row's own node is always a column (it is a vertex of every incident element)
+            rkey[ht_hash((uint32_t)row, RLOG)] = (uint32_t)row;
+            ulist[0] = row;
+        }
+        __syncwarp();
+        int nu = 1;
+        for (int x0 = 0; x0 < ncand; x0 += 32) {
+            const int x = x0 + lane;
+            const int vi = x < ncand ? crow[x] : -1;
+            bool isnew = false;
+            if (vi >= 0 && vi != row) {
+                const uint32_t v = (uint32_t)vi;
+                uint32_t h = ht_hash(v, RLOG);
+                while (true) {
+                    uint32_t k = rkey[h];
+                    if (k == v) break;
+                    if (k == HT_EMPTY) {
+                        k = atomicCAS(&rkey[h], HT_EMPTY, v);
+                        if (k == HT_EMPTY) {
+                            isnew = true;
+                            break;
+                        }
+                        if (k == v) break;
+                    }
+                    h = (h + 1) & hmask;
+                }
+            }
+            const unsigned msk = __ballot_sync(0xffffffffu, isnew);
+            if (isnew) ulist[nu + __popc(msk & lt)] = vi;
+            nu += __popc(msk);
+        }
+        __syncwarp();
+        if (nu <= 32) {
+            // rank by counting (all distinct): no sort needed, lane x owns ulist[x]
+            const int v = lane < nu ? ulist[lane] : INT_MAX;
+            int rank = 0;
+            for (int j = 0; j < nu; ++j) rank += (__shfl_sync(0xffffffffu, v, j) < v) ? 1 : 0;
+            if (lane < nu) {
+                uint32_t h = ht_hash((uint32_t)v, RLOG);
+                while (rkey[h] != (uint32_t)v) h = (h + 1) & hmask;
+                rrank[h] = (uint32_t)rank;
+                tmpcol[(size_t)row * cap + rank] = v;
+                if (v == row) diagnode[row] = rank;
+            }
+        } else {
+            int m = 64;
+            while (m < nu) m <<= 1;
+            for (int x = nu + lane; x < m; x += 32) ulist[x] = INT_MAX;
+            __syncwarp();
+            warp_sort_smem(ulist, m, lane);
+            for (int x = lane; x < nu; x += 32) {
+                const int v = ulist[x];
+                uint32_t h = ht_hash((uint32_t)v, RLOG);
+                while (rkey[h] != (uint32_t)v) h = (h + 1) & hmask;
+                rrank[h] = (uint32_t)x;
+                tmpcol[(size_t)row * cap + x] = v;
+                if (v == row) diagnode[row] = x;
+            }
+        }
+        if (lane == 0) rowlen[row] = nu;
+        localmax = max(localmax, nu);
+        __syncwarp();
+        // position words: lane e takes record e of this row
+        for (int e = lane; e < cnt; e += 32) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int b = 0; b < NLOC; ++b) {
+                const uint32_t v = (uint32_t)crow[e * 4 + b];
+                uint32_t h = ht_hash(v, RLOG);
+                while (rkey[h] != v) h = (h + 1) & hmask;
+                word |= (rrank[h] & 255u) << (8 * b);
+            }
+            recs[e * 33 + r] = word;
+        }
+        __syncwarp();
+        // remove this row's keys (linear probing without deletions in between: every key is still reachable)
+        for (int x = lane; x < nu; x += 32) {
+            const uint32_t v = (uint32_t)ulist[x];
+            uint32_t h = ht_hash(v, RLOG);
+            while (rkey[h] != v) h = (h + 1) & hmask;
+            ulist[x] = (int32_t)h; // remember the slot, clear after everybody has found theirs
+        }
+        __syncwarp();
+        for (int x = lane; x < nu; x += 32) rkey[ulist[x]] = HT_EMPTY;
+        __syncwarp();
+    }
+    for (int e = 0; e < mycnt; ++e) pos[base + (size_t)e * 32 + lane] = recs[e * 33 + lane];
+    if (lane == 0 && localmax > 0) atomicMax(maxrow, localmax);
+}
+
+// tmpcol (fixed stride) -> ncol (CSR): one warp per 32 rows, a row segment at a time
+__global__ void k_compact_cols(const int32_t *__restrict__ tmpcol, int cap, const int32_t *__restrict__ nrowptr, int nrows,
+                               int32_t *__restrict__ ncol)
+{
+    const int blk = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    const int row0 = blk * 32;
+    if (row0 >= nrows) return;
+    const int myrow = row0 + lane;
+    const int rb = myrow <= nrows ? nrowptr[min(myrow, nrows)] : 0;
+    const int rbn = myrow < nrows ? nrowptr[myrow + 1] : rb;
+    for (int r = 0; r < 32 && row0 + r < nrows; ++r) {
+        const int b = __shfl_sync(0xffffffffu, rb, r), L = __shfl_sync(0xffffffffu, rbn, r) - b;
+        for (int x = lane; x < L; x += 32) ncol[(size_t)b + x] = tmpcol[(size_t)(row0 + r) * cap + x];
+    }
+}
+
 void ff_build_incidence(ffcuda_space *s)
 {
     Incidence &I = s->incidence;
@@ -130,27 +431,44 @@ void ff_build_incidence(ffcuda_space *s)
     const IncView V = ff_view(I);
     ff_launch(ctx, "inc_fill", [&] { k_fill_inc<<<ff_blocks(nitems, 256), 256, 0, st>>>(s->e2n, nitems, nloc, nrows, V, cursor.p, I.inc.p); });
     ff_launch(ctx, "inc_sort", [&] { k_sort_inc<<<ff_blocks(nrows, 128), 128, 0, st>>>(V, I.inc.p, nrows); });
+    if (I.ell) {
+        // vertex staging tables for the thread-per-row numeric kernels
+        const int nblk = (nrows + 31) / 32, Lmax = I.maxinc, cstride = Lmax * 4 + 4;
+        size_t per_warp = ((size_t)Lmax * 32 + (size_t)32 * cstride + 2 * 1024 + FF_STAGE_MAX + 4) * 4;
+        int warps = 4;
+        while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
+        FF_REQUIRE(per_warp <= 200 * 1024, "a vertex has too many incident elements for the block staging kernel");
+        I.loc.alloc((size_t)nrec);
+        I.blkvert.alloc((size_t)nblk * FF_STAGE_MAX);
+        I.blkvcnt.alloc((size_t)nblk);
+        DBuf<int32_t> d_st;
+        d_st.alloc(2);
+        FF_CUDA(cudaMemsetAsync(d_st.p, 0, 2 * sizeof(int32_t), st));
+        const size_t shmem = warps * per_warp;
+        const int blocks = ff_blocks((size_t)nblk, warps);
+        if (nloc == 4) {
+            FF_CUDA(cudaFuncSetAttribute(k_block_stage<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+            ff_launch(ctx, "inc_stage", [&] {
+                k_block_stage<4><<<blocks, warps * 32, shmem, st>>>(s->e2n, nrows, V, Lmax, I.loc.p, I.blkvert.p, I.blkvcnt.p, d_st.p);
+            });
+        } else {
+            FF_CUDA(cudaFuncSetAttribute(k_block_stage<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+            ff_launch(ctx, "inc_stage", [&] {
+                k_block_stage<3><<<blocks, warps * 32, shmem, st>>>(s->e2n, nrows, V, Lmax, I.loc.p, I.blkvert.p, I.blkvcnt.p, d_st.p);
+            });
+        }
+        int32_t h_st[2] = {0, 0};
+        FF_CUDA(cudaMemcpyAsync(h_st, d_st.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        FF_CUDA(cudaStreamSynchronize(st));
+        I.maxstage = h_st[0];
+        I.nunstaged = h_st[1];
+    }
     I.built = true;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // stage 2: row pattern.  One warp per node row.
 // ---------------------------------------------------------------------------------------------------------------
-static constexpr uint32_t HT_EMPTY = 0xffffffffu;
-
-__device__ __forceinline__ int warp_sort32(int v, int lane)
-{
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1)
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const int o = __shfl_xor_sync(0xffffffffu, v, j);
-            const bool up = (lane & k) == 0, lower = (lane & j) == 0;
-            v = (lower == up) ? min(v, o) : max(v, o);
-        }
-    return v;
-}
-
 // PASS 0: row length.  PASS 1: columns, positions, diagonal position.
 template <int PASS, typename PosT>
 __global__ void __launch_bounds__(256) k_row_pattern(const int32_t *__restrict__ e2n, int nloc, int nlocp, int nrows, int TS, int LOG,
@@ -339,52 +657,96 @@ extern "C" int ffcuda_symbolic(ffcuda_space *s, ffcuda_pattern **out)
     P = new ffcuda_pattern();
     P->space = s;
     P->ctx = ctx;
+    P->ref.set(ctx);
     P->nrows_node = nrows;
     P->ncols_node = s->nnodes;
     P->ncomp = nc;
     P->n = nrows * nc;
     P->nlocp = (s->order == 1) ? 4 : nloc;
 
-    // --- row lengths
-    int TS = 64, LOG = 6;
-    while (TS < 2 * I.maxinc * nloc) {
-        TS <<= 1;
-        ++LOG;
-    }
-    const size_t per_warp = ((size_t)TS + TS / 2) * 4;
-    FF_REQUIRE(per_warp <= 200 * 1024, "a node has too many incident elements for the shared-memory hash table");
-    int warps = 8;
-    while (warps > 1 && (size_t)warps * per_warp > 96 * 1024) warps >>= 1;
-    const size_t shmem = (size_t)warps * per_warp;
-    const int blocks = min(ff_blocks((size_t)nrows, warps), ctx->sm_count * 16);
     DBuf<int32_t> rowlen, diagnode, d_max;
     rowlen.alloc((size_t)nrows + 1);
     diagnode.alloc((size_t)nrows);
     d_max.alloc(1);
     FF_CUDA(cudaMemsetAsync(rowlen.p + nrows, 0, sizeof(int32_t), st));
     FF_CUDA(cudaMemsetAsync(d_max.p, 0, sizeof(int32_t), st));
-    run_row_pattern<uint8_t>(ctx, P, s->e2n, nloc, TS, LOG, warps, shmem, blocks, V, rowlen.p, diagnode.p, d_max.p, nullptr, 0);
     P->nrowptr.alloc((size_t)nrows + 1);
     int64_t nnzn = 0;
     int32_t h_max = 0;
-    FF_CUDA(cudaMemcpyAsync(&h_max, d_max.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    ff_exclusive_scan_i32(ctx, rowlen.p, P->nrowptr.p, (size_t)nrows + 1, &nnzn); // synchronises the stream
-    P->maxrow_node = h_max;
-    P->nnz_node = nnzn;
-    P->nnz = nnzn * nc * nc;
-    FF_REQUIRE(P->nnz < ((int64_t)1 << 31), "matrix exceeds 2^31 nonzeros (int32 CSR, like MatriceMorse)");
-    rowlen.release();
-
-    // --- columns + positions
-    P->ncol.alloc((size_t)nnzn);
-    if (P->maxrow_node <= 255) {
+    if (s->order == 1) {
+        // --- P1: one pass, one warp per block of 32 rows (k_block_pattern), columns through a fixed-stride scratch
+        const int Lmax = I.maxinc, cstride = Lmax * 4 + 4;
+        const int cap = Lmax * (nloc - 1) + 1; // a row has at most this many distinct columns
+        int TSR = 64, RLOG = 6, UL = 64;
+        while (TSR < 2 * cap) {
+            TSR <<= 1;
+            ++RLOG;
+        }
+        while (UL < cap) UL <<= 1;
+        const size_t per_warp = ((size_t)((Lmax * 33 + 3) & ~3) + (size_t)32 * cstride + 2 * (size_t)TSR + UL) * 4;
+        FF_REQUIRE(per_warp <= 200 * 1024, "a vertex has too many incident elements for the block pattern kernel");
+        int warps = 4;
+        while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
+        const size_t shmem = warps * per_warp;
+        const int nblk = (nrows + 31) / 32, blocks = ff_blocks((size_t)nblk, warps);
+        DBuf<int32_t> tmpcol;
+        tmpcol.alloc((size_t)nrows * cap);
         P->pos8.alloc((size_t)I.nrec * P->nlocp);
-        run_row_pattern<uint8_t>(ctx, P, s->e2n, nloc, TS, LOG, warps, shmem, blocks, V, nullptr, diagnode.p, nullptr, P->pos8.p, 1);
+        uint32_t *posw = reinterpret_cast<uint32_t *>(P->pos8.p);
+        if (nloc == 4) {
+            FF_CUDA(cudaFuncSetAttribute(k_block_pattern<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+            ff_launch(ctx, "sym_block_pattern", [&] {
+                k_block_pattern<4><<<blocks, warps * 32, shmem, st>>>(s->e2n, nrows, V, Lmax, cap, TSR, RLOG, tmpcol.p, rowlen.p, diagnode.p,
+                                                                       posw, d_max.p);
+            });
+        } else {
+            FF_CUDA(cudaFuncSetAttribute(k_block_pattern<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+            ff_launch(ctx, "sym_block_pattern", [&] {
+                k_block_pattern<3><<<blocks, warps * 32, shmem, st>>>(s->e2n, nrows, V, Lmax, cap, TSR, RLOG, tmpcol.p, rowlen.p, diagnode.p,
+                                                                       posw, d_max.p);
+            });
+        }
+        FF_CUDA(cudaMemcpyAsync(&h_max, d_max.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        ff_exclusive_scan_i32(ctx, rowlen.p, P->nrowptr.p, (size_t)nrows + 1, &nnzn); // synchronises the stream
+        P->maxrow_node = h_max;
+        FF_REQUIRE(P->maxrow_node <= 255, "a P1 node with more than 254 neighbours is not supported");
+        P->nnz_node = nnzn;
+        P->nnz = nnzn * nc * nc;
+        FF_REQUIRE(P->nnz < ((int64_t)1 << 31), "matrix exceeds 2^31 nonzeros (int32 CSR, like MatriceMorse)");
+        P->ncol.alloc((size_t)nnzn);
+        ff_launch(ctx, "sym_compact_cols", [&] {
+            k_compact_cols<<<ff_blocks((size_t)nblk * 32, 256), 256, 0, st>>>(tmpcol.p, cap, P->nrowptr.p, nrows, P->ncol.p);
+        });
     } else {
-        FF_REQUIRE(s->order == 2, "a P1 node with more than 254 neighbours is not supported");
-        P->pos16.alloc((size_t)I.nrec * P->nlocp);
-        run_row_pattern<uint16_t>(ctx, P, s->e2n, nloc, TS, LOG, warps, shmem, blocks, V, nullptr, diagnode.p, nullptr, P->pos16.p, 1);
+        // --- P2: one warp per node row, two passes (row lengths, then columns + positions)
+        int TS = 64, LOG = 6;
+        while (TS < 2 * I.maxinc * nloc) {
+            TS <<= 1;
+            ++LOG;
+        }
+        const size_t per_warp = ((size_t)TS + TS / 2) * 4;
+        FF_REQUIRE(per_warp <= 200 * 1024, "a node has too many incident elements for the shared-memory hash table");
+        int warps = 8;
+        while (warps > 1 && (size_t)warps * per_warp > 96 * 1024) warps >>= 1;
+        const size_t shmem = (size_t)warps * per_warp;
+        const int blocks = min(ff_blocks((size_t)nrows, warps), ctx->sm_count * 16);
+        run_row_pattern<uint8_t>(ctx, P, s->e2n, nloc, TS, LOG, warps, shmem, blocks, V, rowlen.p, diagnode.p, d_max.p, nullptr, 0);
+        FF_CUDA(cudaMemcpyAsync(&h_max, d_max.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        ff_exclusive_scan_i32(ctx, rowlen.p, P->nrowptr.p, (size_t)nrows + 1, &nnzn); // synchronises the stream
+        P->maxrow_node = h_max;
+        P->nnz_node = nnzn;
+        P->nnz = nnzn * nc * nc;
+        FF_REQUIRE(P->nnz < ((int64_t)1 << 31), "matrix exceeds 2^31 nonzeros (int32 CSR, like MatriceMorse)");
+        P->ncol.alloc((size_t)nnzn);
+        if (P->maxrow_node <= 255) {
+            P->pos8.alloc((size_t)I.nrec * P->nlocp);
+            run_row_pattern<uint8_t>(ctx, P, s->e2n, nloc, TS, LOG, warps, shmem, blocks, V, nullptr, diagnode.p, nullptr, P->pos8.p, 1);
+        } else {
+            P->pos16.alloc((size_t)I.nrec * P->nlocp);
+            run_row_pattern<uint16_t>(ctx, P, s->e2n, nloc, TS, LOG, warps, shmem, blocks, V, nullptr, diagnode.p, nullptr, P->pos16.p, 1);
+        }
     }
+    rowlen.release();
 
     // --- dof-level CSR
     P->diagpos.alloc((size_t)P->n);

@@ -241,6 +241,50 @@ def test_against_oracle_medium(ctx, case):
         assert np.max(np.abs(x2.download() - ox2)) <= RTOL * np.abs(ox2).max()
 
 
+@pytest.mark.parametrize("kind", ["cube", "square"])
+def test_scrambled_numbering_unstaged_blocks(ctx, kind):
+    """a mesh whose vertex numbering has no locality: blocks of 32 rows touch more than 256 distinct vertices, so the
+    thread-per-row kernels must take their un-staged path (coordinates through global memory); same bars as ever."""
+    m = ol.cube(9, 8, 10) if kind == "cube" else ol.square(40, 37)
+    dim = m["dim"]
+    nv = m["xyz"].shape[0]
+    rng = np.random.default_rng(7)
+    perm = rng.permutation(nv).astype(np.int32)          # old id -> new id
+    inv = np.argsort(perm)
+    m2 = dict(m, xyz=np.ascontiguousarray(m["xyz"][inv]), conn=perm[m["conn"]], bconn=perm[m["bconn"]])
+    terms = (fc.LAP3 if dim == 3 else fc.LAP2) + [(0, fc.ID, 0, fc.ID, 2.5)]
+    lt = [(0, fc.ID, 1.0), (0, fc.DX, 0.5)]
+    labels = fc.ALL6 if dim == 3 else [1, 2, 3, 4]
+    bcs = [(labels, 1, [0.0])]
+    qp, qw = ffcuda.quadrature(dim, 6)
+    (ci, cj, ca), (orp, ocol, oval), ob = _oracle_problem(m2, 1, 1, None, nv, terms, lt, qp, qw, bcs)
+    mesh = ctx.mesh_upload(dim, m2["xyz"], m2["conn"], m2["elab"], m2["bconn"], m2["blab"], m2["belem"], m2["bface"])
+    sp = mesh.space(1, 1)
+    pat = sp.symbolic()
+    rp, col = pat.download()
+    assert np.array_equal(rp, orp) and np.array_equal(col, ocol)
+    A = pat.matrix()
+    A.assemble(terms, qp, qw)
+    b = ctx.vec(nv)
+    sp.assemble_linear(b, lt, qp, qw)
+    for lab, mask, values in bcs:
+        bc = sp.bc_from_labels(lab, mask, values)
+        A.apply_bc(bc, TGV)
+        b.apply_bc(bc, TGV)
+    val = A.download()
+    big = np.abs(oval) > 1e29
+    assert np.array_equal(np.abs(val) > 1e29, big)
+    assert np.max(np.abs(val - oval)[~big]) <= RTOL * _scale(oval)
+    hb = b.download()
+    bbig = np.abs(ob) > 1e20
+    assert np.max(np.abs(hb - ob)[~bbig]) <= RTOL * np.abs(ob[~bbig]).max()
+    x = ctx.vec(nv)
+    it, conv, _ = A.cg(b, x, eps=1e-14, itmax=20 * nv, tgv=TGV)
+    ox, oit, oret, _ = ol.cg(nv, ci, cj, ca, ob, np.zeros(nv), eps=1e-14, itmax=20 * nv, tgv=TGV)
+    assert conv == 1 and oret == 1
+    assert np.max(np.abs(x.download() - ox)) <= 1e-10 * np.abs(ox).max()
+
+
 def test_region_filter_and_accumulate(ctx):
     """int3d(Th, 1)(...) + int3d(Th, 2)(...): region label sets and accumulation into an existing matrix."""
     g = fc.load("lap3d_p1_cube5")
