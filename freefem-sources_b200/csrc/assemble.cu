@@ -669,6 +669,81 @@ __global__ void __launch_bounds__(128) k_rhs(const double *__restrict__ xyz, con
     }
 }
 
+// Lean right-hand side: scalar or vector P1, no region filter, every block staged, symmetric rule (the same
+// sum_q w_q lambda_a for every a).  b_i += |K| (cval[c] L + W grad(lambda_i) . cgrad[c]) over the elements around i.
+template <int DIM, int NC, bool GRAD>
+__global__ void __launch_bounds__(128) k_rhs_p1_lean(const double *__restrict__ xyz, int nrows, const int32_t *__restrict__ cnt,
+                                                     const uint32_t *__restrict__ blkoff, const uint32_t *__restrict__ loc,
+                                                     const int32_t *__restrict__ blkvert, const int32_t *__restrict__ blkvcnt, int SV,
+                                                     double Lval, double Wsum, double *__restrict__ bvec, int accumulate,
+                                                     const __grid_constant__ LinParams Lp)
+{
+    extern __shared__ double stage_all[];
+    constexpr int NV = DIM + 1;
+    constexpr double RFAC = DIM == 3 ? 1.0 / 6.0 : 0.5;
+    const int lane = threadIdx.x & 31;
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    double *stage = stage_all + (size_t)(threadIdx.x >> 5) * DIM * SV;
+    double X[NV][DIM];
+    int mycnt = 0;
+    if (row < nrows) {
+        mycnt = cnt[row];
+        if (DIM == 3) {
+            const double4 p = ldg_vertex(xyz, row);
+            X[0][0] = p.x; X[0][1] = p.y; X[0][DIM - 1] = p.z;
+        } else {
+            const double2 p = __ldg(reinterpret_cast<const double2 *>(xyz) + row);
+            X[0][0] = p.x; X[0][1] = p.y;
+        }
+    }
+    double sdet = 0.0, sn[DIM];
+#pragma unroll
+    for (int x = 0; x < DIM; ++x) sn[x] = 0.0;
+    const int blk = row >> 5, nblk = (nrows + 31) >> 5;
+    if (blk < nblk) {
+        p1_stage<DIM>(xyz, blkvert, blkvcnt, blk, lane, SV, stage);
+        const uint32_t base = blkoff[blk];
+        const int Lb = (int)((blkoff[blk + 1] - base) >> 5);
+        const uint32_t *ploc = loc + base + lane;
+        uint32_t lw = Lb > 0 ? __ldcs(ploc) : 0;
+        for (int e = 0; e < Lb; ++e) {
+            const uint32_t lwc = lw;
+            ploc += 32;
+            if (e + 1 < Lb) lw = __ldcs(ploc);
+            if (e < mycnt) {
+                p1_points_staged<DIM>(stage, SV, lwc, X);
+                if (GRAD) {
+                    // |K| grad(lambda_own) = RFAC N_0 : independent of det, so the normals are simply summed
+                    double N[NV][DIM], det;
+                    p1_normals<DIM>(X, N, det);
+                    sdet += det;
+#pragma unroll
+                    for (int x = 0; x < DIM; ++x) sn[x] += N[0][x];
+                } else if (DIM == 3) {
+                    const double ax = X[1][0] - X[0][0], ay = X[1][1] - X[0][1], az = X[1][DIM - 1] - X[0][DIM - 1];
+                    const double bx = X[2][0] - X[0][0], by = X[2][1] - X[0][1], bz = X[2][DIM - 1] - X[0][DIM - 1];
+                    const double cx = X[DIM][0] - X[0][0], cy = X[DIM][1] - X[0][1], cz = X[DIM][DIM - 1] - X[0][DIM - 1];
+                    sdet += ax * (by * cz - bz * cy) + ay * (bz * cx - bx * cz) + az * (bx * cy - by * cx);
+                } else {
+                    sdet += (X[1][0] - X[0][0]) * (X[2][1] - X[0][1]) - (X[1][1] - X[0][1]) * (X[2][0] - X[0][0]);
+                }
+            }
+        }
+    }
+    if (row < nrows) {
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            double v = Lp.CL[c][0] * Lval * RFAC * sdet;
+            if (GRAD) {
+#pragma unroll
+                for (int x = 0; x < DIM; ++x) v = fma(Lp.CL[c][x + 1] * Wsum * RFAC, sn[x], v);
+            }
+            const size_t d = (size_t)row * NC + c;
+            bvec[d] = accumulate ? bvec[d] + v : v;
+        }
+    }
+}
+
 // ----------------------------------------------------------------------------------------------------
 // host drivers
 // ----------------------------------------------------------------------------------------------------
@@ -835,7 +910,8 @@ extern "C" int ffcuda_assemble_bilinear(ffcuda_matrix *A, ffcuda_space *s, int n
 }
 
 template <int DIM>
-static void launch_rhs(ffcuda_ctx *ctx, ffcuda_vec *b, ffcuda_space *s, const LinParams &Lp, const double *Fh, int hasgrad, int accumulate)
+static void launch_rhs(ffcuda_ctx *ctx, ffcuda_vec *b, ffcuda_space *s, const LinParams &Lp, const double *Fh, const double *hFh,
+                       int hasgrad, bool lean, int accumulate)
 {
     ffcuda_mesh *m = s->mesh;
     const int nrows = s->incidence.nrows;
@@ -844,6 +920,23 @@ static void launch_rhs(ffcuda_ctx *ctx, ffcuda_vec *b, ffcuda_space *s, const Li
     const Incidence &I = s->incidence;
     const int SV = std::max(4, (I.maxstage + 3) & ~3);
     const size_t shmem = I.ell ? (size_t)4 * DIM * SV * 8 : 0;
+    if (lean) {
+        const double Lval = hFh[0], Wsum = -hFh[1];
+        ff_launch(ctx, "rhs_rows", [&] {
+#define FF_RHS_LEAN(NCC)                                                                                                          \
+    if (hasgrad)                                                                                                                  \
+        k_rhs_p1_lean<DIM, NCC, true><<<blocks, 128, shmem, ctx->stream>>>(m->xyz.p, nrows, I.cnt.p, I.blkoff.p, I.loc.p, I.blkvert.p, \
+                                                                           I.blkvcnt.p, SV, Lval, Wsum, b->d.p, accumulate, Lp);  \
+    else                                                                                                                          \
+        k_rhs_p1_lean<DIM, NCC, false><<<blocks, 128, shmem, ctx->stream>>>(m->xyz.p, nrows, I.cnt.p, I.blkoff.p, I.loc.p, I.blkvert.p, \
+                                                                            I.blkvcnt.p, SV, Lval, Wsum, b->d.p, accumulate, Lp);
+            if (s->ncomp == 1) { FF_RHS_LEAN(1) }
+            else if (s->ncomp == 2) { FF_RHS_LEAN(2) }
+            else { FF_RHS_LEAN(3) }
+#undef FF_RHS_LEAN
+        });
+        return;
+    }
     ff_launch(ctx, "rhs_rows", [&] {
         if (s->ncomp == 1)
             k_rhs<DIM, 1><<<blocks, 128, shmem, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, nrows, V, I.loc.p, I.blkvert.p, I.blkvcnt.p, SV, Fh, s->nloc, hasgrad, b->d.p, accumulate, Lp);
@@ -874,7 +967,8 @@ extern "C" int ffcuda_assemble_linear(ffcuda_vec *b, ffcuda_space *s, int nterms
         Lp.CL[terms[t].vcomp][slot] += terms[t].coef;
         if (slot > 0 && terms[t].coef != 0.0) hasgrad = 1;
     }
-    if (dim == 2) hasgrad = 1; // the 2-D geometry helper always evaluates the gradients
+    const int hasgrad_form = hasgrad;
+    if (dim == 2) hasgrad = 1; // the generic 2-D geometry helper always evaluates the gradients
     fill_labels(nlab, labels, Lp.nlab, Lp.labels);
     std::vector<double> Fh((size_t)nloc * ns, 0.0);
     for (int q = 0; q < nq; ++q) {
@@ -887,7 +981,11 @@ extern "C" int ffcuda_assemble_linear(ffcuda_vec *b, ffcuda_space *s, int nterms
     dF.alloc(Fh.size());
     FF_CUDA(cudaMemcpyAsync(dF.p, Fh.data(), dF.bytes(), cudaMemcpyHostToDevice, ctx->stream));
     // (a pageable source is staged before cudaMemcpyAsync returns: Fh may go out of scope)
-    if (dim == 3) launch_rhs<3>(ctx, b, s, Lp, dF.p, hasgrad, accumulate);
-    else launch_rhs<2>(ctx, b, s, Lp, dF.p, hasgrad, accumulate);
+    // lean path: P1, no region filter, all blocks staged, symmetric rule (sum_q w_q lambda_a the same for every a)
+    bool lean = s->order == 1 && Lp.nlab < 0 && s->incidence.ell && s->incidence.nunstaged == 0;
+    for (int a = 1; a < nloc && lean; ++a)
+        if (fabs(Fh[(size_t)a * ns] - Fh[0]) > 1e-15 * fabs(Fh[0])) lean = false;
+    if (dim == 3) launch_rhs<3>(ctx, b, s, Lp, dF.p, Fh.data(), lean ? hasgrad_form : hasgrad, lean, accumulate);
+    else launch_rhs<2>(ctx, b, s, Lp, dF.p, Fh.data(), lean ? hasgrad_form : hasgrad, lean, accumulate);
     FF_API_END(s ? s->ctx : nullptr)
 }

@@ -379,15 +379,26 @@ __global__ void __launch_bounds__(RED_THREADS) k_diag_stats(const int32_t *__res
     __syncthreads();
     if (!last) return;
     __threadfence();
-    if (threadIdx.x == 0) {
+    {   // the last block to retire folds the per-block results, all threads taking part
         double mm = -INFINITY, cc = 0;
-        for (int i = 0; i < (int)gridDim.x; ++i) {
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) {
             mm = fmax(mm, __ldcg(partial + i));
             cc += __ldcg(partial + gridDim.x + i);
         }
-        out[0] = mm;
-        out[1] = cc;
-        flags[F_COUNTER] = 0;
+        for (int o = 16; o; o >>= 1) mm = fmax(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+        __syncthreads();
+        if (l == 0) sh[w] = mm;
+        __syncthreads();
+        if (w == 0) {
+            mm = l < (int)(blockDim.x >> 5) ? sh[l] : -INFINITY;
+            for (int o = 16; o; o >>= 1) mm = fmax(mm, __shfl_xor_sync(0xffffffffu, mm, o));
+        }
+        cc = block_sum(cc, sh);
+        if (threadIdx.x == 0) {
+            out[0] = mm;
+            out[1] = cc;
+            flags[F_COUNTER] = 0;
+        }
     }
 }
 
@@ -633,7 +644,7 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
                 if (hflags[4 * prev + F_CONV_ITER] != 0) done = true;
             }
             slot ^= 1;
-            if (batch < 32) batch *= 2;
+            if (batch < 16) batch *= 2;
         }
         FF_CUDA(cudaStreamSynchronize(st));
     } catch (...) {
