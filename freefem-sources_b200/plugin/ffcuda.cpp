@@ -1,0 +1,747 @@
+// ffcuda.cpp — the FreeFEM side of the drop-in (layer B1): `load "ffcuda"`.
+//
+// A thin shim with no arithmetic of its own.  It is compiled against FreeFEM's headers (where they lie; nothing is
+// copied) and does three things at load time:
+//   1. registers, with preference 100, operators for   matrix A = va(Vh,Vh,...)  /  A = va(Vh,Vh,...)
+//      (built-ins: OpMatrixtoBilinearForm, fflib/lgfem.cpp:6669,6673,6823,6826, pref 0);
+//   2. the same for   real[int] b = va(0,Vh)  /  b = va(0,Vh)   (OpArraytoLinearForm, lgfem.cpp:6668,6672,6686,6688);
+//   3. adds the solver "FFCUDACG" and re-points the name "CG" to it (TheFFSolver::ChangeSolver,
+//      femlib/SparseLinearSolver.hpp:59-72), so that `solver=CG` and `A^-1*b` run on the GPU.
+// At run time an intercepted call walks the varf exactly like AssembleVarForm (fflib/problem.cpp:9744-9855), flattens
+// mesh / dof table / term lists / quadrature rule / Dirichlet sets into plain arrays and calls the C ABI of
+// libffcuda_core.so (include/ffcuda.h).  What the GPU path does not cover (other elements, x-dependent coefficients,
+// boundary integrals, level sets, tgv < 0, sym=1, complex, ...) is NOT claimed: the call is handed, untouched, to the
+// built-in operator it derives from, with a notice at verbosity >= 1 (FFCUDA_STRICT=1 turns that into an error).
+// There is no CPU re-implementation here: without a CUDA device every claimed call throws ErrorExec.
+//
+// Environment: FFCUDA_DEVICE (default 0), FFCUDA_VERBOSE=1 (say which path every call took), FFCUDA_STRICT=1,
+//              FFCUDA_DISABLE=1 (register nothing).
+#include "ff++.hpp"
+#include "AFunction_ext.hpp"
+#include <cstdlib>
+#include <map>
+#include <memory>
+#include <set>
+#include <sstream>
+#include <vector>
+#include "ffcuda.h"
+
+using namespace Fem2D;
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------
+// context, errors
+// ------------------------------------------------------------------------------------------------------------
+ffcuda_ctx *g_ctx = nullptr;
+bool env_on(const char *name)
+{
+    const char *v = getenv(name);
+    return v && *v && *v != '0';
+}
+bool g_verbose = false, g_strict = false;
+
+[[noreturn]] void fail(const std::string &what)
+{
+    const char *e = ffcuda_last_error(g_ctx);
+    std::string msg = "ffcuda: " + what + ((e && *e) ? std::string(" : ") + e : std::string());
+    ExecError(msg.c_str());
+    throw ErrorExec(msg.c_str(), 1); // not reached (ExecError throws)
+}
+#define FFC(call)                        \
+    do {                                 \
+        if ((call) != 0) fail(#call);    \
+    } while (0)
+
+ffcuda_ctx *context()
+{
+    if (!g_ctx) {
+        const char *d = getenv("FFCUDA_DEVICE");
+        if (ffcuda_ctx_create(d ? atoi(d) : 0, &g_ctx) != 0) {
+            g_ctx = nullptr;
+            fail("cannot create a CUDA context (the ffcuda path has no CPU fallback)");
+        }
+    }
+    return g_ctx;
+}
+
+void notice(const char *what, const std::string &why)
+{
+    if (g_strict) ExecError(("ffcuda (FFCUDA_STRICT): " + std::string(what) + " not on the GPU path: " + why).c_str());
+    if (g_verbose || verbosity > 0) cout << "  -- ffcuda: " << what << " left to FreeFEM (" << why << ")" << endl;
+}
+
+struct Unsupported {
+    std::string why;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// FE space on the device, cached per FESpace object (identity = address + UniqueffId, cf. problem.hpp:1678)
+// ------------------------------------------------------------------------------------------------------------
+struct DevSpace {
+    const void *key = nullptr;
+    UniqueffId uid;
+    ffcuda_mesh *mesh = nullptr;
+    ffcuda_space *space = nullptr;
+    int dim = 0, order = 0, ncomp = 0, ndof = 0;
+    ~DevSpace()
+    {
+        if (space) ffcuda_space_destroy(space);
+        if (mesh) ffcuda_mesh_destroy(mesh);
+    }
+};
+std::vector<std::unique_ptr<DevSpace>> g_spaces; // small most-recently-used list
+const size_t kMaxSpaces = 4;
+
+template <class MeshT>
+struct MeshDim;
+template <>
+struct MeshDim<Mesh> {
+    static const int d = 2;
+};
+template <>
+struct MeshDim<Mesh3> {
+    static const int d = 3;
+};
+
+inline void coords(const Mesh &Th, int i, double *p)
+{
+    p[0] = Th(i).x;
+    p[1] = Th(i).y;
+}
+inline void coords(const Mesh3 &Th, int i, double *p)
+{
+    p[0] = Th(i).x;
+    p[1] = Th(i).y;
+    p[2] = Th(i).z;
+}
+inline int belem_of(const Mesh &Th, int ib, int &ie) { return Th.BoundaryElement(ib, ie); }
+inline int belem_of(const Mesh3 &Th, int ib, int &ie) { return Th.BoundaryElement(ib, ie); }
+inline int blabel(const Mesh &Th, int ib) { return Th.bedges[ib].lab; }
+inline int blabel(const Mesh3 &Th, int ib) { return Th.be(ib).lab; }
+inline int bvertex(const Mesh &Th, int ib, int j) { return Th(Th.bedges[ib][j]); }
+inline int bvertex(const Mesh3 &Th, int ib, int j) { return Th(Th.be(ib)[j]); }
+inline int nbe_of(const Mesh &Th) { return Th.neb; }
+inline int nbe_of(const Mesh3 &Th) { return Th.nbe; }
+inline int elabel(const Mesh &Th, int k) { return Th[k].lab; }
+inline int elabel(const Mesh3 &Th, int k) { return Th[k].lab; }
+
+// reference basis of P1/P2 Lagrange at a point (value only), in FreeFEM's local dof order: vertices, then edges
+// ({01,02,03,12,13,23} on tetrahedra, edge opposite to vertex e on triangles)
+void lagrange_values(int dim, int order, const double *l, double *phi)
+{
+    const int nv = dim + 1;
+    if (order == 1) {
+        for (int a = 0; a < nv; ++a) phi[a] = l[a];
+        return;
+    }
+    for (int a = 0; a < nv; ++a) phi[a] = l[a] * (2 * l[a] - 1);
+    static const int e3[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}}, e2[3][2] = {{1, 2}, {2, 0}, {0, 1}};
+    const int ne = dim == 3 ? 6 : 3;
+    for (int e = 0; e < ne; ++e) phi[nv + e] = 4 * l[dim == 3 ? e3[e][0] : e2[e][0]] * l[dim == 3 ? e3[e][1] : e2[e][1]];
+}
+
+inline void basis_values(const FElement &K, const R2 &P, KNMK<double> &val) // 2-D: one flag per operator (FESpace.hpp:840)
+{
+    bool whatd[last_operatortype];
+    for (int i = 0; i < (int)last_operatortype; ++i) whatd[i] = false;
+    whatd[op_id] = true;
+    K.BF(whatd, P, val);
+}
+inline void basis_values(const FElement3 &K, const R3 &P, KNMK<double> &val) // 3-D: bit mask (FESpacen.hpp:451)
+{
+    K.BF(Fop_D0, P, val);
+}
+inline R2 hat_point(const Mesh *, const double *l) { return R2(l[1], l[2]); }
+inline R3 hat_point(const Mesh3 *, const double *l) { return R3(l[1], l[2], l[3]); }
+
+// Is Vh = [Pk]^N with Pk the P1 or P2 Lagrange element, numbered dof = node*N + c, local dof = c*nloc + a ?
+// Decided from what the space does, not from its name: sizes, the dof table, and the values of its basis functions at
+// an interior point of element 0 (a P1nc / P1b / P1dc space has other sizes or other values).
+template <class FESpaceT>
+void classify_space(const FESpaceT &Vh, int dim, int &order, int &ncomp, int &nloc)
+{
+    typedef typename FESpaceT::FElement FElementT;
+    typedef typename FESpaceT::Mesh MeshT;
+    ncomp = Vh.N;
+    if (ncomp < 1 || ncomp > 3) throw Unsupported{"more than 3 components"};
+    if (Vh.NbOfElements <= 0) throw Unsupported{"empty space"};
+    const FElementT K0(Vh[0]);
+    const int nd = K0.NbDoF();
+    if (nd % ncomp) throw Unsupported{"element is not a product of identical components"};
+    nloc = nd / ncomp;
+    const int nv = dim + 1, n2 = dim == 3 ? 10 : 6;
+    if (nloc == nv) order = 1;
+    else if (nloc == n2) order = 2;
+    else throw Unsupported{"finite element is neither P1 nor P2 Lagrange"};
+    if ((long)Vh.NbOfNodes * ncomp != (long)Vh.NbOfDF) throw Unsupported{"dofs are not node*N + component"};
+    // basis fingerprint
+    double l[4] = {0.1, 0.2, 0.3, 0.4};
+    if (dim == 2) {
+        l[0] = 0.2;
+        l[1] = 0.3;
+        l[2] = 0.5;
+    }
+    double phi[10];
+    lagrange_values(dim, order, l, phi);
+    KNMK<double> val(nd, ncomp, (int)last_operatortype);
+    val = 0.;
+    basis_values(K0, hat_point((const MeshT *)0, l), val);
+    for (int c = 0; c < ncomp; ++c)
+        for (int a = 0; a < nloc; ++a)
+            for (int c2 = 0; c2 < ncomp; ++c2) {
+                const double expect = (c == c2) ? phi[a] : 0.0;
+                if (fabs(val(c * nloc + a, c2, (int)op_id) - expect) > 1e-12) throw Unsupported{"basis functions are not [Pk Lagrange]^N, component-major"};
+            }
+    // dof table layout on a sample of elements
+    const int nt = Vh.NbOfElements, step = std::max(1, nt / 64);
+    for (int k = 0; k < nt; k += step) {
+        const FElementT K(Vh[k]);
+        if (K.NbDoF() != nd) throw Unsupported{"variable number of dofs per element"};
+        for (int a = 0; a < nloc; ++a) {
+            const int d0 = K(a);
+            if (d0 % ncomp) throw Unsupported{"dof numbering is not node*N + component"};
+            for (int c = 1; c < ncomp; ++c)
+                if (K(c * nloc + a) != d0 + c) throw Unsupported{"dof numbering is not node*N + component"};
+        }
+    }
+}
+
+template <class FESpaceT>
+DevSpace &device_space(const FESpaceT &Vh)
+{
+    typedef typename FESpaceT::FElement FElementT;
+    typedef typename FESpaceT::Mesh MeshT;
+    const int dim = MeshDim<MeshT>::d;
+    const MeshT &Th = Vh.Th;
+    for (size_t i = 0; i < g_spaces.size(); ++i)
+        if (g_spaces[i]->key == (const void *)&Vh && g_spaces[i]->uid == (const UniqueffId &)Vh) {
+            if (i) std::swap(g_spaces[0], g_spaces[i]);
+            return *g_spaces[0];
+        }
+    int order, ncomp, nloc;
+    classify_space(Vh, dim, order, ncomp, nloc);
+    ffcuda_ctx *ctx = context();
+    const int nv = Th.nv, nt = Th.nt, nbe = nbe_of(Th), nvk = dim + 1;
+    std::vector<double> xyz((size_t)nv * dim);
+    for (int i = 0; i < nv; ++i) coords(Th, i, &xyz[(size_t)i * dim]);
+    std::vector<int32_t> conn((size_t)nt * nvk), elab(nt), bconn((size_t)nbe * dim), blab(nbe), belem(nbe), bface(nbe);
+    for (int k = 0; k < nt; ++k) {
+        for (int j = 0; j < nvk; ++j) conn[(size_t)k * nvk + j] = Th(k, j);
+        elab[k] = elabel(Th, k);
+    }
+    for (int ib = 0; ib < nbe; ++ib) {
+        int ie;
+        belem[ib] = belem_of(Th, ib, ie);
+        bface[ib] = ie;
+        blab[ib] = blabel(Th, ib);
+        for (int j = 0; j < dim; ++j) bconn[(size_t)ib * dim + j] = bvertex(Th, ib, j);
+    }
+    std::unique_ptr<DevSpace> D(new DevSpace());
+    D->key = &Vh;
+    D->uid = (const UniqueffId &)Vh;
+    D->dim = dim;
+    D->order = order;
+    D->ncomp = ncomp;
+    D->ndof = Vh.NbOfDF;
+    FFC(ffcuda_mesh_upload(ctx, dim, nv, xyz.data(), nt, conn.data(), elab.data(), nbe, bconn.data(), blab.data(), belem.data(),
+                           bface.data(), &D->mesh));
+    // the node table as FreeFEM numbered it (2-D P2 is renumbered by FreeFEM: never guessed, always read)
+    std::vector<int32_t> e2n;
+    const int32_t *pe2n = nullptr;
+    bool p1_vertex_numbering = (order == 1);
+    if (order == 1) {
+        for (int k = 0; k < nt && p1_vertex_numbering; k += std::max(1, nt / 256)) {
+            const FElementT K(Vh[k]);
+            for (int a = 0; a < nloc; ++a)
+                if (K(a) / ncomp != Th(k, a)) p1_vertex_numbering = false;
+        }
+    }
+    if (!p1_vertex_numbering) {
+        e2n.resize((size_t)nt * nloc);
+        for (int k = 0; k < nt; ++k) {
+            const FElementT K(Vh[k]);
+            for (int a = 0; a < nloc; ++a) e2n[(size_t)k * nloc + a] = K(a) / ncomp;
+        }
+        pe2n = e2n.data();
+    }
+    FFC(ffcuda_space_create(D->mesh, order, ncomp, pe2n, Vh.NbOfNodes, &D->space));
+    int ndof = 0;
+    FFC(ffcuda_space_info(D->space, &ndof, nullptr, nullptr));
+    if (ndof != Vh.NbOfDF) fail("internal: device space has another number of dofs than the fespace");
+    g_spaces.insert(g_spaces.begin(), std::move(D));
+    if (g_spaces.size() > kMaxSpaces) g_spaces.pop_back();
+    return *g_spaces[0];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// reading a varf
+// ------------------------------------------------------------------------------------------------------------
+struct Quad {
+    std::vector<double> pts, w;
+};
+inline void hat_coords(const R2 &P, double *c)
+{
+    c[0] = P.x;
+    c[1] = P.y;
+}
+inline void hat_coords(const R3 &P, double *c)
+{
+    c[0] = P.x;
+    c[1] = P.y;
+    c[2] = P.z;
+}
+template <class QF>
+Quad flat_quadrature(const QF &q, int dim)
+{
+    Quad Q;
+    for (int i = 0; i < q.n; ++i) {
+        const typename QF::QuadraturePoint &p = q[i];
+        Q.w.push_back(p.a);
+        double c[3];
+        hat_coords((const typename QF::Rd &)p, c); // (x,y[,z]) of the reference point
+        for (int d = 0; d < dim; ++d) Q.pts.push_back(c[d]);
+    }
+    return Q;
+}
+inline Quad volume_rule(Stack s, const CDomainOfIntegration &di, const Mesh *) { return flat_quadrature(di.FIT(s), 2); }
+inline Quad volume_rule(Stack s, const CDomainOfIntegration &di, const Mesh3 *) { return flat_quadrature(di.FIV(s), 3); }
+
+struct Region {
+    bool all = true;
+    std::vector<int32_t> labels;
+};
+Region region_of(Stack stack, const CDomainOfIntegration &di) // Expandsetoflab, fflib/lgfem.cpp:7809
+{
+    Region R;
+    std::set<int> s;
+    for (size_t i = 0; i < di.what.size(); ++i) {
+        R.all = false;
+        if (di.whatis[i] == 0) s.insert((int)GetAny<long>((*di.what[i])(stack)));
+        else {
+            KN<long> labs(GetAny<KN_<long>>((*di.what[i])(stack)));
+            for (long j = 0; j < labs.N(); ++j) s.insert((int)labs[j]);
+        }
+    }
+    R.labels.assign(s.begin(), s.end());
+    if (R.labels.size() > 16) throw Unsupported{"more than 16 region labels in one integral"};
+    return R;
+}
+
+template <class MeshT>
+void check_domain(Stack stack, const CDomainOfIntegration &di, const MeshT &Th)
+{
+    const int dim = MeshDim<MeshT>::d;
+    const CDomainOfIntegration::typeofkind volume = dim == 3 ? CDomainOfIntegration::int3d : CDomainOfIntegration::int2d;
+    if (di.d != dim || di.dHat != dim || di.kind != volume) throw Unsupported{"not a volume integral on the mesh of the space"};
+    if (di.islevelset()) throw Unsupported{"level-set integral"};
+    if (di.withmap()) throw Unsupported{"mapped integration points"};
+    typedef const MeshT *pm;
+    if (GetAny<pm>((*di.Th)(stack)) != &Th) throw Unsupported{"integral on another mesh"};
+}
+
+inline int check_op(int op, int dim)
+{
+    if (op == op_id || op == op_dx || op == op_dy || (op == op_dz && dim == 3)) return op;
+    throw Unsupported{"differential operator other than id, dx, dy, dz"};
+}
+
+double constant_coef(Stack stack, const C_F0 &c)
+{
+    if (!c.LeftValue()->MeshIndependent()) throw Unsupported{"coefficient depends on the mesh point"};
+    if (c.left() != atype<double>()) {
+        if (c.left() == atype<long>()) return (double)GetAny<long>(c.eval(stack));
+        throw Unsupported{"coefficient is not real"};
+    }
+    return GetAny<double>(c.eval(stack));
+}
+
+struct BilinearItem {
+    std::vector<ffcuda_bterm> terms;
+    Quad q;
+    Region reg;
+};
+struct LinearItem {
+    std::vector<ffcuda_lterm> terms;
+    Quad q;
+    Region reg;
+};
+struct BCItem {
+    std::vector<int32_t> labels;
+    int compmask = 0;
+    double values[3] = {0, 0, 0};
+};
+struct Varf {
+    std::vector<BilinearItem> bil;
+    std::vector<LinearItem> lin;
+    std::vector<BCItem> bc;
+    bool other_rhs_items = false; // arrays, A*x, ... (only meaningful for the right-hand side)
+};
+
+template <class MeshT>
+Varf read_varf(Stack stack, const list<C_F0> &largs, const MeshT &Th, int ncomp, bool want_matrix)
+{
+    const int dim = MeshDim<MeshT>::d;
+    Varf V;
+    for (list<C_F0>::const_iterator ii = largs.begin(); ii != largs.end(); ++ii) {
+        Expression e = ii->LeftValue();
+        aType r = ii->left();
+        if (r == atype<const FormBilinear *>()) {
+            if (!want_matrix) continue; // ignored when a right-hand side is assembled (problem.cpp:9761-9779)
+            const FormBilinear *bf = dynamic_cast<const FormBilinear *>(e);
+            if (bf->VF()) throw Unsupported{"discontinuous-Galerkin operators"};
+            check_domain(stack, *bf->di, Th);
+            BilinearItem B;
+            B.q = volume_rule(stack, *bf->di, &Th);
+            B.reg = region_of(stack, *bf->di);
+            const Foperator &op = *bf->b;
+            for (size_t k = 0; k < op.v.size(); ++k) {
+                const pair<MGauche, MDroit> &id = op.v[k].first; // (unknown, test)
+                ffcuda_bterm t;
+                t.ucomp = id.first.first;
+                t.uop = check_op(id.first.second, dim);
+                t.vcomp = id.second.first;
+                t.vop = check_op(id.second.second, dim);
+                if (t.ucomp < 0 || t.ucomp >= ncomp || t.vcomp < 0 || t.vcomp >= ncomp) throw Unsupported{"component out of range"};
+                t.coef = constant_coef(stack, op.v[k].second);
+                B.terms.push_back(t);
+            }
+            V.bil.push_back(B);
+        } else if (r == atype<const FormLinear *>()) {
+            if (want_matrix) continue;
+            const FormLinear *lf = dynamic_cast<const FormLinear *>(e);
+            if (lf->VF()) throw Unsupported{"discontinuous-Galerkin operators"};
+            check_domain(stack, *lf->di, Th);
+            LinearItem L;
+            L.q = volume_rule(stack, *lf->di, &Th);
+            L.reg = region_of(stack, *lf->di);
+            const Ftest &op = *lf->l;
+            for (size_t k = 0; k < op.v.size(); ++k) {
+                ffcuda_lterm t;
+                t.vcomp = op.v[k].first.first;
+                t.vop = check_op(op.v[k].first.second, dim);
+                if (t.vcomp < 0 || t.vcomp >= ncomp) throw Unsupported{"component out of range"};
+                t.coef = constant_coef(stack, op.v[k].second);
+                L.terms.push_back(t);
+            }
+            V.lin.push_back(L);
+        } else if (r == atype<const BC_set *>()) {
+            const BC_set *bc = dynamic_cast<const BC_set *>(e);
+            if (bc->complextype) throw Unsupported{"complex boundary value"};
+            BCItem B;
+            std::set<long> on; // Expandsetoflab, fflib/lgfem.cpp:7792
+            for (size_t i = 0; i < bc->on.size(); ++i)
+                if (bc->onis[i] == 0) on.insert(GetAny<long>((*bc->on[i])(stack)));
+                else {
+                    KN<long> labs(GetAny<KN_<long>>((*bc->on[i])(stack)));
+                    for (long j = 0; j < labs.N(); ++j) on.insert(labs[j]);
+                }
+            if (on.size() > 32) throw Unsupported{"more than 32 labels in one on(...)"};
+            for (std::set<long>::const_iterator it = on.begin(); it != on.end(); ++it) B.labels.push_back((int32_t)*it);
+            for (size_t k = 0; k < bc->bc.size(); ++k) {
+                const int comp = bc->bc[k].first;
+                if (comp < 0 || comp >= ncomp) throw Unsupported{"boundary condition on a component out of range"};
+                if (!bc->bc[k].second->MeshIndependent()) throw Unsupported{"boundary value depends on the mesh point"};
+                B.compmask |= 1 << comp;
+                B.values[comp] = GetAny<double>((*bc->bc[k].second)(stack));
+            }
+            if (ncomp > 1 && B.compmask != (1 << ncomp) - 1)
+                throw Unsupported{"vector space with a boundary condition on some components only"};
+            if (!B.labels.empty()) V.bc.push_back(B);
+        } else {
+            if (want_matrix) throw Unsupported{"varf item other than integrals and on(...)"};
+            V.other_rhs_items = true;
+        }
+    }
+    return V;
+}
+
+void apply_bcs(DevSpace &D, const Varf &V, ffcuda_matrix *A, ffcuda_vec *b, double tgv)
+{
+    for (size_t i = 0; i < V.bc.size(); ++i) {
+        const BCItem &B = V.bc[i];
+        ffcuda_bc *bc = nullptr;
+        FFC(ffcuda_bc_from_labels(D.space, (int)B.labels.size(), B.labels.data(), B.compmask, B.values, &bc));
+        int rc = 0;
+        if (A) rc |= ffcuda_matrix_apply_bc(A, bc, tgv);
+        if (b) rc |= ffcuda_vec_apply_bc(b, bc, tgv);
+        ffcuda_bc_destroy(bc);
+        if (rc) fail("applying the Dirichlet conditions");
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// device copies of matrices, waiting for the solver that will be attached to them
+// ------------------------------------------------------------------------------------------------------------
+struct Resident {
+    ffcuda_matrix *A;
+    ffcuda_pattern *P; // the matrix refers to the pattern's arrays: destroyed after it
+};
+void release_resident(Resident &r)
+{
+    if (r.A) ffcuda_matrix_destroy(r.A);
+    if (r.P) ffcuda_pattern_destroy(r.P);
+    r.A = nullptr;
+    r.P = nullptr;
+}
+std::map<const void *, Resident> g_resident; // HashMatrix* -> device matrix just assembled
+void drop_resident()
+{
+    for (std::map<const void *, Resident>::iterator it = g_resident.begin(); it != g_resident.end(); ++it) release_resident(it->second);
+    g_resident.clear();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// 1. matrix A = va(Vh,Vh,...)
+// ------------------------------------------------------------------------------------------------------------
+template <class MMesh, class v_fes>
+struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes> {
+    typedef OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes> Base;
+    struct Op : public Base::Op {
+        Op(Expression aa, Expression bb, int initt) : Base::Op(aa, bb, initt) {}
+        AnyType operator()(Stack stack) const
+        {
+            typedef typename v_fes::pfes pfes;
+            typedef typename v_fes::FESpace FESpaceT;
+            pfes *pUh = GetAny<pfes *>((*this->b->euh)(stack));
+            pfes *pVh = GetAny<pfes *>((*this->b->evh)(stack));
+            const FESpaceT *PUh = (FESpaceT *)**pUh, *PVh = (FESpaceT *)**pVh;
+            try {
+                if (!PUh || !PVh) throw Unsupported{"null fespace"};
+                if (PUh != PVh) throw Unsupported{"test and unknown spaces differ"};
+                Data_Sparse_Solver ds;
+                ds.factorize = 0;
+                ds.initmat = true;
+                int np = OpCall_FormBilinear_np::n_name_param - NB_NAME_PARM_HMAT;
+                SetEnd_Data_Sparse_Solver<double>(stack, ds, this->b->nargs, np);
+                if (ds.sym) throw Unsupported{"sym=1 (half storage)"};
+                if (!(ds.tgv >= 0)) throw Unsupported{"tgv < 0 (exact elimination)"};
+                const FESpaceT &Vh = *PVh;
+                const MMesh &Th = Vh.Th;
+                if (!isSameMesh(this->b->largs, &Vh.Th, &Vh.Th, stack)) throw Unsupported{"integrals on different meshes"};
+                Varf V = read_varf(stack, this->b->largs, Th, Vh.N, true);
+                DevSpace &D = device_space(Vh);
+
+                // --- the GPU path proper
+                ffcuda_pattern *P = nullptr;
+                ffcuda_matrix *dA = nullptr;
+                FFC(ffcuda_symbolic(D.space, &P));
+                if (ffcuda_matrix_create(P, &dA) != 0) {
+                    ffcuda_pattern_destroy(P);
+                    fail("ffcuda_matrix_create");
+                }
+                int n = 0;
+                int64_t nnz = 0;
+                int rc = ffcuda_pattern_info(P, &n, &nnz);
+                for (size_t i = 0; i < V.bil.size() && !rc; ++i) {
+                    const BilinearItem &B = V.bil[i];
+                    rc = ffcuda_assemble_bilinear(dA, D.space, (int)B.terms.size(), B.terms.data(), (int)B.q.w.size(), B.q.pts.data(),
+                                                  B.q.w.data(), (int)B.reg.labels.size(), B.reg.all ? nullptr : B.reg.labels.data(),
+                                                  i > 0);
+                }
+                std::vector<int32_t> rowptr, colind;
+                std::vector<double> vals;
+                if (!rc) {
+                    try {
+                        apply_bcs(D, V, dA, nullptr, ds.tgv);
+                    } catch (...) {
+                        ffcuda_matrix_destroy(dA);
+                        ffcuda_pattern_destroy(P);
+                        throw;
+                    }
+                    rowptr.resize((size_t)n + 1);
+                    colind.resize((size_t)nnz);
+                    vals.resize((size_t)nnz);
+                    rc = ffcuda_pattern_download(P, rowptr.data(), colind.data()) || ffcuda_matrix_download(dA, vals.data());
+                }
+                if (rc) {
+                    ffcuda_matrix_destroy(dA);
+                    ffcuda_pattern_destroy(P);
+                    fail("assembling the matrix");
+                }
+                // --- hand the result to FreeFEM as its own MatriceMorse (problem.hpp:1678-1693)
+                WhereStackOfPtr2Free(stack) = new StackOfPtr2Free(stack);
+                Matrice_Creuse<double> &A(*GetAny<Matrice_Creuse<double> *>((*this->a)(stack)));
+                if (this->init) A.init();
+                A.A = 0;
+                A.Uh = Vh;
+                A.Vh = Vh;
+                MatriceMorse<double> *M = new MatriceMorse<double>(n, n, 0, 0);
+                M->set(n, n, 0, (size_t)nnz, rowptr.data(), colind.data(), vals.data(), 0, 1); // copies, rebuilds the hash
+                A.A.master(M);
+                drop_resident(); // at most one matrix waits for its solver
+                g_resident[(const void *)static_cast<HashMatrix<int, double> *>(M)] = Resident{dA, P}; // stays on the device for the solver
+                A.pHM()->half = ds.sym;
+                SetSolver(stack, false, *A.A, ds);
+                if (g_verbose) cout << "  -- ffcuda: matrix " << n << " x " << n << ", nnz " << nnz << " assembled on the GPU" << endl;
+                return SetAny<Matrice_Creuse<double> *>(&A);
+            } catch (const Unsupported &u) {
+                notice("matrix = varf(Vh,Vh)", u.why);
+                return Base::Op::operator()(stack);
+            }
+        }
+    };
+    E_F0 *code(const basicAC_F0 &args) const { return new Op(to<Matrice_Creuse<double> *>(args[0]), args[1], this->init); }
+    CudaMatrixOp(int initt) : Base(initt) { this->pref = 100; }
+};
+// ------------------------------------------------------------------------------------------------------------
+// 2. real[int] b = va(0,Vh)
+// ------------------------------------------------------------------------------------------------------------
+template <class MMesh, class v_fes>
+struct CudaRhsOp : public OpArraytoLinearForm<double, MMesh, v_fes> {
+    typedef OpArraytoLinearForm<double, MMesh, v_fes> Base;
+    struct Op : public Base::Op {
+        Op(Expression xx, Expression ll, bool isptrr, bool initt, bool zzero) : Base::Op(xx, ll, isptrr, initt, zzero) {}
+        AnyType operator()(Stack stack) const
+        {
+            typedef v_fes *pfes;
+            typedef typename v_fes::FESpace FESpaceT;
+            pfes &pp = *GetAny<pfes *>((*this->l->ppfes)(stack));
+            FESpaceT *pVh = *pp;
+            try {
+                if (!pVh) throw Unsupported{"null fespace"};
+                if (!this->zero) throw Unsupported{"b += varf(0,Vh)"};
+                FESpaceT &Vh = *pVh;
+                double tgv = ff_tgv;
+                if (this->l->nargs[0]) tgv = GetAny<double>((*this->l->nargs[0])(stack));
+                if (!(tgv >= 0)) throw Unsupported{"tgv < 0 (exact elimination)"};
+                Varf V = read_varf(stack, this->l->largs, Vh.Th, Vh.N, false);
+                if (V.other_rhs_items) throw Unsupported{"right-hand side with array / matrix-vector items"};
+                DevSpace &D = device_space(Vh);
+                const long n = Vh.NbOfDF;
+                // the array, sized as the built-in operator does (problem.hpp:1363-1383)
+                KN<double> *px = 0;
+                if (this->isptr) {
+                    px = GetAny<KN<double> *>((*this->x)(stack));
+                    if (this->init) px->init(n);
+                    if (px->N() != n) px->resize(n);
+                }
+                KN_<double> xx(px ? *(KN_<double> *)px : GetAny<KN_<double>>((*this->x)(stack)));
+                if (xx.N() != n) ExecError("ffcuda: array and fespace sizes differ in b = varf(0,Vh)");
+                ffcuda_vec *db = nullptr;
+                FFC(ffcuda_vec_create(context(), (int)n, &db));
+                int rc = 0;
+                for (size_t i = 0; i < V.lin.size() && !rc; ++i) {
+                    const LinearItem &L = V.lin[i];
+                    rc = ffcuda_assemble_linear(db, D.space, (int)L.terms.size(), L.terms.data(), (int)L.q.w.size(), L.q.pts.data(),
+                                                L.q.w.data(), (int)L.reg.labels.size(), L.reg.all ? nullptr : L.reg.labels.data(), i > 0);
+                }
+                std::vector<double> host((size_t)n);
+                if (!rc) {
+                    try {
+                        apply_bcs(D, V, nullptr, db, tgv);
+                    } catch (...) {
+                        ffcuda_vec_destroy(db);
+                        throw;
+                    }
+                    rc = ffcuda_vec_download(db, host.data());
+                }
+                ffcuda_vec_destroy(db);
+                if (rc) fail("assembling the right-hand side");
+                for (long i = 0; i < n; ++i) xx[i] = host[i]; // KN_ may be strided
+                if (g_verbose) cout << "  -- ffcuda: right-hand side of size " << n << " assembled on the GPU" << endl;
+                return SetAny<KN_<double>>(xx);
+            } catch (const Unsupported &u) {
+                notice("array = varf(0,Vh)", u.why);
+                return Base::Op::operator()(stack);
+            }
+        }
+    };
+    E_F0 *code(const basicAC_F0 &args) const
+    {
+        if (this->isptr) return new Op(to<KN<double> *>(args[0]), args[1], this->isptr, this->init, this->zero);
+        return new Op(to<KN_<double>>(args[0]), args[1], this->isptr, this->init, this->zero);
+    }
+    CudaRhsOp(const basicForEachType *tt, bool isptrr, bool initt, bool zzero = 1) : Base(tt, isptrr, initt, zzero) { this->pref = 100; }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// 3. solver=CG  ->  Jacobi-CG on the device (contract: VirtualSolver<int,double>, femlib/VirtualSolver.hpp:190-243;
+//    reference: SolverCG, femlib/VirtualSolverCG.hpp:112-192)
+// ------------------------------------------------------------------------------------------------------------
+class SolverCudaCG : public VirtualSolver<int, double> {
+  public:
+    // 1 unsym, 2 herm, 4 sym, 8 pos, 16 nopos, 32 seq : what the reference CG declares
+    static const int orTypeSol = 1 | 2 | 4 | 8 | 32;
+    typedef HashMatrix<int, double> HMat;
+    HMat *A;
+    Resident dev;
+    int verb, itermax;
+    double eps, tgv;
+    double *veps;
+    long *getnbiter;
+
+    SolverCudaCG(HMat &AA, const Data_Sparse_Solver &ds, Stack)
+        : A(&AA), dev{nullptr, nullptr}, verb(ds.verb), itermax(ds.itmax > 0 ? ds.itmax : AA.n), eps(ds.epsilon), tgv(ds.tgv),
+          veps(ds.veps), getnbiter(ds.getnbiter)
+    {
+        if (AA.n != AA.m) ExecError("ffcuda: CG needs a square matrix");
+        std::map<const void *, Resident>::iterator it = g_resident.find((const void *)A);
+        if (it != g_resident.end()) { // just assembled by CudaMatrixOp: already on the device
+            dev = it->second;
+            g_resident.erase(it);
+            A->GetReDoNumerics();
+            A->GetReDoSymbolic();
+        }
+    }
+    void upload()
+    {
+        release_resident(dev);
+        if (A->half) ExecError("ffcuda: CG on a half-stored (sym=1) matrix is not on the GPU path");
+        A->CSR(); // sorted, p[] built (HashMatrix.cpp:859-876)
+        if (ffcuda_matrix_from_csr(context(), A->n, (int64_t)A->nnz, A->p, A->j, A->aij, &dev.A) != 0) fail("uploading the matrix");
+    }
+    void UpdateState()
+    {
+        const bool num = A->GetReDoNumerics(), sym = A->GetReDoSymbolic();
+        if (!dev.A || num || sym) upload(); // the script changed the matrix after it was assembled
+    }
+    void dosolver(double *x, double *b, int N, int trans)
+    {
+        (void)trans; // the CG of the reference ignores it as well for symmetric matrices: A^T = A is the user's contract
+        if (!dev.A) upload();
+        if (getnbiter) *getnbiter = 0;
+        int err = 0;
+        for (int k = 0, oo = 0; k < N; ++k, oo += A->n) {
+            int iters = 0, conv = 0;
+            double gcg = 0;
+            if (ffcuda_cg_host(dev.A, b + oo, x + oo, eps, itermax, tgv, &iters, &conv, &gcg) != 0) fail("ffcuda_cg_host");
+            if (verb || g_verbose)
+                cout << " GC (ffcuda): " << (conv ? "converge" : "NO convergence") << " after " << iters << " g=" << gcg << endl;
+            if (!conv) err++;
+            else if (getnbiter) *getnbiter += iters;
+            if (veps) *veps = eps > 0 ? sqrt(gcg) : eps;
+        }
+        if (err) {
+            std::cerr << "Error: ConjugueGradient (ffcuda) do not converge nb end =" << err << std::endl;
+            ffassert(0);
+        }
+    }
+    ~SolverCudaCG() { release_resident(dev); }
+};
+
+} // namespace
+
+static void Load_Init()
+{
+    g_verbose = env_on("FFCUDA_VERBOSE");
+    g_strict = env_on("FFCUDA_STRICT");
+    if (env_on("FFCUDA_DISABLE")) {
+        if (verbosity) cout << " load: ffcuda disabled by FFCUDA_DISABLE" << endl;
+        return;
+    }
+    if (verbosity) cout << " load: ffcuda (GPU assembly of P1/P2 varf + Jacobi-CG; FreeFEM keeps everything else)" << endl;
+    // 1. matrices: "<-" constructs (init = 1), "=" assigns (init = 0)  (fflib/lgfem.cpp:6669,6673,6823,6826)
+    TheOperators->Add("<-", new CudaMatrixOp<Mesh, v_fes>(1), new CudaMatrixOp<Mesh3, v_fes3>(1));
+    TheOperators->Add("=", new CudaMatrixOp<Mesh, v_fes>(0), new CudaMatrixOp<Mesh3, v_fes3>(0));
+    // 2. right-hand sides (fflib/lgfem.cpp:6668,6672,6686,6688)
+    TheOperators->Add("=", new CudaRhsOp<Mesh, v_fes>(atype<KN_<double>>(), false, false),
+                      new CudaRhsOp<Mesh3, v_fes3>(atype<KN_<double>>(), false, false));
+    TheOperators->Add("<-", new CudaRhsOp<Mesh, v_fes>(atype<KN<double> *>(), true, true),
+                      new CudaRhsOp<Mesh3, v_fes3>(atype<KN<double> *>(), true, true));
+    // 3. solver
+    addsolver<SolverCudaCG>("FFCUDACG", 10, 0);
+    TheFFSolver<int, double>::ChangeSolver("CG", "FFCUDACG");
+}
+
+LOADFUNC(Load_Init)

@@ -1,0 +1,204 @@
+"""The drop-in itself: the same .edp script is run by the unmodified FreeFem++ (oracle/_ref/FreeFem++-nw) twice —
+once with `load "ffcuda"` doing its work (FFCUDA_STRICT=1: any delegation to FreeFEM's CPU operators is an error) and
+once with the plugin disabled (FFCUDA_DISABLE=1) — and the dumps are compared: CSR pattern bit-exact, values / rhs
+within 1e-12, CG iteration count and solution as in tests/test_gpu_parity.py.
+
+CPU part (no GPU here): the plugin builds against the reference headers, loads, leaves out-of-scope forms to FreeFEM,
+and refuses — loudly — to compute a claimed form without a CUDA device."""
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FF = os.path.join(ROOT, "oracle", "_ref", "FreeFem++-nw")
+LIBDIR = os.path.join(ROOT, "freefem-sources_b200", "lib")
+PLUGIN = os.path.join(LIBDIR, "ffcuda.so")
+
+needs_ff = pytest.mark.skipif(not (os.path.exists(FF) and os.path.exists(PLUGIN)),
+                              reason="reference binary / plugin not built (needs /root/reference at build time)")
+
+LAP2 = "dx(u)*dx(v)+dy(u)*dy(v)"
+LAP3 = "dx(u)*dx(v)+dy(u)*dy(v)+dz(u)*dz(v)"
+LAME = ("lambda*(dx(u1)+dy(u2)+dz(u3))*(dx(v1)+dy(v2)+dz(v3))"
+        "+2.*mu*(dx(u1)*dx(v1)+dy(u2)*dy(v2)+dz(u3)*dz(v3)"
+        "+0.5*(dy(u1)+dx(u2))*(dy(v1)+dx(v2))+0.5*(dz(u1)+dx(u3))*(dz(v1)+dx(v3))"
+        "+0.5*(dz(u2)+dy(u3))*(dz(v2)+dy(v3)))")
+LAME_PRE = "real E=21.5e4, sigma=0.29; real mu=E/(2*(1+sigma)); real lambda=E*sigma/((1+sigma)*(1-2*sigma));"
+
+DUMP = """
+{ A.CSR; ofstream f("A.txt"); f.precision(17); f << A; }
+{ ofstream f("b.txt"); f.precision(17); for(int i=0;i<b.n;++i) f << b[i] << endl; }
+"""
+SOLVE = """
+verbosity=1; UU[] = 0; UU[] = A^-1*b; verbosity=0;
+{ ofstream f("u.txt"); f.precision(17); for(int i=0;i<UU[].n;++i) f << UU[][i] << endl; }
+"""
+
+
+def script(dim, mesh, fe, bil, lin, bc, pre="", unk="u", tst="v", eps="1e-6", intopt=""):
+    mt, integ = ("mesh", "int2d") if dim == 2 else ("mesh3", "int3d")
+    u0 = unk.strip("[]").split(",")[0]
+    s = f'load "msh3"\nload "ffcuda"\n{pre}\n{mt} Th = {mesh};\nfespace Vh(Th,{fe});\n'
+    s += f"varf va({unk},{tst}) = {integ}(Th{intopt})({bil}) + {integ}(Th{intopt})({lin}){('+' + bc) if bc else ''};\n"
+    s += f"matrix A = va(Vh,Vh,solver=CG,eps={eps});\nreal[int] b = va(0,Vh);\n" + DUMP
+    s += f"Vh {unk};\n" + SOLVE.replace("UU", u0)
+    return s
+
+
+CASES = {
+    "poisson3d_p1": script(3, "cube(7,6,8)", "P1", LAP3, "1.*v", "on(1,2,3,4,5,6,u=0)"),
+    "laplace2d_p1": script(2, "square(23,17)", "P1", LAP2, "1.*v", "on(1,2,3,4,u=0)"),
+    "laplace2d_p1_warp_labels": script(2, "square(9,7,[x+0.2*y*y,y*(1+0.3*x)])", "P1", LAP2 + "+2.*u*v", "3.*v+dx(v)",
+                                       "on(1,u=1)+on(3,u=2)"),
+    "poisson3d_p2": script(3, "cube(3,4,3)", "P2", LAP3, "1.*v", "on(1,2,3,4,5,6,u=0)", eps="1e-14"),
+    "laplace2d_p2": script(2, "square(6,5)", "P2", LAP2, "1.*v", "on(1,2,3,4,u=0)", eps="1e-14"),
+    "heat3d_p1": script(3, "cube(5,5,5)", "P1", "u*v/dt+" + LAP3, "1.*v", "on(1,2,3,4,5,6,u=0)", pre="real dt=0.01;"),
+    "lame3d_p2": script(3, "cube(2,3,2)", "[P2,P2,P2]", LAME, "-0.05*v3", "on(1,u1=0,u2=0,u3=0)", pre=LAME_PRE,
+                        unk="[u1,u2,u3]", tst="[v1,v2,v3]", eps="1e-14"),
+    "mass3d_lumped": script(3, "cube(3,3,3)", "P1", "u*v+0.1*(" + LAP3 + ")", "1.*v", "on(1,u=0)", intopt=",qfV=qfV1lump"),
+}
+
+# re-assembly in a time loop (configs[3] shape, idp/Heat3d.idp): `A = va(Vh,Vh)` on an existing matrix, rhs from the previous
+# solution through a matrix-vector product, solve; the final state is dumped
+HEAT_LOOP = f"""load "msh3"
+load "ffcuda"
+mesh3 Th = cube(5,4,5);
+fespace Vh(Th,P1);
+real dt = 0.01;
+varf va(u,v) = int3d(Th)(u*v/dt+{LAP3}) + on(1,2,3,4,5,6,u=0);
+varf vm(u,v) = int3d(Th)(u*v/dt);
+varf vf(u,v) = int3d(Th)(1.*v) + on(1,2,3,4,5,6,u=0);
+matrix A = va(Vh,Vh,solver=CG,eps=1e-10);
+matrix M = vm(Vh,Vh);
+real[int] f = vf(0,Vh);
+Vh u; u[] = 0;
+real[int] b(Vh.ndof);
+for (int it = 0; it < 3; ++it) {{
+  A = va(Vh,Vh,solver=CG,eps=1e-10);
+  b = M*u[]; b += f;
+  u[] = A^-1*b;
+}}
+{DUMP}
+{{ ofstream g("u.txt"); g.precision(17); for(int i=0;i<u[].n;++i) g << u[][i] << endl; }}
+"""
+
+
+def run_ff(src, env_extra, want_fail=False):
+    with tempfile.TemporaryDirectory() as td:
+        with open(os.path.join(td, "case.edp"), "w") as f:
+            f.write(src)
+        env = dict(os.environ, FF_LOADPATH=LIBDIR, **env_extra)
+        r = subprocess.run([FF, "-nw", "-v", "1", "case.edp"], capture_output=True, text=True, cwd=td, env=env, timeout=600)
+        out = r.stdout + r.stderr
+        if want_fail:
+            return r.returncode, out, None
+        assert r.returncode == 0, out[-3000:]
+        res = {"out": out}
+        with open(os.path.join(td, "A.txt")) as f:
+            lines = [ln for ln in f if not ln.startswith("#")]
+        hdr = lines[0].split()
+        n, nnz = int(hdr[0]), int(hdr[3])
+        a = np.array(" ".join(lines[1:]).split(), dtype=np.float64).reshape(-1, 3)
+        assert a.shape[0] == nnz
+        res.update(n=n, I=a[:, 0].astype(np.int64), J=a[:, 1].astype(np.int64), V=a[:, 2].copy())
+        res["b"] = np.loadtxt(os.path.join(td, "b.txt"), ndmin=1)
+        if os.path.exists(os.path.join(td, "u.txt")):
+            res["u"] = np.loadtxt(os.path.join(td, "u.txt"), ndmin=1)
+        res["iters"] = [int(x) for x in re.findall(r"GC[^\n]*?after\s+(\d+)", out)]
+        return r.returncode, out, res
+
+
+def compare(gpu, cpu, tight):
+    assert gpu["n"] == cpu["n"]
+    assert np.array_equal(gpu["I"], cpu["I"]) and np.array_equal(gpu["J"], cpu["J"])          # bit-exact pattern
+    big = np.abs(cpu["V"]) > 1e29
+    assert np.array_equal(np.abs(gpu["V"]) > 1e29, big)
+    scale = np.abs(cpu["V"][~big]).max()
+    assert np.max(np.abs(gpu["V"] - cpu["V"])[~big]) <= 1e-12 * scale
+    bbig = np.abs(cpu["b"]) > 1e20
+    assert np.array_equal(np.abs(gpu["b"]) > 1e20, bbig)
+    if (~bbig).any():
+        assert np.max(np.abs(gpu["b"] - cpu["b"])[~bbig]) <= 1e-12 * max(np.abs(cpu["b"][~bbig]).max(), 1e-300)
+    assert np.allclose(gpu["b"][bbig], cpu["b"][bbig], rtol=1e-15, atol=0)
+    umax = np.abs(cpu["u"]).max()
+    if tight:   # both converged to round-off
+        assert np.max(np.abs(gpu["u"] - cpu["u"])) <= 1e-12 * umax
+    else:       # the reference's own stopping point: same iteration count, same iterate
+        assert gpu["iters"] == cpu["iters"]
+        assert np.max(np.abs(gpu["u"] - cpu["u"])) <= 1e-12 * umax
+
+
+@needs_ff
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_plugin_matches_freefem(name):
+    src = CASES[name]
+    _, out, gpu = run_ff(src, {"FFCUDA_STRICT": "1", "FFCUDA_VERBOSE": "1"})
+    assert "assembled on the GPU" in out and "GC (ffcuda)" in out       # the GPU path ran, nothing was delegated
+    _, out_cpu, cpu = run_ff(src, {"FFCUDA_DISABLE": "1"})
+    assert "ffcuda" not in out_cpu.replace('load "ffcuda"', "").replace("ffcuda disabled", "")
+    compare(gpu, cpu, tight="eps=1e-14" in src)
+
+
+@needs_ff
+@pytest.mark.gpu
+def test_plugin_heat_time_loop():
+    _, out, gpu = run_ff(HEAT_LOOP, {"FFCUDA_VERBOSE": "1"})
+    assert out.count("assembled on the GPU") >= 6
+    _, _, cpu = run_ff(HEAT_LOOP, {"FFCUDA_DISABLE": "1"})
+    assert np.array_equal(gpu["I"], cpu["I"]) and np.array_equal(gpu["J"], cpu["J"])
+    big = np.abs(cpu["V"]) > 1e29
+    assert np.max(np.abs(gpu["V"] - cpu["V"])[~big]) <= 1e-12 * np.abs(cpu["V"][~big]).max()
+    assert np.max(np.abs(gpu["u"] - cpu["u"])) <= 1e-9 * np.abs(cpu["u"]).max()
+
+
+OUT_OF_SCOPE = """load "msh3"
+load "ffcuda"
+mesh3 Th = cube(3,3,3);
+fespace Vh(Th,P1);
+varf vb(u,v) = int3d(Th)(x*dx(u)*dx(v)+u*v) + on(1,u=0);
+matrix B = vb(Vh,Vh);
+fespace Wh(Th,P0);
+varf vc(u,v) = int3d(Th)(u*v);
+matrix C = vc(Wh,Wh);
+varf vs(u,v) = int2d(Th,2)(u*v) + int2d(Th,2)(1.*v);
+matrix S = vs(Vh,Vh);
+real[int] r = vs(0,Vh);
+cout << "NNZ " << B.nnz << " " << C.nnz << " " << S.nnz << endl;
+"""
+
+CLAIMED = """load "msh3"
+load "ffcuda"
+mesh3 Th = cube(3,3,3);
+fespace Vh(Th,P1);
+varf va(u,v) = int3d(Th)(dx(u)*dx(v)+dy(u)*dy(v)+dz(u)*dz(v)) + on(1,u=0);
+matrix A = va(Vh,Vh);
+cout << "NNZ " << A.nnz << endl;
+"""
+
+
+@needs_ff
+def test_plugin_loads_and_leaves_out_of_scope_forms_to_freefem():
+    """x-dependent coefficient, non-Lagrange element, boundary integral: not claimed, FreeFEM's own operators run
+    (no GPU needed), and the plugin says so."""
+    rc, out, _ = run_ff(OUT_OF_SCOPE, {}, want_fail=True)
+    assert rc == 0, out[-2000:]
+    assert re.search(r"^NNZ 622 162 \d+", out, re.M)
+    assert out.count("left to FreeFEM") >= 4
+    rc, out, _ = run_ff(OUT_OF_SCOPE, {"FFCUDA_STRICT": "1"}, want_fail=True)
+    assert rc != 0 and "FFCUDA_STRICT" in out
+
+
+@needs_ff
+def test_plugin_has_no_cpu_fallback():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    rc, out, _ = run_ff(CLAIMED, {}, want_fail=True)
+    assert rc != 0
+    assert "no CPU fallback" in out and not re.search(r"^NNZ \d", out, re.M)
