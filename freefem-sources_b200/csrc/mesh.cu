@@ -222,21 +222,59 @@ __global__ void k_cube_cells(const CubeLayout C, int32_t *__restrict__ conn, int
     if (PASS == 0) bcount[c] = kf;
 }
 
-static void build_cube(ffcuda_ctx *ctx, int nx, int ny, int nz, int rank, int nranks, ffcuda_mesh **out)
+// The slab partition of cube(nx,ny,nz) along z (host arithmetic only; exported so that it can be checked without a GPU).
+// Vertex layers [L0, L0+nown) are owned by `rank`; it holds the cell layers [c_lo, c_lo+ncl) that touch them (one
+// layer of halo cells on each inner side) and, after its owned vertices, one ghost vertex layer per neighbour.
+struct CubePart {
+    int L0, nown, has_lower, has_upper, c_lo, ncl;
+    int64_t nk, nv_owned, nv_local, nt_local;
+    int nbr[2], send_off[2], recv_off[2], cnt;
+};
+static CubePart cube_partition(int nx, int ny, int nz, int rank, int nranks)
 {
     FF_REQUIRE(nx > 0 && ny > 0 && nz > 0, "cube sizes must be positive");
-    FF_REQUIRE(nranks >= 1 && nz + 1 >= nranks, "cube has fewer vertex layers than ranks");
+    FF_REQUIRE(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / number of ranks");
+    FF_REQUIRE(nz + 1 >= nranks, "cube has fewer vertex layers than ranks");
+    CubePart P;
+    const int64_t L0 = (int64_t)rank * (nz + 1) / nranks, L1 = (int64_t)(rank + 1) * (nz + 1) / nranks;
+    P.L0 = (int)L0;
+    P.nown = (int)(L1 - L0);
+    P.has_lower = rank > 0;
+    P.has_upper = rank < nranks - 1;
+    P.c_lo = std::max(P.L0 - 1, 0);
+    const int c_hi = std::min(P.L0 + P.nown - 1, nz - 1); // inclusive
+    P.ncl = c_hi - P.c_lo + 1;
+    P.nk = (int64_t)(nx + 1) * (ny + 1);
+    P.nv_owned = P.nk * P.nown;
+    P.nv_local = P.nk * (P.nown + P.has_lower + P.has_upper);
+    P.nt_local = (int64_t)6 * nx * ny * P.ncl;
+    P.nbr[0] = P.has_lower ? rank - 1 : -1;
+    P.nbr[1] = P.has_upper ? rank + 1 : -1;
+    P.cnt = (int)P.nk;
+    P.send_off[0] = 0;                                   // first owned layer goes down
+    P.send_off[1] = (int)(P.nk * (P.nown - 1));          // last owned layer goes up
+    P.recv_off[0] = (int)P.nv_owned;                     // ghost layer from below
+    P.recv_off[1] = (int)(P.nv_owned + (P.has_lower ? P.nk : 0)); // ghost layer from above
+    return P;
+}
+
+extern "C" int ffcuda_partition_cube(int nx, int ny, int nz, int rank, int nranks, int64_t *out16)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(out16, "null output");
+    const CubePart P = cube_partition(nx, ny, nz, rank, nranks);
+    const int64_t v[16] = {P.L0, P.nown, P.c_lo, P.ncl, P.nv_owned, P.nv_local, P.nt_local, P.nbr[0], P.nbr[1],
+                           P.send_off[0], P.send_off[1], P.recv_off[0], P.recv_off[1], P.cnt, P.has_lower, P.has_upper};
+    for (int i = 0; i < 16; ++i) out16[i] = v[i];
+    FF_API_END(nullptr)
+}
+
+static void build_cube(ffcuda_ctx *ctx, int nx, int ny, int nz, int rank, int nranks, ffcuda_mesh **out)
+{
+    const CubePart Pt = cube_partition(nx, ny, nz, rank, nranks);
     CubeLayout C;
     C.nx = nx; C.ny = ny; C.nz = nz;
-    const int64_t L0 = (int64_t)rank * (nz + 1) / nranks, L1 = (int64_t)(rank + 1) * (nz + 1) / nranks;
-    C.L0 = (int)L0;
-    C.nown = (int)(L1 - L0);
-    C.has_lower = rank > 0;
-    C.has_upper = rank < nranks - 1;
-    C.c_lo = std::max(C.L0 - 1, 0);
-    const int c_hi = std::min(C.L0 + C.nown - 1, nz - 1); // inclusive
-    C.ncl = c_hi - C.c_lo + 1;
-    const int64_t nk = (int64_t)(nx + 1) * (ny + 1);
+    C.L0 = Pt.L0; C.nown = Pt.nown; C.has_lower = Pt.has_lower; C.has_upper = Pt.has_upper; C.c_lo = Pt.c_lo; C.ncl = Pt.ncl;
     int64_t nc64 = (int64_t)nx * ny * C.ncl;
     FF_REQUIRE(nc64 * 6 < ((int64_t)1 << 27), "cube (slab) too large for one device (limit 2^27 tets); use more ranks");
     ff_enter(ctx);
@@ -246,8 +284,8 @@ static void build_cube(ffcuda_ctx *ctx, int nx, int ny, int nz, int rank, int nr
     m->ref.set(ctx);
     m->dim = 3; m->vstride = 4;
     int nc = (int)nc64;
-    m->nv_owned = (int)(nk * C.nown);
-    m->nv = (int)(nk * (C.nown + C.has_lower + C.has_upper));
+    m->nv_owned = (int)Pt.nv_owned;
+    m->nv = (int)Pt.nv_local;
     m->nt = 6 * nc;
     m->xyz.alloc((size_t)m->nv * 4);
     m->conn.alloc((size_t)m->nt * 4);
@@ -256,12 +294,13 @@ static void build_cube(ffcuda_ctx *ctx, int nx, int ny, int nz, int rank, int nr
     if (nranks > 1) {
         m->distributed = true;
         m->gid.alloc(m->nv);
-        m->nbr[0] = C.has_lower ? rank - 1 : -1;
-        m->nbr[1] = C.has_upper ? rank + 1 : -1;
-        m->send_off[0] = 0; m->send_cnt[0] = (int)nk;
-        m->send_off[1] = (int)(nk * (C.nown - 1)); m->send_cnt[1] = (int)nk;
-        m->recv_off[0] = m->nv_owned; m->recv_cnt[0] = (int)nk;
-        m->recv_off[1] = m->nv_owned + (C.has_lower ? (int)nk : 0); m->recv_cnt[1] = (int)nk;
+        for (int s = 0; s < 2; ++s) {
+            m->nbr[s] = Pt.nbr[s];
+            m->send_off[s] = Pt.send_off[s];
+            m->send_cnt[s] = Pt.cnt;
+            m->recv_off[s] = Pt.recv_off[s];
+            m->recv_cnt[s] = Pt.cnt;
+        }
     }
     ff_launch(ctx, "mesh_cube_vertices", [&] { k_cube_vertices<<<ff_blocks(m->nv, 256), 256, 0, st>>>(m->xyz.p, m->gid.p, C, m->nv); });
     DBuf<int32_t> bcount, boff;

@@ -22,11 +22,22 @@ ffcuda_matrix_from_csr ffcuda_matrix_info ffcuda_matrix_download ffcuda_matrix_u
 ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_destroy ffcuda_assemble_bilinear
 ffcuda_assemble_linear ffcuda_bc_from_pairs ffcuda_bc_from_labels ffcuda_bc_count ffcuda_matrix_apply_bc ffcuda_vec_apply_bc
 ffcuda_vec_set_bc_values ffcuda_bc_destroy ffcuda_spmv ffcuda_cg ffcuda_cg_host ffcuda_comm_unique_id ffcuda_comm_init
-ffcuda_comm_finalize ffcuda_mesh_cube_distributed ffcuda_mesh_local_to_global ffcuda_quadrature""".split()
+ffcuda_comm_finalize ffcuda_mesh_cube_distributed ffcuda_mesh_local_to_global ffcuda_quadrature ffcuda_partition_cube""".split()
 
 
 class FfcudaError(RuntimeError):
     pass
+
+
+PART_FIELDS = ("L0 nown c_lo ncl nv_owned nv_local nt_local nbr_lo nbr_hi send_off_lo send_off_hi recv_off_lo recv_off_hi "
+               "layer has_lower has_upper").split()
+
+
+def partition_cube(nx, ny, nz, rank, nranks):
+    """slab partition of cube(nx,ny,nz) for `rank` of `nranks` (host arithmetic only)."""
+    out = (C.c_int64 * 16)()
+    _ck(lib().ffcuda_partition_cube(nx, ny, nz, rank, nranks, out))
+    return dict(zip(PART_FIELDS, [int(v) for v in out]))
 
 
 def quadrature(dim, qforder=6):

@@ -180,6 +180,11 @@ int ffcuda_comm_finalize(ffcuda_ctx *ctx);
  * rows = owned dofs, columns = owned + ghost dofs; ffcuda_spmv and ffcuda_cg exchange ghosts and
  * all-reduce dot products over NCCL. */
 int ffcuda_mesh_cube_distributed(ffcuda_ctx *ctx, int nx, int ny, int nz, ffcuda_mesh **out);
+/* the partition arithmetic alone (host only, no device needed): out16 = { first owned vertex layer, owned layers,
+ * first local cell layer, local cell layers, owned vertices, local vertices (owned + ghost), local tets,
+ * lower neighbour rank (-1 none), upper neighbour rank, send offset down, send offset up, recv offset from below,
+ * recv offset from above, vertices per exchanged layer, has lower neighbour, has upper neighbour } */
+int ffcuda_partition_cube(int nx, int ny, int nz, int rank, int nranks, int64_t *out16);
 /* global ids of the local vertices (owned first): for gathering results / parity checks */
 int ffcuda_mesh_local_to_global(ffcuda_mesh *m, int *nowned, int *nlocal, int64_t *gid /* nlocal or NULL */);
 
