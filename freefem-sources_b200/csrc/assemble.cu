@@ -423,6 +423,8 @@ __global__ void __launch_bounds__(128) k_asm_p1_lean(const double *__restrict__ 
             pw = __ldcs(ppos);
             lw = __ldcs(ploc);
         }
+        double sdet = 0.0;
+        int dpos = 0;
         for (int e = 0; e < Lb; ++e) {
             const uint32_t pwc = pw, lwc = lw;
             ppos += 32;
@@ -439,15 +441,30 @@ __global__ void __launch_bounds__(128) k_asm_p1_lean(const double *__restrict__ 
                 double w[DIM];
 #pragma unroll
                 for (int x = 0; x < DIM; ++x) w[x] = sgg * N[0][x];
-                const double md = cmd * det, mo = cmo * det;
+                const double mo = cmo * det;
+                sdet += det;
+                dpos = pwc & 255;
+                // the DIM off-diagonal entries of the owner's row of the element matrix; their columns are distinct, so
+                // the read-modify-writes are independent: all loads first, then all stores
+                double v[NV], a[NV];
 #pragma unroll
-                for (int i = 0; i < NV; ++i) {
-                    double v = i == 0 ? md : mo;
+                for (int i = 1; i < NV; ++i) {
+                    v[i] = mo;
 #pragma unroll
-                    for (int x = 0; x < DIM; ++x) v = fma(w[x], N[i][x], v);
-                    acc[(pwc >> (8 * i)) & 255] += v;
+                    for (int x = 0; x < DIM; ++x) v[i] = fma(w[x], N[i][x], v[i]);
+                    a[i] = acc[(pwc >> (8 * i)) & 255];
                 }
+#pragma unroll
+                for (int i = 1; i < NV; ++i) acc[(pwc >> (8 * i)) & 255] = a[i] + v[i];
             }
+        }
+        // The diagonal is not accumulated record by record: the P1 basis is a partition of unity, so the stiffness part
+        // of a row sums to zero, K_ii = -sum_{j != i} K_ij; the mass part is m (M_d - DIM M_o) |K| summed over the star.
+        if (mycnt > 0) {
+            double off = 0.0;
+            for (int j = 0; j < L; ++j)
+                if (j != dpos) off += acc[j];
+            acc[dpos] = (cmd + DIM * cmo) * sdet - off;
         }
     }
     __syncwarp();
@@ -873,6 +890,7 @@ extern "C" int ffcuda_assemble_bilinear(ffcuda_matrix *A, ffcuda_space *s, int n
     ffcuda_pattern *P = A->pattern;
     if (accumulate) ff_matrix_touch(A);
     A->vals_stale = false;
+    A->vals_epoch++;
     DBuf<double> Rg;
     if (s->order == 2) {
         Rg.alloc(R.size());

@@ -205,14 +205,15 @@ struct Incidence {
     DBuf<int32_t> incptr;     // nrows+1 (CSR layout only)
     DBuf<uint32_t> blkoff;    // nblk+1  (ELL layout only)
     DBuf<uint32_t> inc;       // nrec records: (element << 4) | local node, each list sorted by element
-    // ELL layout only - vertex staging tables for the thread-per-row numeric kernels: the distinct vertices touched by
-    // the 32 rows of a block (at most FF_STAGE_MAX, else the block is marked unstaged and read through global
-    // memory), and for every record the 4 block-local slots of its element's vertices
+    // ELL layout only - vertex staging tables for the thread-per-row kernels: the distinct vertices touched by the 32
+    // rows of a block IN ASCENDING ORDER (at most FF_STAGE_MAX, else the block is marked unstaged and read through
+    // global memory), and for every record the 4 block-local slots (= ranks in that list) of its element's vertices
     DBuf<uint32_t> loc;       // nrec words, byte i = slot of the record's i-th vertex in OWNER-FIRST order (see blk_load)
     DBuf<int32_t> blkvert;    // nblk * FF_STAGE_MAX global vertex ids
     DBuf<int32_t> blkvcnt;    // nblk: number of distinct vertices, -1 = unstaged
     int maxstage = 0;         // largest blkvcnt
     int nunstaged = 0;        // number of blocks that could not be staged
+    int nempty = 0;           // rows that no element touches (ELL layout only)
 };
 static constexpr int FF_STAGE_MAX = 256;
 struct IncView {
@@ -275,6 +276,14 @@ struct ffcuda_matrix {
     int stream_nblk = 0, stream_T = 1, stream_grid = 1;
     size_t stream_shmem = 0;
     DBuf<int32_t> stream_rb;
+    // SELL-32 copy for the SpMV (sliced ELLPACK, slices of 32 consecutive rows, entry k of lane l at off + k*32 + l):
+    // structure built once per matrix, values re-packed when vals_epoch moved on
+    int sell_state = 0;       // 0 not prepared, 1 ready, -1 not applicable (too much padding)
+    int sell_nslices = 0;
+    int64_t sell_entries = 0; // padded entries
+    DBuf<int32_t> sell_off, sell_col;
+    DBuf<double> sell_val;
+    uint64_t vals_epoch = 1, sell_epoch = 0; // vals_epoch: bumped by everything that writes vals
     // CG workspace (lazily allocated)
     DBuf<double> wG, wH, wAH, wD1, wX;
     DBuf<int32_t> wcl;

@@ -33,6 +33,7 @@ void ff_matrix_touch(ffcuda_matrix *A)
     if (!A->vals_stale) return;
     FF_CUDA(cudaMemsetAsync(A->vals.p, 0, A->vals.bytes(), A->ctx->stream));
     A->vals_stale = false;
+    A->vals_epoch++;
 }
 
 __global__ void k_maxrow(const int32_t *__restrict__ rowptr, int n, int32_t *__restrict__ out)
@@ -119,6 +120,7 @@ extern "C" int ffcuda_matrix_upload(ffcuda_matrix *A, const double *vals)
     FF_REQUIRE(A && vals, "null argument");
     ff_enter(A->ctx);
     A->vals_stale = false;
+    A->vals_epoch++;
     FF_CUDA(cudaMemcpyAsync(A->vals.p, vals, A->vals.bytes(), cudaMemcpyHostToDevice, A->ctx->stream));
     FF_CUDA(cudaStreamSynchronize(A->ctx->stream));
     FF_API_END(A ? A->ctx : nullptr)
@@ -288,6 +290,7 @@ extern "C" int ffcuda_matrix_apply_bc(ffcuda_matrix *A, ffcuda_bc *bc, double tg
     ffcuda_ctx *ctx = A->ctx;
     ff_enter(ctx);
     ff_matrix_touch(A);
+    A->vals_epoch++;
     if (bc->ndofs)
         ff_launch(ctx, "bc_matrix", [&] {
             k_bc_matrix<<<ff_blocks(bc->ndofs, 256), 256, 0, ctx->stream>>>(bc->dofs.p, bc->ndofs, A->diagpos, A->vals.p, tgv);

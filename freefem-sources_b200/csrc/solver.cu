@@ -14,6 +14,7 @@
 // partials) -> deterministic, no fp64 atomics.  The host enqueues iterations in batches and polls a device flag;
 // kernels of iterations past the converged one are no-ops, so x is exactly the iterate of the stopping iteration.
 #include "common.cuh"
+#include <algorithm>
 #include <cmath>
 
 // d_scal layout (doubles)
@@ -189,6 +190,101 @@ __global__ void __launch_bounds__(RED_THREADS) k_spmv_stream(const int32_t *__re
             }
         }
         __syncthreads(); // sprod is reused by the next row block
+    }
+    if (MODE == 1) {
+        double a[1] = {acc0};
+        grid_sum_finish<1>(a, partial, flags + F_COUNTER, out, sh);
+    }
+    if (MODE == 2) {
+        double a[2] = {acc0, acc1};
+        grid_sum_finish<2>(a, partial, flags + F_COUNTER, out, sh);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SELL-32 SpMV (the default where padding stays small): slices of 32 consecutive rows, one lane per row, entry k of
+// lane l at off + k*32 + l.  Every load of column indices and values is one fully coalesced line per warp, the x
+// gather of a warp reads 32 neighbouring rows' k-th neighbours (near-contiguous on FE numberings: a few L1 wavefronts
+// instead of ~one per lane with CSR), and a row's products are added left to right in a register (the CPU's own
+// order; no shared memory, no shuffles).  Same MODEs as k_spmv_stream.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_sell_len(const int32_t *__restrict__ rowptr, int n, int nslices, int32_t *__restrict__ slen)
+{
+    const int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (sl >= nslices) return;
+    const int row = sl * 32 + lane;
+    int m = row < n ? rowptr[row + 1] - rowptr[row] : 0;
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0) slen[sl] = 32 * m;
+}
+
+// WHAT 0: column indices (padding: the row's own index, value 0), WHAT 1: values
+template <int WHAT>
+__global__ void k_sell_fill(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind, const double *__restrict__ vals,
+                            int n, int nslices, const int32_t *__restrict__ soff, int32_t *__restrict__ scol, double *__restrict__ sval)
+{
+    const int sl = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (sl >= nslices) return;
+    const int row = sl * 32 + lane;
+    const int off = soff[sl], len = (soff[sl + 1] - off) >> 5;
+    const int rb = row < n ? rowptr[row] : 0, rl = row < n ? rowptr[row + 1] - rb : 0;
+    for (int k = 0; k < len; ++k) {
+        const size_t d = (size_t)off + (size_t)k * 32 + lane;
+        if (WHAT == 0) scol[d] = k < rl ? __ldg(colind + rb + k) : (row < n ? row : 0);
+        else sval[d] = k < rl ? __ldg(vals + rb + k) : 0.0;
+    }
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(RED_THREADS) k_spmv_sell(const int32_t *__restrict__ soff, const int32_t *__restrict__ scol,
+                                                           const double *__restrict__ sval, const double *__restrict__ x, int n,
+                                                           int nslices, const double *__restrict__ aux0, const double *__restrict__ aux1,
+                                                           double *__restrict__ y, int iter, double *__restrict__ partial,
+                                                           int *__restrict__ flags, double *__restrict__ out)
+{
+    __shared__ double sh[32];
+    if (MODE == 2) {
+        const int ci = flags[F_CONV_ITER]; // 0: running, -1/-2: stopped before the first iteration, k>0: converged at k
+        if (ci != 0 && iter > ci) return;
+    }
+    double acc0 = 0.0, acc1 = 0.0;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int sl = warp; sl < nslices; sl += nwarps) {
+        const int off = __ldg(soff + sl), len = (__ldg(soff + sl + 1) - off) >> 5;
+        const int32_t *pc = scol + off + lane;
+        const double *pv = sval + off + lane;
+        double s = 0.0;
+        int k = 0;
+        for (; k + 4 <= len; k += 4) {
+            int c[4];
+            double v[4], xv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                c[i] = __ldcs(pc + (size_t)(k + i) * 32);
+                v[i] = __ldcs(pv + (size_t)(k + i) * 32);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) xv[i] = __ldg(x + c[i]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s = __dadd_rn(s, __dmul_rn(v[i], xv[i]));
+        }
+        for (; k < len; ++k) s = __dadd_rn(s, __dmul_rn(__ldcs(pv + (size_t)k * 32), __ldg(x + __ldcs(pc + (size_t)k * 32))));
+        const int row = sl * 32 + lane;
+        if (row < n) {
+            if (MODE == 0) y[row] = s;
+            if (MODE == 1) {
+                const double g = s - aux0[row];
+                y[row] = g;
+                acc0 = fma(g, aux1[row] * g, acc0);
+            }
+            if (MODE == 2) {
+                const double h = x[row];
+                y[row] = s;
+                acc0 = fma(aux0[row], h, acc0);
+                acc1 = fma(h, s, acc1);
+            }
+        }
     }
     if (MODE == 1) {
         double a[1] = {acc0};
@@ -484,6 +580,70 @@ static bool stream_prepare(ffcuda_matrix *A)
     return true;
 }
 
+// ---- SELL-32 set-up: structure once per matrix, values whenever they changed since the last packing
+static constexpr double SELL_MAX_PADDING = 1.15; // padded entries / nnz above which the CSR-stream kernel is used instead
+
+static bool sell_prepare(ffcuda_matrix *A)
+{
+    if (A->sell_state < 0) return false;
+    ffcuda_ctx *ctx = A->ctx;
+    cudaStream_t st = ctx->stream;
+    const int ns = (A->n + 31) / 32;
+    if (A->sell_state == 0) {
+        if (A->nnz == 0 || A->n == 0) {
+            A->sell_state = -1;
+            return false;
+        }
+        DBuf<int32_t> slen;
+        slen.alloc((size_t)ns + 1);
+        FF_CUDA(cudaMemsetAsync(slen.p + ns, 0, sizeof(int32_t), st));
+        ff_launch(ctx, "spmv_sell_len", [&] { k_sell_len<<<ff_blocks((size_t)ns * 32, 256), 256, 0, st>>>(A->rowptr, A->n, ns, slen.p); });
+        A->sell_off.alloc((size_t)ns + 1);
+        int64_t total = 0;
+        ff_exclusive_scan_i32(ctx, slen.p, A->sell_off.p, (size_t)ns + 1, &total); // synchronises the stream
+        // (a padded total beyond int32 wraps to something far from nnz and is rejected by the same test)
+        if (total < A->nnz || (double)total > SELL_MAX_PADDING * (double)A->nnz) {
+            A->sell_off.release();
+            A->sell_state = -1;
+            return false;
+        }
+        A->sell_nslices = ns;
+        A->sell_entries = total;
+        A->sell_col.alloc((size_t)total);
+        A->sell_val.alloc((size_t)total);
+        ff_launch(ctx, "spmv_sell_cols", [&] {
+            k_sell_fill<0><<<ff_blocks((size_t)ns * 32, 256), 256, 0, st>>>(A->rowptr, A->colind, nullptr, A->n, ns, A->sell_off.p, A->sell_col.p, nullptr);
+        });
+        A->sell_state = 1;
+        A->sell_epoch = 0;
+    }
+    if (A->sell_epoch != A->vals_epoch) {
+        ff_launch(ctx, "spmv_sell_vals", [&] {
+            k_sell_fill<1><<<ff_blocks((size_t)ns * 32, 256), 256, 0, st>>>(A->rowptr, nullptr, A->vals.p, A->n, ns, A->sell_off.p, nullptr, A->sell_val.p);
+        });
+        A->sell_epoch = A->vals_epoch;
+    }
+    return true;
+}
+
+static int sell_grid(const ffcuda_matrix *A)
+{
+    const int warps_per_block = RED_THREADS / 32;
+    const int need = (A->sell_nslices + warps_per_block - 1) / warps_per_block;
+    return std::max(1, std::min(need, A->ctx->sm_count * (2048 / RED_THREADS)));
+}
+
+template <int MODE>
+static void sell_launch(ffcuda_matrix *A, const char *name, const double *x, const double *aux0, const double *aux1, double *y, int iter,
+                        double *partial, int *flags, double *out)
+{
+    ffcuda_ctx *ctx = A->ctx;
+    ff_launch(ctx, name, [&] {
+        k_spmv_sell<MODE><<<sell_grid(A), RED_THREADS, 0, ctx->stream>>>(A->sell_off.p, A->sell_col.p, A->sell_val.p, x, A->n,
+                                                                         A->sell_nslices, aux0, aux1, y, iter, partial, flags, out);
+    });
+}
+
 #define FF_DISPATCH_ST(T, ...)                                \
     switch (T) {                                              \
     case 1: { constexpr int TT = 1; __VA_ARGS__; } break;     \
@@ -513,6 +673,10 @@ static void stream_launch(ffcuda_matrix *A, const char *name, const double *x, c
 static void spmv_launch(ffcuda_matrix *A, const double *x, const double *sub, double *y)
 {
     ffcuda_ctx *ctx = A->ctx;
+    if (!sub && sell_prepare(A)) {
+        sell_launch<0>(A, "spmv", x, nullptr, nullptr, y, 0, nullptr, nullptr, nullptr);
+        return;
+    }
     if (!sub && stream_prepare(A)) {
         stream_launch<0>(A, "spmv", x, nullptr, nullptr, y, 0, nullptr, nullptr, nullptr);
         return;
@@ -558,8 +722,9 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
     double *scal = ctx->d_scal;
     int *flags = ctx_flags(ctx);
     const int T = pick_T(A);
-    const bool streamed = stream_prepare(A);
-    const int grid_s = streamed ? A->stream_grid : grid_for(ctx, (size_t)n * T), grid_v = grid_for(ctx, (size_t)n);
+    const bool sell = sell_prepare(A);
+    const bool streamed = !sell && stream_prepare(A);
+    const int grid_s = sell ? sell_grid(A) : streamed ? A->stream_grid : grid_for(ctx, (size_t)n * T), grid_v = grid_for(ctx, (size_t)n);
     ensure_partial(ctx, 2 * (size_t)std::max(grid_s, grid_v) + 16);
     double *partial = ctx->d_partial;
     FF_CUDA(cudaMemsetAsync(scal, 0, 64 * sizeof(double), st));
@@ -598,7 +763,9 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
         ff_halo_exchange(A, A->wX.p);
         xin = A->wX.p;
     }
-    if (streamed)
+    if (sell)
+        sell_launch<1>(A, "cg_init_spmv", xin, b, D1, G, 0, partial, flags, scal + S_GCG0);
+    else if (streamed)
         stream_launch<1>(A, "cg_init_spmv", xin, b, D1, G, 0, partial, flags, scal + S_GCG0);
     else
         FF_DISPATCH_T(T, ff_launch(ctx, "cg_init_spmv", [&] {
@@ -623,7 +790,9 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
             for (int k = 0; k < nb; ++k) {
                 ++it;
                 ff_halo_exchange(A, H);
-                if (streamed)
+                if (sell)
+                    sell_launch<2>(A, "cg_spmv_dots", H, G, nullptr, AH, it, partial, flags, scal + S_GH);
+                else if (streamed)
                     stream_launch<2>(A, "cg_spmv_dots", H, G, nullptr, AH, it, partial, flags, scal + S_GH);
                 else
                     FF_DISPATCH_T(T, ff_launch(ctx, "cg_spmv_dots", [&] {

@@ -35,10 +35,12 @@ __global__ void k_blk_len(const int32_t *__restrict__ cnt, int nrows, int nblk, 
     if (b >= nblk) return;
     const int row = b * 32 + lane;
     int m = row < nrows ? cnt[row] : 0;
+    const unsigned empty = __ballot_sync(0xffffffffu, row < nrows && m == 0);
     for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
     if (lane == 0) {
         blklen[b] = 32 * m;
         if (m > 0) atomicMax(maxinc, m);
+        if (empty) atomicAdd(maxinc + 1, __popc(empty)); // rows without any element
     }
 }
 
@@ -130,6 +132,39 @@ __device__ __forceinline__ void blk_load(const int32_t *__restrict__ conn, const
     __syncwarp();
 }
 
+__device__ __forceinline__ int warp_sort32(int v, int lane)
+{
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const int o = __shfl_xor_sync(0xffffffffu, v, j);
+            const bool up = (lane & k) == 0, lower = (lane & j) == 0;
+            v = (lower == up) ? min(v, o) : max(v, o);
+        }
+    return v;
+}
+
+// bitonic sort of u[0..m) (m a power of two) by one warp in shared memory
+__device__ __forceinline__ void warp_sort_smem(int32_t *u, int m, int lane)
+{
+    for (int k = 2; k <= m; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int x = lane; x < m; x += 32) {
+                const int y = x ^ j;
+                if (y > x) {
+                    const int a = u[x], b = u[y];
+                    const bool up = (x & k) == 0;
+                    if ((a > b) == up) {
+                        u[x] = b;
+                        u[y] = a;
+                    }
+                }
+            }
+            __syncwarp();
+        }
+}
+
 // stage tables of the incidence: distinct vertices of the block (slot numbering) and per-record slot bytes
 template <int NLOC>
 __global__ void __launch_bounds__(128) k_block_stage(const int32_t *__restrict__ conn, int nrows, const IncView V, int Lmax,
@@ -184,6 +219,22 @@ __global__ void __launch_bounds__(128) k_block_stage(const int32_t *__restrict__
     __syncwarp();
     const int nv = *bcnt;
     const bool staged = nv <= FF_STAGE_MAX;
+    if (staged) {
+        // slots are numbered in ASCENDING VERTEX ORDER: the rank of a column inside a row is then a population count
+        // over the row's slot bitmap (k_sym_p1_rows), no search and no hashing in the per-assembly symbolic phase
+        int m = 32;
+        while (m < nv) m <<= 1;
+        for (int x = nv + lane; x < m; x += 32) vlist[x] = INT_MAX;
+        __syncwarp();
+        warp_sort_smem(vlist, m, lane);
+        for (int x = lane; x < nv; x += 32) {
+            const uint32_t v = (uint32_t)vlist[x];
+            uint32_t h = ht_hash(v, BLOG);
+            while (bkey[h] != v) h = (h + 1) & (BT - 1);
+            bslot[h] = (uint32_t)x;
+        }
+        __syncwarp();
+    }
     for (int e = 0; e < Lb; ++e) {
         if (recs[e * 32 + lane] == FF_NOREC) continue;
         uint32_t word = 0;
@@ -205,39 +256,6 @@ __global__ void __launch_bounds__(128) k_block_stage(const int32_t *__restrict__
         if (staged) atomicMax(maxstage, nv);
         else atomicAdd(maxstage + 1, 1);
     }
-}
-
-__device__ __forceinline__ int warp_sort32(int v, int lane)
-{
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1)
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const int o = __shfl_xor_sync(0xffffffffu, v, j);
-            const bool up = (lane & k) == 0, lower = (lane & j) == 0;
-            v = (lower == up) ? min(v, o) : max(v, o);
-        }
-    return v;
-}
-
-// bitonic sort of u[0..m) (m a power of two >= 64) by one warp in shared memory
-__device__ __forceinline__ void warp_sort_smem(int32_t *u, int m, int lane)
-{
-    for (int k = 2; k <= m; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int x = lane; x < m; x += 32) {
-                const int y = x ^ j;
-                if (y > x) {
-                    const int a = u[x], b = u[y];
-                    const bool up = (x & k) == 0;
-                    if ((a > b) == up) {
-                        u[x] = b;
-                        u[y] = a;
-                    }
-                }
-            }
-            __syncwarp();
-        }
 }
 
 // row patterns of the 32 rows of a block in ONE pass: sorted distinct columns into a fixed-stride scratch
@@ -368,6 +386,98 @@ __global__ void __launch_bounds__(128) k_block_pattern(const int32_t *__restrict
     if (lane == 0 && localmax > 0) atomicMax(maxrow, localmax);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// P1, every ELL block staged (the common case): the per-assembly symbolic phase as pure bit arithmetic.
+// The slot bytes of the incidence records (Incidence::loc) number the distinct vertices of a block in ascending vertex
+// order, so a row's column set is a 256-bit bitmap over the block's slots, its length a population count, and the
+// position of a column inside the row the population count of the bits below its slot.  One thread per row, no
+// hashing, no sorting, no atomics on the data path; reads 4 B and writes 4 B per incidence record.
+// ---------------------------------------------------------------------------------------------------------------
+static constexpr int SYM_THREADS = 128;
+static constexpr int SYM_WORDS = FF_STAGE_MAX / 32;
+
+template <int NLOC>
+__global__ void __launch_bounds__(SYM_THREADS) k_sym_p1_rows(int nrows, int nrows_pad, const int32_t *__restrict__ cnt,
+                                                             const uint32_t *__restrict__ blkoff, const uint32_t *__restrict__ loc,
+                                                             uint32_t *__restrict__ pos, uint32_t *__restrict__ bitmaps,
+                                                             int32_t *__restrict__ rowlen, int32_t *__restrict__ diagnode,
+                                                             int32_t *__restrict__ maxrow)
+{
+    __shared__ uint32_t sbm[SYM_WORDS][SYM_THREADS];  // [word][thread]: conflict-free
+    __shared__ uint32_t spre[SYM_WORDS][SYM_THREADS]; // population count of the words below
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int row = blockIdx.x * SYM_THREADS + tid;
+    const int blk = row >> 5, nblk = (nrows + 31) >> 5;
+    if (blk >= nblk) return; // whole warps only
+    const int mycnt = row < nrows ? cnt[row] : 0;
+    const uint32_t base = blkoff[blk];
+    const int Lb = (int)((blkoff[blk + 1] - base) >> 5);
+    const uint32_t *ploc = loc + base + lane;
+#pragma unroll
+    for (int w = 0; w < SYM_WORDS; ++w) sbm[w][tid] = 0u;
+    for (int e = 0; e < Lb; ++e) {
+        const uint32_t lw = __ldg(ploc + (size_t)e * 32);
+        if (e < mycnt) {
+#pragma unroll
+            for (int b = 0; b < NLOC; ++b) {
+                const uint32_t sl = (lw >> (8 * b)) & 255u;
+                sbm[sl >> 5][tid] |= 1u << (sl & 31u);
+            }
+        }
+    }
+    int nu = 0;
+#pragma unroll
+    for (int w = 0; w < SYM_WORDS; ++w) {
+        const uint32_t bits = sbm[w][tid];
+        spre[w][tid] = (uint32_t)nu;
+        nu += __popc(bits);
+        bitmaps[(size_t)w * nrows_pad + row] = bits;
+    }
+    uint32_t *ppos = pos + base + lane;
+    int diag = 0;
+    for (int e = 0; e < mycnt; ++e) {
+        const uint32_t lw = __ldg(ploc + (size_t)e * 32);
+        uint32_t word = 0;
+#pragma unroll
+        for (int b = 0; b < NLOC; ++b) {
+            const uint32_t sl = (lw >> (8 * b)) & 255u, w = sl >> 5;
+            const uint32_t r = spre[w][tid] + __popc(sbm[w][tid] & ((1u << (sl & 31u)) - 1u));
+            word |= r << (8 * b);
+        }
+        if (e == 0) diag = (int)(word & 255u); // byte 0 = the row's own vertex
+        __stcs(ppos + (size_t)e * 32, word);
+    }
+    if (row < nrows) {
+        rowlen[row] = nu;
+        diagnode[row] = diag;
+    }
+    int m = nu;
+    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane == 0 && m > 0) atomicMax(maxrow, m);
+}
+
+// columns of every row from its slot bitmap and the block's (ascending) vertex list; diagonal positions
+__global__ void __launch_bounds__(SYM_THREADS) k_sym_p1_cols(int nrows, int nrows_pad, const uint32_t *__restrict__ bitmaps,
+                                                             const int32_t *__restrict__ nrowptr, const int32_t *__restrict__ blkvert,
+                                                             const int32_t *__restrict__ diagnode, int32_t *__restrict__ ncol,
+                                                             int32_t *__restrict__ diagpos)
+{
+    const int row = blockIdx.x * SYM_THREADS + threadIdx.x;
+    if (row >= nrows) return;
+    const int32_t *bv = blkvert + (size_t)(row >> 5) * FF_STAGE_MAX;
+    int o = nrowptr[row];
+    diagpos[row] = o + diagnode[row];
+#pragma unroll
+    for (int w = 0; w < SYM_WORDS; ++w) {
+        uint32_t bits = __ldcs(bitmaps + (size_t)w * nrows_pad + row);
+        while (bits) {
+            const int b = __ffs(bits) - 1;
+            bits &= bits - 1u;
+            ncol[o++] = __ldg(bv + w * 32 + b);
+        }
+    }
+}
+
 // tmpcol (fixed stride) -> ncol (CSR): one warp per 32 rows, a row segment at a time
 __global__ void k_compact_cols(const int32_t *__restrict__ tmpcol, int cap, const int32_t *__restrict__ nrowptr, int nrows,
                                int32_t *__restrict__ ncol)
@@ -400,8 +510,8 @@ void ff_build_incidence(ffcuda_space *s)
     FF_CUDA(cudaMemsetAsync(I.cnt.p, 0, I.cnt.bytes(), st));
     ff_launch(ctx, "inc_count", [&] { k_count_inc<<<ff_blocks(nitems, 256), 256, 0, st>>>(s->e2n, nitems, nrows, I.cnt.p); });
     DBuf<int32_t> d_max;
-    d_max.alloc(1);
-    FF_CUDA(cudaMemsetAsync(d_max.p, 0, sizeof(int32_t), st));
+    d_max.alloc(2);
+    FF_CUDA(cudaMemsetAsync(d_max.p, 0, 2 * sizeof(int32_t), st));
     int64_t nrec = 0;
     if (I.ell) {
         const int nblk = (nrows + 31) / 32;
@@ -417,10 +527,11 @@ void ff_build_incidence(ffcuda_space *s)
         ff_exclusive_scan_i32(ctx, I.cnt.p, I.incptr.p, (size_t)nrows + 1, &nrec);
     }
     FF_REQUIRE(nrec < ((int64_t)1 << 31), "incidence table exceeds int32");
-    int32_t h_max = 0;
-    FF_CUDA(cudaMemcpyAsync(&h_max, d_max.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    int32_t h_max[2] = {0, 0};
+    FF_CUDA(cudaMemcpyAsync(h_max, d_max.p, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     FF_CUDA(cudaStreamSynchronize(st));
-    I.maxinc = h_max;
+    I.maxinc = h_max[0];
+    I.nempty = h_max[1];
     I.nrec = nrec;
     FF_REQUIRE(I.maxinc > 0, "no element touches any owned node");
     I.inc.alloc((size_t)nrec);
@@ -673,8 +784,40 @@ extern "C" int ffcuda_symbolic(ffcuda_space *s, ffcuda_pattern **out)
     P->nrowptr.alloc((size_t)nrows + 1);
     int64_t nnzn = 0;
     int32_t h_max = 0;
-    if (s->order == 1) {
-        // --- P1: one pass, one warp per block of 32 rows (k_block_pattern), columns through a fixed-stride scratch
+    bool diag_done = false;
+    if (s->order == 1 && I.nunstaged == 0 && I.nempty == 0) {
+        // --- P1, all blocks staged: slot bitmaps (k_sym_p1_rows) -> scan -> columns (k_sym_p1_cols)
+        const int nblk = (nrows + 31) / 32, nrows_pad = nblk * 32;
+        DBuf<uint32_t> bitmaps;
+        bitmaps.alloc((size_t)SYM_WORDS * nrows_pad);
+        P->pos8.alloc((size_t)I.nrec * P->nlocp);
+        uint32_t *posw = reinterpret_cast<uint32_t *>(P->pos8.p);
+        const int blocks = ff_blocks((size_t)nrows_pad, SYM_THREADS);
+        ff_launch(ctx, "sym_p1_rows", [&] {
+            if (nloc == 4)
+                k_sym_p1_rows<4><<<blocks, SYM_THREADS, 0, st>>>(nrows, nrows_pad, I.cnt.p, I.blkoff.p, I.loc.p, posw, bitmaps.p, rowlen.p,
+                                                                 diagnode.p, d_max.p);
+            else
+                k_sym_p1_rows<3><<<blocks, SYM_THREADS, 0, st>>>(nrows, nrows_pad, I.cnt.p, I.blkoff.p, I.loc.p, posw, bitmaps.p, rowlen.p,
+                                                                 diagnode.p, d_max.p);
+        });
+        FF_CUDA(cudaMemcpyAsync(&h_max, d_max.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        ff_exclusive_scan_i32(ctx, rowlen.p, P->nrowptr.p, (size_t)nrows + 1, &nnzn); // synchronises the stream
+        P->maxrow_node = h_max;
+        FF_REQUIRE(P->maxrow_node <= 255, "a P1 node with more than 254 neighbours is not supported");
+        P->nnz_node = nnzn;
+        P->nnz = nnzn * nc * nc;
+        FF_REQUIRE(P->nnz < ((int64_t)1 << 31), "matrix exceeds 2^31 nonzeros (int32 CSR, like MatriceMorse)");
+        P->ncol.alloc((size_t)nnzn);
+        P->diagpos.alloc((size_t)P->n);
+        // scalar spaces: diagpos is final; vector spaces overwrite it in k_expand_rowptr below
+        ff_launch(ctx, "sym_p1_cols", [&] {
+            k_sym_p1_cols<<<blocks, SYM_THREADS, 0, st>>>(nrows, nrows_pad, bitmaps.p, P->nrowptr.p, I.blkvert.p, diagnode.p, P->ncol.p,
+                                                          P->diagpos.p);
+        });
+        diag_done = (nc == 1);
+    } else if (s->order == 1) {
+        // --- P1, general: one pass, one warp per block of 32 rows (k_block_pattern), columns through a fixed-stride scratch
         const int Lmax = I.maxinc, cstride = Lmax * 4 + 4;
         const int cap = Lmax * (nloc - 1) + 1; // a row has at most this many distinct columns
         int TSR = 64, RLOG = 6, UL = 64;
@@ -749,11 +892,11 @@ extern "C" int ffcuda_symbolic(ffcuda_space *s, ffcuda_pattern **out)
     rowlen.release();
 
     // --- dof-level CSR
-    P->diagpos.alloc((size_t)P->n);
+    if (!P->diagpos.p) P->diagpos.alloc((size_t)P->n);
     if (nc == 1) {
         P->rowptr = P->nrowptr.p;
         P->colind = P->ncol.p;
-        ff_launch(ctx, "sym_diagpos", [&] { k_diagpos_scalar<<<ff_blocks(nrows, 256), 256, 0, st>>>(P->nrowptr.p, diagnode.p, nrows, P->diagpos.p); });
+        if (!diag_done) ff_launch(ctx, "sym_diagpos", [&] { k_diagpos_scalar<<<ff_blocks(nrows, 256), 256, 0, st>>>(P->nrowptr.p, diagnode.p, nrows, P->diagpos.p); });
     } else {
         P->rowptr_own.alloc((size_t)P->n + 1);
         P->colind_own.alloc((size_t)P->nnz);
