@@ -64,6 +64,8 @@ struct ffcuda_ctx {
     std::vector<ProfPending> prof_pending;
     int64_t launches = 0;
     int sm_count = 148;
+    int tile_policy = 1;        // 0: never use row tiles, 1: from the second assembly on a fespace, 2: always
+    int tile_rows = 64;         // rows per tile
     // reduction scratch (device) + pinned host mirror
     double *d_scal = nullptr;   // small array of device scalars
     double *h_scal = nullptr;   // pinned
@@ -227,6 +229,19 @@ struct IncView {
 };
 static inline IncView ff_view(const Incidence &I) { return IncView{I.cnt.p, I.incptr.p, I.blkoff.p, I.inc.p, I.ell}; }
 
+// Row tiles of a scalar P1 space (tiles.cu): compact clusters of at most TR rows (consecutive in the Morton order of the
+// vertex coordinates) with everything the tile kernel needs packed in one blob per tile: the distinct vertices the
+// tile touches, every element touching one of its rows ONCE (4 block-local vertex slots), and for every matrix entry
+// of its rows the list of (element, local vertex pair) contributions.  A property of the fespace, built once.
+struct TileSet {
+    int state = 0;            // 0 not built, 1 ready, -1 not applicable (some tile exceeds the kernel's capacities)
+    int tr = 0, ntiles = 0;
+    int max_rows = 0, max_nvt = 0, max_nelem = 0, max_nq = 0, max_ncodes = 0, max_words = 0;
+    int64_t sum_nelem = 0;    // element evaluations per assembly (diagnostics: redundancy = sum_nelem / nt)
+    DBuf<uint32_t> blob;      // tile descriptors, 16-byte aligned each
+    DBuf<uint32_t> toff;      // ntiles+1 offsets into blob in 32-bit words
+};
+
 struct ffcuda_space {
     CtxRef ref; // keep first
     ffcuda_mesh *mesh = nullptr;
@@ -235,7 +250,12 @@ struct ffcuda_space {
     DBuf<int32_t> e2n_own;    // nt*nloc when order 2
     const int32_t *e2n = nullptr;   // = conn for P1
     Incidence incidence;
+    TileSet tiles;
+    int lean_assemblies = 0;  // scalar P1 assemblies seen on this space (the tile set is built from the second one on)
 };
+// tiles.cu: numeric assembly of c grad u.grad v + m u v on a scalar P1 space by row tiles; returns false when the tile
+// path does not apply (the caller then runs the thread-per-row kernel)
+bool ff_asm_p1_tiles(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, double cw, double cmd, double cmo, int accumulate);
 void ff_build_incidence(ffcuda_space *s); // symbolic.cu; no-op when already built
 
 struct ffcuda_pattern {

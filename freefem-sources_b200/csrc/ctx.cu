@@ -1,5 +1,7 @@
 // ctx.cu — context, error reporting, kernel profiler, device-wide scan, device vectors.
 #include "common.cuh"
+#include <algorithm>
+#include <cstdlib>
 
 static thread_local std::string g_thread_err;
 
@@ -56,6 +58,8 @@ extern "C" int ffcuda_ctx_create(int device, ffcuda_ctx **out)
     cudaDeviceProp prop;
     FF_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("FFCUDA_TILES")) ctx->tile_policy = std::max(0, std::min(2, atoi(e)));
+    if (const char *e = getenv("FFCUDA_TILE_ROWS")) ctx->tile_rows = std::max(8, std::min(256, atoi(e)));
     FF_CUDA(cudaMalloc((void **)&ctx->d_scal, 64 * sizeof(double)));
     FF_CUDA(cudaMemset(ctx->d_scal, 0, 64 * sizeof(double)));
     FF_CUDA(cudaMallocHost((void **)&ctx->h_scal, 64 * sizeof(double)));
@@ -166,6 +170,22 @@ extern "C" int ffcuda_ctx_set_stream(ffcuda_ctx *ctx, void *cuda_stream)
 }
 
 extern "C" void *ffcuda_ctx_get_stream(ffcuda_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+extern "C" int ffcuda_ctx_set_option(ffcuda_ctx *ctx, const char *name, int value)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(ctx && name, "ffcuda_ctx_set_option: bad arguments");
+    const std::string n(name);
+    if (n == "tile_policy") {
+        FF_REQUIRE(value >= 0 && value <= 2, "tile_policy must be 0, 1 or 2");
+        ctx->tile_policy = value;
+    } else if (n == "tile_rows") {
+        FF_REQUIRE(value >= 8 && value <= 256, "tile_rows must be in 8..256");
+        ctx->tile_rows = value;
+    } else
+        throw FFError("ffcuda_ctx_set_option: unknown option '" + n + "'");
+    FF_API_END(ctx)
+}
 
 extern "C" int ffcuda_prof_enable(ffcuda_ctx *ctx, int on)
 {

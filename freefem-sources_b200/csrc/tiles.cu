@@ -1,0 +1,757 @@
+// tiles.cu — numeric assembly of scalar P1 forms (c grad u . grad v + m u v) by ROW TILES.
+//
+// Replaces, for the headline configurations, the element loop of AssembleBilinearForm (fflib/problem.cpp:1096-1103,
+// :1398-1405) + Element_Op (:6063-6160, :6337-6437) + HashMatrix::operator+=(MatriceElementaire&)
+// (femlib/HashMatrix.cpp:1295-1332).  Same mathematics as k_asm_p1_lean (assemble.cu); different work decomposition:
+//
+//   * the rows of the matrix are grouped in TILES: compact clusters of <= TR vertices, consecutive in the Morton order
+//     of the vertex coordinates (the clustering is internal: the CSR that is produced is FreeFEM's, row by row);
+//   * one CTA per tile.  Every element touching a row of the tile is evaluated ONCE by one thread (geometry, the
+//     DIM(DIM+1)/2 off-diagonal entries of its element matrix, its measure) into shared memory — the thread-per-row
+//     kernel evaluates every element once per vertex (4x on tetrahedra);
+//   * every matrix entry (i, j) of the tile's rows is OWNED by one thread, which sums the contributions of the elements
+//     around the edge ij in a register, in ascending element order, and stores the entry: no atomics, no
+//     read-modify-write, bit-reproducible;
+//   * the diagonal follows from the partition of unity: K_ii = - sum_j K_ij (+ the mass part).
+//
+// Everything a tile needs sits in ONE contiguous descriptor blob (built once per fespace by k_tile_build): the
+// distinct vertices of the tile (ascending => slot order = column order), one word of 4 slot bytes per element, one
+// word per entry (offset of its contribution list, position in the row, local row) and 16-bit contribution codes
+// (element << 3 | vertex pair).
+#include "common.cuh"
+#include <algorithm>
+#include <cstdlib>
+#include <cub/device/device_radix_sort.cuh>
+
+namespace {
+
+constexpr int TB_THREADS = 256;   // build kernel
+constexpr int SORT_CAP = 8192;    // incidence records of a tile's rows / vertex candidates (sort buffer)
+constexpr int NE_CAP = 2048;      // elements per tile
+constexpr int NV_CAP = 256;       // distinct vertices per tile (8-bit slots)
+constexpr int NQ_CAP = 4096;      // matrix entries per tile
+constexpr int NC_CAP = 16384;     // contribution codes per tile
+constexpr int TR_CAP = 256;       // rows per tile
+constexpr int BMW = NV_CAP / 32;  // bitmap words per row
+constexpr int HDR = 16;           // header words
+// header: 0 nr, 1 nvt, 2 nelem, 3 nq, 4 ncodes, 5 o_grow, 6 o_rinfo, 7 o_tvert, 8 o_telem, 9 o_einfo, 10 o_codes, 11 words
+
+__host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
+
+// ---------------------------------------------------------------------------------------------------------------
+// Morton keys
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ord64(double d)
+{
+    unsigned long long b = (unsigned long long)__double_as_longlong(d);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+static double unord64(unsigned long long u)
+{
+    unsigned long long b = (u >> 63) ? (u & 0x7fffffffffffffffull) : ~u;
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+}
+
+__global__ void k_bbox(const double *__restrict__ xyz, int vstride, int dim, int n, unsigned long long *__restrict__ box)
+{
+    unsigned long long lo[3] = {~0ull, ~0ull, ~0ull}, hi[3] = {0, 0, 0};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        for (int x = 0; x < dim; ++x) {
+            const unsigned long long o = ord64(xyz[(size_t)i * vstride + x]);
+            lo[x] = min(lo[x], o);
+            hi[x] = max(hi[x], o);
+        }
+    for (int x = 0; x < dim; ++x) {
+        for (int o = 16; o; o >>= 1) {
+            lo[x] = min(lo[x], __shfl_xor_sync(0xffffffffu, lo[x], o));
+            hi[x] = max(hi[x], __shfl_xor_sync(0xffffffffu, hi[x], o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(box + x, lo[x]);
+            atomicMax(box + 3 + x, hi[x]);
+        }
+    }
+}
+
+__device__ __forceinline__ uint32_t spread3(uint32_t v) // 10 bits -> every third bit
+{
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t spread2(uint32_t v) // 15 bits -> every second bit
+{
+    v = (v | (v << 8)) & 0x00FF00FFu;
+    v = (v | (v << 4)) & 0x0F0F0F0Fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+
+struct BoxScale {
+    double lo[3], sc[3];
+};
+
+__global__ void k_morton(const double *__restrict__ xyz, int vstride, int dim, int n, const BoxScale B, uint32_t *__restrict__ key,
+                         int32_t *__restrict__ val)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t qmax = dim == 3 ? 1023u : 32767u;
+    uint32_t q[3] = {0, 0, 0};
+    for (int x = 0; x < dim; ++x) {
+        const double t = (xyz[(size_t)i * vstride + x] - B.lo[x]) * B.sc[x] + 0.5;
+        q[x] = (uint32_t)min((double)qmax, max(0.0, t));
+    }
+    key[i] = dim == 3 ? (spread3(q[0]) | (spread3(q[1]) << 1) | (spread3(q[2]) << 2)) : (spread2(q[0]) | (spread2(q[1]) << 1));
+    val[i] = i;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// block-wide helpers of the build kernel (TB_THREADS threads, shared-memory arrays)
+// ---------------------------------------------------------------------------------------------------------------
+__device__ void blk_sort(uint32_t *a, int m) // bitonic, m a power of two
+{
+    for (int k = 2; k <= m; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int x = threadIdx.x; x < m; x += TB_THREADS) {
+                const int y = x ^ j;
+                if (y > x) {
+                    const uint32_t u = a[x], v = a[y];
+                    if ((u > v) == ((x & k) == 0)) {
+                        a[x] = v;
+                        a[y] = u;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// in-place exclusive scan of a[0..n), returns the total; part: TB_THREADS+1 ints
+__device__ int blk_scan(int *a, int n, int *part)
+{
+    const int per = (n + TB_THREADS - 1) / TB_THREADS;
+    const int b = min(n, (int)threadIdx.x * per), e = min(n, b + per);
+    int s = 0;
+    for (int i = b; i < e; ++i) s += a[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) { // one warp scans the TB_THREADS partial sums
+        int carry = 0;
+        for (int c = 0; c < TB_THREADS; c += 32) {
+            const int v = part[c + threadIdx.x];
+            int inc = v;
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, inc, o);
+                if ((int)threadIdx.x >= o) inc += u;
+            }
+            part[c + threadIdx.x] = carry + inc - v;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (threadIdx.x == 0) part[TB_THREADS] = carry;
+    }
+    __syncthreads();
+    int r = part[threadIdx.x];
+    for (int i = b; i < e; ++i) {
+        const int v = a[i];
+        a[i] = r;
+        r += v;
+    }
+    __syncthreads();
+    return part[TB_THREADS];
+}
+
+// sorted a[0..m) (padding = 0xffffffff at the end) -> distinct values, compacted into out[]; returns their number
+__device__ int blk_unique(const uint32_t *a, int m, int *flag, uint32_t *out, int outcap, int *part)
+{
+    for (int x = threadIdx.x; x < m; x += TB_THREADS) flag[x] = (a[x] != 0xffffffffu && (x == 0 || a[x] != a[x - 1])) ? 1 : 0;
+    __syncthreads();
+    const int nu = blk_scan(flag, m, part);
+    for (int x = threadIdx.x; x < m; x += TB_THREADS) {
+        const bool head = a[x] != 0xffffffffu && (x == 0 || a[x] != a[x - 1]);
+        if (head && flag[x] < outcap) out[flag[x]] = a[x];
+    }
+    __syncthreads();
+    return nu;
+}
+
+__device__ __forceinline__ int bsearch_u32(const uint32_t *a, int n, uint32_t v)
+{
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < v) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+template <int NV>
+__device__ __forceinline__ int pair_id(int a, int b) // a < b
+{
+    if (NV == 4) return a == 0 ? b - 1 : (a == 1 ? b + 1 : 5);
+    return a == 0 ? b - 1 : 2;
+}
+
+// One CTA per tile.  WRITE = 0: sizes only (stats[t*8 ..] = nvt, nelem, nq, ncodes, fit, nr).  WRITE = 1: the blob.
+template <int NV, int WRITE>
+__global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__restrict__ rord, const int32_t *__restrict__ tstart,
+                                                           const int32_t *__restrict__ conn, const IncView V,
+                                                           int32_t *__restrict__ stats, const uint32_t *__restrict__ toff,
+                                                           uint32_t *__restrict__ blob)
+{
+    extern __shared__ uint32_t sm[];
+    uint32_t *sbuf = sm;                                   // SORT_CAP   sort buffer; later entry offsets / cursors
+    int *tmp = reinterpret_cast<int *>(sbuf + SORT_CAP);   // SORT_CAP   flags; later the codes (16 bit)
+    uint32_t *elist = reinterpret_cast<uint32_t *>(tmp + SORT_CAP); // NE_CAP element ids, ascending
+    uint32_t *telem = elist + NE_CAP;                      // NE_CAP     slot words
+    uint32_t *vlist = telem + NE_CAP;                      // NV_CAP     vertex ids, ascending
+    uint32_t *bm = vlist + NV_CAP;                         // TR_CAP*BMW row bitmaps over the slots
+    int *rowq = reinterpret_cast<int *>(bm + TR_CAP * BMW); // TR_CAP+1  first entry of every row
+    int *cntq = rowq + TR_CAP + 1;                         // NQ_CAP+1   contributions per entry
+    int *part = cntq + NQ_CAP + 1;                         // TB_THREADS+1
+    int *rslot = part + TB_THREADS + 1;                    // TR_CAP     slot of every row's own vertex
+    uint8_t *s2r = reinterpret_cast<uint8_t *>(rslot + TR_CAP); // NV_CAP row of a slot (255: not a row of the tile)
+    __shared__ int s_n, s_bad;
+    const int t = blockIdx.x, tid = threadIdx.x;
+    const int r0 = tstart[t], nr = tstart[t + 1] - r0;
+    if (tid == 0) {
+        s_n = 0;
+        s_bad = 0;
+    }
+    for (int x = tid; x < SORT_CAP; x += TB_THREADS) sbuf[x] = 0xffffffffu;
+    __syncthreads();
+    // 1. element ids of the incidence records of the tile's rows
+    for (int l = tid; l < nr; l += TB_THREADS) {
+        const int row = rord[r0 + l];
+        const int c = V.cnt[row];
+        const int o = atomicAdd(&s_n, c);
+        if (o + c > SORT_CAP) s_bad = 1;
+        else
+            for (int e = 0; e < c; ++e) sbuf[o + e] = V.inc[V.idx(row, e)] >> 4;
+    }
+    __syncthreads();
+    int fit = (nr <= TR_CAP && !s_bad) ? 1 : 0;
+    int nelem = 0, nvt = 0, nq = 0, ncodes = 0;
+    if (fit) {
+        int m = 32;
+        while (m < s_n) m <<= 1;
+        blk_sort(sbuf, m);
+        nelem = blk_unique(sbuf, m, tmp, elist, NE_CAP, part);
+        if (nelem > NE_CAP) fit = 0;
+    }
+    if (fit) {
+        // 2. distinct vertices, ascending
+        for (int x = tid; x < SORT_CAP; x += TB_THREADS) sbuf[x] = 0xffffffffu;
+        __syncthreads();
+        for (int x = tid; x < nelem * NV; x += TB_THREADS) sbuf[x] = (uint32_t)conn[(size_t)elist[x / NV] * NV + (x % NV)];
+        __syncthreads();
+        int m = 32;
+        while (m < nelem * NV) m <<= 1;
+        blk_sort(sbuf, m);
+        nvt = blk_unique(sbuf, m, tmp, vlist, NV_CAP, part);
+        if (nvt > NV_CAP) fit = 0;
+    }
+    if (fit) {
+        // 3. slots of every element's vertices; rows <-> slots
+        for (int e = tid; e < nelem; e += TB_THREADS) {
+            uint32_t w = 0;
+            for (int a = 0; a < NV; ++a) w |= (uint32_t)bsearch_u32(vlist, nvt, (uint32_t)conn[(size_t)elist[e] * NV + a]) << (8 * a);
+            telem[e] = w;
+        }
+        for (int x = tid; x < NV_CAP; x += TB_THREADS) s2r[x] = 255;
+        for (int x = tid; x < TR_CAP * BMW; x += TB_THREADS) bm[x] = 0u;
+        __syncthreads();
+        for (int l = tid; l < nr; l += TB_THREADS) {
+            const int row = rord[r0 + l];
+            // a row without any element is not in vlist: it gets no slot and an empty row
+            const int sl = nvt > 0 ? bsearch_u32(vlist, nvt, (uint32_t)row) : 0;
+            const bool has = nvt > 0 && vlist[sl] == (uint32_t)row;
+            rslot[l] = has ? sl : -1;
+            if (has) s2r[sl] = (uint8_t)l;
+        }
+        __syncthreads();
+        // 4. column bitmaps of the rows
+        for (int e = tid; e < nelem; e += TB_THREADS) {
+            const uint32_t w = telem[e];
+            for (int a = 0; a < NV; ++a) {
+                const int l = s2r[(w >> (8 * a)) & 255u];
+                if (l == 255) continue;
+                for (int b = 0; b < NV; ++b) {
+                    const uint32_t sb = (w >> (8 * b)) & 255u;
+                    atomicOr(&bm[l * BMW + (sb >> 5)], 1u << (sb & 31u));
+                }
+            }
+        }
+        __syncthreads();
+        for (int l = tid; l <= nr; l += TB_THREADS) {
+            int L = 0;
+            if (l < nr)
+                for (int w = 0; w < BMW; ++w) L += __popc(bm[l * BMW + w]);
+            rowq[l] = L;
+            if (L > 255) s_bad = 1;
+        }
+        __syncthreads();
+        nq = blk_scan(rowq, nr + 1, part);
+        if (nq > NQ_CAP || s_bad) fit = 0;
+    }
+    if (fit) {
+        // 5. contributions per entry: every ordered vertex pair (a, b), a != b, of every element whose vertex a is a row
+        for (int x = tid; x <= nq; x += TB_THREADS) cntq[x] = 0;
+        __syncthreads();
+        for (int e = tid; e < nelem; e += TB_THREADS) {
+            const uint32_t w = telem[e];
+            for (int a = 0; a < NV; ++a) {
+                const int l = s2r[(w >> (8 * a)) & 255u];
+                if (l == 255) continue;
+                for (int b = 0; b < NV; ++b) {
+                    if (b == a) continue;
+                    const uint32_t sb = (w >> (8 * b)) & 255u;
+                    int p = __popc(bm[l * BMW + (sb >> 5)] & ((1u << (sb & 31u)) - 1u));
+                    for (int ww = 0; ww < (int)(sb >> 5); ++ww) p += __popc(bm[l * BMW + ww]);
+                    atomicAdd(&cntq[rowq[l] + p], 1);
+                }
+            }
+        }
+        __syncthreads();
+        for (int x = tid; x < nq; x += TB_THREADS)
+            if (cntq[x] > 255) s_bad = 1;
+        __syncthreads();
+        ncodes = blk_scan(cntq, nq + 1, part); // cntq[q] = offset of entry q's list, cntq[nq] = ncodes
+        if (ncodes > NC_CAP || ncodes > 65535 || s_bad) fit = 0;
+    }
+    if (!WRITE) {
+        if (tid == 0) {
+            int32_t *st = stats + (size_t)t * 8;
+            st[0] = nvt; st[1] = nelem; st[2] = nq; st[3] = ncodes; st[4] = fit; st[5] = nr;
+        }
+        return;
+    }
+    if (!fit) return; // cannot happen: the host only writes tile sets whose tiles all fit
+    // 6. fill the lists (cursor = sbuf), then sort every list: ascending code = ascending element
+    uint16_t *codes = reinterpret_cast<uint16_t *>(tmp);
+    int *cursor = reinterpret_cast<int *>(sbuf);
+    for (int x = tid; x < nq; x += TB_THREADS) cursor[x] = cntq[x];
+    __syncthreads();
+    for (int e = tid; e < nelem; e += TB_THREADS) {
+        const uint32_t w = telem[e];
+        for (int a = 0; a < NV; ++a) {
+            const int l = s2r[(w >> (8 * a)) & 255u];
+            if (l == 255) continue;
+            for (int b = 0; b < NV; ++b) {
+                if (b == a) continue;
+                const uint32_t sb = (w >> (8 * b)) & 255u;
+                int p = __popc(bm[l * BMW + (sb >> 5)] & ((1u << (sb & 31u)) - 1u));
+                for (int ww = 0; ww < (int)(sb >> 5); ++ww) p += __popc(bm[l * BMW + ww]);
+                const int o = atomicAdd(&cursor[rowq[l] + p], 1);
+                codes[o] = (uint16_t)((e << 3) | pair_id<NV>(min(a, b), max(a, b)));
+            }
+        }
+    }
+    __syncthreads();
+    for (int q = tid; q < nq; q += TB_THREADS) {
+        const int o = cntq[q], n = cntq[q + 1] - o;
+        for (int x = 1; x < n; ++x) {
+            const uint16_t v = codes[o + x];
+            int y = x - 1;
+            while (y >= 0 && codes[o + y] > v) {
+                codes[o + y + 1] = codes[o + y];
+                --y;
+            }
+            codes[o + y + 1] = v;
+        }
+    }
+    __syncthreads();
+    // 7. the blob
+    uint32_t *g = blob + toff[t];
+    const int o_grow = HDR, o_rinfo = o_grow + pad4(nr), o_tvert = o_rinfo + pad4(nr + 1), o_telem = o_tvert + pad4(nvt),
+              o_einfo = o_telem + pad4(nelem), o_codes = o_einfo + pad4(nq + 1), words = o_codes + pad4((ncodes + 1) / 2);
+    if (tid == 0) {
+        g[0] = nr; g[1] = nvt; g[2] = nelem; g[3] = nq; g[4] = ncodes; g[5] = o_grow; g[6] = o_rinfo; g[7] = o_tvert;
+        g[8] = o_telem; g[9] = o_einfo; g[10] = o_codes; g[11] = words; g[12] = g[13] = g[14] = g[15] = 0;
+    }
+    for (int l = tid; l < pad4(nr); l += TB_THREADS) g[o_grow + l] = l < nr ? (uint32_t)rord[r0 + l] : 0u;
+    for (int l = tid; l < pad4(nr + 1); l += TB_THREADS) {
+        uint32_t w = 0;
+        if (l < nr) {
+            const int L = rowq[l + 1] - rowq[l], sl = rslot[l];
+            int pd = 0;
+            if (sl >= 0) {
+                pd = __popc(bm[l * BMW + (sl >> 5)] & ((1u << (sl & 31)) - 1u));
+                for (int ww = 0; ww < (sl >> 5); ++ww) pd += __popc(bm[l * BMW + ww]);
+            }
+            w = (uint32_t)rowq[l] | ((uint32_t)pd << 16) | ((uint32_t)L << 24);
+        } else if (l == nr)
+            w = (uint32_t)nq;
+        g[o_rinfo + l] = w;
+    }
+    for (int x = tid; x < pad4(nvt); x += TB_THREADS) g[o_tvert + x] = x < nvt ? vlist[x] : 0u;
+    for (int x = tid; x < pad4(nelem); x += TB_THREADS) g[o_telem + x] = x < nelem ? telem[x] : 0u;
+    // entry words: offset of the list | position in the row << 16 | local row << 24
+    for (int l = tid; l < nr; l += TB_THREADS)
+        for (int q = rowq[l]; q < rowq[l + 1]; ++q) g[o_einfo + q] = (uint32_t)cntq[q] | ((uint32_t)(q - rowq[l]) << 16) | ((uint32_t)l << 24);
+    for (int x = nq + tid; x < pad4(nq + 1); x += TB_THREADS) g[o_einfo + x] = (uint32_t)ncodes;
+    const int cw = pad4((ncodes + 1) / 2);
+    for (int x = tid; x < cw; x += TB_THREADS) {
+        const uint32_t lo = 2 * x < ncodes ? codes[2 * x] : 0u, hi = 2 * x + 1 < ncodes ? codes[2 * x + 1] : 0u;
+        g[o_codes + x] = lo | (hi << 16);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// the numeric kernel
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double tile_rcp(double d) // ~1 ulp reciprocal: hardware seed + two Newton steps
+{
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    double t = fma(-d, r, 1.0);
+    r = fma(r, t, r);
+    t = fma(-d, r, 1.0);
+    return fma(r, t, r);
+}
+
+struct TileSmem { // byte offsets of the shared-memory regions
+    int gbase, coord, vals, sd, nes;
+};
+
+template <int DIM, bool MASS>
+__global__ void __launch_bounds__(256) k_asm_tiles(const uint32_t *__restrict__ toff, const uint32_t *__restrict__ blob,
+                                                   const double *__restrict__ xyz, const int32_t *__restrict__ nrowptr,
+                                                   double *__restrict__ out, int accumulate, double cw, double cmd, double cmo,
+                                                   const TileSmem S)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int NV = DIM + 1, NP = DIM * (DIM + 1) / 2;
+    uint32_t *sb = reinterpret_cast<uint32_t *>(smem_raw);
+    int *gbase = reinterpret_cast<int *>(smem_raw + S.gbase);
+    double *coord = reinterpret_cast<double *>(smem_raw + S.coord); // [slot][DIM]; re-used for the entry sums
+    double *sE = coord;
+    double *sV = reinterpret_cast<double *>(smem_raw + S.vals);     // [pair][NES] (+ [NP][NES] = det when MASS)
+    double *sD = reinterpret_cast<double *>(smem_raw + S.sd);
+    const int NES = S.nes;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    const uint32_t w0 = toff[blockIdx.x];
+    const int nw4 = (int)((toff[blockIdx.x + 1] - w0) >> 2);
+    {
+        const uint4 *g = reinterpret_cast<const uint4 *>(blob + w0);
+        uint4 *d = reinterpret_cast<uint4 *>(sb);
+        for (int i = tid; i < nw4; i += nthr) d[i] = __ldcs(g + i);
+    }
+    __syncthreads();
+    const int nr = sb[0], nvt = sb[1], nelem = sb[2], nq = sb[3];
+    const int32_t *grow = reinterpret_cast<const int32_t *>(sb + sb[5]);
+    const uint32_t *rinfo = sb + sb[6];
+    const int32_t *tvert = reinterpret_cast<const int32_t *>(sb + sb[7]);
+    const uint32_t *telem = sb + sb[8];
+    const uint32_t *einfo = sb + sb[9];
+    const uint16_t *codes = reinterpret_cast<const uint16_t *>(sb + sb[10]);
+    for (int l = tid; l < nr; l += nthr) gbase[l] = __ldg(nrowptr + grow[l]);
+    for (int v = tid; v < nvt; v += nthr) {
+        const int id = tvert[v];
+        if (DIM == 3) {
+            double4 p;
+            asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(p.x), "=d"(p.y), "=d"(p.z), "=d"(p.w) : "l"(xyz + 4 * (size_t)id));
+            coord[3 * v] = p.x; coord[3 * v + 1] = p.y; coord[3 * v + 2] = p.z;
+        } else {
+            const double2 p = __ldg(reinterpret_cast<const double2 *>(xyz) + id);
+            coord[2 * v] = p.x; coord[2 * v + 1] = p.y;
+        }
+    }
+    __syncthreads();
+    // ---- every element of the tile once: off-diagonal entries of its element matrix (+ its determinant)
+    for (int e = tid; e < nelem; e += nthr) {
+        const uint32_t w = telem[e];
+        const double *p0 = coord + DIM * (w & 255u), *p1 = coord + DIM * ((w >> 8) & 255u), *p2 = coord + DIM * ((w >> 16) & 255u);
+        double K[NP], det;
+        if (DIM == 3) {
+            const double *p3 = coord + DIM * (w >> 24);
+            const double x0 = p0[0], y0 = p0[1], z0 = p0[DIM - 1];
+            const double ax = p1[0] - x0, ay = p1[1] - y0, az = p1[DIM - 1] - z0;
+            const double bx = p2[0] - x0, by = p2[1] - y0, bz = p2[DIM - 1] - z0;
+            const double cx = p3[0] - x0, cy = p3[1] - y0, cz = p3[DIM - 1] - z0;
+            // N1 = b x c, N2 = c x a, N3 = a x b, det = a . N1, N0 = -(N1 + N2 + N3)   (Mesh3dn.hpp:126-136)
+            const double n1x = by * cz - bz * cy, n1y = bz * cx - bx * cz, n1z = bx * cy - by * cx;
+            const double n2x = cy * az - cz * ay, n2y = cz * ax - cx * az, n2z = cx * ay - cy * ax;
+            const double n3x = ay * bz - az * by, n3y = az * bx - ax * bz, n3z = ax * by - ay * bx;
+            det = ax * n1x + ay * n1y + az * n1z;
+            const double n0x = -(n1x + n2x + n3x), n0y = -(n1y + n2y + n3y), n0z = -(n1z + n2z + n3z);
+            const double s = cw * tile_rcp(det), mo = MASS ? cmo * det : 0.0;
+            K[0] = fma(n0x * n1x + n0y * n1y + n0z * n1z, s, mo);
+            K[1] = fma(n0x * n2x + n0y * n2y + n0z * n2z, s, mo);
+            K[2] = fma(n0x * n3x + n0y * n3y + n0z * n3z, s, mo);
+            K[3 % NP] = fma(n1x * n2x + n1y * n2y + n1z * n2z, s, mo);
+            K[4 % NP] = fma(n1x * n3x + n1y * n3y + n1z * n3z, s, mo);
+            K[5 % NP] = fma(n2x * n3x + n2y * n3y + n2z * n3z, s, mo);
+        } else {
+            const double x0 = p0[0], y0 = p0[1];
+            const double bx = p1[0] - x0, by = p1[1] - y0, cx = p2[0] - x0, cy = p2[1] - y0;
+            det = bx * cy - by * cx; // N1 = (cy, -cx), N2 = (-by, bx), N0 = -(N1 + N2)   (fem.hpp:321-324)
+            const double n1x = cy, n1y = -cx, n2x = -by, n2y = bx, n0x = -(n1x + n2x), n0y = -(n1y + n2y);
+            const double s = cw * tile_rcp(det), mo = MASS ? cmo * det : 0.0;
+            K[0] = fma(n0x * n1x + n0y * n1y, s, mo);
+            K[1] = fma(n0x * n2x + n0y * n2y, s, mo);
+            K[2] = fma(n1x * n2x + n1y * n2y, s, mo);
+        }
+#pragma unroll
+        for (int k = 0; k < NP; ++k) sV[k * NES + e] = K[k];
+        if (MASS) sV[NP * NES + e] = det;
+    }
+    __syncthreads();
+    // ---- every entry of the tile's rows: sum of the contributions of the elements around its edge
+    for (int q = tid; q < nq; q += nthr) {
+        const uint32_t info = einfo[q];
+        const int o = info & 0xffffu, n = (int)(einfo[q + 1] & 0xffffu) - o;
+        double acc = 0.0, accd = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const uint32_t c = codes[o + k];
+            acc += sV[(c & 7u) * NES + (c >> 3)];
+            if (MASS) accd += sV[NP * NES + (c >> 3)];
+        }
+        sE[q] = acc;
+        if (MASS) sD[q] = accd;
+        if (n > 0) {
+            double *dst = out + (size_t)gbase[info >> 24] + ((info >> 16) & 255u);
+            *dst = accumulate ? *dst + acc : acc;
+        }
+    }
+    __syncthreads();
+    // ---- diagonals: K_ii = -sum_{j != i} K_ij (partition of unity); mass: (m_d + DIM m_o) |K| over the star, and the
+    // sum over the row's edges of the determinants around each edge counts every element of the star DIM times
+    for (int l = tid; l < nr; l += nthr) {
+        const uint32_t ri = rinfo[l];
+        const int q0 = ri & 0xffffu, L = ri >> 24;
+        if (L == 0) continue;
+        double s = 0.0, sd = 0.0;
+        for (int k = 0; k < L; ++k) {
+            s += sE[q0 + k];
+            if (MASS) sd += sD[q0 + k];
+        }
+        const double d = MASS ? (cmd + DIM * cmo) * (sd * (1.0 / DIM)) - s : -s;
+        double *dst = out + (size_t)gbase[l] + ((ri >> 16) & 255u);
+        *dst = accumulate ? *dst + d : d;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host: tile set construction
+// ---------------------------------------------------------------------------------------------------------------
+size_t build_shmem()
+{
+    return (size_t)4 * (SORT_CAP + SORT_CAP + NE_CAP + NE_CAP + NV_CAP + TR_CAP * BMW + (TR_CAP + 1) + (NQ_CAP + 1) + (TB_THREADS + 1) +
+                        TR_CAP) + NV_CAP + 64;
+}
+
+// consecutive Morton blocks packed into tiles of <= tr rows; a block larger than tr is cut
+void chunk_rows(const std::vector<uint32_t> &key, int dim, int tr, std::vector<int32_t> &tstart)
+{
+    const int n = (int)key.size();
+    const int nlev = dim == 3 ? 10 : 15;
+    std::vector<int64_t> hist(nlev + 1, 0);
+    for (int i = 1; i < n; ++i) {
+        const uint32_t d = key[i] ^ key[i - 1];
+        if (d) hist[(31 - __builtin_clz(d)) / dim]++;
+    }
+    // nb[l] = number of non-empty blocks at level l (block id = key >> dim*l); the largest l with n/nb <= 1.3 tr
+    int lev = 0;
+    int64_t nb = 1;
+    for (int l = nlev; l >= 0; --l) {
+        if (l < nlev) nb += hist[l];
+        if ((double)n / (double)nb <= 1.3 * tr) {
+            lev = l;
+            break;
+        }
+    }
+    const int sh = dim * lev;
+    tstart.clear();
+    tstart.push_back(0);
+    int cur = 0; // rows in the open tile
+    int i = 0;
+    while (i < n) {
+        int j = i + 1;
+        const uint32_t b = sh >= 32 ? 0u : key[i] >> sh;
+        while (j < n && (sh >= 32 ? 0u : key[j] >> sh) == b) ++j;
+        int len = j - i;
+        if (cur > 0 && cur + len > tr) { // close the open tile
+            tstart.push_back(i);
+            cur = 0;
+        }
+        while (len > tr) { // cut an oversized block
+            i += tr;
+            len -= tr;
+            tstart.push_back(i);
+        }
+        cur += len;
+        i = j;
+    }
+    if (tstart.back() != n) tstart.push_back(n);
+}
+
+void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s)
+{
+    TileSet &T = s->tiles;
+    T.state = -1;
+    ffcuda_mesh *m = s->mesh;
+    const Incidence &I = s->incidence;
+    if (!I.built || !I.ell || s->order != 1 || s->ncomp != 1) return;
+    cudaStream_t st = ctx->stream;
+    const int dim = m->dim, nrows = s->nnodes_owned;
+    if (nrows <= 0) return;
+    const int tr = std::max(8, std::min(TR_CAP, ctx->tile_rows));
+    // ---- Morton order of the rows' vertices
+    DBuf<unsigned long long> box;
+    box.alloc(6);
+    unsigned long long hbox[6] = {~0ull, ~0ull, ~0ull, 0, 0, 0};
+    FF_CUDA(cudaMemcpyAsync(box.p, hbox, sizeof(hbox), cudaMemcpyHostToDevice, st));
+    ff_launch(ctx, "tile_bbox", [&] { k_bbox<<<ctx->sm_count * 2, 256, 0, st>>>(m->xyz.p, m->vstride, dim, nrows, box.p); });
+    FF_CUDA(ff_memcpy_sync(ctx, hbox, box.p, sizeof(hbox), cudaMemcpyDeviceToHost));
+    BoxScale B;
+    const double qmax = dim == 3 ? 1024.0 : 32768.0;
+    for (int x = 0; x < 3; ++x) {
+        B.lo[x] = 0.0;
+        B.sc[x] = 0.0;
+        if (x < dim) {
+            const double lo = unord64(hbox[x]), hi = unord64(hbox[3 + x]);
+            B.lo[x] = lo;
+            B.sc[x] = hi > lo ? qmax * (1.0 - 1e-9) / (hi - lo) : 0.0;
+        }
+    }
+    DBuf<uint32_t> k0, k1;
+    DBuf<int32_t> v0, rord;
+    k0.alloc(nrows); k1.alloc(nrows); v0.alloc(nrows); rord.alloc(nrows);
+    ff_launch(ctx, "tile_morton", [&] { k_morton<<<ff_blocks(nrows, 256), 256, 0, st>>>(m->xyz.p, m->vstride, dim, nrows, B, k0.p, v0.p); });
+    size_t tb = 0;
+    FF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k0.p, k1.p, v0.p, rord.p, nrows, 0, 30, st));
+    DBuf<unsigned char> tmpbuf;
+    tmpbuf.alloc(tb + 16);
+    ctx->launches++;
+    FF_CUDA(cub::DeviceRadixSort::SortPairs(tmpbuf.p, tb, k0.p, k1.p, v0.p, rord.p, nrows, 0, 30, st));
+    std::vector<uint32_t> hkey(nrows);
+    FF_CUDA(ff_memcpy_sync(ctx, hkey.data(), k1.p, (size_t)nrows * 4, cudaMemcpyDeviceToHost));
+    std::vector<int32_t> tstart;
+    chunk_rows(hkey, dim, tr, tstart);
+    // ---- sizes of every tile; tiles that do not fit are halved
+    const size_t shmem = build_shmem();
+    const int NV = dim + 1;
+    auto kstat = NV == 4 ? k_tile_build<4, 0> : k_tile_build<3, 0>;
+    auto kwrite = NV == 4 ? k_tile_build<4, 1> : k_tile_build<3, 1>;
+    FF_CUDA(cudaFuncSetAttribute(kstat, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    FF_CUDA(cudaFuncSetAttribute(kwrite, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    const IncView V = ff_view(I);
+    DBuf<int32_t> d_tstart, d_stats;
+    std::vector<int32_t> hst;
+    int ntiles = 0;
+    for (int round = 0;; ++round) {
+        ntiles = (int)tstart.size() - 1;
+        d_tstart.alloc(tstart.size());
+        d_stats.alloc((size_t)ntiles * 8);
+        FF_CUDA(cudaMemcpyAsync(d_tstart.p, tstart.data(), tstart.size() * 4, cudaMemcpyHostToDevice, st));
+        ff_launch(ctx, "tile_sizes", [&] {
+            kstat<<<ntiles, TB_THREADS, shmem, st>>>(rord.p, d_tstart.p, m->conn.p, V, d_stats.p, nullptr, nullptr);
+        });
+        hst.resize((size_t)ntiles * 8);
+        FF_CUDA(ff_memcpy_sync(ctx, hst.data(), d_stats.p, hst.size() * 4, cudaMemcpyDeviceToHost));
+        std::vector<int32_t> ns;
+        bool split = false;
+        for (int t = 0; t < ntiles; ++t) {
+            ns.push_back(tstart[t]);
+            if (!hst[(size_t)t * 8 + 4]) {
+                const int nr = tstart[t + 1] - tstart[t];
+                if (nr <= 1 || round >= 8) return; // a single row that does not fit: the thread-per-row kernel keeps the space
+                ns.push_back(tstart[t] + nr / 2);
+                split = true;
+            }
+        }
+        ns.push_back(tstart[ntiles]);
+        if (!split) break;
+        tstart.swap(ns);
+    }
+    // ---- offsets, maxima
+    std::vector<uint32_t> htoff((size_t)ntiles + 1);
+    uint64_t off = 0;
+    T.max_rows = T.max_nvt = T.max_nelem = T.max_nq = T.max_ncodes = T.max_words = 0;
+    T.sum_nelem = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        const int32_t *h = &hst[(size_t)t * 8];
+        const int nvt = h[0], nelem = h[1], nq = h[2], ncodes = h[3], nr = h[5];
+        const int words = HDR + pad4(nr) + pad4(nr + 1) + pad4(nvt) + pad4(nelem) + pad4(nq + 1) + pad4((ncodes + 1) / 2);
+        htoff[t] = (uint32_t)off;
+        off += (uint64_t)words;
+        T.max_rows = std::max(T.max_rows, nr); T.max_nvt = std::max(T.max_nvt, nvt); T.max_nelem = std::max(T.max_nelem, nelem);
+        T.max_nq = std::max(T.max_nq, nq); T.max_ncodes = std::max(T.max_ncodes, ncodes); T.max_words = std::max(T.max_words, words);
+        T.sum_nelem += nelem;
+    }
+    if (off >= ((uint64_t)1 << 32)) return;
+    htoff[ntiles] = (uint32_t)off;
+    T.toff.alloc((size_t)ntiles + 1);
+    T.blob.alloc((size_t)off + 4);
+    FF_CUDA(cudaMemcpyAsync(T.toff.p, htoff.data(), htoff.size() * 4, cudaMemcpyHostToDevice, st));
+    ff_launch(ctx, "tile_build", [&] {
+        kwrite<<<ntiles, TB_THREADS, shmem, st>>>(rord.p, d_tstart.p, m->conn.p, V, nullptr, T.toff.p, T.blob.p);
+    });
+    FF_CUDA(cudaStreamSynchronize(st)); // htoff / tstart are host vectors
+    T.tr = tr;
+    T.ntiles = ntiles;
+    T.state = 1;
+    if (getenv("FFCUDA_VERBOSE"))
+        fprintf(stderr, "ffcuda tiles: %d tiles of <= %d rows, max rows %d vertices %d elements %d entries %d codes %d, "
+                        "%.2f evaluations per element, blob %.1f MB\n",
+                ntiles, tr, T.max_rows, T.max_nvt, T.max_nelem, T.max_nq, T.max_ncodes, (double)T.sum_nelem / std::max(1, m->nt),
+                off * 4.0 / 1e6);
+}
+
+} // namespace
+
+bool ff_asm_p1_tiles(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, double cw, double cmd, double cmo, int accumulate)
+{
+    TileSet &T = s->tiles;
+    s->lean_assemblies++;
+    if (ctx->tile_policy == 0 || T.state < 0) return false;
+    if (T.state == 0) {
+        if (ctx->tile_policy == 1 && s->lean_assemblies < 2) return false;
+        build_tiles(ctx, s);
+        if (T.state != 1) return false;
+    }
+    ffcuda_pattern *P = A->pattern;
+    ffcuda_mesh *m = s->mesh;
+    const int dim = m->dim;
+    const bool mass = (cmd != 0.0 || cmo != 0.0);
+    const int NP = dim * (dim + 1) / 2;
+    TileSmem S;
+    size_t o = (size_t)T.max_words * 4;
+    o = (o + 15) & ~(size_t)15;
+    S.gbase = (int)o;
+    o += (size_t)pad4(T.max_rows) * 4;
+    o = (o + 15) & ~(size_t)15;
+    S.coord = (int)o;
+    o += (size_t)std::max(T.max_nvt * dim, T.max_nq + 1) * 8;
+    S.nes = T.max_nelem | 1; // odd stride
+    S.vals = (int)o;
+    o += (size_t)(NP + (mass ? 1 : 0)) * S.nes * 8;
+    S.sd = (int)o;
+    if (mass) o += (size_t)(T.max_nq + 1) * 8;
+    const size_t shmem = o;
+    if (shmem > 200 * 1024) return false;
+    int threads = 256;
+    if (const char *e = getenv("FFCUDA_TILE_THREADS")) threads = std::max(32, std::min(256, atoi(e) & ~31));
+    auto launch = [&](auto kern) {
+        FF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+        ff_launch(ctx, "asm_rows_p1", [&] {
+            kern<<<T.ntiles, threads, shmem, ctx->stream>>>(T.toff.p, T.blob.p, m->xyz.p, P->nrowptr.p, A->vals.p, accumulate, cw, cmd,
+                                                            cmo, S);
+        });
+    };
+    if (dim == 3) {
+        if (mass) launch(k_asm_tiles<3, true>);
+        else launch(k_asm_tiles<3, false>);
+    } else {
+        if (mass) launch(k_asm_tiles<2, true>);
+        else launch(k_asm_tiles<2, false>);
+    }
+    return true;
+}

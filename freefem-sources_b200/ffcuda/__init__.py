@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libffcuda_core.so")
 OP_ID, OP_DX, OP_DY, OP_DZ = 0, 1, 2, 6
 
 # every symbol include/ffcuda.h declares (checked against the header by tests/test_abi.py)
-SYMBOLS = """ffcuda_ctx_create ffcuda_ctx_destroy ffcuda_last_error ffcuda_ctx_sync ffcuda_ctx_set_stream ffcuda_ctx_get_stream
+SYMBOLS = """ffcuda_ctx_create ffcuda_ctx_destroy ffcuda_last_error ffcuda_ctx_sync ffcuda_ctx_set_stream ffcuda_ctx_get_stream ffcuda_ctx_set_option
 ffcuda_prof_enable ffcuda_prof_reset ffcuda_prof_get ffcuda_launch_count ffcuda_mesh_upload ffcuda_mesh_cube ffcuda_mesh_square
 ffcuda_mesh_info ffcuda_mesh_download ffcuda_mesh_destroy ffcuda_space_create ffcuda_space_info ffcuda_space_download_dofs
 ffcuda_space_destroy ffcuda_symbolic ffcuda_pattern_info ffcuda_pattern_download ffcuda_pattern_destroy ffcuda_matrix_create
@@ -140,6 +140,9 @@ class Context(_Handle):
 
     def set_stream(self, cuda_stream):
         _ck(lib().ffcuda_ctx_set_stream(_h(self), C.c_void_p(cuda_stream)), self.h)
+
+    def set_option(self, name, value):
+        _ck(lib().ffcuda_ctx_set_option(_h(self), name.encode(), int(value)), self.h)
 
     def prof_enable(self, on=True):
         _ck(lib().ffcuda_prof_enable(_h(self), int(on)), self.h)
