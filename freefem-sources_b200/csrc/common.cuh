@@ -238,6 +238,7 @@ struct TileSet {
     int tr = 0, ntiles = 0;
     int max_rows = 0, max_nvt = 0, max_nelem = 0, max_nq = 0, max_ncodes = 0, max_words = 0;
     int64_t sum_nelem = 0;    // element evaluations per assembly (diagnostics: redundancy = sum_nelem / nt)
+    int64_t nnz_node = 0;     // of the pattern whose row pointers are baked into the blobs
     DBuf<uint32_t> blob;      // tile descriptors, 16-byte aligned each
     DBuf<uint32_t> toff;      // ntiles+1 offsets into blob in 32-bit words
 };

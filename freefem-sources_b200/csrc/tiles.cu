@@ -29,12 +29,19 @@ constexpr int TB_THREADS = 256;   // build kernel
 constexpr int SORT_CAP = 8192;    // incidence records of a tile's rows / vertex candidates (sort buffer)
 constexpr int NE_CAP = 2048;      // elements per tile
 constexpr int NV_CAP = 256;       // distinct vertices per tile (8-bit slots)
-constexpr int NQ_CAP = 4096;      // matrix entries per tile
+constexpr int NQ_CAP = 4080;      // matrix entries per tile (2*(NQ_CAP+1) ints share the sort buffer)
 constexpr int NC_CAP = 16384;     // contribution codes per tile
 constexpr int TR_CAP = 256;       // rows per tile
 constexpr int BMW = NV_CAP / 32;  // bitmap words per row
 constexpr int HDR = 16;           // header words
-// header: 0 nr, 1 nvt, 2 nelem, 3 nq, 4 ncodes, 5 o_grow, 6 o_rinfo, 7 o_tvert, 8 o_telem, 9 o_einfo, 10 o_codes, 11 words
+// header: 0 nr, 1 nvt, 2 nelem, 3 nq, 4 ncodes (16-bit units, lists padded to even), 5 o_gbase, 6 o_rinfo, 7 o_coord,
+//         8 o_telem, 9 o_einfo, 10 o_codes, 11 words
+// sections: gbase[nr]   int32  index into vals of the first entry of the row (the pattern's row pointer)
+//           rinfo[nr+1] u32    first entry of the row | position of the diagonal << 16 | row length << 24
+//           coord[nvt]  DIM doubles per slot
+//           telem[nelem] u32   4 slot bytes, element-local vertex order
+//           einfo[nq]   u32    offset of the entry's list in code PAIRS | list length << 15 | local row << 20
+//           codes       u16    (element << 3) | vertex pair
 
 __host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
 
@@ -202,8 +209,9 @@ __device__ __forceinline__ int pair_id(int a, int b) // a < b
 template <int NV, int WRITE>
 __global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__restrict__ rord, const int32_t *__restrict__ tstart,
                                                            const int32_t *__restrict__ conn, const IncView V,
-                                                           int32_t *__restrict__ stats, const uint32_t *__restrict__ toff,
-                                                           uint32_t *__restrict__ blob)
+                                                           const double *__restrict__ xyz, int vstride,
+                                                           const int32_t *__restrict__ nrowptr, int32_t *__restrict__ stats,
+                                                           const uint32_t *__restrict__ toff, uint32_t *__restrict__ blob)
 {
     extern __shared__ uint32_t sm[];
     uint32_t *sbuf = sm;                                   // SORT_CAP   sort buffer; later entry offsets / cursors
@@ -319,11 +327,16 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__rest
             }
         }
         __syncthreads();
-        for (int x = tid; x < nq; x += TB_THREADS)
-            if (cntq[x] > 255) s_bad = 1;
+        int *ncnt = reinterpret_cast<int *>(sbuf); // true list lengths (the scanned array holds the padded ones)
+        for (int x = tid; x <= nq; x += TB_THREADS) {
+            const int c = x < nq ? cntq[x] : 0;
+            if (c > 31) s_bad = 1;
+            ncnt[x] = c;
+            cntq[x] = (c + 1) & ~1; // every list starts on a 32-bit boundary
+        }
         __syncthreads();
         ncodes = blk_scan(cntq, nq + 1, part); // cntq[q] = offset of entry q's list, cntq[nq] = ncodes
-        if (ncodes > NC_CAP || ncodes > 65535 || s_bad) fit = 0;
+        if (ncodes > NC_CAP || ncodes > 65534 || s_bad) fit = 0;
     }
     if (!WRITE) {
         if (tid == 0) {
@@ -335,8 +348,10 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__rest
     if (!fit) return; // cannot happen: the host only writes tile sets whose tiles all fit
     // 6. fill the lists (cursor = sbuf), then sort every list: ascending code = ascending element
     uint16_t *codes = reinterpret_cast<uint16_t *>(tmp);
-    int *cursor = reinterpret_cast<int *>(sbuf);
+    int *ncnt = reinterpret_cast<int *>(sbuf);
+    int *cursor = ncnt + NQ_CAP + 1;
     for (int x = tid; x < nq; x += TB_THREADS) cursor[x] = cntq[x];
+    for (int x = tid; x < (ncodes + 1) / 2 * 2; x += TB_THREADS) codes[x] = 0;
     __syncthreads();
     for (int e = tid; e < nelem; e += TB_THREADS) {
         const uint32_t w = telem[e];
@@ -355,7 +370,7 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__rest
     }
     __syncthreads();
     for (int q = tid; q < nq; q += TB_THREADS) {
-        const int o = cntq[q], n = cntq[q + 1] - o;
+        const int o = cntq[q], n = ncnt[q];
         for (int x = 1; x < n; ++x) {
             const uint16_t v = codes[o + x];
             int y = x - 1;
@@ -369,13 +384,14 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__rest
     __syncthreads();
     // 7. the blob
     uint32_t *g = blob + toff[t];
-    const int o_grow = HDR, o_rinfo = o_grow + pad4(nr), o_tvert = o_rinfo + pad4(nr + 1), o_telem = o_tvert + pad4(nvt),
+    constexpr int DIM = NV - 1;
+    const int o_gbase = HDR, o_rinfo = o_gbase + pad4(nr), o_coord = o_rinfo + pad4(nr + 1), o_telem = o_coord + pad4(2 * DIM * nvt),
               o_einfo = o_telem + pad4(nelem), o_codes = o_einfo + pad4(nq + 1), words = o_codes + pad4((ncodes + 1) / 2);
     if (tid == 0) {
-        g[0] = nr; g[1] = nvt; g[2] = nelem; g[3] = nq; g[4] = ncodes; g[5] = o_grow; g[6] = o_rinfo; g[7] = o_tvert;
+        g[0] = nr; g[1] = nvt; g[2] = nelem; g[3] = nq; g[4] = ncodes; g[5] = o_gbase; g[6] = o_rinfo; g[7] = o_coord;
         g[8] = o_telem; g[9] = o_einfo; g[10] = o_codes; g[11] = words; g[12] = g[13] = g[14] = g[15] = 0;
     }
-    for (int l = tid; l < pad4(nr); l += TB_THREADS) g[o_grow + l] = l < nr ? (uint32_t)rord[r0 + l] : 0u;
+    for (int l = tid; l < pad4(nr); l += TB_THREADS) g[o_gbase + l] = l < nr ? (uint32_t)nrowptr[rord[r0 + l]] : 0u;
     for (int l = tid; l < pad4(nr + 1); l += TB_THREADS) {
         uint32_t w = 0;
         if (l < nr) {
@@ -390,12 +406,20 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__rest
             w = (uint32_t)nq;
         g[o_rinfo + l] = w;
     }
-    for (int x = tid; x < pad4(nvt); x += TB_THREADS) g[o_tvert + x] = x < nvt ? vlist[x] : 0u;
+    for (int x = tid; x < pad4(2 * DIM * nvt); x += TB_THREADS) {
+        uint32_t w = 0;
+        if (x < 2 * DIM * nvt) {
+            const int v = x / (2 * DIM), c = (x % (2 * DIM)) >> 1;
+            const unsigned long long b = (unsigned long long)__double_as_longlong(xyz[(size_t)vlist[v] * vstride + c]);
+            w = (x & 1) ? (uint32_t)(b >> 32) : (uint32_t)b;
+        }
+        g[o_coord + x] = w;
+    }
     for (int x = tid; x < pad4(nelem); x += TB_THREADS) g[o_telem + x] = x < nelem ? telem[x] : 0u;
-    // entry words: offset of the list | position in the row << 16 | local row << 24
+    // entry words: offset of the list in code pairs | list length << 15 | local row << 20
     for (int l = tid; l < nr; l += TB_THREADS)
-        for (int q = rowq[l]; q < rowq[l + 1]; ++q) g[o_einfo + q] = (uint32_t)cntq[q] | ((uint32_t)(q - rowq[l]) << 16) | ((uint32_t)l << 24);
-    for (int x = nq + tid; x < pad4(nq + 1); x += TB_THREADS) g[o_einfo + x] = (uint32_t)ncodes;
+        for (int q = rowq[l]; q < rowq[l + 1]; ++q) g[o_einfo + q] = (uint32_t)(cntq[q] >> 1) | ((uint32_t)ncnt[q] << 15) | ((uint32_t)l << 20);
+    for (int x = nq + tid; x < pad4(nq + 1); x += TB_THREADS) g[o_einfo + x] = 0u;
     const int cw = pad4((ncodes + 1) / 2);
     for (int x = tid; x < cw; x += TB_THREADS) {
         const uint32_t lo = 2 * x < ncodes ? codes[2 * x] : 0u, hi = 2 * x + 1 < ncodes ? codes[2 * x + 1] : 0u;
@@ -416,125 +440,147 @@ __device__ __forceinline__ double tile_rcp(double d) // ~1 ulp reciprocal: hardw
     return fma(r, t, r);
 }
 
-struct TileSmem { // byte offsets of the shared-memory regions
-    int gbase, coord, vals, sd, nes;
+struct TileSmem { // byte offsets of the shared-memory regions behind the two blob buffers
+    int buf1, ent, vals, sd, nes;
 };
 
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// Persistent CTAs: tile t, t + grid, ...  The descriptor blob of the NEXT tile is brought in by one TMA bulk copy
+// (cp.async.bulk, completion on an mbarrier) while the current tile is computed: no thread ever waits on a global load
+// in the steady state.
 template <int DIM, bool MASS>
-__global__ void __launch_bounds__(256) k_asm_tiles(const uint32_t *__restrict__ toff, const uint32_t *__restrict__ blob,
-                                                   const double *__restrict__ xyz, const int32_t *__restrict__ nrowptr,
+__global__ void __launch_bounds__(512) k_asm_tiles(const uint32_t *__restrict__ toff, const uint32_t *__restrict__ blob, int ntiles,
                                                    double *__restrict__ out, int accumulate, double cw, double cmd, double cmo,
                                                    const TileSmem S)
 {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int NV = DIM + 1, NP = DIM * (DIM + 1) / 2;
-    uint32_t *sb = reinterpret_cast<uint32_t *>(smem_raw);
-    int *gbase = reinterpret_cast<int *>(smem_raw + S.gbase);
-    double *coord = reinterpret_cast<double *>(smem_raw + S.coord); // [slot][DIM]; re-used for the entry sums
-    double *sE = coord;
-    double *sV = reinterpret_cast<double *>(smem_raw + S.vals);     // [pair][NES] (+ [NP][NES] = det when MASS)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    constexpr int NP = DIM * (DIM + 1) / 2;
+    double *sE = reinterpret_cast<double *>(smem_raw + S.ent);  // off-diagonal sums of the tile's entries
+    double *sV = reinterpret_cast<double *>(smem_raw + S.vals); // [pair][NES] (+ [NP][NES] = det when MASS)
     double *sD = reinterpret_cast<double *>(smem_raw + S.sd);
     const int NES = S.nes;
     const int tid = threadIdx.x, nthr = blockDim.x;
-    const uint32_t w0 = toff[blockIdx.x];
-    const int nw4 = (int)((toff[blockIdx.x + 1] - w0) >> 2);
-    {
-        const uint4 *g = reinterpret_cast<const uint4 *>(blob + w0);
-        uint4 *d = reinterpret_cast<uint4 *>(sb);
-        for (int i = tid; i < nw4; i += nthr) d[i] = __ldcs(g + i);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[0])));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[1])));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    const int nr = sb[0], nvt = sb[1], nelem = sb[2], nq = sb[3];
-    const int32_t *grow = reinterpret_cast<const int32_t *>(sb + sb[5]);
-    const uint32_t *rinfo = sb + sb[6];
-    const int32_t *tvert = reinterpret_cast<const int32_t *>(sb + sb[7]);
-    const uint32_t *telem = sb + sb[8];
-    const uint32_t *einfo = sb + sb[9];
-    const uint16_t *codes = reinterpret_cast<const uint16_t *>(sb + sb[10]);
-    for (int l = tid; l < nr; l += nthr) gbase[l] = __ldg(nrowptr + grow[l]);
-    for (int v = tid; v < nvt; v += nthr) {
-        const int id = tvert[v];
-        if (DIM == 3) {
-            double4 p;
-            asm("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(p.x), "=d"(p.y), "=d"(p.z), "=d"(p.w) : "l"(xyz + 4 * (size_t)id));
-            coord[3 * v] = p.x; coord[3 * v + 1] = p.y; coord[3 * v + 2] = p.z;
-        } else {
-            const double2 p = __ldg(reinterpret_cast<const double2 *>(xyz) + id);
-            coord[2 * v] = p.x; coord[2 * v + 1] = p.y;
+    auto issue = [&](int b, int t) { // one thread: bulk copy of tile t's blob into buffer b
+        const uint32_t w0 = __ldg(toff + t), bytes = (__ldg(toff + t + 1) - w0) * 4u;
+        const uint32_t bar = smem_u32(&mbar[b]), dst = smem_u32(smem_raw + (b ? S.buf1 : 0));
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                     "l"(blob + w0), "r"(bytes), "r"(bar)
+                     : "memory");
+    };
+    int t = blockIdx.x, b = 0;
+    uint32_t ph0 = 0, ph1 = 0;
+    if (tid == 0 && t < ntiles) issue(0, t);
+    for (; t < ntiles; t += gridDim.x, b ^= 1) {
+        if (tid == 0 && t + (int)gridDim.x < ntiles) issue(b ^ 1, t + gridDim.x); // that buffer was released by the last barrier
+        {
+            const uint32_t bar = smem_u32(&mbar[b]), ph = b ? ph1 : ph0;
+            uint32_t done = 0;
+            while (!done)
+                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(done)
+                             : "r"(bar), "r"(ph)
+                             : "memory");
+            if (b) ph1 ^= 1;
+            else ph0 ^= 1;
         }
-    }
-    __syncthreads();
-    // ---- every element of the tile once: off-diagonal entries of its element matrix (+ its determinant)
-    for (int e = tid; e < nelem; e += nthr) {
-        const uint32_t w = telem[e];
-        const double *p0 = coord + DIM * (w & 255u), *p1 = coord + DIM * ((w >> 8) & 255u), *p2 = coord + DIM * ((w >> 16) & 255u);
-        double K[NP], det;
-        if (DIM == 3) {
-            const double *p3 = coord + DIM * (w >> 24);
-            const double x0 = p0[0], y0 = p0[1], z0 = p0[DIM - 1];
-            const double ax = p1[0] - x0, ay = p1[1] - y0, az = p1[DIM - 1] - z0;
-            const double bx = p2[0] - x0, by = p2[1] - y0, bz = p2[DIM - 1] - z0;
-            const double cx = p3[0] - x0, cy = p3[1] - y0, cz = p3[DIM - 1] - z0;
-            // N1 = b x c, N2 = c x a, N3 = a x b, det = a . N1, N0 = -(N1 + N2 + N3)   (Mesh3dn.hpp:126-136)
-            const double n1x = by * cz - bz * cy, n1y = bz * cx - bx * cz, n1z = bx * cy - by * cx;
-            const double n2x = cy * az - cz * ay, n2y = cz * ax - cx * az, n2z = cx * ay - cy * ax;
-            const double n3x = ay * bz - az * by, n3y = az * bx - ax * bz, n3z = ax * by - ay * bx;
-            det = ax * n1x + ay * n1y + az * n1z;
-            const double n0x = -(n1x + n2x + n3x), n0y = -(n1y + n2y + n3y), n0z = -(n1z + n2z + n3z);
-            const double s = cw * tile_rcp(det), mo = MASS ? cmo * det : 0.0;
-            K[0] = fma(n0x * n1x + n0y * n1y + n0z * n1z, s, mo);
-            K[1] = fma(n0x * n2x + n0y * n2y + n0z * n2z, s, mo);
-            K[2] = fma(n0x * n3x + n0y * n3y + n0z * n3z, s, mo);
-            K[3 % NP] = fma(n1x * n2x + n1y * n2y + n1z * n2z, s, mo);
-            K[4 % NP] = fma(n1x * n3x + n1y * n3y + n1z * n3z, s, mo);
-            K[5 % NP] = fma(n2x * n3x + n2y * n3y + n2z * n3z, s, mo);
-        } else {
-            const double x0 = p0[0], y0 = p0[1];
-            const double bx = p1[0] - x0, by = p1[1] - y0, cx = p2[0] - x0, cy = p2[1] - y0;
-            det = bx * cy - by * cx; // N1 = (cy, -cx), N2 = (-by, bx), N0 = -(N1 + N2)   (fem.hpp:321-324)
-            const double n1x = cy, n1y = -cx, n2x = -by, n2y = bx, n0x = -(n1x + n2x), n0y = -(n1y + n2y);
-            const double s = cw * tile_rcp(det), mo = MASS ? cmo * det : 0.0;
-            K[0] = fma(n0x * n1x + n0y * n1y, s, mo);
-            K[1] = fma(n0x * n2x + n0y * n2y, s, mo);
-            K[2] = fma(n1x * n2x + n1y * n2y, s, mo);
-        }
+        const uint32_t *sb = reinterpret_cast<const uint32_t *>(smem_raw + (b ? S.buf1 : 0));
+        const int nr = sb[0], nelem = sb[2], nq = sb[3];
+        const int32_t *gbase = reinterpret_cast<const int32_t *>(sb + sb[5]);
+        const uint32_t *rinfo = sb + sb[6];
+        const double *coord = reinterpret_cast<const double *>(sb + sb[7]);
+        const uint32_t *telem = sb + sb[8];
+        const uint32_t *einfo = sb + sb[9];
+        const uint32_t *codes2 = sb + sb[10];
+        // ---- every element of the tile once: off-diagonal entries of its element matrix (+ its determinant)
+        for (int e = tid; e < nelem; e += nthr) {
+            const uint32_t w = telem[e];
+            const double *p0 = coord + DIM * (w & 255u), *p1 = coord + DIM * ((w >> 8) & 255u), *p2 = coord + DIM * ((w >> 16) & 255u);
+            double K[NP], det;
+            if (DIM == 3) {
+                const double *p3 = coord + DIM * (w >> 24);
+                const double x0 = p0[0], y0 = p0[1], z0 = p0[DIM - 1];
+                const double ax = p1[0] - x0, ay = p1[1] - y0, az = p1[DIM - 1] - z0;
+                const double bx = p2[0] - x0, by = p2[1] - y0, bz = p2[DIM - 1] - z0;
+                const double cx = p3[0] - x0, cy = p3[1] - y0, cz = p3[DIM - 1] - z0;
+                // N1 = b x c, N2 = c x a, N3 = a x b, det = a . N1, N0 = -(N1 + N2 + N3)   (Mesh3dn.hpp:126-136)
+                const double n1x = by * cz - bz * cy, n1y = bz * cx - bx * cz, n1z = bx * cy - by * cx;
+                const double n2x = cy * az - cz * ay, n2y = cz * ax - cx * az, n2z = cx * ay - cy * ax;
+                const double n3x = ay * bz - az * by, n3y = az * bx - ax * bz, n3z = ax * by - ay * bx;
+                det = ax * n1x + ay * n1y + az * n1z;
+                const double n0x = -(n1x + n2x + n3x), n0y = -(n1y + n2y + n3y), n0z = -(n1z + n2z + n3z);
+                const double s = cw * tile_rcp(det), mo = MASS ? cmo * det : 0.0;
+                K[0] = fma(n0x * n1x + n0y * n1y + n0z * n1z, s, mo);
+                K[1] = fma(n0x * n2x + n0y * n2y + n0z * n2z, s, mo);
+                K[2] = fma(n0x * n3x + n0y * n3y + n0z * n3z, s, mo);
+                K[3 % NP] = fma(n1x * n2x + n1y * n2y + n1z * n2z, s, mo);
+                K[4 % NP] = fma(n1x * n3x + n1y * n3y + n1z * n3z, s, mo);
+                K[5 % NP] = fma(n2x * n3x + n2y * n3y + n2z * n3z, s, mo);
+            } else {
+                const double x0 = p0[0], y0 = p0[1];
+                const double bx = p1[0] - x0, by = p1[1] - y0, cx = p2[0] - x0, cy = p2[1] - y0;
+                det = bx * cy - by * cx; // N1 = (cy, -cx), N2 = (-by, bx), N0 = -(N1 + N2)   (fem.hpp:321-324)
+                const double n1x = cy, n1y = -cx, n2x = -by, n2y = bx, n0x = -(n1x + n2x), n0y = -(n1y + n2y);
+                const double s = cw * tile_rcp(det), mo = MASS ? cmo * det : 0.0;
+                K[0] = fma(n0x * n1x + n0y * n1y, s, mo);
+                K[1] = fma(n0x * n2x + n0y * n2y, s, mo);
+                K[2] = fma(n1x * n2x + n1y * n2y, s, mo);
+            }
 #pragma unroll
-        for (int k = 0; k < NP; ++k) sV[k * NES + e] = K[k];
-        if (MASS) sV[NP * NES + e] = det;
-    }
-    __syncthreads();
-    // ---- every entry of the tile's rows: sum of the contributions of the elements around its edge
-    for (int q = tid; q < nq; q += nthr) {
-        const uint32_t info = einfo[q];
-        const int o = info & 0xffffu, n = (int)(einfo[q + 1] & 0xffffu) - o;
-        double acc = 0.0, accd = 0.0;
-        for (int k = 0; k < n; ++k) {
-            const uint32_t c = codes[o + k];
-            acc += sV[(c & 7u) * NES + (c >> 3)];
-            if (MASS) accd += sV[NP * NES + (c >> 3)];
+            for (int k = 0; k < NP; ++k) sV[k * NES + e] = K[k];
+            if (MASS) sV[NP * NES + e] = det;
         }
-        sE[q] = acc;
-        if (MASS) sD[q] = accd;
-        if (n > 0) {
-            double *dst = out + (size_t)gbase[info >> 24] + ((info >> 16) & 255u);
-            *dst = accumulate ? *dst + acc : acc;
+        __syncthreads();
+        // ---- every entry of the tile's rows: sum of the contributions of the elements around its edge, in a register
+        for (int q = tid; q < nq; q += nthr) {
+            const uint32_t info = einfo[q];
+            const int n = (info >> 15) & 31u;
+            const uint32_t *cp = codes2 + (info & 0x7fffu);
+            double acc = 0.0, accd = 0.0;
+#pragma unroll 1
+            for (int k = 0; k < n; k += 2) {
+                const uint32_t c2 = *cp++;
+                const uint32_t c0 = c2 & 0xffffu, c1 = c2 >> 16;
+                acc += sV[(c0 & 7u) * NES + (c0 >> 3)];
+                if (MASS) accd += sV[NP * NES + (c0 >> 3)];
+                if (k + 1 < n) {
+                    acc += sV[(c1 & 7u) * NES + (c1 >> 3)];
+                    if (MASS) accd += sV[NP * NES + (c1 >> 3)];
+                }
+            }
+            sE[q] = acc;
+            if (MASS) sD[q] = accd;
+            if (n > 0) {
+                const int l = (info >> 20) & 255u;
+                double *dst = out + (size_t)gbase[l] + (q - (int)(rinfo[l] & 0xffffu));
+                *dst = accumulate ? *dst + acc : acc;
+            }
         }
-    }
-    __syncthreads();
-    // ---- diagonals: K_ii = -sum_{j != i} K_ij (partition of unity); mass: (m_d + DIM m_o) |K| over the star, and the
-    // sum over the row's edges of the determinants around each edge counts every element of the star DIM times
-    for (int l = tid; l < nr; l += nthr) {
-        const uint32_t ri = rinfo[l];
-        const int q0 = ri & 0xffffu, L = ri >> 24;
-        if (L == 0) continue;
-        double s = 0.0, sd = 0.0;
-        for (int k = 0; k < L; ++k) {
-            s += sE[q0 + k];
-            if (MASS) sd += sD[q0 + k];
+        __syncthreads();
+        // ---- diagonals: K_ii = -sum_{j != i} K_ij (partition of unity); mass: (m_d + DIM m_o) |K| over the star, and the
+        // sum over the row's edges of the determinants around each edge counts every element of the star DIM times
+        for (int l = tid; l < nr; l += nthr) {
+            const uint32_t ri = rinfo[l];
+            const int q0 = ri & 0xffffu, L = ri >> 24;
+            if (L == 0) continue;
+            double s = 0.0, sd = 0.0;
+            for (int k = 0; k < L; ++k) {
+                s += sE[q0 + k];
+                if (MASS) sd += sD[q0 + k];
+            }
+            const double d = MASS ? (cmd + DIM * cmo) * (sd * (1.0 / DIM)) - s : -s;
+            double *dst = out + (size_t)gbase[l] + ((ri >> 16) & 255u);
+            *dst = accumulate ? *dst + d : d;
         }
-        const double d = MASS ? (cmd + DIM * cmo) * (sd * (1.0 / DIM)) - s : -s;
-        double *dst = out + (size_t)gbase[l] + ((ri >> 16) & 255u);
-        *dst = accumulate ? *dst + d : d;
+        __syncthreads(); // buffer b, sV and sE are free again
     }
 }
 
@@ -592,7 +638,7 @@ void chunk_rows(const std::vector<uint32_t> &key, int dim, int tr, std::vector<i
     if (tstart.back() != n) tstart.push_back(n);
 }
 
-void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s)
+void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr)
 {
     TileSet &T = s->tiles;
     T.state = -1;
@@ -652,7 +698,8 @@ void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s)
         d_stats.alloc((size_t)ntiles * 8);
         FF_CUDA(cudaMemcpyAsync(d_tstart.p, tstart.data(), tstart.size() * 4, cudaMemcpyHostToDevice, st));
         ff_launch(ctx, "tile_sizes", [&] {
-            kstat<<<ntiles, TB_THREADS, shmem, st>>>(rord.p, d_tstart.p, m->conn.p, V, d_stats.p, nullptr, nullptr);
+            kstat<<<ntiles, TB_THREADS, shmem, st>>>(rord.p, d_tstart.p, m->conn.p, V, m->xyz.p, m->vstride, nrowptr, d_stats.p, nullptr,
+                                                     nullptr);
         });
         hst.resize((size_t)ntiles * 8);
         FF_CUDA(ff_memcpy_sync(ctx, hst.data(), d_stats.p, hst.size() * 4, cudaMemcpyDeviceToHost));
@@ -679,7 +726,7 @@ void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s)
     for (int t = 0; t < ntiles; ++t) {
         const int32_t *h = &hst[(size_t)t * 8];
         const int nvt = h[0], nelem = h[1], nq = h[2], ncodes = h[3], nr = h[5];
-        const int words = HDR + pad4(nr) + pad4(nr + 1) + pad4(nvt) + pad4(nelem) + pad4(nq + 1) + pad4((ncodes + 1) / 2);
+        const int words = HDR + pad4(nr) + pad4(nr + 1) + pad4(2 * dim * nvt) + pad4(nelem) + pad4(nq + 1) + pad4((ncodes + 1) / 2);
         htoff[t] = (uint32_t)off;
         off += (uint64_t)words;
         T.max_rows = std::max(T.max_rows, nr); T.max_nvt = std::max(T.max_nvt, nvt); T.max_nelem = std::max(T.max_nelem, nelem);
@@ -692,7 +739,8 @@ void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s)
     T.blob.alloc((size_t)off + 4);
     FF_CUDA(cudaMemcpyAsync(T.toff.p, htoff.data(), htoff.size() * 4, cudaMemcpyHostToDevice, st));
     ff_launch(ctx, "tile_build", [&] {
-        kwrite<<<ntiles, TB_THREADS, shmem, st>>>(rord.p, d_tstart.p, m->conn.p, V, nullptr, T.toff.p, T.blob.p);
+        kwrite<<<ntiles, TB_THREADS, shmem, st>>>(rord.p, d_tstart.p, m->conn.p, V, m->xyz.p, m->vstride, nrowptr, nullptr, T.toff.p,
+                                                  T.blob.p);
     });
     FF_CUDA(cudaStreamSynchronize(st)); // htoff / tstart are host vectors
     T.tr = tr;
@@ -710,26 +758,26 @@ void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s)
 bool ff_asm_p1_tiles(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, double cw, double cmd, double cmo, int accumulate)
 {
     TileSet &T = s->tiles;
+    ffcuda_pattern *P = A->pattern;
     s->lean_assemblies++;
     if (ctx->tile_policy == 0 || T.state < 0) return false;
     if (T.state == 0) {
         if (ctx->tile_policy == 1 && s->lean_assemblies < 2) return false;
-        build_tiles(ctx, s);
+        build_tiles(ctx, s, P->nrowptr.p); // the row pointers are baked in: every pattern of a fespace has the same ones
         if (T.state != 1) return false;
+        T.nnz_node = P->nnz_node;
     }
-    ffcuda_pattern *P = A->pattern;
+    FF_REQUIRE(T.nnz_node == P->nnz_node, "internal: tile set and pattern disagree");
     ffcuda_mesh *m = s->mesh;
     const int dim = m->dim;
     const bool mass = (cmd != 0.0 || cmo != 0.0);
     const int NP = dim * (dim + 1) / 2;
     TileSmem S;
-    size_t o = (size_t)T.max_words * 4;
-    o = (o + 15) & ~(size_t)15;
-    S.gbase = (int)o;
-    o += (size_t)pad4(T.max_rows) * 4;
-    o = (o + 15) & ~(size_t)15;
-    S.coord = (int)o;
-    o += (size_t)std::max(T.max_nvt * dim, T.max_nq + 1) * 8;
+    size_t o = ((size_t)T.max_words * 4 + 127) & ~(size_t)127;
+    S.buf1 = (int)o;
+    o *= 2;
+    S.ent = (int)o;
+    o += (size_t)(T.max_nq + 1) * 8;
     S.nes = T.max_nelem | 1; // odd stride
     S.vals = (int)o;
     o += (size_t)(NP + (mass ? 1 : 0)) * S.nes * 8;
@@ -738,12 +786,14 @@ bool ff_asm_p1_tiles(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, double 
     const size_t shmem = o;
     if (shmem > 200 * 1024) return false;
     int threads = 256;
-    if (const char *e = getenv("FFCUDA_TILE_THREADS")) threads = std::max(32, std::min(256, atoi(e) & ~31));
+    if (const char *e = getenv("FFCUDA_TILE_THREADS")) threads = std::max(32, std::min(512, atoi(e) & ~31));
     auto launch = [&](auto kern) {
         FF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+        int per_sm = 1;
+        FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, shmem));
+        const int grid = std::max(1, std::min(T.ntiles, std::max(1, per_sm) * ctx->sm_count));
         ff_launch(ctx, "asm_rows_p1", [&] {
-            kern<<<T.ntiles, threads, shmem, ctx->stream>>>(T.toff.p, T.blob.p, m->xyz.p, P->nrowptr.p, A->vals.p, accumulate, cw, cmd,
-                                                            cmo, S);
+            kern<<<grid, threads, shmem, ctx->stream>>>(T.toff.p, T.blob.p, T.ntiles, A->vals.p, accumulate, cw, cmd, cmo, S);
         });
     };
     if (dim == 3) {

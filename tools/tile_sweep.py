@@ -39,7 +39,7 @@ def run(policy, rows, threads, terms, tag):
 
 run(0, 64, 256, LAP, "poisson thread-per-row")
 for rows in (32, 48, 64, 96, 128):
-    for threads in (128, 256):
+    for threads in (256, 512):
         run(2, rows, threads, LAP, "poisson tiles")
 run(0, 64, 256, HEAT, "heat thread-per-row")
 run(2, 64, 256, HEAT, "heat tiles")
