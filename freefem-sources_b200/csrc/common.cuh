@@ -236,6 +236,7 @@ static inline IncView ff_view(const Incidence &I) { return IncView{I.cnt.p, I.in
 struct TileSet {
     int state = 0;            // 0 not built, 1 ready, -1 not applicable (some tile exceeds the kernel's capacities)
     int tr = 0, ntiles = 0;
+    int nes = 0;              // stride of the numeric kernel's value table (max_nelem | 1), baked into the codes
     int max_rows = 0, max_nvt = 0, max_nelem = 0, max_nq = 0, max_ncodes = 0, max_words = 0;
     int64_t sum_nelem = 0;    // element evaluations per assembly (diagnostics: redundancy = sum_nelem / nt)
     int64_t nnz_node = 0;     // of the pattern whose row pointers are baked into the blobs

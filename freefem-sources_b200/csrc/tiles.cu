@@ -41,9 +41,10 @@ constexpr int HDR = 16;           // header words
 //           coord[nvt]  DIM doubles per slot
 //           telem[nelem] u32   4 slot bytes, element-local vertex order
 //           einfo[nq]   u32    offset of the entry's list in code PAIRS | list length << 15 | local row << 20
-//           codes       u16    (element << 3) | vertex pair
+//           codes       u16    pair * nes + element: index into the numeric kernel's value table (nes: TileSet::nes)
 
 __host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
+#define DIM_PAIRS(d) ((d) * ((d) + 1) / 2)
 
 // ---------------------------------------------------------------------------------------------------------------
 // Morton keys
@@ -210,8 +211,9 @@ template <int NV, int WRITE>
 __global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__restrict__ rord, const int32_t *__restrict__ tstart,
                                                            const int32_t *__restrict__ conn, const IncView V,
                                                            const double *__restrict__ xyz, int vstride,
-                                                           const int32_t *__restrict__ nrowptr, int32_t *__restrict__ stats,
-                                                           const uint32_t *__restrict__ toff, uint32_t *__restrict__ blob)
+                                                           const int32_t *__restrict__ nrowptr, int nes,
+                                                           int32_t *__restrict__ stats, const uint32_t *__restrict__ toff,
+                                                           uint32_t *__restrict__ blob)
 {
     extern __shared__ uint32_t sm[];
     uint32_t *sbuf = sm;                                   // SORT_CAP   sort buffer; later entry offsets / cursors
@@ -382,6 +384,43 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__rest
         }
     }
     __syncthreads();
+    // The order inside a list is free (any fixed order is reproducible).  The numeric kernel reads the k-th value of 16
+    // consecutive entries in one shared-memory wavefront (64-bit accesses: half a warp at a time), so the lists of every
+    // group of 16 entries are re-ordered greedily to put the k-th values of the group in distinct banks.
+    for (int gq = tid * 16; gq < nq; gq += TB_THREADS * 16) {
+        int maxn = 0;
+        for (int j = 0; j < 16 && gq + j < nq; ++j) maxn = max(maxn, ncnt[gq + j]);
+        for (int k = 0; k < maxn; ++k) {
+            uint32_t used = 0;
+            for (int j = 0; j < 16 && gq + j < nq; ++j) {
+                const int q = gq + j, n = ncnt[q], o = cntq[q];
+                if (k >= n) continue;
+                int best = k;
+                for (int x = k; x < n; ++x) {
+                    const uint32_t c = codes[o + x];
+                    const uint32_t bank = ((c & 7u) * nes + (c >> 3)) & 15u;
+                    if (!((used >> bank) & 1u)) {
+                        best = x;
+                        break;
+                    }
+                }
+                const uint16_t c = codes[o + best];
+                codes[o + best] = codes[o + k];
+                codes[o + k] = c;
+                used |= 1u << ((((uint32_t)c & 7u) * nes + ((uint32_t)c >> 3)) & 15u);
+            }
+        }
+    }
+    __syncthreads();
+    // (element << 3 | pair) -> index of the value in the numeric kernel's [pair][nes] table
+    for (int q = tid; q < nq; q += TB_THREADS) {
+        const int o = cntq[q], n = ncnt[q];
+        for (int x = 0; x < n; ++x) {
+            const uint32_t c = codes[o + x];
+            codes[o + x] = (uint16_t)((c & 7u) * nes + (c >> 3));
+        }
+    }
+    __syncthreads();
     // 7. the blob
     uint32_t *g = blob + toff[t];
     constexpr int DIM = NV - 1;
@@ -461,6 +500,7 @@ __global__ void __launch_bounds__(512) k_asm_tiles(const uint32_t *__restrict__ 
     double *sV = reinterpret_cast<double *>(smem_raw + S.vals); // [pair][NES] (+ [NP][NES] = det when MASS)
     double *sD = reinterpret_cast<double *>(smem_raw + S.sd);
     const int NES = S.nes;
+    const float inv_nes = 1.0f / (float)NES;
     const int tid = threadIdx.x, nthr = blockDim.x;
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[0])));
@@ -549,11 +589,12 @@ __global__ void __launch_bounds__(512) k_asm_tiles(const uint32_t *__restrict__ 
             for (int k = 0; k < n; k += 2) {
                 const uint32_t c2 = *cp++;
                 const uint32_t c0 = c2 & 0xffffu, c1 = c2 >> 16;
-                acc += sV[(c0 & 7u) * NES + (c0 >> 3)];
-                if (MASS) accd += sV[NP * NES + (c0 >> 3)];
+                acc += sV[c0];
+                // element of a code = code mod NES: exact through a float reciprocal at these magnitudes (< 2^14)
+                if (MASS) accd += sV[NP * NES + ((int)c0 - __float2int_rz(((float)c0 + 0.5f) * inv_nes) * NES)];
                 if (k + 1 < n) {
-                    acc += sV[(c1 & 7u) * NES + (c1 >> 3)];
-                    if (MASS) accd += sV[NP * NES + (c1 >> 3)];
+                    acc += sV[c1];
+                    if (MASS) accd += sV[NP * NES + ((int)c1 - __float2int_rz(((float)c1 + 0.5f) * inv_nes) * NES)];
                 }
             }
             sE[q] = acc;
@@ -698,8 +739,8 @@ void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr)
         d_stats.alloc((size_t)ntiles * 8);
         FF_CUDA(cudaMemcpyAsync(d_tstart.p, tstart.data(), tstart.size() * 4, cudaMemcpyHostToDevice, st));
         ff_launch(ctx, "tile_sizes", [&] {
-            kstat<<<ntiles, TB_THREADS, shmem, st>>>(rord.p, d_tstart.p, m->conn.p, V, m->xyz.p, m->vstride, nrowptr, d_stats.p, nullptr,
-                                                     nullptr);
+            kstat<<<ntiles, TB_THREADS, shmem, st>>>(rord.p, d_tstart.p, m->conn.p, V, m->xyz.p, m->vstride, nrowptr, 1, d_stats.p,
+                                                     nullptr, nullptr);
         });
         hst.resize((size_t)ntiles * 8);
         FF_CUDA(ff_memcpy_sync(ctx, hst.data(), d_stats.p, hst.size() * 4, cudaMemcpyDeviceToHost));
@@ -734,13 +775,15 @@ void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr)
         T.sum_nelem += nelem;
     }
     if (off >= ((uint64_t)1 << 32)) return;
+    T.nes = T.max_nelem | 1; // odd stride of the value table
+    if ((DIM_PAIRS(dim) + 1) * T.nes > 65535) return;
     htoff[ntiles] = (uint32_t)off;
     T.toff.alloc((size_t)ntiles + 1);
     T.blob.alloc((size_t)off + 4);
     FF_CUDA(cudaMemcpyAsync(T.toff.p, htoff.data(), htoff.size() * 4, cudaMemcpyHostToDevice, st));
     ff_launch(ctx, "tile_build", [&] {
-        kwrite<<<ntiles, TB_THREADS, shmem, st>>>(rord.p, d_tstart.p, m->conn.p, V, m->xyz.p, m->vstride, nrowptr, nullptr, T.toff.p,
-                                                  T.blob.p);
+        kwrite<<<ntiles, TB_THREADS, shmem, st>>>(rord.p, d_tstart.p, m->conn.p, V, m->xyz.p, m->vstride, nrowptr, T.nes, nullptr,
+                                                  T.toff.p, T.blob.p);
     });
     FF_CUDA(cudaStreamSynchronize(st)); // htoff / tstart are host vectors
     T.tr = tr;
@@ -778,7 +821,8 @@ bool ff_asm_p1_tiles(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, double 
     o *= 2;
     S.ent = (int)o;
     o += (size_t)(T.max_nq + 1) * 8;
-    S.nes = T.max_nelem | 1; // odd stride
+    S.nes = T.nes;
+    o = (o + 127) & ~(size_t)127; // the bank of a value is its index mod 16 (the build kernel orders the lists by it)
     S.vals = (int)o;
     o += (size_t)(NP + (mass ? 1 : 0)) * S.nes * 8;
     S.sd = (int)o;
