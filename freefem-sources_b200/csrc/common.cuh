@@ -65,7 +65,7 @@ struct ffcuda_ctx {
     int64_t launches = 0;
     int sm_count = 148;
     int tile_policy = 1;        // 0: never use row tiles, 1: from the second assembly on a fespace, 2: always
-    int tile_rows = 64;         // rows per tile
+    int tile_rows = 96;         // rows per tile
     // reduction scratch (device) + pinned host mirror
     double *d_scal = nullptr;   // small array of device scalars
     double *h_scal = nullptr;   // pinned

@@ -804,6 +804,9 @@ bool ff_asm_p1_tiles(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, double 
     ffcuda_pattern *P = A->pattern;
     s->lean_assemblies++;
     if (ctx->tile_policy == 0 || T.state < 0) return false;
+    // forms with a mass term need the determinants around every edge as a second sum: measured slower than the
+    // thread-per-row kernel (569 vs 496 us on cube(128)), so they stay there unless tiles are forced (policy 2)
+    if ((cmd != 0.0 || cmo != 0.0) && ctx->tile_policy != 2) return false;
     if (T.state == 0) {
         if (ctx->tile_policy == 1 && s->lean_assemblies < 2) return false;
         build_tiles(ctx, s, P->nrowptr.p); // the row pointers are baked in: every pattern of a fespace has the same ones
@@ -829,7 +832,7 @@ bool ff_asm_p1_tiles(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, double 
     if (mass) o += (size_t)(T.max_nq + 1) * 8;
     const size_t shmem = o;
     if (shmem > 200 * 1024) return false;
-    int threads = 256;
+    int threads = 512;
     if (const char *e = getenv("FFCUDA_TILE_THREADS")) threads = std::max(32, std::min(512, atoi(e) & ~31));
     auto launch = [&](auto kern) {
         FF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));

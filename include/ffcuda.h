@@ -64,7 +64,7 @@ void *ffcuda_ctx_get_stream(ffcuda_ctx *ctx);
 /* tuning knobs (never change results beyond round-off; FreeFEM has no counterpart).  "tile_policy": 0 = scalar P1
  * forms are assembled by the thread-per-row kernel, 1 (default) = by row tiles from the second assembly on the same
  * fespace (the tile set is built once per fespace), 2 = always by row tiles.  "tile_rows": rows per tile (8..256,
- * default 64); takes effect for fespaces whose tile set is not built yet. */
+ * default 96); takes effect for fespaces whose tile set is not built yet. */
 int ffcuda_ctx_set_option(ffcuda_ctx *ctx, const char *name, int value);
 /* built-in kernel profiler: when enabled every kernel launch is bracketed by CUDA events on the launch
  * stream.  ffcuda_prof_get returns accumulated milliseconds and launch count of kernels whose name starts
