@@ -296,6 +296,76 @@ __global__ void __launch_bounds__(RED_THREADS) k_spmv_sell(const int32_t *__rest
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Node-block SpMV for vector spaces ([P,P,P]: dof = node*NC + c).  The NC dof rows of a node share one column
+// structure (the node row of the pattern, every node column expanded to NC consecutive dofs), so the kernel walks the
+// NODE-level CSR: one warp per node row, one 4-byte column index per NC x NC block instead of one per entry, the
+// values read in place from the dof-level CSR (NC coalesced streams), x gathered NC contiguous doubles at a time.
+// Bytes per non-zero: 8 + 4/NC^2 instead of 12.  Same MODEs as k_spmv_stream.
+// ---------------------------------------------------------------------------------------------------
+template <int NC, int MODE>
+__global__ void __launch_bounds__(RED_THREADS) k_spmv_nodeblock(const int32_t *__restrict__ nrowptr, const int32_t *__restrict__ ncol,
+                                                                const int32_t *__restrict__ rowptr, const double *__restrict__ vals,
+                                                                const double *__restrict__ x, int nnode, const double *__restrict__ aux0,
+                                                                const double *__restrict__ aux1, double *__restrict__ y, int iter,
+                                                                double *__restrict__ partial, int *__restrict__ flags,
+                                                                double *__restrict__ out)
+{
+    __shared__ double sh[32];
+    if (MODE == 2) {
+        const int ci = flags[F_CONV_ITER]; // 0: running, -1/-2: stopped before the first iteration, k>0: converged at k
+        if (ci != 0 && iter > ci) return;
+    }
+    double acc0 = 0.0, acc1 = 0.0;
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int i = warp; i < nnode; i += nwarps) {
+        const int nb = __ldg(nrowptr + i), len = NC * (__ldg(nrowptr + i + 1) - nb);
+        const double *v[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) v[c] = vals + __ldg(rowptr + NC * i + c);
+        double s[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) s[c] = 0.0;
+#pragma unroll 2
+        for (int k = lane; k < len; k += 32) {
+            const int jn = NC == 3 ? (int)(((unsigned)k * 0xAAABu) >> 17) : (NC == 2 ? k >> 1 : k); // k / NC for k < 2^15
+            const double xv = __ldg(x + NC * __ldg(ncol + nb + jn) + (k - NC * jn));
+#pragma unroll
+            for (int c = 0; c < NC; ++c) s[c] = fma(__ldcs(v[c] + k), xv, s[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < NC; ++c) s[c] = warp_sum(s[c]);
+        if (lane < NC) {
+            double sv = s[0];
+#pragma unroll
+            for (int c = 1; c < NC; ++c)
+                if (lane == c) sv = s[c];
+            const int row = NC * i + lane;
+            if (MODE == 0) y[row] = sv;
+            if (MODE == 1) {
+                const double g = sv - aux0[row];
+                y[row] = g;
+                acc0 = fma(g, aux1[row] * g, acc0);
+            }
+            if (MODE == 2) {
+                const double h = x[row];
+                y[row] = sv;
+                acc0 = fma(aux0[row], h, acc0);
+                acc1 = fma(h, sv, acc1);
+            }
+        }
+    }
+    if (MODE == 1) {
+        double a[1] = {acc0};
+        grid_sum_finish<1>(a, partial, flags + F_COUNTER, out, sh);
+    }
+    if (MODE == 2) {
+        double a[2] = {acc0, acc1};
+        grid_sum_finish<2>(a, partial, flags + F_COUNTER, out, sh);
+    }
+}
+
 // y = A x  (optionally y = A x - b)
 template <int T>
 __global__ void __launch_bounds__(RED_THREADS) k_spmv(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
@@ -670,9 +740,41 @@ static void stream_launch(ffcuda_matrix *A, const char *name, const double *x, c
     });
 }
 
+// ---- node-block path: matrices assembled on a vector space (values in the pattern's dof-level CSR layout)
+static bool nodeblock_ok(const ffcuda_matrix *A)
+{
+    const ffcuda_pattern *P = A->pattern;
+    return P && (P->ncomp == 2 || P->ncomp == 3) && A->rowptr == P->rowptr && P->maxrow_node * P->ncomp < 32768 && A->nnz > 0;
+}
+static int nodeblock_grid(const ffcuda_matrix *A)
+{
+    const int warps_per_block = RED_THREADS / 32;
+    const int need = (A->pattern->nrows_node + warps_per_block - 1) / warps_per_block;
+    return std::max(1, std::min(need, A->ctx->sm_count * (2048 / RED_THREADS)));
+}
+template <int MODE>
+static void nodeblock_launch(ffcuda_matrix *A, const char *name, const double *x, const double *aux0, const double *aux1, double *y,
+                             int iter, double *partial, int *flags, double *out)
+{
+    ffcuda_ctx *ctx = A->ctx;
+    const ffcuda_pattern *P = A->pattern;
+    ff_launch(ctx, name, [&] {
+        if (P->ncomp == 3)
+            k_spmv_nodeblock<3, MODE><<<nodeblock_grid(A), RED_THREADS, 0, ctx->stream>>>(P->nrowptr.p, P->ncol.p, A->rowptr, A->vals.p, x,
+                                                                                          P->nrows_node, aux0, aux1, y, iter, partial, flags, out);
+        else
+            k_spmv_nodeblock<2, MODE><<<nodeblock_grid(A), RED_THREADS, 0, ctx->stream>>>(P->nrowptr.p, P->ncol.p, A->rowptr, A->vals.p, x,
+                                                                                          P->nrows_node, aux0, aux1, y, iter, partial, flags, out);
+    });
+}
+
 static void spmv_launch(ffcuda_matrix *A, const double *x, const double *sub, double *y)
 {
     ffcuda_ctx *ctx = A->ctx;
+    if (!sub && nodeblock_ok(A)) {
+        nodeblock_launch<0>(A, "spmv", x, nullptr, nullptr, y, 0, nullptr, nullptr, nullptr);
+        return;
+    }
     if (!sub && sell_prepare(A)) {
         sell_launch<0>(A, "spmv", x, nullptr, nullptr, y, 0, nullptr, nullptr, nullptr);
         return;
@@ -722,9 +824,11 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
     double *scal = ctx->d_scal;
     int *flags = ctx_flags(ctx);
     const int T = pick_T(A);
-    const bool sell = sell_prepare(A);
-    const bool streamed = !sell && stream_prepare(A);
-    const int grid_s = sell ? sell_grid(A) : streamed ? A->stream_grid : grid_for(ctx, (size_t)n * T), grid_v = grid_for(ctx, (size_t)n);
+    const bool nblock = nodeblock_ok(A);
+    const bool sell = !nblock && sell_prepare(A);
+    const bool streamed = !nblock && !sell && stream_prepare(A);
+    const int grid_s = nblock ? nodeblock_grid(A) : sell ? sell_grid(A) : streamed ? A->stream_grid : grid_for(ctx, (size_t)n * T),
+              grid_v = grid_for(ctx, (size_t)n);
     ensure_partial(ctx, 2 * (size_t)std::max(grid_s, grid_v) + 16);
     double *partial = ctx->d_partial;
     FF_CUDA(cudaMemsetAsync(scal, 0, 64 * sizeof(double), st));
@@ -763,7 +867,9 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
         ff_halo_exchange(A, A->wX.p);
         xin = A->wX.p;
     }
-    if (sell)
+    if (nblock)
+        nodeblock_launch<1>(A, "cg_init_spmv", xin, b, D1, G, 0, partial, flags, scal + S_GCG0);
+    else if (sell)
         sell_launch<1>(A, "cg_init_spmv", xin, b, D1, G, 0, partial, flags, scal + S_GCG0);
     else if (streamed)
         stream_launch<1>(A, "cg_init_spmv", xin, b, D1, G, 0, partial, flags, scal + S_GCG0);
@@ -790,7 +896,9 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
             for (int k = 0; k < nb; ++k) {
                 ++it;
                 ff_halo_exchange(A, H);
-                if (sell)
+                if (nblock)
+                    nodeblock_launch<2>(A, "cg_spmv_dots", H, G, nullptr, AH, it, partial, flags, scal + S_GH);
+                else if (sell)
                     sell_launch<2>(A, "cg_spmv_dots", H, G, nullptr, AH, it, partial, flags, scal + S_GH);
                 else if (streamed)
                     stream_launch<2>(A, "cg_spmv_dots", H, G, nullptr, AH, it, partial, flags, scal + S_GH);

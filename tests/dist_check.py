@@ -77,9 +77,13 @@ def main():
             assert np.array_equal(g_rows, np.arange(N)), "owned rows do not tile the global numbering"
             lens = np.concatenate([np.diff(p["rp"]) for p in allp])
             assert np.array_equal(lens, np.diff(orp)), "row lengths differ"
-            cols = np.concatenate([p["cols"] for p in allp])
-            assert np.array_equal(cols, ocol), "column indices differ"
+            # a rank's rows are sorted by LOCAL column id (owned first, then ghosts): bring every row to the global order
+            cols = np.concatenate([p["cols"] for p in allp]).astype(np.int64)
             vals = np.concatenate([p["vals"] for p in allp])
+            rowid = np.repeat(np.arange(N, dtype=np.int64), lens)
+            o = np.argsort(rowid * N + cols, kind="stable")
+            cols, vals = cols[o], vals[o]
+            assert np.array_equal(cols, ocol), "column indices differ"
             reg = np.abs(oval) < 1e29
             assert np.array_equal(vals[~reg], oval[~reg])
             assert np.max(np.abs(vals - oval)[reg]) <= 1e-12 * np.abs(oval[reg]).max()
@@ -102,4 +106,12 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:  # a failed rank must not leave the others waiting in a collective until the launcher's timeout
+        import traceback
+
+        traceback.print_exc()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(1)
