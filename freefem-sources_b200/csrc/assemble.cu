@@ -771,6 +771,7 @@ static void launch_p1(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const 
     ffcuda_mesh *m = s->mesh;
     // scalar c grad u.grad v + m u v without region filter: row tiles (tiles.cu) when the space has / may build them
     if (NC == 1 && fast && F.nlab < 0 && ff_asm_p1_tiles(ctx, A, s, F.fast_cw, F.fast_md, F.fast_mo, accumulate)) return;
+    ff_pattern_ensure_pos(P);
     FF_REQUIRE(P->pos8.p, "internal: P1 pattern without 8-bit positions");
     const Incidence &I = s->incidence;
     int S = NC * NC * P->maxrow_node;

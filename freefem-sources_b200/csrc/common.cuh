@@ -326,6 +326,7 @@ struct ffcuda_bc {
     DBuf<double> vals;
 };
 
+void ff_pattern_ensure_pos(ffcuda_pattern *P); // symbolic.cu: per-record positions of a P1 pattern, on demand
 void ff_matrix_touch(ffcuda_matrix *A); // matrix.cu: zero the values if nothing has written them yet
 
 // ---- shared device helpers ----------------------------------------------------------------------

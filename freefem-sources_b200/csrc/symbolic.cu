@@ -16,6 +16,7 @@
 //      binary search (pass 1).  These positions are what lets the numeric phase run without any search or atomic.
 #include "common.cuh"
 #include <climits>
+#include <algorithm>
 
 // ---------------------------------------------------------------------------------------------------------------
 // stage 1: node -> element incidence
@@ -396,7 +397,7 @@ __global__ void __launch_bounds__(128) k_block_pattern(const int32_t *__restrict
 static constexpr int SYM_THREADS = 128;
 static constexpr int SYM_WORDS = FF_STAGE_MAX / 32;
 
-template <int NLOC>
+template <int NLOC, bool WITH_POS>
 __global__ void __launch_bounds__(SYM_THREADS) k_sym_p1_rows(int nrows, int nrows_pad, const int32_t *__restrict__ cnt,
                                                              const uint32_t *__restrict__ blkoff, const uint32_t *__restrict__ loc,
                                                              uint32_t *__restrict__ pos, uint32_t *__restrict__ bitmaps,
@@ -431,11 +432,14 @@ __global__ void __launch_bounds__(SYM_THREADS) k_sym_p1_rows(int nrows, int nrow
         const uint32_t bits = sbm[w][tid];
         spre[w][tid] = (uint32_t)nu;
         nu += __popc(bits);
-        bitmaps[(size_t)w * nrows_pad + row] = bits;
+        if (bitmaps) bitmaps[(size_t)w * nrows_pad + row] = bits;
     }
     uint32_t *ppos = pos + base + lane;
     int diag = 0;
-    for (int e = 0; e < mycnt; ++e) {
+    // WITH_POS = false: only the position of the diagonal (byte 0 of the first record = the row's own vertex); the
+    // per-record positions are produced later, on demand, by the same kernel (ff_pattern_ensure_pos)
+    const int epos = WITH_POS ? mycnt : min(mycnt, 1);
+    for (int e = 0; e < epos; ++e) {
         const uint32_t lw = __ldg(ploc + (size_t)e * 32);
         uint32_t word = 0;
 #pragma unroll
@@ -445,37 +449,56 @@ __global__ void __launch_bounds__(SYM_THREADS) k_sym_p1_rows(int nrows, int nrow
             word |= r << (8 * b);
         }
         if (e == 0) diag = (int)(word & 255u); // byte 0 = the row's own vertex
-        __stcs(ppos + (size_t)e * 32, word);
+        if (WITH_POS) __stcs(ppos + (size_t)e * 32, word);
     }
-    if (row < nrows) {
+    if (row < nrows && rowlen) {
         rowlen[row] = nu;
         diagnode[row] = diag;
     }
-    int m = nu;
-    for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane == 0 && m > 0) atomicMax(maxrow, m);
+    if (maxrow) {
+        int m = nu;
+        for (int o = 16; o; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if (lane == 0 && m > 0) atomicMax(maxrow, m);
+    }
 }
 
-// columns of every row from its slot bitmap and the block's (ascending) vertex list; diagonal positions
+// columns of every row from its slot bitmap and the block's (ascending) vertex list; diagonal positions.  One thread
+// per row expands its bitmap into the warp's shared-memory stage (the 32 rows of a warp are contiguous in ncol), then
+// the warp writes the whole span with coalesced stores.  Rows too long for the stage (span > cap) are written directly.
 __global__ void __launch_bounds__(SYM_THREADS) k_sym_p1_cols(int nrows, int nrows_pad, const uint32_t *__restrict__ bitmaps,
                                                              const int32_t *__restrict__ nrowptr, const int32_t *__restrict__ blkvert,
                                                              const int32_t *__restrict__ diagnode, int32_t *__restrict__ ncol,
-                                                             int32_t *__restrict__ diagpos)
+                                                             int32_t *__restrict__ diagpos, int cap)
 {
-    const int row = blockIdx.x * SYM_THREADS + threadIdx.x;
-    if (row >= nrows) return;
-    const int32_t *bv = blkvert + (size_t)(row >> 5) * FF_STAGE_MAX;
-    int o = nrowptr[row];
-    diagpos[row] = o + diagnode[row];
+    extern __shared__ int32_t scol[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int row = blockIdx.x * SYM_THREADS + tid;
+    const int r0 = row & ~31;
+    if (r0 >= nrows) return; // whole warps only
+    const int rlast = min(r0 + 32, nrows);
+    const int o0 = nrowptr[r0], span = nrowptr[rlast] - o0;
+    const bool staged = span <= cap;
+    int32_t *st = scol + (size_t)warp * cap;
+    if (row < nrows) {
+        const int32_t *bv = blkvert + (size_t)(row >> 5) * FF_STAGE_MAX;
+        int o = nrowptr[row];
+        diagpos[row] = o + diagnode[row];
 #pragma unroll
-    for (int w = 0; w < SYM_WORDS; ++w) {
-        uint32_t bits = __ldcs(bitmaps + (size_t)w * nrows_pad + row);
-        while (bits) {
-            const int b = __ffs(bits) - 1;
-            bits &= bits - 1u;
-            ncol[o++] = __ldg(bv + w * 32 + b);
+        for (int w = 0; w < SYM_WORDS; ++w) {
+            uint32_t bits = __ldcs(bitmaps + (size_t)w * nrows_pad + row);
+            while (bits) {
+                const int b = __ffs(bits) - 1;
+                bits &= bits - 1u;
+                const int32_t c = __ldg(bv + w * 32 + b);
+                if (staged) st[o - o0] = c;
+                else ncol[o] = c;
+                ++o;
+            }
         }
     }
+    __syncwarp();
+    if (staged)
+        for (int j = lane; j < span; j += 32) ncol[o0 + j] = st[j];
 }
 
 // tmpcol (fixed stride) -> ncol (CSR): one warp per 32 rows, a row segment at a time
@@ -790,16 +813,29 @@ extern "C" int ffcuda_symbolic(ffcuda_space *s, ffcuda_pattern **out)
         const int nblk = (nrows + 31) / 32, nrows_pad = nblk * 32;
         DBuf<uint32_t> bitmaps;
         bitmaps.alloc((size_t)SYM_WORDS * nrows_pad);
-        P->pos8.alloc((size_t)I.nrec * P->nlocp);
-        uint32_t *posw = reinterpret_cast<uint32_t *>(P->pos8.p);
+        // The per-record positions (201 MB written at cube(128)) only serve the thread-per-row numeric kernels.  On a
+        // scalar space whose row tiles are built they are produced on demand instead (ff_pattern_ensure_pos).
+        const bool lazy_pos = nc == 1 && s->tiles.state == 1 && ctx->tile_policy != 0;
+        uint32_t *posw = nullptr;
+        if (!lazy_pos) {
+            P->pos8.alloc((size_t)I.nrec * P->nlocp);
+            posw = reinterpret_cast<uint32_t *>(P->pos8.p);
+        }
         const int blocks = ff_blocks((size_t)nrows_pad, SYM_THREADS);
         ff_launch(ctx, "sym_p1_rows", [&] {
-            if (nloc == 4)
-                k_sym_p1_rows<4><<<blocks, SYM_THREADS, 0, st>>>(nrows, nrows_pad, I.cnt.p, I.blkoff.p, I.loc.p, posw, bitmaps.p, rowlen.p,
-                                                                 diagnode.p, d_max.p);
+            if (lazy_pos) {
+                if (nloc == 4)
+                    k_sym_p1_rows<4, false><<<blocks, SYM_THREADS, 0, st>>>(nrows, nrows_pad, I.cnt.p, I.blkoff.p, I.loc.p, nullptr, bitmaps.p,
+                                                                            rowlen.p, diagnode.p, d_max.p);
+                else
+                    k_sym_p1_rows<3, false><<<blocks, SYM_THREADS, 0, st>>>(nrows, nrows_pad, I.cnt.p, I.blkoff.p, I.loc.p, nullptr, bitmaps.p,
+                                                                            rowlen.p, diagnode.p, d_max.p);
+            } else if (nloc == 4)
+                k_sym_p1_rows<4, true><<<blocks, SYM_THREADS, 0, st>>>(nrows, nrows_pad, I.cnt.p, I.blkoff.p, I.loc.p, posw, bitmaps.p, rowlen.p,
+                                                                       diagnode.p, d_max.p);
             else
-                k_sym_p1_rows<3><<<blocks, SYM_THREADS, 0, st>>>(nrows, nrows_pad, I.cnt.p, I.blkoff.p, I.loc.p, posw, bitmaps.p, rowlen.p,
-                                                                 diagnode.p, d_max.p);
+                k_sym_p1_rows<3, true><<<blocks, SYM_THREADS, 0, st>>>(nrows, nrows_pad, I.cnt.p, I.blkoff.p, I.loc.p, posw, bitmaps.p, rowlen.p,
+                                                                       diagnode.p, d_max.p);
         });
         FF_CUDA(cudaMemcpyAsync(&h_max, d_max.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
         ff_exclusive_scan_i32(ctx, rowlen.p, P->nrowptr.p, (size_t)nrows + 1, &nnzn); // synchronises the stream
@@ -811,9 +847,12 @@ extern "C" int ffcuda_symbolic(ffcuda_space *s, ffcuda_pattern **out)
         P->ncol.alloc((size_t)nnzn);
         P->diagpos.alloc((size_t)P->n);
         // scalar spaces: diagpos is final; vector spaces overwrite it in k_expand_rowptr below
+        // stage of the column kernel: the 32 rows of a warp hold at most 32 * maxrow entries; capped so that 8 CTAs fit
+        const int ccap = std::min(32 * std::max(1, P->maxrow_node), 1536);
         ff_launch(ctx, "sym_p1_cols", [&] {
-            k_sym_p1_cols<<<blocks, SYM_THREADS, 0, st>>>(nrows, nrows_pad, bitmaps.p, P->nrowptr.p, I.blkvert.p, diagnode.p, P->ncol.p,
-                                                          P->diagpos.p);
+            k_sym_p1_cols<<<blocks, SYM_THREADS, (size_t)(SYM_THREADS / 32) * ccap * 4, st>>>(nrows, nrows_pad, bitmaps.p, P->nrowptr.p,
+                                                                                              I.blkvert.p, diagnode.p, P->ncol.p, P->diagpos.p,
+                                                                                              ccap);
         });
         diag_done = (nc == 1);
     } else if (s->order == 1) {
@@ -914,6 +953,29 @@ extern "C" int ffcuda_symbolic(ffcuda_space *s, ffcuda_pattern **out)
     *out = P;
     P = nullptr;
     FF_API_END((delete P, s ? s->ctx : nullptr))
+}
+
+// per-record positions of a P1 pattern whose symbolic phase skipped them (see lazy_pos above)
+void ff_pattern_ensure_pos(ffcuda_pattern *P)
+{
+    if (P->pos8.p || P->pos16.p) return;
+    ffcuda_space *s = P->space;
+    ffcuda_ctx *ctx = P->ctx;
+    const Incidence &I = s->incidence;
+    FF_REQUIRE(s->order == 1 && I.built && I.ell && I.nunstaged == 0, "internal: pattern without positions");
+    const int nrows = P->nrows_node, nblk = (nrows + 31) / 32, nrows_pad = nblk * 32;
+    P->pos8.alloc((size_t)I.nrec * P->nlocp);
+    uint32_t *posw = reinterpret_cast<uint32_t *>(P->pos8.p);
+    const int blocks = ff_blocks((size_t)nrows_pad, SYM_THREADS);
+    cudaStream_t st = ctx->stream;
+    ff_launch(ctx, "sym_p1_positions", [&] {
+        if (s->nloc == 4)
+            k_sym_p1_rows<4, true><<<blocks, SYM_THREADS, 0, st>>>(nrows, nrows_pad, I.cnt.p, I.blkoff.p, I.loc.p, posw, nullptr, nullptr, nullptr,
+                                                                   nullptr);
+        else
+            k_sym_p1_rows<3, true><<<blocks, SYM_THREADS, 0, st>>>(nrows, nrows_pad, I.cnt.p, I.blkoff.p, I.loc.p, posw, nullptr, nullptr, nullptr,
+                                                                   nullptr);
+    });
 }
 
 extern "C" int ffcuda_pattern_info(ffcuda_pattern *p, int *n, int64_t *nnz)

@@ -173,3 +173,43 @@ def test_tiles_full_size_properties(ctx):
     assert abs(M - M.T).max() <= 1e-13 * scale
     sp0, pat0, A0 = _assemble(ctx, mesh, fc.LAP3, qp, qw, 0)
     assert np.max(np.abs(A0.download() - val)) <= RTOL * scale
+
+
+def test_lazy_positions_after_tiles_are_built(ctx):
+    """Once a space has its row tiles, the symbolic phase skips the per-record positions (only the thread-per-row kernels
+    read them); a later form that is not on the tile path (mass term, default policy) must get them on demand."""
+    size = (9, 7, 8)
+    m = ol.cube(*size)
+    n = m["xyz"].shape[0]
+    qp, qw = ffcuda.quadrature(3, 6)
+    mesh = ctx.mesh_cube(*size)
+    ctx.set_option("tile_policy", 1)
+    sp = mesh.space(1, 1)
+    pat0 = sp.symbolic()
+    A0 = pat0.matrix()
+    A0.assemble(fc.LAP3, qp, qw)
+    A0.assemble(fc.LAP3, qp, qw)          # builds the tile set
+    rp0, col0 = pat0.download()
+    ctx.prof_enable(True)
+    ctx.prof_reset()
+    pat1 = sp.symbolic()                  # lazy: no positions
+    rp1, col1 = pat1.download()
+    assert np.array_equal(rp0, rp1) and np.array_equal(col0, col1)
+    orp, ocol, oval = _oracle_vals(m, n, fc.LAP3, qp, qw)
+    assert np.array_equal(rp1, orp) and np.array_equal(col1, ocol)
+    A1 = pat1.matrix()
+    A1.assemble(fc.LAP3, qp, qw)          # tiles
+    assert ctx.prof_get("sym_p1_positions")[1] == 0
+    assert np.max(np.abs(A1.download() - oval)) <= RTOL * np.abs(oval).max()
+    A1.assemble(HEAT3, qp, qw)            # mass term: thread-per-row kernel, positions produced now
+    assert ctx.prof_get("sym_p1_positions")[1] == 1
+    ctx.prof_enable(False)
+    _, _, hval = _oracle_vals(m, n, HEAT3, qp, qw)
+    assert np.max(np.abs(A1.download() - hval)) <= RTOL * np.abs(hval).max()
+    # Dirichlet through diagpos of the lazily built pattern
+    bc = sp.bc_from_labels(fc.ALL6, 1, [0.0])
+    A1.apply_bc(bc, TGV)
+    v = A1.download()
+    d, _ = ol.bc_pairs(m, 1, 1, None, fc.ALL6, 1, [0.0])
+    diag_idx = np.array([rp1[i] + np.searchsorted(col1[rp1[i]:rp1[i + 1]], i) for i in np.unique(d)])
+    assert np.all(v[diag_idx] == TGV)
