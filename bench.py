@@ -325,7 +325,7 @@ def ours(args):
         ms, cnt = ctx.prof_get(key)
         prof[key] = (ms / nprof, cnt // nprof)
     kernels_ms = {}
-    for nm in ("inc_count", "inc_blk_len", "inc_fill", "inc_sort", "inc_stage", "sym_p1_rows", "sym_p1_cols", "sym_block_pattern", "sym_compact_cols", "sym_row_count", "sym_row_fill", "sym_diagpos", "scan_tile_sums",
+    for nm in ("inc_count", "inc_blk_len", "inc_fill", "inc_sort", "inc_stage", "sym_p1_rows", "sym_p1_cols", "sym_p1_positions", "sym_block_pattern", "sym_compact_cols", "sym_row_count", "sym_row_fill", "sym_diagpos", "scan_tile_sums",
                "scan_tile_offsets", "scan_tiles", "asm_rows_p1", "rhs_rows", "bc_mark", "bc_compact", "bc_matrix", "bc_vec", "vec_fill",
                "spmv_row_blocks", "spmv_sell_len", "spmv_sell_cols", "spmv_sell_vals", "cg_diag_stats", "cg_precond", "cg_init_spmv", "cg_init_h", "cg_spmv_dots", "cg_update_g", "cg_update_xh"):
         ms, cnt = ctx.prof_get(nm)
@@ -455,7 +455,8 @@ def ours(args):
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures under profiles/
 # (cube(128) on one B200); filled in when a capture exists for the current kernels
-TRAFFIC = {}
+TRAFFIC = {"asm_rows_p1": 914.6e6,   # k_asm_tiles<3,false>: 684.4 MB read + 230.2 MB written (profiles/r01c_ncu_asm_kernels_summary.txt)
+           "cg_spmv_dots": 422.6e6}  # k_spmv_sell<2>: 418.0 MB read + 4.6 MB written (profiles/r01b_ncu_full_summary.txt)
 
 
 def main():
