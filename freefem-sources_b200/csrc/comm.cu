@@ -8,6 +8,8 @@
 //
 // NCCL is bound at run time with dlopen (libnccl.so.2): the single-GPU product and the FreeFEM plugin do not need it.
 #include "common.cuh"
+#include <algorithm>
+#include <cstdlib>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -18,6 +20,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -46,6 +49,7 @@ NcclApi &nccl()
     bind(g_nccl.CommInitRank, "ncclCommInitRank");
     bind(g_nccl.CommDestroy, "ncclCommDestroy");
     bind(g_nccl.AllReduce, "ncclAllReduce");
+    bind(g_nccl.AllGather, "ncclAllGather");
     bind(g_nccl.Send, "ncclSend");
     bind(g_nccl.Recv, "ncclRecv");
     bind(g_nccl.GroupStart, "ncclGroupStart");
@@ -62,6 +66,180 @@ NcclApi &nccl()
             throw FFError(std::string("NCCL error: ") + nccl().GetErrorString(r__) + " at " + __FILE__ + ":" + \
                           std::to_string(__LINE__));                                                         \
     } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// Peer mailboxes.  Every rank owns one device buffer ("mailbox"); all of them are mapped into every process with CUDA
+// IPC at ffcuda_comm_init.  A collective is then a kernel that STORES into the peers' mailboxes over NVLink/NVSwitch,
+// publishes a sequence number behind a system-scope fence and spins on its own mailbox until every peer's number has
+// arrived — no NCCL call, no proxy thread, ~5 us instead of ~25 us for the 8- and 16-byte all-reduces of a CG
+// iteration.  Two parities of every region: a rank can be at most one collective ahead of its slowest peer.
+//   mailbox layout: [RFLAG] u64[2][16]  sequence numbers of the all-reduce contributions
+//                   [RDATA] f64[2][16][4] contributions
+//                   [HFLAG] u64[2][2]   sequence numbers of the halo layers (direction, parity); [HCNT] block counter
+//                   [HDATA] f64[2][2][cap] halo layers
+// Sums are formed in rank order on every rank: bit-identical everywhere, reproducible.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr size_t P2P_HFLAG = FF_P2P_HFLAG, P2P_HCNT = FF_P2P_HCNT, P2P_HDATA = FF_P2P_HDATA;
+constexpr int P2P_MAXR = FF_P2P_MAXR;
+constexpr size_t P2P_HALO_CAP = (size_t)4 << 20; // doubles per region (32 MB): interface layers up to 4 M dofs
+
+struct PeerPtrs {
+    unsigned char *p[P2P_MAXR];
+};
+__device__ __forceinline__ void st_sys_u64(unsigned long long *p, unsigned long long v) { ff_st_release_sys(p, v); }
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long *p) { return ff_ld_acquire_sys(p); }
+__device__ __forceinline__ double ld_sys_f64(const double *p) { return ff_ld_relaxed_sys(p); }
+
+// stand-alone all-reduce of d[0..count) (count <= 4): one warp
+__global__ void k_p2p_allreduce(P2PDesc *D, double *__restrict__ d, int count, int op_max)
+{
+    double t[4];
+    const int lane = threadIdx.x;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[k] = (lane == 0 && k < count) ? d[k] : 0.0;
+    ff_p2p_allreduce_warp<4>(D, t, op_max != 0);
+    if (lane == 0)
+        for (int k = 0; k < count; ++k) d[k] = t[k];
+}
+
+struct HaloArgs {
+    int nbr[2];
+    long long send_off[2], send_cnt[2], recv_off[2], recv_cnt[2]; // in doubles
+};
+
+// all blocks co-resident (grid <= number of SMs): send phase, grid-wide "last block publishes", receive phase
+__global__ void __launch_bounds__(256) k_p2p_halo(const PeerPtrs P, int rank, double *__restrict__ v, const HaloArgs H, size_t cap,
+                                                  unsigned long long seq)
+{
+    const int par = (int)(seq & 1ull);
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
+    for (int s = 0; s < 2; ++s) {
+        if (H.nbr[s] < 0) continue;
+        // my layer towards neighbour s lands in ITS region of the opposite direction
+        double *dst = reinterpret_cast<double *>(P.p[H.nbr[s]] + P2P_HDATA) + (size_t)((1 - s) * 2 + par) * cap;
+        const double *src = v + H.send_off[s];
+        for (size_t i = tid; i < (size_t)H.send_cnt[s]; i += nthr) dst[i] = src[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    unsigned int *cnt = reinterpret_cast<unsigned int *>(P.p[rank] + P2P_HCNT);
+    if (threadIdx.x == 0) last = atomicAdd(cnt, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        __threadfence_system();
+        *cnt = 0;
+        for (int s = 0; s < 2; ++s)
+            if (H.nbr[s] >= 0)
+                st_sys_u64(reinterpret_cast<unsigned long long *>(P.p[H.nbr[s]] + P2P_HFLAG) + (1 - s) * 2 + par, seq);
+    }
+    for (int s = 0; s < 2; ++s) {
+        if (H.nbr[s] < 0) continue;
+        if (threadIdx.x == 0) {
+            const unsigned long long *f = reinterpret_cast<const unsigned long long *>(P.p[rank] + P2P_HFLAG) + s * 2 + par;
+            while (ld_sys_u64(f) != seq) {
+            }
+        }
+        __syncthreads();
+        const double *src = reinterpret_cast<const double *>(P.p[rank] + P2P_HDATA) + (size_t)(s * 2 + par) * cap;
+        double *dst = v + H.recv_off[s];
+        for (size_t i = tid; i < (size_t)H.recv_cnt[s]; i += nthr) dst[i] = ld_sys_f64(src + i);
+    }
+}
+
+PeerPtrs peer_ptrs(const ffcuda_ctx *ctx)
+{
+    PeerPtrs P;
+    for (int r = 0; r < P2P_MAXR; ++r) P.p[r] = static_cast<unsigned char *>(ctx->p2p_peer[r]);
+    return P;
+}
+
+// mailboxes of all ranks: allocate mine, all-gather the IPC handles through NCCL, map the peers'
+void p2p_setup(ffcuda_ctx *ctx)
+{
+    if (ctx->nranks < 2 || ctx->nranks > P2P_MAXR) return;
+    if (const char *e = getenv("FFCUDA_P2P"))
+        if (atoi(e) == 0) return;
+    cudaStream_t st = ctx->stream;
+    const int rank = ctx->rank, n = ctx->nranks;
+    const size_t bytes = P2P_HDATA + 4 * P2P_HALO_CAP * sizeof(double);
+    void *mine = nullptr;
+    // every rank must take the same decision: the outcome of each step is all-reduced (min) before going on
+    int ok = cudaMalloc(&mine, bytes) == cudaSuccess ? 1 : 0;
+    if (ok) ok = cudaMemsetAsync(mine, 0, bytes, st) == cudaSuccess;
+    cudaIpcMemHandle_t h;
+    memset(&h, 0, sizeof(h));
+    if (ok) ok = cudaIpcGetMemHandle(&h, mine) == cudaSuccess;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+    DBuf<unsigned char> d_all;
+    d_all.alloc((size_t)(n + 1) * 80);
+    std::vector<unsigned char> rec(80, 0), all((size_t)n * 80, 0);
+    memcpy(rec.data(), &h, 64);
+    rec[64] = (unsigned char)ok;
+    FF_CUDA(cudaMemcpyAsync(d_all.p + (size_t)n * 80, rec.data(), 80, cudaMemcpyHostToDevice, st));
+    FF_NCCL(nccl().AllGather(d_all.p + (size_t)n * 80, d_all.p, 80, ncclChar, (ncclComm_t)ctx->nccl_comm, st));
+    FF_CUDA(ff_memcpy_sync(ctx, all.data(), d_all.p, (size_t)n * 80, cudaMemcpyDeviceToHost)); // also: every memset is done
+    for (int r = 0; r < n; ++r) ok = ok && all[(size_t)r * 80 + 64];
+    int opened = 0;
+    if (ok) {
+        for (int r = 0; r < n && ok; ++r) {
+            if (r == rank) {
+                ctx->p2p_peer[r] = mine;
+                continue;
+            }
+            cudaIpcMemHandle_t hr;
+            memcpy(&hr, &all[(size_t)r * 80], 64);
+            void *p = nullptr;
+            if (cudaIpcOpenMemHandle(&p, hr, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                ok = 0;
+                break;
+            }
+            ctx->p2p_peer[r] = p;
+            ++opened;
+        }
+    }
+    // second agreement round: did every rank map every peer?
+    DBuf<double> flag;
+    flag.alloc(1);
+    double hv = ok ? 1.0 : 0.0;
+    FF_CUDA(cudaMemcpyAsync(flag.p, &hv, sizeof(double), cudaMemcpyHostToDevice, st));
+    FF_NCCL(nccl().AllReduce(flag.p, flag.p, 1, ncclDouble, ncclMin, (ncclComm_t)ctx->nccl_comm, st));
+    FF_CUDA(ff_memcpy_sync(ctx, &hv, flag.p, sizeof(double), cudaMemcpyDeviceToHost));
+    if (hv < 0.5) {
+        for (int r = 0; r < n; ++r) {
+            if (r != rank && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+            ctx->p2p_peer[r] = nullptr;
+        }
+        if (mine) cudaFree(mine);
+        cudaGetLastError();
+        return;
+    }
+    ctx->p2p_halo_cap = P2P_HALO_CAP;
+    ctx->p2p_seq_halo = 0;
+    P2PDesc D;
+    memset(&D, 0, sizeof(D));
+    for (int r = 0; r < n; ++r) D.peer[r] = static_cast<unsigned char *>(ctx->p2p_peer[r]);
+    D.rank = rank;
+    D.nranks = n;
+    FF_CUDA(ff_memcpy_sync(ctx, ctx->d_scal + FF_P2P_DESC_OFF, &D, sizeof(D), cudaMemcpyHostToDevice));
+    ctx->p2p = true;
+    if (getenv("FFCUDA_VERBOSE")) fprintf(stderr, "ffcuda rank %d: peer mailboxes of %d ranks mapped (%d opened)\n", rank, n, opened);
+}
+
+void p2p_teardown(ffcuda_ctx *ctx)
+{
+    if (!ctx->p2p) return;
+    for (int r = 0; r < ctx->nranks; ++r) {
+        if (!ctx->p2p_peer[r]) continue;
+        if (r == ctx->rank) cudaFree(ctx->p2p_peer[r]);
+        else cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+        ctx->p2p_peer[r] = nullptr;
+    }
+    ctx->p2p = false;
+}
+} // namespace
 
 extern "C" int ffcuda_comm_unique_id(void *id128)
 {
@@ -90,11 +268,13 @@ extern "C" int ffcuda_comm_init(ffcuda_ctx *ctx, int rank, int nranks, const voi
     }
     ctx->rank = rank;
     ctx->nranks = nranks;
+    p2p_setup(ctx); // collective: every rank maps every rank's mailbox, or none does (then NCCL carries the CG traffic)
     FF_API_END(ctx)
 }
 
 void ff_comm_release(ffcuda_ctx *ctx)
 {
+    p2p_teardown(ctx);
     if (ctx->nccl_comm) {
         g_nccl.CommDestroy((ncclComm_t)ctx->nccl_comm);
         ctx->nccl_comm = nullptr;
@@ -130,11 +310,35 @@ void ff_halo_exchange(ffcuda_matrix *A, double *v)
     ffcuda_ctx *ctx = A->ctx;
     FF_REQUIRE(ctx->nccl_comm, "distributed matrix without communicator");
     const int nc = A->pattern->ncomp;
+    // layers that fit the mailbox regions go by peer stores (one kernel for both directions), the others by NCCL; both
+    // ends of a pair see the same count, so they take the same route
+    bool via_p2p[2] = {false, false}, any_p2p = false, any_nccl = false;
+    for (int s = 0; s < 2; ++s) {
+        if (m->nbr[s] < 0) continue;
+        const size_t big = (size_t)std::max(m->send_cnt[s], m->recv_cnt[s]) * nc;
+        via_p2p[s] = ctx->p2p && big <= ctx->p2p_halo_cap;
+        (via_p2p[s] ? any_p2p : any_nccl) = true;
+    }
+    if (any_p2p) {
+        HaloArgs H;
+        for (int s = 0; s < 2; ++s) {
+            H.nbr[s] = via_p2p[s] ? m->nbr[s] : -1;
+            H.send_off[s] = (long long)m->send_off[s] * nc; H.send_cnt[s] = (long long)m->send_cnt[s] * nc;
+            H.recv_off[s] = (long long)m->recv_off[s] * nc; H.recv_cnt[s] = (long long)m->recv_cnt[s] * nc;
+        }
+        const unsigned long long seq = ++ctx->p2p_seq_halo;
+        const size_t most = (size_t)std::max(std::max(H.send_cnt[0], H.send_cnt[1]), std::max(H.recv_cnt[0], H.recv_cnt[1]));
+        const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count / 2, (most + 1023) / 1024));
+        ff_launch(ctx, "halo_p2p", [&] {
+            k_p2p_halo<<<grid, 256, 0, ctx->stream>>>(peer_ptrs(ctx), ctx->rank, v, H, ctx->p2p_halo_cap, seq);
+        });
+    }
+    if (!any_nccl) return;
     NcclApi &N = nccl();
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     FF_NCCL(N.GroupStart());
     for (int s = 0; s < 2; ++s) {
-        if (m->nbr[s] < 0) continue;
+        if (m->nbr[s] < 0 || via_p2p[s]) continue;
         FF_NCCL(N.Send(v + (size_t)m->send_off[s] * nc, (size_t)m->send_cnt[s] * nc, ncclDouble, m->nbr[s], comm, ctx->stream));
         FF_NCCL(N.Recv(v + (size_t)m->recv_off[s] * nc, (size_t)m->recv_cnt[s] * nc, ncclDouble, m->nbr[s], comm, ctx->stream));
     }
@@ -147,6 +351,12 @@ void ff_allreduce(ffcuda_matrix *A, double *d, int count, int op_max)
     if (!dist_mesh(A)) return;
     ffcuda_ctx *ctx = A->ctx;
     FF_REQUIRE(ctx->nccl_comm, "distributed matrix without communicator");
+    if (ctx->p2p && count <= 4) {
+        ff_launch(ctx, "allreduce_p2p", [&] {
+            k_p2p_allreduce<<<1, 32, 0, ctx->stream>>>(reinterpret_cast<P2PDesc *>(ctx->d_scal + FF_P2P_DESC_OFF), d, count, op_max);
+        });
+        return;
+    }
     FF_NCCL(nccl().AllReduce(d, d, (size_t)count, ncclDouble, op_max ? ncclMax : ncclSum, (ncclComm_t)ctx->nccl_comm, ctx->stream));
     ctx->launches++;
 }

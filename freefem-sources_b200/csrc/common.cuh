@@ -74,6 +74,12 @@ struct ffcuda_ctx {
     // multi-GPU
     int rank = 0, nranks = 1;
     void *nccl_comm = nullptr;
+    // peer mailboxes (comm.cu): one buffer per rank, mapped into every process of the box through CUDA IPC; the
+    // all-reduces and halo exchanges of CG are plain stores into the peers' mailboxes over NVLink, no NCCL call
+    bool p2p = false;
+    void *p2p_peer[16] = {};              // p2p_peer[r]: rank r's mailbox in this process' address space
+    size_t p2p_halo_cap = 0;              // doubles per (direction, parity) halo region
+    unsigned long long p2p_seq_halo = 0;
     // lifetime: every handle created on the context holds a reference; ffcuda_ctx_destroy only marks the context
     // closed and the last handle to go tears it down
     int refs = 0;
@@ -109,6 +115,76 @@ struct CtxRef { // first member of every handle struct: released after the handl
         if (c) ff_ctx_unref(c);
     }
 };
+
+// ---- peer mailboxes (comm.cu): layout and the device-side descriptor -------------------------------------
+//   [RFLAG] u64[2][16]     sequence numbers of the all-reduce contributions (parity, rank)
+//   [RDATA] f64[2][16][4]  contributions
+//   [HFLAG] u64[2][2]      sequence numbers of the halo layers (direction, parity); [HCNT] block counter
+//   [HDATA] f64[2][2][cap] halo layers
+constexpr size_t FF_P2P_RFLAG = 0, FF_P2P_RDATA = 4096, FF_P2P_HFLAG = 8192, FF_P2P_HCNT = 8192 + 256, FF_P2P_HDATA = 16384;
+constexpr int FF_P2P_MAXR = 16;
+// lives in device memory at ctx->d_scal + FF_P2P_DESC_OFF (doubles), i.e. FF_P2P_DESC_OFF - 32 doubles behind the CG flags
+constexpr int FF_P2P_DESC_OFF = 64;
+struct P2PDesc {
+    unsigned char *peer[FF_P2P_MAXR]; // rank r's mailbox in this process' address space
+    int rank, nranks;
+    int fused;                        // the dot products of the running CG are all-reduced by their own kernels
+    int pad;
+    unsigned long long seq;           // number of all-reduces so far: advanced on the device, in lockstep on all ranks
+};
+#ifdef __CUDACC__
+__device__ __forceinline__ void ff_st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ff_ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ff_ld_relaxed_sys(const double *p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+// One warp (all 32 lanes): all-reduce of t[0..NV) (lane 0's values are used) over the ranks through the mailboxes;
+// the result is returned in every lane.  Sum in rank order: bit-identical on every rank.
+template <int NV>
+__device__ __forceinline__ void ff_p2p_allreduce_warp(P2PDesc *D, double (&t)[NV], bool op_max)
+{
+    const int lane = threadIdx.x & 31;
+    unsigned long long seq = 0;
+    if (lane == 0) seq = ++D->seq;
+    seq = __shfl_sync(0xffffffffu, seq, 0);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) t[k] = __shfl_sync(0xffffffffu, t[k], 0);
+    const int par = (int)(seq & 1ull), rank = D->rank, nranks = D->nranks;
+    if (lane < nranks) {
+        double *dst = reinterpret_cast<double *>(D->peer[lane] + FF_P2P_RDATA) + (size_t)(par * FF_P2P_MAXR + rank) * 4;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) dst[k] = t[k];
+        __threadfence_system();
+        ff_st_release_sys(reinterpret_cast<unsigned long long *>(D->peer[lane] + FF_P2P_RFLAG) + par * FF_P2P_MAXR + rank, seq);
+        const unsigned long long *mine =
+            reinterpret_cast<const unsigned long long *>(D->peer[rank] + FF_P2P_RFLAG) + par * FF_P2P_MAXR + lane;
+        while (ff_ld_acquire_sys(mine) != seq) {
+        }
+    }
+    __syncwarp();
+    const double *src = reinterpret_cast<const double *>(D->peer[rank] + FF_P2P_RDATA) + (size_t)par * FF_P2P_MAXR * 4;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double s = ff_ld_relaxed_sys(src + k);
+        for (int r = 1; r < nranks; ++r) {
+            const double v = ff_ld_relaxed_sys(src + (size_t)r * 4 + k);
+            s = op_max ? fmax(s, v) : s + v;
+        }
+        t[k] = s;
+    }
+}
+#endif
 
 void ff_report_error(ffcuda_ctx *ctx, const char *msg);
 // every entry point starts with this: selects the device and makes ctx the thread's current context, whose stream

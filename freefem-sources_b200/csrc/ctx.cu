@@ -60,8 +60,8 @@ extern "C" int ffcuda_ctx_create(int device, ffcuda_ctx **out)
     ctx->sm_count = prop.multiProcessorCount;
     if (const char *e = getenv("FFCUDA_TILES")) ctx->tile_policy = std::max(0, std::min(2, atoi(e)));
     if (const char *e = getenv("FFCUDA_TILE_ROWS")) ctx->tile_rows = std::max(8, std::min(256, atoi(e)));
-    FF_CUDA(cudaMalloc((void **)&ctx->d_scal, 64 * sizeof(double)));
-    FF_CUDA(cudaMemset(ctx->d_scal, 0, 64 * sizeof(double)));
+    FF_CUDA(cudaMalloc((void **)&ctx->d_scal, 256 * sizeof(double))); // [0,64): CG scalars and flags, [64, ..): P2PDesc
+    FF_CUDA(cudaMemset(ctx->d_scal, 0, 256 * sizeof(double)));
     FF_CUDA(cudaMallocHost((void **)&ctx->h_scal, 64 * sizeof(double)));
     *out = ctx;
     FF_API_END(ctx)
@@ -320,8 +320,81 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_tiles(const int32_t *__re
     }
 }
 
+// Single-pass variant (decoupled look-back): tiles take tickets from an atomic counter, publish (flag, sum) words —
+// flag 1: the tile's own sum, flag 2: inclusive prefix — and a tile resolves its offset by walking back over its
+// predecessors' words.  One launch and one read of the input instead of three launches and two reads.
+// st[0..ntiles): status words, st[ntiles]: grand total, st[ntiles+1]: ticket counter; all zero on entry.
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_lookback(const int32_t *__restrict__ in, int32_t *__restrict__ out, size_t n,
+                                                                 int ntiles, unsigned long long *__restrict__ st)
+{
+    __shared__ int s_tile;
+    __shared__ long long s_prefix;
+    constexpr unsigned long long MASK = (1ull << 62) - 1ull;
+    if (threadIdx.x == 0) s_tile = (int)atomicAdd(st + ntiles + 1, 1ull);
+    __syncthreads();
+    const int tile = s_tile;
+    const size_t base = (size_t)tile * SCAN_TILE + (size_t)threadIdx.x * SCAN_ITEMS;
+    int32_t v[SCAN_ITEMS];
+    long long s = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < n) ? in[base + i] : 0;
+        s += v[i];
+    }
+    long long tot;
+    long long ex = block_excl_scan(s, &tot);
+    if (threadIdx.x == 0 && tile > 0) atomicExch(st + tile, (1ull << 62) | (unsigned long long)tot);
+    if (threadIdx.x < 32) { // warp 0 walks back over the predecessors' words, 32 at a time
+        const int lane = threadIdx.x;
+        long long prefix = 0;
+        for (int j = tile - 1; tile > 0;) {
+            const int idx = j - lane;
+            unsigned long long w = 2ull << 62; // before the first tile: inclusive prefix 0
+            if (idx >= 0) {
+                do {
+                    w = *reinterpret_cast<volatile unsigned long long *>(st + idx);
+                } while ((w >> 62) == 0);
+            }
+            const unsigned incl = __ballot_sync(0xffffffffu, (w >> 62) == 2);
+            const int first = incl ? __ffs(incl) - 1 : 31;
+            long long val = lane <= first ? (long long)(w & MASK) : 0;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+            prefix += val;
+            if (incl) break;
+            j -= 32;
+        }
+        if (lane == 0) {
+            __threadfence();
+            atomicExch(st + tile, (2ull << 62) | (unsigned long long)(prefix + tot));
+            if (tile == ntiles - 1) st[ntiles] = (unsigned long long)(prefix + tot);
+            s_prefix = prefix;
+        }
+    }
+    __syncthreads();
+    ex += s_prefix;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = (int32_t)ex;
+        ex += v[i];
+    }
+}
+
 void ff_exclusive_scan_i32(ffcuda_ctx *ctx, const int32_t *in, int32_t *out, size_t n, int64_t *total)
 {
+    if (n > 0 && in != out) { // (the three-pass version below also works in place)
+        const int ntiles = (int)((n + SCAN_TILE - 1) / SCAN_TILE);
+        DBuf<unsigned long long> stw;
+        stw.alloc((size_t)ntiles + 2);
+        cudaStream_t st = ctx->stream;
+        FF_CUDA(cudaMemsetAsync(stw.p, 0, stw.bytes(), st));
+        ff_launch(ctx, "scan_lookback", [&] { k_scan_lookback<<<ntiles, SCAN_THREADS, 0, st>>>(in, out, n, ntiles, stw.p); });
+        unsigned long long tot = 0;
+        FF_CUDA(cudaMemcpyAsync(&tot, stw.p + ntiles, sizeof(tot), cudaMemcpyDeviceToHost, st));
+        FF_CUDA(cudaStreamSynchronize(st));
+        if (total) *total = (int64_t)tot;
+        return;
+    }
     if (n == 0) {
         if (total) *total = 0;
         return;

@@ -14,6 +14,7 @@
 // partials) -> deterministic, no fp64 atomics.  The host enqueues iterations in batches and polls a device flag;
 // kernels of iterations past the converged one are no-ops, so x is exactly the iterate of the stopping iteration.
 #include "common.cuh"
+#include <cstddef>
 #include <algorithm>
 #include <cmath>
 
@@ -51,7 +52,7 @@ __device__ __forceinline__ double block_sum(double v, double *sh /* >= 32 double
 // and stores the totals in out[0..NV).  counter must be 0 on entry and is reset to 0 on exit.
 template <int NV>
 __device__ __forceinline__ void grid_sum_finish(const double (&v)[NV], double *__restrict__ partial, int *counter,
-                                                double *__restrict__ out, double *sh)
+                                                double *__restrict__ out, double *sh, bool xrank = false)
 {
     __shared__ bool last;
     double r[NV];
@@ -67,14 +68,25 @@ __device__ __forceinline__ void grid_sum_finish(const double (&v)[NV], double *_
     __syncthreads();
     if (!last) return;
     __threadfence();
+    double tot[NV];
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
         double s = 0;
         for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += __ldcg(partial + (size_t)k * gridDim.x + i);
-        s = block_sum(s, sh);
-        if (threadIdx.x == 0) out[k] = s;
+        tot[k] = block_sum(s, sh); // valid in thread 0
     }
-    if (threadIdx.x == 0) *counter = 0;
+    if (threadIdx.x < 32) {
+        // xrank: the sums of a distributed CG are all-reduced right here, by the last block of the kernel that formed
+        // them, through the peer mailboxes (comm.cu) - no separate collective on the stream.  counter = flags + F_COUNTER,
+        // the descriptor sits FF_P2P_DESC_OFF - 32 doubles behind the flags.
+        P2PDesc *D = reinterpret_cast<P2PDesc *>(reinterpret_cast<double *>(counter - F_COUNTER) + (FF_P2P_DESC_OFF - 32));
+        if (xrank && D->fused) ff_p2p_allreduce_warp<NV>(D, tot, false);
+        if (threadIdx.x == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) out[k] = tot[k];
+            *counter = 0;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -193,11 +205,11 @@ __global__ void __launch_bounds__(RED_THREADS) k_spmv_stream(const int32_t *__re
     }
     if (MODE == 1) {
         double a[1] = {acc0};
-        grid_sum_finish<1>(a, partial, flags + F_COUNTER, out, sh);
+        grid_sum_finish<1>(a, partial, flags + F_COUNTER, out, sh, true);
     }
     if (MODE == 2) {
         double a[2] = {acc0, acc1};
-        grid_sum_finish<2>(a, partial, flags + F_COUNTER, out, sh);
+        grid_sum_finish<2>(a, partial, flags + F_COUNTER, out, sh, true);
     }
 }
 
@@ -288,11 +300,11 @@ __global__ void __launch_bounds__(RED_THREADS) k_spmv_sell(const int32_t *__rest
     }
     if (MODE == 1) {
         double a[1] = {acc0};
-        grid_sum_finish<1>(a, partial, flags + F_COUNTER, out, sh);
+        grid_sum_finish<1>(a, partial, flags + F_COUNTER, out, sh, true);
     }
     if (MODE == 2) {
         double a[2] = {acc0, acc1};
-        grid_sum_finish<2>(a, partial, flags + F_COUNTER, out, sh);
+        grid_sum_finish<2>(a, partial, flags + F_COUNTER, out, sh, true);
     }
 }
 
@@ -358,11 +370,11 @@ __global__ void __launch_bounds__(RED_THREADS) k_spmv_nodeblock(const int32_t *_
     }
     if (MODE == 1) {
         double a[1] = {acc0};
-        grid_sum_finish<1>(a, partial, flags + F_COUNTER, out, sh);
+        grid_sum_finish<1>(a, partial, flags + F_COUNTER, out, sh, true);
     }
     if (MODE == 2) {
         double a[2] = {acc0, acc1};
-        grid_sum_finish<2>(a, partial, flags + F_COUNTER, out, sh);
+        grid_sum_finish<2>(a, partial, flags + F_COUNTER, out, sh, true);
     }
 }
 
@@ -408,7 +420,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_init1(const int32_t *__restr
             acc[0] = fma(g, d1[row] * g, acc[0]);
         }
     }
-    grid_sum_finish<1>(acc, partial, flags + F_COUNTER, scal + S_GCG0, sh);
+    grid_sum_finish<1>(acc, partial, flags + F_COUNTER, scal + S_GCG0, sh, true);
 }
 
 // CG start, second half: H = -D1 G ; eps2 ; "converged before the first iteration"
@@ -457,7 +469,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_spmv(const int32_t *__restri
             acc[1] = fma(h, s, acc[1]);
         }
     }
-    grid_sum_finish<2>(acc, partial, flags + F_COUNTER, scal + S_GH, sh);
+    grid_sum_finish<2>(acc, partial, flags + F_COUNTER, scal + S_GH, sh, true);
 }
 
 // K2: G += rho AH ; <G, D1 G> -> scal[S_GCG0 + (iter & 1)]
@@ -479,7 +491,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_cg_update_g(double *__restrict_
         G[i] = g;
         acc[0] = fma(g, d1[i] * g, acc[0]);
     }
-    grid_sum_finish<1>(acc, partial, flags + F_COUNTER, scal + S_GCG0 + (iter & 1), sh);
+    grid_sum_finish<1>(acc, partial, flags + F_COUNTER, scal + S_GCG0 + (iter & 1), sh, true);
 }
 
 // K3: x += rho H ; H = gamma H - D1 G ; convergence test
@@ -582,6 +594,7 @@ __global__ void k_precond(const int32_t *__restrict__ diagpos, const double *__r
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+bool ff_is_distributed(ffcuda_matrix *A);                              // comm.cu
 void ff_halo_exchange(ffcuda_matrix *A, double *v);                    // comm.cu (no-op on one GPU)
 void ff_allreduce(ffcuda_matrix *A, double *d, int count, int op_max); // comm.cu (no-op on one GPU)
 
@@ -832,6 +845,10 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
     ensure_partial(ctx, 2 * (size_t)std::max(grid_s, grid_v) + 16);
     double *partial = ctx->d_partial;
     FF_CUDA(cudaMemsetAsync(scal, 0, 64 * sizeof(double), st));
+    // distributed solve with peer mailboxes: the kernels that form <G,H>, <H,AH>, <G,CG> all-reduce them themselves
+    const int fused = (ctx->p2p && ff_is_distributed(A)) ? 1 : 0;
+    FF_CUDA(cudaMemcpyAsync(reinterpret_cast<char *>(scal + FF_P2P_DESC_OFF) + offsetof(P2PDesc, fused), &fused, sizeof(int),
+                            cudaMemcpyHostToDevice, st));
 
     // --- gettgv: largest diagonal value, its multiplicity, and the next one (ratio 1e6)
     double *hs = ctx->h_scal;
@@ -877,7 +894,7 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
         FF_DISPATCH_T(T, ff_launch(ctx, "cg_init_spmv", [&] {
                           k_cg_init1<TT><<<grid_s, RED_THREADS, 0, st>>>(A->rowptr, A->colind, A->vals.p, xin, b, D1, G, n, partial, flags, scal);
                       }));
-    ff_allreduce(A, scal + S_GCG0, 1, 0);
+    if (!fused) ff_allreduce(A, scal + S_GCG0, 1, 0);
     ff_launch(ctx, "cg_init_h", [&] { k_cg_init2<<<grid_v, RED_THREADS, 0, st>>>(G, D1, H, n, eps, flags, scal); });
 
     // --- iterations, enqueued in batches; the flag of batch k is inspected while batch k+1 runs
@@ -906,9 +923,9 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
                     FF_DISPATCH_T(T, ff_launch(ctx, "cg_spmv_dots", [&] {
                                       k_cg_spmv<TT><<<grid_s, RED_THREADS, 0, st>>>(A->rowptr, A->colind, A->vals.p, H, G, AH, n, it, partial, flags, scal);
                                   }));
-                ff_allreduce(A, scal + S_GH, 2, 0);
+                if (!fused) ff_allreduce(A, scal + S_GH, 2, 0);
                 ff_launch(ctx, "cg_update_g", [&] { k_cg_update_g<<<grid_v, RED_THREADS, 0, st>>>(G, AH, D1, n, it, partial, flags, scal); });
-                ff_allreduce(A, scal + S_GCG0 + (it & 1), 1, 0);
+                if (!fused) ff_allreduce(A, scal + S_GCG0 + (it & 1), 1, 0);
                 ff_launch(ctx, "cg_update_xh", [&] { k_cg_update_xh<<<grid_v, RED_THREADS, 0, st>>>(x, H, G, D1, n, it, flags, scal); });
             }
             FF_CUDA(cudaMemcpyAsync(hflags + 4 * slot, flags, sizeof(int), cudaMemcpyDeviceToHost, st));

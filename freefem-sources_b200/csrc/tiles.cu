@@ -699,14 +699,13 @@ void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr)
     FF_CUDA(ff_memcpy_sync(ctx, hbox, box.p, sizeof(hbox), cudaMemcpyDeviceToHost));
     BoxScale B;
     const double qmax = dim == 3 ? 1024.0 : 32768.0;
+    // one scale for all directions (the largest extent): Morton cells are cubes in space, so tiles stay compact on
+    // anisotropic boxes too (a slab of a partitioned cube)
+    double ext = 0.0;
+    for (int x = 0; x < dim; ++x) ext = std::max(ext, unord64(hbox[3 + x]) - unord64(hbox[x]));
     for (int x = 0; x < 3; ++x) {
-        B.lo[x] = 0.0;
-        B.sc[x] = 0.0;
-        if (x < dim) {
-            const double lo = unord64(hbox[x]), hi = unord64(hbox[3 + x]);
-            B.lo[x] = lo;
-            B.sc[x] = hi > lo ? qmax * (1.0 - 1e-9) / (hi - lo) : 0.0;
-        }
+        B.lo[x] = x < dim ? unord64(hbox[x]) : 0.0;
+        B.sc[x] = (x < dim && ext > 0.0) ? qmax * (1.0 - 1e-9) / ext : 0.0;
     }
     DBuf<uint32_t> k0, k1;
     DBuf<int32_t> v0, rord;
