@@ -943,6 +943,15 @@ static void launch_rhs(ffcuda_ctx *ctx, ffcuda_vec *b, ffcuda_space *s, const Li
     const size_t shmem = I.ell ? (size_t)4 * DIM * SV * 8 : 0;
     if (lean) {
         const double Lval = hFh[0], Wsum = -hFh[1];
+        {   // row tiles (tiles.cu) when the space has them: every element evaluated once per tile
+            constexpr double RFAC = DIM == 3 ? 1.0 / 6.0 : 0.5;
+            double cval[3] = {0, 0, 0}, cgrad[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+            for (int c = 0; c < s->ncomp; ++c) {
+                cval[c] = Lp.CL[c][0] * Lval * RFAC;
+                for (int x = 0; x < DIM; ++x) cgrad[c * 3 + x] = Lp.CL[c][x + 1] * Wsum * RFAC;
+            }
+            if (ff_rhs_p1_tiles(ctx, b, s, cval, cgrad, hasgrad, accumulate)) return;
+        }
         ff_launch(ctx, "rhs_rows", [&] {
 #define FF_RHS_LEAN(NCC)                                                                                                          \
     if (hasgrad)                                                                                                                  \

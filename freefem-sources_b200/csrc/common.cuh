@@ -314,10 +314,14 @@ struct TileSet {
     int tr = 0, ntiles = 0;
     int nes = 0;              // stride of the numeric kernel's value table (max_nelem | 1), baked into the codes
     int max_rows = 0, max_nvt = 0, max_nelem = 0, max_nq = 0, max_ncodes = 0, max_words = 0;
+    int max_pre = 0, max_rwords = 0; // longest descriptor head (up to the entry words) / record-list blob, in words
     int64_t sum_nelem = 0;    // element evaluations per assembly (diagnostics: redundancy = sum_nelem / nt)
     int64_t nnz_node = 0;     // of the pattern whose row pointers are baked into the blobs
     DBuf<uint32_t> blob;      // tile descriptors, 16-byte aligned each
     DBuf<uint32_t> toff;      // ntiles+1 offsets into blob in 32-bit words
+    DBuf<uint32_t> tpre;      // words of every descriptor's head (row ids, coordinates, element words): all a rhs needs
+    DBuf<uint32_t> rblob;     // record lists of the rows, one blob per tile: (element << 2 | local vertex) of every star
+    DBuf<uint32_t> roff;      // ntiles+1 offsets into rblob
 };
 
 struct ffcuda_space {
@@ -334,6 +338,7 @@ struct ffcuda_space {
 // tiles.cu: numeric assembly of c grad u.grad v + m u v on a scalar P1 space by row tiles; returns false when the tile
 // path does not apply (the caller then runs the thread-per-row kernel)
 bool ff_asm_p1_tiles(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, double cw, double cmd, double cmo, int accumulate);
+bool ff_rhs_p1_tiles(ffcuda_ctx *ctx, ffcuda_vec *b, ffcuda_space *s, const double *cval, const double *cgrad, int hasgrad, int accumulate);
 void ff_build_incidence(ffcuda_space *s); // symbolic.cu; no-op when already built
 
 struct ffcuda_pattern {

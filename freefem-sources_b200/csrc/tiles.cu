@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include <algorithm>
 #include <cstdlib>
+#include <functional>
 #include <cub/device/device_radix_sort.cuh>
 
 namespace {
@@ -213,7 +214,8 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__rest
                                                            const double *__restrict__ xyz, int vstride,
                                                            const int32_t *__restrict__ nrowptr, int nes,
                                                            int32_t *__restrict__ stats, const uint32_t *__restrict__ toff,
-                                                           uint32_t *__restrict__ blob)
+                                                           uint32_t *__restrict__ blob, const uint32_t *__restrict__ roff,
+                                                           uint32_t *__restrict__ rblob)
 {
     extern __shared__ uint32_t sm[];
     uint32_t *sbuf = sm;                                   // SORT_CAP   sort buffer; later entry offsets / cursors
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__rest
     if (!WRITE) {
         if (tid == 0) {
             int32_t *st = stats + (size_t)t * 8;
-            st[0] = nvt; st[1] = nelem; st[2] = nq; st[3] = ncodes; st[4] = fit; st[5] = nr;
+            st[0] = nvt; st[1] = nelem; st[2] = nq; st[3] = ncodes; st[4] = fit; st[5] = nr; st[6] = s_n;
         }
         return;
     }
@@ -424,13 +426,17 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__rest
     // 7. the blob
     uint32_t *g = blob + toff[t];
     constexpr int DIM = NV - 1;
-    const int o_gbase = HDR, o_rinfo = o_gbase + pad4(nr), o_coord = o_rinfo + pad4(nr + 1), o_telem = o_coord + pad4(2 * DIM * nvt),
-              o_einfo = o_telem + pad4(nelem), o_codes = o_einfo + pad4(nq + 1), words = o_codes + pad4((ncodes + 1) / 2);
+    const int o_gbase = HDR, o_grow = o_gbase + pad4(nr), o_rinfo = o_grow + pad4(nr), o_coord = o_rinfo + pad4(nr + 1),
+              o_telem = o_coord + pad4(2 * DIM * nvt), o_einfo = o_telem + pad4(nelem), o_codes = o_einfo + pad4(nq + 1),
+              words = o_codes + pad4((ncodes + 1) / 2);
     if (tid == 0) {
         g[0] = nr; g[1] = nvt; g[2] = nelem; g[3] = nq; g[4] = ncodes; g[5] = o_gbase; g[6] = o_rinfo; g[7] = o_coord;
-        g[8] = o_telem; g[9] = o_einfo; g[10] = o_codes; g[11] = words; g[12] = g[13] = g[14] = g[15] = 0;
+        g[8] = o_telem; g[9] = o_einfo; g[10] = o_codes; g[11] = words; g[12] = o_grow; g[13] = g[14] = g[15] = 0;
     }
-    for (int l = tid; l < pad4(nr); l += TB_THREADS) g[o_gbase + l] = l < nr ? (uint32_t)nrowptr[rord[r0 + l]] : 0u;
+    for (int l = tid; l < pad4(nr); l += TB_THREADS) {
+        g[o_gbase + l] = l < nr ? (uint32_t)nrowptr[rord[r0 + l]] : 0u;
+        g[o_grow + l] = l < nr ? (uint32_t)rord[r0 + l] : 0u;
+    }
     for (int l = tid; l < pad4(nr + 1); l += TB_THREADS) {
         uint32_t w = 0;
         if (l < nr) {
@@ -464,6 +470,29 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__rest
         const uint32_t lo = 2 * x < ncodes ? codes[2 * x] : 0u, hi = 2 * x + 1 < ncodes ? codes[2 * x + 1] : 0u;
         g[o_codes + x] = lo | (hi << 16);
     }
+    // 8. the record lists of the rows (second blob: right-hand sides, mass diagonals): for every row the elements of its
+    // star as (element << 2 | local vertex), ascending element.  header: 0 nrec, 1 o_rroff, 2 o_rrec, 3 words
+    __syncthreads();
+    int *rc = rowq; // the entry offsets are written out: re-used for the record offsets
+    for (int l = tid; l <= nr; l += TB_THREADS) rc[l] = l < nr ? V.cnt[rord[r0 + l]] : 0;
+    __syncthreads();
+    const int nrec = blk_scan(rc, nr + 1, part);
+    uint32_t *rg = rblob + roff[t];
+    const int o_rroff = 4, o_rrec = o_rroff + pad4((nr + 2) / 2), rwords = o_rrec + pad4((nrec + 1) / 2);
+    if (tid == 0) {
+        rg[0] = nrec; rg[1] = o_rroff; rg[2] = o_rrec; rg[3] = rwords;
+    }
+    uint16_t *rr16 = reinterpret_cast<uint16_t *>(rg + o_rroff);
+    for (int l = tid; l < 2 * pad4((nr + 2) / 2); l += TB_THREADS) rr16[l] = (uint16_t)(l <= nr ? rc[l] : nrec);
+    uint16_t *rec16 = reinterpret_cast<uint16_t *>(rg + o_rrec);
+    for (int l = tid; l < nr; l += TB_THREADS) {
+        const int row = rord[r0 + l], c = rc[l + 1] - rc[l];
+        for (int e = 0; e < c; ++e) {
+            const uint32_t ka = V.inc[V.idx(row, e)];
+            rec16[rc[l] + e] = (uint16_t)((bsearch_u32(elist, nelem, ka >> 4) << 2) | (ka & 3u));
+        }
+    }
+    for (int x = nrec + tid; x < 2 * pad4((nrec + 1) / 2); x += TB_THREADS) rec16[x] = 0;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -479,59 +508,113 @@ __device__ __forceinline__ double tile_rcp(double d) // ~1 ulp reciprocal: hardw
     return fma(r, t, r);
 }
 
-struct TileSmem { // byte offsets of the shared-memory regions behind the two blob buffers
-    int buf1, ent, vals, sd, nes;
+struct TileSmem { // byte offsets of the shared-memory regions
+    int buf1;      // second descriptor buffer (the first one is at 0)
+    int rb0, rb1;  // record-list buffers (mass forms, right-hand sides)
+    int ent, vals, nes;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-// Persistent CTAs: tile t, t + grid, ...  The descriptor blob of the NEXT tile is brought in by one TMA bulk copy
-// (cp.async.bulk, completion on an mbarrier) while the current tile is computed: no thread ever waits on a global load
-// in the steady state.
-template <int DIM, bool MASS>
-__global__ void __launch_bounds__(512) k_asm_tiles(const uint32_t *__restrict__ toff, const uint32_t *__restrict__ blob, int ntiles,
-                                                   double *__restrict__ out, int accumulate, double cw, double cmd, double cmo,
-                                                   const TileSmem S)
+__device__ __forceinline__ void tile_mbar_init(unsigned long long *mbar)
 {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) unsigned long long mbar[2];
-    constexpr int NP = DIM * (DIM + 1) / 2;
-    double *sE = reinterpret_cast<double *>(smem_raw + S.ent);  // off-diagonal sums of the tile's entries
-    double *sV = reinterpret_cast<double *>(smem_raw + S.vals); // [pair][NES] (+ [NP][NES] = det when MASS)
-    double *sD = reinterpret_cast<double *>(smem_raw + S.sd);
-    const int NES = S.nes;
-    const float inv_nes = 1.0f / (float)NES;
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    if (tid == 0) {
+    if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[0])));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&mbar[1])));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    auto issue = [&](int b, int t) { // one thread: bulk copy of tile t's blob into buffer b
-        const uint32_t w0 = __ldg(toff + t), bytes = (__ldg(toff + t + 1) - w0) * 4u;
-        const uint32_t bar = smem_u32(&mbar[b]), dst = smem_u32(smem_raw + (b ? S.buf1 : 0));
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                     "l"(blob + w0), "r"(bytes), "r"(bar)
+}
+__device__ __forceinline__ void tile_bulk(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void tile_expect(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tile_wait(uint32_t bar, uint32_t phase)
+{
+    uint32_t done = 0;
+    while (!done)
+        asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done)
+                     : "r"(bar), "r"(phase)
                      : "memory");
+}
+
+// geometry of one P1 element from the tile's coordinate table: unscaled normals N[a][x] = det * d lambda_a / d x, det
+template <int DIM>
+__device__ __forceinline__ void tile_geom(const double *coord, uint32_t w, double (&N)[DIM + 1][DIM], double &det)
+{
+    const double *p0 = coord + DIM * (w & 255u), *p1 = coord + DIM * ((w >> 8) & 255u), *p2 = coord + DIM * ((w >> 16) & 255u);
+    if (DIM == 3) {
+        const double *p3 = coord + DIM * (w >> 24);
+        const double x0 = p0[0], y0 = p0[1], z0 = p0[DIM - 1];
+        const double ax = p1[0] - x0, ay = p1[1] - y0, az = p1[DIM - 1] - z0;
+        const double bx = p2[0] - x0, by = p2[1] - y0, bz = p2[DIM - 1] - z0;
+        const double cx = p3[0] - x0, cy = p3[1] - y0, cz = p3[DIM - 1] - z0;
+        // N1 = b x c, N2 = c x a, N3 = a x b, det = a . N1, N0 = -(N1 + N2 + N3)   (Mesh3dn.hpp:126-136)
+        N[1][0] = by * cz - bz * cy; N[1][1] = bz * cx - bx * cz; N[1][DIM - 1] = bx * cy - by * cx;
+        N[2][0] = cy * az - cz * ay; N[2][1] = cz * ax - cx * az; N[2][DIM - 1] = cx * ay - cy * ax;
+        N[DIM][0] = ay * bz - az * by; N[DIM][1] = az * bx - ax * bz; N[DIM][DIM - 1] = ax * by - ay * bx;
+        det = ax * N[1][0] + ay * N[1][1] + az * N[1][DIM - 1];
+    } else {
+        const double x0 = p0[0], y0 = p0[1];
+        const double bx = p1[0] - x0, by = p1[1] - y0, cx = p2[0] - x0, cy = p2[1] - y0;
+        det = bx * cy - by * cx; // N1 = (cy, -cx), N2 = (-by, bx), N0 = -(N1 + N2)   (fem.hpp:321-324)
+        N[1][0] = cy; N[1][1] = -cx;
+        N[2][0] = -by; N[2][1] = bx;
+    }
+#pragma unroll
+    for (int x = 0; x < DIM; ++x) {
+        double sx = N[1][x];
+#pragma unroll
+        for (int r = 2; r <= DIM; ++r) sx += N[r][x];
+        N[0][x] = -sx;
+    }
+}
+
+// Persistent CTAs: tile t, t + grid, ...  The descriptor blob of the NEXT tile is brought in by one TMA bulk copy
+// (cp.async.bulk, completion on an mbarrier) while the current tile is computed: no thread ever waits on a global load
+// in the steady state.  MASS: the form has a mass term; the record lists of the rows come along (second bulk copy) and
+// give the measure of every row's star for the diagonal.
+template <int DIM, bool MASS>
+__global__ void __launch_bounds__(512) k_asm_tiles(const uint32_t *__restrict__ toff, const uint32_t *__restrict__ blob,
+                                                   const uint32_t *__restrict__ roff, const uint32_t *__restrict__ rblob, int ntiles,
+                                                   double *__restrict__ out, int accumulate, double cw, double cmd, double cmo,
+                                                   const TileSmem S)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    constexpr int NV = DIM + 1, NP = DIM * (DIM + 1) / 2;
+    double *sE = reinterpret_cast<double *>(smem_raw + S.ent);  // off-diagonal sums of the tile's entries
+    double *sV = reinterpret_cast<double *>(smem_raw + S.vals); // [pair][NES] (+ [NP][NES] = det when MASS)
+    const int NES = S.nes;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    tile_mbar_init(mbar);
+    auto issue = [&](int b, int t) { // one thread: bulk copies of tile t's descriptors into buffer b
+        const uint32_t w0 = __ldg(toff + t), bytes = (__ldg(toff + t + 1) - w0) * 4u;
+        const uint32_t bar = smem_u32(&mbar[b]);
+        uint32_t r0 = 0, rbytes = 0;
+        if (MASS) {
+            r0 = __ldg(roff + t);
+            rbytes = (__ldg(roff + t + 1) - r0) * 4u;
+        }
+        tile_expect(bar, bytes + rbytes);
+        tile_bulk(smem_u32(smem_raw + (b ? S.buf1 : 0)), blob + w0, bytes, bar);
+        if (MASS) tile_bulk(smem_u32(smem_raw + (b ? S.rb1 : S.rb0)), rblob + r0, rbytes, bar);
     };
     int t = blockIdx.x, b = 0;
     uint32_t ph0 = 0, ph1 = 0;
     if (tid == 0 && t < ntiles) issue(0, t);
     for (; t < ntiles; t += gridDim.x, b ^= 1) {
         if (tid == 0 && t + (int)gridDim.x < ntiles) issue(b ^ 1, t + gridDim.x); // that buffer was released by the last barrier
-        {
-            const uint32_t bar = smem_u32(&mbar[b]), ph = b ? ph1 : ph0;
-            uint32_t done = 0;
-            while (!done)
-                asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
-                             : "=r"(done)
-                             : "r"(bar), "r"(ph)
-                             : "memory");
-            if (b) ph1 ^= 1;
-            else ph0 ^= 1;
-        }
+        tile_wait(smem_u32(&mbar[b]), b ? ph1 : ph0);
+        if (b) ph1 ^= 1;
+        else ph0 ^= 1;
         const uint32_t *sb = reinterpret_cast<const uint32_t *>(smem_raw + (b ? S.buf1 : 0));
         const int nr = sb[0], nelem = sb[2], nq = sb[3];
         const int32_t *gbase = reinterpret_cast<const int32_t *>(sb + sb[5]);
@@ -542,40 +625,20 @@ __global__ void __launch_bounds__(512) k_asm_tiles(const uint32_t *__restrict__ 
         const uint32_t *codes2 = sb + sb[10];
         // ---- every element of the tile once: off-diagonal entries of its element matrix (+ its determinant)
         for (int e = tid; e < nelem; e += nthr) {
-            const uint32_t w = telem[e];
-            const double *p0 = coord + DIM * (w & 255u), *p1 = coord + DIM * ((w >> 8) & 255u), *p2 = coord + DIM * ((w >> 16) & 255u);
-            double K[NP], det;
-            if (DIM == 3) {
-                const double *p3 = coord + DIM * (w >> 24);
-                const double x0 = p0[0], y0 = p0[1], z0 = p0[DIM - 1];
-                const double ax = p1[0] - x0, ay = p1[1] - y0, az = p1[DIM - 1] - z0;
-                const double bx = p2[0] - x0, by = p2[1] - y0, bz = p2[DIM - 1] - z0;
-                const double cx = p3[0] - x0, cy = p3[1] - y0, cz = p3[DIM - 1] - z0;
-                // N1 = b x c, N2 = c x a, N3 = a x b, det = a . N1, N0 = -(N1 + N2 + N3)   (Mesh3dn.hpp:126-136)
-                const double n1x = by * cz - bz * cy, n1y = bz * cx - bx * cz, n1z = bx * cy - by * cx;
-                const double n2x = cy * az - cz * ay, n2y = cz * ax - cx * az, n2z = cx * ay - cy * ax;
-                const double n3x = ay * bz - az * by, n3y = az * bx - ax * bz, n3z = ax * by - ay * bx;
-                det = ax * n1x + ay * n1y + az * n1z;
-                const double n0x = -(n1x + n2x + n3x), n0y = -(n1y + n2y + n3y), n0z = -(n1z + n2z + n3z);
-                const double s = cw * tile_rcp(det), mo = MASS ? cmo * det : 0.0;
-                K[0] = fma(n0x * n1x + n0y * n1y + n0z * n1z, s, mo);
-                K[1] = fma(n0x * n2x + n0y * n2y + n0z * n2z, s, mo);
-                K[2] = fma(n0x * n3x + n0y * n3y + n0z * n3z, s, mo);
-                K[3 % NP] = fma(n1x * n2x + n1y * n2y + n1z * n2z, s, mo);
-                K[4 % NP] = fma(n1x * n3x + n1y * n3y + n1z * n3z, s, mo);
-                K[5 % NP] = fma(n2x * n3x + n2y * n3y + n2z * n3z, s, mo);
-            } else {
-                const double x0 = p0[0], y0 = p0[1];
-                const double bx = p1[0] - x0, by = p1[1] - y0, cx = p2[0] - x0, cy = p2[1] - y0;
-                det = bx * cy - by * cx; // N1 = (cy, -cx), N2 = (-by, bx), N0 = -(N1 + N2)   (fem.hpp:321-324)
-                const double n1x = cy, n1y = -cx, n2x = -by, n2y = bx, n0x = -(n1x + n2x), n0y = -(n1y + n2y);
-                const double s = cw * tile_rcp(det), mo = MASS ? cmo * det : 0.0;
-                K[0] = fma(n0x * n1x + n0y * n1y, s, mo);
-                K[1] = fma(n0x * n2x + n0y * n2y, s, mo);
-                K[2] = fma(n1x * n2x + n1y * n2y, s, mo);
-            }
+            double N[NV][DIM], det;
+            tile_geom<DIM>(coord, telem[e], N, det);
+            const double s = cw * tile_rcp(det), mo = MASS ? cmo * det : 0.0;
+            int k = 0;
 #pragma unroll
-            for (int k = 0; k < NP; ++k) sV[k * NES + e] = K[k];
+            for (int a2 = 0; a2 < NV; ++a2)
+#pragma unroll
+                for (int b2 = a2 + 1; b2 < NV; ++b2) {
+                    double d = N[a2][0] * N[b2][0];
+#pragma unroll
+                    for (int x = 1; x < DIM; ++x) d = fma(N[a2][x], N[b2][x], d);
+                    sV[k * NES + e] = fma(d, s, mo); // pair order (0,1)(0,2)(0,3)(1,2)(1,3)(2,3) = pair_id
+                    ++k;
+                }
             if (MASS) sV[NP * NES + e] = det;
         }
         __syncthreads();
@@ -584,21 +647,14 @@ __global__ void __launch_bounds__(512) k_asm_tiles(const uint32_t *__restrict__ 
             const uint32_t info = einfo[q];
             const int n = (info >> 15) & 31u;
             const uint32_t *cp = codes2 + (info & 0x7fffu);
-            double acc = 0.0, accd = 0.0;
+            double acc = 0.0;
 #pragma unroll 1
             for (int k = 0; k < n; k += 2) {
                 const uint32_t c2 = *cp++;
-                const uint32_t c0 = c2 & 0xffffu, c1 = c2 >> 16;
-                acc += sV[c0];
-                // element of a code = code mod NES: exact through a float reciprocal at these magnitudes (< 2^14)
-                if (MASS) accd += sV[NP * NES + ((int)c0 - __float2int_rz(((float)c0 + 0.5f) * inv_nes) * NES)];
-                if (k + 1 < n) {
-                    acc += sV[c1];
-                    if (MASS) accd += sV[NP * NES + ((int)c1 - __float2int_rz(((float)c1 + 0.5f) * inv_nes) * NES)];
-                }
+                acc += sV[c2 & 0xffffu];
+                if (k + 1 < n) acc += sV[c2 >> 16];
             }
             sE[q] = acc;
-            if (MASS) sD[q] = accd;
             if (n > 0) {
                 const int l = (info >> 20) & 255u;
                 double *dst = out + (size_t)gbase[l] + (q - (int)(rinfo[l] & 0xffffu));
@@ -606,22 +662,143 @@ __global__ void __launch_bounds__(512) k_asm_tiles(const uint32_t *__restrict__ 
             }
         }
         __syncthreads();
-        // ---- diagonals: K_ii = -sum_{j != i} K_ij (partition of unity); mass: (m_d + DIM m_o) |K| over the star, and the
-        // sum over the row's edges of the determinants around each edge counts every element of the star DIM times
-        for (int l = tid; l < nr; l += nthr) {
-            const uint32_t ri = rinfo[l];
-            const int q0 = ri & 0xffffu, L = ri >> 24;
-            if (L == 0) continue;
-            double s = 0.0, sd = 0.0;
-            for (int k = 0; k < L; ++k) {
-                s += sE[q0 + k];
-                if (MASS) sd += sD[q0 + k];
+        // ---- diagonals: K_ii = -sum_{j != i} K_ij (partition of unity: the off-diagonal entries carry m_o |K| each, DIM
+        // per element); mass: + (m_d + DIM m_o) sum of |K| over the star (record lists, 4 lanes per row)
+        if (!MASS) {
+            for (int l = tid; l < nr; l += nthr) {
+                const uint32_t ri = rinfo[l];
+                const int q0 = ri & 0xffffu, L = ri >> 24;
+                if (L == 0) continue;
+                double sx = 0.0;
+                for (int k = 0; k < L; ++k) sx += sE[q0 + k];
+                double *dst = out + (size_t)gbase[l] + ((ri >> 16) & 255u);
+                *dst = accumulate ? *dst - sx : -sx;
             }
-            const double d = MASS ? (cmd + DIM * cmo) * (sd * (1.0 / DIM)) - s : -s;
-            double *dst = out + (size_t)gbase[l] + ((ri >> 16) & 255u);
-            *dst = accumulate ? *dst + d : d;
+        } else {
+            for (int i0 = 0; i0 < 4 * nr; i0 += nthr) {
+                const int idx = i0 + tid, l = idx >> 2, j = idx & 3;
+                double sx = 0.0, sd = 0.0;
+                uint32_t ri = 0;
+                if (l < nr) {
+                    ri = rinfo[l];
+                    const int q0 = ri & 0xffffu, L = ri >> 24;
+                    for (int k = j; k < L; k += 4) sx += sE[q0 + k];
+                    const uint32_t *rb = reinterpret_cast<const uint32_t *>(smem_raw + (b ? S.rb1 : S.rb0));
+                    const uint16_t *rro = reinterpret_cast<const uint16_t *>(rb + rb[1]), *rec = reinterpret_cast<const uint16_t *>(rb + rb[2]);
+                    const int o1 = rro[l + 1];
+                    for (int r = rro[l] + j; r < o1; r += 4) sd += sV[NP * NES + (rec[r] >> 2)];
+                }
+                sx += __shfl_xor_sync(0xffffffffu, sx, 1);
+                sx += __shfl_xor_sync(0xffffffffu, sx, 2);
+                sd += __shfl_xor_sync(0xffffffffu, sd, 1);
+                sd += __shfl_xor_sync(0xffffffffu, sd, 2);
+                if (l < nr && j == 0 && (ri >> 24) != 0) {
+                    const double d = (cmd + DIM * cmo) * sd - sx;
+                    double *dst = out + (size_t)gbase[l] + ((ri >> 16) & 255u);
+                    *dst = accumulate ? *dst + d : d;
+                }
+            }
         }
         __syncthreads(); // buffer b, sV and sE are free again
+    }
+}
+
+// Right-hand side of a P1 space by tiles: b_i = sum over the star of i of |K| (c_0 <lambda> + sum_x c_x d_x lambda_i),
+// i.e. (RFAC c_0 <lambda>) sum det + (RFAC W) sum_x c_x sum N_i[x]  (AssembleLinearForm, fflib/problem.cpp:10878-11227,
+// Element_rhs :7917-7985).  Every element is evaluated once per tile (its determinant, with gradient terms its
+// normals); 4 lanes per row add the star's values through the row's record list.  Only the head of the tile descriptor
+// (row ids, coordinates, element words) is copied, plus the record lists.
+struct RhsCoef {
+    double cval[3];     // per component: RFAC * c_0 * <lambda>
+    double cgrad[3][3]; // per component: RFAC * W * c_x
+};
+
+template <int DIM, bool GRAD>
+__global__ void __launch_bounds__(512) k_rhs_tiles(const uint32_t *__restrict__ toff, const uint32_t *__restrict__ tpre,
+                                                   const uint32_t *__restrict__ blob, const uint32_t *__restrict__ roff,
+                                                   const uint32_t *__restrict__ rblob, int ntiles, double *__restrict__ bvec, int nc,
+                                                   int accumulate, const __grid_constant__ RhsCoef C, const TileSmem S)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar[2];
+    constexpr int NV = DIM + 1;
+    double *sV = reinterpret_cast<double *>(smem_raw + S.vals); // det[NES] (+ N[a][x][NES] when GRAD)
+    const int NES = S.nes;
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    tile_mbar_init(mbar);
+    auto issue = [&](int b, int t) {
+        const uint32_t w0 = __ldg(toff + t), bytes = __ldg(tpre + t) * 4u;
+        const uint32_t r0 = __ldg(roff + t), rbytes = (__ldg(roff + t + 1) - r0) * 4u;
+        const uint32_t bar = smem_u32(&mbar[b]);
+        tile_expect(bar, bytes + rbytes);
+        tile_bulk(smem_u32(smem_raw + (b ? S.buf1 : 0)), blob + w0, bytes, bar);
+        tile_bulk(smem_u32(smem_raw + (b ? S.rb1 : S.rb0)), rblob + r0, rbytes, bar);
+    };
+    int t = blockIdx.x, b = 0;
+    uint32_t ph0 = 0, ph1 = 0;
+    if (tid == 0 && t < ntiles) issue(0, t);
+    for (; t < ntiles; t += gridDim.x, b ^= 1) {
+        if (tid == 0 && t + (int)gridDim.x < ntiles) issue(b ^ 1, t + gridDim.x);
+        tile_wait(smem_u32(&mbar[b]), b ? ph1 : ph0);
+        if (b) ph1 ^= 1;
+        else ph0 ^= 1;
+        const uint32_t *sb = reinterpret_cast<const uint32_t *>(smem_raw + (b ? S.buf1 : 0));
+        const uint32_t *rb = reinterpret_cast<const uint32_t *>(smem_raw + (b ? S.rb1 : S.rb0));
+        const int nr = sb[0], nelem = sb[2];
+        const int32_t *grow = reinterpret_cast<const int32_t *>(sb + sb[12]);
+        const double *coord = reinterpret_cast<const double *>(sb + sb[7]);
+        const uint32_t *telem = sb + sb[8];
+        const uint16_t *rro = reinterpret_cast<const uint16_t *>(rb + rb[1]), *rec = reinterpret_cast<const uint16_t *>(rb + rb[2]);
+        for (int e = tid; e < nelem; e += nthr) {
+            double N[NV][DIM], det;
+            tile_geom<DIM>(coord, telem[e], N, det);
+            sV[e] = det;
+            if (GRAD) {
+#pragma unroll
+                for (int a = 0; a < NV; ++a)
+#pragma unroll
+                    for (int x = 0; x < DIM; ++x) sV[(1 + a * DIM + x) * NES + e] = N[a][x];
+            }
+        }
+        __syncthreads();
+        for (int i0 = 0; i0 < 4 * nr; i0 += nthr) {
+            const int idx = i0 + tid, l = idx >> 2, j = idx & 3;
+            double sd = 0.0, sn[DIM];
+#pragma unroll
+            for (int x = 0; x < DIM; ++x) sn[x] = 0.0;
+            if (l < nr) {
+                const int o1 = rro[l + 1];
+                for (int r = rro[l] + j; r < o1; r += 4) {
+                    const uint32_t c = rec[r];
+                    sd += sV[c >> 2];
+                    if (GRAD) {
+#pragma unroll
+                        for (int x = 0; x < DIM; ++x) sn[x] += sV[(1 + (c & 3u) * DIM + x) * NES + (c >> 2)];
+                    }
+                }
+            }
+            sd += __shfl_xor_sync(0xffffffffu, sd, 1);
+            sd += __shfl_xor_sync(0xffffffffu, sd, 2);
+            if (GRAD) {
+#pragma unroll
+                for (int x = 0; x < DIM; ++x) {
+                    sn[x] += __shfl_xor_sync(0xffffffffu, sn[x], 1);
+                    sn[x] += __shfl_xor_sync(0xffffffffu, sn[x], 2);
+                }
+            }
+            if (l < nr && j == 0) {
+                for (int c = 0; c < nc; ++c) {
+                    double v = C.cval[c] * sd;
+                    if (GRAD) {
+#pragma unroll
+                        for (int x = 0; x < DIM; ++x) v = fma(C.cgrad[c][x], sn[x], v);
+                    }
+                    double *dst = bvec + (size_t)grow[l] * nc + c;
+                    *dst = accumulate ? *dst + v : v;
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -739,7 +916,7 @@ void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr)
         FF_CUDA(cudaMemcpyAsync(d_tstart.p, tstart.data(), tstart.size() * 4, cudaMemcpyHostToDevice, st));
         ff_launch(ctx, "tile_sizes", [&] {
             kstat<<<ntiles, TB_THREADS, shmem, st>>>(rord.p, d_tstart.p, m->conn.p, V, m->xyz.p, m->vstride, nrowptr, 1, d_stats.p,
-                                                     nullptr, nullptr);
+                                                     nullptr, nullptr, nullptr, nullptr);
         });
         hst.resize((size_t)ntiles * 8);
         FF_CUDA(ff_memcpy_sync(ctx, hst.data(), d_stats.p, hst.size() * 4, cudaMemcpyDeviceToHost));
@@ -759,30 +936,45 @@ void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr)
         tstart.swap(ns);
     }
     // ---- offsets, maxima
-    std::vector<uint32_t> htoff((size_t)ntiles + 1);
-    uint64_t off = 0;
+    std::vector<uint32_t> htoff((size_t)ntiles + 1), hroff((size_t)ntiles + 1), hpre((size_t)ntiles + 1, 0);
+    uint64_t off = 0, roffs = 0;
+    T.max_pre = T.max_rwords = 0;
     T.max_rows = T.max_nvt = T.max_nelem = T.max_nq = T.max_ncodes = T.max_words = 0;
     T.sum_nelem = 0;
     for (int t = 0; t < ntiles; ++t) {
         const int32_t *h = &hst[(size_t)t * 8];
         const int nvt = h[0], nelem = h[1], nq = h[2], ncodes = h[3], nr = h[5];
-        const int words = HDR + pad4(nr) + pad4(nr + 1) + pad4(2 * dim * nvt) + pad4(nelem) + pad4(nq + 1) + pad4((ncodes + 1) / 2);
+        const int nrec = h[6];
+        const int pre = HDR + 2 * pad4(nr) + pad4(nr + 1) + pad4(2 * dim * nvt) + pad4(nelem); // up to the entry words
+        const int words = pre + pad4(nq + 1) + pad4((ncodes + 1) / 2);
+        const int rwords = 4 + pad4((nr + 2) / 2) + pad4((nrec + 1) / 2);
         htoff[t] = (uint32_t)off;
+        hroff[t] = (uint32_t)roffs;
+        hpre[t] = (uint32_t)pre;
         off += (uint64_t)words;
+        roffs += (uint64_t)rwords;
+        T.max_pre = std::max(T.max_pre, pre);
+        T.max_rwords = std::max(T.max_rwords, rwords);
         T.max_rows = std::max(T.max_rows, nr); T.max_nvt = std::max(T.max_nvt, nvt); T.max_nelem = std::max(T.max_nelem, nelem);
         T.max_nq = std::max(T.max_nq, nq); T.max_ncodes = std::max(T.max_ncodes, ncodes); T.max_words = std::max(T.max_words, words);
         T.sum_nelem += nelem;
     }
-    if (off >= ((uint64_t)1 << 32)) return;
+    if (off >= ((uint64_t)1 << 32) || roffs >= ((uint64_t)1 << 32)) return;
+    hroff[ntiles] = (uint32_t)roffs;
     T.nes = T.max_nelem | 1; // odd stride of the value table
     if ((DIM_PAIRS(dim) + 1) * T.nes > 65535) return;
     htoff[ntiles] = (uint32_t)off;
     T.toff.alloc((size_t)ntiles + 1);
+    T.roff.alloc((size_t)ntiles + 1);
+    T.tpre.alloc((size_t)ntiles + 1);
     T.blob.alloc((size_t)off + 4);
+    T.rblob.alloc((size_t)roffs + 4);
     FF_CUDA(cudaMemcpyAsync(T.toff.p, htoff.data(), htoff.size() * 4, cudaMemcpyHostToDevice, st));
+    FF_CUDA(cudaMemcpyAsync(T.roff.p, hroff.data(), hroff.size() * 4, cudaMemcpyHostToDevice, st));
+    FF_CUDA(cudaMemcpyAsync(T.tpre.p, hpre.data(), hpre.size() * 4, cudaMemcpyHostToDevice, st));
     ff_launch(ctx, "tile_build", [&] {
         kwrite<<<ntiles, TB_THREADS, shmem, st>>>(rord.p, d_tstart.p, m->conn.p, V, m->xyz.p, m->vstride, nrowptr, T.nes, nullptr,
-                                                  T.toff.p, T.blob.p);
+                                                  T.toff.p, T.blob.p, T.roff.p, T.rblob.p);
     });
     FF_CUDA(cudaStreamSynchronize(st)); // htoff / tstart are host vectors
     T.tr = tr;
@@ -790,11 +982,38 @@ void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr)
     T.state = 1;
     if (getenv("FFCUDA_VERBOSE"))
         fprintf(stderr, "ffcuda tiles: %d tiles of <= %d rows, max rows %d vertices %d elements %d entries %d codes %d, "
-                        "%.2f evaluations per element, blob %.1f MB\n",
+                        "%.2f evaluations per element, blobs %.1f + %.1f MB\n",
                 ntiles, tr, T.max_rows, T.max_nvt, T.max_nelem, T.max_nq, T.max_ncodes, (double)T.sum_nelem / std::max(1, m->nt),
-                off * 4.0 / 1e6);
+                off * 4.0 / 1e6, roffs * 4.0 / 1e6);
 }
 
+} // namespace
+
+namespace {
+// tile set of the space, built on demand; false when the tile path does not apply (policy, capacities)
+bool tiles_ready(ffcuda_ctx *ctx, ffcuda_space *s, ffcuda_pattern *P)
+{
+    TileSet &T = s->tiles;
+    if (ctx->tile_policy == 0 || T.state < 0) return false;
+    if (T.state == 0) {
+        if (!P) return false; // the row pointers of a pattern are baked in: the first matrix assembly builds the set
+        if (ctx->tile_policy == 1 && s->lean_assemblies < 2) return false;
+        build_tiles(ctx, s, P->nrowptr.p); // every pattern of a fespace has the same row pointers
+        if (T.state != 1) return false;
+        T.nnz_node = P->nnz_node;
+    }
+    return true;
+}
+
+template <class K>
+void tile_launch(ffcuda_ctx *ctx, const char *name, K kern, int threads, size_t shmem, int ntiles, const std::function<void(int)> &go)
+{
+    FF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    int per_sm = 1;
+    FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, shmem));
+    const int grid = std::max(1, std::min(ntiles, std::max(1, per_sm) * ctx->sm_count));
+    ff_launch(ctx, name, [&] { go(grid); });
+}
 } // namespace
 
 bool ff_asm_p1_tiles(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, double cw, double cmd, double cmo, int accumulate)
@@ -802,16 +1021,10 @@ bool ff_asm_p1_tiles(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, double 
     TileSet &T = s->tiles;
     ffcuda_pattern *P = A->pattern;
     s->lean_assemblies++;
-    if (ctx->tile_policy == 0 || T.state < 0) return false;
-    // forms with a mass term need the determinants around every edge as a second sum: measured slower than the
-    // thread-per-row kernel (569 vs 496 us on cube(128)), so they stay there unless tiles are forced (policy 2)
+    // forms with a mass term are (measured) slower by tiles than by rows (0.60-0.67 vs 0.50 ms on cube(128): the star sums
+    // of the diagonal and the second descriptor blob): they stay on the thread-per-row kernel unless tiles are forced
     if ((cmd != 0.0 || cmo != 0.0) && ctx->tile_policy != 2) return false;
-    if (T.state == 0) {
-        if (ctx->tile_policy == 1 && s->lean_assemblies < 2) return false;
-        build_tiles(ctx, s, P->nrowptr.p); // the row pointers are baked in: every pattern of a fespace has the same ones
-        if (T.state != 1) return false;
-        T.nnz_node = P->nnz_node;
-    }
+    if (!tiles_ready(ctx, s, P)) return false;
     FF_REQUIRE(T.nnz_node == P->nnz_node, "internal: tile set and pattern disagree");
     ffcuda_mesh *m = s->mesh;
     const int dim = m->dim;
@@ -821,33 +1034,82 @@ bool ff_asm_p1_tiles(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, double 
     size_t o = ((size_t)T.max_words * 4 + 127) & ~(size_t)127;
     S.buf1 = (int)o;
     o *= 2;
+    S.rb0 = S.rb1 = (int)o;
+    if (mass) {
+        const size_t rb = ((size_t)T.max_rwords * 4 + 127) & ~(size_t)127;
+        S.rb1 = (int)(o + rb);
+        o += 2 * rb;
+    }
     S.ent = (int)o;
     o += (size_t)(T.max_nq + 1) * 8;
     S.nes = T.nes;
     o = (o + 127) & ~(size_t)127; // the bank of a value is its index mod 16 (the build kernel orders the lists by it)
     S.vals = (int)o;
     o += (size_t)(NP + (mass ? 1 : 0)) * S.nes * 8;
-    S.sd = (int)o;
-    if (mass) o += (size_t)(T.max_nq + 1) * 8;
     const size_t shmem = o;
     if (shmem > 200 * 1024) return false;
     int threads = 512;
     if (const char *e = getenv("FFCUDA_TILE_THREADS")) threads = std::max(32, std::min(512, atoi(e) & ~31));
-    auto launch = [&](auto kern) {
-        FF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-        int per_sm = 1;
-        FF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, shmem));
-        const int grid = std::max(1, std::min(T.ntiles, std::max(1, per_sm) * ctx->sm_count));
-        ff_launch(ctx, "asm_rows_p1", [&] {
-            kern<<<grid, threads, shmem, ctx->stream>>>(T.toff.p, T.blob.p, T.ntiles, A->vals.p, accumulate, cw, cmd, cmo, S);
+    auto run = [&](auto kern) {
+        tile_launch(ctx, "asm_rows_p1", kern, threads, shmem, T.ntiles, [&](int grid) {
+            kern<<<grid, threads, shmem, ctx->stream>>>(T.toff.p, T.blob.p, T.roff.p, T.rblob.p, T.ntiles, A->vals.p, accumulate, cw, cmd,
+                                                        cmo, S);
         });
     };
     if (dim == 3) {
-        if (mass) launch(k_asm_tiles<3, true>);
-        else launch(k_asm_tiles<3, false>);
+        if (mass) run(k_asm_tiles<3, true>);
+        else run(k_asm_tiles<3, false>);
     } else {
-        if (mass) launch(k_asm_tiles<2, true>);
-        else launch(k_asm_tiles<2, false>);
+        if (mass) run(k_asm_tiles<2, true>);
+        else run(k_asm_tiles<2, false>);
+    }
+    return true;
+}
+
+// b (+)= sum over the stars: cval[c] * sum det + sum_x cgrad[c][x] * sum N_i[x]; only on spaces whose tile set exists
+bool ff_rhs_p1_tiles(ffcuda_ctx *ctx, ffcuda_vec *b, ffcuda_space *s, const double *cval, const double *cgrad /* [nc][3] */, int hasgrad,
+                     int accumulate)
+{
+    TileSet &T = s->tiles;
+    if (ctx->tile_policy == 0 || T.state != 1) return false;
+    // gradient terms move 12 more values per element through shared memory: measured slower than the thread-per-row
+    // kernel (350 vs 231 us on cube(128)); value-only forms: 162 vs 217 us
+    if (hasgrad && ctx->tile_policy != 2) return false;
+    const int dim = s->mesh->dim, nc = s->ncomp;
+    RhsCoef C;
+    memset(&C, 0, sizeof(C));
+    for (int c = 0; c < nc; ++c) {
+        C.cval[c] = cval[c];
+        for (int x = 0; x < 3; ++x) C.cgrad[c][x] = cgrad[c * 3 + x];
+    }
+    TileSmem S;
+    size_t o = ((size_t)T.max_pre * 4 + 127) & ~(size_t)127;
+    S.buf1 = (int)o;
+    o *= 2;
+    const size_t rb = ((size_t)T.max_rwords * 4 + 127) & ~(size_t)127;
+    S.rb0 = (int)o;
+    S.rb1 = (int)(o + rb);
+    o += 2 * rb;
+    S.ent = (int)o;
+    S.nes = T.nes;
+    S.vals = (int)o;
+    o += (size_t)(1 + (hasgrad ? (dim + 1) * dim : 0)) * S.nes * 8;
+    const size_t shmem = o;
+    if (shmem > 200 * 1024) return false;
+    int threads = 128;
+    if (const char *e = getenv("FFCUDA_RHS_THREADS")) threads = std::max(32, std::min(512, atoi(e) & ~31));
+    auto run = [&](auto kern) {
+        tile_launch(ctx, "rhs_rows", kern, threads, shmem, T.ntiles, [&](int grid) {
+            kern<<<grid, threads, shmem, ctx->stream>>>(T.toff.p, T.tpre.p, T.blob.p, T.roff.p, T.rblob.p, T.ntiles, b->d.p, nc, accumulate,
+                                                        C, S);
+        });
+    };
+    if (dim == 3) {
+        if (hasgrad) run(k_rhs_tiles<3, true>);
+        else run(k_rhs_tiles<3, false>);
+    } else {
+        if (hasgrad) run(k_rhs_tiles<2, true>);
+        else run(k_rhs_tiles<2, false>);
     }
     return true;
 }

@@ -213,3 +213,39 @@ def test_lazy_positions_after_tiles_are_built(ctx):
     d, _ = ol.bc_pairs(m, 1, 1, None, fc.ALL6, 1, [0.0])
     diag_idx = np.array([rp1[i] + np.searchsorted(col1[rp1[i]:rp1[i + 1]], i) for i in np.unique(d)])
     assert np.all(v[diag_idx] == TGV)
+
+
+RHS_CASES = [("cube", (9, 7, 8), [(0, fc.ID, 1.0)]), ("cube", (6, 6, 5), [(0, fc.ID, 2.0), (0, fc.DX, 0.5), (0, fc.DZ, -1.5)]),
+             ("square", (23, 17), [(0, fc.ID, 1.0)]), ("square", (14, 19), [(0, fc.DY, 3.0), (0, fc.ID, -0.25)])]
+
+
+@pytest.mark.parametrize("rows", [16, 96])
+@pytest.mark.parametrize("case", RHS_CASES, ids=[f"{k}{'x'.join(map(str, s))}_{len(t)}t" for k, s, t in RHS_CASES])
+def test_rhs_by_tiles_against_oracle(ctx, case, rows):
+    """right-hand side through the row tiles (value and gradient terms) = oracle = thread-per-row kernel; accumulation"""
+    kind, size, lt = case
+    dim = 3 if kind == "cube" else 2
+    m = ol.cube(*size) if kind == "cube" else ol.square(*size)
+    mesh = ctx.mesh_cube(*size) if kind == "cube" else ctx.mesh_square(*size)
+    qp, qw = ffcuda.quadrature(dim, 6)
+    n = m["xyz"].shape[0]
+    ob = ol.assemble_rhs(m, 1, 1, None, n, lt, qp, qw)
+    sp, pat, A = _assemble(ctx, mesh, fc.LAP3 if dim == 3 else fc.LAP2, qp, qw, 2, rows)   # builds the tile set
+    ctx.prof_enable(True)
+    ctx.prof_reset()
+    b = ctx.vec(n)
+    sp.assemble_linear(b, lt, qp, qw)
+    hb = b.download()
+    assert np.max(np.abs(hb - ob)) <= RTOL * np.abs(ob).max()
+    sp.assemble_linear(b, lt, qp, qw, accumulate=True)
+    assert np.max(np.abs(b.download() - 2 * ob)) <= 2 * RTOL * np.abs(ob).max()
+    ctx.prof_enable(False)
+    ctx.set_option("tile_policy", 0)
+    b0 = ctx.vec(n)
+    sp.assemble_linear(b0, lt, qp, qw)
+    assert np.max(np.abs(b0.download() - hb)) <= RTOL * np.abs(ob).max()
+    # reproducible
+    ctx.set_option("tile_policy", 2)
+    b1 = ctx.vec(n)
+    sp.assemble_linear(b1, lt, qp, qw)
+    assert np.array_equal(b1.download(), hb)
