@@ -331,18 +331,35 @@ __global__ void __launch_bounds__(RED_THREADS) k_spmv_nodeblock(const int32_t *_
     double acc0 = 0.0, acc1 = 0.0;
     const int lane = threadIdx.x & 31;
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    for (int i = warp; i < nnode; i += nwarps) {
-        const int nb = __ldg(nrowptr + i), len = NC * (__ldg(nrowptr + i + 1) - nb);
+    // the header of the next node row (node-level and dof-level row pointers) is fetched while the current one is summed
+    int i = warp;
+    int nb = 0, ne = 0;
+    size_t vo[NC];
+    if (i < nnode) {
+        nb = __ldg(nrowptr + i);
+        ne = __ldg(nrowptr + i + 1);
+#pragma unroll
+        for (int c = 0; c < NC; ++c) vo[c] = (size_t)__ldg(rowptr + NC * i + c);
+    }
+    for (; i < nnode; i += nwarps) {
+        const int len = NC * (ne - nb), nbc = nb;
         const double *v[NC];
 #pragma unroll
-        for (int c = 0; c < NC; ++c) v[c] = vals + __ldg(rowptr + NC * i + c);
+        for (int c = 0; c < NC; ++c) v[c] = vals + vo[c];
+        const int inext = i + nwarps;
+        if (inext < nnode) {
+            nb = __ldg(nrowptr + inext);
+            ne = __ldg(nrowptr + inext + 1);
+#pragma unroll
+            for (int c = 0; c < NC; ++c) vo[c] = (size_t)__ldg(rowptr + NC * inext + c);
+        }
         double s[NC];
 #pragma unroll
         for (int c = 0; c < NC; ++c) s[c] = 0.0;
-#pragma unroll 2
+#pragma unroll 4
         for (int k = lane; k < len; k += 32) {
             const int jn = NC == 3 ? (int)(((unsigned)k * 0xAAABu) >> 17) : (NC == 2 ? k >> 1 : k); // k / NC for k < 2^15
-            const double xv = __ldg(x + NC * __ldg(ncol + nb + jn) + (k - NC * jn));
+            const double xv = __ldg(x + NC * __ldg(ncol + nbc + jn) + (k - NC * jn));
 #pragma unroll
             for (int c = 0; c < NC; ++c) s[c] = fma(__ldcs(v[c] + k), xv, s[c]);
         }

@@ -175,20 +175,6 @@ __device__ int blk_scan(int *a, int n, int *part)
     return part[TB_THREADS];
 }
 
-// sorted a[0..m) (padding = 0xffffffff at the end) -> distinct values, compacted into out[]; returns their number
-__device__ int blk_unique(const uint32_t *a, int m, int *flag, uint32_t *out, int outcap, int *part)
-{
-    for (int x = threadIdx.x; x < m; x += TB_THREADS) flag[x] = (a[x] != 0xffffffffu && (x == 0 || a[x] != a[x - 1])) ? 1 : 0;
-    __syncthreads();
-    const int nu = blk_scan(flag, m, part);
-    for (int x = threadIdx.x; x < m; x += TB_THREADS) {
-        const bool head = a[x] != 0xffffffffu && (x == 0 || a[x] != a[x - 1]);
-        if (head && flag[x] < outcap) out[flag[x]] = a[x];
-    }
-    __syncthreads();
-    return nu;
-}
-
 __device__ __forceinline__ int bsearch_u32(const uint32_t *a, int n, uint32_t v)
 {
     int lo = 0, hi = n - 1;
@@ -236,38 +222,97 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__rest
         s_n = 0;
         s_bad = 0;
     }
-    for (int x = tid; x < SORT_CAP; x += TB_THREADS) sbuf[x] = 0xffffffffu;
+    // hash tables (open addressing, 1024 slots, in the sort buffer's tail): vertex id -> local row, later vertex id set
+    constexpr int HT = 1024;
+    uint32_t *hkey = sbuf + SORT_CAP - 2 * HT, *hval = hkey + HT;
+    for (int x = tid; x < HT; x += TB_THREADS) hkey[x] = 0xffffffffu;
     __syncthreads();
-    // 1. element ids of the incidence records of the tile's rows
     for (int l = tid; l < nr; l += TB_THREADS) {
-        const int row = rord[r0 + l];
-        const int c = V.cnt[row];
-        const int o = atomicAdd(&s_n, c);
-        if (o + c > SORT_CAP) s_bad = 1;
-        else
-            for (int e = 0; e < c; ++e) sbuf[o + e] = V.inc[V.idx(row, e)] >> 4;
+        const uint32_t v = (uint32_t)rord[r0 + l];
+        uint32_t h = (v * 0x9E3779B1u) >> 22;
+        while (atomicCAS(&hkey[h], 0xffffffffu, v) != 0xffffffffu) h = (h + 1) & (HT - 1);
+        hval[h] = (uint32_t)l;
+        atomicAdd(&s_n, V.cnt[rord[r0 + l]]);
     }
     __syncthreads();
-    int fit = (nr <= TR_CAP && !s_bad) ? 1 : 0;
+    // 1. elements of the tile.  A record (row l, element k) contributes k when l is the smallest local row among the
+    // element's vertices that are rows of the tile: every element exactly once, no sort over all the records
+    int fit = (nr <= TR_CAP && s_n <= 65535) ? 1 : 0;
     int nelem = 0, nvt = 0, nq = 0, ncodes = 0;
+    __shared__ int s_ne, s_nv;
+    if (tid == 0) s_ne = s_nv = 0;
+    __syncthreads();
     if (fit) {
-        int m = 32;
-        while (m < s_n) m <<= 1;
-        blk_sort(sbuf, m);
-        nelem = blk_unique(sbuf, m, tmp, elist, NE_CAP, part);
+        for (int l = tid; l < nr; l += TB_THREADS) {
+            const int row = rord[r0 + l];
+            const int c = V.cnt[row];
+            for (int e = 0; e < c; ++e) {
+                const uint32_t ka = V.inc[V.idx(row, e)];
+                const uint32_t k = ka >> 4;
+                const int a = ka & 15;
+                bool first = true;
+                for (int bb = 0; bb < NV && first; ++bb) {
+                    if (bb == a) continue;
+                    const uint32_t v = (uint32_t)conn[(size_t)k * NV + bb];
+                    uint32_t h = (v * 0x9E3779B1u) >> 22;
+                    while (hkey[h] != 0xffffffffu) {
+                        if (hkey[h] == v) {
+                            if ((int)hval[h] < l) first = false;
+                            break;
+                        }
+                        h = (h + 1) & (HT - 1);
+                    }
+                }
+                if (first) {
+                    const int o = atomicAdd(&s_ne, 1);
+                    if (o < NE_CAP) elist[o] = k;
+                }
+            }
+        }
+        __syncthreads();
+        nelem = s_ne;
         if (nelem > NE_CAP) fit = 0;
     }
     if (fit) {
-        // 2. distinct vertices, ascending
-        for (int x = tid; x < SORT_CAP; x += TB_THREADS) sbuf[x] = 0xffffffffu;
-        __syncthreads();
-        for (int x = tid; x < nelem * NV; x += TB_THREADS) sbuf[x] = (uint32_t)conn[(size_t)elist[x / NV] * NV + (x % NV)];
-        __syncthreads();
         int m = 32;
-        while (m < nelem * NV) m <<= 1;
-        blk_sort(sbuf, m);
-        nvt = blk_unique(sbuf, m, tmp, vlist, NV_CAP, part);
+        while (m < nelem) m <<= 1;
+        for (int x = nelem + tid; x < m; x += TB_THREADS) elist[x] = 0xffffffffu;
+        __syncthreads();
+        blk_sort(elist, m); // ascending element ids
+        // 2. distinct vertices: hash set, then sorted
+        for (int x = tid; x < HT; x += TB_THREADS) hkey[x] = 0xffffffffu;
+        __syncthreads();
+        for (int x = tid; x < nelem * NV; x += TB_THREADS) {
+            const uint32_t v = (uint32_t)conn[(size_t)elist[x / NV] * NV + (x % NV)];
+            uint32_t h = (v * 0x9E3779B1u) >> 22;
+            while (true) {
+                const uint32_t k = hkey[h];
+                if (k == v) break;
+                if (k == 0xffffffffu) {
+                    // more than NV_CAP distinct vertices: the tile is unfit, stop filling (the table cannot overflow:
+                    // at most TB_THREADS insertions are in flight past the test)
+                    if (*reinterpret_cast<volatile int *>(&s_nv) > NV_CAP) break;
+                    const uint32_t old = atomicCAS(&hkey[h], 0xffffffffu, v);
+                    if (old == 0xffffffffu) {
+                        const int o = atomicAdd(&s_nv, 1);
+                        if (o < NV_CAP) vlist[o] = v;
+                        break;
+                    }
+                    if (old == v) break;
+                }
+                h = (h + 1) & (HT - 1);
+            }
+        }
+        __syncthreads();
+        nvt = s_nv;
         if (nvt > NV_CAP) fit = 0;
+    }
+    if (fit) {
+        int m = 32;
+        while (m < nvt) m <<= 1;
+        for (int x = nvt + tid; x < m; x += TB_THREADS) vlist[x] = 0xffffffffu;
+        __syncthreads();
+        blk_sort(vlist, m);
     }
     if (fit) {
         // 3. slots of every element's vertices; rows <-> slots
