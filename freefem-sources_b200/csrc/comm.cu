@@ -110,7 +110,7 @@ struct HaloArgs {
 
 // all blocks co-resident (grid <= number of SMs): send phase, grid-wide "last block publishes", receive phase
 __global__ void __launch_bounds__(256) k_p2p_halo(const PeerPtrs P, int rank, double *__restrict__ v, const HaloArgs H, size_t cap,
-                                                  unsigned long long seq)
+                                                  unsigned long long seq, P2PDesc *D)
 {
     const int par = (int)(seq & 1ull);
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
@@ -138,7 +138,12 @@ __global__ void __launch_bounds__(256) k_p2p_halo(const PeerPtrs P, int rank, do
         if (H.nbr[s] < 0) continue;
         if (threadIdx.x == 0) {
             const unsigned long long *f = reinterpret_cast<const unsigned long long *>(P.p[rank] + P2P_HFLAG) + s * 2 + par;
+            const long long t0 = clock64();
             while (ld_sys_u64(f) != seq) {
+                if (clock64() - t0 > FF_P2P_SPIN_LIMIT) { // crashed neighbour: do not hang the device
+                    D->timed_out = 1;
+                    break;
+                }
             }
         }
         __syncthreads();
@@ -330,7 +335,8 @@ void ff_halo_exchange(ffcuda_matrix *A, double *v)
         const size_t most = (size_t)std::max(std::max(H.send_cnt[0], H.send_cnt[1]), std::max(H.recv_cnt[0], H.recv_cnt[1]));
         const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count / 2, (most + 1023) / 1024));
         ff_launch(ctx, "halo_p2p", [&] {
-            k_p2p_halo<<<grid, 256, 0, ctx->stream>>>(peer_ptrs(ctx), ctx->rank, v, H, ctx->p2p_halo_cap, seq);
+            k_p2p_halo<<<grid, 256, 0, ctx->stream>>>(peer_ptrs(ctx), ctx->rank, v, H, ctx->p2p_halo_cap, seq,
+                                                      reinterpret_cast<P2PDesc *>(ctx->d_scal + FF_P2P_DESC_OFF));
         });
     }
     if (!any_nccl) return;

@@ -125,11 +125,12 @@ constexpr size_t FF_P2P_RFLAG = 0, FF_P2P_RDATA = 4096, FF_P2P_HFLAG = 8192, FF_
 constexpr int FF_P2P_MAXR = 16;
 // lives in device memory at ctx->d_scal + FF_P2P_DESC_OFF (doubles), i.e. FF_P2P_DESC_OFF - 32 doubles behind the CG flags
 constexpr int FF_P2P_DESC_OFF = 64;
+constexpr long long FF_P2P_SPIN_LIMIT = 60000000000ll; // clock cycles (~30 s: ranks may legitimately arrive seconds apart)
 struct P2PDesc {
     unsigned char *peer[FF_P2P_MAXR]; // rank r's mailbox in this process' address space
     int rank, nranks;
     int fused;                        // the dot products of the running CG are all-reduced by their own kernels
-    int pad;
+    int timed_out;                    // a spin on a peer's sequence number gave up: the solve reports an error
     unsigned long long seq;           // number of all-reduces so far: advanced on the device, in lockstep on all ranks
 };
 #ifdef __CUDACC__
@@ -169,7 +170,13 @@ __device__ __forceinline__ void ff_p2p_allreduce_warp(P2PDesc *D, double (&t)[NV
         ff_st_release_sys(reinterpret_cast<unsigned long long *>(D->peer[lane] + FF_P2P_RFLAG) + par * FF_P2P_MAXR + rank, seq);
         const unsigned long long *mine =
             reinterpret_cast<const unsigned long long *>(D->peer[rank] + FF_P2P_RFLAG) + par * FF_P2P_MAXR + lane;
+        // a peer that never arrives (crashed rank) must not hang the device: give up after ~30 s and flag it
+        const long long t0 = clock64();
         while (ff_ld_acquire_sys(mine) != seq) {
+            if (clock64() - t0 > FF_P2P_SPIN_LIMIT) {
+                D->timed_out = 1;
+                break;
+            }
         }
     }
     __syncwarp();

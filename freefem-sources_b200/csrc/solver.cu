@@ -968,6 +968,12 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
     FF_CUDA(cudaMemcpyAsync(hflags, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
     FF_CUDA(cudaMemcpyAsync(hs, scal, 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
     FF_CUDA(cudaStreamSynchronize(st));
+    if (ctx->p2p && ff_is_distributed(A)) {
+        int to = 0;
+        FF_CUDA(ff_memcpy_sync(ctx, &to, reinterpret_cast<char *>(scal + FF_P2P_DESC_OFF) + offsetof(P2PDesc, timed_out), sizeof(int),
+                               cudaMemcpyDeviceToHost));
+        FF_REQUIRE(to == 0, "CG: a peer rank did not answer within the spin limit (multi-GPU exchange timed out)");
+    }
     const int ci = hflags[F_CONV_ITER];
     FF_REQUIRE(ci != -2, "CG: <g,Cg> is NaN (bad matrix)");
     const int ret = ci == -1 ? 2 : (ci > 0 ? 1 : 0);

@@ -33,7 +33,10 @@ def main():
     dist.broadcast(idt, 0)
     ctx.comm_init(rank, world, bytes(idt.cpu().tolist()))
     ok = True
-    for dims in [(6, 5, 7), (16, 12, 21)]:
+    # every mesh twice: thread-per-row kernels (tile_policy 1: one assembly per fespace never builds the tiles) and row
+    # tiles for the matrix and the right-hand side (tile_policy 2)
+    for dims, policy in [((6, 5, 7), 1), ((16, 12, 21), 1), ((6, 5, 7), 2), ((16, 12, 21), 2)]:
+        ctx.set_option("tile_policy", policy)
         nx, ny, nz = dims
         qp, qw = ffcuda.quadrature(3, 6)
         mesh = ctx.mesh_cube(nx, ny, nz, distributed=True)
@@ -97,7 +100,7 @@ def main():
             assert its == {oit} and all(p["conv"] == 1 for p in allp), (its, oit)
             uu = np.concatenate([p["u"] for p in allp])
             assert np.max(np.abs(uu - ox)) <= 1e-12 * np.abs(ox).max()
-            print(f"dist_check cube{dims} on {world} GPUs: n={N} nnz={len(ocol)} cg_iters={oit} OK", flush=True)
+            print(f"dist_check cube{dims} tile_policy={policy} on {world} GPUs: n={N} nnz={len(ocol)} cg_iters={oit} OK", flush=True)
     dist.barrier()
     ctx.comm_finalize()
     dist.destroy_process_group()
