@@ -480,7 +480,9 @@ __global__ void __launch_bounds__(128) k_asm_p1_lean(const double *__restrict__ 
 // ----------------------------------------------------------------------------------------------------
 // P2: one group of GL lanes per node row, lane b handles the pair (a, b)
 // ----------------------------------------------------------------------------------------------------
-template <int DIM, int NC, int GL, typename PosT>
+// GG: the form only couples gradients (d_x u d_y v terms: Laplace, Lame, ...): the value row/column of the per-pair
+// tensor is not formed and the coefficient contraction runs over the DIM x DIM gradient block without per-term tests
+template <int DIM, int NC, int GL, typename PosT, bool GG>
 __global__ void __launch_bounds__(128) k_asm_p2(const double *__restrict__ xyz, const int32_t *__restrict__ conn,
                                                 const int32_t *__restrict__ elab, int nrows,
                                                 const int32_t *__restrict__ nrowptr, const int32_t *__restrict__ incptr,
@@ -527,17 +529,19 @@ __global__ void __launch_bounds__(128) k_asm_p2(const double *__restrict__ xyz, 
             const int pb = pos[(size_t)e * NL + b];
             const double *R = sR + (a * NL + b) * RS;
             double M[NS][NS];
-            M[0][0] = R[0];
+            if (!GG) {
+                M[0][0] = R[0];
 #pragma unroll
-            for (int x = 0; x < DIM; ++x) {
-                double s0 = 0, s1 = 0;
+                for (int x = 0; x < DIM; ++x) {
+                    double s0 = 0, s1 = 0;
 #pragma unroll
-                for (int r = 0; r < DIM; ++r) {
-                    s0 = fma(R[r + 1], G.g[r][x], s0);          // value(a) * d_x(b)
-                    s1 = fma(R[(r + 1) * NS], G.g[r][x], s1);   // d_x(a) * value(b)
+                    for (int r = 0; r < DIM; ++r) {
+                        s0 = fma(R[r + 1], G.g[r][x], s0);          // value(a) * d_x(b)
+                        s1 = fma(R[(r + 1) * NS], G.g[r][x], s1);   // d_x(a) * value(b)
+                    }
+                    M[0][x + 1] = s0;
+                    M[x + 1][0] = s1;
                 }
-                M[0][x + 1] = s0;
-                M[x + 1][0] = s1;
             }
             // Y[r][x] = sum_r' R[r][r'] g[r'][x] ; M[sv][su] = sum_r g[r][sv] Y[r][su]
             double Y[DIM][DIM];
@@ -564,11 +568,18 @@ __global__ void __launch_bounds__(128) k_asm_p2(const double *__restrict__ xyz, 
 #pragma unroll
                 for (int cu = 0; cu < NC; ++cu) {
                     double v = 0.0;
+                    if (GG) {
 #pragma unroll
-                    for (int sv = 0; sv < NS; ++sv)
+                        for (int sv = 1; sv < NS; ++sv)
 #pragma unroll
-                        for (int su = 0; su < NS; ++su)
-                            if (F.mask >> (sv * 4 + su) & 1u) v = fma(F.C[cv][cu][sv][su], M[sv][su], v);
+                            for (int su = 1; su < NS; ++su) v = fma(F.C[cv][cu][sv][su], M[sv][su], v);
+                    } else {
+#pragma unroll
+                        for (int sv = 0; sv < NS; ++sv)
+#pragma unroll
+                            for (int su = 0; su < NS; ++su)
+                                if (F.mask >> (sv * 4 + su) & 1u) v = fma(F.C[cv][cu][sv][su], M[sv][su], v);
+                    }
                     acc[cv * (NC * L) + pb * NC + cu] += G.mes * v;
                 }
         }
@@ -820,7 +831,8 @@ static void launch_p2(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const 
     int groups = threads / GL;
     size_t shmem = ((size_t)NL * NL * RS + (size_t)groups * S) * 8;
     FF_REQUIRE(shmem <= 220 * 1024, "matrix rows too long for the shared-memory row accumulators");
-    auto kern = k_asm_p2<DIM, NC, GL, PosT>;
+    const bool gg = (F.mask & 0x111Fu) == 0; // no term involves the value of u or v
+    auto kern = gg ? k_asm_p2<DIM, NC, GL, PosT, true> : k_asm_p2<DIM, NC, GL, PosT, false>;
     FF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     int blocks = ff_blocks((size_t)P->nrows_node, groups);
     const Incidence &I = s->incidence;
