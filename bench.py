@@ -325,7 +325,7 @@ def ours(args):
         ms, cnt = ctx.prof_get(key)
         prof[key] = (ms / nprof, cnt // nprof)
     kernels_ms = {}
-    for nm in ("inc_count", "inc_blk_len", "inc_fill", "inc_sort", "inc_stage", "sym_p1_rows", "sym_p1_cols", "sym_p1_positions", "sym_block_pattern", "sym_compact_cols", "sym_row_count", "sym_row_fill", "sym_diagpos", "scan_tile_sums",
+    for nm in ("inc_count", "inc_blk_len", "inc_fill", "inc_sort", "inc_stage", "sym_p1_fused", "sym_p1_rows", "sym_p1_cols", "sym_p1_positions", "sym_block_pattern", "sym_compact_cols", "sym_row_count", "sym_row_fill", "sym_diagpos", "scan_tile_sums",
                "scan_tile_offsets", "scan_tiles", "scan_lookback", "asm_rows_p1", "rhs_rows", "bc_mark", "bc_compact", "bc_matrix", "bc_vec", "vec_fill",
                "spmv_row_blocks", "spmv_sell_len", "spmv_sell_cols", "spmv_sell_vals", "cg_diag_stats", "cg_precond", "cg_init_spmv", "cg_init_h", "cg_spmv_dots", "cg_update_g", "cg_update_xh"):
         ms, cnt = ctx.prof_get(nm)
