@@ -1,6 +1,7 @@
 // matrix.cu — device-resident CSR matrices and Dirichlet (penalty) conditions.
 // AssembleBC (fflib/problem.cpp:9881-10194) + HashMatrix::SetBC (femlib/HashMatrix.cpp:1195-1238), tgv >= 0.
 #include "common.cuh"
+#include <cmath>
 #include <algorithm>
 
 extern "C" int ffcuda_matrix_create(ffcuda_pattern *p, ffcuda_matrix **out)
@@ -276,6 +277,36 @@ __global__ void k_bc_matrix(const int32_t *__restrict__ dofs, int n, const int32
     if (i < n) vals[diagpos[dofs[i]]] = tgv;
 }
 
+// Exact elimination, HashMatrix::SetBC with tgv < 0 (femlib/HashMatrix.cpp:1195-1238).
+// rows: one warp per Dirichlet dof: diagonal = dval (1, or 0 when tgv < -9), the rest of the row 0 (kept for -3 / -30)
+__global__ void k_bc_rows_exact(const int32_t *__restrict__ dofs, int n, const int32_t *__restrict__ rowptr,
+                                const int32_t *__restrict__ colind, double *__restrict__ vals, double dval, int keeprow)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int d = dofs[i];
+    for (int k = rowptr[d] + lane; k < rowptr[d + 1]; k += 32) {
+        if (colind[k] == d) vals[k] = dval;
+        else if (!keeprow) vals[k] = 0.0;
+    }
+}
+__global__ void k_bc_mask(const int32_t *__restrict__ dofs, int n, unsigned char *__restrict__ on)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) on[dofs[i]] = 1;
+}
+// columns (tgv = -2, -20, -3, -30): one warp per row of the matrix; the diagonal goes too when tgv < -19
+__global__ void k_bc_cols_exact(int nrows, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ colind,
+                                const unsigned char *__restrict__ on, double *__restrict__ vals, int withdiag)
+{
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (r >= nrows) return;
+    for (int k = rowptr[r] + lane; k < rowptr[r + 1]; k += 32) {
+        const int c = colind[k];
+        if (on[c] && (c != r || withdiag)) vals[k] = 0.0;
+    }
+}
+
 __global__ void k_bc_vec(const int32_t *__restrict__ dofs, const double *__restrict__ g, int n, double *__restrict__ b, double scale)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -286,15 +317,36 @@ extern "C" int ffcuda_matrix_apply_bc(ffcuda_matrix *A, ffcuda_bc *bc, double tg
 {
     FF_API_BEGIN
     FF_REQUIRE(A && bc, "null argument");
-    FF_REQUIRE(tgv >= 0, "only the penalty form of Dirichlet conditions (tgv >= 0) is on the ffcuda path");
+    FF_REQUIRE(tgv == tgv, "tgv is NaN");
     ffcuda_ctx *ctx = A->ctx;
     ff_enter(ctx);
     ff_matrix_touch(A);
     A->vals_epoch++;
-    if (bc->ndofs)
+    if (tgv >= 0) {
+        if (bc->ndofs)
+            ff_launch(ctx, "bc_matrix", [&] {
+                k_bc_matrix<<<ff_blocks(bc->ndofs, 256), 256, 0, ctx->stream>>>(bc->dofs.p, bc->ndofs, A->diagpos, A->vals.p, tgv);
+            });
+    } else if (bc->ndofs) {
+        FF_REQUIRE(A->n == A->ncols, "exact elimination (tgv < 0) needs a square, non-distributed matrix");
+        auto near = [&](double v) { return fabs(tgv - v) < 1.0e-10; };
+        const int keeprow = near(-3.0) || near(-30.0);
+        const int cols = near(-2.0) || near(-20.0) || near(-3.0) || near(-30.0);
         ff_launch(ctx, "bc_matrix", [&] {
-            k_bc_matrix<<<ff_blocks(bc->ndofs, 256), 256, 0, ctx->stream>>>(bc->dofs.p, bc->ndofs, A->diagpos, A->vals.p, tgv);
+            k_bc_rows_exact<<<ff_blocks((size_t)bc->ndofs * 32, 256), 256, 0, ctx->stream>>>(bc->dofs.p, bc->ndofs, A->rowptr, A->colind,
+                                                                                              A->vals.p, tgv < -9.0 ? 0.0 : 1.0, keeprow);
         });
+        if (cols) {
+            DBuf<unsigned char> on;
+            on.alloc((size_t)A->ncols);
+            FF_CUDA(cudaMemsetAsync(on.p, 0, on.bytes(), ctx->stream));
+            ff_launch(ctx, "bc_mark", [&] { k_bc_mask<<<ff_blocks(bc->ndofs, 256), 256, 0, ctx->stream>>>(bc->dofs.p, bc->ndofs, on.p); });
+            ff_launch(ctx, "bc_matrix", [&] {
+                k_bc_cols_exact<<<ff_blocks((size_t)A->n * 32, 256), 256, 0, ctx->stream>>>(A->n, A->rowptr, A->colind, on.p, A->vals.p,
+                                                                                            tgv < -19.0);
+            });
+        }
+    }
     FF_API_END(A ? A->ctx : nullptr)
 }
 
@@ -306,7 +358,8 @@ extern "C" int ffcuda_vec_apply_bc(ffcuda_vec *b, ffcuda_bc *bc, double tgv)
     ff_enter(ctx);
     if (bc->ndofs)
         ff_launch(ctx, "bc_vec", [&] {
-            k_bc_vec<<<ff_blocks(bc->ndofs, 256), 256, 0, ctx->stream>>>(bc->dofs.p, bc->vals.p, bc->ndofs, b->d.p, tgv);
+            // AssembleBC: B[dof] = tgv1 * g, tgv1 = tgv for the penalty form, 1 for exact elimination (problem.cpp:10099)
+            k_bc_vec<<<ff_blocks(bc->ndofs, 256), 256, 0, ctx->stream>>>(bc->dofs.p, bc->vals.p, bc->ndofs, b->d.p, tgv < 0 ? 1.0 : tgv);
         });
     FF_API_END(b ? b->ctx : nullptr)
 }

@@ -10,7 +10,7 @@
 // At run time an intercepted call walks the varf exactly like AssembleVarForm (fflib/problem.cpp:9744-9855), flattens
 // mesh / dof table / term lists / quadrature rule / Dirichlet sets into plain arrays and calls the C ABI of
 // libffcuda_core.so (include/ffcuda.h).  What the GPU path does not cover (other elements, x-dependent coefficients,
-// boundary integrals, level sets, tgv < 0, sym=1, complex, ...) is NOT claimed: the call is handed, untouched, to the
+// boundary integrals, level sets, sym=1, complex, ...) is NOT claimed: the call is handed, untouched, to the
 // built-in operator it derives from, with a notice at verbosity >= 1 (FFCUDA_STRICT=1 turns that into an error).
 // There is no CPU re-implementation here: without a CUDA device every claimed call throws ErrorExec.
 //
@@ -515,7 +515,7 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
                 int np = OpCall_FormBilinear_np::n_name_param - NB_NAME_PARM_HMAT;
                 SetEnd_Data_Sparse_Solver<double>(stack, ds, this->b->nargs, np);
                 if (ds.sym) throw Unsupported{"sym=1 (half storage)"};
-                if (!(ds.tgv >= 0)) throw Unsupported{"tgv < 0 (exact elimination)"};
+                if (ds.tgv != ds.tgv) throw Unsupported{"tgv is NaN"};
                 const FESpaceT &Vh = *PVh;
                 const MMesh &Th = Vh.Th;
                 if (!isSameMesh(this->b->largs, &Vh.Th, &Vh.Th, stack)) throw Unsupported{"integrals on different meshes"};
@@ -604,7 +604,7 @@ struct CudaRhsOp : public OpArraytoLinearForm<double, MMesh, v_fes> {
                 FESpaceT &Vh = *pVh;
                 double tgv = ff_tgv;
                 if (this->l->nargs[0]) tgv = GetAny<double>((*this->l->nargs[0])(stack));
-                if (!(tgv >= 0)) throw Unsupported{"tgv < 0 (exact elimination)"};
+                if (tgv != tgv) throw Unsupported{"tgv is NaN"};
                 Varf V = read_varf(stack, this->l->largs, Vh.Th, Vh.N, false);
                 if (V.other_rhs_items) throw Unsupported{"right-hand side with array / matrix-vector items"};
                 DevSpace &D = device_space(Vh);

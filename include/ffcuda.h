@@ -149,7 +149,12 @@ int ffcuda_assemble_linear(ffcuda_vec *b, ffcuda_space *s, int nterms, const ffc
                            int nq, const double *qpts, const double *qw,
                            int nlab, const int32_t *labels, int accumulate);
 
-/* ---- Dirichlet conditions (penalty, tgv >= 0) ------------------------------------------------------ */
+/* ---- Dirichlet conditions ------------------------------------------------------------------------------
+ * tgv >= 0: penalty, A(d,d) = tgv and b[d] = tgv*g(d).  tgv < 0: exact elimination exactly as HashMatrix::SetBC
+ * (femlib/HashMatrix.cpp:1195-1238) and AssembleBC (fflib/problem.cpp:10099,10176): rows of the Dirichlet dofs zeroed
+ * with A(d,d) = 1 (tgv = -1), rows and columns (-2), columns only (-3), the -10/-20/-30 variants with A(d,d) = 0;
+ * b[d] = g(d).  When several ffcuda_bc are applied with tgv = -2/-3 the result equals SetBC on their union as long as
+ * every one is applied to the matrix before the right-hand side is used (column zeroing is idempotent). */
 /* explicit (dof, value) pairs as AssembleBC produced them on the host (later pairs win) */
 int ffcuda_bc_from_pairs(ffcuda_space *s, int n, const int32_t *dofs, const double *vals, ffcuda_bc **out);
 /* on(labels..., u_c = values[c]) for the components in compmask, evaluated on the device */
@@ -157,8 +162,8 @@ int ffcuda_bc_from_labels(ffcuda_space *s, int nlab, const int32_t *labels, int 
                           ffcuda_bc **out);
 /* several ffcuda_bc may be applied in sequence (one per on(...) item of the varf) */
 int ffcuda_bc_count(ffcuda_bc *bc, int *ndofs);
-int ffcuda_matrix_apply_bc(ffcuda_matrix *A, ffcuda_bc *bc, double tgv); /* A(d,d) = tgv      */
-int ffcuda_vec_apply_bc(ffcuda_vec *b, ffcuda_bc *bc, double tgv);       /* b[d] = tgv*g(d)    */
+int ffcuda_matrix_apply_bc(ffcuda_matrix *A, ffcuda_bc *bc, double tgv); /* A(d,d) = tgv | exact elimination */
+int ffcuda_vec_apply_bc(ffcuda_vec *b, ffcuda_bc *bc, double tgv);       /* b[d] = tgv*g(d) | g(d)           */
 int ffcuda_vec_set_bc_values(ffcuda_vec *x, ffcuda_bc *bc);              /* x[d] = g(d)        */
 void ffcuda_bc_destroy(ffcuda_bc *bc);
 

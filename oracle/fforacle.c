@@ -505,19 +505,38 @@ int ffo_bc_pairs(int dim, int nt, const int32_t *conn, int order, int ncomp, con
     return n;
 }
 
+/* HashMatrix::SetBC (femlib/HashMatrix.cpp:1195-1238).  tgv >= 0: diag = tgv.  tgv < 0 (exact elimination): on the rows
+ * of the Dirichlet dofs diag = 1 (0 when tgv < -9), the other entries 0 unless tgv is -3 / -30; for tgv = -2, -20, -3,
+ * -30 the columns of those dofs are zeroed too (the diagonal as well when tgv < -19). */
 void ffo_bc_matrix_coo(int64_t nnz, const int32_t *coo_i, const int32_t *coo_j, double *coo_a,
                        int n, int nbc, const int32_t *dofs, double tgv)
 {
     char *on = (char *)calloc((size_t)n, 1);
     for (int k = 0; k < nbc; ++k) on[dofs[k]] = 1;
-    for (int64_t k = 0; k < nnz; ++k)
-        if (coo_i[k] == coo_j[k] && on[coo_i[k]]) coo_a[k] = tgv;
+    if (tgv >= 0) {
+        for (int64_t k = 0; k < nnz; ++k)
+            if (coo_i[k] == coo_j[k] && on[coo_i[k]]) coo_a[k] = tgv;
+    } else {
+        const int keeprow = fabs(tgv + 3.0) <= 1.0e-10 || fabs(tgv + 30.0) <= 1.0e-10;
+        const int cols = fabs(tgv + 2.0) < 1.0e-10 || fabs(tgv + 20.0) < 1.0e-10 || fabs(tgv + 3.0) < 1.0e-10 ||
+                         fabs(tgv + 30.0) < 1.0e-10;
+        for (int64_t k = 0; k < nnz; ++k)
+            if (on[coo_i[k]]) {
+                if (coo_j[k] == coo_i[k]) coo_a[k] = tgv < -9.0 ? 0.0 : 1.0;
+                else if (!keeprow) coo_a[k] = 0.0;
+            }
+        if (cols)
+            for (int64_t k = 0; k < nnz; ++k)
+                if (on[coo_j[k]] && (coo_i[k] != coo_j[k] || tgv < -19.0)) coo_a[k] = 0.0;
+    }
     free(on);
 }
 
+/* AssembleBC: B[dof] = tgv1 * g with tgv1 = tgv >= 0 ? tgv : 1 (fflib/problem.cpp:10099,10176; rank 0 / sequential) */
 void ffo_bc_rhs(double *b, int nbc, const int32_t *dofs, const double *vals, double tgv)
 {
-    for (int k = 0; k < nbc; ++k) b[dofs[k]] = tgv * vals[k];
+    const double tgv1 = tgv < 0 ? 1.0 : tgv;
+    for (int k = 0; k < nbc; ++k) b[dofs[k]] = tgv1 * vals[k];
 }
 
 /* ------------------------------------------------------------------ SpMV + CG ----------- */

@@ -57,7 +57,15 @@ CASES = {
     "lame3d_p1_cube3": (1, 3, lame_terms(), [(2, ID, -0.05)], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
     "lame3d_p2_warp": (2, 3, lame_terms(), [(2, ID, -0.05)], "qfV5",
                        [([1], 7, [0.0, 0.0, 0.0]), ([3], 7, [0.01, 0.0, -0.02])]),
+    # exact elimination (tgv < 0, CASE_TGV below)
+    "lap3d_p1_tgvm1": (1, 1, LAP3, [(0, ID, 2.0)], "qfV5", [([1], 1, [1.0]), ([6], 1, [-1.0])]),
+    "lap3d_p1_tgvm2": (1, 1, LAP3, [(0, ID, 1.0)], "qfV5", [(ALL6, 1, [0.0])]),
+    "lap2d_p2_tgvm2": (2, 1, LAP2, [(0, ID, 1.0)], "qf5pT", [([1, 2, 3, 4], 1, [0.0])]),
+    "lame3d_p1_tgvm1": (1, 3, lame_terms(), [(2, ID, -0.05)], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
+    "lap3d_p1_tgvm3": (1, 1, LAP3, [(0, ID, 1.0)], "qfV5", [([1, 3], 1, [0.0])]),
 }
+# Dirichlet treatment of a case: penalty tgv = 1e30 unless listed here (HashMatrix::SetBC with tgv < 0)
+CASE_TGV = {"lap3d_p1_tgvm1": -1.0, "lap3d_p1_tgvm2": -2.0, "lap2d_p2_tgvm2": -2.0, "lame3d_p1_tgvm1": -1.0, "lap3d_p1_tgvm3": -3.0}
 
 
 def load(name):
@@ -85,3 +93,5 @@ def elem2node(g, order, ncomp):
     for c in range(ncomp):
         assert np.array_equal(dof[:, c * nl:(c + 1) * nl], e2n * ncomp + c)
     return np.ascontiguousarray(e2n, dtype=np.int32)
+# cases whose script does not solve (non-symmetric after tgv = -1 / -3 elimination)
+NO_SOLVE_TGV = {"lap3d_p1_tgvm1", "lame3d_p1_tgvm1", "lap3d_p1_tgvm3"}

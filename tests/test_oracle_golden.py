@@ -35,13 +35,16 @@ def _bc(g, order, ncomp, e2n, bcs):
 @pytest.mark.parametrize("name", sorted(fc.CASES))
 def test_matrix_rhs_solution(name):
     order, ncomp, bt, lt, qname, bcs = fc.CASES[name]
+    TGV = fc.CASE_TGV.get(name, 1e30)  # noqa: N806 (shadows the module constant for the exact-elimination fixtures)
     g = fc.load(name)
     dim, n = g["dim"], g["ndof"]
     e2n = fc.elem2node(g, order, ncomp)
     qp, qw = ol.quadrature(dim, qname)
     ci, cj, ca = ol.assemble_coo(_mesh(g), order, ncomp, e2n, bt, qp, qw)
     # HashMatrix insertion order (storage order before any CSR()/COO() call): bit-exact
-    assert np.array_equal(ci, g["ins_i"]) and np.array_equal(cj, g["ins_j"])
+    # (SetBC with tgv < 0 sorts the storage: those fixtures hold the sorted order only)
+    if name not in fc.CASE_TGV:
+        assert np.array_equal(ci, g["ins_i"]) and np.array_equal(cj, g["ins_j"])
     # the script's `[I,J,C]=A` sorted the reference storage by (i,j); do the same (Sortij)
     o = np.argsort(ci.astype(np.int64) * n + cj, kind="stable")
     ci, cj, ca = ci[o], cj[o], ca[o]
@@ -81,9 +84,10 @@ def test_matrix_rhs_solution(name):
         assert np.max(np.abs(x - g["u14"])) <= RTOL * np.abs(g["u14"]).max()
 
 
-@pytest.mark.parametrize("name", sorted(k for k in fc.CASES if fc.CASES[k][5]))
+@pytest.mark.parametrize("name", sorted(k for k in fc.CASES if fc.CASES[k][5] and k not in fc.NO_SOLVE_TGV))
 def test_cg_on_reference_matrix(name):
     """ffo_cg fed with the reference's own A and b must reproduce its iterate: same count, u to 1e-12."""
+    TGV = fc.CASE_TGV.get(name, 1e30)  # noqa: N806
     g = fc.load(name)
     n = g["ndof"]
     x, it, ret, _ = ol.cg(n, g["coo_i"], g["coo_j"], g["coo_a"], g["b"], np.zeros(n), eps=1e-6, itmax=0, tgv=TGV)
