@@ -379,9 +379,20 @@ __device__ __forceinline__ double fast_rcp(double d)
     return fma(r, t, r);
 }
 
-// The lean kernel behind the headline configurations: scalar P1, form = c grad u . grad v (+ m u v), no region filter,
-// every ELL block staged.  Per record it reads 8 bytes (position word + slot word), everything else is shared memory
-// and fp64 registers; records are prefetched one iteration ahead.
+// shared-memory accesses through 32-bit shared-space addresses kept in registers (the compiler otherwise re-derives the
+// generic bases - thread id, kernel parameters, window base - inside the record loop: ~25 of its 140 instructions)
+__device__ __forceinline__ double lds_f64(uint32_t a)
+{
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts_f64(uint32_t a, double v) { asm volatile("st.shared.f64 [%0], %1;" ::"r"(a), "d"(v) : "memory"); }
+
+// The lean thread-per-row kernel: scalar P1, form = c grad u . grad v (+ m u v), no region filter, every ELL block
+// staged.  It serves the assemblies that are not on the tile path (first assembly on a fespace, forms with a mass term).
+// Per record it reads 8 bytes (position word + slot word), everything else is shared memory and fp64 registers; records
+// are prefetched two iterations ahead; the stage holds the block's vertices as (x, y, z) triples (one address per vertex).
 template <int DIM>
 __global__ void __launch_bounds__(128) k_asm_p1_lean(const double *__restrict__ xyz, int nrows, const int32_t *__restrict__ nrowptr,
                                                      const int32_t *__restrict__ cnt, const uint32_t *__restrict__ blkoff,
@@ -394,11 +405,14 @@ __global__ void __launch_bounds__(128) k_asm_p1_lean(const double *__restrict__ 
     constexpr int NV = DIM + 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarp = blockDim.x >> 5;
     const int row = blockIdx.x * blockDim.x + tid;
-    const double *stage = smem_d + (size_t)warp * DIM * SV;
+    double *stage = smem_d + (size_t)warp * DIM * SV;               // [slot][DIM]
     double *sacc = smem_d + (size_t)nwarp * DIM * SV;
     double *acc = sacc + (size_t)tid * S;
+    const uint32_t stage_a = (uint32_t)__cvta_generic_to_shared(stage), acc_a = (uint32_t)__cvta_generic_to_shared(acc);
     int L = 0, rb = 0, mycnt = 0;
-    double X[NV][DIM];
+    double X0[DIM];
+#pragma unroll
+    for (int x = 0; x < DIM; ++x) X0[x] = 0.0;
     if (row < nrows) {
         rb = nrowptr[row];
         L = nrowptr[row + 1] - rb;
@@ -406,36 +420,60 @@ __global__ void __launch_bounds__(128) k_asm_p1_lean(const double *__restrict__ 
         for (int j = 0; j < L; ++j) acc[j] = 0.0;
         if (DIM == 3) {
             const double4 p = ldg_vertex(xyz, row);
-            X[0][0] = p.x; X[0][1] = p.y; X[0][DIM - 1] = p.z;
+            X0[0] = p.x; X0[1] = p.y; X0[DIM - 1] = p.z;
         } else {
             const double2 p = __ldg(reinterpret_cast<const double2 *>(xyz) + row);
-            X[0][0] = p.x; X[0][1] = p.y;
+            X0[0] = p.x; X0[1] = p.y;
         }
     }
     const int blk = row >> 5, nblk = (nrows + 31) >> 5;
     if (blk < nblk) {
-        p1_stage<DIM>(xyz, blkvert, blkvcnt, blk, lane, SV, const_cast<double *>(stage));
+        {   // stage the block's distinct vertices
+            const int vcnt = blkvcnt[blk];
+            for (int s = lane; s < vcnt; s += 32) {
+                const int v = __ldg(blkvert + (size_t)blk * FF_STAGE_MAX + s);
+                if (DIM == 3) {
+                    const double4 p = ldg_vertex(xyz, v);
+                    stage[DIM * s] = p.x; stage[DIM * s + 1] = p.y; stage[DIM * s + DIM - 1] = p.z;
+                } else {
+                    const double2 p = __ldg(reinterpret_cast<const double2 *>(xyz) + v);
+                    stage[DIM * s] = p.x; stage[DIM * s + 1] = p.y;
+                }
+            }
+            __syncwarp();
+        }
         const uint32_t base = blkoff[blk];
         const int Lb = (int)((blkoff[blk + 1] - base) >> 5);
         const uint32_t *ppos = pos + base + lane, *ploc = loc + base + lane;
-        uint32_t pw = 0, lw = 0;
+        uint32_t pw0 = 0, lw0 = 0, pw1 = 0, lw1 = 0; // records e and e+1
         if (Lb > 0) {
-            pw = __ldcs(ppos);
-            lw = __ldcs(ploc);
+            pw0 = __ldcs(ppos);
+            lw0 = __ldcs(ploc);
+        }
+        if (Lb > 1) {
+            pw1 = __ldcs(ppos + 32);
+            lw1 = __ldcs(ploc + 32);
         }
         double sdet = 0.0;
         int dpos = 0;
         for (int e = 0; e < Lb; ++e) {
-            const uint32_t pwc = pw, lwc = lw;
-            ppos += 32;
-            ploc += 32;
-            if (e + 1 < Lb) { // prefetch the next record (padding records hold unused words)
-                pw = __ldcs(ppos);
-                lw = __ldcs(ploc);
+            const uint32_t pwc = pw0, lwc = lw0;
+            pw0 = pw1;
+            lw0 = lw1;
+            if (e + 2 < Lb) { // prefetch two records ahead (padding records hold unused words)
+                pw1 = __ldcs(ppos + (size_t)(e + 2) * 32);
+                lw1 = __ldcs(ploc + (size_t)(e + 2) * 32);
             }
             if (e < mycnt) {
-                double N[NV][DIM], det;
-                p1_points_staged<DIM>(stage, SV, lwc, X);
+                double X[NV][DIM], N[NV][DIM], det;
+#pragma unroll
+                for (int x = 0; x < DIM; ++x) X[0][x] = X0[x];
+#pragma unroll
+                for (int b = 1; b <= DIM; ++b) {
+                    const uint32_t va = stage_a + ((lwc >> (8 * b)) & 255u) * (DIM * 8);
+#pragma unroll
+                    for (int x = 0; x < DIM; ++x) X[b][x] = lds_f64(va + 8 * x);
+                }
                 p1_normals<DIM>(X, N, det);
                 const double sgg = cw * fast_rcp(det);
                 double w[DIM];
@@ -447,15 +485,17 @@ __global__ void __launch_bounds__(128) k_asm_p1_lean(const double *__restrict__ 
                 // the DIM off-diagonal entries of the owner's row of the element matrix; their columns are distinct, so
                 // the read-modify-writes are independent: all loads first, then all stores
                 double v[NV], a[NV];
+                uint32_t pa[NV];
 #pragma unroll
                 for (int i = 1; i < NV; ++i) {
                     v[i] = mo;
 #pragma unroll
                     for (int x = 0; x < DIM; ++x) v[i] = fma(w[x], N[i][x], v[i]);
-                    a[i] = acc[(pwc >> (8 * i)) & 255];
+                    pa[i] = acc_a + ((pwc >> (8 * i)) & 255u) * 8;
+                    a[i] = lds_f64(pa[i]);
                 }
 #pragma unroll
-                for (int i = 1; i < NV; ++i) acc[(pwc >> (8 * i)) & 255] = a[i] + v[i];
+                for (int i = 1; i < NV; ++i) sts_f64(pa[i], a[i] + v[i]);
             }
         }
         // The diagonal is not accumulated record by record: the P1 basis is a partition of unity, so the stiffness part

@@ -1066,9 +1066,9 @@ bool ff_asm_p1_tiles(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, double 
     TileSet &T = s->tiles;
     ffcuda_pattern *P = A->pattern;
     s->lean_assemblies++;
-    // forms with a mass term are (measured) slower by tiles than by rows (0.60-0.67 vs 0.50 ms on cube(128): the star sums
-    // of the diagonal and the second descriptor blob): they stay on the thread-per-row kernel unless tiles are forced
-    if ((cmd != 0.0 || cmo != 0.0) && ctx->tile_policy != 2) return false;
+    // (forms with a mass term: the diagonal needs the measure of every row's star, taken from the record lists of the
+    // second descriptor blob: 0.45 ms by tiles against 0.48 ms by rows on cube(128) - and the symbolic phase of a space
+    // with tiles is the cheap fused one)
     if (!tiles_ready(ctx, s, P)) return false;
     FF_REQUIRE(T.nnz_node == P->nnz_node, "internal: tile set and pattern disagree");
     ffcuda_mesh *m = s->mesh;

@@ -177,7 +177,7 @@ def test_tiles_full_size_properties(ctx):
 
 def test_lazy_positions_after_tiles_are_built(ctx):
     """Once a space has its row tiles, the symbolic phase skips the per-record positions (only the thread-per-row kernels
-    read them); a later form that is not on the tile path (mass term, default policy) must get them on demand."""
+    read them); a later form that is not on the tile path (region filter) must get them on demand."""
     size = (9, 7, 8)
     m = ol.cube(*size)
     n = m["xyz"].shape[0]
@@ -201,7 +201,7 @@ def test_lazy_positions_after_tiles_are_built(ctx):
     A1.assemble(fc.LAP3, qp, qw)          # tiles
     assert ctx.prof_get("sym_p1_positions")[1] == 0
     assert np.max(np.abs(A1.download() - oval)) <= RTOL * np.abs(oval).max()
-    A1.assemble(HEAT3, qp, qw)            # mass term: thread-per-row kernel, positions produced now
+    A1.assemble(HEAT3, qp, qw, labels=[0])  # region filter: thread-per-row kernel, positions produced now (all elements are in region 0)
     assert ctx.prof_get("sym_p1_positions")[1] == 1
     ctx.prof_enable(False)
     _, _, hval = _oracle_vals(m, n, HEAT3, qp, qw)

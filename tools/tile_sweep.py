@@ -42,4 +42,5 @@ for rows in (32, 48, 64, 96, 128):
     for threads in (256, 512):
         run(2, rows, threads, LAP, "poisson tiles")
 run(0, 64, 256, HEAT, "heat thread-per-row")
-run(2, 64, 256, HEAT, "heat tiles")
+for rows, threads in ((64, 512), (96, 256), (96, 512), (48, 256)):
+    run(2, rows, threads, HEAT, "heat tiles")
