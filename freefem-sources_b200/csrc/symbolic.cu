@@ -166,20 +166,44 @@ __device__ __forceinline__ void warp_sort_smem(int32_t *u, int m, int lane)
         }
 }
 
-// stage tables of the incidence: distinct vertices of the block (slot numbering) and per-record slot bytes
+// stage tables of the incidence: distinct vertices of the block (slot numbering) and per-record slot bytes.
+// One warp per block of 32 rows; shared memory holds only the warp's hash table and vertex list (5 KB), the records and
+// the connectivity are read twice (second time from L1/L2): 3x the occupancy of the version that parked them in
+// shared memory, which was latency bound (2.8 ms on cube(128)).
 template <int NLOC>
-__global__ void __launch_bounds__(128) k_block_stage(const int32_t *__restrict__ conn, int nrows, const IncView V, int Lmax,
+__device__ __forceinline__ void owner_first(const int32_t *__restrict__ conn, uint32_t r, int (&c)[4])
+{
+    const size_t k = r >> 4;
+    const int a = r & 15;
+    if (NLOC == 4) {
+        const int4 q = __ldg(reinterpret_cast<const int4 *>(conn) + k);
+        // c[i] = q[a ^ i]
+        c[0] = a == 0 ? q.x : a == 1 ? q.y : a == 2 ? q.z : q.w;
+        c[1] = a == 0 ? q.y : a == 1 ? q.x : a == 2 ? q.w : q.z;
+        c[2] = a == 0 ? q.z : a == 1 ? q.w : a == 2 ? q.x : q.y;
+        c[3] = a == 0 ? q.w : a == 1 ? q.z : a == 2 ? q.y : q.x;
+    } else {
+        const int q0 = __ldg(conn + 3 * k), q1 = __ldg(conn + 3 * k + 1), q2 = __ldg(conn + 3 * k + 2);
+        // c[i] = q[(a + i) % 3]
+        c[0] = a == 0 ? q0 : a == 1 ? q1 : q2;
+        c[1] = a == 0 ? q1 : a == 1 ? q2 : q0;
+        c[2] = a == 0 ? q2 : a == 1 ? q0 : q1;
+        c[3] = -1;
+    }
+}
+
+static constexpr int STAGE_BT = 512, STAGE_BLOG = 9; // hash table of a block: at most FF_STAGE_MAX = 256 keys
+static constexpr int STAGE_WORDS = 2 * STAGE_BT + FF_STAGE_MAX + 4;
+
+template <int NLOC>
+__global__ void __launch_bounds__(256) k_block_stage(const int32_t *__restrict__ conn, int nrows, const IncView V,
                                                      uint32_t *__restrict__ loc, int32_t *__restrict__ blkvert,
                                                      int32_t *__restrict__ blkvcnt, int32_t *__restrict__ maxstage)
 {
     extern __shared__ uint32_t smem_u[];
-    constexpr int BT = 1024, BLOG = 10;
+    constexpr int BT = STAGE_BT, BLOG = STAGE_BLOG;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cstride = Lmax * 4 + 4;
-    const size_t per_warp = (size_t)Lmax * 32 + (size_t)32 * cstride + 2 * BT + FF_STAGE_MAX + 4;
-    uint32_t *recs = smem_u + (size_t)w * per_warp;
-    int32_t *cand = reinterpret_cast<int32_t *>(recs + (size_t)Lmax * 32);
-    uint32_t *bkey = reinterpret_cast<uint32_t *>(cand + (size_t)32 * cstride);
+    uint32_t *bkey = smem_u + (size_t)w * STAGE_WORDS;
     uint32_t *bslot = bkey + BT;
     int32_t *vlist = reinterpret_cast<int32_t *>(bslot + BT);
     int *bcnt = vlist + FF_STAGE_MAX;
@@ -189,16 +213,19 @@ __global__ void __launch_bounds__(128) k_block_stage(const int32_t *__restrict__
     const int Lb = (int)((V.blkoff[blk + 1] - base) >> 5);
     for (int x = lane; x < BT; x += 32) bkey[x] = HT_EMPTY;
     if (lane == 0) *bcnt = 0;
-    blk_load<NLOC>(conn, V, base, Lb, lane, cstride, recs, cand);
-    // insert: lane = row, walking its own records
+    __syncwarp();
+    // pass 1: the distinct vertices of the block's records
     for (int e = 0; e < Lb; ++e) {
+        const uint32_t r = __ldg(V.inc + base + (size_t)e * 32 + lane);
+        if (r == FF_NOREC) continue;
+        int c[4];
+        owner_first<NLOC>(conn, r, c);
 #pragma unroll
         for (int b = 0; b < NLOC; ++b) {
-            const int vi = cand[(size_t)lane * cstride + e * 4 + b];
             // more than FF_STAGE_MAX distinct vertices: the block will be marked unstaged, stop filling the table
-            // (at most 32 lanes overshoot by one insertion each: the 1024-slot table cannot fill up)
-            if (vi < 0 || *reinterpret_cast<volatile int *>(bcnt) > FF_STAGE_MAX) continue;
-            const uint32_t v = (uint32_t)vi;
+            // (at most 32 lanes overshoot by one insertion each: the 512-slot table cannot fill up)
+            if (*reinterpret_cast<volatile int *>(bcnt) > FF_STAGE_MAX) continue;
+            const uint32_t v = (uint32_t)c[b];
             uint32_t h = ht_hash(v, BLOG);
             while (true) {
                 uint32_t k = bkey[h];
@@ -208,7 +235,7 @@ __global__ void __launch_bounds__(128) k_block_stage(const int32_t *__restrict__
                     if (k == HT_EMPTY) {
                         const int slot = atomicAdd(bcnt, 1);
                         bslot[h] = (uint32_t)slot;
-                        if (slot < FF_STAGE_MAX) vlist[slot] = vi;
+                        if (slot < FF_STAGE_MAX) vlist[slot] = (int32_t)v;
                         break;
                     }
                     if (k == v) break;
@@ -236,13 +263,17 @@ __global__ void __launch_bounds__(128) k_block_stage(const int32_t *__restrict__
         }
         __syncwarp();
     }
+    // pass 2: slot words of the records (owner-first order)
     for (int e = 0; e < Lb; ++e) {
-        if (recs[e * 32 + lane] == FF_NOREC) continue;
+        const uint32_t r = __ldg(V.inc + base + (size_t)e * 32 + lane);
+        if (r == FF_NOREC) continue;
         uint32_t word = 0;
         if (staged) {
+            int c[4];
+            owner_first<NLOC>(conn, r, c);
 #pragma unroll
             for (int b = 0; b < NLOC; ++b) {
-                const uint32_t v = (uint32_t)cand[(size_t)lane * cstride + e * 4 + b];
+                const uint32_t v = (uint32_t)c[b];
                 uint32_t h = ht_hash(v, BLOG);
                 while (bkey[h] != v) h = (h + 1) & (BT - 1);
                 word |= bslot[h] << (8 * b);
@@ -704,28 +735,25 @@ void ff_build_incidence(ffcuda_space *s)
     ff_launch(ctx, "inc_sort", [&] { k_sort_inc<<<ff_blocks(nrows, 128), 128, 0, st>>>(V, I.inc.p, nrows); });
     if (I.ell) {
         // vertex staging tables for the thread-per-row numeric kernels
-        const int nblk = (nrows + 31) / 32, Lmax = I.maxinc, cstride = Lmax * 4 + 4;
-        size_t per_warp = ((size_t)Lmax * 32 + (size_t)32 * cstride + 2 * 1024 + FF_STAGE_MAX + 4) * 4;
-        int warps = 4;
-        while (warps > 1 && warps * per_warp > 200 * 1024) warps >>= 1;
-        FF_REQUIRE(per_warp <= 200 * 1024, "a vertex has too many incident elements for the block staging kernel");
+        const int nblk = (nrows + 31) / 32;
+        const int warps = 8;
         I.loc.alloc((size_t)nrec);
         I.blkvert.alloc((size_t)nblk * FF_STAGE_MAX);
         I.blkvcnt.alloc((size_t)nblk);
         DBuf<int32_t> d_st;
         d_st.alloc(2);
         FF_CUDA(cudaMemsetAsync(d_st.p, 0, 2 * sizeof(int32_t), st));
-        const size_t shmem = warps * per_warp;
+        const size_t shmem = (size_t)warps * STAGE_WORDS * 4;
         const int blocks = ff_blocks((size_t)nblk, warps);
         if (nloc == 4) {
             FF_CUDA(cudaFuncSetAttribute(k_block_stage<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
             ff_launch(ctx, "inc_stage", [&] {
-                k_block_stage<4><<<blocks, warps * 32, shmem, st>>>(s->e2n, nrows, V, Lmax, I.loc.p, I.blkvert.p, I.blkvcnt.p, d_st.p);
+                k_block_stage<4><<<blocks, warps * 32, shmem, st>>>(s->e2n, nrows, V, I.loc.p, I.blkvert.p, I.blkvcnt.p, d_st.p);
             });
         } else {
             FF_CUDA(cudaFuncSetAttribute(k_block_stage<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
             ff_launch(ctx, "inc_stage", [&] {
-                k_block_stage<3><<<blocks, warps * 32, shmem, st>>>(s->e2n, nrows, V, Lmax, I.loc.p, I.blkvert.p, I.blkvcnt.p, d_st.p);
+                k_block_stage<3><<<blocks, warps * 32, shmem, st>>>(s->e2n, nrows, V, I.loc.p, I.blkvert.p, I.blkvcnt.p, d_st.p);
             });
         }
         int32_t h_st[2] = {0, 0};
