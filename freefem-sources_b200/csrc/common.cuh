@@ -58,6 +58,8 @@ struct ProfPending {
 struct ffcuda_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_stream = nullptr; // device -> host copies that overlap the work of `stream` (ffcuda_pattern_download_async)
+    cudaEvent_t copy_event = nullptr;
     std::string err;
     bool prof = false;
     std::map<std::string, ProfEntry> prof_acc;
@@ -370,6 +372,7 @@ struct ffcuda_pattern {
     DBuf<uint16_t> pos16;     // used instead when maxrow_node > 255
     int nlocp = 0;            // padded nloc in the pos table (4 for P1, nloc for P2)
     DBuf<int32_t> diagpos;    // n: index into vals of A(i,i)
+    bool copy_pending = false; // an asynchronous download of rowptr / colind may still be in flight on ctx->copy_stream
 };
 
 struct ffcuda_matrix {

@@ -129,6 +129,11 @@ static void ctx_teardown(ffcuda_ctx *ctx)
     if (ctx->d_scal) cudaFree(ctx->d_scal);
     if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
     if (ctx->d_partial) cudaFree(ctx->d_partial);
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+        cudaEventDestroy(ctx->copy_event);
+    }
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     if (g_cur_ctx == ctx) g_cur_ctx = nullptr;
     delete ctx;
@@ -157,6 +162,7 @@ extern "C" int ffcuda_ctx_sync(ffcuda_ctx *ctx)
     FF_API_BEGIN
     FF_REQUIRE(ctx, "null context");
     FF_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->copy_stream) FF_CUDA(cudaStreamSynchronize(ctx->copy_stream));
     FF_API_END(ctx)
 }
 

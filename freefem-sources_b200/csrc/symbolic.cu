@@ -1197,9 +1197,31 @@ extern "C" int ffcuda_pattern_download(ffcuda_pattern *p, int32_t *rowptr, int32
     FF_API_END(p ? p->ctx : nullptr)
 }
 
+// The copies run on a second stream behind an event of the context's stream: the numeric assembly that follows the
+// symbolic phase overlaps the transfer of the pattern.  Complete after ffcuda_ctx_sync.
+extern "C" int ffcuda_pattern_download_async(ffcuda_pattern *p, int32_t *rowptr, int32_t *colind)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(p, "null pattern");
+    ffcuda_ctx *ctx = p->ctx;
+    ff_enter(ctx);
+    if (!ctx->copy_stream) {
+        FF_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+        FF_CUDA(cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
+    }
+    FF_CUDA(cudaEventRecord(ctx->copy_event, ctx->stream));
+    FF_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0));
+    if (rowptr)
+        FF_CUDA(cudaMemcpyAsync(rowptr, p->rowptr, ((size_t)p->n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    if (colind) FF_CUDA(cudaMemcpyAsync(colind, p->colind, (size_t)p->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->copy_stream));
+    p->copy_pending = true;
+    FF_API_END(p ? p->ctx : nullptr)
+}
+
 extern "C" void ffcuda_pattern_destroy(ffcuda_pattern *p)
 {
     if (!p) return;
+    if (p->copy_pending && p->ctx && p->ctx->copy_stream) cudaStreamSynchronize(p->ctx->copy_stream);
     ff_enter(p->ctx);
     delete p;
 }

@@ -17,7 +17,7 @@ OP_ID, OP_DX, OP_DY, OP_DZ = 0, 1, 2, 6
 SYMBOLS = """ffcuda_ctx_create ffcuda_ctx_destroy ffcuda_last_error ffcuda_ctx_sync ffcuda_ctx_set_stream ffcuda_ctx_get_stream ffcuda_ctx_set_option
 ffcuda_prof_enable ffcuda_prof_reset ffcuda_prof_get ffcuda_launch_count ffcuda_mesh_upload ffcuda_mesh_cube ffcuda_mesh_square
 ffcuda_mesh_info ffcuda_mesh_download ffcuda_mesh_destroy ffcuda_space_create ffcuda_space_info ffcuda_space_download_dofs
-ffcuda_space_destroy ffcuda_symbolic ffcuda_pattern_info ffcuda_pattern_download ffcuda_pattern_destroy ffcuda_matrix_create
+ffcuda_space_destroy ffcuda_symbolic ffcuda_pattern_info ffcuda_pattern_download ffcuda_pattern_download_async ffcuda_pattern_destroy ffcuda_matrix_create
 ffcuda_matrix_from_csr ffcuda_matrix_info ffcuda_matrix_download ffcuda_matrix_upload ffcuda_matrix_destroy ffcuda_vec_create
 ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_destroy ffcuda_assemble_bilinear
 ffcuda_assemble_linear ffcuda_bc_from_pairs ffcuda_bc_from_labels ffcuda_bc_count ffcuda_matrix_apply_bc ffcuda_vec_apply_bc
@@ -306,6 +306,10 @@ class Pattern(_Handle):
         assert rp.dtype == np.int32 and ci.dtype == np.int32 and len(rp) == n + 1 and len(ci) == nnz
         _ck(lib().ffcuda_pattern_download(_h(self), _p(rp), _p(ci)), self.ctx.h)
         return rp, ci
+
+    def download_async(self, rp, ci):
+        """copies behind the work enqueued so far, on a second stream; rp / ci (pinned numpy arrays) are valid after ctx.sync()"""
+        _ck(lib().ffcuda_pattern_download_async(_h(self), _p(rp), _p(ci)), self.ctx.h)
 
     def matrix(self):
         out = C.c_void_p()

@@ -112,6 +112,10 @@ void ffcuda_space_destroy(ffcuda_space *s);
 int ffcuda_symbolic(ffcuda_space *s, ffcuda_pattern **out);
 int ffcuda_pattern_info(ffcuda_pattern *p, int *n, int64_t *nnz);
 int ffcuda_pattern_download(ffcuda_pattern *p, int32_t *rowptr /* n+1 */, int32_t *colind /* nnz */);
+/* same copies on a second stream, behind the work enqueued so far: the call returns at once and the numeric assembly
+ * that follows overlaps the transfer.  The buffers (pinned host memory, or the copy degrades to a synchronous one) are
+ * valid after ffcuda_ctx_sync. */
+int ffcuda_pattern_download_async(ffcuda_pattern *p, int32_t *rowptr, int32_t *colind);
 void ffcuda_pattern_destroy(ffcuda_pattern *p);
 
 /* ---- matrices and vectors (device resident) ------------------------------------------------------- */

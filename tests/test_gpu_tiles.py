@@ -249,3 +249,24 @@ def test_rhs_by_tiles_against_oracle(ctx, case, rows):
     b1 = ctx.vec(n)
     sp.assemble_linear(b1, lt, qp, qw)
     assert np.array_equal(b1.download(), hb)
+
+
+def test_pattern_download_async_overlaps_and_matches(ctx):
+    """the asynchronous pattern download (second stream, behind the symbolic phase) returns the same CSR as the blocking one"""
+    import torch
+
+    mesh = ctx.mesh_cube(14, 11, 9)
+    qp, qw = ffcuda.quadrature(3, 6)
+    sp = mesh.space(1, 1)
+    pat = sp.symbolic()
+    n, nnz = pat.info()
+    rp = torch.empty(n + 1, dtype=torch.int32, pin_memory=True).numpy()
+    ci = torch.empty(nnz, dtype=torch.int32, pin_memory=True).numpy()
+    rp[:] = -1
+    ci[:] = -1
+    pat.download_async(rp, ci)
+    A = pat.matrix()
+    A.assemble(fc.LAP3, qp, qw)       # overlaps the copies
+    ctx.sync()
+    rp0, ci0 = pat.download()
+    assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0)
