@@ -528,7 +528,7 @@ __global__ void __launch_bounds__(128) k_asm_p2(const double *__restrict__ xyz, 
                                                 const int32_t *__restrict__ nrowptr, const int32_t *__restrict__ incptr,
                                                 const uint32_t *__restrict__ inc, const PosT *__restrict__ pos,
                                                 const double *__restrict__ Rg, double *__restrict__ vals, int S, int accumulate,
-                                                const __grid_constant__ FormParams F)
+                                                const __grid_constant__ FormParams F, const int32_t *__restrict__ rowperm, int row0)
 {
     constexpr int NL = DIM == 3 ? 10 : 6;
     constexpr int NS = DIM + 1;
@@ -543,10 +543,13 @@ __global__ void __launch_bounds__(128) k_asm_p2(const double *__restrict__ xyz, 
     }
     const int grp = tid / GL, b = tid % GL;
     const int groups = blockDim.x / GL;
-    const int row = blockIdx.x * groups + grp;
+    // rows are taken in the order of rowperm (longest first, see launch_p2): the groups of a block then own rows of
+    // about the same cost, and the launch over the short rows can run with small accumulators.  nrows = end of the range.
+    const int ridx = row0 + blockIdx.x * groups + grp;
     double *acc = sacc + (size_t)grp * S;
     __syncthreads();
-    if (row >= nrows) return;
+    if (ridx >= nrows) return;
+    const int row = rowperm ? rowperm[ridx] : ridx;
     const int rb = nrowptr[row], L = nrowptr[row + 1] - rb;
     const int nflat = NC * NC * L;
     for (int j = b; j < nflat; j += GL) acc[j] = 0.0;
@@ -856,6 +859,9 @@ static void launch_p1(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const 
     });
 }
 
+// rows of a P2 space sorted by decreasing length (tiles.cu: CUB radix sort), built once per space
+void ff_p2_row_order(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr, int nrows, int maxrow);
+
 template <int DIM, int NC, typename PosT>
 static void launch_p2(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const FormParams &F, const double *Rg, const PosT *pos,
                       int accumulate)
@@ -865,21 +871,32 @@ static void launch_p2(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const 
     constexpr int RS = (DIM + 1) * (DIM + 1) + 1;
     ffcuda_pattern *P = A->pattern;
     ffcuda_mesh *m = s->mesh;
-    int S = NC * NC * P->maxrow_node;
-    int threads = 128;
-    while (threads > GL && (size_t)(threads / GL) * S * 8 > 96 * 1024) threads >>= 1;
-    int groups = threads / GL;
-    size_t shmem = ((size_t)NL * NL * RS + (size_t)groups * S) * 8;
-    FF_REQUIRE(shmem <= 220 * 1024, "matrix rows too long for the shared-memory row accumulators");
     const bool gg = (F.mask & 0x111Fu) == 0; // no term involves the value of u or v
     auto kern = gg ? k_asm_p2<DIM, NC, GL, PosT, true> : k_asm_p2<DIM, NC, GL, PosT, false>;
-    FF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-    int blocks = ff_blocks((size_t)P->nrows_node, groups);
     const Incidence &I = s->incidence;
-    ff_launch(ctx, "asm_rows_p2", [&] {
-        kern<<<blocks, threads, shmem, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, P->nrows_node, P->nrowptr.p, I.incptr.p,
-                                                      I.inc.p, pos, Rg, A->vals.p, S, accumulate, F);
-    });
+    // Vertex nodes have ~5x the elements and ~2.5x the row length of edge nodes, and the numbering interleaves them: with
+    // rows in natural order a block waits for its one vertex row while its other groups idle (13 % achieved occupancy,
+    // ncu r01d), and every group pays the shared-memory accumulator of the longest row.  Rows are therefore taken in order
+    // of decreasing length, in two launches: the long rows, then the short ones with accumulators sized for them.
+    ff_p2_row_order(ctx, s, P->nrowptr.p, P->nrows_node, P->maxrow_node);
+    const int nrows = P->nrows_node, nlong = s->p2_nlong;
+    auto run = [&](int r0, int r1, int maxL) {
+        if (r1 <= r0) return;
+        int S = NC * NC * maxL;
+        int threads = 128;
+        while (threads > GL && (size_t)(threads / GL) * S * 8 > 96 * 1024) threads >>= 1;
+        const int groups = threads / GL;
+        const size_t shmem = ((size_t)NL * NL * RS + (size_t)groups * S) * 8;
+        FF_REQUIRE(shmem <= 220 * 1024, "matrix rows too long for the shared-memory row accumulators");
+        FF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+        const int blocks = ff_blocks((size_t)(r1 - r0), groups);
+        ff_launch(ctx, "asm_rows_p2", [&] {
+            kern<<<blocks, threads, shmem, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, r1, P->nrowptr.p, I.incptr.p, I.inc.p, pos, Rg,
+                                                          A->vals.p, S, accumulate, F, s->p2_rowperm.p, r0);
+        });
+    };
+    run(0, nlong, P->maxrow_node);
+    run(nlong, nrows, s->p2_short_maxrow);
 }
 
 template <int DIM>

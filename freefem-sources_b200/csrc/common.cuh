@@ -345,6 +345,9 @@ struct ffcuda_space {
     int lean_assemblies = 0;  // scalar P1 assemblies seen on this space (the tile set is built from the second one on)
     int64_t sym_nnz_node = 0; // pattern size found by the first symbolic phase on this space (scalar P1, staged)
     int sym_maxrow = 0;
+    // P2: node rows sorted by decreasing length (assemble.cu launch_p2), rows [0, p2_nlong) are the long ones
+    DBuf<int32_t> p2_rowperm;
+    int p2_nlong = 0, p2_short_maxrow = 0;
 };
 // tiles.cu: numeric assembly of c grad u.grad v + m u v on a scalar P1 space by row tiles; returns false when the tile
 // path does not apply (the caller then runs the thread-per-row kernel)

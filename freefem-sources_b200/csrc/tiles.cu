@@ -1158,3 +1158,51 @@ bool ff_rhs_p1_tiles(ffcuda_ctx *ctx, ffcuda_vec *b, ffcuda_space *s, const doub
     }
     return true;
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// P2 row order (used by launch_p2 in assemble.cu): node rows by decreasing length, split into long / short
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_row_len_keys(const int32_t *__restrict__ nrowptr, int n, uint32_t *__restrict__ key, int32_t *__restrict__ val)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    key[i] = (uint32_t)(nrowptr[i + 1] - nrowptr[i]);
+    val[i] = i;
+}
+// keys sorted in decreasing order: out[0] = number of keys > T, out[1] = the largest key <= T (0 if none)
+__global__ void k_split_desc(const uint32_t *__restrict__ key, int n, uint32_t T, int32_t *__restrict__ out)
+{
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (key[mid] > T) lo = mid + 1;
+        else hi = mid;
+    }
+    out[0] = lo;
+    out[1] = lo < n ? (int32_t)key[lo] : 0;
+}
+} // namespace
+
+void ff_p2_row_order(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr, int nrows, int maxrow)
+{
+    if (s->p2_rowperm.p) return;
+    cudaStream_t st = ctx->stream;
+    DBuf<uint32_t> k0, k1;
+    DBuf<int32_t> v0, d_out;
+    k0.alloc(nrows); k1.alloc(nrows); v0.alloc(nrows); d_out.alloc(2);
+    s->p2_rowperm.alloc(nrows);
+    ff_launch(ctx, "p2_row_keys", [&] { k_row_len_keys<<<ff_blocks(nrows, 256), 256, 0, st>>>(nrowptr, nrows, k0.p, v0.p); });
+    size_t tb = 0;
+    FF_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, k0.p, k1.p, v0.p, s->p2_rowperm.p, nrows, 0, 32, st));
+    DBuf<unsigned char> tmpbuf;
+    tmpbuf.alloc(tb + 16);
+    ctx->launches++;
+    FF_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmpbuf.p, tb, k0.p, k1.p, v0.p, s->p2_rowperm.p, nrows, 0, 32, st));
+    // long rows: more than 60 % of the longest (vertex nodes against edge nodes on tetrahedra / triangles)
+    ff_launch(ctx, "p2_row_split", [&] { k_split_desc<<<1, 1, 0, st>>>(k1.p, nrows, (uint32_t)(0.6 * maxrow), d_out.p); });
+    int32_t h[2] = {0, 0};
+    FF_CUDA(ff_memcpy_sync(ctx, h, d_out.p, sizeof(h), cudaMemcpyDeviceToHost));
+    s->p2_nlong = h[0];
+    s->p2_short_maxrow = std::max(1, h[1]);
+}
