@@ -422,8 +422,18 @@ struct ffcuda_bc {
     DBuf<double> vals;
 };
 
+void ff_pattern_ensure_colind(ffcuda_pattern *P); // symbolic.cu: dof-level column indices of a vector-space pattern, on demand
 void ff_pattern_ensure_pos(ffcuda_pattern *P); // symbolic.cu: per-record positions of a P1 pattern, on demand
 void ff_matrix_touch(ffcuda_matrix *A); // matrix.cu: zero the values if nothing has written them yet
+// column indices of a matrix (those of its pattern, materialised on first use for vector spaces)
+static inline const int32_t *ff_matrix_colind(ffcuda_matrix *A)
+{
+    if (!A->colind && A->pattern) {
+        ff_pattern_ensure_colind(A->pattern);
+        A->colind = A->pattern->colind;
+    }
+    return A->colind;
+}
 
 // ---- shared device helpers ----------------------------------------------------------------------
 void ff_exclusive_scan_i32(ffcuda_ctx *ctx, const int32_t *in, int32_t *out, size_t n, int64_t *total);

@@ -81,7 +81,7 @@ extern "C" int ffcuda_matrix_from_csr(ffcuda_ctx *ctx, int n, int64_t nnz, const
     A->rowptr = A->rowptr_own.p;
     A->colind = A->colind_own.p;
     A->diagpos = A->diagpos_own.p;
-    ff_launch(ctx, "matrix_find_diag", [&] { k_find_diag<<<ff_blocks(n, 256), 256, 0, st>>>(A->rowptr, A->colind, n, A->diagpos_own.p); });
+    ff_launch(ctx, "matrix_find_diag", [&] { k_find_diag<<<ff_blocks(n, 256), 256, 0, st>>>(A->rowptr, ff_matrix_colind(A), n, A->diagpos_own.p); });
     DBuf<int32_t> d_max;
     d_max.alloc(1);
     FF_CUDA(cudaMemsetAsync(d_max.p, 0, sizeof(int32_t), st));
@@ -333,7 +333,7 @@ extern "C" int ffcuda_matrix_apply_bc(ffcuda_matrix *A, ffcuda_bc *bc, double tg
         const int keeprow = near(-3.0) || near(-30.0);
         const int cols = near(-2.0) || near(-20.0) || near(-3.0) || near(-30.0);
         ff_launch(ctx, "bc_matrix", [&] {
-            k_bc_rows_exact<<<ff_blocks((size_t)bc->ndofs * 32, 256), 256, 0, ctx->stream>>>(bc->dofs.p, bc->ndofs, A->rowptr, A->colind,
+            k_bc_rows_exact<<<ff_blocks((size_t)bc->ndofs * 32, 256), 256, 0, ctx->stream>>>(bc->dofs.p, bc->ndofs, A->rowptr, ff_matrix_colind(A),
                                                                                               A->vals.p, tgv < -9.0 ? 0.0 : 1.0, keeprow);
         });
         if (cols) {
@@ -342,7 +342,7 @@ extern "C" int ffcuda_matrix_apply_bc(ffcuda_matrix *A, ffcuda_bc *bc, double tg
             FF_CUDA(cudaMemsetAsync(on.p, 0, on.bytes(), ctx->stream));
             ff_launch(ctx, "bc_mark", [&] { k_bc_mask<<<ff_blocks(bc->ndofs, 256), 256, 0, ctx->stream>>>(bc->dofs.p, bc->ndofs, on.p); });
             ff_launch(ctx, "bc_matrix", [&] {
-                k_bc_cols_exact<<<ff_blocks((size_t)A->n * 32, 256), 256, 0, ctx->stream>>>(A->n, A->rowptr, A->colind, on.p, A->vals.p,
+                k_bc_cols_exact<<<ff_blocks((size_t)A->n * 32, 256), 256, 0, ctx->stream>>>(A->n, A->rowptr, ff_matrix_colind(A), on.p, A->vals.p,
                                                                                             tgv < -19.0);
             });
         }

@@ -712,7 +712,7 @@ static bool sell_prepare(ffcuda_matrix *A)
         A->sell_col.alloc((size_t)total);
         A->sell_val.alloc((size_t)total);
         ff_launch(ctx, "spmv_sell_cols", [&] {
-            k_sell_fill<0><<<ff_blocks((size_t)ns * 32, 256), 256, 0, st>>>(A->rowptr, A->colind, nullptr, A->n, ns, A->sell_off.p, A->sell_col.p, nullptr);
+            k_sell_fill<0><<<ff_blocks((size_t)ns * 32, 256), 256, 0, st>>>(A->rowptr, ff_matrix_colind(A), nullptr, A->n, ns, A->sell_off.p, A->sell_col.p, nullptr);
         });
         A->sell_state = 1;
         A->sell_epoch = 0;
@@ -764,7 +764,7 @@ static void stream_launch(ffcuda_matrix *A, const char *name, const double *x, c
         if (A->stream_shmem > 48 * 1024)
             FF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)A->stream_shmem));
         ff_launch(ctx, name, [&] {
-            kern<<<A->stream_grid, RED_THREADS, A->stream_shmem, ctx->stream>>>(A->rowptr, A->colind, A->vals.p, x, A->stream_rb.p,
+            kern<<<A->stream_grid, RED_THREADS, A->stream_shmem, ctx->stream>>>(A->rowptr, ff_matrix_colind(A), A->vals.p, x, A->stream_rb.p,
                                                                                  A->stream_nblk, aux0, aux1, y, iter, partial, flags, out);
         });
     });
@@ -816,7 +816,7 @@ static void spmv_launch(ffcuda_matrix *A, const double *x, const double *sub, do
     const int T = pick_T(A);
     const int grid = grid_for(ctx, (size_t)A->n * T);
     FF_DISPATCH_T(T, ff_launch(ctx, "spmv", [&] {
-                      k_spmv<TT><<<grid, RED_THREADS, 0, ctx->stream>>>(A->rowptr, A->colind, A->vals.p, x, sub, y, A->n);
+                      k_spmv<TT><<<grid, RED_THREADS, 0, ctx->stream>>>(A->rowptr, ff_matrix_colind(A), A->vals.p, x, sub, y, A->n);
                   }));
 }
 
@@ -909,7 +909,7 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
         stream_launch<1>(A, "cg_init_spmv", xin, b, D1, G, 0, partial, flags, scal + S_GCG0);
     else
         FF_DISPATCH_T(T, ff_launch(ctx, "cg_init_spmv", [&] {
-                          k_cg_init1<TT><<<grid_s, RED_THREADS, 0, st>>>(A->rowptr, A->colind, A->vals.p, xin, b, D1, G, n, partial, flags, scal);
+                          k_cg_init1<TT><<<grid_s, RED_THREADS, 0, st>>>(A->rowptr, ff_matrix_colind(A), A->vals.p, xin, b, D1, G, n, partial, flags, scal);
                       }));
     if (!fused) ff_allreduce(A, scal + S_GCG0, 1, 0);
     ff_launch(ctx, "cg_init_h", [&] { k_cg_init2<<<grid_v, RED_THREADS, 0, st>>>(G, D1, H, n, eps, flags, scal); });
@@ -938,7 +938,7 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
                     stream_launch<2>(A, "cg_spmv_dots", H, G, nullptr, AH, it, partial, flags, scal + S_GH);
                 else
                     FF_DISPATCH_T(T, ff_launch(ctx, "cg_spmv_dots", [&] {
-                                      k_cg_spmv<TT><<<grid_s, RED_THREADS, 0, st>>>(A->rowptr, A->colind, A->vals.p, H, G, AH, n, it, partial, flags, scal);
+                                      k_cg_spmv<TT><<<grid_s, RED_THREADS, 0, st>>>(A->rowptr, ff_matrix_colind(A), A->vals.p, H, G, AH, n, it, partial, flags, scal);
                                   }));
                 if (!fused) ff_allreduce(A, scal + S_GH, 2, 0);
                 ff_launch(ctx, "cg_update_g", [&] { k_cg_update_g<<<grid_v, RED_THREADS, 0, st>>>(G, AH, D1, n, it, partial, flags, scal); });

@@ -1136,21 +1136,32 @@ extern "C" int ffcuda_symbolic(ffcuda_space *s, ffcuda_pattern **out)
         if (!diag_done) ff_launch(ctx, "sym_diagpos", [&] { k_diagpos_scalar<<<ff_blocks(nrows, 256), 256, 0, st>>>(P->nrowptr.p, diagnode.p, nrows, P->diagpos.p); });
     } else {
         P->rowptr_own.alloc((size_t)P->n + 1);
-        P->colind_own.alloc((size_t)P->nnz);
         ff_launch(ctx, "sym_expand_rowptr", [&] {
             k_expand_rowptr<<<ff_blocks((size_t)nrows + 1, 256), 256, 0, st>>>(P->nrowptr.p, nrows, nc, P->rowptr_own.p, diagnode.p, P->diagpos.p);
         });
-        ff_launch(ctx, "sym_expand_colind", [&] {
-            k_expand_colind<<<ff_blocks((size_t)nrows * 32, 256), 256, 0, st>>>(P->nrowptr.p, P->ncol.p, nrows, nc, P->colind_own.p);
-        });
         P->rowptr = P->rowptr_own.p;
-        P->colind = P->colind_own.p;
+        // the dof-level column indices (4 bytes per entry: 2.2 GB at config 3) are only materialised when somebody reads
+        // them (download to the host, a kernel that is not the node-block SpMV): ff_pattern_ensure_colind
+        P->colind = nullptr;
     }
     // no synchronisation here: everything downstream is ordered on the same stream (the temporaries above are
     // released through the stream-ordered allocator)
     *out = P;
     P = nullptr;
     FF_API_END((delete P, s ? s->ctx : nullptr))
+}
+
+// dof-level column indices of a vector-space pattern, expanded from the node-level ones on first use
+void ff_pattern_ensure_colind(ffcuda_pattern *P)
+{
+    if (P->colind) return;
+    ffcuda_ctx *ctx = P->ctx;
+    P->colind_own.alloc((size_t)P->nnz);
+    ff_launch(ctx, "sym_expand_colind", [&] {
+        k_expand_colind<<<ff_blocks((size_t)P->nrows_node * 32, 256), 256, 0, ctx->stream>>>(P->nrowptr.p, P->ncol.p, P->nrows_node,
+                                                                                             P->ncomp, P->colind_own.p);
+    });
+    P->colind = P->colind_own.p;
 }
 
 // per-record positions of a P1 pattern whose symbolic phase skipped them (see lazy_pos above)
@@ -1191,6 +1202,7 @@ extern "C" int ffcuda_pattern_download(ffcuda_pattern *p, int32_t *rowptr, int32
     FF_REQUIRE(p, "null pattern");
     ff_enter(p->ctx);
     cudaStream_t st = p->ctx->stream;
+    if (colind) ff_pattern_ensure_colind(p);
     if (rowptr) FF_CUDA(cudaMemcpyAsync(rowptr, p->rowptr, ((size_t)p->n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     if (colind) FF_CUDA(cudaMemcpyAsync(colind, p->colind, (size_t)p->nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     FF_CUDA(cudaStreamSynchronize(st));
@@ -1209,6 +1221,7 @@ extern "C" int ffcuda_pattern_download_async(ffcuda_pattern *p, int32_t *rowptr,
         FF_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
         FF_CUDA(cudaEventCreateWithFlags(&ctx->copy_event, cudaEventDisableTiming));
     }
+    if (colind) ff_pattern_ensure_colind(p);
     FF_CUDA(cudaEventRecord(ctx->copy_event, ctx->stream));
     FF_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_event, 0));
     if (rowptr)
