@@ -243,7 +243,8 @@ __device__ __forceinline__ void p1_points_global(const double *__restrict__ xyz,
 // permutation of the element's order): the thread evaluates the simplex with its own vertex as origin, so the row of
 // the element matrix it needs is always "row 0": N[0] is its own normal, no selection by local index.
 // FAST: scalar space, form = c grad u . grad v (+ m u v) with a symmetric quadrature rule -> a handful of constants.
-template <int DIM, int NC, bool FAST>
+// GG: only gradient-gradient terms (no value of u or v): the coefficient contraction runs without per-term mask tests
+template <int DIM, int NC, bool FAST, bool GG>
 __global__ void __launch_bounds__(128) k_asm_p1(const double *__restrict__ xyz, const int32_t *__restrict__ conn,
                                                 const int32_t *__restrict__ elab, int nrows,
                                                 const int32_t *__restrict__ nrowptr, const IncView V,
@@ -285,8 +286,8 @@ __global__ void __launch_bounds__(128) k_asm_p1(const double *__restrict__ xyz, 
         const uint32_t *rpos = pos + base + lane;
         const uint32_t *rloc = loc + base + lane;
         const bool need_inc = !FAST || !staged || F.nlab >= 0;
-        const bool gradgrad = (F.mask & 0xEEE0u) != 0, valgrad = (F.mask & 0x000Eu) != 0, gradval = (F.mask & 0x1110u) != 0,
-                   valval = (F.mask & 1u) != 0;
+        const bool gradgrad = GG || (F.mask & 0xEEE0u) != 0, valgrad = !GG && (F.mask & 0x000Eu) != 0,
+                   gradval = !GG && (F.mask & 0x1110u) != 0, valval = !GG && (F.mask & 1u) != 0;
         for (int e = 0; e < Lb; ++e) {
             if (e >= mycnt) continue;
             const uint32_t pw = __ldcs(rpos + (size_t)e * 32);
@@ -331,7 +332,7 @@ __global__ void __launch_bounds__(128) k_asm_p1(const double *__restrict__ xyz, 
                             double t = 0.0;
 #pragma unroll
                             for (int sv = 0; sv < DIM; ++sv)
-                                if (F.mask >> ((sv + 1) * 4 + su + 1) & 1u) t = fma(F.C[cv][cu][sv + 1][su + 1], N[0][sv], t);
+                                if (GG || (F.mask >> ((sv + 1) * 4 + su + 1) & 1u)) t = fma(F.C[cv][cu][sv + 1][su + 1], N[0][sv], t);
                             wa[su] = t * sgg;
                             if (valgrad) wa[su] = fma(F.C[cv][cu][0][su + 1], La, wa[su]);
                         }
@@ -846,7 +847,8 @@ static void launch_p1(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const 
         });
         return;
     }
-    auto kern = (NC == 1 && fast) ? k_asm_p1<DIM, NC, (NC == 1)> : k_asm_p1<DIM, NC, false>;
+    const bool gg = (F.mask & 0x111Fu) == 0 && (F.mask & 0xEEE0u) != 0;
+    auto kern = (NC == 1 && fast) ? k_asm_p1<DIM, NC, (NC == 1), false> : (gg ? k_asm_p1<DIM, NC, false, true> : k_asm_p1<DIM, NC, false, false>);
     FF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     // rows are taken in whole ELL blocks of 32: the grid covers ceil(nrows/32) warps
     const int nwarps = (P->nrows_node + 31) / 32;
