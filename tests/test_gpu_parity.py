@@ -470,3 +470,64 @@ def test_config4_heat_reassembly_is_reproducible(ctx):
     for _ in range(3):
         A.assemble(terms, qp, qw)
         assert np.array_equal(A.download(), v0)
+
+
+def test_config3_lame_p2_cube64_full_size_properties(ctx):
+    """BASELINE config 3 at its full size (548 M nnz, ~14 GB on the device): everything is checked through products on the
+    device (the matrix never travels): nnz formula, rigid-body translations in the kernel of the un-constrained operator,
+    symmetry through x'Ay = y'Ax."""
+    n = 64
+    mesh = ctx.mesh_cube(n, n, n)
+    sp = mesh.space(2, 3)
+    pat = sp.symbolic()
+    ndof, nnz = pat.info()
+    assert ndof == 3 * (2 * n + 1) ** 3
+    assert nnz == 9 * (230 * n ** 3 + 138 * n ** 2 + 24 * n + 1)
+    qp, qw = ffcuda.quadrature(3, 6)
+    A = pat.matrix()
+    A.assemble(fc.lame_terms(), qp, qw)
+    y = ctx.vec(ndof)
+
+    def mul(v):
+        A.spmv(ctx.vec_from(v), y)
+        return y.download().copy()
+
+    scale = 2.0 * fc.MU + fc.LAMBDA          # size of the entries (h cancels in 3-D: entries ~ h * modulus, rows sum ~30 of them)
+    for c in range(3):                        # translations
+        t = np.zeros(ndof)
+        t[c::3] = 1.0
+        assert np.max(np.abs(mul(t))) <= 1e-10 * scale
+    # symmetry: x'Ay = y'Ax with deterministic vectors
+    i = np.arange(ndof, dtype=np.float64)
+    xv, yv = np.sin(0.37 * i), np.cos(0.11 * i + 0.5)
+    axy, ayx = float(xv @ mul(yv)), float(yv @ mul(xv))
+    assert abs(axy - ayx) <= 1e-11 * max(abs(axy), abs(ayx), scale * np.sqrt(ndof))
+
+
+def test_config5_cube256_single_gpu_full_size_properties(ctx):
+    """BASELINE config 5 (cube(256), 100 M tets, 253 M nnz) on ONE device: pattern size, row sums of the stiffness matrix,
+    volume from the right-hand side, and the CG iteration count the 8-GPU run of bench.py reports (525)."""
+    n = 256
+    mesh = ctx.mesh_cube(n, n, n)
+    sp = mesh.space(1, 1)
+    pat = sp.symbolic()
+    ndof, nnz = pat.info()
+    assert ndof == (n + 1) ** 3 and nnz == _nnz_cube_p1(n) == 253036801
+    qp, qw = ffcuda.quadrature(3, 6)
+    A = pat.matrix()
+    A.assemble(fc.LAP3, qp, qw)
+    A.assemble(fc.LAP3, qp, qw)               # second assembly: row tiles
+    y = ctx.vec(ndof)
+    A.spmv(ctx.vec_from(np.ones(ndof)), y)
+    assert np.max(np.abs(y.download())) <= 1e-12 * 4.0 / n * 8   # entries ~ h
+    b = ctx.vec(ndof)
+    sp.assemble_linear(b, [(0, fc.ID, 1.0)], qp, qw)
+    assert abs(b.download().sum() - 1.0) <= 1e-12
+    bc = sp.bc_from_labels(fc.ALL6, 1, [0.0])
+    A.apply_bc(bc, TGV)
+    b.apply_bc(bc, TGV)
+    x = ctx.vec(ndof)
+    it, conv, _ = A.cg(b, x, eps=1e-6, itmax=0, tgv=TGV)
+    assert conv == 1 and it == 525
+    u = x.download()
+    assert u.min() >= -1e-25 and 0.05 < u.max() < 0.06        # max of the torsion function of the unit cube ~ 0.0562
