@@ -375,6 +375,8 @@ struct ffcuda_pattern {
     DBuf<uint16_t> pos16;     // used instead when maxrow_node > 255
     int nlocp = 0;            // padded nloc in the pos table (4 for P1, nloc for P2)
     DBuf<int32_t> diagpos;    // n: index into vals of A(i,i)
+    DBuf<int32_t> lower_rowptr; // row pointers of the lower triangle (sym=1 hand-off), built on first use
+    int64_t lower_nnz = 0;
     bool copy_pending = false; // an asynchronous download of rowptr / colind may still be in flight on ctx->copy_stream
 };
 

@@ -1,6 +1,7 @@
 // matrix.cu — device-resident CSR matrices and Dirichlet (penalty) conditions.
 // AssembleBC (fflib/problem.cpp:9881-10194) + HashMatrix::SetBC (femlib/HashMatrix.cpp:1195-1238), tgv >= 0.
 #include "common.cuh"
+#include <vector>
 #include <cmath>
 #include <algorithm>
 
@@ -93,6 +94,140 @@ extern "C" int ffcuda_matrix_from_csr(ffcuda_ctx *ctx, int n, int64_t nnz, const
     *out = A;
     A = nullptr;
     FF_API_END((delete A, ctx))
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Half storage (sym=1): MatriceMorse keeps the entries (i, j <= i) only - MatriceElementaireSymetrique /
+// HashMatrix::operator+= (femlib/HashMatrix.cpp:1319-1325), mirrored by addMatMul (:1087-1154).  On the device a
+// matrix is always stored in full; the lower triangle is cut out when it is handed to the host, and a half-stored host
+// matrix is expanded when it comes in.
+// ---------------------------------------------------------------------------------------------------
+__global__ void k_lower_len(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ diagpos, int n, int32_t *__restrict__ len)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > n) return;
+    len[i] = i < n ? diagpos[i] - rowptr[i] + 1 : 0; // sorted rows: everything up to and including the diagonal
+}
+template <class T>
+__global__ void k_lower_copy(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ hrowptr, const T *__restrict__ src,
+                             T *__restrict__ dst, int n)
+{
+    const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (i >= n) return;
+    const int b = rowptr[i], hb = hrowptr[i], len = hrowptr[i + 1] - hb;
+    for (int k = lane; k < len; k += 32) dst[hb + k] = src[b + k];
+}
+
+// rowptr of the lower triangle (device, n+1), built on first use and kept with the pattern
+static const int32_t *lower_rowptr(ffcuda_pattern *P)
+{
+    if (P->lower_rowptr.p) return P->lower_rowptr.p;
+    ffcuda_ctx *ctx = P->ctx;
+    FF_REQUIRE(P->diagpos.p, "pattern without diagonal index");
+    DBuf<int32_t> len;
+    len.alloc((size_t)P->n + 1);
+    ff_launch(ctx, "lower_len", [&] { k_lower_len<<<ff_blocks((size_t)P->n + 1, 256), 256, 0, ctx->stream>>>(P->rowptr, P->diagpos.p, P->n, len.p); });
+    P->lower_rowptr.alloc((size_t)P->n + 1);
+    int64_t tot = 0;
+    ff_exclusive_scan_i32(ctx, len.p, P->lower_rowptr.p, (size_t)P->n + 1, &tot);
+    P->lower_nnz = tot;
+    return P->lower_rowptr.p;
+}
+
+extern "C" int ffcuda_pattern_lower_nnz(ffcuda_pattern *p, int64_t *nnz_lower)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(p && nnz_lower, "null argument");
+    ff_enter(p->ctx);
+    lower_rowptr(p);
+    *nnz_lower = p->lower_nnz;
+    FF_API_END(p ? p->ctx : nullptr)
+}
+
+extern "C" int ffcuda_pattern_download_lower(ffcuda_pattern *p, int32_t *rowptr, int32_t *colind)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(p, "null pattern");
+    ffcuda_ctx *ctx = p->ctx;
+    ff_enter(ctx);
+    const int32_t *hrp = lower_rowptr(p);
+    if (rowptr) FF_CUDA(cudaMemcpyAsync(rowptr, hrp, ((size_t)p->n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    if (colind) {
+        ff_pattern_ensure_colind(p);
+        DBuf<int32_t> tmp;
+        tmp.alloc((size_t)p->lower_nnz);
+        ff_launch(ctx, "lower_copy", [&] {
+            k_lower_copy<int32_t><<<ff_blocks((size_t)p->n * 32, 256), 256, 0, ctx->stream>>>(p->rowptr, hrp, p->colind, tmp.p, p->n);
+        });
+        FF_CUDA(cudaMemcpyAsync(colind, tmp.p, (size_t)p->lower_nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+        FF_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    FF_CUDA(cudaStreamSynchronize(ctx->stream));
+    FF_API_END(p ? p->ctx : nullptr)
+}
+
+extern "C" int ffcuda_matrix_download_lower(ffcuda_matrix *A, double *vals)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A && vals && A->pattern, "ffcuda_matrix_download_lower: needs a matrix created on a pattern");
+    ffcuda_ctx *ctx = A->ctx;
+    ff_enter(ctx);
+    ff_matrix_touch(A);
+    ffcuda_pattern *p = A->pattern;
+    const int32_t *hrp = lower_rowptr(p);
+    DBuf<double> tmp;
+    tmp.alloc((size_t)p->lower_nnz);
+    ff_launch(ctx, "lower_copy", [&] {
+        k_lower_copy<double><<<ff_blocks((size_t)p->n * 32, 256), 256, 0, ctx->stream>>>(p->rowptr, hrp, A->vals.p, tmp.p, p->n);
+    });
+    FF_CUDA(cudaMemcpyAsync(vals, tmp.p, (size_t)p->lower_nnz * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    FF_CUDA(cudaStreamSynchronize(ctx->stream));
+    FF_API_END(A ? A->ctx : nullptr)
+}
+
+// a half-stored host matrix (sorted lower triangle) -> full device matrix; the mirror entries are laid out on the host
+// (one pass over the entries: the upper part of row j receives its columns i > j in increasing order)
+extern "C" int ffcuda_matrix_from_csr_lower(ffcuda_ctx *ctx, int n, int64_t nnz_lower, const int32_t *rowptr, const int32_t *colind,
+                                            const double *vals, ffcuda_matrix **out)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(ctx && out && rowptr && colind && vals && n > 0 && nnz_lower >= 0, "ffcuda_matrix_from_csr_lower: bad arguments");
+    std::vector<int64_t> cnt((size_t)n + 1, 0);
+    int64_t nstrict = 0;
+    for (int i = 0; i < n; ++i) {
+        cnt[i + 1] += rowptr[i + 1] - rowptr[i];
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k) {
+            const int j = colind[k];
+            FF_REQUIRE(j >= 0 && j <= i, "ffcuda_matrix_from_csr_lower: an entry lies above the diagonal");
+            if (j < i) {
+                cnt[j + 1]++;
+                nstrict++;
+            }
+        }
+    }
+    const int64_t nnz = nnz_lower + nstrict;
+    FF_REQUIRE(nnz < ((int64_t)1 << 31), "matrix exceeds 2^31 nonzeros");
+    std::vector<int32_t> frp((size_t)n + 1), fci((size_t)nnz);
+    std::vector<double> fv((size_t)nnz);
+    frp[0] = 0;
+    for (int i = 0; i < n; ++i) frp[i + 1] = (int32_t)(frp[i] + cnt[i + 1]);
+    std::vector<int32_t> cur((size_t)n);
+    for (int i = 0; i < n; ++i) cur[i] = frp[i] + (rowptr[i + 1] - rowptr[i]); // the upper part starts behind the lower one
+    for (int i = 0; i < n; ++i) {
+        int o = frp[i];
+        for (int k = rowptr[i]; k < rowptr[i + 1]; ++k, ++o) {
+            const int j = colind[k];
+            fci[o] = j;
+            fv[o] = vals[k];
+            if (j < i) {
+                fci[cur[j]] = i;
+                fv[cur[j]] = vals[k];
+                cur[j]++;
+            }
+        }
+    }
+    if (ffcuda_matrix_from_csr(ctx, n, nnz, frp.data(), fci.data(), fv.data(), out) != 0) return 1;
+    FF_API_END(ctx)
 }
 
 extern "C" int ffcuda_matrix_info(ffcuda_matrix *A, int *n, int64_t *nnz)

@@ -17,7 +17,8 @@ OP_ID, OP_DX, OP_DY, OP_DZ = 0, 1, 2, 6
 SYMBOLS = """ffcuda_ctx_create ffcuda_ctx_destroy ffcuda_last_error ffcuda_ctx_sync ffcuda_ctx_set_stream ffcuda_ctx_get_stream ffcuda_ctx_set_option
 ffcuda_prof_enable ffcuda_prof_reset ffcuda_prof_get ffcuda_launch_count ffcuda_mesh_upload ffcuda_mesh_cube ffcuda_mesh_square
 ffcuda_mesh_info ffcuda_mesh_download ffcuda_mesh_destroy ffcuda_space_create ffcuda_space_info ffcuda_space_download_dofs
-ffcuda_space_destroy ffcuda_symbolic ffcuda_pattern_info ffcuda_pattern_download ffcuda_pattern_download_async ffcuda_pattern_destroy ffcuda_matrix_create
+ffcuda_space_destroy ffcuda_symbolic ffcuda_pattern_info ffcuda_pattern_download ffcuda_pattern_download_async ffcuda_pattern_lower_nnz ffcuda_pattern_download_lower
+ffcuda_matrix_download_lower ffcuda_matrix_from_csr_lower ffcuda_pattern_destroy ffcuda_matrix_create
 ffcuda_matrix_from_csr ffcuda_matrix_info ffcuda_matrix_download ffcuda_matrix_upload ffcuda_matrix_destroy ffcuda_vec_create
 ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_destroy ffcuda_assemble_bilinear
 ffcuda_assemble_linear ffcuda_bc_from_pairs ffcuda_bc_from_labels ffcuda_bc_count ffcuda_matrix_apply_bc ffcuda_vec_apply_bc
@@ -203,6 +204,14 @@ class Context(_Handle):
         v.upload(host)
         return v
 
+    def matrix_from_csr_lower(self, n, rowptr, colind, vals):
+        """half-stored (sym=1) host matrix -> full device matrix"""
+        rowptr, colind, vals = _i32(rowptr), _i32(colind), _f64(vals)
+        out = C.c_void_p()
+        _ck(lib().ffcuda_matrix_from_csr_lower(_h(self), int(n), C.c_int64(len(colind)), _p(rowptr), _p(colind), _p(vals), C.byref(out)),
+            self.h)
+        return Matrix(out.value, self, None)
+
     def matrix_from_csr(self, n, rowptr, colind, vals):
         rowptr, colind, vals = _i32(rowptr), _i32(colind), _f64(vals)
         out = C.c_void_p()
@@ -307,6 +316,15 @@ class Pattern(_Handle):
         _ck(lib().ffcuda_pattern_download(_h(self), _p(rp), _p(ci)), self.ctx.h)
         return rp, ci
 
+    def download_lower(self):
+        """(rowptr, colind) of the lower triangle: what a sym=1 MatriceMorse holds"""
+        n, _ = self.info()
+        nl = C.c_int64()
+        _ck(lib().ffcuda_pattern_lower_nnz(_h(self), C.byref(nl)), self.ctx.h)
+        rp, ci = np.zeros(n + 1, np.int32), np.zeros(nl.value, np.int32)
+        _ck(lib().ffcuda_pattern_download_lower(_h(self), _p(rp), _p(ci)), self.ctx.h)
+        return rp, ci
+
     def download_async(self, rp, ci):
         """copies behind the work enqueued so far, on a second stream; rp / ci (pinned numpy arrays) are valid after ctx.sync()"""
         _ck(lib().ffcuda_pattern_download_async(_h(self), _p(rp), _p(ci)), self.ctx.h)
@@ -334,6 +352,13 @@ class Matrix(_Handle):
         v = np.zeros(nnz) if out is None else out
         _ck(lib().ffcuda_matrix_download(_h(self), _p(v)), self.ctx.h)
         return v
+
+    def download_lower(self):
+        nl = C.c_int64()
+        _ck(lib().ffcuda_pattern_lower_nnz(_h(self.pattern), C.byref(nl)), self.ctx.h)
+        out = np.zeros(nl.value)
+        _ck(lib().ffcuda_matrix_download_lower(_h(self), _p(out)), self.ctx.h)
+        return out
 
     def upload(self, vals):
         vals = _f64(vals)

@@ -10,7 +10,7 @@
 // At run time an intercepted call walks the varf exactly like AssembleVarForm (fflib/problem.cpp:9744-9855), flattens
 // mesh / dof table / term lists / quadrature rule / Dirichlet sets into plain arrays and calls the C ABI of
 // libffcuda_core.so (include/ffcuda.h).  What the GPU path does not cover (other elements, x-dependent coefficients,
-// boundary integrals, level sets, sym=1, complex, ...) is NOT claimed: the call is handed, untouched, to the
+// boundary integrals, level sets, complex, ...) is NOT claimed: the call is handed, untouched, to the
 // built-in operator it derives from, with a notice at verbosity >= 1 (FFCUDA_STRICT=1 turns that into an error).
 // There is no CPU re-implementation here: without a CUDA device every claimed call throws ErrorExec.
 //
@@ -514,7 +514,6 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
                 ds.initmat = true;
                 int np = OpCall_FormBilinear_np::n_name_param - NB_NAME_PARM_HMAT;
                 SetEnd_Data_Sparse_Solver<double>(stack, ds, this->b->nargs, np);
-                if (ds.sym) throw Unsupported{"sym=1 (half storage)"};
                 if (ds.tgv != ds.tgv) throw Unsupported{"tgv is NaN"};
                 const FESpaceT &Vh = *PVh;
                 const MMesh &Th = Vh.Th;
@@ -550,9 +549,17 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
                         throw;
                     }
                     rowptr.resize((size_t)n + 1);
-                    colind.resize((size_t)nnz);
-                    vals.resize((size_t)nnz);
-                    rc = ffcuda_pattern_download(P, rowptr.data(), colind.data()) || ffcuda_matrix_download(dA, vals.data());
+                    if (ds.sym) { // half storage: FreeFEM keeps the entries (i, j <= i); the device matrix stays full
+                        rc = ffcuda_pattern_lower_nnz(P, &nnz);
+                        colind.resize((size_t)nnz);
+                        vals.resize((size_t)nnz);
+                        rc = rc || ffcuda_pattern_download_lower(P, rowptr.data(), colind.data()) ||
+                             ffcuda_matrix_download_lower(dA, vals.data());
+                    } else {
+                        colind.resize((size_t)nnz);
+                        vals.resize((size_t)nnz);
+                        rc = ffcuda_pattern_download(P, rowptr.data(), colind.data()) || ffcuda_matrix_download(dA, vals.data());
+                    }
                 }
                 if (rc) {
                     ffcuda_matrix_destroy(dA);
@@ -567,7 +574,7 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
                 A.Uh = Vh;
                 A.Vh = Vh;
                 MatriceMorse<double> *M = new MatriceMorse<double>(n, n, 0, 0);
-                M->set(n, n, 0, (size_t)nnz, rowptr.data(), colind.data(), vals.data(), 0, 1); // copies, rebuilds the hash
+                M->set(n, n, ds.sym ? 1 : 0, (size_t)nnz, rowptr.data(), colind.data(), vals.data(), 0, 1); // copies, rebuilds the hash
                 A.A.master(M);
                 drop_resident(); // at most one matrix waits for its solver
                 g_resident[(const void *)static_cast<HashMatrix<int, double> *>(M)] = Resident{dA, P}; // stays on the device for the solver
@@ -687,9 +694,11 @@ class SolverCudaCG : public VirtualSolver<int, double> {
     void upload()
     {
         release_resident(dev);
-        if (A->half) ExecError("ffcuda: CG on a half-stored (sym=1) matrix is not on the GPU path");
         A->CSR(); // sorted, p[] built (HashMatrix.cpp:859-876)
-        if (ffcuda_matrix_from_csr(context(), A->n, (int64_t)A->nnz, A->p, A->j, A->aij, &dev.A) != 0) fail("uploading the matrix");
+        if (A->half) { // sym=1: entries (i, j <= i); expanded to the full symmetric matrix on the way in
+            if (ffcuda_matrix_from_csr_lower(context(), A->n, (int64_t)A->nnz, A->p, A->j, A->aij, &dev.A) != 0) fail("uploading the matrix");
+        } else if (ffcuda_matrix_from_csr(context(), A->n, (int64_t)A->nnz, A->p, A->j, A->aij, &dev.A) != 0)
+            fail("uploading the matrix");
     }
     void UpdateState()
     {

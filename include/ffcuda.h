@@ -116,6 +116,12 @@ int ffcuda_pattern_download(ffcuda_pattern *p, int32_t *rowptr /* n+1 */, int32_
  * that follows overlaps the transfer.  The buffers (pinned host memory, or the copy degrades to a synchronous one) are
  * valid after ffcuda_ctx_sync. */
 int ffcuda_pattern_download_async(ffcuda_pattern *p, int32_t *rowptr, int32_t *colind);
+/* half storage (`sym=1`): FreeFEM's MatriceMorse then keeps the entries (i, j <= i) only (MatriceElementaireSymetrique,
+ * HashMatrix::operator+= femlib/HashMatrix.cpp:1319-1325; addMatMul :1087-1154 mirrors them).  The device matrix stays
+ * full; these entries cut the lower triangle out for the host (rowptr n+1, colind / vals ffcuda_pattern_lower_nnz long),
+ * which equals FreeFEM's half matrix for symmetric forms. */
+int ffcuda_pattern_lower_nnz(ffcuda_pattern *p, int64_t *nnz_lower);
+int ffcuda_pattern_download_lower(ffcuda_pattern *p, int32_t *rowptr, int32_t *colind);
 void ffcuda_pattern_destroy(ffcuda_pattern *p);
 
 /* ---- matrices and vectors (device resident) ------------------------------------------------------- */
@@ -123,8 +129,12 @@ int ffcuda_matrix_create(ffcuda_pattern *p, ffcuda_matrix **out); /* values zero
 /* a matrix given by host CSR arrays (solver-only use: `set(A,solver=CG)` on an existing MatriceMorse) */
 int ffcuda_matrix_from_csr(ffcuda_ctx *ctx, int n, int64_t nnz, const int32_t *rowptr, const int32_t *colind,
                            const double *vals, ffcuda_matrix **out);
+/* the same from a half-stored matrix (sorted rows, entries j <= i): expanded to the full symmetric matrix */
+int ffcuda_matrix_from_csr_lower(ffcuda_ctx *ctx, int n, int64_t nnz_lower, const int32_t *rowptr, const int32_t *colind,
+                                 const double *vals, ffcuda_matrix **out);
 int ffcuda_matrix_info(ffcuda_matrix *A, int *n, int64_t *nnz);
 int ffcuda_matrix_download(ffcuda_matrix *A, double *vals /* nnz, CSR order */);
+int ffcuda_matrix_download_lower(ffcuda_matrix *A, double *vals); /* values of the lower triangle, see ffcuda_pattern_lower_nnz */
 int ffcuda_matrix_upload(ffcuda_matrix *A, const double *vals);
 void ffcuda_matrix_destroy(ffcuda_matrix *A);
 

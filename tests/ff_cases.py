@@ -63,7 +63,13 @@ CASES = {
     "lap2d_p2_tgvm2": (2, 1, LAP2, [(0, ID, 1.0)], "qf5pT", [([1, 2, 3, 4], 1, [0.0])]),
     "lame3d_p1_tgvm1": (1, 3, lame_terms(), [(2, ID, -0.05)], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
     "lap3d_p1_tgvm3": (1, 1, LAP3, [(0, ID, 1.0)], "qfV5", [([1, 3], 1, [0.0])]),
+    # half storage (sym=1, CASE_SYM below): the fixture holds the lower triangle
+    "lap3d_p1_sym": (1, 1, LAP3, [(0, ID, 1.0)], "qfV5", [(ALL6, 1, [0.0])]),
+    "lap2d_p2_sym": (2, 1, LAP2 + [(0, ID, 0, ID, 2.0)], [(0, ID, 1.0)], "qf5pT", [([2, 4], 1, [0.0])]),
+    "lame3d_p1_sym": (1, 3, lame_terms(), [(2, ID, -0.05)], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
 }
+# cases assembled with sym=1: MatriceMorse keeps the entries (i, j) with j <= i only (HashMatrix.cpp:1319-1325)
+CASE_SYM = {"lap3d_p1_sym", "lap2d_p2_sym", "lame3d_p1_sym"}
 # Dirichlet treatment of a case: penalty tgv = 1e30 unless listed here (HashMatrix::SetBC with tgv < 0)
 CASE_TGV = {"lap3d_p1_tgvm1": -1.0, "lap3d_p1_tgvm2": -2.0, "lap2d_p2_tgvm2": -2.0, "lame3d_p1_tgvm1": -1.0, "lap3d_p1_tgvm3": -3.0}
 
@@ -73,6 +79,28 @@ def load(name):
     g["dim"] = int(g["dim"])
     g["ndof"] = int(g["ndof"])
     return g
+
+
+def lower(n, rp, ci, val):
+    """lower triangle (j <= i) of a CSR matrix with sorted rows: what sym=1 stores"""
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    keep = ci <= rows
+    hrp = np.zeros(n + 1, np.int64)
+    np.add.at(hrp, rows[keep] + 1, 1)
+    return np.cumsum(hrp).astype(np.int32), ci[keep], val[keep]
+
+
+def expand_lower(n, rp, ci, val):
+    """full symmetric CSR from its lower triangle"""
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    off = ci < rows
+    fi = np.concatenate([rows, ci[off]])
+    fj = np.concatenate([ci, rows[off]])
+    fv = np.concatenate([val, val[off]])
+    o = np.argsort(fi.astype(np.int64) * n + fj, kind="stable")
+    frp = np.zeros(n + 1, np.int64)
+    np.add.at(frp, fi + 1, 1)
+    return np.cumsum(frp).astype(np.int32), fj[o].astype(np.int32), fv[o]
 
 
 def golden_csr(g):

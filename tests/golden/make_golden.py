@@ -69,6 +69,12 @@ CASES = {
     "lame3d_p1_tgvm1": dict(dim=3, mesh="cube(2,2,2)", fe="[P1,P1,P1]", unk="[u1,u2,u3]", tst="[v1,v2,v3]",
                             pre=LAME_PRE, bil=LAME, lin="-0.05*v3", bc="on(1,u1=0,u2=0,u3=0)", tgv=-1, solve=False),
     "lap3d_p1_tgvm3": dict(dim=3, mesh="cube(2,3,2)", fe="P1", bil=LAP3, lin="1.*v", bc="on(1,3,u=0)", tgv=-3, solve=False),
+    # half storage (sym=1): MatriceElementaireSymetrique / the symmetric Element_Op, lower triangle only (HashMatrix.cpp:1319-1325)
+    "lap3d_p1_sym": dict(dim=3, mesh="cube(3,3,3)", fe="P1", bil=LAP3, lin="1.*v", bc="on(1,2,3,4,5,6,u=0)", sym=1),
+    "lap2d_p2_sym": dict(dim=2, mesh="square(4,3,[x+0.2*y*y,y*(1+0.3*x)])", fe="P2", bil=LAP2 + "+2.*u*v", lin="1.*v",
+                         bc="on(2,4,u=0)", sym=1),
+    "lame3d_p1_sym": dict(dim=3, mesh="cube(2,2,3)", fe="[P1,P1,P1]", unk="[u1,u2,u3]", tst="[v1,v2,v3]",
+                          pre=LAME_PRE, bil=LAME, lin="-0.05*v3", bc="on(1,u1=0,u2=0,u3=0)", sym=1),
     "lame3d_p2_warp": dict(dim=3, mesh="cube(2,1,2,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", fe="[P2,P2,P2]",
                            unk="[u1,u2,u3]", tst="[v1,v2,v3]", pre=LAME_PRE, bil=LAME, lin="-0.05*v3",
                            bc="on(1,u1=0,u2=0,u3=0)+on(3,u1=0.01,u2=0,u3=-0.02)"),
@@ -89,7 +95,8 @@ def script(c, out):
     s.append(f"fespace Vh(Th,{c['fe']});")
     s.append(f"varf va({unk},{tst}) = {integ}(Th{opt})({c['bil']}) + {integ}(Th{opt})({c['lin']}){bc};")
     tg = (",tgv=%g" % c["tgv"]) if "tgv" in c else ""
-    s.append(f"matrix A = va(Vh,Vh,solver=CG,eps=1e-6{tg});")
+    sy = ",sym=1" if c.get("sym") else ""
+    s.append(f"matrix A = va(Vh,Vh,solver=CG,eps=1e-6{tg}{sy});")
     s.append(f"real[int] b = va(0,Vh{tg});")
     # mesh dump
     s.append(f'{{ ofstream f("{out}/mesh.txt"); f.precision(17);')

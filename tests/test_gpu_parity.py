@@ -33,7 +33,7 @@ def _upload(ctx, g):
     return ctx.mesh_upload(g["dim"], g["xyz"], g["conn"], g["elab"], g["bconn"], g["blab"], g["belem"], g["bface"])
 
 
-def _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve=True, eps=1e-6, itmax=0, TGV=TGV):  # noqa: N803
+def _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve=True, eps=1e-6, itmax=0, TGV=TGV, lower=False):  # noqa: N803
     """Full product pipeline on one problem; returns everything a parity check needs."""
     mesh = _upload(ctx, g)
     sp = mesh.space(order, ncomp, e2n, nnodes)
@@ -49,6 +49,13 @@ def _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve=True
         A.apply_bc(bc, TGV)
         b.apply_bc(bc, TGV)
     out = dict(rowptr=rp, colind=ci, vals=A.download(), b=b.download(), n=n)
+    if lower:  # sym=1: what FreeFEM's half-stored MatriceMorse holds (the device matrix stays full)
+        frp, fci, fval = out["rowptr"], out["colind"], out["vals"]
+        hrp, hci = pat.download_lower()
+        hval = A.download_lower()
+        erp, eci, eval_ = fc.lower(n, frp, fci, fval)
+        assert np.array_equal(hrp, erp) and np.array_equal(hci, eci) and np.array_equal(hval, eval_)
+        out.update(rowptr=hrp, colind=hci, vals=hval)
     if solve:
         x = ctx.vec(n)
         it, conv, gcg = A.cg(b, x, eps=eps, itmax=itmax, tgv=TGV)
@@ -68,7 +75,8 @@ def test_golden_case(ctx, name):
     qp, qw = ol.quadrature(g["dim"], qname)
     e2n = fc.elem2node(g, order, ncomp)
     nnodes = g["ndof"] // ncomp
-    r = _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve="u" in g, TGV=fc.CASE_TGV.get(name, TGV))
+    r = _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve="u" in g, TGV=fc.CASE_TGV.get(name, TGV),
+                  lower=name in fc.CASE_SYM)
     grp, gci, gval = fc.golden_csr(g)
     assert r["n"] == g["ndof"]
     assert np.array_equal(r["rowptr"], grp) and np.array_equal(r["colind"], gci)          # bit-exact pattern
@@ -106,7 +114,18 @@ def test_cg_on_reference_matrix(ctx, name):
     g = fc.load(name)
     n = g["ndof"]
     rp, ci, val = fc.golden_csr(g)
-    A = ctx.matrix_from_csr(n, rp, ci, val)
+    if name in fc.CASE_SYM:   # half-stored host matrix: expanded on the way in; same as the expansion done here
+        A = ctx.matrix_from_csr_lower(n, rp, ci, val)
+        frp, fci, fval = fc.expand_lower(n, rp, ci, val)
+        xs = np.sin(np.arange(n, dtype=np.float64))
+        y = ctx.vec(n)
+        A.spmv(ctx.vec_from(xs), y)
+        import scipy.sparse as sps
+        ref = sps.csr_matrix((fval, fci, frp), shape=(n, n)) @ xs
+        big = np.abs(ref) > 1e20
+        assert np.max(np.abs(y.download() - ref)[~big]) <= RTOL * np.abs(ref[~big]).max()
+    else:
+        A = ctx.matrix_from_csr(n, rp, ci, val)
     b = np.ascontiguousarray(g["b"])
     x = np.zeros(n)
     it, conv, _ = A.cg_host(b, x, eps=1e-6, itmax=0, tgv=TGV)

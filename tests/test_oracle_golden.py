@@ -41,9 +41,15 @@ def test_matrix_rhs_solution(name):
     e2n = fc.elem2node(g, order, ncomp)
     qp, qw = ol.quadrature(dim, qname)
     ci, cj, ca = ol.assemble_coo(_mesh(g), order, ncomp, e2n, bt, qp, qw)
+    if name in fc.CASE_SYM:
+        # sym=1: the symmetric element routine visits the local couples (il, jl <= il) and stores each at (max, min) of the
+        # global dofs (HashMatrix.cpp:1319-1325); for a symmetric form that is the lower triangle of the full matrix.  The
+        # insertion order differs from the filtered full order, so only the sorted storage is pinned for these fixtures.
+        keep = cj <= ci
+        ci, cj, ca = ci[keep], cj[keep], ca[keep]
     # HashMatrix insertion order (storage order before any CSR()/COO() call): bit-exact
     # (SetBC with tgv < 0 sorts the storage: those fixtures hold the sorted order only)
-    if name not in fc.CASE_TGV:
+    if name not in fc.CASE_TGV and name not in fc.CASE_SYM:
         assert np.array_equal(ci, g["ins_i"]) and np.array_equal(cj, g["ins_j"])
     # the script's `[I,J,C]=A` sorted the reference storage by (i,j); do the same (Sortij)
     o = np.argsort(ci.astype(np.int64) * n + cj, kind="stable")
@@ -69,12 +75,17 @@ def test_matrix_rhs_solution(name):
     # entries by 1 ulp (term summation order) and CG at eps=1e-6 is not converged to round-off, so that
     # ulp is amplified by the iteration (observed: 1.5e-8, one iteration more); there the pin on ffo_cg is
     # test_cg_on_reference_matrix below and here only the converged residual is checked.
+    if name in fc.CASE_SYM:  # addMatMul mirrors the off-diagonal entries of a half-stored matrix (HashMatrix.cpp:1087-1154)
+        off = cj < ci
+        ci, cj, ca = np.concatenate([ci, cj[off]]), np.concatenate([cj, ci[off]]), np.concatenate([ca, ca[off]])
     if "u" in g:
         x, it, ret, _ = ol.cg(n, ci, cj, ca, b, np.zeros(n), eps=1e-6, itmax=0, tgv=TGV)
         assert ret in (1, 2)
         if ncomp == 1:
             assert it == int(g["cg_iters"])
-            assert np.max(np.abs(x - g["u"])) <= RTOL * np.abs(g["u"]).max()
+            # (half storage: the mirrored product adds in another order than ffo_spmv_coo on the expanded matrix, and an
+            # eps=1e-6 iterate amplifies that ulp up to the residual level)
+            assert np.max(np.abs(x - g["u"])) <= (1e-9 if name in fc.CASE_SYM else RTOL) * np.abs(g["u"]).max()
         else:
             assert abs(it - int(g["cg_iters"])) <= 2
             assert np.max(np.abs(x - g["u"])) <= 1e-6 * np.abs(g["u"]).max()
@@ -90,9 +101,13 @@ def test_cg_on_reference_matrix(name):
     TGV = fc.CASE_TGV.get(name, 1e30)  # noqa: N806
     g = fc.load(name)
     n = g["ndof"]
+    if name in fc.CASE_SYM:
+        off = g["coo_j"] < g["coo_i"]
+        g = dict(g, coo_i=np.concatenate([g["coo_i"], g["coo_j"][off]]), coo_j=np.concatenate([g["coo_j"], g["coo_i"][off]]),
+                 coo_a=np.concatenate([g["coo_a"], g["coo_a"][off]]))
     x, it, ret, _ = ol.cg(n, g["coo_i"], g["coo_j"], g["coo_a"], g["b"], np.zeros(n), eps=1e-6, itmax=0, tgv=TGV)
-    assert ret in (1, 2) and it == int(g["cg_iters"])
-    assert np.max(np.abs(x - g["u"])) <= RTOL * np.abs(g["u"]).max()
+    assert ret in (1, 2) and abs(it - int(g["cg_iters"])) <= (1 if name in fc.CASE_SYM else 0)
+    assert np.max(np.abs(x - g["u"])) <= (1e-6 if name in fc.CASE_SYM else RTOL) * np.abs(g["u"]).max()
     x, it, ret, _ = ol.cg(n, g["coo_i"], g["coo_j"], g["coo_a"], g["b"], np.zeros(n), eps=1e-14, itmax=0, tgv=TGV)
     assert ret in (1, 2) and it == int(g["cg_iters14"])
     assert np.max(np.abs(x - g["u14"])) <= RTOL * np.abs(g["u14"]).max()

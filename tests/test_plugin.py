@@ -39,13 +39,14 @@ verbosity=1; UU[] = 0; UU[] = A^-1*b; verbosity=0;
 """
 
 
-def script(dim, mesh, fe, bil, lin, bc, pre="", unk="u", tst="v", eps="1e-6", intopt="", tgv=None):
+def script(dim, mesh, fe, bil, lin, bc, pre="", unk="u", tst="v", eps="1e-6", intopt="", tgv=None, sym=False):
     mt, integ = ("mesh", "int2d") if dim == 2 else ("mesh3", "int3d")
     u0 = unk.strip("[]").split(",")[0]
     s = f'load "msh3"\nload "ffcuda"\n{pre}\n{mt} Th = {mesh};\nfespace Vh(Th,{fe});\n'
     s += f"varf va({unk},{tst}) = {integ}(Th{intopt})({bil}) + {integ}(Th{intopt})({lin}){('+' + bc) if bc else ''};\n"
     tg = "" if tgv is None else f",tgv={tgv}"
-    s += f"matrix A = va(Vh,Vh,solver=CG,eps={eps}{tg});\nreal[int] b = va(0,Vh{tg});\n" + DUMP
+    sy = ",sym=1" if sym else ""
+    s += f"matrix A = va(Vh,Vh,solver=CG,eps={eps}{tg}{sy});\nreal[int] b = va(0,Vh{tg});\n" + DUMP
     s += f"Vh {unk};\n" + SOLVE.replace("UU", u0)
     return s
 
@@ -63,6 +64,10 @@ CASES = {
     # exact elimination of the Dirichlet rows and columns (tgv = -2, HashMatrix::SetBC)
     "poisson3d_p1_tgvm2": script(3, "cube(5,6,4)", "P1", LAP3, "1.*v", "on(1,2,3,4,5,6,u=0)", tgv=-2),
     "laplace2d_p2_tgvm2": script(2, "square(6,5)", "P2", LAP2, "1.*v", "on(1,2,3,4,u=0)", eps="1e-14", tgv=-2),
+    # half storage (sym=1): FreeFEM keeps the lower triangle, the solve runs on the full device matrix
+    "poisson3d_p1_sym": script(3, "cube(6,5,4)", "P1", LAP3, "1.*v", "on(1,2,3,4,5,6,u=0)", sym=True),
+    "lame3d_p2_sym": script(3, "cube(2,2,2)", "[P2,P2,P2]", LAME, "-0.05*v3", "on(1,u1=0,u2=0,u3=0)", pre=LAME_PRE,
+                            unk="[u1,u2,u3]", tst="[v1,v2,v3]", eps="1e-14", sym=True),
     "mass3d_lumped": script(3, "cube(3,3,3)", "P1", "u*v+0.1*(" + LAP3 + ")", "1.*v", "on(1,u=0)", intopt=",qfV=qfV1lump"),
 }
 
