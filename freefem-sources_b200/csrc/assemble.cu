@@ -1090,3 +1090,207 @@ extern "C" int ffcuda_assemble_linear(ffcuda_vec *b, ffcuda_space *s, int nterms
     else launch_rhs<2>(ctx, b, s, Lp, dF.p, Fh.data(), lean ? hasgrad_form : hasgrad, lean, accumulate);
     FF_API_END(s ? s->ctx : nullptr)
 }
+
+// ----------------------------------------------------------------------------------------------------
+// Boundary integrals of a linear form: int2d(Th3, labels)(c v) / int1d(Th, labels)(c v) - Neumann / traction data.
+// Element_rhs on border elements (fflib/problem.cpp:8439-8513 2-D, :8517-8587 3-D): for every boundary element with a
+// listed label, B[dof] += measure(face) * c * sum_q w_q phi_dof(PBord(face, q)).  Value terms only (vop = id), for which
+// only the nodes lying on the face receive something.
+// Deterministic without atomics on doubles: the node -> boundary-element incidence (a property of the space, built
+// once: integer count / scan / fill, lists sorted by boundary element) and one thread per node adding its list in order.
+// ----------------------------------------------------------------------------------------------------
+static constexpr int MAXBL = 32;
+struct BndParams {
+    double Fb[4][10];  // [face of the element][local node]: sum_q w_q phi(PBord(face, q))
+    double coef[3];    // per component
+    int nlab;          // < 0: every boundary element
+    int labels[MAXBL];
+};
+
+// local nodes of the element that lie on its face f (opposite vertex f): P1: the dim vertices; P2: + the edges of the face
+template <int DIM>
+__device__ __forceinline__ int face_nodes(int order, int f, int (&out)[6])
+{
+    int n = 0;
+    for (int a = 0; a <= DIM; ++a)
+        if (a != f) out[n++] = a;
+    if (order == 2) {
+        if (DIM == 3) {
+            const int e3[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+            for (int e = 0; e < 6; ++e)
+                if (e3[e][0] != f && e3[e][1] != f) out[n++] = 4 + e;
+        } else {
+            out[n++] = 3 + f; // dof 3+e lies on the edge opposite vertex e
+        }
+    }
+    return n;
+}
+
+// PASS 0: count the items of every node; PASS 1: fill (item = boundary element << 4 | local node)
+template <int DIM, int PASS>
+__global__ void k_bnd_items(int nbe, const int32_t *__restrict__ belem, const int32_t *__restrict__ bface,
+                            const int32_t *__restrict__ e2n, int nloc, int order, int nrows, int32_t *__restrict__ cntptr,
+                            int32_t *__restrict__ cursor, uint32_t *__restrict__ items)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nbe) return;
+    int loc[6];
+    const int n = face_nodes<DIM>(order, bface[e], loc);
+    const int32_t *N = e2n + (size_t)nloc * belem[e];
+    for (int j = 0; j < n; ++j) {
+        const int node = N[loc[j]];
+        if (node >= nrows) continue;
+        if (PASS == 0) atomicAdd(&cntptr[node], 1);
+        else items[cntptr[node] + atomicAdd(&cursor[node], 1)] = ((uint32_t)e << 4) | (uint32_t)loc[j];
+    }
+}
+__global__ void k_bnd_sort(const int32_t *__restrict__ ptr, uint32_t *__restrict__ items, int nrows)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    const int b = ptr[i], n = ptr[i + 1] - b;
+    for (int x = 1; x < n; ++x) {
+        const uint32_t v = items[b + x];
+        int y = x - 1;
+        while (y >= 0 && items[b + y] > v) {
+            items[b + y + 1] = items[b + y];
+            --y;
+        }
+        items[b + y + 1] = v;
+    }
+}
+// measure of every boundary element whose label is listed (0 otherwise): |N|/2 of the face, length of the edge
+template <int DIM>
+__global__ void k_bnd_measure(int nbe, const int32_t *__restrict__ belem, const int32_t *__restrict__ bface,
+                              const int32_t *__restrict__ blab, const int32_t *__restrict__ conn, const double *__restrict__ xyz,
+                              int vstride, const __grid_constant__ BndParams Bp, double *__restrict__ meas)
+{
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nbe) return;
+    bool ok = Bp.nlab < 0;
+    for (int i = 0; i < Bp.nlab; ++i) ok |= (Bp.labels[i] == blab[e]);
+    double m = 0.0;
+    if (ok) {
+        const int32_t *K = conn + (size_t)(DIM + 1) * belem[e];
+        const int f = bface[e];
+        int v[DIM], n = 0;
+        for (int a = 0; a <= DIM; ++a)
+            if (a != f) v[n++] = K[a];
+        const double *A = xyz + (size_t)v[0] * vstride, *B = xyz + (size_t)v[1] * vstride;
+        if (DIM == 3) {
+            const double *Cc = xyz + (size_t)v[DIM - 1] * vstride;
+            const double ux = B[0] - A[0], uy = B[1] - A[1], uz = B[DIM - 1] - A[DIM - 1];
+            const double wx = Cc[0] - A[0], wy = Cc[1] - A[1], wz = Cc[DIM - 1] - A[DIM - 1];
+            const double nx = uy * wz - uz * wy, ny = uz * wx - ux * wz, nz = ux * wy - uy * wx;
+            m = 0.5 * sqrt(nx * nx + ny * ny + nz * nz);
+        } else {
+            m = sqrt((B[0] - A[0]) * (B[0] - A[0]) + (B[1] - A[1]) * (B[1] - A[1]));
+        }
+    }
+    meas[e] = m;
+}
+__global__ void k_bnd_gather(int nrows, const int32_t *__restrict__ ptr, const uint32_t *__restrict__ items,
+                             const int32_t *__restrict__ bface, const double *__restrict__ meas, int nc,
+                             const __grid_constant__ BndParams Bp, double *__restrict__ b, int accumulate)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    double s = 0.0;
+    for (int k = ptr[i]; k < ptr[i + 1]; ++k) {
+        const uint32_t it = items[k];
+        const int e = it >> 4, a = it & 15;
+        s += meas[e] * Bp.Fb[bface[e]][a];
+    }
+    if (!accumulate || ptr[i + 1] > ptr[i])
+        for (int c = 0; c < nc; ++c) {
+            double *dst = b + (size_t)i * nc + c;
+            *dst = accumulate ? *dst + Bp.coef[c] * s : Bp.coef[c] * s;
+        }
+}
+
+template <int DIM>
+static void bnd_incidence(ffcuda_ctx *ctx, ffcuda_space *s)
+{
+    if (s->bnd_ptr.p) return;
+    ffcuda_mesh *m = s->mesh;
+    cudaStream_t st = ctx->stream;
+    const int nrows = s->nnodes_owned, nbe = m->nbe;
+    DBuf<int32_t> cnt, cursor;
+    cnt.alloc((size_t)nrows + 1);
+    cursor.alloc((size_t)nrows + 1);
+    FF_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), st));
+    FF_CUDA(cudaMemsetAsync(cursor.p, 0, cursor.bytes(), st));
+    ff_launch(ctx, "bnd_count", [&] {
+        k_bnd_items<DIM, 0><<<ff_blocks(nbe, 256), 256, 0, st>>>(nbe, m->belem.p, m->bface.p, s->e2n, s->nloc, s->order, nrows, cnt.p, nullptr, nullptr);
+    });
+    s->bnd_ptr.alloc((size_t)nrows + 1);
+    int64_t tot = 0;
+    ff_exclusive_scan_i32(ctx, cnt.p, s->bnd_ptr.p, (size_t)nrows + 1, &tot);
+    s->bnd_items.alloc((size_t)std::max<int64_t>(tot, 1));
+    ff_launch(ctx, "bnd_fill", [&] {
+        k_bnd_items<DIM, 1><<<ff_blocks(nbe, 256), 256, 0, st>>>(nbe, m->belem.p, m->bface.p, s->e2n, s->nloc, s->order, nrows, s->bnd_ptr.p, cursor.p,
+                                                                s->bnd_items.p);
+    });
+    ff_launch(ctx, "bnd_sort", [&] { k_bnd_sort<<<ff_blocks(nrows, 256), 256, 0, st>>>(s->bnd_ptr.p, s->bnd_items.p, nrows); });
+}
+
+extern "C" int ffcuda_assemble_linear_boundary(ffcuda_vec *b, ffcuda_space *s, int nterms, const ffcuda_lterm *terms, int nq,
+                                               const double *qpts, const double *qw, int nlab, const int32_t *labels, int accumulate)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(b && s, "ffcuda_assemble_linear_boundary: null argument");
+    FF_REQUIRE(nq > 0 && qpts && qw, "face quadrature rule missing");
+    ffcuda_ctx *ctx = s->ctx;
+    ff_enter(ctx);
+    ffcuda_mesh *m = s->mesh;
+    const int dim = m->dim, nloc = s->nloc, nc = s->ncomp;
+    FF_REQUIRE(b->n >= s->nnodes_owned * nc, "right-hand side vector too short");
+    FF_REQUIRE(m->nbe > 0 && m->belem.p && m->bface.p, "the mesh has no boundary elements");
+    BndParams Bp;
+    memset(&Bp, 0, sizeof(Bp));
+    for (int t = 0; t < nterms; ++t) {
+        FF_REQUIRE(terms[t].vcomp >= 0 && terms[t].vcomp < nc, "term component out of range");
+        FF_REQUIRE(terms[t].vop == FFCUDA_OP_ID, "boundary integrals: only value terms (c * v) are on the ffcuda path");
+        Bp.coef[terms[t].vcomp] += terms[t].coef;
+    }
+    if (!labels) Bp.nlab = -1;
+    else {
+        FF_REQUIRE(nlab <= MAXBL, "at most 32 boundary labels per integral");
+        Bp.nlab = nlab;
+        for (int i = 0; i < nlab; ++i) Bp.labels[i] = labels[i];
+    }
+    // Fb[f][a] = sum_q w_q phi_a(PBord(f, q)); PBord: femlib/Mesh3dn.hpp:76 (faces nvfaceTet), Mesh2dn.hpp:65 (edges nvedgeTria)
+    static const int nvface[4][3] = {{3, 2, 1}, {0, 2, 3}, {3, 1, 0}, {0, 1, 2}};
+    static const int nvedge[3][2] = {{1, 2}, {2, 0}, {0, 1}};
+    static const double hat3[4][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    static const double hat2[3][2] = {{0, 0}, {1, 0}, {0, 1}};
+    for (int f = 0; f <= dim; ++f)
+        for (int q = 0; q < nq; ++q) {
+            double P[3] = {0, 0, 0}, B[10][4];
+            if (dim == 3) {
+                const double x = qpts[2 * q], y = qpts[2 * q + 1];
+                for (int d = 0; d < 3; ++d) P[d] = hat3[nvface[f][0]][d] * (1 - x - y) + hat3[nvface[f][1]][d] * x + hat3[nvface[f][2]][d] * y;
+            } else {
+                const double x = qpts[q];
+                for (int d = 0; d < 2; ++d) P[d] = hat2[nvedge[f][0]][d] * (1 - x) + hat2[nvedge[f][1]][d] * x;
+            }
+            ref_basis(dim, s->order, P, B);
+            for (int a = 0; a < nloc; ++a) Bp.Fb[f][a] += qw[q] * B[a][0];
+        }
+    cudaStream_t st = ctx->stream;
+    if (dim == 3) bnd_incidence<3>(ctx, s);
+    else bnd_incidence<2>(ctx, s);
+    DBuf<double> meas;
+    meas.alloc((size_t)m->nbe);
+    ff_launch(ctx, "bnd_measure", [&] {
+        if (dim == 3)
+            k_bnd_measure<3><<<ff_blocks(m->nbe, 256), 256, 0, st>>>(m->nbe, m->belem.p, m->bface.p, m->blab.p, m->conn.p, m->xyz.p, m->vstride, Bp, meas.p);
+        else
+            k_bnd_measure<2><<<ff_blocks(m->nbe, 256), 256, 0, st>>>(m->nbe, m->belem.p, m->bface.p, m->blab.p, m->conn.p, m->xyz.p, m->vstride, Bp, meas.p);
+    });
+    const int nrows = s->nnodes_owned;
+    ff_launch(ctx, "bnd_gather", [&] {
+        k_bnd_gather<<<ff_blocks(nrows, 256), 256, 0, st>>>(nrows, s->bnd_ptr.p, s->bnd_items.p, m->bface.p, meas.p, nc, Bp, b->d.p, accumulate);
+    });
+    FF_API_END(s ? s->ctx : nullptr)
+}

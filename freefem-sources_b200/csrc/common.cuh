@@ -345,6 +345,9 @@ struct ffcuda_space {
     int lean_assemblies = 0;  // scalar P1 assemblies seen on this space (the tile set is built from the second one on)
     int64_t sym_nnz_node = 0; // pattern size found by the first symbolic phase on this space (scalar P1, staged)
     int sym_maxrow = 0;
+    // node -> boundary-element incidence (assemble.cu, boundary integrals of linear forms), built on first use
+    DBuf<int32_t> bnd_ptr;
+    DBuf<uint32_t> bnd_items;
     // P2: node rows sorted by decreasing length (assemble.cu launch_p2), rows [0, p2_nlong) are the long ones
     DBuf<int32_t> p2_rowperm;
     int p2_nlong = 0, p2_short_maxrow = 0;

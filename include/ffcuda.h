@@ -20,6 +20,7 @@
  *                                  Element_Op :6063-6160, :6337-6437, MatriceElementairePleine::call
  *                                  femlib/MatriceCreuse_tpl.hpp:233-258
  *   ffcuda_assemble_linear      <- AssembleLinearForm fflib/problem.cpp:10555, :10878-11227, Element_rhs :7839-7985
+ *   ffcuda_assemble_linear_boundary <- Element_rhs on border elements fflib/problem.cpp:8439-8587
  *   ffcuda_bc_* / *_apply_bc    <- AssembleBC fflib/problem.cpp:9881-10034, :10039-10194, HashMatrix::SetBC
  *                                  femlib/HashMatrix.cpp:1195-1238 (tgv >= 0 branch)
  *   ffcuda_quadrature           <- CDomainOfIntegration::FIT/FIV fflib/problem.cpp:14102-14145, QF_Simplex
@@ -162,6 +163,14 @@ int ffcuda_assemble_bilinear(ffcuda_matrix *A, ffcuda_space *s, int nterms, cons
 int ffcuda_assemble_linear(ffcuda_vec *b, ffcuda_space *s, int nterms, const ffcuda_lterm *terms,
                            int nq, const double *qpts, const double *qw,
                            int nlab, const int32_t *labels, int accumulate);
+/* b (+)= boundary integrals int2d(Th3, labels)(c v) / int1d(Th, labels)(c v) of a linear form (Neumann, traction data):
+ * Element_rhs on border elements, fflib/problem.cpp:8439-8513 (2-D), :8517-8587 (3-D).  Value terms only (vop = id),
+ * constant c.  qpts: nq x (dim-1) reference coordinates of the face rule FreeFEM selected (default: 7 points on a face,
+ * 3 Gauss points on an edge), qw: weights summing to 1; labels NULL = every boundary element.  The mesh must have been
+ * uploaded with its boundary elements (belem / bface given or recovered). */
+int ffcuda_assemble_linear_boundary(ffcuda_vec *b, ffcuda_space *s, int nterms, const ffcuda_lterm *terms,
+                                    int nq, const double *qpts, const double *qw,
+                                    int nlab, const int32_t *labels, int accumulate);
 
 /* ---- Dirichlet conditions ------------------------------------------------------------------------------
  * tgv >= 0: penalty, A(d,d) = tgv and b[d] = tgv*g(d).  tgv < 0: exact elimination exactly as HashMatrix::SetBC

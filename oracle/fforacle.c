@@ -474,6 +474,59 @@ void ffo_assemble_rhs(int dim, int nv, const double *xyz, int nt, const int32_t 
     }
 }
 
+/* Boundary integrals of a linear form, int2d(Th3,labels)(...) / int1d(Th,labels)(...): Element_rhs on a border element
+ * (fflib/problem.cpp:8517-8587 in 3-D, :8439-8513 in 2-D): for every boundary element with a listed label, every
+ * quadrature point of the face rule, every dof of the ADJACENT ELEMENT: B[dof] += (face measure * w_q) * c * d^op phi_i(Pt),
+ * Pt = PBord(ie, pi) (femlib/Mesh3dn.hpp:76, Mesh2dn.hpp:65).  Adds to b (the caller zeroes it). */
+void ffo_assemble_rhs_boundary(int dim, const double *xyz, const int32_t *conn, int order, int ncomp,
+                               const int32_t *elem2node, int nbe, const int32_t *blab, const int32_t *belem,
+                               const int32_t *bface, int nterms, const ffo_lterm *terms, int nq, const double *qpts,
+                               const double *qw, int nlab, const int32_t *labels, double *b)
+{
+    static const double hat3[4][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    static const double hat2[3][2] = {{0, 0}, {1, 0}, {0, 1}};
+    const int nloc = ffo_nloc(dim, order), nvk = dim + 1;
+    for (int ib = 0; ib < nbe; ++ib) {
+        if (!in_labels(blab[ib], nlab, labels)) continue;
+        const int it = belem[ib], ie = bface[ib];
+        const int32_t *K = conn + (size_t)nvk * it;
+        const int32_t *N = elem2node ? elem2node + (size_t)nloc * it : K;
+        double X[12], G[4][3], val[10][4];
+        elem_coords(dim, xyz, K, X);
+        geom(dim, X, G);
+        double le;
+        if (dim == 3) { /* T.N(ie): cross product of two edges of the face, norm = 2 * area */
+            const double *A = X + 3 * nvfaceTet[ie][0], *B = X + 3 * nvfaceTet[ie][1], *Cc = X + 3 * nvfaceTet[ie][2];
+            double u[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, v[3] = {Cc[0] - A[0], Cc[1] - A[1], Cc[2] - A[2]}, nn[3];
+            cross3(u, v, nn);
+            le = sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+        } else {
+            const double *A = X + 2 * nvedgeTri[ie][0], *B = X + 2 * nvedgeTri[ie][1];
+            le = sqrt((B[0] - A[0]) * (B[0] - A[0]) + (B[1] - A[1]) * (B[1] - A[1]));
+        }
+        for (int q = 0; q < nq; ++q) {
+            double P[3], coef;
+            if (dim == 3) {
+                const double x = qpts[2 * q], y = qpts[2 * q + 1];
+                for (int d = 0; d < 3; ++d)
+                    P[d] = hat3[nvfaceTet[ie][0]][d] * (1 - x - y) + hat3[nvfaceTet[ie][1]][d] * x + hat3[nvfaceTet[ie][2]][d] * y;
+                coef = le * qw[q] * 0.5;
+            } else {
+                const double x = qpts[q];
+                for (int d = 0; d < 2; ++d) P[d] = hat2[nvedgeTri[ie][0]][d] * (1 - x) + hat2[nvedgeTri[ie][1]][d] * x;
+                coef = le * qw[q];
+            }
+            basis(dim, order, P, G, val);
+            for (int c = 0; c < ncomp; ++c)
+                for (int a = 0; a < nloc; ++a)
+                    for (int t = 0; t < nterms; ++t) {
+                        double w_i = (terms[t].vcomp == c) ? val[a][opslot(terms[t].vop)] : 0.;
+                        b[N[a] * ncomp + c] += coef * terms[t].coef * w_i;
+                    }
+        }
+    }
+}
+
 /* ------------------------------------------------------------------ Dirichlet ----------- */
 int ffo_bc_pairs(int dim, int nt, const int32_t *conn, int order, int ncomp, const int32_t *elem2node,
                  int nbe, const int32_t *blab, const int32_t *belem, const int32_t *bface,

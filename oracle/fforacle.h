@@ -73,6 +73,12 @@ void ffo_assemble_rhs(int dim, int nv, const double *xyz, int nt, const int32_t 
                       int order, int ncomp, const int32_t *elem2node, int ndof,
                       int nterms, const ffo_lterm *terms, int nq, const double *qpts, const double *qw,
                       int nlab, const int32_t *labels, double *b);
+/* boundary integrals of a linear form (Element_rhs on border elements, problem.cpp:8439-8587); ADDS to b.
+ * qpts: nq x (dim-1) reference coordinates on the face / edge */
+void ffo_assemble_rhs_boundary(int dim, const double *xyz, const int32_t *conn, int order, int ncomp,
+                               const int32_t *elem2node, int nbe, const int32_t *blab, const int32_t *belem,
+                               const int32_t *bface, int nterms, const ffo_lterm *terms, int nq, const double *qpts,
+                               const double *qw, int nlab, const int32_t *labels, double *b);
 
 /* Dirichlet dofs as AssembleBC visits them: for each boundary element (in order) whose label is in
  * labels[], for each component c with compmask bit c set, each dof lying on that face -> (dof, value[c]).

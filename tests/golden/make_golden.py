@@ -69,6 +69,16 @@ CASES = {
     "lame3d_p1_tgvm1": dict(dim=3, mesh="cube(2,2,2)", fe="[P1,P1,P1]", unk="[u1,u2,u3]", tst="[v1,v2,v3]",
                             pre=LAME_PRE, bil=LAME, lin="-0.05*v3", bc="on(1,u1=0,u2=0,u3=0)", tgv=-1, solve=False),
     "lap3d_p1_tgvm3": dict(dim=3, mesh="cube(2,3,2)", fe="P1", bil=LAP3, lin="1.*v", bc="on(1,3,u=0)", tgv=-3, solve=False),
+    # Neumann / traction data: boundary integrals of the linear form (Element_rhs on border elements, problem.cpp:8439-8587)
+    "lap3d_p1_neumann": dict(dim=3, mesh="cube(3,3,3,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", fe="P1", bil=LAP3, lin="1.*v",
+                             blin="+int2d(Th,2,3)(2.5*v)", bc="on(1,u=0)"),
+    "lap2d_p2_neumann": dict(dim=2, mesh="square(4,3,[x+0.2*y*y,y*(1+0.3*x)])", fe="P2", bil=LAP2, lin="1.*v",
+                             blin="+int1d(Th,2)(1.5*v)", bc="on(4,u=0)"),
+    "lame3d_p1_traction": dict(dim=3, mesh="cube(2,3,2)", fe="[P1,P1,P1]", unk="[u1,u2,u3]", tst="[v1,v2,v3]",
+                               pre=LAME_PRE, bil=LAME, lin="-0.05*v3", blin="+int2d(Th,2)(0.3*v1-0.2*v3)",
+                               bc="on(1,u1=0,u2=0,u3=0)"),
+    "lap3d_p2_neumann": dict(dim=3, mesh="cube(2,2,2)", fe="P2", bil=LAP3 + "+u*v", lin="1.*v", blin="+int2d(Th,6)(-1.*v)",
+                             bc=""),
     # half storage (sym=1): MatriceElementaireSymetrique / the symmetric Element_Op, lower triangle only (HashMatrix.cpp:1319-1325)
     "lap3d_p1_sym": dict(dim=3, mesh="cube(3,3,3)", fe="P1", bil=LAP3, lin="1.*v", bc="on(1,2,3,4,5,6,u=0)", sym=1),
     "lap2d_p2_sym": dict(dim=2, mesh="square(4,3,[x+0.2*y*y,y*(1+0.3*x)])", fe="P2", bil=LAP2 + "+2.*u*v", lin="1.*v",
@@ -93,7 +103,7 @@ def script(c, out):
     s.append(c.get("pre", ""))
     s.append(f"{mtype} Th = {c['mesh']};")
     s.append(f"fespace Vh(Th,{c['fe']});")
-    s.append(f"varf va({unk},{tst}) = {integ}(Th{opt})({c['bil']}) + {integ}(Th{opt})({c['lin']}){bc};")
+    s.append(f"varf va({unk},{tst}) = {integ}(Th{opt})({c['bil']}) + {integ}(Th{opt})({c['lin']}){c.get('blin', '')}{bc};")
     tg = (",tgv=%g" % c["tgv"]) if "tgv" in c else ""
     sy = ",sym=1" if c.get("sym") else ""
     s.append(f"matrix A = va(Vh,Vh,solver=CG,eps=1e-6{tg}{sy});")

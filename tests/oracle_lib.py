@@ -146,6 +146,31 @@ def assemble_rhs(mesh, order, ncomp, elem2node, ndof, terms, qpts, qw, labels=No
     return b
 
 
+def assemble_rhs_boundary(mesh, order, ncomp, elem2node, b, terms, qpts, qw, labels=None):
+    """adds the boundary integrals int2d(Th3,labels)(...) / int1d(Th,labels)(...) of a linear form to b (returns a copy)"""
+    dim = mesh["dim"]
+    xyz, conn = _f64(mesh["xyz"]), _i32(mesh["conn"])
+    blab, belem, bface = _i32(mesh["blab"]), _i32(mesh["belem"]), _i32(mesh["bface"])
+    e2n, lab = _i32(elem2node), _i32(labels)
+    b = _f64(b).copy()
+    lt = lterms(terms)
+    qpts, qw = _f64(qpts), _f64(qw)
+    lib().ffo_assemble_rhs_boundary(dim, _p(xyz, C.c_double), _p(conn, C.c_int32), order, ncomp, _p(e2n, C.c_int32), len(blab),
+                                    _p(blab, C.c_int32), _p(belem, C.c_int32), _p(bface, C.c_int32), len(terms), lt, len(qw),
+                                    _p(qpts, C.c_double), _p(qw, C.c_double), 0 if lab is None else len(lab), _p(lab, C.c_int32),
+                                    _p(b, C.c_double))
+    return b
+
+
+def face_quadrature(dim):
+    """default rule of a boundary integral (qforder = 6): 7-point rule on the faces of tetrahedra, 3-point Gauss-Legendre
+    on the edges of triangles (QuadratureFormular.cpp: QuadratureFormular_T_5, QF_GaussLegendre3)"""
+    if dim == 3:
+        return quadrature(2, "qf5pT")
+    r = np.sqrt(3.0 / 5.0)
+    return np.array([[(1 - r) / 2], [0.5], [(1 + r) / 2]]), np.array([5.0 / 18, 8.0 / 18, 5.0 / 18])
+
+
 def bc_pairs(mesh, order, ncomp, elem2node, labels, compmask, values):
     dim = mesh["dim"]
     conn = _i32(mesh["conn"])

@@ -33,7 +33,8 @@ def _upload(ctx, g):
     return ctx.mesh_upload(g["dim"], g["xyz"], g["conn"], g["elab"], g["bconn"], g["blab"], g["belem"], g["bface"])
 
 
-def _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve=True, eps=1e-6, itmax=0, TGV=TGV, lower=False):  # noqa: N803
+def _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve=True, eps=1e-6, itmax=0, TGV=TGV, lower=False,  # noqa: N803
+              blin=None):
     """Full product pipeline on one problem; returns everything a parity check needs."""
     mesh = _upload(ctx, g)
     sp = mesh.space(order, ncomp, e2n, nnodes)
@@ -44,6 +45,9 @@ def _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve=True
     n = pat.info()[0]
     b = ctx.vec(n)
     sp.assemble_linear(b, lt, qp, qw)
+    if blin:  # boundary integrals of the linear form (Neumann / traction data)
+        fq, fw = ol.face_quadrature(g["dim"])
+        sp.assemble_linear_boundary(b, blin[1], fq, fw, blin[0], accumulate=True)
     bcl = [sp.bc_from_labels(labels, mask, values) for labels, mask, values in bcs]
     for bc in bcl:
         A.apply_bc(bc, TGV)
@@ -76,7 +80,7 @@ def test_golden_case(ctx, name):
     e2n = fc.elem2node(g, order, ncomp)
     nnodes = g["ndof"] // ncomp
     r = _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve="u" in g, TGV=fc.CASE_TGV.get(name, TGV),
-                  lower=name in fc.CASE_SYM)
+                  lower=name in fc.CASE_SYM, blin=fc.CASE_BLIN.get(name))
     grp, gci, gval = fc.golden_csr(g)
     assert r["n"] == g["ndof"]
     assert np.array_equal(r["rowptr"], grp) and np.array_equal(r["colind"], gci)          # bit-exact pattern
@@ -94,7 +98,7 @@ def test_golden_case(ctx, name):
         # (a) the reference's own stopping point (eps=1e-6).  An eps=1e-6 iterate is NOT converged to round-off: CG
         # amplifies a 1-ulp difference in A (our assembly sums in another order) up to the residual level, so the
         # 1e-12 bar is only attainable where few iterations are taken (all P1 scalar fixtures); see (b) for the rest.
-        if ncomp == 1:
+        if ncomp == 1 and name not in fc.CASE_BLIN:
             assert r["iters"] == int(g["cg_iters"])
             assert np.max(np.abs(r["u"] - g["u"])) <= (RTOL if order == 1 else 1e-9) * umax
         else:
@@ -550,3 +554,29 @@ def test_config5_cube256_single_gpu_full_size_properties(ctx):
     assert conv == 1 and it == 525
     u = x.download()
     assert u.min() >= -1e-25 and 0.05 < u.max() < 0.06        # max of the torsion function of the unit cube ~ 0.0562
+
+
+def test_boundary_linear_form_properties_and_errors(ctx):
+    """int2d(Th3, labels)(c v) on cube(n): the sum of the vector is c times the area of the labelled faces, only nodes of
+    those faces are touched, accumulation adds, the result is reproducible, gradient terms are refused."""
+    n = 12
+    mesh = ctx.mesh_cube(n, n, n)
+    fq, fw = ol.face_quadrature(3)
+    for order in (1, 2):
+        sp = mesh.space(order, 1)
+        nd = sp.info()[0]
+        b = ctx.vec(nd)
+        sp.assemble_linear_boundary(b, [(0, fc.ID, 2.0)], fq, fw, [2, 5], accumulate=False)
+        hb = b.download()
+        assert abs(hb.sum() - 2.0 * 2.0) <= 1e-12          # two unit faces
+        assert np.count_nonzero(hb) <= 2 * (order * n + 1) ** 2
+        sp.assemble_linear_boundary(b, [(0, fc.ID, 2.0)], fq, fw, [2, 5], accumulate=True)
+        assert np.max(np.abs(b.download() - 2 * hb)) <= 1e-15 * np.abs(hb).max() * 4
+        b2 = ctx.vec(nd)
+        sp.assemble_linear_boundary(b2, [(0, fc.ID, 2.0)], fq, fw, [2, 5], accumulate=False)
+        assert np.array_equal(b2.download(), hb)
+        b3 = ctx.vec(nd)
+        sp.assemble_linear_boundary(b3, [(0, fc.ID, 1.0)], fq, fw, None, accumulate=False)   # every boundary element
+        assert abs(b3.download().sum() - 6.0) <= 1e-12
+        with pytest.raises(ffcuda.FfcudaError):
+            sp.assemble_linear_boundary(b, [(0, fc.DX, 1.0)], fq, fw, [2])
