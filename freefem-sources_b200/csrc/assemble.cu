@@ -1234,6 +1234,44 @@ static void bnd_incidence(ffcuda_ctx *ctx, ffcuda_space *s)
     ff_launch(ctx, "bnd_sort", [&] { k_bnd_sort<<<ff_blocks(nrows, 256), 256, 0, st>>>(s->bnd_ptr.p, s->bnd_items.p, nrows); });
 }
 
+// basis values at the point of face f of the reference element that the face rule's node qp maps to:
+// PBord, femlib/Mesh3dn.hpp:76 (faces nvfaceTet), Mesh2dn.hpp:65 (edges nvedgeTria)
+static void face_ref_basis(int dim, int order, int f, const double *qp, double B[10][4])
+{
+    static const int nvface[4][3] = {{3, 2, 1}, {0, 2, 3}, {3, 1, 0}, {0, 1, 2}};
+    static const int nvedge[3][2] = {{1, 2}, {2, 0}, {0, 1}};
+    static const double hat3[4][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    static const double hat2[3][2] = {{0, 0}, {1, 0}, {0, 1}};
+    double P[3] = {0, 0, 0};
+    if (dim == 3) {
+        const double x = qp[0], y = qp[1];
+        for (int d = 0; d < 3; ++d) P[d] = hat3[nvface[f][0]][d] * (1 - x - y) + hat3[nvface[f][1]][d] * x + hat3[nvface[f][2]][d] * y;
+    } else {
+        const double x = qp[0];
+        for (int d = 0; d < 2; ++d) P[d] = hat2[nvedge[f][0]][d] * (1 - x) + hat2[nvedge[f][1]][d] * x;
+    }
+    ref_basis(dim, order, P, B);
+}
+static void bnd_fill_labels(BndParams &Bp, int nlab, const int32_t *labels)
+{
+    if (!labels) Bp.nlab = -1;
+    else {
+        FF_REQUIRE(nlab <= MAXBL, "at most 32 boundary labels per integral");
+        Bp.nlab = nlab;
+        for (int i = 0; i < nlab; ++i) Bp.labels[i] = labels[i];
+    }
+}
+static void bnd_measures(ffcuda_ctx *ctx, ffcuda_mesh *m, const BndParams &Bp, double *meas)
+{
+    cudaStream_t st = ctx->stream;
+    ff_launch(ctx, "bnd_measure", [&] {
+        if (m->dim == 3)
+            k_bnd_measure<3><<<ff_blocks(m->nbe, 256), 256, 0, st>>>(m->nbe, m->belem.p, m->bface.p, m->blab.p, m->conn.p, m->xyz.p, m->vstride, Bp, meas);
+        else
+            k_bnd_measure<2><<<ff_blocks(m->nbe, 256), 256, 0, st>>>(m->nbe, m->belem.p, m->bface.p, m->blab.p, m->conn.p, m->xyz.p, m->vstride, Bp, meas);
+    });
+}
+
 extern "C" int ffcuda_assemble_linear_boundary(ffcuda_vec *b, ffcuda_space *s, int nterms, const ffcuda_lterm *terms, int nq,
                                                const double *qpts, const double *qw, int nlab, const int32_t *labels, int accumulate)
 {
@@ -1253,28 +1291,12 @@ extern "C" int ffcuda_assemble_linear_boundary(ffcuda_vec *b, ffcuda_space *s, i
         FF_REQUIRE(terms[t].vop == FFCUDA_OP_ID, "boundary integrals: only value terms (c * v) are on the ffcuda path");
         Bp.coef[terms[t].vcomp] += terms[t].coef;
     }
-    if (!labels) Bp.nlab = -1;
-    else {
-        FF_REQUIRE(nlab <= MAXBL, "at most 32 boundary labels per integral");
-        Bp.nlab = nlab;
-        for (int i = 0; i < nlab; ++i) Bp.labels[i] = labels[i];
-    }
-    // Fb[f][a] = sum_q w_q phi_a(PBord(f, q)); PBord: femlib/Mesh3dn.hpp:76 (faces nvfaceTet), Mesh2dn.hpp:65 (edges nvedgeTria)
-    static const int nvface[4][3] = {{3, 2, 1}, {0, 2, 3}, {3, 1, 0}, {0, 1, 2}};
-    static const int nvedge[3][2] = {{1, 2}, {2, 0}, {0, 1}};
-    static const double hat3[4][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-    static const double hat2[3][2] = {{0, 0}, {1, 0}, {0, 1}};
+    bnd_fill_labels(Bp, nlab, labels);
+    // Fb[f][a] = sum_q w_q phi_a(PBord(f, q))
     for (int f = 0; f <= dim; ++f)
         for (int q = 0; q < nq; ++q) {
-            double P[3] = {0, 0, 0}, B[10][4];
-            if (dim == 3) {
-                const double x = qpts[2 * q], y = qpts[2 * q + 1];
-                for (int d = 0; d < 3; ++d) P[d] = hat3[nvface[f][0]][d] * (1 - x - y) + hat3[nvface[f][1]][d] * x + hat3[nvface[f][2]][d] * y;
-            } else {
-                const double x = qpts[q];
-                for (int d = 0; d < 2; ++d) P[d] = hat2[nvedge[f][0]][d] * (1 - x) + hat2[nvedge[f][1]][d] * x;
-            }
-            ref_basis(dim, s->order, P, B);
+            double B[10][4];
+            face_ref_basis(dim, s->order, f, qpts + (size_t)q * (dim - 1), B);
             for (int a = 0; a < nloc; ++a) Bp.Fb[f][a] += qw[q] * B[a][0];
         }
     cudaStream_t st = ctx->stream;
@@ -1282,15 +1304,113 @@ extern "C" int ffcuda_assemble_linear_boundary(ffcuda_vec *b, ffcuda_space *s, i
     else bnd_incidence<2>(ctx, s);
     DBuf<double> meas;
     meas.alloc((size_t)m->nbe);
-    ff_launch(ctx, "bnd_measure", [&] {
-        if (dim == 3)
-            k_bnd_measure<3><<<ff_blocks(m->nbe, 256), 256, 0, st>>>(m->nbe, m->belem.p, m->bface.p, m->blab.p, m->conn.p, m->xyz.p, m->vstride, Bp, meas.p);
-        else
-            k_bnd_measure<2><<<ff_blocks(m->nbe, 256), 256, 0, st>>>(m->nbe, m->belem.p, m->bface.p, m->blab.p, m->conn.p, m->xyz.p, m->vstride, Bp, meas.p);
-    });
+    bnd_measures(ctx, m, Bp, meas.p);
     const int nrows = s->nnodes_owned;
     ff_launch(ctx, "bnd_gather", [&] {
         k_bnd_gather<<<ff_blocks(nrows, 256), 256, 0, st>>>(nrows, s->bnd_ptr.p, s->bnd_items.p, m->bface.p, meas.p, nc, Bp, b->d.p, accumulate);
+    });
+    FF_API_END(s ? s->ctx : nullptr)
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Boundary integrals of a bilinear form (Robin terms): int2d(Th3, labels)(c u v) / int1d(Th, labels)(c u v).
+// AssembleBilinearForm's loop over the border elements (fflib/problem.cpp:1317-1326, 2-D :1030-1040) hands the ADJACENT
+// element to Element_Op's border branch (:6518-6560, 2-D :6216-6290) and adds all its couples; every such couple is
+// already in the pattern of the space, and for value terms only the couples of nodes lying on the face receive
+// something: A(i, j) += measure(face) * c * sum_q w_q phi_i phi_j at PBord(face, q).
+// Same ownership as the linear case: one thread per node row walks the row's boundary items in order (sorted by
+// boundary element), finds each face node's column by bisection in the sorted node row and adds in place.
+// ----------------------------------------------------------------------------------------------------
+struct BndBilParams {
+    double Mb[4][10][10]; // [face][local node a (row)][local node b (column)]: sum_q w_q phi_a phi_b
+    double C[3][3];       // [vcomp][ucomp]
+};
+template <int DIM>
+__global__ void k_bnd_bilinear(int nrows, const int32_t *__restrict__ ptr, const uint32_t *__restrict__ items,
+                               const int32_t *__restrict__ belem, const int32_t *__restrict__ bface, const double *__restrict__ meas,
+                               const int32_t *__restrict__ e2n, int nloc, int order, int nc, const int32_t *__restrict__ nrowptr,
+                               const int32_t *__restrict__ ncol, const __grid_constant__ BndBilParams Bq, double *__restrict__ vals)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    const int k0 = ptr[i], k1 = ptr[i + 1];
+    if (k0 == k1) return;
+    const int rb = nrowptr[i], L = nrowptr[i + 1] - rb;
+    double *row = vals + (size_t)nc * nc * rb;
+    for (int k = k0; k < k1; ++k) {
+        const uint32_t it = items[k];
+        const int e = it >> 4, a = it & 15;
+        const double m = meas[e];
+        if (m == 0.0) continue; // label not listed
+        const int f = bface[e];
+        const int32_t *N = e2n + (size_t)nloc * belem[e];
+        int loc[6];
+        const int nf = face_nodes<DIM>(order, f, loc);
+        for (int x = 0; x < nf; ++x) {
+            const int b = loc[x], j = N[b];
+            int lo = 0, hi = L - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (ncol[rb + mid] < j) lo = mid + 1;
+                else hi = mid;
+            }
+            const double w = m * Bq.Mb[f][a][b];
+            for (int cv = 0; cv < nc; ++cv)
+                for (int cu = 0; cu < nc; ++cu)
+                    if (Bq.C[cv][cu] != 0.0) row[(size_t)cv * nc * L + (size_t)lo * nc + cu] += Bq.C[cv][cu] * w;
+        }
+    }
+}
+
+extern "C" int ffcuda_assemble_bilinear_boundary(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms, int nq,
+                                                 const double *qpts, const double *qw, int nlab, const int32_t *labels, int accumulate)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A && s && A->pattern && A->pattern->space == s, "ffcuda_assemble_bilinear_boundary: matrix was not created on this space");
+    FF_REQUIRE(nterms >= 0 && (nterms == 0 || terms), "bad term list");
+    FF_REQUIRE(nq > 0 && qpts && qw, "face quadrature rule missing");
+    ffcuda_ctx *ctx = s->ctx;
+    ff_enter(ctx);
+    ffcuda_mesh *m = s->mesh;
+    ffcuda_pattern *P = A->pattern;
+    const int dim = m->dim, nloc = s->nloc, nc = s->ncomp;
+    FF_REQUIRE(m->nbe > 0 && m->belem.p && m->bface.p, "the mesh has no boundary elements");
+    BndBilParams Bq;
+    memset(&Bq, 0, sizeof(Bq));
+    for (int t = 0; t < nterms; ++t) {
+        const ffcuda_bterm &T = terms[t];
+        FF_REQUIRE(T.ucomp >= 0 && T.ucomp < nc && T.vcomp >= 0 && T.vcomp < nc, "term component out of range");
+        FF_REQUIRE(T.uop == FFCUDA_OP_ID && T.vop == FFCUDA_OP_ID, "boundary integrals: only value terms (c * u * v) are on the ffcuda path");
+        Bq.C[T.vcomp][T.ucomp] += T.coef;
+    }
+    BndParams Bp;
+    memset(&Bp, 0, sizeof(Bp));
+    bnd_fill_labels(Bp, nlab, labels);
+    for (int f = 0; f <= dim; ++f)
+        for (int q = 0; q < nq; ++q) {
+            double B[10][4];
+            face_ref_basis(dim, s->order, f, qpts + (size_t)q * (dim - 1), B);
+            for (int a = 0; a < nloc; ++a)
+                for (int b = 0; b < nloc; ++b) Bq.Mb[f][a][b] += qw[q] * B[a][0] * B[b][0];
+        }
+    cudaStream_t st = ctx->stream;
+    if (accumulate) ff_matrix_touch(A);
+    else FF_CUDA(cudaMemsetAsync(A->vals.p, 0, A->vals.bytes(), st));
+    A->vals_stale = false;
+    A->vals_epoch++;
+    if (dim == 3) bnd_incidence<3>(ctx, s);
+    else bnd_incidence<2>(ctx, s);
+    DBuf<double> meas;
+    meas.alloc((size_t)m->nbe);
+    bnd_measures(ctx, m, Bp, meas.p);
+    const int nrows = s->nnodes_owned;
+    ff_launch(ctx, "bnd_bilinear", [&] {
+        if (dim == 3)
+            k_bnd_bilinear<3><<<ff_blocks(nrows, 128), 128, 0, st>>>(nrows, s->bnd_ptr.p, s->bnd_items.p, m->belem.p, m->bface.p, meas.p, s->e2n, nloc,
+                                                                   s->order, nc, P->nrowptr.p, P->ncol.p, Bq, A->vals.p);
+        else
+            k_bnd_bilinear<2><<<ff_blocks(nrows, 128), 128, 0, st>>>(nrows, s->bnd_ptr.p, s->bnd_items.p, m->belem.p, m->bface.p, meas.p, s->e2n, nloc,
+                                                                   s->order, nc, P->nrowptr.p, P->ncol.p, Bq, A->vals.p);
     });
     FF_API_END(s ? s->ctx : nullptr)
 }

@@ -306,12 +306,26 @@ Quad flat_quadrature(const QF &q, int dim)
 }
 inline Quad volume_rule(Stack s, const CDomainOfIntegration &di, const Mesh *) { return flat_quadrature(di.FIT(s), 2); }
 inline Quad volume_rule(Stack s, const CDomainOfIntegration &di, const Mesh3 *) { return flat_quadrature(di.FIV(s), 3); }
+// rule of a boundary integral in the face coordinates ffcuda_assemble_*_boundary expects (P = A(1-x-y) + Bx + Cy on a face,
+// P = A(1-x) + Bx on an edge).  3-D: T.PBord(ie, pi) is exactly that; 2-D: Element_rhs / Element_Op take
+// Pt = PA*pi.x + PB*(1-pi.x) (fflib/problem.cpp:8646-8649, :6229-6232), hence 1 - x
+inline Quad border_rule(Stack s, const CDomainOfIntegration &di, const Mesh3 *) { return flat_quadrature(di.FIT(s), 2); }
+inline Quad border_rule(Stack s, const CDomainOfIntegration &di, const Mesh *)
+{
+    const QuadratureFormular1d &q = di.FIE(s);
+    Quad Q;
+    for (int i = 0; i < q.n; ++i) {
+        Q.w.push_back(q[i].a);
+        Q.pts.push_back(1.0 - q[i].x);
+    }
+    return Q;
+}
 
 struct Region {
     bool all = true;
     std::vector<int32_t> labels;
 };
-Region region_of(Stack stack, const CDomainOfIntegration &di) // Expandsetoflab, fflib/lgfem.cpp:7809
+Region region_of(Stack stack, const CDomainOfIntegration &di, size_t maxlab = 16) // Expandsetoflab, fflib/lgfem.cpp:7809
 {
     Region R;
     std::set<int> s;
@@ -324,16 +338,27 @@ Region region_of(Stack stack, const CDomainOfIntegration &di) // Expandsetoflab,
         }
     }
     R.labels.assign(s.begin(), s.end());
-    if (R.labels.size() > 16) throw Unsupported{"more than 16 region labels in one integral"};
+    if (R.labels.size() > maxlab) throw Unsupported{"too many region / boundary labels in one integral"};
     return R;
 }
 
 template <class MeshT>
-void check_domain(Stack stack, const CDomainOfIntegration &di, const MeshT &Th)
+void check_domain_options(Stack stack, const CDomainOfIntegration &di, const MeshT &Th);
+// returns true for an integral over boundary elements (int2d on a mesh3, int1d on a mesh), false for a volume integral
+template <class MeshT>
+bool check_domain(Stack stack, const CDomainOfIntegration &di, const MeshT &Th)
 {
     const int dim = MeshDim<MeshT>::d;
     const CDomainOfIntegration::typeofkind volume = dim == 3 ? CDomainOfIntegration::int3d : CDomainOfIntegration::int2d;
-    if (di.d != dim || di.dHat != dim || di.kind != volume) throw Unsupported{"not a volume integral on the mesh of the space"};
+    const CDomainOfIntegration::typeofkind border = dim == 3 ? CDomainOfIntegration::int2d : CDomainOfIntegration::int1d;
+    if (di.d != dim || di.dHat != dim || (di.kind != volume && di.kind != border))
+        throw Unsupported{"neither a volume nor a boundary integral on the mesh of the space"};
+    check_domain_options(stack, di, Th);
+    return di.kind == border;
+}
+template <class MeshT>
+void check_domain_options(Stack stack, const CDomainOfIntegration &di, const MeshT &Th)
+{
     if (di.islevelset()) throw Unsupported{"level-set integral"};
     if (di.withmap()) throw Unsupported{"mapped integration points"};
     typedef const MeshT *pm;
@@ -360,11 +385,13 @@ struct BilinearItem {
     std::vector<ffcuda_bterm> terms;
     Quad q;
     Region reg;
+    bool border = false; // integral over the boundary elements with the labels of reg (Robin terms)
 };
 struct LinearItem {
     std::vector<ffcuda_lterm> terms;
     Quad q;
     Region reg;
+    bool border = false; // Neumann / traction data
 };
 struct BCItem {
     std::vector<int32_t> labels;
@@ -390,10 +417,10 @@ Varf read_varf(Stack stack, const list<C_F0> &largs, const MeshT &Th, int ncomp,
             if (!want_matrix) continue; // ignored when a right-hand side is assembled (problem.cpp:9761-9779)
             const FormBilinear *bf = dynamic_cast<const FormBilinear *>(e);
             if (bf->VF()) throw Unsupported{"discontinuous-Galerkin operators"};
-            check_domain(stack, *bf->di, Th);
             BilinearItem B;
-            B.q = volume_rule(stack, *bf->di, &Th);
-            B.reg = region_of(stack, *bf->di);
+            B.border = check_domain(stack, *bf->di, Th);
+            B.q = B.border ? border_rule(stack, *bf->di, &Th) : volume_rule(stack, *bf->di, &Th);
+            B.reg = region_of(stack, *bf->di, B.border ? 32 : 16);
             const Foperator &op = *bf->b;
             for (size_t k = 0; k < op.v.size(); ++k) {
                 const pair<MGauche, MDroit> &id = op.v[k].first; // (unknown, test)
@@ -403,6 +430,7 @@ Varf read_varf(Stack stack, const list<C_F0> &largs, const MeshT &Th, int ncomp,
                 t.vcomp = id.second.first;
                 t.vop = check_op(id.second.second, dim);
                 if (t.ucomp < 0 || t.ucomp >= ncomp || t.vcomp < 0 || t.vcomp >= ncomp) throw Unsupported{"component out of range"};
+                if (B.border && (t.uop != op_id || t.vop != op_id)) throw Unsupported{"derivatives in a boundary integral"};
                 t.coef = constant_coef(stack, op.v[k].second);
                 B.terms.push_back(t);
             }
@@ -411,16 +439,17 @@ Varf read_varf(Stack stack, const list<C_F0> &largs, const MeshT &Th, int ncomp,
             if (want_matrix) continue;
             const FormLinear *lf = dynamic_cast<const FormLinear *>(e);
             if (lf->VF()) throw Unsupported{"discontinuous-Galerkin operators"};
-            check_domain(stack, *lf->di, Th);
             LinearItem L;
-            L.q = volume_rule(stack, *lf->di, &Th);
-            L.reg = region_of(stack, *lf->di);
+            L.border = check_domain(stack, *lf->di, Th);
+            L.q = L.border ? border_rule(stack, *lf->di, &Th) : volume_rule(stack, *lf->di, &Th);
+            L.reg = region_of(stack, *lf->di, L.border ? 32 : 16);
             const Ftest &op = *lf->l;
             for (size_t k = 0; k < op.v.size(); ++k) {
                 ffcuda_lterm t;
                 t.vcomp = op.v[k].first.first;
                 t.vop = check_op(op.v[k].first.second, dim);
                 if (t.vcomp < 0 || t.vcomp >= ncomp) throw Unsupported{"component out of range"};
+                if (L.border && t.vop != op_id) throw Unsupported{"derivatives in a boundary integral"};
                 t.coef = constant_coef(stack, op.v[k].second);
                 L.terms.push_back(t);
             }
@@ -519,6 +548,19 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
                 const MMesh &Th = Vh.Th;
                 if (!isSameMesh(this->b->largs, &Vh.Th, &Vh.Th, stack)) throw Unsupported{"integrals on different meshes"};
                 Varf V = read_varf(stack, this->b->largs, Th, Vh.N, true);
+                // the pattern of the device matrix is that of the whole space: FreeFEM's is the same only when the volume
+                // integrals visit every element (HashMatrix creates the couples of the visited elements only)
+                {
+                    bool full = false;
+                    std::set<int> labs;
+                    for (size_t i = 0; i < V.bil.size(); ++i)
+                        if (!V.bil[i].border) {
+                            full = full || V.bil[i].reg.all;
+                            labs.insert(V.bil[i].reg.labels.begin(), V.bil[i].reg.labels.end());
+                        }
+                    for (int k = 0; k < Th.nt && !full; ++k)
+                        if (!labs.count(Th[k].lab)) throw Unsupported{"the volume integrals do not visit every element (sub-pattern)"};
+                }
                 DevSpace &D = device_space(Vh);
 
                 // --- the GPU path proper
@@ -532,12 +574,18 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
                 int n = 0;
                 int64_t nnz = 0;
                 int rc = ffcuda_pattern_info(P, &n, &nnz);
-                for (size_t i = 0; i < V.bil.size() && !rc; ++i) {
-                    const BilinearItem &B = V.bil[i];
-                    rc = ffcuda_assemble_bilinear(dA, D.space, (int)B.terms.size(), B.terms.data(), (int)B.q.w.size(), B.q.pts.data(),
-                                                  B.q.w.data(), (int)B.reg.labels.size(), B.reg.all ? nullptr : B.reg.labels.data(),
-                                                  i > 0);
-                }
+                // volume integrals first, then the boundary ones (Robin terms) on top; the sum does not depend on the order
+                // the varf lists them in beyond round-off
+                bool first = true;
+                for (int border = 0; border < 2; ++border)
+                    for (size_t i = 0; i < V.bil.size() && !rc; ++i) {
+                        const BilinearItem &B = V.bil[i];
+                        if ((int)B.border != border) continue;
+                        rc = (border ? ffcuda_assemble_bilinear_boundary : ffcuda_assemble_bilinear)(
+                            dA, D.space, (int)B.terms.size(), B.terms.data(), (int)B.q.w.size(), B.q.pts.data(), B.q.w.data(),
+                            (int)B.reg.labels.size(), B.reg.all ? nullptr : B.reg.labels.data(), first ? 0 : 1);
+                        first = false;
+                    }
                 std::vector<int32_t> rowptr, colind;
                 std::vector<double> vals;
                 if (!rc) {
@@ -628,11 +676,16 @@ struct CudaRhsOp : public OpArraytoLinearForm<double, MMesh, v_fes> {
                 ffcuda_vec *db = nullptr;
                 FFC(ffcuda_vec_create(context(), (int)n, &db));
                 int rc = 0;
-                for (size_t i = 0; i < V.lin.size() && !rc; ++i) {
-                    const LinearItem &L = V.lin[i];
-                    rc = ffcuda_assemble_linear(db, D.space, (int)L.terms.size(), L.terms.data(), (int)L.q.w.size(), L.q.pts.data(),
-                                                L.q.w.data(), (int)L.reg.labels.size(), L.reg.all ? nullptr : L.reg.labels.data(), i > 0);
-                }
+                bool first = true;
+                for (int border = 0; border < 2; ++border)
+                    for (size_t i = 0; i < V.lin.size() && !rc; ++i) {
+                        const LinearItem &L = V.lin[i];
+                        if ((int)L.border != border) continue;
+                        rc = (border ? ffcuda_assemble_linear_boundary : ffcuda_assemble_linear)(
+                            db, D.space, (int)L.terms.size(), L.terms.data(), (int)L.q.w.size(), L.q.pts.data(), L.q.w.data(),
+                            (int)L.reg.labels.size(), L.reg.all ? nullptr : L.reg.labels.data(), first ? 0 : 1);
+                        first = false;
+                    }
                 std::vector<double> host((size_t)n);
                 if (!rc) {
                     try {

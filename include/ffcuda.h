@@ -21,6 +21,7 @@
  *                                  femlib/MatriceCreuse_tpl.hpp:233-258
  *   ffcuda_assemble_linear      <- AssembleLinearForm fflib/problem.cpp:10555, :10878-11227, Element_rhs :7839-7985
  *   ffcuda_assemble_linear_boundary <- Element_rhs on border elements fflib/problem.cpp:8439-8587
+ *   ffcuda_assemble_bilinear_boundary <- AssembleBilinearForm border loop fflib/problem.cpp:1317-1326, Element_Op :6518-6560
  *   ffcuda_bc_* / *_apply_bc    <- AssembleBC fflib/problem.cpp:9881-10034, :10039-10194, HashMatrix::SetBC
  *                                  femlib/HashMatrix.cpp:1195-1238 (tgv >= 0 branch)
  *   ffcuda_quadrature           <- CDomainOfIntegration::FIT/FIV fflib/problem.cpp:14102-14145, QF_Simplex
@@ -171,6 +172,13 @@ int ffcuda_assemble_linear(ffcuda_vec *b, ffcuda_space *s, int nterms, const ffc
 int ffcuda_assemble_linear_boundary(ffcuda_vec *b, ffcuda_space *s, int nterms, const ffcuda_lterm *terms,
                                     int nq, const double *qpts, const double *qw,
                                     int nlab, const int32_t *labels, int accumulate);
+/* A (+)= boundary integrals int2d(Th3, labels)(c u v) / int1d(Th, labels)(c u v) of a bilinear form (Robin terms):
+ * the border loop of AssembleBilinearForm, fflib/problem.cpp:1317-1326 (3-D), :1030-1040 (2-D), with Element_Op's border
+ * branch :6518-6560 / :6216-6290.  Value terms only (uop = vop = id), constant c.  The couples FreeFEM creates for a border
+ * element are those of the adjacent element, all present in the pattern of the space.  qpts / qw / labels as above. */
+int ffcuda_assemble_bilinear_boundary(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms,
+                                      int nq, const double *qpts, const double *qw,
+                                      int nlab, const int32_t *labels, int accumulate);
 
 /* ---- Dirichlet conditions ------------------------------------------------------------------------------
  * tgv >= 0: penalty, A(d,d) = tgv and b[d] = tgv*g(d).  tgv < 0: exact elimination exactly as HashMatrix::SetBC

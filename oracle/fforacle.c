@@ -474,17 +474,42 @@ void ffo_assemble_rhs(int dim, int nv, const double *xyz, int nt, const int32_t 
     }
 }
 
+/* measure factor and reference point of a border quadrature node: T.N(ie) (cross product of two edges of the face,
+ * norm = 2 * area, hence the 0.5) / edge length, and Pt = PBord(ie, pi) (femlib/Mesh3dn.hpp:76, Mesh2dn.hpp:65) */
+static double face_measure(int dim, const double *X, int ie)
+{
+    if (dim == 3) {
+        const double *A = X + 3 * nvfaceTet[ie][0], *B = X + 3 * nvfaceTet[ie][1], *Cc = X + 3 * nvfaceTet[ie][2];
+        double u[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, v[3] = {Cc[0] - A[0], Cc[1] - A[1], Cc[2] - A[2]}, nn[3];
+        cross3(u, v, nn);
+        return 0.5 * sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+    }
+    const double *A = X + 2 * nvedgeTri[ie][0], *B = X + 2 * nvedgeTri[ie][1];
+    return sqrt((B[0] - A[0]) * (B[0] - A[0]) + (B[1] - A[1]) * (B[1] - A[1]));
+}
+static void face_point(int dim, int ie, const double *qp, double *P)
+{
+    static const double hat3[4][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    static const double hat2[3][2] = {{0, 0}, {1, 0}, {0, 1}};
+    if (dim == 3) {
+        const double x = qp[0], y = qp[1];
+        for (int d = 0; d < 3; ++d)
+            P[d] = hat3[nvfaceTet[ie][0]][d] * (1 - x - y) + hat3[nvfaceTet[ie][1]][d] * x + hat3[nvfaceTet[ie][2]][d] * y;
+    } else {
+        const double x = qp[0];
+        for (int d = 0; d < 2; ++d) P[d] = hat2[nvedgeTri[ie][0]][d] * (1 - x) + hat2[nvedgeTri[ie][1]][d] * x;
+    }
+}
+
 /* Boundary integrals of a linear form, int2d(Th3,labels)(...) / int1d(Th,labels)(...): Element_rhs on a border element
  * (fflib/problem.cpp:8517-8587 in 3-D, :8439-8513 in 2-D): for every boundary element with a listed label, every
  * quadrature point of the face rule, every dof of the ADJACENT ELEMENT: B[dof] += (face measure * w_q) * c * d^op phi_i(Pt),
- * Pt = PBord(ie, pi) (femlib/Mesh3dn.hpp:76, Mesh2dn.hpp:65).  Adds to b (the caller zeroes it). */
+ * Pt = PBord(ie, pi).  Adds to b (the caller zeroes it). */
 void ffo_assemble_rhs_boundary(int dim, const double *xyz, const int32_t *conn, int order, int ncomp,
                                const int32_t *elem2node, int nbe, const int32_t *blab, const int32_t *belem,
                                const int32_t *bface, int nterms, const ffo_lterm *terms, int nq, const double *qpts,
                                const double *qw, int nlab, const int32_t *labels, double *b)
 {
-    static const double hat3[4][3] = {{0, 0, 0}, {1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
-    static const double hat2[3][2] = {{0, 0}, {1, 0}, {0, 1}};
     const int nloc = ffo_nloc(dim, order), nvk = dim + 1;
     for (int ib = 0; ib < nbe; ++ib) {
         if (!in_labels(blab[ib], nlab, labels)) continue;
@@ -494,28 +519,11 @@ void ffo_assemble_rhs_boundary(int dim, const double *xyz, const int32_t *conn, 
         double X[12], G[4][3], val[10][4];
         elem_coords(dim, xyz, K, X);
         geom(dim, X, G);
-        double le;
-        if (dim == 3) { /* T.N(ie): cross product of two edges of the face, norm = 2 * area */
-            const double *A = X + 3 * nvfaceTet[ie][0], *B = X + 3 * nvfaceTet[ie][1], *Cc = X + 3 * nvfaceTet[ie][2];
-            double u[3] = {B[0] - A[0], B[1] - A[1], B[2] - A[2]}, v[3] = {Cc[0] - A[0], Cc[1] - A[1], Cc[2] - A[2]}, nn[3];
-            cross3(u, v, nn);
-            le = sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
-        } else {
-            const double *A = X + 2 * nvedgeTri[ie][0], *B = X + 2 * nvedgeTri[ie][1];
-            le = sqrt((B[0] - A[0]) * (B[0] - A[0]) + (B[1] - A[1]) * (B[1] - A[1]));
-        }
+        const double le = face_measure(dim, X, ie);
         for (int q = 0; q < nq; ++q) {
-            double P[3], coef;
-            if (dim == 3) {
-                const double x = qpts[2 * q], y = qpts[2 * q + 1];
-                for (int d = 0; d < 3; ++d)
-                    P[d] = hat3[nvfaceTet[ie][0]][d] * (1 - x - y) + hat3[nvfaceTet[ie][1]][d] * x + hat3[nvfaceTet[ie][2]][d] * y;
-                coef = le * qw[q] * 0.5;
-            } else {
-                const double x = qpts[q];
-                for (int d = 0; d < 2; ++d) P[d] = hat2[nvedgeTri[ie][0]][d] * (1 - x) + hat2[nvedgeTri[ie][1]][d] * x;
-                coef = le * qw[q];
-            }
+            double P[3];
+            face_point(dim, ie, qpts + (size_t)q * (dim - 1), P);
+            const double coef = le * qw[q];
             basis(dim, order, P, G, val);
             for (int c = 0; c < ncomp; ++c)
                 for (int a = 0; a < nloc; ++a)
@@ -525,6 +533,66 @@ void ffo_assemble_rhs_boundary(int dim, const double *xyz, const int32_t *conn, 
                     }
         }
     }
+}
+
+/* Boundary integrals of a bilinear form (Robin terms), int2d(Th3,labels)(c u v) / int1d(Th,labels)(c u v):
+ * AssembleBilinearForm's loop over the border elements (fflib/problem.cpp:1317-1326 in 3-D, :1030-1040 in 2-D) calls
+ * MatriceElementairePleine::call(k, ie, label) on the ADJACENT ELEMENT k, whose Element_Op border branch
+ * (:6518-6560 3-D, :6216-6290 2-D) fills the whole n x m element matrix at the face quadrature nodes, and
+ * HashMatrix::operator+= then creates/accumulates every (il, jl) couple of that element, zero or not.
+ * Output: COO with one entry per distinct couple (first-encounter order); returns their number. */
+int64_t ffo_assemble_coo_boundary(int dim, const double *xyz, const int32_t *conn, int order, int ncomp,
+                                  const int32_t *elem2node, int nbe, const int32_t *blab, const int32_t *belem,
+                                  const int32_t *bface, int nterms, const ffo_bterm *terms, int nq, const double *qpts,
+                                  const double *qw, int nlab, const int32_t *labels,
+                                  int32_t *coo_i, int32_t *coo_j, double *coo_a)
+{
+    const int nloc = ffo_nloc(dim, order), nd = nloc * ncomp, nvk = dim + 1;
+    uint64_t mask;
+    hent *tab = hnew((uint64_t)(nbe > 0 ? nbe : 1) * (uint64_t)nd * nd * 2 + 64, &mask);
+    double *mat = (double *)malloc(sizeof(double) * (size_t)nd * nd);
+    int32_t *gd = (int32_t *)malloc(sizeof(int32_t) * (size_t)nd);
+    int64_t nnz = 0;
+    for (int ib = 0; ib < nbe; ++ib) {
+        if (!in_labels(blab[ib], nlab, labels)) continue;
+        const int it = belem[ib], ie = bface[ib];
+        const int32_t *K = conn + (size_t)nvk * it;
+        const int32_t *N = elem2node ? elem2node + (size_t)nloc * it : K;
+        double X[12], G[4][3], val[10][4];
+        elem_coords(dim, xyz, K, X);
+        geom(dim, X, G);
+        const double le = face_measure(dim, X, ie);
+        for (int i = 0; i < nd * nd; ++i) mat[i] = 0.;
+        for (int q = 0; q < nq; ++q) {
+            double P[3];
+            face_point(dim, ie, qpts + (size_t)q * (dim - 1), P);
+            const double coef = le * qw[q];
+            basis(dim, order, P, G, val);
+            for (int t = 0; t < nterms; ++t) {
+                const int so = opslot(terms[t].uop), to = opslot(terms[t].vop);
+                const double ccc = terms[t].coef * coef;
+                const int fi = terms[t].vcomp * nloc, fj = terms[t].ucomp * nloc;
+                for (int a = 0; a < nloc; ++a)
+                    for (int b = 0; b < nloc; ++b) mat[(fi + a) * nd + fj + b] += ccc * val[a][to] * val[b][so];
+            }
+        }
+        for (int c = 0; c < ncomp; ++c)
+            for (int a = 0; a < nloc; ++a) gd[c * nloc + a] = N[a] * ncomp + c;
+        for (int il = 0; il < nd; ++il)
+            for (int jl = 0; jl < nd; ++jl) {
+                uint64_t key = ((uint64_t)(uint32_t)gd[il] << 32) | (uint32_t)gd[jl];
+                int isnew;
+                int32_t *pv = hfind(tab, mask, key, &isnew);
+                if (isnew) {
+                    *pv = (int32_t)nnz;
+                    coo_i[nnz] = gd[il]; coo_j[nnz] = gd[jl]; coo_a[nnz] = 0.;
+                    nnz++;
+                }
+                coo_a[*pv] += mat[il * nd + jl];
+            }
+    }
+    free(tab); free(mat); free(gd);
+    return nnz;
 }
 
 /* ------------------------------------------------------------------ Dirichlet ----------- */

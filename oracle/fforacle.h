@@ -80,6 +80,15 @@ void ffo_assemble_rhs_boundary(int dim, const double *xyz, const int32_t *conn, 
                                const int32_t *bface, int nterms, const ffo_lterm *terms, int nq, const double *qpts,
                                const double *qw, int nlab, const int32_t *labels, double *b);
 
+/* boundary integrals of a bilinear form (Robin terms: AssembleBilinearForm border loop problem.cpp:1317-1326, Element_Op
+ * border branch :6518-6560 / :6216-6290): COO with one entry per distinct (il, jl) couple of the elements adjacent to the
+ * labelled boundary elements, zero or not.  Arrays sized (labelled boundary elements) * (nloc*ncomp)^2.  Returns count. */
+int64_t ffo_assemble_coo_boundary(int dim, const double *xyz, const int32_t *conn, int order, int ncomp,
+                                  const int32_t *elem2node, int nbe, const int32_t *blab, const int32_t *belem,
+                                  const int32_t *bface, int nterms, const ffo_bterm *terms, int nq, const double *qpts,
+                                  const double *qw, int nlab, const int32_t *labels,
+                                  int32_t *coo_i, int32_t *coo_j, double *coo_a);
+
 /* Dirichlet dofs as AssembleBC visits them: for each boundary element (in order) whose label is in
  * labels[], for each component c with compmask bit c set, each dof lying on that face -> (dof, value[c]).
  * Later pairs overwrite earlier ones.  out arrays sized nbe*ncomp*nlocface at most.  Returns count. */

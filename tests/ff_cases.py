@@ -68,6 +68,11 @@ CASES = {
     "lap2d_p2_neumann": (2, 1, LAP2, [(0, ID, 1.0)], "qf5pT", [([4], 1, [0.0])]),
     "lame3d_p1_traction": (1, 3, lame_terms(), [(2, ID, -0.05)], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
     "lap3d_p2_neumann": (2, 1, LAP3 + [(0, ID, 0, ID, 1.0)], [(0, ID, 1.0)], "qfV5", []),
+    # Robin terms: boundary integrals in the bilinear form (CASE_BBIL below)
+    "lap3d_p1_robin": (1, 1, LAP3, [(0, ID, 1.0)], "qfV5", [([1], 1, [0.0])]),
+    "lap2d_p2_robin": (2, 1, LAP2, [(0, ID, 1.0)], "qf5pT", [([4], 1, [0.0])]),
+    "lame3d_p1_robin": (1, 3, lame_terms(), [(2, ID, -0.05)], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
+    "lap3d_p2_robin": (2, 1, LAP3, [(0, ID, 1.0)], "qfV5", []),
     # half storage (sym=1, CASE_SYM below): the fixture holds the lower triangle
     "lap3d_p1_sym": (1, 1, LAP3, [(0, ID, 1.0)], "qfV5", [(ALL6, 1, [0.0])]),
     "lap2d_p2_sym": (2, 1, LAP2 + [(0, ID, 0, ID, 2.0)], [(0, ID, 1.0)], "qf5pT", [([2, 4], 1, [0.0])]),
@@ -76,6 +81,11 @@ CASES = {
 # boundary integrals of the linear form: name -> (labels, terms)
 CASE_BLIN = {"lap3d_p1_neumann": ([2, 3], [(0, ID, 2.5)]), "lap2d_p2_neumann": ([2], [(0, ID, 1.5)]),
              "lame3d_p1_traction": ([2], [(0, ID, 0.3), (2, ID, -0.2)]), "lap3d_p2_neumann": ([6], [(0, ID, -1.0)])}
+CASE_BLIN["lap3d_p1_robin"] = ([2, 3], [(0, ID, 2.5)])
+# boundary integrals of the bilinear form (Robin terms): name -> (labels, terms (ucomp, uop, vcomp, vop, c))
+CASE_BBIL = {"lap3d_p1_robin": ([2, 3], [(0, ID, 0, ID, 1.5)]), "lap2d_p2_robin": ([2, 3], [(0, ID, 0, ID, 0.7)]),
+             "lame3d_p1_robin": ([2], [(0, ID, 0, ID, 1e4), (1, ID, 1, ID, 1e4), (2, ID, 2, ID, 5e3), (0, ID, 2, ID, 2e3)]),
+             "lap3d_p2_robin": ([6, 1], [(0, ID, 0, ID, 2.0)])}
 # cases assembled with sym=1: MatriceMorse keeps the entries (i, j) with j <= i only (HashMatrix.cpp:1319-1325)
 CASE_SYM = {"lap3d_p1_sym", "lap2d_p2_sym", "lame3d_p1_sym"}
 # Dirichlet treatment of a case: penalty tgv = 1e30 unless listed here (HashMatrix::SetBC with tgv < 0)
@@ -130,4 +140,4 @@ def elem2node(g, order, ncomp):
         assert np.array_equal(dof[:, c * nl:(c + 1) * nl], e2n * ncomp + c)
     return np.ascontiguousarray(e2n, dtype=np.int32)
 # cases whose script does not solve (non-symmetric after tgv = -1 / -3 elimination)
-NO_SOLVE_TGV = {"lap3d_p1_tgvm1", "lame3d_p1_tgvm1", "lap3d_p1_tgvm3"}
+NO_SOLVE_TGV = {"lap3d_p1_tgvm1", "lame3d_p1_tgvm1", "lap3d_p1_tgvm3", "lame3d_p1_robin"}  # (the last: non-symmetric Robin coupling)

@@ -79,6 +79,17 @@ CASES = {
                                bc="on(1,u1=0,u2=0,u3=0)"),
     "lap3d_p2_neumann": dict(dim=3, mesh="cube(2,2,2)", fe="P2", bil=LAP3 + "+u*v", lin="1.*v", blin="+int2d(Th,6)(-1.*v)",
                              bc=""),
+    # Robin terms: boundary integrals of the bilinear form (AssembleBilinearForm border loop problem.cpp:1317-1326,
+    # Element_Op border branch :6518-6560, 2-D :6216-6290)
+    "lap3d_p1_robin": dict(dim=3, mesh="cube(3,3,3,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", fe="P1", bil=LAP3, lin="1.*v",
+                           blin="+int2d(Th,2,3)(1.5*u*v)+int2d(Th,2,3)(2.5*v)", bc="on(1,u=0)"),
+    "lap2d_p2_robin": dict(dim=2, mesh="square(4,3,[x+0.2*y*y,y*(1+0.3*x)])", fe="P2", bil=LAP2, lin="1.*v",
+                           blin="+int1d(Th,2,3)(0.7*u*v)", bc="on(4,u=0)"),
+    "lame3d_p1_robin": dict(dim=3, mesh="cube(2,3,2)", fe="[P1,P1,P1]", unk="[u1,u2,u3]", tst="[v1,v2,v3]",
+                            pre=LAME_PRE, bil=LAME, lin="-0.05*v3",
+                            blin="+int2d(Th,2)(1e4*u1*v1+1e4*u2*v2+5e3*u3*v3+2e3*u1*v3)", bc="on(1,u1=0,u2=0,u3=0)",
+                            solve=False),
+    "lap3d_p2_robin": dict(dim=3, mesh="cube(2,2,2)", fe="P2", bil=LAP3, lin="1.*v", blin="+int2d(Th,6,1)(2.*u*v)", bc=""),
     # half storage (sym=1): MatriceElementaireSymetrique / the symmetric Element_Op, lower triangle only (HashMatrix.cpp:1319-1325)
     "lap3d_p1_sym": dict(dim=3, mesh="cube(3,3,3)", fe="P1", bil=LAP3, lin="1.*v", bc="on(1,2,3,4,5,6,u=0)", sym=1),
     "lap2d_p2_sym": dict(dim=2, mesh="square(4,3,[x+0.2*y*y,y*(1+0.3*x)])", fe="P2", bil=LAP2 + "+2.*u*v", lin="1.*v",

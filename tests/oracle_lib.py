@@ -33,6 +33,7 @@ def lib():
     if _LIB is None:
         _LIB = C.CDLL(build())
         _LIB.ffo_assemble_coo.restype = C.c_int64
+        _LIB.ffo_assemble_coo_boundary.restype = C.c_int64
     return _LIB
 
 
@@ -160,6 +161,42 @@ def assemble_rhs_boundary(mesh, order, ncomp, elem2node, b, terms, qpts, qw, lab
                                     _p(qpts, C.c_double), _p(qw, C.c_double), 0 if lab is None else len(lab), _p(lab, C.c_int32),
                                     _p(b, C.c_double))
     return b
+
+
+def assemble_coo_boundary(mesh, order, ncomp, elem2node, terms, qpts, qw, labels=None):
+    """COO of the boundary integrals int2d(Th3,labels)(c u v) / int1d(Th,labels)(c u v) of a bilinear form (Robin terms):
+    one entry per distinct couple of the elements adjacent to the labelled boundary elements"""
+    dim = mesh["dim"]
+    xyz, conn = _f64(mesh["xyz"]), _i32(mesh["conn"])
+    blab, belem, bface = _i32(mesh["blab"]), _i32(mesh["belem"]), _i32(mesh["bface"])
+    e2n, lab = _i32(elem2node), _i32(labels)
+    nd = nloc(dim, order) * ncomp
+    cap = max(len(blab), 1) * nd * nd
+    ci, cj, ca = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap)
+    bt = bterms(terms)
+    qpts, qw = _f64(qpts), _f64(qw)
+    nnz = lib().ffo_assemble_coo_boundary(dim, _p(xyz, C.c_double), _p(conn, C.c_int32), order, ncomp, _p(e2n, C.c_int32),
+                                          len(blab), _p(blab, C.c_int32), _p(belem, C.c_int32), _p(bface, C.c_int32),
+                                          len(terms), bt, len(qw), _p(qpts, C.c_double), _p(qw, C.c_double),
+                                          0 if lab is None else len(lab), _p(lab, C.c_int32),
+                                          _p(ci, C.c_int32), _p(cj, C.c_int32), _p(ca, C.c_double))
+    return ci[:nnz].copy(), cj[:nnz].copy(), ca[:nnz].copy()
+
+
+def coo_add(n, a, b):
+    """HashMatrix accumulation of two COO matrices with distinct couples each: couples of a keep their place, new couples
+    of b are appended (the order of a COO list is irrelevant once sorted into CSR)"""
+    (ai, aj, aa), (bi, bj, ba) = a, b
+    ka = ai.astype(np.int64) * n + aj
+    kb = bi.astype(np.int64) * n + bj
+    order = np.argsort(ka, kind="stable")
+    pos = np.searchsorted(ka[order], kb)
+    pos = np.minimum(pos, len(ka) - 1) if len(ka) else pos
+    hit = (ka[order][pos] == kb) if len(ka) else np.zeros(len(kb), bool)
+    out = aa.copy()
+    out[order[pos[hit]]] += ba[hit]
+    return (np.concatenate([ai, bi[~hit]]).astype(np.int32), np.concatenate([aj, bj[~hit]]).astype(np.int32),
+            np.concatenate([out, ba[~hit]]))
 
 
 def face_quadrature(dim):

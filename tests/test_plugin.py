@@ -39,11 +39,11 @@ verbosity=1; UU[] = 0; UU[] = A^-1*b; verbosity=0;
 """
 
 
-def script(dim, mesh, fe, bil, lin, bc, pre="", unk="u", tst="v", eps="1e-6", intopt="", tgv=None, sym=False):
+def script(dim, mesh, fe, bil, lin, bc, pre="", unk="u", tst="v", eps="1e-6", intopt="", tgv=None, sym=False, extra=""):
     mt, integ = ("mesh", "int2d") if dim == 2 else ("mesh3", "int3d")
     u0 = unk.strip("[]").split(",")[0]
     s = f'load "msh3"\nload "ffcuda"\n{pre}\n{mt} Th = {mesh};\nfespace Vh(Th,{fe});\n'
-    s += f"varf va({unk},{tst}) = {integ}(Th{intopt})({bil}) + {integ}(Th{intopt})({lin}){('+' + bc) if bc else ''};\n"
+    s += f"varf va({unk},{tst}) = {integ}(Th{intopt})({bil}) + {integ}(Th{intopt})({lin}){extra}{('+' + bc) if bc else ''};\n"
     tg = "" if tgv is None else f",tgv={tgv}"
     sy = ",sym=1" if sym else ""
     s += f"matrix A = va(Vh,Vh,solver=CG,eps={eps}{tg}{sy});\nreal[int] b = va(0,Vh{tg});\n" + DUMP
@@ -68,6 +68,14 @@ CASES = {
     "poisson3d_p1_sym": script(3, "cube(6,5,4)", "P1", LAP3, "1.*v", "on(1,2,3,4,5,6,u=0)", sym=True),
     "lame3d_p2_sym": script(3, "cube(2,2,2)", "[P2,P2,P2]", LAME, "-0.05*v3", "on(1,u1=0,u2=0,u3=0)", pre=LAME_PRE,
                             unk="[u1,u2,u3]", tst="[v1,v2,v3]", eps="1e-14", sym=True),
+    # boundary integrals: Neumann data and Robin terms (int2d on a mesh3, int1d on a mesh), 1-D rule chosen by the user
+    "poisson3d_p1_robin": script(3, "cube(5,4,6,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", "P1", LAP3, "1.*v", "on(1,u=0)",
+                                 extra="+int2d(Th,2,3)(1.5*u*v)+int2d(Th,2,3)(2.5*v)+int2d(Th,6)(-1.*v)"),
+    "laplace2d_p2_robin": script(2, "square(6,5,[x+0.2*y*y,y*(1+0.3*x)])", "P2", LAP2, "1.*v", "on(4,u=0)", eps="1e-14",
+                                 extra="+int1d(Th,2,3)(0.7*u*v)+int1d(Th,2,qfe=qf2pE)(1.5*v)"),
+    "lame3d_p1_traction": script(3, "cube(3,4,3)", "[P1,P1,P1]", LAME, "-0.05*v3", "on(1,u1=0,u2=0,u3=0)", pre=LAME_PRE,
+                                 unk="[u1,u2,u3]", tst="[v1,v2,v3]", eps="1e-14",
+                                 extra="+int2d(Th,3)(1e3*(u1*v1+u2*v2+u3*v3))+int2d(Th,2)(0.3*v1-0.2*v3)"),
     "mass3d_lumped": script(3, "cube(3,3,3)", "P1", "u*v+0.1*(" + LAP3 + ")", "1.*v", "on(1,u=0)", intopt=",qfV=qfV1lump"),
 }
 
@@ -174,7 +182,7 @@ matrix B = vb(Vh,Vh);
 fespace Wh(Th,P0);
 varf vc(u,v) = int3d(Th)(u*v);
 matrix C = vc(Wh,Wh);
-varf vs(u,v) = int2d(Th,2)(u*v) + int2d(Th,2)(1.*v);
+varf vs(u,v) = int2d(Th,2)(u*v) + int2d(Th,2)(x*v);
 matrix S = vs(Vh,Vh);
 real[int] r = vs(0,Vh);
 cout << "NNZ " << B.nnz << " " << C.nnz << " " << S.nnz << endl;
@@ -192,7 +200,7 @@ cout << "NNZ " << A.nnz << endl;
 
 @needs_ff
 def test_plugin_loads_and_leaves_out_of_scope_forms_to_freefem():
-    """x-dependent coefficient, non-Lagrange element, boundary integral: not claimed, FreeFEM's own operators run
+    """x-dependent coefficient, non-Lagrange element, boundary integral without a volume integral: not claimed, FreeFEM's own operators run
     (no GPU needed), and the plugin says so."""
     rc, out, _ = run_ff(OUT_OF_SCOPE, {}, want_fail=True)
     assert rc == 0, out[-2000:]
