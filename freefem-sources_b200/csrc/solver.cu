@@ -13,6 +13,7 @@
 // Dot products: per-block partial sums in a fixed tree, finished by the last block to retire (fixed order over the
 // partials) -> deterministic, no fp64 atomics.  The host enqueues iterations in batches and polls a device flag;
 // kernels of iterations past the converged one are no-ops, so x is exactly the iterate of the stopping iteration.
+#include <deque>
 #include "common.cuh"
 #include <cstddef>
 #include <algorithm>
@@ -834,6 +835,41 @@ extern "C" int ffcuda_spmv(ffcuda_matrix *A, ffcuda_vec *x, ffcuda_vec *y)
     FF_API_END(A ? A->ctx : nullptr)
 }
 
+// gettgv (femlib/HashMatrix.cpp:1341-1371): largest diagonal value, its multiplicity, and the next one (ratio 1e6)
+static void detect_tgv(ffcuda_matrix *A, double *partial, double *ttgv_out, long *ntgv_out)
+{
+    ffcuda_ctx *ctx = A->ctx;
+    cudaStream_t st = ctx->stream;
+    const int n = A->n;
+    const int grid_v = grid_for(ctx, (size_t)n);
+    double *scal = ctx->d_scal;
+    int *flags = ctx_flags(ctx);
+    double *hs = ctx->h_scal;
+    ff_launch(ctx, "cg_diag_stats", [&] { k_diag_stats<<<grid_v, RED_THREADS, 0, st>>>(A->diagpos, A->vals.p, n, 0, 0.0, partial, flags, scal + S_TMP0); });
+    ff_allreduce(A, scal + S_TMP0, 1, 1);
+    FF_CUDA(cudaMemcpyAsync(hs, scal + S_TMP0, sizeof(double), cudaMemcpyDeviceToHost, st));
+    FF_CUDA(cudaStreamSynchronize(st));
+    double ttgv = hs[0];
+    ff_launch(ctx, "cg_diag_stats", [&] { k_diag_stats<<<grid_v, RED_THREADS, 0, st>>>(A->diagpos, A->vals.p, n, 1, ttgv, partial, flags, scal + S_TMP0); });
+    ff_allreduce(A, scal + S_TMP0, 1, 1);
+    ff_allreduce(A, scal + S_TMP1, 1, 0);
+    FF_CUDA(cudaMemcpyAsync(hs, scal + S_TMP0, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    FF_CUDA(cudaStreamSynchronize(st));
+    double max1 = hs[0];
+    long ntgv = (long)hs[1];
+    if (!(ttgv > 0)) { // the reference starts its scan from ttgv = max1 = 0
+        ttgv = 0;
+        ntgv = 0;
+    }
+    if (!(max1 > 0)) max1 = 0;
+    if (max1 * 1e6 > ttgv) {
+        ttgv = 0;
+        ntgv = 0;
+    }
+    *ttgv_out = ttgv;
+    *ntgv_out = ntgv;
+}
+
 static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, int itmax, double tgv, int *iters, int *converged,
                       double *gcg_out)
 {
@@ -867,29 +903,10 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
     FF_CUDA(cudaMemcpyAsync(reinterpret_cast<char *>(scal + FF_P2P_DESC_OFF) + offsetof(P2PDesc, fused), &fused, sizeof(int),
                             cudaMemcpyHostToDevice, st));
 
-    // --- gettgv: largest diagonal value, its multiplicity, and the next one (ratio 1e6)
     double *hs = ctx->h_scal;
-    ff_launch(ctx, "cg_diag_stats", [&] { k_diag_stats<<<grid_v, RED_THREADS, 0, st>>>(A->diagpos, A->vals.p, n, 0, 0.0, partial, flags, scal + S_TMP0); });
-    ff_allreduce(A, scal + S_TMP0, 1, 1);
-    FF_CUDA(cudaMemcpyAsync(hs, scal + S_TMP0, sizeof(double), cudaMemcpyDeviceToHost, st));
-    FF_CUDA(cudaStreamSynchronize(st));
-    double ttgv = hs[0];
-    ff_launch(ctx, "cg_diag_stats", [&] { k_diag_stats<<<grid_v, RED_THREADS, 0, st>>>(A->diagpos, A->vals.p, n, 1, ttgv, partial, flags, scal + S_TMP0); });
-    ff_allreduce(A, scal + S_TMP0, 1, 1);
-    ff_allreduce(A, scal + S_TMP1, 1, 0);
-    FF_CUDA(cudaMemcpyAsync(hs, scal + S_TMP0, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
-    FF_CUDA(cudaStreamSynchronize(st));
-    double max1 = hs[0];
-    long ntgv = (long)hs[1];
-    if (!(ttgv > 0)) { // the reference starts its scan from ttgv = max1 = 0
-        ttgv = 0;
-        ntgv = 0;
-    }
-    if (!(max1 > 0)) max1 = 0;
-    if (max1 * 1e6 > ttgv) {
-        ttgv = 0;
-        ntgv = 0;
-    }
+    double ttgv = 0;
+    long ntgv = 0;
+    detect_tgv(A, partial, &ttgv, &ntgv);
     ff_launch(ctx, "cg_precond", [&] {
         k_precond<<<ff_blocks(n, 256), 256, 0, st>>>(A->diagpos, A->vals.p, n, D1, ntgv > 0, ttgv, tgv, b, x);
     });
@@ -1007,6 +1024,342 @@ extern "C" int ffcuda_cg_host(ffcuda_matrix *A, const double *b, double *x, doub
     FF_CUDA(cudaMemcpyAsync(db.p, b, db.bytes(), cudaMemcpyHostToDevice, ctx->stream));
     FF_CUDA(cudaMemcpyAsync(dx.p, x, dx.bytes(), cudaMemcpyHostToDevice, ctx->stream));
     cg_device(A, db.p, dx.p, eps, itmax, tgv, iters, converged, gcg);
+    FF_CUDA(cudaMemcpyAsync(x, dx.p, dx.bytes(), cudaMemcpyDeviceToHost, ctx->stream));
+    FF_CUDA(cudaStreamSynchronize(ctx->stream));
+    FF_API_END(A ? A->ctx : nullptr)
+}
+
+// ---------------------------------------------------------------------------------------------------
+// GMRES: SolverGMRES::dosolver (femlib/VirtualSolverCG.hpp:236-255) = SetInitWithBC + fgmres (femlib/CG.cpp:347-517):
+// flexible GMRES(m) with the Jacobi preconditioner on the right (leftC is forced to 0 there), modified Gram-Schmidt,
+// Givens rotations, stop when |g[it+1]| / normb < |eps|, normb = norm of the right-hand side with the tgv rows zeroed.
+// Like the CG, every scalar stays on the device: the Hessenberg column, the rotations and the convergence test are
+// done by the last block to retire of the kernel that forms the last norm; the Gram-Schmidt chain is one kernel per
+// basis vector (subtract the previous projection, form the next dot product in the same pass: 2 reads + 1 write of n
+// per step); kernels enqueued after convergence are no-ops, so the host polls a flag every few iterations only.
+// gs layout (doubles): H (m+2)x(m+1) row-major | rot0 m+2 | rot1 m+2 | g m+1 | y m+1 | normb, aux, relres
+// ---------------------------------------------------------------------------------------------------
+struct GmresLayout {
+    int m;
+    __host__ __device__ size_t H(int i, int j) const { return (size_t)i * (m + 1) + j; }
+    __host__ __device__ size_t rot0() const { return (size_t)(m + 2) * (m + 1); }
+    __host__ __device__ size_t rot1() const { return rot0() + m + 2; }
+    __host__ __device__ size_t g() const { return rot1() + m + 2; }
+    __host__ __device__ size_t y() const { return g() + m + 1; }
+    __host__ __device__ size_t normb() const { return y() + m + 1; }
+    __host__ __device__ size_t aux() const { return normb() + 1; }
+    __host__ __device__ size_t relres() const { return normb() + 2; }
+    __host__ __device__ size_t size() const { return normb() + 4; }
+};
+
+// totals of NV per-thread values over the whole grid, fixed summation shape; returns true in thread 0 of the last block to
+// retire (tot[] valid there); that thread must reset *counter to 0 when it is done
+template <int NV>
+__device__ __forceinline__ bool grid_sum_last(const double (&v)[NV], double *__restrict__ partial, int *counter, double (&tot)[NV], double *sh)
+{
+    __shared__ bool last;
+    double r[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) r[k] = block_sum(v[k], sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) partial[(size_t)k * gridDim.x + blockIdx.x] = r[k];
+        __threadfence();
+        last = (atomicAdd(counter, 1) == (int)gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return false;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        double s = 0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += __ldcg(partial + (size_t)k * gridDim.x + i);
+        tot[k] = block_sum(s, sh);
+    }
+    return threadIdx.x == 0;
+}
+
+// normb = || b with the tgv rows zeroed ||  (fgmres: wi = rhs; wi[wbc] = 0; normb = nrm2(Cl wi), Cl = Id)
+__global__ void __launch_bounds__(RED_THREADS) k_gm_normb(const double *__restrict__ b, const int32_t *__restrict__ diagpos,
+                                                          const double *__restrict__ vals, int has_tgv, double ttgv, int n,
+                                                          double *__restrict__ partial, int *__restrict__ flags, double *__restrict__ out)
+{
+    __shared__ double sh[32];
+    double v[1] = {0.0}, tot[1];
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += stride) {
+        const int p = diagpos[i];
+        const bool bc = has_tgv && p >= 0 && vals[p] == ttgv;
+        const double x = bc ? 0.0 : b[i];
+        v[0] += x * x;
+    }
+    if (grid_sum_last<1>(v, partial, flags + F_COUNTER, tot, sh)) {
+        *out = sqrt(tot[0]);
+        flags[F_COUNTER] = 0;
+    }
+}
+
+// start of a cycle: W = -(A x - b), g[0] = || W ||, all other cycle scalars restart
+__global__ void __launch_bounds__(RED_THREADS) k_gm_resid(const double *__restrict__ b, const double *__restrict__ Ax, double *__restrict__ W,
+                                                          int n, double eps, GmresLayout L, double *__restrict__ gs,
+                                                          double *__restrict__ partial, int *__restrict__ flags)
+{
+    __shared__ double sh[32];
+    double v[1] = {0.0}, tot[1];
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += stride) {
+        const double r = -(Ax[i] + -1.0 * b[i]);
+        W[i] = r;
+        v[0] += r * r;
+    }
+    if (grid_sum_last<1>(v, partial, flags + F_COUNTER, tot, sh)) {
+        gs[L.g()] = sqrt(tot[0]);
+        if (gs[L.normb()] < 1.e-20 || eps < 0) gs[L.normb()] = 1.0;
+        flags[F_COUNTER] = 0;
+    }
+}
+
+// dst = (1 / *s) * src  (Vi[0] = (1./g[0])*zi, Vi[it+1] = (1./aux)*wi)
+__global__ void k_gm_scale(double *__restrict__ dst, const double *__restrict__ src, const double *__restrict__ s, int n,
+                           const int *__restrict__ flags)
+{
+    if (flags[F_CONV_ITER] != 0) return;
+    const double a = 1.0 / *s;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += stride) dst[i] = a * src[i];
+}
+
+// Vp = C V, C = diag1 (HMatVirtPrecon::addmatmul on a zeroed vector)
+__global__ void k_gm_precond(double *__restrict__ Vp, const double *__restrict__ V, const double *__restrict__ d1, int n,
+                             const int *__restrict__ flags)
+{
+    if (flags[F_CONV_ITER] != 0) return;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += stride) Vp[i] = d1[i] * V[i];
+}
+
+// one step of the modified Gram-Schmidt chain: W -= h_prev * Vprev (when there is a previous step), then h = <W, Vcur>
+__global__ void __launch_bounds__(RED_THREADS) k_gm_mgs(double *__restrict__ W, const double *__restrict__ Vprev, const double *__restrict__ Vcur,
+                                                        const double *__restrict__ hprev, double *__restrict__ hout, int n,
+                                                        double *__restrict__ partial, int *__restrict__ flags)
+{
+    if (flags[F_CONV_ITER] != 0) return;
+    __shared__ double sh[32];
+    double v[1] = {0.0}, tot[1];
+    const double a = Vprev ? -*hprev : 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += stride) {
+        double w = W[i];
+        if (Vprev) {
+            w += a * Vprev[i];
+            W[i] = w;
+        }
+        v[0] += w * Vcur[i];
+    }
+    if (grid_sum_last<1>(v, partial, flags + F_COUNTER, tot, sh)) {
+        *hout = tot[0];
+        flags[F_COUNTER] = 0;
+    }
+}
+
+// end of the chain: W -= H(it,it) * V_it, aux = || W ||, then the Hessenberg column goes through the rotations, the new
+// rotation is formed, g is updated and the stopping test is taken (CG.cpp:436-471); flags[F_CONV_ITER] = it + 1 on convergence
+__global__ void __launch_bounds__(RED_THREADS) k_gm_mgs_last(double *__restrict__ W, const double *__restrict__ Vprev, int n, int it, double eps,
+                                                             GmresLayout L, double *__restrict__ gs, double *__restrict__ partial,
+                                                             int *__restrict__ flags)
+{
+    if (flags[F_CONV_ITER] != 0) return;
+    __shared__ double sh[32];
+    double v[1] = {0.0}, tot[1];
+    const double a = -gs[L.H(it, it)];
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)n; i += stride) {
+        const double w = W[i] + a * Vprev[i];
+        W[i] = w;
+        v[0] += w * w;
+    }
+    if (grid_sum_last<1>(v, partial, flags + F_COUNTER, tot, sh)) {
+        double *H = gs, *rot0 = gs + L.rot0(), *rot1 = gs + L.rot1(), *g = gs + L.g();
+        const double aux = sqrt(tot[0]);
+        gs[L.aux()] = aux;
+        H[L.H(it + 1, it)] = aux;
+        for (int i = 0; i < it; i++) {
+            const double aa = rot0[i] * H[L.H(i, it)] + rot1[i] * H[L.H(i + 1, it)];
+            const double bb = -rot1[i] * H[L.H(i, it)] + rot0[i] * H[L.H(i + 1, it)];
+            H[L.H(i, it)] = aa;
+            H[L.H(i + 1, it)] = bb;
+        }
+        const double hii = H[L.H(it, it)], hi1 = H[L.H(it + 1, it)];
+        const double sq = sqrt(hii * hii + hi1 * hi1);
+        rot0[it] = hii / sq;
+        rot1[it] = hi1 / sq;
+        H[L.H(it, it)] = rot0[it] * hii + rot1[it] * hi1;
+        H[L.H(it + 1, it)] = 0.0;
+        g[it + 1] = -rot1[it] * g[it];
+        g[it] = rot0[it] * g[it];
+        const double relres = fabs(g[it + 1]);
+        gs[L.relres()] = relres;
+        flags[F_COUNTER] = 0;
+        __threadfence();
+        if (relres / gs[L.normb()] < fabs(eps)) flags[F_CONV_ITER] = it + 1;
+    }
+}
+
+// y by back substitution on the rotated Hessenberg matrix (CG.cpp:477-483)
+__global__ void k_gm_backsolve(int it, GmresLayout L, double *__restrict__ gs)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    const double *H = gs, *g = gs + L.g();
+    double *y = gs + L.y();
+    for (int i = it; i >= 0; i--) {
+        double g1 = g[i];
+        for (int j = i + 1; j < it + 1; j++) g1 = g1 - H[L.H(i, j)] * y[j];
+        y[i] = g1 / H[L.H(i, i)];
+    }
+}
+
+// x = (sum_i y_i Vp_i) + x0, x0 = x (CG.cpp:485-495)
+__global__ void k_gm_update_x(double *__restrict__ x, const double *const *__restrict__ Vp, const double *__restrict__ y, int it, int n)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < (size_t)n; k += stride) {
+        double w = 0.0;
+        for (int i = 0; i < it + 1; ++i) w += y[i] * Vp[i][k];
+        x[k] = w + x[k];
+    }
+}
+
+static void gmres_device(ffcuda_matrix *A, const double *b, double *x, double eps, int itmax, int restart, double tgv, int *iters,
+                         int *converged, double *relres_out)
+{
+    ffcuda_ctx *ctx = A->ctx;
+    cudaStream_t st = ctx->stream;
+    const int n = A->n;
+    FF_REQUIRE(A->diagpos, "matrix has no diagonal index");
+    FF_REQUIRE(!ff_is_distributed(A) && A->ncols == n, "GMRES runs on one GPU (the distributed solve is the CG)");
+    ff_matrix_touch(A);
+    if (itmax <= 0) itmax = n;
+    if (restart <= 0) restart = 1000; // Data_Sparse_Solver::NbSpace default (femlib/VirtualSolver.hpp:79)
+    const int m = (int)std::min<int64_t>(restart, (int64_t)itmax + 2); // storage only: the inner loop leaves at it > itmax
+    GmresLayout L{m};
+    const int grid_v = grid_for(ctx, (size_t)n);
+    ensure_partial(ctx, 2 * (size_t)std::max(grid_v, 1024) + 16);
+    double *partial = ctx->d_partial;
+    int *flags = ctx_flags(ctx);
+    FF_CUDA(cudaMemsetAsync(ctx->d_scal, 0, 64 * sizeof(double), st));
+    DBuf<double> gs, D1, W, R;
+    gs.alloc(L.size());
+    D1.alloc(n);
+    W.alloc(n);
+    R.alloc(n);
+    FF_CUDA(cudaMemsetAsync(gs.p, 0, gs.bytes(), st));
+    double ttgv = 0;
+    long ntgv = 0;
+    detect_tgv(A, partial, &ttgv, &ntgv);
+    ff_launch(ctx, "gmres_precond", [&] {
+        k_precond<<<ff_blocks(n, 256), 256, 0, st>>>(A->diagpos, A->vals.p, n, D1.p, ntgv > 0, ttgv, tgv, b, x);
+    });
+    ff_launch(ctx, "gmres_normb", [&] {
+        k_gm_normb<<<grid_v, RED_THREADS, 0, st>>>(b, A->diagpos, A->vals.p, ntgv > 0, ttgv, n, partial, flags, gs.p + L.normb());
+    });
+    // Krylov vectors in chunks of 16, allocated as the basis grows (the default dimension is 1000)
+    constexpr int CH = 16;
+    std::deque<DBuf<double>> cV, cP;
+    std::vector<double *> hP((size_t)m + 1, nullptr);
+    DBuf<double *> dP;
+    dP.alloc((size_t)m + 1);
+    auto vecV = [&](int i) -> double * {
+        while ((int)cV.size() * CH <= i) {
+            cV.emplace_back();
+            cV.back().alloc((size_t)CH * n);
+        }
+        return cV[i / CH].p + (size_t)(i % CH) * n;
+    };
+    auto vecP = [&](int i) -> double * {
+        while ((int)cP.size() * CH <= i) {
+            cP.emplace_back();
+            cP.back().alloc((size_t)CH * n);
+            for (int k = 0; k < CH && (cP.size() - 1) * CH + k <= (size_t)m; ++k) hP[(cP.size() - 1) * CH + k] = cP.back().p + (size_t)k * n;
+            FF_CUDA(ff_memcpy_sync(ctx, dP.p, hP.data(), hP.size() * sizeof(double *), cudaMemcpyHostToDevice));
+        }
+        return hP[i];
+    };
+    int *hflags = reinterpret_cast<int *>(ctx->h_scal + 32);
+    const int poll = 8;
+    bool conv = false;
+    int iter = 0;
+    while (true) {
+        spmv_launch(A, x, nullptr, R.p);
+        ff_launch(ctx, "gmres_resid", [&] { k_gm_resid<<<grid_v, RED_THREADS, 0, st>>>(b, R.p, W.p, n, eps, L, gs.p, partial, flags); });
+        double *V0 = vecV(0);
+        ff_launch(ctx, "gmres_scale", [&] { k_gm_scale<<<grid_v, RED_THREADS, 0, st>>>(V0, W.p, gs.p + L.g(), n, flags); });
+        int it = 0, it_used = m;
+        for (; it < m; ++it) {
+            double *Vit = vecV(it), *Vnext = vecV(it + 1), *Pit = vecP(it);
+            ff_launch(ctx, "gmres_precond_apply", [&] { k_gm_precond<<<grid_v, RED_THREADS, 0, st>>>(Pit, Vit, D1.p, n, flags); });
+            spmv_launch(A, Pit, nullptr, W.p);
+            for (int i = 0; i <= it; ++i) {
+                const double *Vprev = i ? vecV(i - 1) : nullptr;
+                const double *Vcur = vecV(i);
+                ff_launch(ctx, "gmres_mgs", [&] {
+                    k_gm_mgs<<<grid_v, RED_THREADS, 0, st>>>(W.p, Vprev, Vcur, gs.p + L.H(i ? i - 1 : 0, it), gs.p + L.H(i, it), n, partial, flags);
+                });
+            }
+            ff_launch(ctx, "gmres_mgs_last", [&] { k_gm_mgs_last<<<grid_v, RED_THREADS, 0, st>>>(W.p, Vit, n, it, eps, L, gs.p, partial, flags); });
+            ff_launch(ctx, "gmres_scale", [&] { k_gm_scale<<<grid_v, RED_THREADS, 0, st>>>(Vnext, W.p, gs.p + L.aux(), n, flags); });
+            const bool leave = it > itmax; // `if( it > nbitermx) break;`
+            if (leave || it == m - 1 || it % poll == poll - 1) {
+                FF_CUDA(cudaMemcpyAsync(hflags, flags, sizeof(int), cudaMemcpyDeviceToHost, st));
+                FF_CUDA(cudaStreamSynchronize(st));
+                if (hflags[F_CONV_ITER] != 0) {
+                    conv = true;
+                    it_used = hflags[F_CONV_ITER] - 1;
+                    break;
+                }
+            }
+            if (leave) {
+                it_used = it;
+                break;
+            }
+        }
+        iter += it_used; // neither a convergence nor a forced exit counts the iteration they happen in
+        const int ity = std::min(it_used, m - 1);
+        ff_launch(ctx, "gmres_backsolve", [&] { k_gm_backsolve<<<1, 32, 0, st>>>(ity, L, gs.p); });
+        ff_launch(ctx, "gmres_update_x", [&] { k_gm_update_x<<<grid_v, RED_THREADS, 0, st>>>(x, dP.p, gs.p + L.y(), ity, n); });
+        if (conv || iter > itmax) break;
+    }
+    double hr[4];
+    FF_CUDA(ff_memcpy_sync(ctx, hr, gs.p + L.normb(), 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    FF_REQUIRE(hr[2] == hr[2], "GMRES: the residual is NaN (bad matrix)");
+    if (iters) *iters = iter;
+    if (converged) *converged = conv ? 1 : 0;
+    if (relres_out) *relres_out = hr[2] / hr[0];
+}
+
+extern "C" int ffcuda_gmres(ffcuda_matrix *A, ffcuda_vec *b, ffcuda_vec *x, double eps, int itmax, int restart, double tgv, int *iters,
+                            int *converged, double *relres)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A && b && x, "ffcuda_gmres: null argument");
+    FF_REQUIRE(b->n >= A->n && x->n >= A->n, "ffcuda_gmres: vectors shorter than the matrix");
+    ff_enter(A->ctx);
+    gmres_device(A, b->d.p, x->d.p, eps, itmax, restart, tgv, iters, converged, relres);
+    FF_API_END(A ? A->ctx : nullptr)
+}
+
+extern "C" int ffcuda_gmres_host(ffcuda_matrix *A, const double *b, double *x, double eps, int itmax, int restart, double tgv,
+                                 int *iters, int *converged, double *relres)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A && b && x, "ffcuda_gmres_host: null argument");
+    ffcuda_ctx *ctx = A->ctx;
+    ff_enter(ctx);
+    DBuf<double> db, dx;
+    db.alloc(A->n);
+    dx.alloc(A->n);
+    FF_CUDA(cudaMemcpyAsync(db.p, b, db.bytes(), cudaMemcpyHostToDevice, ctx->stream));
+    FF_CUDA(cudaMemcpyAsync(dx.p, x, dx.bytes(), cudaMemcpyHostToDevice, ctx->stream));
+    gmres_device(A, db.p, dx.p, eps, itmax, restart, tgv, iters, converged, relres);
     FF_CUDA(cudaMemcpyAsync(x, dx.p, dx.bytes(), cudaMemcpyDeviceToHost, ctx->stream));
     FF_CUDA(cudaStreamSynchronize(ctx->stream));
     FF_API_END(A ? A->ctx : nullptr)

@@ -22,7 +22,7 @@ ffcuda_matrix_download_lower ffcuda_matrix_from_csr_lower ffcuda_pattern_destroy
 ffcuda_matrix_from_csr ffcuda_matrix_info ffcuda_matrix_download ffcuda_matrix_upload ffcuda_matrix_destroy ffcuda_vec_create
 ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_destroy ffcuda_assemble_bilinear
 ffcuda_assemble_linear ffcuda_assemble_linear_boundary ffcuda_assemble_bilinear_boundary ffcuda_bc_from_pairs ffcuda_bc_from_labels ffcuda_bc_count ffcuda_matrix_apply_bc ffcuda_vec_apply_bc
-ffcuda_vec_set_bc_values ffcuda_bc_destroy ffcuda_spmv ffcuda_cg ffcuda_cg_host ffcuda_comm_unique_id ffcuda_comm_init
+ffcuda_vec_set_bc_values ffcuda_bc_destroy ffcuda_spmv ffcuda_cg ffcuda_cg_host ffcuda_gmres ffcuda_gmres_host ffcuda_comm_unique_id ffcuda_comm_init
 ffcuda_comm_finalize ffcuda_mesh_cube_distributed ffcuda_mesh_local_to_global ffcuda_quadrature ffcuda_partition_cube""".split()
 
 
@@ -409,6 +409,20 @@ class Matrix(_Handle):
         _ck(lib().ffcuda_cg_host(_h(self), _p(b), _p(x), C.c_double(eps), int(itmax), C.c_double(tgv), C.byref(it),
                                  C.byref(conv), C.byref(g)), self.ctx.h)
         return it.value, conv.value, g.value
+
+    def gmres(self, b, x, eps=1e-6, itmax=0, restart=0, tgv=1e30):
+        """SolverGMRES of FreeFEM on the device (right Jacobi, modified Gram-Schmidt); returns (iterations, converged, relres)"""
+        it, conv, r = C.c_int(), C.c_int(), C.c_double()
+        _ck(lib().ffcuda_gmres(_h(self), _h(b), _h(x), C.c_double(eps), int(itmax), int(restart), C.c_double(tgv), C.byref(it),
+                               C.byref(conv), C.byref(r)), self.ctx.h)
+        return it.value, conv.value, r.value
+
+    def gmres_host(self, b, x, eps=1e-6, itmax=0, restart=0, tgv=1e30):
+        assert b.dtype == np.float64 and x.dtype == np.float64 and b.flags.c_contiguous and x.flags.c_contiguous
+        it, conv, r = C.c_int(), C.c_int(), C.c_double()
+        _ck(lib().ffcuda_gmres_host(_h(self), _p(b), _p(x), C.c_double(eps), int(itmax), int(restart), C.c_double(tgv),
+                                    C.byref(it), C.byref(conv), C.byref(r)), self.ctx.h)
+        return it.value, conv.value, r.value
 
 
 class Vec(_Handle):

@@ -782,6 +782,60 @@ class SolverCudaCG : public VirtualSolver<int, double> {
     ~SolverCudaCG() { release_resident(dev); }
 };
 
+// ------------------------------------------------------------------------------------------------------------
+// 4. solver=GMRES  ->  right-preconditioned (Jacobi) flexible GMRES on the device (reference: SolverGMRES,
+//    femlib/VirtualSolverCG.hpp:196-258, fgmres femlib/CG.cpp:347-517).  A user preconditioner (precon=) or a transposed
+//    solve (A'^-1) are not on the path: FreeFEM's own SolverGMRES runs them.
+// ------------------------------------------------------------------------------------------------------------
+class SolverCudaGMRES : public SolverCudaCG {
+  public:
+    static const int orTypeSol = 1 | 2 | 4 | 8 | 16 | 32; // what the reference GMRES declares
+    int restart;
+    SolverGMRES<int, double> *host; // FreeFEM's own solver for what is left to it
+    bool precon;
+    SolverCudaGMRES(HMat &AA, const Data_Sparse_Solver &ds, Stack stack)
+        : SolverCudaCG(AA, ds, stack), restart(ds.NbSpace), host(nullptr), precon(ds.precon != 0)
+    {
+        if (precon) host = new SolverGMRES<int, double>(AA, ds, stack); // (Data_Sparse_Solver cannot be kept: built now)
+    }
+    void dosolver(double *x, double *b, int N, int trans)
+    {
+        if (trans || precon) {
+            notice("GMRES", trans ? "transposed solve" : "user preconditioner");
+            if (!host) {
+                Data_Sparse_Solver ds; // the parameters this solver was created with
+                ds.epsilon = eps;
+                ds.itmax = itermax;
+                ds.NbSpace = restart;
+                ds.tgv = tgv;
+                ds.verb = verb;
+                host = new SolverGMRES<int, double>(*A, ds, nullptr);
+            }
+            host->dosolver(x, b, N, trans);
+            return;
+        }
+        if (!dev.A) upload();
+        if (getnbiter) *getnbiter = 0;
+        int err = 0;
+        for (int k = 0, oo = 0; k < N; ++k, oo += A->n) {
+            int iters = 0, conv = 0;
+            double rel = 0;
+            if (ffcuda_gmres_host(dev.A, b + oo, x + oo, eps, itermax, restart, tgv, &iters, &conv, &rel) != 0) fail("ffcuda_gmres_host");
+            if (verb || g_verbose)
+                cout << "  **  fgmres (ffcuda) " << (conv ? "has converged in " : "has not converged in ") << iters
+                     << " iterations The relative residual is " << rel << endl;
+            if (!conv) err++;
+            if (getnbiter) *getnbiter = iters;
+            if (veps) *veps = eps;
+        }
+        if (err) {
+            std::cerr << "Error: fgmres (ffcuda) do not converge nb end =" << err << std::endl;
+            ffassert(0);
+        }
+    }
+    ~SolverCudaGMRES() { delete host; }
+};
+
 } // namespace
 
 static void Load_Init()
@@ -792,7 +846,7 @@ static void Load_Init()
         if (verbosity) cout << " load: ffcuda disabled by FFCUDA_DISABLE" << endl;
         return;
     }
-    if (verbosity) cout << " load: ffcuda (GPU assembly of P1/P2 varf + Jacobi-CG; FreeFEM keeps everything else)" << endl;
+    if (verbosity) cout << " load: ffcuda (GPU assembly of P1/P2 varf + Jacobi-CG / GMRES; FreeFEM keeps everything else)" << endl;
     // 1. matrices: "<-" constructs (init = 1), "=" assigns (init = 0)  (fflib/lgfem.cpp:6669,6673,6823,6826)
     TheOperators->Add("<-", new CudaMatrixOp<Mesh, v_fes>(1), new CudaMatrixOp<Mesh3, v_fes3>(1));
     TheOperators->Add("=", new CudaMatrixOp<Mesh, v_fes>(0), new CudaMatrixOp<Mesh3, v_fes3>(0));
@@ -804,6 +858,8 @@ static void Load_Init()
     // 3. solver
     addsolver<SolverCudaCG>("FFCUDACG", 10, 0);
     TheFFSolver<int, double>::ChangeSolver("CG", "FFCUDACG");
+    addsolver<SolverCudaGMRES>("FFCUDAGMRES", 10, 0);
+    TheFFSolver<int, double>::ChangeSolver("GMRES", "FFCUDAGMRES");
 }
 
 LOADFUNC(Load_Init)

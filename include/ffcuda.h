@@ -24,6 +24,7 @@
  *   ffcuda_assemble_bilinear_boundary <- AssembleBilinearForm border loop fflib/problem.cpp:1317-1326, Element_Op :6518-6560
  *   ffcuda_bc_* / *_apply_bc    <- AssembleBC fflib/problem.cpp:9881-10034, :10039-10194, HashMatrix::SetBC
  *                                  femlib/HashMatrix.cpp:1195-1238 (tgv >= 0 branch)
+ *   ffcuda_gmres                <- SolverGMRES femlib/VirtualSolverCG.hpp:196-258, fgmres femlib/CG.cpp:347-517
  *   ffcuda_quadrature           <- CDomainOfIntegration::FIT/FIV fflib/problem.cpp:14102-14145, QF_Simplex
  *                                  femlib/QuadratureFormular.cpp:73-115 and the rule tables :138-188, :699-743
  *   ffcuda_spmv                 <- HashMatrix::addMatMul femlib/HashMatrix.cpp:1087-1154
@@ -209,6 +210,16 @@ int ffcuda_cg(ffcuda_matrix *A, ffcuda_vec *b, ffcuda_vec *x, double eps, int it
 /* same with host vectors (the call the FreeFEM solver plugin makes) */
 int ffcuda_cg_host(ffcuda_matrix *A, const double *b, double *x, double eps, int itmax, double tgv,
                    int *iters, int *converged, double *gcg);
+
+/* GMRES for non-symmetric matrices: SolverGMRES (femlib/VirtualSolverCG.hpp:196-258) = SetInitWithBC + fgmres
+ * (femlib/CG.cpp:347-517), flexible GMRES(restart) with the Jacobi preconditioner on the right, modified Gram-Schmidt;
+ * stops when |g[it+1]| / ||b (tgv rows zeroed)|| < |eps| (eps < 0: absolute).  restart <= 0: FreeFEM's default 1000
+ * (dimKrylov=), itmax <= 0: n.  x = initial guess on entry.  *iters = fgmres's iteration counter, *converged = 0/1,
+ * *relres = the last relative residual.  One GPU. */
+int ffcuda_gmres(ffcuda_matrix *A, ffcuda_vec *b, ffcuda_vec *x, double eps, int itmax, int restart, double tgv,
+                 int *iters, int *converged, double *relres);
+int ffcuda_gmres_host(ffcuda_matrix *A, const double *b, double *x, double eps, int itmax, int restart, double tgv,
+                      int *iters, int *converged, double *relres);
 
 /* ---- multi-GPU (one process per GPU; the caller's launcher provides rank/size and moves the 128-byte
  *      NCCL id between ranks, e.g. with torch.distributed) ------------------------------------------- */

@@ -737,3 +737,119 @@ int ffo_cg(int n, int64_t nnz, const int32_t *ai, const int32_t *aj, const doubl
     free(G); free(CG); free(H); free(d1); free(diag); free(has);
     return ret;
 }
+
+/* ------------------------------------------------------------------ GMRES ---------------- */
+/* SolverGMRES::dosolver (femlib/VirtualSolverCG.hpp:236-255) = SetInitWithBC, then fgmres (femlib/CG.cpp:347-517) with the
+ * Jacobi preconditioner of HMatVirtPrecon (VirtualSolverCG.hpp:24-70) applied on the right (leftC is forced to 0, :374):
+ * flexible GMRES(nbkrylov), modified Gram-Schmidt, Givens rotations, stop when |g[it+1]| / normb < |eps| where
+ * normb = || rhs with the tgv rows zeroed ||.  x holds the initial guess on entry.  Returns 1 when converged;
+ * *iters = the reference's `iter` (completed inner iterations before the one that converged). */
+static double nrm2(int n, const double *x)
+{
+    double s = 0.;
+    for (int i = 0; i < n; ++i) s += x[i] * x[i];
+    return sqrt(s);
+}
+int ffo_gmres(int n, int64_t nnz, const int32_t *ai, const int32_t *aj, const double *aa,
+              const double *b, double *x, double eps, int itmax, int nbkrylov, double tgv, int *iters, double *relres_out)
+{
+    double *diag = (double *)calloc((size_t)n, sizeof(double));
+    char *has = (char *)calloc((size_t)n, 1);
+    for (int64_t k = 0; k < nnz; ++k)
+        if (ai[k] == aj[k]) { diag[ai[k]] = aa[k]; has[ai[k]] = 1; }
+    double ttgv = 0, max1 = 0; int ntgv = 0; /* gettgv, as in ffo_cg */
+    for (int i = 0; i < n; ++i)
+        if (has[i]) {
+            double a = diag[i];
+            if (a > ttgv) { max1 = ttgv; ttgv = a; ntgv = 1; }
+            else if (a == ttgv) ++ntgv;
+            else if (a > max1) max1 = a;
+        }
+    if (max1 * 1e6 > ttgv) { ttgv = 0; ntgv = 0; }
+    double *d1 = (double *)malloc(sizeof(double) * (size_t)n);
+    char *wbc = (char *)calloc((size_t)n, 1);
+    for (int i = 0; i < n; ++i) d1[i] = (diag[i] * diag[i] < 1e-60) ? 1. : 1. / diag[i];
+    if (ntgv) {
+        double tgve = ttgv <= 0 ? 1e200 : ttgv;
+        for (int i = 0; i < n; ++i)
+            if (diag[i] == tgve) { wbc[i] = 1; x[i] = b[i] / tgv; } /* wcl + SetInitWithBC */
+    }
+    if (itmax <= 0) itmax = n;
+    if (nbkrylov > itmax + 2) nbkrylov = itmax + 2; /* storage only: the inner loop leaves at it > itmax */
+    const int m = nbkrylov;
+    double *rot0 = (double *)calloc((size_t)m + 2, sizeof(double)), *rot1 = (double *)calloc((size_t)m + 2, sizeof(double));
+    double *g = (double *)calloc((size_t)m + 1, sizeof(double)), *g1 = (double *)calloc((size_t)m + 1, sizeof(double));
+    double *y = (double *)calloc((size_t)m + 1, sizeof(double));
+    double *Hn = (double *)calloc((size_t)(m + 2) * (m + 1), sizeof(double));
+#define HN(i, j) Hn[(size_t)(i) * (m + 1) + (j)]
+    double **Vi = (double **)calloc((size_t)m + 1, sizeof(double *)), **Vpi = (double **)calloc((size_t)m + 1, sizeof(double *));
+    double *uni = (double *)malloc(sizeof(double) * (size_t)n), *x0 = (double *)malloc(sizeof(double) * (size_t)n);
+    double *ri = (double *)malloc(sizeof(double) * (size_t)n), *vi = (double *)malloc(sizeof(double) * (size_t)n);
+    double *wi = (double *)malloc(sizeof(double) * (size_t)n);
+    for (int i = 0; i < n; ++i) wi[i] = wbc[i] ? 0. : b[i];
+    double normb = nrm2(n, wi), relres = 1e100;
+    for (int i = 0; i < n; ++i) uni[i] = x[i];
+    int noconv = 1, iter = 0;
+    while (noconv) {
+        for (int i = 0; i < n; ++i) x0[i] = uni[i];
+        ffo_spmv_coo(n, nnz, ai, aj, aa, uni, ri);
+        for (int i = 0; i < n; ++i) ri[i] += -1. * b[i];
+        for (int i = 0; i < n; ++i) ri[i] *= -1.;
+        g[0] = nrm2(n, ri); /* zi = Id ri */
+        if (normb < 1.e-20 || eps < 0) normb = 1.;
+        if (!Vi[0]) Vi[0] = (double *)malloc(sizeof(double) * (size_t)n);
+        { const double s = 1. / g[0]; for (int i = 0; i < n; ++i) Vi[0][i] = s * ri[i]; }
+        int it;
+        for (it = 0; it < m; it++, iter++) {
+            if (!Vpi[it]) Vpi[it] = (double *)malloc(sizeof(double) * (size_t)n);
+            if (!Vi[it + 1]) Vi[it + 1] = (double *)malloc(sizeof(double) * (size_t)n);
+            for (int i = 0; i < n; ++i) { vi[i] = 0.; vi[i] += d1[i] * Vi[it][i]; } /* C.matmul */
+            for (int i = 0; i < n; ++i) Vpi[it][i] = vi[i];
+            ffo_spmv_coo(n, nnz, ai, aj, aa, vi, wi);
+            for (int i = 0; i < it + 1; i++) {
+                HN(i, it) = dotp(n, wi, Vi[i]);
+                const double a = -HN(i, it);
+                for (int k = 0; k < n; ++k) wi[k] += a * Vi[i][k];
+            }
+            const double aux = HN(it + 1, it) = nrm2(n, wi);
+            { const double s = 1. / aux; for (int k = 0; k < n; ++k) Vi[it + 1][k] = s * wi[k]; }
+            for (int i = 0; i < it; i++) {
+                double aa_ = rot0[i] * HN(i, it) + rot1[i] * HN(i + 1, it);
+                double bb_ = -rot1[i] * HN(i, it) + rot0[i] * HN(i + 1, it);
+                HN(i, it) = aa_;
+                HN(i + 1, it) = bb_;
+            }
+            const double sq = sqrt(HN(it, it) * HN(it, it) + HN(it + 1, it) * HN(it + 1, it));
+            rot0[it] = HN(it, it) / sq;
+            rot1[it] = HN(it + 1, it) / sq;
+            HN(it, it) = rot0[it] * HN(it, it) + rot1[it] * HN(it + 1, it);
+            HN(it + 1, it) = 0.;
+            g[it + 1] = -rot1[it] * g[it];
+            g[it] = rot0[it] * g[it];
+            relres = fabs(g[it + 1]);
+            if (relres / normb < fabs(eps)) { noconv = 0; break; }
+            if (it > itmax) break;
+        }
+        if (it > m - 1) it = m - 1;
+        for (int i = it; i >= 0; i--) {
+            g1[i] = g[i];
+            for (int j = i + 1; j < it + 1; j++) g1[i] = g1[i] - HN(i, j) * y[j];
+            y[i] = g1[i] / HN(i, i);
+        }
+        for (int k = 0; k < n; ++k) wi[k] = 0.;
+        for (int i = 0; i < it + 1; i++)
+            for (int k = 0; k < n; ++k) wi[k] += y[i] * Vpi[i][k];
+        for (int k = 0; k < n; ++k) uni[k] = wi[k];
+        for (int k = 0; k < n; ++k) uni[k] += x0[k];
+        for (int k = 0; k < n; ++k) x[k] = uni[k];
+        if (!noconv) break;
+        if (iter > itmax) break;
+    }
+#undef HN
+    if (iters) *iters = iter;
+    if (relres_out) *relres_out = relres / normb;
+    for (int i = 0; i <= m; ++i) { free(Vi[i]); free(Vpi[i]); }
+    free(Vi); free(Vpi); free(uni); free(x0); free(ri); free(vi); free(wi); free(Hn); free(rot0); free(rot1); free(g); free(g1);
+    free(y); free(d1); free(wbc); free(diag); free(has);
+    return !noconv;
+}

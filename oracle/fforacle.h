@@ -112,6 +112,11 @@ void ffo_spmv_coo(int n, int64_t nnz, const int32_t *ai, const int32_t *aj, cons
 int ffo_cg(int n, int64_t nnz, const int32_t *ai, const int32_t *aj, const double *aa,
            const double *b, double *x, double eps, int itmax, double tgv, int *iters, double *gcg_out);
 
+/* SolverGMRES (femlib/VirtualSolverCG.hpp:196-258) = SetInitWithBC + fgmres (femlib/CG.cpp:347-517): right-preconditioned
+ * (Jacobi) flexible GMRES(nbkrylov) with modified Gram-Schmidt.  x = initial guess on entry.  Returns 1 when converged. */
+int ffo_gmres(int n, int64_t nnz, const int32_t *ai, const int32_t *aj, const double *aa,
+              const double *b, double *x, double eps, int itmax, int nbkrylov, double tgv, int *iters, double *relres_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -73,6 +73,10 @@ CASES = {
     "lap2d_p2_robin": (2, 1, LAP2, [(0, ID, 1.0)], "qf5pT", [([4], 1, [0.0])]),
     "lame3d_p1_robin": (1, 3, lame_terms(), [(2, ID, -0.05)], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
     "lap3d_p2_robin": (2, 1, LAP3, [(0, ID, 1.0)], "qfV5", []),
+    # non-symmetric forms, solved by GMRES in the fixture (CASE_GMRES below)
+    "convdiff3d_p1_gmres": (1, 1, LAP3 + [(0, DX, 0, ID, 8.0), (0, DY, 0, ID, 3.0), (0, DZ, 0, ID, -2.0)], [(0, ID, 1.0)], "qfV5",
+                            [(ALL6, 1, [0.0])]),
+    "convdiff2d_p2_gmres": (2, 1, LAP2 + [(0, DX, 0, ID, 5.0), (0, ID, 0, ID, 1.0)], [(0, ID, 1.0)], "qf5pT", [([1, 3], 1, [0.0])]),
     # half storage (sym=1, CASE_SYM below): the fixture holds the lower triangle
     "lap3d_p1_sym": (1, 1, LAP3, [(0, ID, 1.0)], "qfV5", [(ALL6, 1, [0.0])]),
     "lap2d_p2_sym": (2, 1, LAP2 + [(0, ID, 0, ID, 2.0)], [(0, ID, 1.0)], "qf5pT", [([2, 4], 1, [0.0])]),
@@ -86,6 +90,8 @@ CASE_BLIN["lap3d_p1_robin"] = ([2, 3], [(0, ID, 2.5)])
 CASE_BBIL = {"lap3d_p1_robin": ([2, 3], [(0, ID, 0, ID, 1.5)]), "lap2d_p2_robin": ([2, 3], [(0, ID, 0, ID, 0.7)]),
              "lame3d_p1_robin": ([2], [(0, ID, 0, ID, 1e4), (1, ID, 1, ID, 1e4), (2, ID, 2, ID, 5e3), (0, ID, 2, ID, 2e3)]),
              "lap3d_p2_robin": ([6, 1], [(0, ID, 0, ID, 2.0)])}
+# fixtures solved with solver=GMRES: name -> dimKrylov (FreeFEM's default is 1000)
+CASE_GMRES = {"convdiff3d_p1_gmres": 1000, "convdiff2d_p2_gmres": 25}
 # cases assembled with sym=1: MatriceMorse keeps the entries (i, j) with j <= i only (HashMatrix.cpp:1319-1325)
 CASE_SYM = {"lap3d_p1_sym", "lap2d_p2_sym", "lame3d_p1_sym"}
 # Dirichlet treatment of a case: penalty tgv = 1e30 unless listed here (HashMatrix::SetBC with tgv < 0)
@@ -140,4 +146,5 @@ def elem2node(g, order, ncomp):
         assert np.array_equal(dof[:, c * nl:(c + 1) * nl], e2n * ncomp + c)
     return np.ascontiguousarray(e2n, dtype=np.int32)
 # cases whose script does not solve (non-symmetric after tgv = -1 / -3 elimination)
-NO_SOLVE_TGV = {"lap3d_p1_tgvm1", "lame3d_p1_tgvm1", "lap3d_p1_tgvm3", "lame3d_p1_robin"}  # (the last: non-symmetric Robin coupling)
+NO_SOLVE_TGV = {"lap3d_p1_tgvm1", "lame3d_p1_tgvm1", "lap3d_p1_tgvm3", "lame3d_p1_robin",  # (non-symmetric Robin coupling)
+                "convdiff3d_p1_gmres", "convdiff2d_p2_gmres"}  # (GMRES fixtures have their own solve tests)

@@ -90,6 +90,12 @@ CASES = {
                             blin="+int2d(Th,2)(1e4*u1*v1+1e4*u2*v2+5e3*u3*v3+2e3*u1*v3)", bc="on(1,u1=0,u2=0,u3=0)",
                             solve=False),
     "lap3d_p2_robin": dict(dim=3, mesh="cube(2,2,2)", fe="P2", bil=LAP3, lin="1.*v", blin="+int2d(Th,6,1)(2.*u*v)", bc=""),
+    # non-symmetric forms solved by GMRES (SolverGMRES / fgmres, femlib/CG.cpp:347-517); the second one restarts
+    "convdiff3d_p1_gmres": dict(dim=3, mesh="cube(4,4,4,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", fe="P1",
+                                bil=LAP3 + "+8.*dx(u)*v+3.*dy(u)*v-2.*dz(u)*v", lin="1.*v", bc="on(1,2,3,4,5,6,u=0)",
+                                solver="GMRES"),
+    "convdiff2d_p2_gmres": dict(dim=2, mesh="square(5,4)", fe="P2", bil=LAP2 + "+5.*dx(u)*v+u*v", lin="1.*v",
+                                bc="on(1,3,u=0)", solver="GMRES", sopt=",dimKrylov=25"),
     # half storage (sym=1): MatriceElementaireSymetrique / the symmetric Element_Op, lower triangle only (HashMatrix.cpp:1319-1325)
     "lap3d_p1_sym": dict(dim=3, mesh="cube(3,3,3)", fe="P1", bil=LAP3, lin="1.*v", bc="on(1,2,3,4,5,6,u=0)", sym=1),
     "lap2d_p2_sym": dict(dim=2, mesh="square(4,3,[x+0.2*y*y,y*(1+0.3*x)])", fe="P2", bil=LAP2 + "+2.*u*v", lin="1.*v",
@@ -117,7 +123,8 @@ def script(c, out):
     s.append(f"varf va({unk},{tst}) = {integ}(Th{opt})({c['bil']}) + {integ}(Th{opt})({c['lin']}){c.get('blin', '')}{bc};")
     tg = (",tgv=%g" % c["tgv"]) if "tgv" in c else ""
     sy = ",sym=1" if c.get("sym") else ""
-    s.append(f"matrix A = va(Vh,Vh,solver=CG,eps=1e-6{tg}{sy});")
+    solver, sopt = c.get("solver", "CG"), c.get("sopt", "")
+    s.append(f"matrix A = va(Vh,Vh,solver={solver},eps=1e-6{tg}{sy}{sopt});")
     s.append(f"real[int] b = va(0,Vh{tg});")
     # mesh dump
     s.append(f'{{ ofstream f("{out}/mesh.txt"); f.precision(17);')
@@ -144,7 +151,7 @@ def script(c, out):
         s.append(f"{u0}[] = A^-1*b; verbosity=0;")
         s.append(f'{{ ofstream f("{out}/u.txt"); f.precision(17); for(int i=0;i<{u0}[].n;++i) f << {u0}[][i] << endl; }}')
         # second solve converged to round-off: the comparison point that does not depend on where eps=1e-6 stops
-        s.append(f"verbosity=1; set(A,solver=CG,eps=1e-14); {u0}[] = 0; {u0}[] = A^-1*b; verbosity=0;")
+        s.append(f"verbosity=1; set(A,solver={solver},eps=1e-14{sopt}); {u0}[] = 0; {u0}[] = A^-1*b; verbosity=0;")
         s.append(f'{{ ofstream f("{out}/u14.txt"); f.precision(17); for(int i=0;i<{u0}[].n;++i) f << {u0}[][i] << endl; }}')
     return "\n".join(s) + "\n"
 
@@ -199,7 +206,7 @@ def run_case(name):
                    edp=np.array(src))
         if c.get("solve", True):
             out["u"] = np.array(toks(os.path.join(td, "u.txt")), dtype=np.float64)
-            mm = re.findall(r"GC:\s+converge after\s+(\d+)", r.stdout)
+            mm = re.findall(r"fgmres has converged in\s+(\d+)" if c.get("solver") == "GMRES" else r"GC:\s+converge after\s+(\d+)", r.stdout)
             assert len(mm) == 2, r.stdout[-2000:]
             out["cg_iters"] = np.int32(int(mm[0]))
             out["u14"] = np.array(toks(os.path.join(td, "u14.txt")), dtype=np.float64)

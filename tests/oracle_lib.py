@@ -252,3 +252,13 @@ def cg(n, ci, cj, ca, b, x0, eps=1e-6, itmax=0, tgv=1e30):
     ret = lib().ffo_cg(n, C.c_int64(len(ci)), _p(ci, C.c_int32), _p(cj, C.c_int32), _p(ca, C.c_double), _p(b, C.c_double),
                        _p(x, C.c_double), C.c_double(eps), itmax, C.c_double(tgv), C.byref(it), C.byref(g))
     return x, it.value, ret, g.value
+
+
+def gmres(n, ci, cj, ca, b, x0, eps=1e-6, itmax=0, nbkrylov=1000, tgv=1e30):
+    """SolverGMRES of the reference (fgmres, right Jacobi preconditioner): returns x, iterations, converged, relative residual"""
+    ci, cj, ca, b = _i32(ci), _i32(cj), _f64(ca), _f64(b)
+    x = _f64(x0).copy()
+    it, r = C.c_int(), C.c_double()
+    ret = lib().ffo_gmres(n, C.c_int64(len(ci)), _p(ci, C.c_int32), _p(cj, C.c_int32), _p(ca, C.c_double), _p(b, C.c_double),
+                          _p(x, C.c_double), C.c_double(eps), itmax, nbkrylov, C.c_double(tgv), C.byref(it), C.byref(r))
+    return x, it.value, ret, r.value

@@ -34,7 +34,7 @@ def _upload(ctx, g):
 
 
 def _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve=True, eps=1e-6, itmax=0, TGV=TGV, lower=False,  # noqa: N803
-              blin=None, bbil=None):
+              blin=None, bbil=None, gmres=None):
     """Full product pipeline on one problem; returns everything a parity check needs."""
     mesh = _upload(ctx, g)
     sp = mesh.space(order, ncomp, e2n, nnodes)
@@ -63,7 +63,15 @@ def _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve=True
         erp, eci, eval_ = fc.lower(n, frp, fci, fval)
         assert np.array_equal(hrp, erp) and np.array_equal(hci, eci) and np.array_equal(hval, eval_)
         out.update(rowptr=hrp, colind=hci, vals=hval)
-    if solve:
+    if solve and gmres:  # non-symmetric form: GMRES(gmres) as solver=GMRES,dimKrylov=... does in the fixture's script
+        x = ctx.vec(n)
+        it, conv, rel = A.gmres(b, x, eps=eps, itmax=itmax, restart=gmres, tgv=TGV)
+        out.update(u=x.download(), iters=it, conv=conv, gcg=rel)
+        x14 = ctx.vec(n)
+        it14, conv14, _ = A.gmres(b, x14, eps=1e-14, itmax=itmax, restart=gmres, tgv=TGV)
+        assert conv14 == 1
+        out.update(u14=x14.download(), iters14=it14)
+    elif solve:
         x = ctx.vec(n)
         it, conv, gcg = A.cg(b, x, eps=eps, itmax=itmax, tgv=TGV)
         out.update(u=x.download(), iters=it, conv=conv, gcg=gcg)
@@ -83,7 +91,7 @@ def test_golden_case(ctx, name):
     e2n = fc.elem2node(g, order, ncomp)
     nnodes = g["ndof"] // ncomp
     r = _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve="u" in g, TGV=fc.CASE_TGV.get(name, TGV),
-                  lower=name in fc.CASE_SYM, blin=fc.CASE_BLIN.get(name), bbil=fc.CASE_BBIL.get(name))
+                  lower=name in fc.CASE_SYM, blin=fc.CASE_BLIN.get(name), bbil=fc.CASE_BBIL.get(name), gmres=fc.CASE_GMRES.get(name))
     grp, gci, gval = fc.golden_csr(g)
     assert r["n"] == g["ndof"]
     assert np.array_equal(r["rowptr"], grp) and np.array_equal(r["colind"], gci)          # bit-exact pattern
@@ -101,7 +109,10 @@ def test_golden_case(ctx, name):
         # (a) the reference's own stopping point (eps=1e-6).  An eps=1e-6 iterate is NOT converged to round-off: CG
         # amplifies a 1-ulp difference in A (our assembly sums in another order) up to the residual level, so the
         # 1e-12 bar is only attainable where few iterations are taken (all P1 scalar fixtures); see (b) for the rest.
-        if ncomp == 1 and name not in fc.CASE_BLIN and name not in fc.CASE_BBIL:
+        if name in fc.CASE_GMRES:
+            assert abs(r["iters"] - int(g["cg_iters"])) <= 1
+            assert np.max(np.abs(r["u"] - g["u"])) <= 1e-7 * umax
+        elif ncomp == 1 and name not in fc.CASE_BLIN and name not in fc.CASE_BBIL:
             assert r["iters"] == int(g["cg_iters"])
             assert np.max(np.abs(r["u"] - g["u"])) <= (RTOL if order == 1 else 1e-9) * umax
         else:
@@ -631,3 +642,59 @@ def test_boundary_bilinear_form_properties_and_errors(ctx):
         import scipy.sparse as sps
         D = sps.csr_matrix((v, col, rp), shape=(nd, nd)) - sps.coo_matrix((ca, (ci, cj)), shape=(nd, nd)).tocsr()
         assert abs(D).max() <= 1e-13 * np.abs(ca).max()
+
+
+@pytest.mark.parametrize("name", sorted(fc.CASE_GMRES))
+def test_gmres_on_reference_matrix(ctx, name):
+    """the GMRES entry the plugin calls (host CSR in, host vectors in/out) fed with the reference's own A and b: fgmres's
+    iteration count at both tolerances (restart included), the iterates to 1e-10 / 1e-12."""
+    g = fc.load(name)
+    n = g["ndof"]
+    rp, ci, val = fc.golden_csr(g)
+    A = ctx.matrix_from_csr(n, rp, ci, val)
+    for eps, ku, kit in ((1e-6, "u", "cg_iters"), (1e-14, "u14", "cg_iters14")):
+        x = np.zeros(n)
+        it, conv, rel = A.gmres_host(g["b"].copy(), x, eps=eps, restart=fc.CASE_GMRES[name])
+        assert conv == 1 and it == int(g[kit]) and rel < eps
+        assert np.max(np.abs(x - g[ku])) <= (1e-10 if eps > 1e-10 else RTOL) * np.abs(g[ku]).max()
+    # reproducible run to run (fixed summation shapes, no atomics on doubles)
+    x1, x2 = np.zeros(n), np.zeros(n)
+    A.gmres_host(g["b"].copy(), x1, eps=1e-10, restart=fc.CASE_GMRES[name])
+    A.gmres_host(g["b"].copy(), x2, eps=1e-10, restart=fc.CASE_GMRES[name])
+    assert np.array_equal(x1, x2)
+
+
+def test_gmres_convection_diffusion_cube(ctx):
+    """a larger non-symmetric problem (cube(24), 15 625 unknowns) against the oracle's restatement of fgmres: same iteration
+    count within 1, solution to 1e-9 at eps=1e-12; a restart length of 30; itmax reached -> not converged, no exception."""
+    N = 24
+    bt = fc.LAP3 + [(0, fc.DX, 0, fc.ID, 20.0), (0, fc.DY, 0, fc.ID, -10.0), (0, fc.ID, 0, fc.ID, 1.0)]
+    lt = [(0, fc.ID, 1.0)]
+    qp, qw = ffcuda.quadrature(3, 6)
+    mesh = ctx.mesh_cube(N, N, N)
+    sp = mesh.space(1, 1)
+    pat = sp.symbolic()
+    n = pat.info()[0]
+    A = pat.matrix()
+    A.assemble(bt, qp, qw)
+    b = ctx.vec(n)
+    sp.assemble_linear(b, lt, qp, qw)
+    bc = sp.bc_from_labels([1, 2, 3, 4, 5, 6], 1, [0.0])
+    A.apply_bc(bc, TGV)
+    b.apply_bc(bc, TGV)
+    rp, col = pat.download()
+    val, hb = A.download(), b.download()
+    rows = np.repeat(np.arange(n, dtype=np.int32), np.diff(rp))
+    for restart in (1000, 30):
+        x = ctx.vec(n)
+        it, conv, rel = A.gmres(b, x, eps=1e-12, restart=restart, tgv=TGV)
+        xo, ito, reto, _ = ol.gmres(n, rows, col, val, hb, np.zeros(n), eps=1e-12, nbkrylov=restart, tgv=TGV)
+        assert conv == 1 and reto == 1 and abs(it - ito) <= 1 and rel < 1e-12
+        u = x.download()
+        assert np.max(np.abs(u - xo)) <= 1e-9 * np.abs(xo).max()
+        r = hb - __import__("scipy.sparse").sparse.csr_matrix((val, col, rp), shape=(n, n)) @ u
+        inner = np.abs(hb) < 1e20
+        assert np.linalg.norm(r[inner]) <= 1e-10 * np.linalg.norm(hb[inner])
+    x = ctx.vec(n)
+    it, conv, rel = A.gmres(b, x, eps=1e-12, itmax=5, restart=1000, tgv=TGV)
+    assert conv == 0 and it <= 8

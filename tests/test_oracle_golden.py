@@ -86,7 +86,12 @@ def test_matrix_rhs_solution(name):
     if name in fc.CASE_SYM:  # addMatMul mirrors the off-diagonal entries of a half-stored matrix (HashMatrix.cpp:1087-1154)
         off = cj < ci
         ci, cj, ca = np.concatenate([ci, cj[off]]), np.concatenate([cj, ci[off]]), np.concatenate([ca, ca[off]])
-    if "u" in g:
+    if name in fc.CASE_GMRES:  # own restated assembly + own restated GMRES against the reference's solution
+        for eps, ku, kit in ((1e-6, "u", "cg_iters"), (1e-14, "u14", "cg_iters14")):
+            x, it, ret, _ = ol.gmres(n, ci, cj, ca, b, np.zeros(n), eps=eps, nbkrylov=fc.CASE_GMRES[name], tgv=TGV)
+            assert ret == 1 and abs(it - int(g[kit])) <= 1
+            assert np.max(np.abs(x - g[ku])) <= (1e-7 if eps > 1e-10 else RTOL) * np.abs(g[ku]).max()
+    elif "u" in g:
         x, it, ret, _ = ol.cg(n, ci, cj, ca, b, np.zeros(n), eps=1e-6, itmax=0, tgv=TGV)
         assert ret in (1, 2)
         if ncomp == 1 and name not in fc.CASE_BLIN and name not in fc.CASE_BBIL:
@@ -160,3 +165,15 @@ def test_known_answers_from_survey():
     assert list(map(list, ol.square(2, 1)["conn"])) == [[0, 1, 4], [0, 4, 3], [1, 2, 5], [1, 5, 4]]
     g2 = fc.load("lap2d_p1_sq4")
     assert g2["ndof"] == 25 and len(g2["coo_i"]) == 137
+
+
+@pytest.mark.parametrize("name", sorted(fc.CASE_GMRES))
+def test_gmres_on_reference_matrix(name):
+    """ffo_gmres fed with the reference's own A (in its storage order) and b must reproduce fgmres: same iteration count at
+    both tolerances, the iterate to 1e-12 (restart included for the dimKrylov=25 fixture)."""
+    g = fc.load(name)
+    n = g["ndof"]
+    for eps, ku, kit in ((1e-6, "u", "cg_iters"), (1e-14, "u14", "cg_iters14")):
+        x, it, ret, rel = ol.gmres(n, g["coo_i"], g["coo_j"], g["coo_a"], g["b"], np.zeros(n), eps=eps, nbkrylov=fc.CASE_GMRES[name])
+        assert ret == 1 and it == int(g[kit]) and rel < eps
+        assert np.max(np.abs(x - g[ku])) <= (1e-10 if eps > 1e-10 else RTOL) * np.abs(g[ku]).max()

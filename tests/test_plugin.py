@@ -39,14 +39,14 @@ verbosity=1; UU[] = 0; UU[] = A^-1*b; verbosity=0;
 """
 
 
-def script(dim, mesh, fe, bil, lin, bc, pre="", unk="u", tst="v", eps="1e-6", intopt="", tgv=None, sym=False, extra=""):
+def script(dim, mesh, fe, bil, lin, bc, pre="", unk="u", tst="v", eps="1e-6", intopt="", tgv=None, sym=False, extra="", solver="CG"):
     mt, integ = ("mesh", "int2d") if dim == 2 else ("mesh3", "int3d")
     u0 = unk.strip("[]").split(",")[0]
     s = f'load "msh3"\nload "ffcuda"\n{pre}\n{mt} Th = {mesh};\nfespace Vh(Th,{fe});\n'
     s += f"varf va({unk},{tst}) = {integ}(Th{intopt})({bil}) + {integ}(Th{intopt})({lin}){extra}{('+' + bc) if bc else ''};\n"
     tg = "" if tgv is None else f",tgv={tgv}"
     sy = ",sym=1" if sym else ""
-    s += f"matrix A = va(Vh,Vh,solver=CG,eps={eps}{tg}{sy});\nreal[int] b = va(0,Vh{tg});\n" + DUMP
+    s += f"matrix A = va(Vh,Vh,solver={solver},eps={eps}{tg}{sy});\nreal[int] b = va(0,Vh{tg});\n" + DUMP
     s += f"Vh {unk};\n" + SOLVE.replace("UU", u0)
     return s
 
@@ -76,6 +76,11 @@ CASES = {
     "lame3d_p1_traction": script(3, "cube(3,4,3)", "[P1,P1,P1]", LAME, "-0.05*v3", "on(1,u1=0,u2=0,u3=0)", pre=LAME_PRE,
                                  unk="[u1,u2,u3]", tst="[v1,v2,v3]", eps="1e-14",
                                  extra="+int2d(Th,3)(1e3*(u1*v1+u2*v2+u3*v3))+int2d(Th,2)(0.3*v1-0.2*v3)"),
+    # non-symmetric forms with solver=GMRES (fgmres; the second case restarts every 12 iterations)
+    "convdiff3d_p1_gmres": script(3, "cube(6,5,7)", "P1", LAP3 + "+8.*dx(u)*v+3.*dy(u)*v-2.*dz(u)*v", "1.*v",
+                                  "on(1,2,3,4,5,6,u=0)", solver="GMRES"),
+    "convdiff2d_p2_gmres": script(2, "square(7,6)", "P2", LAP2 + "+5.*dx(u)*v+u*v", "1.*v", "on(1,3,u=0)", eps="1e-14",
+                                  solver="GMRES,dimKrylov=40"),
     "mass3d_lumped": script(3, "cube(3,3,3)", "P1", "u*v+0.1*(" + LAP3 + ")", "1.*v", "on(1,u=0)", intopt=",qfV=qfV1lump"),
 }
 
@@ -125,7 +130,7 @@ def run_ff(src, env_extra, want_fail=False):
         res["b"] = np.loadtxt(os.path.join(td, "b.txt"), ndmin=1)
         if os.path.exists(os.path.join(td, "u.txt")):
             res["u"] = np.loadtxt(os.path.join(td, "u.txt"), ndmin=1)
-        res["iters"] = [int(x) for x in re.findall(r"GC[^\n]*?after\s+(\d+)", out)]
+        res["iters"] = [int(x) for x in re.findall(r"(?:GC[^\n]*?after|fgmres[^\n]*?converged in)\s+(\d+)", out)]
         return r.returncode, out, res
 
 
@@ -155,9 +160,10 @@ def compare(gpu, cpu, tight):
 def test_plugin_matches_freefem(name):
     src = CASES[name]
     _, out, gpu = run_ff(src, {"FFCUDA_STRICT": "1", "FFCUDA_VERBOSE": "1"})
-    assert "assembled on the GPU" in out and "GC (ffcuda)" in out       # the GPU path ran, nothing was delegated
+    tag = "fgmres (ffcuda)" if "solver=GMRES" in src else "GC (ffcuda)"
+    assert "assembled on the GPU" in out and tag in out                  # the GPU path ran, nothing was delegated
     _, out_cpu, cpu = run_ff(src, {"FFCUDA_DISABLE": "1"})
-    assert "assembled on the GPU" not in out_cpu and "GC (ffcuda)" not in out_cpu and "ffcuda disabled" in out_cpu
+    assert "assembled on the GPU" not in out_cpu and "(ffcuda)" not in out_cpu and "ffcuda disabled" in out_cpu
     compare(gpu, cpu, tight="eps=1e-14" in src)
 
 
