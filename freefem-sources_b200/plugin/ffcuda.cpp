@@ -520,6 +520,132 @@ void drop_resident()
     g_resident.clear();
 }
 
+// the pattern of the device matrix is that of the whole space: FreeFEM's is the same only when the volume integrals
+// visit every element (HashMatrix creates the couples of the visited elements only)
+template <class MeshT>
+void check_full_pattern(const Varf &V, const MeshT &Th)
+{
+    bool full = false;
+    std::set<int> labs;
+    for (size_t i = 0; i < V.bil.size(); ++i)
+        if (!V.bil[i].border) {
+            full = full || V.bil[i].reg.all;
+            labs.insert(V.bil[i].reg.labels.begin(), V.bil[i].reg.labels.end());
+        }
+    for (int k = 0; k < Th.nt && !full; ++k)
+        if (!labs.count(Th[k].lab)) throw Unsupported{"the volume integrals do not visit every element (sub-pattern)"};
+}
+
+// the GPU path proper for a matrix: symbolic, numeric assembly of every bilinear item, Dirichlet conditions, then the
+// CSR arrays come back and become a MatriceMorse of FreeFEM's own (HashMatrix::set copies and rebuilds the hash); the
+// device copy is returned in res for the solver that will be attached
+MatriceMorse<double> *gpu_matrix(DevSpace &D, const Varf &V, const Data_Sparse_Solver &ds, Resident &res, int &n, int64_t &nnz)
+{
+    ffcuda_pattern *P = nullptr;
+    ffcuda_matrix *dA = nullptr;
+    FFC(ffcuda_symbolic(D.space, &P));
+    if (ffcuda_matrix_create(P, &dA) != 0) {
+        ffcuda_pattern_destroy(P);
+        fail("ffcuda_matrix_create");
+    }
+    int rc = ffcuda_pattern_info(P, &n, &nnz);
+    // volume integrals first, then the boundary ones (Robin terms) on top; the sum does not depend on the order the
+    // varf lists them in beyond round-off
+    bool first = true;
+    for (int border = 0; border < 2; ++border)
+        for (size_t i = 0; i < V.bil.size() && !rc; ++i) {
+            const BilinearItem &B = V.bil[i];
+            if ((int)B.border != border) continue;
+            rc = (border ? ffcuda_assemble_bilinear_boundary : ffcuda_assemble_bilinear)(
+                dA, D.space, (int)B.terms.size(), B.terms.data(), (int)B.q.w.size(), B.q.pts.data(), B.q.w.data(),
+                (int)B.reg.labels.size(), B.reg.all ? nullptr : B.reg.labels.data(), first ? 0 : 1);
+            first = false;
+        }
+    std::vector<int32_t> rowptr, colind;
+    std::vector<double> vals;
+    if (!rc) {
+        try {
+            apply_bcs(D, V, dA, nullptr, ds.tgv);
+        } catch (...) {
+            ffcuda_matrix_destroy(dA);
+            ffcuda_pattern_destroy(P);
+            throw;
+        }
+        rowptr.resize((size_t)n + 1);
+        if (ds.sym) { // half storage: FreeFEM keeps the entries (i, j <= i); the device matrix stays full
+            rc = ffcuda_pattern_lower_nnz(P, &nnz);
+            colind.resize((size_t)nnz);
+            vals.resize((size_t)nnz);
+            rc = rc || ffcuda_pattern_download_lower(P, rowptr.data(), colind.data()) || ffcuda_matrix_download_lower(dA, vals.data());
+        } else {
+            colind.resize((size_t)nnz);
+            vals.resize((size_t)nnz);
+            rc = ffcuda_pattern_download(P, rowptr.data(), colind.data()) || ffcuda_matrix_download(dA, vals.data());
+        }
+    }
+    if (rc) {
+        ffcuda_matrix_destroy(dA);
+        ffcuda_pattern_destroy(P);
+        fail("assembling the matrix");
+    }
+    MatriceMorse<double> *M = new MatriceMorse<double>(n, n, 0, 0);
+    M->set(n, n, ds.sym ? 1 : 0, (size_t)nnz, rowptr.data(), colind.data(), vals.data(), 0, 1); // copies, rebuilds the hash
+    res = Resident{dA, P};
+    return M;
+}
+
+// the GPU path proper for a right-hand side: every linear item (volume integrals, then boundary integrals), an optional
+// change of sign (problem/solve: a(u,v) - l(v) = 0), Dirichlet values; x0 (optional, size n) gets x0[d] = g(d) as
+// AssembleBC does for the initial guess
+void gpu_rhs(DevSpace &D, const Varf &V, double tgv, bool negate, long n, std::vector<double> &host, double *x0)
+{
+    ffcuda_vec *db = nullptr;
+    FFC(ffcuda_vec_create(context(), (int)n, &db));
+    int rc = 0;
+    bool first = true;
+    for (int border = 0; border < 2; ++border)
+        for (size_t i = 0; i < V.lin.size() && !rc; ++i) {
+            const LinearItem &L = V.lin[i];
+            if ((int)L.border != border) continue;
+            std::vector<ffcuda_lterm> terms(L.terms);
+            if (negate)
+                for (size_t k = 0; k < terms.size(); ++k) terms[k].coef = -terms[k].coef;
+            rc = (border ? ffcuda_assemble_linear_boundary : ffcuda_assemble_linear)(
+                db, D.space, (int)terms.size(), terms.data(), (int)L.q.w.size(), L.q.pts.data(), L.q.w.data(),
+                (int)L.reg.labels.size(), L.reg.all ? nullptr : L.reg.labels.data(), first ? 0 : 1);
+            first = false;
+        }
+    if (first && !rc) rc = ffcuda_vec_fill(db, 0.0);
+    host.resize((size_t)n);
+    ffcuda_vec *dx = nullptr;
+    if (!rc) {
+        try {
+            apply_bcs(D, V, nullptr, db, tgv);
+            if (x0 && !V.bc.empty()) {
+                FFC(ffcuda_vec_create(context(), (int)n, &dx));
+                if (ffcuda_vec_upload(dx, x0) != 0) fail("uploading the initial guess");
+                for (size_t i = 0; i < V.bc.size(); ++i) {
+                    const BCItem &B = V.bc[i];
+                    ffcuda_bc *bc = nullptr;
+                    FFC(ffcuda_bc_from_labels(D.space, (int)B.labels.size(), B.labels.data(), B.compmask, B.values, &bc));
+                    int r2 = ffcuda_vec_set_bc_values(dx, bc);
+                    ffcuda_bc_destroy(bc);
+                    if (r2) fail("setting the Dirichlet values of the initial guess");
+                }
+                if (ffcuda_vec_download(dx, x0) != 0) fail("downloading the initial guess");
+            }
+        } catch (...) {
+            ffcuda_vec_destroy(db);
+            if (dx) ffcuda_vec_destroy(dx);
+            throw;
+        }
+        rc = ffcuda_vec_download(db, host.data());
+    }
+    ffcuda_vec_destroy(db);
+    if (dx) ffcuda_vec_destroy(dx);
+    if (rc) fail("assembling the right-hand side");
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // 1. matrix A = va(Vh,Vh,...)
 // ------------------------------------------------------------------------------------------------------------
@@ -548,72 +674,12 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
                 const MMesh &Th = Vh.Th;
                 if (!isSameMesh(this->b->largs, &Vh.Th, &Vh.Th, stack)) throw Unsupported{"integrals on different meshes"};
                 Varf V = read_varf(stack, this->b->largs, Th, Vh.N, true);
-                // the pattern of the device matrix is that of the whole space: FreeFEM's is the same only when the volume
-                // integrals visit every element (HashMatrix creates the couples of the visited elements only)
-                {
-                    bool full = false;
-                    std::set<int> labs;
-                    for (size_t i = 0; i < V.bil.size(); ++i)
-                        if (!V.bil[i].border) {
-                            full = full || V.bil[i].reg.all;
-                            labs.insert(V.bil[i].reg.labels.begin(), V.bil[i].reg.labels.end());
-                        }
-                    for (int k = 0; k < Th.nt && !full; ++k)
-                        if (!labs.count(Th[k].lab)) throw Unsupported{"the volume integrals do not visit every element (sub-pattern)"};
-                }
+                check_full_pattern(V, Th);
                 DevSpace &D = device_space(Vh);
-
-                // --- the GPU path proper
-                ffcuda_pattern *P = nullptr;
-                ffcuda_matrix *dA = nullptr;
-                FFC(ffcuda_symbolic(D.space, &P));
-                if (ffcuda_matrix_create(P, &dA) != 0) {
-                    ffcuda_pattern_destroy(P);
-                    fail("ffcuda_matrix_create");
-                }
                 int n = 0;
                 int64_t nnz = 0;
-                int rc = ffcuda_pattern_info(P, &n, &nnz);
-                // volume integrals first, then the boundary ones (Robin terms) on top; the sum does not depend on the order
-                // the varf lists them in beyond round-off
-                bool first = true;
-                for (int border = 0; border < 2; ++border)
-                    for (size_t i = 0; i < V.bil.size() && !rc; ++i) {
-                        const BilinearItem &B = V.bil[i];
-                        if ((int)B.border != border) continue;
-                        rc = (border ? ffcuda_assemble_bilinear_boundary : ffcuda_assemble_bilinear)(
-                            dA, D.space, (int)B.terms.size(), B.terms.data(), (int)B.q.w.size(), B.q.pts.data(), B.q.w.data(),
-                            (int)B.reg.labels.size(), B.reg.all ? nullptr : B.reg.labels.data(), first ? 0 : 1);
-                        first = false;
-                    }
-                std::vector<int32_t> rowptr, colind;
-                std::vector<double> vals;
-                if (!rc) {
-                    try {
-                        apply_bcs(D, V, dA, nullptr, ds.tgv);
-                    } catch (...) {
-                        ffcuda_matrix_destroy(dA);
-                        ffcuda_pattern_destroy(P);
-                        throw;
-                    }
-                    rowptr.resize((size_t)n + 1);
-                    if (ds.sym) { // half storage: FreeFEM keeps the entries (i, j <= i); the device matrix stays full
-                        rc = ffcuda_pattern_lower_nnz(P, &nnz);
-                        colind.resize((size_t)nnz);
-                        vals.resize((size_t)nnz);
-                        rc = rc || ffcuda_pattern_download_lower(P, rowptr.data(), colind.data()) ||
-                             ffcuda_matrix_download_lower(dA, vals.data());
-                    } else {
-                        colind.resize((size_t)nnz);
-                        vals.resize((size_t)nnz);
-                        rc = ffcuda_pattern_download(P, rowptr.data(), colind.data()) || ffcuda_matrix_download(dA, vals.data());
-                    }
-                }
-                if (rc) {
-                    ffcuda_matrix_destroy(dA);
-                    ffcuda_pattern_destroy(P);
-                    fail("assembling the matrix");
-                }
+                Resident res{nullptr, nullptr};
+                MatriceMorse<double> *M = gpu_matrix(D, V, ds, res, n, nnz);
                 // --- hand the result to FreeFEM as its own MatriceMorse (problem.hpp:1678-1693)
                 WhereStackOfPtr2Free(stack) = new StackOfPtr2Free(stack);
                 Matrice_Creuse<double> &A(*GetAny<Matrice_Creuse<double> *>((*this->a)(stack)));
@@ -621,11 +687,9 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
                 A.A = 0;
                 A.Uh = Vh;
                 A.Vh = Vh;
-                MatriceMorse<double> *M = new MatriceMorse<double>(n, n, 0, 0);
-                M->set(n, n, ds.sym ? 1 : 0, (size_t)nnz, rowptr.data(), colind.data(), vals.data(), 0, 1); // copies, rebuilds the hash
                 A.A.master(M);
                 drop_resident(); // at most one matrix waits for its solver
-                g_resident[(const void *)static_cast<HashMatrix<int, double> *>(M)] = Resident{dA, P}; // stays on the device for the solver
+                g_resident[(const void *)static_cast<HashMatrix<int, double> *>(M)] = res; // stays on the device for the solver
                 A.pHM()->half = ds.sym;
                 SetSolver(stack, false, *A.A, ds);
                 if (g_verbose) cout << "  -- ffcuda: matrix " << n << " x " << n << ", nnz " << nnz << " assembled on the GPU" << endl;
@@ -673,31 +737,8 @@ struct CudaRhsOp : public OpArraytoLinearForm<double, MMesh, v_fes> {
                 }
                 KN_<double> xx(px ? *(KN_<double> *)px : GetAny<KN_<double>>((*this->x)(stack)));
                 if (xx.N() != n) ExecError("ffcuda: array and fespace sizes differ in b = varf(0,Vh)");
-                ffcuda_vec *db = nullptr;
-                FFC(ffcuda_vec_create(context(), (int)n, &db));
-                int rc = 0;
-                bool first = true;
-                for (int border = 0; border < 2; ++border)
-                    for (size_t i = 0; i < V.lin.size() && !rc; ++i) {
-                        const LinearItem &L = V.lin[i];
-                        if ((int)L.border != border) continue;
-                        rc = (border ? ffcuda_assemble_linear_boundary : ffcuda_assemble_linear)(
-                            db, D.space, (int)L.terms.size(), L.terms.data(), (int)L.q.w.size(), L.q.pts.data(), L.q.w.data(),
-                            (int)L.reg.labels.size(), L.reg.all ? nullptr : L.reg.labels.data(), first ? 0 : 1);
-                        first = false;
-                    }
-                std::vector<double> host((size_t)n);
-                if (!rc) {
-                    try {
-                        apply_bcs(D, V, nullptr, db, tgv);
-                    } catch (...) {
-                        ffcuda_vec_destroy(db);
-                        throw;
-                    }
-                    rc = ffcuda_vec_download(db, host.data());
-                }
-                ffcuda_vec_destroy(db);
-                if (rc) fail("assembling the right-hand side");
+                std::vector<double> host;
+                gpu_rhs(D, V, tgv, false, n, host, nullptr);
                 for (long i = 0; i < n; ++i) xx[i] = host[i]; // KN_ may be strided
                 if (g_verbose) cout << "  -- ffcuda: right-hand side of size " << n << " assembled on the GPU" << endl;
                 return SetAny<KN_<double>>(xx);
@@ -836,6 +877,200 @@ class SolverCudaGMRES : public SolverCudaCG {
     ~SolverCudaGMRES() { delete host; }
 };
 
+// ------------------------------------------------------------------------------------------------------------
+// 5. problem / solve  (Problem::eval, fflib/problem.cpp:12198-12450; types registered at fflib/lgfem.cpp:6308-6309,
+//    keywords at :6541-6542).  `solve Poisson(u,v,solver=CG) = int3d(Th)(...) - int3d(Th)(f*v) + on(...)` builds a
+//    Problem object at parse time through TypeSolve::SetParam and runs Problem::operator() at execution time.  The
+//    plugin makes SetParam build a subclass whose operator() takes the GPU path for what it claims (one real P1/P2
+//    space, same unknown and test space, items read_varf accepts) and calls Problem::operator() for everything else.
+//    Steps of eval kept here: solver parameters, spaces of the unknowns, Data<FESpace> bookkeeping on the stack
+//    (matrix kept across calls when init= says so), X initialised from the previous solution (InitProblem :11826-11902,
+//    Nb = 1), A and B assembled (on the device), B = -B, |B_i| < 1e-60 -> 0, Dirichlet rows (AssembleBC), DefSolver,
+//    A.Solve(X, B), solution handed to the FE function (DispatchSolution :12086-12101, Nb = 1).
+// ------------------------------------------------------------------------------------------------------------
+template <class T>
+struct FeTypes;
+template <>
+struct FeTypes<Mesh> {
+    typedef FESpace FES;
+    typedef v_fes vfes;
+};
+template <>
+struct FeTypes<Mesh3> {
+    typedef FESpace3 FES;
+    typedef v_fes3 vfes;
+};
+
+// dimension of a real problem as dimProblem finds it (fflib/problem.cpp:13118): 2, 3, or 0 for what is not claimed here
+int claimed_dim(const ListOfId &l)
+{
+    typedef pair<FEbase<double, v_fes> *, int> pfer_;
+    typedef pair<FEbase<double, v_fes3> *, int> pf3r_;
+    int dim = 0;
+    bool other = false;
+    auto look = [&](const UnId &idi) {
+        C_F0 c = ::Find(idi.id);
+        if (BCastTo<pfer_>(c)) {
+            if (dim == 3) other = true;
+            dim = 2;
+        } else if (BCastTo<pf3r_>(c)) {
+            if (dim == 2) other = true;
+            dim = 3;
+        } else
+            other = true;
+    };
+    for (size_t i = 0; i < l.size(); ++i)
+        if (l[i].e == 0) { // (named parameters carry an expression)
+            if (l[i].array) {
+                const ListOfId &a = *l[i].array;
+                for (size_t j = 0; j < a.size(); ++j)
+                    if (a[j].r == 0 && a[j].re == 0 && a[j].array == 0) look(a[j]);
+                    else other = true;
+            } else
+                look(l[i]);
+        }
+    return other ? 0 : dim;
+}
+
+template <class Base>
+struct CudaProblem : public Base {
+    int cdim;
+    CudaProblem(const C_args *ca, const ListOfId &l, size_t &top) : Base(ca, l, top), cdim(claimed_dim(l)) {}
+
+    template <class MeshT>
+    AnyType run(Stack stack, Problem::Data<typename FeTypes<MeshT>::FES> *data) const
+    {
+        typedef typename FeTypes<MeshT>::FES FES;
+        typedef typename FeTypes<MeshT>::vfes vfes;
+        typedef pair<FEbase<double, vfes> *, int> pfer_;
+        if (this->nargs[0]) throw Unsupported{"save= parameter"};
+        if (this->nargs[1]) throw Unsupported{"cadna= parameter"};
+        const int nvar = (int)this->var.size();
+        if (nvar < 2 || nvar % 2) throw Unsupported{"odd number of unknown / test functions"};
+        std::vector<pfer_> u_hh((size_t)nvar);
+        for (int i = 0; i < nvar; ++i) u_hh[i] = GetAny<pfer_>((*(this->var[i]))(stack));
+        // one fespace for the unknowns, one for the test functions: components 0..N-1 of the same FE function each
+        const int N = nvar / 2;
+        for (int i = 0; i < nvar; ++i) {
+            if (u_hh[i].second != i % N) throw Unsupported{"unknowns from several fespaces"};
+            if (u_hh[i].first != u_hh[i - i % N].first) throw Unsupported{"unknowns from several FE functions"};
+        }
+        FEbase<double, vfes> *uh = u_hh[0].first, *vh = u_hh[N].first;
+        const FES *Uhp = uh->newVh(), *Vhp = vh->newVh();
+        if (!Uhp || !Vhp) throw Unsupported{"null fespace"};
+        if (Uhp != Vhp) throw Unsupported{"test and unknown spaces differ"};
+        if (Uhp->N != N) throw Unsupported{"number of unknowns differs from the components of the fespace"};
+        const MeshT &Th = Uhp->Th;
+        if (!isSameMesh(this->op->largs, &Th, &Th, stack)) throw Unsupported{"integrals on different meshes"};
+        // everything that may be refused is read before anything is changed
+        Varf VA = read_varf(stack, this->op->largs, Th, N, true);
+        Varf VB = read_varf(stack, this->op->largs, Th, N, false);
+        if (VB.other_rhs_items) throw Unsupported{"array / matrix-vector items in the problem"};
+        check_full_pattern(VA, Th);
+        if (data->pTh == &Th && (const FES *)data->Uh != Uhp) throw Unsupported{"the problem was set up on another fespace of this mesh"};
+        DevSpace &D = device_space(*Uhp);
+
+        MeshPoint *mps = MeshPointStack(stack), mp = *mps;
+        Data_Sparse_Solver ds;
+        const int np = 3 + NB_NAME_PARM_MAT; // Problem::n_name_param - NB_NAME_PARM_HMAT (fflib/problem.hpp:501)
+        SetEnd_Data_Sparse_Solver<double>(stack, ds, this->nargs, np);
+        if (ds.tgv != ds.tgv) throw Unsupported{"tgv is NaN"};
+        WhereStackOfPtr2Free(stack) = new StackOfPtr2Free(stack);
+        if (&Th != data->pTh) {
+            ds.initmat = true;
+            data->pTh = &Th;
+            data->Uh = Uhp;
+            data->Vh = Vhp;
+        }
+        const FES &Uh(*data->Uh);
+        const long n = Uh.NbOfDF;
+        // X: the previous solution when the FE function lives on this mesh (InitProblem, Nb = 1)
+        KN<double> *X = new KN<double>(n);
+        if (!(const FES *)uh->Vh || &uh->Vh->Th != &Th || !uh->x() || uh->x()->N() != n) *X = 0.;
+        else *X = *uh->x();
+        KN<double> *B = nullptr;
+        try {
+            if (ds.initmat) {
+                int nn = 0;
+                int64_t nnz = 0;
+                Resident res{nullptr, nullptr};
+                MatriceMorse<double> *M = gpu_matrix(D, VA, ds, res, nn, nnz);
+                data->AR.master(M);
+                drop_resident();
+                g_resident[(const void *)static_cast<HashMatrix<int, double> *>(M)] = res;
+                if (g_verbose) cout << "  -- ffcuda: problem matrix " << nn << " x " << nn << ", nnz " << nnz << " assembled on the GPU" << endl;
+            }
+            if (!data->AR) throw Unsupported{"init= without a matrix"};
+            MatriceCreuse<double> &A(*data->AR);
+            std::vector<double> hb;
+            gpu_rhs(D, VB, ds.tgv, true, n, hb, VB.bc.empty() ? nullptr : (double *)*X);
+            B = new KN<double>(n);
+            for (long i = 0; i < n; ++i) (*B)[i] = std::abs(hb[i]) < 1.e-60 ? 0. : hb[i];
+            dynamic_cast<HashMatrix<int, double> *>(&A)->half = ds.sym;
+            if (ds.initmat) DefSolver(stack, A, ds);
+            if (g_verbose) cout << "  -- ffcuda: problem right-hand side of size " << n << " assembled on the GPU" << endl;
+            A.Solve(*X, *B);
+        } catch (const Unsupported &) {
+            delete X;
+            delete B;
+            throw;
+        } catch (...) {
+            if (verbosity) cout << " catch an erreur in  solve  =>  set  sol = 0 !!!!!!! " << endl;
+            *X = 0.;
+            *uh = X;
+            delete B;
+            throw;
+        }
+        *uh = X; // DispatchSolution, Nb = 1: the FE function owns X now
+        delete B;
+        if (verbosity) cout << "  -- Solve : \n          min " << uh->x()->min() << "  max " << uh->x()->max() << endl;
+        *mps = mp;
+        return SetAny<const Problem *>(this);
+    }
+
+    AnyType operator()(Stack stack) const
+    {
+        if (this->complextype || this->VF || !cdim) {
+            notice("problem / solve", this->complextype ? "complex problem" : this->VF ? "discontinuous-Galerkin operators" : "not a real 2-D / 3-D problem");
+            return Problem::operator()(stack);
+        }
+        try {
+            if (cdim == 2) return run<Mesh>(stack, this->dataptr(stack));
+            return run<Mesh3>(stack, this->dataptr3(stack));
+        } catch (const Unsupported &u) {
+            notice("problem / solve", u.why);
+            return Problem::operator()(stack);
+        }
+    }
+};
+
+// TypeSolve (fflib/problem.hpp:1040-1094) with SetParam building the subclass above.  The `solve` and `problem` keywords
+// hold pointers to the type objects created at start-up (zzzfff->AddF, lgfem.cpp:6541-6542) and mylex refuses a second
+// registration of a keyword, so those very objects are re-pointed to this class: it adds no data member and overrides
+// one virtual function, the objects keep their addresses and contents.
+template <bool exec_init, class P>
+struct CudaTypeSolve : public TypeSolve<exec_init, P> {
+    Type_Expr SetParam(const C_F0 &c, const ListOfId *l, size_t &top) const
+    {
+        if (c.left() != atype<const C_args *>()) CompileError(" Problem  a(...) = invalid type ", c.left());
+        const C_args *ca = dynamic_cast<const C_args *>(c.LeftValue());
+        P *pb = new CudaProblem<P>(ca, *l, top);
+        return Type_Expr(this, pb);
+    }
+};
+template <bool exec_init, class P>
+void repoint_solve_type()
+{
+    static_assert(sizeof(CudaTypeSolve<exec_init, P>) == sizeof(TypeSolve<exec_init, P>), "CudaTypeSolve must not add data");
+    basicForEachType *t = map_type[typeid(const P *).name()];
+    if (!t || !dynamic_cast<TypeSolve<exec_init, P> *>(t)) {
+        cerr << " ffcuda: the type of problem / solve is not the one expected; they stay with FreeFEM" << endl;
+        return;
+    }
+    static CudaTypeSolve<exec_init, P> model;
+    *reinterpret_cast<void **>(t) = *reinterpret_cast<void **>(&model); // the virtual table pointer
+}
+
 } // namespace
 
 static void Load_Init()
@@ -860,6 +1095,11 @@ static void Load_Init()
     TheFFSolver<int, double>::ChangeSolver("CG", "FFCUDACG");
     addsolver<SolverCudaGMRES>("FFCUDAGMRES", 10, 0);
     TheFFSolver<int, double>::ChangeSolver("GMRES", "FFCUDAGMRES");
+    // 4. problem / solve
+    if (!env_on("FFCUDA_NO_PROBLEM")) {
+        repoint_solve_type<false, Problem>();
+        repoint_solve_type<true, Solve>();
+    }
 }
 
 LOADFUNC(Load_Init)

@@ -225,3 +225,98 @@ def test_plugin_has_no_cpu_fallback():
     rc, out, _ = run_ff(CLAIMED, {}, want_fail=True)
     assert rc != 0
     assert "no CPU fallback" in out and not re.search(r"^NNZ \d", out, re.M)
+
+
+# problem / solve statements (Problem::eval, fflib/problem.cpp:12198-12450): the tutorial shape `solve Poisson(u,v,...) = a - l + on`
+SOLVE_DUMP = '{ ofstream f("u.txt"); f.precision(17); for(int i=0;i<UU[].n;++i) f << UU[][i] << endl; }\n'
+SOLVE_CASES = {
+    # examples/tutorial/Laplace.edp shape
+    "laplace2d_p1": """mesh Th = square(24,19);
+fespace Vh(Th,P1); Vh u,v;
+solve Poisson(u,v,solver=CG,eps=1e-14) = int2d(Th)(dx(u)*dx(v)+dy(u)*dy(v)) - int2d(Th)(1.*v) + on(1,2,3,4,u=0);
+""",
+    "poisson3d_p2_robin_neumann": f"""mesh3 Th = cube(4,3,4,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)]);
+fespace Vh(Th,P2); Vh u,v;
+solve Pb(u,v,solver=CG,eps=1e-14) = int3d(Th)({LAP3}) + int2d(Th,2)(2.*u*v) - int3d(Th)(1.*v) - int2d(Th,3)(0.5*v) + on(1,u=1);
+""",
+    "lame3d_p1_vector": f"""{LAME_PRE}
+mesh3 Th = cube(3,4,3);
+fespace Vh(Th,[P1,P1,P1]); Vh [u1,u2,u3],[v1,v2,v3];
+solve Lame([u1,u2,u3],[v1,v2,v3],solver=CG,eps=1e-14) = int3d(Th)({LAME}) - int3d(Th)(-0.05*v3) + on(1,u1=0,u2=0,u3=0);
+""",
+    "problem_reused_init": f"""mesh3 Th = cube(5,4,5);
+fespace Vh(Th,P1); Vh u=0,v;
+problem Pb(u,v,solver=CG,eps=1e-14,init=1) = int3d(Th)(u*v+{LAP3}) - int3d(Th)(1.*v) + on(1,2,u=0.5);
+problem Pa(u,v,solver=CG,eps=1e-14) = int3d(Th)(3.*u*v+{LAP3}) - int3d(Th)(2.*v) + on(1,2,u=0.5);
+for (int it = 0; it < 3; ++it) {{ Pa; }}
+""",
+    "default_solver": """mesh Th = square(9,8);
+fespace Vh(Th,P2); Vh u,v;
+solve Pb(u,v) = int2d(Th)(dx(u)*dx(v)+dy(u)*dy(v)+u*v) - int2d(Th)(1.*v) - int1d(Th,2)(0.3*v) + on(4,u=0);
+""",
+    "convdiff2d_gmres": """mesh Th = square(12,11);
+fespace Vh(Th,P1); Vh u,v;
+solve Pb(u,v,solver=GMRES,eps=1e-14) = int2d(Th)(dx(u)*dx(v)+dy(u)*dy(v)+6.*dx(u)*v+2.*dy(u)*v) - int2d(Th)(1.*v) + on(1,2,3,4,u=0);
+""",
+}
+
+
+def run_solve(body, u0, env_extra):
+    src = 'load "msh3"\nload "ffcuda"\n' + body + SOLVE_DUMP.replace("UU", u0)
+    with tempfile.TemporaryDirectory() as td:
+        with open(os.path.join(td, "case.edp"), "w") as f:
+            f.write(src)
+        env = dict(os.environ, FF_LOADPATH=LIBDIR, **env_extra)
+        r = subprocess.run([FF, "-nw", "-v", "1", "case.edp"], capture_output=True, text=True, cwd=td, env=env, timeout=600)
+        out = r.stdout + r.stderr
+        u = np.loadtxt(os.path.join(td, "u.txt"), ndmin=1) if os.path.exists(os.path.join(td, "u.txt")) else None
+        return r.returncode, out, u
+
+
+@needs_ff
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(SOLVE_CASES))
+def test_plugin_problem_solve_matches_freefem(name):
+    body = SOLVE_CASES[name]
+    u0 = "u1" if "u1" in body else "u"
+    rc, out, gpu = run_solve(body, u0, {"FFCUDA_STRICT": "1", "FFCUDA_VERBOSE": "1"})
+    assert rc == 0, out[-3000:]
+    assert "problem matrix" in out and "problem right-hand side" in out and "assembled on the GPU" in out
+    if "solver=CG" in body:
+        assert "GC (ffcuda)" in out
+    if "solver=GMRES" in body:
+        assert "fgmres (ffcuda)" in out
+    if name == "problem_reused_init":   # Pa rebuilds its matrix at every call (no init=): 3 matrices, 3 right-hand sides
+        assert out.count("problem matrix") == 3 and out.count("problem right-hand side") == 3
+    rc, out_cpu, cpu = run_solve(body, u0, {"FFCUDA_DISABLE": "1"})
+    assert rc == 0 and "(ffcuda)" not in out_cpu and "assembled on the GPU" not in out_cpu
+    assert np.max(np.abs(gpu - cpu)) <= 1e-11 * np.abs(cpu).max()
+
+
+SOLVE_FALLBACK = """mesh Th = square(10,9);
+fespace Vh(Th,P1); Vh u,v;
+solve Poisson(u,v,solver=LU) = int2d(Th)(dx(u)*dx(v)+dy(u)*dy(v)) - int2d(Th)(x*v) + on(1,2,3,4,u=0);
+fespace Wh(Th,P1dc); Wh w,ww;
+solve Proj(w,ww) = int2d(Th)(w*ww) - int2d(Th)(u*ww);
+cout << "WW " << w[].sum << endl;
+"""
+
+
+@needs_ff
+def test_plugin_problem_solve_left_to_freefem_when_not_claimed():
+    """the re-pointed problem/solve types hand everything they do not claim (x-dependent data, other elements) to
+    Problem::eval unchanged: same numbers with the plugin loaded (no GPU needed) and with the plugin disabled."""
+    rc, out, u = run_solve(SOLVE_FALLBACK, "u", {})
+    assert rc == 0, out[-3000:]
+    assert out.count("problem / solve left to FreeFEM") >= 2
+    rc, out2, u2 = run_solve(SOLVE_FALLBACK, "u", {"FFCUDA_DISABLE": "1"})
+    assert rc == 0 and np.array_equal(u, u2)
+    assert re.search(r"^WW (\S+)", out, re.M).group(1) == re.search(r"^WW (\S+)", out2, re.M).group(1)
+    rc, out, _ = run_solve(SOLVE_CASES["laplace2d_p1"], "u", {}) if not _has_cuda() else (1, "no CPU fallback", None)
+    assert rc != 0 and "no CPU fallback" in out
+
+
+def _has_cuda():
+    import torch
+
+    return torch.cuda.is_available()
