@@ -1414,3 +1414,101 @@ extern "C" int ffcuda_assemble_bilinear_boundary(ffcuda_matrix *A, ffcuda_space 
     });
     FF_API_END(s ? s->ctx : nullptr)
 }
+
+// ----------------------------------------------------------------------------------------------------
+// Linear forms with data that depend on the mesh point: int3d(Th)(f(x,y,z) v), int2d(Th)(uold v / dt), ...
+// Element_rhs (fflib/problem.cpp:7839-7985) evaluates the coefficient expression at every quadrature node of every
+// element; the caller (the plugin, through FreeFEM's own expression evaluator) hands exactly those values over:
+// fq[(c * nt + k) * nq + q] = coefficient of v_c at node q of element k (0 for elements outside the integral's region).
+// Value terms only:  b[dof(node a of k, c)] += |K| sum_q w_q fq[c][k][q] phi_a(q).
+// Two passes, no atomics: per element the nloc x ncomp weighted sums (coalesced over elements), then the row-owner
+// gather over the node -> element incidence of the space (fixed order: lists are sorted by element).
+// ----------------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void k_rhs_qvalues_elem(int nt, const int32_t *__restrict__ conn, const double *__restrict__ xyz, int vstride, int nloc, int nc,
+                                   int nq, const double *__restrict__ wphi /* [q][a] = w_q phi_a(q) */, const double *__restrict__ fq,
+                                   double *__restrict__ G /* [k][a][c] */)
+{
+    extern __shared__ double swphi[];
+    for (int i = threadIdx.x; i < nq * nloc; i += blockDim.x) swphi[i] = wphi[i];
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nt) return;
+    double X[DIM + 1][DIM], N[DIM + 1][DIM], det;
+    const int32_t *K = conn + (size_t)(DIM + 1) * k;
+#pragma unroll
+    for (int a = 0; a <= DIM; ++a) {
+        const double *P = xyz + (size_t)K[a] * vstride;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) X[a][d] = P[d];
+    }
+    p1_normals<DIM>(X, N, det);
+    const double mes = det * (DIM == 3 ? 1.0 / 6.0 : 0.5);
+    for (int c = 0; c < nc; ++c) {
+        const double *f = fq + ((size_t)c * nt + k) * nq;
+        for (int a = 0; a < nloc; ++a) {
+            double s = 0.0;
+            for (int q = 0; q < nq; ++q) s = fma(swphi[q * nloc + a], f[q], s);
+            G[((size_t)k * nloc + a) * nc + c] = mes * s;
+        }
+    }
+}
+__global__ void k_rhs_qvalues_gather(int nrows, const IncView V, int nloc, int nc, const double *__restrict__ G, double *__restrict__ b,
+                                     int accumulate)
+{
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    const int cnt = V.cnt[row];
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int e = 0; e < cnt; ++e) {
+        const uint32_t rec = V.inc[V.idx(row, e)];
+        const double *g = G + ((size_t)(rec >> 4) * nloc + (rec & 15u)) * nc;
+        for (int c = 0; c < nc; ++c) s[c] += g[c];
+    }
+    for (int c = 0; c < nc; ++c) {
+        double *dst = b + (size_t)row * nc + c;
+        *dst = accumulate ? *dst + s[c] : s[c];
+    }
+}
+
+extern "C" int ffcuda_assemble_linear_qvalues(ffcuda_vec *b, ffcuda_space *s, int nq, const double *qpts, const double *qw,
+                                              const double *fq, int accumulate)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(b && s && fq, "ffcuda_assemble_linear_qvalues: null argument");
+    FF_REQUIRE(nq > 0 && nq <= 256 && qpts && qw, "quadrature rule missing (or more than 256 nodes)");
+    ffcuda_ctx *ctx = s->ctx;
+    ff_enter(ctx);
+    ff_build_incidence(s);
+    ffcuda_mesh *m = s->mesh;
+    FF_REQUIRE(!m->distributed, "ffcuda_assemble_linear_qvalues: single-GPU meshes only");
+    FF_REQUIRE(b->n >= s->nnodes_owned * s->ncomp, "right-hand side vector too short");
+    const int dim = m->dim, nloc = s->nloc, nc = s->ncomp, nt = m->nt;
+    std::vector<double> wphi((size_t)nq * nloc);
+    for (int q = 0; q < nq; ++q) {
+        double B[10][4];
+        ref_basis(dim, s->order, qpts + (size_t)q * dim, B);
+        for (int a = 0; a < nloc; ++a) wphi[(size_t)q * nloc + a] = qw[q] * B[a][0];
+    }
+    cudaStream_t st = ctx->stream;
+    DBuf<double> dW, dF, G;
+    dW.alloc(wphi.size());
+    dF.alloc((size_t)nc * nt * nq);
+    G.alloc((size_t)nt * nloc * nc);
+    FF_CUDA(cudaMemcpyAsync(dW.p, wphi.data(), dW.bytes(), cudaMemcpyHostToDevice, st));
+    FF_CUDA(cudaMemcpyAsync(dF.p, fq, dF.bytes(), cudaMemcpyHostToDevice, st));
+    const size_t shmem = wphi.size() * sizeof(double);
+    ff_launch(ctx, "rhs_qvalues_elem", [&] {
+        if (dim == 3)
+            k_rhs_qvalues_elem<3><<<ff_blocks(nt, 128), 128, shmem, st>>>(nt, m->conn.p, m->xyz.p, m->vstride, nloc, nc, nq, dW.p, dF.p, G.p);
+        else
+            k_rhs_qvalues_elem<2><<<ff_blocks(nt, 128), 128, shmem, st>>>(nt, m->conn.p, m->xyz.p, m->vstride, nloc, nc, nq, dW.p, dF.p, G.p);
+    });
+    const int nrows = s->nnodes_owned;
+    const IncView V = ff_view(s->incidence);
+    ff_launch(ctx, "rhs_qvalues_gather", [&] {
+        k_rhs_qvalues_gather<<<ff_blocks(nrows, 128), 128, 0, st>>>(nrows, V, nloc, nc, G.p, b->d.p, accumulate);
+    });
+    FF_CUDA(cudaStreamSynchronize(st)); // fq is the caller's pageable memory
+    FF_API_END(s ? s->ctx : nullptr)
+}

@@ -387,8 +387,13 @@ struct BilinearItem {
     Region reg;
     bool border = false; // integral over the boundary elements with the labels of reg (Robin terms)
 };
+struct QTerm { // value term whose coefficient depends on the mesh point: evaluated at the quadrature nodes by FreeFEM's evaluator
+    int vcomp;
+    C_F0 coef;
+};
 struct LinearItem {
     std::vector<ffcuda_lterm> terms;
+    std::vector<QTerm> qterms;
     Quad q;
     Region reg;
     bool border = false; // Neumann / traction data
@@ -450,6 +455,15 @@ Varf read_varf(Stack stack, const list<C_F0> &largs, const MeshT &Th, int ncomp,
                 t.vop = check_op(op.v[k].first.second, dim);
                 if (t.vcomp < 0 || t.vcomp >= ncomp) throw Unsupported{"component out of range"};
                 if (L.border && t.vop != op_id) throw Unsupported{"derivatives in a boundary integral"};
+                if (!op.v[k].second.LeftValue()->MeshIndependent()) {
+                    // f(x,y,z) v, uold v / dt, ...: the values Element_rhs would compute go to the device as a table
+                    if (L.border) throw Unsupported{"boundary integral whose coefficient depends on the mesh point"};
+                    if (t.vop != op_id) throw Unsupported{"derivative of the test function times a coefficient that depends on the mesh point"};
+                    if (op.v[k].second.left() != atype<double>() && op.v[k].second.left() != atype<long>())
+                        throw Unsupported{"coefficient is not real"};
+                    L.qterms.push_back(QTerm{t.vcomp, op.v[k].second});
+                    continue;
+                }
                 t.coef = constant_coef(stack, op.v[k].second);
                 L.terms.push_back(t);
             }
@@ -597,7 +611,48 @@ MatriceMorse<double> *gpu_matrix(DevSpace &D, const Varf &V, const Data_Sparse_S
 // the GPU path proper for a right-hand side: every linear item (volume integrals, then boundary integrals), an optional
 // change of sign (problem/solve: a(u,v) - l(v) = 0), Dirichlet values; x0 (optional, size n) gets x0[d] = g(d) as
 // AssembleBC does for the initial guess
-void gpu_rhs(DevSpace &D, const Varf &V, double tgv, bool negate, long n, std::vector<double> &host, double *x0)
+// values of the mesh-point dependent coefficients of a linear item at every quadrature node of every element, obtained the
+// way Element_rhs obtains them (fflib/problem.cpp:7876-7884, :7951-7960): MeshPointStack set to the node, expression
+// evaluated.  fq[(c * nt + k) * nq + q], summed over the terms of component c; elements outside the region stay 0.
+inline R2 ref_point(const Mesh *, const double *p) { return R2(p[0], p[1]); }
+inline R3 ref_point(const Mesh3 *, const double *p) { return R3(p[0], p[1], p[2]); }
+template <class FESpaceT>
+std::vector<double> eval_qvalues(Stack stack, const FESpaceT &Vh, const LinearItem &L, bool negate)
+{
+    typedef typename FESpaceT::Mesh MeshT;
+    typedef typename FESpaceT::FElement FElementT;
+    const MeshT &Th = Vh.Th;
+    const int dim = MeshDim<MeshT>::d, nq = (int)L.q.w.size(), nt = Th.nt, nc = Vh.N;
+    std::vector<double> fq((size_t)nc * nt * nq, 0.0);
+    std::set<int> labs(L.reg.labels.begin(), L.reg.labels.end());
+    MeshPoint *mps = MeshPointStack(stack), mp = *mps;
+    const double sgn = negate ? -1.0 : 1.0;
+    try {
+        for (int k = 0; k < nt; ++k) {
+            if (!L.reg.all && !labs.count(Th[k].lab)) continue;
+            const FElementT Kv(Vh[k]);
+            const typename MeshT::Element &T = Kv.T;
+            for (int q = 0; q < nq; ++q) {
+                typename MeshT::RdHat Pt(ref_point(&Th, L.q.pts.data() + (size_t)q * dim));
+                mps->set(T(Pt), Pt, Kv);
+                for (size_t t = 0; t < L.qterms.size(); ++t) {
+                    const C_F0 &c = L.qterms[t].coef;
+                    const double v = c.left() == atype<long>() ? (double)GetAny<long>(c.eval(stack)) : GetAny<double>(c.eval(stack));
+                    fq[((size_t)L.qterms[t].vcomp * nt + k) * nq + q] += sgn * v;
+                }
+            }
+        }
+    } catch (...) {
+        *mps = mp;
+        throw;
+    }
+    *mps = mp;
+    return fq;
+}
+
+template <class FESpaceT>
+void gpu_rhs(Stack stack, const FESpaceT &Vh, DevSpace &D, const Varf &V, double tgv, bool negate, long n, std::vector<double> &host,
+             double *x0)
 {
     ffcuda_vec *db = nullptr;
     FFC(ffcuda_vec_create(context(), (int)n, &db));
@@ -610,10 +665,23 @@ void gpu_rhs(DevSpace &D, const Varf &V, double tgv, bool negate, long n, std::v
             std::vector<ffcuda_lterm> terms(L.terms);
             if (negate)
                 for (size_t k = 0; k < terms.size(); ++k) terms[k].coef = -terms[k].coef;
-            rc = (border ? ffcuda_assemble_linear_boundary : ffcuda_assemble_linear)(
-                db, D.space, (int)terms.size(), terms.data(), (int)L.q.w.size(), L.q.pts.data(), L.q.w.data(),
-                (int)L.reg.labels.size(), L.reg.all ? nullptr : L.reg.labels.data(), first ? 0 : 1);
-            first = false;
+            if (!terms.empty() || L.qterms.empty()) {
+                rc = (border ? ffcuda_assemble_linear_boundary : ffcuda_assemble_linear)(
+                    db, D.space, (int)terms.size(), terms.data(), (int)L.q.w.size(), L.q.pts.data(), L.q.w.data(),
+                    (int)L.reg.labels.size(), L.reg.all ? nullptr : L.reg.labels.data(), first ? 0 : 1);
+                first = false;
+            }
+            if (!L.qterms.empty() && !rc) {
+                std::vector<double> fq;
+                try {
+                    fq = eval_qvalues(stack, Vh, L, negate);
+                } catch (...) {
+                    ffcuda_vec_destroy(db);
+                    throw;
+                }
+                rc = ffcuda_assemble_linear_qvalues(db, D.space, (int)L.q.w.size(), L.q.pts.data(), L.q.w.data(), fq.data(), first ? 0 : 1);
+                first = false;
+            }
         }
     if (first && !rc) rc = ffcuda_vec_fill(db, 0.0);
     host.resize((size_t)n);
@@ -738,7 +806,7 @@ struct CudaRhsOp : public OpArraytoLinearForm<double, MMesh, v_fes> {
                 KN_<double> xx(px ? *(KN_<double> *)px : GetAny<KN_<double>>((*this->x)(stack)));
                 if (xx.N() != n) ExecError("ffcuda: array and fespace sizes differ in b = varf(0,Vh)");
                 std::vector<double> host;
-                gpu_rhs(D, V, tgv, false, n, host, nullptr);
+                gpu_rhs(stack, Vh, D, V, tgv, false, n, host, nullptr);
                 for (long i = 0; i < n; ++i) xx[i] = host[i]; // KN_ may be strided
                 if (g_verbose) cout << "  -- ffcuda: right-hand side of size " << n << " assembled on the GPU" << endl;
                 return SetAny<KN_<double>>(xx);
@@ -1003,7 +1071,7 @@ struct CudaProblem : public Base {
             if (!data->AR) throw Unsupported{"init= without a matrix"};
             MatriceCreuse<double> &A(*data->AR);
             std::vector<double> hb;
-            gpu_rhs(D, VB, ds.tgv, true, n, hb, VB.bc.empty() ? nullptr : (double *)*X);
+            gpu_rhs(stack, Uh, D, VB, ds.tgv, true, n, hb, VB.bc.empty() ? nullptr : (double *)*X);
             B = new KN<double>(n);
             for (long i = 0; i < n; ++i) (*B)[i] = std::abs(hb[i]) < 1.e-60 ? 0. : hb[i];
             dynamic_cast<HashMatrix<int, double> *>(&A)->half = ds.sym;

@@ -173,6 +173,12 @@ int ffcuda_assemble_linear(ffcuda_vec *b, ffcuda_space *s, int nterms, const ffc
 int ffcuda_assemble_linear_boundary(ffcuda_vec *b, ffcuda_space *s, int nterms, const ffcuda_lterm *terms,
                                     int nq, const double *qpts, const double *qw,
                                     int nlab, const int32_t *labels, int accumulate);
+/* b (+)= volume integral of a linear form whose data depend on the mesh point (f(x,y,z) v, uold v / dt, ...): Element_rhs
+ * (fflib/problem.cpp:7839-7985) evaluates the coefficient at every quadrature node of every element, and the caller hands
+ * those very values over: fq[(c * nt + k) * nq + q] (HOST array) = coefficient of the value of v_c at node q of element k,
+ * summed over the terms, 0 where the element is outside the integral's region.  Value terms only. */
+int ffcuda_assemble_linear_qvalues(ffcuda_vec *b, ffcuda_space *s, int nq, const double *qpts, const double *qw,
+                                   const double *fq, int accumulate);
 /* A (+)= boundary integrals int2d(Th3, labels)(c u v) / int1d(Th, labels)(c u v) of a bilinear form (Robin terms):
  * the border loop of AssembleBilinearForm, fflib/problem.cpp:1317-1326 (3-D), :1030-1040 (2-D), with Element_Op's border
  * branch :6518-6560 / :6216-6290.  Value terms only (uop = vop = id), constant c.  The couples FreeFEM creates for a border

@@ -73,6 +73,10 @@ void ffo_assemble_rhs(int dim, int nv, const double *xyz, int nt, const int32_t 
                       int order, int ncomp, const int32_t *elem2node, int ndof,
                       int nterms, const ffo_lterm *terms, int nq, const double *qpts, const double *qw,
                       int nlab, const int32_t *labels, double *b);
+/* linear form with data depending on the mesh point (Element_rhs, problem.cpp:7917-7985): fq[(c*nt + k)*nq + q] = value of
+ * the coefficient of v_c at quadrature node q of element k; ADDS to b */
+void ffo_assemble_rhs_qvalues(int dim, const double *xyz, int nt, const int32_t *conn, int order, int ncomp,
+                              const int32_t *elem2node, int nq, const double *qpts, const double *qw, const double *fq, double *b);
 /* boundary integrals of a linear form (Element_rhs on border elements, problem.cpp:8439-8587); ADDS to b.
  * qpts: nq x (dim-1) reference coordinates on the face / edge */
 void ffo_assemble_rhs_boundary(int dim, const double *xyz, const int32_t *conn, int order, int ncomp,

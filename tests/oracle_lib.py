@@ -147,6 +147,25 @@ def assemble_rhs(mesh, order, ncomp, elem2node, ndof, terms, qpts, qw, labels=No
     return b
 
 
+def quad_points_xyz(mesh, qpts):
+    """physical coordinates of the quadrature nodes of every element: (nt, nq, dim)"""
+    xyz, conn = _f64(mesh["xyz"]), _i32(mesh["conn"])
+    qpts = _f64(qpts)
+    lam = np.concatenate([1.0 - qpts.sum(axis=1, keepdims=True), qpts], axis=1)      # (nq, dim+1) barycentric
+    return np.einsum("qa,kad->kqd", lam, xyz[conn])
+
+
+def assemble_rhs_qvalues(mesh, order, ncomp, elem2node, b, qpts, qw, fq):
+    """adds int(f v) with f given at the quadrature nodes, fq[c, k, q], to b (returns a copy)"""
+    dim = mesh["dim"]
+    xyz, conn = _f64(mesh["xyz"]), _i32(mesh["conn"])
+    e2n = _i32(elem2node)
+    b, qpts, qw, fq = _f64(b).copy(), _f64(qpts), _f64(qw), _f64(fq)
+    lib().ffo_assemble_rhs_qvalues(dim, _p(xyz, C.c_double), conn.shape[0], _p(conn, C.c_int32), order, ncomp, _p(e2n, C.c_int32),
+                                   len(qw), _p(qpts, C.c_double), _p(qw, C.c_double), _p(fq, C.c_double), _p(b, C.c_double))
+    return b
+
+
 def assemble_rhs_boundary(mesh, order, ncomp, elem2node, b, terms, qpts, qw, labels=None):
     """adds the boundary integrals int2d(Th3,labels)(...) / int1d(Th,labels)(...) of a linear form to b (returns a copy)"""
     dim = mesh["dim"]

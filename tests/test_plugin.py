@@ -81,6 +81,11 @@ CASES = {
                                   "on(1,2,3,4,5,6,u=0)", solver="GMRES"),
     "convdiff2d_p2_gmres": script(2, "square(7,6)", "P2", LAP2 + "+5.*dx(u)*v+u*v", "1.*v", "on(1,3,u=0)", eps="1e-14",
                                   solver="GMRES,dimKrylov=40"),
+    # right-hand side data depending on the mesh point (evaluated at the quadrature nodes by FreeFEM's evaluator, integrated on the GPU)
+    "poisson3d_p1_fxyz": script(3, "cube(5,4,6,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", "P1", LAP3, "(x*y+sin(z))*v+2.*v",
+                                "on(1,2,3,4,5,6,u=0)", eps="1e-14"),
+    "lame3d_p2_fvec": script(3, "cube(2,3,2)", "[P2,P2,P2]", LAME, "x*v1-0.05*(1+y)*v3", "on(1,u1=0,u2=0,u3=0)", pre=LAME_PRE,
+                             unk="[u1,u2,u3]", tst="[v1,v2,v3]", eps="1e-14"),
     "mass3d_lumped": script(3, "cube(3,3,3)", "P1", "u*v+0.1*(" + LAP3 + ")", "1.*v", "on(1,u=0)", intopt=",qfV=qfV1lump"),
 }
 
@@ -250,6 +255,20 @@ problem Pb(u,v,solver=CG,eps=1e-14,init=1) = int3d(Th)(u*v+{LAP3}) - int3d(Th)(1
 problem Pa(u,v,solver=CG,eps=1e-14) = int3d(Th)(3.*u*v+{LAP3}) - int3d(Th)(2.*v) + on(1,2,u=0.5);
 for (int it = 0; it < 3; ++it) {{ Pa; }}
 """,
+    # examples/tutorial/Laplace.edp as it is written there: the data is a function of x and y
+    "tutorial_laplace_fxy": """mesh Th = square(20,20);
+fespace Vh(Th,P2); Vh u,v;
+func f = x*y;
+solve Poisson(u,v,solver=CG,eps=1e-14) = int2d(Th)(dx(u)*dx(v)+dy(u)*dy(v)) - int2d(Th)(f*v) + on(1,2,3,4,u=0);
+""",
+    # idp/Heat3d.idp shape: the previous time step enters the right-hand side as an FE function
+    "heat3d_time_loop_uold": f"""mesh3 Th = cube(5,4,5);
+fespace Vh(Th,P1); Vh u=0,v,uold;
+real dt = 0.1;
+int it = 0;
+problem Heat(u,v,solver=CG,eps=1e-14,init=it) = int3d(Th)(u*v/dt+{LAP3}) - int3d(Th)(uold*v/dt) - int3d(Th)((1+x)*v) + on(1,2,u=0);
+for (it = 0; it < 4; ++it) {{ uold = u; Heat; }}
+""",
     "default_solver": """mesh Th = square(9,8);
 fespace Vh(Th,P2); Vh u,v;
 solve Pb(u,v) = int2d(Th)(dx(u)*dx(v)+dy(u)*dy(v)+u*v) - int2d(Th)(1.*v) - int1d(Th,2)(0.3*v) + on(4,u=0);
@@ -286,6 +305,8 @@ def test_plugin_problem_solve_matches_freefem(name):
         assert "GC (ffcuda)" in out
     if "solver=GMRES" in body:
         assert "fgmres (ffcuda)" in out
+    if name == "heat3d_time_loop_uold":  # init=it: the matrix is built once, the right-hand side at every step
+        assert out.count("problem matrix") == 1 and out.count("problem right-hand side") == 4
     if name == "problem_reused_init":   # Pa rebuilds its matrix at every call (no init=): 3 matrices, 3 right-hand sides
         assert out.count("problem matrix") == 3 and out.count("problem right-hand side") == 3
     rc, out_cpu, cpu = run_solve(body, u0, {"FFCUDA_DISABLE": "1"})
@@ -295,7 +316,7 @@ def test_plugin_problem_solve_matches_freefem(name):
 
 SOLVE_FALLBACK = """mesh Th = square(10,9);
 fespace Vh(Th,P1); Vh u,v;
-solve Poisson(u,v,solver=LU) = int2d(Th)(dx(u)*dx(v)+dy(u)*dy(v)) - int2d(Th)(x*v) + on(1,2,3,4,u=0);
+solve Poisson(u,v,solver=LU) = int2d(Th)((1+x)*(dx(u)*dx(v)+dy(u)*dy(v))) - int2d(Th)(x*v) + on(1,2,3,4,u=0);
 fespace Wh(Th,P1dc); Wh w,ww;
 solve Proj(w,ww) = int2d(Th)(w*ww) - int2d(Th)(u*ww);
 cout << "WW " << w[].sum << endl;
