@@ -244,14 +244,17 @@ __device__ __forceinline__ void p1_points_global(const double *__restrict__ xyz,
 // the element matrix it needs is always "row 0": N[0] is its own normal, no selection by local index.
 // FAST: scalar space, form = c grad u . grad v (+ m u v) with a symmetric quadrature rule -> a handful of constants.
 // GG: only gradient-gradient terms (no value of u or v): the coefficient contraction runs without per-term mask tests
-template <int DIM, int NC, bool FAST, bool GG>
+// EM: the form is multiplied by a coefficient that depends on the mesh point; its moments against the rule on every element
+// (emom, 24 doubles per element: sum_q w_q c_q | sum_q w_q c_q lambda_a | sum_q w_q c_q lambda_a lambda_b, k_emom below) take the
+// place of the constants F.W, F.Lh, F.Mh - exact for P1, whose gradients do not depend on the quadrature node
+template <int DIM, int NC, bool FAST, bool GG, bool EM = false>
 __global__ void __launch_bounds__(128) k_asm_p1(const double *__restrict__ xyz, const int32_t *__restrict__ conn,
                                                 const int32_t *__restrict__ elab, int nrows,
                                                 const int32_t *__restrict__ nrowptr, const IncView V,
                                                 const uint32_t *__restrict__ loc, const int32_t *__restrict__ blkvert,
                                                 const int32_t *__restrict__ blkvcnt, const uint32_t *__restrict__ pos,
                                                 double *__restrict__ vals, int S, int SV, int accumulate,
-                                                const __grid_constant__ FormParams F)
+                                                const __grid_constant__ FormParams F, const double *__restrict__ emom = nullptr)
 {
     extern __shared__ double smem_d[];
     constexpr int NV = DIM + 1;
@@ -285,7 +288,7 @@ __global__ void __launch_bounds__(128) k_asm_p1(const double *__restrict__ xyz, 
         const uint32_t *rinc = V.inc + base + lane;
         const uint32_t *rpos = pos + base + lane;
         const uint32_t *rloc = loc + base + lane;
-        const bool need_inc = !FAST || !staged || F.nlab >= 0;
+        const bool need_inc = EM || !FAST || !staged || F.nlab >= 0;
         const bool gradgrad = GG || (F.mask & 0xEEE0u) != 0, valgrad = !GG && (F.mask & 0x000Eu) != 0,
                    gradval = !GG && (F.mask & 0x1110u) != 0, valval = !GG && (F.mask & 1u) != 0;
         for (int e = 0; e < Lb; ++e) {
@@ -319,8 +322,9 @@ __global__ void __launch_bounds__(128) k_asm_p1(const double *__restrict__ xyz, 
                 }
             } else {
                 // |K| W g_0[sv] g_i[su] = (W RFAC / det) N_0[sv] N_i[su] ; |K| L g_i[su] = RFAC L N_i[su] ; |K| M = RFAC det M
-                const double sgg = gradgrad ? F.W * RFAC * __drcp_rn(det) : 0.0;
-                const double La = F.Lh[a] * RFAC;
+                const double *em = EM ? emom + (size_t)24 * k : nullptr;
+                const double sgg = gradgrad ? (EM ? em[0] : F.W) * RFAC * __drcp_rn(det) : 0.0;
+                const double La = (EM ? em[1 + a] : F.Lh[a]) * RFAC;
 #pragma unroll
                 for (int cv = 0; cv < NC; ++cv)
 #pragma unroll
@@ -348,8 +352,8 @@ __global__ void __launch_bounds__(128) k_asm_p1(const double *__restrict__ xyz, 
                             double v = wa[0] * N[i][0];
 #pragma unroll
                             for (int su = 1; su < DIM; ++su) v = fma(wa[su], N[i][su], v);
-                            if (gradval) v = fma(ca0, F.Lh[o], v);
-                            if (valval) v = fma(cm, F.Mh[a][o], v);
+                            if (gradval) v = fma(ca0, EM ? em[1 + o] : F.Lh[o], v);
+                            if (valval) v = fma(cm, EM ? em[5 + 4 * a + o] : F.Mh[a][o], v);
                             const int pb = (pw >> (8 * i)) & 255;
                             acc[cv * (NC * L) + pb * NC + cu] += v;
                         }
@@ -820,10 +824,12 @@ __global__ void __launch_bounds__(128) k_rhs_p1_lean(const double *__restrict__ 
 // host drivers
 // ----------------------------------------------------------------------------------------------------
 template <int DIM, int NC>
-static void launch_p1(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const FormParams &F, int accumulate, bool fast)
+static void launch_p1(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const FormParams &F, int accumulate, bool fast,
+                      const double *emom = nullptr)
 {
     ffcuda_pattern *P = A->pattern;
     ffcuda_mesh *m = s->mesh;
+    if (emom) fast = false; // per-element moments: the general thread-per-row kernel
     // scalar c grad u.grad v + m u v without region filter: row tiles (tiles.cu) when the space has / may build them
     if (NC == 1 && fast && F.nlab < 0 && ff_asm_p1_tiles(ctx, A, s, F.fast_cw, F.fast_md, F.fast_mo, accumulate)) return;
     ff_pattern_ensure_pos(P);
@@ -848,7 +854,9 @@ static void launch_p1(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const 
         return;
     }
     const bool gg = (F.mask & 0x111Fu) == 0 && (F.mask & 0xEEE0u) != 0;
-    auto kern = (NC == 1 && fast) ? k_asm_p1<DIM, NC, (NC == 1), false> : (gg ? k_asm_p1<DIM, NC, false, true> : k_asm_p1<DIM, NC, false, false>);
+    auto kern = emom ? (gg ? k_asm_p1<DIM, NC, false, true, true> : k_asm_p1<DIM, NC, false, false, true>)
+                     : (NC == 1 && fast) ? k_asm_p1<DIM, NC, (NC == 1), false>
+                                         : (gg ? k_asm_p1<DIM, NC, false, true> : k_asm_p1<DIM, NC, false, false>);
     FF_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     // rows are taken in whole ELL blocks of 32: the grid covers ceil(nrows/32) warps
     const int nwarps = (P->nrows_node + 31) / 32;
@@ -857,7 +865,7 @@ static void launch_p1(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const 
     ff_launch(ctx, "asm_rows_p1", [&] {
         kern<<<blocks, threads, shmem, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, P->nrows_node, P->nrowptr.p, V, I.loc.p,
                                                       I.blkvert.p, I.blkvcnt.p, reinterpret_cast<const uint32_t *>(P->pos8.p),
-                                                      A->vals.p, S, SV, accumulate, F);
+                                                      A->vals.p, S, SV, accumulate, F, emom);
     });
 }
 
@@ -902,12 +910,43 @@ static void launch_p2(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const 
 }
 
 template <int DIM>
-static void dispatch_p1(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const FormParams &F, int accumulate, bool fast)
+static void dispatch_p1(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const FormParams &F, int accumulate, bool fast,
+                        const double *emom = nullptr)
 {
     const int nc = s->ncomp;
-    if (nc == 1) launch_p1<DIM, 1>(ctx, A, s, F, accumulate, fast);
-    else if (nc == 2) launch_p1<DIM, 2>(ctx, A, s, F, accumulate, false);
-    else launch_p1<DIM, 3>(ctx, A, s, F, accumulate, false);
+    if (nc == 1) launch_p1<DIM, 1>(ctx, A, s, F, accumulate, fast, emom);
+    else if (nc == 2) launch_p1<DIM, 2>(ctx, A, s, F, accumulate, false, emom);
+    else launch_p1<DIM, 3>(ctx, A, s, F, accumulate, false, emom);
+}
+
+// moments of a coefficient given at the quadrature nodes against the rule, per element (P1): em[0] = sum_q w_q c_q,
+// em[1+a] = sum_q w_q c_q lambda_a(q), em[5+4a+b] = sum_q w_q c_q lambda_a(q) lambda_b(q); 24 doubles per element
+__global__ void k_emom(int nt, int nq, int nv, const double *__restrict__ wl /* [q][0] = w_q, [q][1+a] = lambda_a(q); stride 5 */,
+                       const double *__restrict__ cq, double *__restrict__ emom)
+{
+    extern __shared__ double swl[];
+    for (int i = threadIdx.x; i < nq * 5; i += blockDim.x) swl[i] = wl[i];
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nt) return;
+    double m[24];
+#pragma unroll
+    for (int i = 0; i < 24; ++i) m[i] = 0.0;
+    const double *c = cq + (size_t)k * nq;
+    for (int q = 0; q < nq; ++q) {
+        const double wc = swl[q * 5] * c[q];
+        m[0] += wc;
+#pragma unroll
+        for (int a = 0; a < 4; ++a) {
+            const double la = a < nv ? swl[q * 5 + 1 + a] : 0.0;
+            m[1 + a] = fma(wc, la, m[1 + a]);
+#pragma unroll
+            for (int b = 0; b < 4; ++b) m[5 + 4 * a + b] = fma(wc * la, b < nv ? swl[q * 5 + 1 + b] : 0.0, m[5 + 4 * a + b]);
+        }
+    }
+    double *o = emom + (size_t)24 * k;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) o[i] = m[i];
 }
 
 template <int DIM, typename PosT>
@@ -920,11 +959,32 @@ static void dispatch_p2(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, cons
     else launch_p2<DIM, 3, PosT>(ctx, A, s, F, Rg, pos, accumulate);
 }
 
+static int assemble_bilinear_impl(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms, int nq, const double *qpts,
+                                  const double *qw, int nlab, const int32_t *labels, int accumulate, const double *cq);
+
 extern "C" int ffcuda_assemble_bilinear(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms, int nq,
                                         const double *qpts, const double *qw, int nlab, const int32_t *labels, int accumulate)
 {
+    return assemble_bilinear_impl(A, s, nterms, terms, nq, qpts, qw, nlab, labels, accumulate, nullptr);
+}
+
+extern "C" int ffcuda_assemble_bilinear_qcoef(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms, int nq,
+                                              const double *qpts, const double *qw, const double *cq, int accumulate)
+{
+    if (!cq) {
+        ff_report_error(s ? s->ctx : nullptr, "ffcuda_assemble_bilinear_qcoef: null coefficient table");
+        return 1;
+    }
+    return assemble_bilinear_impl(A, s, nterms, terms, nq, qpts, qw, 0, nullptr, accumulate, cq);
+}
+
+static int assemble_bilinear_impl(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms, int nq, const double *qpts,
+                                  const double *qw, int nlab, const int32_t *labels, int accumulate, const double *cq)
+{
     FF_API_BEGIN
     FF_REQUIRE(A && s && A->pattern && A->pattern->space == s, "ffcuda_assemble_bilinear: matrix was not created on this space");
+    FF_REQUIRE(!cq || (s->order == 1 && !s->mesh->distributed && nq <= 256),
+               "coefficients given at the quadrature nodes: P1 spaces on one GPU only (P2 forms with such coefficients are not on the ffcuda path)");
     FF_REQUIRE(nterms >= 0 && (nterms == 0 || terms), "bad term list");
     FF_REQUIRE(nq > 0 && qpts && qw, "quadrature rule missing");
     ffcuda_ctx *ctx = s->ctx;
@@ -988,8 +1048,30 @@ extern "C" int ffcuda_assemble_bilinear(ffcuda_matrix *A, ffcuda_space *s, int n
             F.fast_md = F.C[0][0][0][0] * F.Mh[0][0] * rfac;
             F.fast_mo = F.C[0][0][0][0] * F.Mh[0][1] * rfac;
         }
-        if (dim == 3) dispatch_p1<3>(ctx, A, s, F, accumulate, fast);
-        else dispatch_p1<2>(ctx, A, s, F, accumulate, fast);
+        DBuf<double> emom;
+        if (cq) { // moments of the coefficient on every element
+            const int nt = s->mesh->nt;
+            std::vector<double> wl((size_t)nq * 5, 0.0);
+            for (int q = 0; q < nq; ++q) {
+                double B[10][4];
+                ref_basis(dim, 1, qpts + (size_t)q * dim, B);
+                wl[(size_t)q * 5] = qw[q];
+                for (int a = 0; a <= dim; ++a) wl[(size_t)q * 5 + 1 + a] = B[a][0];
+            }
+            DBuf<double> dwl, dcq;
+            dwl.alloc(wl.size());
+            dcq.alloc((size_t)nt * nq);
+            emom.alloc((size_t)nt * 24);
+            FF_CUDA(cudaMemcpyAsync(dwl.p, wl.data(), dwl.bytes(), cudaMemcpyHostToDevice, ctx->stream));
+            FF_CUDA(cudaMemcpyAsync(dcq.p, cq, dcq.bytes(), cudaMemcpyHostToDevice, ctx->stream));
+            ff_launch(ctx, "asm_coef_moments", [&] {
+                k_emom<<<ff_blocks(nt, 128), 128, wl.size() * sizeof(double), ctx->stream>>>(nt, nq, dim + 1, dwl.p, dcq.p, emom.p);
+            });
+            FF_CUDA(cudaStreamSynchronize(ctx->stream)); // cq is the caller's pageable memory
+            fast = false;
+        }
+        if (dim == 3) dispatch_p1<3>(ctx, A, s, F, accumulate, fast, emom.p);
+        else dispatch_p1<2>(ctx, A, s, F, accumulate, fast, emom.p);
     } else if (P->pos8.p) {
         if (dim == 3) dispatch_p2<3, uint8_t>(ctx, A, s, F, Rg.p, P->pos8.p, accumulate);
         else dispatch_p2<2, uint8_t>(ctx, A, s, F, Rg.p, P->pos8.p, accumulate);

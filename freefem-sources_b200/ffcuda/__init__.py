@@ -20,7 +20,7 @@ ffcuda_mesh_info ffcuda_mesh_download ffcuda_mesh_destroy ffcuda_space_create ff
 ffcuda_space_destroy ffcuda_symbolic ffcuda_pattern_info ffcuda_pattern_download ffcuda_pattern_download_async ffcuda_pattern_lower_nnz ffcuda_pattern_download_lower
 ffcuda_matrix_download_lower ffcuda_matrix_from_csr_lower ffcuda_pattern_destroy ffcuda_matrix_create
 ffcuda_matrix_from_csr ffcuda_matrix_info ffcuda_matrix_download ffcuda_matrix_upload ffcuda_matrix_destroy ffcuda_vec_create
-ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_destroy ffcuda_assemble_bilinear
+ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_destroy ffcuda_assemble_bilinear ffcuda_assemble_bilinear_qcoef
 ffcuda_assemble_linear ffcuda_assemble_linear_qvalues ffcuda_assemble_linear_boundary ffcuda_assemble_bilinear_boundary ffcuda_bc_from_pairs ffcuda_bc_from_labels ffcuda_bc_count ffcuda_matrix_apply_bc ffcuda_vec_apply_bc
 ffcuda_vec_set_bc_values ffcuda_bc_destroy ffcuda_spmv ffcuda_cg ffcuda_cg_host ffcuda_gmres ffcuda_gmres_host ffcuda_comm_unique_id ffcuda_comm_init
 ffcuda_comm_finalize ffcuda_mesh_cube_distributed ffcuda_mesh_local_to_global ffcuda_quadrature ffcuda_partition_cube""".split()
@@ -385,6 +385,15 @@ class Matrix(_Handle):
         qpts, qw, lab = _f64(qpts), _f64(qw), _i32(labels)
         _ck(lib().ffcuda_assemble_bilinear(_h(self), _h(self.pattern.space), len(terms), arr, len(qw), _p(qpts), _p(qw),
                                            0 if lab is None else len(lab), _p(lab), int(accumulate)), self.ctx.h)
+
+    def assemble_qcoef(self, terms, qpts, qw, cq, accumulate=False):
+        """A (+)= the form multiplied by the coefficient whose values at the quadrature nodes are cq[k, q] (P1 spaces)"""
+        arr = (BTerm * max(len(terms), 1))()
+        for k, (uc, uo, vc, vo, c) in enumerate(terms):
+            arr[k] = BTerm(uc, uo, vc, vo, c)
+        qpts, qw, cq = _f64(qpts), _f64(qw), _f64(cq)
+        _ck(lib().ffcuda_assemble_bilinear_qcoef(_h(self), _h(self.pattern.space), len(terms), arr, len(qw), _p(qpts), _p(qw),
+                                                 _p(cq), int(accumulate)), self.ctx.h)
 
     def assemble_boundary(self, terms, qpts, qw, labels=None, accumulate=True):
         """A (+)= int2d(Th3, labels)(c u v) / int1d(Th, labels)(c u v) (Robin terms); qpts: nq x (dim-1) face coordinates"""

@@ -381,8 +381,13 @@ double constant_coef(Stack stack, const C_F0 &c)
     return GetAny<double>(c.eval(stack));
 }
 
+struct QBTerm { // term of a bilinear form whose coefficient depends on the mesh point
+    ffcuda_bterm t; // (coef unused)
+    C_F0 coef;
+};
 struct BilinearItem {
     std::vector<ffcuda_bterm> terms;
+    std::vector<QBTerm> qterms;
     Quad q;
     Region reg;
     bool border = false; // integral over the boundary elements with the labels of reg (Robin terms)
@@ -436,6 +441,16 @@ Varf read_varf(Stack stack, const list<C_F0> &largs, const MeshT &Th, int ncomp,
                 t.vop = check_op(id.second.second, dim);
                 if (t.ucomp < 0 || t.ucomp >= ncomp || t.vcomp < 0 || t.vcomp >= ncomp) throw Unsupported{"component out of range"};
                 if (B.border && (t.uop != op_id || t.vop != op_id)) throw Unsupported{"derivatives in a boundary integral"};
+                if (!op.v[k].second.LeftValue()->MeshIndependent()) {
+                    // kappa(x,y,z) grad u . grad v, rho(x) u v, a P0 / P1 function as coefficient: evaluated at the quadrature
+                    // nodes by FreeFEM's evaluator, integrated on the device (P1 spaces; checked in gpu_matrix)
+                    if (B.border) throw Unsupported{"boundary integral whose coefficient depends on the mesh point"};
+                    if (op.v[k].second.left() != atype<double>() && op.v[k].second.left() != atype<long>())
+                        throw Unsupported{"coefficient is not real"};
+                    t.coef = 0.0;
+                    B.qterms.push_back(QBTerm{t, op.v[k].second});
+                    continue;
+                }
                 t.coef = constant_coef(stack, op.v[k].second);
                 B.terms.push_back(t);
             }
@@ -534,6 +549,19 @@ void drop_resident()
     g_resident.clear();
 }
 
+// bilinear terms whose coefficient depends on the mesh point are on the path for P1 spaces only (decided on the host, before
+// any device work, so that a refusal costs nothing)
+template <class FESpaceT>
+void check_qterms_supported(const FESpaceT &Vh, const Varf &V)
+{
+    bool any = false;
+    for (size_t i = 0; i < V.bil.size(); ++i) any = any || !V.bil[i].qterms.empty();
+    if (!any) return;
+    int order, ncomp, nloc;
+    classify_space(Vh, MeshDim<typename FESpaceT::Mesh>::d, order, ncomp, nloc);
+    if (order != 1) throw Unsupported{"P2 form whose coefficient depends on the mesh point"};
+}
+
 // the pattern of the device matrix is that of the whole space: FreeFEM's is the same only when the volume integrals
 // visit every element (HashMatrix creates the couples of the visited elements only)
 template <class MeshT>
@@ -550,11 +578,111 @@ void check_full_pattern(const Varf &V, const MeshT &Th)
         if (!labs.count(Th[k].lab)) throw Unsupported{"the volume integrals do not visit every element (sub-pattern)"};
 }
 
+// values of mesh-point dependent coefficient expressions at every quadrature node of every element, obtained the way
+// Element_rhs / Element_Op obtain them (fflib/problem.cpp:7876-7884, :7951-7960, :6380-6407): MeshPointStack set to the
+// node, expression evaluated.  out[e][k * nq + q] for expression e; elements outside the region stay 0.
+inline R2 ref_point(const Mesh *, const double *p) { return R2(p[0], p[1]); }
+inline R3 ref_point(const Mesh3 *, const double *p) { return R3(p[0], p[1], p[2]); }
+template <class FESpaceT>
+std::vector<std::vector<double>> eval_at_nodes(Stack stack, const FESpaceT &Vh, const std::vector<const C_F0 *> &exprs, const Quad &Q,
+                                               const Region &reg)
+{
+    typedef typename FESpaceT::Mesh MeshT;
+    typedef typename FESpaceT::FElement FElementT;
+    const MeshT &Th = Vh.Th;
+    const int dim = MeshDim<MeshT>::d, nq = (int)Q.w.size(), nt = Th.nt;
+    std::vector<std::vector<double>> out(exprs.size(), std::vector<double>((size_t)nt * nq, 0.0));
+    std::set<int> labs(reg.labels.begin(), reg.labels.end());
+    MeshPoint *mps = MeshPointStack(stack), mp = *mps;
+    try {
+        for (int k = 0; k < nt; ++k) {
+            if (!reg.all && !labs.count(Th[k].lab)) continue;
+            const FElementT Kv(Vh[k]);
+            const typename MeshT::Element &T = Kv.T;
+            for (int q = 0; q < nq; ++q) {
+                typename MeshT::RdHat Pt(ref_point(&Th, Q.pts.data() + (size_t)q * dim));
+                mps->set(T(Pt), Pt, Kv);
+                for (size_t e = 0; e < exprs.size(); ++e) {
+                    const C_F0 &c = *exprs[e];
+                    out[e][(size_t)k * nq + q] = c.left() == atype<long>() ? (double)GetAny<long>(c.eval(stack)) : GetAny<double>(c.eval(stack));
+                }
+            }
+        }
+    } catch (...) {
+        *mps = mp;
+        throw;
+    }
+    *mps = mp;
+    return out;
+}
+// table of a linear item: fq[(c * nt + k) * nq + q], summed over the terms of component c
+template <class FESpaceT>
+std::vector<double> eval_qvalues(Stack stack, const FESpaceT &Vh, const LinearItem &L, bool negate)
+{
+    const size_t per = (size_t)Vh.Th.nt * L.q.w.size();
+    std::vector<const C_F0 *> ex;
+    for (size_t t = 0; t < L.qterms.size(); ++t) ex.push_back(&L.qterms[t].coef);
+    std::vector<std::vector<double>> v = eval_at_nodes(stack, Vh, ex, L.q, L.reg);
+    std::vector<double> fq((size_t)Vh.N * per, 0.0);
+    const double sgn = negate ? -1.0 : 1.0;
+    for (size_t t = 0; t < L.qterms.size(); ++t) {
+        double *dst = fq.data() + (size_t)L.qterms[t].vcomp * per;
+        for (size_t i = 0; i < per; ++i) dst[i] += sgn * v[t][i];
+    }
+    return fq;
+}
+
 // the GPU path proper for a matrix: symbolic, numeric assembly of every bilinear item, Dirichlet conditions, then the
 // CSR arrays come back and become a MatriceMorse of FreeFEM's own (HashMatrix::set copies and rebuilds the hash); the
 // device copy is returned in res for the solver that will be attached
-MatriceMorse<double> *gpu_matrix(DevSpace &D, const Varf &V, const Data_Sparse_Solver &ds, Resident &res, int &n, int64_t &nnz)
+template <class FESpaceT>
+MatriceMorse<double> *gpu_matrix(Stack stack, const FESpaceT &Vh, DevSpace &D, const Varf &V, const Data_Sparse_Solver &ds, Resident &res,
+                                 int &n, int64_t &nnz)
 {
+    // terms whose coefficient depends on the mesh point: values at the quadrature nodes first (this is what may be refused)
+    struct QGroup {
+        size_t item;
+        std::vector<double> cq;
+        std::vector<ffcuda_bterm> terms;
+    };
+    std::vector<QGroup> groups;
+    for (size_t i = 0; i < V.bil.size(); ++i) {
+        const BilinearItem &B = V.bil[i];
+        if (B.qterms.empty()) continue;
+        if (D.order != 1) throw Unsupported{"P2 form whose coefficient depends on the mesh point"};
+        std::vector<const C_F0 *> ex;
+        for (size_t t = 0; t < B.qterms.size(); ++t) ex.push_back(&B.qterms[t].coef);
+        std::vector<std::vector<double>> v = eval_at_nodes(stack, Vh, ex, B.q, B.reg);
+        // terms whose tables are proportional share one coefficient function ((1+x)*lambda, (1+x)*mu, ...): one pass each group
+        const size_t first_group = groups.size();
+        for (size_t t = 0; t < B.qterms.size(); ++t) {
+            const std::vector<double> &a = v[t];
+            size_t imax = 0;
+            for (size_t k = 1; k < a.size(); ++k)
+                if (std::abs(a[k]) > std::abs(a[imax])) imax = k;
+            if (a.empty() || a[imax] == 0.0) continue; // the coefficient vanishes at every node
+            bool placed = false;
+            for (size_t gi = first_group; gi < groups.size() && !placed; ++gi) {
+                const std::vector<double> &r = groups[gi].cq;
+                if (r[imax] == 0.0) continue;
+                const double alpha = a[imax] / r[imax];
+                double err = 0.0;
+                for (size_t k = 0; k < a.size(); ++k) err = std::max(err, std::abs(a[k] - alpha * r[k]));
+                if (err <= 1e-14 * std::abs(a[imax])) { // (the products are rounded separately: a few ulp)
+                    ffcuda_bterm bt = B.qterms[t].t;
+                    bt.coef = alpha;
+                    groups[gi].terms.push_back(bt);
+                    placed = true;
+                }
+            }
+            if (!placed) {
+                ffcuda_bterm bt = B.qterms[t].t;
+                bt.coef = 1.0;
+                groups.push_back(QGroup{i, a, std::vector<ffcuda_bterm>(1, bt)});
+            }
+        }
+    }
+
     ffcuda_pattern *P = nullptr;
     ffcuda_matrix *dA = nullptr;
     FFC(ffcuda_symbolic(D.space, &P));
@@ -570,11 +698,20 @@ MatriceMorse<double> *gpu_matrix(DevSpace &D, const Varf &V, const Data_Sparse_S
         for (size_t i = 0; i < V.bil.size() && !rc; ++i) {
             const BilinearItem &B = V.bil[i];
             if ((int)B.border != border) continue;
+            if (B.terms.empty() && !B.qterms.empty()) continue; // nothing constant in this item
             rc = (border ? ffcuda_assemble_bilinear_boundary : ffcuda_assemble_bilinear)(
                 dA, D.space, (int)B.terms.size(), B.terms.data(), (int)B.q.w.size(), B.q.pts.data(), B.q.w.data(),
                 (int)B.reg.labels.size(), B.reg.all ? nullptr : B.reg.labels.data(), first ? 0 : 1);
             first = false;
         }
+    for (size_t gi = 0; gi < groups.size() && !rc; ++gi) {
+        const BilinearItem &B = V.bil[groups[gi].item];
+        rc = ffcuda_assemble_bilinear_qcoef(dA, D.space, (int)groups[gi].terms.size(), groups[gi].terms.data(), (int)B.q.w.size(),
+                                            B.q.pts.data(), B.q.w.data(), groups[gi].cq.data(), first ? 0 : 1);
+        first = false;
+    }
+    if (g_verbose && !groups.empty())
+        cout << "  -- ffcuda: " << groups.size() << " coefficient function(s) depending on the mesh point, evaluated at the quadrature nodes" << endl;
     std::vector<int32_t> rowptr, colind;
     std::vector<double> vals;
     if (!rc) {
@@ -611,45 +748,6 @@ MatriceMorse<double> *gpu_matrix(DevSpace &D, const Varf &V, const Data_Sparse_S
 // the GPU path proper for a right-hand side: every linear item (volume integrals, then boundary integrals), an optional
 // change of sign (problem/solve: a(u,v) - l(v) = 0), Dirichlet values; x0 (optional, size n) gets x0[d] = g(d) as
 // AssembleBC does for the initial guess
-// values of the mesh-point dependent coefficients of a linear item at every quadrature node of every element, obtained the
-// way Element_rhs obtains them (fflib/problem.cpp:7876-7884, :7951-7960): MeshPointStack set to the node, expression
-// evaluated.  fq[(c * nt + k) * nq + q], summed over the terms of component c; elements outside the region stay 0.
-inline R2 ref_point(const Mesh *, const double *p) { return R2(p[0], p[1]); }
-inline R3 ref_point(const Mesh3 *, const double *p) { return R3(p[0], p[1], p[2]); }
-template <class FESpaceT>
-std::vector<double> eval_qvalues(Stack stack, const FESpaceT &Vh, const LinearItem &L, bool negate)
-{
-    typedef typename FESpaceT::Mesh MeshT;
-    typedef typename FESpaceT::FElement FElementT;
-    const MeshT &Th = Vh.Th;
-    const int dim = MeshDim<MeshT>::d, nq = (int)L.q.w.size(), nt = Th.nt, nc = Vh.N;
-    std::vector<double> fq((size_t)nc * nt * nq, 0.0);
-    std::set<int> labs(L.reg.labels.begin(), L.reg.labels.end());
-    MeshPoint *mps = MeshPointStack(stack), mp = *mps;
-    const double sgn = negate ? -1.0 : 1.0;
-    try {
-        for (int k = 0; k < nt; ++k) {
-            if (!L.reg.all && !labs.count(Th[k].lab)) continue;
-            const FElementT Kv(Vh[k]);
-            const typename MeshT::Element &T = Kv.T;
-            for (int q = 0; q < nq; ++q) {
-                typename MeshT::RdHat Pt(ref_point(&Th, L.q.pts.data() + (size_t)q * dim));
-                mps->set(T(Pt), Pt, Kv);
-                for (size_t t = 0; t < L.qterms.size(); ++t) {
-                    const C_F0 &c = L.qterms[t].coef;
-                    const double v = c.left() == atype<long>() ? (double)GetAny<long>(c.eval(stack)) : GetAny<double>(c.eval(stack));
-                    fq[((size_t)L.qterms[t].vcomp * nt + k) * nq + q] += sgn * v;
-                }
-            }
-        }
-    } catch (...) {
-        *mps = mp;
-        throw;
-    }
-    *mps = mp;
-    return fq;
-}
-
 template <class FESpaceT>
 void gpu_rhs(Stack stack, const FESpaceT &Vh, DevSpace &D, const Varf &V, double tgv, bool negate, long n, std::vector<double> &host,
              double *x0)
@@ -743,11 +841,12 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
                 if (!isSameMesh(this->b->largs, &Vh.Th, &Vh.Th, stack)) throw Unsupported{"integrals on different meshes"};
                 Varf V = read_varf(stack, this->b->largs, Th, Vh.N, true);
                 check_full_pattern(V, Th);
+                check_qterms_supported(Vh, V);
                 DevSpace &D = device_space(Vh);
                 int n = 0;
                 int64_t nnz = 0;
                 Resident res{nullptr, nullptr};
-                MatriceMorse<double> *M = gpu_matrix(D, V, ds, res, n, nnz);
+                MatriceMorse<double> *M = gpu_matrix(stack, Vh, D, V, ds, res, n, nnz);
                 // --- hand the result to FreeFEM as its own MatriceMorse (problem.hpp:1678-1693)
                 WhereStackOfPtr2Free(stack) = new StackOfPtr2Free(stack);
                 Matrice_Creuse<double> &A(*GetAny<Matrice_Creuse<double> *>((*this->a)(stack)));
@@ -1035,6 +1134,7 @@ struct CudaProblem : public Base {
         Varf VB = read_varf(stack, this->op->largs, Th, N, false);
         if (VB.other_rhs_items) throw Unsupported{"array / matrix-vector items in the problem"};
         check_full_pattern(VA, Th);
+        check_qterms_supported(*Uhp, VA);
         if (data->pTh == &Th && (const FES *)data->Uh != Uhp) throw Unsupported{"the problem was set up on another fespace of this mesh"};
         DevSpace &D = device_space(*Uhp);
 
@@ -1062,7 +1162,7 @@ struct CudaProblem : public Base {
                 int nn = 0;
                 int64_t nnz = 0;
                 Resident res{nullptr, nullptr};
-                MatriceMorse<double> *M = gpu_matrix(D, VA, ds, res, nn, nnz);
+                MatriceMorse<double> *M = gpu_matrix(stack, Uh, D, VA, ds, res, nn, nnz);
                 data->AR.master(M);
                 drop_resident();
                 g_resident[(const void *)static_cast<HashMatrix<int, double> *>(M)] = res;

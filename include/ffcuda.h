@@ -162,6 +162,13 @@ int ffcuda_quadrature(int dim, int qforder, int *nq, double *qpts, double *qw);
 int ffcuda_assemble_bilinear(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms,
                              int nq, const double *qpts, const double *qw,
                              int nlab, const int32_t *labels, int accumulate);
+/* A (+)= the same with every term multiplied by ONE coefficient that depends on the mesh point (kappa(x,y,z), a P0 / P1
+ * FE function, ...), given by the values Element_Op would compute (fflib/problem.cpp:6407): cq[k * nq + q] (HOST array) at
+ * quadrature node q of element k.  P1 spaces (scalar or vector): the gradients of P1 functions do not depend on the node,
+ * so the element integrals reduce exactly to the moments sum_q w_q c_q, sum_q w_q c_q lambda_a, sum_q w_q c_q lambda_a
+ * lambda_b of the coefficient, formed on the device.  Forms with several coefficient functions: one call per function. */
+int ffcuda_assemble_bilinear_qcoef(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms,
+                                   int nq, const double *qpts, const double *qw, const double *cq, int accumulate);
 int ffcuda_assemble_linear(ffcuda_vec *b, ffcuda_space *s, int nterms, const ffcuda_lterm *terms,
                            int nq, const double *qpts, const double *qw,
                            int nlab, const int32_t *labels, int accumulate);

@@ -360,11 +360,38 @@ static void elem_coords(int dim, const double *xyz, const int32_t *K, double *X)
 }
 
 /* ------------------------------------------------------------------ bilinear form ------- */
+static int64_t assemble_coo_impl(int dim, int nv, const double *xyz, int nt, const int32_t *conn, const int32_t *elab,
+                                 int order, int ncomp, const int32_t *elem2node,
+                                 int nterms, const ffo_bterm *terms, int nq, const double *qpts, const double *qw,
+                                 int nlab, const int32_t *labels, const double *cq,
+                                 int32_t *coo_i, int32_t *coo_j, double *coo_a);
+
 int64_t ffo_assemble_coo(int dim, int nv, const double *xyz, int nt, const int32_t *conn, const int32_t *elab,
                          int order, int ncomp, const int32_t *elem2node,
                          int nterms, const ffo_bterm *terms, int nq, const double *qpts, const double *qw,
                          int nlab, const int32_t *labels,
                          int32_t *coo_i, int32_t *coo_j, double *coo_a)
+{
+    return assemble_coo_impl(dim, nv, xyz, nt, conn, elab, order, ncomp, elem2node, nterms, terms, nq, qpts, qw, nlab, labels, NULL,
+                             coo_i, coo_j, coo_a);
+}
+
+/* the same with every term multiplied by a coefficient that depends on the mesh point, given by its values at the
+ * quadrature nodes cq[k * nq + q] - what GetAny<R>(ll.second.eval(stack)) returns inside Element_Op (problem.cpp:6407) */
+int64_t ffo_assemble_coo_qcoef(int dim, int nv, const double *xyz, int nt, const int32_t *conn, const int32_t *elab,
+                               int order, int ncomp, const int32_t *elem2node,
+                               int nterms, const ffo_bterm *terms, int nq, const double *qpts, const double *qw,
+                               const double *cq, int32_t *coo_i, int32_t *coo_j, double *coo_a)
+{
+    return assemble_coo_impl(dim, nv, xyz, nt, conn, elab, order, ncomp, elem2node, nterms, terms, nq, qpts, qw, 0, NULL, cq,
+                             coo_i, coo_j, coo_a);
+}
+
+static int64_t assemble_coo_impl(int dim, int nv, const double *xyz, int nt, const int32_t *conn, const int32_t *elab,
+                                 int order, int ncomp, const int32_t *elem2node,
+                                 int nterms, const ffo_bterm *terms, int nq, const double *qpts, const double *qw,
+                                 int nlab, const int32_t *labels, const double *cq,
+                                 int32_t *coo_i, int32_t *coo_j, double *coo_a)
 {
     (void)nv;
     const int nloc = ffo_nloc(dim, order), nd = nloc * ncomp;
@@ -389,6 +416,7 @@ int64_t ffo_assemble_coo(int dim, int nv, const double *xyz, int nt, const int32
             for (int t = 0; t < nterms; ++t) {
                 int so = opslot(terms[t].uop), to = opslot(terms[t].vop);
                 double ccc = terms[t].coef;
+                if (cq) ccc *= cq[(size_t)k * nq + q];
                 ccc *= coef;
                 int fi = terms[t].vcomp * nloc, fj = terms[t].ucomp * nloc;
                 for (int a = 0; a < nloc; ++a)

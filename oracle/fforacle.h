@@ -84,6 +84,13 @@ void ffo_assemble_rhs_boundary(int dim, const double *xyz, const int32_t *conn, 
                                const int32_t *bface, int nterms, const ffo_lterm *terms, int nq, const double *qpts,
                                const double *qw, int nlab, const int32_t *labels, double *b);
 
+/* ffo_assemble_coo with every term multiplied by a coefficient depending on the mesh point, given at the quadrature
+ * nodes: cq[k * nq + q] (Element_Op evaluates the coefficient expression there, problem.cpp:6407) */
+int64_t ffo_assemble_coo_qcoef(int dim, int nv, const double *xyz, int nt, const int32_t *conn, const int32_t *elab,
+                               int order, int ncomp, const int32_t *elem2node,
+                               int nterms, const ffo_bterm *terms, int nq, const double *qpts, const double *qw,
+                               const double *cq, int32_t *coo_i, int32_t *coo_j, double *coo_a);
+
 /* boundary integrals of a bilinear form (Robin terms: AssembleBilinearForm border loop problem.cpp:1317-1326, Element_Op
  * border branch :6518-6560 / :6216-6290): COO with one entry per distinct (il, jl) couple of the elements adjacent to the
  * labelled boundary elements, zero or not.  Arrays sized (labelled boundary elements) * (nloc*ncomp)^2.  Returns count. */

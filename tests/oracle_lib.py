@@ -34,6 +34,7 @@ def lib():
         _LIB = C.CDLL(build())
         _LIB.ffo_assemble_coo.restype = C.c_int64
         _LIB.ffo_assemble_coo_boundary.restype = C.c_int64
+        _LIB.ffo_assemble_coo_qcoef.restype = C.c_int64
     return _LIB
 
 
@@ -122,6 +123,23 @@ def assemble_coo(mesh, order, ncomp, elem2node, terms, qpts, qw, labels=None):
                                  order, ncomp, _p(e2n, C.c_int32), len(terms), bt, len(qw), _p(qpts, C.c_double),
                                  _p(qw, C.c_double), 0 if lab is None else len(lab), _p(lab, C.c_int32),
                                  _p(ci, C.c_int32), _p(cj, C.c_int32), _p(ca, C.c_double))
+    return ci[:nnz].copy(), cj[:nnz].copy(), ca[:nnz].copy()
+
+
+def assemble_coo_qcoef(mesh, order, ncomp, elem2node, terms, qpts, qw, cq):
+    """assemble_coo with every term multiplied by the coefficient whose values at the quadrature nodes are cq[k, q]"""
+    dim = mesh["dim"]
+    xyz, conn, elab = _f64(mesh["xyz"]), _i32(mesh["conn"]), _i32(mesh["elab"])
+    nt = conn.shape[0]
+    nd = nloc(dim, order) * ncomp
+    cap = nt * nd * nd
+    ci, cj, ca = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap)
+    e2n = _i32(elem2node)
+    bt = bterms(terms)
+    qpts, qw, cq = _f64(qpts), _f64(qw), _f64(cq)
+    nnz = lib().ffo_assemble_coo_qcoef(dim, xyz.shape[0], _p(xyz, C.c_double), nt, _p(conn, C.c_int32), _p(elab, C.c_int32),
+                                       order, ncomp, _p(e2n, C.c_int32), len(terms), bt, len(qw), _p(qpts, C.c_double),
+                                       _p(qw, C.c_double), _p(cq, C.c_double), _p(ci, C.c_int32), _p(cj, C.c_int32), _p(ca, C.c_double))
     return ci[:nnz].copy(), cj[:nnz].copy(), ca[:nnz].copy()
 
 

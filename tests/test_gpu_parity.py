@@ -34,7 +34,7 @@ def _upload(ctx, g):
 
 
 def _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve=True, eps=1e-6, itmax=0, TGV=TGV, lower=False,  # noqa: N803
-              blin=None, bbil=None, gmres=None, fqfun=None):
+              blin=None, bbil=None, gmres=None, fqfun=None, qcoef=()):
     """Full product pipeline on one problem; returns everything a parity check needs."""
     mesh = _upload(ctx, g)
     sp = mesh.space(order, ncomp, e2n, nnodes)
@@ -42,6 +42,8 @@ def _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve=True
     rp, ci = pat.download()
     A = pat.matrix()
     A.assemble(bt, qp, qw)
+    for cfun, cterms in qcoef:  # groups of terms multiplied by a coefficient given at the quadrature nodes
+        A.assemble_qcoef(cterms, qp, qw, cfun(ol.quad_points_xyz(g, qp)), accumulate=True)
     if bbil:  # boundary integrals of the bilinear form (Robin terms)
         fq, fw = ol.face_quadrature(g["dim"])
         A.assemble_boundary(bbil[1], fq, fw, bbil[0], accumulate=True)
@@ -93,7 +95,7 @@ def test_golden_case(ctx, name):
     e2n = fc.elem2node(g, order, ncomp)
     nnodes = g["ndof"] // ncomp
     r = _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve="u" in g, TGV=fc.CASE_TGV.get(name, TGV),
-                  lower=name in fc.CASE_SYM, blin=fc.CASE_BLIN.get(name), bbil=fc.CASE_BBIL.get(name), gmres=fc.CASE_GMRES.get(name), fqfun=fc.CASE_FQ.get(name))
+                  lower=name in fc.CASE_SYM, blin=fc.CASE_BLIN.get(name), bbil=fc.CASE_BBIL.get(name), gmres=fc.CASE_GMRES.get(name), fqfun=fc.CASE_FQ.get(name), qcoef=fc.CASE_QCOEF.get(name, ()))
     grp, gci, gval = fc.golden_csr(g)
     assert r["n"] == g["ndof"]
     assert np.array_equal(r["rowptr"], grp) and np.array_equal(r["colind"], gci)          # bit-exact pattern

@@ -41,6 +41,9 @@ def test_matrix_rhs_solution(name):
     e2n = fc.elem2node(g, order, ncomp)
     qp, qw = ol.quadrature(dim, qname)
     ci, cj, ca = ol.assemble_coo(_mesh(g), order, ncomp, e2n, bt, qp, qw)
+    for cfun, cterms in fc.CASE_QCOEF.get(name, []):  # groups of terms with a coefficient depending on the mesh point
+        cq = cfun(ol.quad_points_xyz(_mesh(g), qp))
+        ci, cj, ca = ol.coo_add(n, (ci, cj, ca), ol.assemble_coo_qcoef(_mesh(g), order, ncomp, e2n, cterms, qp, qw, cq))
     if name in fc.CASE_BBIL:  # Robin terms: the border loop runs after the volume loop, in the order of the varf
         blabels, bbt = fc.CASE_BBIL[name]
         fq, fw = ol.face_quadrature(dim)

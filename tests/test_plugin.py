@@ -86,6 +86,11 @@ CASES = {
                                 "on(1,2,3,4,5,6,u=0)", eps="1e-14"),
     "lame3d_p2_fvec": script(3, "cube(2,3,2)", "[P2,P2,P2]", LAME, "x*v1-0.05*(1+y)*v3", "on(1,u1=0,u2=0,u3=0)", pre=LAME_PRE,
                              unk="[u1,u2,u3]", tst="[v1,v2,v3]", eps="1e-14"),
+    # bilinear coefficients depending on the mesh point on P1 spaces (moments of the coefficient on every element)
+    "diff3d_p1_kappa": script(3, "cube(5,4,6,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", "P1", "(1+x*y+z*z)*(" + LAP3 + ")+2.*u*v", "1.*v",
+                              "on(1,2,u=0)", eps="1e-14"),
+    "lame3d_p1_evar": script(3, "cube(3,4,3)", "[P1,P1,P1]", "(1+x)*(" + LAME + ")+0.5*(1+y*y)*(u1*v1+u2*v2+u3*v3)", "-0.05*v3",
+                             "on(1,u1=0,u2=0,u3=0)", pre=LAME_PRE, unk="[u1,u2,u3]", tst="[v1,v2,v3]", eps="1e-14"),
     "mass3d_lumped": script(3, "cube(3,3,3)", "P1", "u*v+0.1*(" + LAP3 + ")", "1.*v", "on(1,u=0)", intopt=",qfV=qfV1lump"),
 }
 
@@ -188,8 +193,9 @@ OUT_OF_SCOPE = """load "msh3"
 load "ffcuda"
 mesh3 Th = cube(3,3,3);
 fespace Vh(Th,P1);
+fespace Vh2(Th,P2);
 varf vb(u,v) = int3d(Th)(x*dx(u)*dx(v)+u*v) + on(1,u=0);
-matrix B = vb(Vh,Vh);
+matrix B = vb(Vh2,Vh2);
 fespace Wh(Th,P0);
 varf vc(u,v) = int3d(Th)(u*v);
 matrix C = vc(Wh,Wh);
@@ -211,11 +217,11 @@ cout << "NNZ " << A.nnz << endl;
 
 @needs_ff
 def test_plugin_loads_and_leaves_out_of_scope_forms_to_freefem():
-    """x-dependent coefficient, non-Lagrange element, boundary integral without a volume integral: not claimed, FreeFEM's own operators run
+    """x-dependent coefficient on a P2 space, non-Lagrange element, boundary integral without a volume integral: not claimed, FreeFEM's own operators run
     (no GPU needed), and the plugin says so."""
     rc, out, _ = run_ff(OUT_OF_SCOPE, {}, want_fail=True)
     assert rc == 0, out[-2000:]
-    assert re.search(r"^NNZ 622 162 \d+", out, re.M)
+    assert re.search(r"^NNZ 7525 162 \d+", out, re.M)
     assert out.count("left to FreeFEM") >= 4
     rc, out, _ = run_ff(OUT_OF_SCOPE, {"FFCUDA_STRICT": "1"}, want_fail=True)
     assert rc != 0 and "FFCUDA_STRICT" in out
@@ -269,6 +275,12 @@ int it = 0;
 problem Heat(u,v,solver=CG,eps=1e-14,init=it) = int3d(Th)(u*v/dt+{LAP3}) - int3d(Th)(uold*v/dt) - int3d(Th)((1+x)*v) + on(1,2,u=0);
 for (it = 0; it < 4; ++it) {{ uold = u; Heat; }}
 """,
+    # a P0 material coefficient and a P1 function in the reaction term
+    "materials_p0_p1_coefficients": """mesh Th = square(14,12);
+fespace Vh(Th,P1); Vh u,v,rho=1+x*y;
+fespace Ph(Th,P0); Ph kappa = 1 + 9*(x>0.5)*(y<0.5);
+solve Pb(u,v,solver=CG,eps=1e-14) = int2d(Th)(kappa*(dx(u)*dx(v)+dy(u)*dy(v))+rho*u*v) - int2d(Th)(rho*v) + on(1,u=0);
+""",
     "default_solver": """mesh Th = square(9,8);
 fespace Vh(Th,P2); Vh u,v;
 solve Pb(u,v) = int2d(Th)(dx(u)*dx(v)+dy(u)*dy(v)+u*v) - int2d(Th)(1.*v) - int1d(Th,2)(0.3*v) + on(4,u=0);
@@ -315,7 +327,7 @@ def test_plugin_problem_solve_matches_freefem(name):
 
 
 SOLVE_FALLBACK = """mesh Th = square(10,9);
-fespace Vh(Th,P1); Vh u,v;
+fespace Vh(Th,P2); Vh u,v;
 solve Poisson(u,v,solver=LU) = int2d(Th)((1+x)*(dx(u)*dx(v)+dy(u)*dy(v))) - int2d(Th)(x*v) + on(1,2,3,4,u=0);
 fespace Wh(Th,P1dc); Wh w,ww;
 solve Proj(w,ww) = int2d(Th)(w*ww) - int2d(Th)(u*ww);
