@@ -68,6 +68,7 @@ struct ffcuda_ctx {
     int sm_count = 148;
     int tile_policy = 1;        // 0: never use row tiles, 1: from the second assembly on a fespace, 2: always
     int tile_rows = 96;         // rows per tile
+    int gmres_coop = 1;         // 1: one cooperative kernel per Arnoldi step when the vectors fit its registers, 0: one kernel per basis vector
     // reduction scratch (device) + pinned host mirror
     double *d_scal = nullptr;   // small array of device scalars
     double *h_scal = nullptr;   // pinned

@@ -188,6 +188,9 @@ extern "C" int ffcuda_ctx_set_option(ffcuda_ctx *ctx, const char *name, int valu
     } else if (n == "tile_rows") {
         FF_REQUIRE(value >= 8 && value <= 256, "tile_rows must be in 8..256");
         ctx->tile_rows = value;
+    } else if (n == "gmres_coop") {
+        FF_REQUIRE(value == 0 || value == 1, "gmres_coop must be 0 or 1");
+        ctx->gmres_coop = value;
     } else
         throw FFError("ffcuda_ctx_set_option: unknown option '" + n + "'");
     FF_API_END(ctx)

@@ -14,6 +14,7 @@
 // partials) -> deterministic, no fp64 atomics.  The host enqueues iterations in batches and polls a device flag;
 // kernels of iterations past the converged one are no-ops, so x is exactly the iterate of the stopping iteration.
 #include <deque>
+#include <cooperative_groups.h>
 #include "common.cuh"
 #include <cstddef>
 #include <algorithm>
@@ -1205,6 +1206,107 @@ __global__ void __launch_bounds__(RED_THREADS) k_gm_mgs_last(double *__restrict_
     }
 }
 
+// One Arnoldi step in ONE cooperative kernel (grid = co-resident CTAs, grid-wide barriers): the whole modified
+// Gram-Schmidt chain, the norm, the Givens update and the next basis vector.  Every thread keeps its entries of w in
+// registers for the whole chain (KW per thread), so a step of the chain reads one basis vector (the one before comes from
+// L2) and costs one grid barrier; the dot products are summed in a fixed shape (per-block partials, every block adds
+// them in the same order), so the result is reproducible and every block holds the same h.
+namespace cg = cooperative_groups;
+template <int KW>
+__global__ void __launch_bounds__(RED_THREADS, 2)
+    k_gm_arnoldi(double *__restrict__ W, const double *const *__restrict__ Vtab, int n, int it, double eps, GmresLayout L,
+                 double *__restrict__ gs, double *__restrict__ partial /* 2 x gridDim */, int *__restrict__ flags)
+{
+    if (flags[F_CONV_ITER] != 0) return; // (uniform over the grid: no barrier is left waiting)
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sh[32];
+    __shared__ double sbc;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gstride = gridDim.x * blockDim.x; // (n < 2^31 / KW entries)
+    double w[KW];
+#pragma unroll
+    for (int j = 0; j < KW; ++j) {
+        const int idx = gtid + j * gstride;
+        w[j] = idx < n ? W[idx] : 0.0;
+    }
+    double hprev = 0.0;
+    int par = 0;
+    // grid-wide sum of one value per thread: partials of every block, barrier, every block adds them in the same order
+    auto grid_total = [&](double v) -> double {
+        const double r = block_sum(v, sh);
+        if (threadIdx.x == 0) partial[(size_t)par * gridDim.x + blockIdx.x] = r;
+        grid.sync();
+        double s = 0.0;
+        for (int i = threadIdx.x; i < (int)gridDim.x; i += blockDim.x) s += __ldcg(partial + (size_t)par * gridDim.x + i);
+        const double t = block_sum(s, sh);
+        if (threadIdx.x == 0) sbc = t;
+        __syncthreads();
+        par ^= 1;
+        return sbc;
+    };
+    for (int i = 0; i <= it; ++i) {
+        const double *Vcur = Vtab[i], *Vprev = i ? Vtab[i - 1] : nullptr;
+        const double a = -hprev;
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < KW; ++j) {
+            const int idx = gtid + j * gstride;
+            if (idx < n) {
+                if (i) w[j] += a * Vprev[idx];
+                acc += w[j] * Vcur[idx];
+            }
+        }
+        hprev = grid_total(acc);
+        if (blockIdx.x == 0 && threadIdx.x == 0) gs[L.H(i, it)] = hprev;
+    }
+    {
+        const double *Vit = Vtab[it];
+        const double a = -hprev;
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < KW; ++j) {
+            const int idx = gtid + j * gstride;
+            if (idx < n) {
+                w[j] += a * Vit[idx];
+                acc += w[j] * w[j];
+            }
+        }
+        const double aux = sqrt(grid_total(acc));
+        const double s = 1.0 / aux;
+        double *Vnext = const_cast<double *>(Vtab[it + 1]);
+#pragma unroll
+        for (int j = 0; j < KW; ++j) {
+            const int idx = gtid + j * gstride;
+            if (idx < n) {
+                W[idx] = w[j];
+                Vnext[idx] = s * w[j];
+            }
+        }
+        if (blockIdx.x == 0 && threadIdx.x == 0) { // Hessenberg column through the rotations, new rotation, g, stopping test
+            double *H = gs, *rot0 = gs + L.rot0(), *rot1 = gs + L.rot1(), *g = gs + L.g();
+            gs[L.aux()] = aux;
+            H[L.H(it + 1, it)] = aux;
+            for (int i = 0; i < it; i++) {
+                const double aa = rot0[i] * H[L.H(i, it)] + rot1[i] * H[L.H(i + 1, it)];
+                const double bb = -rot1[i] * H[L.H(i, it)] + rot0[i] * H[L.H(i + 1, it)];
+                H[L.H(i, it)] = aa;
+                H[L.H(i + 1, it)] = bb;
+            }
+            const double hii = H[L.H(it, it)], hi1 = H[L.H(it + 1, it)];
+            const double sq = sqrt(hii * hii + hi1 * hi1);
+            rot0[it] = hii / sq;
+            rot1[it] = hi1 / sq;
+            H[L.H(it, it)] = rot0[it] * hii + rot1[it] * hi1;
+            H[L.H(it + 1, it)] = 0.0;
+            g[it + 1] = -rot1[it] * g[it];
+            g[it] = rot0[it] * g[it];
+            const double relres = fabs(g[it + 1]);
+            gs[L.relres()] = relres;
+            __threadfence();
+            if (relres / gs[L.normb()] < fabs(eps)) flags[F_CONV_ITER] = it + 1;
+        }
+    }
+}
+
 // y by back substitution on the rotated Hessenberg matrix (CG.cpp:477-483)
 __global__ void k_gm_backsolve(int it, GmresLayout L, double *__restrict__ gs)
 {
@@ -1265,16 +1367,44 @@ static void gmres_device(ffcuda_matrix *A, const double *b, double *x, double ep
     // Krylov vectors in chunks of 16, allocated as the basis grows (the default dimension is 1000)
     constexpr int CH = 16;
     std::deque<DBuf<double>> cV, cP;
-    std::vector<double *> hP((size_t)m + 1, nullptr);
-    DBuf<double *> dP;
+    std::vector<double *> hP((size_t)m + 1, nullptr), hV((size_t)m + 2, nullptr);
+    DBuf<double *> dP, dV;
     dP.alloc((size_t)m + 1);
+    dV.alloc((size_t)m + 2);
     auto vecV = [&](int i) -> double * {
         while ((int)cV.size() * CH <= i) {
             cV.emplace_back();
             cV.back().alloc((size_t)CH * n);
+            for (int k = 0; k < CH && (cV.size() - 1) * CH + k <= (size_t)m + 1; ++k) hV[(cV.size() - 1) * CH + k] = cV.back().p + (size_t)k * n;
+            FF_CUDA(ff_memcpy_sync(ctx, dV.p, hV.data(), hV.size() * sizeof(double *), cudaMemcpyHostToDevice));
         }
         return cV[i / CH].p + (size_t)(i % CH) * n;
     };
+    // the cooperative Arnoldi kernel: as many CTAs as are co-resident, the entries of w in registers (KW per thread)
+    int coop_grid = 0, coop_kw = 0;
+    if (ctx->gmres_coop) {
+        int dev = 0, can = 0;
+        FF_CUDA(cudaGetDevice(&dev));
+        FF_CUDA(cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, dev));
+        if (can) {
+            for (int kw : {4, 8, 16, 32}) {
+                int per_sm = 0;
+                cudaError_t e = kw == 4    ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gm_arnoldi<4>, RED_THREADS, 0)
+                                : kw == 8  ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gm_arnoldi<8>, RED_THREADS, 0)
+                                : kw == 16 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gm_arnoldi<16>, RED_THREADS, 0)
+                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gm_arnoldi<32>, RED_THREADS, 0);
+                FF_CUDA(e);
+                const int g = std::min(per_sm, 2) * ctx->sm_count;
+                if (g > 0 && (size_t)g * RED_THREADS * kw >= (size_t)n) {
+                    coop_grid = (int)std::min<size_t>((size_t)g, ((size_t)n + (size_t)RED_THREADS * kw - 1) / ((size_t)RED_THREADS * kw));
+                    coop_kw = kw;
+                    break;
+                }
+            }
+        }
+    }
+    if (coop_grid) ensure_partial(ctx, 2 * (size_t)std::max({grid_v, 1024, coop_grid}) + 16);
+    partial = ctx->d_partial;
     auto vecP = [&](int i) -> double * {
         while ((int)cP.size() * CH <= i) {
             cP.emplace_back();
@@ -1298,15 +1428,28 @@ static void gmres_device(ffcuda_matrix *A, const double *b, double *x, double ep
             double *Vit = vecV(it), *Vnext = vecV(it + 1), *Pit = vecP(it);
             ff_launch(ctx, "gmres_precond_apply", [&] { k_gm_precond<<<grid_v, RED_THREADS, 0, st>>>(Pit, Vit, D1.p, n, flags); });
             spmv_launch(A, Pit, nullptr, W.p);
-            for (int i = 0; i <= it; ++i) {
-                const double *Vprev = i ? vecV(i - 1) : nullptr;
-                const double *Vcur = vecV(i);
-                ff_launch(ctx, "gmres_mgs", [&] {
-                    k_gm_mgs<<<grid_v, RED_THREADS, 0, st>>>(W.p, Vprev, Vcur, gs.p + L.H(i ? i - 1 : 0, it), gs.p + L.H(i, it), n, partial, flags);
-                });
+            if (coop_grid) {
+                double *Wp = W.p, *gsp = gs.p;
+                const double *const *vt = dV.p;
+                int nn = n, iit = it;
+                double e = eps;
+                void *args[] = {&Wp, &vt, &nn, &iit, &e, &L, &gsp, &partial, &flags};
+                const void *fn = coop_kw == 4    ? (const void *)k_gm_arnoldi<4>
+                                 : coop_kw == 8  ? (const void *)k_gm_arnoldi<8>
+                                 : coop_kw == 16 ? (const void *)k_gm_arnoldi<16>
+                                                 : (const void *)k_gm_arnoldi<32>;
+                ff_launch(ctx, "gmres_arnoldi", [&] { FF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(coop_grid), dim3(RED_THREADS), args, 0, st)); });
+            } else {
+                for (int i = 0; i <= it; ++i) {
+                    const double *Vprev = i ? vecV(i - 1) : nullptr;
+                    const double *Vcur = vecV(i);
+                    ff_launch(ctx, "gmres_mgs", [&] {
+                        k_gm_mgs<<<grid_v, RED_THREADS, 0, st>>>(W.p, Vprev, Vcur, gs.p + L.H(i ? i - 1 : 0, it), gs.p + L.H(i, it), n, partial, flags);
+                    });
+                }
+                ff_launch(ctx, "gmres_mgs_last", [&] { k_gm_mgs_last<<<grid_v, RED_THREADS, 0, st>>>(W.p, Vit, n, it, eps, L, gs.p, partial, flags); });
+                ff_launch(ctx, "gmres_scale", [&] { k_gm_scale<<<grid_v, RED_THREADS, 0, st>>>(Vnext, W.p, gs.p + L.aux(), n, flags); });
             }
-            ff_launch(ctx, "gmres_mgs_last", [&] { k_gm_mgs_last<<<grid_v, RED_THREADS, 0, st>>>(W.p, Vit, n, it, eps, L, gs.p, partial, flags); });
-            ff_launch(ctx, "gmres_scale", [&] { k_gm_scale<<<grid_v, RED_THREADS, 0, st>>>(Vnext, W.p, gs.p + L.aux(), n, flags); });
             const bool leave = it > itmax; // `if( it > nbitermx) break;`
             if (leave || it == m - 1 || it % poll == poll - 1) {
                 FF_CUDA(cudaMemcpyAsync(hflags, flags, sizeof(int), cudaMemcpyDeviceToHost, st));

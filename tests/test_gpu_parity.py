@@ -656,11 +656,14 @@ def test_gmres_on_reference_matrix(ctx, name):
     n = g["ndof"]
     rp, ci, val = fc.golden_csr(g)
     A = ctx.matrix_from_csr(n, rp, ci, val)
-    for eps, ku, kit in ((1e-6, "u", "cg_iters"), (1e-14, "u14", "cg_iters14")):
-        x = np.zeros(n)
-        it, conv, rel = A.gmres_host(g["b"].copy(), x, eps=eps, restart=fc.CASE_GMRES[name])
-        assert conv == 1 and it == int(g[kit]) and rel < eps
-        assert np.max(np.abs(x - g[ku])) <= (1e-10 if eps > 1e-10 else RTOL) * np.abs(g[ku]).max()
+    for coop in (1, 0):   # one cooperative kernel per Arnoldi step (default) / one kernel per basis vector
+        ctx.set_option("gmres_coop", coop)
+        for eps, ku, kit in ((1e-6, "u", "cg_iters"), (1e-14, "u14", "cg_iters14")):
+            x = np.zeros(n)
+            it, conv, rel = A.gmres_host(g["b"].copy(), x, eps=eps, restart=fc.CASE_GMRES[name])
+            assert conv == 1 and it == int(g[kit]) and rel < eps
+            assert np.max(np.abs(x - g[ku])) <= (1e-10 if eps > 1e-10 else RTOL) * np.abs(g[ku]).max()
+    ctx.set_option("gmres_coop", 1)
     # reproducible run to run (fixed summation shapes, no atomics on doubles)
     x1, x2 = np.zeros(n), np.zeros(n)
     A.gmres_host(g["b"].copy(), x1, eps=1e-10, restart=fc.CASE_GMRES[name])
@@ -689,7 +692,8 @@ def test_gmres_convection_diffusion_cube(ctx):
     rp, col = pat.download()
     val, hb = A.download(), b.download()
     rows = np.repeat(np.arange(n, dtype=np.int32), np.diff(rp))
-    for restart in (1000, 30):
+    for restart, coop in ((1000, 1), (30, 1), (30, 0)):
+        ctx.set_option("gmres_coop", coop)
         x = ctx.vec(n)
         it, conv, rel = A.gmres(b, x, eps=1e-12, restart=restart, tgv=TGV)
         xo, ito, reto, _ = ol.gmres(n, rows, col, val, hb, np.zeros(n), eps=1e-12, nbkrylov=restart, tgv=TGV)
@@ -699,6 +703,7 @@ def test_gmres_convection_diffusion_cube(ctx):
         r = hb - __import__("scipy.sparse").sparse.csr_matrix((val, col, rp), shape=(n, n)) @ u
         inner = np.abs(hb) < 1e20
         assert np.linalg.norm(r[inner]) <= 1e-10 * np.linalg.norm(hb[inner])
+    ctx.set_option("gmres_coop", 1)
     x = ctx.vec(n)
     it, conv, rel = A.gmres(b, x, eps=1e-12, itmax=5, restart=1000, tgv=TGV)
     assert conv == 0 and it <= 8

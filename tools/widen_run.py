@@ -44,7 +44,8 @@ def main():
     bc = sp.bc_from_labels([1, 2, 3, 4, 5, 6], 1, [0.0])
     A.apply_bc(bc, 1e30)
     b.apply_bc(bc, 1e30)
-    for restart in (1000, 50):
+    for restart, coop in ((1000, 1), (50, 1), (50, 0)):
+        ctx.set_option("gmres_coop", coop)
         x = ctx.vec(n)
         A.gmres(b, x, eps=1e-6, restart=restart)    # warm-up (SELL copy, allocator)
         x = ctx.vec(n)
@@ -52,9 +53,9 @@ def main():
         ctx.prof_reset()
         l0 = ctx.launch_count()
         t, (it, conv, rel) = wall(ctx, lambda: A.gmres(b, x, eps=1e-6, restart=restart))
-        kern = {k: ctx.prof_get(k) for k in ("gmres_mgs", "gmres_mgs_last", "gmres_scale", "gmres_precond_apply", "spmv", "gmres_update_x", "")}
+        kern = {k: ctx.prof_get(k) for k in ("gmres_arnoldi", "gmres_mgs", "gmres_mgs_last", "gmres_scale", "gmres_precond_apply", "spmv", "gmres_update_x", "")}
         ctx.prof_enable(False)
-        print(json.dumps({"what": "gmres convection-diffusion", "mesh": f"cube({N})", "n": n, "nnz": nnz, "restart": restart, "iters": it,
+        print(json.dumps({"what": "gmres convection-diffusion", "mesh": f"cube({N})", "n": n, "nnz": nnz, "restart": restart, "cooperative_arnoldi": coop, "iters": it,
                           "converged": conv, "relres": rel, "wall_ms": round(t, 2), "launches": int(ctx.launch_count() - l0),
                           "kernels_ms_and_launches": {k: [round(v[0], 3), int(v[1])] for k, v in kern.items()}}), flush=True)
     # --- boundary integrals: Neumann data on two faces, Robin term on two faces
