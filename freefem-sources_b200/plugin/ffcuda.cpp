@@ -407,7 +407,18 @@ struct BCItem {
     std::vector<int32_t> labels;
     int compmask = 0;
     double values[3] = {0, 0, 0};
+    // on(..., u = g(x,y,z)): the (dof, value) pairs AssembleBC would produce, in its order (later pairs win)
+    bool pairs = false;
+    std::vector<int32_t> pdofs;
+    std::vector<double> pvals;
 };
+ffcuda_bc *make_bc(ffcuda_space *space, const BCItem &B)
+{
+    ffcuda_bc *bc = nullptr;
+    if (B.pairs) FFC(ffcuda_bc_from_pairs(space, (int)B.pdofs.size(), B.pdofs.data(), B.pvals.data(), &bc));
+    else FFC(ffcuda_bc_from_labels(space, (int)B.labels.size(), B.labels.data(), B.compmask, B.values, &bc));
+    return bc;
+}
 struct Varf {
     std::vector<BilinearItem> bil;
     std::vector<LinearItem> lin;
@@ -415,8 +426,80 @@ struct Varf {
     bool other_rhs_items = false; // arrays, A*x, ... (only meaningful for the right-hand side)
 };
 
-template <class MeshT>
-Varf read_varf(Stack stack, const list<C_F0> &largs, const MeshT &Th, int ncomp, bool want_matrix)
+// Dirichlet data depending on the mesh point, on(labels, u = g(x,y,z)): AssembleBC (fflib/problem.cpp:9881-10034 2-D,
+// :10039-10194 3-D) visits the boundary elements in order and, on each one whose label is listed, evaluates g at the
+// interpolation point of every dof lying on that face (for P1 / P2 Lagrange: the node itself) with the mesh point set to
+// that boundary element (label, unit normal); a later boundary element overwrites an earlier one.  The same here, through
+// FreeFEM's evaluator; the pairs go to ffcuda_bc_from_pairs.  O(boundary) evaluations.
+inline R3 unit_normal(const Mesh3 &, const Tet &T, int ie)
+{
+    R3 NN = T.N(ie);
+    NN /= NN.norme();
+    return NN;
+}
+inline R2 unit_normal(const Mesh &, const Triangle &T, int ie)
+{
+    R2 E = T.Edge(ie);
+    const double le = sqrt((E, E));
+    return R2(E.y, -E.x) / le;
+}
+template <class FESpaceT>
+void dirichlet_pairs(Stack stack, const FESpaceT &Vh, const BC_set *bc, BCItem &B)
+{
+    typedef typename FESpaceT::Mesh MeshT;
+    typedef typename FESpaceT::FElement FElementT;
+    typedef typename MeshT::RdHat RdHat;
+    const MeshT &Th = Vh.Th;
+    const int dim = MeshDim<MeshT>::d;
+    int order, ncomp, nloc;
+    classify_space(Vh, dim, order, ncomp, nloc);
+    static const int edge3[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}}; // Mesh3dn.cpp:73
+    static const int edge2[3][2] = {{1, 2}, {2, 0}, {0, 1}};                       // dof 3+e on the edge opposite vertex e
+    std::vector<Expression> ex((size_t)ncomp, (Expression)0);
+    for (size_t k = 0; k < bc->bc.size(); ++k) ex[bc->bc[k].first] = bc->bc[k].second;
+    std::set<int> on(B.labels.begin(), B.labels.end());
+    MeshPoint *mps = MeshPointStack(stack), mp = *mps;
+    B.pairs = true;
+    try {
+        const int nbe = nbe_of(Th);
+        for (int ib = 0; ib < nbe; ++ib) {
+            int ie;
+            const int it = belem_of(Th, ib, ie);
+            const int r = blabel(Th, ib);
+            if (!on.count(r)) continue;
+            const FElementT K(Vh[it]);
+            const typename MeshT::Rd NN = unit_normal(Th, K.T, ie);
+            for (int a = 0; a < nloc; ++a) {
+                double l[4] = {0, 0, 0, 0}; // barycentric coordinates of local node a
+                bool onface;
+                if (a <= dim) {
+                    l[a] = 1.0;
+                    onface = a != ie;
+                } else {
+                    const int e = a - (dim + 1);
+                    const int i0 = dim == 3 ? edge3[e][0] : edge2[e][0], i1 = dim == 3 ? edge3[e][1] : edge2[e][1];
+                    l[i0] = l[i1] = 0.5;
+                    onface = i0 != ie && i1 != ie;
+                }
+                if (!onface) continue;
+                const RdHat PtHat(hat_point((const MeshT *)0, l));
+                mps->set(K.T(PtHat), PtHat, K, r, NN, ie);
+                for (int c = 0; c < ncomp; ++c)
+                    if (B.compmask >> c & 1) {
+                        B.pdofs.push_back((int32_t)K(c * nloc + a));
+                        B.pvals.push_back(GetAny<double>((*ex[c])(stack)));
+                    }
+            }
+        }
+    } catch (...) {
+        *mps = mp;
+        throw;
+    }
+    *mps = mp;
+}
+
+template <class MeshT, class FESpaceT>
+Varf read_varf(Stack stack, const list<C_F0> &largs, const MeshT &Th, int ncomp, bool want_matrix, const FESpaceT &Vh)
 {
     const int dim = MeshDim<MeshT>::d;
     Varf V;
@@ -496,15 +579,19 @@ Varf read_varf(Stack stack, const list<C_F0> &largs, const MeshT &Th, int ncomp,
                 }
             if (on.size() > 32) throw Unsupported{"more than 32 labels in one on(...)"};
             for (std::set<long>::const_iterator it = on.begin(); it != on.end(); ++it) B.labels.push_back((int32_t)*it);
+            bool varying = false;
             for (size_t k = 0; k < bc->bc.size(); ++k) {
                 const int comp = bc->bc[k].first;
                 if (comp < 0 || comp >= ncomp) throw Unsupported{"boundary condition on a component out of range"};
-                if (!bc->bc[k].second->MeshIndependent()) throw Unsupported{"boundary value depends on the mesh point"};
                 B.compmask |= 1 << comp;
-                B.values[comp] = GetAny<double>((*bc->bc[k].second)(stack));
+                if (!bc->bc[k].second->MeshIndependent()) varying = true;
             }
             if (ncomp > 1 && B.compmask != (1 << ncomp) - 1)
                 throw Unsupported{"vector space with a boundary condition on some components only"};
+            if (varying) {
+                if (!B.labels.empty()) dirichlet_pairs(stack, Vh, bc, B);
+            } else
+                for (size_t k = 0; k < bc->bc.size(); ++k) B.values[bc->bc[k].first] = GetAny<double>((*bc->bc[k].second)(stack));
             if (!B.labels.empty()) V.bc.push_back(B);
         } else {
             if (want_matrix) throw Unsupported{"varf item other than integrals and on(...)"};
@@ -518,8 +605,7 @@ void apply_bcs(DevSpace &D, const Varf &V, ffcuda_matrix *A, ffcuda_vec *b, doub
 {
     for (size_t i = 0; i < V.bc.size(); ++i) {
         const BCItem &B = V.bc[i];
-        ffcuda_bc *bc = nullptr;
-        FFC(ffcuda_bc_from_labels(D.space, (int)B.labels.size(), B.labels.data(), B.compmask, B.values, &bc));
+        ffcuda_bc *bc = make_bc(D.space, B);
         int rc = 0;
         if (A) rc |= ffcuda_matrix_apply_bc(A, bc, tgv);
         if (b) rc |= ffcuda_vec_apply_bc(b, bc, tgv);
@@ -792,8 +878,7 @@ void gpu_rhs(Stack stack, const FESpaceT &Vh, DevSpace &D, const Varf &V, double
                 if (ffcuda_vec_upload(dx, x0) != 0) fail("uploading the initial guess");
                 for (size_t i = 0; i < V.bc.size(); ++i) {
                     const BCItem &B = V.bc[i];
-                    ffcuda_bc *bc = nullptr;
-                    FFC(ffcuda_bc_from_labels(D.space, (int)B.labels.size(), B.labels.data(), B.compmask, B.values, &bc));
+                    ffcuda_bc *bc = make_bc(D.space, B);
                     int r2 = ffcuda_vec_set_bc_values(dx, bc);
                     ffcuda_bc_destroy(bc);
                     if (r2) fail("setting the Dirichlet values of the initial guess");
@@ -839,7 +924,7 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
                 const FESpaceT &Vh = *PVh;
                 const MMesh &Th = Vh.Th;
                 if (!isSameMesh(this->b->largs, &Vh.Th, &Vh.Th, stack)) throw Unsupported{"integrals on different meshes"};
-                Varf V = read_varf(stack, this->b->largs, Th, Vh.N, true);
+                Varf V = read_varf(stack, this->b->largs, Th, Vh.N, true, Vh);
                 check_full_pattern(V, Th);
                 check_qterms_supported(Vh, V);
                 DevSpace &D = device_space(Vh);
@@ -891,7 +976,7 @@ struct CudaRhsOp : public OpArraytoLinearForm<double, MMesh, v_fes> {
                 double tgv = ff_tgv;
                 if (this->l->nargs[0]) tgv = GetAny<double>((*this->l->nargs[0])(stack));
                 if (tgv != tgv) throw Unsupported{"tgv is NaN"};
-                Varf V = read_varf(stack, this->l->largs, Vh.Th, Vh.N, false);
+                Varf V = read_varf(stack, this->l->largs, Vh.Th, Vh.N, false, Vh);
                 if (V.other_rhs_items) throw Unsupported{"right-hand side with array / matrix-vector items"};
                 DevSpace &D = device_space(Vh);
                 const long n = Vh.NbOfDF;
@@ -1130,8 +1215,8 @@ struct CudaProblem : public Base {
         const MeshT &Th = Uhp->Th;
         if (!isSameMesh(this->op->largs, &Th, &Th, stack)) throw Unsupported{"integrals on different meshes"};
         // everything that may be refused is read before anything is changed
-        Varf VA = read_varf(stack, this->op->largs, Th, N, true);
-        Varf VB = read_varf(stack, this->op->largs, Th, N, false);
+        Varf VA = read_varf(stack, this->op->largs, Th, N, true, *Uhp);
+        Varf VB = read_varf(stack, this->op->largs, Th, N, false, *Uhp);
         if (VB.other_rhs_items) throw Unsupported{"array / matrix-vector items in the problem"};
         check_full_pattern(VA, Th);
         check_qterms_supported(*Uhp, VA);

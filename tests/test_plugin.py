@@ -91,6 +91,14 @@ CASES = {
                               "on(1,2,u=0)", eps="1e-14"),
     "lame3d_p1_evar": script(3, "cube(3,4,3)", "[P1,P1,P1]", "(1+x)*(" + LAME + ")+0.5*(1+y*y)*(u1*v1+u2*v2+u3*v3)", "-0.05*v3",
                              "on(1,u1=0,u2=0,u3=0)", pre=LAME_PRE, unk="[u1,u2,u3]", tst="[v1,v2,v3]", eps="1e-14"),
+    # Dirichlet data depending on the mesh point (evaluated at the boundary nodes by FreeFEM's evaluator, boundary element by
+    # boundary element as AssembleBC does)
+    "poisson3d_p1_dirichlet_g": script(3, "cube(5,4,6,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", "P1", LAP3, "1.*v",
+                                       "on(1,2,3,u=x*y+z)+on(4,5,6,u=1+N.x)", eps="1e-14"),
+    "laplace2d_p2_dirichlet_g": script(2, "square(6,5,[x+0.2*y*y,y*(1+0.3*x)])", "P2", LAP2, "1.*v", "on(1,3,u=sin(x)+y)+on(2,u=2.)",
+                                       eps="1e-14", tgv=-2),
+    "lame3d_p2_dirichlet_g": script(3, "cube(2,3,2)", "[P2,P2,P2]", LAME, "-0.05*v3", "on(1,u1=0.01*x,u2=0,u3=-0.02*z)", pre=LAME_PRE,
+                                    unk="[u1,u2,u3]", tst="[v1,v2,v3]", eps="1e-14"),
     "mass3d_lumped": script(3, "cube(3,3,3)", "P1", "u*v+0.1*(" + LAP3 + ")", "1.*v", "on(1,u=0)", intopt=",qfV=qfV1lump"),
 }
 
@@ -280,6 +288,11 @@ for (it = 0; it < 4; ++it) {{ uold = u; Heat; }}
 fespace Vh(Th,P1); Vh u,v,rho=1+x*y;
 fespace Ph(Th,P0); Ph kappa = 1 + 9*(x>0.5)*(y<0.5);
 solve Pb(u,v,solver=CG,eps=1e-14) = int2d(Th)(kappa*(dx(u)*dx(v)+dy(u)*dy(v))+rho*u*v) - int2d(Th)(rho*v) + on(1,u=0);
+""",
+    "dirichlet_data_function": """mesh Th = square(15,13);
+fespace Vh(Th,P2); Vh u,v;
+func g = cos(3*x)*y;
+solve Pb(u,v,solver=CG,eps=1e-14) = int2d(Th)(dx(u)*dx(v)+dy(u)*dy(v)) - int2d(Th)(1.*v) + on(1,2,3,4,u=g);
 """,
     "default_solver": """mesh Th = square(9,8);
 fespace Vh(Th,P2); Vh u,v;
