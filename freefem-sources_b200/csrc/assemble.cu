@@ -1594,3 +1594,177 @@ extern "C" int ffcuda_assemble_linear_qvalues(ffcuda_vec *b, ffcuda_space *s, in
     FF_CUDA(cudaStreamSynchronize(st)); // fq is the caller's pageable memory
     FF_API_END(s ? s->ctx : nullptr)
 }
+
+// ----------------------------------------------------------------------------------------------------
+// Boundary integrals whose data depend on the mesh point: int2d(Th3, labels)(g(x,y,z) v), int1d(Th, labels)(alpha(x,y) u v).
+// Element_rhs / Element_Op evaluate the coefficient at every face quadrature node (fflib/problem.cpp:8551-8570, :6526-6556);
+// the caller hands those values over (0 on boundary elements whose label is not listed), the sums over the nodes are
+// formed inside the owner gathers of the constant-coefficient kernels above.
+// ----------------------------------------------------------------------------------------------------
+__global__ void k_bnd_gather_q(int nrows, const int32_t *__restrict__ ptr, const uint32_t *__restrict__ items,
+                               const int32_t *__restrict__ bface, const double *__restrict__ meas, int nc, int nq, int nloc, int nbe,
+                               const double *__restrict__ wphi /* [f][q][a] = w_q phi_a(PBord(f, q)) */,
+                               const double *__restrict__ gq /* [c][e][q] */, double *__restrict__ b, int accumulate)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int k = ptr[i]; k < ptr[i + 1]; ++k) {
+        const uint32_t it = items[k];
+        const int e = it >> 4, a = it & 15;
+        const double *w = wphi + (size_t)bface[e] * nq * nloc + a;
+        for (int c = 0; c < nc; ++c) {
+            const double *g = gq + ((size_t)c * nbe + e) * nq;
+            double t = 0.0;
+            for (int q = 0; q < nq; ++q) t = fma(w[(size_t)q * nloc], g[q], t);
+            s[c] += meas[e] * t;
+        }
+    }
+    if (!accumulate || ptr[i + 1] > ptr[i])
+        for (int c = 0; c < nc; ++c) {
+            double *dst = b + (size_t)i * nc + c;
+            *dst = accumulate ? *dst + s[c] : s[c];
+        }
+}
+template <int DIM>
+__global__ void k_bnd_bilinear_q(int nrows, const int32_t *__restrict__ ptr, const uint32_t *__restrict__ items,
+                                 const int32_t *__restrict__ belem, const int32_t *__restrict__ bface, const double *__restrict__ meas,
+                                 const int32_t *__restrict__ e2n, int nloc, int order, int nc, int nq,
+                                 const int32_t *__restrict__ nrowptr, const int32_t *__restrict__ ncol,
+                                 const double *__restrict__ wpp /* [f][q][a][b] = w_q phi_a phi_b */, const double *__restrict__ cq /* [e][q] */,
+                                 const __grid_constant__ BndBilParams Bq, double *__restrict__ vals)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    const int k0 = ptr[i], k1 = ptr[i + 1];
+    if (k0 == k1) return;
+    const int rb = nrowptr[i], L = nrowptr[i + 1] - rb;
+    double *row = vals + (size_t)nc * nc * rb;
+    for (int k = k0; k < k1; ++k) {
+        const uint32_t it = items[k];
+        const int e = it >> 4, a = it & 15;
+        const double m = meas[e];
+        if (m == 0.0) continue; // label not listed
+        const int f = bface[e];
+        const int32_t *N = e2n + (size_t)nloc * belem[e];
+        const double *c = cq + (size_t)e * nq;
+        int loc[6];
+        const int nf = face_nodes<DIM>(order, f, loc);
+        for (int x = 0; x < nf; ++x) {
+            const int b = loc[x], j = N[b];
+            int lo = 0, hi = L - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (ncol[rb + mid] < j) lo = mid + 1;
+                else hi = mid;
+            }
+            double t = 0.0;
+            for (int q = 0; q < nq; ++q) t = fma(wpp[(((size_t)f * nq + q) * nloc + a) * nloc + b], c[q], t);
+            const double w = m * t;
+            for (int cv = 0; cv < nc; ++cv)
+                for (int cu = 0; cu < nc; ++cu)
+                    if (Bq.C[cv][cu] != 0.0) row[(size_t)cv * nc * L + (size_t)lo * nc + cu] += Bq.C[cv][cu] * w;
+        }
+    }
+}
+
+extern "C" int ffcuda_assemble_linear_boundary_qvalues(ffcuda_vec *b, ffcuda_space *s, int nq, const double *qpts, const double *qw,
+                                                       const double *gq, int accumulate)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(b && s && gq, "ffcuda_assemble_linear_boundary_qvalues: null argument");
+    FF_REQUIRE(nq > 0 && qpts && qw, "face quadrature rule missing");
+    ffcuda_ctx *ctx = s->ctx;
+    ff_enter(ctx);
+    ffcuda_mesh *m = s->mesh;
+    const int dim = m->dim, nloc = s->nloc, nc = s->ncomp, nbe = m->nbe;
+    FF_REQUIRE(b->n >= s->nnodes_owned * nc, "right-hand side vector too short");
+    FF_REQUIRE(nbe > 0 && m->belem.p && m->bface.p, "the mesh has no boundary elements");
+    std::vector<double> wphi((size_t)(dim + 1) * nq * nloc);
+    for (int f = 0; f <= dim; ++f)
+        for (int q = 0; q < nq; ++q) {
+            double B[10][4];
+            face_ref_basis(dim, s->order, f, qpts + (size_t)q * (dim - 1), B);
+            for (int a = 0; a < nloc; ++a) wphi[((size_t)f * nq + q) * nloc + a] = qw[q] * B[a][0];
+        }
+    BndParams Bp;
+    memset(&Bp, 0, sizeof(Bp));
+    Bp.nlab = -1; // every boundary element: the table is 0 where the integral does not go
+    cudaStream_t st = ctx->stream;
+    if (dim == 3) bnd_incidence<3>(ctx, s);
+    else bnd_incidence<2>(ctx, s);
+    DBuf<double> meas, dW, dG;
+    meas.alloc((size_t)nbe);
+    dW.alloc(wphi.size());
+    dG.alloc((size_t)nc * nbe * nq);
+    FF_CUDA(cudaMemcpyAsync(dW.p, wphi.data(), dW.bytes(), cudaMemcpyHostToDevice, st));
+    FF_CUDA(cudaMemcpyAsync(dG.p, gq, dG.bytes(), cudaMemcpyHostToDevice, st));
+    bnd_measures(ctx, m, Bp, meas.p);
+    const int nrows = s->nnodes_owned;
+    ff_launch(ctx, "bnd_gather_q", [&] {
+        k_bnd_gather_q<<<ff_blocks(nrows, 256), 256, 0, st>>>(nrows, s->bnd_ptr.p, s->bnd_items.p, m->bface.p, meas.p, nc, nq, nloc, nbe, dW.p, dG.p,
+                                                            b->d.p, accumulate);
+    });
+    FF_CUDA(cudaStreamSynchronize(st)); // gq is the caller's pageable memory
+    FF_API_END(s ? s->ctx : nullptr)
+}
+
+extern "C" int ffcuda_assemble_bilinear_boundary_qcoef(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms, int nq,
+                                                       const double *qpts, const double *qw, const double *cq, int nlab,
+                                                       const int32_t *labels, int accumulate)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A && s && cq && A->pattern && A->pattern->space == s, "ffcuda_assemble_bilinear_boundary_qcoef: bad arguments");
+    FF_REQUIRE(nterms >= 0 && (nterms == 0 || terms), "bad term list");
+    FF_REQUIRE(nq > 0 && qpts && qw, "face quadrature rule missing");
+    ffcuda_ctx *ctx = s->ctx;
+    ff_enter(ctx);
+    ffcuda_mesh *m = s->mesh;
+    ffcuda_pattern *P = A->pattern;
+    const int dim = m->dim, nloc = s->nloc, nc = s->ncomp, nbe = m->nbe;
+    FF_REQUIRE(nbe > 0 && m->belem.p && m->bface.p, "the mesh has no boundary elements");
+    BndBilParams Bq;
+    memset(&Bq, 0, sizeof(Bq));
+    for (int t = 0; t < nterms; ++t) {
+        const ffcuda_bterm &T = terms[t];
+        FF_REQUIRE(T.ucomp >= 0 && T.ucomp < nc && T.vcomp >= 0 && T.vcomp < nc, "term component out of range");
+        FF_REQUIRE(T.uop == FFCUDA_OP_ID && T.vop == FFCUDA_OP_ID, "boundary integrals: only value terms (c * u * v) are on the ffcuda path");
+        Bq.C[T.vcomp][T.ucomp] += T.coef;
+    }
+    BndParams Bp;
+    memset(&Bp, 0, sizeof(Bp));
+    bnd_fill_labels(Bp, nlab, labels);
+    std::vector<double> wpp((size_t)(dim + 1) * nq * nloc * nloc);
+    for (int f = 0; f <= dim; ++f)
+        for (int q = 0; q < nq; ++q) {
+            double B[10][4];
+            face_ref_basis(dim, s->order, f, qpts + (size_t)q * (dim - 1), B);
+            for (int a = 0; a < nloc; ++a)
+                for (int b = 0; b < nloc; ++b) wpp[(((size_t)f * nq + q) * nloc + a) * nloc + b] = qw[q] * B[a][0] * B[b][0];
+        }
+    cudaStream_t st = ctx->stream;
+    if (accumulate) ff_matrix_touch(A);
+    else FF_CUDA(cudaMemsetAsync(A->vals.p, 0, A->vals.bytes(), st));
+    A->vals_stale = false;
+    A->vals_epoch++;
+    if (dim == 3) bnd_incidence<3>(ctx, s);
+    else bnd_incidence<2>(ctx, s);
+    DBuf<double> meas, dW, dC;
+    meas.alloc((size_t)nbe);
+    dW.alloc(wpp.size());
+    dC.alloc((size_t)nbe * nq);
+    FF_CUDA(cudaMemcpyAsync(dW.p, wpp.data(), dW.bytes(), cudaMemcpyHostToDevice, st));
+    FF_CUDA(cudaMemcpyAsync(dC.p, cq, dC.bytes(), cudaMemcpyHostToDevice, st));
+    bnd_measures(ctx, m, Bp, meas.p);
+    const int nrows = s->nnodes_owned;
+    ff_launch(ctx, "bnd_bilinear_q", [&] {
+        if (dim == 3)
+            k_bnd_bilinear_q<3><<<ff_blocks(nrows, 128), 128, 0, st>>>(nrows, s->bnd_ptr.p, s->bnd_items.p, m->belem.p, m->bface.p, meas.p, s->e2n,
+                                                                     nloc, s->order, nc, nq, P->nrowptr.p, P->ncol.p, dW.p, dC.p, Bq, A->vals.p);
+        else
+            k_bnd_bilinear_q<2><<<ff_blocks(nrows, 128), 128, 0, st>>>(nrows, s->bnd_ptr.p, s->bnd_items.p, m->belem.p, m->bface.p, meas.p, s->e2n,
+                                                                     nloc, s->order, nc, nq, P->nrowptr.p, P->ncol.p, dW.p, dC.p, Bq, A->vals.p);
+    });
+    FF_CUDA(cudaStreamSynchronize(st)); // cq is the caller's pageable memory
+    FF_API_END(s ? s->ctx : nullptr)
+}

@@ -21,7 +21,7 @@ ffcuda_space_destroy ffcuda_symbolic ffcuda_pattern_info ffcuda_pattern_download
 ffcuda_matrix_download_lower ffcuda_matrix_from_csr_lower ffcuda_pattern_destroy ffcuda_matrix_create
 ffcuda_matrix_from_csr ffcuda_matrix_info ffcuda_matrix_download ffcuda_matrix_upload ffcuda_matrix_destroy ffcuda_vec_create
 ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_destroy ffcuda_assemble_bilinear ffcuda_assemble_bilinear_qcoef
-ffcuda_assemble_linear ffcuda_assemble_linear_qvalues ffcuda_assemble_linear_boundary ffcuda_assemble_bilinear_boundary ffcuda_bc_from_pairs ffcuda_bc_from_labels ffcuda_bc_count ffcuda_matrix_apply_bc ffcuda_vec_apply_bc
+ffcuda_assemble_linear ffcuda_assemble_linear_qvalues ffcuda_assemble_linear_boundary ffcuda_assemble_bilinear_boundary ffcuda_assemble_linear_boundary_qvalues ffcuda_assemble_bilinear_boundary_qcoef ffcuda_bc_from_pairs ffcuda_bc_from_labels ffcuda_bc_count ffcuda_matrix_apply_bc ffcuda_vec_apply_bc
 ffcuda_vec_set_bc_values ffcuda_bc_destroy ffcuda_spmv ffcuda_cg ffcuda_cg_host ffcuda_gmres ffcuda_gmres_host ffcuda_comm_unique_id ffcuda_comm_init
 ffcuda_comm_finalize ffcuda_mesh_cube_distributed ffcuda_mesh_local_to_global ffcuda_quadrature ffcuda_partition_cube""".split()
 
@@ -300,6 +300,11 @@ class Space(_Handle):
         qpts, qw, fq = _f64(qpts), _f64(qw), _f64(fq)
         _ck(lib().ffcuda_assemble_linear_qvalues(_h(b), _h(self), len(qw), _p(qpts), _p(qw), _p(fq), int(accumulate)), self.ctx.h)
 
+    def assemble_linear_boundary_qvalues(self, b, qpts, qw, gq, accumulate=True):
+        """b (+)= boundary integral of g v with g given at the face quadrature nodes: gq[c, ib, q] (0 where it does not go)"""
+        qpts, qw, gq = _f64(qpts), _f64(qw), _f64(gq)
+        _ck(lib().ffcuda_assemble_linear_boundary_qvalues(_h(b), _h(self), len(qw), _p(qpts), _p(qw), _p(gq), int(accumulate)), self.ctx.h)
+
     def assemble_linear_boundary(self, b, terms, qpts, qw, labels=None, accumulate=True):
         """b (+)= int2d(Th3, labels)(c v) / int1d(Th, labels)(c v); qpts: nq x (dim-1) face reference coordinates"""
         arr = (LTerm * max(len(terms), 1))()
@@ -394,6 +399,15 @@ class Matrix(_Handle):
         qpts, qw, cq = _f64(qpts), _f64(qw), _f64(cq)
         _ck(lib().ffcuda_assemble_bilinear_qcoef(_h(self), _h(self.pattern.space), len(terms), arr, len(qw), _p(qpts), _p(qw),
                                                  _p(cq), int(accumulate)), self.ctx.h)
+
+    def assemble_boundary_qcoef(self, terms, qpts, qw, cq, labels=None, accumulate=True):
+        """A (+)= boundary integral of alpha u v with alpha given at the face quadrature nodes: cq[ib, q]"""
+        arr = (BTerm * max(len(terms), 1))()
+        for k, (uc, uo, vc, vo, c) in enumerate(terms):
+            arr[k] = BTerm(uc, uo, vc, vo, c)
+        qpts, qw, cq, lab = _f64(qpts), _f64(qw), _f64(cq), _i32(labels)
+        _ck(lib().ffcuda_assemble_bilinear_boundary_qcoef(_h(self), _h(self.pattern.space), len(terms), arr, len(qw), _p(qpts), _p(qw),
+                                                          _p(cq), 0 if lab is None else len(lab), _p(lab), int(accumulate)), self.ctx.h)
 
     def assemble_boundary(self, terms, qpts, qw, labels=None, accumulate=True):
         """A (+)= int2d(Th3, labels)(c u v) / int1d(Th, labels)(c u v) (Robin terms); qpts: nq x (dim-1) face coordinates"""

@@ -527,7 +527,6 @@ Varf read_varf(Stack stack, const list<C_F0> &largs, const MeshT &Th, int ncomp,
                 if (!op.v[k].second.LeftValue()->MeshIndependent()) {
                     // kappa(x,y,z) grad u . grad v, rho(x) u v, a P0 / P1 function as coefficient: evaluated at the quadrature
                     // nodes by FreeFEM's evaluator, integrated on the device (P1 spaces; checked in gpu_matrix)
-                    if (B.border) throw Unsupported{"boundary integral whose coefficient depends on the mesh point"};
                     if (op.v[k].second.left() != atype<double>() && op.v[k].second.left() != atype<long>())
                         throw Unsupported{"coefficient is not real"};
                     t.coef = 0.0;
@@ -555,7 +554,6 @@ Varf read_varf(Stack stack, const list<C_F0> &largs, const MeshT &Th, int ncomp,
                 if (L.border && t.vop != op_id) throw Unsupported{"derivatives in a boundary integral"};
                 if (!op.v[k].second.LeftValue()->MeshIndependent()) {
                     // f(x,y,z) v, uold v / dt, ...: the values Element_rhs would compute go to the device as a table
-                    if (L.border) throw Unsupported{"boundary integral whose coefficient depends on the mesh point"};
                     if (t.vop != op_id) throw Unsupported{"derivative of the test function times a coefficient that depends on the mesh point"};
                     if (op.v[k].second.left() != atype<double>() && op.v[k].second.left() != atype<long>())
                         throw Unsupported{"coefficient is not real"};
@@ -641,7 +639,7 @@ template <class FESpaceT>
 void check_qterms_supported(const FESpaceT &Vh, const Varf &V)
 {
     bool any = false;
-    for (size_t i = 0; i < V.bil.size(); ++i) any = any || !V.bil[i].qterms.empty();
+    for (size_t i = 0; i < V.bil.size(); ++i) any = any || (!V.bil[i].qterms.empty() && !V.bil[i].border);
     if (!any) return;
     int order, ncomp, nloc;
     classify_space(Vh, MeshDim<typename FESpaceT::Mesh>::d, order, ncomp, nloc);
@@ -701,14 +699,59 @@ std::vector<std::vector<double>> eval_at_nodes(Stack stack, const FESpaceT &Vh, 
     *mps = mp;
     return out;
 }
+// the same at the face quadrature nodes of the boundary elements whose label is listed (Element_rhs / Element_Op on a border
+// element, fflib/problem.cpp:8540-8551, :8646-8652, :6520-6528): Pt = PBord(ie, q), mesh point set with the label and the
+// unit normal of the boundary element.  out[e][ib * nq + q]; Q holds the face rule in the library's coordinates
+// (P = A(1-x-y) + Bx + Cy on a face, P = A(1-x) + Bx on an edge, A, B, C the vertices of the face in FreeFEM's order).
+inline R3 bord_point(const Tet &T, int ie, const double *p) { return T.PBord(ie, R2(p[0], p[1])); }
+inline R2 bord_point(const Triangle &, int ie, const double *p)
+{
+    const R2 PA(TriangleHat[VerticesOfTriangularEdge[ie][0]]), PB(TriangleHat[VerticesOfTriangularEdge[ie][1]]);
+    return PA * (1.0 - p[0]) + PB * p[0];
+}
+template <class FESpaceT>
+std::vector<std::vector<double>> eval_at_bnodes(Stack stack, const FESpaceT &Vh, const std::vector<const C_F0 *> &exprs, const Quad &Q,
+                                                const Region &reg)
+{
+    typedef typename FESpaceT::Mesh MeshT;
+    typedef typename FESpaceT::FElement FElementT;
+    const MeshT &Th = Vh.Th;
+    const int dim = MeshDim<MeshT>::d, nq = (int)Q.w.size(), nbe = nbe_of(Th);
+    std::vector<std::vector<double>> out(exprs.size(), std::vector<double>((size_t)nbe * nq, 0.0));
+    std::set<int> labs(reg.labels.begin(), reg.labels.end());
+    MeshPoint *mps = MeshPointStack(stack), mp = *mps;
+    try {
+        for (int ib = 0; ib < nbe; ++ib) {
+            const int r = blabel(Th, ib);
+            if (!reg.all && !labs.count(r)) continue;
+            int ie;
+            const int it = belem_of(Th, ib, ie);
+            const FElementT K(Vh[it]);
+            const typename MeshT::Rd NN = unit_normal(Th, K.T, ie);
+            for (int q = 0; q < nq; ++q) {
+                const typename MeshT::RdHat Pt(bord_point(K.T, ie, Q.pts.data() + (size_t)q * (dim - 1)));
+                mps->set(K.T(Pt), Pt, K, r, NN, ie);
+                for (size_t e = 0; e < exprs.size(); ++e) {
+                    const C_F0 &c = *exprs[e];
+                    out[e][(size_t)ib * nq + q] = c.left() == atype<long>() ? (double)GetAny<long>(c.eval(stack)) : GetAny<double>(c.eval(stack));
+                }
+            }
+        }
+    } catch (...) {
+        *mps = mp;
+        throw;
+    }
+    *mps = mp;
+    return out;
+}
 // table of a linear item: fq[(c * nt + k) * nq + q], summed over the terms of component c
 template <class FESpaceT>
 std::vector<double> eval_qvalues(Stack stack, const FESpaceT &Vh, const LinearItem &L, bool negate)
 {
-    const size_t per = (size_t)Vh.Th.nt * L.q.w.size();
+    const size_t per = (size_t)(L.border ? nbe_of(Vh.Th) : Vh.Th.nt) * L.q.w.size();
     std::vector<const C_F0 *> ex;
     for (size_t t = 0; t < L.qterms.size(); ++t) ex.push_back(&L.qterms[t].coef);
-    std::vector<std::vector<double>> v = eval_at_nodes(stack, Vh, ex, L.q, L.reg);
+    std::vector<std::vector<double>> v = L.border ? eval_at_bnodes(stack, Vh, ex, L.q, L.reg) : eval_at_nodes(stack, Vh, ex, L.q, L.reg);
     std::vector<double> fq((size_t)Vh.N * per, 0.0);
     const double sgn = negate ? -1.0 : 1.0;
     for (size_t t = 0; t < L.qterms.size(); ++t) {
@@ -735,10 +778,10 @@ MatriceMorse<double> *gpu_matrix(Stack stack, const FESpaceT &Vh, DevSpace &D, c
     for (size_t i = 0; i < V.bil.size(); ++i) {
         const BilinearItem &B = V.bil[i];
         if (B.qterms.empty()) continue;
-        if (D.order != 1) throw Unsupported{"P2 form whose coefficient depends on the mesh point"};
+        if (D.order != 1 && !B.border) throw Unsupported{"P2 form whose coefficient depends on the mesh point"};
         std::vector<const C_F0 *> ex;
         for (size_t t = 0; t < B.qterms.size(); ++t) ex.push_back(&B.qterms[t].coef);
-        std::vector<std::vector<double>> v = eval_at_nodes(stack, Vh, ex, B.q, B.reg);
+        std::vector<std::vector<double>> v = B.border ? eval_at_bnodes(stack, Vh, ex, B.q, B.reg) : eval_at_nodes(stack, Vh, ex, B.q, B.reg);
         // terms whose tables are proportional share one coefficient function ((1+x)*lambda, (1+x)*mu, ...): one pass each group
         const size_t first_group = groups.size();
         for (size_t t = 0; t < B.qterms.size(); ++t) {
@@ -790,12 +833,19 @@ MatriceMorse<double> *gpu_matrix(Stack stack, const FESpaceT &Vh, DevSpace &D, c
                 (int)B.reg.labels.size(), B.reg.all ? nullptr : B.reg.labels.data(), first ? 0 : 1);
             first = false;
         }
-    for (size_t gi = 0; gi < groups.size() && !rc; ++gi) {
-        const BilinearItem &B = V.bil[groups[gi].item];
-        rc = ffcuda_assemble_bilinear_qcoef(dA, D.space, (int)groups[gi].terms.size(), groups[gi].terms.data(), (int)B.q.w.size(),
-                                            B.q.pts.data(), B.q.w.data(), groups[gi].cq.data(), first ? 0 : 1);
-        first = false;
-    }
+    for (int border = 0; border < 2; ++border)
+        for (size_t gi = 0; gi < groups.size() && !rc; ++gi) {
+            const BilinearItem &B = V.bil[groups[gi].item];
+            if ((int)B.border != border) continue;
+            if (border)
+                rc = ffcuda_assemble_bilinear_boundary_qcoef(dA, D.space, (int)groups[gi].terms.size(), groups[gi].terms.data(),
+                                                             (int)B.q.w.size(), B.q.pts.data(), B.q.w.data(), groups[gi].cq.data(),
+                                                             (int)B.reg.labels.size(), B.reg.all ? nullptr : B.reg.labels.data(), first ? 0 : 1);
+            else
+                rc = ffcuda_assemble_bilinear_qcoef(dA, D.space, (int)groups[gi].terms.size(), groups[gi].terms.data(), (int)B.q.w.size(),
+                                                    B.q.pts.data(), B.q.w.data(), groups[gi].cq.data(), first ? 0 : 1);
+            first = false;
+        }
     if (g_verbose && !groups.empty())
         cout << "  -- ffcuda: " << groups.size() << " coefficient function(s) depending on the mesh point, evaluated at the quadrature nodes" << endl;
     std::vector<int32_t> rowptr, colind;
@@ -863,7 +913,8 @@ void gpu_rhs(Stack stack, const FESpaceT &Vh, DevSpace &D, const Varf &V, double
                     ffcuda_vec_destroy(db);
                     throw;
                 }
-                rc = ffcuda_assemble_linear_qvalues(db, D.space, (int)L.q.w.size(), L.q.pts.data(), L.q.w.data(), fq.data(), first ? 0 : 1);
+                rc = (border ? ffcuda_assemble_linear_boundary_qvalues : ffcuda_assemble_linear_qvalues)(
+                    db, D.space, (int)L.q.w.size(), L.q.pts.data(), L.q.w.data(), fq.data(), first ? 0 : 1);
                 first = false;
             }
         }

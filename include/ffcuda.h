@@ -193,6 +193,15 @@ int ffcuda_assemble_linear_qvalues(ffcuda_vec *b, ffcuda_space *s, int nq, const
 int ffcuda_assemble_bilinear_boundary(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms,
                                       int nq, const double *qpts, const double *qw,
                                       int nlab, const int32_t *labels, int accumulate);
+/* the two boundary integrals with data that depend on the mesh point, given by the values FreeFEM's evaluator returns at
+ * the face quadrature nodes (fflib/problem.cpp:8551-8570, :6526-6556): gq[(c * nbe + ib) * nq + q] (HOST) = coefficient of
+ * the value of v_c at node q of boundary element ib, 0 where the integral does not go; cq[ib * nq + q] (HOST) = the ONE
+ * coefficient function multiplying every listed term (labels as above). */
+int ffcuda_assemble_linear_boundary_qvalues(ffcuda_vec *b, ffcuda_space *s, int nq, const double *qpts, const double *qw,
+                                            const double *gq, int accumulate);
+int ffcuda_assemble_bilinear_boundary_qcoef(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms,
+                                            int nq, const double *qpts, const double *qw, const double *cq,
+                                            int nlab, const int32_t *labels, int accumulate);
 
 /* ---- Dirichlet conditions ------------------------------------------------------------------------------
  * tgv >= 0: penalty, A(d,d) = tgv and b[d] = tgv*g(d).  tgv < 0: exact elimination exactly as HashMatrix::SetBC

@@ -555,10 +555,29 @@ static void face_point(int dim, int ie, const double *qp, double *P)
  * (fflib/problem.cpp:8517-8587 in 3-D, :8439-8513 in 2-D): for every boundary element with a listed label, every
  * quadrature point of the face rule, every dof of the ADJACENT ELEMENT: B[dof] += (face measure * w_q) * c * d^op phi_i(Pt),
  * Pt = PBord(ie, pi).  Adds to b (the caller zeroes it). */
+static void rhs_boundary_impl(int dim, const double *xyz, const int32_t *conn, int order, int ncomp,
+                              const int32_t *elem2node, int nbe, const int32_t *blab, const int32_t *belem,
+                              const int32_t *bface, int nterms, const ffo_lterm *terms, int nq, const double *qpts,
+                              const double *qw, int nlab, const int32_t *labels, const double *gq, double *b);
 void ffo_assemble_rhs_boundary(int dim, const double *xyz, const int32_t *conn, int order, int ncomp,
                                const int32_t *elem2node, int nbe, const int32_t *blab, const int32_t *belem,
                                const int32_t *bface, int nterms, const ffo_lterm *terms, int nq, const double *qpts,
                                const double *qw, int nlab, const int32_t *labels, double *b)
+{
+    rhs_boundary_impl(dim, xyz, conn, order, ncomp, elem2node, nbe, blab, belem, bface, nterms, terms, nq, qpts, qw, nlab, labels, NULL, b);
+}
+/* the same with data depending on the mesh point: gq[(c * nbe + ib) * nq + q] = coefficient of the value of v_c at node q
+ * of boundary element ib (0 where the label is not listed), as evaluated inside Element_rhs (problem.cpp:8551-8570) */
+void ffo_assemble_rhs_boundary_qvalues(int dim, const double *xyz, const int32_t *conn, int order, int ncomp,
+                                       const int32_t *elem2node, int nbe, const int32_t *blab, const int32_t *belem,
+                                       const int32_t *bface, int nq, const double *qpts, const double *qw, const double *gq, double *b)
+{
+    rhs_boundary_impl(dim, xyz, conn, order, ncomp, elem2node, nbe, blab, belem, bface, 0, NULL, nq, qpts, qw, 0, NULL, gq, b);
+}
+static void rhs_boundary_impl(int dim, const double *xyz, const int32_t *conn, int order, int ncomp,
+                              const int32_t *elem2node, int nbe, const int32_t *blab, const int32_t *belem,
+                              const int32_t *bface, int nterms, const ffo_lterm *terms, int nq, const double *qpts,
+                              const double *qw, int nlab, const int32_t *labels, const double *gq, double *b)
 {
     const int nloc = ffo_nloc(dim, order), nvk = dim + 1;
     for (int ib = 0; ib < nbe; ++ib) {
@@ -576,11 +595,13 @@ void ffo_assemble_rhs_boundary(int dim, const double *xyz, const int32_t *conn, 
             const double coef = le * qw[q];
             basis(dim, order, P, G, val);
             for (int c = 0; c < ncomp; ++c)
-                for (int a = 0; a < nloc; ++a)
+                for (int a = 0; a < nloc; ++a) {
                     for (int t = 0; t < nterms; ++t) {
                         double w_i = (terms[t].vcomp == c) ? val[a][opslot(terms[t].vop)] : 0.;
                         b[N[a] * ncomp + c] += coef * terms[t].coef * w_i;
                     }
+                    if (gq) b[N[a] * ncomp + c] += coef * gq[((size_t)c * nbe + ib) * nq + q] * val[a][0];
+                }
         }
     }
 }
@@ -591,11 +612,35 @@ void ffo_assemble_rhs_boundary(int dim, const double *xyz, const int32_t *conn, 
  * (:6518-6560 3-D, :6216-6290 2-D) fills the whole n x m element matrix at the face quadrature nodes, and
  * HashMatrix::operator+= then creates/accumulates every (il, jl) couple of that element, zero or not.
  * Output: COO with one entry per distinct couple (first-encounter order); returns their number. */
+static int64_t coo_boundary_impl(int dim, const double *xyz, const int32_t *conn, int order, int ncomp,
+                                 const int32_t *elem2node, int nbe, const int32_t *blab, const int32_t *belem,
+                                 const int32_t *bface, int nterms, const ffo_bterm *terms, int nq, const double *qpts,
+                                 const double *qw, int nlab, const int32_t *labels, const double *cq,
+                                 int32_t *coo_i, int32_t *coo_j, double *coo_a);
 int64_t ffo_assemble_coo_boundary(int dim, const double *xyz, const int32_t *conn, int order, int ncomp,
                                   const int32_t *elem2node, int nbe, const int32_t *blab, const int32_t *belem,
                                   const int32_t *bface, int nterms, const ffo_bterm *terms, int nq, const double *qpts,
                                   const double *qw, int nlab, const int32_t *labels,
                                   int32_t *coo_i, int32_t *coo_j, double *coo_a)
+{
+    return coo_boundary_impl(dim, xyz, conn, order, ncomp, elem2node, nbe, blab, belem, bface, nterms, terms, nq, qpts, qw, nlab, labels,
+                             NULL, coo_i, coo_j, coo_a);
+}
+/* the same with every term multiplied by a coefficient depending on the mesh point, cq[ib * nq + q]; labels as above */
+int64_t ffo_assemble_coo_boundary_qcoef(int dim, const double *xyz, const int32_t *conn, int order, int ncomp,
+                                        const int32_t *elem2node, int nbe, const int32_t *blab, const int32_t *belem,
+                                        const int32_t *bface, int nterms, const ffo_bterm *terms, int nq, const double *qpts,
+                                        const double *qw, int nlab, const int32_t *labels, const double *cq,
+                                        int32_t *coo_i, int32_t *coo_j, double *coo_a)
+{
+    return coo_boundary_impl(dim, xyz, conn, order, ncomp, elem2node, nbe, blab, belem, bface, nterms, terms, nq, qpts, qw, nlab, labels,
+                             cq, coo_i, coo_j, coo_a);
+}
+static int64_t coo_boundary_impl(int dim, const double *xyz, const int32_t *conn, int order, int ncomp,
+                                 const int32_t *elem2node, int nbe, const int32_t *blab, const int32_t *belem,
+                                 const int32_t *bface, int nterms, const ffo_bterm *terms, int nq, const double *qpts,
+                                 const double *qw, int nlab, const int32_t *labels, const double *cq,
+                                 int32_t *coo_i, int32_t *coo_j, double *coo_a)
 {
     const int nloc = ffo_nloc(dim, order), nd = nloc * ncomp, nvk = dim + 1;
     uint64_t mask;
@@ -620,7 +665,7 @@ int64_t ffo_assemble_coo_boundary(int dim, const double *xyz, const int32_t *con
             basis(dim, order, P, G, val);
             for (int t = 0; t < nterms; ++t) {
                 const int so = opslot(terms[t].uop), to = opslot(terms[t].vop);
-                const double ccc = terms[t].coef * coef;
+                const double ccc = terms[t].coef * (cq ? cq[(size_t)ib * nq + q] : 1.) * coef;
                 const int fi = terms[t].vcomp * nloc, fj = terms[t].ucomp * nloc;
                 for (int a = 0; a < nloc; ++a)
                     for (int b = 0; b < nloc; ++b) mat[(fi + a) * nd + fj + b] += ccc * val[a][to] * val[b][so];

@@ -100,6 +100,18 @@ int64_t ffo_assemble_coo_boundary(int dim, const double *xyz, const int32_t *con
                                   const double *qw, int nlab, const int32_t *labels,
                                   int32_t *coo_i, int32_t *coo_j, double *coo_a);
 
+/* boundary integrals with data depending on the mesh point, given at the face quadrature nodes (problem.cpp:8551-8570,
+ * :6526-6556): gq[(c * nbe + ib) * nq + q] for the linear form (adds to b), cq[ib * nq + q] multiplying every term of the
+ * bilinear form */
+void ffo_assemble_rhs_boundary_qvalues(int dim, const double *xyz, const int32_t *conn, int order, int ncomp,
+                                       const int32_t *elem2node, int nbe, const int32_t *blab, const int32_t *belem,
+                                       const int32_t *bface, int nq, const double *qpts, const double *qw, const double *gq, double *b);
+int64_t ffo_assemble_coo_boundary_qcoef(int dim, const double *xyz, const int32_t *conn, int order, int ncomp,
+                                        const int32_t *elem2node, int nbe, const int32_t *blab, const int32_t *belem,
+                                        const int32_t *bface, int nterms, const ffo_bterm *terms, int nq, const double *qpts,
+                                        const double *qw, int nlab, const int32_t *labels, const double *cq,
+                                        int32_t *coo_i, int32_t *coo_j, double *coo_a);
+
 /* Dirichlet dofs as AssembleBC visits them: for each boundary element (in order) whose label is in
  * labels[], for each component c with compmask bit c set, each dof lying on that face -> (dof, value[c]).
  * Later pairs overwrite earlier ones.  out arrays sized nbe*ncomp*nlocface at most.  Returns count. */

@@ -85,6 +85,10 @@ CASES = {
     "diff3d_p1_kappa": (1, 1, [(0, ID, 0, ID, 2.0)], [(0, ID, 1.0)], "qfV5", [([1, 2], 1, [0.0])]),
     "reac2d_p1_rho": (1, 1, LAP2, [(0, ID, 1.0)], "qf5pT", [([4], 1, [0.0])]),
     "lame3d_p1_evar": (1, 3, [], [(2, ID, -0.05)], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
+    # boundary integrals with data depending on the mesh point (CASE_BQ below)
+    "lap3d_p1_bnd_g": (1, 1, LAP3, [(0, ID, 1.0)], "qfV5", [([1], 1, [0.0])]),
+    "lap2d_p2_bnd_g": (2, 1, LAP2, [(0, ID, 1.0)], "qf5pT", [([4], 1, [0.0])]),
+    "lame3d_p1_bnd_g": (1, 3, lame_terms(), [(2, ID, -0.05)], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
     # half storage (sym=1, CASE_SYM below): the fixture holds the lower triangle
     "lap3d_p1_sym": (1, 1, LAP3, [(0, ID, 1.0)], "qfV5", [(ALL6, 1, [0.0])]),
     "lap2d_p2_sym": (2, 1, LAP2 + [(0, ID, 0, ID, 2.0)], [(0, ID, 1.0)], "qf5pT", [([2, 4], 1, [0.0])]),
@@ -111,6 +115,17 @@ CASE_QCOEF = {
     "diff3d_p1_kappa": [(lambda P: 1 + P[..., 0] * P[..., 1] + P[..., 2] ** 2, LAP3)],
     "reac2d_p1_rho": [(lambda P: 1 + np.sin(P[..., 0]) * P[..., 1], [(0, ID, 0, ID, 1.0)])],
     "lame3d_p1_evar": [(lambda P: 1 + P[..., 0], lame_terms())],
+}
+CASE_BLIN["lap3d_p1_bnd_g"] = ([6], [(0, ID, 0.5)])
+# boundary data depending on the mesh point: name -> dict(lin=(labels, g at points P (..., dim) -> (ncomp, ...)),
+#                                                        bil=(labels, coefficient at P, terms))
+CASE_BQ = {
+    "lap3d_p1_bnd_g": dict(lin=([2, 3], lambda P: (P[..., 1] + np.sin(P[..., 2]))[None]),
+                           bil=([2, 3], lambda P: 1 + P[..., 0] * P[..., 2], [(0, ID, 0, ID, 1.0)])),
+    "lap2d_p2_bnd_g": dict(lin=([2], lambda P: np.exp(P[..., 1])[None]),
+                           bil=([2, 3], lambda P: 1 + P[..., 0] * P[..., 1], [(0, ID, 0, ID, 1.0)])),
+    "lame3d_p1_bnd_g": dict(lin=([2], lambda P: np.stack([0.3 * P[..., 2], 0 * P[..., 0], -0.2 * (1 + P[..., 1])])),
+                            bil=([3], lambda P: 1 + P[..., 0], [(c, ID, c, ID, 1e3) for c in range(3)])),
 }
 # cases assembled with sym=1: MatriceMorse keeps the entries (i, j) with j <= i only (HashMatrix.cpp:1319-1325)
 CASE_SYM = {"lap3d_p1_sym", "lap2d_p2_sym", "lame3d_p1_sym"}
@@ -173,4 +188,4 @@ NO_SOLVE_TGV = {"lap3d_p1_tgvm1", "lame3d_p1_tgvm1", "lap3d_p1_tgvm3", "lame3d_p
 def loose_iterate(name):
     """fixtures whose eps=1e-6 iterate is compared loosely (1e-6) because their right-hand side or matrix carries extra ulp
     differences (boundary terms, data evaluated with another libm); their eps=1e-14 solutions are held to 1e-12 like all others"""
-    return name in CASE_BLIN or name in CASE_BBIL or name in CASE_FQ or name in CASE_QCOEF
+    return name in CASE_BLIN or name in CASE_BBIL or name in CASE_FQ or name in CASE_QCOEF or name in CASE_BQ

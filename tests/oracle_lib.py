@@ -35,6 +35,7 @@ def lib():
         _LIB.ffo_assemble_coo.restype = C.c_int64
         _LIB.ffo_assemble_coo_boundary.restype = C.c_int64
         _LIB.ffo_assemble_coo_qcoef.restype = C.c_int64
+        _LIB.ffo_assemble_coo_boundary_qcoef.restype = C.c_int64
     return _LIB
 
 
@@ -234,6 +235,54 @@ def coo_add(n, a, b):
     out[order[pos[hit]]] += ba[hit]
     return (np.concatenate([ai, bi[~hit]]).astype(np.int32), np.concatenate([aj, bj[~hit]]).astype(np.int32),
             np.concatenate([out, ba[~hit]]))
+
+
+_NVFACE = np.array([[3, 2, 1], [0, 2, 3], [3, 1, 0], [0, 1, 2]])
+_NVEDGE = np.array([[1, 2], [2, 0], [0, 1]])
+
+
+def bquad_points_xyz(mesh, fqpts):
+    """physical coordinates of the face quadrature nodes of every boundary element, PBord(ie, q): (nbe, nq, dim)"""
+    dim = mesh["dim"]
+    xyz, conn = _f64(mesh["xyz"]), _i32(mesh["conn"])
+    belem, bface = _i32(mesh["belem"]), _i32(mesh["bface"])
+    fq = _f64(fqpts).reshape(len(fqpts), dim - 1)
+    lam = np.concatenate([1.0 - fq.sum(axis=1, keepdims=True), fq], axis=1)          # (nq, dim) weights of the face vertices
+    fv = (_NVFACE if dim == 3 else _NVEDGE)[bface]                                   # (nbe, dim) local vertices of the face
+    verts = np.take_along_axis(conn[belem], fv, axis=1)                              # (nbe, dim) global vertices
+    return np.einsum("qa,ead->eqd", lam, xyz[verts])
+
+
+def assemble_rhs_boundary_qvalues(mesh, order, ncomp, elem2node, b, qpts, qw, gq):
+    """adds the boundary integral of g v with g given at the face quadrature nodes, gq[c, ib, q], to b (returns a copy)"""
+    dim = mesh["dim"]
+    xyz, conn = _f64(mesh["xyz"]), _i32(mesh["conn"])
+    blab, belem, bface = _i32(mesh["blab"]), _i32(mesh["belem"]), _i32(mesh["bface"])
+    e2n = _i32(elem2node)
+    b, qpts, qw, gq = _f64(b).copy(), _f64(qpts), _f64(qw), _f64(gq)
+    lib().ffo_assemble_rhs_boundary_qvalues(dim, _p(xyz, C.c_double), _p(conn, C.c_int32), order, ncomp, _p(e2n, C.c_int32), len(blab),
+                                            _p(blab, C.c_int32), _p(belem, C.c_int32), _p(bface, C.c_int32), len(qw),
+                                            _p(qpts, C.c_double), _p(qw, C.c_double), _p(gq, C.c_double), _p(b, C.c_double))
+    return b
+
+
+def assemble_coo_boundary_qcoef(mesh, order, ncomp, elem2node, terms, qpts, qw, cq, labels=None):
+    """assemble_coo_boundary with every term multiplied by the coefficient given at the face quadrature nodes, cq[ib, q]"""
+    dim = mesh["dim"]
+    xyz, conn = _f64(mesh["xyz"]), _i32(mesh["conn"])
+    blab, belem, bface = _i32(mesh["blab"]), _i32(mesh["belem"]), _i32(mesh["bface"])
+    e2n, lab = _i32(elem2node), _i32(labels)
+    nd = nloc(dim, order) * ncomp
+    cap = max(len(blab), 1) * nd * nd
+    ci, cj, ca = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap)
+    bt = bterms(terms)
+    qpts, qw, cq = _f64(qpts), _f64(qw), _f64(cq)
+    nnz = lib().ffo_assemble_coo_boundary_qcoef(dim, _p(xyz, C.c_double), _p(conn, C.c_int32), order, ncomp, _p(e2n, C.c_int32),
+                                                len(blab), _p(blab, C.c_int32), _p(belem, C.c_int32), _p(bface, C.c_int32),
+                                                len(terms), bt, len(qw), _p(qpts, C.c_double), _p(qw, C.c_double),
+                                                0 if lab is None else len(lab), _p(lab, C.c_int32), _p(cq, C.c_double),
+                                                _p(ci, C.c_int32), _p(cj, C.c_int32), _p(ca, C.c_double))
+    return ci[:nnz].copy(), cj[:nnz].copy(), ca[:nnz].copy()
 
 
 def face_quadrature(dim):

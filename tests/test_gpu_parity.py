@@ -34,7 +34,7 @@ def _upload(ctx, g):
 
 
 def _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve=True, eps=1e-6, itmax=0, TGV=TGV, lower=False,  # noqa: N803
-              blin=None, bbil=None, gmres=None, fqfun=None, qcoef=()):
+              blin=None, bbil=None, gmres=None, fqfun=None, qcoef=(), bq=None):
     """Full product pipeline on one problem; returns everything a parity check needs."""
     mesh = _upload(ctx, g)
     sp = mesh.space(order, ncomp, e2n, nnodes)
@@ -47,9 +47,18 @@ def _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve=True
     if bbil:  # boundary integrals of the bilinear form (Robin terms)
         fq, fw = ol.face_quadrature(g["dim"])
         A.assemble_boundary(bbil[1], fq, fw, bbil[0], accumulate=True)
+    if bq:  # Robin term whose coefficient depends on the mesh point
+        blabels, cfun, bbt = bq["bil"]
+        fq, fw = ol.face_quadrature(g["dim"])
+        A.assemble_boundary_qcoef(bbt, fq, fw, cfun(ol.bquad_points_xyz(g, fq)), blabels, accumulate=True)
     n = pat.info()[0]
     b = ctx.vec(n)
     sp.assemble_linear(b, lt, qp, qw)
+    if bq:  # Neumann data depending on the mesh point (0 outside the listed labels)
+        blabels, gfun = bq["lin"]
+        fq, fw = ol.face_quadrature(g["dim"])
+        gq = gfun(ol.bquad_points_xyz(g, fq)) * np.isin(g["blab"], blabels)[None, :, None]
+        sp.assemble_linear_boundary_qvalues(b, fq, fw, gq, accumulate=True)
     if fqfun:  # data depending on the mesh point, handed over at the quadrature nodes
         sp.assemble_linear_qvalues(b, qp, qw, fqfun(ol.quad_points_xyz(g, qp)), accumulate=True)
     if blin:  # boundary integrals of the linear form (Neumann / traction data)
@@ -95,7 +104,7 @@ def test_golden_case(ctx, name):
     e2n = fc.elem2node(g, order, ncomp)
     nnodes = g["ndof"] // ncomp
     r = _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve="u" in g, TGV=fc.CASE_TGV.get(name, TGV),
-                  lower=name in fc.CASE_SYM, blin=fc.CASE_BLIN.get(name), bbil=fc.CASE_BBIL.get(name), gmres=fc.CASE_GMRES.get(name), fqfun=fc.CASE_FQ.get(name), qcoef=fc.CASE_QCOEF.get(name, ()))
+                  lower=name in fc.CASE_SYM, blin=fc.CASE_BLIN.get(name), bbil=fc.CASE_BBIL.get(name), gmres=fc.CASE_GMRES.get(name), fqfun=fc.CASE_FQ.get(name), qcoef=fc.CASE_QCOEF.get(name, ()), bq=fc.CASE_BQ.get(name))
     grp, gci, gval = fc.golden_csr(g)
     assert r["n"] == g["ndof"]
     assert np.array_equal(r["rowptr"], grp) and np.array_equal(r["colind"], gci)          # bit-exact pattern

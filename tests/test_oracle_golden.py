@@ -48,6 +48,11 @@ def test_matrix_rhs_solution(name):
         blabels, bbt = fc.CASE_BBIL[name]
         fq, fw = ol.face_quadrature(dim)
         ci, cj, ca = ol.coo_add(n, (ci, cj, ca), ol.assemble_coo_boundary(_mesh(g), order, ncomp, e2n, bbt, fq, fw, blabels))
+    if name in fc.CASE_BQ:  # Robin term whose coefficient depends on the mesh point
+        blabels, cfun, bbt = fc.CASE_BQ[name]["bil"]
+        fq, fw = ol.face_quadrature(dim)
+        cq = cfun(ol.bquad_points_xyz(_mesh(g), fq))
+        ci, cj, ca = ol.coo_add(n, (ci, cj, ca), ol.assemble_coo_boundary_qcoef(_mesh(g), order, ncomp, e2n, bbt, fq, fw, cq, blabels))
     if name in fc.CASE_SYM:
         # sym=1: the symmetric element routine visits the local couples (il, jl <= il) and stores each at (max, min) of the
         # global dofs (HashMatrix.cpp:1319-1325); for a symmetric form that is the lower triangle of the full matrix.  The
@@ -79,6 +84,11 @@ def test_matrix_rhs_solution(name):
         blabels, bterms = fc.CASE_BLIN[name]
         fq, fw = ol.face_quadrature(dim)
         b = ol.assemble_rhs_boundary(_mesh(g), order, ncomp, e2n, b, bterms, fq, fw, blabels)
+    if name in fc.CASE_BQ:  # Neumann data depending on the mesh point: 0 outside the listed labels
+        blabels, gfun = fc.CASE_BQ[name]["lin"]
+        fq, fw = ol.face_quadrature(dim)
+        gq = gfun(ol.bquad_points_xyz(_mesh(g), fq)) * np.isin(g["blab"], blabels)[None, :, None]
+        b = ol.assemble_rhs_boundary_qvalues(_mesh(g), order, ncomp, e2n, b, fq, fw, gq)
     b = ol.bc_rhs(b, dofs, vals, TGV)
     big = np.abs(g["b"]) > 1e20
     assert np.array_equal(np.abs(b) > 1e20, big)

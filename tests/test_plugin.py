@@ -99,6 +99,14 @@ CASES = {
                                        eps="1e-14", tgv=-2),
     "lame3d_p2_dirichlet_g": script(3, "cube(2,3,2)", "[P2,P2,P2]", LAME, "-0.05*v3", "on(1,u1=0.01*x,u2=0,u3=-0.02*z)", pre=LAME_PRE,
                                     unk="[u1,u2,u3]", tst="[v1,v2,v3]", eps="1e-14"),
+    # boundary integrals whose data depend on the mesh point (Neumann g(x) v, Robin alpha(x) u v), P1 and P2
+    "poisson3d_p2_bnd_g": script(3, "cube(3,3,4,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", "P2", LAP3, "1.*v", "on(1,u=0)", eps="1e-14",
+                                 extra="+int2d(Th,2,3)((1+x*z)*u*v)+int2d(Th,2,3)((y+sin(z))*v)+int2d(Th,6)(0.5*v-N.z*x*v)"),
+    "laplace2d_p1_bnd_g": script(2, "square(9,7,[x+0.2*y*y,y*(1+0.3*x)])", "P1", LAP2, "1.*v", "on(4,u=0)", eps="1e-14",
+                                 extra="+int1d(Th,2,3,qfe=qf3pE)((1+x*y)*u*v)+int1d(Th,2,qfe=qf1pElump)(exp(y)*v)"),
+    "lame3d_p1_bnd_g": script(3, "cube(3,4,3)", "[P1,P1,P1]", LAME, "-0.05*v3", "on(1,u1=0,u2=0,u3=0)", pre=LAME_PRE,
+                              unk="[u1,u2,u3]", tst="[v1,v2,v3]", eps="1e-14",
+                              extra="+int2d(Th,3)(1e3*(1+x)*(u1*v1+u2*v2+u3*v3))+int2d(Th,2)(0.3*z*v1-0.2*(1+y)*v3)"),
     "mass3d_lumped": script(3, "cube(3,3,3)", "P1", "u*v+0.1*(" + LAP3 + ")", "1.*v", "on(1,u=0)", intopt=",qfV=qfV1lump"),
 }
 
@@ -207,7 +215,7 @@ matrix B = vb(Vh2,Vh2);
 fespace Wh(Th,P0);
 varf vc(u,v) = int3d(Th)(u*v);
 matrix C = vc(Wh,Wh);
-varf vs(u,v) = int2d(Th,2)(u*v) + int2d(Th,2)(x*v);
+varf vs(u,v) = int2d(Th,2)(u*v) + int2d(Th,2)(x*dx(v));
 matrix S = vs(Vh,Vh);
 real[int] r = vs(0,Vh);
 cout << "NNZ " << B.nnz << " " << C.nnz << " " << S.nnz << endl;
