@@ -74,6 +74,7 @@ struct FormParams {
     double Lh[4];         // sum_q w_q lambda_a
     double Mh[4][4];      // sum_q w_q lambda_a lambda_b
     double fast_cw, fast_md, fast_mo; // FAST P1 path: c*W*RFAC, m*M_diag*RFAC, m*M_offdiag*RFAC
+    double iso_a, iso_b, iso_c;       // ISO P2 path (ncomp = dim): C = a d(cv,sv)d(cu,su) + b d(cv,cu)d(sv,su) + c d(cv,su)d(cu,sv)
     uint32_t mask;        // bit (sv*4+su) set when some C[.][.][sv][su] != 0
     int nlab;             // <0: all regions
     int labels[MAXLAB];
@@ -527,7 +528,10 @@ __global__ void __launch_bounds__(128) k_asm_p1_lean(const double *__restrict__ 
 // ----------------------------------------------------------------------------------------------------
 // GG: the form only couples gradients (d_x u d_y v terms: Laplace, Lame, ...): the value row/column of the per-pair
 // tensor is not formed and the coefficient contraction runs over the DIM x DIM gradient block without per-term tests
-template <int DIM, int NC, int GL, typename PosT, bool GG>
+// ISO (with GG, ncomp = dim): the coefficient tensor is isotropic - lambda div u div v + 2 mu eps(u):eps(v), vector Laplacians,
+// div-div terms - so the contraction with the DIM x DIM block M of a node pair collapses from (NC DIM)^2 to 2 NC^2 + DIM
+// operations: v[cv][cu] = a M[cv][cu] + c M[cu][cv] + (cv == cu) b tr M
+template <int DIM, int NC, int GL, typename PosT, bool GG, bool ISO = false>
 __global__ void __launch_bounds__(128) k_asm_p2(const double *__restrict__ xyz, const int32_t *__restrict__ conn,
                                                 const int32_t *__restrict__ elab, int nrows,
                                                 const int32_t *__restrict__ nrowptr, const int32_t *__restrict__ incptr,
@@ -616,7 +620,16 @@ __global__ void __launch_bounds__(128) k_asm_p2(const double *__restrict__ xyz, 
 #pragma unroll
                 for (int cu = 0; cu < NC; ++cu) {
                     double v = 0.0;
-                    if (GG) {
+                    if (ISO) {
+                        v = F.iso_a * M[cv + 1][cu + 1];
+                        v = fma(F.iso_c, M[cu + 1][cv + 1], v);
+                        if (cv == cu) {
+                            double tr = M[1][1];
+#pragma unroll
+                            for (int x = 2; x < NS; ++x) tr += M[x][x];
+                            v = fma(F.iso_b, tr, v);
+                        }
+                    } else if (GG) {
 #pragma unroll
                         for (int sv = 1; sv < NS; ++sv)
 #pragma unroll
@@ -882,7 +895,24 @@ static void launch_p2(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const 
     ffcuda_pattern *P = A->pattern;
     ffcuda_mesh *m = s->mesh;
     const bool gg = (F.mask & 0x111Fu) == 0; // no term involves the value of u or v
-    auto kern = gg ? k_asm_p2<DIM, NC, GL, PosT, true> : k_asm_p2<DIM, NC, GL, PosT, false>;
+    // isotropic coefficient tensor (ncomp = dim): exact structural test on the summed coefficients
+    bool iso = gg && NC == DIM;
+    FormParams Fi = F;
+    if (iso) {
+        const double a = F.C[0][1][1][2], c = F.C[0][1][2][1], bb = F.C[0][0][2][2];
+        for (int cv = 0; cv < NC && iso; ++cv)
+            for (int cu = 0; cu < NC && iso; ++cu)
+                for (int sv = 1; sv <= DIM && iso; ++sv)
+                    for (int su = 1; su <= DIM; ++su) {
+                        const double want = (cv + 1 == sv && cu + 1 == su ? a : 0.0) + (cv == cu && sv == su ? bb : 0.0) +
+                                            (cv + 1 == su && cu + 1 == sv ? c : 0.0);
+                        if (F.C[cv][cu][sv][su] != want && fabs(F.C[cv][cu][sv][su] - want) > 4e-16 * fabs(want)) iso = false;
+                    }
+        Fi.iso_a = a;
+        Fi.iso_b = bb;
+        Fi.iso_c = c;
+    }
+    auto kern = iso ? k_asm_p2<DIM, NC, GL, PosT, true, (NC == DIM)> : gg ? k_asm_p2<DIM, NC, GL, PosT, true> : k_asm_p2<DIM, NC, GL, PosT, false>;
     const Incidence &I = s->incidence;
     // Vertex nodes have ~5x the elements and ~2.5x the row length of edge nodes, and the numbering interleaves them: with
     // rows in natural order a block waits for its one vertex row while its other groups idle (13 % achieved occupancy,
@@ -902,7 +932,7 @@ static void launch_p2(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const 
         const int blocks = ff_blocks((size_t)(r1 - r0), groups);
         ff_launch(ctx, "asm_rows_p2", [&] {
             kern<<<blocks, threads, shmem, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, r1, P->nrowptr.p, I.incptr.p, I.inc.p, pos, Rg,
-                                                          A->vals.p, S, accumulate, F, s->p2_rowperm.p, r0);
+                                                          A->vals.p, S, accumulate, Fi, s->p2_rowperm.p, r0);
         });
     };
     run(0, nlong, P->maxrow_node);
