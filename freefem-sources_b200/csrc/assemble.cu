@@ -531,13 +531,17 @@ __global__ void __launch_bounds__(128) k_asm_p1_lean(const double *__restrict__ 
 // ISO (with GG, ncomp = dim): the coefficient tensor is isotropic - lambda div u div v + 2 mu eps(u):eps(v), vector Laplacians,
 // div-div terms - so the contraction with the DIM x DIM block M of a node pair collapses from (NC DIM)^2 to 2 NC^2 + DIM
 // operations: v[cv][cu] = a M[cv][cu] + c M[cu][cv] + (cv == cu) b tr M
-template <int DIM, int NC, int GL, typename PosT, bool GG, bool ISO = false>
+// QC: every term is multiplied by a coefficient that depends on the mesh point, given at the quadrature nodes (cq[k][q]): the
+// per-pair tensor of the element, sum_q c_q w_q d^sa phi_a(q) d^sb phi_b(q), is formed on the fly from the constant table
+// Tq[q][a][b][sa][sb] (L1/L2 resident, 16 contiguous doubles per lane) instead of being read from the shared reference tensor
+template <int DIM, int NC, int GL, typename PosT, bool GG, bool ISO = false, bool QC = false>
 __global__ void __launch_bounds__(128) k_asm_p2(const double *__restrict__ xyz, const int32_t *__restrict__ conn,
                                                 const int32_t *__restrict__ elab, int nrows,
                                                 const int32_t *__restrict__ nrowptr, const int32_t *__restrict__ incptr,
                                                 const uint32_t *__restrict__ inc, const PosT *__restrict__ pos,
                                                 const double *__restrict__ Rg, double *__restrict__ vals, int S, int accumulate,
-                                                const __grid_constant__ FormParams F, const int32_t *__restrict__ rowperm, int row0)
+                                                const __grid_constant__ FormParams F, const int32_t *__restrict__ rowperm, int row0,
+                                                const double *__restrict__ Tq = nullptr, const double *__restrict__ cq = nullptr, int nqc = 0)
 {
     constexpr int NL = DIM == 3 ? 10 : 6;
     constexpr int NS = DIM + 1;
@@ -579,7 +583,21 @@ __global__ void __launch_bounds__(128) k_asm_p2(const double *__restrict__ xyz, 
                 load_geom2(xyz, v0, v1, v2, reinterpret_cast<Geom<2> &>(G));
             }
             const int pb = pos[(size_t)e * NL + b];
-            const double *R = sR + (a * NL + b) * RS;
+            double Rl[QC ? NS * NS : 1];
+            if (QC) {
+#pragma unroll
+                for (int st = 0; st < NS * NS; ++st) Rl[st] = 0.0;
+                const double *c = cq + (size_t)k * nqc;
+                const double *T = Tq + ((size_t)a * NL + b) * (NS * NS);
+                for (int q = 0; q < nqc; ++q) {
+                    const double cv_ = __ldg(c + q);
+                    const double *Tp = T + (size_t)q * NL * NL * NS * NS;
+#pragma unroll
+                    for (int st = GG ? NS + 1 : 0; st < NS * NS; ++st)
+                        if (!GG || st % NS) Rl[st] = fma(cv_, __ldg(Tp + st), Rl[st]);
+                }
+            }
+            const double *R = QC ? Rl : sR + (a * NL + b) * RS;
             double M[NS][NS];
             if (!GG) {
                 M[0][0] = R[0];
@@ -887,7 +905,7 @@ void ff_p2_row_order(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr, i
 
 template <int DIM, int NC, typename PosT>
 static void launch_p2(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const FormParams &F, const double *Rg, const PosT *pos,
-                      int accumulate)
+                      int accumulate, const double *Tq = nullptr, const double *cq = nullptr, int nqc = 0)
 {
     constexpr int GL = DIM == 3 ? 16 : 8;
     constexpr int NL = DIM == 3 ? 10 : 6;
@@ -896,7 +914,7 @@ static void launch_p2(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const 
     ffcuda_mesh *m = s->mesh;
     const bool gg = (F.mask & 0x111Fu) == 0; // no term involves the value of u or v
     // isotropic coefficient tensor (ncomp = dim): exact structural test on the summed coefficients
-    bool iso = gg && NC == DIM;
+    bool iso = gg && NC == DIM && !cq;
     FormParams Fi = F;
     if (iso) {
         const double a = F.C[0][1][1][2], c = F.C[0][1][2][1], bb = F.C[0][0][2][2];
@@ -912,7 +930,10 @@ static void launch_p2(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const 
         Fi.iso_b = bb;
         Fi.iso_c = c;
     }
-    auto kern = iso ? k_asm_p2<DIM, NC, GL, PosT, true, (NC == DIM)> : gg ? k_asm_p2<DIM, NC, GL, PosT, true> : k_asm_p2<DIM, NC, GL, PosT, false>;
+    auto kern = cq    ? (gg ? k_asm_p2<DIM, NC, GL, PosT, true, false, true> : k_asm_p2<DIM, NC, GL, PosT, false, false, true>)
+                : iso ? k_asm_p2<DIM, NC, GL, PosT, true, (NC == DIM)>
+                : gg  ? k_asm_p2<DIM, NC, GL, PosT, true>
+                      : k_asm_p2<DIM, NC, GL, PosT, false>;
     const Incidence &I = s->incidence;
     // Vertex nodes have ~5x the elements and ~2.5x the row length of edge nodes, and the numbering interleaves them: with
     // rows in natural order a block waits for its one vertex row while its other groups idle (13 % achieved occupancy,
@@ -932,7 +953,7 @@ static void launch_p2(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const 
         const int blocks = ff_blocks((size_t)(r1 - r0), groups);
         ff_launch(ctx, "asm_rows_p2", [&] {
             kern<<<blocks, threads, shmem, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, r1, P->nrowptr.p, I.incptr.p, I.inc.p, pos, Rg,
-                                                          A->vals.p, S, accumulate, Fi, s->p2_rowperm.p, r0);
+                                                          A->vals.p, S, accumulate, Fi, s->p2_rowperm.p, r0, Tq, cq, nqc);
         });
     };
     run(0, nlong, P->maxrow_node);
@@ -981,12 +1002,12 @@ __global__ void k_emom(int nt, int nq, int nv, const double *__restrict__ wl /* 
 
 template <int DIM, typename PosT>
 static void dispatch_p2(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const FormParams &F, const double *Rg, const PosT *pos,
-                        int accumulate)
+                        int accumulate, const double *Tq = nullptr, const double *cq = nullptr, int nqc = 0)
 {
     const int nc = s->ncomp;
-    if (nc == 1) launch_p2<DIM, 1, PosT>(ctx, A, s, F, Rg, pos, accumulate);
-    else if (nc == 2) launch_p2<DIM, 2, PosT>(ctx, A, s, F, Rg, pos, accumulate);
-    else launch_p2<DIM, 3, PosT>(ctx, A, s, F, Rg, pos, accumulate);
+    if (nc == 1) launch_p2<DIM, 1, PosT>(ctx, A, s, F, Rg, pos, accumulate, Tq, cq, nqc);
+    else if (nc == 2) launch_p2<DIM, 2, PosT>(ctx, A, s, F, Rg, pos, accumulate, Tq, cq, nqc);
+    else launch_p2<DIM, 3, PosT>(ctx, A, s, F, Rg, pos, accumulate, Tq, cq, nqc);
 }
 
 static int assemble_bilinear_impl(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms, int nq, const double *qpts,
@@ -1013,8 +1034,7 @@ static int assemble_bilinear_impl(ffcuda_matrix *A, ffcuda_space *s, int nterms,
 {
     FF_API_BEGIN
     FF_REQUIRE(A && s && A->pattern && A->pattern->space == s, "ffcuda_assemble_bilinear: matrix was not created on this space");
-    FF_REQUIRE(!cq || (s->order == 1 && !s->mesh->distributed && nq <= 256),
-               "coefficients given at the quadrature nodes: P1 spaces on one GPU only (P2 forms with such coefficients are not on the ffcuda path)");
+    FF_REQUIRE(!cq || (!s->mesh->distributed && nq <= 256), "coefficients given at the quadrature nodes: one GPU, at most 256 nodes");
     FF_REQUIRE(nterms >= 0 && (nterms == 0 || terms), "bad term list");
     FF_REQUIRE(nq > 0 && qpts && qw, "quadrature rule missing");
     ffcuda_ctx *ctx = s->ctx;
@@ -1102,12 +1122,33 @@ static int assemble_bilinear_impl(ffcuda_matrix *A, ffcuda_space *s, int nterms,
         }
         if (dim == 3) dispatch_p1<3>(ctx, A, s, F, accumulate, fast, emom.p);
         else dispatch_p1<2>(ctx, A, s, F, accumulate, fast, emom.p);
-    } else if (P->pos8.p) {
-        if (dim == 3) dispatch_p2<3, uint8_t>(ctx, A, s, F, Rg.p, P->pos8.p, accumulate);
-        else dispatch_p2<2, uint8_t>(ctx, A, s, F, Rg.p, P->pos8.p, accumulate);
     } else {
-        if (dim == 3) dispatch_p2<3, uint16_t>(ctx, A, s, F, Rg.p, P->pos16.p, accumulate);
-        else dispatch_p2<2, uint16_t>(ctx, A, s, F, Rg.p, P->pos16.p, accumulate);
+        // P2 with a coefficient at the quadrature nodes: the table w_q d^sa phi_a(q) d^sb phi_b(q) and the values go to the device
+        DBuf<double> dT, dcq;
+        if (cq) {
+            std::vector<double> T((size_t)nq * nloc * nloc * ns * ns);
+            for (int q = 0; q < nq; ++q) {
+                double B[10][4];
+                ref_basis(dim, 2, qpts + (size_t)q * dim, B);
+                for (int a = 0; a < nloc; ++a)
+                    for (int b = 0; b < nloc; ++b)
+                        for (int sa = 0; sa < ns; ++sa)
+                            for (int sb = 0; sb < ns; ++sb)
+                                T[((((size_t)q * nloc + a) * nloc + b) * ns + sa) * ns + sb] = qw[q] * B[a][sa] * B[b][sb];
+            }
+            dT.alloc(T.size());
+            dcq.alloc((size_t)s->mesh->nt * nq);
+            FF_CUDA(cudaMemcpyAsync(dT.p, T.data(), dT.bytes(), cudaMemcpyHostToDevice, ctx->stream));
+            FF_CUDA(cudaMemcpyAsync(dcq.p, cq, dcq.bytes(), cudaMemcpyHostToDevice, ctx->stream));
+            FF_CUDA(cudaStreamSynchronize(ctx->stream)); // both sources are pageable host memory
+        }
+        if (P->pos8.p) {
+            if (dim == 3) dispatch_p2<3, uint8_t>(ctx, A, s, F, Rg.p, P->pos8.p, accumulate, dT.p, dcq.p, nq);
+            else dispatch_p2<2, uint8_t>(ctx, A, s, F, Rg.p, P->pos8.p, accumulate, dT.p, dcq.p, nq);
+        } else {
+            if (dim == 3) dispatch_p2<3, uint16_t>(ctx, A, s, F, Rg.p, P->pos16.p, accumulate, dT.p, dcq.p, nq);
+            else dispatch_p2<2, uint16_t>(ctx, A, s, F, Rg.p, P->pos16.p, accumulate, dT.p, dcq.p, nq);
+        }
     }
     // Rg is released through the stream-ordered allocator: no synchronisation needed
     FF_API_END(s ? s->ctx : nullptr)

@@ -633,8 +633,8 @@ void drop_resident()
     g_resident.clear();
 }
 
-// bilinear terms whose coefficient depends on the mesh point are on the path for P1 spaces only (decided on the host, before
-// any device work, so that a refusal costs nothing)
+// bilinear terms whose coefficient depends on the mesh point cost a pass of FreeFEM's evaluator over the quadrature nodes:
+// the space is classified first, on the host, so that a refusal costs nothing
 template <class FESpaceT>
 void check_qterms_supported(const FESpaceT &Vh, const Varf &V)
 {
@@ -642,8 +642,7 @@ void check_qterms_supported(const FESpaceT &Vh, const Varf &V)
     for (size_t i = 0; i < V.bil.size(); ++i) any = any || (!V.bil[i].qterms.empty() && !V.bil[i].border);
     if (!any) return;
     int order, ncomp, nloc;
-    classify_space(Vh, MeshDim<typename FESpaceT::Mesh>::d, order, ncomp, nloc);
-    if (order != 1) throw Unsupported{"P2 form whose coefficient depends on the mesh point"};
+    classify_space(Vh, MeshDim<typename FESpaceT::Mesh>::d, order, ncomp, nloc); // refuses what is not P1 / P2 Lagrange
 }
 
 // the pattern of the device matrix is that of the whole space: FreeFEM's is the same only when the volume integrals
@@ -778,7 +777,6 @@ MatriceMorse<double> *gpu_matrix(Stack stack, const FESpaceT &Vh, DevSpace &D, c
     for (size_t i = 0; i < V.bil.size(); ++i) {
         const BilinearItem &B = V.bil[i];
         if (B.qterms.empty()) continue;
-        if (D.order != 1 && !B.border) throw Unsupported{"P2 form whose coefficient depends on the mesh point"};
         std::vector<const C_F0 *> ex;
         for (size_t t = 0; t < B.qterms.size(); ++t) ex.push_back(&B.qterms[t].coef);
         std::vector<std::vector<double>> v = B.border ? eval_at_bnodes(stack, Vh, ex, B.q, B.reg) : eval_at_nodes(stack, Vh, ex, B.q, B.reg);

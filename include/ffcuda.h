@@ -164,9 +164,10 @@ int ffcuda_assemble_bilinear(ffcuda_matrix *A, ffcuda_space *s, int nterms, cons
                              int nlab, const int32_t *labels, int accumulate);
 /* A (+)= the same with every term multiplied by ONE coefficient that depends on the mesh point (kappa(x,y,z), a P0 / P1
  * FE function, ...), given by the values Element_Op would compute (fflib/problem.cpp:6407): cq[k * nq + q] (HOST array) at
- * quadrature node q of element k.  P1 spaces (scalar or vector): the gradients of P1 functions do not depend on the node,
- * so the element integrals reduce exactly to the moments sum_q w_q c_q, sum_q w_q c_q lambda_a, sum_q w_q c_q lambda_a
- * lambda_b of the coefficient, formed on the device.  Forms with several coefficient functions: one call per function. */
+ * quadrature node q of element k.  P1: the gradients do not depend on the node, so the element integrals reduce exactly to
+ * the moments sum_q w_q c_q, sum_q w_q c_q lambda_a, sum_q w_q c_q lambda_a lambda_b of the coefficient, formed on the
+ * device.  P2: the per-pair tensors sum_q c_q w_q d phi_a(q) d phi_b(q) are formed on the fly from the node values.
+ * Forms with several coefficient functions: one call per function. */
 int ffcuda_assemble_bilinear_qcoef(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms,
                                    int nq, const double *qpts, const double *qw, const double *cq, int accumulate);
 int ffcuda_assemble_linear(ffcuda_vec *b, ffcuda_space *s, int nterms, const ffcuda_lterm *terms,

@@ -89,6 +89,9 @@ CASES = {
     "lap3d_p1_bnd_g": (1, 1, LAP3, [(0, ID, 1.0)], "qfV5", [([1], 1, [0.0])]),
     "lap2d_p2_bnd_g": (2, 1, LAP2, [(0, ID, 1.0)], "qf5pT", [([4], 1, [0.0])]),
     "lame3d_p1_bnd_g": (1, 3, lame_terms(), [(2, ID, -0.05)], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
+    "diff3d_p2_kappa": (2, 1, [(0, ID, 0, ID, 2.0)], [(0, ID, 1.0)], "qfV5", [([1, 2], 1, [0.0])]),
+    "reac2d_p2_rho": (2, 1, LAP2, [(0, ID, 1.0)], "qf5pT", [([4], 1, [0.0])]),
+    "lame3d_p2_evar": (2, 3, [], [(2, ID, -0.05)], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
     # half storage (sym=1, CASE_SYM below): the fixture holds the lower triangle
     "lap3d_p1_sym": (1, 1, LAP3, [(0, ID, 1.0)], "qfV5", [(ALL6, 1, [0.0])]),
     "lap2d_p2_sym": (2, 1, LAP2 + [(0, ID, 0, ID, 2.0)], [(0, ID, 1.0)], "qf5pT", [([2, 4], 1, [0.0])]),
@@ -115,6 +118,9 @@ CASE_QCOEF = {
     "diff3d_p1_kappa": [(lambda P: 1 + P[..., 0] * P[..., 1] + P[..., 2] ** 2, LAP3)],
     "reac2d_p1_rho": [(lambda P: 1 + np.sin(P[..., 0]) * P[..., 1], [(0, ID, 0, ID, 1.0)])],
     "lame3d_p1_evar": [(lambda P: 1 + P[..., 0], lame_terms())],
+    "diff3d_p2_kappa": [(lambda P: 1 + P[..., 0] * P[..., 1] + P[..., 2] ** 2, LAP3)],
+    "reac2d_p2_rho": [(lambda P: 1 + np.sin(P[..., 0]) * P[..., 1], [(0, ID, 0, ID, 1.0), (0, DX, 0, ID, 0.5), (0, ID, 0, DX, 0.5)])],
+    "lame3d_p2_evar": [(lambda P: 1 + P[..., 0], lame_terms())],
 }
 CASE_BLIN["lap3d_p1_bnd_g"] = ([6], [(0, ID, 0.5)])
 # boundary data depending on the mesh point: name -> dict(lin=(labels, g at points P (..., dim) -> (ncomp, ...)),

@@ -117,6 +117,13 @@ CASES = {
     "lame3d_p1_bnd_g": dict(dim=3, mesh="cube(2,3,2)", fe="[P1,P1,P1]", unk="[u1,u2,u3]", tst="[v1,v2,v3]", pre=LAME_PRE, bil=LAME,
                             lin="-0.05*v3", blin="+int2d(Th,3)(1e3*(1+x)*(u1*v1+u2*v2+u3*v3))+int2d(Th,2)(0.3*z*v1-0.2*(1+y)*v3)",
                             bc="on(1,u1=0,u2=0,u3=0)"),
+    # the same on P2 spaces (the per-pair tensors are formed from the coefficient values at the quadrature nodes)
+    "diff3d_p2_kappa": dict(dim=3, mesh="cube(2,2,2,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", fe="P2",
+                            bil="(1+x*y+z*z)*(" + LAP3 + ")+2.*u*v", lin="1.*v", bc="on(1,2,u=0)"),
+    "reac2d_p2_rho": dict(dim=2, mesh="square(4,3,[x+0.2*y*y,y*(1+0.3*x)])", fe="P2", bil=LAP2 + "+(1+sin(x)*y)*(u*v+0.5*dx(u)*v+0.5*u*dx(v))",
+                          lin="1.*v", bc="on(4,u=0)"),
+    "lame3d_p2_evar": dict(dim=3, mesh="cube(2,2,2)", fe="[P2,P2,P2]", unk="[u1,u2,u3]", tst="[v1,v2,v3]", pre=LAME_PRE,
+                           bil="(1+x)*(" + LAME + ")", lin="-0.05*v3", bc="on(1,u1=0,u2=0,u3=0)"),
     # half storage (sym=1): MatriceElementaireSymetrique / the symmetric Element_Op, lower triangle only (HashMatrix.cpp:1319-1325)
     "lap3d_p1_sym": dict(dim=3, mesh="cube(3,3,3)", fe="P1", bil=LAP3, lin="1.*v", bc="on(1,2,3,4,5,6,u=0)", sym=1),
     "lap2d_p2_sym": dict(dim=2, mesh="square(4,3,[x+0.2*y*y,y*(1+0.3*x)])", fe="P2", bil=LAP2 + "+2.*u*v", lin="1.*v",

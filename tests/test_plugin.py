@@ -107,6 +107,10 @@ CASES = {
     "lame3d_p1_bnd_g": script(3, "cube(3,4,3)", "[P1,P1,P1]", LAME, "-0.05*v3", "on(1,u1=0,u2=0,u3=0)", pre=LAME_PRE,
                               unk="[u1,u2,u3]", tst="[v1,v2,v3]", eps="1e-14",
                               extra="+int2d(Th,3)(1e3*(1+x)*(u1*v1+u2*v2+u3*v3))+int2d(Th,2)(0.3*z*v1-0.2*(1+y)*v3)"),
+    "diff3d_p2_kappa": script(3, "cube(3,3,4,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", "P2", "(1+x*y+z*z)*(" + LAP3 + ")+2.*u*v", "1.*v",
+                              "on(1,2,u=0)", eps="1e-14"),
+    "lame3d_p2_evar": script(3, "cube(2,3,2)", "[P2,P2,P2]", "(1+x)*(" + LAME + ")+0.5*(1+y*y)*(u1*v1+u2*v2+u3*v3)", "-0.05*v3",
+                             "on(1,u1=0,u2=0,u3=0)", pre=LAME_PRE, unk="[u1,u2,u3]", tst="[v1,v2,v3]", eps="1e-14"),
     "mass3d_lumped": script(3, "cube(3,3,3)", "P1", "u*v+0.1*(" + LAP3 + ")", "1.*v", "on(1,u=0)", intopt=",qfV=qfV1lump"),
 }
 
@@ -211,7 +215,7 @@ mesh3 Th = cube(3,3,3);
 fespace Vh(Th,P1);
 fespace Vh2(Th,P2);
 varf vb(u,v) = int3d(Th)(x*dx(u)*dx(v)+u*v) + on(1,u=0);
-matrix B = vb(Vh2,Vh2);
+matrix B = vb(Vh2,Vh);
 fespace Wh(Th,P0);
 varf vc(u,v) = int3d(Th)(u*v);
 matrix C = vc(Wh,Wh);
@@ -233,11 +237,11 @@ cout << "NNZ " << A.nnz << endl;
 
 @needs_ff
 def test_plugin_loads_and_leaves_out_of_scope_forms_to_freefem():
-    """x-dependent coefficient on a P2 space, non-Lagrange element, boundary integral without a volume integral: not claimed, FreeFEM's own operators run
+    """different unknown and test spaces, non-Lagrange element, boundary integral without a volume integral: not claimed, FreeFEM's own operators run
     (no GPU needed), and the plugin says so."""
     rc, out, _ = run_ff(OUT_OF_SCOPE, {}, want_fail=True)
     assert rc == 0, out[-2000:]
-    assert re.search(r"^NNZ 7525 162 \d+", out, re.M)
+    assert re.search(r"^NNZ 2314 162 \d+", out, re.M)
     assert out.count("left to FreeFEM") >= 4
     rc, out, _ = run_ff(OUT_OF_SCOPE, {"FFCUDA_STRICT": "1"}, want_fail=True)
     assert rc != 0 and "FFCUDA_STRICT" in out
@@ -348,7 +352,7 @@ def test_plugin_problem_solve_matches_freefem(name):
 
 
 SOLVE_FALLBACK = """mesh Th = square(10,9);
-fespace Vh(Th,P2); Vh u,v;
+fespace Vh(Th,P1nc); Vh u,v;
 solve Poisson(u,v,solver=LU) = int2d(Th)((1+x)*(dx(u)*dx(v)+dy(u)*dy(v))) - int2d(Th)(x*v) + on(1,2,3,4,u=0);
 fespace Wh(Th,P1dc); Wh w,ww;
 solve Proj(w,ww) = int2d(Th)(w*ww) - int2d(Th)(u*ww);
