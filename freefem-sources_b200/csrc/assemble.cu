@@ -1839,3 +1839,108 @@ extern "C" int ffcuda_assemble_bilinear_boundary_qcoef(ffcuda_matrix *A, ffcuda_
     FF_CUDA(cudaStreamSynchronize(st)); // cq is the caller's pageable memory
     FF_API_END(s ? s->ctx : nullptr)
 }
+
+// ----------------------------------------------------------------------------------------------------
+// Linear forms with data depending on the mesh point AND derivatives of the test function (the residual of a Newton step,
+// int(dx(uk) dx(v) + ...)): fq[((c * (DIM+1) + s) * nt + k) * nq + q] = coefficient of d^s v_c at node q of element k.
+// d_x phi_a(q) = sum_r dhat_r phi_a(q) grad(lambda_r)[x], grad(lambda_r) = N_r / det.  Same two passes as the value-only
+// entry above: per element the nloc x ncomp weighted sums, then the row-owner gather.
+// ----------------------------------------------------------------------------------------------------
+template <int DIM>
+__global__ void k_rhs_qterms_elem(int nt, const int32_t *__restrict__ conn, const double *__restrict__ xyz, int vstride, int nloc, int nc,
+                                  int nq, const double *__restrict__ wB /* [q][a][s] = w_q dhat^s phi_a(q) */,
+                                  const double *__restrict__ fq, double *__restrict__ G /* [k][a][c] */)
+{
+    extern __shared__ double swB[];
+    constexpr int NS = DIM + 1;
+    for (int i = threadIdx.x; i < nq * nloc * NS; i += blockDim.x) swB[i] = wB[i];
+    __syncthreads();
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nt) return;
+    double X[DIM + 1][DIM], N[DIM + 1][DIM], det;
+    const int32_t *K = conn + (size_t)(DIM + 1) * k;
+#pragma unroll
+    for (int a = 0; a <= DIM; ++a) {
+        const double *P = xyz + (size_t)K[a] * vstride;
+#pragma unroll
+        for (int d = 0; d < DIM; ++d) X[a][d] = P[d];
+    }
+    p1_normals<DIM>(X, N, det);
+    const double mes = det * (DIM == 3 ? 1.0 / 6.0 : 0.5), rdet = 1.0 / det;
+    for (int c = 0; c < nc; ++c) {
+        double acc[10];
+#pragma unroll
+        for (int a = 0; a < 10; ++a) acc[a] = 0.0;
+        for (int q = 0; q < nq; ++q) {
+            double h[NS]; // h[0] = f_0, h[r] = sum_x grad(lambda_r)[x] f_x : coefficients of phi_a and of dhat_r phi_a
+            h[0] = fq[(((size_t)c * NS) * nt + k) * nq + q];
+            double fx[DIM];
+#pragma unroll
+            for (int x = 0; x < DIM; ++x) fx[x] = fq[(((size_t)c * NS + 1 + x) * nt + k) * nq + q];
+#pragma unroll
+            for (int r = 1; r <= DIM; ++r) {
+                double t = 0.0;
+#pragma unroll
+                for (int x = 0; x < DIM; ++x) t = fma(N[r][x], fx[x], t);
+                h[r] = t * rdet;
+            }
+            const double *w = swB + (size_t)q * nloc * NS;
+#pragma unroll
+            for (int a = 0; a < 10; ++a)
+                if (a < nloc) {
+#pragma unroll
+                    for (int s2 = 0; s2 < NS; ++s2) acc[a] = fma(w[a * NS + s2], h[s2], acc[a]);
+                }
+        }
+#pragma unroll
+        for (int a = 0; a < 10; ++a)
+            if (a < nloc) G[((size_t)k * nloc + a) * nc + c] = mes * acc[a];
+    }
+}
+
+extern "C" int ffcuda_assemble_linear_qterms(ffcuda_vec *b, ffcuda_space *s, int nq, const double *qpts, const double *qw,
+                                             const double *fq, int accumulate)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(b && s && fq, "ffcuda_assemble_linear_qterms: null argument");
+    FF_REQUIRE(nq > 0 && nq <= 256 && qpts && qw, "quadrature rule missing (or more than 256 nodes)");
+    ffcuda_ctx *ctx = s->ctx;
+    ff_enter(ctx);
+    ff_build_incidence(s);
+    ffcuda_mesh *m = s->mesh;
+    FF_REQUIRE(!m->distributed, "ffcuda_assemble_linear_qterms: single-GPU meshes only");
+    FF_REQUIRE(b->n >= s->nnodes_owned * s->ncomp, "right-hand side vector too short");
+    const int dim = m->dim, nloc = s->nloc, nc = s->ncomp, nt = m->nt, ns = dim + 1;
+    std::vector<double> wB((size_t)nq * nloc * ns);
+    for (int q = 0; q < nq; ++q) {
+        double B[10][4];
+        ref_basis(dim, s->order, qpts + (size_t)q * dim, B);
+        for (int a = 0; a < nloc; ++a)
+            for (int s2 = 0; s2 < ns; ++s2) wB[((size_t)q * nloc + a) * ns + s2] = qw[q] * B[a][s2];
+    }
+    cudaStream_t st = ctx->stream;
+    DBuf<double> dW, dF, G;
+    dW.alloc(wB.size());
+    dF.alloc((size_t)nc * ns * nt * nq);
+    G.alloc((size_t)nt * nloc * nc);
+    FF_CUDA(cudaMemcpyAsync(dW.p, wB.data(), dW.bytes(), cudaMemcpyHostToDevice, st));
+    FF_CUDA(cudaMemcpyAsync(dF.p, fq, dF.bytes(), cudaMemcpyHostToDevice, st));
+    const size_t shmem = wB.size() * sizeof(double);
+    FF_REQUIRE(shmem <= 96 * 1024, "quadrature rule too large for the shared-memory basis table");
+    ff_launch(ctx, "rhs_qterms_elem", [&] {
+        if (dim == 3) {
+            FF_CUDA(cudaFuncSetAttribute(k_rhs_qterms_elem<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+            k_rhs_qterms_elem<3><<<ff_blocks(nt, 128), 128, shmem, st>>>(nt, m->conn.p, m->xyz.p, m->vstride, nloc, nc, nq, dW.p, dF.p, G.p);
+        } else {
+            FF_CUDA(cudaFuncSetAttribute(k_rhs_qterms_elem<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+            k_rhs_qterms_elem<2><<<ff_blocks(nt, 128), 128, shmem, st>>>(nt, m->conn.p, m->xyz.p, m->vstride, nloc, nc, nq, dW.p, dF.p, G.p);
+        }
+    });
+    const int nrows = s->nnodes_owned;
+    const IncView V = ff_view(s->incidence);
+    ff_launch(ctx, "rhs_qvalues_gather", [&] {
+        k_rhs_qvalues_gather<<<ff_blocks(nrows, 128), 128, 0, st>>>(nrows, V, nloc, nc, G.p, b->d.p, accumulate);
+    });
+    FF_CUDA(cudaStreamSynchronize(st)); // fq is the caller's pageable memory
+    FF_API_END(s ? s->ctx : nullptr)
+}

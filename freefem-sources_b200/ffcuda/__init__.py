@@ -21,7 +21,7 @@ ffcuda_space_destroy ffcuda_symbolic ffcuda_pattern_info ffcuda_pattern_download
 ffcuda_matrix_download_lower ffcuda_matrix_from_csr_lower ffcuda_pattern_destroy ffcuda_matrix_create
 ffcuda_matrix_from_csr ffcuda_matrix_info ffcuda_matrix_download ffcuda_matrix_upload ffcuda_matrix_destroy ffcuda_vec_create
 ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_destroy ffcuda_assemble_bilinear ffcuda_assemble_bilinear_qcoef
-ffcuda_assemble_linear ffcuda_assemble_linear_qvalues ffcuda_assemble_linear_boundary ffcuda_assemble_bilinear_boundary ffcuda_assemble_linear_boundary_qvalues ffcuda_assemble_bilinear_boundary_qcoef ffcuda_bc_from_pairs ffcuda_bc_from_labels ffcuda_bc_count ffcuda_matrix_apply_bc ffcuda_vec_apply_bc
+ffcuda_assemble_linear ffcuda_assemble_linear_qvalues ffcuda_assemble_linear_qterms ffcuda_assemble_linear_boundary ffcuda_assemble_bilinear_boundary ffcuda_assemble_linear_boundary_qvalues ffcuda_assemble_bilinear_boundary_qcoef ffcuda_bc_from_pairs ffcuda_bc_from_labels ffcuda_bc_count ffcuda_matrix_apply_bc ffcuda_vec_apply_bc
 ffcuda_vec_set_bc_values ffcuda_bc_destroy ffcuda_spmv ffcuda_cg ffcuda_cg_host ffcuda_gmres ffcuda_gmres_host ffcuda_comm_unique_id ffcuda_comm_init
 ffcuda_comm_finalize ffcuda_mesh_cube_distributed ffcuda_mesh_local_to_global ffcuda_quadrature ffcuda_partition_cube""".split()
 
@@ -299,6 +299,11 @@ class Space(_Handle):
         """b (+)= int(f v) with f given at the quadrature nodes: fq[c, k, q] (ncomp x nt x nq)"""
         qpts, qw, fq = _f64(qpts), _f64(qw), _f64(fq)
         _ck(lib().ffcuda_assemble_linear_qvalues(_h(b), _h(self), len(qw), _p(qpts), _p(qw), _p(fq), int(accumulate)), self.ctx.h)
+
+    def assemble_linear_qterms(self, b, qpts, qw, fq, accumulate=False):
+        """b (+)= int(sum_s f_s d^s v) with the f_s given at the quadrature nodes: fq[c, s, k, q] (ncomp x (dim+1) x nt x nq)"""
+        qpts, qw, fq = _f64(qpts), _f64(qw), _f64(fq)
+        _ck(lib().ffcuda_assemble_linear_qterms(_h(b), _h(self), len(qw), _p(qpts), _p(qw), _p(fq), int(accumulate)), self.ctx.h)
 
     def assemble_linear_boundary_qvalues(self, b, qpts, qw, gq, accumulate=True):
         """b (+)= boundary integral of g v with g given at the face quadrature nodes: gq[c, ib, q] (0 where it does not go)"""

@@ -392,8 +392,9 @@ struct BilinearItem {
     Region reg;
     bool border = false; // integral over the boundary elements with the labels of reg (Robin terms)
 };
-struct QTerm { // value term whose coefficient depends on the mesh point: evaluated at the quadrature nodes by FreeFEM's evaluator
+struct QTerm { // term whose coefficient depends on the mesh point: evaluated at the quadrature nodes by FreeFEM's evaluator
     int vcomp;
+    int slot; // 0 = value of the test function, 1..dim = dx, dy, dz
     C_F0 coef;
 };
 struct LinearItem {
@@ -554,10 +555,10 @@ Varf read_varf(Stack stack, const list<C_F0> &largs, const MeshT &Th, int ncomp,
                 if (L.border && t.vop != op_id) throw Unsupported{"derivatives in a boundary integral"};
                 if (!op.v[k].second.LeftValue()->MeshIndependent()) {
                     // f(x,y,z) v, uold v / dt, ...: the values Element_rhs would compute go to the device as a table
-                    if (t.vop != op_id) throw Unsupported{"derivative of the test function times a coefficient that depends on the mesh point"};
                     if (op.v[k].second.left() != atype<double>() && op.v[k].second.left() != atype<long>())
                         throw Unsupported{"coefficient is not real"};
-                    L.qterms.push_back(QTerm{t.vcomp, op.v[k].second});
+                    const int slot = t.vop == op_id ? 0 : t.vop == op_dx ? 1 : t.vop == op_dy ? 2 : 3;
+                    L.qterms.push_back(QTerm{t.vcomp, slot, op.v[k].second});
                     continue;
                 }
                 t.coef = constant_coef(stack, op.v[k].second);
@@ -743,18 +744,20 @@ std::vector<std::vector<double>> eval_at_bnodes(Stack stack, const FESpaceT &Vh,
     *mps = mp;
     return out;
 }
-// table of a linear item: fq[(c * nt + k) * nq + q], summed over the terms of component c
+// table of a linear item: fq[(c * nt + k) * nq + q], summed over the terms of component c; with derivatives of the test
+// function (grad = true): fq[((c * (dim+1) + slot) * nt + k) * nq + q]
 template <class FESpaceT>
-std::vector<double> eval_qvalues(Stack stack, const FESpaceT &Vh, const LinearItem &L, bool negate)
+std::vector<double> eval_qvalues(Stack stack, const FESpaceT &Vh, const LinearItem &L, bool negate, bool grad = false)
 {
     const size_t per = (size_t)(L.border ? nbe_of(Vh.Th) : Vh.Th.nt) * L.q.w.size();
+    const int ns = grad ? MeshDim<typename FESpaceT::Mesh>::d + 1 : 1;
     std::vector<const C_F0 *> ex;
     for (size_t t = 0; t < L.qterms.size(); ++t) ex.push_back(&L.qterms[t].coef);
     std::vector<std::vector<double>> v = L.border ? eval_at_bnodes(stack, Vh, ex, L.q, L.reg) : eval_at_nodes(stack, Vh, ex, L.q, L.reg);
-    std::vector<double> fq((size_t)Vh.N * per, 0.0);
+    std::vector<double> fq((size_t)Vh.N * ns * per, 0.0);
     const double sgn = negate ? -1.0 : 1.0;
     for (size_t t = 0; t < L.qterms.size(); ++t) {
-        double *dst = fq.data() + (size_t)L.qterms[t].vcomp * per;
+        double *dst = fq.data() + ((size_t)L.qterms[t].vcomp * ns + (grad ? L.qterms[t].slot : 0)) * per;
         for (size_t i = 0; i < per; ++i) dst[i] += sgn * v[t][i];
     }
     return fq;
@@ -905,13 +908,15 @@ void gpu_rhs(Stack stack, const FESpaceT &Vh, DevSpace &D, const Varf &V, double
             }
             if (!L.qterms.empty() && !rc) {
                 std::vector<double> fq;
+                bool grad = false;
+                for (size_t t = 0; t < L.qterms.size(); ++t) grad = grad || L.qterms[t].slot != 0;
                 try {
-                    fq = eval_qvalues(stack, Vh, L, negate);
+                    fq = eval_qvalues(stack, Vh, L, negate, grad);
                 } catch (...) {
                     ffcuda_vec_destroy(db);
                     throw;
                 }
-                rc = (border ? ffcuda_assemble_linear_boundary_qvalues : ffcuda_assemble_linear_qvalues)(
+                rc = (border ? ffcuda_assemble_linear_boundary_qvalues : grad ? ffcuda_assemble_linear_qterms : ffcuda_assemble_linear_qvalues)(
                     db, D.space, (int)L.q.w.size(), L.q.pts.data(), L.q.w.data(), fq.data(), first ? 0 : 1);
                 first = false;
             }

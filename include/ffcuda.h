@@ -187,6 +187,10 @@ int ffcuda_assemble_linear_boundary(ffcuda_vec *b, ffcuda_space *s, int nterms, 
  * summed over the terms, 0 where the element is outside the integral's region.  Value terms only. */
 int ffcuda_assemble_linear_qvalues(ffcuda_vec *b, ffcuda_space *s, int nq, const double *qpts, const double *qw,
                                    const double *fq, int accumulate);
+/* the same with derivatives of the test function (the residual of a Newton step, int(dx(uk) dx(v) + ...)):
+ * fq[((c * (dim+1) + s) * nt + k) * nq + q] (HOST) = coefficient of d^s v_c, s = 0 value, 1..dim = dx, dy, dz */
+int ffcuda_assemble_linear_qterms(ffcuda_vec *b, ffcuda_space *s, int nq, const double *qpts, const double *qw,
+                                  const double *fq, int accumulate);
 /* A (+)= boundary integrals int2d(Th3, labels)(c u v) / int1d(Th, labels)(c u v) of a bilinear form (Robin terms):
  * the border loop of AssembleBilinearForm, fflib/problem.cpp:1317-1326 (3-D), :1030-1040 (2-D), with Element_Op's border
  * branch :6518-6560 / :6216-6290.  Value terms only (uop = vop = id), constant c.  The couples FreeFEM creates for a border

@@ -524,6 +524,29 @@ void ffo_assemble_rhs_qvalues(int dim, const double *xyz, int nt, const int32_t 
     }
 }
 
+/* the same with derivatives of the test function: fq[((c * (dim+1) + s) * nt + k) * nq + q] = coefficient of d^s v_c
+ * (s = 0 value, 1..dim = dx, dy, dz) at node q of element k - e.g. the residual of a Newton step, int(dx(uk) dx(v) + ...) */
+void ffo_assemble_rhs_qterms(int dim, const double *xyz, int nt, const int32_t *conn, int order, int ncomp,
+                             const int32_t *elem2node, int nq, const double *qpts, const double *qw, const double *fq, double *b)
+{
+    const int nloc = ffo_nloc(dim, order), nvk = dim + 1, ns = dim + 1;
+    for (int k = 0; k < nt; ++k) {
+        const int32_t *K = conn + (size_t)nvk * k;
+        const int32_t *N = elem2node ? elem2node + (size_t)nloc * k : K;
+        double X[12], G[4][3], val[10][4];
+        elem_coords(dim, xyz, K, X);
+        double mes = geom(dim, X, G);
+        for (int q = 0; q < nq; ++q) {
+            double coef = mes * qw[q];
+            basis(dim, order, qpts + (size_t)q * dim, G, val);
+            for (int c = 0; c < ncomp; ++c)
+                for (int a = 0; a < nloc; ++a)
+                    for (int sl = 0; sl < ns; ++sl)
+                        b[N[a] * ncomp + c] += coef * fq[(((size_t)c * ns + sl) * nt + k) * nq + q] * val[a][sl];
+        }
+    }
+}
+
 /* measure factor and reference point of a border quadrature node: T.N(ie) (cross product of two edges of the face,
  * norm = 2 * area, hence the 0.5) / edge length, and Pt = PBord(ie, pi) (femlib/Mesh3dn.hpp:76, Mesh2dn.hpp:65) */
 static double face_measure(int dim, const double *X, int ie)

@@ -77,6 +77,9 @@ void ffo_assemble_rhs(int dim, int nv, const double *xyz, int nt, const int32_t 
  * the coefficient of v_c at quadrature node q of element k; ADDS to b */
 void ffo_assemble_rhs_qvalues(int dim, const double *xyz, int nt, const int32_t *conn, int order, int ncomp,
                               const int32_t *elem2node, int nq, const double *qpts, const double *qw, const double *fq, double *b);
+/* ... and with derivatives of the test function: fq[((c*(dim+1) + s)*nt + k)*nq + q], s = 0 value, 1..dim = dx, dy, dz */
+void ffo_assemble_rhs_qterms(int dim, const double *xyz, int nt, const int32_t *conn, int order, int ncomp,
+                             const int32_t *elem2node, int nq, const double *qpts, const double *qw, const double *fq, double *b);
 /* boundary integrals of a linear form (Element_rhs on border elements, problem.cpp:8439-8587); ADDS to b.
  * qpts: nq x (dim-1) reference coordinates on the face / edge */
 void ffo_assemble_rhs_boundary(int dim, const double *xyz, const int32_t *conn, int order, int ncomp,

@@ -92,6 +92,10 @@ CASES = {
     "diff3d_p2_kappa": (2, 1, [(0, ID, 0, ID, 2.0)], [(0, ID, 1.0)], "qfV5", [([1, 2], 1, [0.0])]),
     "reac2d_p2_rho": (2, 1, LAP2, [(0, ID, 1.0)], "qf5pT", [([4], 1, [0.0])]),
     "lame3d_p2_evar": (2, 3, [], [(2, ID, -0.05)], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
+    # right-hand sides with derivatives of the test function times data depending on the mesh point (CASE_FQT below)
+    "resid2d_p1_grad": (1, 1, LAP2, [], "qf5pT", [([4], 1, [0.0])]),
+    "resid3d_p2_grad": (2, 1, LAP3, [], "qfV5", [([1, 2], 1, [0.0])]),
+    "resid3d_p1_vec_grad": (1, 3, lame_terms(), [], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
     # half storage (sym=1, CASE_SYM below): the fixture holds the lower triangle
     "lap3d_p1_sym": (1, 1, LAP3, [(0, ID, 1.0)], "qfV5", [(ALL6, 1, [0.0])]),
     "lap2d_p2_sym": (2, 1, LAP2 + [(0, ID, 0, ID, 2.0)], [(0, ID, 1.0)], "qf5pT", [([2, 4], 1, [0.0])]),
@@ -132,6 +136,18 @@ CASE_BQ = {
                            bil=([2, 3], lambda P: 1 + P[..., 0] * P[..., 1], [(0, ID, 0, ID, 1.0)])),
     "lame3d_p1_bnd_g": dict(lin=([2], lambda P: np.stack([0.3 * P[..., 2], 0 * P[..., 0], -0.2 * (1 + P[..., 1])])),
                             bil=([3], lambda P: 1 + P[..., 0], [(c, ID, c, ID, 1e3) for c in range(3)])),
+}
+# data of the linear form per (component, slot): P (..., dim) -> (ncomp, dim+1, ...); slot 0 = value, 1..dim = dx, dy, dz
+def _z(P):
+    return 0 * P[..., 0]
+
+
+CASE_FQT = {
+    "resid2d_p1_grad": lambda P: np.stack([np.stack([P[..., 0] * P[..., 1], np.sin(P[..., 0]), -P[..., 1]])]),
+    "resid3d_p2_grad": lambda P: np.stack([np.stack([P[..., 0], -P[..., 1] * P[..., 2], _z(P), 1 + P[..., 2]])]),
+    "resid3d_p1_vec_grad": lambda P: np.stack([np.stack([_z(P), P[..., 0], P[..., 2], _z(P)]),
+                                               np.stack([P[..., 1], _z(P), _z(P), _z(P)]),
+                                               np.stack([_z(P), _z(P), _z(P), -0.05 * (1 + P[..., 0])])]),
 }
 # cases assembled with sym=1: MatriceMorse keeps the entries (i, j) with j <= i only (HashMatrix.cpp:1319-1325)
 CASE_SYM = {"lap3d_p1_sym", "lap2d_p2_sym", "lame3d_p1_sym"}
@@ -194,4 +210,4 @@ NO_SOLVE_TGV = {"lap3d_p1_tgvm1", "lame3d_p1_tgvm1", "lap3d_p1_tgvm3", "lame3d_p
 def loose_iterate(name):
     """fixtures whose eps=1e-6 iterate is compared loosely (1e-6) because their right-hand side or matrix carries extra ulp
     differences (boundary terms, data evaluated with another libm); their eps=1e-14 solutions are held to 1e-12 like all others"""
-    return name in CASE_BLIN or name in CASE_BBIL or name in CASE_FQ or name in CASE_QCOEF or name in CASE_BQ
+    return name in CASE_BLIN or name in CASE_BBIL or name in CASE_FQ or name in CASE_QCOEF or name in CASE_BQ or name in CASE_FQT

@@ -124,6 +124,13 @@ CASES = {
                           lin="1.*v", bc="on(4,u=0)"),
     "lame3d_p2_evar": dict(dim=3, mesh="cube(2,2,2)", fe="[P2,P2,P2]", unk="[u1,u2,u3]", tst="[v1,v2,v3]", pre=LAME_PRE,
                            bil="(1+x)*(" + LAME + ")", lin="-0.05*v3", bc="on(1,u1=0,u2=0,u3=0)"),
+    # ... and with derivatives of the test function (the residual of a Newton step: int(dx(uk) dx(v) + ...))
+    "resid2d_p1_grad": dict(dim=2, mesh="square(5,4,[x+0.2*y*y,y*(1+0.3*x)])", fe="P1", bil=LAP2, lin="x*y*v+sin(x)*dx(v)-y*dy(v)",
+                            bc="on(4,u=0)"),
+    "resid3d_p2_grad": dict(dim=3, mesh="cube(2,2,2,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", fe="P2", bil=LAP3, lin="(1+z)*dz(v)+x*v-y*z*dx(v)",
+                            bc="on(1,2,u=0)"),
+    "resid3d_p1_vec_grad": dict(dim=3, mesh="cube(2,3,2)", fe="[P1,P1,P1]", unk="[u1,u2,u3]", tst="[v1,v2,v3]", pre=LAME_PRE, bil=LAME,
+                                lin="x*dx(v1)+y*v2-0.05*(1+x)*dz(v3)+z*dy(v1)", bc="on(1,u1=0,u2=0,u3=0)"),
     # half storage (sym=1): MatriceElementaireSymetrique / the symmetric Element_Op, lower triangle only (HashMatrix.cpp:1319-1325)
     "lap3d_p1_sym": dict(dim=3, mesh="cube(3,3,3)", fe="P1", bil=LAP3, lin="1.*v", bc="on(1,2,3,4,5,6,u=0)", sym=1),
     "lap2d_p2_sym": dict(dim=2, mesh="square(4,3,[x+0.2*y*y,y*(1+0.3*x)])", fe="P2", bil=LAP2 + "+2.*u*v", lin="1.*v",

@@ -185,6 +185,18 @@ def assemble_rhs_qvalues(mesh, order, ncomp, elem2node, b, qpts, qw, fq):
     return b
 
 
+def assemble_rhs_qterms(mesh, order, ncomp, elem2node, b, qpts, qw, fq):
+    """adds int(sum_s f_s d^s v) with the f_s given at the quadrature nodes, fq[c, s, k, q] (s = 0 value, 1..dim derivatives)"""
+    dim = mesh["dim"]
+    xyz, conn = _f64(mesh["xyz"]), _i32(mesh["conn"])
+    e2n = _i32(elem2node)
+    b, qpts, qw, fq = _f64(b).copy(), _f64(qpts), _f64(qw), _f64(fq)
+    assert fq.shape[1] == dim + 1
+    lib().ffo_assemble_rhs_qterms(dim, _p(xyz, C.c_double), conn.shape[0], _p(conn, C.c_int32), order, ncomp, _p(e2n, C.c_int32),
+                                  len(qw), _p(qpts, C.c_double), _p(qw, C.c_double), _p(fq, C.c_double), _p(b, C.c_double))
+    return b
+
+
 def assemble_rhs_boundary(mesh, order, ncomp, elem2node, b, terms, qpts, qw, labels=None):
     """adds the boundary integrals int2d(Th3,labels)(...) / int1d(Th,labels)(...) of a linear form to b (returns a copy)"""
     dim = mesh["dim"]

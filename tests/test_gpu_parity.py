@@ -34,7 +34,7 @@ def _upload(ctx, g):
 
 
 def _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve=True, eps=1e-6, itmax=0, TGV=TGV, lower=False,  # noqa: N803
-              blin=None, bbil=None, gmres=None, fqfun=None, qcoef=(), bq=None):
+              blin=None, bbil=None, gmres=None, fqfun=None, qcoef=(), bq=None, fqt=None):
     """Full product pipeline on one problem; returns everything a parity check needs."""
     mesh = _upload(ctx, g)
     sp = mesh.space(order, ncomp, e2n, nnodes)
@@ -61,6 +61,8 @@ def _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve=True
         sp.assemble_linear_boundary_qvalues(b, fq, fw, gq, accumulate=True)
     if fqfun:  # data depending on the mesh point, handed over at the quadrature nodes
         sp.assemble_linear_qvalues(b, qp, qw, fqfun(ol.quad_points_xyz(g, qp)), accumulate=True)
+    if fqt:  # ... with derivatives of the test function
+        sp.assemble_linear_qterms(b, qp, qw, fqt(ol.quad_points_xyz(g, qp)), accumulate=True)
     if blin:  # boundary integrals of the linear form (Neumann / traction data)
         fq, fw = ol.face_quadrature(g["dim"])
         sp.assemble_linear_boundary(b, blin[1], fq, fw, blin[0], accumulate=True)
@@ -104,7 +106,7 @@ def test_golden_case(ctx, name):
     e2n = fc.elem2node(g, order, ncomp)
     nnodes = g["ndof"] // ncomp
     r = _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, nnodes, solve="u" in g, TGV=fc.CASE_TGV.get(name, TGV),
-                  lower=name in fc.CASE_SYM, blin=fc.CASE_BLIN.get(name), bbil=fc.CASE_BBIL.get(name), gmres=fc.CASE_GMRES.get(name), fqfun=fc.CASE_FQ.get(name), qcoef=fc.CASE_QCOEF.get(name, ()), bq=fc.CASE_BQ.get(name))
+                  lower=name in fc.CASE_SYM, blin=fc.CASE_BLIN.get(name), bbil=fc.CASE_BBIL.get(name), gmres=fc.CASE_GMRES.get(name), fqfun=fc.CASE_FQ.get(name), qcoef=fc.CASE_QCOEF.get(name, ()), bq=fc.CASE_BQ.get(name), fqt=fc.CASE_FQT.get(name))
     grp, gci, gval = fc.golden_csr(g)
     assert r["n"] == g["ndof"]
     assert np.array_equal(r["rowptr"], grp) and np.array_equal(r["colind"], gci)          # bit-exact pattern

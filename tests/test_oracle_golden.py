@@ -80,6 +80,8 @@ def test_matrix_rhs_solution(name):
     if name in fc.CASE_FQ:  # data evaluated at the quadrature nodes, as Element_rhs does
         fq = fc.CASE_FQ[name](ol.quad_points_xyz(_mesh(g), qp))
         b = ol.assemble_rhs_qvalues(_mesh(g), order, ncomp, e2n, b, qp, qw, fq)
+    if name in fc.CASE_FQT:  # ... with derivatives of the test function
+        b = ol.assemble_rhs_qterms(_mesh(g), order, ncomp, e2n, b, qp, qw, fc.CASE_FQT[name](ol.quad_points_xyz(_mesh(g), qp)))
     if name in fc.CASE_BLIN:
         blabels, bterms = fc.CASE_BLIN[name]
         fq, fw = ol.face_quadrature(dim)
