@@ -1212,8 +1212,9 @@ __global__ void __launch_bounds__(RED_THREADS) k_gm_mgs_last(double *__restrict_
 // L2) and costs one grid barrier; the dot products are summed in a fixed shape (per-block partials, every block adds
 // them in the same order), so the result is reproducible and every block holds the same h.
 namespace cg = cooperative_groups;
+static constexpr int ARN_THREADS = 512; // one CTA per SM: half as many partial sums and barrier participants as 2 x 256
 template <int KW>
-__global__ void __launch_bounds__(RED_THREADS, 2)
+__global__ void __launch_bounds__(ARN_THREADS, 1)
     k_gm_arnoldi(double *__restrict__ W, const double *const *__restrict__ Vtab, int n, int it, double eps, GmresLayout L,
                  double *__restrict__ gs, double *__restrict__ partial /* 2 x gridDim */, int *__restrict__ flags)
 {
@@ -1389,14 +1390,14 @@ static void gmres_device(ffcuda_matrix *A, const double *b, double *x, double ep
         if (can) {
             for (int kw : {4, 8, 16, 32}) {
                 int per_sm = 0;
-                cudaError_t e = kw == 4    ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gm_arnoldi<4>, RED_THREADS, 0)
-                                : kw == 8  ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gm_arnoldi<8>, RED_THREADS, 0)
-                                : kw == 16 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gm_arnoldi<16>, RED_THREADS, 0)
-                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gm_arnoldi<32>, RED_THREADS, 0);
+                cudaError_t e = kw == 4    ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gm_arnoldi<4>, ARN_THREADS, 0)
+                                : kw == 8  ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gm_arnoldi<8>, ARN_THREADS, 0)
+                                : kw == 16 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gm_arnoldi<16>, ARN_THREADS, 0)
+                                           : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_gm_arnoldi<32>, ARN_THREADS, 0);
                 FF_CUDA(e);
-                const int g = std::min(per_sm, 2) * ctx->sm_count;
-                if (g > 0 && (size_t)g * RED_THREADS * kw >= (size_t)n) {
-                    coop_grid = (int)std::min<size_t>((size_t)g, ((size_t)n + (size_t)RED_THREADS * kw - 1) / ((size_t)RED_THREADS * kw));
+                const int g = std::min(per_sm, 1) * ctx->sm_count;
+                if (g > 0 && (size_t)g * ARN_THREADS * kw >= (size_t)n) {
+                    coop_grid = (int)std::min<size_t>((size_t)g, ((size_t)n + (size_t)ARN_THREADS * kw - 1) / ((size_t)ARN_THREADS * kw));
                     coop_kw = kw;
                     break;
                 }
@@ -1438,7 +1439,7 @@ static void gmres_device(ffcuda_matrix *A, const double *b, double *x, double ep
                                  : coop_kw == 8  ? (const void *)k_gm_arnoldi<8>
                                  : coop_kw == 16 ? (const void *)k_gm_arnoldi<16>
                                                  : (const void *)k_gm_arnoldi<32>;
-                ff_launch(ctx, "gmres_arnoldi", [&] { FF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(coop_grid), dim3(RED_THREADS), args, 0, st)); });
+                ff_launch(ctx, "gmres_arnoldi", [&] { FF_CUDA(cudaLaunchCooperativeKernel(fn, dim3(coop_grid), dim3(ARN_THREADS), args, 0, st)); });
             } else {
                 for (int i = 0; i <= it; ++i) {
                     const double *Vprev = i ? vecV(i - 1) : nullptr;
