@@ -1397,7 +1397,7 @@ static void gmres_device(ffcuda_matrix *A, const double *b, double *x, double ep
                 FF_CUDA(e);
                 const int g = std::min(per_sm, 1) * ctx->sm_count;
                 if (g > 0 && (size_t)g * ARN_THREADS * kw >= (size_t)n) {
-                    coop_grid = (int)std::min<size_t>((size_t)g, ((size_t)n + (size_t)ARN_THREADS * kw - 1) / ((size_t)ARN_THREADS * kw));
+                    coop_grid = (int)std::min<size_t>((size_t)g, ((size_t)n + ARN_THREADS - 1) / ARN_THREADS); // every SM, as long as a thread has an entry
                     coop_kw = kw;
                     break;
                 }
