@@ -39,7 +39,7 @@ bool env_on(const char *name)
     const char *v = getenv(name);
     return v && *v && *v != '0';
 }
-bool g_verbose = false, g_strict = false;
+bool g_verbose = false, g_strict = false, g_check = false;
 
 [[noreturn]] void fail(const std::string &what)
 {
@@ -986,6 +986,36 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
                 int64_t nnz = 0;
                 Resident res{nullptr, nullptr};
                 MatriceMorse<double> *M = gpu_matrix(stack, Vh, D, V, ds, res, n, nnz);
+                if (g_check) { // FFCUDA_CHECK=1: FreeFEM's own operator runs as well, the two matrices are compared, FreeFEM's is kept
+                    M->CSR();
+                    const std::vector<int> p0(M->p, M->p + n + 1), j0(M->j, M->j + M->nnz);
+                    const std::vector<double> a0(M->aij, M->aij + M->nnz);
+                    delete M;
+                    release_resident(res);
+                    AnyType r = Base::Op::operator()(stack);
+                    Matrice_Creuse<double> &Af(*GetAny<Matrice_Creuse<double> *>((*this->a)(stack)));
+                    HashMatrix<int, double> *H = Af.pHM();
+                    if (!H) ExecError("ffcuda check: FreeFEM's operator did not produce a sparse matrix");
+                    H->CSR();
+                    bool same = H->n == n && (size_t)H->nnz == j0.size();
+                    for (int i = 0; same && i <= n; ++i) same = H->p[i] == p0[i];
+                    for (size_t k = 0; same && k < j0.size(); ++k) same = H->j[k] == j0[k];
+                    if (!same) ExecError("ffcuda check: the sparsity pattern differs from FreeFEM's");
+                    double amax = 0, dmax = 0;
+                    for (size_t k = 0; k < a0.size(); ++k) {
+                        const double a = H->aij[k];
+                        if (std::abs(a) > 1e29 || std::abs(a0[k]) > 1e29) {
+                            if (a != a0[k]) dmax = 1e300;
+                            continue;
+                        }
+                        amax = std::max(amax, std::abs(a));
+                        dmax = std::max(dmax, std::abs(a - a0[k]));
+                    }
+                    cout << "  -- ffcuda check: matrix " << n << " x " << n << ", nnz " << j0.size() << ": pattern identical, max |dA| / max |A| = "
+                         << (amax > 0 ? dmax / amax : dmax) << endl;
+                    if (dmax > 1e-12 * amax) ExecError("ffcuda check: matrix values differ from FreeFEM's by more than 1e-12");
+                    return r;
+                }
                 // --- hand the result to FreeFEM as its own MatriceMorse (problem.hpp:1678-1693)
                 WhereStackOfPtr2Free(stack) = new StackOfPtr2Free(stack);
                 Matrice_Creuse<double> &A(*GetAny<Matrice_Creuse<double> *>((*this->a)(stack)));
@@ -1045,6 +1075,22 @@ struct CudaRhsOp : public OpArraytoLinearForm<double, MMesh, v_fes> {
                 if (xx.N() != n) ExecError("ffcuda: array and fespace sizes differ in b = varf(0,Vh)");
                 std::vector<double> host;
                 gpu_rhs(stack, Vh, D, V, tgv, false, n, host, nullptr);
+                if (g_check) { // FFCUDA_CHECK=1: FreeFEM's own operator runs as well, the two vectors are compared, FreeFEM's is kept
+                    AnyType r = Base::Op::operator()(stack);
+                    KN_<double> xf(px ? *(KN_<double> *)px : GetAny<KN_<double>>((*this->x)(stack)));
+                    double bmax = 0, dmax = 0;
+                    for (long i = 0; i < n; ++i) {
+                        if (std::abs(xf[i]) > 1e20 || std::abs(host[i]) > 1e20) {
+                            if (std::abs(xf[i] - host[i]) > 1e-14 * std::abs(xf[i])) dmax = 1e300;
+                            continue;
+                        }
+                        bmax = std::max(bmax, std::abs(xf[i]));
+                        dmax = std::max(dmax, std::abs(xf[i] - host[i]));
+                    }
+                    cout << "  -- ffcuda check: right-hand side of size " << n << ": max |db| / max |b| = " << (bmax > 0 ? dmax / bmax : dmax) << endl;
+                    if (dmax > 1e-12 * bmax) ExecError("ffcuda check: right-hand side differs from FreeFEM's by more than 1e-12");
+                    return r;
+                }
                 for (long i = 0; i < n; ++i) xx[i] = host[i]; // KN_ may be strided
                 if (g_verbose) cout << "  -- ffcuda: right-hand side of size " << n << " assembled on the GPU" << endl;
                 return SetAny<KN_<double>>(xx);
@@ -1384,6 +1430,7 @@ static void Load_Init()
 {
     g_verbose = env_on("FFCUDA_VERBOSE");
     g_strict = env_on("FFCUDA_STRICT");
+    g_check = env_on("FFCUDA_CHECK");
     if (env_on("FFCUDA_DISABLE")) {
         if (verbosity) cout << " load: ffcuda disabled by FFCUDA_DISABLE" << endl;
         return;

@@ -388,3 +388,16 @@ def _has_cuda():
     import torch
 
     return torch.cuda.is_available()
+
+
+@needs_ff
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["poisson3d_p1", "lame3d_p2", "poisson3d_p2_bnd_g", "diff3d_p2_kappa", "laplace2d_p2_dirichlet_g"])
+def test_plugin_check_mode(name):
+    """FFCUDA_CHECK=1: every intercepted varf statement also runs FreeFEM's own operator and compares (pattern identical,
+    values / right-hand side within 1e-12) inside the FreeFEM process - the drop-in validating itself on the user's script."""
+    rc, out, res = run_ff(CASES[name], {"FFCUDA_CHECK": "1"})
+    assert rc == 0
+    m = re.search(r"ffcuda check: matrix .*pattern identical, max \|dA\| / max \|A\| = (\S+)", out)
+    b = re.search(r"ffcuda check: right-hand side .* max \|db\| / max \|b\| = (\S+)", out)
+    assert m and b and float(m.group(1)) <= 1e-12 and float(b.group(1)) <= 1e-12
