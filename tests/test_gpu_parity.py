@@ -718,3 +718,53 @@ def test_gmres_convection_diffusion_cube(ctx):
     x = ctx.vec(n)
     it, conv, rel = A.gmres(b, x, eps=1e-12, itmax=5, restart=1000, tgv=TGV)
     assert conv == 0 and it <= 8
+
+
+@pytest.mark.parametrize("order,ncomp,N", [(1, 1, 24), (1, 3, 12), (2, 1, 10), (2, 3, 6)])
+def test_tables_of_a_constant_equal_the_constant_forms(ctx, order, ncomp, N):
+    """size-independent property of the entries that take data at the quadrature nodes: with a constant in the table they
+    must reproduce the constant-coefficient entries (matrix: heat-like form with a non-symmetric first-order term; rhs with
+    value and derivative terms; Neumann and Robin boundary integrals) on meshes far larger than the fixtures."""
+    qp, qw = ffcuda.quadrature(3, 6)
+    fq3, fw3 = ol.face_quadrature(3)
+    mesh = ctx.mesh_cube(N, N, N)
+    sp = mesh.space(order, ncomp)
+    pat = sp.symbolic()
+    n = pat.info()[0]
+    nt, nbe = 6 * N ** 3, 12 * N * N
+    bt = []
+    for c in range(ncomp):
+        bt += [(c, fc.DX, c, fc.DX, 1.0), (c, fc.DY, c, fc.DY, 1.0), (c, fc.DZ, c, fc.DZ, 1.0), (c, fc.ID, c, fc.ID, 2.0),
+               (c, fc.DX, (c + 1) % ncomp, fc.ID, 0.5), (c, fc.ID, c, fc.DY, -0.25)]
+    kappa = 1.75
+    A0, A1 = pat.matrix(), pat.matrix()
+    A0.assemble([(uc, uo, vc, vo, kappa * v) for uc, uo, vc, vo, v in bt], qp, qw)
+    A1.assemble_qcoef(bt, qp, qw, np.full((nt, len(qw)), kappa))
+    v0, v1 = A0.download(), A1.download()
+    assert np.max(np.abs(v0 - v1)) <= 1e-13 * np.abs(v0).max()
+    # Robin term on top
+    A0.assemble_boundary([(c, fc.ID, c, fc.ID, 3.0 * kappa) for c in range(ncomp)], fq3, fw3, [2, 5], accumulate=True)
+    A1.assemble_boundary_qcoef([(c, fc.ID, c, fc.ID, 3.0) for c in range(ncomp)], fq3, fw3, np.full((nbe, len(fw3)), kappa), [2, 5])
+    v0, v1 = A0.download(), A1.download()
+    assert np.max(np.abs(v0 - v1)) <= 1e-13 * np.abs(v0).max()
+    # right-hand sides
+    lt = [(c, fc.ID, 1.0 + c) for c in range(ncomp)] + [(0, fc.DX, 0.5), (ncomp - 1, fc.DZ, -2.0)]
+    b0, b1, b2 = ctx.vec(n), ctx.vec(n), ctx.vec(n)
+    sp.assemble_linear(b0, lt, qp, qw)
+    fqt = np.zeros((ncomp, 4, nt, len(qw)))
+    for c, op, v in lt:
+        fqt[c, {fc.ID: 0, fc.DX: 1, fc.DY: 2, fc.DZ: 3}[op]] += v
+    sp.assemble_linear_qterms(b1, qp, qw, fqt)
+    h0, h1 = b0.download(), b1.download()
+    assert np.max(np.abs(h0 - h1)) <= 1e-13 * np.abs(h0).max()
+    sp.assemble_linear(b0, lt[:ncomp], qp, qw)
+    sp.assemble_linear_qvalues(b2, qp, qw, fqt[:, 0])   # (slot 0 of fqt holds the value terms only)
+    h0, h2 = b0.download(), b2.download()
+    assert np.max(np.abs(h0 - h2)) <= 1e-13 * np.abs(h0).max()
+    # Neumann data on two faces
+    blab = mesh.download()["blab"]
+    sp.assemble_linear_boundary(b0, [(c, fc.ID, 0.7) for c in range(ncomp)], fq3, fw3, [1, 6], accumulate=False)
+    gq = np.full((ncomp, nbe, len(fw3)), 0.7) * np.isin(blab, [1, 6])[None, :, None]
+    sp.assemble_linear_boundary_qvalues(b2, fq3, fw3, gq, accumulate=False)
+    h0, h2 = b0.download(), b2.download()
+    assert np.max(np.abs(h0 - h2)) <= 1e-13 * np.abs(h0).max() and np.abs(h0).max() > 0
