@@ -1256,6 +1256,14 @@ __global__ void __launch_bounds__(ARN_THREADS, 1)
                 acc += w[j] * Vcur[idx];
             }
         }
+        if (i < it) { // the next basis vector does not depend on h: pull it into L2 while the barrier is crossed
+            const double *Vn = Vtab[i + 1];
+#pragma unroll
+            for (int j = 0; j < KW; ++j) {
+                const int idx = gtid + j * gstride;
+                if (idx < n && (threadIdx.x & 3) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(Vn + idx));
+            }
+        }
         hprev = grid_total(acc);
         if (blockIdx.x == 0 && threadIdx.x == 0) gs[L.H(i, it)] = hprev;
     }
