@@ -40,6 +40,7 @@ bool env_on(const char *name)
     return v && *v && *v != '0';
 }
 bool g_verbose = false, g_strict = false, g_check = false;
+int g_sample_min = 2048, g_sample_n = 512; // grouping of coefficient tables: sampled above g_sample_min units, on ~g_sample_n of them
 
 [[noreturn]] void fail(const std::string &what)
 {
@@ -669,17 +670,18 @@ inline R2 ref_point(const Mesh *, const double *p) { return R2(p[0], p[1]); }
 inline R3 ref_point(const Mesh3 *, const double *p) { return R3(p[0], p[1], p[2]); }
 template <class FESpaceT>
 std::vector<std::vector<double>> eval_at_nodes(Stack stack, const FESpaceT &Vh, const std::vector<const C_F0 *> &exprs, const Quad &Q,
-                                               const Region &reg)
+                                               const Region &reg, const std::vector<int> *units = nullptr)
 {
     typedef typename FESpaceT::Mesh MeshT;
     typedef typename FESpaceT::FElement FElementT;
     const MeshT &Th = Vh.Th;
-    const int dim = MeshDim<MeshT>::d, nq = (int)Q.w.size(), nt = Th.nt;
+    const int dim = MeshDim<MeshT>::d, nq = (int)Q.w.size(), nt = units ? (int)units->size() : Th.nt;
     std::vector<std::vector<double>> out(exprs.size(), std::vector<double>((size_t)nt * nq, 0.0));
     std::set<int> labs(reg.labels.begin(), reg.labels.end());
     MeshPoint *mps = MeshPointStack(stack), mp = *mps;
     try {
-        for (int k = 0; k < nt; ++k) {
+        for (int ku = 0; ku < nt; ++ku) {
+            const int k = units ? (*units)[ku] : ku; // (out is indexed by the position in the list)
             if (!reg.all && !labs.count(Th[k].lab)) continue;
             const FElementT Kv(Vh[k]);
             const typename MeshT::Element &T = Kv.T;
@@ -688,7 +690,7 @@ std::vector<std::vector<double>> eval_at_nodes(Stack stack, const FESpaceT &Vh, 
                 mps->set(T(Pt), Pt, Kv);
                 for (size_t e = 0; e < exprs.size(); ++e) {
                     const C_F0 &c = *exprs[e];
-                    out[e][(size_t)k * nq + q] = c.left() == atype<long>() ? (double)GetAny<long>(c.eval(stack)) : GetAny<double>(c.eval(stack));
+                    out[e][(size_t)ku * nq + q] = c.left() == atype<long>() ? (double)GetAny<long>(c.eval(stack)) : GetAny<double>(c.eval(stack));
                 }
             }
         }
@@ -711,17 +713,18 @@ inline R2 bord_point(const Triangle &, int ie, const double *p)
 }
 template <class FESpaceT>
 std::vector<std::vector<double>> eval_at_bnodes(Stack stack, const FESpaceT &Vh, const std::vector<const C_F0 *> &exprs, const Quad &Q,
-                                                const Region &reg)
+                                                const Region &reg, const std::vector<int> *units = nullptr)
 {
     typedef typename FESpaceT::Mesh MeshT;
     typedef typename FESpaceT::FElement FElementT;
     const MeshT &Th = Vh.Th;
-    const int dim = MeshDim<MeshT>::d, nq = (int)Q.w.size(), nbe = nbe_of(Th);
+    const int dim = MeshDim<MeshT>::d, nq = (int)Q.w.size(), nbe = units ? (int)units->size() : nbe_of(Th);
     std::vector<std::vector<double>> out(exprs.size(), std::vector<double>((size_t)nbe * nq, 0.0));
     std::set<int> labs(reg.labels.begin(), reg.labels.end());
     MeshPoint *mps = MeshPointStack(stack), mp = *mps;
     try {
-        for (int ib = 0; ib < nbe; ++ib) {
+        for (int iu = 0; iu < nbe; ++iu) {
+            const int ib = units ? (*units)[iu] : iu;
             const int r = blabel(Th, ib);
             if (!reg.all && !labs.count(r)) continue;
             int ie;
@@ -733,7 +736,7 @@ std::vector<std::vector<double>> eval_at_bnodes(Stack stack, const FESpaceT &Vh,
                 mps->set(K.T(Pt), Pt, K, r, NN, ie);
                 for (size_t e = 0; e < exprs.size(); ++e) {
                     const C_F0 &c = *exprs[e];
-                    out[e][(size_t)ib * nq + q] = c.left() == atype<long>() ? (double)GetAny<long>(c.eval(stack)) : GetAny<double>(c.eval(stack));
+                    out[e][(size_t)iu * nq + q] = c.left() == atype<long>() ? (double)GetAny<long>(c.eval(stack)) : GetAny<double>(c.eval(stack));
                 }
             }
         }
@@ -770,46 +773,105 @@ template <class FESpaceT>
 MatriceMorse<double> *gpu_matrix(Stack stack, const FESpaceT &Vh, DevSpace &D, const Varf &V, const Data_Sparse_Solver &ds, Resident &res,
                                  int &n, int64_t &nnz)
 {
-    // terms whose coefficient depends on the mesh point: values at the quadrature nodes first (this is what may be refused)
+    // terms whose coefficient depends on the mesh point: values at the quadrature nodes first (this is what may be refused).
+    // Terms whose tables are proportional share one coefficient function ((1+x)*lambda, (1+x)*mu, ...): one device pass per
+    // group.  The groups are found on a sample of the elements, then one chunked pass over the mesh evaluates every
+    // expression, keeps ONE table per group and checks every other term against its group (host memory: groups, not
+    // terms); if the sample misled (a coefficient that vanishes or is proportional on the sample only) the exact
+    // grouping on full tables is taken instead.
     struct QGroup {
         size_t item;
         std::vector<double> cq;
         std::vector<ffcuda_bterm> terms;
     };
     std::vector<QGroup> groups;
-    for (size_t i = 0; i < V.bil.size(); ++i) {
-        const BilinearItem &B = V.bil[i];
-        if (B.qterms.empty()) continue;
-        std::vector<const C_F0 *> ex;
-        for (size_t t = 0; t < B.qterms.size(); ++t) ex.push_back(&B.qterms[t].coef);
-        std::vector<std::vector<double>> v = B.border ? eval_at_bnodes(stack, Vh, ex, B.q, B.reg) : eval_at_nodes(stack, Vh, ex, B.q, B.reg);
-        // terms whose tables are proportional share one coefficient function ((1+x)*lambda, (1+x)*mu, ...): one pass each group
-        const size_t first_group = groups.size();
-        for (size_t t = 0; t < B.qterms.size(); ++t) {
+    struct Place {
+        int group;     // index into the item's own groups, -1: vanishes
+        double alpha;  // multiple of the group's table
+        double amax;
+    };
+    auto place_terms = [](const std::vector<std::vector<double>> &v, std::vector<Place> &pl, std::vector<int> &reps) {
+        pl.assign(v.size(), Place{-1, 0.0, 0.0});
+        reps.clear();
+        for (size_t t = 0; t < v.size(); ++t) {
             const std::vector<double> &a = v[t];
             size_t imax = 0;
             for (size_t k = 1; k < a.size(); ++k)
                 if (std::abs(a[k]) > std::abs(a[imax])) imax = k;
             if (a.empty() || a[imax] == 0.0) continue; // the coefficient vanishes at every node
-            bool placed = false;
-            for (size_t gi = first_group; gi < groups.size() && !placed; ++gi) {
-                const std::vector<double> &r = groups[gi].cq;
+            pl[t].amax = std::abs(a[imax]);
+            for (size_t gi = 0; gi < reps.size() && pl[t].group < 0; ++gi) {
+                const std::vector<double> &r = v[reps[gi]];
                 if (r[imax] == 0.0) continue;
                 const double alpha = a[imax] / r[imax];
                 double err = 0.0;
                 for (size_t k = 0; k < a.size(); ++k) err = std::max(err, std::abs(a[k] - alpha * r[k]));
                 if (err <= 1e-14 * std::abs(a[imax])) { // (the products are rounded separately: a few ulp)
-                    ffcuda_bterm bt = B.qterms[t].t;
-                    bt.coef = alpha;
-                    groups[gi].terms.push_back(bt);
-                    placed = true;
+                    pl[t].group = (int)gi;
+                    pl[t].alpha = alpha;
                 }
             }
-            if (!placed) {
-                ffcuda_bterm bt = B.qterms[t].t;
-                bt.coef = 1.0;
-                groups.push_back(QGroup{i, a, std::vector<ffcuda_bterm>(1, bt)});
+            if (pl[t].group < 0) {
+                pl[t].group = (int)reps.size();
+                pl[t].alpha = 1.0;
+                reps.push_back((int)t);
             }
+        }
+    };
+    for (size_t i = 0; i < V.bil.size(); ++i) {
+        const BilinearItem &B = V.bil[i];
+        if (B.qterms.empty()) continue;
+        std::vector<const C_F0 *> ex;
+        for (size_t t = 0; t < B.qterms.size(); ++t) ex.push_back(&B.qterms[t].coef);
+        const int nunits = B.border ? nbe_of(Vh.Th) : Vh.Th.nt, nq = (int)B.q.w.size();
+        auto eval = [&](const std::vector<int> *units) {
+            return B.border ? eval_at_bnodes(stack, Vh, ex, B.q, B.reg, units) : eval_at_nodes(stack, Vh, ex, B.q, B.reg, units);
+        };
+        std::vector<Place> pl;
+        std::vector<int> reps;
+        std::vector<std::vector<double>> tables; // one per group
+        bool ok = false;
+        if (nunits > g_sample_min && ex.size() > 1) {
+            std::vector<int> sample;
+            const int step = std::max(1, nunits / std::max(1, g_sample_n));
+            for (int k = 0; k < nunits; k += step) sample.push_back(k);
+            place_terms(eval(&sample), pl, reps);
+            tables.assign(reps.size(), std::vector<double>((size_t)nunits * nq, 0.0));
+            ok = true;
+            const int CH = 8192;
+            std::vector<int> chunk;
+            for (int k0 = 0; k0 < nunits && ok; k0 += CH) {
+                chunk.clear();
+                for (int k = k0; k < std::min(nunits, k0 + CH); ++k) chunk.push_back(k);
+                const std::vector<std::vector<double>> vc = eval(&chunk);
+                const size_t len = chunk.size() * (size_t)nq, off = (size_t)k0 * nq;
+                for (size_t gi = 0; gi < reps.size(); ++gi) std::copy(vc[reps[gi]].begin(), vc[reps[gi]].begin() + len, tables[gi].begin() + off);
+                for (size_t t = 0; t < ex.size() && ok; ++t) {
+                    if (pl[t].group >= 0 && reps[pl[t].group] == (int)t) continue;
+                    const double *r = pl[t].group >= 0 ? vc[reps[pl[t].group]].data() : nullptr;
+                    for (size_t k = 0; k < len; ++k) {
+                        const double want = r ? pl[t].alpha * r[k] : 0.0;
+                        if (std::abs(vc[t][k] - want) > 1e-13 * std::max(pl[t].amax, std::abs(want))) {
+                            ok = false; // the sample misled: exact grouping below
+                            break;
+                        }
+                    }
+                }
+            }
+        }
+        if (!ok) {
+            std::vector<std::vector<double>> v = eval(nullptr);
+            place_terms(v, pl, reps);
+            tables.clear();
+            for (size_t gi = 0; gi < reps.size(); ++gi) tables.push_back(std::move(v[reps[gi]]));
+        }
+        const size_t first_group = groups.size();
+        for (size_t gi = 0; gi < reps.size(); ++gi) groups.push_back(QGroup{i, std::move(tables[gi]), std::vector<ffcuda_bterm>()});
+        for (size_t t = 0; t < ex.size(); ++t) {
+            if (pl[t].group < 0) continue;
+            ffcuda_bterm bt = B.qterms[t].t;
+            bt.coef = pl[t].alpha;
+            groups[first_group + pl[t].group].terms.push_back(bt);
         }
     }
 
@@ -1431,6 +1493,8 @@ static void Load_Init()
     g_verbose = env_on("FFCUDA_VERBOSE");
     g_strict = env_on("FFCUDA_STRICT");
     g_check = env_on("FFCUDA_CHECK");
+    if (const char *e = getenv("FFCUDA_SAMPLE_MIN")) g_sample_min = atoi(e); // (testing knobs of the coefficient grouping)
+    if (const char *e = getenv("FFCUDA_SAMPLE_N")) g_sample_n = atoi(e);
     if (env_on("FFCUDA_DISABLE")) {
         if (verbosity) cout << " load: ffcuda disabled by FFCUDA_DISABLE" << endl;
         return;

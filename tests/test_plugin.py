@@ -401,3 +401,31 @@ def test_plugin_check_mode(name):
     m = re.search(r"ffcuda check: matrix .*pattern identical, max \|dA\| / max \|A\| = (\S+)", out)
     b = re.search(r"ffcuda check: right-hand side .* max \|db\| / max \|b\| = (\S+)", out)
     assert m and b and float(m.group(1)) <= 1e-12 and float(b.group(1)) <= 1e-12
+
+
+@needs_ff
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["lame3d_p1_evar", "diff3d_p2_kappa"])
+def test_plugin_coefficient_grouping_on_a_sample(name):
+    """the grouping of proportional coefficient tables decided on a sparse sample of the elements and verified on the chunked
+    full pass (forced here on small meshes: FFCUDA_SAMPLE_MIN=1, ~5 sampled elements) gives the same matrices"""
+    src = CASES[name]
+    _, out, gpu = run_ff(src, {"FFCUDA_STRICT": "1", "FFCUDA_VERBOSE": "1", "FFCUDA_SAMPLE_MIN": "1", "FFCUDA_SAMPLE_N": "5"})
+    assert "coefficient function(s) depending on the mesh point" in out
+    _, _, cpu = run_ff(src, {"FFCUDA_DISABLE": "1"})
+    compare(gpu, cpu, tight=True)
+
+
+@needs_ff
+@pytest.mark.gpu
+def test_plugin_coefficient_grouping_sample_misled():
+    """a coefficient that vanishes on the sample but not on the mesh: the chunked pass notices, the exact grouping is taken"""
+    body = """mesh Th = square(14,12);
+fespace Vh(Th,P1); Vh u,v;
+solve Pb(u,v,solver=CG,eps=1e-14) = int2d(Th)((1+x)*(dx(u)*dx(v)+dy(u)*dy(v)) + 50.*(x>0.93)*(y>0.9)*u*v) - int2d(Th)(1.*v) + on(1,u=0);
+"""
+    env = {"FFCUDA_STRICT": "1", "FFCUDA_VERBOSE": "1", "FFCUDA_SAMPLE_MIN": "1", "FFCUDA_SAMPLE_N": "3"}
+    rc, out, gpu = run_solve(body, "u", env)
+    assert rc == 0 and "problem matrix" in out
+    rc, _, cpu = run_solve(body, "u", {"FFCUDA_DISABLE": "1"})
+    assert rc == 0 and np.max(np.abs(gpu - cpu)) <= 1e-11 * np.abs(cpu).max()
