@@ -196,8 +196,9 @@ def toks(path):
         return f.read().split()
 
 
-def run_case(name):
-    c = CASES[name]
+def run_case(name, case=None, save=True):
+    """runs the reference on CASES[name] (or on the given case dict) and returns the dump; save=False: nothing is written"""
+    c = case if case is not None else CASES[name]
     dim = c["dim"]
     with tempfile.TemporaryDirectory() as td:
         edp = os.path.join(td, "case.edp")
@@ -246,6 +247,8 @@ def run_case(name):
             out["cg_iters"] = np.int32(int(mm[0]))
             out["u14"] = np.array(toks(os.path.join(td, "u14.txt")), dtype=np.float64)
             out["cg_iters14"] = np.int32(int(mm[1]))
+        if not save:
+            return out
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
         print(f"{name}: nv={nv} nt={nt} nbe={nbe} ndof={ndof} nnz={nnz}"
               + (f" cg_iters={int(out['cg_iters'])}" if "cg_iters" in out else ""))
