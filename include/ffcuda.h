@@ -22,8 +22,13 @@
  *   ffcuda_assemble_linear      <- AssembleLinearForm fflib/problem.cpp:10555, :10878-11227, Element_rhs :7839-7985
  *   ffcuda_assemble_linear_boundary <- Element_rhs on border elements fflib/problem.cpp:8439-8587
  *   ffcuda_assemble_bilinear_boundary <- AssembleBilinearForm border loop fflib/problem.cpp:1317-1326, Element_Op :6518-6560
+ *   ffcuda_assemble_linear_qvalues / _qterms <- coefficient evaluation at the quadrature nodes inside Element_rhs
+ *                                  fflib/problem.cpp:7876-7884, :7951-7975 (data depending on the mesh point)
+ *   ffcuda_assemble_bilinear_qcoef <- the same inside Element_Op fflib/problem.cpp:6380-6407
+ *   ffcuda_assemble_linear_boundary_qvalues / ffcuda_assemble_bilinear_boundary_qcoef <- the same on border elements
+ *                                  fflib/problem.cpp:8551-8570, :6526-6556
  *   ffcuda_bc_* / *_apply_bc    <- AssembleBC fflib/problem.cpp:9881-10034, :10039-10194, HashMatrix::SetBC
- *                                  femlib/HashMatrix.cpp:1195-1238 (tgv >= 0 branch)
+ *                                  femlib/HashMatrix.cpp:1195-1238 (penalty and exact elimination)
  *   ffcuda_gmres                <- SolverGMRES femlib/VirtualSolverCG.hpp:196-258, fgmres femlib/CG.cpp:347-517
  *   ffcuda_quadrature           <- CDomainOfIntegration::FIT/FIV fflib/problem.cpp:14102-14145, QF_Simplex
  *                                  femlib/QuadratureFormular.cpp:73-115 and the rule tables :138-188, :699-743
