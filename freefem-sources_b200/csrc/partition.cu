@@ -1,0 +1,152 @@
+// partition.cu — vertex partition of a general (unstructured) mesh and the bookkeeping of a rank's local problem.
+// HOST ONLY (no device needed; CPU-tested under gloo, tests/test_partition_gloo.py): the arithmetic the distributed path
+// will be built on for meshes that are not the synthetic cube (SURVEY.md §8 e: FreeFEM itself splits the ELEMENT RANGE,
+// fflib/problem.cpp:1133-1138, and all-reduces the whole matrix; METIS is only a download recipe, 3rdparty/getall:118).
+//
+// Model (the same as the z-slab partition of mesh.cu): a rank OWNS vertices = matrix rows; it holds every element that
+// touches an owned vertex, so its rows assemble without communication; the other vertices of those elements are its
+// GHOSTS (columns only), refreshed before every SpMV.  Local numbering: owned vertices first (ascending global id),
+// then the ghosts grouped by owner rank (ascending), ascending global id inside a group - so what a neighbour sends
+// arrives as ONE contiguous range, and only the sender gathers.
+#include "common.cuh"
+#include <algorithm>
+#include <numeric>
+
+namespace {
+
+// recursive coordinate bisection: ids[lo, hi) go to parts [p0, p0 + np); split across the longest extent of the bounding
+// box at the rank that gives the lower side floor(np / 2) / np of the vertices; ties broken by vertex id (deterministic)
+void rcb(int dim, const double *xyz, std::vector<int32_t> &ids, size_t lo, size_t hi, int p0, int np, int32_t *part)
+{
+    if (np == 1) {
+        for (size_t i = lo; i < hi; ++i) part[ids[i]] = p0;
+        return;
+    }
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    for (size_t i = lo; i < hi; ++i)
+        for (int d = 0; d < dim; ++d) {
+            const double x = xyz[(size_t)ids[i] * dim + d];
+            mn[d] = std::min(mn[d], x);
+            mx[d] = std::max(mx[d], x);
+        }
+    int ax = 0;
+    for (int d = 1; d < dim; ++d)
+        if (mx[d] - mn[d] > mx[ax] - mn[ax]) ax = d;
+    const int npl = np / 2;
+    const size_t mid = lo + (size_t)(((hi - lo) * (uint64_t)npl) / (uint64_t)np);
+    auto less = [&](int32_t a, int32_t b) {
+        const double xa = xyz[(size_t)a * dim + ax], xb = xyz[(size_t)b * dim + ax];
+        return xa < xb || (xa == xb && a < b);
+    };
+    std::nth_element(ids.begin() + lo, ids.begin() + mid, ids.begin() + hi, less);
+    rcb(dim, xyz, ids, lo, mid, p0, npl, part);
+    rcb(dim, xyz, ids, mid, hi, p0 + npl, np - npl, part);
+}
+
+struct LocalLists {
+    std::vector<int32_t> l2g;      // local -> global vertex: owned (ascending), then ghosts by (owner, id)
+    std::vector<int32_t> elems;    // global ids of the local elements, ascending
+    std::vector<int32_t> nbr;      // neighbour ranks, ascending
+    std::vector<int32_t> recv_off; // per neighbour: first local index of the ghosts it owns
+    std::vector<int32_t> recv_cnt;
+    std::vector<int32_t> send_ptr; // per neighbour: range in send_idx
+    std::vector<int32_t> send_idx; // owned LOCAL indices to send, in the receiver's ghost order (ascending global id)
+    int nowned = 0;
+};
+
+LocalLists local_lists(int nvk, int nv, int nt, const int32_t *conn, const int32_t *part, int rank, int nranks)
+{
+    LocalLists L;
+    std::vector<uint8_t> ghost((size_t)nv, 0);
+    for (int k = 0; k < nt; ++k) {
+        const int32_t *K = conn + (size_t)nvk * k;
+        bool mine = false;
+        for (int a = 0; a < nvk; ++a) mine = mine || part[K[a]] == rank;
+        if (!mine) continue;
+        L.elems.push_back(k);
+        for (int a = 0; a < nvk; ++a)
+            if (part[K[a]] != rank) ghost[K[a]] = 1;
+    }
+    for (int v = 0; v < nv; ++v)
+        if (part[v] == rank) L.l2g.push_back(v);
+    L.nowned = (int)L.l2g.size();
+    std::vector<int32_t> gh;
+    for (int v = 0; v < nv; ++v)
+        if (ghost[v]) gh.push_back(v);
+    std::stable_sort(gh.begin(), gh.end(), [&](int32_t a, int32_t b) { return part[a] < part[b]; }); // (ids stay ascending inside)
+    for (size_t i = 0; i < gh.size(); ++i) {
+        const int o = part[gh[i]];
+        if (L.nbr.empty() || L.nbr.back() != o) {
+            L.nbr.push_back(o);
+            L.recv_off.push_back(L.nowned + (int)i);
+            L.recv_cnt.push_back(0);
+        }
+        L.recv_cnt.back()++;
+        L.l2g.push_back(gh[i]);
+    }
+    // what the neighbours need from me: my owned vertices that are ghosts of theirs = vertices of mine in an element that
+    // touches a vertex of theirs.  The relation is symmetric (an element with vertices of both ranks is local to both), so
+    // the neighbour sets coincide; the list for neighbour r, ascending global id, is r's ghost range owned by me.
+    std::vector<std::vector<int32_t>> need((size_t)nranks);
+    {
+        std::vector<int32_t> stamp((size_t)nv, -1); // last neighbour a vertex was listed for (lists are built rank by rank)
+        for (size_t x = 0; x < L.nbr.size(); ++x) {
+            const int r = L.nbr[x];
+            for (size_t e = 0; e < L.elems.size(); ++e) {
+                const int32_t *K = conn + (size_t)nvk * L.elems[e];
+                bool theirs = false;
+                for (int a = 0; a < nvk; ++a) theirs = theirs || part[K[a]] == r;
+                if (!theirs) continue;
+                for (int a = 0; a < nvk; ++a)
+                    if (part[K[a]] == rank && stamp[K[a]] != r) {
+                        stamp[K[a]] = r;
+                        need[r].push_back(K[a]);
+                    }
+            }
+            std::sort(need[r].begin(), need[r].end());
+        }
+    }
+    // global -> owned local index: owned vertices are ascending, so a binary search does
+    L.send_ptr.push_back(0);
+    for (size_t x = 0; x < L.nbr.size(); ++x) {
+        for (int32_t g : need[L.nbr[x]])
+            L.send_idx.push_back((int32_t)(std::lower_bound(L.l2g.begin(), L.l2g.begin() + L.nowned, g) - L.l2g.begin()));
+        L.send_ptr.push_back((int32_t)L.send_idx.size());
+    }
+    return L;
+}
+
+} // namespace
+
+extern "C" int ffcuda_partition_rcb(int dim, int nv, const double *xyz, int nparts, int32_t *part)
+{
+    FF_API_BEGIN
+    FF_REQUIRE((dim == 2 || dim == 3) && nv >= 0 && nparts >= 1 && (nv == 0 || (xyz && part)), "ffcuda_partition_rcb: bad arguments");
+    std::vector<int32_t> ids((size_t)nv);
+    std::iota(ids.begin(), ids.end(), 0);
+    rcb(dim, xyz, ids, 0, (size_t)nv, 0, nparts, part);
+    FF_API_END(nullptr)
+}
+
+extern "C" int ffcuda_partition_local(int dim, int nv, int nt, const int32_t *conn, const int32_t *part, int rank, int nranks,
+                                      int64_t *sizes8, int32_t *l2g, int32_t *elems, int32_t *nbr, int32_t *recv_off, int32_t *recv_cnt,
+                                      int32_t *send_ptr, int32_t *send_idx)
+{
+    FF_API_BEGIN
+    FF_REQUIRE((dim == 2 || dim == 3) && conn && part && sizes8 && rank >= 0 && rank < nranks, "ffcuda_partition_local: bad arguments");
+    const LocalLists L = local_lists(dim + 1, nv, nt, conn, part, rank, nranks);
+    const int64_t s[8] = {L.nowned, (int64_t)L.l2g.size() - L.nowned, (int64_t)L.elems.size(), (int64_t)L.nbr.size(),
+                          (int64_t)L.send_idx.size(), 0, 0, 0};
+    for (int i = 0; i < 8; ++i) sizes8[i] = s[i];
+    auto put = [](int32_t *dst, const std::vector<int32_t> &v) {
+        if (dst) std::copy(v.begin(), v.end(), dst);
+    };
+    put(l2g, L.l2g);
+    put(elems, L.elems);
+    put(nbr, L.nbr);
+    put(recv_off, L.recv_off);
+    put(recv_cnt, L.recv_cnt);
+    put(send_ptr, L.send_ptr);
+    put(send_idx, L.send_idx);
+    FF_API_END(nullptr)
+}

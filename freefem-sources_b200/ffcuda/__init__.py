@@ -23,7 +23,8 @@ ffcuda_matrix_from_csr ffcuda_matrix_info ffcuda_matrix_download ffcuda_matrix_u
 ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_destroy ffcuda_assemble_bilinear ffcuda_assemble_bilinear_qcoef
 ffcuda_assemble_linear ffcuda_assemble_linear_qvalues ffcuda_assemble_linear_qterms ffcuda_assemble_linear_boundary ffcuda_assemble_bilinear_boundary ffcuda_assemble_linear_boundary_qvalues ffcuda_assemble_bilinear_boundary_qcoef ffcuda_bc_from_pairs ffcuda_bc_from_labels ffcuda_bc_count ffcuda_matrix_apply_bc ffcuda_vec_apply_bc
 ffcuda_vec_set_bc_values ffcuda_bc_destroy ffcuda_spmv ffcuda_cg ffcuda_cg_host ffcuda_gmres ffcuda_gmres_host ffcuda_comm_unique_id ffcuda_comm_init
-ffcuda_comm_finalize ffcuda_mesh_cube_distributed ffcuda_mesh_local_to_global ffcuda_quadrature ffcuda_partition_cube""".split()
+ffcuda_comm_finalize ffcuda_mesh_cube_distributed ffcuda_mesh_local_to_global ffcuda_quadrature ffcuda_partition_cube
+ffcuda_partition_rcb ffcuda_partition_local""".split()
 
 
 class FfcudaError(RuntimeError):
@@ -39,6 +40,30 @@ def partition_cube(nx, ny, nz, rank, nranks):
     out = (C.c_int64 * 16)()
     _ck(lib().ffcuda_partition_cube(nx, ny, nz, rank, nranks, out))
     return dict(zip(PART_FIELDS, [int(v) for v in out]))
+
+
+def partition_rcb(xyz, nparts):
+    """recursive coordinate bisection of the vertices (host arithmetic only): part[v] in [0, nparts)"""
+    xyz = _f64(xyz)
+    part = np.zeros(xyz.shape[0], np.int32)
+    _ck(lib().ffcuda_partition_rcb(xyz.shape[1], xyz.shape[0], _p(xyz), int(nparts), _p(part)))
+    return part
+
+
+def partition_local(dim, nv, conn, part, rank, nranks):
+    """the local problem of `rank` for a vertex partition (host arithmetic only): owned + ghost vertices, local elements,
+    neighbours with their contiguous receive ranges and the gather lists to send"""
+    conn, part = _i32(conn), _i32(part)
+    sz = (C.c_int64 * 8)()
+    args = (dim, nv, conn.shape[0], _p(conn), _p(part), rank, nranks, sz)
+    _ck(lib().ffcuda_partition_local(*args, None, None, None, None, None, None, None))
+    no, ng, ne, nn, ns = (int(sz[i]) for i in range(5))
+    out = dict(nowned=no, l2g=np.zeros(no + ng, np.int32), elems=np.zeros(ne, np.int32), nbr=np.zeros(nn, np.int32),
+               recv_off=np.zeros(nn, np.int32), recv_cnt=np.zeros(nn, np.int32), send_ptr=np.zeros(nn + 1, np.int32),
+               send_idx=np.zeros(ns, np.int32))
+    _ck(lib().ffcuda_partition_local(*args, _p(out["l2g"]), _p(out["elems"]), _p(out["nbr"]), _p(out["recv_off"]), _p(out["recv_cnt"]),
+                                     _p(out["send_ptr"]), _p(out["send_idx"])))
+    return out
 
 
 def quadrature(dim, qforder=6):

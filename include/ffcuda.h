@@ -269,6 +269,20 @@ int ffcuda_mesh_cube_distributed(ffcuda_ctx *ctx, int nx, int ny, int nz, ffcuda
  * lower neighbour rank (-1 none), upper neighbour rank, send offset down, send offset up, recv offset from below,
  * recv offset from above, vertices per exchanged layer, has lower neighbour, has upper neighbour } */
 int ffcuda_partition_cube(int nx, int ny, int nz, int rank, int nranks, int64_t *out16);
+/* General (unstructured) meshes, host only, no device needed - the arithmetic a distributed upload is built on:
+ * recursive coordinate bisection of the vertices into nparts parts of equal size (+-1 per split; deterministic: ties by
+ * vertex id), and the local problem of `rank` for any vertex partition: it owns the vertices with part[v] == rank (= its
+ * matrix rows), holds every element touching one of them (rows assemble without communication), the other vertices of
+ * those elements are its ghosts.  Local numbering: owned vertices (ascending global id), then ghosts grouped by owner
+ * rank, ascending id inside - a neighbour's data arrives as one contiguous range, only the sender gathers.
+ * sizes8 = { owned, ghosts, local elements, neighbours, total send count, 0, 0, 0 }; call once with the arrays NULL for
+ * the sizes, then with l2g[owned+ghosts], elems[local elements], nbr/recv_off/recv_cnt[neighbours],
+ * send_ptr[neighbours+1], send_idx[total send count] (owned LOCAL indices, in the receiver's ghost order).
+ * (FreeFEM's own counterpart splits the element range and all-reduces the whole matrix, fflib/problem.cpp:1133-1138.) */
+int ffcuda_partition_rcb(int dim, int nv, const double *xyz, int nparts, int32_t *part);
+int ffcuda_partition_local(int dim, int nv, int nt, const int32_t *conn, const int32_t *part, int rank, int nranks,
+                           int64_t *sizes8, int32_t *l2g, int32_t *elems, int32_t *nbr, int32_t *recv_off, int32_t *recv_cnt,
+                           int32_t *send_ptr, int32_t *send_idx);
 /* global ids of the local vertices (owned first): for gathering results / parity checks */
 int ffcuda_mesh_local_to_global(ffcuda_mesh *m, int *nowned, int *nlocal, int64_t *gid /* nlocal or NULL */);
 

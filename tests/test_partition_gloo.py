@@ -105,3 +105,122 @@ def test_reference_arm_under_multi_rank_launch():
     assert line["impl"] == "reference" and line["n_gpus"] == 2 and line["value"] > 0 and line["unit"] == "nnz/s"
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["cores"] == 1
     assert outs[1] == ""
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# general (unstructured) meshes: recursive coordinate bisection + the local problem of every rank (host arithmetic only)
+# ------------------------------------------------------------------------------------------------------------------
+def _general_mesh(kind):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import numpy as np
+    import oracle_lib as ol
+
+    m = ol.cube(6, 5, 4) if kind == "cube" else ol.square(11, 9)
+    # an unstructured-looking numbering: vertices and elements shuffled, coordinates warped
+    rng = np.random.default_rng(7)
+    nv, nt = m["xyz"].shape[0], m["conn"].shape[0]
+    pv, pe = rng.permutation(nv), rng.permutation(nt)
+    inv = np.empty(nv, np.int64)
+    inv[pv] = np.arange(nv)
+    xyz = m["xyz"][pv].copy()
+    xyz[:, 0] += 0.15 * xyz[:, 1] ** 2
+    conn = inv[m["conn"]][pe].astype(np.int32)
+    return dict(dim=m["dim"], xyz=xyz, conn=conn, elab=np.zeros(nt, np.int32))
+
+
+def _worker_general(rank, world, port, kind, q):
+    import numpy as np
+    import torch.distributed as dist
+
+    sys.path.insert(0, os.path.join(ROOT, "freefem-sources_b200"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ffcuda
+    import ff_cases as fc
+    import oracle_lib as ol
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        m = _general_mesh(kind)
+        dim, xyz, conn = m["dim"], m["xyz"], m["conn"]
+        nv, nt = xyz.shape[0], conn.shape[0]
+        part = ffcuda.partition_rcb(xyz, world)                      # the same on every rank (deterministic)
+        sizes = np.bincount(part, minlength=world)
+        assert sizes.sum() == nv and sizes.max() - sizes.min() <= 2
+        me = ffcuda.partition_local(dim, nv, conn, part, rank, world)
+        no, l2g = me["nowned"], me["l2g"]
+        # owned = my part, ascending; local elements = exactly those touching an owned vertex; ghosts = their other vertices
+        assert np.array_equal(l2g[:no], np.flatnonzero(part == rank))
+        touch = (part[conn] == rank).any(axis=1)
+        assert np.array_equal(me["elems"], np.flatnonzero(touch))
+        gh = np.setdiff1d(np.unique(conn[touch]), l2g[:no])
+        assert np.array_equal(np.sort(l2g[no:]), gh)
+        key = part[l2g[no:]].astype(np.int64) * nv + l2g[no:]
+        assert np.all(np.diff(key) > 0)                              # grouped by owner, ascending id inside
+        for x, r in enumerate(me["nbr"]):
+            rng_ = l2g[me["recv_off"][x]:me["recv_off"][x] + me["recv_cnt"][x]]
+            assert np.all(part[rng_] == r)
+        allp = [None] * world
+        dist.all_gather_object(allp, me)
+        # halo lists mirror each other: what I gather for r is r's contiguous ghost range owned by me, in order
+        for x, r in enumerate(me["nbr"]):
+            other = allp[r]
+            assert rank in other["nbr"]
+            y = list(other["nbr"]).index(rank)
+            mine_send = l2g[me["send_idx"][me["send_ptr"][x]:me["send_ptr"][x + 1]]]
+            their_recv = other["l2g"][other["recv_off"][y]:other["recv_off"][y] + other["recv_cnt"][y]]
+            assert np.array_equal(mine_send, their_recv)
+        # every vertex owned exactly once, every element local somewhere
+        owned_all = np.concatenate([p["l2g"][:p["nowned"]] for p in allp])
+        assert np.array_equal(np.sort(owned_all), np.arange(nv))
+        assert np.array_equal(np.unique(np.concatenate([p["elems"] for p in allp])), np.arange(nt))
+        # a halo exchange carried out over gloo: ghosts end up with the owners' values
+        xg = np.sin(np.arange(nv, dtype=np.float64))
+        xl = np.zeros(len(l2g))
+        xl[:no] = xg[l2g[:no]]
+        payload = {int(r): xl[me["send_idx"][me["send_ptr"][x]:me["send_ptr"][x + 1]]] for x, r in enumerate(me["nbr"])}
+        allpay = [None] * world
+        dist.all_gather_object(allpay, payload)
+        for x, r in enumerate(me["nbr"]):
+            xl[me["recv_off"][x]:me["recv_off"][x] + me["recv_cnt"][x]] = allpay[r][rank]
+        assert np.array_equal(xl, xg[l2g])
+        # assembly without communication: the P1 Laplace matrix of the LOCAL mesh has, in its owned rows, exactly the rows
+        # of the global matrix (pattern and values), and the local product with the exchanged vector is the global one
+        qp, qw = ol.quadrature(dim, "qfV5" if dim == 3 else "qf5pT")
+        lap = fc.LAP3 if dim == 3 else fc.LAP2
+        g2l = -np.ones(nv, np.int64)
+        g2l[l2g] = np.arange(len(l2g))
+        ml = dict(dim=dim, xyz=xyz[l2g], conn=g2l[conn[me["elems"]]].astype(np.int32), elab=np.zeros(len(me["elems"]), np.int32))
+        li, lj, la = ol.assemble_coo(ml, 1, 1, None, lap, qp, qw)
+        gi, gj, ga = ol.assemble_coo(m, 1, 1, None, lap, qp, qw)
+        import scipy.sparse as sps
+        Ag = sps.coo_matrix((ga, (gi, gj)), shape=(nv, nv)).tocsr()
+        rows = li < no
+        Al = sps.coo_matrix((la[rows], (li[rows], l2g[lj[rows]])), shape=(no, nv)).tocsr()
+        Aref = Ag[l2g[:no]]
+        Al.sort_indices()
+        Aref.sort_indices()
+        assert np.array_equal(Al.indptr, Aref.indptr) and np.array_equal(Al.indices, Aref.indices)     # structural zeros included
+        assert np.max(np.abs(Al.data - Aref.data)) <= 1e-13 * np.abs(Aref.data).max()
+        yl = sps.coo_matrix((la[rows], (li[rows], lj[rows])), shape=(no, len(l2g))).tocsr() @ xl
+        assert np.max(np.abs(yl - (Ag @ xg)[l2g[:no]])) <= 1e-12 * np.abs(Ag @ xg).max()
+        q.put((rank, "ok"))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, repr(e) + traceback.format_exc()[-600:]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,kind", [(2, "cube"), (3, "cube"), (2, "square"), (4, "square")])
+def test_general_partition_is_consistent_across_ranks(world, kind):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() + 17 * world + len(kind)) % 2000
+    procs = [ctx.Process(target=_worker_general, args=(r, world, port, kind, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(res) == [(r, "ok") for r in range(world)], res
