@@ -224,3 +224,44 @@ def test_general_partition_is_consistent_across_ranks(world, kind):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(r, "ok") for r in range(world)], res
+
+
+def test_general_partition_edge_cases():
+    """single process: one part, as many parts as vertices, identical coordinates (ties by vertex id), and the local lists
+    of an arbitrary (random, non-geometric) vertex partition checked against a brute-force construction."""
+    import numpy as np
+
+    sys.path.insert(0, os.path.join(ROOT, "freefem-sources_b200"))
+    import ffcuda
+
+    m = _general_mesh("square")
+    xyz, conn, nv = m["xyz"], m["conn"], m["xyz"].shape[0]
+    assert np.all(ffcuda.partition_rcb(xyz, 1) == 0)
+    p = ffcuda.partition_rcb(xyz, nv)
+    assert np.array_equal(np.sort(p), np.arange(nv))                         # one vertex per part
+    p = ffcuda.partition_rcb(np.zeros((10, 3)), 4)                            # all points equal: split by id, sizes 2 3 2 3
+    assert np.array_equal(p, [0, 0, 1, 1, 1, 2, 2, 3, 3, 3])
+    p5 = ffcuda.partition_rcb(xyz, 5)
+    assert np.bincount(p5, minlength=5).max() - np.bincount(p5, minlength=5).min() <= 2
+    # parts of an RCB partition are boxes in the split direction: the first split separates the point set by a plane
+    p2 = ffcuda.partition_rcb(xyz, 2)
+    ext = xyz.max(axis=0) - xyz.min(axis=0)
+    ax = int(np.argmax(ext))
+    assert xyz[p2 == 0, ax].max() <= xyz[p2 == 1, ax].min()
+    rng = np.random.default_rng(1)
+    part = rng.integers(0, 3, nv).astype(np.int32)
+    for rank in range(3):
+        L = ffcuda.partition_local(2, nv, conn, part, rank, 3)
+        touch = (part[conn] == rank).any(axis=1)
+        assert np.array_equal(L["elems"], np.flatnonzero(touch))
+        assert np.array_equal(L["l2g"][:L["nowned"]], np.flatnonzero(part == rank))
+        gh = np.setdiff1d(np.unique(conn[touch]), np.flatnonzero(part == rank))
+        assert np.array_equal(np.sort(L["l2g"][L["nowned"]:]), gh)
+        assert L["send_ptr"][0] == 0 and L["send_ptr"][-1] == len(L["send_idx"]) and np.all(L["send_idx"] < L["nowned"])
+        for x, r in enumerate(L["nbr"]):
+            sent = L["l2g"][L["send_idx"][L["send_ptr"][x]:L["send_ptr"][x + 1]]]
+            other = ffcuda.partition_local(2, nv, conn, part, int(r), 3)
+            y = list(other["nbr"]).index(rank)
+            assert np.array_equal(sent, other["l2g"][other["recv_off"][y]:other["recv_off"][y] + other["recv_cnt"][y]])
+    with pytest.raises(ffcuda.FfcudaError):
+        ffcuda.partition_rcb(xyz, 0)
