@@ -1090,9 +1090,11 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
                 g_resident[(const void *)static_cast<HashMatrix<int, double> *>(M)] = res; // stays on the device for the solver
                 A.pHM()->half = ds.sym;
                 SetSolver(stack, false, *A.A, ds);
+                drop_resident(); // not adopted (the solver is not ours): a later set(A,solver=CG) uploads the matrix as it is THEN
                 if (g_verbose) cout << "  -- ffcuda: matrix " << n << " x " << n << ", nnz " << nnz << " assembled on the GPU" << endl;
                 return SetAny<Matrice_Creuse<double> *>(&A);
             } catch (const Unsupported &u) {
+                drop_resident();
                 notice("matrix = varf(Vh,Vh)", u.why);
                 return Base::Op::operator()(stack);
             }
@@ -1185,18 +1187,32 @@ class SolverCudaCG : public VirtualSolver<int, double> {
     double eps, tgv;
     double *veps;
     long *getnbiter;
+    VirtualSolver<int, double> *hostcg; // FreeFEM's own SolverCG when the script gives a preconditioner (precon=)
 
-    SolverCudaCG(HMat &AA, const Data_Sparse_Solver &ds, Stack)
+    SolverCudaCG(HMat &AA, const Data_Sparse_Solver &ds, Stack stack, bool is_cg = true)
         : A(&AA), dev{nullptr, nullptr}, verb(ds.verb), itermax(ds.itmax > 0 ? ds.itmax : AA.n), eps(ds.epsilon), tgv(ds.tgv),
-          veps(ds.veps), getnbiter(ds.getnbiter)
+          veps(ds.veps), getnbiter(ds.getnbiter), hostcg(nullptr)
     {
         if (AA.n != AA.m) ExecError("ffcuda: CG needs a square matrix");
         std::map<const void *, Resident>::iterator it = g_resident.find((const void *)A);
-        if (it != g_resident.end()) { // just assembled by CudaMatrixOp: already on the device
-            dev = it->second;
+        if (it != g_resident.end()) { // assembled by the statement that attaches this solver: already on the device
+            int dn = 0;
+            int64_t dnnz = 0;
+            // (the entry only lives during that statement; the size test guards against a stale entry all the same)
+            if (ffcuda_matrix_info(it->second.A, &dn, &dnnz) == 0 && dn == AA.n && !(is_cg && ds.precon)) {
+                dev = it->second;
+                A->GetReDoNumerics();
+                A->GetReDoSymbolic();
+            } else
+                release_resident(it->second);
             g_resident.erase(it);
-            A->GetReDoNumerics();
-            A->GetReDoSymbolic();
+        }
+        // solver=CG, precon=P: the preconditioner is a FreeFEM expression evaluated by the interpreter on host vectors
+        // (HMatVirtPrecon, femlib/VirtualSolverCG.hpp:27-63, with its tgv-row fix :50-62); FreeFEM's own CG runs it, as
+        // its GMRES does for SolverCudaGMRES.  Never silently replaced by Jacobi.
+        if (is_cg && ds.precon) {
+            notice("solver=CG", "user preconditioner (precon=)");
+            hostcg = new SolverCG<int, double>(AA, ds, stack);
         }
     }
     void upload()
@@ -1210,12 +1226,17 @@ class SolverCudaCG : public VirtualSolver<int, double> {
     }
     void UpdateState()
     {
+        if (hostcg) return; // works on the host matrix
         const bool num = A->GetReDoNumerics(), sym = A->GetReDoSymbolic();
         if (!dev.A || num || sym) upload(); // the script changed the matrix after it was assembled
     }
     void dosolver(double *x, double *b, int N, int trans)
     {
-        (void)trans; // the CG of the reference ignores it as well for symmetric matrices: A^T = A is the user's contract
+        if (hostcg) {
+            hostcg->dosolver(x, b, N, trans);
+            return;
+        }
+        (void)trans; // A'^-1 with CG: the matrix is symmetric by the user's contract (the reference multiplies by A^T, the same)
         if (!dev.A) upload();
         if (getnbiter) *getnbiter = 0;
         int err = 0;
@@ -1234,7 +1255,11 @@ class SolverCudaCG : public VirtualSolver<int, double> {
             ffassert(0);
         }
     }
-    ~SolverCudaCG() { release_resident(dev); }
+    ~SolverCudaCG()
+    {
+        release_resident(dev);
+        delete hostcg;
+    }
 };
 
 // ------------------------------------------------------------------------------------------------------------
@@ -1249,7 +1274,7 @@ class SolverCudaGMRES : public SolverCudaCG {
     SolverGMRES<int, double> *host; // FreeFEM's own solver for what is left to it
     bool precon;
     SolverCudaGMRES(HMat &AA, const Data_Sparse_Solver &ds, Stack stack)
-        : SolverCudaCG(AA, ds, stack), restart(ds.NbSpace), host(nullptr), precon(ds.precon != 0)
+        : SolverCudaCG(AA, ds, stack, false), restart(ds.NbSpace), host(nullptr), precon(ds.precon != 0)
     {
         if (precon) host = new SolverGMRES<int, double>(AA, ds, stack); // (Data_Sparse_Solver cannot be kept: built now)
     }
@@ -1422,7 +1447,10 @@ struct CudaProblem : public Base {
             B = new KN<double>(n);
             for (long i = 0; i < n; ++i) (*B)[i] = std::abs(hb[i]) < 1.e-60 ? 0. : hb[i];
             dynamic_cast<HashMatrix<int, double> *>(&A)->half = ds.sym;
-            if (ds.initmat) DefSolver(stack, A, ds);
+            if (ds.initmat) {
+                DefSolver(stack, A, ds);
+                drop_resident(); // see CudaMatrixOp: a device copy nobody adopted must not outlive the statement
+            }
             if (g_verbose) cout << "  -- ffcuda: problem right-hand side of size " << n << " assembled on the GPU" << endl;
             A.Solve(*X, *B);
         } catch (const Unsupported &) {
@@ -1483,7 +1511,25 @@ void repoint_solve_type()
         return;
     }
     static CudaTypeSolve<exec_init, P> model;
-    *reinterpret_cast<void **>(t) = *reinterpret_cast<void **>(&model); // the virtual table pointer
+    // The keywords `problem` / `solve` hold pointers to the type objects created at start-up and the lexer refuses a second
+    // registration, so the object is given the dynamic type of the subclass (no data member, one overridden virtual
+    // function).  This relies on the Itanium C++ ABI (vptr = first word of a polymorphic object with a polymorphic primary
+    // base).  Self-test at load time: the first word of the model must be its vptr (two models share it and differ from the
+    // base's), and after the switch the object must answer as a CudaTypeSolve through RTTI; otherwise everything is put
+    // back and problem / solve stay with FreeFEM.
+    static CudaTypeSolve<exec_init, P> model2;
+    void *const vp = *reinterpret_cast<void **>(static_cast<basicForEachType *>(&model));
+    void *const vp2 = *reinterpret_cast<void **>(static_cast<basicForEachType *>(&model2));
+    void *const old = *reinterpret_cast<void **>(t);
+    if (vp != vp2 || vp == old || static_cast<void *>(static_cast<basicForEachType *>(&model)) != static_cast<void *>(&model)) {
+        cerr << " ffcuda: unexpected object layout; problem / solve stay with FreeFEM" << endl;
+        return;
+    }
+    *reinterpret_cast<void **>(t) = vp;
+    if (!dynamic_cast<CudaTypeSolve<exec_init, P> *>(t) || typeid(*t) != typeid(model)) {
+        *reinterpret_cast<void **>(t) = old;
+        cerr << " ffcuda: the type switch of problem / solve did not take; they stay with FreeFEM" << endl;
+    }
 }
 
 } // namespace

@@ -429,3 +429,81 @@ solve Pb(u,v,solver=CG,eps=1e-14) = int2d(Th)((1+x)*(dx(u)*dx(v)+dy(u)*dy(v)) + 
     assert rc == 0 and "problem matrix" in out
     rc, _, cpu = run_solve(body, "u", {"FFCUDA_DISABLE": "1"})
     assert rc == 0 and np.max(np.abs(gpu - cpu)) <= 1e-11 * np.abs(cpu).max()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# solver=CG with a user preconditioner, set(A,solver=CG) after the script changed the matrix, A'^-1
+# (precon= must never be silently replaced by Jacobi; a stale device copy must never be
+# adopted)
+# ---------------------------------------------------------------------------------------------------------------
+PRECON_NOT_CLAIMED = """mesh Th = square(12,11);
+fespace Vh(Th,P1nc); Vh u,v;
+varf va(u,v) = int2d(Th)(dx(u)*dx(v)+dy(u)*dy(v)+u*v) + int2d(Th)(1.*v) + on(1,2,3,4,u=0);
+matrix M = va(Vh,Vh);
+real[int] dm(Vh.ndof); dm = M.diag;
+func real[int] Pre(real[int] &xx) { for (int i=0;i<xx.n;++i) xx[i] = (dm[i] > 1e20 ? 1. : 0.5)*xx[i]/dm[i]; return xx; }
+matrix A = va(Vh,Vh,solver=CG,eps=1e-8,precon=Pre);
+real[int] b = va(0,Vh);
+verbosity=1; u[] = 0; u[] = A^-1*b; verbosity=0;
+{ ofstream f("u.txt"); f.precision(17); for(int i=0;i<u[].n;++i) f << u[][i] << endl; }
+"""
+
+
+@needs_ff
+def test_plugin_cg_user_preconditioner_runs_freefems_cg():
+    """P1nc is not on the GPU path, so this runs without a device: with the plugin loaded `solver=CG` resolves to
+    SolverCudaCG, which must hand a `precon=` solve to FreeFEM's own SolverCG (and say so) - same iterations, same bits."""
+    rc, out, u = run_solve(PRECON_NOT_CLAIMED, "u", {})
+    assert rc == 0, out[-3000:]
+    assert "solver=CG left to FreeFEM (user preconditioner" in out
+    rc2, out2, u2 = run_solve(PRECON_NOT_CLAIMED, "u", {"FFCUDA_DISABLE": "1"})
+    assert rc2 == 0
+    it = re.findall(r"GC[^\n]*?after\s+(\d+)", out)
+    it2 = re.findall(r"GC[^\n]*?after\s+(\d+)", out2)
+    assert it and it == it2
+    assert np.array_equal(u, u2)
+    rc, out, _ = run_solve(PRECON_NOT_CLAIMED, "u", {"FFCUDA_STRICT": "1"})
+    assert rc != 0 and "FFCUDA_STRICT" in out
+
+
+SET_SOLVER_CASES = {
+    # the matrix is assembled on the GPU with the default solver, CHANGED by the script, and only then given to CG: the
+    # solve must see the changed values (no stale device copy)
+    "set_after_scaling": """mesh3 Th = cube(5,4,6);
+fespace Vh(Th,P1); Vh u,v;
+varf va(u,v) = int3d(Th)(dx(u)*dx(v)+dy(u)*dy(v)+dz(u)*dz(v)+u*v) + int3d(Th)(1.*v) + on(1,u=0);
+matrix A = va(Vh,Vh);
+real[int] b = va(0,Vh);
+A = 3.*A;
+set(A,solver=CG,eps=1e-12);
+""",
+    "set_after_diag_edit": """mesh Th = square(9,8);
+fespace Vh(Th,P2); Vh u,v;
+varf va(u,v) = int2d(Th)(dx(u)*dx(v)+dy(u)*dy(v)) + int2d(Th)(1.*v) + on(1,2,3,4,u=0);
+matrix A = va(Vh,Vh,solver=CG,eps=1e-12);
+real[int] b = va(0,Vh);
+for (int i=0;i<Vh.ndof;i+=7) A(i,i) = 2.*A(i,i);
+set(A,solver=CG,eps=1e-12);
+""",
+    "transposed_solve": """mesh3 Th = cube(4,5,4);
+fespace Vh(Th,P1); Vh u,v;
+varf va(u,v) = int3d(Th)(dx(u)*dx(v)+dy(u)*dy(v)+dz(u)*dz(v)) + int3d(Th)(1.*v) + on(1,2,3,4,5,6,u=0);
+matrix A = va(Vh,Vh,solver=CG,eps=1e-12);
+real[int] b = va(0,Vh);
+u[] = A'^-1*b;
+real[int] keep = u[];
+""",
+}
+
+
+@needs_ff
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(SET_SOLVER_CASES))
+def test_plugin_set_solver_and_transposed(name):
+    body = SET_SOLVER_CASES[name] + "verbosity=1; u[] = 0; u[] = A^-1*b; verbosity=0;\n"
+    rc, out, gpu = run_solve(body, "u", {"FFCUDA_VERBOSE": "1"})
+    assert rc == 0, out[-3000:]
+    assert "assembled on the GPU" in out and "GC (ffcuda)" in out
+    rc, out_cpu, cpu = run_solve(body, "u", {"FFCUDA_DISABLE": "1"})
+    assert rc == 0 and "(ffcuda)" not in out_cpu
+    assert np.max(np.abs(gpu - cpu)) <= 1e-10 * np.abs(cpu).max()
