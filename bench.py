@@ -50,6 +50,46 @@ METRIC = ("assembly nnz/s + CG SpMV GB/s vs HBM roofline (value = assembly nnz/s
 FF_BIN = os.path.join(ROOT, "oracle", "_ref", "FreeFem++-nw")
 
 
+def load_traffic():
+    """per-kernel DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum per launch) written by tools/ncu_extract.py from
+    the `ncu --set full` capture of the committed build: the newest profiles/*_traffic.json.  Nothing is hard-coded."""
+    import glob
+
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return {}, None
+    try:
+        with open(files[-1]) as f:
+            return json.load(f), os.path.relpath(files[-1], ROOT)
+    except Exception:
+        return {}, None
+
+
+CUBE_STENCIL = [(0, 0, 0)] + [(sx * a, sx * b, sx * c) for sx in (1, -1)
+                              for (a, b, c) in ((1, 0, 0), (0, 1, 0), (0, 0, 1), (1, 1, 0), (0, 1, 1), (1, 0, 1), (1, 1, 1))]
+
+
+def cube_pattern_mismatches(np, nx, ny, nz, row_gid, rp, gcols):
+    """rows of the P1 matrix on BuildCube's mesh in closed form (fflib/msh3.cpp:7683-7742: every cell is cut in 6 tets
+    around the diagonal 0-7, so vertex (i,j,k) is coupled with itself and +-(1,0,0) (0,1,0) (0,0,1) (1,1,0) (0,1,1)
+    (1,0,1) (1,1,1) when that vertex is in the box; HashMatrix keeps every couple of an element, zero or not).  Compares
+    row lengths and an order-independent 64-bit hash of every row's global column set; returns the number of rows that differ."""
+    g = row_gid.astype(np.int64)
+    sx, sxy = nx + 1, (nx + 1) * (ny + 1)
+    i, j, k = g % sx, (g // sx) % (ny + 1), g // sxy
+    mul = np.uint64(0x9E3779B97F4A7C15)
+    cnt = np.zeros(len(g), np.int64)
+    hsh = np.zeros(len(g), np.uint64)
+    for (a, b, c) in CUBE_STENCIL:
+        ok = (i + a >= 0) & (i + a <= nx) & (j + b >= 0) & (j + b <= ny) & (k + c >= 0) & (k + c <= nz)
+        nid = (g + a + b * sx + c * sxy).astype(np.uint64)
+        cnt += ok
+        hsh += np.where(ok, (nid + np.uint64(1)) * mul, np.uint64(0))
+    lens = np.diff(rp.astype(np.int64))
+    got = np.add.reduceat((gcols.astype(np.uint64) + np.uint64(1)) * mul, rp[:-1].astype(np.int64)) if len(gcols) else hsh * np.uint64(0)
+    return int(np.count_nonzero((lens != cnt) | (got != hsh)))
+
+
 def peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -103,8 +143,11 @@ class ClockSampler:
 # reference arm / CPU baseline: the unmodified FreeFem++ on a bounded sample
 # ------------------------------------------------------------------------------------------------------------------
 EDP = """load "msh3"
+%s
 int n = %d;
+real tm0 = clock();
 mesh3 Th = cube(n,n,n);
+real tm1 = clock();
 fespace Vh(Th,P1);
 varf va(u,v) = int3d(Th)(dx(u)*dx(v)+dy(u)*dy(v)+dz(u)*dz(v)) + int3d(Th)(1.*v) + on(1,2,3,4,5,6,u=0);
 verbosity = 1;
@@ -118,23 +161,26 @@ u[] = A^-1*b;
 real t3 = clock();
 cout.precision(12);
 cout << "FFBENCH nt " << Th.nt << " n " << Vh.ndof << " nnz " << A.nnz << " tA " << t1-t0 << " tb " << t2-t1
-     << " tcg " << t3-t2 << " uu " << u[]'*u[] << endl;
+     << " tcg " << t3-t2 << " uu " << u[]'*u[] << " tmesh " << tm1-tm0 << endl;
 """
 
 
-def run_reference_once(m):
-    """one run of the reference on cube(m): dict(nnz, n, iters, tA, tb, tcg)."""
+def run_reference_once(m, plugin=False):
+    """one run of the reference on cube(m): dict(nnz, n, iters, tA, tb, tcg).  plugin=True: the same script with
+    `load "ffcuda"` (the drop-in as a script author sees it: FreeFEM's interpreter, host mesh, MatriceMorse hand-off)."""
     with tempfile.TemporaryDirectory() as td:
         edp = os.path.join(td, "bench.edp")
         with open(edp, "w") as f:
-            f.write(EDP % m)
-        r = subprocess.run([FF_BIN, "-nw", "-v", "1", edp], capture_output=True, text=True, cwd=td)
-    mm = re.search(r"FFBENCH nt (\d+) n (\d+) nnz (\d+) tA (\S+) tb (\S+) tcg (\S+) uu (\S+)", r.stdout)
-    it = re.search(r"GC:\s+converge after\s+(\d+)", r.stdout)
+            f.write(EDP % ('load "ffcuda"' if plugin else "", m))
+        env = dict(os.environ, FF_LOADPATH=os.path.join(ROOT, "freefem-sources_b200", "lib"))
+        r = subprocess.run([FF_BIN, "-nw", "-v", "1", edp], capture_output=True, text=True, cwd=td, env=env)
+    mm = re.search(r"FFBENCH nt (\d+) n (\d+) nnz (\d+) tA (\S+) tb (\S+) tcg (\S+) uu (\S+) tmesh (\S+)", r.stdout)
+    it = re.search(r"GC[^\n]*?converge after\s+(\d+)", r.stdout)
     if r.returncode != 0 or not mm or not it:
         raise RuntimeError("reference run failed: " + (r.stdout[-500:] + r.stderr[-500:]))
     return dict(nt=int(mm.group(1)), n=int(mm.group(2)), nnz=int(mm.group(3)), tA=float(mm.group(4)), tb=float(mm.group(5)),
-                tcg=float(mm.group(6)), uu=float(mm.group(7)), iters=int(it.group(1)))
+                tcg=float(mm.group(6)), uu=float(mm.group(7)), tmesh=float(mm.group(8)), iters=int(it.group(1)),
+                gpu_path="assembled on the GPU" in r.stdout or "(ffcuda)" in r.stdout)
 
 
 def run_port_once(m):
@@ -155,7 +201,7 @@ def run_port_once(m):
     t2 = time.perf_counter()
     x, it, _, _ = ol.cg(n, ci, cj, ca, b, np.zeros(n), eps=EPS, itmax=0, tgv=TGV)
     t3 = time.perf_counter()
-    return dict(nt=6 * m ** 3, n=n, nnz=len(ci), tA=t1 - t0, tb=t2 - t1, tcg=t3 - t2, uu=float(x @ x), iters=it)
+    return dict(nt=6 * m ** 3, n=n, nnz=len(ci), tA=t1 - t0, tb=t2 - t1, tcg=t3 - t2, uu=float(x @ x), iters=it, tmesh=0.0)
 
 
 def cpu_figures(r):
@@ -177,12 +223,25 @@ def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    m = args.ref_n
+    # The workload itself (cube(n), n = 128: ~15 s of mesh generation + ~60-110 s of assembly and CG per run on one
+    # core) when the run fits a few minutes, else a bounded sample cube(m): a calibration run on cube(40) decides.  The
+    # reference has no warm state between statements (every `matrix A = ...` starts from nothing), so warm-up runs are
+    # only made on the bounded sample.
     runs = []
     kind = "reference"
-    for _ in range(args.warmup):
+    cal, kind = cpu_run(40)
+    scale = (args.n / 40.0) ** 3
+    est_full = (cal["tA"] + cal["tb"] + cal["tcg"] * (args.n / 40.0) + cal["tmesh"]) * scale * 1.3
+    budget = 240.0
+    if args.ref_n > 0:
+        m, nruns, nwarm = args.ref_n, args.steps, args.warmup
+    elif est_full <= budget:
+        m, nruns, nwarm = args.n, max(1, min(args.steps, int(budget // est_full))), 0
+    else:
+        m, nruns, nwarm = 64, max(1, min(args.steps, 3)), 0
+    for _ in range(nwarm):
         _, kind = cpu_run(m)
-    for _ in range(args.steps):
+    for _ in range(nruns):
         r, kind = cpu_run(m)
         runs.append(r)
     t = statistics.mean(r["tA"] + r["tb"] for r in runs)
@@ -191,11 +250,14 @@ def reference_arm(args):
     value = r0["nnz"] / t
     fig = cpu_figures(dict(r0, tA=statistics.mean(r["tA"] for r in runs), tb=statistics.mean(r["tb"] for r in runs),
                            tcg=statistics.mean(r["tcg"] for r in runs)))
-    sample = f"3-D P1 Poisson cube({m}) ({r0['nt']} tets, nnz {r0['nnz']}, {r0['iters']} CG it): same .edp as the workload, bounded size"
+    sample = (f"3-D P1 Poisson cube({m}) ({r0['nt']} tets, nnz {r0['nnz']}, {r0['iters']} CG it): "
+              + ("the workload itself" if m == args.n else "same .edp as the workload, bounded size")
+              + f", {len(runs)} timed run(s) of {r0['tA'] + r0['tb'] + r0['tcg'] + r0['tmesh']:.0f} s each")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "nnz/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
+        "steps_run": len(runs), "same_size_as_workload": m == args.n,
         "config": {"workload": workload_name(args.n, args.gpus), "sample": sample, "threads": 1,
                    "timed": "clock() deltas around `matrix A = va(Vh,Vh)` and `real[int] b = va(0,Vh)` inside FreeFem++"},
         "assembly": {"nnz_per_s": fig["assembly_nnz_per_s"]}, "spmv": {"gbs": fig["spmv_gbs"], "bytes_model": "16*nnz+16*n (COO)"},
@@ -254,6 +316,7 @@ def ours(args):
     mesh = ctx.mesh_cube(nx, ny, nz, distributed=(world > 1))
     space = mesh.space(1, 1)
     hbm, hbm_src = peaks()
+    TRAFFIC, traffic_src = load_traffic()
 
     def barrier():
         if dist is not None:
@@ -288,6 +351,20 @@ def ours(args):
         if dist is not None:
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item() / steps, ctx.launch_count() - l0, out
+
+    # ---- what the resident data cost: the first statements on a fresh fespace (wall clock around a synchronised step)
+    def wall_step(sp):
+        barrier()
+        t0 = time.perf_counter()
+        out = assemble_on(sp)
+        barrier()
+        return (time.perf_counter() - t0) * 1e3, out
+
+    cold_sp = mesh.space(1, 1)
+    cold1_ms, _ = wall_step(cold_sp)        # node->element incidence + symbolic + thread-per-row kernels
+    cold2_ms, _ = wall_step(cold_sp)        # second assembly on the fespace: the row tiles / fans are built here
+    cold3_ms, _ = wall_step(cold_sp)        # steady state (wall clock, for comparison with the two above)
+    del cold_sp
 
     # ---- the timed steps: assembly, device resident
     sampler = ClockSampler(local)
@@ -410,17 +487,121 @@ def ours(args):
                "d2h_bytes_per_step": int(h_val.nbytes + h_b.nbytes), "pinned": True,
                "api": "ffcuda_mesh_cube_distributed (inputs generated on the device) -> assembly -> matrix/vec_download"}
 
-    # ---- CPU baseline beside it (rank 0, N=1 only): the unmodified reference on a bounded sample
+    # ---- parity of THIS run's result (every rank; size-independent properties + closed forms)
+    def allsum(v):
+        tt = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt)
+        return tt.item()
+
+    def allmax(v):
+        tt = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return tt.item()
+
+    parity = {}
+    if not args.no_parity:
+        rp_h, ci_h = pat.download()
+        if world > 1:
+            nown, gid = mesh.local_to_global()
+        else:
+            gid = np.arange(nv_loc, dtype=np.int64)
+        bad_rows = cube_pattern_mismatches(np, nx, ny, nz, gid[:n_loc], rp_h, gid[ci_h])
+        A0 = pat.matrix()
+        A0.assemble(LAP3, qp, qw)                       # no Dirichlet rows: constants are in the kernel of the stiffness matrix
+        ones = ctx.vec_from(np.ones(nv_loc))
+        y0 = ctx.vec(n_loc)
+        A0.spmv(ones, y0)
+        a0max = allmax(np.abs(A0.download()).max())
+        rowsum = allmax(np.abs(y0.download()).max()) / a0max
+        b0 = ctx.vec(n_loc)
+        space.assemble_linear(b0, RHS, qp, qw)
+        sum_b = allsum(b0.download().sum())           # f = 1 on the unit cube: the measures of the elements add up to 1
+        u_h = x.download()[:n_loc]
+        uu = allsum(float(u_h @ u_h))
+        del A0, ones, y0, b0
+        parity = {"pattern_rows_differing_from_closed_form": int(allsum(bad_rows)), "rows_checked": n_glob,
+                  "row_sum_max_over_amax": rowsum, "sum_b_minus_volume": abs(sum_b - 1.0), "cg_iters": iters, "uu": uu}
+        ok = parity["pattern_rows_differing_from_closed_form"] == 0 and rowsum <= 1e-12 and abs(sum_b - 1.0) <= 1e-12 and conv == 1
+        if world > 1:
+            # the same mesh solved on ONE GPU (rank 0, its own context): iteration count and |u|^2 must agree
+            if rank == 0:
+                c1 = ffcuda.Context(local)
+                m1 = c1.mesh_cube(nx, ny, nz)
+                s1 = m1.space(1, 1)
+                p1 = s1.symbolic()
+                A1 = p1.matrix()
+                A1.assemble(LAP3, qp, qw)
+                n1 = p1.info()[0]
+                b1 = c1.vec(n1)
+                s1.assemble_linear(b1, RHS, qp, qw)
+                bc1 = s1.bc_from_labels(ALL6, 1, [0.0])
+                A1.apply_bc(bc1, TGV)
+                b1.apply_bc(bc1, TGV)
+                x1 = c1.vec(n1)
+                it1, conv1, _ = A1.cg(b1, x1, eps=EPS, itmax=0, tgv=TGV)
+                u1 = x1.download()
+                parity["single_gpu_cg_iters"] = it1
+                parity["single_gpu_uu_rel_diff"] = abs(float(u1 @ u1) - uu) / max(abs(uu), 1e-300)
+                ok = ok and it1 == iters and parity["single_gpu_uu_rel_diff"] <= 1e-10
+                del x1, b1, A1, p1, s1, m1, u1
+                c1.close()
+            barrier()
+        parity["status"] = "ok" if ok else "FAIL"
+
+    # ---- strong scaling: BASELINE.json configs[4] (cube(256), a fixed problem) on the N GPUs of this run
+    strong = None
+    if args.strong and args.n == 128 and world in (1, 2, 4, 8):
+        if world == 8:      # the weak-scaling workload at N = 8 IS cube(256)
+            strong = {"workload": workload_name(128, 8), "ms_per_step": ms_step, "value": value, "cg_iters": iters,
+                      "cg_ms_per_iter": ms_cg / max(iters, 1), "note": "same run as the weak-scaling line"}
+        else:
+            sm_ = ctx.mesh_cube(256, 256, 256, distributed=(world > 1))
+            ss_ = sm_.space(1, 1)
+            ms_s, _, (sp_, sA_, sb_) = timed(lambda: assemble_on(ss_), max(2, min(args.steps, 5)), 3)
+            sn_, snnz_ = sp_.info()
+            sx_ = ctx.vec(sm_.info()[1])
+
+            def ssolve():
+                sx_.fill(0.0)
+                return sA_.cg(sb_, sx_, eps=EPS, itmax=0, tgv=TGV)
+
+            ms_scg, _, (sit_, sconv_, _) = timed(ssolve, 1, 1)
+            strong = {"workload": workload_name(128, 8), "ms_per_step": ms_s, "value": allsum(snnz_) / (ms_s * 1e-3), "cg_iters": sit_,
+                      "cg_converged": sconv_ == 1, "cg_ms_per_iter": ms_scg / max(sit_, 1)}
+            del sx_, sb_, sA_, sp_, ss_, sm_
+
+    # ---- CPU baseline beside it (rank 0, N=1 only): the unmodified reference on the workload itself (one run, ~1.5-2 min
+    # on one core), or on a bounded sample with --ref-n; and the same script with `load "ffcuda"`: what a script author sees
     cpu = None
+    e2e_plugin = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        r, kind = cpu_run(args.ref_n)
+        m_cpu = args.ref_n if args.ref_n > 0 else args.n
+        r, kind = cpu_run(m_cpu)
         fig = cpu_figures(r)
-        cpu = {"value": fig["value"], "unit": "nnz/s", "cores": 1, "kind": kind,
-               "sample": f"3-D P1 Poisson cube({args.ref_n}) ({r['nt']} tets, nnz {r['nnz']}, {r['iters']} CG it, "
-                         f"{r['tA'] + r['tb'] + r['tcg']:.1f} s): same .edp as the workload at a bounded size "
-                         "(assembly is O(nt): nnz/s is size-independent)",
+        cpu = {"value": fig["value"], "unit": "nnz/s", "cores": 1, "kind": kind, "same_size_as_workload": m_cpu == args.n,
+               "sample": f"3-D P1 Poisson cube({m_cpu}) ({r['nt']} tets, nnz {r['nnz']}, {r['iters']} CG it, "
+                         f"{r['tA'] + r['tb'] + r['tcg']:.1f} s + {r['tmesh']:.1f} s of mesh generation): "
+                         + ("the workload itself, one run" if m_cpu == args.n else "same .edp as the workload at a bounded size"),
                "assembly_nnz_per_s": fig["assembly_nnz_per_s"], "spmv_gbs": fig["spmv_gbs"],
+               "matrix_s": r["tA"], "rhs_s": r["tb"], "cg_s": r["tcg"], "cg_iters": r["iters"],
                "cg_ms_per_iter": r["tcg"] * 1e3 / max(r["iters"], 1)}
+        if kind == "reference" and os.path.exists(os.path.join(ROOT, "freefem-sources_b200", "lib", "ffcuda.so")):
+            try:
+                del A, b, x, pat
+                rp_ = run_reference_once(m_cpu, plugin=True)
+                e2e_plugin = {"script": "the cpu_baseline .edp with `load \"ffcuda\"` as its second line, run by the unmodified FreeFem++",
+                              "size": f"cube({m_cpu})", "gpu_path_taken": bool(rp_["gpu_path"]),
+                              "matrix_s": rp_["tA"], "rhs_s": rp_["tb"], "cg_s": rp_["tcg"], "cg_iters": rp_["iters"],
+                              "value": rp_["nnz"] / (rp_["tA"] + rp_["tb"]), "unit": "nnz/s",
+                              "speedup_assembly": (r["tA"] + r["tb"]) / max(rp_["tA"] + rp_["tb"], 1e-9),
+                              "speedup_cg": r["tcg"] / max(rp_["tcg"], 1e-9),
+                              "uu_rel_diff_vs_reference": abs(rp_["uu"] - r["uu"]) / max(abs(r["uu"]), 1e-300),
+                              "timed": "clock() deltas inside FreeFem++ (CPU time of the interpreter process: mesh flattening, upload, "
+                                       "kernels, download and the MatriceMorse hand-off are all inside)"}
+            except Exception as e:  # the plugin leg must never take the bench line down
+                e2e_plugin = {"error": str(e)[-300:]}
 
     if rank == 0:
         allk = max(prof[""][0], 1e-9)
@@ -430,7 +611,9 @@ def ours(args):
             "data": "synthetic",
             "config": {"workload": workload_name(args.n, world), "nt": 6 * nx * ny * nz, "ndof": n_glob, "nnz": nnz_glob,
                        "quadrature": "14-point (qforder 6)", "tgv": TGV,
-                       "resident": "mesh, element->dof map and its transpose (node->element incidence, built once per fespace)",
+                       "resident": "mesh, element->dof map, its transpose (node->element incidence) and the row tiles / fans of "
+                                   "the fespace (Morton clusters of rows with their elements grouped in fans, built once per fespace at "
+                                   "its second assembly: `cold` gives what they cost)",
                        "l2": "inputs larger than L2 per GPU: connectivity %.0f MB + CSR %.0f MB vs 126 MB L2"
                              % (16.0 * nt_loc / 1e6, 12.0 * nnz_loc / 1e6),
                        "partition": "z-slabs, one process per GPU" if world > 1 else "single GPU"},
@@ -445,27 +628,29 @@ def ours(args):
                      "plain_spmv_gbs": B_spmv / (ms_spmv_plain * 1e-3) / 1e9 * world,
                      "plain_spmv_frac": B_spmv / (ms_spmv_plain * 1e-3) / 1e9 / hbm},
             "roofline": {"bound": "hbm", "kernel": "asm_rows_p1", "achieved": asm_gbs, "peak": hbm, "unit": "GB/s",
-                         "frac": asm_gbs / hbm, "traffic": TRAFFIC.get("asm_rows_p1") if args.n == 128 else None,
+                         "frac": asm_gbs / hbm, "traffic": (TRAFFIC.get("asm_rows_p1") or {}).get("traffic") if args.n == 128 else None,
+                         "traffic_source": traffic_src,
                          "peak_source": hbm_src, "share_of_step_kernels": t_asmk / max(asm_step_kernels, 1e-9), "per": "GPU"},
             "roofline_spmv": {"bound": "hbm", "kernel": "cg_spmv_dots", "achieved": spmv_gbs, "peak": hbm, "unit": "GB/s",
-                              "frac": spmv_gbs / hbm, "traffic": TRAFFIC.get("cg_spmv_dots") if args.n == 128 else None,
+                              "frac": spmv_gbs / hbm, "traffic": (TRAFFIC.get("cg_spmv_dots") or {}).get("traffic") if args.n == 128 else None,
                               "peak_source": hbm_src, "share_of_cg_kernels": prof["cg_spmv_dots"][0] / max(prof["cg_"][0], 1e-9),
                               "per": "GPU"},
             "kernels_ms_and_launches_per_pass": kernels_ms,
+            "cold": {"first_step_ms": cold1_ms, "second_step_ms": cold2_ms, "steady_step_wall_ms": cold3_ms,
+                     "tile_build_ms": max(0.0, cold2_ms - cold3_ms), "incidence_and_first_kernels_extra_ms": max(0.0, cold1_ms - cold3_ms),
+
+                     "note": "wall clock around synchronised steps on a fresh fespace of the resident mesh; `value` is the steady state"},
+            "parity": parity, "strong_scaling": strong,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         if cpu:
             line["cpu_baseline"] = cpu
+        if e2e_plugin:
+            line["e2e_plugin"] = e2e_plugin
         print(json.dumps(line), flush=True)
     if dist is not None:
         ctx.comm_finalize()
         dist.destroy_process_group()
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` captures under profiles/
-# (cube(128) on one B200); filled in when a capture exists for the current kernels
-TRAFFIC = {"asm_rows_p1": 914.6e6,   # k_asm_tiles<3,false>: 684.4 MB read + 230.2 MB written (profiles/r01c_ncu_asm_kernels_summary.txt)
-           "cg_spmv_dots": 422.6e6}  # k_spmv_sell<2>: 418.0 MB read + 4.6 MB written (profiles/r01b_ncu_full_summary.txt)
 
 
 def main():
@@ -475,7 +660,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--n", type=int, default=128, help="cells per edge per GPU (128 = BASELINE.json configs[1])")
-    ap.add_argument("--ref-n", type=int, default=40, help="cube size of the bounded CPU sample")
+    ap.add_argument("--ref-n", type=int, default=0,
+                    help="cube size of a bounded CPU sample (0: the workload itself; the reference arm falls back to a sample if a run does not fit)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the parity object")
+    ap.add_argument("--no-strong", dest="strong", action="store_false", help="skip the strong-scaling leg (cube(256) on the N GPUs)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-clocks", action="store_true", help="do not sample nvidia-smi clocks during the timed region")
     args = ap.parse_args()

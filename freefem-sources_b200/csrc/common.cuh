@@ -68,6 +68,7 @@ struct ffcuda_ctx {
     int sm_count = 148;
     int tile_policy = 1;        // 0: never use row tiles, 1: from the second assembly on a fespace, 2: always
     int tile_rows = 96;         // rows per tile
+    int tile_fans = 1;          // 3-D stiffness forms: elements of a tile evaluated in fans around their longest edge (0: element by element)
     int gmres_coop = 1;         // 1: one cooperative kernel per Arnoldi step when the vectors fit its registers, 0: one kernel per basis vector
     // reduction scratch (device) + pinned host mirror
     double *d_scal = nullptr;   // small array of device scalars
@@ -332,6 +333,11 @@ struct TileSet {
     DBuf<uint32_t> tpre;      // words of every descriptor's head (row ids, coordinates, element words): all a rhs needs
     DBuf<uint32_t> rblob;     // record lists of the rows, one blob per tile: (element << 2 | local vertex) of every star
     DBuf<uint32_t> roff;      // ntiles+1 offsets into rblob
+    // fan set (tiles.cu, 3-D): the same tiles with their elements grouped in fans around a common edge
+    int fan_state = 0;        // 1 ready, -1 not applicable
+    int fan_max_head = 0, fan_max_b = 0, fan_max_nvals = 0, fan_max_nq = 0; // largest part A / part B (words), value table, entries
+    int64_t fan_sum_fans = 0;
+    DBuf<uint32_t> fblob, foff, fhead; // descriptors, ntiles+1 offsets (words), words of every descriptor's head (the part copied to shared memory)
 };
 
 struct ffcuda_space {

@@ -59,6 +59,7 @@ extern "C" int ffcuda_ctx_create(int device, ffcuda_ctx **out)
     FF_CUDA(cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
     if (const char *e = getenv("FFCUDA_TILES")) ctx->tile_policy = std::max(0, std::min(2, atoi(e)));
+    if (const char *e = getenv("FFCUDA_TILE_FANS")) ctx->tile_fans = atoi(e) != 0;
     if (const char *e = getenv("FFCUDA_TILE_ROWS")) ctx->tile_rows = std::max(8, std::min(256, atoi(e)));
     FF_CUDA(cudaMalloc((void **)&ctx->d_scal, 256 * sizeof(double))); // [0,64): CG scalars and flags, [64, ..): P2PDesc
     FF_CUDA(cudaMemset(ctx->d_scal, 0, 256 * sizeof(double)));
@@ -185,6 +186,9 @@ extern "C" int ffcuda_ctx_set_option(ffcuda_ctx *ctx, const char *name, int valu
     if (n == "tile_policy") {
         FF_REQUIRE(value >= 0 && value <= 2, "tile_policy must be 0, 1 or 2");
         ctx->tile_policy = value;
+    } else if (n == "tile_fans") {
+        FF_REQUIRE(value == 0 || value == 1, "tile_fans must be 0 or 1");
+        ctx->tile_fans = value;
     } else if (n == "tile_rows") {
         FF_REQUIRE(value >= 8 && value <= 256, "tile_rows must be in 8..256");
         ctx->tile_rows = value;

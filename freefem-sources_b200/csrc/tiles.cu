@@ -44,6 +44,11 @@ constexpr int HDR = 16;           // header words
 //           einfo[nq]   u32    offset of the entry's list in code PAIRS | list length << 15 | local row << 20
 //           codes       u16    pair * nes + element: index into the numeric kernel's value table (nes: TileSet::nes)
 
+// words of the build kernels' common scratch (BuildScratch)
+__host__ __device__ constexpr int build_words()
+{
+    return SORT_CAP + SORT_CAP + NE_CAP + NE_CAP + NV_CAP + TR_CAP * BMW + (TR_CAP + 1) + (NQ_CAP + 1) + (TB_THREADS + 1) + TR_CAP + NV_CAP / 4 + 16;
+}
 __host__ __device__ inline int pad4(int x) { return (x + 3) & ~3; }
 #define DIM_PAIRS(d) ((d) * ((d) + 1) / 2)
 
@@ -193,34 +198,53 @@ __device__ __forceinline__ int pair_id(int a, int b) // a < b
     return a == 0 ? b - 1 : 2;
 }
 
-// One CTA per tile.  WRITE = 0: sizes only (stats[t*8 ..] = nvt, nelem, nq, ncodes, fit, nr).  WRITE = 1: the blob.
-template <int NV, int WRITE>
-__global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__restrict__ rord, const int32_t *__restrict__ tstart,
-                                                           const int32_t *__restrict__ conn, const IncView V,
-                                                           const double *__restrict__ xyz, int vstride,
-                                                           const int32_t *__restrict__ nrowptr, int nes,
-                                                           int32_t *__restrict__ stats, const uint32_t *__restrict__ toff,
-                                                           uint32_t *__restrict__ blob, const uint32_t *__restrict__ roff,
-                                                           uint32_t *__restrict__ rblob)
+// Scratch of the build kernels (dynamic shared memory, build_shmem() bytes)
+struct BuildScratch {
+    uint32_t *sbuf;  // SORT_CAP   sort buffer; later entry offsets / cursors
+    int *tmp;        // SORT_CAP   flags; later the codes (16 bit) / fan records
+    uint32_t *elist; // NE_CAP     element ids, ascending
+    uint32_t *telem; // NE_CAP     slot words
+    uint32_t *vlist; // NV_CAP     vertex ids, ascending
+    uint32_t *bm;    // TR_CAP*BMW row bitmaps over the slots
+    int *rowq;       // TR_CAP+1   first entry of every row
+    int *cntq;       // NQ_CAP+1   contributions per entry
+    int *part;       // TB_THREADS+1
+    int *rslot;      // TR_CAP     slot of every row's own vertex
+    uint8_t *s2r;    // NV_CAP     row of a slot (255: not a row of the tile)
+};
+__device__ __forceinline__ BuildScratch build_scratch(uint32_t *sm)
 {
-    extern __shared__ uint32_t sm[];
-    uint32_t *sbuf = sm;                                   // SORT_CAP   sort buffer; later entry offsets / cursors
-    int *tmp = reinterpret_cast<int *>(sbuf + SORT_CAP);   // SORT_CAP   flags; later the codes (16 bit)
-    uint32_t *elist = reinterpret_cast<uint32_t *>(tmp + SORT_CAP); // NE_CAP element ids, ascending
-    uint32_t *telem = elist + NE_CAP;                      // NE_CAP     slot words
-    uint32_t *vlist = telem + NE_CAP;                      // NV_CAP     vertex ids, ascending
-    uint32_t *bm = vlist + NV_CAP;                         // TR_CAP*BMW row bitmaps over the slots
-    int *rowq = reinterpret_cast<int *>(bm + TR_CAP * BMW); // TR_CAP+1  first entry of every row
-    int *cntq = rowq + TR_CAP + 1;                         // NQ_CAP+1   contributions per entry
-    int *part = cntq + NQ_CAP + 1;                         // TB_THREADS+1
-    int *rslot = part + TB_THREADS + 1;                    // TR_CAP     slot of every row's own vertex
-    uint8_t *s2r = reinterpret_cast<uint8_t *>(rslot + TR_CAP); // NV_CAP row of a slot (255: not a row of the tile)
-    __shared__ int s_n, s_bad;
-    const int t = blockIdx.x, tid = threadIdx.x;
-    const int r0 = tstart[t], nr = tstart[t + 1] - r0;
+    BuildScratch S;
+    S.sbuf = sm;
+    S.tmp = reinterpret_cast<int *>(S.sbuf + SORT_CAP);
+    S.elist = reinterpret_cast<uint32_t *>(S.tmp + SORT_CAP);
+    S.telem = S.elist + NE_CAP;
+    S.vlist = S.telem + NE_CAP;
+    S.bm = S.vlist + NV_CAP;
+    S.rowq = reinterpret_cast<int *>(S.bm + TR_CAP * BMW);
+    S.cntq = S.rowq + TR_CAP + 1;
+    S.part = S.cntq + NQ_CAP + 1;
+    S.rslot = S.part + TB_THREADS + 1;
+    S.s2r = reinterpret_cast<uint8_t *>(S.rslot + TR_CAP);
+    return S;
+}
+
+// Steps 1-4 of a tile's construction, shared by the build kernels: the elements touching a row of the tile (ascending),
+// the distinct vertices they touch (ascending: slot order = column order), the slot word of every element, the column
+// bitmap of every row and the first entry of every row.  Returns whether the tile fits the capacities.
+template <int NV>
+__device__ int tile_topology(const BuildScratch &S, const int32_t *__restrict__ rord, int r0, int nr, const int32_t *__restrict__ conn,
+                             const IncView &V, int &nelem, int &nvt, int &nq, int &nrec)
+{
+    uint32_t *sbuf = S.sbuf, *elist = S.elist, *telem = S.telem, *vlist = S.vlist, *bm = S.bm;
+    int *rowq = S.rowq, *part = S.part, *rslot = S.rslot;
+    uint8_t *s2r = S.s2r;
+    __shared__ int s_n, s_bad, s_ne, s_nv;
+    const int tid = threadIdx.x;
     if (tid == 0) {
         s_n = 0;
         s_bad = 0;
+        s_ne = s_nv = 0;
     }
     // hash tables (open addressing, 1024 slots, in the sort buffer's tail): vertex id -> local row, later vertex id set
     constexpr int HT = 1024;
@@ -235,13 +259,11 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__rest
         atomicAdd(&s_n, V.cnt[rord[r0 + l]]);
     }
     __syncthreads();
+    nrec = s_n;
     // 1. elements of the tile.  A record (row l, element k) contributes k when l is the smallest local row among the
     // element's vertices that are rows of the tile: every element exactly once, no sort over all the records
     int fit = (nr <= TR_CAP && s_n <= 65535) ? 1 : 0;
-    int nelem = 0, nvt = 0, nq = 0, ncodes = 0;
-    __shared__ int s_ne, s_nv;
-    if (tid == 0) s_ne = s_nv = 0;
-    __syncthreads();
+    nelem = 0; nvt = 0; nq = 0;
     if (fit) {
         for (int l = tid; l < nr; l += TB_THREADS) {
             const int row = rord[r0 + l];
@@ -357,6 +379,38 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__rest
         nq = blk_scan(rowq, nr + 1, part);
         if (nq > NQ_CAP || s_bad) fit = 0;
     }
+    return fit;
+}
+
+// position of slot sb inside row l (number of set bits of the row's bitmap below it)
+__device__ __forceinline__ int row_pos(const uint32_t *bm, int l, uint32_t sb)
+{
+    int p = __popc(bm[l * BMW + (sb >> 5)] & ((1u << (sb & 31u)) - 1u));
+    for (int ww = 0; ww < (int)(sb >> 5); ++ww) p += __popc(bm[l * BMW + ww]);
+    return p;
+}
+
+// One CTA per tile.  WRITE = 0: sizes only (stats[t*8 ..] = nvt, nelem, nq, ncodes, fit, nr).  WRITE = 1: the blob.
+template <int NV, int WRITE>
+__global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__restrict__ rord, const int32_t *__restrict__ tstart,
+                                                           const int32_t *__restrict__ conn, const IncView V,
+                                                           const double *__restrict__ xyz, int vstride,
+                                                           const int32_t *__restrict__ nrowptr, int nes,
+                                                           int32_t *__restrict__ stats, const uint32_t *__restrict__ toff,
+                                                           uint32_t *__restrict__ blob, const uint32_t *__restrict__ roff,
+                                                           uint32_t *__restrict__ rblob)
+{
+    extern __shared__ uint32_t sm[];
+    const BuildScratch S = build_scratch(sm);
+    uint32_t *sbuf = S.sbuf, *elist = S.elist, *telem = S.telem, *vlist = S.vlist, *bm = S.bm;
+    int *tmp = S.tmp, *rowq = S.rowq, *cntq = S.cntq, *part = S.part, *rslot = S.rslot;
+    uint8_t *s2r = S.s2r;
+    __shared__ int s_bad;
+    const int t = blockIdx.x, tid = threadIdx.x;
+    const int r0 = tstart[t], nr = tstart[t + 1] - r0;
+    if (tid == 0) s_bad = 0;
+    int nelem = 0, nvt = 0, nq = 0, ncodes = 0, s_nrec = 0;
+    int fit = tile_topology<NV>(S, rord, r0, nr, conn, V, nelem, nvt, nq, s_nrec);
     if (fit) {
         // 5. contributions per entry: every ordered vertex pair (a, b), a != b, of every element whose vertex a is a row
         for (int x = tid; x <= nq; x += TB_THREADS) cntq[x] = 0;
@@ -390,7 +444,7 @@ __global__ void __launch_bounds__(TB_THREADS) k_tile_build(const int32_t *__rest
     if (!WRITE) {
         if (tid == 0) {
             int32_t *st = stats + (size_t)t * 8;
-            st[0] = nvt; st[1] = nelem; st[2] = nq; st[3] = ncodes; st[4] = fit; st[5] = nr; st[6] = s_n;
+            st[0] = nvt; st[1] = nelem; st[2] = nq; st[3] = ncodes; st[4] = fit; st[5] = nr; st[6] = s_nrec;
         }
         return;
     }
@@ -848,6 +902,527 @@ __global__ void __launch_bounds__(512) k_rhs_tiles(const uint32_t *__restrict__ 
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// FANS (3-D scalar P1 stiffness forms, the headline kernel of round 2).
+//
+// ncu on the round-1 tile kernel: 72 % of the shared-memory pipe, 25 % of the FP64 pipe - per evaluated element 12 LDS.64
+// of coordinates, 6 STS.64 of values, and 12 LDS.64 + 6 code reads on the gather side.  A warp LDS.64 costs two cycles of
+// the 128 B/clk pipe whatever the addresses (tools/micro/pipes.cu), and so does a shuffle, so the only way down is fewer
+// bytes through shared memory per element.  Elements are therefore taken in FANS: runs of <= KMAX elements around a
+// common edge (the AXIS, the longest edge of each element: the main diagonal of the cell in BuildCube's meshes), ordered
+// around it so that consecutive elements share a face.  One thread walks one fan:
+//   * axis end points p, q loaded once, one new ring vertex r_{t+1} per element (3 LDS.64 instead of 12);
+//   * a x (r_{t+1} - p) is the normal of a face of element t AND (negated) of element t+1: computed once;
+//   * the contributions to the axis edge are summed over the whole fan in a register, those to the spokes p-r_t, q-r_t
+//     over the two elements that share them: 3k+3 values stored for k elements instead of 6k, and the entry gather
+//     reads as many fewer.
+// Everything that is used once (fan records, entry rows, contribution codes) is read straight from global memory with
+// coalesced loads; only the coordinates of the tile's vertices, the row tables and the group tables go through shared
+// memory (one TMA bulk copy per tile, double-buffered).  Contribution codes are stored TRANSPOSED per group of 32
+// consecutive entries (code word kk of lane l at kk*32 + l, lists padded with the index of a zero) : no per-entry
+// offsets, 128-byte loads.  Same owner-gather as before: no atomics on doubles, fixed order, bit-reproducible.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int KMAX = 7;          // elements per fan (8 ring vertices)
+constexpr int NVAL_CAP = 20000;  // value slots per tile
+constexpr int FHDR = 16;
+// tile blob v2 (32-bit words): header [0 nr, 1 nvt, 2 nfan, 3 nq, 4 ngf (fan groups), 5 nge (entry groups), 6 nvals,
+//   7 o_gbase, 8 o_rinfo, 9 o_coord, 10 o_fans, 11 o_fgrp, 12 o_egrp, 13 o_erow, 14 o_codes, 15 words]
+//   HEAD (copied to shared memory): header, gbase[nr], rinfo[nr], fgrp[ngf] (first value slot | kmax << 16),
+//        egrp[nge+1] (first code word of the group), coord[3 nvt] doubles
+//   then, read from global memory: fans[nfan] uint4, erow[nq] bytes, codes
+
+// elements of a run (all share the axis) -> arcs of <= KMAX elements, consecutive elements share a ring vertex
+struct FanOut {
+    uint32_t *rec; // 4 words per fan
+    int *count;
+};
+__device__ void emit_fan(const FanOut &F, uint32_t p, uint32_t q, const uint32_t *ring, int k, uint32_t key16)
+{
+    const int idx = atomicAdd(F.count, 1);
+    if (idx >= NE_CAP) return;
+    uint32_t r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = i <= k ? ring[i] : 0u;
+    uint32_t *w = F.rec + 4 * idx;
+    w[0] = p | (q << 8) | (r[0] << 16) | (r[1] << 24);
+    w[1] = r[2] | (r[3] << 8) | (r[4] << 16) | (r[5] << 24);
+    w[2] = r[6] | (r[7] << 8) | ((uint32_t)k << 16);
+    w[3] = ((uint32_t)(KMAX - k) << 24) | (key16 << 8) | r[0]; // sort key: longest first, then axis, then first ring vertex
+}
+
+template <int WRITE>
+__global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restrict__ rord, const int32_t *__restrict__ tstart,
+                                                          const int32_t *__restrict__ conn, const IncView V,
+                                                          const double *__restrict__ xyz, int vstride,
+                                                          const int32_t *__restrict__ nrowptr, int32_t *__restrict__ stats,
+                                                          const uint32_t *__restrict__ foff, uint32_t *__restrict__ fblob)
+{
+    extern __shared__ uint32_t sm[];
+    const BuildScratch S = build_scratch(sm);
+    uint32_t *sbuf = S.sbuf, *telem = S.telem, *vlist = S.vlist, *bm = S.bm;
+    int *rowq = S.rowq, *cntq = S.cntq, *part = S.part, *rslot = S.rslot;
+    uint8_t *s2r = S.s2r;
+    uint32_t *frec = reinterpret_cast<uint32_t *>(S.tmp); // 4 words per fan (NE_CAP fans at most)
+    __shared__ int s_nf, s_bad, s_nvals;
+    const int t = blockIdx.x, tid = threadIdx.x;
+    const int r0 = tstart[t], nr = tstart[t + 1] - r0;
+    if (tid == 0) {
+        s_nf = 0;
+        s_bad = 0;
+        s_nvals = 0;
+    }
+    int nelem = 0, nvt = 0, nq = 0, nrec = 0, nfan = 0, ngf = 0, nge = 0, nvals = 0, ncw = 0;
+    int fit = tile_topology<4>(S, rord, r0, nr, conn, V, nelem, nvt, nq, nrec);
+    // the sort buffer (SORT_CAP = 8192 words), by use:
+    uint32_t *ekey = sbuf;          // [0, 2048): element sort keys; from F3 on: fan order (order[rank] = fan index)
+    uint32_t *fkey = sbuf + NE_CAP; // [2048, 4096): fan sort keys (F3 only)
+    uint32_t *skey = sbuf + NE_CAP; // [2048, 6144): entries sorted by decreasing list length: (63 - length) << 12 | entry (from F6 on)
+    int *egl = reinterpret_cast<int *>(sbuf + 6144);      // [6144, 6400): first code word of every entry group
+    int *fgt = reinterpret_cast<int *>(sbuf + 6400);      // [6400, 6464): fan groups: first value slot | kmax << 16
+    int *epos = reinterpret_cast<int *>(sm) + build_words(); // NQ_CAP+16: sorted position of every entry (extra scratch of this kernel)
+    int *cursor = epos + 4096;                               // NQ_CAP+16: fill cursors of the entries (F7 only)
+    static_assert(NE_CAP == 2048 && NQ_CAP + 1 <= 4096 && SORT_CAP >= 6464, "scratch layout of k_fan_build");
+    if (fit) {
+        // F1. axis of every element: its longest edge (ties: the smallest pair of global vertex ids, the same choice in
+        // every element around the edge)
+        for (int e = tid; e < nelem; e += TB_THREADS) {
+            const uint32_t w = telem[e];
+            uint32_t sl[4], gv[4];
+            double X[4][3];
+#pragma unroll
+            for (int a = 0; a < 4; ++a) {
+                sl[a] = (w >> (8 * a)) & 255u;
+                gv[a] = vlist[sl[a]];
+#pragma unroll
+                for (int c = 0; c < 3; ++c) X[a][c] = xyz[(size_t)gv[a] * vstride + c];
+            }
+            double best = -1.0;
+            uint32_t blo = 0, bhi = 0, bsl = 0;
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = a + 1; b < 4; ++b) {
+                    const int i0 = gv[a] < gv[b] ? a : b, i1 = gv[a] < gv[b] ? b : a; // canonical order: same rounding everywhere
+                    const double dx = X[i1][0] - X[i0][0], dy = X[i1][1] - X[i0][1], dz = X[i1][2] - X[i0][2];
+                    const double l2 = dx * dx + dy * dy + dz * dz;
+                    const uint32_t lo = gv[i0], hi = gv[i1];
+                    if (l2 > best || (l2 == best && (lo < blo || (lo == blo && hi < bhi)))) {
+                        best = l2;
+                        blo = lo;
+                        bhi = hi;
+                        bsl = (min(sl[a], sl[b]) << 8) | max(sl[a], sl[b]);
+                    }
+                }
+            ekey[e] = (bsl << 11) | (uint32_t)e;
+        }
+        int m = 32;
+        while (m < nelem) m <<= 1;
+        for (int x = nelem + tid; x < m; x += TB_THREADS) ekey[x] = 0xffffffffu;
+        __syncthreads();
+        blk_sort(ekey, m);
+        // F2. one thread per run of elements with the same axis: chains around the axis
+        const FanOut F{frec, &s_nf};
+        for (int x = tid; x < nelem; x += TB_THREADS) {
+            const uint32_t key16 = ekey[x] >> 11;
+            if (x > 0 && (ekey[x - 1] >> 11) == key16) continue;
+            const uint32_t p = key16 >> 8, q = key16 & 255u;
+            int y = x;
+            while (y < nelem && (ekey[y] >> 11) == key16) {
+                // chunk of at most 32 elements of the run
+                uint32_t ru[32], rv[32];
+                int mrun = 0;
+                while (y < nelem && mrun < 32 && (ekey[y] >> 11) == key16) {
+                    const uint32_t w = telem[ekey[y] & 2047u];
+                    uint32_t o[2];
+                    int no = 0;
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const uint32_t sa = (w >> (8 * a)) & 255u;
+                        if (sa != p && sa != q && no < 2) o[no++] = sa;
+                    }
+                    ru[mrun] = o[0];
+                    rv[mrun] = o[1];
+                    ++mrun;
+                    ++y;
+                }
+                uint32_t used = 0;
+                for (int i = 0; i < mrun; ++i) {
+                    if ((used >> i) & 1u) continue;
+                    // arc through element i: ring[h .. h+k], grown at both ends
+                    uint32_t ring[2 * KMAX + 2];
+                    int h = KMAX, k = 1;
+                    ring[h] = ru[i];
+                    ring[h + 1] = rv[i];
+                    used |= 1u << i;
+                    bool grown = true;
+                    while (grown && k < KMAX) {
+                        grown = false;
+                        for (int j = 0; j < mrun && k < KMAX; ++j) {
+                            if ((used >> j) & 1u) continue;
+                            const uint32_t tail = ring[h + k], head = ring[h];
+                            if (ru[j] == tail || rv[j] == tail) {
+                                ring[h + k + 1] = ru[j] == tail ? rv[j] : ru[j];
+                                ++k;
+                                used |= 1u << j;
+                                grown = true;
+                            } else if (ru[j] == head || rv[j] == head) {
+                                --h;
+                                ring[h] = ru[j] == head ? rv[j] : ru[j];
+                                ++k;
+                                used |= 1u << j;
+                                grown = true;
+                            }
+                        }
+                    }
+                    // canonical direction (the walk above depends on nothing but the sorted run, this is for the key)
+                    emit_fan(F, p, q, ring + h, k, key16);
+                }
+            }
+        }
+        __syncthreads();
+        nfan = s_nf;
+        if (nfan > NE_CAP) fit = 0;
+    }
+    if (fit) {
+        // F3. fans sorted by decreasing length (keys are unique: a vertex starts one arc of an axis at most ... if not,
+        // equal keys still land on distinct ranks below)
+        int m = 32;
+        while (m < nfan) m <<= 1;
+        for (int x = tid; x < m; x += TB_THREADS) fkey[x] = x < nfan ? frec[4 * x + 3] : 0xffffffffu;
+        __syncthreads();
+        blk_sort(fkey, m);
+        for (int x = tid; x < nfan; x += TB_THREADS) ekey[x] = 0xffffffffu; // order[rank] = fan index
+        __syncthreads();
+        for (int x = tid; x < nfan; x += TB_THREADS) {
+            int rk = bsearch_u32(fkey, nfan, frec[4 * x + 3]);
+            while (atomicCAS(&ekey[rk], 0xffffffffu, (uint32_t)x) != 0xffffffffu) ++rk; // equal keys (non-manifold input): next rank
+        }
+        __syncthreads();
+        // F4. value slots: fan of rank f = 32 G + lane, value j at vb[G] + 32 j + lane, 3 kmax(G) + 3 values per lane
+        ngf = (nfan + 31) >> 5;
+        if (tid == 0) {
+            int vb = 1; // slot 0 holds a zero (padding of the code lists)
+            for (int G = 0; G < ngf && G < 64; ++G) {
+                const int kmax = (int)((frec[4 * ekey[G * 32] + 2] >> 16) & 15u);
+                fgt[G] = vb | (kmax << 16);
+                vb += 32 * (3 * kmax + 3);
+                if (vb > 65535) break;
+            }
+            s_nvals = vb;
+        }
+        __syncthreads();
+        nvals = s_nvals;
+        if (nvals > NVAL_CAP || ngf > 64) fit = 0;
+    }
+    // every value of every fan contributes to the entries (row x, column y) and (row y, column x) of its edge x-y
+    auto for_contribs = [&](auto &&add) {
+        for (int f = tid; f < nfan; f += TB_THREADS) {
+            const uint32_t *w = frec + 4 * ekey[f];
+            const int G = f >> 5, lane = f & 31;
+            const int vb = fgt[G] & 0xffff, kmax = fgt[G] >> 16, K1 = kmax + 1;
+            const int k = (int)((w[2] >> 16) & 15u);
+            const uint32_t p = w[0] & 255u, q = (w[0] >> 8) & 255u;
+            const unsigned long long rr = (unsigned long long)(w[0] >> 16) | ((unsigned long long)w[1] << 16) |
+                                          ((unsigned long long)(w[2] & 0xffffu) << 48);
+            const int v0 = vb + lane;
+            add(p, q, v0);
+            for (int tt = 0; tt <= k; ++tt) {
+                const uint32_t r = (uint32_t)(rr >> (8 * tt)) & 255u;
+                add(p, r, v0 + 32 * (1 + tt));
+                add(q, r, v0 + 32 * (1 + K1 + tt));
+                if (tt < k) add(r, (uint32_t)(rr >> (8 * (tt + 1))) & 255u, v0 + 32 * (1 + 2 * K1 + tt));
+            }
+        }
+    };
+    if (fit) {
+        // F5. contributions per entry
+        for (int x = tid; x <= nq; x += TB_THREADS) cntq[x] = 0;
+        __syncthreads();
+        for_contribs([&](uint32_t x, uint32_t y, int) {
+            int l = s2r[x];
+            if (l != 255) atomicAdd(&cntq[rowq[l] + row_pos(bm, l, y)], 1);
+            l = s2r[y];
+            if (l != 255) atomicAdd(&cntq[rowq[l] + row_pos(bm, l, x)], 1);
+        });
+        __syncthreads();
+        // F6. entries sorted by decreasing list length, taken in groups of 32 (one warp): the group's lists are padded to
+        // the longest = the first one, rounded up to even (two 16-bit codes per word) - next to no padding
+        nge = (nq + 31) >> 5;
+        for (int x = tid; x < 4096; x += TB_THREADS) {
+            uint32_t key = 0xffffffffu;
+            if (x < nq) {
+                if (cntq[x] > 62) s_bad = 1;
+                key = ((uint32_t)(63 - min(cntq[x], 62)) << 12) | (uint32_t)x;
+            }
+            skey[x] = key;
+        }
+        __syncthreads();
+        blk_sort(skey, 4096);
+        for (int e = tid; e < nq; e += TB_THREADS) epos[skey[e] & 0xfffu] = e;
+        for (int g = tid; g <= nge; g += TB_THREADS) egl[g] = g < nge ? ((cntq[skey[g * 32] & 0xfffu] + 1) >> 1) * 32 : 0; // words
+        __syncthreads();
+        if (nge + 1 > 256) fit = 0;
+        else ncw = blk_scan(egl, nge + 1, part);
+        if (s_bad) fit = 0;
+    }
+    if (!WRITE) {
+        if (tid == 0) {
+            int32_t *st = stats + (size_t)t * 12;
+            st[0] = nvt; st[1] = nelem; st[2] = nq; st[3] = nfan; st[4] = fit; st[5] = nr; st[6] = nvals; st[7] = ncw; st[8] = ngf; st[9] = nge;
+        }
+        return;
+    }
+    if (!fit) return; // (the host only writes fan sets whose tiles all fit)
+    // F7. the blob
+    // part A (what the fans need): header, fan groups, coordinates, fan records.  part B (what the gather needs): header,
+    // row bases, row words, entry groups, entry words, codes.  Two bulk copies with their own barriers: A of the next tile
+    // is fetched while this tile's entries are summed, B of the next tile while its fans are evaluated.
+    uint32_t *gA = fblob + foff[t];
+    const int o_fgrp = FHDR, o_coord = o_fgrp + pad4(ngf), o_fans = o_coord + pad4(6 * nvt), wordsA = o_fans + 4 * nfan;
+    uint32_t *g = gA + wordsA; // part B: offsets below are relative to it
+    const int o_gbase = 8, o_rinfo = o_gbase + pad4(nr), o_egrp = o_rinfo + pad4(nr), o_einfo = o_egrp + pad4(nge + 1),
+              o_codes = o_einfo + pad4(nq), wordsB = o_codes + pad4(ncw);
+    if (tid == 0) {
+        gA[0] = nr; gA[1] = nvt; gA[2] = nfan; gA[3] = nq; gA[4] = ngf; gA[5] = nge; gA[6] = nvals; gA[7] = o_fgrp; gA[8] = o_coord;
+        gA[9] = o_fans; gA[10] = wordsA; gA[11] = wordsB; gA[12] = gA[13] = gA[14] = gA[15] = 0;
+        g[0] = nr; g[1] = nq; g[2] = nge; g[3] = o_gbase; g[4] = o_rinfo; g[5] = o_egrp; g[6] = o_einfo; g[7] = o_codes;
+    }
+    for (int l = tid; l < pad4(nr); l += TB_THREADS) {
+        g[o_gbase + l] = l < nr ? (uint32_t)nrowptr[rord[r0 + l]] : 0u;
+        uint32_t w = 0;
+        if (l < nr) {
+            const int L = rowq[l + 1] - rowq[l], sl = rslot[l];
+            const int pd = sl >= 0 ? row_pos(bm, l, (uint32_t)sl) : 0;
+            w = (uint32_t)rowq[l] | ((uint32_t)pd << 16) | ((uint32_t)L << 24);
+            // entry words, in sorted order: position in the row | local row << 8 | entry (CSR order) << 16 | diagonal << 31
+            for (int qq = rowq[l]; qq < rowq[l + 1]; ++qq) {
+                const int pos = qq - rowq[l];
+                g[o_einfo + epos[qq]] = (uint32_t)pos | ((uint32_t)l << 8) | ((uint32_t)qq << 16) | ((sl >= 0 && pos == pd) ? 0x80000000u : 0u);
+            }
+        }
+        g[o_rinfo + l] = w;
+    }
+    for (int x = nq + tid; x < pad4(nq); x += TB_THREADS) g[o_einfo + x] = 0x80000000u;
+    for (int x = tid; x < pad4(ngf); x += TB_THREADS) gA[o_fgrp + x] = x < ngf ? (uint32_t)fgt[x] : 0u;
+    for (int x = tid; x < pad4(nge + 1); x += TB_THREADS) g[o_egrp + x] = x <= nge ? (uint32_t)egl[x] : (uint32_t)ncw;
+    for (int x = tid; x < pad4(6 * nvt); x += TB_THREADS) {
+        uint32_t w = 0;
+        if (x < 6 * nvt) {
+            const int v = x / 6, c = (x % 6) >> 1;
+            const unsigned long long b = (unsigned long long)__double_as_longlong(xyz[(size_t)vlist[v] * vstride + c]);
+            w = (x & 1) ? (uint32_t)(b >> 32) : (uint32_t)b;
+        }
+        gA[o_coord + x] = w;
+    }
+    for (int f = tid; f < nfan; f += TB_THREADS) {
+        const uint32_t *w = frec + 4 * ekey[f];
+        gA[o_fans + 4 * f] = w[0];
+        gA[o_fans + 4 * f + 1] = w[1];
+        gA[o_fans + 4 * f + 2] = w[2];
+        gA[o_fans + 4 * f + 3] = 0u;
+    }
+    for (int x = tid; x < pad4(ncw); x += TB_THREADS) g[o_codes + x] = 0u;
+    for (int x = tid; x <= nq; x += TB_THREADS) cursor[x] = 0;
+    __syncthreads();
+    uint16_t *gc = reinterpret_cast<uint16_t *>(g + o_codes);
+    auto code_at = [&](int qq, int c) -> uint16_t & {
+        const int e = epos[qq];
+        return gc[2 * (egl[e >> 5] + (c >> 1) * 32 + (e & 31)) + (c & 1)];
+    };
+    for_contribs([&](uint32_t x, uint32_t y, int slot) {
+        int l = s2r[x];
+        if (l != 255) {
+            const int qq = rowq[l] + row_pos(bm, l, y);
+            code_at(qq, atomicAdd(&cursor[qq], 1)) = (uint16_t)slot;
+        }
+        l = s2r[y];
+        if (l != 255) {
+            const int qq = rowq[l] + row_pos(bm, l, x);
+            code_at(qq, atomicAdd(&cursor[qq], 1)) = (uint16_t)slot;
+        }
+    });
+    __syncthreads();
+    // every list in ascending order of the value slots: the summation order does not depend on the order of arrival
+    for (int qq = tid; qq < nq; qq += TB_THREADS) {
+        const int n = cntq[qq];
+        for (int x = 1; x < n; ++x) {
+            const uint16_t v = code_at(qq, x);
+            int y = x - 1;
+            while (y >= 0 && code_at(qq, y) > v) {
+                code_at(qq, y + 1) = code_at(qq, y);
+                --y;
+            }
+            code_at(qq, y + 1) = v;
+        }
+    }
+    __syncthreads();
+    // ... then, inside every half-warp of 16 (sorted) entries, re-ordered greedily so that the values read together (the
+    // k-th of each list) sit in distinct banks: bank of a 64-bit value = slot mod 16
+    for (int ge = tid * 16; ge < nq; ge += TB_THREADS * 16) {
+        const int maxn = cntq[skey[ge] & 0xfffu];
+        for (int k = 0; k < maxn; ++k) {
+            uint32_t usedb = 0;
+            for (int j = 0; j < 16 && ge + j < nq; ++j) {
+                const int qq = skey[ge + j] & 0xfffu, n = cntq[qq];
+                if (k >= n) continue;
+                int best = k;
+                for (int x = k; x < n; ++x) {
+                    if (!((usedb >> (code_at(qq, x) & 15u)) & 1u)) {
+                        best = x;
+                        break;
+                    }
+                }
+                const uint16_t c = code_at(qq, best);
+                code_at(qq, best) = code_at(qq, k);
+                code_at(qq, k) = c;
+                usedb |= 1u << (c & 15u);
+            }
+        }
+    }
+}
+
+struct FanSmem { // byte offsets of the shared-memory regions (part A of the descriptor at 0)
+    int bufB, vals, ent;
+};
+
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_asm_fans(const uint32_t *__restrict__ foff, const uint32_t *__restrict__ fhead,
+                                                            const uint32_t *__restrict__ fblob, int ntiles, double *__restrict__ out,
+                                                            int accumulate, double cw, const FanSmem S)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar[2]; // [0]: part A arrived, [1]: part B arrived
+    double *sV = reinterpret_cast<double *>(smem_raw + S.vals); // values of the fans (slot 0 = 0)
+    double *sE = reinterpret_cast<double *>(smem_raw + S.ent);  // off-diagonal sums of the tile's entries, CSR order
+    const uint32_t *sA = reinterpret_cast<const uint32_t *>(smem_raw);
+    const uint32_t *sB = reinterpret_cast<const uint32_t *>(smem_raw + S.bufB);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = THREADS / 32;
+    tile_mbar_init(mbar);
+    auto issueA = [&](int t) {
+        const uint32_t bytes = __ldg(fhead + t) * 4u;
+        tile_expect(smem_u32(&mbar[0]), bytes);
+        tile_bulk(smem_u32(smem_raw), fblob + __ldg(foff + t), bytes, smem_u32(&mbar[0]));
+    };
+    auto issueB = [&](int t) {
+        const uint32_t w0 = __ldg(foff + t), wa = __ldg(fhead + t), bytes = (__ldg(foff + t + 1) - w0 - wa) * 4u;
+        tile_expect(smem_u32(&mbar[1]), bytes);
+        tile_bulk(smem_u32(smem_raw + S.bufB), fblob + w0 + wa, bytes, smem_u32(&mbar[1]));
+    };
+    int t = blockIdx.x;
+    uint32_t ph = 0;
+    if (tid == 0) {
+        sV[0] = 0.0;
+        if (t < ntiles) {
+            issueA(t);
+            issueB(t);
+        }
+    }
+    for (; t < ntiles; t += gridDim.x, ph ^= 1) {
+        tile_wait(smem_u32(&mbar[0]), ph);
+        {
+            const int nfan = sA[2], ngf = sA[4];
+            const uint32_t *fgrp = sA + sA[7];
+            const double *coord = reinterpret_cast<const double *>(sA + sA[8]);
+            const uint4 *fans = reinterpret_cast<const uint4 *>(sA + sA[9]);
+            // ---- fans: every element of the tile once
+            for (int G = warp; G < ngf; G += NW) {
+                const int f = G * 32 + lane;
+                uint4 fw = make_uint4(0u, 0u, 0u, 0u);
+                if (f < nfan) fw = fans[f];
+                const uint32_t fg = fgrp[G];
+                const int kmax = (int)(fg >> 16), K1 = kmax + 1;
+                const int k = (int)((fw.z >> 16) & 15u);
+                double *v = sV + (fg & 0xffffu) + lane;
+                const unsigned long long rr = (unsigned long long)(fw.x >> 16) | ((unsigned long long)fw.y << 16) |
+                                              ((unsigned long long)(fw.z & 0xffffu) << 48);
+                const double *P = coord + 3 * (fw.x & 255u), *Q = coord + 3 * ((fw.x >> 8) & 255u), *R = coord + 3 * ((uint32_t)rr & 255u);
+                const double px = P[0], py = P[1], pz = P[2];
+                const double ax = Q[0] - px, ay = Q[1] - py, az = Q[2] - pz;
+                double bx = R[0] - px, by = R[1] - py, bz = R[2] - pz;
+                double cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx; // a x b
+                double accA = 0.0, carp = 0.0, carq = 0.0;
+                double *vp = v + 32, *vq = v + 32 * (1 + K1), *vr = v + 32 * (1 + 2 * K1);
+#pragma unroll 2
+                for (int tt = 0; tt < kmax; ++tt) {
+                    double K01 = 0.0, K02 = 0.0, K03 = 0.0, K12 = 0.0, K13 = 0.0, K23 = 0.0;
+                    if (tt < k) {
+                        const double *R1 = coord + 3 * ((uint32_t)(rr >> (8 * (tt + 1))) & 255u);
+                        const double ex = R1[0] - px, ey = R1[1] - py, ez = R1[2] - pz; // the new ring vertex
+                        const double fx = ay * ez - az * ey, fy = az * ex - ax * ez, fz = ax * ey - ay * ex; // a x e
+                        // element (p, q, r_t, r_t+1): N1 = b x e, N2 = e x a = -(a x e), N3 = a x b, N0 = -(N1 + N2 + N3)
+                        const double n1x = by * ez - bz * ey, n1y = bz * ex - bx * ez, n1z = bx * ey - by * ex;
+                        const double det = ax * n1x + ay * n1y + az * n1z;
+                        const double n0x = fx - n1x - cx, n0y = fy - n1y - cy, n0z = fz - n1z - cz;
+                        const double s = cw * tile_rcp(fabs(det));
+                        K01 = s * (n0x * n1x + n0y * n1y + n0z * n1z);
+                        K02 = -s * (n0x * fx + n0y * fy + n0z * fz);
+                        K03 = s * (n0x * cx + n0y * cy + n0z * cz);
+                        K12 = -s * (n1x * fx + n1y * fy + n1z * fz);
+                        K13 = s * (n1x * cx + n1y * cy + n1z * cz);
+                        K23 = -s * (fx * cx + fy * cy + fz * cz);
+                        bx = ex; by = ey; bz = ez;
+                        cx = fx; cy = fy; cz = fz;
+                    }
+                    accA += K01;
+                    vp[32 * tt] = carp + K02; // spoke p - r_t: elements t-1 and t
+                    carp = K03;
+                    vq[32 * tt] = carq + K12; // spoke q - r_t
+                    carq = K13;
+                    vr[32 * tt] = K23;        // ring edge r_t - r_t+1
+                }
+                vp[32 * kmax] = carp;
+                vq[32 * kmax] = carq;
+                v[0] = accA;
+            }
+        }
+        __syncthreads(); // the values are complete; part A is free
+        if (tid == 0 && t + (int)gridDim.x < ntiles) issueA(t + gridDim.x);
+        tile_wait(smem_u32(&mbar[1]), ph);
+        const int nr = sB[0], nq = sB[1], nge = sB[2];
+        const int32_t *gbase = reinterpret_cast<const int32_t *>(sB + sB[3]);
+        const uint32_t *rinfo = sB + sB[4];
+        const uint32_t *egrp = sB + sB[5];
+        const uint32_t *einfo = sB + sB[6];
+        const uint32_t *codes = sB + sB[7];
+        // ---- entries, sorted by list length: 32 per warp, transposed code lists; the sums go to their place in the CSR
+        // rows (global memory) and to sE in CSR order (row sums for the diagonals)
+        for (int g = warp; g < nge; g += NW) {
+            const int e = g * 32 + lane;
+            const uint32_t w0 = egrp[g], nk = (egrp[g + 1] - w0) >> 5;
+            const uint32_t *cp = codes + w0 + lane;
+            double acc = 0.0;
+#pragma unroll 1
+            for (uint32_t kk = 0; kk < nk; ++kk) {
+                const uint32_t c = cp[kk * 32];
+                acc += sV[c & 0xffffu];
+                acc += sV[c >> 16];
+            }
+            if (e < nq) {
+                const uint32_t info = einfo[e];
+                sE[(info >> 16) & 0xfffu] = acc;
+                if (!(info >> 31)) {
+                    double *dst = out + (size_t)gbase[(info >> 8) & 255u] + (info & 255u);
+                    *dst = accumulate ? *dst + acc : acc;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- diagonals: K_ii = -sum_{j != i} K_ij (partition of unity)
+        for (int l = tid; l < nr; l += THREADS) {
+            const uint32_t ri = rinfo[l];
+            const int q0 = ri & 0xffffu, L = ri >> 24;
+            if (L == 0) continue;
+            double sx = 0.0;
+            for (int kq = 0; kq < L; ++kq) sx += sE[q0 + kq];
+            double *dst = out + (size_t)gbase[l] + ((ri >> 16) & 255u);
+            *dst = accumulate ? *dst - sx : -sx;
+        }
+        __syncthreads(); // part B, sV and sE are free again
+        if (tid == 0 && t + (int)gridDim.x < ntiles) issueB(t + gridDim.x);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host: tile set construction
 // ---------------------------------------------------------------------------------------------------------------
 size_t build_shmem()
@@ -900,6 +1475,8 @@ void chunk_rows(const std::vector<uint32_t> &key, int dim, int tr, std::vector<i
     }
     if (tstart.back() != n) tstart.push_back(n);
 }
+
+void build_fans(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr, const int32_t *d_rord, const int32_t *d_tstart, int ntiles);
 
 void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr)
 {
@@ -1025,11 +1602,74 @@ void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr)
     T.tr = tr;
     T.ntiles = ntiles;
     T.state = 1;
+    build_fans(ctx, s, nrowptr, rord.p, d_tstart.p, ntiles);
     if (getenv("FFCUDA_VERBOSE"))
         fprintf(stderr, "ffcuda tiles: %d tiles of <= %d rows, max rows %d vertices %d elements %d entries %d codes %d, "
                         "%.2f evaluations per element, blobs %.1f + %.1f MB\n",
                 ntiles, tr, T.max_rows, T.max_nvt, T.max_nelem, T.max_nq, T.max_ncodes, (double)T.sum_nelem / std::max(1, m->nt),
                 off * 4.0 / 1e6, roffs * 4.0 / 1e6);
+}
+
+// fan set of a 3-D scalar P1 space on the tiles of the tile set (same rows per tile); T.fan_state = 1 when every tile fits
+void build_fans(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr, const int32_t *d_rord, const int32_t *d_tstart, int ntiles)
+{
+    TileSet &T = s->tiles;
+    T.fan_state = -1;
+    ffcuda_mesh *m = s->mesh;
+    if (m->dim != 3 || ctx->tile_fans == 0) return;
+    cudaStream_t st = ctx->stream;
+    const size_t shmem = (size_t)4 * (build_words() + 2 * 4096);
+    FF_CUDA(cudaFuncSetAttribute(k_fan_build<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    FF_CUDA(cudaFuncSetAttribute(k_fan_build<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    const IncView V = ff_view(s->incidence);
+    DBuf<int32_t> d_stats;
+    d_stats.alloc((size_t)ntiles * 12);
+    ff_launch(ctx, "fan_sizes", [&] {
+        k_fan_build<0><<<ntiles, TB_THREADS, shmem, st>>>(d_rord, d_tstart, m->conn.p, V, m->xyz.p, m->vstride, nrowptr, d_stats.p, nullptr, nullptr);
+    });
+    std::vector<int32_t> hst((size_t)ntiles * 12);
+    FF_CUDA(ff_memcpy_sync(ctx, hst.data(), d_stats.p, hst.size() * 4, cudaMemcpyDeviceToHost));
+    std::vector<uint32_t> hoff((size_t)ntiles + 1), hhead((size_t)ntiles + 1, 0);
+    uint64_t off = 0;
+    T.fan_max_head = T.fan_max_b = T.fan_max_nvals = T.fan_max_nq = 0;
+    T.fan_sum_fans = 0;
+    int64_t sum_vals = 0, sum_cw = 0;
+    for (int t = 0; t < ntiles; ++t) {
+        const int32_t *h = &hst[(size_t)t * 12];
+        const int nvt = h[0], nq = h[2], nfan = h[3], fit = h[4], nr = h[5], nvals = h[6], ncw = h[7], ngf = h[8], nge = h[9];
+        if (!fit) return; // some tile exceeds a capacity: the round-1 tile kernel keeps the space
+        const int head = FHDR + pad4(ngf) + pad4(6 * nvt) + 4 * nfan;                               // part A
+        const int wordsB = 8 + 2 * pad4(nr) + pad4(nge + 1) + pad4(nq) + pad4(ncw);                     // part B
+        const int words = head + wordsB;
+        T.fan_max_b = std::max(T.fan_max_b, wordsB);
+        hoff[t] = (uint32_t)off;
+        hhead[t] = (uint32_t)head;
+        off += (uint64_t)words;
+        T.fan_max_head = std::max(T.fan_max_head, head);
+        T.fan_max_nvals = std::max(T.fan_max_nvals, nvals);
+        T.fan_max_nq = std::max(T.fan_max_nq, nq);
+        T.fan_sum_fans += nfan;
+        sum_vals += nvals;
+        sum_cw += ncw;
+    }
+    if (off >= ((uint64_t)1 << 32)) return;
+    hoff[ntiles] = (uint32_t)off;
+    T.foff.alloc((size_t)ntiles + 1);
+    T.fhead.alloc((size_t)ntiles + 1);
+    T.fblob.alloc((size_t)off + 4);
+    FF_CUDA(cudaMemcpyAsync(T.foff.p, hoff.data(), hoff.size() * 4, cudaMemcpyHostToDevice, st));
+    FF_CUDA(cudaMemcpyAsync(T.fhead.p, hhead.data(), hhead.size() * 4, cudaMemcpyHostToDevice, st));
+    ff_launch(ctx, "fan_build", [&] {
+        k_fan_build<1><<<ntiles, TB_THREADS, shmem, st>>>(d_rord, d_tstart, m->conn.p, V, m->xyz.p, m->vstride, nrowptr, nullptr, T.foff.p, T.fblob.p);
+    });
+    FF_CUDA(cudaStreamSynchronize(st)); // hoff / hhead are host vectors
+    T.fan_state = 1;
+    if (getenv("FFCUDA_VERBOSE"))
+        fprintf(stderr, "ffcuda fans: %lld fans for %lld element evaluations (%.2f per fan), %.2f values and %.2f code words per row, "
+                        "max part A %d words, part B %d words, max values %d, blob %.1f MB\n",
+                (long long)T.fan_sum_fans, (long long)T.sum_nelem, (double)T.sum_nelem / std::max<int64_t>(1, T.fan_sum_fans),
+                (double)sum_vals / std::max(1, s->nnodes_owned), (double)sum_cw / std::max(1, s->nnodes_owned), T.fan_max_head, T.fan_max_b,
+                T.fan_max_nvals, off * 4.0 / 1e6);
 }
 
 } // namespace
@@ -1074,6 +1714,30 @@ bool ff_asm_p1_tiles(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, double 
     ffcuda_mesh *m = s->mesh;
     const int dim = m->dim;
     const bool mass = (cmd != 0.0 || cmo != 0.0);
+    if (!mass && dim == 3 && T.fan_state == 1 && ctx->tile_fans != 0) {
+        FanSmem FS;
+        size_t o = ((size_t)T.fan_max_head * 4 + 127) & ~(size_t)127;
+        FS.bufB = (int)o;
+        o += ((size_t)T.fan_max_b * 4 + 127) & ~(size_t)127;
+        FS.vals = (int)o; // 128-byte aligned: the bank of a value is its slot mod 16 (the build kernel orders the lists by it)
+        o += ((size_t)T.fan_max_nvals * 8 + 127) & ~(size_t)127;
+        FS.ent = (int)o;
+        o += (size_t)(T.fan_max_nq + 1) * 8;
+        const size_t shmem = o;
+        if (shmem <= 200 * 1024) {
+            int threads = 128;
+            if (const char *e = getenv("FFCUDA_FAN_THREADS")) threads = atoi(e);
+            auto runf = [&](auto kern, int thr) {
+                tile_launch(ctx, "asm_rows_p1", kern, thr, shmem, T.ntiles, [&](int grid) {
+                    kern<<<grid, thr, shmem, ctx->stream>>>(T.foff.p, T.fhead.p, T.fblob.p, T.ntiles, A->vals.p, accumulate, cw, FS);
+                });
+            };
+            if (threads == 256) runf(k_asm_fans<256, 2>, 256);
+            else if (threads == 64) runf(k_asm_fans<64, 8>, 64);
+            else runf(k_asm_fans<128, 4>, 128);
+            return true;
+        }
+    }
     const int NP = dim * (dim + 1) / 2;
     TileSmem S;
     size_t o = ((size_t)T.max_words * 4 + 127) & ~(size_t)127;

@@ -1,0 +1,73 @@
+#!/usr/bin/env python3
+"""Quick check + timing of the fan tile kernel: parity vs the oracle on small cubes, timing on cube(n).
+usage: python tools/fan_check.py [n=128] [small_only]"""
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "freefem-sources_b200"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import numpy as np  # noqa: E402
+import ffcuda  # noqa: E402
+import ff_cases as fc  # noqa: E402
+import oracle_lib as ol  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+ctx = ffcuda.Context(0)
+ctx.set_option("tile_policy", 2)
+qp, qw = ffcuda.quadrature(3, 6)
+for size in [(1, 1, 1), (2, 3, 1), (5, 4, 6), (11, 9, 13), (24, 24, 24)]:
+    for rows in (96, 32, 256):
+        ctx.set_option("tile_rows", rows)
+        m = ol.cube(*size)
+        N = m["xyz"].shape[0]
+        ci, cj, ca = ol.assemble_coo(m, 1, 1, None, fc.LAP3, qp, qw)
+        orp, ocol, oval = ol.coo_to_csr(N, ci, cj, ca)
+        mesh = ctx.mesh_cube(*size)
+        sp = mesh.space(1, 1)
+        pat = sp.symbolic()
+        A = pat.matrix()
+        A.assemble(fc.LAP3, qp, qw)
+        val = A.download()
+        rp, col = pat.download()
+        assert np.array_equal(rp, orp) and np.array_equal(col, ocol)
+        err = np.max(np.abs(val - oval)) / np.abs(oval).max()
+        A.assemble(fc.LAP3, qp, qw)
+        same = np.array_equal(A.download(), val)
+        print(f"cube{size} rows={rows}: rel err {err:.2e} reproducible={same}", flush=True)
+        assert err <= 1e-12 and same
+if len(sys.argv) > 2:
+    sys.exit(0)
+ctx.set_option("tile_rows", int(os.environ.get("ROWS", "96")))
+mesh = ctx.mesh_cube(n, n, n)
+sp = mesh.space(1, 1)
+pat = sp.symbolic()
+A = pat.matrix()
+t0 = time.time()
+A.assemble(fc.LAP3, qp, qw)
+ctx.sync()
+print(f"first assembly incl. tile+fan build: {time.time() - t0:.3f} s", flush=True)
+ctx.prof_enable(True)
+ctx.prof_reset()
+for _ in range(10):
+    A.assemble(fc.LAP3, qp, qw)
+ctx.sync()
+ms, cnt = ctx.prof_get("asm_rows_p1")
+nv, nt = mesh.info()[1], mesh.info()[2]
+N, nnz = pat.info()
+B = 16.0 * nt + 24.0 * nv + 12.0 * nnz + 4.0 * (N + 1)
+print(f"asm_rows_p1: {ms / cnt:.4f} ms per launch, {B / (ms / cnt * 1e-3) / 1e9:.0f} GB/s algorithmic, frac {B / (ms / cnt * 1e-3) / 1e9 / 6454.3:.3f}")
+import scipy.sparse as sps  # noqa: E402
+
+rp, col = pat.download()
+M = sps.csr_matrix((A.download(), col, rp), shape=(N, N))
+print("row sums", np.max(np.abs(M @ np.ones(N))), "sym", abs(M - M.T).max())
+ctx.set_option("tile_fans", 0)
+ctx.prof_reset()
+A2 = pat.matrix()
+for _ in range(5):
+    A2.assemble(fc.LAP3, qp, qw)
+ctx.sync()
+ms, cnt = ctx.prof_get("asm_rows_p1")
+print(f"round-1 tile kernel: {ms / cnt:.4f} ms; max diff vs fans {np.max(np.abs(A2.download() - A.download())):.3e}")
