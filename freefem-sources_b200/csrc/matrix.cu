@@ -262,6 +262,155 @@ extern "C" int ffcuda_matrix_upload(ffcuda_matrix *A, const double *vals)
     FF_API_END(A ? A->ctx : nullptr)
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Hand-off formats straight from the device CSR: borrowed device pointers for consumers that
+// stay on the GPU (PETSc's MatCreateSeqAIJCUSPARSE-style constructors take exactly these three arrays), the COO triple
+// of `[I,J,C] = A` (fflib/lgmat.cpp) with the row indices expanded on the device, and FreeFEM's Morse text format
+// (`ofstream << A` after A.CSR, femlib/HashMatrix.hpp:485-508; read back by HashMatrix(istream&), HashMatrix.cpp:137-188).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+__global__ void k_expand_rows(const int32_t *__restrict__ rowptr, int n, int32_t *__restrict__ rows, int base)
+{
+    // one warp per row: rows[rowptr[i] .. rowptr[i+1]) = i
+    const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (w >= n) return;
+    const int b = rowptr[w], e = rowptr[w + 1];
+    for (int k = b + lane; k < e; k += 32) rows[k] = w + base;
+}
+__global__ void k_shift_i32(const int32_t *__restrict__ in, int64_t n, int base, int32_t *__restrict__ out)
+{
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i] + base;
+}
+} // namespace
+
+extern "C" int ffcuda_matrix_export_device(ffcuda_matrix *A, const int32_t **d_rowptr, const int32_t **d_colind, const double **d_vals,
+                                           int *n, int64_t *nnz)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A && d_rowptr && d_colind && d_vals, "null argument");
+    ff_enter(A->ctx);
+    ff_matrix_touch(A);
+    *d_rowptr = A->rowptr;
+    *d_colind = ff_matrix_colind(A);
+    *d_vals = A->vals.p;
+    if (n) *n = A->n;
+    if (nnz) *nnz = A->nnz;
+    FF_CUDA(cudaStreamSynchronize(A->ctx->stream)); // the arrays are final when the call returns (any stream may read them)
+    FF_API_END(A ? A->ctx : nullptr)
+}
+
+extern "C" int ffcuda_matrix_download_coo(ffcuda_matrix *A, int32_t *I, int32_t *J, double *C, int index_base)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A && I && J && C, "null argument");
+    FF_REQUIRE(index_base == 0 || index_base == 1, "index_base must be 0 or 1");
+    ffcuda_ctx *ctx = A->ctx;
+    ff_enter(ctx);
+    ff_matrix_touch(A);
+    const int32_t *colind = ff_matrix_colind(A);
+    DBuf<int32_t> rows, cols;
+    rows.alloc((size_t)std::max<int64_t>(A->nnz, 1));
+    ff_launch(ctx, "export_rows", [&] {
+        k_expand_rows<<<ff_blocks((size_t)A->n * 32, 256), 256, 0, ctx->stream>>>(A->rowptr, A->n, rows.p, index_base);
+    });
+    const int32_t *jsrc = colind;
+    if (index_base) {
+        cols.alloc((size_t)std::max<int64_t>(A->nnz, 1));
+        ff_launch(ctx, "export_cols", [&] { k_shift_i32<<<ff_blocks((size_t)A->nnz, 256), 256, 0, ctx->stream>>>(colind, A->nnz, 1, cols.p); });
+        jsrc = cols.p;
+    }
+    FF_CUDA(cudaMemcpyAsync(I, rows.p, (size_t)A->nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FF_CUDA(cudaMemcpyAsync(J, jsrc, (size_t)A->nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    FF_CUDA(cudaMemcpyAsync(C, A->vals.p, (size_t)A->nnz * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FF_CUDA(cudaStreamSynchronize(ctx->stream));
+    FF_API_END(A ? A->ctx : nullptr)
+}
+
+extern "C" int ffcuda_matrix_write_morse(ffcuda_matrix *A, const char *path, int half)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A && path, "null argument");
+    ffcuda_ctx *ctx = A->ctx;
+    ff_enter(ctx);
+    ff_matrix_touch(A);
+    const int32_t *colind = ff_matrix_colind(A);
+    FILE *f = fopen(path, "w");
+    FF_REQUIRE(f != nullptr, std::string("cannot open ") + path);
+    // chunks of rows through pinned staging buffers: the next chunk is copied while this one is formatted
+    std::vector<int32_t> rp((size_t)A->n + 1);
+    FF_CUDA(ff_memcpy_sync(ctx, rp.data(), A->rowptr, rp.size() * 4, cudaMemcpyDeviceToHost));
+    int64_t nnz_out = A->nnz;
+    if (half) { // entries (i, j <= i) only, as FreeFEM stores a symmetric matrix
+        nnz_out = 0;
+    }
+    const int64_t CH = (int64_t)1 << 22;
+    int32_t *hj[2] = {nullptr, nullptr};
+    double *hv[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    std::string err;
+    try {
+        for (int b = 0; b < 2; ++b) {
+            FF_CUDA(cudaMallocHost((void **)&hj[b], (size_t)CH * 4));
+            FF_CUDA(cudaMallocHost((void **)&hv[b], (size_t)CH * 8));
+            FF_CUDA(cudaEventCreateWithFlags(&ev[b], cudaEventDisableTiming));
+        }
+        if (half) { // count first (columns are sorted: the prefix of every row up to the diagonal)
+            for (int64_t k0 = 0; k0 < A->nnz; k0 += CH) {
+                const int64_t m = std::min(CH, A->nnz - k0);
+                FF_CUDA(ff_memcpy_sync(ctx, hj[0], colind + k0, (size_t)m * 4, cudaMemcpyDeviceToHost));
+                int row = (int)(std::upper_bound(rp.begin(), rp.end(), (int32_t)k0) - rp.begin()) - 1;
+                for (int64_t k = 0; k < m; ++k) {
+                    while (k0 + k >= rp[(size_t)row + 1]) ++row;
+                    if (hj[0][k] <= row) ++nnz_out;
+                }
+            }
+        }
+        fprintf(f, "# Sparse Matrix (Morse)  %p\n# first line: n m (is symmetic) nnz \n"
+                   "# after for each nonzero coefficient:   i j a_ij where (i,j) \\in  {1,...,n}x{1,...,m} \n",
+                (void *)A);
+        fprintf(f, "%d %d %d  %lld\n", A->n, A->ncols > 0 && !A->pattern ? A->ncols : A->n, half ? 1 : 0, (long long)nnz_out);
+        auto fetch = [&](int b, int64_t k0) {
+            const int64_t m = std::min(CH, A->nnz - k0);
+            FF_CUDA(cudaMemcpyAsync(hj[b], colind + k0, (size_t)m * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            FF_CUDA(cudaMemcpyAsync(hv[b], A->vals.p + k0, (size_t)m * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            FF_CUDA(cudaEventRecord(ev[b], ctx->stream));
+        };
+        if (A->nnz > 0) fetch(0, 0);
+        int b = 0, row = 0;
+        std::vector<char> line((size_t)1 << 20);
+        for (int64_t k0 = 0; k0 < A->nnz; k0 += CH, b ^= 1) {
+            if (k0 + CH < A->nnz) fetch(b ^ 1, k0 + CH);
+            FF_CUDA(cudaEventSynchronize(ev[b]));
+            const int64_t m = std::min(CH, A->nnz - k0);
+            size_t pos = 0;
+            for (int64_t k = 0; k < m; ++k) {
+                while (k0 + k >= rp[(size_t)row + 1]) ++row;
+                if (half && hj[b][k] > row) continue;
+                const double v = std::fabs(hv[b][k]) < 1e-305 ? 0.0 : hv[b][k]; // RNM::removeeps
+                pos += (size_t)snprintf(line.data() + pos, 80, "%9d %9d %.20g\n", row + 1, hj[b][k] + 1, v);
+                if (pos + 128 > line.size()) {
+                    fwrite(line.data(), 1, pos, f);
+                    pos = 0;
+                }
+            }
+            fwrite(line.data(), 1, pos, f);
+        }
+    } catch (const std::exception &e) {
+        err = e.what();
+    }
+    for (int b = 0; b < 2; ++b) {
+        if (hj[b]) cudaFreeHost(hj[b]);
+        if (hv[b]) cudaFreeHost(hv[b]);
+        if (ev[b]) cudaEventDestroy(ev[b]);
+    }
+    const bool bad = ferror(f) != 0;
+    fclose(f);
+    if (!err.empty()) throw FFError(err);
+    FF_REQUIRE(!bad, std::string("error while writing ") + path);
+    FF_API_END(A ? A->ctx : nullptr)
+}
+
 extern "C" void ffcuda_matrix_destroy(ffcuda_matrix *A)
 {
     if (!A) return;

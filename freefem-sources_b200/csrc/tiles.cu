@@ -1123,13 +1123,16 @@ __global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restr
             const uint32_t p = w[0] & 255u, q = (w[0] >> 8) & 255u;
             const unsigned long long rr = (unsigned long long)(w[0] >> 16) | ((unsigned long long)w[1] << 16) |
                                           ((unsigned long long)(w[2] & 0xffffu) << 48);
-            const int v0 = vb + lane;
-            add(p, q, v0);
+            // value j of the fan in lane l sits at vb + 32 j + ((l + j) & 31): a warp store is a permutation of 32 consecutive
+            // doubles (no bank conflict), and the values of ONE fan fall in different banks (the entries of a row that
+            // read them together do not collide)
+            auto slot = [&](int j) { return vb + 32 * j + ((lane + j) & 31); };
+            add(p, q, slot(0));
             for (int tt = 0; tt <= k; ++tt) {
                 const uint32_t r = (uint32_t)(rr >> (8 * tt)) & 255u;
-                add(p, r, v0 + 32 * (1 + tt));
-                add(q, r, v0 + 32 * (1 + K1 + tt));
-                if (tt < k) add(r, (uint32_t)(rr >> (8 * (tt + 1))) & 255u, v0 + 32 * (1 + 2 * K1 + tt));
+                add(p, r, slot(1 + tt));
+                add(q, r, slot(1 + K1 + tt));
+                if (tt < k) add(r, (uint32_t)(rr >> (8 * (tt + 1))) & 255u, slot(1 + 2 * K1 + tt));
             }
         }
     };
@@ -1203,7 +1206,9 @@ __global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restr
     }
     for (int x = nq + tid; x < pad4(nq); x += TB_THREADS) g[o_einfo + x] = 0x80000000u;
     for (int x = tid; x < pad4(ngf); x += TB_THREADS) gA[o_fgrp + x] = x < ngf ? (uint32_t)fgt[x] : 0u;
-    for (int x = tid; x < pad4(nge + 1); x += TB_THREADS) g[o_egrp + x] = x <= nge ? (uint32_t)egl[x] : (uint32_t)ncw;
+    // entry groups: first code word | code words per lane << 24
+    for (int x = tid; x < pad4(nge + 1); x += TB_THREADS)
+        g[o_egrp + x] = x < nge ? ((uint32_t)egl[x] | ((uint32_t)((egl[x + 1] - egl[x]) >> 5) << 24)) : (uint32_t)ncw;
     for (int x = tid; x < pad4(6 * nvt); x += TB_THREADS) {
         uint32_t w = 0;
         if (x < 6 * nvt) {
@@ -1332,7 +1337,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_asm_fans(const uint32_t *__re
                 const uint32_t fg = fgrp[G];
                 const int kmax = (int)(fg >> 16), K1 = kmax + 1;
                 const int k = (int)((fw.z >> 16) & 15u);
-                double *v = sV + (fg & 0xffffu) + lane;
+                double *v = sV + (fg & 0xffffu); // value j of this lane at v[32 j + ((lane + j) & 31)]
                 const unsigned long long rr = (unsigned long long)(fw.x >> 16) | ((unsigned long long)fw.y << 16) |
                                               ((unsigned long long)(fw.z & 0xffffu) << 48);
                 const double *P = coord + 3 * (fw.x & 255u), *Q = coord + 3 * ((fw.x >> 8) & 255u), *R = coord + 3 * ((uint32_t)rr & 255u);
@@ -1341,13 +1346,19 @@ __global__ void __launch_bounds__(THREADS, MINB) k_asm_fans(const uint32_t *__re
                 double bx = R[0] - px, by = R[1] - py, bz = R[2] - pz;
                 double cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx; // a x b
                 double accA = 0.0, carp = 0.0, carq = 0.0;
-                double *vp = v + 32, *vq = v + 32 * (1 + K1), *vr = v + 32 * (1 + 2 * K1);
+                int jp = 1, jq = 1 + K1, jr = 1 + 2 * K1;
+                // the coordinates of the next ring vertex are fetched one step ahead (slot 0 past the end: harmless)
+                const double *R1 = coord + 3 * ((uint32_t)(rr >> 8) & 255u);
+                double nx = R1[0], ny = R1[1], nz = R1[2];
 #pragma unroll 2
                 for (int tt = 0; tt < kmax; ++tt) {
                     double K01 = 0.0, K02 = 0.0, K03 = 0.0, K12 = 0.0, K13 = 0.0, K23 = 0.0;
+                    const double ex = nx - px, ey = ny - py, ez = nz - pz; // the new ring vertex
+                    {
+                        const double *R2 = coord + 3 * ((uint32_t)(rr >> (8 * min(tt + 2, 7))) & 255u);
+                        nx = R2[0]; ny = R2[1]; nz = R2[2];
+                    }
                     if (tt < k) {
-                        const double *R1 = coord + 3 * ((uint32_t)(rr >> (8 * (tt + 1))) & 255u);
-                        const double ex = R1[0] - px, ey = R1[1] - py, ez = R1[2] - pz; // the new ring vertex
                         const double fx = ay * ez - az * ey, fy = az * ex - ax * ez, fz = ax * ey - ay * ex; // a x e
                         // element (p, q, r_t, r_t+1): N1 = b x e, N2 = e x a = -(a x e), N3 = a x b, N0 = -(N1 + N2 + N3)
                         const double n1x = by * ez - bz * ey, n1y = bz * ex - bx * ez, n1z = bx * ey - by * ex;
@@ -1364,15 +1375,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_asm_fans(const uint32_t *__re
                         cx = fx; cy = fy; cz = fz;
                     }
                     accA += K01;
-                    vp[32 * tt] = carp + K02; // spoke p - r_t: elements t-1 and t
+                    v[32 * jp + ((lane + jp) & 31)] = carp + K02; // spoke p - r_t: elements t-1 and t
                     carp = K03;
-                    vq[32 * tt] = carq + K12; // spoke q - r_t
+                    v[32 * jq + ((lane + jq) & 31)] = carq + K12; // spoke q - r_t
                     carq = K13;
-                    vr[32 * tt] = K23;        // ring edge r_t - r_t+1
+                    v[32 * jr + ((lane + jr) & 31)] = K23;        // ring edge r_t - r_t+1
+                    ++jp; ++jq; ++jr;
                 }
-                vp[32 * kmax] = carp;
-                vq[32 * kmax] = carq;
-                v[0] = accA;
+                v[32 * jp + ((lane + jp) & 31)] = carp;
+                v[32 * jq + ((lane + jq) & 31)] = carq;
+                v[lane] = accA;
             }
         }
         __syncthreads(); // the values are complete; part A is free
@@ -1388,14 +1400,31 @@ __global__ void __launch_bounds__(THREADS, MINB) k_asm_fans(const uint32_t *__re
         // rows (global memory) and to sE in CSR order (row sums for the diagonals)
         for (int g = warp; g < nge; g += NW) {
             const int e = g * 32 + lane;
-            const uint32_t w0 = egrp[g], nk = (egrp[g + 1] - w0) >> 5;
-            const uint32_t *cp = codes + w0 + lane;
+            const uint32_t eg = egrp[g], nk = eg >> 24;
+            const uint32_t *cp = codes + (eg & 0xffffffu) + lane;
             double acc = 0.0;
+            // (lists are short - 1 to 3 words for most groups: the loads of a group are issued together, then added in
+            // list order)
+            if (nk == 1) {
+                const uint32_t c0 = cp[0];
+                const double v0 = sV[c0 & 0xffffu], v1 = sV[c0 >> 16];
+                acc = v0 + v1;
+            } else if (nk == 2) {
+                const uint32_t c0 = cp[0], c1 = cp[32];
+                const double v0 = sV[c0 & 0xffffu], v1 = sV[c0 >> 16], v2 = sV[c1 & 0xffffu], v3 = sV[c1 >> 16];
+                acc = ((v0 + v1) + v2) + v3;
+            } else if (nk == 3) {
+                const uint32_t c0 = cp[0], c1 = cp[32], c2 = cp[64];
+                const double v0 = sV[c0 & 0xffffu], v1 = sV[c0 >> 16], v2 = sV[c1 & 0xffffu], v3 = sV[c1 >> 16], v4 = sV[c2 & 0xffffu],
+                             v5 = sV[c2 >> 16];
+                acc = ((((v0 + v1) + v2) + v3) + v4) + v5;
+            } else {
 #pragma unroll 1
-            for (uint32_t kk = 0; kk < nk; ++kk) {
-                const uint32_t c = cp[kk * 32];
-                acc += sV[c & 0xffffu];
-                acc += sV[c >> 16];
+                for (uint32_t kk = 0; kk < nk; ++kk) {
+                    const uint32_t c = cp[kk * 32];
+                    acc += sV[c & 0xffffu];
+                    acc += sV[c >> 16];
+                }
             }
             if (e < nq) {
                 const uint32_t info = einfo[e];
@@ -1734,7 +1763,7 @@ bool ff_asm_p1_tiles(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, double 
             };
             if (threads == 256) runf(k_asm_fans<256, 2>, 256);
             else if (threads == 64) runf(k_asm_fans<64, 8>, 64);
-            else runf(k_asm_fans<128, 4>, 128);
+            else runf(k_asm_fans<128, 5>, 128);
             return true;
         }
     }

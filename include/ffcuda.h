@@ -144,6 +144,20 @@ int ffcuda_matrix_info(ffcuda_matrix *A, int *n, int64_t *nnz);
 int ffcuda_matrix_download(ffcuda_matrix *A, double *vals /* nnz, CSR order */);
 int ffcuda_matrix_download_lower(ffcuda_matrix *A, double *vals); /* values of the lower triangle, see ffcuda_pattern_lower_nnz */
 int ffcuda_matrix_upload(ffcuda_matrix *A, const double *vals);
+/* ---- hand-off formats straight from the device CSR ----
+ * ffcuda_matrix_export_device: BORROWED device pointers to the CSR triple (int32 rowptr[n+1], int32 colind[nnz], fp64
+ *   vals[nnz]; valid until the matrix is destroyed or re-assembled): what a consumer that stays on the GPU takes, e.g.
+ *   PETSc's MatCreateSeqAIJCUSPARSE / MatSeqAIJCUSPARSESetPreallocationCSR-style constructors (the reference reaches
+ *   PETSc through host arrays, plugin/mpi/PETSc-code.hpp) - no host round trip.
+ * ffcuda_matrix_download_coo: the triple of `[I,J,C] = A` (fflib/lgmat.cpp), row indices expanded on the device, CSR order,
+ *   index_base 0 or 1.
+ * ffcuda_matrix_write_morse: FreeFEM's Morse text format, the output of `ofstream f; f << A` after `A.CSR`
+ *   (femlib/HashMatrix.hpp:485-508: header `n m half  nnz`, then `i j a_ij` 1-based, values with 20 digits), readable by
+ *   HashMatrix(istream&) (femlib/HashMatrix.cpp:137-188); half != 0 writes the entries (i, j <= i) only. */
+int ffcuda_matrix_export_device(ffcuda_matrix *A, const int32_t **d_rowptr, const int32_t **d_colind, const double **d_vals,
+                                int *n, int64_t *nnz);
+int ffcuda_matrix_download_coo(ffcuda_matrix *A, int32_t *I, int32_t *J, double *C, int index_base);
+int ffcuda_matrix_write_morse(ffcuda_matrix *A, const char *path, int half);
 void ffcuda_matrix_destroy(ffcuda_matrix *A);
 
 int ffcuda_vec_create(ffcuda_ctx *ctx, int n, ffcuda_vec **out); /* zeroed */
