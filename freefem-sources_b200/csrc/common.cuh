@@ -269,6 +269,7 @@ struct ffcuda_mesh {
     DBuf<int32_t> conn;       // nt*(dim+1)
     DBuf<int32_t> elab;       // nt
     DBuf<int32_t> bconn, blab, belem, bface;
+    DBuf<int32_t> adj;        // element adjacency (ffcuda_mesh_adjacency), built on first use
     // distributed (slab partition): local vertices [0,nv_owned) are owned, the rest are ghosts
     int nv_owned = 0;
     DBuf<int64_t> gid;        // global vertex id of each local vertex

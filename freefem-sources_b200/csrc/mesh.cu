@@ -2,6 +2,7 @@
 // cube / square meshes with FreeFEM's exact vertex, element and boundary-element ordering
 // (BuildCube fflib/msh3.cpp:7879-8132 with kind=6; Carre_ fflib/lgmesh.cpp:1229-1384 with flags=0).
 #include "common.cuh"
+#include <cub/device/device_radix_sort.cuh>
 #include <algorithm>
 #include <array>
 #include <memory>
@@ -471,6 +472,119 @@ extern "C" int ffcuda_mesh_download(ffcuda_mesh *m, double *xyz, int32_t *conn, 
     if (belem && m->nbe) FF_CUDA(cudaMemcpyAsync(belem, m->belem.p, m->belem.bytes(), cudaMemcpyDeviceToHost, st));
     if (bface && m->nbe) FF_CUDA(cudaMemcpyAsync(bface, m->bface.p, m->bface.bytes(), cudaMemcpyDeviceToHost, st));
     FF_CUDA(cudaStreamSynchronize(st));
+    FF_API_END(m ? m->ctx : nullptr)
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Element adjacency on the device: GenericMesh::BuildAdj (femlib/GenericMesh.hpp:837-930).  adj[nea*k + i] = nea*k' + i'
+// when face i of element k (the face opposite vertex i: nvfaceTet {3,2,1},{0,2,3},{3,1,0},{0,1,2}, femlib/Mesh3dn.cpp:72;
+// edges {1,2},{2,0},{0,1} of a triangle) is face i' of element k', -1 on the boundary, -2 for a face shared by more than
+// two elements (the reference breaks those lists the same way, :887-911).  The reference inserts every face in a hash
+// table one after the other; here: one 64-bit hash per face (of its sorted vertices), a radix sort of (hash, face), and
+// one thread per sorted position comparing the vertices themselves with its neighbours in the run (a hash collision
+// between different faces only makes the run longer).
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+template <int NV>
+__device__ __forceinline__ void face_verts(const int32_t *__restrict__ conn, int f, int (&v)[NV - 1])
+{
+    const int k = f / NV, i = f % NV;
+    int o = 0;
+#pragma unroll
+    for (int a = 0; a < NV; ++a)
+        if (a != i) v[o++] = conn[(size_t)k * NV + a];
+    // sorted
+#pragma unroll
+    for (int x = 0; x < NV - 1; ++x)
+#pragma unroll
+        for (int y = x + 1; y < NV - 1; ++y)
+            if (v[y] < v[x]) {
+                const int t = v[x];
+                v[x] = v[y];
+                v[y] = t;
+            }
+}
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x)
+{
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull; x ^= x >> 33;
+    return x;
+}
+template <int NV>
+__global__ void k_face_keys(const int32_t *__restrict__ conn, int nfaces, unsigned long long *__restrict__ key, int32_t *__restrict__ val)
+{
+    const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f >= nfaces) return;
+    int v[NV - 1];
+    face_verts<NV>(conn, f, v);
+    unsigned long long h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int x = 0; x < NV - 1; ++x) h = mix64(h ^ (unsigned long long)(unsigned)v[x]) + 0x632BE59BD9B4E019ull * (x + 1);
+    key[f] = h;
+    val[f] = f;
+}
+template <int NV>
+__global__ void k_face_match(const int32_t *__restrict__ conn, int nfaces, const unsigned long long *__restrict__ key,
+                             const int32_t *__restrict__ val, int32_t *__restrict__ adj)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= nfaces) return;
+    const int f = val[x];
+    int v[NV - 1];
+    face_verts<NV>(conn, f, v);
+    const unsigned long long h = key[x];
+    int mate = -1, nsame = 0;
+    // the run of equal hashes around x (length 1 or 2 on a manifold mesh)
+    int lo = x;
+    while (lo > 0 && key[lo - 1] == h) --lo;
+    for (int y = lo; y < nfaces && key[y] == h; ++y) {
+        if (y == x) continue;
+        int w[NV - 1];
+        face_verts<NV>(conn, val[y], w);
+        bool same = true;
+#pragma unroll
+        for (int c = 0; c < NV - 1; ++c) same = same && (w[c] == v[c]);
+        if (same) {
+            ++nsame;
+            mate = val[y];
+        }
+    }
+    adj[f] = nsame == 0 ? -1 : (nsame == 1 ? mate : -2);
+}
+} // namespace
+
+extern "C" int ffcuda_mesh_adjacency(ffcuda_mesh *m, int32_t *adj /* host, (dim+1)*nt, may be NULL */, const int32_t **d_adj /* may be NULL */)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(m, "null mesh");
+    ffcuda_ctx *ctx = m->ctx;
+    ff_enter(ctx);
+    cudaStream_t st = ctx->stream;
+    const int NV = m->dim + 1;
+    FF_REQUIRE((int64_t)m->nt * NV < ((int64_t)1 << 31), "too many faces for 32-bit face ids");
+    const int nf = m->nt * NV;
+    if (!m->adj.p && nf > 0) {
+        DBuf<unsigned long long> k0, k1;
+        DBuf<int32_t> v0, v1;
+        k0.alloc(nf); k1.alloc(nf); v0.alloc(nf); v1.alloc(nf);
+        m->adj.alloc(nf);
+        ff_launch(ctx, "adj_face_keys", [&] {
+            if (NV == 4) k_face_keys<4><<<ff_blocks(nf, 256), 256, 0, st>>>(m->conn.p, nf, k0.p, v0.p);
+            else k_face_keys<3><<<ff_blocks(nf, 256), 256, 0, st>>>(m->conn.p, nf, k0.p, v0.p);
+        });
+        size_t tb = 0;
+        FF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k0.p, k1.p, v0.p, v1.p, nf, 0, 64, st));
+        DBuf<unsigned char> tmp;
+        tmp.alloc(tb + 16);
+        ctx->launches++;
+        FF_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k0.p, k1.p, v0.p, v1.p, nf, 0, 64, st));
+        ff_launch(ctx, "adj_face_match", [&] {
+            if (NV == 4) k_face_match<4><<<ff_blocks(nf, 256), 256, 0, st>>>(m->conn.p, nf, k1.p, v1.p, m->adj.p);
+            else k_face_match<3><<<ff_blocks(nf, 256), 256, 0, st>>>(m->conn.p, nf, k1.p, v1.p, m->adj.p);
+        });
+    }
+    if (adj && nf > 0) FF_CUDA(cudaMemcpyAsync(adj, m->adj.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
+    FF_CUDA(cudaStreamSynchronize(st));
+    if (d_adj) *d_adj = m->adj.p;
     FF_API_END(m ? m->ctx : nullptr)
 }
 

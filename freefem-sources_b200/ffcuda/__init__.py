@@ -24,7 +24,7 @@ ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_
 ffcuda_assemble_linear ffcuda_assemble_linear_qvalues ffcuda_assemble_linear_qterms ffcuda_assemble_linear_boundary ffcuda_assemble_bilinear_boundary ffcuda_assemble_linear_boundary_qvalues ffcuda_assemble_bilinear_boundary_qcoef ffcuda_bc_from_pairs ffcuda_bc_from_labels ffcuda_bc_count ffcuda_matrix_apply_bc ffcuda_vec_apply_bc
 ffcuda_vec_set_bc_values ffcuda_bc_destroy ffcuda_spmv ffcuda_cg ffcuda_cg_host ffcuda_gmres ffcuda_gmres_host ffcuda_comm_unique_id ffcuda_comm_init
 ffcuda_comm_finalize ffcuda_mesh_cube_distributed ffcuda_mesh_local_to_global ffcuda_quadrature ffcuda_partition_cube
-ffcuda_partition_rcb ffcuda_partition_local""".split()
+ffcuda_partition_rcb ffcuda_partition_local ffcuda_matrix_export_device ffcuda_matrix_download_coo ffcuda_matrix_write_morse ffcuda_mesh_adjacency""".split()
 
 
 class FfcudaError(RuntimeError):
@@ -262,6 +262,13 @@ class Mesh(_Handle):
                                        _p(m["belem"]), _p(m["bface"])), self.ctx.h)
         return m
 
+    def adjacency(self):
+        """element adjacency as GenericMesh::BuildAdj numbers it: adj[(dim+1)*k+i] = (dim+1)*k'+i' | -1 (boundary) | -2"""
+        dim, _, nt, _ = self.info()
+        adj = np.zeros((dim + 1) * nt, np.int32)
+        _ck(lib().ffcuda_mesh_adjacency(_h(self), _p(adj), None), self.ctx.h)
+        return adj
+
     def local_to_global(self):
         no, nl = C.c_int(), C.c_int()
         _ck(lib().ffcuda_mesh_local_to_global(_h(self), C.byref(no), C.byref(nl), None), self.ctx.h)
@@ -408,6 +415,24 @@ class Matrix(_Handle):
         out = np.zeros(nl.value)
         _ck(lib().ffcuda_matrix_download_lower(_h(self), _p(out)), self.ctx.h)
         return out
+
+    def export_device(self):
+        """borrowed device pointers (ints) to the CSR triple: (rowptr, colind, vals, n, nnz)"""
+        rp, ci, va = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        n, nnz = C.c_int(), C.c_int64()
+        _ck(lib().ffcuda_matrix_export_device(_h(self), C.byref(rp), C.byref(ci), C.byref(va), C.byref(n), C.byref(nnz)), self.ctx.h)
+        return rp.value, ci.value, va.value, n.value, nnz.value
+
+    def download_coo(self, index_base=0):
+        """the triple of `[I,J,C] = A`: row indices expanded on the device"""
+        _, nnz = self.info()
+        I, J, V = np.zeros(nnz, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz)
+        _ck(lib().ffcuda_matrix_download_coo(_h(self), _p(I), _p(J), _p(V), int(index_base)), self.ctx.h)
+        return I, J, V
+
+    def write_morse(self, path, half=False):
+        """FreeFEM's Morse text format (`ofstream << A` after A.CSR) straight from the device CSR"""
+        _ck(lib().ffcuda_matrix_write_morse(_h(self), os.fsencode(path), 1 if half else 0), self.ctx.h)
 
     def upload(self, vals):
         vals = _f64(vals)

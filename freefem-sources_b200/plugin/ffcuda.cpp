@@ -911,8 +911,12 @@ MatriceMorse<double> *gpu_matrix(Stack stack, const FESpaceT &Vh, DevSpace &D, c
         }
     if (g_verbose && !groups.empty())
         cout << "  -- ffcuda: " << groups.size() << " coefficient function(s) depending on the mesh point, evaluated at the quadrature nodes" << endl;
-    std::vector<int32_t> rowptr, colind;
-    std::vector<double> vals;
+    // --- hand-off: FreeFEM's own MatriceMorse, its arrays filled straight from the device.  HashMatrix::set
+    // (femlib/HashMatrix.cpp:698-728) would copy the three arrays once more and leave the matrix marked `unsorted`, so
+    // that the first A.CSR (solver upload, `ofstream << A`, UMFPACK...) heap-sorts nnz entries on one core
+    // (Sortij, :671-682).  The device CSR is already sorted by (i, j): the arrays i, j, aij, p are downloaded in place,
+    // the hash is rebuilt once (ReHash, :631-642: A(i,j) look-ups work) and the matrix is marked sorted_ij / type_CSR.
+    MatriceMorse<double> *M = nullptr;
     if (!rc) {
         try {
             apply_bcs(D, V, dA, nullptr, ds.tgv);
@@ -921,25 +925,32 @@ MatriceMorse<double> *gpu_matrix(Stack stack, const FESpaceT &Vh, DevSpace &D, c
             ffcuda_pattern_destroy(P);
             throw;
         }
-        rowptr.resize((size_t)n + 1);
-        if (ds.sym) { // half storage: FreeFEM keeps the entries (i, j <= i); the device matrix stays full
-            rc = ffcuda_pattern_lower_nnz(P, &nnz);
-            colind.resize((size_t)nnz);
-            vals.resize((size_t)nnz);
-            rc = rc || ffcuda_pattern_download_lower(P, rowptr.data(), colind.data()) || ffcuda_matrix_download_lower(dA, vals.data());
-        } else {
-            colind.resize((size_t)nnz);
-            vals.resize((size_t)nnz);
-            rc = ffcuda_pattern_download(P, rowptr.data(), colind.data()) || ffcuda_matrix_download(dA, vals.data());
+        if (ds.sym) rc = ffcuda_pattern_lower_nnz(P, &nnz); // half storage: FreeFEM keeps the entries (i, j <= i); the device matrix stays full
+        if (!rc) {
+            M = new MatriceMorse<double>(n, n, 0, 0);
+            HashMatrix<int, double> *H = M;
+            H->clear();
+            H->half = ds.sym ? 1 : 0;
+            H->Increaze((size_t)nnz);
+            H->nnz = (size_t)nnz;
+            H->setp(n + 1);
+            if (ds.sym) rc = ffcuda_pattern_download_lower(P, H->p, H->j) || ffcuda_matrix_download_lower(dA, H->aij);
+            else rc = ffcuda_pattern_download(P, H->p, H->j) || ffcuda_matrix_download(dA, H->aij);
+            if (!rc) {
+                for (int i = 0; i < n; ++i)
+                    for (int k = H->p[i]; k < H->p[i + 1]; ++k) H->i[k] = i;
+                H->ReHash();
+                H->state = HashMatrix<int, double>::sorted_ij;
+                H->type_state = HashMatrix<int, double>::type_CSR;
+            }
         }
     }
     if (rc) {
+        delete M;
         ffcuda_matrix_destroy(dA);
         ffcuda_pattern_destroy(P);
         fail("assembling the matrix");
     }
-    MatriceMorse<double> *M = new MatriceMorse<double>(n, n, 0, 0);
-    M->set(n, n, ds.sym ? 1 : 0, (size_t)nnz, rowptr.data(), colind.data(), vals.data(), 0, 1); // copies, rebuilds the hash
     res = Resident{dA, P};
     return M;
 }

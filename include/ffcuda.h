@@ -98,6 +98,11 @@ int ffcuda_mesh_info(ffcuda_mesh *m, int *dim, int *nv, int *nt, int *nbe);
 /* any output pointer may be NULL */
 int ffcuda_mesh_download(ffcuda_mesh *m, double *xyz, int32_t *conn, int32_t *elab, int32_t *bconn,
                          int32_t *blab, int32_t *belem, int32_t *bface);
+/* element adjacency, GenericMesh::BuildAdj (femlib/GenericMesh.hpp:837-930): adj[(dim+1)*k + i] = (dim+1)*k' + i' when face i
+ * of element k (opposite its vertex i) is face i' of element k'; -1 on the boundary; -2 for a face shared by more than two
+ * elements.  Built on the device on first use (face hashes, radix sort, match) and kept with the mesh; `adj` (host) and
+ * `d_adj` (borrowed device pointer) may be NULL. */
+int ffcuda_mesh_adjacency(ffcuda_mesh *m, int32_t *adj, const int32_t **d_adj);
 void ffcuda_mesh_destroy(ffcuda_mesh *m);
 
 /* ---- finite-element space ------------------------------------------------------------------------ */

@@ -768,3 +768,94 @@ def test_tables_of_a_constant_equal_the_constant_forms(ctx, order, ncomp, N):
     sp.assemble_linear_boundary_qvalues(b2, fq3, fw3, gq, accumulate=False)
     h0, h2 = b0.download(), b2.download()
     assert np.max(np.abs(h0 - h2)) <= 1e-13 * np.abs(h0).max() and np.abs(h0).max() > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# hand-off formats straight from the device CSR
+# ---------------------------------------------------------------------------------------------------------------
+def test_device_export_coo_and_morse_text(ctx, tmp_path):
+    """borrowed device pointers (read back through torch, no library call), the [I,J,C] triple, and the Morse text file
+    parsed the way HashMatrix(istream&) reads it (femlib/HashMatrix.cpp:137-188): all equal the oracle's CSR."""
+    import torch
+
+    size = (7, 5, 6)
+    m = ol.cube(*size)
+    n = m["xyz"].shape[0]
+    qp, qw = ffcuda.quadrature(3, 6)
+    terms = fc.LAP3 + [(0, fc.ID, 0, fc.ID, 3.0)]
+    ci, cj, ca = ol.assemble_coo(m, 1, 1, None, terms, qp, qw)
+    orp, ocol, oval = ol.coo_to_csr(n, ci, cj, ca)
+    mesh = ctx.mesh_cube(*size)
+    sp = mesh.space(1, 1)
+    pat = sp.symbolic()
+    A = pat.matrix()
+    A.assemble(terms, qp, qw)
+    rp_ptr, ci_ptr, va_ptr, dn, dnnz = A.export_device()
+    assert dn == n and dnnz == len(ocol) and rp_ptr and ci_ptr and va_ptr
+
+    def view(ptr, count, dtype, itemsize):
+        # wrap the borrowed pointer without copying through the library (cudaMemcpy by torch)
+        out = torch.empty(count, dtype=dtype, device="cuda")
+        torch.cuda.current_stream().synchronize()
+        import ctypes
+
+        rt = ctypes.CDLL("libcudart.so")
+        rc = rt.cudaMemcpy(ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(ptr), ctypes.c_size_t(count * itemsize), 3)
+        assert rc == 0
+        return out.cpu().numpy()
+
+    assert np.array_equal(view(rp_ptr, n + 1, torch.int32, 4), orp)
+    assert np.array_equal(view(ci_ptr, dnnz, torch.int32, 4), ocol)
+    dv = view(va_ptr, dnnz, torch.float64, 8)
+    assert np.max(np.abs(dv - oval)) <= RTOL * np.abs(oval).max()
+    # [I,J,C] = A
+    for base in (0, 1):
+        I, J, V = A.download_coo(base)
+        assert np.array_equal(I, np.repeat(np.arange(n, dtype=np.int32), np.diff(orp)) + base)
+        assert np.array_equal(J, ocol + base) and np.array_equal(V, dv)
+    # Morse text: header `n m half  nnz`, then 1-based `i j a_ij`, 20 significant digits (values round-trip exactly)
+    for half in (False, True):
+        path = str(tmp_path / f"A{int(half)}.txt")
+        A.write_morse(path, half=half)
+        lines = [ln for ln in open(path) if not ln.startswith("#")]
+        hn, hm, hh, hz = lines[0].split()
+        a = np.array(" ".join(lines[1:]).split(), dtype=np.float64).reshape(-1, 3)
+        rows = np.repeat(np.arange(n), np.diff(orp))
+        keep = ocol <= rows if half else np.ones(len(ocol), bool)
+        assert (int(hn), int(hm), int(hh), int(hz)) == (n, n, int(half), int(keep.sum())) and a.shape[0] == int(keep.sum())
+        assert np.array_equal(a[:, 0].astype(np.int64), rows[keep] + 1) and np.array_equal(a[:, 1].astype(np.int64), ocol[keep] + 1)
+        assert np.array_equal(a[:, 2], dv[keep])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# mesh side (SURVEY.md section 8 f-4): element adjacency on the device = GenericMesh::BuildAdj
+# ---------------------------------------------------------------------------------------------------------------
+def _adjacency_by_dictionary(conn):
+    """BuildAdj restated (femlib/GenericMesh.hpp:837-886): faces keyed by their sorted vertices, visited element by element"""
+    nt, nv = conn.shape
+    adj = np.full(nt * nv, -1, np.int64)
+    seen = {}
+    for k in range(nt):
+        for i in range(nv):
+            key = tuple(sorted(int(conn[k, a]) for a in range(nv) if a != i))
+            f = k * nv + i
+            if key in seen:
+                g = seen[key]
+                adj[f], adj[g] = g, f
+            else:
+                seen[key] = f
+    return adj
+
+
+@pytest.mark.parametrize("kind,size", [("cube", (4, 3, 5)), ("cube", (1, 1, 1)), ("square", (7, 5)), ("square", (1, 1))])
+def test_mesh_adjacency_matches_buildadj(ctx, kind, size):
+    m = ol.cube(*size) if kind == "cube" else ol.square(*size)
+    mesh = ctx.mesh_cube(*size) if kind == "cube" else ctx.mesh_square(*size)
+    adj = mesh.adjacency()
+    ref = _adjacency_by_dictionary(m["conn"])
+    assert np.array_equal(adj, ref)
+    # symmetric link, boundary faces = the boundary elements of the mesh, second call served from the cache
+    inner = adj >= 0
+    assert np.array_equal(adj[adj[inner]], np.nonzero(inner)[0])
+    assert int((~inner).sum()) == m["bconn"].shape[0]
+    assert np.array_equal(mesh.adjacency(), adj)
