@@ -82,7 +82,7 @@ NcclApi &nccl()
 namespace {
 constexpr size_t P2P_HFLAG = FF_P2P_HFLAG, P2P_HCNT = FF_P2P_HCNT, P2P_HDATA = FF_P2P_HDATA;
 constexpr int P2P_MAXR = FF_P2P_MAXR;
-constexpr size_t P2P_HALO_CAP = (size_t)4 << 20; // doubles per region (32 MB): interface layers up to 4 M dofs
+constexpr size_t P2P_HALO_CAP = (size_t)1 << 20; // doubles per (source rank, parity) region (8 MB): interfaces up to 1 M dofs per pair of ranks
 
 struct PeerPtrs {
     unsigned char *p[P2P_MAXR];
@@ -104,22 +104,32 @@ __global__ void k_p2p_allreduce(P2PDesc *D, double *__restrict__ d, int count, i
 }
 
 struct HaloArgs {
-    int nbr[2];
-    long long send_off[2], send_cnt[2], recv_off[2], recv_cnt[2]; // in doubles
+    int n, nc;                     // neighbours, components per node
+    int nbr[P2P_MAXR];
+    int send_off[P2P_MAXR], send_cnt[P2P_MAXR], recv_off[P2P_MAXR], recv_cnt[P2P_MAXR]; // in nodes
+    const int32_t *send_idx;       // gather lists (null: send_off is a contiguous range of v)
 };
 
-// all blocks co-resident (grid <= number of SMs): send phase, grid-wide "last block publishes", receive phase
+// value i of the layer for neighbour x: node-major, nc components per node
+__device__ __forceinline__ double halo_pick(const double *__restrict__ v, const HaloArgs &H, int x, size_t i)
+{
+    const size_t node = i / (size_t)H.nc, c = i - node * (size_t)H.nc;
+    const size_t src = H.send_idx ? (size_t)H.send_idx[H.send_off[x] + node] : (size_t)H.send_off[x] + node;
+    return v[src * H.nc + c];
+}
+
+// all blocks co-resident (grid <= number of SMs): pack + send phase (my values go straight into the neighbours' mailboxes,
+// region [my rank][parity]: the gather IS the peer store), grid-wide "last block publishes", receive phase
 __global__ void __launch_bounds__(256) k_p2p_halo(const PeerPtrs P, int rank, double *__restrict__ v, const HaloArgs H, size_t cap,
                                                   unsigned long long seq, P2PDesc *D)
 {
     const int par = (int)(seq & 1ull);
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (size_t)gridDim.x * blockDim.x;
-    for (int s = 0; s < 2; ++s) {
-        if (H.nbr[s] < 0) continue;
-        // my layer towards neighbour s lands in ITS region of the opposite direction
-        double *dst = reinterpret_cast<double *>(P.p[H.nbr[s]] + P2P_HDATA) + (size_t)((1 - s) * 2 + par) * cap;
-        const double *src = v + H.send_off[s];
-        for (size_t i = tid; i < (size_t)H.send_cnt[s]; i += nthr) dst[i] = src[i];
+    for (int x = 0; x < H.n; ++x) {
+        if (H.nbr[x] < 0) continue;
+        double *dst = reinterpret_cast<double *>(P.p[H.nbr[x]] + P2P_HDATA) + (size_t)(rank * 2 + par) * cap;
+        const size_t cnt = (size_t)H.send_cnt[x] * H.nc;
+        for (size_t i = tid; i < cnt; i += nthr) dst[i] = halo_pick(v, H, x, i);
     }
     __threadfence_system();
     __syncthreads();
@@ -127,17 +137,18 @@ __global__ void __launch_bounds__(256) k_p2p_halo(const PeerPtrs P, int rank, do
     unsigned int *cnt = reinterpret_cast<unsigned int *>(P.p[rank] + P2P_HCNT);
     if (threadIdx.x == 0) last = atomicAdd(cnt, 1u) == gridDim.x - 1;
     __syncthreads();
-    if (last && threadIdx.x == 0) {
+    if (last && threadIdx.x < H.n && H.nbr[threadIdx.x] >= 0) {
         __threadfence_system();
-        *cnt = 0;
-        for (int s = 0; s < 2; ++s)
-            if (H.nbr[s] >= 0)
-                st_sys_u64(reinterpret_cast<unsigned long long *>(P.p[H.nbr[s]] + P2P_HFLAG) + (1 - s) * 2 + par, seq);
+        st_sys_u64(reinterpret_cast<unsigned long long *>(P.p[H.nbr[threadIdx.x]] + P2P_HFLAG) + rank * 2 + par, seq);
     }
-    for (int s = 0; s < 2; ++s) {
-        if (H.nbr[s] < 0) continue;
+    if (last) {
+        __syncthreads();
+        if (threadIdx.x == 0) *cnt = 0;
+    }
+    for (int x = 0; x < H.n; ++x) {
+        if (H.nbr[x] < 0) continue;
         if (threadIdx.x == 0) {
-            const unsigned long long *f = reinterpret_cast<const unsigned long long *>(P.p[rank] + P2P_HFLAG) + s * 2 + par;
+            const unsigned long long *f = reinterpret_cast<const unsigned long long *>(P.p[rank] + P2P_HFLAG) + H.nbr[x] * 2 + par;
             const long long t0 = clock64();
             while (ld_sys_u64(f) != seq) {
                 if (clock64() - t0 > FF_P2P_SPIN_LIMIT) { // crashed neighbour: do not hang the device
@@ -147,10 +158,18 @@ __global__ void __launch_bounds__(256) k_p2p_halo(const PeerPtrs P, int rank, do
             }
         }
         __syncthreads();
-        const double *src = reinterpret_cast<const double *>(P.p[rank] + P2P_HDATA) + (size_t)(s * 2 + par) * cap;
-        double *dst = v + H.recv_off[s];
-        for (size_t i = tid; i < (size_t)H.recv_cnt[s]; i += nthr) dst[i] = ld_sys_f64(src + i);
+        const double *src = reinterpret_cast<const double *>(P.p[rank] + P2P_HDATA) + (size_t)(H.nbr[x] * 2 + par) * cap;
+        double *dst = v + (size_t)H.recv_off[x] * H.nc;
+        const size_t cnt2 = (size_t)H.recv_cnt[x] * H.nc;
+        for (size_t i = tid; i < cnt2; i += nthr) dst[i] = ld_sys_f64(src + i);
     }
+}
+
+// NCCL route with gather lists: the layers are packed into a staging buffer first
+__global__ void k_halo_pack(const double *__restrict__ v, const HaloArgs H, int x, double *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < (size_t)H.send_cnt[x] * H.nc) out[i] = halo_pick(v, H, x, i);
 }
 
 PeerPtrs peer_ptrs(const ffcuda_ctx *ctx)
@@ -168,7 +187,7 @@ void p2p_setup(ffcuda_ctx *ctx)
         if (atoi(e) == 0) return;
     cudaStream_t st = ctx->stream;
     const int rank = ctx->rank, n = ctx->nranks;
-    const size_t bytes = P2P_HDATA + 4 * P2P_HALO_CAP * sizeof(double);
+    const size_t bytes = P2P_HDATA + (size_t)2 * P2P_MAXR * P2P_HALO_CAP * sizeof(double);
     void *mine = nullptr;
     // every rank must take the same decision: the outcome of each step is all-reduced (min) before going on
     int ok = cudaMalloc(&mine, bytes) == cudaSuccess ? 1 : 0;
@@ -315,24 +334,31 @@ void ff_halo_exchange(ffcuda_matrix *A, double *v)
     ffcuda_ctx *ctx = A->ctx;
     FF_REQUIRE(ctx->nccl_comm, "distributed matrix without communicator");
     const int nc = A->pattern->ncomp;
-    // layers that fit the mailbox regions go by peer stores (one kernel for both directions), the others by NCCL; both
-    // ends of a pair see the same count, so they take the same route
-    bool via_p2p[2] = {false, false}, any_p2p = false, any_nccl = false;
-    for (int s = 0; s < 2; ++s) {
-        if (m->nbr[s] < 0) continue;
-        const size_t big = (size_t)std::max(m->send_cnt[s], m->recv_cnt[s]) * nc;
-        via_p2p[s] = ctx->p2p && big <= ctx->p2p_halo_cap;
-        (via_p2p[s] ? any_p2p : any_nccl) = true;
+    HaloArgs H;
+    memset(&H, 0, sizeof(H));
+    H.n = m->nnbr;
+    H.nc = nc;
+    H.send_idx = m->send_idx.p;
+    // layers that fit the mailbox regions go by peer stores (one kernel for all neighbours), the others by NCCL; both
+    // ends of a pair see the same counts, so they take the same route
+    bool via_p2p[P2P_MAXR], any_p2p = false, any_nccl = false;
+    size_t most = 0;
+    for (int x = 0; x < m->nnbr; ++x) {
+        via_p2p[x] = false;
+        H.nbr[x] = -1;
+        H.send_off[x] = m->send_off[x]; H.send_cnt[x] = m->send_cnt[x];
+        H.recv_off[x] = m->recv_off[x]; H.recv_cnt[x] = m->recv_cnt[x];
+        if (m->nbr[x] < 0) continue;
+        const size_t big = (size_t)std::max(m->send_cnt[x], m->recv_cnt[x]) * nc;
+        via_p2p[x] = ctx->p2p && big <= ctx->p2p_halo_cap;
+        (via_p2p[x] ? any_p2p : any_nccl) = true;
+        if (via_p2p[x]) {
+            H.nbr[x] = m->nbr[x];
+            most = std::max(most, big);
+        }
     }
     if (any_p2p) {
-        HaloArgs H;
-        for (int s = 0; s < 2; ++s) {
-            H.nbr[s] = via_p2p[s] ? m->nbr[s] : -1;
-            H.send_off[s] = (long long)m->send_off[s] * nc; H.send_cnt[s] = (long long)m->send_cnt[s] * nc;
-            H.recv_off[s] = (long long)m->recv_off[s] * nc; H.recv_cnt[s] = (long long)m->recv_cnt[s] * nc;
-        }
         const unsigned long long seq = ++ctx->p2p_seq_halo;
-        const size_t most = (size_t)std::max(std::max(H.send_cnt[0], H.send_cnt[1]), std::max(H.recv_cnt[0], H.recv_cnt[1]));
         const int grid = (int)std::max<size_t>(1, std::min<size_t>((size_t)ctx->sm_count / 2, (most + 1023) / 1024));
         ff_launch(ctx, "halo_p2p", [&] {
             k_p2p_halo<<<grid, 256, 0, ctx->stream>>>(peer_ptrs(ctx), ctx->rank, v, H, ctx->p2p_halo_cap, seq,
@@ -342,11 +368,25 @@ void ff_halo_exchange(ffcuda_matrix *A, double *v)
     if (!any_nccl) return;
     NcclApi &N = nccl();
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+    DBuf<double> stage;
+    std::vector<size_t> soff((size_t)m->nnbr + 1, 0);
+    if (m->send_idx.p) { // gather lists: pack first
+        for (int x = 0; x < m->nnbr; ++x) soff[(size_t)x + 1] = soff[x] + ((m->nbr[x] >= 0 && !via_p2p[x]) ? (size_t)m->send_cnt[x] * nc : 0);
+        stage.alloc(std::max<size_t>(soff[m->nnbr], 1));
+        for (int x = 0; x < m->nnbr; ++x) {
+            if (m->nbr[x] < 0 || via_p2p[x] || m->send_cnt[x] == 0) continue;
+            H.nbr[x] = m->nbr[x];
+            ff_launch(ctx, "halo_pack", [&] {
+                k_halo_pack<<<ff_blocks((size_t)m->send_cnt[x] * nc, 256), 256, 0, ctx->stream>>>(v, H, x, stage.p + soff[x]);
+            });
+        }
+    }
     FF_NCCL(N.GroupStart());
-    for (int s = 0; s < 2; ++s) {
-        if (m->nbr[s] < 0 || via_p2p[s]) continue;
-        FF_NCCL(N.Send(v + (size_t)m->send_off[s] * nc, (size_t)m->send_cnt[s] * nc, ncclDouble, m->nbr[s], comm, ctx->stream));
-        FF_NCCL(N.Recv(v + (size_t)m->recv_off[s] * nc, (size_t)m->recv_cnt[s] * nc, ncclDouble, m->nbr[s], comm, ctx->stream));
+    for (int x = 0; x < m->nnbr; ++x) {
+        if (m->nbr[x] < 0 || via_p2p[x]) continue;
+        const double *src = m->send_idx.p ? stage.p + soff[x] : v + (size_t)m->send_off[x] * nc;
+        FF_NCCL(N.Send(src, (size_t)m->send_cnt[x] * nc, ncclDouble, m->nbr[x], comm, ctx->stream));
+        FF_NCCL(N.Recv(v + (size_t)m->recv_off[x] * nc, (size_t)m->recv_cnt[x] * nc, ncclDouble, m->nbr[x], comm, ctx->stream));
     }
     FF_NCCL(N.GroupEnd());
     ctx->launches++;

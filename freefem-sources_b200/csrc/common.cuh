@@ -123,8 +123,8 @@ struct CtxRef { // first member of every handle struct: released after the handl
 // ---- peer mailboxes (comm.cu): layout and the device-side descriptor -------------------------------------
 //   [RFLAG] u64[2][16]     sequence numbers of the all-reduce contributions (parity, rank)
 //   [RDATA] f64[2][16][4]  contributions
-//   [HFLAG] u64[2][2]      sequence numbers of the halo layers (direction, parity); [HCNT] block counter
-//   [HDATA] f64[2][2][cap] halo layers
+//   [HFLAG] u64[16][2]     sequence numbers of the halo layers (source rank, parity); [HCNT] block counter
+//   [HDATA] f64[16][2][cap] halo layers (source rank, parity)
 constexpr size_t FF_P2P_RFLAG = 0, FF_P2P_RDATA = 4096, FF_P2P_HFLAG = 8192, FF_P2P_HCNT = 8192 + 256, FF_P2P_HDATA = 16384;
 constexpr int FF_P2P_MAXR = 16;
 // lives in device memory at ctx->d_scal + FF_P2P_DESC_OFF (doubles), i.e. FF_P2P_DESC_OFF - 32 doubles behind the CG flags
@@ -270,12 +270,25 @@ struct ffcuda_mesh {
     DBuf<int32_t> elab;       // nt
     DBuf<int32_t> bconn, blab, belem, bface;
     DBuf<int32_t> adj;        // element adjacency (ffcuda_mesh_adjacency), built on first use
-    // distributed (slab partition): local vertices [0,nv_owned) are owned, the rest are ghosts
+    // distributed: local vertices [0,nv_owned) are owned, the rest are ghosts, grouped by owner rank.  Per neighbour x:
+    // the ghosts owned by nbr[x] are the contiguous range [recv_off, recv_off + recv_cnt); what nbr[x] needs from me is
+    // either the contiguous range [send_off, send_off + send_cnt) of my owned vertices (slab partition of a cube) or the
+    // gather list send_idx[send_off .. send_off + send_cnt) (any partition: ffcuda_mesh_upload_distributed), in the
+    // order of ITS ghost range
     int nv_owned = 0;
     DBuf<int64_t> gid;        // global vertex id of each local vertex
-    int nbr[2] = {-1, -1};    // lower / upper neighbour rank
-    int send_off[2] = {0, 0}, send_cnt[2] = {0, 0};   // owned vertices to send (contiguous ranges)
-    int recv_off[2] = {0, 0}, recv_cnt[2] = {0, 0};   // ghost ranges to receive into
+    static constexpr int MAXNBR = 16;
+    int nnbr = 0;
+    int nbr[MAXNBR];          // neighbour ranks (-1: no neighbour in this slot)
+    int send_off[MAXNBR], send_cnt[MAXNBR], recv_off[MAXNBR], recv_cnt[MAXNBR];
+    DBuf<int32_t> send_idx;   // gather lists (null: contiguous ranges)
+    ffcuda_mesh()
+    {
+        for (int x = 0; x < MAXNBR; ++x) {
+            nbr[x] = -1;
+            send_off[x] = send_cnt[x] = recv_off[x] = recv_cnt[x] = 0;
+        }
+    }
     bool distributed = false;
 };
 

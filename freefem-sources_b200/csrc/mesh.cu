@@ -295,6 +295,7 @@ static void build_cube(ffcuda_ctx *ctx, int nx, int ny, int nz, int rank, int nr
     if (nranks > 1) {
         m->distributed = true;
         m->gid.alloc(m->nv);
+        m->nnbr = 2;
         for (int s = 0; s < 2; ++s) {
             m->nbr[s] = Pt.nbr[s];
             m->send_off[s] = Pt.send_off[s];
@@ -320,6 +321,58 @@ static void build_cube(ffcuda_ctx *ctx, int nx, int ny, int nz, int rank, int nr
     });
     FF_CUDA(cudaStreamSynchronize(st));
     *out = m.release();
+}
+
+// The local problem of one rank for ANY vertex partition (the output of ffcuda_partition_local, or of METIS / the user's
+// own partitioner): owned vertices first, ghosts grouped by owner; local elements = every element touching an owned
+// vertex, so the owned rows assemble without communication.  Reference counterpart: the element-range split of
+// fflib/problem.cpp:1133-1138 (+ an all-reduce of the whole matrix), plugin/seq/metis.cpp for the partition vector.
+extern "C" int ffcuda_mesh_upload_distributed(ffcuda_ctx *ctx, int dim, int nv_owned, int nv_local, const double *xyz, int nt,
+                                              const int32_t *conn, const int32_t *elab, int nbe, const int32_t *bconn,
+                                              const int32_t *blab, const int32_t *belem, const int32_t *bface, const int64_t *gid,
+                                              int nnbr, const int32_t *nbr, const int32_t *recv_off, const int32_t *recv_cnt,
+                                              const int32_t *send_ptr, const int32_t *send_idx, ffcuda_mesh **out)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(ctx && out, "ffcuda_mesh_upload_distributed: null context/output");
+    FF_REQUIRE(ctx->nranks == 1 || ctx->nccl_comm, "ffcuda_mesh_upload_distributed: call ffcuda_comm_init first");
+    FF_REQUIRE(nv_owned > 0 && nv_owned <= nv_local, "every rank must own at least one vertex");
+    FF_REQUIRE(nnbr >= 0 && nnbr <= ffcuda_mesh::MAXNBR, "at most 16 neighbour ranks");
+    FF_REQUIRE(nnbr == 0 || (nbr && recv_off && recv_cnt && send_ptr && (send_idx || send_ptr[nnbr] == 0)), "halo arrays missing");
+    int covered = nv_owned;
+    for (int x = 0; x < nnbr; ++x) {
+        FF_REQUIRE(nbr[x] >= 0 && nbr[x] < ctx->nranks && nbr[x] != ctx->rank, "bad neighbour rank");
+        FF_REQUIRE(recv_off[x] == covered && recv_cnt[x] > 0, "ghost ranges must follow the owned vertices, in neighbour order, without gaps");
+        covered += recv_cnt[x];
+        FF_REQUIRE(send_ptr[x + 1] >= send_ptr[x], "send_ptr must be non-decreasing");
+    }
+    FF_REQUIRE(covered == nv_local, "ghost ranges do not cover the ghost vertices");
+    for (int k = 0; k < (nnbr ? send_ptr[nnbr] : 0); ++k) FF_REQUIRE(send_idx[k] >= 0 && send_idx[k] < nv_owned, "send list entry is not an owned vertex");
+    ffcuda_mesh *m = nullptr;
+    const int rc = ffcuda_mesh_upload(ctx, dim, nv_local, xyz, nt, conn, elab, nbe, bconn, blab, belem, bface, &m);
+    if (rc) throw FFError(ffcuda_last_error(ctx));
+    std::unique_ptr<ffcuda_mesh> guard(m);
+    ff_enter(ctx);
+    m->nv_owned = nv_owned;
+    m->distributed = ctx->nranks > 1;
+    m->gid.alloc(nv_local);
+    if (gid) FF_CUDA(cudaMemcpyAsync(m->gid.p, gid, (size_t)nv_local * 8, cudaMemcpyHostToDevice, ctx->stream));
+    else FF_CUDA(cudaMemsetAsync(m->gid.p, 0, (size_t)nv_local * 8, ctx->stream));
+    m->nnbr = nnbr;
+    for (int x = 0; x < nnbr; ++x) {
+        m->nbr[x] = nbr[x];
+        m->recv_off[x] = recv_off[x];
+        m->recv_cnt[x] = recv_cnt[x];
+        m->send_off[x] = send_ptr[x];
+        m->send_cnt[x] = send_ptr[x + 1] - send_ptr[x];
+    }
+    if (nnbr && send_ptr[nnbr] > 0) {
+        m->send_idx.alloc((size_t)send_ptr[nnbr]);
+        FF_CUDA(cudaMemcpyAsync(m->send_idx.p, send_idx, (size_t)send_ptr[nnbr] * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    FF_CUDA(cudaStreamSynchronize(ctx->stream));
+    *out = guard.release();
+    FF_API_END(ctx)
 }
 
 extern "C" int ffcuda_mesh_cube(ffcuda_ctx *ctx, int nx, int ny, int nz, ffcuda_mesh **out)

@@ -24,7 +24,7 @@ ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_
 ffcuda_assemble_linear ffcuda_assemble_linear_qvalues ffcuda_assemble_linear_qterms ffcuda_assemble_linear_boundary ffcuda_assemble_bilinear_boundary ffcuda_assemble_linear_boundary_qvalues ffcuda_assemble_bilinear_boundary_qcoef ffcuda_bc_from_pairs ffcuda_bc_from_labels ffcuda_bc_count ffcuda_matrix_apply_bc ffcuda_vec_apply_bc
 ffcuda_vec_set_bc_values ffcuda_bc_destroy ffcuda_spmv ffcuda_cg ffcuda_cg_host ffcuda_gmres ffcuda_gmres_host ffcuda_comm_unique_id ffcuda_comm_init
 ffcuda_comm_finalize ffcuda_mesh_cube_distributed ffcuda_mesh_local_to_global ffcuda_quadrature ffcuda_partition_cube
-ffcuda_partition_rcb ffcuda_partition_local ffcuda_matrix_export_device ffcuda_matrix_download_coo ffcuda_matrix_write_morse ffcuda_mesh_adjacency""".split()
+ffcuda_partition_rcb ffcuda_partition_local ffcuda_matrix_export_device ffcuda_matrix_download_coo ffcuda_matrix_write_morse ffcuda_mesh_adjacency ffcuda_mesh_upload_distributed""".split()
 
 
 class FfcudaError(RuntimeError):
@@ -205,6 +205,20 @@ class Context(_Handle):
         out = C.c_void_p()
         _ck(lib().ffcuda_mesh_upload(_h(self), dim, xyz.shape[0], _p(xyz), conn.shape[0], _p(conn), _p(elab), nbe, _p(bconn),
                                      _p(blab), _p(belem), _p(bface), C.byref(out)), self.h)
+        return Mesh(out.value, self)
+
+    def mesh_upload_distributed(self, dim, nv_owned, xyz, conn, elab, bconn, blab, belem, bface, gid, nbr, recv_off, recv_cnt,
+                                send_ptr, send_idx):
+        """the local problem of this rank for any vertex partition (arrays in LOCAL numbering, see include/ffcuda.h)"""
+        xyz, conn, elab = _f64(xyz), _i32(conn), _i32(elab)
+        bconn, blab, belem, bface = _i32(bconn), _i32(blab), _i32(belem), _i32(bface)
+        gid = np.ascontiguousarray(gid, dtype=np.int64)
+        nbr, recv_off, recv_cnt, send_ptr, send_idx = _i32(nbr), _i32(recv_off), _i32(recv_cnt), _i32(send_ptr), _i32(send_idx)
+        nbe = 0 if blab is None else len(blab)
+        out = C.c_void_p()
+        _ck(lib().ffcuda_mesh_upload_distributed(_h(self), dim, int(nv_owned), xyz.shape[0], _p(xyz), conn.shape[0], _p(conn), _p(elab),
+                                                 nbe, _p(bconn), _p(blab), _p(belem), _p(bface), _p(gid), len(nbr), _p(nbr),
+                                                 _p(recv_off), _p(recv_cnt), _p(send_ptr), _p(send_idx), C.byref(out)), self.h)
         return Mesh(out.value, self)
 
     def mesh_cube(self, nx, ny, nz, distributed=False):

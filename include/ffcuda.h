@@ -302,6 +302,17 @@ int ffcuda_partition_rcb(int dim, int nv, const double *xyz, int nparts, int32_t
 int ffcuda_partition_local(int dim, int nv, int nt, const int32_t *conn, const int32_t *part, int rank, int nranks,
                            int64_t *sizes8, int32_t *l2g, int32_t *elems, int32_t *nbr, int32_t *recv_off, int32_t *recv_cnt,
                            int32_t *send_ptr, int32_t *send_idx);
+/* The local problem of this rank for ANY vertex partition (the arrays ffcuda_partition_local returns, local numbering: owned
+ * vertices first, then the ghosts grouped by owner rank): xyz[nv_local*dim], conn with LOCAL vertex ids, the boundary
+ * elements whose element is local, gid[nv_local] global ids, and the halo description - per neighbour x the contiguous ghost
+ * range [recv_off[x], +recv_cnt[x]) and the gather list send_idx[send_ptr[x] .. send_ptr[x+1]) of owned vertices it needs, in
+ * the order of ITS ghost range.  Any number of neighbours up to 16; the halo exchange packs and stores into the peers'
+ * mailboxes in one kernel (NCCL send/recv after a pack kernel as the fallback).  P1 spaces (scalar or vector). */
+int ffcuda_mesh_upload_distributed(ffcuda_ctx *ctx, int dim, int nv_owned, int nv_local, const double *xyz, int nt,
+                                   const int32_t *conn, const int32_t *elab, int nbe, const int32_t *bconn, const int32_t *blab,
+                                   const int32_t *belem, const int32_t *bface, const int64_t *gid, int nnbr, const int32_t *nbr,
+                                   const int32_t *recv_off, const int32_t *recv_cnt, const int32_t *send_ptr,
+                                   const int32_t *send_idx, ffcuda_mesh **out);
 /* global ids of the local vertices (owned first): for gathering results / parity checks */
 int ffcuda_mesh_local_to_global(ffcuda_mesh *m, int *nowned, int *nlocal, int64_t *gid /* nlocal or NULL */);
 

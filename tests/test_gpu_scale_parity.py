@@ -124,3 +124,16 @@ def test_dist_check_under_torchrun(world):
            "--master-port", str(port), os.path.join(ROOT, "tests", "dist_check.py")]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DIST_CHECK_PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_dist_check_rcb_under_torchrun(world):
+    """tests/dist_check_rcb.py: an RCB-partitioned cube with shuffled numbering (gather lists, up to world-1 neighbours per
+    rank, vector space) against the oracle on the whole mesh.  Self-skips when the box has fewer devices."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} CUDA devices")
+    port = 29640 + world
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "dist_check_rcb.py")]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST_CHECK_RCB_PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
