@@ -351,6 +351,8 @@ struct TileSet {
     int fan_state = 0;        // 1 ready, -1 not applicable
     int fan_max_head = 0, fan_max_b = 0, fan_max_nvals = 0, fan_max_nq = 0; // largest part A / part B (words), value table, entries
     int64_t fan_sum_fans = 0;
+    int fan_max_c = 0, fan_max_rvals = 0; // part C (right-hand sides): largest descriptor (words) and value table
+    DBuf<uint32_t> fcblob, fcoff;         // part C descriptors and their offsets
     DBuf<uint32_t> fblob, foff, fhead; // descriptors, ntiles+1 offsets (words), words of every descriptor's head (the part copied to shared memory)
 };
 

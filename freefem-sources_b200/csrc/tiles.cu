@@ -954,7 +954,8 @@ __global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restr
                                                           const int32_t *__restrict__ conn, const IncView V,
                                                           const double *__restrict__ xyz, int vstride,
                                                           const int32_t *__restrict__ nrowptr, int32_t *__restrict__ stats,
-                                                          const uint32_t *__restrict__ foff, uint32_t *__restrict__ fblob)
+                                                          const uint32_t *__restrict__ foff, uint32_t *__restrict__ fblob,
+                                                          const uint32_t *__restrict__ fcoff, uint32_t *__restrict__ fcblob)
 {
     extern __shared__ uint32_t sm[];
     const BuildScratch S = build_scratch(sm);
@@ -980,6 +981,11 @@ __global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restr
     int *fgt = reinterpret_cast<int *>(sbuf + 6400);      // [6400, 6464): fan groups: first value slot | kmax << 16
     int *epos = reinterpret_cast<int *>(sm) + build_words(); // NQ_CAP+16: sorted position of every entry (extra scratch of this kernel)
     int *cursor = epos + 4096;                               // NQ_CAP+16: fill cursors of the entries (F7 only)
+    int *rcnt = cursor + 4096;                               // TR_CAP: fans around every row's vertex (right-hand sides, part C)
+    uint32_t *rkey = reinterpret_cast<uint32_t *>(rcnt + TR_CAP); // TR_CAP: rows sorted by decreasing count
+    int *rpos = reinterpret_cast<int *>(rkey + TR_CAP);      // TR_CAP: sorted position of every row
+    int *rgl = rpos + TR_CAP;                                // TR_CAP/32 + 1: first code word of every row group
+    int *rfg = rgl + 16;                                     // 64: fan groups of the right-hand side: first value slot
     static_assert(NE_CAP == 2048 && NQ_CAP + 1 <= 4096 && SORT_CAP >= 6464, "scratch layout of k_fan_build");
     if (fit) {
         // F1. axis of every element: its longest edge (ties: the smallest pair of global vertex ids, the same choice in
@@ -1167,10 +1173,72 @@ __global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restr
         else ncw = blk_scan(egl, nge + 1, part);
         if (s_bad) fit = 0;
     }
+    // F8. right-hand sides (part C, its own blob): a fan gives the sum of |det| over its elements to its axis vertices
+    // (value 0) and det_{t-1} + det_t to its ring vertex t (value 1 + t); a row adds one value per fan around its vertex.
+    // Rows sorted by decreasing number of fans, groups of 32 rows, transposed code lists as for the entries.
+    int nvals_r = 0, ncw_r = 0, ngr = 0;
+    auto for_vertex_sums = [&](auto &&add) {
+        for (int f = tid; f < nfan; f += TB_THREADS) {
+            const uint32_t *w = frec + 4 * ekey[f];
+            const int G = f >> 5, lane = f & 31;
+            const int vb = rfg[G];
+            const int k = (int)((w[2] >> 16) & 15u);
+            const unsigned long long rr = (unsigned long long)(w[0] >> 16) | ((unsigned long long)w[1] << 16) |
+                                          ((unsigned long long)(w[2] & 0xffffu) << 48);
+            auto slot = [&](int j) { return vb + 32 * j + ((lane + j) & 31); };
+            add(w[0] & 255u, slot(0));
+            add((w[0] >> 8) & 255u, slot(0));
+            for (int tt = 0; tt <= k; ++tt) add((uint32_t)(rr >> (8 * tt)) & 255u, slot(1 + tt));
+        }
+    };
+    if (fit) {
+        if (tid == 0) {
+            int vb = 1;
+            for (int G = 0; G < ngf; ++G) {
+                rfg[G] = vb;
+                vb += 32 * ((fgt[G] >> 16) + 2);
+            }
+            s_nvals = vb;
+        }
+        for (int l = tid; l < TR_CAP; l += TB_THREADS) rcnt[l] = 0;
+        __syncthreads();
+        nvals_r = s_nvals;
+        for_vertex_sums([&](uint32_t x, int) {
+            const int l = s2r[x];
+            if (l != 255) atomicAdd(&rcnt[l], 1);
+        });
+        __syncthreads();
+        ngr = (nr + 31) >> 5;
+        for (int l = tid; l < TR_CAP; l += TB_THREADS) {
+            uint32_t key = 0xffffffffu;
+            if (l < nr) {
+                if (rcnt[l] > 126) s_bad = 1;
+                key = ((uint32_t)(127 - min(rcnt[l], 126)) << 12) | (uint32_t)l;
+            }
+            rkey[l] = key;
+        }
+        __syncthreads();
+        blk_sort(rkey, TR_CAP);
+        for (int e = tid; e < nr; e += TB_THREADS) rpos[rkey[e] & 0xfffu] = e;
+        for (int g = tid; g <= ngr; g += TB_THREADS) rgl[g] = g < ngr ? ((rcnt[rkey[g * 32] & 0xfffu] + 1) >> 1) * 32 : 0;
+        __syncthreads();
+        if (tid == 0) { // (at most 9 groups)
+            int o = 0;
+            for (int g = 0; g <= ngr; ++g) {
+                const int w = rgl[g];
+                rgl[g] = o;
+                o += w;
+            }
+        }
+        __syncthreads();
+        ncw_r = rgl[ngr];
+        if (s_bad) fit = 0;
+    }
     if (!WRITE) {
         if (tid == 0) {
             int32_t *st = stats + (size_t)t * 12;
             st[0] = nvt; st[1] = nelem; st[2] = nq; st[3] = nfan; st[4] = fit; st[5] = nr; st[6] = nvals; st[7] = ncw; st[8] = ngf; st[9] = nge;
+            st[10] = nvals_r; st[11] = ncw_r;
         }
         return;
     }
@@ -1280,6 +1348,44 @@ __global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restr
                 code_at(qq, best) = code_at(qq, k);
                 code_at(qq, k) = c;
                 usedb |= 1u << (c & 15u);
+            }
+        }
+    }
+    // part C: header [0 nr, 1 ngr, 2 nvals, 3 o_grow, 4 o_rgrp, 5 o_codes, 6 words, 7 o_fgrp], fan groups (first value slot |
+    // kmax << 16), global row ids in sorted order, row groups (first code word | words per lane << 24), codes
+    {
+        uint32_t *gC = fcblob + fcoff[t];
+        const int o_fg = 8, o_grow = o_fg + pad4(ngf), o_rgrp = o_grow + pad4(nr), o_rc = o_rgrp + pad4(ngr + 1), wordsC = o_rc + pad4(ncw_r);
+        if (tid == 0) {
+            gC[0] = nr; gC[1] = ngr; gC[2] = nvals_r; gC[3] = o_grow; gC[4] = o_rgrp; gC[5] = o_rc; gC[6] = wordsC; gC[7] = o_fg;
+        }
+        for (int x = tid; x < pad4(ngf); x += TB_THREADS) gC[o_fg + x] = x < ngf ? ((uint32_t)rfg[x] | ((uint32_t)(fgt[x] >> 16) << 16)) : 0u;
+        for (int e = tid; e < pad4(nr); e += TB_THREADS) gC[o_grow + e] = e < nr ? (uint32_t)rord[r0 + (rkey[e] & 0xfffu)] : 0u;
+        for (int x = tid; x < pad4(ngr + 1); x += TB_THREADS)
+            gC[o_rgrp + x] = x < ngr ? ((uint32_t)rgl[x] | ((uint32_t)((rgl[x + 1] - rgl[x]) >> 5) << 24)) : (uint32_t)ncw_r;
+        for (int x = tid; x < pad4(ncw_r); x += TB_THREADS) gC[o_rc + x] = 0u;
+        for (int l = tid; l < TR_CAP; l += TB_THREADS) cursor[l] = 0;
+        __syncthreads();
+        uint16_t *gcr = reinterpret_cast<uint16_t *>(gC + o_rc);
+        auto rcode_at = [&](int l, int c) -> uint16_t & {
+            const int e = rpos[l];
+            return gcr[2 * (rgl[e >> 5] + (c >> 1) * 32 + (e & 31)) + (c & 1)];
+        };
+        for_vertex_sums([&](uint32_t x, int slot) {
+            const int l = s2r[x];
+            if (l != 255) rcode_at(l, atomicAdd(&cursor[l], 1)) = (uint16_t)slot;
+        });
+        __syncthreads();
+        for (int l = tid; l < nr; l += TB_THREADS) { // ascending value slots: a fixed summation order
+            const int n = rcnt[l];
+            for (int x = 1; x < n; ++x) {
+                const uint16_t v = rcode_at(l, x);
+                int y = x - 1;
+                while (y >= 0 && rcode_at(l, y) > v) {
+                    rcode_at(l, y + 1) = rcode_at(l, y);
+                    --y;
+                }
+                rcode_at(l, y + 1) = v;
             }
         }
     }
@@ -1448,6 +1554,112 @@ __global__ void __launch_bounds__(THREADS, MINB) k_asm_fans(const uint32_t *__re
         }
         __syncthreads(); // part B, sV and sE are free again
         if (tid == 0 && t + (int)gridDim.x < ntiles) issueB(t + gridDim.x);
+    }
+}
+
+// Right-hand side of value-only linear forms on the fans: b_i = cval * sum of |det K| over the star of i.  Part A of the
+// tile descriptor (fans, coordinates) and part C (rows sorted by the number of fans around them, code lists).
+template <int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_rhs_fans(const uint32_t *__restrict__ foff, const uint32_t *__restrict__ fhead,
+                                                            const uint32_t *__restrict__ fblob, const uint32_t *__restrict__ fcoff,
+                                                            const uint32_t *__restrict__ fcblob, int ntiles, double *__restrict__ bvec,
+                                                            int accumulate, double cval, const FanSmem S)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) unsigned long long mbar[2]; // [0]: part A arrived, [1]: part C arrived
+    double *sV = reinterpret_cast<double *>(smem_raw + S.vals);
+    const uint32_t *sA = reinterpret_cast<const uint32_t *>(smem_raw);
+    const uint32_t *sC = reinterpret_cast<const uint32_t *>(smem_raw + S.bufB);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = THREADS / 32;
+    tile_mbar_init(mbar);
+    auto issueA = [&](int t) {
+        const uint32_t bytes = __ldg(fhead + t) * 4u;
+        tile_expect(smem_u32(&mbar[0]), bytes);
+        tile_bulk(smem_u32(smem_raw), fblob + __ldg(foff + t), bytes, smem_u32(&mbar[0]));
+    };
+    auto issueC = [&](int t) {
+        const uint32_t w0 = __ldg(fcoff + t), bytes = (__ldg(fcoff + t + 1) - w0) * 4u;
+        tile_expect(smem_u32(&mbar[1]), bytes);
+        tile_bulk(smem_u32(smem_raw + S.bufB), fcblob + w0, bytes, smem_u32(&mbar[1]));
+    };
+    int t = blockIdx.x;
+    uint32_t ph = 0;
+    if (tid == 0) {
+        sV[0] = 0.0;
+        if (t < ntiles) {
+            issueA(t);
+            issueC(t);
+        }
+    }
+    for (; t < ntiles; t += gridDim.x, ph ^= 1) {
+        tile_wait(smem_u32(&mbar[0]), ph);
+        tile_wait(smem_u32(&mbar[1]), ph); // (the fan groups of the right-hand side are in part C)
+        {
+            const int nfan = sA[2], ngf = sA[4];
+            const double *coord = reinterpret_cast<const double *>(sA + sA[8]);
+            const uint4 *fans = reinterpret_cast<const uint4 *>(sA + sA[9]);
+            const uint32_t *fgrp = sC + sC[7];
+            for (int G = warp; G < ngf; G += NW) {
+                const int f = G * 32 + lane;
+                uint4 fw = make_uint4(0u, 0u, 0u, 0u);
+                if (f < nfan) fw = fans[f];
+                const uint32_t fg = fgrp[G];
+                const int kmax = (int)(fg >> 16);
+                const int k = (int)((fw.z >> 16) & 15u);
+                double *v = sV + (fg & 0xffffu);
+                const unsigned long long rr = (unsigned long long)(fw.x >> 16) | ((unsigned long long)fw.y << 16) |
+                                              ((unsigned long long)(fw.z & 0xffffu) << 48);
+                const double *P = coord + 3 * (fw.x & 255u), *Q = coord + 3 * ((fw.x >> 8) & 255u), *R = coord + 3 * ((uint32_t)rr & 255u);
+                const double px = P[0], py = P[1], pz = P[2];
+                const double ax = Q[0] - px, ay = Q[1] - py, az = Q[2] - pz;
+                double bx = R[0] - px, by = R[1] - py, bz = R[2] - pz;
+                double tot = 0.0, prev = 0.0;
+#pragma unroll 2
+                for (int tt = 0; tt < kmax; ++tt) {
+                    double d = 0.0;
+                    if (tt < k) {
+                        const double *R1 = coord + 3 * ((uint32_t)(rr >> (8 * (tt + 1))) & 255u);
+                        const double ex = R1[0] - px, ey = R1[1] - py, ez = R1[2] - pz;
+                        // det of (a, b, e) = a . (b x e)
+                        d = fabs(ax * (by * ez - bz * ey) + ay * (bz * ex - bx * ez) + az * (bx * ey - by * ex));
+                        bx = ex; by = ey; bz = ez;
+                    }
+                    tot += d;
+                    v[32 * (1 + tt) + ((lane + 1 + tt) & 31)] = prev + d; // ring vertex t: elements t-1 and t
+                    prev = d;
+                }
+                v[32 * (1 + kmax) + ((lane + 1 + kmax) & 31)] = prev;
+                v[lane] = tot;
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && t + (int)gridDim.x < ntiles) issueA(t + gridDim.x);
+        {
+            const int nr = sC[0], ngr = sC[1];
+            const int32_t *grow = reinterpret_cast<const int32_t *>(sC + sC[3]);
+            const uint32_t *rgrp = sC + sC[4];
+            const uint32_t *codes = sC + sC[5];
+            for (int g = warp; g < ngr; g += NW) {
+                const int e = g * 32 + lane;
+                const uint32_t eg = rgrp[g], nk = eg >> 24;
+                const uint32_t *cp = codes + (eg & 0xffffffu) + lane;
+                double acc = 0.0;
+#pragma unroll 2
+                for (uint32_t kk = 0; kk < nk; ++kk) {
+                    const uint32_t c = cp[kk * 32];
+                    acc += sV[c & 0xffffu];
+                    acc += sV[c >> 16];
+                }
+                if (e < nr) {
+                    double *dst = bvec + grow[e];
+                    const double val = cval * acc;
+                    *dst = accumulate ? *dst + val : val;
+                }
+            }
+        }
+        __syncthreads();
+        if (tid == 0 && t + (int)gridDim.x < ntiles) issueC(t + gridDim.x);
     }
 }
 
@@ -1647,19 +1859,21 @@ void build_fans(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr, const 
     ffcuda_mesh *m = s->mesh;
     if (m->dim != 3 || ctx->tile_fans == 0) return;
     cudaStream_t st = ctx->stream;
-    const size_t shmem = (size_t)4 * (build_words() + 2 * 4096);
+    const size_t shmem = (size_t)4 * (build_words() + 2 * 4096 + 3 * TR_CAP + 16 + 64);
     FF_CUDA(cudaFuncSetAttribute(k_fan_build<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     FF_CUDA(cudaFuncSetAttribute(k_fan_build<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     const IncView V = ff_view(s->incidence);
     DBuf<int32_t> d_stats;
     d_stats.alloc((size_t)ntiles * 12);
     ff_launch(ctx, "fan_sizes", [&] {
-        k_fan_build<0><<<ntiles, TB_THREADS, shmem, st>>>(d_rord, d_tstart, m->conn.p, V, m->xyz.p, m->vstride, nrowptr, d_stats.p, nullptr, nullptr);
+        k_fan_build<0><<<ntiles, TB_THREADS, shmem, st>>>(d_rord, d_tstart, m->conn.p, V, m->xyz.p, m->vstride, nrowptr, d_stats.p, nullptr, nullptr,
+                                                          nullptr, nullptr);
     });
     std::vector<int32_t> hst((size_t)ntiles * 12);
     FF_CUDA(ff_memcpy_sync(ctx, hst.data(), d_stats.p, hst.size() * 4, cudaMemcpyDeviceToHost));
-    std::vector<uint32_t> hoff((size_t)ntiles + 1), hhead((size_t)ntiles + 1, 0);
-    uint64_t off = 0;
+    std::vector<uint32_t> hoff((size_t)ntiles + 1), hhead((size_t)ntiles + 1, 0), hcoff((size_t)ntiles + 1);
+    uint64_t off = 0, coff = 0;
+    T.fan_max_c = T.fan_max_rvals = 0;
     T.fan_max_head = T.fan_max_b = T.fan_max_nvals = T.fan_max_nq = 0;
     T.fan_sum_fans = 0;
     int64_t sum_vals = 0, sum_cw = 0;
@@ -1674,6 +1888,11 @@ void build_fans(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr, const 
         hoff[t] = (uint32_t)off;
         hhead[t] = (uint32_t)head;
         off += (uint64_t)words;
+        const int wordsC = 8 + pad4(ngf) + pad4(nr) + pad4(((nr + 31) >> 5) + 1) + pad4(h[11]);
+        hcoff[t] = (uint32_t)coff;
+        coff += (uint64_t)wordsC;
+        T.fan_max_c = std::max(T.fan_max_c, wordsC);
+        T.fan_max_rvals = std::max(T.fan_max_rvals, (int)h[10]);
         T.fan_max_head = std::max(T.fan_max_head, head);
         T.fan_max_nvals = std::max(T.fan_max_nvals, nvals);
         T.fan_max_nq = std::max(T.fan_max_nq, nq);
@@ -1681,15 +1900,20 @@ void build_fans(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr, const 
         sum_vals += nvals;
         sum_cw += ncw;
     }
-    if (off >= ((uint64_t)1 << 32)) return;
+    if (off >= ((uint64_t)1 << 32) || coff >= ((uint64_t)1 << 32)) return;
     hoff[ntiles] = (uint32_t)off;
+    hcoff[ntiles] = (uint32_t)coff;
+    T.fcoff.alloc((size_t)ntiles + 1);
+    T.fcblob.alloc((size_t)coff + 4);
+    FF_CUDA(cudaMemcpyAsync(T.fcoff.p, hcoff.data(), hcoff.size() * 4, cudaMemcpyHostToDevice, st));
     T.foff.alloc((size_t)ntiles + 1);
     T.fhead.alloc((size_t)ntiles + 1);
     T.fblob.alloc((size_t)off + 4);
     FF_CUDA(cudaMemcpyAsync(T.foff.p, hoff.data(), hoff.size() * 4, cudaMemcpyHostToDevice, st));
     FF_CUDA(cudaMemcpyAsync(T.fhead.p, hhead.data(), hhead.size() * 4, cudaMemcpyHostToDevice, st));
     ff_launch(ctx, "fan_build", [&] {
-        k_fan_build<1><<<ntiles, TB_THREADS, shmem, st>>>(d_rord, d_tstart, m->conn.p, V, m->xyz.p, m->vstride, nrowptr, nullptr, T.foff.p, T.fblob.p);
+        k_fan_build<1><<<ntiles, TB_THREADS, shmem, st>>>(d_rord, d_tstart, m->conn.p, V, m->xyz.p, m->vstride, nrowptr, nullptr, T.foff.p, T.fblob.p,
+                                                          T.fcoff.p, T.fcblob.p);
     });
     FF_CUDA(cudaStreamSynchronize(st)); // hoff / hhead are host vectors
     T.fan_state = 1;
@@ -1810,6 +2034,24 @@ bool ff_rhs_p1_tiles(ffcuda_ctx *ctx, ffcuda_vec *b, ffcuda_space *s, const doub
 {
     TileSet &T = s->tiles;
     if (ctx->tile_policy == 0 || T.state != 1) return false;
+    if (!hasgrad && s->ncomp == 1 && s->mesh->dim == 3 && T.fan_state == 1 && ctx->tile_fans != 0) {
+        FanSmem FS;
+        size_t o = ((size_t)T.fan_max_head * 4 + 127) & ~(size_t)127;
+        FS.bufB = (int)o;
+        o += ((size_t)T.fan_max_c * 4 + 127) & ~(size_t)127;
+        FS.vals = (int)o;
+        o += ((size_t)T.fan_max_rvals * 8 + 127) & ~(size_t)127;
+        FS.ent = (int)o;
+        const size_t shmem = o;
+        if (shmem <= 200 * 1024) {
+            auto kern = k_rhs_fans<128, 6>;
+            tile_launch(ctx, "rhs_rows", kern, 128, shmem, T.ntiles, [&](int grid) {
+                kern<<<grid, 128, shmem, ctx->stream>>>(T.foff.p, T.fhead.p, T.fblob.p, T.fcoff.p, T.fcblob.p, T.ntiles, b->d.p, accumulate,
+                                                        cval[0], FS);
+            });
+            return true;
+        }
+    }
     // gradient terms move 12 more values per element through shared memory: measured slower than the thread-per-row
     // kernel (350 vs 231 us on cube(128)); value-only forms: 162 vs 217 us
     if (hasgrad && ctx->tile_policy != 2) return false;

@@ -35,8 +35,15 @@ for size in [(1, 1, 1), (2, 3, 1), (5, 4, 6), (11, 9, 13), (24, 24, 24)]:
         err = np.max(np.abs(val - oval)) / np.abs(oval).max()
         A.assemble(fc.LAP3, qp, qw)
         same = np.array_equal(A.download(), val)
-        print(f"cube{size} rows={rows}: rel err {err:.2e} reproducible={same}", flush=True)
-        assert err <= 1e-12 and same
+        b = ctx.vec(N)
+        sp.assemble_linear(b, [(0, fc.ID, 2.5)], qp, qw)
+        ob = ol.assemble_rhs(m, 1, 1, None, N, [(0, fc.ID, 2.5)], qp, qw)
+        hb = b.download()
+        errb = np.max(np.abs(hb - ob)) / np.abs(ob).max()
+        sp.assemble_linear(b, [(0, fc.ID, 2.5)], qp, qw)
+        sameb = np.array_equal(b.download(), hb)
+        print(f"cube{size} rows={rows}: rel err {err:.2e} reproducible={same}; rhs rel err {errb:.2e} reproducible={sameb}", flush=True)
+        assert err <= 1e-12 and same and errb <= 1e-12 and sameb
 if len(sys.argv) > 2:
     sys.exit(0)
 ctx.set_option("tile_rows", int(os.environ.get("ROWS", "96")))
@@ -58,6 +65,13 @@ nv, nt = mesh.info()[1], mesh.info()[2]
 N, nnz = pat.info()
 B = 16.0 * nt + 24.0 * nv + 12.0 * nnz + 4.0 * (N + 1)
 print(f"asm_rows_p1: {ms / cnt:.4f} ms per launch, {B / (ms / cnt * 1e-3) / 1e9:.0f} GB/s algorithmic, frac {B / (ms / cnt * 1e-3) / 1e9 / 6454.3:.3f}")
+b = ctx.vec(N)
+ctx.prof_reset()
+for _ in range(10):
+    sp.assemble_linear(b, [(0, fc.ID, 1.0)], qp, qw)
+ctx.sync()
+ms, cnt = ctx.prof_get("rhs_rows")
+print(f"rhs_rows: {ms / cnt:.4f} ms per launch; sum b = {b.download().sum():.15f}")
 import scipy.sparse as sps  # noqa: E402
 
 rp, col = pat.download()
