@@ -65,6 +65,16 @@ nv, nt = mesh.info()[1], mesh.info()[2]
 N, nnz = pat.info()
 B = 16.0 * nt + 24.0 * nv + 12.0 * nnz + 4.0 * (N + 1)
 print(f"asm_rows_p1: {ms / cnt:.4f} ms per launch, {B / (ms / cnt * 1e-3) / 1e9:.0f} GB/s algorithmic, frac {B / (ms / cnt * 1e-3) / 1e9 / 6454.3:.3f}")
+ctx.prof_reset()
+for _ in range(10):
+    patx = sp.symbolic()
+ctx.sync()
+for nm in ("sym_p1_fused", "sym_p1_rows", "sym_p1_cols", "sym_", "scan_"):
+    ms, cnt = ctx.prof_get(nm)
+    print(f"{nm}: {ms / max(cnt, 1):.4f} ms per launch ({cnt} launches)")
+rpx, colx = patx.download()
+rp0, col0 = pat.download()
+assert np.array_equal(rpx, rp0) and np.array_equal(colx, col0)
 b = ctx.vec(N)
 ctx.prof_reset()
 for _ in range(10):
