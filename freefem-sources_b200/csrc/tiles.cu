@@ -106,6 +106,36 @@ __device__ __forceinline__ uint32_t spread2(uint32_t v) // 15 bits -> every seco
     return v;
 }
 
+// mean extent of the element edges along every axis (the metric of the mesh): the Morton quantisation is scaled by it so
+// that tiles are compact in INDEX space - a cube(128,128,256) slab has vertices twice as dense along z
+template <int NV>
+__global__ void k_edge_extents(const double *__restrict__ xyz, int vstride, const int32_t *__restrict__ conn, int nt, double fix,
+                               unsigned long long *__restrict__ acc)
+{
+    constexpr int DIM = NV - 1;
+    double s[3] = {0.0, 0.0, 0.0};
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nt; k += gridDim.x * blockDim.x) {
+        double X[NV][3];
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) X[a][c] = xyz[(size_t)conn[(size_t)k * NV + a] * vstride + c];
+#pragma unroll
+        for (int a = 0; a < NV; ++a)
+#pragma unroll
+            for (int b = a + 1; b < NV; ++b)
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) s[c] += fabs(X[a][c] - X[b][c]);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        for (int o = 16; o; o >>= 1) s[c] += __shfl_xor_sync(0xffffffffu, s[c], o);
+        // fixed point, integer atomics: the sum does not depend on the order of arrival (the tiles, hence the summation
+        // order of the assembly, are the same in every run)
+        if ((threadIdx.x & 31) == 0) atomicAdd(acc + c, (unsigned long long)llrint(s[c] * fix));
+    }
+}
+
 struct BoxScale {
     double lo[3], sc[3];
 };
@@ -1739,13 +1769,35 @@ void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr)
     FF_CUDA(ff_memcpy_sync(ctx, hbox, box.p, sizeof(hbox), cudaMemcpyDeviceToHost));
     BoxScale B;
     const double qmax = dim == 3 ? 1024.0 : 32768.0;
-    // one scale for all directions (the largest extent): Morton cells are cubes in space, so tiles stay compact on
-    // anisotropic boxes too (a slab of a partitioned cube)
+    // Morton cells should hold the same number of vertices along every axis: the axes are scaled by the inverse of the
+    // mean edge extent along them (a sample of the elements), then one common factor maps the largest scaled extent to the
+    // key range.  Isotropic meshes get one scale for all directions (tiles = cubes in space, also on a thin slab of a
+    // partitioned cube); cube(128,128,256) gets z stretched by 2 (r01: 0.443 ms instead of 0.380 ms for the same 128^3 cells).
+    double hmean[3] = {1.0, 1.0, 1.0};
+    {
+        DBuf<unsigned long long> acc;
+        acc.alloc(3);
+        FF_CUDA(cudaMemsetAsync(acc.p, 0, 3 * sizeof(unsigned long long), st));
+        const int nsample = std::min(m->nt, 1 << 20);
+        double bext = 0.0;
+        for (int x = 0; x < dim; ++x) bext = std::max(bext, unord64(hbox[3 + x]) - unord64(hbox[x]));
+        const double fix = bext > 0.0 ? 68719476736.0 / bext : 1.0; // 2^36 per box extent: 6 * 2^20 edges stay below 2^63
+        ff_launch(ctx, "tile_metric", [&] {
+            if (dim == 3) k_edge_extents<4><<<ctx->sm_count * 2, 256, 0, st>>>(m->xyz.p, m->vstride, m->conn.p, nsample, fix, acc.p);
+            else k_edge_extents<3><<<ctx->sm_count * 2, 256, 0, st>>>(m->xyz.p, m->vstride, m->conn.p, nsample, fix, acc.p);
+        });
+        unsigned long long hi[3];
+        FF_CUDA(ff_memcpy_sync(ctx, hi, acc.p, sizeof(hi), cudaMemcpyDeviceToHost));
+        const double h[3] = {(double)hi[0], (double)hi[1], (double)hi[2]};
+        double hmax = 0.0;
+        for (int x = 0; x < dim; ++x) hmax = std::max(hmax, h[x]);
+        for (int x = 0; x < dim; ++x) hmean[x] = (h[x] > 1e-3 * hmax && hmax > 0.0) ? h[x] / hmax : 1.0; // (degenerate direction: left alone)
+    }
     double ext = 0.0;
-    for (int x = 0; x < dim; ++x) ext = std::max(ext, unord64(hbox[3 + x]) - unord64(hbox[x]));
+    for (int x = 0; x < dim; ++x) ext = std::max(ext, (unord64(hbox[3 + x]) - unord64(hbox[x])) / hmean[x]);
     for (int x = 0; x < 3; ++x) {
         B.lo[x] = x < dim ? unord64(hbox[x]) : 0.0;
-        B.sc[x] = (x < dim && ext > 0.0) ? qmax * (1.0 - 1e-9) / ext : 0.0;
+        B.sc[x] = (x < dim && ext > 0.0) ? qmax * (1.0 - 1e-9) / (ext * hmean[x]) : 0.0;
     }
     DBuf<uint32_t> k0, k1;
     DBuf<int32_t> v0, rord;
