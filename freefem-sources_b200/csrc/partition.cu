@@ -122,6 +122,8 @@ extern "C" int ffcuda_partition_rcb(int dim, int nv, const double *xyz, int npar
 {
     FF_API_BEGIN
     FF_REQUIRE((dim == 2 || dim == 3) && nv >= 0 && nparts >= 1 && (nv == 0 || (xyz && part)), "ffcuda_partition_rcb: bad arguments");
+    // every part must own a vertex (the distributed mesh rejects empty ranks: ffcuda_mesh_upload_distributed)
+    FF_REQUIRE(nv == 0 || nparts <= nv, "ffcuda_partition_rcb: more parts than vertices");
     std::vector<int32_t> ids((size_t)nv);
     std::iota(ids.begin(), ids.end(), 0);
     rcb(dim, xyz, ids, 0, (size_t)nv, 0, nparts, part);
@@ -133,7 +135,12 @@ extern "C" int ffcuda_partition_local(int dim, int nv, int nt, const int32_t *co
                                       int32_t *send_ptr, int32_t *send_idx)
 {
     FF_API_BEGIN
-    FF_REQUIRE((dim == 2 || dim == 3) && conn && part && sizes8 && rank >= 0 && rank < nranks, "ffcuda_partition_local: bad arguments");
+    FF_REQUIRE((dim == 2 || dim == 3) && nv >= 0 && nt >= 0 && sizes8 && rank >= 0 && rank < nranks && (nt == 0 || conn) && (nv == 0 || part),
+               "ffcuda_partition_local: bad arguments");
+    // the inputs index host arrays: a partition vector made for another number of parts, or a connectivity of another mesh,
+    // must come back as an error through the ABI, not as an out-of-bounds write
+    for (int v = 0; v < nv; ++v) FF_REQUIRE(part[v] >= 0 && part[v] < nranks, "ffcuda_partition_local: part[] entry outside [0, nranks)");
+    for (size_t i = 0; i < (size_t)nt * (dim + 1); ++i) FF_REQUIRE(conn[i] >= 0 && conn[i] < nv, "ffcuda_partition_local: conn[] entry outside [0, nv)");
     const LocalLists L = local_lists(dim + 1, nv, nt, conn, part, rank, nranks);
     const int64_t s[8] = {L.nowned, (int64_t)L.l2g.size() - L.nowned, (int64_t)L.elems.size(), (int64_t)L.nbr.size(),
                           (int64_t)L.send_idx.size(), 0, 0, 0};

@@ -265,3 +265,13 @@ def test_general_partition_edge_cases():
             assert np.array_equal(sent, other["l2g"][other["recv_off"][y]:other["recv_off"][y] + other["recv_cnt"][y]])
     with pytest.raises(ffcuda.FfcudaError):
         ffcuda.partition_rcb(xyz, 0)
+    # malformed inputs come back as errors through the ABI: a partition vector made for more parts than ranks,
+    # a connectivity entry outside the mesh, more parts than vertices
+    with pytest.raises(ffcuda.FfcudaError):
+        ffcuda.partition_local(2, nv, conn, ffcuda.partition_rcb(xyz, 5), 0, 3)
+    bad = conn.copy()
+    bad[3, 1] = nv
+    with pytest.raises(ffcuda.FfcudaError):
+        ffcuda.partition_local(2, nv, bad, part, 0, 3)
+    with pytest.raises(ffcuda.FfcudaError):
+        ffcuda.partition_rcb(xyz[:4], 5)
