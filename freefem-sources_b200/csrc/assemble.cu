@@ -523,6 +523,32 @@ __global__ void __launch_bounds__(128) k_asm_p1_lean(const double *__restrict__ 
     }
 }
 
+// Geometry of every element once per assembly (P2 rows): gradients of the barycentric coordinates and the measure, GS
+// doubles per element.  k_asm_p2 visits an element once per (node row, lane) - 10 rows x 10 lanes on tetrahedra - and used
+// to re-derive the inverse Jacobian each time (ncu r01d: FP64 pipe 34 %, a third of it this geometry): now one 80-byte
+// broadcast load per visit.
+template <int DIM>
+__global__ void k_elem_geom(const double *__restrict__ xyz, const int32_t *__restrict__ conn, int nt, double *__restrict__ egeo)
+{
+    constexpr int GS = DIM == 3 ? 10 : 6;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nt) return;
+    Geom<DIM> G;
+    if (DIM == 3) {
+        const int4 K = __ldg(reinterpret_cast<const int4 *>(conn) + k);
+        load_geom3(xyz, K.x, K.y, K.z, K.w, reinterpret_cast<Geom<3> &>(G));
+    } else {
+        load_geom2(xyz, __ldg(conn + 3 * (size_t)k), __ldg(conn + 3 * (size_t)k + 1), __ldg(conn + 3 * (size_t)k + 2), reinterpret_cast<Geom<2> &>(G));
+    }
+    double *o = egeo + (size_t)k * GS;
+#pragma unroll
+    for (int r = 0; r < DIM; ++r)
+#pragma unroll
+        for (int x = 0; x < DIM; ++x) o[r * DIM + x] = G.g[r][x];
+    o[DIM * DIM] = G.mes;
+    if (DIM == 2) o[5] = 0.0;
+}
+
 // ----------------------------------------------------------------------------------------------------
 // P2: one group of GL lanes per node row, lane b handles the pair (a, b)
 // ----------------------------------------------------------------------------------------------------
@@ -541,7 +567,8 @@ __global__ void __launch_bounds__(128) k_asm_p2(const double *__restrict__ xyz, 
                                                 const uint32_t *__restrict__ inc, const PosT *__restrict__ pos,
                                                 const double *__restrict__ Rg, double *__restrict__ vals, int S, int accumulate,
                                                 const __grid_constant__ FormParams F, const int32_t *__restrict__ rowperm, int row0,
-                                                const double *__restrict__ Tq = nullptr, const double *__restrict__ cq = nullptr, int nqc = 0)
+                                                const double *__restrict__ Tq = nullptr, const double *__restrict__ cq = nullptr, int nqc = 0,
+                                                const double *__restrict__ egeo = nullptr)
 {
     constexpr int NL = DIM == 3 ? 10 : 6;
     constexpr int NS = DIM + 1;
@@ -575,7 +602,22 @@ __global__ void __launch_bounds__(128) k_asm_p2(const double *__restrict__ xyz, 
         const int k = ka >> 4, a = ka & 15;
         if (region_ok(F.nlab, F.labels, elab, k) && b < NL) {
             Geom<DIM> G;
-            if (DIM == 3) {
+            if (egeo) { // computed once per element by k_elem_geom: the lanes of the group read the same 16-byte words (broadcast)
+                constexpr int GS = DIM == 3 ? 10 : 6;
+                const double2 *gp = reinterpret_cast<const double2 *>(egeo + (size_t)k * GS);
+                double t[GS];
+#pragma unroll
+                for (int i = 0; i < GS / 2; ++i) {
+                    const double2 v2 = __ldg(gp + i);
+                    t[2 * i] = v2.x;
+                    t[2 * i + 1] = v2.y;
+                }
+#pragma unroll
+                for (int r = 0; r < DIM; ++r)
+#pragma unroll
+                    for (int x = 0; x < DIM; ++x) G.g[r][x] = t[r * DIM + x];
+                G.mes = t[DIM * DIM];
+            } else if (DIM == 3) {
                 const int4 K = __ldg(reinterpret_cast<const int4 *>(conn) + k);
                 load_geom3(xyz, K.x, K.y, K.z, K.w, reinterpret_cast<Geom<3> &>(G));
             } else {
@@ -941,6 +983,14 @@ static void launch_p2(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const 
     // of decreasing length, in two launches: the long rows, then the short ones with accumulators sized for them.
     ff_p2_row_order(ctx, s, P->nrowptr.p, P->nrows_node, P->maxrow_node);
     const int nrows = P->nrows_node, nlong = s->p2_nlong;
+    // geometry of every element, once per assembly
+    constexpr int GS = DIM == 3 ? 10 : 6;
+    DBuf<double> egeo;
+    const bool pregeo = !(getenv("FFCUDA_P2_PREGEOM") && atoi(getenv("FFCUDA_P2_PREGEOM")) == 0);
+    if (pregeo) {
+        egeo.alloc((size_t)m->nt * GS);
+        ff_launch(ctx, "asm_p2_geom", [&] { k_elem_geom<DIM><<<ff_blocks((size_t)m->nt, 256), 256, 0, ctx->stream>>>(m->xyz.p, m->conn.p, m->nt, egeo.p); });
+    }
     auto run = [&](int r0, int r1, int maxL) {
         if (r1 <= r0) return;
         int S = NC * NC * maxL;
@@ -953,7 +1003,7 @@ static void launch_p2(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, const 
         const int blocks = ff_blocks((size_t)(r1 - r0), groups);
         ff_launch(ctx, "asm_rows_p2", [&] {
             kern<<<blocks, threads, shmem, ctx->stream>>>(m->xyz.p, m->conn.p, m->elab.p, r1, P->nrowptr.p, I.incptr.p, I.inc.p, pos, Rg,
-                                                          A->vals.p, S, accumulate, Fi, s->p2_rowperm.p, r0, Tq, cq, nqc);
+                                                          A->vals.p, S, accumulate, Fi, s->p2_rowperm.p, r0, Tq, cq, nqc, egeo.p);
         });
     };
     run(0, nlong, P->maxrow_node);
