@@ -398,13 +398,13 @@ def ours(args):
         solve()
     torch.cuda.synchronize()
     prof = {}
-    for key in ("inc_", "sym_", "scan_", "asm_rows", "bc_", "rhs_rows", "vec_fill", "cg_spmv_dots", "cg_update_g", "cg_update_xh", "cg_", ""):
+    for key in ("inc_", "sym_", "scan_", "asm_rows", "bc_", "rhs_rows", "vec_fill", "cg_spmv_dots", "cg_update_g", "cg_update_xh", "cg_", "halo_", ""):
         ms, cnt = ctx.prof_get(key)
         prof[key] = (ms / nprof, cnt // nprof)
     kernels_ms = {}
     for nm in ("inc_count", "inc_blk_len", "inc_fill", "inc_sort", "inc_stage", "sym_p1_fused", "sym_p1_rows", "sym_p1_cols", "sym_p1_positions", "sym_block_pattern", "sym_compact_cols", "sym_row_count", "sym_row_fill", "sym_diagpos", "scan_tile_sums",
                "scan_tile_offsets", "scan_tiles", "scan_lookback", "asm_rows_p1", "rhs_rows", "bc_mark", "bc_compact", "bc_matrix", "bc_vec", "vec_fill",
-               "spmv_row_blocks", "spmv_sell_len", "spmv_sell_cols", "spmv_sell_vals", "cg_diag_stats", "cg_precond", "cg_init_spmv", "cg_init_h", "cg_spmv_dots", "cg_update_g", "cg_update_xh"):
+               "halo_p2p", "halo_pack", "allreduce_p2p", "spmv_row_blocks", "spmv_sell_len", "spmv_sell_cols", "spmv_sell_vals", "cg_diag_stats", "cg_precond", "cg_init_spmv", "cg_init_h", "cg_spmv_dots", "cg_update_g", "cg_update_xh"):
         ms, cnt = ctx.prof_get(nm)
         if cnt:
             kernels_ms[nm] = [round(ms / nprof, 4), cnt // nprof]
@@ -617,7 +617,7 @@ def ours(args):
                        "l2": "inputs larger than L2 per GPU: connectivity %.0f MB + CSR %.0f MB vs 126 MB L2"
                              % (16.0 * nt_loc / 1e6, 12.0 * nnz_loc / 1e6),
                        "partition": "z-slabs, one process per GPU" if world > 1 else "single GPU"},
-            "phases_ms": {"incidence_once_per_fespace": prof["inc_"][0], "symbolic": prof["sym_"][0] + prof["scan_"][0], "numeric_assembly": prof["asm_rows"][0], "bc": prof["bc_"][0],
+            "phases_ms": {"halo_exchange_in_cg": prof["halo_"][0], "incidence_once_per_fespace": prof["inc_"][0], "symbolic": prof["sym_"][0] + prof["scan_"][0], "numeric_assembly": prof["asm_rows"][0], "bc": prof["bc_"][0],
                           "rhs": prof["rhs_rows"][0], "assembly_step_kernels": asm_step_kernels, "cg_kernels": prof["cg_"][0]},
             "assembly": {"numeric_nnz_per_s": nnz_glob / (t_asmk * 1e-3), "numeric_ms": t_asmk, "algorithmic_GB": B_asm / 1e9,
                          "gbs": asm_gbs * world, "frac_of_hbm": asm_gbs / hbm},

@@ -49,11 +49,19 @@ def run(ctx, label, mesh, dim, order, ncomp, terms, rhs, bcs, reps=3, itmax=0):
         bc = sp.bc_from_labels(*bcs)
         t_bc, _ = wall(ctx, lambda: (A.apply_bc(bc, 1e30), b.apply_bc(bc, 1e30)))
         prof_asm = {k: ctx.prof_get(k) for k in NAMES_ASM}
-        ctx.prof_reset()
-        x = ctx.vec(n)
-        t_cg, (it, conv, gcg) = wall(ctx, lambda: A.cg(b, x, eps=1e-6, itmax=itmax, tgv=1e30))
-        prof_cg = {k: ctx.prof_get(k) for k in NAMES_CG}
         ctx.prof_enable(False)
+        x = ctx.vec(n)
+        t_cg, (it, conv, gcg) = wall(ctx, lambda: A.cg(b, x, eps=1e-6, itmax=itmax, tgv=1e30))   # as a user runs it (CUDA-graph batches)
+        prof_cg = {}
+        if rep == reps - 1:   # kernel breakdown: the same solve once more under the event profiler (plain launches)
+            ctx.prof_enable(True)
+            ctx.prof_reset()
+            x2 = ctx.vec(n)
+            A.cg(b, x2, eps=1e-6, itmax=itmax, tgv=1e30)
+            ctx.sync()
+            prof_cg = {k: ctx.prof_get(k) for k in NAMES_CG}
+            ctx.prof_enable(False)
+            del x2
         if rep < reps - 1:
             del A, pat, b, x, bc
     kern = {k: [round(v[0], 4), int(v[1])] for k, v in prof_asm.items() if v[1]}
