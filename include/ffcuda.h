@@ -35,6 +35,13 @@
  *   ffcuda_spmv                 <- HashMatrix::addMatMul femlib/HashMatrix.cpp:1087-1154
  *   ffcuda_cg                   <- SolverCG::dosolver femlib/VirtualSolverCG.hpp:112-192, HMatVirtPrecon :13-111,
  *                                  ConjugueGradient femlib/CG.cpp:195-265, gettgv HashMatrix.cpp:1341-1371
+ *   ffcuda_matrix_export_device / _download_coo / _write_morse <- hand-off formats: PETSc through host arrays
+ *                                  plugin/mpi/PETSc-code.hpp, `[I,J,C]=A` fflib/lgmat.cpp, `ofstream << A`
+ *                                  femlib/HashMatrix.hpp:485-508 (reader femlib/HashMatrix.cpp:137-188)
+ *   ffcuda_mesh_adjacency       <- GenericMesh::BuildAdj femlib/GenericMesh.hpp:837-930
+ *   ffcuda_partition_rcb / _local, ffcuda_mesh_upload_distributed, ffcuda_mesh_cube_distributed, ffcuda_comm_*
+ *                               <- element-range split fflib/problem.cpp:1133-1138, partition vector plugin/seq/metis.cpp,
+ *                                  MPI_Allreduce per dot product plugin/mpi/MPICG.cpp:93-101
  */
 #ifndef FFCUDA_H
 #define FFCUDA_H
