@@ -53,17 +53,29 @@ extern "C" int ffcuda_ctx_create(int device, ffcuda_ctx **out)
     FF_CUDA(cudaSetDevice(device));
     ctx = new ffcuda_ctx();
     ctx->device = device;
-    FF_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
-    ctx->stream = ctx->own_stream;
-    cudaDeviceProp prop;
-    FF_CUDA(cudaGetDeviceProperties(&prop, device));
-    ctx->sm_count = prop.multiProcessorCount;
-    if (const char *e = getenv("FFCUDA_TILES")) ctx->tile_policy = std::max(0, std::min(2, atoi(e)));
-    if (const char *e = getenv("FFCUDA_TILE_FANS")) ctx->tile_fans = atoi(e) != 0;
-    if (const char *e = getenv("FFCUDA_TILE_ROWS")) ctx->tile_rows = std::max(8, std::min(256, atoi(e)));
-    FF_CUDA(cudaMalloc((void **)&ctx->d_scal, 256 * sizeof(double))); // [0,64): CG scalars and flags, [64, ..): P2PDesc
-    FF_CUDA(cudaMemset(ctx->d_scal, 0, 256 * sizeof(double)));
-    FF_CUDA(cudaMallocHost((void **)&ctx->h_scal, 64 * sizeof(double)));
+    try {
+        FF_CUDA(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+        ctx->stream = ctx->own_stream;
+        cudaDeviceProp prop;
+        FF_CUDA(cudaGetDeviceProperties(&prop, device));
+        ctx->sm_count = prop.multiProcessorCount;
+        if (const char *e = getenv("FFCUDA_TILES")) ctx->tile_policy = std::max(0, std::min(2, atoi(e)));
+        if (const char *e = getenv("FFCUDA_TILE_FANS")) ctx->tile_fans = atoi(e) != 0;
+        if (const char *e = getenv("FFCUDA_TILE_ROWS")) ctx->tile_rows = std::max(8, std::min(256, atoi(e)));
+        FF_CUDA(cudaMalloc((void **)&ctx->d_scal, 256 * sizeof(double))); // [0,64): CG scalars and flags, [64, ..): P2PDesc
+        // zeroed on the context's own (non-blocking) stream: the legacy stream does not order with it
+        FF_CUDA(cudaMemsetAsync(ctx->d_scal, 0, 256 * sizeof(double), ctx->stream));
+        FF_CUDA(cudaStreamSynchronize(ctx->stream));
+        FF_CUDA(cudaMallocHost((void **)&ctx->h_scal, 64 * sizeof(double)));
+    } catch (...) { // nothing of a half-built context survives an error
+        if (ctx->h_scal) cudaFreeHost(ctx->h_scal);
+        if (ctx->d_scal) cudaFree(ctx->d_scal);
+        if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        ctx = nullptr;
+        cudaGetLastError();
+        throw;
+    }
     *out = ctx;
     FF_API_END(ctx)
 }

@@ -840,6 +840,12 @@ extern "C" int ffcuda_spmv(ffcuda_matrix *A, ffcuda_vec *x, ffcuda_vec *y)
     ff_matrix_touch(A);
     ff_halo_exchange(A, x->d.p);
     spmv_launch(A, x->d.p, nullptr, y->d.p);
+    if (A->ctx->p2p && ff_is_distributed(A)) { // a neighbour that never answered must not pass as a result
+        int to = 0;
+        FF_CUDA(ff_memcpy_sync(A->ctx, &to, reinterpret_cast<char *>(A->ctx->d_scal + FF_P2P_DESC_OFF) + offsetof(P2PDesc, timed_out),
+                               sizeof(int), cudaMemcpyDeviceToHost));
+        FF_REQUIRE(to == 0, "ffcuda_spmv: a peer rank did not answer within the spin limit (halo exchange timed out)");
+    }
     FF_API_END(A ? A->ctx : nullptr)
 }
 
@@ -910,6 +916,8 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
     const int fused = (ctx->p2p && ff_is_distributed(A)) ? 1 : 0;
     FF_CUDA(cudaMemcpyAsync(reinterpret_cast<char *>(scal + FF_P2P_DESC_OFF) + offsetof(P2PDesc, fused), &fused, sizeof(int),
                             cudaMemcpyHostToDevice, st));
+    if (ctx->p2p) // a time-out of an earlier solve is that solve's error, not this one's
+        FF_CUDA(cudaMemsetAsync(reinterpret_cast<char *>(scal + FF_P2P_DESC_OFF) + offsetof(P2PDesc, timed_out), 0, sizeof(int), st));
 
     double *hs = ctx->h_scal;
     double ttgv = 0;

@@ -17,6 +17,8 @@
 // Environment: FFCUDA_DEVICE (default 0), FFCUDA_VERBOSE=1 (say which path every call took), FFCUDA_STRICT=1,
 //              FFCUDA_DISABLE=1 (register nothing).
 #include "ff++.hpp"
+#include <chrono>
+#include <thread>
 #include "AFunction_ext.hpp"
 #include <cstdlib>
 #include <map>
@@ -64,6 +66,50 @@ ffcuda_ctx *context()
         }
     }
     return g_ctx;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host helpers: wall-clock marks (printed with FFCUDA_VERBOSE) and a chunked parallel loop for the O(mesh) / O(nnz) host
+// passes of the hand-over (mesh flattening, row expansion, hash chains) - FreeFEM's interpreter is one thread, these
+// loops only read FreeFEM's structures or write our own arrays
+// ------------------------------------------------------------------------------------------------------------
+struct Marks {
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    std::string line;
+    void mark(const char *what)
+    {
+        const auto t1 = std::chrono::steady_clock::now();
+        char buf[96];
+        snprintf(buf, sizeof buf, " %s %.1f ms", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        line += buf;
+        t0 = t1;
+    }
+};
+int host_threads()
+{
+    static int n = 0;
+    if (!n) {
+        const char *e = getenv("FFCUDA_HOST_THREADS");
+        n = e ? atoi(e) : (int)std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        if (n < 1) n = 1;
+    }
+    return n;
+}
+template <class F>
+void par_for(size_t n, F f) // f(begin, end) on disjoint chunks
+{
+    const int nt = (int)std::min<size_t>((size_t)host_threads(), std::max<size_t>(1, n / 65536));
+    if (nt <= 1) {
+        f((size_t)0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t chunk = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; ++t) {
+        const size_t b = std::min(n, (size_t)t * chunk), e = std::min(n, b + chunk);
+        if (b < e) th.emplace_back([=] { f(b, e); });
+    }
+    for (size_t t = 0; t < th.size(); ++t) th[t].join();
 }
 
 void notice(const char *what, const std::string &why)
@@ -224,13 +270,18 @@ DevSpace &device_space(const FESpaceT &Vh)
     classify_space(Vh, dim, order, ncomp, nloc);
     ffcuda_ctx *ctx = context();
     const int nv = Th.nv, nt = Th.nt, nbe = nbe_of(Th), nvk = dim + 1;
+    Marks mk;
     std::vector<double> xyz((size_t)nv * dim);
-    for (int i = 0; i < nv; ++i) coords(Th, i, &xyz[(size_t)i * dim]);
+    par_for((size_t)nv, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) coords(Th, (int)i, &xyz[i * dim]);
+    });
     std::vector<int32_t> conn((size_t)nt * nvk), elab(nt), bconn((size_t)nbe * dim), blab(nbe), belem(nbe), bface(nbe);
-    for (int k = 0; k < nt; ++k) {
-        for (int j = 0; j < nvk; ++j) conn[(size_t)k * nvk + j] = Th(k, j);
-        elab[k] = elabel(Th, k);
-    }
+    par_for((size_t)nt, [&](size_t b, size_t e) {
+        for (size_t k = b; k < e; ++k) {
+            for (int j = 0; j < nvk; ++j) conn[k * nvk + j] = Th((int)k, j);
+            elab[k] = elabel(Th, (int)k);
+        }
+    });
     for (int ib = 0; ib < nbe; ++ib) {
         int ie;
         belem[ib] = belem_of(Th, ib, ie);
@@ -245,8 +296,10 @@ DevSpace &device_space(const FESpaceT &Vh)
     D->order = order;
     D->ncomp = ncomp;
     D->ndof = Vh.NbOfDF;
+    mk.mark("mesh flattened");
     FFC(ffcuda_mesh_upload(ctx, dim, nv, xyz.data(), nt, conn.data(), elab.data(), nbe, bconn.data(), blab.data(), belem.data(),
                            bface.data(), &D->mesh));
+    mk.mark("uploaded");
     // the node table as FreeFEM numbered it (2-D P2 is renumbered by FreeFEM: never guessed, always read)
     std::vector<int32_t> e2n;
     const int32_t *pe2n = nullptr;
@@ -270,6 +323,8 @@ DevSpace &device_space(const FESpaceT &Vh)
     int ndof = 0;
     FFC(ffcuda_space_info(D->space, &ndof, nullptr, nullptr));
     if (ndof != Vh.NbOfDF) fail("internal: device space has another number of dofs than the fespace");
+    mk.mark("space");
+    if (g_verbose) cout << "  -- ffcuda: fespace on the device (" << host_threads() << " host threads):" << mk.line << endl;
     g_spaces.insert(g_spaces.begin(), std::move(D));
     if (g_spaces.size() > kMaxSpaces) g_spaces.pop_back();
     return *g_spaces[0];
@@ -927,6 +982,7 @@ MatriceMorse<double> *gpu_matrix(Stack stack, const FESpaceT &Vh, DevSpace &D, c
         }
         if (ds.sym) rc = ffcuda_pattern_lower_nnz(P, &nnz); // half storage: FreeFEM keeps the entries (i, j <= i); the device matrix stays full
         if (!rc) {
+            Marks hmk;
             M = new MatriceMorse<double>(n, n, 0, 0);
             HashMatrix<int, double> *H = M;
             H->clear();
@@ -934,14 +990,52 @@ MatriceMorse<double> *gpu_matrix(Stack stack, const FESpaceT &Vh, DevSpace &D, c
             H->Increaze((size_t)nnz);
             H->nnz = (size_t)nnz;
             H->setp(n + 1);
+            // the arrays are fresh from the allocator: their pages are touched by several threads before the driver copies
+            // into them (a single-threaded first touch of 0.9 GB was most of the 0.28 s the downloads took at cube(128))
+            {
+                auto touch = [&](void *ptr, size_t bytes) {
+                    char *c = static_cast<char *>(ptr);
+                    par_for((bytes + 4095) / 4096, [&](size_t b, size_t e) {
+                        for (size_t pg = b; pg < e; ++pg) c[pg * 4096] = 0;
+                    });
+                };
+                touch(H->i, (size_t)nnz * sizeof(int));
+                touch(H->j, (size_t)nnz * sizeof(int));
+                touch(H->aij, (size_t)nnz * sizeof(double));
+                touch(H->next, (size_t)nnz * sizeof(size_t));
+                touch(H->head, (size_t)H->nhash * sizeof(size_t));
+                hmk.mark("arrays allocated and touched");
+            }
             if (ds.sym) rc = ffcuda_pattern_download_lower(P, H->p, H->j) || ffcuda_matrix_download_lower(dA, H->aij);
             else rc = ffcuda_pattern_download(P, H->p, H->j) || ffcuda_matrix_download(dA, H->aij);
             if (!rc) {
-                for (int i = 0; i < n; ++i)
-                    for (int k = H->p[i]; k < H->p[i + 1]; ++k) H->i[k] = i;
-                H->ReHash();
+                hmk.mark("downloaded");
+                par_for((size_t)n, [&](size_t b, size_t e) {
+                    for (size_t i = b; i < e; ++i)
+                        for (int k = H->p[i]; k < H->p[i + 1]; ++k) H->i[k] = (int)i;
+                });
+                // the hash chains of ReHash (femlib/HashMatrix.cpp:631-642: next[k] = head[h]; head[h] = k), built by several
+                // threads with an atomic exchange on the heads: the same chains up to the order inside a chain, which only
+                // the look-up walks
+                {
+                    size_t *head = H->head, *next = H->next;
+                    const size_t nhash = H->nhash;
+                    par_for(nhash, [&](size_t b, size_t e) {
+                        for (size_t h = b; h < e; ++h) head[h] = HashMatrix<int, double>::empty;
+                    });
+                    const int *pi = H->i, *pj = H->j;
+                    const size_t nn = (size_t)H->n;
+                    par_for((size_t)nnz, [&](size_t b, size_t e) {
+                        for (size_t k = b; k < e; ++k) {
+                            const size_t h = ((size_t)pi[k] + (size_t)pj[k] * nn) % nhash; // HashMatrix::hash, fortran = 0
+                            next[k] = __atomic_exchange_n(&head[h], k, __ATOMIC_RELAXED);
+                        }
+                    });
+                }
                 H->state = HashMatrix<int, double>::sorted_ij;
                 H->type_state = HashMatrix<int, double>::type_CSR;
+                hmk.mark("rows expanded, hash chains built");
+                if (g_verbose) cout << "  -- ffcuda: hand-over of the matrix:" << hmk.line << endl;
             }
         }
     }
