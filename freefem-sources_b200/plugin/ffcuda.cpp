@@ -18,6 +18,7 @@
 //              FFCUDA_DISABLE=1 (register nothing).
 #include "ff++.hpp"
 #include <chrono>
+#include <sys/mman.h>
 #include <thread>
 #include "AFunction_ext.hpp"
 #include <cstdlib>
@@ -987,23 +988,39 @@ MatriceMorse<double> *gpu_matrix(Stack stack, const FESpaceT &Vh, DevSpace &D, c
             HashMatrix<int, double> *H = M;
             H->clear();
             H->half = ds.sym ? 1 : 0;
-            H->Increaze((size_t)nnz);
-            H->nnz = (size_t)nnz;
-            H->setp(n + 1);
-            // the arrays are fresh from the allocator: their pages are touched by several threads before the driver copies
-            // into them (a single-threaded first touch of 0.9 GB was most of the 0.28 s the downloads took at cube(128))
+            // the arrays of HashMatrix::Increaze (femlib/HashMatrix.cpp:606-628: i, j, aij, next of nnz entries, head of
+            // max(n,m) * min(max(1, nnz/max(n,m)), 50) hash heads), allocated here so that their pages can be asked for as
+            // huge pages and touched by several threads before the driver copies into them (first touch of 1.1 GB by one
+            // thread, head[] filled by ReHash on one thread: 0.34 s at cube(128) when Increaze did it)
             {
+                const size_t mnx = (size_t)n, nzzx = std::max<size_t>((size_t)nnz, 1);
+                const double nnzl = std::min(std::max(1., double(nzzx) / double(mnx)), 50.);
+                const size_t nh = (size_t)(mnx * nnzl);
+                delete[] H->i; delete[] H->j; delete[] H->aij; delete[] H->next; delete[] H->head;
+                H->i = new int[nzzx];
+                H->j = new int[nzzx];
+                H->aij = new double[nzzx];
+                H->next = new size_t[nzzx];
+                H->head = new size_t[nh];
+                H->nnzmax = nzzx;
+                H->nhash = nh;
+                H->nnz = (size_t)nnz;
+                H->setp(n + 1);
                 auto touch = [&](void *ptr, size_t bytes) {
                     char *c = static_cast<char *>(ptr);
+#ifdef MADV_HUGEPAGE
+                    const uintptr_t a0 = ((uintptr_t)c + 4095) & ~(uintptr_t)4095, a1 = ((uintptr_t)c + bytes) & ~(uintptr_t)4095;
+                    if (a1 > a0) madvise((void *)a0, a1 - a0, MADV_HUGEPAGE);
+#endif
                     par_for((bytes + 4095) / 4096, [&](size_t b, size_t e) {
                         for (size_t pg = b; pg < e; ++pg) c[pg * 4096] = 0;
                     });
                 };
-                touch(H->i, (size_t)nnz * sizeof(int));
-                touch(H->j, (size_t)nnz * sizeof(int));
-                touch(H->aij, (size_t)nnz * sizeof(double));
-                touch(H->next, (size_t)nnz * sizeof(size_t));
-                touch(H->head, (size_t)H->nhash * sizeof(size_t));
+                touch(H->i, nzzx * sizeof(int));
+                touch(H->j, nzzx * sizeof(int));
+                touch(H->aij, nzzx * sizeof(double));
+                touch(H->next, nzzx * sizeof(size_t));
+                touch(H->head, nh * sizeof(size_t));
                 hmk.mark("arrays allocated and touched");
             }
             if (ds.sym) rc = ffcuda_pattern_download_lower(P, H->p, H->j) || ffcuda_matrix_download_lower(dA, H->aij);
