@@ -564,6 +564,14 @@ __global__ void __launch_bounds__(SYM_THREADS) k_sym_p1_fused(int nrows, const i
     int nu = 0, diag = 0;
 #pragma unroll
     for (int w = 0; w < SYM_WORDS; ++w) sbm[w][tid] = 0u;
+    // the block's ascending vertex list (the columns) is requested now and used at the very end: the expansion of the
+    // bitmaps into columns was a chain of dependent global loads (a third of the stall samples in the r02 capture)
+    __shared__ int32_t sbv[SYM_THREADS / 32][FF_STAGE_MAX];
+    if (blk < nblk) {
+        const int32_t *bvg = blkvert + (size_t)blk * FF_STAGE_MAX;
+#pragma unroll
+        for (int j = 0; j < FF_STAGE_MAX / 32; ++j) sbv[warp][j * 32 + lane] = __ldg(bvg + j * 32 + lane);
+    }
     if (blk < nblk) {
         const int mycnt = row < nrows ? cnt[row] : 0;
         const uint32_t base = blkoff[blk];
@@ -662,7 +670,7 @@ __global__ void __launch_bounds__(SYM_THREADS) k_sym_p1_fused(int nrows, const i
     const bool staged = span <= cap;
     int32_t *stg = scol + (size_t)warp * cap;
     if (row < nrows && nu > 0) {
-        const int32_t *bv = blkvert + (size_t)blk * FF_STAGE_MAX;
+        const int32_t *bv = sbv[warp];
         int oo = o;
 #pragma unroll
         for (int w = 0; w < SYM_WORDS; ++w) {
@@ -670,7 +678,7 @@ __global__ void __launch_bounds__(SYM_THREADS) k_sym_p1_fused(int nrows, const i
             while (bits) {
                 const int b = __ffs(bits) - 1;
                 bits &= bits - 1u;
-                const int32_t c = __ldg(bv + w * 32 + b);
+                const int32_t c = bv[w * 32 + b];
                 if (staged) stg[oo - o0] = c;
                 else ncol[oo] = c;
                 ++oo;

@@ -1381,14 +1381,16 @@ __global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restr
             }
         }
     }
-    // part C: header [0 nr, 1 ngr, 2 nvals, 3 o_grow, 4 o_rgrp, 5 o_codes, 6 words, 7 o_fgrp], fan groups (first value slot |
+    // part C: header [0 nr, 1 ngr, 2 nvals, 3 o_grow, 4 o_rgrp, 5 o_codes, 6 o_rloc, 7 o_fgrp], fan groups (first value slot |
     // kmax << 16), global row ids in sorted order, row groups (first code word | words per lane << 24), codes
     {
         uint32_t *gC = fcblob + fcoff[t];
-        const int o_fg = 8, o_grow = o_fg + pad4(ngf), o_rgrp = o_grow + pad4(nr), o_rc = o_rgrp + pad4(ngr + 1), wordsC = o_rc + pad4(ncw_r);
+        const int o_fg = 8, o_grow = o_fg + pad4(ngf), o_rgrp = o_grow + pad4(nr), o_rc = o_rgrp + pad4(ngr + 1), o_rloc = o_rc + pad4(ncw_r);
         if (tid == 0) {
-            gC[0] = nr; gC[1] = ngr; gC[2] = nvals_r; gC[3] = o_grow; gC[4] = o_rgrp; gC[5] = o_rc; gC[6] = wordsC; gC[7] = o_fg;
+            gC[0] = nr; gC[1] = ngr; gC[2] = nvals_r; gC[3] = o_grow; gC[4] = o_rgrp; gC[5] = o_rc; gC[6] = o_rloc; gC[7] = o_fg;
         }
+        // local row of every sorted row (mass forms: the diagonal needs the row's entries and its star's measure together)
+        for (int e = tid; e < pad4(nr); e += TB_THREADS) gC[o_rloc + e] = e < nr ? (rkey[e] & 0xfffu) : 0u;
         for (int x = tid; x < pad4(ngf); x += TB_THREADS) gC[o_fg + x] = x < ngf ? ((uint32_t)rfg[x] | ((uint32_t)(fgt[x] >> 16) << 16)) : 0u;
         for (int e = tid; e < pad4(nr); e += TB_THREADS) gC[o_grow + e] = e < nr ? (uint32_t)rord[r0 + (rkey[e] & 0xfffu)] : 0u;
         for (int x = tid; x < pad4(ngr + 1); x += TB_THREADS)
@@ -1423,12 +1425,17 @@ __global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restr
 
 struct FanSmem { // byte offsets of the shared-memory regions (part A of the descriptor at 0)
     int bufB, vals, ent;
+    int bufC, wvals; // mass forms: part C of the descriptor and the vertex sums of |det|
 };
 
-template <int THREADS, int MINB>
+// MASS: the form has a mass term m u v (heat, config 4): every off-diagonal entry of an element also gets m_o |K| (cmo * det),
+// the diagonal (m_d + 3 m_o) times the measure of the row's star - the vertex sums of |det| of the right-hand-side
+// kernel (part C of the descriptor), gathered per row next to the row sum of its entries.
+template <int THREADS, int MINB, bool MASS>
 __global__ void __launch_bounds__(THREADS, MINB) k_asm_fans(const uint32_t *__restrict__ foff, const uint32_t *__restrict__ fhead,
-                                                            const uint32_t *__restrict__ fblob, int ntiles, double *__restrict__ out,
-                                                            int accumulate, double cw, const FanSmem S)
+                                                            const uint32_t *__restrict__ fblob, const uint32_t *__restrict__ fcoff,
+                                                            const uint32_t *__restrict__ fcblob, int ntiles, double *__restrict__ out,
+                                                            int accumulate, double cw, double cmd, double cmo, const FanSmem S)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) unsigned long long mbar[2]; // [0]: part A arrived, [1]: part B arrived
@@ -1436,6 +1443,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_asm_fans(const uint32_t *__re
     double *sE = reinterpret_cast<double *>(smem_raw + S.ent);  // off-diagonal sums of the tile's entries, CSR order
     const uint32_t *sA = reinterpret_cast<const uint32_t *>(smem_raw);
     const uint32_t *sB = reinterpret_cast<const uint32_t *>(smem_raw + S.bufB);
+    const uint32_t *sC = reinterpret_cast<const uint32_t *>(smem_raw + S.bufC);
+    double *sW = reinterpret_cast<double *>(smem_raw + S.wvals);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     constexpr int NW = THREADS / 32;
     tile_mbar_init(mbar);
@@ -1446,13 +1455,20 @@ __global__ void __launch_bounds__(THREADS, MINB) k_asm_fans(const uint32_t *__re
     };
     auto issueB = [&](int t) {
         const uint32_t w0 = __ldg(foff + t), wa = __ldg(fhead + t), bytes = (__ldg(foff + t + 1) - w0 - wa) * 4u;
-        tile_expect(smem_u32(&mbar[1]), bytes);
+        uint32_t c0 = 0, cbytes = 0;
+        if (MASS) {
+            c0 = __ldg(fcoff + t);
+            cbytes = (__ldg(fcoff + t + 1) - c0) * 4u;
+        }
+        tile_expect(smem_u32(&mbar[1]), bytes + cbytes);
         tile_bulk(smem_u32(smem_raw + S.bufB), fblob + w0 + wa, bytes, smem_u32(&mbar[1]));
+        if (MASS) tile_bulk(smem_u32(smem_raw + S.bufC), fcblob + c0, cbytes, smem_u32(&mbar[1]));
     };
     int t = blockIdx.x;
     uint32_t ph = 0;
     if (tid == 0) {
         sV[0] = 0.0;
+        if (MASS) sW[0] = 0.0;
         if (t < ntiles) {
             issueA(t);
             issueB(t);
@@ -1460,6 +1476,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_asm_fans(const uint32_t *__re
     }
     for (; t < ntiles; t += gridDim.x, ph ^= 1) {
         tile_wait(smem_u32(&mbar[0]), ph);
+        if (MASS) tile_wait(smem_u32(&mbar[1]), ph); // (the fan groups of the vertex sums are in part C)
         {
             const int nfan = sA[2], ngf = sA[4];
             const uint32_t *fgrp = sA + sA[7];
@@ -1482,6 +1499,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_asm_fans(const uint32_t *__re
                 double bx = R[0] - px, by = R[1] - py, bz = R[2] - pz;
                 double cx = ay * bz - az * by, cy = az * bx - ax * bz, cz = ax * by - ay * bx; // a x b
                 double accA = 0.0, carp = 0.0, carq = 0.0;
+                double wtot = 0.0, wprev = 0.0; // MASS: sum of |det| over the fan, |det| of the previous element
+                double *wv = MASS ? sW + ((sC + sC[7])[G] & 0xffffu) : nullptr;
                 int jp = 1, jq = 1 + K1, jr = 1 + 2 * K1;
                 // the coordinates of the next ring vertex are fetched one step ahead (slot 0 past the end: harmless)
                 const double *R1 = coord + 3 * ((uint32_t)(rr >> 8) & 255u);
@@ -1500,7 +1519,8 @@ __global__ void __launch_bounds__(THREADS, MINB) k_asm_fans(const uint32_t *__re
                         const double n1x = by * ez - bz * ey, n1y = bz * ex - bx * ez, n1z = bx * ey - by * ex;
                         const double det = ax * n1x + ay * n1y + az * n1z;
                         const double n0x = fx - n1x - cx, n0y = fy - n1y - cy, n0z = fz - n1z - cz;
-                        const double s = cw * tile_rcp(fabs(det));
+                        const double adet = fabs(det);
+                        const double s = cw * tile_rcp(adet);
                         K01 = s * (n0x * n1x + n0y * n1y + n0z * n1z);
                         K02 = -s * (n0x * fx + n0y * fy + n0z * fz);
                         K03 = s * (n0x * cx + n0y * cy + n0z * cz);
@@ -1509,6 +1529,16 @@ __global__ void __launch_bounds__(THREADS, MINB) k_asm_fans(const uint32_t *__re
                         K23 = -s * (fx * cx + fy * cy + fz * cz);
                         bx = ex; by = ey; bz = ez;
                         cx = fx; cy = fy; cz = fz;
+                        if (MASS) {
+                            const double mo = cmo * adet;
+                            K01 += mo; K02 += mo; K03 += mo; K12 += mo; K13 += mo; K23 += mo;
+                            wtot += adet;
+                            wv[32 * (1 + tt) + ((lane + 1 + tt) & 31)] = wprev + adet; // ring vertex t: elements t-1 and t
+                            wprev = adet;
+                        }
+                    } else if (MASS) {
+                        wv[32 * (1 + tt) + ((lane + 1 + tt) & 31)] = wprev;
+                        wprev = 0.0;
                     }
                     accA += K01;
                     v[32 * jp + ((lane + jp) & 31)] = carp + K02; // spoke p - r_t: elements t-1 and t
@@ -1521,6 +1551,10 @@ __global__ void __launch_bounds__(THREADS, MINB) k_asm_fans(const uint32_t *__re
                 v[32 * jp + ((lane + jp) & 31)] = carp;
                 v[32 * jq + ((lane + jq) & 31)] = carq;
                 v[lane] = accA;
+                if (MASS) {
+                    wv[32 * (1 + kmax) + ((lane + 1 + kmax) & 31)] = wprev;
+                    wv[lane] = wtot;
+                }
             }
         }
         __syncthreads(); // the values are complete; part A is free
@@ -1572,17 +1606,47 @@ __global__ void __launch_bounds__(THREADS, MINB) k_asm_fans(const uint32_t *__re
             }
         }
         __syncthreads();
-        // ---- diagonals: K_ii = -sum_{j != i} K_ij (partition of unity)
-        for (int l = tid; l < nr; l += THREADS) {
-            const uint32_t ri = rinfo[l];
-            const int q0 = ri & 0xffffu, L = ri >> 24;
-            if (L == 0) continue;
-            double sx = 0.0;
-            for (int kq = 0; kq < L; ++kq) sx += sE[q0 + kq];
-            double *dst = out + (size_t)gbase[l] + ((ri >> 16) & 255u);
-            *dst = accumulate ? *dst - sx : -sx;
+        // ---- diagonals: K_ii = -sum_{j != i} K_ij (partition of unity: with a mass term every off-diagonal entry carries
+        // m_o |K| per element, 3 per element in the row sum) + (m_d + 3 m_o) * measure of the star
+        if (!MASS) {
+            for (int l = tid; l < nr; l += THREADS) {
+                const uint32_t ri = rinfo[l];
+                const int q0 = ri & 0xffffu, L = ri >> 24;
+                if (L == 0) continue;
+                double sx = 0.0;
+                for (int kq = 0; kq < L; ++kq) sx += sE[q0 + kq];
+                double *dst = out + (size_t)gbase[l] + ((ri >> 16) & 255u);
+                *dst = accumulate ? *dst - sx : -sx;
+            }
+        } else {
+            const int ngr = sC[1];
+            const uint32_t *rgrp = sC + sC[4], *rcodes = sC + sC[5], *rloc = sC + sC[6];
+            for (int g = warp; g < ngr; g += NW) { // rows in part C's order (sorted by the number of fans around them)
+                const int e = g * 32 + lane;
+                const uint32_t eg = rgrp[g], nk = eg >> 24;
+                const uint32_t *cp = rcodes + (eg & 0xffffffu) + lane;
+                double sd = 0.0;
+#pragma unroll 2
+                for (uint32_t kk = 0; kk < nk; ++kk) {
+                    const uint32_t c = cp[kk * 32];
+                    sd += sW[c & 0xffffu];
+                    sd += sW[c >> 16];
+                }
+                if (e < nr) {
+                    const int l = (int)rloc[e];
+                    const uint32_t ri = rinfo[l];
+                    const int q0 = ri & 0xffffu, L = ri >> 24;
+                    if (L != 0) {
+                        double sx = 0.0;
+                        for (int kq = 0; kq < L; ++kq) sx += sE[q0 + kq];
+                        const double d = (cmd + 3.0 * cmo) * sd - sx;
+                        double *dst = out + (size_t)gbase[l] + ((ri >> 16) & 255u);
+                        *dst = accumulate ? *dst + d : d;
+                    }
+                }
+            }
         }
-        __syncthreads(); // part B, sV and sE are free again
+        __syncthreads(); // part B (and C), sV, sW and sE are free again
         if (tid == 0 && t + (int)gridDim.x < ntiles) issueB(t + gridDim.x);
     }
 }
@@ -1940,7 +2004,7 @@ void build_fans(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr, const 
         hoff[t] = (uint32_t)off;
         hhead[t] = (uint32_t)head;
         off += (uint64_t)words;
-        const int wordsC = 8 + pad4(ngf) + pad4(nr) + pad4(((nr + 31) >> 5) + 1) + pad4(h[11]);
+        const int wordsC = 8 + pad4(ngf) + 2 * pad4(nr) + pad4(((nr + 31) >> 5) + 1) + pad4(h[11]);
         hcoff[t] = (uint32_t)coff;
         coff += (uint64_t)wordsC;
         T.fan_max_c = std::max(T.fan_max_c, wordsC);
@@ -2019,7 +2083,7 @@ bool ff_asm_p1_tiles(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, double 
     ffcuda_mesh *m = s->mesh;
     const int dim = m->dim;
     const bool mass = (cmd != 0.0 || cmo != 0.0);
-    if (!mass && dim == 3 && T.fan_state == 1 && ctx->tile_fans != 0) {
+    if (dim == 3 && T.fan_state == 1 && ctx->tile_fans != 0) {
         FanSmem FS;
         size_t o = ((size_t)T.fan_max_head * 4 + 127) & ~(size_t)127;
         FS.bufB = (int)o;
@@ -2027,19 +2091,28 @@ bool ff_asm_p1_tiles(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, double 
         FS.vals = (int)o; // 128-byte aligned: the bank of a value is its slot mod 16 (the build kernel orders the lists by it)
         o += ((size_t)T.fan_max_nvals * 8 + 127) & ~(size_t)127;
         FS.ent = (int)o;
-        o += (size_t)(T.fan_max_nq + 1) * 8;
+        o += ((size_t)(T.fan_max_nq + 1) * 8 + 127) & ~(size_t)127;
+        FS.bufC = FS.wvals = 0;
+        if (mass) {
+            FS.bufC = (int)o;
+            o += ((size_t)T.fan_max_c * 4 + 127) & ~(size_t)127;
+            FS.wvals = (int)o;
+            o += ((size_t)T.fan_max_rvals * 8 + 127) & ~(size_t)127;
+        }
         const size_t shmem = o;
         if (shmem <= 200 * 1024) {
             int threads = 128;
             if (const char *e = getenv("FFCUDA_FAN_THREADS")) threads = atoi(e);
             auto runf = [&](auto kern, int thr) {
                 tile_launch(ctx, "asm_rows_p1", kern, thr, shmem, T.ntiles, [&](int grid) {
-                    kern<<<grid, thr, shmem, ctx->stream>>>(T.foff.p, T.fhead.p, T.fblob.p, T.ntiles, A->vals.p, accumulate, cw, FS);
+                    kern<<<grid, thr, shmem, ctx->stream>>>(T.foff.p, T.fhead.p, T.fblob.p, T.fcoff.p, T.fcblob.p, T.ntiles, A->vals.p, accumulate,
+                                                            cw, cmd, cmo, FS);
                 });
             };
-            if (threads == 256) runf(k_asm_fans<256, 2>, 256);
-            else if (threads == 64) runf(k_asm_fans<64, 8>, 64);
-            else runf(k_asm_fans<128, 5>, 128);
+            if (mass) runf(k_asm_fans<128, 3, true>, 128);
+            else if (threads == 256) runf(k_asm_fans<256, 2, false>, 256);
+            else if (threads == 64) runf(k_asm_fans<64, 8, false>, 64);
+            else runf(k_asm_fans<128, 5, false>, 128);
             return true;
         }
     }

@@ -270,3 +270,44 @@ def test_pattern_download_async_overlaps_and_matches(ctx):
     ctx.sync()
     rp0, ci0 = pat.download()
     assert np.array_equal(rp, rp0) and np.array_equal(ci, ci0)
+
+
+@pytest.mark.parametrize("size", [(7, 6, 9), (20, 17, 13)])
+def test_fans_against_oracle_and_round1_tiles(ctx, size):
+    """3-D: the fan kernels (stiffness, heat form with its mass term, value-only right-hand side) against the oracle and
+    against the element-by-element tile kernels of round 1 (tile_fans = 0): same pattern, values 1e-12, bit-identical from
+    run to run; the fan kernels are the ones that run (asm_rows_p1 / rhs_rows launches of a space with tiles)."""
+    m = ol.cube(*size)
+    n = m["xyz"].shape[0]
+    qp, qw = ffcuda.quadrature(3, 6)
+    heat = [(0, fc.ID, 0, fc.ID, 100.0)] + fc.LAP3
+    rhs = [(0, fc.ID, 2.5)]
+    ob = ol.assemble_rhs(m, 1, 1, None, n, rhs, qp, qw)
+    res = {}
+    for fans in (1, 0):
+        ctx.set_option("tile_fans", fans)
+        mesh = ctx.mesh_cube(*size)
+        sp, pat, A = _assemble(ctx, mesh, fc.LAP3, qp, qw, 2, 96)
+        rp, col = pat.download()
+        orp, ocol, oval = _oracle_vals(m, n, fc.LAP3, qp, qw)
+        assert np.array_equal(rp, orp) and np.array_equal(col, ocol)
+        v = A.download()
+        assert np.max(np.abs(v - oval)) <= RTOL * np.abs(oval).max()
+        A.assemble(heat, qp, qw)
+        hv = A.download()
+        _, _, ohv = _oracle_vals(m, n, heat, qp, qw)
+        assert np.max(np.abs(hv - ohv)) <= RTOL * np.abs(ohv).max()
+        A.assemble(heat, qp, qw)
+        assert np.array_equal(A.download(), hv)          # bit-reproducible
+        A.assemble(fc.LAP3, qp, qw, accumulate=True)      # accumulate on top of the heat matrix
+        assert np.max(np.abs(A.download() - (ohv + oval))) <= RTOL * np.abs(ohv).max()
+        b = ctx.vec(n)
+        sp.assemble_linear(b, rhs, qp, qw)
+        hb = b.download()
+        assert np.max(np.abs(hb - ob)) <= RTOL * np.abs(ob).max()
+        sp.assemble_linear(b, rhs, qp, qw, accumulate=True)
+        assert np.max(np.abs(b.download() - 2 * ob)) <= RTOL * np.abs(ob).max()
+        res[fans] = (v, hv, hb)
+    ctx.set_option("tile_fans", 1)
+    for a, b_ in zip(res[0], res[1]):
+        assert np.max(np.abs(a - b_)) <= RTOL * np.abs(a).max()

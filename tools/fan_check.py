@@ -35,6 +35,14 @@ for size in [(1, 1, 1), (2, 3, 1), (5, 4, 6), (11, 9, 13), (24, 24, 24)]:
         err = np.max(np.abs(val - oval)) / np.abs(oval).max()
         A.assemble(fc.LAP3, qp, qw)
         same = np.array_equal(A.download(), val)
+        heat = [(0, fc.ID, 0, fc.ID, 100.0)] + fc.LAP3
+        hi, hj, ha = ol.assemble_coo(m, 1, 1, None, heat, qp, qw)
+        _, _, hval = ol.coo_to_csr(N, hi, hj, ha)
+        A.assemble(heat, qp, qw)
+        hv = A.download()
+        errh = np.max(np.abs(hv - hval)) / np.abs(hval).max()
+        A.assemble(heat, qp, qw)
+        assert errh <= 1e-12 and np.array_equal(A.download(), hv), ("heat form", errh)
         b = ctx.vec(N)
         sp.assemble_linear(b, [(0, fc.ID, 2.5)], qp, qw)
         ob = ol.assemble_rhs(m, 1, 1, None, N, [(0, fc.ID, 2.5)], qp, qw)
@@ -87,7 +95,23 @@ import scipy.sparse as sps  # noqa: E402
 rp, col = pat.download()
 M = sps.csr_matrix((A.download(), col, rp), shape=(N, N))
 print("row sums", np.max(np.abs(M @ np.ones(N))), "sym", abs(M - M.T).max())
+heat = [(0, fc.ID, 0, fc.ID, 100.0)] + fc.LAP3
+AH = pat.matrix()
+AH.assemble(heat, qp, qw)
+ctx.prof_reset()
+for _ in range(5):
+    AH.assemble(heat, qp, qw)
+ctx.sync()
+ms, cnt = ctx.prof_get("asm_rows_p1")
+print(f"heat form on the fans: {ms / cnt:.4f} ms per launch")
+hv = AH.download()
 ctx.set_option("tile_fans", 0)
+ctx.prof_reset()
+for _ in range(3):
+    AH.assemble(heat, qp, qw)
+ctx.sync()
+ms, cnt = ctx.prof_get("asm_rows_p1")
+print(f"heat form, round-1 tile kernel: {ms / cnt:.4f} ms; max rel diff {np.max(np.abs(AH.download() - hv)) / np.abs(hv).max():.2e}")
 ctx.prof_reset()
 A2 = pat.matrix()
 for _ in range(5):
