@@ -348,6 +348,7 @@ struct TileSet {
     DBuf<uint32_t> rblob;     // record lists of the rows, one blob per tile: (element << 2 | local vertex) of every star
     DBuf<uint32_t> roff;      // ntiles+1 offsets into rblob
     // fan set (tiles.cu, 3-D): the same tiles with their elements grouped in fans around a common edge
+    bool has_blob = true;     // the element-by-element descriptors (blob / rblob) exist (not built on 3-D spaces that run on the fans)
     int fan_state = 0;        // 1 ready, -1 not applicable
     int fan_max_head = 0, fan_max_b = 0, fan_max_nvals = 0, fan_max_nq = 0; // largest part A / part B (words), value table, entries
     int64_t fan_sum_fans = 0;

@@ -1016,6 +1016,7 @@ __global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restr
     int *rpos = reinterpret_cast<int *>(rkey + TR_CAP);      // TR_CAP: sorted position of every row
     int *rgl = rpos + TR_CAP;                                // TR_CAP/32 + 1: first code word of every row group
     int *rfg = rgl + 16;                                     // 64: fan groups of the right-hand side: first value slot
+    uint32_t *scw = reinterpret_cast<uint32_t *>(rfg + 64);  // 4096 words: the code lists while they are filled and ordered
     static_assert(NE_CAP == 2048 && NQ_CAP + 1 <= 4096 && SORT_CAP >= 6464, "scratch layout of k_fan_build");
     if (fit) {
         // F1. axis of every element: its longest edge (ties: the smallest pair of global vertex ids, the same choice in
@@ -1186,7 +1187,9 @@ __global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restr
         // F6. entries sorted by decreasing list length, taken in groups of 32 (one warp): the group's lists are padded to
         // the longest = the first one, rounded up to even (two 16-bit codes per word) - next to no padding
         nge = (nq + 31) >> 5;
-        for (int x = tid; x < 4096; x += TB_THREADS) {
+        int m4 = 32; // (the sort works on the next power of two, not on the capacity: 1024 for a typical tile)
+        while (m4 < nq) m4 <<= 1;
+        for (int x = tid; x < m4; x += TB_THREADS) {
             uint32_t key = 0xffffffffu;
             if (x < nq) {
                 if (cntq[x] > 62) s_bad = 1;
@@ -1195,7 +1198,7 @@ __global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restr
             skey[x] = key;
         }
         __syncthreads();
-        blk_sort(skey, 4096);
+        blk_sort(skey, m4);
         for (int e = tid; e < nq; e += TB_THREADS) epos[skey[e] & 0xfffu] = e;
         for (int g = tid; g <= nge; g += TB_THREADS) egl[g] = g < nge ? ((cntq[skey[g * 32] & 0xfffu] + 1) >> 1) * 32 : 0; // words
         __syncthreads();
@@ -1239,7 +1242,9 @@ __global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restr
         });
         __syncthreads();
         ngr = (nr + 31) >> 5;
-        for (int l = tid; l < TR_CAP; l += TB_THREADS) {
+        int mr = 32;
+        while (mr < nr) mr <<= 1;
+        for (int l = tid; l < mr; l += TB_THREADS) {
             uint32_t key = 0xffffffffu;
             if (l < nr) {
                 if (rcnt[l] > 126) s_bad = 1;
@@ -1248,7 +1253,7 @@ __global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restr
             rkey[l] = key;
         }
         __syncthreads();
-        blk_sort(rkey, TR_CAP);
+        blk_sort(rkey, mr);
         for (int e = tid; e < nr; e += TB_THREADS) rpos[rkey[e] & 0xfffu] = e;
         for (int g = tid; g <= ngr; g += TB_THREADS) rgl[g] = g < ngr ? ((rcnt[rkey[g * 32] & 0xfffu] + 1) >> 1) * 32 : 0;
         __syncthreads();
@@ -1323,10 +1328,14 @@ __global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restr
         gA[o_fans + 4 * f + 2] = w[2];
         gA[o_fans + 4 * f + 3] = 0u;
     }
-    for (int x = tid; x < pad4(ncw); x += TB_THREADS) g[o_codes + x] = 0u;
+    // the lists are filled, sorted and re-ordered in shared memory when they fit (4096 words: always on the tile sizes in
+    // use) and written out with coalesced stores; straight in global memory otherwise
+    const bool cw_sh = pad4(ncw) <= 4096;
+    uint32_t *cwbuf = cw_sh ? scw : g + o_codes;
+    for (int x = tid; x < pad4(ncw); x += TB_THREADS) cwbuf[x] = 0u;
     for (int x = tid; x <= nq; x += TB_THREADS) cursor[x] = 0;
     __syncthreads();
-    uint16_t *gc = reinterpret_cast<uint16_t *>(g + o_codes);
+    uint16_t *gc = reinterpret_cast<uint16_t *>(cwbuf);
     auto code_at = [&](int qq, int c) -> uint16_t & {
         const int e = epos[qq];
         return gc[2 * (egl[e >> 5] + (c >> 1) * 32 + (e & 31)) + (c & 1)];
@@ -1381,6 +1390,10 @@ __global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restr
             }
         }
     }
+    __syncthreads();
+    if (cw_sh)
+        for (int x = tid; x < pad4(ncw); x += TB_THREADS) g[o_codes + x] = scw[x];
+    __syncthreads();
     // part C: header [0 nr, 1 ngr, 2 nvals, 3 o_grow, 4 o_rgrp, 5 o_codes, 6 o_rloc, 7 o_fgrp], fan groups (first value slot |
     // kmax << 16), global row ids in sorted order, row groups (first code word | words per lane << 24), codes
     {
@@ -1395,10 +1408,12 @@ __global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restr
         for (int e = tid; e < pad4(nr); e += TB_THREADS) gC[o_grow + e] = e < nr ? (uint32_t)rord[r0 + (rkey[e] & 0xfffu)] : 0u;
         for (int x = tid; x < pad4(ngr + 1); x += TB_THREADS)
             gC[o_rgrp + x] = x < ngr ? ((uint32_t)rgl[x] | ((uint32_t)((rgl[x + 1] - rgl[x]) >> 5) << 24)) : (uint32_t)ncw_r;
-        for (int x = tid; x < pad4(ncw_r); x += TB_THREADS) gC[o_rc + x] = 0u;
+        const bool cr_sh = pad4(ncw_r) <= 4096;
+        uint32_t *crbuf = cr_sh ? scw : gC + o_rc;
+        for (int x = tid; x < pad4(ncw_r); x += TB_THREADS) crbuf[x] = 0u;
         for (int l = tid; l < TR_CAP; l += TB_THREADS) cursor[l] = 0;
         __syncthreads();
-        uint16_t *gcr = reinterpret_cast<uint16_t *>(gC + o_rc);
+        uint16_t *gcr = reinterpret_cast<uint16_t *>(crbuf);
         auto rcode_at = [&](int l, int c) -> uint16_t & {
             const int e = rpos[l];
             return gcr[2 * (rgl[e >> 5] + (c >> 1) * 32 + (e & 31)) + (c & 1)];
@@ -1420,6 +1435,9 @@ __global__ void __launch_bounds__(TB_THREADS) k_fan_build(const int32_t *__restr
                 rcode_at(l, y + 1) = v;
             }
         }
+        __syncthreads();
+        if (cr_sh)
+            for (int x = tid; x < pad4(ncw_r); x += TB_THREADS) gC[o_rc + x] = scw[x];
     }
 }
 
@@ -1939,6 +1957,20 @@ void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr)
         T.sum_nelem += nelem;
     }
     if (off >= ((uint64_t)1 << 32) || roffs >= ((uint64_t)1 << 32)) return;
+    // 3-D spaces with fans: the stiffness / heat matrices and the value-only right-hand sides run on the fan descriptors;
+    // the element-by-element descriptors (0.8 GB and 17 ms at cube(128)) are not built
+    T.has_blob = true;
+    if (dim == 3 && ctx->tile_fans != 0 && ctx->tile_policy != 2) {
+        build_fans(ctx, s, nrowptr, rord.p, d_tstart.p, ntiles);
+        if (T.fan_state == 1) {
+            T.has_blob = false;
+            T.nes = T.max_nelem | 1;
+            T.tr = tr;
+            T.ntiles = ntiles;
+            T.state = 1;
+            return;
+        }
+    }
     hroff[ntiles] = (uint32_t)roffs;
     T.nes = T.max_nelem | 1; // odd stride of the value table
     if ((DIM_PAIRS(dim) + 1) * T.nes > 65535) return;
@@ -1959,7 +1991,7 @@ void build_tiles(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr)
     T.tr = tr;
     T.ntiles = ntiles;
     T.state = 1;
-    build_fans(ctx, s, nrowptr, rord.p, d_tstart.p, ntiles);
+    if (T.fan_state == 0) build_fans(ctx, s, nrowptr, rord.p, d_tstart.p, ntiles);
     if (getenv("FFCUDA_VERBOSE"))
         fprintf(stderr, "ffcuda tiles: %d tiles of <= %d rows, max rows %d vertices %d elements %d entries %d codes %d, "
                         "%.2f evaluations per element, blobs %.1f + %.1f MB\n",
@@ -1975,7 +2007,7 @@ void build_fans(ffcuda_ctx *ctx, ffcuda_space *s, const int32_t *nrowptr, const 
     ffcuda_mesh *m = s->mesh;
     if (m->dim != 3 || ctx->tile_fans == 0) return;
     cudaStream_t st = ctx->stream;
-    const size_t shmem = (size_t)4 * (build_words() + 2 * 4096 + 3 * TR_CAP + 16 + 64);
+    const size_t shmem = (size_t)4 * (build_words() + 2 * 4096 + 3 * TR_CAP + 16 + 64 + 4096);
     FF_CUDA(cudaFuncSetAttribute(k_fan_build<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     FF_CUDA(cudaFuncSetAttribute(k_fan_build<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
     const IncView V = ff_view(s->incidence);
@@ -2116,6 +2148,7 @@ bool ff_asm_p1_tiles(ffcuda_ctx *ctx, ffcuda_matrix *A, ffcuda_space *s, double 
             return true;
         }
     }
+    if (!T.has_blob) return false; // (no element-by-element descriptors on this space: the thread-per-row kernel takes the form)
     const int NP = dim * (dim + 1) / 2;
     TileSmem S;
     size_t o = ((size_t)T.max_words * 4 + 127) & ~(size_t)127;
@@ -2180,6 +2213,7 @@ bool ff_rhs_p1_tiles(ffcuda_ctx *ctx, ffcuda_vec *b, ffcuda_space *s, const doub
     // gradient terms move 12 more values per element through shared memory: measured slower than the thread-per-row
     // kernel (350 vs 231 us on cube(128)); value-only forms: 162 vs 217 us
     if (hasgrad && ctx->tile_policy != 2) return false;
+    if (!T.has_blob) return false;
     const int dim = s->mesh->dim, nc = s->ncomp;
     RhsCoef C;
     memset(&C, 0, sizeof(C));

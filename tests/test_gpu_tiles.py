@@ -77,10 +77,11 @@ def test_tiles_policy_default_switches_on_second_assembly(ctx):
     v1 = A.download().copy()
     ctx.prof_enable(True)
     ctx.prof_reset()
-    A.assemble(fc.LAP3, qp, qw)   # second assembly on the fespace: the tile set is built and used
-    assert ctx.prof_get("tile_build")[1] == 1
+    A.assemble(fc.LAP3, qp, qw)   # second assembly on the fespace: the tiles are built and used
+    # (3-D, default policy: the fan descriptors only; the element-by-element ones are built with tile_policy 2 or tile_fans 0)
+    assert ctx.prof_get("fan_build")[1] == 1 and ctx.prof_get("tile_build")[1] == 0
     A.assemble(fc.LAP3, qp, qw)   # built once
-    assert ctx.prof_get("tile_build")[1] == 1
+    assert ctx.prof_get("fan_build")[1] == 1
     ctx.prof_enable(False)
     assert np.max(np.abs(A.download() - v1)) <= RTOL * np.abs(v1).max()
 
