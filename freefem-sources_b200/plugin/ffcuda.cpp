@@ -1668,6 +1668,14 @@ static void Load_Init()
         return;
     }
     if (verbosity) cout << " load: ffcuda (GPU assembly of P1/P2 varf + Jacobi-CG / GMRES; FreeFEM keeps everything else)" << endl;
+    // The CUDA context (driver initialisation, module load: about a second in a fresh process) is created here, while the
+    // script is being parsed, not inside the first `matrix A = ...` statement.  Without a device nothing happens now: the
+    // first claimed form raises the "no CPU fallback" error as before.  FFCUDA_LAZY_INIT=1 keeps the old behaviour.
+    if (!env_on("FFCUDA_LAZY_INIT") && !g_ctx) {
+        const char *d = getenv("FFCUDA_DEVICE");
+        ffcuda_ctx *c = nullptr;
+        if (ffcuda_ctx_create(d ? atoi(d) : 0, &c) == 0) g_ctx = c;
+    }
     // 1. matrices: "<-" constructs (init = 1), "=" assigns (init = 0)  (fflib/lgfem.cpp:6669,6673,6823,6826)
     TheOperators->Add("<-", new CudaMatrixOp<Mesh, v_fes>(1), new CudaMatrixOp<Mesh3, v_fes3>(1));
     TheOperators->Add("=", new CudaMatrixOp<Mesh, v_fes>(0), new CudaMatrixOp<Mesh3, v_fes3>(0));

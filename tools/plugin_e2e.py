@@ -9,6 +9,11 @@ with tempfile.TemporaryDirectory() as td:
     open(edp, "w").write(bench.EDP % ('load "ffcuda"', n))
     env = dict(os.environ, FF_LOADPATH=os.path.join(ROOT, "freefem-sources_b200", "lib"), FFCUDA_VERBOSE="1")
     r = subprocess.run([bench.FF_BIN, "-nw", "-v", "1", edp], capture_output=True, text=True, cwd=td, env=env)
+    try:
+        st = [float(x) for x in open(os.path.join(td, "ffstamps.txt")).read().split()]
+        print("wall: matrix %.3f s, rhs %.3f s, cg %.3f s" % (st[1] - st[0], st[2] - st[1], st[3] - st[2]))
+    except Exception as e:
+        print("no stamps", e)
     for ln in (r.stdout + r.stderr).splitlines():
         if "ffcuda" in ln or "FFBENCH" in ln or "GC" in ln:
             print(ln[:260])
