@@ -69,6 +69,7 @@ struct ffcuda_ctx {
     int tile_policy = 1;        // 0: never use row tiles, 1: from the second assembly on a fespace, 2: always
     int tile_rows = 96;         // rows per tile
     int tile_fans = 1;          // 3-D stiffness forms: elements of a tile evaluated in fans around their longest edge (0: element by element)
+    double last_cg_eps2 = 0.0;  // stopping threshold of the last CG solve on this context (ffcuda_cg_stop_threshold)
     int gmres_coop = 1;         // 1: one cooperative kernel per Arnoldi step when the vectors fit its registers, 0: one kernel per basis vector
     // reduction scratch (device) + pinned host mirror
     double *d_scal = nullptr;   // small array of device scalars

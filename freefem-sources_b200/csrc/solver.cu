@@ -1082,6 +1082,15 @@ static void cg_device(ffcuda_matrix *A, const double *b, double *x, double eps, 
     if (iters) *iters = nit;
     if (converged) *converged = ret;
     if (gcg_out) *gcg_out = hs[S_GCG0 + (nit & 1)];
+    ctx->last_cg_eps2 = hs[S_EPS2]; // the absolute threshold the solve stopped on (eps^2 * gCg0 for eps > 0)
+}
+
+extern "C" int ffcuda_cg_stop_threshold(ffcuda_matrix *A, double *eps2)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A && eps2, "ffcuda_cg_stop_threshold: null argument");
+    *eps2 = A->ctx->last_cg_eps2;
+    FF_API_END(A ? A->ctx : nullptr)
 }
 
 extern "C" int ffcuda_cg(ffcuda_matrix *A, ffcuda_vec *b, ffcuda_vec *x, double eps, int itmax, double tgv, int *iters,

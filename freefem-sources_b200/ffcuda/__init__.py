@@ -24,7 +24,7 @@ ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_
 ffcuda_assemble_linear ffcuda_assemble_linear_qvalues ffcuda_assemble_linear_qterms ffcuda_assemble_linear_boundary ffcuda_assemble_bilinear_boundary ffcuda_assemble_linear_boundary_qvalues ffcuda_assemble_bilinear_boundary_qcoef ffcuda_bc_from_pairs ffcuda_bc_from_labels ffcuda_bc_count ffcuda_matrix_apply_bc ffcuda_vec_apply_bc
 ffcuda_vec_set_bc_values ffcuda_bc_destroy ffcuda_spmv ffcuda_cg ffcuda_cg_host ffcuda_gmres ffcuda_gmres_host ffcuda_comm_unique_id ffcuda_comm_init
 ffcuda_comm_finalize ffcuda_mesh_cube_distributed ffcuda_mesh_local_to_global ffcuda_quadrature ffcuda_partition_cube
-ffcuda_partition_rcb ffcuda_partition_local ffcuda_matrix_export_device ffcuda_matrix_download_coo ffcuda_matrix_write_morse ffcuda_mesh_adjacency ffcuda_mesh_upload_distributed""".split()
+ffcuda_partition_rcb ffcuda_partition_local ffcuda_matrix_export_device ffcuda_matrix_download_coo ffcuda_matrix_write_morse ffcuda_mesh_adjacency ffcuda_mesh_upload_distributed ffcuda_cg_stop_threshold""".split()
 
 
 class FfcudaError(RuntimeError):
@@ -429,6 +429,11 @@ class Matrix(_Handle):
         out = np.zeros(nl.value)
         _ck(lib().ffcuda_matrix_download_lower(_h(self), _p(out)), self.ctx.h)
         return out
+
+    def cg_stop_threshold(self):
+        v = C.c_double()
+        _ck(lib().ffcuda_cg_stop_threshold(_h(self), C.byref(v)), self.ctx.h)
+        return v.value
 
     def export_device(self):
         """borrowed device pointers (ints) to the CSR triple: (rowptr, colind, vals, n, nnz)"""

@@ -1370,7 +1370,11 @@ class SolverCudaCG : public VirtualSolver<int, double> {
                 cout << " GC (ffcuda): " << (conv ? "converge" : "NO convergence") << " after " << iters << " g=" << gcg << endl;
             if (!conv) err++;
             else if (getnbiter) *getnbiter += iters;
-            if (veps) *veps = eps > 0 ? sqrt(gcg) : eps;
+            if (veps) { // what FreeFEM's SolverCG hands back: the absolute threshold ConjugueGradient stopped on (CG.cpp:226)
+                double eps2 = 0;
+                if (eps > 0 && ffcuda_cg_stop_threshold(dev.A, &eps2) == 0) *veps = sqrt(eps2);
+                else *veps = eps;
+            }
         }
         if (err) {
             std::cerr << "Error: ConjugueGradient (ffcuda) do not converge nb end =" << err << std::endl;

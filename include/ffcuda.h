@@ -269,6 +269,11 @@ int ffcuda_cg(ffcuda_matrix *A, ffcuda_vec *b, ffcuda_vec *x, double eps, int it
 int ffcuda_cg_host(ffcuda_matrix *A, const double *b, double *x, double eps, int itmax, double tgv,
                    int *iters, int *converged, double *gcg);
 
+/* the ABSOLUTE threshold on <g,Cg> the last CG solve of A's context stopped on: eps^2 * <g0,Cg0> for eps > 0 (ConjugueGradient
+ * rewrites its eps to the square root of this, femlib/CG.cpp:226, and SolverCG hands it back through `veps=`,
+ * femlib/VirtualSolverCG.hpp:186), eps^2 for eps < 0 */
+int ffcuda_cg_stop_threshold(ffcuda_matrix *A, double *eps2);
+
 /* GMRES for non-symmetric matrices: SolverGMRES (femlib/VirtualSolverCG.hpp:196-258) = SetInitWithBC + fgmres
  * (femlib/CG.cpp:347-517), flexible GMRES(restart) with the Jacobi preconditioner on the right, modified Gram-Schmidt;
  * stops when |g[it+1]| / ||b (tgv rows zeroed)|| < |eps| (eps < 0: absolute).  restart <= 0: FreeFEM's default 1000

@@ -507,3 +507,30 @@ def test_plugin_set_solver_and_transposed(name):
     rc, out_cpu, cpu = run_solve(body, "u", {"FFCUDA_DISABLE": "1"})
     assert rc == 0 and "(ffcuda)" not in out_cpu
     assert np.max(np.abs(gpu - cpu)) <= 1e-10 * np.abs(cpu).max()
+
+
+VEPS_CASE = """mesh3 Th = cube(5,4,6);
+fespace Vh(Th,P1); Vh u,v;
+varf va(u,v) = int3d(Th)(dx(u)*dx(v)+dy(u)*dy(v)+dz(u)*dz(v)) + int3d(Th)(1.*v) + on(1,2,3,4,5,6,u=0);
+real ve = 1e-6;
+matrix A = va(Vh,Vh,solver=CG,veps=ve);
+real[int] b = va(0,Vh);
+verbosity=1; u[] = 0; u[] = A^-1*b; verbosity=0;
+cout.precision(15);
+cout << "VEPS " << ve << endl;
+"""
+
+
+@needs_ff
+@pytest.mark.gpu
+def test_plugin_veps_is_the_stopping_threshold():
+    """`veps=` comes back as FreeFEM's SolverCG leaves it: the ABSOLUTE threshold sqrt(eps^2 <g0,Cg0>) ConjugueGradient stopped
+    on (femlib/CG.cpp:226, VirtualSolverCG.hpp:186), not the residual reached."""
+    rc, out, gpu = run_solve(VEPS_CASE, "u", {"FFCUDA_VERBOSE": "1"})
+    assert rc == 0 and "GC (ffcuda)" in out, out[-2000:]
+    rc, out_cpu, cpu = run_solve(VEPS_CASE, "u", {"FFCUDA_DISABLE": "1"})
+    assert rc == 0
+    vg = float(re.search(r"^VEPS (\S+)", out, re.M).group(1))
+    vc = float(re.search(r"^VEPS (\S+)", out_cpu, re.M).group(1))
+    assert vc != 1e-6 and abs(vg - vc) <= 1e-10 * abs(vc)
+    assert np.max(np.abs(gpu - cpu)) <= 1e-11 * np.abs(cpu).max()
