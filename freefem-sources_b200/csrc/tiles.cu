@@ -1,23 +1,27 @@
-// tiles.cu — numeric assembly of scalar P1 forms (c grad u . grad v + m u v) by ROW TILES.
+// tiles.cu — numeric assembly of scalar P1 forms (c grad u . grad v + m u v) and their right-hand sides by ROW TILES.
 //
 // Replaces, for the headline configurations, the element loop of AssembleBilinearForm (fflib/problem.cpp:1096-1103,
 // :1398-1405) + Element_Op (:6063-6160, :6337-6437) + HashMatrix::operator+=(MatriceElementaire&)
-// (femlib/HashMatrix.cpp:1295-1332).  Same mathematics as k_asm_p1_lean (assemble.cu); different work decomposition:
+// (femlib/HashMatrix.cpp:1295-1332), and AssembleLinearForm / Element_rhs (:10878-11227, :7917-7985).  Same mathematics
+// as the thread-per-row kernels of assemble.cu; different work decomposition:
 //
 //   * the rows of the matrix are grouped in TILES: compact clusters of <= TR vertices, consecutive in the Morton order
-//     of the vertex coordinates (the clustering is internal: the CSR that is produced is FreeFEM's, row by row);
-//   * one CTA per tile.  Every element touching a row of the tile is evaluated ONCE by one thread (geometry, the
-//     DIM(DIM+1)/2 off-diagonal entries of its element matrix, its measure) into shared memory — the thread-per-row
-//     kernel evaluates every element once per vertex (4x on tetrahedra);
+//     of the vertex coordinates, the axes scaled by the mean edge extent (the clustering is internal: the CSR that is
+//     produced is FreeFEM's, row by row);
+//   * one CTA per tile (persistent).  Every element touching a row of the tile is evaluated ONCE per tile into shared
+//     memory — the thread-per-row kernel evaluates every element once per vertex (4x on tetrahedra);
 //   * every matrix entry (i, j) of the tile's rows is OWNED by one thread, which sums the contributions of the elements
-//     around the edge ij in a register, in ascending element order, and stores the entry: no atomics, no
-//     read-modify-write, bit-reproducible;
+//     around the edge ij in a register, in a fixed order, and stores the entry: no atomics, no read-modify-write,
+//     bit-reproducible;
 //   * the diagonal follows from the partition of unity: K_ii = - sum_j K_ij (+ the mass part).
 //
-// Everything a tile needs sits in ONE contiguous descriptor blob (built once per fespace by k_tile_build): the
-// distinct vertices of the tile (ascending => slot order = column order), one word of 4 slot bytes per element, one
-// word per entry (offset of its contribution list, position in the row, local row) and 16-bit contribution codes
-// (element << 3 | vertex pair).
+// Two generations of kernels live here:
+//   round 1  k_tile_build / k_asm_tiles / k_rhs_tiles: element by element, one descriptor blob per tile (2-D spaces, and
+//            3-D with tile_fans = 0 or tile_policy = 2);
+//   round 2  k_fan_build / k_asm_fans / k_rhs_fans (3-D): the elements of a tile in FANS around their longest edge — one
+//            new vertex per element, shared face normals, contributions pre-summed along the fan — entries sorted by list
+//            length with transposed code lists, descriptor in parts with their own bulk copies.  See the comment above
+//            k_fan_build and DESIGN.md section 3.
 #include "common.cuh"
 #include <algorithm>
 #include <cstdlib>

@@ -72,3 +72,33 @@ def test_gmres_restatement_on_a_random_nonsymmetric_matrix():
     assert ret == 1 and it >= its[2] and np.max(np.abs(x - xe)) <= 1e-10 * np.abs(xe).max()
     x, it, ret, rel = ol.gmres(n, ci, cj, ca, b, np.zeros(n), eps=1e-12, itmax=3, nbkrylov=1000)
     assert ret == 0 and it <= 6
+
+
+def test_bench_closed_form_cube_pattern_matches_the_oracle():
+    """bench.py's `parity` object compares every rank's rows with BuildCube's pattern in closed form (row lengths and an
+    order-independent hash of the global column set): the closed form itself is pinned here against the oracle's CSR, on
+    anisotropic cubes, with rows given in any order and columns in any order inside a row, and it notices a wrong column."""
+    import importlib.util
+    import os
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    rng = np.random.default_rng(3)
+    for dims in [(1, 1, 1), (3, 2, 4), (5, 7, 3)]:
+        m = ol.cube(*dims)
+        n = m["xyz"].shape[0]
+        qp, qw = ol.quadrature(3, "qfV5")
+        ci, cj, ca = ol.assemble_coo(m, 1, 1, None, [(0, 1, 0, 1, 1.0)], qp, qw)
+        rp, col, _ = ol.coo_to_csr(n, ci, cj, ca)
+        assert bench.cube_pattern_mismatches(np, *dims, np.arange(n), rp, col) == 0
+        # a rank's view: a subset of the rows in another order, columns shuffled inside every row
+        rows = rng.permutation(n)[: max(1, n // 2)]
+        lens = np.diff(rp)[rows]
+        rp2 = np.concatenate([[0], np.cumsum(lens)]).astype(np.int32)
+        col2 = np.concatenate([rng.permutation(col[rp[r]:rp[r + 1]]) for r in rows])
+        assert bench.cube_pattern_mismatches(np, *dims, rows, rp2, col2) == 0
+        bad = col2.copy()
+        bad[0] = (bad[0] + 1) % n if (bad[0] + 1) % n not in col2[rp2[0]:rp2[1]] else (bad[0] + 2) % n
+        assert bench.cube_pattern_mismatches(np, *dims, rows, rp2, bad) >= 1
