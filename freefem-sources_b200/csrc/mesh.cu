@@ -605,6 +605,454 @@ __global__ void k_face_match(const int32_t *__restrict__ conn, int nfaces, const
 }
 } // namespace
 
+// ---------------------------------------------------------------------------------------------------------------
+// Boundary links of a tetrahedral mesh on the device: the boundary part of GenericMesh::BuildAdj
+// (femlib/GenericMesh.hpp:914-1017).  Every boundary triangle gets its (element, face) and the orientation the reference
+// leaves it with: a true boundary face takes the orientation of its element's face; an internal boundary face points to
+// the element on the side where the face runs the other way, and between two regions the minority is turned round.
+// Same sorted (hash, face) array as the adjacency; one thread per boundary triangle bisects it.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ int sort3_sign(int (&v)[3])
+{ // SortArray<T,3> (femlib/HashTable.hpp:65-80): the sorted triple and the parity of the permutation
+    int s = 1, t;
+    if (v[0] > v[1]) { s = -s; t = v[0]; v[0] = v[1]; v[1] = t; }
+    if (v[1] > v[2]) {
+        s = -s; t = v[1]; v[1] = v[2]; v[2] = t;
+        if (v[0] > v[1]) { s = -s; t = v[0]; v[0] = v[1]; v[1] = t; }
+    }
+    return s;
+}
+__device__ __forceinline__ unsigned long long face_hash3(const int (&v)[3])
+{
+    unsigned long long h = 0x9E3779B97F4A7C15ull;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) h = mix64(h ^ (unsigned long long)(unsigned)v[x]) + 0x632BE59BD9B4E019ull * (x + 1);
+    return h;
+}
+__device__ __forceinline__ int tet_face_sign(const int32_t *__restrict__ conn, int id, int (&v)[3])
+{
+    const int k = id >> 2, f = id & 3;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) v[j] = conn[4 * (size_t)k + c_nvfaceTet[f][j]];
+    return sort3_sign(v);
+}
+
+// other[b] = the second element face of an internal boundary face between two regions (else -1); reg[2b], reg[2b+1] its regions
+__global__ void k_bface_link(const int32_t *__restrict__ conn, const int32_t *__restrict__ elab, int nfaces,
+                             const unsigned long long *__restrict__ key, const int32_t *__restrict__ val, int nbe,
+                             int32_t *__restrict__ bconn, int32_t *__restrict__ belem, int32_t *__restrict__ bface,
+                             int32_t *__restrict__ other, int32_t *__restrict__ reg, int *__restrict__ flags)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= nbe) return;
+    int v[3] = {bconn[3 * (size_t)b], bconn[3 * (size_t)b + 1], bconn[3 * (size_t)b + 2]};
+    const int sens = sort3_sign(v);
+    const unsigned long long h = face_hash3(v);
+    int lo = 0, hi = nfaces;
+    while (lo < hi) {
+        const int mid = (int)(((long long)lo + hi) >> 1);
+        if (key[mid] < h) lo = mid + 1; else hi = mid;
+    }
+    int first = -1, last = -1, cnt = 0;
+    for (int y = lo; y < nfaces && key[y] == h; ++y) {
+        int w[3];
+        tet_face_sign(conn, val[y], w);
+        if (w[0] == v[0] && w[1] == v[1] && w[2] == v[2]) {
+            const int id = val[y];
+            first = cnt ? min(first, id) : id;
+            last = cnt ? max(last, id) : id;
+            ++cnt;
+        }
+    }
+    other[b] = -1;
+    if (cnt == 0) { // not a face of the mesh
+        belem[b] = bface[b] = -1;
+        atomicOr(flags, 1);
+        return;
+    }
+    int w[3], nk = first;
+    if (cnt == 1) {
+        if (tet_face_sign(conn, nk, w) != sens) { // the orientation of the element's face
+            const int t = bconn[3 * (size_t)b];
+            bconn[3 * (size_t)b] = bconn[3 * (size_t)b + 1];
+            bconn[3 * (size_t)b + 1] = t;
+        }
+    } else {
+        if (cnt > 2) atomicOr(flags, 4); // non-manifold: first and last of the run are taken
+        int nkk = first;
+        nk = last; // the later element is looked at first
+        if (sens == tet_face_sign(conn, nk, w)) { const int t = nk; nk = nkk; nkk = t; }
+        const int rk = elab[nk >> 2], rkk = elab[nkk >> 2];
+        if (rk != rkk) {
+            other[b] = nkk;
+            reg[2 * (size_t)b] = rk;
+            reg[2 * (size_t)b + 1] = rkk;
+            atomicOr(flags, 2);
+        }
+    }
+    belem[b] = nk >> 2;
+    bface[b] = nk & 3;
+}
+
+__global__ void k_bface_turn(const int32_t *__restrict__ turn, int nturn, const int32_t *__restrict__ other,
+                             int32_t *__restrict__ bconn, int32_t *__restrict__ belem, int32_t *__restrict__ bface)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= nturn) return;
+    const int b = turn[x];
+    const int t = bconn[3 * (size_t)b];
+    bconn[3 * (size_t)b] = bconn[3 * (size_t)b + 1];
+    bconn[3 * (size_t)b + 1] = t;
+    belem[b] = other[b] >> 2;
+    bface[b] = other[b] & 3;
+}
+
+void sorted_face_keys(ffcuda_mesh *m, DBuf<unsigned long long> &k1, DBuf<int32_t> &v1)
+{
+    ffcuda_ctx *ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    const int NV = m->dim + 1;
+    FF_REQUIRE((int64_t)m->nt * NV < ((int64_t)1 << 31), "too many faces for 32-bit face ids");
+    const int nf = m->nt * NV;
+    DBuf<unsigned long long> k0;
+    DBuf<int32_t> v0;
+    k0.alloc(nf); k1.alloc(nf); v0.alloc(nf); v1.alloc(nf);
+    ff_launch(ctx, "adj_face_keys", [&] {
+        if (NV == 4) k_face_keys<4><<<ff_blocks(nf, 256), 256, 0, st>>>(m->conn.p, nf, k0.p, v0.p);
+        else k_face_keys<3><<<ff_blocks(nf, 256), 256, 0, st>>>(m->conn.p, nf, k0.p, v0.p);
+    });
+    size_t tb = 0;
+    FF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k0.p, k1.p, v0.p, v1.p, nf, 0, 64, st));
+    DBuf<unsigned char> tmp;
+    tmp.alloc(tb + 16);
+    ctx->launches++;
+    FF_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k0.p, k1.p, v0.p, v1.p, nf, 0, 64, st));
+    FF_CUDA(cudaStreamSynchronize(st)); // the temporaries go out of scope
+}
+
+// belem / bface / final orientation of the boundary triangles of a 3-D mesh whose bconn, blab are set
+void boundary_links_3d(ffcuda_mesh *m)
+{
+    ffcuda_ctx *ctx = m->ctx;
+    cudaStream_t st = ctx->stream;
+    if (m->nbe == 0) return;
+    DBuf<unsigned long long> k1;
+    DBuf<int32_t> v1, other, reg;
+    sorted_face_keys(m, k1, v1);
+    const int nf = m->nt * 4, nbe = m->nbe;
+    other.alloc(nbe); reg.alloc((size_t)2 * nbe);
+    DBuf<int> flags;
+    flags.alloc(1);
+    FF_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int), st));
+    ff_launch(ctx, "mesh_bface_link", [&] {
+        k_bface_link<<<ff_blocks(nbe, 256), 256, 0, st>>>(m->conn.p, m->elab.p, nf, k1.p, v1.p, nbe, m->bconn.p, m->belem.p,
+                                                          m->bface.p, other.p, reg.p, flags.p);
+    });
+    int hf = 0;
+    FF_CUDA(ff_memcpy_sync(ctx, &hf, flags.p, sizeof(int), cudaMemcpyDeviceToHost));
+    FF_REQUIRE(!(hf & 1), "a boundary element is not a face of the mesh");
+    if (!(hf & 2)) return;
+    // internal faces between two regions: per pair of regions the minority is turned round (GenericMesh.hpp:958-984);
+    // a few faces, counted on the host
+    std::vector<int32_t> ho(nbe), hr((size_t)2 * nbe);
+    FF_CUDA(ff_memcpy_sync(ctx, ho.data(), other.p, (size_t)nbe * 4, cudaMemcpyDeviceToHost));
+    FF_CUDA(ff_memcpy_sync(ctx, hr.data(), reg.p, (size_t)nbe * 8, cudaMemcpyDeviceToHost));
+    std::unordered_map<uint64_t, std::pair<int64_t, int64_t>> cnt;
+    auto pkey = [](int a, int b) { return ((uint64_t)(uint32_t)std::min(a, b) << 32) | (uint32_t)std::max(a, b); };
+    for (int b = 0; b < nbe; ++b)
+        if (ho[b] >= 0) {
+            auto &c = cnt[pkey(hr[2 * (size_t)b], hr[2 * (size_t)b + 1])];
+            (hr[2 * (size_t)b] > hr[2 * (size_t)b + 1] ? c.second : c.first)++;
+        }
+    bool mixed = false;
+    for (auto &kv : cnt) mixed = mixed || (kv.second.first && kv.second.second);
+    if (!mixed) return;
+    std::vector<int32_t> turn;
+    for (int b = 0; b < nbe; ++b)
+        if (ho[b] >= 0) {
+            const auto &c = cnt[pkey(hr[2 * (size_t)b], hr[2 * (size_t)b + 1])];
+            const int sr = hr[2 * (size_t)b] > hr[2 * (size_t)b + 1] ? -1 : 1;
+            if ((c.first < c.second && sr == 1) || (c.first > c.second && sr == -1)) turn.push_back(b);
+        }
+    if (turn.empty()) return;
+    DBuf<int32_t> dturn;
+    dturn.alloc(turn.size());
+    FF_CUDA(cudaMemcpyAsync(dturn.p, turn.data(), turn.size() * 4, cudaMemcpyHostToDevice, st));
+    ff_launch(ctx, "mesh_bface_turn", [&] {
+        k_bface_turn<<<ff_blocks(turn.size(), 256), 256, 0, st>>>(dturn.p, (int)turn.size(), other.p, m->bconn.p, m->belem.p, m->bface.p);
+    });
+    FF_CUDA(cudaStreamSynchronize(st));
+}
+} // namespace
+
+// ---------------------------------------------------------------------------------------------------------------
+// buildlayers (fflib/msh3.cpp:895-1757): the layered tetrahedral mesh over a 2-D mesh that is on the device.  2-D vertex i
+// with ni[i] layers becomes the column of 3-D vertices first[i] .. first[i] + ni[i]; at level s (taken from the top) a
+// column stands at position (s ni)/Nmax, so columns with fewer layers repeat positions and the prism over a triangle
+// degenerates to a pyramid (2 tets) or a tetrahedron; quadrilateral faces are cut by the diagonal through the largest 3-D
+// vertex number, which makes neighbouring prisms agree.  The reference walks triangles and levels one after the other; here
+// every (triangle, level) and (boundary edge, level) is a thread: count, scan, fill — same element and face order.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+__constant__ int c_pentaCut[6][12] = {{0, 5, 1, 2, 0, 4, 1, 5, 0, 5, 3, 4}, {0, 5, 1, 2, 0, 3, 1, 5, 1, 5, 3, 4},
+                                      {0, 3, 1, 2, 1, 5, 2, 3, 1, 5, 3, 4}, {0, 4, 1, 2, 0, 4, 2, 5, 0, 5, 3, 4},
+                                      {0, 4, 1, 2, 0, 4, 2, 3, 2, 5, 3, 4}, {0, 3, 1, 2, 1, 4, 2, 3, 2, 5, 3, 4}}; // dpent1 :1694-1701, 0-based
+__constant__ int c_pentaSel[8] = {0, -1, 1, 2, 3, 4, -1, 5};                                                   // pdd :1693
+
+struct LayerMaps { // (old,new) pairs: region, labelmid, labelup, labeldown; the last pair of a label wins
+    const int32_t *p[4];
+    int n[4];
+};
+__device__ __forceinline__ int map_label(const LayerMaps &M, int which, int lab)
+{
+    int out = lab;
+    for (int k = 0; k < M.n[which]; ++k)
+        if (M.p[which][2 * k] == lab) out = M.p[which][2 * k + 1];
+    return out;
+}
+
+__global__ void k_layer_vertices(const double *__restrict__ xy, const int32_t *__restrict__ first, const int32_t *__restrict__ ni,
+                                 const double *__restrict__ zmin, const double *__restrict__ zmax, int nv2, int nlayer,
+                                 double *__restrict__ xyz4)
+{
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = (int)(t / (size_t)(nlayer + 1)), j = (int)(t - (size_t)i * (nlayer + 1));
+    if (i >= nv2) return;
+    const int N = ni[i];
+    if (j > N) return;
+    const double dz = N == 0 ? 0. : __ddiv_rn(__dsub_rn(zmax[i], zmin[i]), (double)N);
+    reinterpret_cast<double4 *>(xyz4)[first[i] + j] =
+        make_double4(xy[2 * (size_t)i], xy[2 * (size_t)i + 1], __dadd_rn(zmin[i], __dmul_rn(dz, (double)j)), 0.0);
+}
+
+// tets of the prism P[0..2] (lower) / P[3..5] (upper); returns their number
+__device__ __forceinline__ int prism_tets(const int (&P)[6], int (&o)[3][4])
+{
+    const int cas = (P[0] != P[3]) + 2 * (P[1] != P[4]) + 4 * (P[2] != P[5]);
+    if (cas == 0) return 0;
+    o[0][0] = P[0]; o[0][1] = P[1]; o[0][2] = P[2];
+    if (cas == 1 || cas == 2 || cas == 4) {
+        o[0][3] = P[cas == 1 ? 3 : (cas == 2 ? 4 : 5)];
+        return 1;
+    }
+    if (cas != 7) {
+        const int a = cas == 6 ? 1 : 0, b = cas == 3 ? 1 : 2;
+        const bool one = max(P[a], P[b + 3]) > max(P[b], P[a + 3]);
+        o[0][3] = one ? P[b + 3] : P[a + 3];
+        o[1][0] = P[5]; o[1][1] = P[4]; o[1][2] = P[3]; o[1][3] = one ? P[a] : P[b];
+        return 2;
+    }
+    const int i1 = max(P[0], P[5]) > max(P[2], P[3]) ? 0 : 1;
+    const int i2 = max(P[0], P[4]) > max(P[1], P[3]) ? 0 : 1;
+    const int i3 = max(P[1], P[5]) > max(P[2], P[4]) ? 0 : 1;
+    const int cut = c_pentaSel[i1 + 2 * i2 + 4 * i3];
+    if (cut < 0) return -1;
+#pragma unroll
+    for (int t = 0; t < 3; ++t)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) o[t][q] = P[c_pentaCut[cut][4 * t + q]];
+    return 3;
+}
+
+template <int PASS>
+__global__ void k_layer_tets(const int32_t *__restrict__ tri, const int32_t *__restrict__ trilab, const int32_t *__restrict__ first,
+                             const int32_t *__restrict__ ni, int nt2, int nlayer, const LayerMaps M, int32_t *__restrict__ cnt,
+                             const int32_t *__restrict__ off, int32_t *__restrict__ conn, int32_t *__restrict__ elab, int *__restrict__ bad)
+{
+    const size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= (size_t)nt2 * nlayer) return;
+    const int k = (int)(it / nlayer), s = nlayer - 1 - (int)(it - (size_t)k * nlayer);
+    int P[6], o[3][4];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int v = tri[3 * (size_t)k + j], N = ni[v], f = first[v];
+        P[j] = f + (s * N) / nlayer;
+        P[j + 3] = f + ((s + 1) * N) / nlayer;
+    }
+    const int c = prism_tets(P, o);
+    if (c < 0) {
+        atomicOr(bad, 1);
+        if (PASS == 0) cnt[it] = 0;
+        return;
+    }
+    if (PASS == 0) {
+        cnt[it] = c;
+        return;
+    }
+    const int lab = map_label(M, 0, trilab[k]);
+    const size_t base = (size_t)off[it];
+    for (int t = 0; t < c; ++t) {
+        reinterpret_cast<int4 *>(conn)[base + t] = make_int4(o[t][0], o[t][1], o[t][2], o[t][3]);
+        elab[base + t] = lab;
+    }
+}
+
+// faces at zmax (first nt2) and zmin (next nt2, orientation reversed): :1111-1150
+__global__ void k_layer_caps(const int32_t *__restrict__ tri, const int32_t *__restrict__ trilab, const int32_t *__restrict__ first,
+                             int nt2, const LayerMaps M, int32_t *__restrict__ bconn, int32_t *__restrict__ blab)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nt2) return;
+    const int lab = trilab[k];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int v = tri[3 * (size_t)k + j];
+        bconn[3 * (size_t)k + j] = first[v + 1] - 1;
+        bconn[3 * ((size_t)nt2 + k) + 2 - j] = first[v];
+    }
+    blab[k] = map_label(M, 2, lab);
+    blab[(size_t)nt2 + k] = map_label(M, 3, lab);
+}
+
+// lateral faces over the boundary edges: :1154-1316
+template <int PASS>
+__global__ void k_layer_sides(const int32_t *__restrict__ tri, const int32_t *__restrict__ bedge_lab, const int32_t *__restrict__ bedge_elem,
+                              const int32_t *__restrict__ bedge_face, const int32_t *__restrict__ first, const int32_t *__restrict__ ni,
+                              int nbe2, int nlayer, const LayerMaps M, int32_t *__restrict__ cnt, const int32_t *__restrict__ off,
+                              int base0, int32_t *__restrict__ bconn, int32_t *__restrict__ blab)
+{
+    const size_t it = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (it >= (size_t)nbe2 * nlayer) return;
+    const int e = (int)(it / nlayer), s = nlayer - 1 - (int)(it - (size_t)e * nlayer);
+    const int el = bedge_elem[e], f = bedge_face[e];
+    const int i1 = tri[3 * (size_t)el + (f + 1) % 3], i2 = tri[3 * (size_t)el + (f + 2) % 3]; // VerticesNumberOfEdge femlib/fem.hpp:561
+    const int a = first[i1] + (s * ni[i1]) / nlayer, d = first[i1] + ((s + 1) * ni[i1]) / nlayer;
+    const int b = first[i2] + (s * ni[i2]) / nlayer, c = first[i2] + ((s + 1) * ni[i2]) / nlayer;
+    const int type = (a != d ? 1 : 0) + (b != c ? 2 : 0);
+    const int n = type == 0 ? 0 : (type == 3 ? 2 : 1);
+    if (PASS == 0) {
+        cnt[it] = n;
+        return;
+    }
+    if (n == 0) return;
+    const int lab = map_label(M, 1, bedge_lab[e]);
+    int32_t *o = bconn + 3 * ((size_t)base0 + off[it]);
+    int32_t *l = blab + (size_t)base0 + off[it];
+    if (type == 1) { o[0] = a; o[1] = b; o[2] = d; l[0] = lab; }
+    else if (type == 2) { o[0] = a; o[1] = b; o[2] = c; l[0] = lab; }
+    else {
+        const bool one = max(a, c) > max(b, d);
+        o[0] = a; o[1] = b; o[2] = one ? c : d;
+        o[3] = c; o[4] = d; o[5] = one ? a : b;
+        l[0] = l[1] = lab;
+    }
+}
+} // namespace
+
+extern "C" int ffcuda_mesh_buildlayers(ffcuda_mesh *m2, int nlayer, const int32_t *ni, const double *zmin, const double *zmax,
+                                       int nreg, const int32_t *regmap, int nmid, const int32_t *midmap, int nup,
+                                       const int32_t *upmap, int ndown, const int32_t *downmap, ffcuda_mesh **out)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(m2 && out, "ffcuda_mesh_buildlayers: null mesh/output");
+    FF_REQUIRE(m2->dim == 2 && !m2->distributed, "ffcuda_mesh_buildlayers: the base mesh must be a 2-D mesh on one device");
+    FF_REQUIRE(nlayer > 0 && nlayer < (1 << 15), "ffcuda_mesh_buildlayers: the number of layers must lie in [1, 32767]");
+    FF_REQUIRE(nreg >= 0 && nmid >= 0 && nup >= 0 && ndown >= 0, "negative map size");
+    FF_REQUIRE((!nreg || regmap) && (!nmid || midmap) && (!nup || upmap) && (!ndown || downmap), "label map missing");
+    FF_REQUIRE(m2->nbe == 0 || (m2->belem.p && m2->bface.p), "the base mesh has no boundary links");
+    ffcuda_ctx *ctx = m2->ctx;
+    ff_enter(ctx);
+    cudaStream_t st = ctx->stream;
+    const int nv2 = m2->nv, nt2 = m2->nt, nbe2 = m2->nbe;
+    // columns: first[i] (host prefix sum over the 2-D vertices; fflib/msh3.cpp:1016-1052)
+    std::vector<int32_t> hni(nv2), hfirst((size_t)nv2 + 1);
+    int64_t acc = 0;
+    for (int i = 0; i < nv2; ++i) {
+        hni[i] = ni ? ni[i] : nlayer;
+        FF_REQUIRE(hni[i] >= 0 && hni[i] <= nlayer, "ffcuda_mesh_buildlayers: ni[] must lie in [0, nlayer]");
+        hfirst[i] = (int32_t)acc;
+        acc += hni[i] + 1;
+        FF_REQUIRE(acc < ((int64_t)1 << 31), "too many vertices");
+    }
+    hfirst[nv2] = (int32_t)acc;
+    FF_REQUIRE((int64_t)nt2 * nlayer * 3 < ((int64_t)1 << 27), "layered mesh too large for one device (limit 2^27 tets)");
+    std::vector<double> hz((size_t)2 * nv2);
+    for (int i = 0; i < nv2; ++i) {
+        hz[i] = zmin ? zmin[i] : 0.;
+        hz[(size_t)nv2 + i] = zmax ? zmax[i] : 1.;
+    }
+    DBuf<int32_t> dni, dfirst, dmaps;
+    DBuf<double> dz;
+    dni.alloc(nv2); dfirst.alloc((size_t)nv2 + 1); dz.alloc((size_t)2 * nv2);
+    FF_CUDA(cudaMemcpyAsync(dni.p, hni.data(), (size_t)nv2 * 4, cudaMemcpyHostToDevice, st));
+    FF_CUDA(cudaMemcpyAsync(dfirst.p, hfirst.data(), ((size_t)nv2 + 1) * 4, cudaMemcpyHostToDevice, st));
+    FF_CUDA(cudaMemcpyAsync(dz.p, hz.data(), (size_t)2 * nv2 * 8, cudaMemcpyHostToDevice, st));
+    std::vector<int32_t> hmaps;
+    const int mn[4] = {nreg, nmid, nup, ndown};
+    const int32_t *mp[4] = {regmap, midmap, upmap, downmap};
+    size_t moff[4];
+    for (int w = 0; w < 4; ++w) {
+        moff[w] = hmaps.size();
+        hmaps.insert(hmaps.end(), mp[w], mp[w] + (mn[w] ? 2 * (size_t)mn[w] : 0));
+    }
+    dmaps.alloc(std::max<size_t>(hmaps.size(), 1));
+    if (!hmaps.empty()) FF_CUDA(cudaMemcpyAsync(dmaps.p, hmaps.data(), hmaps.size() * 4, cudaMemcpyHostToDevice, st));
+    LayerMaps M;
+    for (int w = 0; w < 4; ++w) {
+        M.p[w] = dmaps.p + moff[w];
+        M.n[w] = mn[w];
+    }
+    std::unique_ptr<ffcuda_mesh> m(new ffcuda_mesh());
+    m->ctx = ctx;
+    m->ref.set(ctx);
+    m->dim = 3; m->vstride = 4;
+    m->nv = m->nv_owned = (int)acc;
+    m->xyz.alloc((size_t)m->nv * 4);
+    ff_launch(ctx, "mesh_layer_vertices", [&] {
+        k_layer_vertices<<<ff_blocks((size_t)nv2 * (nlayer + 1), 256), 256, 0, st>>>(m2->xyz.p, dfirst.p, dni.p, dz.p, dz.p + nv2, nv2, nlayer, m->xyz.p);
+    });
+    // tetrahedra: count per (triangle, level), scan, fill
+    const size_t nit = (size_t)nt2 * nlayer;
+    DBuf<int32_t> cnt, off;
+    cnt.alloc(nit); off.alloc(nit);
+    DBuf<int> bad;
+    bad.alloc(1);
+    FF_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), st));
+    ff_launch(ctx, "mesh_layer_tets_count", [&] {
+        k_layer_tets<0><<<ff_blocks(nit, 256), 256, 0, st>>>(m2->conn.p, m2->elab.p, dfirst.p, dni.p, nt2, nlayer, M, cnt.p, nullptr, nullptr, nullptr, bad.p);
+    });
+    int64_t tot = 0;
+    ff_exclusive_scan_i32(ctx, cnt.p, off.p, nit, &tot);
+    int hbad = 0;
+    FF_CUDA(ff_memcpy_sync(ctx, &hbad, bad.p, sizeof(int), cudaMemcpyDeviceToHost));
+    FF_REQUIRE(!hbad, "internal: a prism has no conforming cut");
+    FF_REQUIRE(tot > 0, "ffcuda_mesh_buildlayers: no tetrahedron (every column has zero layers)");
+    m->nt = (int)tot;
+    m->conn.alloc((size_t)m->nt * 4);
+    m->elab.alloc(m->nt);
+    ff_launch(ctx, "mesh_layer_tets", [&] {
+        k_layer_tets<1><<<ff_blocks(nit, 256), 256, 0, st>>>(m2->conn.p, m2->elab.p, dfirst.p, dni.p, nt2, nlayer, M, nullptr, off.p, m->conn.p, m->elab.p, bad.p);
+    });
+    // boundary: caps, then the lateral faces
+    const size_t nis = (size_t)nbe2 * nlayer;
+    DBuf<int32_t> scnt, soff;
+    int64_t stot = 0;
+    if (nis) {
+        scnt.alloc(nis); soff.alloc(nis);
+        ff_launch(ctx, "mesh_layer_sides_count", [&] {
+            k_layer_sides<0><<<ff_blocks(nis, 256), 256, 0, st>>>(m2->conn.p, m2->blab.p, m2->belem.p, m2->bface.p, dfirst.p, dni.p, nbe2, nlayer, M,
+                                                                   scnt.p, nullptr, 0, nullptr, nullptr);
+        });
+        ff_exclusive_scan_i32(ctx, scnt.p, soff.p, nis, &stot);
+    }
+    m->nbe = 2 * nt2 + (int)stot;
+    m->bconn.alloc((size_t)m->nbe * 3);
+    m->blab.alloc(m->nbe); m->belem.alloc(m->nbe); m->bface.alloc(m->nbe);
+    ff_launch(ctx, "mesh_layer_caps", [&] {
+        k_layer_caps<<<ff_blocks(nt2, 256), 256, 0, st>>>(m2->conn.p, m2->elab.p, dfirst.p, nt2, M, m->bconn.p, m->blab.p);
+    });
+    if (stot)
+        ff_launch(ctx, "mesh_layer_sides", [&] {
+            k_layer_sides<1><<<ff_blocks(nis, 256), 256, 0, st>>>(m2->conn.p, m2->blab.p, m2->belem.p, m2->bface.p, dfirst.p, dni.p, nbe2, nlayer, M,
+                                                                   nullptr, soff.p, 2 * nt2, m->bconn.p, m->blab.p);
+        });
+    boundary_links_3d(m.get()); // what Mesh3's BuildAdj does to the boundary triangles (orientation, element, face)
+    FF_CUDA(cudaStreamSynchronize(st));
+    *out = m.release();
+    FF_API_END(m2 ? m2->ctx : nullptr)
+}
+
 extern "C" int ffcuda_mesh_adjacency(ffcuda_mesh *m, int32_t *adj /* host, (dim+1)*nt, may be NULL */, const int32_t **d_adj /* may be NULL */)
 {
     FF_API_BEGIN
@@ -616,24 +1064,15 @@ extern "C" int ffcuda_mesh_adjacency(ffcuda_mesh *m, int32_t *adj /* host, (dim+
     FF_REQUIRE((int64_t)m->nt * NV < ((int64_t)1 << 31), "too many faces for 32-bit face ids");
     const int nf = m->nt * NV;
     if (!m->adj.p && nf > 0) {
-        DBuf<unsigned long long> k0, k1;
-        DBuf<int32_t> v0, v1;
-        k0.alloc(nf); k1.alloc(nf); v0.alloc(nf); v1.alloc(nf);
+        DBuf<unsigned long long> k1;
+        DBuf<int32_t> v1;
+        sorted_face_keys(m, k1, v1);
         m->adj.alloc(nf);
-        ff_launch(ctx, "adj_face_keys", [&] {
-            if (NV == 4) k_face_keys<4><<<ff_blocks(nf, 256), 256, 0, st>>>(m->conn.p, nf, k0.p, v0.p);
-            else k_face_keys<3><<<ff_blocks(nf, 256), 256, 0, st>>>(m->conn.p, nf, k0.p, v0.p);
-        });
-        size_t tb = 0;
-        FF_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, k0.p, k1.p, v0.p, v1.p, nf, 0, 64, st));
-        DBuf<unsigned char> tmp;
-        tmp.alloc(tb + 16);
-        ctx->launches++;
-        FF_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb, k0.p, k1.p, v0.p, v1.p, nf, 0, 64, st));
         ff_launch(ctx, "adj_face_match", [&] {
             if (NV == 4) k_face_match<4><<<ff_blocks(nf, 256), 256, 0, st>>>(m->conn.p, nf, k1.p, v1.p, m->adj.p);
             else k_face_match<3><<<ff_blocks(nf, 256), 256, 0, st>>>(m->conn.p, nf, k1.p, v1.p, m->adj.p);
         });
+        FF_CUDA(cudaStreamSynchronize(st)); // k1, v1 go out of scope
     }
     if (adj && nf > 0) FF_CUDA(cudaMemcpyAsync(adj, m->adj.p, (size_t)nf * 4, cudaMemcpyDeviceToHost, st));
     FF_CUDA(cudaStreamSynchronize(st));

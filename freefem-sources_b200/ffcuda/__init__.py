@@ -15,7 +15,7 @@ OP_ID, OP_DX, OP_DY, OP_DZ = 0, 1, 2, 6
 
 # every symbol include/ffcuda.h declares (checked against the header by tests/test_abi.py)
 SYMBOLS = """ffcuda_ctx_create ffcuda_ctx_destroy ffcuda_last_error ffcuda_ctx_sync ffcuda_ctx_set_stream ffcuda_ctx_get_stream ffcuda_ctx_set_option
-ffcuda_prof_enable ffcuda_prof_reset ffcuda_prof_get ffcuda_launch_count ffcuda_mesh_upload ffcuda_mesh_cube ffcuda_mesh_square
+ffcuda_prof_enable ffcuda_prof_reset ffcuda_prof_get ffcuda_launch_count ffcuda_mesh_upload ffcuda_mesh_cube ffcuda_mesh_square ffcuda_mesh_buildlayers
 ffcuda_mesh_info ffcuda_mesh_download ffcuda_mesh_destroy ffcuda_space_create ffcuda_space_info ffcuda_space_download_dofs
 ffcuda_space_destroy ffcuda_symbolic ffcuda_pattern_info ffcuda_pattern_download ffcuda_pattern_download_async ffcuda_pattern_lower_nnz ffcuda_pattern_download_lower
 ffcuda_matrix_download_lower ffcuda_matrix_from_csr_lower ffcuda_pattern_destroy ffcuda_matrix_create
@@ -282,6 +282,17 @@ class Mesh(_Handle):
         adj = np.zeros((dim + 1) * nt, np.int32)
         _ck(lib().ffcuda_mesh_adjacency(_h(self), _p(adj), None), self.ctx.h)
         return adj
+
+    def buildlayers(self, nlayer, ni=None, zmin=None, zmax=None, regmap=(), midmap=(), upmap=(), downmap=()):
+        """`buildlayers(Th2, nlayer, ...)` on the device (self = the 2-D mesh); maps are flat (old,new,...) sequences"""
+        ni, zmin, zmax = _i32(ni), _f64(zmin), _f64(zmax)
+        maps = [np.ascontiguousarray(np.asarray(m_, dtype=np.int32).ravel()) for m_ in (regmap, midmap, upmap, downmap)]
+        margs = []
+        for m_ in maps:
+            margs += [int(m_.size // 2), _p(m_) if m_.size else None]
+        out = C.c_void_p()
+        _ck(lib().ffcuda_mesh_buildlayers(_h(self), int(nlayer), _p(ni), _p(zmin), _p(zmax), *margs, C.byref(out)), self.ctx.h)
+        return Mesh(out.value, self.ctx)
 
     def local_to_global(self):
         no, nl = C.c_int(), C.c_int()

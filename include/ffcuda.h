@@ -39,6 +39,8 @@
  *                                  plugin/mpi/PETSc-code.hpp, `[I,J,C]=A` fflib/lgmat.cpp, `ofstream << A`
  *                                  femlib/HashMatrix.hpp:485-508 (reader femlib/HashMatrix.cpp:137-188)
  *   ffcuda_mesh_adjacency       <- GenericMesh::BuildAdj femlib/GenericMesh.hpp:837-930
+ *   ffcuda_mesh_buildlayers     <- build_layer fflib/msh3.cpp:895-1757 (operator BuildLayeMesh_Op :4536-4760) and the
+ *                                  boundary part of BuildAdj femlib/GenericMesh.hpp:914-1017
  *   ffcuda_partition_rcb / _local, ffcuda_mesh_upload_distributed, ffcuda_mesh_cube_distributed, ffcuda_comm_*
  *                               <- element-range split fflib/problem.cpp:1133-1138, partition vector plugin/seq/metis.cpp,
  *                                  MPI_Allreduce per dot product plugin/mpi/MPICG.cpp:93-101
@@ -110,6 +112,16 @@ int ffcuda_mesh_download(ffcuda_mesh *m, double *xyz, int32_t *conn, int32_t *el
  * elements.  Built on the device on first use (face hashes, radix sort, match) and kept with the mesh; `adj` (host) and
  * `d_adj` (borrowed device pointer) may be NULL. */
 int ffcuda_mesh_adjacency(ffcuda_mesh *m, int32_t *adj, const int32_t **d_adj);
+/* buildlayers(Th2, nlayer, zbound=[zmin,zmax], coef=..., region=, labelmid=, labelup=, labeldown=) on the device
+ * (fflib/msh3.cpp:895-1757; `mesh3 Th = buildlayers(...)` of idp/Heat3d.idp:16): the layered tetrahedral mesh over the
+ * 2-D mesh m2 (uploaded, or ffcuda_mesh_square), same vertex / element / boundary-element order, labels and boundary
+ * orientation as FreeFEM's.  Host inputs per 2-D vertex, as the operator derives them (:4566-4657): ni[] layers over the
+ * vertex (NULL: nlayer everywhere), zmin[], zmax[] (NULL: 0 and 1).  Label maps are (old,new) pairs, n* = number of pairs:
+ * regmap for the tetrahedra (from the triangle labels), midmap for the lateral faces (from the boundary-edge labels), upmap /
+ * downmap for the faces at zmax / zmin (from the triangle labels); labels without a pair are kept. */
+int ffcuda_mesh_buildlayers(ffcuda_mesh *m2, int nlayer, const int32_t *ni, const double *zmin, const double *zmax,
+                            int nreg, const int32_t *regmap, int nmid, const int32_t *midmap, int nup, const int32_t *upmap,
+                            int ndown, const int32_t *downmap, ffcuda_mesh **out);
 void ffcuda_mesh_destroy(ffcuda_mesh *m);
 
 /* ---- finite-element space ------------------------------------------------------------------------ */

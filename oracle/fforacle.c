@@ -188,6 +188,263 @@ void ffo_square(int nx, int ny, double *xy, int32_t *conn, int32_t *elab,
     }
 }
 
+/* ------------------------------------------------------------------ buildlayers --------- */
+/* fflib/msh3.cpp:978-1668.  A 2-D vertex i with ni[i] layers becomes the column of 3-D vertices first[i] .. first[i]+ni[i];
+ * level s of Nmax (taken from the top, jNmax = Nmax-1 .. 0) maps to the column position (s*ni)/Nmax (integer division),
+ * so a column with fewer layers repeats positions and the prism over a triangle degenerates to a pyramid or a
+ * tetrahedron.  Quadrilateral faces are cut by the diagonal that holds the largest 3-D vertex number. */
+static int bl_lab(int lab, int n, const int32_t *pairs)
+{
+    int out = lab;
+    for (int k = 0; k < n; ++k)
+        if (pairs[2 * k] == lab) out = pairs[2 * k + 1];
+    return out;
+}
+static int bl_max(int a, int b) { return a > b ? a : b; }
+
+/* prism over one triangle at one level: P[0..2] lower, P[3..5] upper 3-D vertex numbers; returns the tets (0..3) */
+static int bl_prism(const int P[6], int out[3][4])
+{
+    /* pentahedron cuts of dpent1 (fflib/msh3.cpp:1694-1701), 1-based in the source: data */
+    static const int mu[6][12] = {{1, 6, 2, 3, 1, 5, 2, 6, 1, 6, 4, 5}, {1, 6, 2, 3, 1, 4, 2, 6, 2, 6, 4, 5},
+                                  {1, 4, 2, 3, 2, 6, 3, 4, 2, 6, 4, 5}, {1, 5, 2, 3, 1, 5, 3, 6, 1, 6, 4, 5},
+                                  {1, 5, 2, 3, 1, 5, 3, 4, 3, 6, 4, 5}, {1, 4, 2, 3, 2, 5, 3, 4, 3, 6, 4, 5}};
+    static const int pdd[8] = {1, 0, 2, 3, 4, 5, 0, 6};
+    int cas = 0;
+    for (int j = 0; j < 3; ++j)
+        if (P[j] != P[j + 3]) cas += 1 << j;
+    if (cas == 0) return 0;
+    if (cas == 1 || cas == 2 || cas == 4) {
+        const int top = cas == 1 ? 3 : (cas == 2 ? 4 : 5);
+        out[0][0] = P[0]; out[0][1] = P[1]; out[0][2] = P[2]; out[0][3] = P[top];
+        return 1;
+    }
+    if (cas != 7) { /* pyramid: the two columns a < b that rise, c merged */
+        const int a = cas == 6 ? 1 : 0, b = cas == 3 ? 1 : 2;
+        const int first = bl_max(P[a], P[b + 3]) > bl_max(P[b], P[a + 3]);
+        out[0][0] = P[0]; out[0][1] = P[1]; out[0][2] = P[2]; out[0][3] = first ? P[b + 3] : P[a + 3];
+        out[1][0] = P[5]; out[1][1] = P[4]; out[1][2] = P[3]; out[1][3] = first ? P[a] : P[b];
+        return 2;
+    }
+    const int i1 = bl_max(P[0], P[5]) > bl_max(P[2], P[3]) ? 1 : 2;
+    const int i2 = bl_max(P[0], P[4]) > bl_max(P[1], P[3]) ? 1 : 2;
+    const int i3 = bl_max(P[1], P[5]) > bl_max(P[2], P[4]) ? 1 : 2;
+    const int cut = pdd[(i1 - 1) + 2 * (i2 - 1) + 4 * (i3 - 1)];
+    if (cut == 0) return -1; /* cyclic choice: cannot happen with "largest number" diagonals */
+    for (int t = 0; t < 3; ++t)
+        for (int q = 0; q < 4; ++q) out[t][q] = P[mu[cut - 1][4 * t + q] - 1];
+    return 3;
+}
+
+/* side quadrilateral over the 2-D edge (i1,i2) at one level: a,b lower (over i1, i2), d,c upper; returns the triangles (0..2) */
+static int bl_side(int a, int b, int c, int d, int out[2][3])
+{
+    const int type = (a != d ? 1 : 0) + (b != c ? 2 : 0);
+    if (type == 0) return 0;
+    if (type == 1) { out[0][0] = a; out[0][1] = b; out[0][2] = d; return 1; }
+    if (type == 2) { out[0][0] = a; out[0][1] = b; out[0][2] = c; return 1; }
+    if (bl_max(a, c) > bl_max(b, d)) {
+        out[0][0] = a; out[0][1] = b; out[0][2] = c;
+        out[1][0] = c; out[1][1] = d; out[1][2] = a;
+    } else {
+        out[0][0] = a; out[0][1] = b; out[0][2] = d;
+        out[1][0] = c; out[1][1] = d; out[1][2] = b;
+    }
+    return 2;
+}
+
+static void bl_edge_vertices(const int32_t *tri, int el, int f, int *i1, int *i2)
+{ /* Mesh::VerticesNumberOfEdge femlib/fem.hpp:561-564 */
+    *i1 = tri[3 * el + (f + 1) % 3];
+    *i2 = tri[3 * el + (f + 2) % 3];
+}
+
+void ffo_buildlayers_sizes(int nv2, int nt2, const int32_t *tri, int nbe2, const int32_t *bedge_elem, const int32_t *bedge_face,
+                           int nlayer, const int32_t *ni, int *nv, int *nt, int *nbe)
+{
+    int64_t v = 0, t = 0, b = 2 * (int64_t)nt2;
+    for (int i = 0; i < nv2; ++i) v += ni[i] + 1;
+    /* the counts of :936-976 are upper bounds when columns degenerate; the exact ones are what the fill produces */
+    for (int k = 0; k < nt2; ++k)
+        for (int s = nlayer - 1; s >= 0; --s) {
+            int P[6], o[3][4];
+            for (int j = 0; j < 3; ++j) {
+                const int N = ni[tri[3 * k + j]];
+                P[j] = (s * N) / nlayer;
+                P[j + 3] = ((s + 1) * N) / nlayer;
+                /* distinct columns: make numbers of different columns differ */
+                P[j] += 1000003 * j; P[j + 3] += 1000003 * j;
+            }
+            int c = bl_prism(P, o);
+            t += c > 0 ? c : 0;
+        }
+    for (int e = 0; e < nbe2; ++e) {
+        int i1, i2, o[2][3];
+        bl_edge_vertices(tri, bedge_elem[e], bedge_face[e], &i1, &i2);
+        for (int s = nlayer - 1; s >= 0; --s)
+            b += bl_side((s * ni[i1]) / nlayer, 1000003 + (s * ni[i2]) / nlayer, 1000003 + ((s + 1) * ni[i2]) / nlayer,
+                         ((s + 1) * ni[i1]) / nlayer, o);
+    }
+    *nv = (int)v; *nt = (int)t; *nbe = (int)b;
+}
+
+void ffo_buildlayers(int nv2, const double *xy, int nt2, const int32_t *tri, const int32_t *trilab, int nbe2,
+                     const int32_t *bedge_lab, const int32_t *bedge_elem, const int32_t *bedge_face, int nlayer,
+                     const int32_t *ni, const double *zmin, const double *zmax, int nreg, const int32_t *regmap, int nmid,
+                     const int32_t *midmap, int nup, const int32_t *upmap, int ndown, const int32_t *downmap, double *xyz,
+                     int32_t *conn, int32_t *elab, int32_t *bconn, int32_t *blab, int32_t *belem, int32_t *bface)
+{
+    int *first = (int *)malloc(sizeof(int) * ((size_t)nv2 + 1));
+    int nv = 0;
+    for (int i = 0; i < nv2; ++i) { /* :1016-1050 */
+        const int N = ni[i];
+        const double dz = N == 0 ? 0. : (zmax[i] - zmin[i]) / N;
+        first[i] = nv;
+        for (int j = 0; j <= N; ++j, ++nv) {
+            xyz[3 * nv + 0] = xy[2 * i];
+            xyz[3 * nv + 1] = xy[2 * i + 1];
+            xyz[3 * nv + 2] = zmin[i] + dz * j;
+        }
+    }
+    first[nv2] = nv;
+    int nb = 0;
+    for (int k = 0; k < nt2; ++k, ++nb) { /* faces at zmax :1111-1128 */
+        for (int j = 0; j < 3; ++j) bconn[3 * nb + j] = first[tri[3 * k + j] + 1] - 1;
+        blab[nb] = bl_lab(trilab[k], nup, upmap);
+    }
+    for (int k = 0; k < nt2; ++k, ++nb) { /* faces at zmin, orientation reversed :1132-1150 */
+        for (int j = 0; j < 3; ++j) bconn[3 * nb + 2 - j] = first[tri[3 * k + j]];
+        blab[nb] = bl_lab(trilab[k], ndown, downmap);
+    }
+    for (int e = 0; e < nbe2; ++e) { /* lateral faces :1154-1316 */
+        int i1, i2, o[2][3];
+        bl_edge_vertices(tri, bedge_elem[e], bedge_face[e], &i1, &i2);
+        const int lab = bl_lab(bedge_lab[e], nmid, midmap);
+        for (int s = nlayer - 1; s >= 0; --s) {
+            const int c = bl_side(first[i1] + (s * ni[i1]) / nlayer, first[i2] + (s * ni[i2]) / nlayer,
+                                  first[i2] + ((s + 1) * ni[i2]) / nlayer, first[i1] + ((s + 1) * ni[i1]) / nlayer, o);
+            for (int t = 0; t < c; ++t, ++nb) {
+                for (int j = 0; j < 3; ++j) bconn[3 * nb + j] = o[t][j];
+                blab[nb] = lab;
+            }
+        }
+    }
+    int nt = 0;
+    for (int k = 0; k < nt2; ++k) { /* tetrahedra :1330-1666 */
+        const int lab = bl_lab(trilab[k], nreg, regmap);
+        for (int s = nlayer - 1; s >= 0; --s) {
+            int P[6], o[3][4];
+            for (int j = 0; j < 3; ++j) {
+                const int v = tri[3 * k + j];
+                P[j] = first[v] + (s * ni[v]) / nlayer;
+                P[j + 3] = first[v] + ((s + 1) * ni[v]) / nlayer;
+            }
+            const int c = bl_prism(P, o);
+            for (int t = 0; t < c; ++t, ++nt) {
+                for (int q = 0; q < 4; ++q) conn[4 * nt + q] = o[t][q];
+                elab[nt] = lab;
+            }
+        }
+    }
+    free(first);
+    if (belem) ffo_boundary_links(nt, conn, elab, nb, bconn, belem, bface);
+}
+
+/* The boundary part of GenericMesh::BuildAdj (femlib/GenericMesh.hpp:914-1017) for tetrahedral meshes: every boundary
+ * triangle gets its (element, face) — BoundaryElementHeadLink — and the orientation the reference leaves it with.
+ * sign of a vertex triple = parity of the permutation that sorts it (SortArray<T,3>, femlib/HashTable.hpp:65-80). */
+typedef struct { int32_t v[3]; int32_t id; } bl_face;
+static int bl_face_cmp(const void *pa, const void *pb)
+{
+    const bl_face *a = (const bl_face *)pa, *b = (const bl_face *)pb;
+    for (int i = 0; i < 3; ++i)
+        if (a->v[i] != b->v[i]) return a->v[i] < b->v[i] ? -1 : 1;
+    return a->id < b->id ? -1 : (a->id > b->id ? 1 : 0);
+}
+static int bl_sort3(int32_t *v)
+{
+    int32_t t;
+    int s = 1;
+    if (v[0] > v[1]) { s = -s; t = v[0]; v[0] = v[1]; v[1] = t; }
+    if (v[1] > v[2]) {
+        s = -s; t = v[1]; v[1] = v[2]; v[2] = t;
+        if (v[0] > v[1]) { s = -s; t = v[0]; v[0] = v[1]; v[1] = t; }
+    }
+    return s;
+}
+static int bl_face_sign(const int32_t *conn, int id)
+{
+    int32_t v[3];
+    for (int j = 0; j < 3; ++j) v[j] = conn[4 * (id / 4) + nvfaceTet[id % 4][j]];
+    return bl_sort3(v);
+}
+
+void ffo_boundary_links(int nt, const int32_t *conn, const int32_t *elab, int nbe, int32_t *bconn, int32_t *belem, int32_t *bface)
+{
+    const size_t nf = (size_t)nt * 4;
+    bl_face *F = (bl_face *)malloc(sizeof(bl_face) * (nf ? nf : 1));
+    for (size_t id = 0; id < nf; ++id) {
+        for (int j = 0; j < 3; ++j) F[id].v[j] = conn[4 * (id / 4) + nvfaceTet[id % 4][j]];
+        bl_sort3(F[id].v);
+        F[id].id = (int32_t)id;
+    }
+    qsort(F, nf, sizeof(bl_face), bl_face_cmp);
+    /* region pairs of the internal boundary faces: (first, second) counts of :958-965 */
+    typedef struct { int a, b, first, second; } pair_t;
+    pair_t *pairs = (pair_t *)malloc(sizeof(pair_t) * ((size_t)nbe + 1));
+    int npairs = 0, uncorrect = 0;
+    for (int step = 0; step < 2; ++step) {
+        for (int b = 0; b < nbe; ++b) {
+            bl_face key;
+            for (int j = 0; j < 3; ++j) key.v[j] = bconn[3 * b + j];
+            const int sens = bl_sort3(key.v);
+            key.id = -1;
+            size_t lo = 0, hi = nf;
+            while (lo < hi) {
+                size_t mid = (lo + hi) / 2;
+                if (bl_face_cmp(&F[mid], &key) < 0) lo = mid + 1; else hi = mid;
+            }
+            belem[b] = bface[b] = -1;
+            if (!(lo < nf && F[lo].v[0] == key.v[0] && F[lo].v[1] == key.v[1] && F[lo].v[2] == key.v[2])) continue;
+            const int two = lo + 1 < nf && F[lo + 1].v[0] == key.v[0] && F[lo + 1].v[1] == key.v[1] && F[lo + 1].v[2] == key.v[2];
+            int nk = F[lo].id;
+            if (!two) { /* true boundary face: same orientation as the face of its element :989-1000 */
+                if (bl_face_sign(conn, nk) != sens && step == 0) {
+                    int32_t t = bconn[3 * b]; bconn[3 * b] = bconn[3 * b + 1]; bconn[3 * b + 1] = t;
+                }
+            } else { /* internal face: the element on the side where the face runs the other way :934-986 */
+                int nkk = F[lo].id;
+                nk = F[lo + 1].id; /* the later of the two elements is looked at first */
+                if (sens == bl_face_sign(conn, nk)) { int t = nk; nk = nkk; nkk = t; }
+                int regk = elab[nk / 4], regkk = elab[nkk / 4];
+                if (regk != regkk) {
+                    const int lo_r = regk < regkk ? regk : regkk, hi_r = regk < regkk ? regkk : regk;
+                    int q = 0;
+                    while (q < npairs && !(pairs[q].a == lo_r && pairs[q].b == hi_r)) ++q;
+                    if (q == npairs) { pairs[q].a = lo_r; pairs[q].b = hi_r; pairs[q].first = pairs[q].second = 0; ++npairs; }
+                    if (step == 0) {
+                        if (regk > regkk) pairs[q].second++; else pairs[q].first++;
+                    } else { /* the minority turns round :966-984 */
+                        const int sr = regk > regkk ? -1 : 1;
+                        if ((pairs[q].first < pairs[q].second && sr == 1) || (pairs[q].first > pairs[q].second && sr == -1)) {
+                            int32_t t = bconn[3 * b]; bconn[3 * b] = bconn[3 * b + 1]; bconn[3 * b + 1] = t;
+                            nk = nkk;
+                        }
+                    }
+                }
+            }
+            belem[b] = nk / 4;
+            bface[b] = nk % 4;
+        }
+        uncorrect = 0;
+        for (int q = 0; q < npairs; ++q)
+            if (pairs[q].first && pairs[q].second) ++uncorrect;
+        if (uncorrect == 0) break;
+    }
+    free(pairs);
+    free(F);
+}
+
 /* ------------------------------------------------------------------ dof numbering ------- */
 int ffo_nloc(int dim, int order)
 {

@@ -49,6 +49,26 @@ void ffo_square_sizes(int nx, int ny, int *nv, int *nt, int *nbe);
 void ffo_square(int nx, int ny, double *xy, int32_t *conn, int32_t *elab,
                 int32_t *bconn, int32_t *blab, int32_t *belem, int32_t *bface);
 
+/* buildlayers (fflib/msh3.cpp:895-934 build_layer, :936-976 sizes, :978-1668 vertices / boundary / tetrahedra,
+ * :1670-1757 dpent1_mesh): the layered 3-D mesh over a 2-D mesh.  Inputs: the 2-D mesh (vertices only enter through
+ * zmin/zmax/ni; xy, triangles with labels, boundary edges with labels and belem/bface = Mesh::BoundaryElement),
+ * nlayer (= Nmax), per 2-D vertex ni (0..nlayer), zmin, zmax, and the label maps as (old,new) pairs (the last pair of a
+ * label wins, labels without a pair keep their value: BuildLayeMesh_Op fflib/msh3.cpp:4608-4645).
+ * The boundary triangles come out as the reference's mesh holds them after BuildAdj (ffo_boundary_links). */
+void ffo_buildlayers_sizes(int nv2, int nt2, const int32_t *tri, int nbe2, const int32_t *bedge_elem, const int32_t *bedge_face,
+                           int nlayer, const int32_t *ni, int *nv, int *nt, int *nbe);
+void ffo_buildlayers(int nv2, const double *xy, int nt2, const int32_t *tri, const int32_t *trilab, int nbe2,
+                     const int32_t *bedge_lab, const int32_t *bedge_elem, const int32_t *bedge_face, int nlayer,
+                     const int32_t *ni, const double *zmin, const double *zmax, int nreg, const int32_t *regmap, int nmid,
+                     const int32_t *midmap, int nup, const int32_t *upmap, int ndown, const int32_t *downmap, double *xyz,
+                     int32_t *conn, int32_t *elab, int32_t *bconn, int32_t *blab, int32_t *belem, int32_t *bface);
+
+/* Boundary part of GenericMesh::BuildAdj (femlib/GenericMesh.hpp:914-1017), tetrahedra: (element, face) of every boundary
+ * triangle and its final orientation (bconn is modified in place: a true boundary face takes the orientation of its
+ * element's face; internal faces pick the element on the side where the face runs the other way, the minority between
+ * two regions is turned round). */
+void ffo_boundary_links(int nt, const int32_t *conn, const int32_t *elab, int nbe, int32_t *bconn, int32_t *belem, int32_t *bface);
+
 /* 3-D P2 node numbering (vertices and edges in first-encounter order). elem2node: nt*10. Returns nnodes. */
 int ffo_p2_nodes_3d(int nv, int nt, const int32_t *conn, int32_t *elem2node);
 

@@ -101,6 +101,33 @@ def square(nx, ny):
     return m
 
 
+def buildlayers(mesh2, nlayer, ni=None, zmin=None, zmax=None, regmap=(), midmap=(), upmap=(), downmap=()):
+    """layered mesh over the 2-D mesh dict (keys xyz, conn, elab, blab, belem, bface); maps are flat (old,new,...) lists"""
+    xy, tri, trilab = _f64(mesh2["xyz"]), _i32(mesh2["conn"]), _i32(mesh2["elab"])
+    bl, be, bf = _i32(mesh2["blab"]), _i32(mesh2["belem"]), _i32(mesh2["bface"])
+    nv2, nt2, nbe2 = xy.shape[0], tri.shape[0], bl.shape[0]
+    ni = np.full(nv2, nlayer, np.int32) if ni is None else _i32(ni)
+    zmin = np.zeros(nv2) if zmin is None else _f64(zmin)
+    zmax = np.ones(nv2) if zmax is None else _f64(zmax)
+    maps = [_i32(np.asarray(m_, dtype=np.int32).ravel()) for m_ in (regmap, midmap, upmap, downmap)]
+    nv, nt, nbe = C.c_int(), C.c_int(), C.c_int()
+    lib().ffo_buildlayers_sizes(nv2, nt2, _p(tri, C.c_int32), nbe2, _p(be, C.c_int32), _p(bf, C.c_int32), nlayer,
+                                _p(ni, C.c_int32), C.byref(nv), C.byref(nt), C.byref(nbe))
+    nv, nt, nbe = nv.value, nt.value, nbe.value
+    m = dict(dim=3, xyz=np.zeros((nv, 3)), conn=np.zeros((nt, 4), np.int32), elab=np.zeros(nt, np.int32),
+             bconn=np.zeros((nbe, 3), np.int32), blab=np.zeros(nbe, np.int32), belem=np.zeros(nbe, np.int32),
+             bface=np.zeros(nbe, np.int32))
+    margs = []
+    for m_ in maps:
+        margs += [m_.size // 2, _p(m_, C.c_int32)]
+    lib().ffo_buildlayers(nv2, _p(xy, C.c_double), nt2, _p(tri, C.c_int32), _p(trilab, C.c_int32), nbe2, _p(bl, C.c_int32),
+                          _p(be, C.c_int32), _p(bf, C.c_int32), nlayer, _p(ni, C.c_int32), _p(zmin, C.c_double),
+                          _p(zmax, C.c_double), *margs, _p(m["xyz"], C.c_double), _p(m["conn"], C.c_int32),
+                          _p(m["elab"], C.c_int32), _p(m["bconn"], C.c_int32), _p(m["blab"], C.c_int32),
+                          _p(m["belem"], C.c_int32), _p(m["bface"], C.c_int32))
+    return m
+
+
 def p2_nodes_3d(nv, conn):
     conn = _i32(conn)
     nt = conn.shape[0]

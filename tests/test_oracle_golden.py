@@ -195,3 +195,42 @@ def test_gmres_on_reference_matrix(name):
         x, it, ret, rel = ol.gmres(n, g["coo_i"], g["coo_j"], g["coo_a"], g["b"], np.zeros(n), eps=eps, nbkrylov=fc.CASE_GMRES[name])
         assert ret == 1 and it == int(g[kit]) and rel < eps
         assert np.max(np.abs(x - g[ku])) <= (1e-10 if eps > 1e-10 else RTOL) * np.abs(g[ku]).max()
+
+
+LAYER_CASES = ["layers_coef", "layers_disk", "layers_heat3d", "layers_one", "layers_plain"]
+
+
+def layers_inputs(g):
+    """(2-D mesh dict, keyword arguments) of a buildlayers fixture (tests/golden/make_golden_layers.py)"""
+    m2 = dict(dim=2, xyz=g["xy"], conn=g["tri"], elab=g["trilab"], bconn=g["bedge"], blab=g["bedge_lab"], belem=g["bedge_elem"],
+              bface=g["bedge_face"])
+    kw = dict(ni=g["ni"], zmin=g["zmin"], zmax=g["zmax"], regmap=g["regmap"], midmap=g["midmap"], upmap=g["upmap"],
+              downmap=g["downmap"])
+    return m2, kw
+
+
+@pytest.mark.parametrize("name", LAYER_CASES)
+def test_buildlayers_bit_exact(name):
+    """the layered mesh of the reference (fflib/msh3.cpp:895-1757 + the boundary orientation BuildAdj leaves): vertices to the
+    bit, elements, labels, boundary triangles with their orientation, (element, face) links"""
+    g = fc.load(name)
+    m2, kw = layers_inputs(g)
+    m = ol.buildlayers(m2, int(g["nlayer"]), **kw)
+    for k in ("xyz", "conn", "elab", "bconn", "blab", "belem", "bface"):
+        assert m[k].shape == g[k].shape, k
+        assert np.array_equal(m[k], g[k]), k
+
+
+def test_boundary_links_turn_the_minority_between_two_regions():
+    """BuildAdj's second pass (femlib/GenericMesh.hpp:966-984) on a hand-made mesh: two tets glued on a face that is listed
+    three times as an internal boundary element between regions 1 and 2, twice running one way and once the other -> the
+    single one is turned round and linked to the other element"""
+    conn = np.array([[0, 1, 2, 3], [1, 0, 2, 4]], np.int32)
+    elab = np.array([1, 2], np.int32)
+    bconn = np.array([[0, 1, 2], [1, 2, 0], [1, 0, 2]], np.int32)
+    be, bf = np.zeros(3, np.int32), np.zeros(3, np.int32)
+    import ctypes as C
+    ol.lib().ffo_boundary_links(2, conn.ctypes.data_as(C.c_void_p), elab.ctypes.data_as(C.c_void_p), 3,
+                                bconn.ctypes.data_as(C.c_void_p), be.ctypes.data_as(C.c_void_p), bf.ctypes.data_as(C.c_void_p))
+    assert np.array_equal(bconn, [[0, 1, 2], [1, 2, 0], [0, 1, 2]])
+    assert be[0] == be[1] == be[2] and bf[0] == bf[1] == bf[2] == 3
