@@ -174,6 +174,72 @@ inline int nbe_of(const Mesh3 &Th) { return Th.nbe; }
 inline int elabel(const Mesh &Th, int k) { return Th[k].lab; }
 inline int elabel(const Mesh3 &Th, int k) { return Th[k].lab; }
 
+// ------------------------------------------------------------------------------------------------------------
+// meshes generated on the device (cube / buildlayers below): the device copy is kept until a fespace on the mesh adopts
+// it, so that such a mesh is never flattened and uploaded.  Identity = address + sizes + a sample of coordinates and
+// connectivity (a mesh object freed and another allocated at the same address does not pass).
+// ------------------------------------------------------------------------------------------------------------
+struct Generated {
+    const void *th = nullptr;
+    int nv = 0, nt = 0, nbe = 0;
+    std::vector<double> sx;
+    std::vector<int32_t> sc;
+    ffcuda_mesh *dm = nullptr;
+};
+std::vector<Generated> g_generated;
+const size_t kMaxGenerated = 2;
+const int kSample = 64;
+
+template <class MeshT>
+void sample_mesh(const MeshT &Th, std::vector<double> &sx, std::vector<int32_t> &sc)
+{
+    const int dim = MeshDim<MeshT>::d, nvk = dim + 1;
+    sx.clear();
+    sc.clear();
+    for (int q = 0; q < kSample; ++q) {
+        const int i = (int)((long long)q * Th.nv / kSample), k = (int)((long long)q * Th.nt / kSample);
+        double p[3];
+        coords(Th, i, p);
+        for (int d = 0; d < dim; ++d) sx.push_back(p[d]);
+        for (int j = 0; j < nvk; ++j) sc.push_back(Th(k, j));
+    }
+}
+
+template <class MeshT>
+void keep_generated(const MeshT &Th, ffcuda_mesh *dm)
+{
+    Generated G;
+    G.th = &Th;
+    G.nv = Th.nv;
+    G.nt = Th.nt;
+    G.nbe = Th.nbe;
+    sample_mesh(Th, G.sx, G.sc);
+    G.dm = dm;
+    g_generated.insert(g_generated.begin(), G);
+    while (g_generated.size() > kMaxGenerated) {
+        ffcuda_mesh_destroy(g_generated.back().dm);
+        g_generated.pop_back();
+    }
+}
+
+template <class MeshT>
+ffcuda_mesh *take_generated(const MeshT &Th, int nbe)
+{
+    for (size_t x = 0; x < g_generated.size(); ++x) {
+        Generated &G = g_generated[x];
+        if (G.th != (const void *)&Th || G.nv != Th.nv || G.nt != Th.nt || G.nbe != nbe) continue;
+        std::vector<double> sx;
+        std::vector<int32_t> sc;
+        sample_mesh(Th, sx, sc);
+        if (sx != G.sx || sc != G.sc) continue;
+        ffcuda_mesh *dm = G.dm;
+        g_generated.erase(g_generated.begin() + x);
+        return dm;
+    }
+    return nullptr;
+}
+inline ffcuda_mesh *take_generated(const Mesh &, int) { return nullptr; } // only 3-D meshes are generated here
+
 // reference basis of P1/P2 Lagrange at a point (value only), in FreeFEM's local dof order: vertices, then edges
 // ({01,02,03,12,13,23} on tetrahedra, edge opposite to vertex e on triangles)
 void lagrange_values(int dim, int order, const double *l, double *phi)
@@ -272,6 +338,10 @@ DevSpace &device_space(const FESpaceT &Vh)
     ffcuda_ctx *ctx = context();
     const int nv = Th.nv, nt = Th.nt, nbe = nbe_of(Th), nvk = dim + 1;
     Marks mk;
+    std::unique_ptr<DevSpace> D(new DevSpace());
+    D->mesh = take_generated(Th, nbe); // generated on the device by this plugin: already there
+    if (D->mesh) mk.mark("mesh already on the device");
+    else {
     std::vector<double> xyz((size_t)nv * dim);
     par_for((size_t)nv, [&](size_t b, size_t e) {
         for (size_t i = b; i < e; ++i) coords(Th, (int)i, &xyz[i * dim]);
@@ -290,17 +360,17 @@ DevSpace &device_space(const FESpaceT &Vh)
         blab[ib] = blabel(Th, ib);
         for (int j = 0; j < dim; ++j) bconn[(size_t)ib * dim + j] = bvertex(Th, ib, j);
     }
-    std::unique_ptr<DevSpace> D(new DevSpace());
+    mk.mark("mesh flattened");
+    FFC(ffcuda_mesh_upload(ctx, dim, nv, xyz.data(), nt, conn.data(), elab.data(), nbe, bconn.data(), blab.data(), belem.data(),
+                           bface.data(), &D->mesh));
+    mk.mark("uploaded");
+    }
     D->key = &Vh;
     D->uid = (const UniqueffId &)Vh;
     D->dim = dim;
     D->order = order;
     D->ncomp = ncomp;
     D->ndof = Vh.NbOfDF;
-    mk.mark("mesh flattened");
-    FFC(ffcuda_mesh_upload(ctx, dim, nv, xyz.data(), nt, conn.data(), elab.data(), nbe, bconn.data(), blab.data(), belem.data(),
-                           bface.data(), &D->mesh));
-    mk.mark("uploaded");
     // the node table as FreeFEM numbered it (2-D P2 is renumbered by FreeFEM: never guessed, always read)
     std::vector<int32_t> e2n;
     const int32_t *pe2n = nullptr;
@@ -1658,6 +1728,278 @@ void repoint_solve_type()
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// cube(nx,ny,nz) and buildlayers(Th2,n,...) with the mesh generated on the device.
+// FreeFEM builds the arrays in 0.15 s at cube(64) and then spends 1.8 s in GenericMesh::BuildAdj (one hash-table
+// insertion per face, femlib/GenericMesh.hpp:837-1046) — 2 minutes at cube(256).  Here the vertices, tetrahedra, boundary
+// triangles (final orientation), the adjacency and the boundary links come from the device (csrc/mesh.cu) and are put
+// into a Mesh3 the way build_layer does it (fflib/msh3.cpp:895-934): set(), fill, BuildBound, [adjacency arrays filled
+// instead of BuildAdj], Buildbnormalv, BuildjElementConteningVertex, BuildGTree.  The device mesh stays resident for the
+// first fespace on it.  Same operator signatures and named parameters as the built-ins, preference 100; what is not
+// covered (label= / flags= of cube, transfo= / facemerge= / ptmerge= of buildlayers) runs the built-in expression,
+// which is always compiled alongside.
+// ------------------------------------------------------------------------------------------------------------
+// a CUDA context if there is a device, without raising (the mesh generators fall back to FreeFEM's own code)
+bool device_available()
+{
+    if (g_ctx) return true;
+    const char *d = getenv("FFCUDA_DEVICE");
+    ffcuda_ctx *c = nullptr;
+    if (ffcuda_ctx_create(d ? atoi(d) : 0, &c) != 0) return false;
+    g_ctx = c;
+    return true;
+}
+
+template <class LabelOfVertex>
+Mesh3 *mesh3_from_device(ffcuda_mesh *dm, LabelOfVertex vlab, Marks &mk)
+{
+    int dim = 0, nv = 0, nt = 0, nbe = 0;
+    FFC(ffcuda_mesh_info(dm, &dim, &nv, &nt, &nbe));
+    if (dim != 3) fail("internal: the generated mesh is not 3-D");
+    std::vector<double> xyz((size_t)nv * 3);
+    std::vector<int32_t> conn((size_t)nt * 4), elab(nt), bconn((size_t)nbe * 3), blab(nbe), belem(nbe), bface(nbe);
+    FFC(ffcuda_mesh_download(dm, xyz.data(), conn.data(), elab.data(), bconn.data(), blab.data(), belem.data(), bface.data()));
+    Mesh3 *Th = new Mesh3;
+    Th->set(nv, nt, nbe);
+    int *adj = new int[(size_t)4 * nt], *head = new int[std::max(nbe, 1)];
+    static_assert(sizeof(int) == sizeof(int32_t), "int is expected to be 32 bits");
+    FFC(ffcuda_mesh_adjacency(dm, reinterpret_cast<int32_t *>(adj), nullptr));
+    mk.mark("generated + downloaded");
+    par_for((size_t)nv, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; ++i) {
+            Vertex3 &V = Th->vertices[i];
+            V.x = xyz[3 * i];
+            V.y = xyz[3 * i + 1];
+            V.z = xyz[3 * i + 2];
+            V.lab = vlab((int)i);
+        }
+    });
+    par_for((size_t)nt, [&](size_t b, size_t e) {
+        for (size_t k = b; k < e; ++k) {
+            int iv[4] = {conn[4 * k], conn[4 * k + 1], conn[4 * k + 2], conn[4 * k + 3]};
+            Th->elements[k].set(Th->vertices, iv, elab[k]);
+        }
+    });
+    for (int ib = 0; ib < nbe; ++ib) {
+        int iv[3] = {bconn[3 * (size_t)ib], bconn[3 * (size_t)ib + 1], bconn[3 * (size_t)ib + 2]};
+        Th->borderelements[ib].set(Th->vertices, iv, blab[ib]);
+        head[ib] = 4 * belem[ib] + bface[ib];
+    }
+    Th->BuildBound();
+    // what BuildAdj leaves behind (femlib/GenericMesh.hpp:837-1046): k*4+i -> k'*4+i', -1 on the boundary; the boundary
+    // triangles already have their final orientation
+    Th->TheAdjacencesLink = adj;
+    Th->BoundaryElementHeadLink = head;
+    Th->nadjnomanifold = 0;
+    Th->Buildbnormalv();
+    Th->BuildjElementConteningVertex();
+    Th->BuildGTree();
+    mk.mark("Mesh3");
+    return Th;
+}
+
+struct CudaCubeOp : public E_F0mps {
+    Expression builtin, enx, eny, enz;
+    static const int n_name_param = 3;
+    static basicAC_F0::name_and_type name_param[];
+    Expression nargs[n_name_param];
+    CudaCubeOp(const basicAC_F0 &args, Expression b, Expression nx, Expression ny, Expression nz) : builtin(b), enx(nx), eny(ny), enz(nz)
+    {
+        args.SetNameParam(n_name_param, name_param, nargs);
+    }
+    AnyType operator()(Stack stack) const
+    {
+        const long nx = GetAny<long>((*enx)(stack)), ny = GetAny<long>((*eny)(stack)), nz = GetAny<long>((*enz)(stack));
+        std::string why;
+        if (nargs[1]) why = "label=";
+        else if (nargs[2] && GetAny<long>((*nargs[2])(stack)) != 6) why = "flags=";
+        else if (nx < 1 || ny < 1 || nz < 1 || (double)nx * ny * nz * 6 >= (double)(1 << 27)) why = "size";
+        else if (!device_available()) why = "no CUDA device";
+        if (!why.empty()) {
+            notice("cube", why);
+            return (*builtin)(stack);
+        }
+        const long region = nargs[0] ? GetAny<long>((*nargs[0])(stack)) : 0;
+        Marks mk;
+        ffcuda_mesh *dm = nullptr;
+        FFC(ffcuda_mesh_cube(context(), (int)nx, (int)ny, (int)nz, &dm));
+        const int n1 = (int)nx + 1, n2 = (int)ny + 1;
+        Mesh3 *Th = nullptr;
+        try {
+            // vertex labels of BuildCube: one bit per face the vertex lies on (fflib/msh3.cpp:8010-8016)
+            Th = mesh3_from_device(dm, [=](int p) {
+                const int i = p % n1, j = (p / n1) % n2, k = p / (n1 * n2);
+                return 1 * (i == 0) + 2 * (i == nx) + 4 * (j == 0) + 8 * (j == ny) + 16 * (k == 0) + 32 * (k == nz);
+            }, mk);
+        } catch (...) {
+            ffcuda_mesh_destroy(dm);
+            throw;
+        }
+        if (region != 0) { // the device copy carries region 0: not kept
+            for (int k = 0; k < Th->nt; ++k) Th->elements[k].lab = (int)region;
+            ffcuda_mesh_destroy(dm);
+        } else
+            keep_generated(*Th, dm);
+        if (g_verbose) cout << "  -- ffcuda: cube(" << nx << "," << ny << "," << nz << ") on the device:" << mk.line << endl;
+        Add2StackOfPtr2FreeRC(stack, Th);
+        return Th;
+    }
+};
+basicAC_F0::name_and_type CudaCubeOp::name_param[] = {{"region", &typeid(long)}, {"label", &typeid(KN_<long>)}, {"flags", &typeid(long)}};
+
+struct CudaCube : public OneOperator {
+    const OneOperator *builtin;
+    explicit CudaCube(const OneOperator *b) : OneOperator(atype<pmesh3>(), atype<long>(), atype<long>(), atype<long>()), builtin(b) { pref = 100; }
+    E_F0 *code(const basicAC_F0 &args) const
+    {
+        return new CudaCubeOp(args, builtin->code(args), t[0]->CastTo(args[0]), t[1]->CastTo(args[1]), t[2]->CastTo(args[2]));
+    }
+};
+
+struct CudaLayersOp : public E_F0mps {
+    Expression builtin, eTh, enmax, ezmin, ezmax;
+    static const int n_name_param = 13;
+    static basicAC_F0::name_and_type name_param[];
+    Expression nargs[n_name_param];
+    CudaLayersOp(const basicAC_F0 &args, Expression b, Expression th, Expression nm) : builtin(b), eTh(th), enmax(nm), ezmin(0), ezmax(0)
+    {
+        args.SetNameParam(n_name_param, name_param, nargs);
+        if (nargs[0]) { // zbound=[zmin,zmax]; the built-in expression reports a malformed array
+            const E_Array *a = dynamic_cast<const E_Array *>(nargs[0]);
+            if (a && a->size() == 2) {
+                ezmin = to<double>((*a)[0]);
+                ezmax = to<double>((*a)[1]);
+            }
+        }
+    }
+    std::vector<int32_t> pairs(Stack stack, int a, int b) const
+    { // region= / reftet= and friends: (old,new) pairs
+        std::vector<int32_t> out;
+        Expression e = nargs[a] ? nargs[a] : nargs[b];
+        if (e) {
+            KN_<long> v = GetAny<KN_<long>>((*e)(stack));
+            if (v.N() % 2) ExecError("buildlayers: a label array needs an even number of entries");
+            for (int i = 0; i < v.N(); ++i) out.push_back((int32_t)v[i]);
+        }
+        return out;
+    }
+    AnyType operator()(Stack stack) const
+    {
+        std::string why;
+        if (nargs[1]) why = "transfo=";
+        else if (nargs[7] || nargs[8]) why = "facemerge= / ptmerge=";
+        else if (nargs[0] && !(ezmin && ezmax)) why = "zbound";
+        else if (!device_available()) why = "no CUDA device";
+        if (!why.empty()) {
+            notice("buildlayers", why);
+            return (*builtin)(stack);
+        }
+        MeshPoint *mp(MeshPointStack(stack)), mps = *mp;
+        const Mesh *pTh = GetAny<const Mesh *>((*eTh)(stack));
+        const int nlayer = (int)GetAny<long>((*enmax)(stack));
+        ffassert(pTh && nlayer > 0);
+        const Mesh &Th = *pTh;
+        const int nbv = Th.nv, nbt = Th.nt, neb = Th.neb;
+        // zmin, zmax, coef at the vertices, evaluated like BuildLayeMesh_Op does (fflib/msh3.cpp:4556-4585)
+        std::vector<double> zmin(nbv, 0.), zmax(nbv, 1.), clayer(nbv, -1.);
+        double maxdz = 0;
+        for (int it = 0; it < nbt; ++it)
+            for (int iv = 0; iv < 3; ++iv) {
+                const int i = Th(it, iv);
+                if (clayer[i] < 0) {
+                    mp->setP(&Th, it, iv);
+                    if (ezmin) zmin[i] = GetAny<double>((*ezmin)(stack));
+                    if (ezmax) zmax[i] = GetAny<double>((*ezmax)(stack));
+                    maxdz = std::max(maxdz, std::abs(zmin[i] - zmax[i]));
+                    const double c = nargs[2] ? GetAny<double>((*nargs[2])(stack)) : 1.;
+                    clayer[i] = std::max(0., std::min(1., c));
+                }
+            }
+        *mp = mps;
+        std::vector<int32_t> ni(nbv);
+        const double epsz = maxdz * 1e-6;
+        for (int i = 0; i < nbv; ++i) { // :4647-4657
+            ni[i] = std::max(0, std::min(nlayer, (int)lrint(nlayer * std::max(clayer[i], 0.))));
+            if (std::abs(zmin[i] - zmax[i]) < epsz) ni[i] = 0;
+        }
+        bool empty_prism = nlayer >= (1 << 15) || (double)nbt * nlayer * 3 >= (double)(1 << 27);
+        for (int i = 0; i < nbv; ++i) empty_prism = empty_prism || clayer[i] < 0; // a vertex of no triangle: FreeFEM asserts (:4587)
+        for (int it = 0; it < nbt && !empty_prism; ++it)
+            empty_prism = ni[Th(it, 0)] == 0 && ni[Th(it, 1)] == 0 && ni[Th(it, 2)] == 0;
+        if (empty_prism) { // FreeFEM stops the run there (:4662-4673), or the mesh is too large for one device: its business
+            notice("buildlayers", "a triangle without layers, or size");
+            return (*builtin)(stack);
+        }
+        const std::vector<int32_t> reg = pairs(stack, 3, 9), mid = pairs(stack, 4, 10), up = pairs(stack, 5, 11), down = pairs(stack, 6, 12);
+        // the 2-D mesh as the device takes it
+        Marks mk;
+        std::vector<double> xy((size_t)nbv * 2);
+        std::vector<int32_t> tri((size_t)nbt * 3), trilab(nbt), bconn((size_t)neb * 2), blab(neb), belem(neb), bface(neb), vlab2(nbv);
+        for (int i = 0; i < nbv; ++i) {
+            xy[2 * (size_t)i] = Th(i).x;
+            xy[2 * (size_t)i + 1] = Th(i).y;
+            vlab2[i] = Th(i).lab;
+        }
+        for (int k = 0; k < nbt; ++k) {
+            for (int j = 0; j < 3; ++j) tri[3 * (size_t)k + j] = Th(k, j);
+            trilab[k] = Th[k].lab;
+        }
+        for (int ib = 0; ib < neb; ++ib) {
+            int ie;
+            belem[ib] = Th.BoundaryElement(ib, ie);
+            bface[ib] = ie;
+            blab[ib] = Th.bedges[ib].lab;
+            for (int j = 0; j < 2; ++j) bconn[2 * (size_t)ib + j] = Th(Th.bedges[ib][j]);
+        }
+        ffcuda_mesh *d2 = nullptr, *dm = nullptr;
+        FFC(ffcuda_mesh_upload(context(), 2, nbv, xy.data(), nbt, tri.data(), trilab.data(), neb, bconn.data(), blab.data(), belem.data(),
+                               bface.data(), &d2));
+        const int rc = ffcuda_mesh_buildlayers(d2, nlayer, ni.data(), zmin.data(), zmax.data(), (int)reg.size() / 2, reg.data(),
+                                               (int)mid.size() / 2, mid.data(), (int)up.size() / 2, up.data(), (int)down.size() / 2,
+                                               down.data(), &dm);
+        ffcuda_mesh_destroy(d2);
+        if (rc) fail("ffcuda_mesh_buildlayers");
+        // 3-D vertex -> its 2-D vertex: the columns follow each other (fflib/msh3.cpp:1016-1050); label of the 2-D vertex
+        std::vector<int32_t> col;
+        col.reserve((size_t)nbv * (nlayer + 1));
+        for (int i = 0; i < nbv; ++i) col.insert(col.end(), (size_t)ni[i] + 1, vlab2[i]);
+        Mesh3 *Th3 = nullptr;
+        try {
+            Th3 = mesh3_from_device(dm, [&](int p) { return col[p]; }, mk);
+        } catch (...) {
+            ffcuda_mesh_destroy(dm);
+            throw;
+        }
+        keep_generated(*Th3, dm);
+        if (g_verbose) cout << "  -- ffcuda: buildlayers(" << nbt << " triangles, " << nlayer << " layers) on the device:" << mk.line << endl;
+        Add2StackOfPtr2FreeRC(stack, Th3);
+        return Th3;
+    }
+};
+basicAC_F0::name_and_type CudaLayersOp::name_param[] = { // BuildLayeMesh_Op::name_param, fflib/msh3.cpp:4254-4268
+    {"zbound", &typeid(E_Array)},          {"transfo", &typeid(E_Array)},        {"coef", &typeid(double)},
+    {"reftet", &typeid(KN_<long>)},        {"reffacemid", &typeid(KN_<long>)},   {"reffaceup", &typeid(KN_<long>)},
+    {"reffacelow", &typeid(KN_<long>)},    {"facemerge", &typeid(long)},         {"ptmerge", &typeid(double)},
+    {"region", &typeid(KN_<long>)},        {"labelmid", &typeid(KN_<long>)},     {"labelup", &typeid(KN_<long>)},
+    {"labeldown", &typeid(KN_<long>)}};
+
+struct CudaLayers : public OneOperator {
+    const OneOperator *builtin;
+    explicit CudaLayers(const OneOperator *b) : OneOperator(atype<pmesh3>(), atype<pmesh>(), atype<long>()), builtin(b) { pref = 100; }
+    E_F0 *code(const basicAC_F0 &args) const
+    {
+        return new CudaLayersOp(args, builtin->code(args), t[0]->CastTo(args[0]), t[1]->CastTo(args[1]));
+    }
+};
+
+// the built-in operator of a global function for exact argument types (before ours is added)
+const OneOperator *builtin_operator(const char *name, const ArrayOfaType &at)
+{
+    C_F0 f = Global.Find(name); // (a Polymorphic answers Empty(): not asked)
+    const Polymorphic *p = dynamic_cast<const Polymorphic *>(f.LeftValue());
+    return p ? p->FindWithOutCast("(", at) : nullptr;
+}
+
 } // namespace
 
 static void Load_Init()
@@ -1697,6 +2039,13 @@ static void Load_Init()
     if (!env_on("FFCUDA_NO_PROBLEM")) {
         repoint_solve_type<false, Problem>();
         repoint_solve_type<true, Solve>();
+    }
+    // 5. mesh generators on the device (cube without transformation, buildlayers)
+    if (!env_on("FFCUDA_NO_MESH")) {
+        if (const OneOperator *b = builtin_operator("cube", ArrayOfaType(atype<long>(), atype<long>(), atype<long>())))
+            Global.Add("cube", "(", new CudaCube(b));
+        if (const OneOperator *b = builtin_operator("buildlayers", ArrayOfaType(atype<pmesh>(), atype<long>())))
+            Global.Add("buildlayers", "(", new CudaLayers(b));
     }
 }
 

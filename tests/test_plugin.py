@@ -534,3 +534,79 @@ def test_plugin_veps_is_the_stopping_threshold():
     vc = float(re.search(r"^VEPS (\S+)", out_cpu, re.M).group(1))
     assert vc != 1e-6 and abs(vg - vc) <= 1e-10 * abs(vc)
     assert np.max(np.abs(gpu - cpu)) <= 1e-11 * np.abs(cpu).max()
+
+
+# ---- mesh generators on the device: `cube(nx,ny,nz)` and `buildlayers(Th2,n,...)` ----------------------
+MESH_DUMP = """
+{ ofstream f("NAME.txt"); f.precision(17);
+  f << Th.nv << " " << Th.nt << " " << Th.nbe << " " << Th.mesure << " " << Th.bordermesure << endl;
+  for(int i=0;i<Th.nv;++i) f << Th(i).x << " " << Th(i).y << " " << Th(i).z << " " << Th(i).label << endl;
+  for(int k=0;k<Th.nt;++k){ for(int i=0;i<4;++i) f << Th[k][i] << " "; f << Th[k].label << " " << Th[k].mesure << endl; }
+  for(int e=0;e<Th.nbe;++e){ for(int i=0;i<3;++i) f << Th.be(e)[i] << " ";
+     f << Th.be(e).label << " " << Th.be(e).Element << " " << Th.be(e).whoinElement << endl; }
+  for(int k=0;k<Th.nt;++k) for(int e=0;e<4;++e){ int ee=e; int kk=Th[k].adj(ee); f << kk << " " << ee << endl; }
+}
+"""
+MESHGEN = {
+    "cube": 'mesh3 Th = cube(5,4,3);',
+    "cube_region": 'mesh3 Th = cube(2,3,4,region=7);',
+    "layers_heat3d": 'mesh Th2=square(6,6); int[int] refm=[1,1,2,1,3,1,4,1]; int[int] refu=[0,1];\n'
+                     'mesh3 Th=buildlayers(Th2,6,zbound=[0.,1.],labelmid=refm,labelup=refu,labeldown=refu);',
+    "layers_coef": 'mesh Th2=square(5,4,[x+0.1*y,y*(1+0.2*x)],flags=1); int[int] rr=[0,7]; int[int] rm=[1,11,3,13,1,21];\n'
+                   'int[int] ru=[0,31]; int[int] rd=[0,41,5,6];\n'
+                   'mesh3 Th=buildlayers(Th2,4,zbound=[0.1*x*y,1.+0.3*y-0.2*x],coef=1.02-x,region=rr,labelmid=rm,labelup=ru,labeldown=rd);',
+    "layers_disk": 'border C(t=0,2*pi){x=cos(t);y=sin(t);label=9;}\nborder D(t=0,2*pi){x=0.3*cos(t)+0.1;y=0.3*sin(t);label=8;}\n'
+                   'mesh Th2=buildmesh(C(24)+D(10)); int[int] rr=[0,3,1,4];\n'
+                   'mesh3 Th=buildlayers(Th2,5,zbound=[-0.2*(1-x*x-y*y),0.5+0.5*(1-x*x-y*y)+0.1*x],coef=0.15+0.85*(x*x+0.5*y*y),reftet=rr);',
+}
+
+
+def _mesh_script(gen):
+    s = 'load "msh3"\nload "ffcuda"\n' + gen + "\n" + MESH_DUMP.replace("NAME", "mesh")
+    s += "fespace Vh(Th,P1);\nvarf va(u,v) = int3d(Th)(" + LAP3 + "+u*v) + int3d(Th)(1.*v);\n"
+    s += "matrix A = va(Vh,Vh,solver=CG,eps=1e-14);\nreal[int] b = va(0,Vh);\n" + DUMP + "Vh u;\n" + SOLVE.replace("UU", "u")
+    return s
+
+
+def _run_mesh(src, env_extra):
+    with tempfile.TemporaryDirectory() as td:
+        with open(os.path.join(td, "case.edp"), "w") as f:
+            f.write(src)
+        env = dict(os.environ, FF_LOADPATH=LIBDIR, **env_extra)
+        r = subprocess.run([FF, "-nw", "-v", "1", "case.edp"], capture_output=True, text=True, cwd=td, env=env, timeout=600)
+        out = r.stdout + r.stderr
+        assert r.returncode == 0, out[-3000:]
+        return out, open(os.path.join(td, "mesh.txt")).read(), open(os.path.join(td, "A.txt")).read(), np.loadtxt(os.path.join(td, "u.txt"))
+
+
+@needs_ff
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(MESHGEN))
+def test_plugin_device_mesh_generators(name):
+    """the Mesh3 a script gets from `cube` / `buildlayers` with the plugin loaded is the one FreeFEM builds: vertices,
+    labels, elements, measures, boundary elements with orientation and links, adjacency (Th[k].adj) — the dumps are equal
+    as text; the first fespace on it adopts the device copy (no upload) and assembles the same matrix"""
+    src = _mesh_script(MESHGEN[name])
+    out, mesh, a, u = _run_mesh(src, {"FFCUDA_STRICT": "1", "FFCUDA_VERBOSE": "1"})
+    assert ("cube(" if name.startswith("cube") else "buildlayers(") in out and "on the device" in out
+    if name != "cube_region":
+        assert "mesh already on the device" in out
+    out0, mesh0, a0, u0 = _run_mesh(src, {"FFCUDA_DISABLE": "1"})
+    assert "on the device" not in out0
+    assert mesh == mesh0
+    ga = np.array(" ".join(ln for ln in a.splitlines()[1:] if not ln.startswith("#")).split(), dtype=np.float64)
+    ca = np.array(" ".join(ln for ln in a0.splitlines()[1:] if not ln.startswith("#")).split(), dtype=np.float64)
+    assert ga.shape == ca.shape and np.max(np.abs(ga - ca)) <= 1e-12 * np.abs(ca).max()
+    assert np.max(np.abs(u - u0)) <= 1e-12 * np.abs(u0).max()
+
+
+@needs_ff
+def test_plugin_mesh_generators_fall_back_without_a_device_or_for_options():
+    """no device, or an option the device generator does not cover (label= of cube): FreeFEM's own generator runs and the
+    plugin says so"""
+    src = ('load "msh3"\nload "ffcuda"\nint[int] ll=[1,1,1,1,2,2]; mesh3 Th = cube(2,3,2,label=ll);\nmesh Th2=square(2,2);\n'
+           'mesh3 T3=buildlayers(Th2,2,transfo=[x,y,2*z]);\ncout << "SIZES " << Th.nt << " " << T3.nt << endl;\n')
+    rc, out, _ = run_ff(src, {"FFCUDA_VERBOSE": "1"}, want_fail=True)
+    assert rc == 0, out[-2000:]
+    assert "SIZES 72 48" in out
+    assert out.count("left to FreeFEM") == 2

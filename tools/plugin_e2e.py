@@ -11,7 +11,7 @@ with tempfile.TemporaryDirectory() as td:
     r = subprocess.run([bench.FF_BIN, "-nw", "-v", "1", edp], capture_output=True, text=True, cwd=td, env=env)
     try:
         st = [float(x) for x in open(os.path.join(td, "ffstamps.txt")).read().split()]
-        print("wall: matrix %.3f s, rhs %.3f s, cg %.3f s" % (st[1] - st[0], st[2] - st[1], st[3] - st[2]))
+        print("wall: mesh %.3f s, matrix %.3f s, rhs %.3f s, cg %.3f s" % (st[1] - st[0], st[3] - st[2], st[4] - st[3], st[5] - st[4]))
     except Exception as e:
         print("no stamps", e)
     for ln in (r.stdout + r.stderr).splitlines():
