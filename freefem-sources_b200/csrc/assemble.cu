@@ -18,6 +18,7 @@
 // contracted per element with the inverse Jacobian.  Same mathematics as the reference loop, different
 // summation order (differences ~1e-16 relative).
 #include "common.cuh"
+#include <memory>
 #include <algorithm>
 #include <cmath>
 
@@ -1333,12 +1334,20 @@ __device__ __forceinline__ int face_nodes(int order, int f, int (&out)[6])
 template <int DIM, int PASS>
 __global__ void k_bnd_items(int nbe, const int32_t *__restrict__ belem, const int32_t *__restrict__ bface,
                             const int32_t *__restrict__ e2n, int nloc, int order, int nrows, int32_t *__restrict__ cntptr,
-                            int32_t *__restrict__ cursor, uint32_t *__restrict__ items)
+                            int32_t *__restrict__ cursor, uint32_t *__restrict__ items, int allnodes)
 {
     const int e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= nbe) return;
-    int loc[6];
-    const int n = face_nodes<DIM>(order, bface[e], loc);
+    int loc[10];
+    int n;
+    if (allnodes) { // every node of the adjacent element: terms with derivatives reach the nodes off the face too
+        n = nloc;
+        for (int j = 0; j < nloc; ++j) loc[j] = j;
+    } else {
+        int fl[6];
+        n = face_nodes<DIM>(order, bface[e], fl);
+        for (int j = 0; j < n; ++j) loc[j] = fl[j];
+    }
     const int32_t *N = e2n + (size_t)nloc * belem[e];
     for (int j = 0; j < n; ++j) {
         const int node = N[loc[j]];
@@ -1412,9 +1421,11 @@ __global__ void k_bnd_gather(int nrows, const int32_t *__restrict__ ptr, const u
 }
 
 template <int DIM>
-static void bnd_incidence(ffcuda_ctx *ctx, ffcuda_space *s)
+static void bnd_incidence(ffcuda_ctx *ctx, ffcuda_space *s, bool allnodes = false)
 {
-    if (s->bnd_ptr.p) return;
+    DBuf<int32_t> &bptr = allnodes ? s->bnd2_ptr : s->bnd_ptr;
+    DBuf<uint32_t> &bitems = allnodes ? s->bnd2_items : s->bnd_items;
+    if (bptr.p) return;
     ffcuda_mesh *m = s->mesh;
     cudaStream_t st = ctx->stream;
     const int nrows = s->nnodes_owned, nbe = m->nbe;
@@ -1424,17 +1435,18 @@ static void bnd_incidence(ffcuda_ctx *ctx, ffcuda_space *s)
     FF_CUDA(cudaMemsetAsync(cnt.p, 0, cnt.bytes(), st));
     FF_CUDA(cudaMemsetAsync(cursor.p, 0, cursor.bytes(), st));
     ff_launch(ctx, "bnd_count", [&] {
-        k_bnd_items<DIM, 0><<<ff_blocks(nbe, 256), 256, 0, st>>>(nbe, m->belem.p, m->bface.p, s->e2n, s->nloc, s->order, nrows, cnt.p, nullptr, nullptr);
+        k_bnd_items<DIM, 0><<<ff_blocks(nbe, 256), 256, 0, st>>>(nbe, m->belem.p, m->bface.p, s->e2n, s->nloc, s->order, nrows, cnt.p, nullptr, nullptr,
+                                                                (int)allnodes);
     });
-    s->bnd_ptr.alloc((size_t)nrows + 1);
+    bptr.alloc((size_t)nrows + 1);
     int64_t tot = 0;
-    ff_exclusive_scan_i32(ctx, cnt.p, s->bnd_ptr.p, (size_t)nrows + 1, &tot);
-    s->bnd_items.alloc((size_t)std::max<int64_t>(tot, 1));
+    ff_exclusive_scan_i32(ctx, cnt.p, bptr.p, (size_t)nrows + 1, &tot);
+    bitems.alloc((size_t)std::max<int64_t>(tot, 1));
     ff_launch(ctx, "bnd_fill", [&] {
-        k_bnd_items<DIM, 1><<<ff_blocks(nbe, 256), 256, 0, st>>>(nbe, m->belem.p, m->bface.p, s->e2n, s->nloc, s->order, nrows, s->bnd_ptr.p, cursor.p,
-                                                                s->bnd_items.p);
+        k_bnd_items<DIM, 1><<<ff_blocks(nbe, 256), 256, 0, st>>>(nbe, m->belem.p, m->bface.p, s->e2n, s->nloc, s->order, nrows, bptr.p, cursor.p,
+                                                                bitems.p, (int)allnodes);
     });
-    ff_launch(ctx, "bnd_sort", [&] { k_bnd_sort<<<ff_blocks(nrows, 256), 256, 0, st>>>(s->bnd_ptr.p, s->bnd_items.p, nrows); });
+    ff_launch(ctx, "bnd_sort", [&] { k_bnd_sort<<<ff_blocks(nrows, 256), 256, 0, st>>>(bptr.p, bitems.p, nrows); });
 }
 
 // basis values at the point of face f of the reference element that the face rule's node qp maps to:
@@ -1475,6 +1487,313 @@ static void bnd_measures(ffcuda_ctx *ctx, ffcuda_mesh *m, const BndParams &Bp, d
     });
 }
 
+// ----------------------------------------------------------------------------------------------------
+// Boundary integrals with DERIVATIVES of the unknown or of the test function (int2d(Th,lab)(dx(u) v), Nitsche terms,
+// int2d(Th,lab)(c dz(v))): the border branch of Element_Op / Element_rhs evaluates the basis functions of the adjacent
+// element at the face quadrature points with whatever operators the terms ask for (fflib/problem.cpp:6518-6560,
+// :8517-8587), so every node of that element receives something, not only those lying on the face.  Same ownership as the
+// value terms: one thread per node row walks its items — here taken from the incidence over ALL nodes of the adjacent
+// elements (bnd2) — in order, evaluates its own basis function and those of the element's nodes at every face point
+// (gradients of the barycentric coordinates from the vertices, P2 by the product rule) and adds into its row, columns found
+// by bisection.  O(boundary) work: clarity over speed.
+// ----------------------------------------------------------------------------------------------------
+struct BndGenTerm {
+    int ucomp, uslot, vcomp, vslot; // slot: 0 value, 1..3 d/dx, d/dy, d/dz
+    double coef;
+};
+static constexpr int MAXBT = 48;
+struct BndGenParams {
+    int nterms, nq;
+    BndGenTerm t[MAXBT];
+    double w[16];        // weights of the face rule
+    double lam[4][16][4]; // [face][q][vertex]: barycentric coordinates, in the element, of face point q (PBord)
+};
+
+// gradients of the barycentric coordinates of element K
+template <int DIM>
+__device__ __forceinline__ void bary_gradients(const int32_t *__restrict__ K, const double *__restrict__ xyz, int vstride, double (&G)[DIM + 1][DIM])
+{
+    double X[DIM + 1][DIM];
+    for (int a = 0; a <= DIM; ++a)
+        for (int d = 0; d < DIM; ++d) X[a][d] = xyz[(size_t)K[a] * vstride + d];
+    if (DIM == 2) {
+        const double ax = X[1][0] - X[0][0], ay = X[1][1] - X[0][1], bx = X[2][0] - X[0][0], by = X[2][1] - X[0][1];
+        const double det = ax * by - ay * bx;
+        G[1][0] = by / det;  G[1][1] = -bx / det;
+        G[2][0] = -ay / det; G[2][1] = ax / det;
+    } else {
+        double e[3][3];
+        for (int r = 0; r < 3; ++r)
+            for (int d = 0; d < 3; ++d) e[r][d] = X[r + 1][d] - X[0][d];
+        double c[3][3]; // c[r] = e[r+1] x e[r+2]
+        for (int r = 0; r < 3; ++r) {
+            const double *u = e[(r + 1) % 3], *v = e[(r + 2) % 3];
+            c[r][0] = u[1] * v[2] - u[2] * v[1];
+            c[r][1] = u[2] * v[0] - u[0] * v[2];
+            c[r][2] = u[0] * v[1] - u[1] * v[0];
+        }
+        const double det = e[0][0] * c[0][0] + e[0][1] * c[0][1] + e[0][2] * c[0][2];
+        for (int r = 0; r < 3; ++r)
+            for (int d = 0; d < DIM; ++d) G[r + 1][d] = c[r][d] / det;
+    }
+    for (int d = 0; d < DIM; ++d) {
+        double sgrad = 0.0;
+        for (int a = 1; a <= DIM; ++a) sgrad += G[a][d];
+        G[0][d] = -sgrad;
+    }
+}
+
+// value and gradient of the basis function of local node a at the point with barycentric coordinates l: out[0] value,
+// out[1..DIM] derivatives.  P2 edges: {01,02,03,12,13,23} on a tetrahedron, edge opposite vertex e on a triangle
+// (femlib/P012_3d.cpp:199-300, femlib/FESpace.cpp:1219)
+template <int DIM>
+__device__ __forceinline__ void basis_at(int order, int a, const double *__restrict__ l, const double (&G)[DIM + 1][DIM], double (&out)[4])
+{
+    out[0] = out[1] = out[2] = out[3] = 0.0;
+    if (order == 1) {
+        out[0] = l[a];
+        for (int d = 0; d < DIM; ++d) out[1 + d] = G[a][d];
+        return;
+    }
+    if (a <= DIM) {
+        out[0] = l[a] * (2.0 * l[a] - 1.0);
+        for (int d = 0; d < DIM; ++d) out[1 + d] = (4.0 * l[a] - 1.0) * G[a][d];
+        return;
+    }
+    int p, r;
+    if (DIM == 3) {
+        const int e3[6][2] = {{0, 1}, {0, 2}, {0, 3}, {1, 2}, {1, 3}, {2, 3}};
+        p = e3[a - 4][0];
+        r = e3[a - 4][1];
+    } else {
+        p = (a - 3 + 1) % 3;
+        r = (a - 3 + 2) % 3;
+    }
+    out[0] = 4.0 * l[p] * l[r];
+    for (int d = 0; d < DIM; ++d) out[1 + d] = 4.0 * (l[p] * G[r][d] + l[r] * G[p][d]);
+}
+
+template <int DIM>
+__global__ void k_bnd_bilinear_gen(int nrows, const int32_t *__restrict__ ptr, const uint32_t *__restrict__ items,
+                                   const int32_t *__restrict__ belem, const int32_t *__restrict__ bface, const double *__restrict__ meas,
+                                   const int32_t *__restrict__ conn, const double *__restrict__ xyz, int vstride,
+                                   const int32_t *__restrict__ e2n, int nloc, int order, int nc, const int32_t *__restrict__ nrowptr,
+                                   const int32_t *__restrict__ ncol, const BndGenParams *__restrict__ Gp, const double *__restrict__ cq,
+                                   double *__restrict__ vals)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    const int k0 = ptr[i], k1 = ptr[i + 1];
+    if (k0 == k1) return;
+    const int rb = nrowptr[i], L = nrowptr[i + 1] - rb;
+    double *row = vals + (size_t)nc * nc * rb;
+    const int nq = Gp->nq, nterms = Gp->nterms;
+    for (int k = k0; k < k1; ++k) {
+        const uint32_t it = items[k];
+        const int e = it >> 4, a = it & 15;
+        const double m = meas[e];
+        if (m == 0.0) continue; // label not listed
+        const int f = bface[e], el = belem[e];
+        const int32_t *N = e2n + (size_t)nloc * el;
+        double G[DIM + 1][DIM];
+        bary_gradients<DIM>(conn + (size_t)(DIM + 1) * el, xyz, vstride, G);
+        for (int b = 0; b < nloc; ++b) {
+            double acc[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+            for (int q = 0; q < nq; ++q) {
+                double va[4], ub[4];
+                basis_at<DIM>(order, a, Gp->lam[f][q], G, va);
+                basis_at<DIM>(order, b, Gp->lam[f][q], G, ub);
+                const double w = m * Gp->w[q] * (cq ? cq[(size_t)e * nq + q] : 1.0);
+                for (int t = 0; t < nterms; ++t) {
+                    const BndGenTerm &T = Gp->t[t];
+                    acc[T.vcomp][T.ucomp] += (T.coef * w) * va[T.vslot] * ub[T.uslot];
+                }
+            }
+            const int j = N[b];
+            int lo = 0, hi = L - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (ncol[rb + mid] < j) lo = mid + 1;
+                else hi = mid;
+            }
+            for (int cv = 0; cv < nc; ++cv)
+                for (int cu = 0; cu < nc; ++cu)
+                    if (acc[cv][cu] != 0.0) row[(size_t)cv * nc * L + (size_t)lo * nc + cu] += acc[cv][cu];
+        }
+    }
+}
+
+template <int DIM>
+__global__ void k_bnd_linear_gen(int nrows, const int32_t *__restrict__ ptr, const uint32_t *__restrict__ items,
+                                 const int32_t *__restrict__ belem, const int32_t *__restrict__ bface, const double *__restrict__ meas,
+                                 const int32_t *__restrict__ conn, const double *__restrict__ xyz, int vstride, int order, int nc,
+                                 const BndGenParams *__restrict__ Gp, double *__restrict__ bvec, int accumulate)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    double s[3] = {0, 0, 0};
+    const int nq = Gp->nq, nterms = Gp->nterms;
+    for (int k = ptr[i]; k < ptr[i + 1]; ++k) {
+        const uint32_t it = items[k];
+        const int e = it >> 4, a = it & 15;
+        const double m = meas[e];
+        if (m == 0.0) continue;
+        const int f = bface[e], el = belem[e];
+        double G[DIM + 1][DIM];
+        bary_gradients<DIM>(conn + (size_t)(DIM + 1) * el, xyz, vstride, G);
+        for (int q = 0; q < nq; ++q) {
+            double va[4];
+            basis_at<DIM>(order, a, Gp->lam[f][q], G, va);
+            const double w = m * Gp->w[q];
+            for (int t = 0; t < nterms; ++t) {
+                const BndGenTerm &T = Gp->t[t];
+                s[T.vcomp] += (T.coef * w) * va[T.vslot];
+            }
+        }
+    }
+    if (!accumulate || ptr[i + 1] > ptr[i])
+        for (int c = 0; c < nc; ++c) {
+            double *dst = bvec + (size_t)i * nc + c;
+            *dst = accumulate ? *dst + s[c] : s[c];
+        }
+}
+
+static int op_slot(int op)
+{
+    switch (op) {
+    case FFCUDA_OP_ID: return 0;
+    case FFCUDA_OP_DX: return 1;
+    case FFCUDA_OP_DY: return 2;
+    case FFCUDA_OP_DZ: return 3;
+    }
+    throw FFError("boundary integrals: operator code not supported (value and first derivatives only)");
+}
+
+// face rule -> barycentric coordinates in the element (PBord: femlib/Mesh3dn.hpp:76 faces nvfaceTet, Mesh2dn.hpp:65 edges)
+static void bnd_gen_rule(BndGenParams &Gp, int dim, int nq, const double *qpts, const double *qw)
+{
+    static const int nvface[4][3] = {{3, 2, 1}, {0, 2, 3}, {3, 1, 0}, {0, 1, 2}};
+    static const int nvedge[3][2] = {{1, 2}, {2, 0}, {0, 1}};
+    FF_REQUIRE(nq <= 16, "boundary integrals with derivatives: at most 16 quadrature points on a face");
+    Gp.nq = nq;
+    for (int q = 0; q < nq; ++q) Gp.w[q] = qw[q];
+    for (int f = 0; f <= dim; ++f)
+        for (int q = 0; q < nq; ++q) {
+            for (int a = 0; a < 4; ++a) Gp.lam[f][q][a] = 0.0;
+            if (dim == 3) {
+                const double x = qpts[2 * q], y = qpts[2 * q + 1];
+                Gp.lam[f][q][nvface[f][0]] = 1 - x - y;
+                Gp.lam[f][q][nvface[f][1]] = x;
+                Gp.lam[f][q][nvface[f][2]] = y;
+            } else {
+                const double x = qpts[q];
+                Gp.lam[f][q][nvedge[f][0]] = 1 - x;
+                Gp.lam[f][q][nvedge[f][1]] = x;
+            }
+        }
+}
+
+static bool bnd_has_derivative(int nterms, const ffcuda_bterm *terms)
+{
+    for (int t = 0; t < nterms; ++t)
+        if (terms[t].uop != FFCUDA_OP_ID || terms[t].vop != FFCUDA_OP_ID) return true;
+    return false;
+}
+
+// the general bilinear path: constant coefficients (cq == nullptr) or one coefficient table cq[e * nq + q] (host)
+static void bnd_bilinear_general(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms, int nq, const double *qpts,
+                                 const double *qw, const double *cq, int nlab, const int32_t *labels, int accumulate)
+{
+    ffcuda_ctx *ctx = s->ctx;
+    ffcuda_mesh *m = s->mesh;
+    ffcuda_pattern *P = A->pattern;
+    cudaStream_t st = ctx->stream;
+    const int dim = m->dim, nc = s->ncomp, nbe = m->nbe;
+    FF_REQUIRE(nterms <= MAXBT, "boundary integrals with derivatives: at most 48 terms per integral");
+    FF_REQUIRE(dim == 2 || dim == 3, "bad dimension");
+    std::unique_ptr<BndGenParams> Gp(new BndGenParams());
+    memset(Gp.get(), 0, sizeof(BndGenParams));
+    bnd_gen_rule(*Gp, dim, nq, qpts, qw);
+    Gp->nterms = nterms;
+    for (int t = 0; t < nterms; ++t) {
+        const ffcuda_bterm &T = terms[t];
+        FF_REQUIRE(T.ucomp >= 0 && T.ucomp < nc && T.vcomp >= 0 && T.vcomp < nc, "term component out of range");
+        Gp->t[t] = BndGenTerm{T.ucomp, op_slot(T.uop), T.vcomp, op_slot(T.vop), T.coef};
+        FF_REQUIRE(dim == 3 || (Gp->t[t].uslot < 3 && Gp->t[t].vslot < 3), "dz on a 2-D mesh");
+    }
+    BndParams Bp;
+    memset(&Bp, 0, sizeof(Bp));
+    bnd_fill_labels(Bp, nlab, labels);
+    if (accumulate) ff_matrix_touch(A);
+    else FF_CUDA(cudaMemsetAsync(A->vals.p, 0, A->vals.bytes(), st));
+    A->vals_stale = false;
+    A->vals_epoch++;
+    if (dim == 3) bnd_incidence<3>(ctx, s, true);
+    else bnd_incidence<2>(ctx, s, true);
+    DBuf<double> meas, dC;
+    DBuf<BndGenParams> dG;
+    meas.alloc((size_t)nbe);
+    dG.alloc(1);
+    FF_CUDA(cudaMemcpyAsync(dG.p, Gp.get(), sizeof(BndGenParams), cudaMemcpyHostToDevice, st));
+    if (cq) {
+        dC.alloc((size_t)nbe * nq);
+        FF_CUDA(cudaMemcpyAsync(dC.p, cq, dC.bytes(), cudaMemcpyHostToDevice, st));
+    }
+    bnd_measures(ctx, m, Bp, meas.p);
+    const int nrows = s->nnodes_owned;
+    ff_launch(ctx, "bnd_bilinear_gen", [&] {
+        if (dim == 3)
+            k_bnd_bilinear_gen<3><<<ff_blocks(nrows, 128), 128, 0, st>>>(nrows, s->bnd2_ptr.p, s->bnd2_items.p, m->belem.p, m->bface.p, meas.p,
+                                                                       m->conn.p, m->xyz.p, m->vstride, s->e2n, s->nloc, s->order, nc,
+                                                                       P->nrowptr.p, P->ncol.p, dG.p, dC.p, A->vals.p);
+        else
+            k_bnd_bilinear_gen<2><<<ff_blocks(nrows, 128), 128, 0, st>>>(nrows, s->bnd2_ptr.p, s->bnd2_items.p, m->belem.p, m->bface.p, meas.p,
+                                                                       m->conn.p, m->xyz.p, m->vstride, s->e2n, s->nloc, s->order, nc,
+                                                                       P->nrowptr.p, P->ncol.p, dG.p, dC.p, A->vals.p);
+    });
+    FF_CUDA(cudaStreamSynchronize(st)); // host buffers (Gp, cq) are the caller's / ours on the stack
+}
+
+static void bnd_linear_general(ffcuda_vec *b, ffcuda_space *s, int nterms, const ffcuda_lterm *terms, int nq, const double *qpts,
+                               const double *qw, int nlab, const int32_t *labels, int accumulate)
+{
+    ffcuda_ctx *ctx = s->ctx;
+    ffcuda_mesh *m = s->mesh;
+    cudaStream_t st = ctx->stream;
+    const int dim = m->dim, nc = s->ncomp, nbe = m->nbe;
+    FF_REQUIRE(nterms <= MAXBT, "boundary integrals with derivatives: at most 48 terms per integral");
+    std::unique_ptr<BndGenParams> Gp(new BndGenParams());
+    memset(Gp.get(), 0, sizeof(BndGenParams));
+    bnd_gen_rule(*Gp, dim, nq, qpts, qw);
+    Gp->nterms = nterms;
+    for (int t = 0; t < nterms; ++t) {
+        FF_REQUIRE(terms[t].vcomp >= 0 && terms[t].vcomp < nc, "term component out of range");
+        Gp->t[t] = BndGenTerm{0, 0, terms[t].vcomp, op_slot(terms[t].vop), terms[t].coef};
+        FF_REQUIRE(dim == 3 || Gp->t[t].vslot < 3, "dz on a 2-D mesh");
+    }
+    BndParams Bp;
+    memset(&Bp, 0, sizeof(Bp));
+    bnd_fill_labels(Bp, nlab, labels);
+    if (dim == 3) bnd_incidence<3>(ctx, s, true);
+    else bnd_incidence<2>(ctx, s, true);
+    DBuf<double> meas;
+    DBuf<BndGenParams> dG;
+    meas.alloc((size_t)nbe);
+    dG.alloc(1);
+    FF_CUDA(cudaMemcpyAsync(dG.p, Gp.get(), sizeof(BndGenParams), cudaMemcpyHostToDevice, st));
+    bnd_measures(ctx, m, Bp, meas.p);
+    const int nrows = s->nnodes_owned;
+    ff_launch(ctx, "bnd_linear_gen", [&] {
+        if (dim == 3)
+            k_bnd_linear_gen<3><<<ff_blocks(nrows, 128), 128, 0, st>>>(nrows, s->bnd2_ptr.p, s->bnd2_items.p, m->belem.p, m->bface.p, meas.p,
+                                                                     m->conn.p, m->xyz.p, m->vstride, s->order, nc, dG.p, b->d.p, accumulate);
+        else
+            k_bnd_linear_gen<2><<<ff_blocks(nrows, 128), 128, 0, st>>>(nrows, s->bnd2_ptr.p, s->bnd2_items.p, m->belem.p, m->bface.p, meas.p,
+                                                                     m->conn.p, m->xyz.p, m->vstride, s->order, nc, dG.p, b->d.p, accumulate);
+    });
+    FF_CUDA(cudaStreamSynchronize(st));
+}
+
 extern "C" int ffcuda_assemble_linear_boundary(ffcuda_vec *b, ffcuda_space *s, int nterms, const ffcuda_lterm *terms, int nq,
                                                const double *qpts, const double *qw, int nlab, const int32_t *labels, int accumulate)
 {
@@ -1487,11 +1806,17 @@ extern "C" int ffcuda_assemble_linear_boundary(ffcuda_vec *b, ffcuda_space *s, i
     const int dim = m->dim, nloc = s->nloc, nc = s->ncomp;
     FF_REQUIRE(b->n >= s->nnodes_owned * nc, "right-hand side vector too short");
     FF_REQUIRE(m->nbe > 0 && m->belem.p && m->bface.p, "the mesh has no boundary elements");
+    FF_REQUIRE(nterms >= 0 && (nterms == 0 || terms), "bad term list");
+    bool derivative = false;
+    for (int t = 0; t < nterms; ++t) derivative = derivative || terms[t].vop != FFCUDA_OP_ID;
+    if (derivative) { // c * dx(v) ...: every node of the adjacent element receives something
+        bnd_linear_general(b, s, nterms, terms, nq, qpts, qw, nlab, labels, accumulate);
+        return 0;
+    }
     BndParams Bp;
     memset(&Bp, 0, sizeof(Bp));
     for (int t = 0; t < nterms; ++t) {
         FF_REQUIRE(terms[t].vcomp >= 0 && terms[t].vcomp < nc, "term component out of range");
-        FF_REQUIRE(terms[t].vop == FFCUDA_OP_ID, "boundary integrals: only value terms (c * v) are on the ffcuda path");
         Bp.coef[terms[t].vcomp] += terms[t].coef;
     }
     bnd_fill_labels(Bp, nlab, labels);
@@ -1578,12 +1903,15 @@ extern "C" int ffcuda_assemble_bilinear_boundary(ffcuda_matrix *A, ffcuda_space 
     ffcuda_pattern *P = A->pattern;
     const int dim = m->dim, nloc = s->nloc, nc = s->ncomp;
     FF_REQUIRE(m->nbe > 0 && m->belem.p && m->bface.p, "the mesh has no boundary elements");
+    if (bnd_has_derivative(nterms, terms)) { // dx(u) v, u dz(v), ...: the general path
+        bnd_bilinear_general(A, s, nterms, terms, nq, qpts, qw, nullptr, nlab, labels, accumulate);
+        return 0;
+    }
     BndBilParams Bq;
     memset(&Bq, 0, sizeof(Bq));
     for (int t = 0; t < nterms; ++t) {
         const ffcuda_bterm &T = terms[t];
         FF_REQUIRE(T.ucomp >= 0 && T.ucomp < nc && T.vcomp >= 0 && T.vcomp < nc, "term component out of range");
-        FF_REQUIRE(T.uop == FFCUDA_OP_ID && T.vop == FFCUDA_OP_ID, "boundary integrals: only value terms (c * u * v) are on the ffcuda path");
         Bq.C[T.vcomp][T.ucomp] += T.coef;
     }
     BndParams Bp;
@@ -1844,12 +2172,15 @@ extern "C" int ffcuda_assemble_bilinear_boundary_qcoef(ffcuda_matrix *A, ffcuda_
     ffcuda_pattern *P = A->pattern;
     const int dim = m->dim, nloc = s->nloc, nc = s->ncomp, nbe = m->nbe;
     FF_REQUIRE(nbe > 0 && m->belem.p && m->bface.p, "the mesh has no boundary elements");
+    if (bnd_has_derivative(nterms, terms)) { // N.x * dx(u) * v, ...: the general path with the coefficient table
+        bnd_bilinear_general(A, s, nterms, terms, nq, qpts, qw, cq, nlab, labels, accumulate);
+        return 0;
+    }
     BndBilParams Bq;
     memset(&Bq, 0, sizeof(Bq));
     for (int t = 0; t < nterms; ++t) {
         const ffcuda_bterm &T = terms[t];
         FF_REQUIRE(T.ucomp >= 0 && T.ucomp < nc && T.vcomp >= 0 && T.vcomp < nc, "term component out of range");
-        FF_REQUIRE(T.uop == FFCUDA_OP_ID && T.vop == FFCUDA_OP_ID, "boundary integrals: only value terms (c * u * v) are on the ffcuda path");
         Bq.C[T.vcomp][T.ucomp] += T.coef;
     }
     BndParams Bp;

@@ -373,6 +373,8 @@ struct ffcuda_space {
     // node -> boundary-element incidence (assemble.cu, boundary integrals of linear forms), built on first use
     DBuf<int32_t> bnd_ptr;
     DBuf<uint32_t> bnd_items;
+    DBuf<int32_t> bnd2_ptr;   // the same with ALL nodes of the element adjacent to a boundary element (terms with derivatives)
+    DBuf<uint32_t> bnd2_items;
     // P2: node rows sorted by decreasing length (assemble.cu launch_p2), rows [0, p2_nlong) are the long ones
     DBuf<int32_t> p2_rowperm;
     int p2_nlong = 0, p2_short_maxrow = 0;

@@ -651,7 +651,8 @@ Varf read_varf(Stack stack, const list<C_F0> &largs, const MeshT &Th, int ncomp,
                 t.vcomp = id.second.first;
                 t.vop = check_op(id.second.second, dim);
                 if (t.ucomp < 0 || t.ucomp >= ncomp || t.vcomp < 0 || t.vcomp >= ncomp) throw Unsupported{"component out of range"};
-                if (B.border && (t.uop != op_id || t.vop != op_id)) throw Unsupported{"derivatives in a boundary integral"};
+                // (derivatives in a boundary integral - dx(u) v, N.x dx(u) v, ... - reach every node of the adjacent element: the
+                //  library takes its general path for them, fflib/problem.cpp:6518-6560)
                 if (!op.v[k].second.LeftValue()->MeshIndependent()) {
                     // kappa(x,y,z) grad u . grad v, rho(x) u v, a P0 / P1 function as coefficient: evaluated at the quadrature
                     // nodes by FreeFEM's evaluator, integrated on the device (P1 spaces; checked in gpu_matrix)
@@ -679,8 +680,8 @@ Varf read_varf(Stack stack, const list<C_F0> &largs, const MeshT &Th, int ncomp,
                 t.vcomp = op.v[k].first.first;
                 t.vop = check_op(op.v[k].first.second, dim);
                 if (t.vcomp < 0 || t.vcomp >= ncomp) throw Unsupported{"component out of range"};
-                if (L.border && t.vop != op_id) throw Unsupported{"derivatives in a boundary integral"};
                 if (!op.v[k].second.LeftValue()->MeshIndependent()) {
+                    if (L.border && t.vop != op_id) throw Unsupported{"derivative of the test function times mesh-dependent data in a boundary integral"};
                     // f(x,y,z) v, uold v / dt, ...: the values Element_rhs would compute go to the device as a table
                     if (op.v[k].second.left() != atype<double>() && op.v[k].second.left() != atype<long>())
                         throw Unsupported{"coefficient is not real"};

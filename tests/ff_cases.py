@@ -100,6 +100,11 @@ CASES = {
     "lap3d_p1_sym": (1, 1, LAP3, [(0, ID, 1.0)], "qfV5", [(ALL6, 1, [0.0])]),
     "lap2d_p2_sym": (2, 1, LAP2 + [(0, ID, 0, ID, 2.0)], [(0, ID, 1.0)], "qf5pT", [([2, 4], 1, [0.0])]),
     "lame3d_p1_sym": (1, 3, lame_terms(), [(2, ID, -0.05)], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
+    # boundary integrals with derivatives of the unknown / test function (CASE_BBIL / CASE_BLIN / CASE_BQ below)
+    "lap3d_p1_bnd_grad": (1, 1, LAP3, [(0, ID, 1.0)], "qfV5", [([1], 1, [0.0])]),
+    "lap2d_p2_bnd_grad": (2, 1, LAP2, [(0, ID, 1.0)], "qf5pT", [([4], 1, [0.0])]),
+    "lame3d_p1_bnd_grad": (1, 3, lame_terms(), [(2, ID, -0.05)], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
+    "lap3d_p2_bnd_gradq": (2, 1, LAP3, [(0, ID, 1.0)], "qfV5", [([1], 1, [0.0])]),
 }
 # boundary integrals of the linear form: name -> (labels, terms)
 CASE_BLIN = {"lap3d_p1_neumann": ([2, 3], [(0, ID, 2.5)]), "lap2d_p2_neumann": ([2], [(0, ID, 1.5)]),
@@ -137,6 +142,15 @@ CASE_BQ = {
     "lame3d_p1_bnd_g": dict(lin=([2], lambda P: np.stack([0.3 * P[..., 2], 0 * P[..., 0], -0.2 * (1 + P[..., 1])])),
                             bil=([3], lambda P: 1 + P[..., 0], [(c, ID, c, ID, 1e3) for c in range(3)])),
 }
+# ... with derivatives on the faces: dx(u) v, u dy(v), dz(u) dx(v) (every node of the adjacent element is reached)
+CASE_BBIL["lap3d_p1_bnd_grad"] = ([2, 3], [(0, DX, 0, ID, 1.5), (0, ID, 0, DY, 0.5), (0, DZ, 0, DX, 2.0), (0, ID, 0, ID, 0.25)])
+CASE_BLIN["lap3d_p1_bnd_grad"] = ([6], [(0, DZ, 0.3), (0, ID, -1.0)])
+CASE_BBIL["lap2d_p2_bnd_grad"] = ([2, 3], [(0, DX, 0, ID, 0.7), (0, DY, 0, DY, 0.2)])
+CASE_BLIN["lap2d_p2_bnd_grad"] = ([2], [(0, DX, 1.5), (0, ID, 0.5)])
+CASE_BBIL["lame3d_p1_bnd_grad"] = ([3], [(0, DX, 1, ID, 1e3), (2, ID, 0, DZ, 1e3), (1, ID, 1, ID, 1e3)])
+CASE_BLIN["lame3d_p1_bnd_grad"] = ([2], [(0, DY, 0.3), (2, ID, -0.2)])
+CASE_BQ["lap3d_p2_bnd_gradq"] = dict(lin=([2], lambda P: (0 * P[..., 0])[None]),
+                                     bil=([2, 3], lambda P: 1 + P[..., 0] * P[..., 2], [(0, DX, 0, ID, 1.0), (0, ID, 0, DZ, 0.5)]))
 # data of the linear form per (component, slot): P (..., dim) -> (ncomp, dim+1, ...); slot 0 = value, 1..dim = dx, dy, dz
 def _z(P):
     return 0 * P[..., 0]
@@ -205,7 +219,8 @@ def elem2node(g, order, ncomp):
     return np.ascontiguousarray(e2n, dtype=np.int32)
 # cases whose script does not solve (non-symmetric after tgv = -1 / -3 elimination)
 NO_SOLVE_TGV = {"lap3d_p1_tgvm1", "lame3d_p1_tgvm1", "lap3d_p1_tgvm3", "lame3d_p1_robin",  # (non-symmetric Robin coupling)
-                "convdiff3d_p1_gmres", "convdiff2d_p2_gmres"}  # (GMRES fixtures have their own solve tests)
+                "convdiff3d_p1_gmres", "convdiff2d_p2_gmres",  # (GMRES fixtures have their own solve tests)
+                "lap3d_p1_bnd_grad", "lap2d_p2_bnd_grad", "lame3d_p1_bnd_grad", "lap3d_p2_bnd_gradq"}  # (non-symmetric, not solved)
 
 
 def loose_iterate(name):

@@ -140,6 +140,17 @@ CASES = {
     "lame3d_p2_warp": dict(dim=3, mesh="cube(2,1,2,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", fe="[P2,P2,P2]",
                            unk="[u1,u2,u3]", tst="[v1,v2,v3]", pre=LAME_PRE, bil=LAME, lin="-0.05*v3",
                            bc="on(1,u1=0,u2=0,u3=0)+on(3,u1=0.01,u2=0,u3=-0.02)"),
+    # boundary integrals with derivatives of the unknown / of the test function (every node of the adjacent element is reached)
+    "lap3d_p1_bnd_grad": dict(dim=3, mesh="cube(3,3,3,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", fe="P1", bil=LAP3, lin="1.*v",
+                              blin="+int2d(Th,2,3)(1.5*dx(u)*v+0.5*u*dy(v)+2.*dz(u)*dx(v)+0.25*u*v)+int2d(Th,6)(0.3*dz(v)-1.*v)",
+                              bc="on(1,u=0)", solve=False),
+    "lap2d_p2_bnd_grad": dict(dim=2, mesh="square(4,3,[x+0.2*y*y,y*(1+0.3*x)])", fe="P2", bil=LAP2, lin="1.*v",
+                              blin="+int1d(Th,2,3)(0.7*dx(u)*v+0.2*dy(u)*dy(v))+int1d(Th,2)(1.5*dx(v)+0.5*v)", bc="on(4,u=0)", solve=False),
+    "lame3d_p1_bnd_grad": dict(dim=3, mesh="cube(2,3,2)", fe="[P1,P1,P1]", unk="[u1,u2,u3]", tst="[v1,v2,v3]", pre=LAME_PRE, bil=LAME,
+                               lin="-0.05*v3", blin="+int2d(Th,3)(1e3*(dx(u1)*v2+u3*dz(v1)+u2*v2))+int2d(Th,2)(0.3*dy(v1)-0.2*v3)",
+                               bc="on(1,u1=0,u2=0,u3=0)", solve=False),
+    "lap3d_p2_bnd_gradq": dict(dim=3, mesh="cube(2,2,2,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", fe="P2", bil=LAP3, lin="1.*v",
+                               blin="+int2d(Th,2,3)((1+x*z)*(dx(u)*v+0.5*u*dz(v)))", bc="on(1,u=0)", solve=False),
 }
 
 

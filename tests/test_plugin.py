@@ -114,6 +114,16 @@ CASES = {
     "resid3d_p2_grad": script(3, "cube(3,3,4,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", "P2", LAP3, "(1+z)*dz(v)+x*v-y*z*dx(v)+2.*dy(v)",
                               "on(1,2,u=0)", eps="1e-14"),
     "mass3d_lumped": script(3, "cube(3,3,3)", "P1", "u*v+0.1*(" + LAP3 + ")", "1.*v", "on(1,u=0)", intopt=",qfV=qfV1lump"),
+    # boundary integrals with derivatives of the unknown / of the test function (constant coefficients and the unit normal):
+    # every node of the element behind the face is reached (Element_Op's border branch, problem.cpp:6518-6560)
+    "poisson3d_p1_bnd_grad": script(3, "cube(5,4,6,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", "P1", LAP3, "1.*v", "on(1,u=0)", solver="GMRES",
+                                    extra="+int2d(Th,2,3)(0.3*dx(u)*v+0.2*u*dy(v)+0.1*dz(u)*dx(v)+0.25*u*v)"
+                                          "+int2d(Th,4)(-0.5*(N.x*dx(u)+N.y*dy(u)+N.z*dz(u))*v)+int2d(Th,6)(0.3*dz(v)-1.*v)"),
+    "laplace2d_p2_bnd_grad": script(2, "square(6,5,[x+0.2*y*y,y*(1+0.3*x)])", "P2", LAP2, "1.*v", "on(4,u=0)", solver="GMRES", eps="1e-14",
+                                    extra="+int1d(Th,2,3)(0.3*dx(u)*v+0.1*dy(u)*dy(v))+int1d(Th,2)(1.5*dx(v)+0.5*v)"),
+    "lame3d_p1_bnd_grad": script(3, "cube(3,4,3)", "[P1,P1,P1]", LAME, "-0.05*v3", "on(1,4,5,u1=0,u2=0,u3=0)", pre=LAME_PRE,
+                                 unk="[u1,u2,u3]", tst="[v1,v2,v3]", solver="GMRES", eps="1e-14",
+                                 extra="+int2d(Th,3)(1e3*(dx(u1)*v2+u3*dz(v1)+u2*v2))+int2d(Th,2)(0.3*dy(v1)-0.2*v3)"),
 }
 
 # re-assembly in a time loop (configs[3] shape, idp/Heat3d.idp): `A = va(Vh,Vh)` on an existing matrix, rhs from the previous
