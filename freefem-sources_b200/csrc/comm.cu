@@ -326,6 +326,26 @@ static ffcuda_mesh *dist_mesh(ffcuda_matrix *A)
 
 bool ff_is_distributed(ffcuda_matrix *A) { return dist_mesh(A) != nullptr; }
 
+// the halo lists that apply to a matrix: those of its space when it has its own (P2 on a distributed mesh), else the mesh's
+struct HaloView {
+    int nnbr = 0;
+    const int *nbr = nullptr, *send_off = nullptr, *send_cnt = nullptr, *recv_off = nullptr, *recv_cnt = nullptr;
+    const int32_t *send_idx = nullptr;
+};
+static HaloView halo_view(ffcuda_matrix *A, ffcuda_mesh *m)
+{
+    HaloView H;
+    ffcuda_space *s = A->pattern->space;
+    if (s->own_halo) {
+        H.nnbr = s->nnbr; H.nbr = s->nbr; H.send_off = s->send_off; H.send_cnt = s->send_cnt; H.recv_off = s->recv_off; H.recv_cnt = s->recv_cnt;
+        H.send_idx = s->send_idx.p;
+    } else {
+        H.nnbr = m->nnbr; H.nbr = m->nbr; H.send_off = m->send_off; H.send_cnt = m->send_cnt; H.recv_off = m->recv_off; H.recv_cnt = m->recv_cnt;
+        H.send_idx = m->send_idx.p;
+    }
+    return H;
+}
+
 // v holds owned values in [0, n) ; fills the ghost ranges [n, ncols) from the neighbours' owned boundary layers
 void ff_halo_exchange(ffcuda_matrix *A, double *v)
 {
@@ -333,27 +353,28 @@ void ff_halo_exchange(ffcuda_matrix *A, double *v)
     if (!m) return;
     ffcuda_ctx *ctx = A->ctx;
     FF_REQUIRE(ctx->nccl_comm, "distributed matrix without communicator");
+    const HaloView V = halo_view(A, m);
     const int nc = A->pattern->ncomp;
     HaloArgs H;
     memset(&H, 0, sizeof(H));
-    H.n = m->nnbr;
+    H.n = V.nnbr;
     H.nc = nc;
-    H.send_idx = m->send_idx.p;
+    H.send_idx = V.send_idx;
     // layers that fit the mailbox regions go by peer stores (one kernel for all neighbours), the others by NCCL; both
     // ends of a pair see the same counts, so they take the same route
     bool via_p2p[P2P_MAXR], any_p2p = false, any_nccl = false;
     size_t most = 0;
-    for (int x = 0; x < m->nnbr; ++x) {
+    for (int x = 0; x < V.nnbr; ++x) {
         via_p2p[x] = false;
         H.nbr[x] = -1;
-        H.send_off[x] = m->send_off[x]; H.send_cnt[x] = m->send_cnt[x];
-        H.recv_off[x] = m->recv_off[x]; H.recv_cnt[x] = m->recv_cnt[x];
-        if (m->nbr[x] < 0) continue;
-        const size_t big = (size_t)std::max(m->send_cnt[x], m->recv_cnt[x]) * nc;
+        H.send_off[x] = V.send_off[x]; H.send_cnt[x] = V.send_cnt[x];
+        H.recv_off[x] = V.recv_off[x]; H.recv_cnt[x] = V.recv_cnt[x];
+        if (V.nbr[x] < 0) continue;
+        const size_t big = (size_t)std::max(V.send_cnt[x], V.recv_cnt[x]) * nc;
         via_p2p[x] = ctx->p2p && big <= ctx->p2p_halo_cap;
         (via_p2p[x] ? any_p2p : any_nccl) = true;
         if (via_p2p[x]) {
-            H.nbr[x] = m->nbr[x];
+            H.nbr[x] = V.nbr[x];
             most = std::max(most, big);
         }
     }
@@ -369,24 +390,24 @@ void ff_halo_exchange(ffcuda_matrix *A, double *v)
     NcclApi &N = nccl();
     ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
     DBuf<double> stage;
-    std::vector<size_t> soff((size_t)m->nnbr + 1, 0);
-    if (m->send_idx.p) { // gather lists: pack first
-        for (int x = 0; x < m->nnbr; ++x) soff[(size_t)x + 1] = soff[x] + ((m->nbr[x] >= 0 && !via_p2p[x]) ? (size_t)m->send_cnt[x] * nc : 0);
-        stage.alloc(std::max<size_t>(soff[m->nnbr], 1));
-        for (int x = 0; x < m->nnbr; ++x) {
-            if (m->nbr[x] < 0 || via_p2p[x] || m->send_cnt[x] == 0) continue;
-            H.nbr[x] = m->nbr[x];
+    std::vector<size_t> soff((size_t)V.nnbr + 1, 0);
+    if (V.send_idx) { // gather lists: pack first
+        for (int x = 0; x < V.nnbr; ++x) soff[(size_t)x + 1] = soff[x] + ((V.nbr[x] >= 0 && !via_p2p[x]) ? (size_t)V.send_cnt[x] * nc : 0);
+        stage.alloc(std::max<size_t>(soff[V.nnbr], 1));
+        for (int x = 0; x < V.nnbr; ++x) {
+            if (V.nbr[x] < 0 || via_p2p[x] || V.send_cnt[x] == 0) continue;
+            H.nbr[x] = V.nbr[x];
             ff_launch(ctx, "halo_pack", [&] {
-                k_halo_pack<<<ff_blocks((size_t)m->send_cnt[x] * nc, 256), 256, 0, ctx->stream>>>(v, H, x, stage.p + soff[x]);
+                k_halo_pack<<<ff_blocks((size_t)V.send_cnt[x] * nc, 256), 256, 0, ctx->stream>>>(v, H, x, stage.p + soff[x]);
             });
         }
     }
     FF_NCCL(N.GroupStart());
-    for (int x = 0; x < m->nnbr; ++x) {
-        if (m->nbr[x] < 0 || via_p2p[x]) continue;
-        const double *src = m->send_idx.p ? stage.p + soff[x] : v + (size_t)m->send_off[x] * nc;
-        FF_NCCL(N.Send(src, (size_t)m->send_cnt[x] * nc, ncclDouble, m->nbr[x], comm, ctx->stream));
-        FF_NCCL(N.Recv(v + (size_t)m->recv_off[x] * nc, (size_t)m->recv_cnt[x] * nc, ncclDouble, m->nbr[x], comm, ctx->stream));
+    for (int x = 0; x < V.nnbr; ++x) {
+        if (V.nbr[x] < 0 || via_p2p[x]) continue;
+        const double *src = V.send_idx ? stage.p + soff[x] : v + (size_t)V.send_off[x] * nc;
+        FF_NCCL(N.Send(src, (size_t)V.send_cnt[x] * nc, ncclDouble, V.nbr[x], comm, ctx->stream));
+        FF_NCCL(N.Recv(v + (size_t)V.recv_off[x] * nc, (size_t)V.recv_cnt[x] * nc, ncclDouble, V.nbr[x], comm, ctx->stream));
     }
     FF_NCCL(N.GroupEnd());
     ctx->launches++;

@@ -378,6 +378,13 @@ struct ffcuda_space {
     // P2: node rows sorted by decreasing length (assemble.cu launch_p2), rows [0, p2_nlong) are the long ones
     DBuf<int32_t> p2_rowperm;
     int p2_nlong = 0, p2_short_maxrow = 0;
+    // a space on a distributed mesh whose nodes are not the vertices (P2: ffcuda_space_create_distributed) carries its own
+    // node-level halo lists, same meaning as the vertex-level ones of the mesh; own_halo false: the mesh's lists apply
+    bool own_halo = false;
+    int nnbr = 0;
+    int nbr[ffcuda_mesh::MAXNBR], send_off[ffcuda_mesh::MAXNBR], send_cnt[ffcuda_mesh::MAXNBR], recv_off[ffcuda_mesh::MAXNBR],
+        recv_cnt[ffcuda_mesh::MAXNBR];
+    DBuf<int32_t> send_idx;
 };
 // tiles.cu: numeric assembly of c grad u.grad v + m u v on a scalar P1 space by row tiles; returns false when the tile
 // path does not apply (the caller then runs the thread-per-row kernel)

@@ -157,3 +157,33 @@ extern "C" int ffcuda_partition_local(int dim, int nv, int nt, const int32_t *co
     put(send_idx, L.send_idx);
     FF_API_END(nullptr)
 }
+
+// The same for ANY element -> node table and node partition (P2: nloc = 10 nodes per tetrahedron, 6 per triangle; an edge
+// node goes to the rank of one of its end points, so the local elements are those of the vertex partition).
+extern "C" int ffcuda_partition_local_nodes(int nloc, int nnodes, int nt, const int32_t *elem2node, const int32_t *part, int rank, int nranks,
+                                            int64_t *sizes8, int32_t *l2g, int32_t *elems, int32_t *nbr, int32_t *recv_off,
+                                            int32_t *recv_cnt, int32_t *send_ptr, int32_t *send_idx)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(nloc >= 2 && nloc <= 10 && nnodes >= 0 && nt >= 0 && sizes8 && rank >= 0 && rank < nranks && (nt == 0 || elem2node) &&
+                   (nnodes == 0 || part),
+               "ffcuda_partition_local_nodes: bad arguments");
+    for (int v = 0; v < nnodes; ++v) FF_REQUIRE(part[v] >= 0 && part[v] < nranks, "ffcuda_partition_local_nodes: part[] entry outside [0, nranks)");
+    for (size_t i = 0; i < (size_t)nt * nloc; ++i)
+        FF_REQUIRE(elem2node[i] >= 0 && elem2node[i] < nnodes, "ffcuda_partition_local_nodes: table entry outside [0, nnodes)");
+    const LocalLists L = local_lists(nloc, nnodes, nt, elem2node, part, rank, nranks);
+    const int64_t s[8] = {L.nowned, (int64_t)L.l2g.size() - L.nowned, (int64_t)L.elems.size(), (int64_t)L.nbr.size(),
+                          (int64_t)L.send_idx.size(), 0, 0, 0};
+    for (int i = 0; i < 8; ++i) sizes8[i] = s[i];
+    auto put = [](int32_t *dst, const std::vector<int32_t> &v) {
+        if (dst) std::copy(v.begin(), v.end(), dst);
+    };
+    put(l2g, L.l2g);
+    put(elems, L.elems);
+    put(nbr, L.nbr);
+    put(recv_off, L.recv_off);
+    put(recv_cnt, L.recv_cnt);
+    put(send_ptr, L.send_ptr);
+    put(send_idx, L.send_idx);
+    FF_API_END(nullptr)
+}

@@ -1172,10 +1172,56 @@ __device__ __forceinline__ bool grid_sum_last(const double (&v)[NV], double *__r
     return threadIdx.x == 0;
 }
 
+// what the last block does with a finished sum; on several GPUs the sums are all-reduced first and the k_gm_fin_* kernels
+// (one thread) do the same
+__device__ __forceinline__ void gm_cycle_start(double sum, double eps, const GmresLayout &L, double *__restrict__ gs)
+{
+    gs[L.g()] = sqrt(sum);
+    if (gs[L.normb()] < 1.e-20 || eps < 0) gs[L.normb()] = 1.0;
+}
+// the new Hessenberg column goes through the rotations, the new rotation is formed, g is updated and the stopping test is
+// taken (CG.cpp:436-471); flags[F_CONV_ITER] = it + 1 on convergence
+__device__ __forceinline__ void gm_hessenberg_step(double sum, int it, double eps, const GmresLayout &L, double *__restrict__ gs, int *__restrict__ flags)
+{
+    double *H = gs, *rot0 = gs + L.rot0(), *rot1 = gs + L.rot1(), *g = gs + L.g();
+    const double aux = sqrt(sum);
+    gs[L.aux()] = aux;
+    H[L.H(it + 1, it)] = aux;
+    for (int i = 0; i < it; i++) {
+        const double aa = rot0[i] * H[L.H(i, it)] + rot1[i] * H[L.H(i + 1, it)];
+        const double bb = -rot1[i] * H[L.H(i, it)] + rot0[i] * H[L.H(i + 1, it)];
+        H[L.H(i, it)] = aa;
+        H[L.H(i + 1, it)] = bb;
+    }
+    const double hii = H[L.H(it, it)], hi1 = H[L.H(it + 1, it)];
+    const double sq = sqrt(hii * hii + hi1 * hi1);
+    rot0[it] = hii / sq;
+    rot1[it] = hi1 / sq;
+    H[L.H(it, it)] = rot0[it] * hii + rot1[it] * hi1;
+    H[L.H(it + 1, it)] = 0.0;
+    g[it + 1] = -rot1[it] * g[it];
+    g[it] = rot0[it] * g[it];
+    const double relres = fabs(g[it + 1]);
+    gs[L.relres()] = relres;
+    __threadfence();
+    if (relres / gs[L.normb()] < fabs(eps)) flags[F_CONV_ITER] = it + 1;
+}
+__global__ void k_gm_fin_normb(const double *__restrict__ raw, double *__restrict__ out) { *out = sqrt(*raw); }
+__global__ void k_gm_fin_resid(const double *__restrict__ raw, double eps, GmresLayout L, double *__restrict__ gs) { gm_cycle_start(*raw, eps, L, gs); }
+__global__ void k_gm_fin_mgs(const double *__restrict__ raw, double *__restrict__ hout, const int *__restrict__ flags)
+{
+    if (flags[F_CONV_ITER] == 0) *hout = *raw;
+}
+__global__ void k_gm_fin_last(const double *__restrict__ raw, int it, double eps, GmresLayout L, double *__restrict__ gs, int *__restrict__ flags)
+{
+    if (flags[F_CONV_ITER] == 0) gm_hessenberg_step(*raw, it, eps, L, gs, flags);
+}
+
 // normb = || b with the tgv rows zeroed ||  (fgmres: wi = rhs; wi[wbc] = 0; normb = nrm2(Cl wi), Cl = Id)
 __global__ void __launch_bounds__(RED_THREADS) k_gm_normb(const double *__restrict__ b, const int32_t *__restrict__ diagpos,
                                                           const double *__restrict__ vals, int has_tgv, double ttgv, int n,
-                                                          double *__restrict__ partial, int *__restrict__ flags, double *__restrict__ out)
+                                                          double *__restrict__ partial, int *__restrict__ flags, double *__restrict__ out,
+                                                          double *__restrict__ raw /* distributed: the local sum goes here, see k_gm_fin_* */)
 {
     __shared__ double sh[32];
     double v[1] = {0.0}, tot[1];
@@ -1187,7 +1233,8 @@ __global__ void __launch_bounds__(RED_THREADS) k_gm_normb(const double *__restri
         v[0] += x * x;
     }
     if (grid_sum_last<1>(v, partial, flags + F_COUNTER, tot, sh)) {
-        *out = sqrt(tot[0]);
+        if (raw) *raw = tot[0];
+        else *out = sqrt(tot[0]);
         flags[F_COUNTER] = 0;
     }
 }
@@ -1195,7 +1242,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_gm_normb(const double *__restri
 // start of a cycle: W = -(A x - b), g[0] = || W ||, all other cycle scalars restart
 __global__ void __launch_bounds__(RED_THREADS) k_gm_resid(const double *__restrict__ b, const double *__restrict__ Ax, double *__restrict__ W,
                                                           int n, double eps, GmresLayout L, double *__restrict__ gs,
-                                                          double *__restrict__ partial, int *__restrict__ flags)
+                                                          double *__restrict__ partial, int *__restrict__ flags, double *__restrict__ raw)
 {
     __shared__ double sh[32];
     double v[1] = {0.0}, tot[1];
@@ -1206,8 +1253,8 @@ __global__ void __launch_bounds__(RED_THREADS) k_gm_resid(const double *__restri
         v[0] += r * r;
     }
     if (grid_sum_last<1>(v, partial, flags + F_COUNTER, tot, sh)) {
-        gs[L.g()] = sqrt(tot[0]);
-        if (gs[L.normb()] < 1.e-20 || eps < 0) gs[L.normb()] = 1.0;
+        if (raw) *raw = tot[0];
+        else gm_cycle_start(tot[0], eps, L, gs);
         flags[F_COUNTER] = 0;
     }
 }
@@ -1234,7 +1281,7 @@ __global__ void k_gm_precond(double *__restrict__ Vp, const double *__restrict__
 // one step of the modified Gram-Schmidt chain: W -= h_prev * Vprev (when there is a previous step), then h = <W, Vcur>
 __global__ void __launch_bounds__(RED_THREADS) k_gm_mgs(double *__restrict__ W, const double *__restrict__ Vprev, const double *__restrict__ Vcur,
                                                         const double *__restrict__ hprev, double *__restrict__ hout, int n,
-                                                        double *__restrict__ partial, int *__restrict__ flags)
+                                                        double *__restrict__ partial, int *__restrict__ flags, double *__restrict__ raw)
 {
     if (flags[F_CONV_ITER] != 0) return;
     __shared__ double sh[32];
@@ -1250,7 +1297,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_gm_mgs(double *__restrict__ W, 
         v[0] += w * Vcur[i];
     }
     if (grid_sum_last<1>(v, partial, flags + F_COUNTER, tot, sh)) {
-        *hout = tot[0];
+        *(raw ? raw : hout) = tot[0];
         flags[F_COUNTER] = 0;
     }
 }
@@ -1259,7 +1306,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_gm_mgs(double *__restrict__ W, 
 // rotation is formed, g is updated and the stopping test is taken (CG.cpp:436-471); flags[F_CONV_ITER] = it + 1 on convergence
 __global__ void __launch_bounds__(RED_THREADS) k_gm_mgs_last(double *__restrict__ W, const double *__restrict__ Vprev, int n, int it, double eps,
                                                              GmresLayout L, double *__restrict__ gs, double *__restrict__ partial,
-                                                             int *__restrict__ flags)
+                                                             int *__restrict__ flags, double *__restrict__ raw)
 {
     if (flags[F_CONV_ITER] != 0) return;
     __shared__ double sh[32];
@@ -1272,29 +1319,9 @@ __global__ void __launch_bounds__(RED_THREADS) k_gm_mgs_last(double *__restrict_
         v[0] += w * w;
     }
     if (grid_sum_last<1>(v, partial, flags + F_COUNTER, tot, sh)) {
-        double *H = gs, *rot0 = gs + L.rot0(), *rot1 = gs + L.rot1(), *g = gs + L.g();
-        const double aux = sqrt(tot[0]);
-        gs[L.aux()] = aux;
-        H[L.H(it + 1, it)] = aux;
-        for (int i = 0; i < it; i++) {
-            const double aa = rot0[i] * H[L.H(i, it)] + rot1[i] * H[L.H(i + 1, it)];
-            const double bb = -rot1[i] * H[L.H(i, it)] + rot0[i] * H[L.H(i + 1, it)];
-            H[L.H(i, it)] = aa;
-            H[L.H(i + 1, it)] = bb;
-        }
-        const double hii = H[L.H(it, it)], hi1 = H[L.H(it + 1, it)];
-        const double sq = sqrt(hii * hii + hi1 * hi1);
-        rot0[it] = hii / sq;
-        rot1[it] = hi1 / sq;
-        H[L.H(it, it)] = rot0[it] * hii + rot1[it] * hi1;
-        H[L.H(it + 1, it)] = 0.0;
-        g[it + 1] = -rot1[it] * g[it];
-        g[it] = rot0[it] * g[it];
-        const double relres = fabs(g[it + 1]);
-        gs[L.relres()] = relres;
         flags[F_COUNTER] = 0;
-        __threadfence();
-        if (relres / gs[L.normb()] < fabs(eps)) flags[F_CONV_ITER] = it + 1;
+        if (raw) *raw = tot[0];
+        else gm_hessenberg_step(tot[0], it, eps, L, gs, flags);
     }
 }
 
@@ -1439,7 +1466,14 @@ static void gmres_device(ffcuda_matrix *A, const double *b, double *x, double ep
     cudaStream_t st = ctx->stream;
     const int n = A->n;
     FF_REQUIRE(A->diagpos, "matrix has no diagonal index");
-    FF_REQUIRE(!ff_is_distributed(A) && A->ncols == n, "GMRES runs on one GPU (the distributed solve is the CG)");
+    // several GPUs (a matrix on a distributed mesh): the rows are shared out, so every dot product / norm is a local sum, an
+    // all-reduce (peer mailboxes, else NCCL: ff_allreduce) and a one-thread kernel that does what the last block does on one
+    // GPU; the vectors A is applied to carry the ghost columns and get them by a halo exchange first.  The sums are formed in
+    // rank order on every rank: every rank holds the same Hessenberg matrix and takes the same decisions.  Reference role:
+    // MPI_Allreduce per dot product, plugin/mpi/MPICG.cpp:93-101 (MPILinearGMRES there), idp/MPIGMRESmacro.idp.
+    const bool dist = ff_is_distributed(A);
+    const int ncols = A->ncols;
+    FF_REQUIRE(dist || ncols == n, "GMRES: the matrix has ghost columns but no distributed mesh");
     ff_matrix_touch(A);
     if (itmax <= 0) itmax = n;
     if (restart <= 0) restart = 1000; // Data_Sparse_Solver::NbSpace default (femlib/VirtualSolver.hpp:79)
@@ -1450,11 +1484,15 @@ static void gmres_device(ffcuda_matrix *A, const double *b, double *x, double ep
     double *partial = ctx->d_partial;
     int *flags = ctx_flags(ctx);
     FF_CUDA(cudaMemsetAsync(ctx->d_scal, 0, 64 * sizeof(double), st));
-    DBuf<double> gs, D1, W, R;
+    DBuf<double> gs, D1, W, R, XG;
     gs.alloc(L.size());
     D1.alloc(n);
     W.alloc(n);
     R.alloc(n);
+    if (dist) XG.alloc(ncols); // x with its ghost columns
+    double *raw = dist ? ctx->d_scal + S_TMP2 : nullptr; // local sums on their way through the all-reduce
+    if (dist && ctx->p2p) // a time-out of an earlier solve is that solve's error, not this one's
+        FF_CUDA(cudaMemsetAsync(reinterpret_cast<char *>(ctx->d_scal + FF_P2P_DESC_OFF) + offsetof(P2PDesc, timed_out), 0, sizeof(int), st));
     FF_CUDA(cudaMemsetAsync(gs.p, 0, gs.bytes(), st));
     double ttgv = 0;
     long ntgv = 0;
@@ -1463,8 +1501,12 @@ static void gmres_device(ffcuda_matrix *A, const double *b, double *x, double ep
         k_precond<<<ff_blocks(n, 256), 256, 0, st>>>(A->diagpos, A->vals.p, n, D1.p, ntgv > 0, ttgv, tgv, b, x);
     });
     ff_launch(ctx, "gmres_normb", [&] {
-        k_gm_normb<<<grid_v, RED_THREADS, 0, st>>>(b, A->diagpos, A->vals.p, ntgv > 0, ttgv, n, partial, flags, gs.p + L.normb());
+        k_gm_normb<<<grid_v, RED_THREADS, 0, st>>>(b, A->diagpos, A->vals.p, ntgv > 0, ttgv, n, partial, flags, gs.p + L.normb(), raw);
     });
+    if (dist) {
+        ff_allreduce(A, raw, 1, 0);
+        ff_launch(ctx, "gmres_fin", [&] { k_gm_fin_normb<<<1, 1, 0, st>>>(raw, gs.p + L.normb()); });
+    }
     // Krylov vectors in chunks of 16, allocated as the basis grows (the default dimension is 1000)
     constexpr int CH = 16;
     std::deque<DBuf<double>> cV, cP;
@@ -1483,7 +1525,7 @@ static void gmres_device(ffcuda_matrix *A, const double *b, double *x, double ep
     };
     // the cooperative Arnoldi kernel: as many CTAs as are co-resident, the entries of w in registers (KW per thread)
     int coop_grid = 0, coop_kw = 0;
-    if (ctx->gmres_coop) {
+    if (ctx->gmres_coop && !dist) {
         int dev = 0, can = 0;
         FF_CUDA(cudaGetDevice(&dev));
         FF_CUDA(cudaDeviceGetAttribute(&can, cudaDevAttrCooperativeLaunch, dev));
@@ -1509,8 +1551,8 @@ static void gmres_device(ffcuda_matrix *A, const double *b, double *x, double ep
     auto vecP = [&](int i) -> double * {
         while ((int)cP.size() * CH <= i) {
             cP.emplace_back();
-            cP.back().alloc((size_t)CH * n);
-            for (int k = 0; k < CH && (cP.size() - 1) * CH + k <= (size_t)m; ++k) hP[(cP.size() - 1) * CH + k] = cP.back().p + (size_t)k * n;
+            cP.back().alloc((size_t)CH * ncols); // A is applied to these: room for the ghost columns
+            for (int k = 0; k < CH && (cP.size() - 1) * CH + k <= (size_t)m; ++k) hP[(cP.size() - 1) * CH + k] = cP.back().p + (size_t)k * ncols;
             FF_CUDA(ff_memcpy_sync(ctx, dP.p, hP.data(), hP.size() * sizeof(double *), cudaMemcpyHostToDevice));
         }
         return hP[i];
@@ -1520,14 +1562,25 @@ static void gmres_device(ffcuda_matrix *A, const double *b, double *x, double ep
     bool conv = false;
     int iter = 0;
     while (true) {
-        spmv_launch(A, x, nullptr, R.p);
-        ff_launch(ctx, "gmres_resid", [&] { k_gm_resid<<<grid_v, RED_THREADS, 0, st>>>(b, R.p, W.p, n, eps, L, gs.p, partial, flags); });
+        const double *xin = x;
+        if (dist) {
+            FF_CUDA(cudaMemcpyAsync(XG.p, x, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            ff_halo_exchange(A, XG.p);
+            xin = XG.p;
+        }
+        spmv_launch(A, xin, nullptr, R.p);
+        ff_launch(ctx, "gmres_resid", [&] { k_gm_resid<<<grid_v, RED_THREADS, 0, st>>>(b, R.p, W.p, n, eps, L, gs.p, partial, flags, raw); });
+        if (dist) {
+            ff_allreduce(A, raw, 1, 0);
+            ff_launch(ctx, "gmres_fin", [&] { k_gm_fin_resid<<<1, 1, 0, st>>>(raw, eps, L, gs.p); });
+        }
         double *V0 = vecV(0);
         ff_launch(ctx, "gmres_scale", [&] { k_gm_scale<<<grid_v, RED_THREADS, 0, st>>>(V0, W.p, gs.p + L.g(), n, flags); });
         int it = 0, it_used = m;
         for (; it < m; ++it) {
             double *Vit = vecV(it), *Vnext = vecV(it + 1), *Pit = vecP(it);
             ff_launch(ctx, "gmres_precond_apply", [&] { k_gm_precond<<<grid_v, RED_THREADS, 0, st>>>(Pit, Vit, D1.p, n, flags); });
+            if (dist) ff_halo_exchange(A, Pit);
             spmv_launch(A, Pit, nullptr, W.p);
             if (coop_grid) {
                 double *Wp = W.p, *gsp = gs.p;
@@ -1545,10 +1598,18 @@ static void gmres_device(ffcuda_matrix *A, const double *b, double *x, double ep
                     const double *Vprev = i ? vecV(i - 1) : nullptr;
                     const double *Vcur = vecV(i);
                     ff_launch(ctx, "gmres_mgs", [&] {
-                        k_gm_mgs<<<grid_v, RED_THREADS, 0, st>>>(W.p, Vprev, Vcur, gs.p + L.H(i ? i - 1 : 0, it), gs.p + L.H(i, it), n, partial, flags);
+                        k_gm_mgs<<<grid_v, RED_THREADS, 0, st>>>(W.p, Vprev, Vcur, gs.p + L.H(i ? i - 1 : 0, it), gs.p + L.H(i, it), n, partial, flags, raw);
                     });
+                    if (dist) {
+                        ff_allreduce(A, raw, 1, 0);
+                        ff_launch(ctx, "gmres_fin", [&] { k_gm_fin_mgs<<<1, 1, 0, st>>>(raw, gs.p + L.H(i, it), flags); });
+                    }
                 }
-                ff_launch(ctx, "gmres_mgs_last", [&] { k_gm_mgs_last<<<grid_v, RED_THREADS, 0, st>>>(W.p, Vit, n, it, eps, L, gs.p, partial, flags); });
+                ff_launch(ctx, "gmres_mgs_last", [&] { k_gm_mgs_last<<<grid_v, RED_THREADS, 0, st>>>(W.p, Vit, n, it, eps, L, gs.p, partial, flags, raw); });
+                if (dist) {
+                    ff_allreduce(A, raw, 1, 0);
+                    ff_launch(ctx, "gmres_fin", [&] { k_gm_fin_last<<<1, 1, 0, st>>>(raw, it, eps, L, gs.p, flags); });
+                }
                 ff_launch(ctx, "gmres_scale", [&] { k_gm_scale<<<grid_v, RED_THREADS, 0, st>>>(Vnext, W.p, gs.p + L.aux(), n, flags); });
             }
             const bool leave = it > itmax; // `if( it > nbitermx) break;`
@@ -1574,6 +1635,12 @@ static void gmres_device(ffcuda_matrix *A, const double *b, double *x, double ep
     }
     double hr[4];
     FF_CUDA(ff_memcpy_sync(ctx, hr, gs.p + L.normb(), 3 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (dist && ctx->p2p) {
+        int to = 0;
+        FF_CUDA(ff_memcpy_sync(ctx, &to, reinterpret_cast<char *>(ctx->d_scal + FF_P2P_DESC_OFF) + offsetof(P2PDesc, timed_out), sizeof(int),
+                               cudaMemcpyDeviceToHost));
+        FF_REQUIRE(to == 0, "GMRES: a peer rank did not answer within the spin limit (multi-GPU exchange timed out)");
+    }
     FF_REQUIRE(hr[2] == hr[2], "GMRES: the residual is NaN (bad matrix)");
     if (iters) *iters = iter;
     if (converged) *converged = conv ? 1 : 0;

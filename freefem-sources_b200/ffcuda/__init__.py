@@ -17,7 +17,7 @@ OP_ID, OP_DX, OP_DY, OP_DZ = 0, 1, 2, 6
 SYMBOLS = """ffcuda_ctx_create ffcuda_ctx_destroy ffcuda_last_error ffcuda_ctx_sync ffcuda_ctx_set_stream ffcuda_ctx_get_stream ffcuda_ctx_set_option
 ffcuda_prof_enable ffcuda_prof_reset ffcuda_prof_get ffcuda_launch_count ffcuda_mesh_upload ffcuda_mesh_cube ffcuda_mesh_square ffcuda_mesh_buildlayers
 ffcuda_mesh_info ffcuda_mesh_download ffcuda_mesh_destroy ffcuda_space_create ffcuda_space_info ffcuda_space_download_dofs
-ffcuda_space_destroy ffcuda_symbolic ffcuda_pattern_info ffcuda_pattern_download ffcuda_pattern_download_async ffcuda_pattern_lower_nnz ffcuda_pattern_download_lower
+ffcuda_space_destroy ffcuda_space_create_distributed ffcuda_partition_local_nodes ffcuda_symbolic ffcuda_pattern_info ffcuda_pattern_download ffcuda_pattern_download_async ffcuda_pattern_lower_nnz ffcuda_pattern_download_lower
 ffcuda_matrix_download_lower ffcuda_matrix_from_csr_lower ffcuda_pattern_destroy ffcuda_matrix_create
 ffcuda_matrix_from_csr ffcuda_matrix_info ffcuda_matrix_download ffcuda_matrix_upload ffcuda_matrix_destroy ffcuda_vec_create
 ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_destroy ffcuda_assemble_bilinear ffcuda_assemble_bilinear_qcoef
@@ -63,6 +63,21 @@ def partition_local(dim, nv, conn, part, rank, nranks):
                send_idx=np.zeros(ns, np.int32))
     _ck(lib().ffcuda_partition_local(*args, _p(out["l2g"]), _p(out["elems"]), _p(out["nbr"]), _p(out["recv_off"]), _p(out["recv_cnt"]),
                                      _p(out["send_ptr"]), _p(out["send_idx"])))
+    return out
+
+
+def partition_local_nodes(elem2node, nnodes, part, rank, nranks):
+    """the same for any element -> node table and node partition (P2 spaces on a distributed mesh)"""
+    e2n, part = _i32(elem2node), _i32(part)
+    sz = (C.c_int64 * 8)()
+    args = (e2n.shape[1], int(nnodes), e2n.shape[0], _p(e2n), _p(part), rank, nranks, sz)
+    _ck(lib().ffcuda_partition_local_nodes(*args, None, None, None, None, None, None, None))
+    no, ng, ne, nn, ns = (int(sz[i]) for i in range(5))
+    out = dict(nowned=no, l2g=np.zeros(no + ng, np.int32), elems=np.zeros(ne, np.int32), nbr=np.zeros(nn, np.int32),
+               recv_off=np.zeros(nn, np.int32), recv_cnt=np.zeros(nn, np.int32), send_ptr=np.zeros(nn + 1, np.int32),
+               send_idx=np.zeros(ns, np.int32))
+    _ck(lib().ffcuda_partition_local_nodes(*args, _p(out["l2g"]), _p(out["elems"]), _p(out["nbr"]), _p(out["recv_off"]),
+                                           _p(out["recv_cnt"]), _p(out["send_ptr"]), _p(out["send_idx"])))
     return out
 
 
@@ -300,6 +315,14 @@ class Mesh(_Handle):
         gid = np.zeros(nl.value, np.int64)
         _ck(lib().ffcuda_mesh_local_to_global(_h(self), C.byref(no), C.byref(nl), _p(gid)), self.ctx.h)
         return no.value, gid
+
+    def space_distributed(self, order, ncomp, elem2node, nowned, nlocal, nbr, recv_off, recv_cnt, send_ptr, send_idx):
+        """a space with its own node table and node-level halo lists on a distributed mesh (P2): ffcuda_space_create_distributed"""
+        e2n, nbr, ro, rc, sp, si = (_i32(a) for a in (elem2node, nbr, recv_off, recv_cnt, send_ptr, send_idx))
+        out = C.c_void_p()
+        _ck(lib().ffcuda_space_create_distributed(_h(self), order, ncomp, _p(e2n), int(nowned), int(nlocal), len(nbr), _p(nbr), _p(ro), _p(rc),
+                                                  _p(sp), _p(si), C.byref(out)), self.ctx.h)
+        return Space(out.value, self.ctx, self)
 
     def space(self, order=1, ncomp=1, elem2node=None, nnodes=0):
         e2n = _i32(elem2node)

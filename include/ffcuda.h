@@ -326,6 +326,20 @@ int ffcuda_partition_rcb(int dim, int nv, const double *xyz, int nparts, int32_t
 int ffcuda_partition_local(int dim, int nv, int nt, const int32_t *conn, const int32_t *part, int rank, int nranks,
                            int64_t *sizes8, int32_t *l2g, int32_t *elems, int32_t *nbr, int32_t *recv_off, int32_t *recv_cnt,
                            int32_t *send_ptr, int32_t *send_idx);
+/* The same for any element -> node table (nloc nodes per element) and node partition - P2 spaces on a distributed mesh:
+ * elem2node = the GLOBAL table (FreeFEM's numbering), part[node] = rank of the vertex, or of one end point of the edge (then
+ * the local elements are those of the vertex partition, in the same order, and every owned row assembles without
+ * communication).  Same outputs; l2g = local -> global NODE. */
+int ffcuda_partition_local_nodes(int nloc, int nnodes, int nt, const int32_t *elem2node, const int32_t *part, int rank, int nranks,
+                                 int64_t *sizes8, int32_t *l2g, int32_t *elems, int32_t *nbr, int32_t *recv_off, int32_t *recv_cnt,
+                                 int32_t *send_ptr, int32_t *send_idx);
+/* A space on a distributed mesh with its own node table and node-level halo lists (P2, scalar or vector): elem2node =
+ * nt_local x nloc LOCAL node ids (owned nodes first, ghosts grouped by owner rank), lists as ffcuda_partition_local_nodes
+ * returns them.  Rows = owned nodes, columns = local nodes; ffcuda_spmv / ffcuda_cg / ffcuda_gmres exchange the ghost
+ * nodes. */
+int ffcuda_space_create_distributed(ffcuda_mesh *m, int order, int ncomp, const int32_t *elem2node, int nnodes_owned,
+                                    int nnodes_local, int nnbr, const int32_t *nbr, const int32_t *recv_off, const int32_t *recv_cnt,
+                                    const int32_t *send_ptr, const int32_t *send_idx, ffcuda_space **out);
 /* The local problem of this rank for ANY vertex partition (the arrays ffcuda_partition_local returns, local numbering: owned
  * vertices first, then the ghosts grouped by owner rank): xyz[nv_local*dim], conn with LOCAL vertex ids, the boundary
  * elements whose element is local, gid[nv_local] global ids, and the halo description - per neighbour x the contiguous ghost

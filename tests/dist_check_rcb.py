@@ -7,7 +7,8 @@ local problem (ffcuda_partition_local), uploads it (ffcuda_mesh_upload_distribut
 communication and runs the distributed CG (halo exchange with gather lists and any number of neighbours).  Rank 0
 gathers the owned rows with global column ids and compares with the CPU oracle on the whole mesh: pattern bit-exact,
 values / rhs / SpMV 1e-12, CG iteration count equal and solution 1e-12 — the same bars as on one GPU.  Also a
-[P1,P1,P1] Lame matrix (vector space on a distributed mesh: node-blocked halo)."""
+[P1,P1,P1] Lame matrix (vector space on a distributed mesh: node-blocked halo) and, on the small mesh, a non-symmetric
+convection-diffusion matrix solved by the distributed GMRES(30) (restarts included) against the oracle's fgmres."""
 import os
 import sys
 
@@ -24,6 +25,7 @@ ID, DX, DY, DZ = 0, 1, 2, 6
 LAP = [(0, DX, 0, DX, 1.0), (0, DY, 0, DY, 1.0), (0, DZ, 0, DZ, 1.0), (0, ID, 0, ID, 0.5)]
 RHS = [(0, ID, 1.0)]
 ALL6 = [1, 2, 3, 4, 5, 6]
+CONV = LAP + [(0, DX, 0, ID, 8.0), (0, DY, 0, ID, 3.0), (0, DZ, 0, ID, -2.0)]
 
 
 def scrambled_cube(dims, seed):
@@ -112,6 +114,13 @@ def main():
         A3.spmv(ctx.vec_from(np.cos(0.37 * g3.astype(np.float64))), y3)
         pack = dict(rp=rp, cols=gid[ci], vals=A.download(), b=b.download(), u=x.download()[:n], y=ys.download(), gid=gid[:n], it=it,
                     conv=conv, y3=y3.download(), nbrs=len(me["nbr"]))
+        if policy == 1:  # distributed GMRES on a non-symmetric matrix (same pattern object, values re-assembled)
+            A.assemble(CONV, qp, qw)
+            A.apply_bc(bc, 1e30)
+            for eps, tag in ((1e-6, "g6"), (1e-14, "g14")):
+                xg = ctx.vec(len(gid))
+                git, gconv, _ = A.gmres(b, xg, eps=eps, itmax=0, restart=30, tgv=1e30)
+                pack[tag] = (xg.download()[:n], git, gconv)
         allp = [None] * world
         dist.all_gather_object(allp, pack)
         if rank == 0:
@@ -146,6 +155,17 @@ def main():
             assert its == {oit} and all(p["conv"] == 1 for p in allp), (its, oit)
             uu = np.concatenate([p["u"] for p in allp])[inv]
             assert np.max(np.abs(uu - ox)) <= 1e-12 * np.abs(ox).max()
+            if policy == 1:
+                gi, gj, ga = ol.assemble_coo(m, 1, 1, None, CONV, qp, qw)
+                ga = ol.bc_matrix_coo(gi, gj, ga, N, d, 1e30)
+                for eps, tag, tol in ((1e-6, "g6", 1e-7), (1e-14, "g14", 1e-10)):
+                    ogx, ogit, ogret, _ = ol.gmres(N, gi, gj, ga, ob, np.zeros(N), eps=eps, nbkrylov=30, tgv=1e30)
+                    gits = {p[tag][1] for p in allp}
+                    assert ogret == 1 and all(p[tag][2] == 1 for p in allp) and len(gits) == 1, (gits, ogit)
+                    assert abs(gits.pop() - ogit) <= 1, (tag, ogit)
+                    gu = np.concatenate([p[tag][0] for p in allp])[inv]
+                    assert np.max(np.abs(gu - ogx)) <= tol * np.abs(ogx).max(), (tag, np.max(np.abs(gu - ogx)) / np.abs(ogx).max())
+                print(f"dist_check_rcb cube{dims}: distributed GMRES(30) on {world} GPUs: {ogit} iterations OK", flush=True)
             # Lame
             li, lj, la = ol.assemble_coo(m, 1, 3, None, fc.lame_terms(), qp, qw)
             oy3 = ol.spmv_coo(3 * N, li, lj, la, np.cos(0.37 * np.arange(3 * N, dtype=np.float64)))

@@ -227,3 +227,14 @@ def loose_iterate(name):
     """fixtures whose eps=1e-6 iterate is compared loosely (1e-6) because their right-hand side or matrix carries extra ulp
     differences (boundary terms, data evaluated with another libm); their eps=1e-14 solutions are held to 1e-12 like all others"""
     return name in CASE_BLIN or name in CASE_BBIL or name in CASE_FQ or name in CASE_QCOEF or name in CASE_BQ or name in CASE_FQT
+
+
+def p2_node_partition(conn, e2n, part):
+    """rank of every P2 node of a tetrahedral mesh for the vertex partition `part`: a vertex node goes with its vertex, an
+    edge node with its end point of smaller global id (then every element around an owned node is local to its rank)"""
+    nn = int(e2n.max()) + 1
+    pn = np.empty(nn, np.int32)
+    pn[e2n[:, :4]] = part[conn]
+    for e, (p, r) in enumerate([(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]):
+        pn[e2n[:, 4 + e]] = part[np.minimum(conn[:, p], conn[:, r])]
+    return pn

@@ -137,3 +137,16 @@ def test_dist_check_rcb_under_torchrun(world):
            "--master-port", str(port), os.path.join(ROOT, "tests", "dist_check_rcb.py")]
     r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "DIST_CHECK_RCB_PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_dist_check_p2_under_torchrun(world):
+    """tests/dist_check_p2.py: P2 and [P2,P2,P2] spaces on an RCB-partitioned cube with shuffled numbering (node-level halo lists:
+    vertices and edges) against the oracle on the whole mesh.  Self-skips when the box has fewer devices."""
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} CUDA devices")
+    port = 29660 + world
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tests", "dist_check_p2.py")]
+    r = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "DIST_CHECK_P2_PASSED" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

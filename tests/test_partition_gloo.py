@@ -275,3 +275,55 @@ def test_general_partition_edge_cases():
         ffcuda.partition_local(2, nv, bad, part, 0, 3)
     with pytest.raises(ffcuda.FfcudaError):
         ffcuda.partition_rcb(xyz[:4], 5)
+
+
+def test_node_partition_p2_local_problem():
+    """P2 spaces on a distributed mesh (ffcuda_partition_local_nodes): for every rank of a 3-way RCB partition of a cube the
+    node-level local problem has the elements of the vertex-level one, owns each node exactly once, its send lists are the
+    neighbours' ghost ranges in order, and the P2 Laplace matrix of the LOCAL mesh with the LOCAL node table holds, in its
+    owned rows, exactly the rows of the global matrix (structural zeros included): assembly needs no communication."""
+    import numpy as np
+    import scipy.sparse as sps
+
+    sys.path.insert(0, os.path.join(ROOT, "freefem-sources_b200"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ffcuda
+    import ff_cases as fc
+    import oracle_lib as ol
+
+    m = _general_mesh("cube")
+    xyz, conn, nv = m["xyz"], m["conn"], m["xyz"].shape[0]
+    e2n, nn = ol.p2_nodes_3d(nv, conn)
+    world = 3
+    part = ffcuda.partition_rcb(xyz, world)
+    pn = fc.p2_node_partition(conn, e2n, part)
+    qp, qw = ol.quadrature(3, "qfV5")
+    gi, gj, ga = ol.assemble_coo(m, 2, 1, e2n, fc.LAP3, qp, qw)
+    Ag = sps.coo_matrix((ga, (gi, gj)), shape=(nn, nn)).tocsr()
+    Ls = [ffcuda.partition_local_nodes(e2n, nn, pn, r, world) for r in range(world)]
+    assert np.array_equal(np.sort(np.concatenate([L["l2g"][:L["nowned"]] for L in Ls])), np.arange(nn))
+    for rank, L in enumerate(Ls):
+        Lv = ffcuda.partition_local(3, nv, conn, part, rank, world)
+        assert np.array_equal(L["elems"], Lv["elems"])
+        no, l2g = L["nowned"], L["l2g"]
+        assert np.array_equal(l2g[:no], np.flatnonzero(pn == rank))
+        for x, r in enumerate(L["nbr"]):
+            other = Ls[int(r)]
+            y = list(other["nbr"]).index(rank)
+            sent = l2g[L["send_idx"][L["send_ptr"][x]:L["send_ptr"][x + 1]]]
+            assert np.array_equal(sent, other["l2g"][other["recv_off"][y]:other["recv_off"][y] + other["recv_cnt"][y]])
+        g2l_v = -np.ones(nv, np.int64)
+        g2l_v[Lv["l2g"]] = np.arange(len(Lv["l2g"]))
+        g2l_n = -np.ones(nn, np.int64)
+        g2l_n[l2g] = np.arange(len(l2g))
+        ml = dict(dim=3, xyz=xyz[Lv["l2g"]], conn=g2l_v[conn[L["elems"]]].astype(np.int32), elab=np.zeros(len(L["elems"]), np.int32))
+        e2n_l = g2l_n[e2n[L["elems"]]].astype(np.int32)
+        assert e2n_l.min() >= 0
+        li, lj, la = ol.assemble_coo(ml, 2, 1, e2n_l, fc.LAP3, qp, qw)
+        rows = li < no
+        Al = sps.coo_matrix((la[rows], (li[rows], l2g[lj[rows]])), shape=(no, nn)).tocsr()
+        Aref = Ag[l2g[:no]]
+        Al.sort_indices()
+        Aref.sort_indices()
+        assert np.array_equal(Al.indptr, Aref.indptr) and np.array_equal(Al.indices, Aref.indices)
+        assert np.max(np.abs(Al.data - Aref.data)) <= 1e-13 * np.abs(Aref.data).max()
