@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <nccl.h>
 
 namespace {
@@ -201,6 +202,13 @@ void p2p_setup(ffcuda_ctx *ctx)
     std::vector<unsigned char> rec(80, 0), all((size_t)n * 80, 0);
     memcpy(rec.data(), &h, 64);
     rec[64] = (unsigned char)ok;
+    // ranks that are threads of ONE process (the FreeFEM plugin driving several GPUs) cannot open each other's IPC handles:
+    // they exchange the pointer itself and enable peer access between the two devices
+    const int32_t mypid = (int32_t)getpid();
+    const uint64_t myptr = (uint64_t)(uintptr_t)mine;
+    memcpy(rec.data() + 65, &mypid, 4);
+    memcpy(rec.data() + 69, &myptr, 8);
+    rec[77] = (unsigned char)ctx->device;
     FF_CUDA(cudaMemcpyAsync(d_all.p + (size_t)n * 80, rec.data(), 80, cudaMemcpyHostToDevice, st));
     FF_NCCL(nccl().AllGather(d_all.p + (size_t)n * 80, d_all.p, 80, ncclChar, (ncclComm_t)ctx->nccl_comm, st));
     FF_CUDA(ff_memcpy_sync(ctx, all.data(), d_all.p, (size_t)n * 80, cudaMemcpyDeviceToHost)); // also: every memset is done
@@ -210,6 +218,28 @@ void p2p_setup(ffcuda_ctx *ctx)
         for (int r = 0; r < n && ok; ++r) {
             if (r == rank) {
                 ctx->p2p_peer[r] = mine;
+                continue;
+            }
+            int32_t rpid = 0;
+            uint64_t rptr = 0;
+            memcpy(&rpid, &all[(size_t)r * 80 + 65], 4);
+            memcpy(&rptr, &all[(size_t)r * 80 + 69], 8);
+            if (rpid == mypid) {
+                const int rdev = all[(size_t)r * 80 + 77];
+                int can = 0;
+                cudaError_t e = cudaDeviceCanAccessPeer(&can, ctx->device, rdev);
+                if (e == cudaSuccess && can) {
+                    e = cudaDeviceEnablePeerAccess(rdev, 0);
+                    if (e == cudaErrorPeerAccessAlreadyEnabled) e = cudaSuccess;
+                }
+                cudaGetLastError();
+                if (e != cudaSuccess || !can) {
+                    ok = 0;
+                    break;
+                }
+                ctx->p2p_peer[r] = (void *)(uintptr_t)rptr;
+                ctx->p2p_inproc[r] = true;
+                ++opened;
                 continue;
             }
             cudaIpcMemHandle_t hr;
@@ -233,8 +263,9 @@ void p2p_setup(ffcuda_ctx *ctx)
     FF_CUDA(ff_memcpy_sync(ctx, &hv, flag.p, sizeof(double), cudaMemcpyDeviceToHost));
     if (hv < 0.5) {
         for (int r = 0; r < n; ++r) {
-            if (r != rank && ctx->p2p_peer[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+            if (r != rank && ctx->p2p_peer[r] && !ctx->p2p_inproc[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
             ctx->p2p_peer[r] = nullptr;
+            ctx->p2p_inproc[r] = false;
         }
         if (mine) cudaFree(mine);
         cudaGetLastError();
@@ -258,8 +289,9 @@ void p2p_teardown(ffcuda_ctx *ctx)
     for (int r = 0; r < ctx->nranks; ++r) {
         if (!ctx->p2p_peer[r]) continue;
         if (r == ctx->rank) cudaFree(ctx->p2p_peer[r]);
-        else cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
+        else if (!ctx->p2p_inproc[r]) cudaIpcCloseMemHandle(ctx->p2p_peer[r]);
         ctx->p2p_peer[r] = nullptr;
+        ctx->p2p_inproc[r] = false;
     }
     ctx->p2p = false;
 }
@@ -324,7 +356,8 @@ static ffcuda_mesh *dist_mesh(ffcuda_matrix *A)
     return (m && m->distributed) ? m : nullptr;
 }
 
-bool ff_is_distributed(ffcuda_matrix *A) { return dist_mesh(A) != nullptr; }
+// rows of one rank: a matrix on a distributed mesh, or one handed over with its own halo lists
+bool ff_is_distributed(ffcuda_matrix *A) { return (A->own_halo && A->ctx->nranks > 1) || dist_mesh(A) != nullptr; }
 
 // the halo lists that apply to a matrix: those of its space when it has its own (P2 on a distributed mesh), else the mesh's
 struct HaloView {
@@ -335,6 +368,11 @@ struct HaloView {
 static HaloView halo_view(ffcuda_matrix *A, ffcuda_mesh *m)
 {
     HaloView H;
+    if (A->own_halo) {
+        H.nnbr = A->nnbr; H.nbr = A->nbr; H.send_off = A->send_off; H.send_cnt = A->send_cnt; H.recv_off = A->recv_off; H.recv_cnt = A->recv_cnt;
+        H.send_idx = A->send_idx.p;
+        return H;
+    }
     ffcuda_space *s = A->pattern->space;
     if (s->own_halo) {
         H.nnbr = s->nnbr; H.nbr = s->nbr; H.send_off = s->send_off; H.send_cnt = s->send_cnt; H.recv_off = s->recv_off; H.recv_cnt = s->recv_cnt;
@@ -349,12 +387,12 @@ static HaloView halo_view(ffcuda_matrix *A, ffcuda_mesh *m)
 // v holds owned values in [0, n) ; fills the ghost ranges [n, ncols) from the neighbours' owned boundary layers
 void ff_halo_exchange(ffcuda_matrix *A, double *v)
 {
+    if (!ff_is_distributed(A)) return;
     ffcuda_mesh *m = dist_mesh(A);
-    if (!m) return;
     ffcuda_ctx *ctx = A->ctx;
     FF_REQUIRE(ctx->nccl_comm, "distributed matrix without communicator");
     const HaloView V = halo_view(A, m);
-    const int nc = A->pattern->ncomp;
+    const int nc = A->pattern ? A->pattern->ncomp : 1;
     HaloArgs H;
     memset(&H, 0, sizeof(H));
     H.n = V.nnbr;
@@ -406,8 +444,10 @@ void ff_halo_exchange(ffcuda_matrix *A, double *v)
     for (int x = 0; x < V.nnbr; ++x) {
         if (V.nbr[x] < 0 || via_p2p[x]) continue;
         const double *src = V.send_idx ? stage.p + soff[x] : v + (size_t)V.send_off[x] * nc;
-        FF_NCCL(N.Send(src, (size_t)V.send_cnt[x] * nc, ncclDouble, V.nbr[x], comm, ctx->stream));
-        FF_NCCL(N.Recv(v + (size_t)V.recv_off[x] * nc, (size_t)V.recv_cnt[x] * nc, ncclDouble, V.nbr[x], comm, ctx->stream));
+        // (a layer of length zero - a matrix whose structure is not symmetric - is skipped on both ends: counts mirror each other)
+        if (V.send_cnt[x] > 0) FF_NCCL(N.Send(src, (size_t)V.send_cnt[x] * nc, ncclDouble, V.nbr[x], comm, ctx->stream));
+        if (V.recv_cnt[x] > 0)
+            FF_NCCL(N.Recv(v + (size_t)V.recv_off[x] * nc, (size_t)V.recv_cnt[x] * nc, ncclDouble, V.nbr[x], comm, ctx->stream));
     }
     FF_NCCL(N.GroupEnd());
     ctx->launches++;
@@ -415,7 +455,7 @@ void ff_halo_exchange(ffcuda_matrix *A, double *v)
 
 void ff_allreduce(ffcuda_matrix *A, double *d, int count, int op_max)
 {
-    if (!dist_mesh(A)) return;
+    if (!ff_is_distributed(A)) return;
     ffcuda_ctx *ctx = A->ctx;
     FF_REQUIRE(ctx->nccl_comm, "distributed matrix without communicator");
     if (ctx->p2p && count <= 4) {

@@ -83,6 +83,7 @@ struct ffcuda_ctx {
     // all-reduces and halo exchanges of CG are plain stores into the peers' mailboxes over NVLink, no NCCL call
     bool p2p = false;
     void *p2p_peer[16] = {};              // p2p_peer[r]: rank r's mailbox in this process' address space
+    bool p2p_inproc[16] = {};             // rank r lives in this process (one thread per GPU): its pointer is used as it is
     size_t p2p_halo_cap = 0;              // doubles per (direction, parity) halo region
     unsigned long long p2p_seq_halo = 0;
     // lifetime: every handle created on the context holds a reference; ffcuda_ctx_destroy only marks the context
@@ -444,6 +445,13 @@ struct ffcuda_matrix {
     // CG workspace (lazily allocated)
     DBuf<double> wG, wH, wAH, wD1, wX;
     DBuf<int32_t> wcl;
+    // a matrix handed over as the rows of one rank (ffcuda_matrix_from_csr_distributed) carries its own halo lists: rows =
+    // owned dofs, columns = owned then ghost dofs; same meaning as the lists of a distributed mesh / space
+    bool own_halo = false;
+    int nnbr = 0;
+    int nbr[ffcuda_mesh::MAXNBR], send_off[ffcuda_mesh::MAXNBR], send_cnt[ffcuda_mesh::MAXNBR], recv_off[ffcuda_mesh::MAXNBR],
+        recv_cnt[ffcuda_mesh::MAXNBR];
+    DBuf<int32_t> send_idx;
 };
 
 struct ffcuda_vec {

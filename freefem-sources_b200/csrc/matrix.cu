@@ -1,6 +1,7 @@
 // matrix.cu — device-resident CSR matrices and Dirichlet (penalty) conditions.
 // AssembleBC (fflib/problem.cpp:9881-10194) + HashMatrix::SetBC (femlib/HashMatrix.cpp:1195-1238), tgv >= 0.
 #include "common.cuh"
+#include <memory>
 #include <vector>
 #include <cmath>
 #include <algorithm>
@@ -94,6 +95,57 @@ extern "C" int ffcuda_matrix_from_csr(ffcuda_ctx *ctx, int n, int64_t nnz, const
     *out = A;
     A = nullptr;
     FF_API_END((delete A, ctx))
+}
+
+// The rows of ONE rank of a matrix that is shared out by rows (any origin: the FreeFEM plugin splits a host MatriceMorse
+// into row blocks, one per GPU): n_owned rows, columns in local numbering - owned dofs first (column i is row i), then the
+// ghost dofs grouped by owner rank - and the halo lists in the form ffcuda_partition_local returns them (a neighbour may
+// have an empty range in one direction when the structure is not symmetric; both ranks must list each other).  ffcuda_spmv /
+// ffcuda_cg / ffcuda_gmres on such a matrix exchange the ghost values and all-reduce the dot products.
+extern "C" int ffcuda_matrix_from_csr_distributed(ffcuda_ctx *ctx, int n_owned, int ncols, int64_t nnz, const int32_t *rowptr,
+                                                  const int32_t *colind, const double *vals, int nnbr, const int32_t *nbr,
+                                                  const int32_t *recv_off, const int32_t *recv_cnt, const int32_t *send_ptr,
+                                                  const int32_t *send_idx, ffcuda_matrix **out)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(ctx && out && rowptr && colind && n_owned > 0 && ncols >= n_owned, "ffcuda_matrix_from_csr_distributed: bad arguments");
+    FF_REQUIRE(ctx->nranks == 1 || ctx->nccl_comm, "ffcuda_matrix_from_csr_distributed: call ffcuda_comm_init first");
+    FF_REQUIRE(nnbr >= 0 && nnbr <= ffcuda_mesh::MAXNBR, "at most 16 neighbour ranks");
+    FF_REQUIRE(nnbr == 0 || (nbr && recv_off && recv_cnt && send_ptr && (send_idx || send_ptr[nnbr] == 0)), "halo arrays missing");
+    int covered = n_owned;
+    for (int x = 0; x < nnbr; ++x) {
+        FF_REQUIRE(nbr[x] >= 0 && nbr[x] < ctx->nranks && nbr[x] != ctx->rank, "bad neighbour rank");
+        FF_REQUIRE(recv_off[x] == covered && recv_cnt[x] >= 0, "ghost ranges must follow the owned dofs, in neighbour order, without gaps");
+        covered += recv_cnt[x];
+        FF_REQUIRE(send_ptr[x + 1] >= send_ptr[x], "send_ptr must be non-decreasing");
+    }
+    FF_REQUIRE(covered == ncols, "ghost ranges do not cover the ghost columns");
+    for (int k = 0; k < (nnbr ? send_ptr[nnbr] : 0); ++k) FF_REQUIRE(send_idx[k] >= 0 && send_idx[k] < n_owned, "send list entry is not an owned dof");
+    for (int64_t k = 0; k < nnz; ++k) FF_REQUIRE(colind[k] >= 0 && colind[k] < ncols, "column index outside the local columns");
+    ffcuda_matrix *A = nullptr;
+    if (ffcuda_matrix_from_csr(ctx, n_owned, nnz, rowptr, colind, vals, &A) != 0) throw FFError(ffcuda_last_error(ctx));
+    std::unique_ptr<ffcuda_matrix> guard(A);
+    ff_enter(ctx);
+    A->ncols = ncols;
+    A->own_halo = true;
+    A->nnbr = nnbr;
+    for (int x = 0; x < ffcuda_mesh::MAXNBR; ++x) {
+        A->nbr[x] = -1;
+        A->send_off[x] = A->send_cnt[x] = A->recv_off[x] = A->recv_cnt[x] = 0;
+    }
+    for (int x = 0; x < nnbr; ++x) {
+        A->nbr[x] = nbr[x];
+        A->recv_off[x] = recv_off[x];
+        A->recv_cnt[x] = recv_cnt[x];
+        A->send_off[x] = send_ptr[x];
+        A->send_cnt[x] = send_ptr[x + 1] - send_ptr[x];
+    }
+    if (nnbr && send_ptr[nnbr] > 0) {
+        A->send_idx.alloc((size_t)send_ptr[nnbr]);
+        FF_CUDA(ff_memcpy_sync(ctx, A->send_idx.p, send_idx, (size_t)send_ptr[nnbr] * 4, cudaMemcpyHostToDevice));
+    }
+    *out = guard.release();
+    FF_API_END(ctx)
 }
 
 // ---------------------------------------------------------------------------------------------------

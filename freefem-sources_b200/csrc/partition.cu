@@ -187,3 +187,84 @@ extern "C" int ffcuda_partition_local_nodes(int nloc, int nnodes, int nt, const 
     put(send_idx, L.send_idx);
     FF_API_END(nullptr)
 }
+
+// A host CSR matrix shared out by contiguous row blocks (what the FreeFEM plugin does with a MatriceMorse to solve it on
+// several GPUs; for cube / square meshes in FreeFEM's numbering the blocks are slabs): rank r owns the rows
+// [n r / nranks, n (r+1) / nranks).  Its local problem: ghost columns = the columns of its rows outside its block, ascending
+// (hence grouped by owner); what it sends to rank o = its columns that appear in o's rows, ascending (= o's ghost order).
+// A rank is a neighbour when something goes in either direction (structure need not be symmetric).  Host arithmetic only.
+// sizes8 = { owned rows, ghosts, local nnz, neighbours, total send count, first owned row, 0, 0 }; call once with the arrays
+// NULL for the sizes.  lrowptr[owned+1] and lcolind[local nnz] are the local CSR structure (the values are the slice
+// vals[rowptr[first] .. rowptr[first + owned]) of the caller's array, untouched).
+extern "C" int ffcuda_partition_rows_local(int n, const int32_t *rowptr, const int32_t *colind, int rank, int nranks, int64_t *sizes8,
+                                           int32_t *l2g, int32_t *lrowptr, int32_t *lcolind, int32_t *nbr, int32_t *recv_off,
+                                           int32_t *recv_cnt, int32_t *send_ptr, int32_t *send_idx)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(n > 0 && rowptr && colind && sizes8 && nranks >= 1 && rank >= 0 && rank < nranks, "ffcuda_partition_rows_local: bad arguments");
+    FF_REQUIRE(nranks <= n, "ffcuda_partition_rows_local: more ranks than rows");
+    auto first = [&](int r) { return (int)((int64_t)n * r / nranks); };
+    const int lo = first(rank), hi = first(rank + 1), nown = hi - lo;
+    std::vector<int32_t> ghosts;
+    for (int64_t k = rowptr[lo]; k < rowptr[hi]; ++k) {
+        const int32_t j = colind[k];
+        FF_REQUIRE(j >= 0 && j < n, "ffcuda_partition_rows_local: column index outside [0, n)");
+        if (j < lo || j >= hi) ghosts.push_back(j);
+    }
+    std::sort(ghosts.begin(), ghosts.end());
+    ghosts.erase(std::unique(ghosts.begin(), ghosts.end()), ghosts.end());
+    std::vector<std::vector<int32_t>> send((size_t)nranks);
+    {
+        std::vector<int32_t> stamp((size_t)nown, -1);
+        for (int o = 0; o < nranks; ++o) {
+            if (o == rank) continue;
+            for (int64_t k = rowptr[first(o)]; k < rowptr[first(o + 1)]; ++k) {
+                const int32_t j = colind[k];
+                if (j >= lo && j < hi && stamp[j - lo] != o) {
+                    stamp[j - lo] = o;
+                    send[o].push_back(j - lo);
+                }
+            }
+            std::sort(send[o].begin(), send[o].end());
+        }
+    }
+    std::vector<int32_t> vnbr, voff, vcnt, vsp(1, 0), vsi;
+    size_t g = 0;
+    for (int o = 0; o < nranks; ++o) {
+        if (o == rank) continue;
+        size_t g1 = g;
+        while (g1 < ghosts.size() && ghosts[g1] < first(o + 1)) ++g1;
+        if (g1 > g || !send[o].empty()) {
+            vnbr.push_back(o);
+            voff.push_back(nown + (int32_t)g);
+            vcnt.push_back((int32_t)(g1 - g));
+            vsi.insert(vsi.end(), send[o].begin(), send[o].end());
+            vsp.push_back((int32_t)vsi.size());
+        }
+        g = g1;
+    }
+    FF_REQUIRE((int)vnbr.size() <= 16, "ffcuda_partition_rows_local: a row block has more than 16 neighbour blocks");
+    const int64_t lnnz = (int64_t)rowptr[hi] - rowptr[lo];
+    const int64_t sz[8] = {nown, (int64_t)ghosts.size(), lnnz, (int64_t)vnbr.size(), (int64_t)vsi.size(), lo, 0, 0};
+    for (int i = 0; i < 8; ++i) sizes8[i] = sz[i];
+    if (l2g) {
+        for (int i = 0; i < nown; ++i) l2g[i] = lo + i;
+        std::copy(ghosts.begin(), ghosts.end(), l2g + nown);
+    }
+    if (lrowptr)
+        for (int i = 0; i <= nown; ++i) lrowptr[i] = rowptr[lo + i] - rowptr[lo];
+    if (lcolind)
+        for (int64_t k = 0; k < lnnz; ++k) {
+            const int32_t j = colind[rowptr[lo] + k];
+            lcolind[k] = (j >= lo && j < hi) ? j - lo : nown + (int32_t)(std::lower_bound(ghosts.begin(), ghosts.end(), j) - ghosts.begin());
+        }
+    auto put = [](int32_t *dst, const std::vector<int32_t> &v) {
+        if (dst) std::copy(v.begin(), v.end(), dst);
+    };
+    put(nbr, vnbr);
+    put(recv_off, voff);
+    put(recv_cnt, vcnt);
+    put(send_ptr, vsp);
+    put(send_idx, vsi);
+    FF_API_END(nullptr)
+}

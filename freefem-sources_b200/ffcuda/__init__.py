@@ -17,7 +17,7 @@ OP_ID, OP_DX, OP_DY, OP_DZ = 0, 1, 2, 6
 SYMBOLS = """ffcuda_ctx_create ffcuda_ctx_destroy ffcuda_last_error ffcuda_ctx_sync ffcuda_ctx_set_stream ffcuda_ctx_get_stream ffcuda_ctx_set_option
 ffcuda_prof_enable ffcuda_prof_reset ffcuda_prof_get ffcuda_launch_count ffcuda_mesh_upload ffcuda_mesh_cube ffcuda_mesh_square ffcuda_mesh_buildlayers
 ffcuda_mesh_info ffcuda_mesh_download ffcuda_mesh_destroy ffcuda_space_create ffcuda_space_info ffcuda_space_download_dofs
-ffcuda_space_destroy ffcuda_space_create_distributed ffcuda_partition_local_nodes ffcuda_symbolic ffcuda_pattern_info ffcuda_pattern_download ffcuda_pattern_download_async ffcuda_pattern_lower_nnz ffcuda_pattern_download_lower
+ffcuda_space_destroy ffcuda_partition_rows_local ffcuda_matrix_from_csr_distributed ffcuda_space_create_distributed ffcuda_partition_local_nodes ffcuda_symbolic ffcuda_pattern_info ffcuda_pattern_download ffcuda_pattern_download_async ffcuda_pattern_lower_nnz ffcuda_pattern_download_lower
 ffcuda_matrix_download_lower ffcuda_matrix_from_csr_lower ffcuda_pattern_destroy ffcuda_matrix_create
 ffcuda_matrix_from_csr ffcuda_matrix_info ffcuda_matrix_download ffcuda_matrix_upload ffcuda_matrix_destroy ffcuda_vec_create
 ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_destroy ffcuda_assemble_bilinear ffcuda_assemble_bilinear_qcoef
@@ -78,6 +78,21 @@ def partition_local_nodes(elem2node, nnodes, part, rank, nranks):
                send_idx=np.zeros(ns, np.int32))
     _ck(lib().ffcuda_partition_local_nodes(*args, _p(out["l2g"]), _p(out["elems"]), _p(out["nbr"]), _p(out["recv_off"]),
                                            _p(out["recv_cnt"]), _p(out["send_ptr"]), _p(out["send_idx"])))
+    return out
+
+
+def partition_rows_local(n, rowptr, colind, rank, nranks):
+    """the local problem of `rank` when a host CSR matrix is shared out by contiguous row blocks (host arithmetic only)"""
+    rowptr, colind = _i32(rowptr), _i32(colind)
+    sz = (C.c_int64 * 8)()
+    args = (int(n), _p(rowptr), _p(colind), rank, nranks, sz)
+    _ck(lib().ffcuda_partition_rows_local(*args, None, None, None, None, None, None, None, None))
+    no, ng, lnnz, nn, ns, lo = (int(sz[i]) for i in range(6))
+    out = dict(nowned=no, first=lo, l2g=np.zeros(no + ng, np.int32), rowptr=np.zeros(no + 1, np.int32), colind=np.zeros(lnnz, np.int32),
+               nbr=np.zeros(nn, np.int32), recv_off=np.zeros(nn, np.int32), recv_cnt=np.zeros(nn, np.int32),
+               send_ptr=np.zeros(nn + 1, np.int32), send_idx=np.zeros(ns, np.int32))
+    _ck(lib().ffcuda_partition_rows_local(*args, _p(out["l2g"]), _p(out["rowptr"]), _p(out["colind"]), _p(out["nbr"]), _p(out["recv_off"]),
+                                          _p(out["recv_cnt"]), _p(out["send_ptr"]), _p(out["send_idx"])))
     return out
 
 
@@ -257,6 +272,15 @@ class Context(_Handle):
         v = self.vec(len(host))
         v.upload(host)
         return v
+
+    def matrix_from_csr_distributed(self, L, vals):
+        """rows of this rank from the local problem L (partition_rows_local) and the values of its rows"""
+        vals = _f64(vals)
+        out = C.c_void_p()
+        _ck(lib().ffcuda_matrix_from_csr_distributed(_h(self), L["nowned"], len(L["l2g"]), C.c_int64(len(L["colind"])), _p(L["rowptr"]),
+                                                     _p(L["colind"]), _p(vals), len(L["nbr"]), _p(L["nbr"]), _p(L["recv_off"]),
+                                                     _p(L["recv_cnt"]), _p(L["send_ptr"]), _p(L["send_idx"]), C.byref(out)), self.h)
+        return Matrix(out.value, self, None)
 
     def matrix_from_csr_lower(self, n, rowptr, colind, vals):
         """half-stored (sym=1) host matrix -> full device matrix"""

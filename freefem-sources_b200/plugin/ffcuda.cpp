@@ -119,6 +119,86 @@ void notice(const char *what, const std::string &why)
     if (g_verbose || verbosity > 0) cout << "  -- ffcuda: " << what << " left to FreeFEM (" << why << ")" << endl;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// several GPUs from the one FreeFEM process (FFCUDA_NGPU=N): one context per device, one host thread per device while a
+// distributed call runs (the library is one rank per context; ranks that are threads of one process share their peer
+// mailboxes by pointer, csrc/comm.cu).  Used by the solvers: a MatriceMorse is shared out by contiguous row blocks
+// (ffcuda_partition_rows_local), every GPU holds its rows, the CG / GMRES iterations exchange ghost values and all-reduce
+// their dot products (reference role: MPI_Allreduce per dot product, plugin/mpi/MPICG.cpp:93-101).  The assembly statements
+// stay on one GPU: their result has to end in FreeFEM's host matrix anyway.
+// ------------------------------------------------------------------------------------------------------------
+int g_ngpu = 1;          // FFCUDA_NGPU
+long g_ngpu_min_n = 0;   // FFCUDA_NGPU_MIN_N: matrices with fewer rows are solved on one GPU
+std::vector<ffcuda_ctx *> g_gang;
+
+// f(rank) for every rank, rank 0 on the calling thread; the first error (if any) is raised after all of them returned
+template <class F>
+void on_ranks(int n, F f)
+{
+    std::vector<std::string> err((size_t)n);
+    std::vector<std::thread> th;
+    auto run = [&](int r) {
+        try {
+            f(r);
+        } catch (const std::exception &e) {
+            err[r] = e.what();
+        } catch (const ErrorExec &e) {
+            err[r] = "error in rank thread";
+        } catch (...) {
+            err[r] = "unknown error in rank thread";
+        }
+    };
+    for (int r = 1; r < n; ++r) th.emplace_back(run, r);
+    run(0);
+    for (size_t t = 0; t < th.size(); ++t) th[t].join();
+    for (int r = 0; r < n; ++r)
+        if (!err[r].empty()) ExecError(("ffcuda (GPU " + std::to_string(r) + "): " + err[r]).c_str());
+}
+
+struct RankError : std::runtime_error {
+    explicit RankError(const std::string &s) : std::runtime_error(s) {}
+};
+inline void rank_check(int rc, ffcuda_ctx *c, const char *what)
+{
+    if (rc == 0) return;
+    const char *e = ffcuda_last_error(c);
+    throw RankError(std::string(what) + ((e && *e) ? std::string(": ") + e : std::string()));
+}
+
+// the contexts of the gang, with their communicator; false (and a notice) when fewer devices answer
+bool gang_ready()
+{
+    if (g_ngpu < 2) return false;
+    if ((int)g_gang.size() == g_ngpu) return true;
+    if (!g_gang.empty()) return false; // an earlier attempt failed: one GPU from then on
+    const char *d = getenv("FFCUDA_DEVICE");
+    const int base = d ? atoi(d) : 0;
+    std::vector<ffcuda_ctx *> gang((size_t)g_ngpu, nullptr);
+    gang[0] = context();
+    bool ok = true;
+    for (int r = 1; r < g_ngpu && ok; ++r) ok = ffcuda_ctx_create(base + r, &gang[r]) == 0;
+    unsigned char id[128];
+    ok = ok && ffcuda_comm_unique_id(id) == 0;
+    if (ok) {
+        try {
+            on_ranks(g_ngpu, [&](int r) { rank_check(ffcuda_comm_init(gang[r], r, g_ngpu, id), gang[r], "ffcuda_comm_init"); });
+        } catch (...) {
+            ok = false;
+        }
+    }
+    if (!ok) {
+        for (int r = 1; r < g_ngpu; ++r)
+            if (gang[r]) ffcuda_ctx_destroy(gang[r]);
+        g_gang.assign(1, gang[0]); // marks the failed attempt
+        g_ngpu = 1;
+        notice("FFCUDA_NGPU", "the devices or their communicator are not available: one GPU");
+        return false;
+    }
+    g_gang = gang;
+    if (g_verbose) cout << "  -- ffcuda: " << g_ngpu << " GPUs driven from this process (one host thread per GPU during distributed solves)" << endl;
+    return true;
+}
+
 struct Unsupported {
     std::string why;
 };
@@ -1381,6 +1461,8 @@ class SolverCudaCG : public VirtualSolver<int, double> {
     double *veps;
     long *getnbiter;
     VirtualSolver<int, double> *hostcg; // FreeFEM's own SolverCG when the script gives a preconditioner (precon=)
+    std::vector<ffcuda_matrix *> dmat;  // FFCUDA_NGPU > 1: the row block of every GPU
+    std::vector<int> dfirst;            // first row of every block (+ n)
 
     SolverCudaCG(HMat &AA, const Data_Sparse_Solver &ds, Stack stack, bool is_cg = true)
         : A(&AA), dev{nullptr, nullptr}, verb(ds.verb), itermax(ds.itmax > 0 ? ds.itmax : AA.n), eps(ds.epsilon), tgv(ds.tgv),
@@ -1408,8 +1490,46 @@ class SolverCudaCG : public VirtualSolver<int, double> {
             hostcg = new SolverCG<int, double>(AA, ds, stack);
         }
     }
+    // several GPUs: full storage, enough rows, the gang answers
+    bool want_gang() const { return g_ngpu > 1 && !A->half && A->n >= g_ngpu_min_n && A->n >= 64 * g_ngpu && gang_ready(); }
+    void release_dist()
+    {
+        for (size_t r = 0; r < dmat.size(); ++r)
+            if (dmat[r]) ffcuda_matrix_destroy(dmat[r]);
+        dmat.clear();
+        dfirst.clear();
+    }
+    // the MatriceMorse shared out by contiguous row blocks, one per GPU (values: slices of FreeFEM's own array)
+    void upload_dist()
+    {
+        release_dist();
+        release_resident(dev);
+        A->CSR();
+        const int n = A->n, N = g_ngpu;
+        dmat.assign((size_t)N, nullptr);
+        dfirst.assign((size_t)N + 1, n);
+        Marks mk;
+        on_ranks(N, [&](int r) {
+            int64_t sz[8];
+            rank_check(ffcuda_partition_rows_local(n, A->p, A->j, r, N, sz, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr),
+                       nullptr, "ffcuda_partition_rows_local");
+            const int no = (int)sz[0], ng = (int)sz[1], nn = (int)sz[3];
+            std::vector<int32_t> l2g((size_t)no + ng), rp((size_t)no + 1), ci((size_t)sz[2]), nbr((size_t)nn), ro((size_t)nn), rc((size_t)nn),
+                sp((size_t)nn + 1), si((size_t)sz[4]);
+            rank_check(ffcuda_partition_rows_local(n, A->p, A->j, r, N, sz, l2g.data(), rp.data(), ci.data(), nbr.data(), ro.data(), rc.data(),
+                                                   sp.data(), si.data()),
+                       nullptr, "ffcuda_partition_rows_local");
+            dfirst[r] = (int)sz[5];
+            rank_check(ffcuda_matrix_from_csr_distributed(g_gang[r], no, no + ng, sz[2], rp.data(), ci.data(), A->aij + A->p[sz[5]], nn,
+                                                          nbr.data(), ro.data(), rc.data(), sp.data(), si.data(), &dmat[r]),
+                       g_gang[r], "ffcuda_matrix_from_csr_distributed");
+        });
+        mk.mark("row blocks on the GPUs");
+        if (g_verbose) cout << "  -- ffcuda: matrix " << n << " x " << n << " shared out over " << N << " GPUs:" << mk.line << endl;
+    }
     void upload()
     {
+        release_dist();
         release_resident(dev);
         A->CSR(); // sorted, p[] built (HashMatrix.cpp:859-876)
         if (A->half) { // sym=1: entries (i, j <= i); expanded to the full symmetric matrix on the way in
@@ -1421,6 +1541,10 @@ class SolverCudaCG : public VirtualSolver<int, double> {
     {
         if (hostcg) return; // works on the host matrix
         const bool num = A->GetReDoNumerics(), sym = A->GetReDoSymbolic();
+        if (want_gang()) {
+            if (dmat.empty() || num || sym) upload_dist();
+            return;
+        }
         if (!dev.A || num || sym) upload(); // the script changed the matrix after it was assembled
     }
     void dosolver(double *x, double *b, int N, int trans)
@@ -1430,20 +1554,33 @@ class SolverCudaCG : public VirtualSolver<int, double> {
             return;
         }
         (void)trans; // A'^-1 with CG: the matrix is symmetric by the user's contract (the reference multiplies by A^T, the same)
-        if (!dev.A) upload();
+        const bool gang = want_gang();
+        if (gang && dmat.empty()) upload_dist();
+        if (!gang && !dev.A) upload();
         if (getnbiter) *getnbiter = 0;
         int err = 0;
         for (int k = 0, oo = 0; k < N; ++k, oo += A->n) {
             int iters = 0, conv = 0;
             double gcg = 0;
-            if (ffcuda_cg_host(dev.A, b + oo, x + oo, eps, itermax, tgv, &iters, &conv, &gcg) != 0) fail("ffcuda_cg_host");
+            if (gang) { // every GPU iterates on its rows; the scalars are the same on all of them
+                std::vector<int> its((size_t)g_ngpu, 0), cv((size_t)g_ngpu, 0);
+                std::vector<double> gg((size_t)g_ngpu, 0.);
+                on_ranks(g_ngpu, [&](int r) {
+                    rank_check(ffcuda_cg_host(dmat[r], b + oo + dfirst[r], x + oo + dfirst[r], eps, itermax, tgv, &its[r], &cv[r], &gg[r]), g_gang[r],
+                               "ffcuda_cg_host");
+                });
+                iters = its[0];
+                conv = cv[0];
+                gcg = gg[0];
+            } else if (ffcuda_cg_host(dev.A, b + oo, x + oo, eps, itermax, tgv, &iters, &conv, &gcg) != 0) fail("ffcuda_cg_host");
             if (verb || g_verbose)
-                cout << " GC (ffcuda): " << (conv ? "converge" : "NO convergence") << " after " << iters << " g=" << gcg << endl;
+                cout << " GC (ffcuda" << (gang ? ", " + std::to_string(g_ngpu) + " GPUs" : std::string()) << "): "
+                     << (conv ? "converge" : "NO convergence") << " after " << iters << " g=" << gcg << endl;
             if (!conv) err++;
             else if (getnbiter) *getnbiter += iters;
             if (veps) { // what FreeFEM's SolverCG hands back: the absolute threshold ConjugueGradient stopped on (CG.cpp:226)
                 double eps2 = 0;
-                if (eps > 0 && ffcuda_cg_stop_threshold(dev.A, &eps2) == 0) *veps = sqrt(eps2);
+                if (eps > 0 && ffcuda_cg_stop_threshold(gang ? dmat[0] : dev.A, &eps2) == 0) *veps = sqrt(eps2);
                 else *veps = eps;
             }
         }
@@ -1454,6 +1591,7 @@ class SolverCudaCG : public VirtualSolver<int, double> {
     }
     ~SolverCudaCG()
     {
+        release_dist();
         release_resident(dev);
         delete hostcg;
     }
@@ -1491,15 +1629,28 @@ class SolverCudaGMRES : public SolverCudaCG {
             host->dosolver(x, b, N, trans);
             return;
         }
-        if (!dev.A) upload();
+        const bool gang = want_gang();
+        if (gang && dmat.empty()) upload_dist();
+        if (!gang && !dev.A) upload();
         if (getnbiter) *getnbiter = 0;
         int err = 0;
         for (int k = 0, oo = 0; k < N; ++k, oo += A->n) {
             int iters = 0, conv = 0;
             double rel = 0;
-            if (ffcuda_gmres_host(dev.A, b + oo, x + oo, eps, itermax, restart, tgv, &iters, &conv, &rel) != 0) fail("ffcuda_gmres_host");
+            if (gang) {
+                std::vector<int> its((size_t)g_ngpu, 0), cv((size_t)g_ngpu, 0);
+                std::vector<double> rr((size_t)g_ngpu, 0.);
+                on_ranks(g_ngpu, [&](int r) {
+                    rank_check(ffcuda_gmres_host(dmat[r], b + oo + dfirst[r], x + oo + dfirst[r], eps, itermax, restart, tgv, &its[r], &cv[r], &rr[r]),
+                               g_gang[r], "ffcuda_gmres_host");
+                });
+                iters = its[0];
+                conv = cv[0];
+                rel = rr[0];
+            } else if (ffcuda_gmres_host(dev.A, b + oo, x + oo, eps, itermax, restart, tgv, &iters, &conv, &rel) != 0) fail("ffcuda_gmres_host");
             if (verb || g_verbose)
-                cout << "  **  fgmres (ffcuda) " << (conv ? "has converged in " : "has not converged in ") << iters
+                cout << "  **  fgmres (ffcuda" << (gang ? ", " + std::to_string(g_ngpu) + " GPUs" : std::string()) << ") "
+                     << (conv ? "has converged in " : "has not converged in ") << iters
                      << " iterations The relative residual is " << rel << endl;
             if (!conv) err++;
             if (getnbiter) *getnbiter = iters;
@@ -2010,6 +2161,8 @@ static void Load_Init()
     g_check = env_on("FFCUDA_CHECK");
     if (const char *e = getenv("FFCUDA_SAMPLE_MIN")) g_sample_min = atoi(e); // (testing knobs of the coefficient grouping)
     if (const char *e = getenv("FFCUDA_SAMPLE_N")) g_sample_n = atoi(e);
+    if (const char *e = getenv("FFCUDA_NGPU")) g_ngpu = std::max(1, std::min(16, atoi(e)));
+    if (const char *e = getenv("FFCUDA_NGPU_MIN_N")) g_ngpu_min_n = atol(e);
     if (env_on("FFCUDA_DISABLE")) {
         if (verbosity) cout << " load: ffcuda disabled by FFCUDA_DISABLE" << endl;
         return;

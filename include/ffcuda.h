@@ -337,6 +337,22 @@ int ffcuda_partition_local_nodes(int nloc, int nnodes, int nt, const int32_t *el
  * nt_local x nloc LOCAL node ids (owned nodes first, ghosts grouped by owner rank), lists as ffcuda_partition_local_nodes
  * returns them.  Rows = owned nodes, columns = local nodes; ffcuda_spmv / ffcuda_cg / ffcuda_gmres exchange the ghost
  * nodes. */
+/* A host CSR matrix (n x n, sorted rows) shared out by contiguous row blocks - rank r owns the rows [n r / nranks, n (r+1) / nranks):
+ * the local problem of `rank` (host arithmetic only).  sizes8 = { owned rows, ghosts, local nnz, neighbours, total send count,
+ * first owned row, 0, 0 }; call once with the arrays NULL for the sizes, then with l2g[owned + ghosts] (local -> global dof),
+ * lrowptr[owned + 1], lcolind[local nnz] (local numbering; the values are the slice vals[rowptr[first] ...] of the caller's
+ * array), nbr / recv_off / recv_cnt[neighbours], send_ptr[neighbours + 1], send_idx[total send count]. */
+int ffcuda_partition_rows_local(int n, const int32_t *rowptr, const int32_t *colind, int rank, int nranks, int64_t *sizes8,
+                                int32_t *l2g, int32_t *lrowptr, int32_t *lcolind, int32_t *nbr, int32_t *recv_off, int32_t *recv_cnt,
+                                int32_t *send_ptr, int32_t *send_idx);
+/* The rows of one rank of a matrix shared out by rows, from host CSR arrays in LOCAL numbering (owned dofs first: column i is
+ * row i; then the ghost dofs grouped by owner rank) with its halo lists in the form ffcuda_partition_local returns them
+ * (an empty range in one direction is allowed - non-symmetric structure - but both ranks must list each other).  What the
+ * FreeFEM plugin uses to solve on several GPUs a matrix that lives on the host (FFCUDA_NGPU). */
+int ffcuda_matrix_from_csr_distributed(ffcuda_ctx *ctx, int n_owned, int ncols, int64_t nnz, const int32_t *rowptr,
+                                       const int32_t *colind, const double *vals, int nnbr, const int32_t *nbr,
+                                       const int32_t *recv_off, const int32_t *recv_cnt, const int32_t *send_ptr,
+                                       const int32_t *send_idx, ffcuda_matrix **out);
 int ffcuda_space_create_distributed(ffcuda_mesh *m, int order, int ncomp, const int32_t *elem2node, int nnodes_owned,
                                     int nnodes_local, int nnbr, const int32_t *nbr, const int32_t *recv_off, const int32_t *recv_cnt,
                                     const int32_t *send_ptr, const int32_t *send_idx, ffcuda_space **out);

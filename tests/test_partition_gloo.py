@@ -327,3 +327,58 @@ def test_node_partition_p2_local_problem():
         Aref.sort_indices()
         assert np.array_equal(Al.indptr, Aref.indptr) and np.array_equal(Al.indices, Aref.indices)
         assert np.max(np.abs(Al.data - Aref.data)) <= 1e-13 * np.abs(Aref.data).max()
+
+
+@pytest.mark.parametrize("world,structure", [(2, "sym"), (3, "sym"), (4, "nonsym")])
+def test_row_block_partition_of_a_host_matrix(world, structure):
+    """ffcuda_partition_rows_local (what the plugin does with a MatriceMorse on several GPUs): the blocks tile the rows, ghost
+    ranges are grouped by owner in ascending order, every send list is the neighbour's ghost range in its order, neighbours
+    list each other even when the structure is not symmetric, and block products with exchanged ghosts give the global
+    product."""
+    import numpy as np
+    import scipy.sparse as sps
+
+    sys.path.insert(0, os.path.join(ROOT, "freefem-sources_b200"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import ffcuda
+    import ff_cases as fc
+    import oracle_lib as ol
+
+    m = ol.cube(4, 3, 6)
+    n = m["xyz"].shape[0]
+    qp, qw = ol.quadrature(3, "qfV5")
+    gi, gj, ga = ol.assemble_coo(m, 1, 1, None, fc.LAP3 + [(0, fc.DX, 0, fc.ID, 3.0)], qp, qw)
+    A = sps.coo_matrix((ga, (gi, gj)), shape=(n, n)).tocsr()
+    if structure == "nonsym":   # lower triangle only: a block needs nothing from the blocks after it, they need its values
+        coo = A.tocoo()
+        keep = coo.col <= coo.row
+        A = sps.coo_matrix((coo.data[keep], (coo.row[keep], coo.col[keep])), shape=(n, n)).tocsr()
+    A.sort_indices()
+    rp, ci, va = A.indptr.astype(np.int32), A.indices.astype(np.int32), A.data
+    Ls = [ffcuda.partition_rows_local(n, rp, ci, r, world) for r in range(world)]
+    assert [L["first"] for L in Ls] == [n * r // world for r in range(world)]
+    assert sum(L["nowned"] for L in Ls) == n
+    xg = np.sin(np.arange(n, dtype=np.float64))
+    y = A @ xg
+    for r, L in enumerate(Ls):
+        no, l2g, lo = L["nowned"], L["l2g"], L["first"]
+        assert np.array_equal(l2g[:no], np.arange(lo, lo + no)) and np.all(np.diff(l2g[no:]) > 0)
+        assert np.array_equal(l2g[L["colind"]], ci[rp[lo]:rp[lo + no]])
+        assert np.array_equal(L["rowptr"], rp[lo:lo + no + 1] - rp[lo])
+        off = no
+        for x, o in enumerate(L["nbr"]):
+            assert L["recv_off"][x] == off
+            off += L["recv_cnt"][x]
+            gh = l2g[L["recv_off"][x]:L["recv_off"][x] + L["recv_cnt"][x]]
+            assert np.all((gh >= Ls[o]["first"]) & (gh < Ls[o]["first"] + Ls[o]["nowned"]))
+            other = Ls[int(o)]
+            assert r in other["nbr"]                                   # mutual, whatever the direction of the data
+            yx = list(other["nbr"]).index(r)
+            sent = other["l2g"][other["send_idx"][other["send_ptr"][yx]:other["send_ptr"][yx + 1]]]
+            assert np.array_equal(sent, gh)
+        assert off == len(l2g)
+        # the block product with the exchanged ghost values
+        Al = sps.csr_matrix((va[rp[lo]:rp[lo + no]], L["colind"], L["rowptr"]), shape=(no, len(l2g)))
+        assert np.max(np.abs(Al @ xg[l2g] - y[lo:lo + no])) <= 1e-13 * np.abs(y).max()
+    if structure == "nonsym":
+        assert any(0 in L["recv_cnt"] or 0 in np.diff(L["send_ptr"]) for L in Ls)   # a one-way neighbour exists

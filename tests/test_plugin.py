@@ -620,3 +620,32 @@ def test_plugin_mesh_generators_fall_back_without_a_device_or_for_options():
     assert rc == 0, out[-2000:]
     assert "SIZES 72 48" in out
     assert out.count("left to FreeFEM") == 2
+
+
+# ---- several GPUs driven from the one FreeFEM process (FFCUDA_NGPU): the solvers share the matrix out by row blocks ------------
+NGPU_CASES = {
+    "cg": script(3, "cube(9,8,10)", "P1", LAP3, "1.*v", "on(1,2,3,4,5,6,u=0)", eps="1e-14"),
+    "cg_p2_vector": script(3, "cube(2,3,2)", "[P2,P2,P2]", LAME, "-0.05*v3", "on(1,u1=0,u2=0,u3=0)", pre=LAME_PRE,
+                           unk="[u1,u2,u3]", tst="[v1,v2,v3]", eps="1e-14"),
+    "gmres": script(3, "cube(8,7,9)", "P1", LAP3 + "+8.*dx(u)*v+3.*dy(u)*v-2.*dz(u)*v", "1.*v", "on(1,2,3,4,5,6,u=0)", eps="1e-14",
+                    solver="GMRES,dimKrylov=30"),
+}
+
+
+@needs_ff
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(NGPU_CASES))
+def test_plugin_solves_on_two_gpus(name):
+    """FFCUDA_NGPU=2: `u[] = A^-1*b` runs the distributed CG / GMRES on two GPUs from the one FreeFem++ process (row blocks of the
+    host MatriceMorse, one host thread per GPU, ghost exchange + all-reduced dot products); same converged solution as
+    FreeFEM's own solver.  Self-skips on a box with one device."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 CUDA devices")
+    src = NGPU_CASES[name]
+    _, out, gpu = run_ff(src, {"FFCUDA_NGPU": "2", "FFCUDA_VERBOSE": "1"})
+    assert "2 GPUs driven from this process" in out and "shared out over 2 GPUs" in out
+    assert ("fgmres (ffcuda, 2 GPUs)" if "GMRES" in src else "GC (ffcuda, 2 GPUs)") in out
+    _, _, cpu = run_ff(src, {"FFCUDA_DISABLE": "1"})
+    compare(gpu, cpu, tight=True)
