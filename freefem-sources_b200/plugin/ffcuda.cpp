@@ -176,7 +176,9 @@ bool gang_ready()
     std::vector<ffcuda_ctx *> gang((size_t)g_ngpu, nullptr);
     gang[0] = context();
     bool ok = true;
+    Marks mk;
     for (int r = 1; r < g_ngpu && ok; ++r) ok = ffcuda_ctx_create(base + r, &gang[r]) == 0;
+    mk.mark("contexts");
     unsigned char id[128];
     ok = ok && ffcuda_comm_unique_id(id) == 0;
     if (ok) {
@@ -185,6 +187,7 @@ bool gang_ready()
         } catch (...) {
             ok = false;
         }
+        mk.mark("communicator + peer mailboxes");
     }
     if (!ok) {
         for (int r = 1; r < g_ngpu; ++r)
@@ -195,7 +198,8 @@ bool gang_ready()
         return false;
     }
     g_gang = gang;
-    if (g_verbose) cout << "  -- ffcuda: " << g_ngpu << " GPUs driven from this process (one host thread per GPU during distributed solves)" << endl;
+    if (g_verbose)
+        cout << "  -- ffcuda: " << g_ngpu << " GPUs driven from this process (one host thread per GPU during distributed solves):" << mk.line << endl;
     return true;
 }
 
@@ -1565,10 +1569,13 @@ class SolverCudaCG : public VirtualSolver<int, double> {
             if (gang) { // every GPU iterates on its rows; the scalars are the same on all of them
                 std::vector<int> its((size_t)g_ngpu, 0), cv((size_t)g_ngpu, 0);
                 std::vector<double> gg((size_t)g_ngpu, 0.);
+                Marks mk;
                 on_ranks(g_ngpu, [&](int r) {
                     rank_check(ffcuda_cg_host(dmat[r], b + oo + dfirst[r], x + oo + dfirst[r], eps, itermax, tgv, &its[r], &cv[r], &gg[r]), g_gang[r],
                                "ffcuda_cg_host");
                 });
+                mk.mark("CG");
+                if (g_verbose) cout << "  -- ffcuda: solve on " << g_ngpu << " GPUs:" << mk.line << endl;
                 iters = its[0];
                 conv = cv[0];
                 gcg = gg[0];
@@ -2175,6 +2182,13 @@ static void Load_Init()
         const char *d = getenv("FFCUDA_DEVICE");
         ffcuda_ctx *c = nullptr;
         if (ffcuda_ctx_create(d ? atoi(d) : 0, &c) == 0) g_ctx = c;
+        // ... and with FFCUDA_NGPU > 1 the other contexts and the communicator (seconds of NCCL start-up), for the same reason
+        if (g_ctx && g_ngpu > 1) {
+            try {
+                gang_ready();
+            } catch (...) { // (FFCUDA_STRICT turns the notice into an error: raised again by the first solve)
+            }
+        }
     }
     // 1. matrices: "<-" constructs (init = 1), "=" assigns (init = 0)  (fflib/lgfem.cpp:6669,6673,6823,6826)
     TheOperators->Add("<-", new CudaMatrixOp<Mesh, v_fes>(1), new CudaMatrixOp<Mesh3, v_fes3>(1));
