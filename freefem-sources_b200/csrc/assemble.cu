@@ -98,6 +98,19 @@ static void fill_labels(int nlab, const int32_t *labels, int &onlab, int *olabel
     for (int i = 0; i < nlab; ++i) olabels[i] = labels[i];
 }
 
+// A table of the caller (cq / fq / gq of the entries below): a HOST array, copied to the device here, or a DEVICE pointer
+// (ffcuda_vec_ptr of a table formed by ffcuda_fe_table), used where it lies.
+static const double *table_on_device(const double *t, size_t count, DBuf<double> &buf, cudaStream_t st)
+{
+    cudaPointerAttributes at;
+    const cudaError_t e = cudaPointerGetAttributes(&at, t);
+    if (e != cudaSuccess) (void)cudaGetLastError(); // (plain host memory is reported as an error by old drivers)
+    else if (at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged) return t;
+    buf.alloc(count);
+    FF_CUDA(cudaMemcpyAsync(buf.p, t, buf.bytes(), cudaMemcpyHostToDevice, st));
+    return buf.p;
+}
+
 // ----------------------------------------------------------------------------------------------------
 // device: geometry
 // ----------------------------------------------------------------------------------------------------
@@ -1161,12 +1174,11 @@ static int assemble_bilinear_impl(ffcuda_matrix *A, ffcuda_space *s, int nterms,
             }
             DBuf<double> dwl, dcq;
             dwl.alloc(wl.size());
-            dcq.alloc((size_t)nt * nq);
             emom.alloc((size_t)nt * 24);
             FF_CUDA(cudaMemcpyAsync(dwl.p, wl.data(), dwl.bytes(), cudaMemcpyHostToDevice, ctx->stream));
-            FF_CUDA(cudaMemcpyAsync(dcq.p, cq, dcq.bytes(), cudaMemcpyHostToDevice, ctx->stream));
+            const double *pcq = table_on_device(cq, (size_t)nt * nq, dcq, ctx->stream);
             ff_launch(ctx, "asm_coef_moments", [&] {
-                k_emom<<<ff_blocks(nt, 128), 128, wl.size() * sizeof(double), ctx->stream>>>(nt, nq, dim + 1, dwl.p, dcq.p, emom.p);
+                k_emom<<<ff_blocks(nt, 128), 128, wl.size() * sizeof(double), ctx->stream>>>(nt, nq, dim + 1, dwl.p, pcq, emom.p);
             });
             FF_CUDA(cudaStreamSynchronize(ctx->stream)); // cq is the caller's pageable memory
             fast = false;
@@ -1176,6 +1188,7 @@ static int assemble_bilinear_impl(ffcuda_matrix *A, ffcuda_space *s, int nterms,
     } else {
         // P2 with a coefficient at the quadrature nodes: the table w_q d^sa phi_a(q) d^sb phi_b(q) and the values go to the device
         DBuf<double> dT, dcq;
+        const double *pcq = nullptr;
         if (cq) {
             std::vector<double> T((size_t)nq * nloc * nloc * ns * ns);
             for (int q = 0; q < nq; ++q) {
@@ -1188,17 +1201,16 @@ static int assemble_bilinear_impl(ffcuda_matrix *A, ffcuda_space *s, int nterms,
                                 T[((((size_t)q * nloc + a) * nloc + b) * ns + sa) * ns + sb] = qw[q] * B[a][sa] * B[b][sb];
             }
             dT.alloc(T.size());
-            dcq.alloc((size_t)s->mesh->nt * nq);
             FF_CUDA(cudaMemcpyAsync(dT.p, T.data(), dT.bytes(), cudaMemcpyHostToDevice, ctx->stream));
-            FF_CUDA(cudaMemcpyAsync(dcq.p, cq, dcq.bytes(), cudaMemcpyHostToDevice, ctx->stream));
+            pcq = table_on_device(cq, (size_t)s->mesh->nt * nq, dcq, ctx->stream);
             FF_CUDA(cudaStreamSynchronize(ctx->stream)); // both sources are pageable host memory
         }
         if (P->pos8.p) {
-            if (dim == 3) dispatch_p2<3, uint8_t>(ctx, A, s, F, Rg.p, P->pos8.p, accumulate, dT.p, dcq.p, nq);
-            else dispatch_p2<2, uint8_t>(ctx, A, s, F, Rg.p, P->pos8.p, accumulate, dT.p, dcq.p, nq);
+            if (dim == 3) dispatch_p2<3, uint8_t>(ctx, A, s, F, Rg.p, P->pos8.p, accumulate, dT.p, pcq, nq);
+            else dispatch_p2<2, uint8_t>(ctx, A, s, F, Rg.p, P->pos8.p, accumulate, dT.p, pcq, nq);
         } else {
-            if (dim == 3) dispatch_p2<3, uint16_t>(ctx, A, s, F, Rg.p, P->pos16.p, accumulate, dT.p, dcq.p, nq);
-            else dispatch_p2<2, uint16_t>(ctx, A, s, F, Rg.p, P->pos16.p, accumulate, dT.p, dcq.p, nq);
+            if (dim == 3) dispatch_p2<3, uint16_t>(ctx, A, s, F, Rg.p, P->pos16.p, accumulate, dT.p, pcq, nq);
+            else dispatch_p2<2, uint16_t>(ctx, A, s, F, Rg.p, P->pos16.p, accumulate, dT.p, pcq, nq);
         }
     }
     // Rg is released through the stream-ordered allocator: no synchronisation needed
@@ -1735,21 +1747,18 @@ static void bnd_bilinear_general(ffcuda_matrix *A, ffcuda_space *s, int nterms, 
     meas.alloc((size_t)nbe);
     dG.alloc(1);
     FF_CUDA(cudaMemcpyAsync(dG.p, Gp.get(), sizeof(BndGenParams), cudaMemcpyHostToDevice, st));
-    if (cq) {
-        dC.alloc((size_t)nbe * nq);
-        FF_CUDA(cudaMemcpyAsync(dC.p, cq, dC.bytes(), cudaMemcpyHostToDevice, st));
-    }
+    const double *pC = cq ? table_on_device(cq, (size_t)nbe * nq, dC, st) : nullptr;
     bnd_measures(ctx, m, Bp, meas.p);
     const int nrows = s->nnodes_owned;
     ff_launch(ctx, "bnd_bilinear_gen", [&] {
         if (dim == 3)
             k_bnd_bilinear_gen<3><<<ff_blocks(nrows, 128), 128, 0, st>>>(nrows, s->bnd2_ptr.p, s->bnd2_items.p, m->belem.p, m->bface.p, meas.p,
                                                                        m->conn.p, m->xyz.p, m->vstride, s->e2n, s->nloc, s->order, nc,
-                                                                       P->nrowptr.p, P->ncol.p, dG.p, dC.p, A->vals.p);
+                                                                       P->nrowptr.p, P->ncol.p, dG.p, pC, A->vals.p);
         else
             k_bnd_bilinear_gen<2><<<ff_blocks(nrows, 128), 128, 0, st>>>(nrows, s->bnd2_ptr.p, s->bnd2_items.p, m->belem.p, m->bface.p, meas.p,
                                                                        m->conn.p, m->xyz.p, m->vstride, s->e2n, s->nloc, s->order, nc,
-                                                                       P->nrowptr.p, P->ncol.p, dG.p, dC.p, A->vals.p);
+                                                                       P->nrowptr.p, P->ncol.p, dG.p, pC, A->vals.p);
     });
     FF_CUDA(cudaStreamSynchronize(st)); // host buffers (Gp, cq) are the caller's / ours on the stack
 }
@@ -2024,16 +2033,15 @@ extern "C" int ffcuda_assemble_linear_qvalues(ffcuda_vec *b, ffcuda_space *s, in
     cudaStream_t st = ctx->stream;
     DBuf<double> dW, dF, G;
     dW.alloc(wphi.size());
-    dF.alloc((size_t)nc * nt * nq);
     G.alloc((size_t)nt * nloc * nc);
     FF_CUDA(cudaMemcpyAsync(dW.p, wphi.data(), dW.bytes(), cudaMemcpyHostToDevice, st));
-    FF_CUDA(cudaMemcpyAsync(dF.p, fq, dF.bytes(), cudaMemcpyHostToDevice, st));
+    const double *pF = table_on_device(fq, (size_t)nc * nt * nq, dF, st);
     const size_t shmem = wphi.size() * sizeof(double);
     ff_launch(ctx, "rhs_qvalues_elem", [&] {
         if (dim == 3)
-            k_rhs_qvalues_elem<3><<<ff_blocks(nt, 128), 128, shmem, st>>>(nt, m->conn.p, m->xyz.p, m->vstride, nloc, nc, nq, dW.p, dF.p, G.p);
+            k_rhs_qvalues_elem<3><<<ff_blocks(nt, 128), 128, shmem, st>>>(nt, m->conn.p, m->xyz.p, m->vstride, nloc, nc, nq, dW.p, pF, G.p);
         else
-            k_rhs_qvalues_elem<2><<<ff_blocks(nt, 128), 128, shmem, st>>>(nt, m->conn.p, m->xyz.p, m->vstride, nloc, nc, nq, dW.p, dF.p, G.p);
+            k_rhs_qvalues_elem<2><<<ff_blocks(nt, 128), 128, shmem, st>>>(nt, m->conn.p, m->xyz.p, m->vstride, nloc, nc, nq, dW.p, pF, G.p);
     });
     const int nrows = s->nnodes_owned;
     const IncView V = ff_view(s->incidence);
@@ -2145,13 +2153,12 @@ extern "C" int ffcuda_assemble_linear_boundary_qvalues(ffcuda_vec *b, ffcuda_spa
     DBuf<double> meas, dW, dG;
     meas.alloc((size_t)nbe);
     dW.alloc(wphi.size());
-    dG.alloc((size_t)nc * nbe * nq);
     FF_CUDA(cudaMemcpyAsync(dW.p, wphi.data(), dW.bytes(), cudaMemcpyHostToDevice, st));
-    FF_CUDA(cudaMemcpyAsync(dG.p, gq, dG.bytes(), cudaMemcpyHostToDevice, st));
+    const double *pG = table_on_device(gq, (size_t)nc * nbe * nq, dG, st);
     bnd_measures(ctx, m, Bp, meas.p);
     const int nrows = s->nnodes_owned;
     ff_launch(ctx, "bnd_gather_q", [&] {
-        k_bnd_gather_q<<<ff_blocks(nrows, 256), 256, 0, st>>>(nrows, s->bnd_ptr.p, s->bnd_items.p, m->bface.p, meas.p, nc, nq, nloc, nbe, dW.p, dG.p,
+        k_bnd_gather_q<<<ff_blocks(nrows, 256), 256, 0, st>>>(nrows, s->bnd_ptr.p, s->bnd_items.p, m->bface.p, meas.p, nc, nq, nloc, nbe, dW.p, pG,
                                                             b->d.p, accumulate);
     });
     FF_CUDA(cudaStreamSynchronize(st)); // gq is the caller's pageable memory
@@ -2204,18 +2211,17 @@ extern "C" int ffcuda_assemble_bilinear_boundary_qcoef(ffcuda_matrix *A, ffcuda_
     DBuf<double> meas, dW, dC;
     meas.alloc((size_t)nbe);
     dW.alloc(wpp.size());
-    dC.alloc((size_t)nbe * nq);
     FF_CUDA(cudaMemcpyAsync(dW.p, wpp.data(), dW.bytes(), cudaMemcpyHostToDevice, st));
-    FF_CUDA(cudaMemcpyAsync(dC.p, cq, dC.bytes(), cudaMemcpyHostToDevice, st));
+    const double *pC = table_on_device(cq, (size_t)nbe * nq, dC, st);
     bnd_measures(ctx, m, Bp, meas.p);
     const int nrows = s->nnodes_owned;
     ff_launch(ctx, "bnd_bilinear_q", [&] {
         if (dim == 3)
             k_bnd_bilinear_q<3><<<ff_blocks(nrows, 128), 128, 0, st>>>(nrows, s->bnd_ptr.p, s->bnd_items.p, m->belem.p, m->bface.p, meas.p, s->e2n,
-                                                                     nloc, s->order, nc, nq, P->nrowptr.p, P->ncol.p, dW.p, dC.p, Bq, A->vals.p);
+                                                                     nloc, s->order, nc, nq, P->nrowptr.p, P->ncol.p, dW.p, pC, Bq, A->vals.p);
         else
             k_bnd_bilinear_q<2><<<ff_blocks(nrows, 128), 128, 0, st>>>(nrows, s->bnd_ptr.p, s->bnd_items.p, m->belem.p, m->bface.p, meas.p, s->e2n,
-                                                                     nloc, s->order, nc, nq, P->nrowptr.p, P->ncol.p, dW.p, dC.p, Bq, A->vals.p);
+                                                                     nloc, s->order, nc, nq, P->nrowptr.p, P->ncol.p, dW.p, pC, Bq, A->vals.p);
     });
     FF_CUDA(cudaStreamSynchronize(st)); // cq is the caller's pageable memory
     FF_API_END(s ? s->ctx : nullptr)
@@ -2302,19 +2308,18 @@ extern "C" int ffcuda_assemble_linear_qterms(ffcuda_vec *b, ffcuda_space *s, int
     cudaStream_t st = ctx->stream;
     DBuf<double> dW, dF, G;
     dW.alloc(wB.size());
-    dF.alloc((size_t)nc * ns * nt * nq);
     G.alloc((size_t)nt * nloc * nc);
     FF_CUDA(cudaMemcpyAsync(dW.p, wB.data(), dW.bytes(), cudaMemcpyHostToDevice, st));
-    FF_CUDA(cudaMemcpyAsync(dF.p, fq, dF.bytes(), cudaMemcpyHostToDevice, st));
+    const double *pF = table_on_device(fq, (size_t)nc * ns * nt * nq, dF, st);
     const size_t shmem = wB.size() * sizeof(double);
     FF_REQUIRE(shmem <= 96 * 1024, "quadrature rule too large for the shared-memory basis table");
     ff_launch(ctx, "rhs_qterms_elem", [&] {
         if (dim == 3) {
             FF_CUDA(cudaFuncSetAttribute(k_rhs_qterms_elem<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-            k_rhs_qterms_elem<3><<<ff_blocks(nt, 128), 128, shmem, st>>>(nt, m->conn.p, m->xyz.p, m->vstride, nloc, nc, nq, dW.p, dF.p, G.p);
+            k_rhs_qterms_elem<3><<<ff_blocks(nt, 128), 128, shmem, st>>>(nt, m->conn.p, m->xyz.p, m->vstride, nloc, nc, nq, dW.p, pF, G.p);
         } else {
             FF_CUDA(cudaFuncSetAttribute(k_rhs_qterms_elem<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
-            k_rhs_qterms_elem<2><<<ff_blocks(nt, 128), 128, shmem, st>>>(nt, m->conn.p, m->xyz.p, m->vstride, nloc, nc, nq, dW.p, dF.p, G.p);
+            k_rhs_qterms_elem<2><<<ff_blocks(nt, 128), 128, shmem, st>>>(nt, m->conn.p, m->xyz.p, m->vstride, nloc, nc, nq, dW.p, pF, G.p);
         }
     });
     const int nrows = s->nnodes_owned;
@@ -2324,4 +2329,158 @@ extern "C" int ffcuda_assemble_linear_qterms(ffcuda_vec *b, ffcuda_space *s, int
     });
     FF_CUDA(cudaStreamSynchronize(st)); // fq is the caller's pageable memory
     FF_API_END(s ? s->ctx : nullptr)
+}
+
+// ----------------------------------------------------------------------------------------------------
+// FE functions as data of a form, handed over as DOF ARRAYS: int3d(Th)(f v), int3d(Th)(kappa grad u . grad v),
+// the residual int3d(Th)(dx(uk) dx(v) + ...) of a Newton step with f, kappa, uk P0 / P1 / P2 functions on the mesh of the
+// form.  The reference evaluates such a coefficient through the interpreter at every quadrature node of every element
+// (Element_Op / Element_rhs, fflib/problem.cpp:6380-6407, :7951-7975, calling pfer2R / pf3r2R -> FElement::operator()(PHat,
+// u, comp, op), femlib/FESpace.cpp:1078-1099, :1637-1654, femlib/P012_3d.cpp:98-122): sum_a u[K(a)] d^op phi_a(PHat).  Here
+// the same sum is formed on the device from the dof vector, one thread per (unit, node), and lands in the table layout the
+// q-table entries above consume (they take it where it lies: table_on_device).
+// ----------------------------------------------------------------------------------------------------
+struct FeTabLabels {
+    int nlab; // < 0: every unit
+    int labels[MAXBL];
+};
+template <int DIM, bool BND>
+__global__ void __launch_bounds__(256)
+k_fe_table(size_t nitems, int nq, int nloc, int slot /* 0: value, 1..DIM: d/dx_slot */, const int32_t *__restrict__ conn,
+           const double *__restrict__ xyz, int vstride, const int32_t *__restrict__ ulab, const int32_t *__restrict__ belem,
+           const int32_t *__restrict__ bface, const int32_t *__restrict__ e2n /* nt x nloc or null */, int dstride, int doff,
+           const double *__restrict__ dofs, const double *__restrict__ Bq /* [face][q][a][4]: value, dhat_1..3 */, double scale,
+           const FeTabLabels L, double *__restrict__ out, int accumulate)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nitems) return;
+    const int u = (int)(i / (size_t)nq), q = (int)(i - (size_t)u * nq);
+    bool in = L.nlab < 0;
+    if (!in) {
+        const int l = ulab[u];
+        for (int j = 0; j < L.nlab; ++j) in |= (L.labels[j] == l);
+    }
+    double val = 0.0;
+    if (in) {
+        const int k = BND ? belem[u] : u, f = BND ? bface[u] : 0;
+        const int32_t *K = conn + (size_t)(DIM + 1) * k;
+        const double *B = Bq + ((size_t)f * nq + q) * nloc * 4;
+        double g[DIM]; // g[r-1] = d lambda_r / d x_slot
+        if (slot > 0) {
+            double X[DIM + 1][DIM], N[DIM + 1][DIM], det;
+#pragma unroll
+            for (int a = 0; a <= DIM; ++a)
+#pragma unroll
+                for (int d = 0; d < DIM; ++d) X[a][d] = xyz[(size_t)K[a] * vstride + d];
+            p1_normals<DIM>(X, N, det);
+            const double rdet = 1.0 / det;
+#pragma unroll
+            for (int r = 1; r <= DIM; ++r) {
+                double nx = N[r][0];
+#pragma unroll
+                for (int d = 1; d < DIM; ++d)
+                    if (slot - 1 == d) nx = N[r][d];
+                g[r - 1] = nx * rdet;
+            }
+        }
+        for (int a = 0; a < nloc; ++a) {
+            const int node = e2n ? e2n[(size_t)k * nloc + a] : (nloc == 1 ? k : K[a]);
+            const double ua = dofs[(size_t)node * dstride + doff];
+            double w;
+            if (slot == 0) w = B[a * 4];
+            else {
+                w = 0.0;
+#pragma unroll
+                for (int r = 1; r <= DIM; ++r) w = fma(B[a * 4 + r], g[r - 1], w);
+            }
+            val = fma(ua, w, val);
+        }
+        val *= scale;
+    }
+    out[i] = accumulate ? out[i] + val : val;
+}
+
+extern "C" int ffcuda_fe_table(ffcuda_mesh *m, int order, const int32_t *e2n, int dstride, int doff, ffcuda_vec *dofs, int op,
+                               int border, int nq, const double *qpts, double scale, int nlab, const int32_t *labels,
+                               ffcuda_vec *table, int64_t offset, int accumulate)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(m && dofs && table && qpts, "ffcuda_fe_table: null argument");
+    FF_REQUIRE(!m->distributed, "ffcuda_fe_table: single-GPU meshes only");
+    FF_REQUIRE(order >= 0 && order <= 2, "ffcuda_fe_table: the function must be P0, P1 or P2 Lagrange");
+    FF_REQUIRE(nq > 0 && nq <= 256, "quadrature rule missing (or more than 256 nodes)");
+    FF_REQUIRE(dstride >= 1 && doff >= 0 && doff < dstride, "ffcuda_fe_table: bad dof stride / offset");
+    ffcuda_ctx *ctx = m->ctx;
+    ff_enter(ctx);
+    const int dim = m->dim, nt = m->nt;
+    const int nloc = order == 0 ? 1 : order == 1 ? dim + 1 : (dim == 3 ? 10 : 6);
+    const int slot = op_slot(dim, op);
+    FF_REQUIRE(order != 2 || e2n, "ffcuda_fe_table: a P2 function needs its element -> node table");
+    const int nunits = border ? m->nbe : nt;
+    FF_REQUIRE(!border || (m->nbe > 0 && m->belem.p && m->bface.p && m->blab.p), "the mesh has no boundary elements");
+    FF_REQUIRE(offset >= 0 && (size_t)offset + (size_t)nunits * nq <= (size_t)table->n, "ffcuda_fe_table: table too short");
+    // the largest node the table refers to must lie inside the dof vector
+    int64_t maxnode = order == 0 ? nt - 1 : m->nv - 1;
+    if (e2n) {
+        maxnode = -1;
+        for (size_t i = 0; i < (size_t)nt * nloc; ++i) {
+            FF_REQUIRE(e2n[i] >= 0, "ffcuda_fe_table: negative node in the element -> node table");
+            maxnode = std::max<int64_t>(maxnode, e2n[i]);
+        }
+    }
+    FF_REQUIRE(maxnode * dstride + doff < (int64_t)dofs->n, "ffcuda_fe_table: dof vector too short for this space");
+    FeTabLabels L;
+    memset(&L, 0, sizeof(L));
+    if (!labels) L.nlab = -1;
+    else {
+        FF_REQUIRE(nlab >= 0 && nlab <= MAXBL, "at most 32 labels per integral");
+        L.nlab = nlab;
+        for (int i = 0; i < nlab; ++i) L.labels[i] = labels[i];
+    }
+    // reference values and derivatives at the nodes of the rule (volume: one "face"; border: PBord of each face)
+    const int nf = border ? dim + 1 : 1;
+    std::vector<double> Bq((size_t)nf * nq * nloc * 4, 0.0);
+    for (int f = 0; f < nf; ++f)
+        for (int q = 0; q < nq; ++q) {
+            double B[10][4];
+            for (int a = 0; a < 10; ++a)
+                for (int s2 = 0; s2 < 4; ++s2) B[a][s2] = 0.0;
+            if (order == 0) B[0][0] = 1.0; // constant on the element: derivatives vanish
+            else if (border) face_ref_basis(dim, order, f, qpts + (size_t)q * (dim - 1), B);
+            else ref_basis(dim, order, qpts + (size_t)q * dim, B);
+            for (int a = 0; a < nloc; ++a)
+                for (int s2 = 0; s2 <= dim; ++s2) Bq[(((size_t)f * nq + q) * nloc + a) * 4 + s2] = B[a][s2];
+        }
+    cudaStream_t st = ctx->stream;
+    DBuf<double> dB;
+    DBuf<int32_t> dE;
+    dB.alloc(Bq.size());
+    FF_CUDA(cudaMemcpyAsync(dB.p, Bq.data(), dB.bytes(), cudaMemcpyHostToDevice, st));
+    if (e2n) {
+        dE.alloc((size_t)nt * nloc);
+        FF_CUDA(cudaMemcpyAsync(dE.p, e2n, dE.bytes(), cudaMemcpyHostToDevice, st));
+    }
+    const size_t nitems = (size_t)nunits * nq;
+    double *out = table->d.p + offset;
+    const int32_t *ulab = border ? m->blab.p : m->elab.p;
+    FF_REQUIRE(L.nlab < 0 || ulab, "ffcuda_fe_table: the mesh carries no labels");
+    if (nitems)
+        ff_launch(ctx, "fe_table", [&] {
+            const int nb = ff_blocks(nitems, 256);
+            if (dim == 3 && border)
+                k_fe_table<3, true><<<nb, 256, 0, st>>>(nitems, nq, nloc, slot, m->conn.p, m->xyz.p, m->vstride, ulab, m->belem.p, m->bface.p, dE.p,
+                                                        dstride, doff, dofs->d.p, dB.p, scale, L, out, accumulate);
+            else if (dim == 3)
+                k_fe_table<3, false><<<nb, 256, 0, st>>>(nitems, nq, nloc, slot, m->conn.p, m->xyz.p, m->vstride, ulab, nullptr, nullptr, dE.p,
+                                                         dstride, doff, dofs->d.p, dB.p, scale, L, out, accumulate);
+            else if (border)
+                k_fe_table<2, true><<<nb, 256, 0, st>>>(nitems, nq, nloc, slot, m->conn.p, m->xyz.p, m->vstride, ulab, m->belem.p, m->bface.p, dE.p,
+                                                        dstride, doff, dofs->d.p, dB.p, scale, L, out, accumulate);
+            else
+                k_fe_table<2, false><<<nb, 256, 0, st>>>(nitems, nq, nloc, slot, m->conn.p, m->xyz.p, m->vstride, ulab, nullptr, nullptr, dE.p,
+                                                         dstride, doff, dofs->d.p, dB.p, scale, L, out, accumulate);
+            FF_CUDA(cudaGetLastError());
+        });
+    FF_CUDA(cudaStreamSynchronize(st)); // Bq and e2n are host memory of this call / of the caller
+    FF_API_END(m ? m->ctx : nullptr)
 }

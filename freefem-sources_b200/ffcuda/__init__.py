@@ -24,7 +24,7 @@ ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_
 ffcuda_assemble_linear ffcuda_assemble_linear_qvalues ffcuda_assemble_linear_qterms ffcuda_assemble_linear_boundary ffcuda_assemble_bilinear_boundary ffcuda_assemble_linear_boundary_qvalues ffcuda_assemble_bilinear_boundary_qcoef ffcuda_bc_from_pairs ffcuda_bc_from_labels ffcuda_bc_count ffcuda_matrix_apply_bc ffcuda_vec_apply_bc
 ffcuda_vec_set_bc_values ffcuda_bc_destroy ffcuda_spmv ffcuda_cg ffcuda_cg_host ffcuda_gmres ffcuda_gmres_host ffcuda_comm_unique_id ffcuda_comm_init
 ffcuda_comm_finalize ffcuda_mesh_cube_distributed ffcuda_mesh_local_to_global ffcuda_quadrature ffcuda_partition_cube
-ffcuda_partition_rcb ffcuda_partition_local ffcuda_matrix_export_device ffcuda_matrix_download_coo ffcuda_matrix_write_morse ffcuda_mesh_adjacency ffcuda_mesh_upload_distributed ffcuda_cg_stop_threshold""".split()
+ffcuda_partition_rcb ffcuda_partition_local ffcuda_matrix_export_device ffcuda_matrix_download_coo ffcuda_matrix_write_morse ffcuda_mesh_adjacency ffcuda_mesh_upload_distributed ffcuda_cg_stop_threshold ffcuda_fe_table""".split()
 
 
 class FfcudaError(RuntimeError):
@@ -158,6 +158,14 @@ def _f64(a):
 
 def _p(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def _table(t):
+    """a q-table argument: a numpy array (host) or a device Vec (its pointer is handed over: the table is used where it lies)"""
+    if isinstance(t, Vec):
+        return t, C.c_void_p(t.ptr())
+    t = _f64(t)
+    return t, _p(t)
 
 
 def _h(obj):
@@ -315,6 +323,16 @@ class Mesh(_Handle):
                                        _p(m["belem"]), _p(m["bface"])), self.ctx.h)
         return m
 
+    def fe_table(self, order, dofs, table, qpts, op=0, border=False, e2n=None, dstride=1, doff=0, scale=1.0, labels=None, offset=0,
+                 accumulate=False):
+        """table[offset + u*nq + q] (+)= scale * d^op f(P_q of unit u) for the P0/P1/P2 function whose dofs are the device Vec `dofs`"""
+        qpts, e2n, lab = _f64(qpts), _i32(e2n), _i32(labels)
+        dim = self.info()[0]
+        nq = qpts.size // (dim - 1 if border else dim)
+        _ck(lib().ffcuda_fe_table(_h(self), int(order), _p(e2n), int(dstride), int(doff), _h(dofs), int(op), int(bool(border)), int(nq),
+                                  _p(qpts), C.c_double(scale), 0 if lab is None else len(lab), _p(lab), _h(table), C.c_int64(offset),
+                                  int(accumulate)), self.ctx.h)
+
     def adjacency(self):
         """element adjacency as GenericMesh::BuildAdj numbers it: adj[(dim+1)*k+i] = (dim+1)*k'+i' | -1 (boundary) | -2"""
         dim, _, nt, _ = self.info()
@@ -401,18 +419,21 @@ class Space(_Handle):
 
     def assemble_linear_qvalues(self, b, qpts, qw, fq, accumulate=False):
         """b (+)= int(f v) with f given at the quadrature nodes: fq[c, k, q] (ncomp x nt x nq)"""
-        qpts, qw, fq = _f64(qpts), _f64(qw), _f64(fq)
-        _ck(lib().ffcuda_assemble_linear_qvalues(_h(b), _h(self), len(qw), _p(qpts), _p(qw), _p(fq), int(accumulate)), self.ctx.h)
+        qpts, qw = _f64(qpts), _f64(qw)
+        fq, pfq = _table(fq)
+        _ck(lib().ffcuda_assemble_linear_qvalues(_h(b), _h(self), len(qw), _p(qpts), _p(qw), pfq, int(accumulate)), self.ctx.h)
 
     def assemble_linear_qterms(self, b, qpts, qw, fq, accumulate=False):
         """b (+)= int(sum_s f_s d^s v) with the f_s given at the quadrature nodes: fq[c, s, k, q] (ncomp x (dim+1) x nt x nq)"""
-        qpts, qw, fq = _f64(qpts), _f64(qw), _f64(fq)
-        _ck(lib().ffcuda_assemble_linear_qterms(_h(b), _h(self), len(qw), _p(qpts), _p(qw), _p(fq), int(accumulate)), self.ctx.h)
+        qpts, qw = _f64(qpts), _f64(qw)
+        fq, pfq = _table(fq)
+        _ck(lib().ffcuda_assemble_linear_qterms(_h(b), _h(self), len(qw), _p(qpts), _p(qw), pfq, int(accumulate)), self.ctx.h)
 
     def assemble_linear_boundary_qvalues(self, b, qpts, qw, gq, accumulate=True):
         """b (+)= boundary integral of g v with g given at the face quadrature nodes: gq[c, ib, q] (0 where it does not go)"""
-        qpts, qw, gq = _f64(qpts), _f64(qw), _f64(gq)
-        _ck(lib().ffcuda_assemble_linear_boundary_qvalues(_h(b), _h(self), len(qw), _p(qpts), _p(qw), _p(gq), int(accumulate)), self.ctx.h)
+        qpts, qw = _f64(qpts), _f64(qw)
+        gq, pgq = _table(gq)
+        _ck(lib().ffcuda_assemble_linear_boundary_qvalues(_h(b), _h(self), len(qw), _p(qpts), _p(qw), pgq, int(accumulate)), self.ctx.h)
 
     def assemble_linear_boundary(self, b, terms, qpts, qw, labels=None, accumulate=True):
         """b (+)= int2d(Th3, labels)(c v) / int1d(Th, labels)(c v); qpts: nq x (dim-1) face reference coordinates"""
@@ -528,18 +549,20 @@ class Matrix(_Handle):
         arr = (BTerm * max(len(terms), 1))()
         for k, (uc, uo, vc, vo, c) in enumerate(terms):
             arr[k] = BTerm(uc, uo, vc, vo, c)
-        qpts, qw, cq = _f64(qpts), _f64(qw), _f64(cq)
+        qpts, qw = _f64(qpts), _f64(qw)
+        cq, pcq = _table(cq)
         _ck(lib().ffcuda_assemble_bilinear_qcoef(_h(self), _h(self.pattern.space), len(terms), arr, len(qw), _p(qpts), _p(qw),
-                                                 _p(cq), int(accumulate)), self.ctx.h)
+                                                 pcq, int(accumulate)), self.ctx.h)
 
     def assemble_boundary_qcoef(self, terms, qpts, qw, cq, labels=None, accumulate=True):
         """A (+)= boundary integral of alpha u v with alpha given at the face quadrature nodes: cq[ib, q]"""
         arr = (BTerm * max(len(terms), 1))()
         for k, (uc, uo, vc, vo, c) in enumerate(terms):
             arr[k] = BTerm(uc, uo, vc, vo, c)
-        qpts, qw, cq, lab = _f64(qpts), _f64(qw), _f64(cq), _i32(labels)
+        qpts, qw, lab = _f64(qpts), _f64(qw), _i32(labels)
+        cq, pcq = _table(cq)
         _ck(lib().ffcuda_assemble_bilinear_boundary_qcoef(_h(self), _h(self.pattern.space), len(terms), arr, len(qw), _p(qpts), _p(qw),
-                                                          _p(cq), 0 if lab is None else len(lab), _p(lab), int(accumulate)), self.ctx.h)
+                                                          pcq, 0 if lab is None else len(lab), _p(lab), int(accumulate)), self.ctx.h)
 
     def assemble_boundary(self, terms, qpts, qw, labels=None, accumulate=True):
         """A (+)= int2d(Th3, labels)(c u v) / int1d(Th, labels)(c u v) (Robin terms); qpts: nq x (dim-1) face coordinates"""

@@ -18,6 +18,7 @@
 //              FFCUDA_DISABLE=1 (register nothing).
 #include "ff++.hpp"
 #include <chrono>
+#include <climits>
 #include <sys/mman.h>
 #include <thread>
 #include "AFunction_ext.hpp"
@@ -874,6 +875,198 @@ void check_full_pattern(const Varf &V, const MeshT &Th)
         if (!labs.count(Th[k].lab)) throw Unsupported{"the volume integrals do not visit every element (sub-pattern)"};
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// FE functions as data of a form, shipped as DOF ARRAYS: f in int3d(Th)(f*v), kappa in
+// int3d(Th)(kappa*(dx(u)*dx(v)+...)), uk in the Newton residual int3d(Th)(dx(uk)*dx(v)+...).  A coefficient that IS the
+// value or a first derivative of a P0 / P1 / P2 Lagrange function living on the mesh of the form compiles to the node
+// E_F0_Func1(pfer2R<R,op> | pf3r2R<R,op,v_fes3>, <the FE function>) (fflib/lgfem.cpp:2053-2088, 6993-7000,
+// fflib/lgmesh3.cpp:2169, 3094, 3136-3138; `f*v` keeps the node as it is: operator*(C_F0,C_F0) drops the constant 1,
+// fflib/AFunction.hpp:3159).  Such a term needs no interpreter call per quadrature node: the dof array goes to the device
+// and ffcuda_fe_table forms the very sums FElement::operator()(PHat,u,comp,op) forms.  The functions behind the nodes are
+// not exported by name, so their addresses are read, at load time, from the nodes FreeFEM itself compiles for a dummy FE
+// function.  Anything else (uold/dt, f*g, functions on another mesh, other elements) stays on the interpreter path above.
+// FFCUDA_NO_FE_DOFS=1 switches the recognition off.
+// ------------------------------------------------------------------------------------------------------------
+template <class MeshT>
+struct FeTypesOf;
+template <>
+struct FeTypesOf<Mesh> {
+    typedef v_fes vfes;
+};
+template <>
+struct FeTypesOf<Mesh3> {
+    typedef v_fes3 vfes;
+};
+struct FeNodeFunctions {
+    Function1 f[4]; // value, dx, dy, dz (0: not found)
+};
+FeNodeFunctions g_fe2 = {{0, 0, 0, 0}}, g_fe3 = {{0, 0, 0, 0}};
+bool g_fe_dofs = true, g_explain = false;
+template <class PF>
+void find_fe_node_functions(FeNodeFunctions &F, int dim)
+{
+    static const char *names[4] = {nullptr, "dx", "dy", "dz"};
+    for (int k = 0; k <= dim; ++k) {
+        F.f[k] = 0;
+        try {
+            C_F0 dummy(CConstant<PF>(PF((typename PF::first_type)0, 0))); // never evaluated
+            C_F0 r;
+            if (k == 0) r = atype<double>()->CastTo(dummy);
+            else {
+                C_F0 g = Global.Find(names[k]);
+                const Polymorphic *pop = dynamic_cast<const Polymorphic *>(g.LeftValue());
+                if (!pop) continue;
+                r = C_F0(pop, "(", dummy);
+            }
+            if (r.left() != atype<double>()) continue;
+            const E_F0_Func1 *n = dynamic_cast<const E_F0_Func1 *>(r.LeftValue());
+            if (n) F.f[k] = n->f;
+        } catch (...) { // (no such cast / overload in this FreeFEM: the term stays on the interpreter path)
+        }
+    }
+}
+inline const FeNodeFunctions &fe_node_functions(const Mesh *) { return g_fe2; }
+inline const FeNodeFunctions &fe_node_functions(const Mesh3 *) { return g_fe3; }
+
+// the FE functions met in one statement: dof array and node table go to the device once per function
+template <class FESpaceT>
+struct FeFunctions {
+    struct Fun {
+        const KN<double> *x;
+        const FESpaceT *Wh;
+        int order, ncomp, nloc;
+        bool default_numbering;       // P0: node = element, P1: node = vertex (no table needed)
+        std::vector<int32_t> e2n;     // nt x nloc otherwise
+        ffcuda_vec *dofs;
+    };
+    std::vector<Fun> funs;
+    ~FeFunctions()
+    {
+        for (size_t i = 0; i < funs.size(); ++i)
+            if (funs[i].dofs) ffcuda_vec_destroy(funs[i].dofs);
+    }
+    ffcuda_vec *on_device(int i)
+    {
+        Fun &F = funs[i];
+        if (!F.dofs) {
+            FFC(ffcuda_vec_create(context(), (int)F.x->N(), &F.dofs));
+            const double *src = (const double *)*F.x;
+            std::vector<double> packed;
+            if (F.x->step != 1) { // (a KN owns contiguous storage; kept for safety)
+                packed.resize((size_t)F.x->N());
+                for (long j = 0; j < F.x->N(); ++j) packed[j] = (*F.x)[j];
+                src = packed.data();
+            }
+            if (ffcuda_vec_upload(F.dofs, src) != 0) fail("uploading the dofs of an FE function");
+        }
+        return F.dofs;
+    }
+};
+struct FeRef {
+    int fun, comp, op; // op: FFCUDA_OP_*
+    bool operator==(const FeRef &o) const { return fun == o.fun && comp == o.comp && op == o.op; }
+};
+
+// Is Wh a P0 space as FreeFEM numbers it (one dof per element, dof = element, basis = 1) ?
+template <class FESpaceT>
+bool is_p0_space(const FESpaceT &Wh)
+{
+    typedef typename FESpaceT::FElement FElementT;
+    typedef typename FESpaceT::Mesh MeshT;
+    if (Wh.N != 1 || Wh.NbOfElements <= 0 || (long)Wh.NbOfDF != (long)Wh.Th.nt) return false;
+    const int nt = Wh.Th.nt, step = std::max(1, nt / 256);
+    for (int k = 0; k < nt; k += step) {
+        const FElementT K(Wh[k]);
+        if (K.NbDoF() != 1 || K(0) != k) return false;
+    }
+    const FElementT K0(Wh[0]);
+    KNMK<double> val(1, 1, (int)last_operatortype);
+    val = 0.;
+    double l[4] = {0.1, 0.2, 0.3, 0.4};
+    if (MeshDim<MeshT>::d == 2) l[0] = 0.2, l[1] = 0.3, l[2] = 0.5;
+    basis_values(K0, hat_point((const MeshT *)0, l), val);
+    return fabs(val(0, 0, (int)op_id) - 1.0) <= 1e-14;
+}
+
+// c = value / dx / dy / dz of an FE function we can evaluate on the device ?  (no device call here)
+template <class FESpaceT>
+bool fe_reference(Stack stack, const C_F0 &c, const FESpaceT &Vh, FeFunctions<FESpaceT> &cache, FeRef &out)
+{
+    typedef typename FESpaceT::Mesh MeshT;
+    typedef typename FESpaceT::FElement FElementT;
+    typedef typename FeTypesOf<MeshT>::vfes vfes;
+    typedef pair<FEbase<double, vfes> *, int> PF;
+    const int dim = MeshDim<MeshT>::d;
+    if (!g_fe_dofs || c.left() != atype<double>()) return false;
+    const E_F0_Func1 *node = dynamic_cast<const E_F0_Func1 *>(c.LeftValue());
+    if (!node || !node->f || !node->a) return false;
+    const FeNodeFunctions &F = fe_node_functions((const MeshT *)0);
+    static const int ops[4] = {FFCUDA_OP_ID, FFCUDA_OP_DX, FFCUDA_OP_DY, FFCUDA_OP_DZ};
+    int k = -1;
+    for (int j = 0; j <= dim; ++j)
+        if (F.f[j] && node->f == F.f[j]) k = j;
+    if (k < 0) return false;
+    PF pp = GetAny<PF>((*node->a)(stack));
+    FEbase<double, vfes> *fe = pp.first;
+    if (!fe || !fe->x() || !fe->Vh) return false;
+    const FESpaceT *Wh = &*fe->Vh;
+    if (&Wh->Th != &Vh.Th) return false; // a function on another mesh is interpolated by FreeFEM: interpreter path
+    if ((long)fe->x()->N() != (long)Wh->NbOfDF) return false;
+    const KN<double> *x = fe->x();
+    int fi = -1;
+    for (size_t i = 0; i < cache.funs.size(); ++i)
+        if (cache.funs[i].x == x && cache.funs[i].Wh == Wh) fi = (int)i;
+    if (fi < 0) {
+        typename FeFunctions<FESpaceT>::Fun N;
+        N.x = x;
+        N.Wh = Wh;
+        N.dofs = nullptr;
+        if (is_p0_space(*Wh)) {
+            N.order = 0;
+            N.ncomp = 1;
+            N.nloc = 1;
+            N.default_numbering = true;
+        } else {
+            try {
+                classify_space(*Wh, dim, N.order, N.ncomp, N.nloc);
+            } catch (const Unsupported &) {
+                return false;
+            }
+            const int nt = Wh->Th.nt;
+            N.default_numbering = N.order == 1;
+            N.e2n.resize((size_t)nt * N.nloc);
+            par_for((size_t)nt, [&](size_t b, size_t e) {
+                for (size_t kk = b; kk < e; ++kk) {
+                    const FElementT K((*Wh)[(int)kk]);
+                    for (int a = 0; a < N.nloc; ++a) N.e2n[kk * N.nloc + a] = K(a) / N.ncomp;
+                }
+            });
+            for (int kk = 0; kk < nt && N.default_numbering; ++kk)
+                for (int a = 0; a < N.nloc; ++a)
+                    if (N.e2n[(size_t)kk * N.nloc + a] != Wh->Th(kk, a)) N.default_numbering = false;
+            if (N.default_numbering) std::vector<int32_t>().swap(N.e2n);
+        }
+        cache.funs.push_back(N);
+        fi = (int)cache.funs.size() - 1;
+    }
+    if (pp.second < 0 || pp.second >= cache.funs[fi].ncomp) return false;
+    out.fun = fi;
+    out.comp = pp.second;
+    out.op = ops[k];
+    return true;
+}
+
+// table[offset + unit*nq + q] += scale * (datum at node q of the unit), on the device
+template <class FESpaceT>
+void fe_table_add(DevSpace &D, FeFunctions<FESpaceT> &cache, const FeRef &r, bool border, const Quad &Q, const Region &reg, double scale,
+                  ffcuda_vec *table, int64_t offset)
+{
+    typename FeFunctions<FESpaceT>::Fun &F = cache.funs[r.fun];
+    ffcuda_vec *dofs = cache.on_device(r.fun);
+    FFC(ffcuda_fe_table(D.mesh, F.order, F.default_numbering ? nullptr : F.e2n.data(), F.ncomp, r.comp, dofs, r.op, border ? 1 : 0,
+                        (int)Q.w.size(), Q.pts.data(), scale, (int)reg.labels.size(), reg.all ? nullptr : reg.labels.data(), table, offset, 1));
+}
+
 // values of mesh-point dependent coefficient expressions at every quadrature node of every element, obtained the way
 // Element_rhs / Element_Op obtain them (fflib/problem.cpp:7876-7884, :7951-7960, :6380-6407): MeshPointStack set to the
 // node, expression evaluated.  out[e][k * nq + q] for expression e; elements outside the region stay 0.
@@ -958,6 +1151,162 @@ std::vector<std::vector<double>> eval_at_bnodes(Stack stack, const FESpaceT &Vh,
     *mps = mp;
     return out;
 }
+// A coefficient that is an AFFINE combination of FE data with mesh-independent factors — uold/dt, -f (what `- int3d(Th)(f*v)`
+// of a problem turns into: (-1)*f), f1 + 2*f2, 2 + kappa (LinearComb::add merges the coefficients of equal terms into one sum,
+// femlib/DOperator.hpp:127-131) — is taken apart without reading FreeFEM's private operator nodes: E_F0::Optimize (the public
+// pass FieldOfForm itself runs, fflib/AFunction2.cpp:839, AFunction.hpp:2607-2614) lists the sub-expressions, the FE nodes
+// among them are the candidates L_i, and beta, alpha_i of  c = beta + sum alpha_i L_i  are fitted on the values the
+// interpreter gives at the quadrature nodes of a sample of the units (~g_sample_n of them, at least one per label).  The
+// decomposition is accepted only if it reproduces c at EVERY sampled node to 1e-13: (1+x)*f, f*g, f^2, sin(f) are refused
+// and stay on the interpreter path.
+struct FeAffine {
+    double beta = 0.0;
+    std::vector<std::pair<FeRef, double>> parts;
+};
+template <class FESpaceT>
+bool fe_affine(Stack stack, const C_F0 &c, const FESpaceT &Vh, FeFunctions<FESpaceT> &cache, const Quad &Q, const Region &reg, bool border,
+               FeAffine &out)
+{
+    typedef typename FESpaceT::Mesh MeshT;
+    const MeshT &Th = Vh.Th;
+    out = FeAffine();
+    FeRef r0;
+    if (fe_reference(stack, c, Vh, cache, r0)) {
+        out.parts.push_back(std::make_pair(r0, 1.0));
+        return true;
+    }
+    if (!g_fe_dofs || c.left() != atype<double>()) return false;
+    deque<pair<Expression, int>> ll;
+    E_F0::MapOfE_F0 mm;
+    size_t top = 64; // (offset 0 means "not found" in E_F0::find)
+    try {
+        c.LeftValue()->Optimize(ll, mm, top);
+    } catch (...) {
+        return false;
+    }
+    std::vector<C_F0> leaves;
+    std::vector<FeRef> refs;
+    for (size_t i = 0; i < ll.size(); ++i) {
+        if (!dynamic_cast<const E_F0_Func1 *>(ll[i].first)) continue;
+        C_F0 e(Type_Expr(atype<double>(), ll[i].first));
+        FeRef rr;
+        if (!fe_reference(stack, e, Vh, cache, rr)) continue;
+        bool seen = false;
+        for (size_t j = 0; j < refs.size(); ++j) seen = seen || refs[j] == rr;
+        if (seen) continue;
+        leaves.push_back(e);
+        refs.push_back(rr);
+    }
+    if (leaves.empty() || leaves.size() > 8) return false;
+    // the sample: units of the integral's domain, evenly spread, and the first unit of every label
+    const int nunits = border ? nbe_of(Th) : Th.nt;
+    std::set<int> labs(reg.labels.begin(), reg.labels.end()), met;
+    std::vector<int> inside, sample;
+    for (int k = 0; k < nunits; ++k) {
+        const int lab = border ? blabel(Th, k) : elabel(Th, k);
+        if (!reg.all && !labs.count(lab)) continue;
+        inside.push_back(k);
+        if (met.insert(lab).second) sample.push_back(k);
+    }
+    if (inside.empty()) return false;
+    const size_t step = std::max<size_t>(1, inside.size() / (size_t)std::max(1, g_sample_n));
+    for (size_t i = 0; i < inside.size(); i += step) sample.push_back(inside[i]);
+    std::sort(sample.begin(), sample.end());
+    sample.erase(std::unique(sample.begin(), sample.end()), sample.end());
+    std::vector<const C_F0 *> ex(1, &c);
+    for (size_t j = 0; j < leaves.size(); ++j) ex.push_back(&leaves[j]);
+    const std::vector<std::vector<double>> v = border ? eval_at_bnodes(stack, Vh, ex, Q, reg, &sample) : eval_at_nodes(stack, Vh, ex, Q, reg, &sample);
+    const size_t rows = v[0].size(), m = leaves.size() + 1;
+    if (rows < 4 * m) return false;
+    // least squares for (beta, alpha_1..): columns scaled to unit maximum, normal equations in long double
+    std::vector<double> sc(m, 1.0);
+    double ymax = 0.0;
+    for (size_t k = 0; k < rows; ++k) ymax = std::max(ymax, std::abs(v[0][k]));
+    for (size_t j = 1; j < m; ++j) {
+        sc[j] = 0.0;
+        for (size_t k = 0; k < rows; ++k) sc[j] = std::max(sc[j], std::abs(v[j][k]));
+        if (sc[j] == 0.0) sc[j] = 1.0; // a function that vanishes on the sample: its column is 0, its alpha comes out 0
+    }
+    std::vector<long double> G(m * (m + 1), 0.0L);
+    for (size_t k = 0; k < rows; ++k) {
+        long double a[9];
+        a[0] = 1.0L;
+        for (size_t j = 1; j < m; ++j) a[j] = (long double)v[j][k] / sc[j];
+        for (size_t i = 0; i < m; ++i) {
+            for (size_t j = 0; j < m; ++j) G[i * (m + 1) + j] += a[i] * a[j];
+            G[i * (m + 1) + m] += a[i] * (long double)v[0][k];
+        }
+    }
+    std::vector<long double> x(m, 0.0L);
+    std::vector<bool> dead(m, false);
+    for (size_t i = 0; i < m; ++i) { // Gauss-Jordan with partial pivoting; a vanishing column is dropped (alpha = 0)
+        size_t piv = i;
+        for (size_t r = i + 1; r < m; ++r)
+            if (fabsl(G[r * (m + 1) + i]) > fabsl(G[piv * (m + 1) + i])) piv = r;
+        if (fabsl(G[piv * (m + 1) + i]) <= 1e-9L * (long double)rows) {
+            bool zero_col = true;
+            for (size_t k = 0; k < rows && zero_col && i > 0; ++k) zero_col = v[i][k] == 0.0;
+            if (i > 0 && zero_col) {
+                dead[i] = true;
+                continue;
+            }
+            return false; // collinear candidates (or a constant function next to beta): no unique decomposition
+        }
+        if (piv != i)
+            for (size_t j = 0; j <= m; ++j) std::swap(G[i * (m + 1) + j], G[piv * (m + 1) + j]);
+        for (size_t r = 0; r < m; ++r) {
+            if (r == i) continue;
+            const long double f = G[r * (m + 1) + i] / G[i * (m + 1) + i];
+            for (size_t j = i; j <= m; ++j) G[r * (m + 1) + j] -= f * G[i * (m + 1) + j];
+        }
+    }
+    for (size_t i = 0; i < m; ++i) x[i] = dead[i] ? 0.0L : G[i * (m + 1) + m] / G[i * (m + 1) + i];
+    double beta = (double)x[0], mag = std::abs(beta);
+    std::vector<double> alpha(m, 0.0);
+    for (size_t j = 1; j < m; ++j) {
+        alpha[j] = (double)(x[j] / sc[j]);
+        mag += std::abs(alpha[j]) * sc[j];
+    }
+    if (!(mag < 1e300) || mag > 1e6 * std::max(ymax, 1e-300)) return false; // (cancellation between the parts would cost digits)
+    for (size_t k = 0; k < rows; ++k) {
+        double fit = beta;
+        for (size_t j = 1; j < m; ++j) fit += alpha[j] * v[j][k];
+        if (std::abs(fit - v[0][k]) > 1e-13 * std::max(mag, ymax)) return false; // not affine in the FE data
+    }
+    if (std::abs(beta) <= 1e-13 * std::max(mag, ymax)) beta = 0.0;
+    out.beta = beta;
+    for (size_t j = 1; j < m; ++j)
+        if (alpha[j] != 0.0) out.parts.push_back(std::make_pair(refs[j - 1], alpha[j]));
+    return true;
+}
+
+// FFCUDA_EXPLAIN=1: how every term with mesh-dependent data of a statement will be treated (printed before any device call)
+template <class FESpaceT>
+void explain_varf(Stack stack, const FESpaceT &Vh, const Varf &V)
+{
+    FeFunctions<FESpaceT> cache;
+    auto say = [&](const char *kind, size_t i, size_t t, const C_F0 &c, const Quad &Q, const Region &reg, bool border) {
+        FeAffine A;
+        cout << "  -- ffcuda explain: " << kind << " item " << i << " term " << t << ": ";
+        if (fe_affine(stack, c, Vh, cache, Q, reg, border, A)) {
+            cout << "FE data on the device: " << A.beta;
+            for (size_t j = 0; j < A.parts.size(); ++j) {
+                const FeRef &r = A.parts[j].first;
+                cout << " + " << A.parts[j].second << " * [function #" << r.fun << " (P" << cache.funs[r.fun].order << ", "
+                     << cache.funs[r.fun].ncomp << " comp., " << cache.funs[r.fun].x->N() << " dofs"
+                     << (cache.funs[r.fun].default_numbering ? "" : ", own node table") << ") comp. " << r.comp << " op " << r.op << "]";
+            }
+            cout << endl;
+        } else cout << "evaluated by the interpreter at the quadrature nodes" << endl;
+    };
+    for (size_t i = 0; i < V.bil.size(); ++i)
+        for (size_t t = 0; t < V.bil[i].qterms.size(); ++t)
+            say(V.bil[i].border ? "boundary bilinear" : "bilinear", i, t, V.bil[i].qterms[t].coef, V.bil[i].q, V.bil[i].reg, V.bil[i].border);
+    for (size_t i = 0; i < V.lin.size(); ++i)
+        for (size_t t = 0; t < V.lin[i].qterms.size(); ++t)
+            say(V.lin[i].border ? "boundary linear" : "linear", i, t, V.lin[i].qterms[t].coef, V.lin[i].q, V.lin[i].reg, V.lin[i].border);
+}
+
 // table of a linear item: fq[(c * nt + k) * nq + q], summed over the terms of component c; with derivatives of the test
 // function (grad = true): fq[((c * (dim+1) + slot) * nt + k) * nq + q]
 template <class FESpaceT>
@@ -1029,11 +1378,45 @@ MatriceMorse<double> *gpu_matrix(Stack stack, const FESpaceT &Vh, DevSpace &D, c
             }
         }
     };
+    // coefficients that are FE functions on this mesh (kappa, a P0 / P1 / P2 function): one device table per function, formed
+    // from its dof array; the terms it multiplies keep the coefficient 1
+    struct FeGroup {
+        size_t item;
+        FeRef ref;
+        std::vector<ffcuda_bterm> terms;
+    };
+    std::vector<FeGroup> fegroups;
+    FeFunctions<FESpaceT> fefuns;
+    std::vector<std::vector<ffcuda_bterm>> cterms(V.bil.size()); // constant terms of every item (+ constant parts of FE data)
+    for (size_t i = 0; i < V.bil.size(); ++i) cterms[i] = V.bil[i].terms;
     for (size_t i = 0; i < V.bil.size(); ++i) {
         const BilinearItem &B = V.bil[i];
         if (B.qterms.empty()) continue;
         std::vector<const C_F0 *> ex;
-        for (size_t t = 0; t < B.qterms.size(); ++t) ex.push_back(&B.qterms[t].coef);
+        std::vector<const QBTerm *> rest; // the terms left to the interpreter
+        for (size_t t = 0; t < B.qterms.size(); ++t) {
+            FeAffine af;
+            if (fe_affine(stack, B.qterms[t].coef, Vh, fefuns, B.q, B.reg, B.border, af)) {
+                for (size_t j = 0; j < af.parts.size(); ++j) {
+                    const FeRef &r = af.parts[j].first;
+                    size_t gi = 0;
+                    while (gi < fegroups.size() && !(fegroups[gi].item == i && fegroups[gi].ref == r)) ++gi;
+                    if (gi == fegroups.size()) fegroups.push_back(FeGroup{i, r, std::vector<ffcuda_bterm>()});
+                    ffcuda_bterm bt = B.qterms[t].t;
+                    bt.coef = af.parts[j].second;
+                    fegroups[gi].terms.push_back(bt);
+                }
+                if (af.beta != 0.0) {
+                    ffcuda_bterm bt = B.qterms[t].t;
+                    bt.coef = af.beta;
+                    cterms[i].push_back(bt);
+                }
+                continue;
+            }
+            rest.push_back(&B.qterms[t]);
+            ex.push_back(&B.qterms[t].coef);
+        }
+        if (rest.empty()) continue;
         const int nunits = B.border ? nbe_of(Vh.Th) : Vh.Th.nt, nq = (int)B.q.w.size();
         auto eval = [&](const std::vector<int> *units) {
             return B.border ? eval_at_bnodes(stack, Vh, ex, B.q, B.reg, units) : eval_at_nodes(stack, Vh, ex, B.q, B.reg, units);
@@ -1080,7 +1463,7 @@ MatriceMorse<double> *gpu_matrix(Stack stack, const FESpaceT &Vh, DevSpace &D, c
         for (size_t gi = 0; gi < reps.size(); ++gi) groups.push_back(QGroup{i, std::move(tables[gi]), std::vector<ffcuda_bterm>()});
         for (size_t t = 0; t < ex.size(); ++t) {
             if (pl[t].group < 0) continue;
-            ffcuda_bterm bt = B.qterms[t].t;
+            ffcuda_bterm bt = rest[t]->t;
             bt.coef = pl[t].alpha;
             groups[first_group + pl[t].group].terms.push_back(bt);
         }
@@ -1101,9 +1484,9 @@ MatriceMorse<double> *gpu_matrix(Stack stack, const FESpaceT &Vh, DevSpace &D, c
         for (size_t i = 0; i < V.bil.size() && !rc; ++i) {
             const BilinearItem &B = V.bil[i];
             if ((int)B.border != border) continue;
-            if (B.terms.empty() && !B.qterms.empty()) continue; // nothing constant in this item
+            if (cterms[i].empty() && !B.qterms.empty()) continue; // nothing constant in this item
             rc = (border ? ffcuda_assemble_bilinear_boundary : ffcuda_assemble_bilinear)(
-                dA, D.space, (int)B.terms.size(), B.terms.data(), (int)B.q.w.size(), B.q.pts.data(), B.q.w.data(),
+                dA, D.space, (int)cterms[i].size(), cterms[i].data(), (int)B.q.w.size(), B.q.pts.data(), B.q.w.data(),
                 (int)B.reg.labels.size(), B.reg.all ? nullptr : B.reg.labels.data(), first ? 0 : 1);
             first = false;
         }
@@ -1120,8 +1503,38 @@ MatriceMorse<double> *gpu_matrix(Stack stack, const FESpaceT &Vh, DevSpace &D, c
                                                     B.q.pts.data(), B.q.w.data(), groups[gi].cq.data(), first ? 0 : 1);
             first = false;
         }
+    for (int border = 0; border < 2; ++border)
+        for (size_t gi = 0; gi < fegroups.size() && !rc; ++gi) {
+            const BilinearItem &B = V.bil[fegroups[gi].item];
+            if ((int)B.border != border) continue;
+            const size_t per = (size_t)(border ? nbe_of(Vh.Th) : Vh.Th.nt) * B.q.w.size();
+            ffcuda_vec *tab = nullptr;
+            try {
+                if (per > (size_t)INT_MAX) throw Unsupported{"table of FE data larger than 2^31 entries"};
+                FFC(ffcuda_vec_create(context(), (int)per, &tab));
+                fe_table_add(D, fefuns, fegroups[gi].ref, border != 0, B.q, B.reg, 1.0, tab, 0);
+            } catch (...) {
+                if (tab) ffcuda_vec_destroy(tab);
+                ffcuda_matrix_destroy(dA);
+                ffcuda_pattern_destroy(P);
+                throw;
+            }
+            const double *cq = (const double *)ffcuda_vec_ptr(tab);
+            if (border)
+                rc = ffcuda_assemble_bilinear_boundary_qcoef(dA, D.space, (int)fegroups[gi].terms.size(), fegroups[gi].terms.data(),
+                                                             (int)B.q.w.size(), B.q.pts.data(), B.q.w.data(), cq, (int)B.reg.labels.size(),
+                                                             B.reg.all ? nullptr : B.reg.labels.data(), first ? 0 : 1);
+            else
+                rc = ffcuda_assemble_bilinear_qcoef(dA, D.space, (int)fegroups[gi].terms.size(), fegroups[gi].terms.data(), (int)B.q.w.size(),
+                                                    B.q.pts.data(), B.q.w.data(), cq, first ? 0 : 1);
+            ffcuda_vec_destroy(tab);
+            first = false;
+        }
     if (g_verbose && !groups.empty())
         cout << "  -- ffcuda: " << groups.size() << " coefficient function(s) depending on the mesh point, evaluated at the quadrature nodes" << endl;
+    if (g_verbose && !fegroups.empty())
+        cout << "  -- ffcuda: " << fegroups.size() << " coefficient(s) that are FE functions (" << fefuns.funs.size()
+             << " dof array(s) sent), evaluated at the quadrature nodes on the device" << endl;
     // --- hand-off: FreeFEM's own MatriceMorse, its arrays filled straight from the device.  HashMatrix::set
     // (femlib/HashMatrix.cpp:698-728) would copy the three arrays once more and leave the matrix marked `unsorted`, so
     // that the first A.CSR (solver upload, `ofstream << A`, UMFPACK...) heap-sorts nnz entries on one core
@@ -1230,8 +1643,9 @@ void gpu_rhs(Stack stack, const FESpaceT &Vh, DevSpace &D, const Varf &V, double
 {
     ffcuda_vec *db = nullptr;
     FFC(ffcuda_vec_create(context(), (int)n, &db));
-    int rc = 0;
+    int rc = 0, nfe = 0;
     bool first = true;
+    FeFunctions<FESpaceT> fefuns;
     for (int border = 0; border < 2; ++border)
         for (size_t i = 0; i < V.lin.size() && !rc; ++i) {
             const LinearItem &L = V.lin[i];
@@ -1239,13 +1653,58 @@ void gpu_rhs(Stack stack, const FESpaceT &Vh, DevSpace &D, const Varf &V, double
             std::vector<ffcuda_lterm> terms(L.terms);
             if (negate)
                 for (size_t k = 0; k < terms.size(); ++k) terms[k].coef = -terms[k].coef;
+            // data that are FE functions on this mesh: their dof arrays go to the device, the table is formed there
+            std::vector<FeAffine> aff(L.qterms.size());
+            bool all_fe = !L.qterms.empty() && !rc;
+            try {
+                for (size_t t = 0; t < L.qterms.size() && all_fe; ++t)
+                    all_fe = fe_affine(stack, L.qterms[t].coef, Vh, fefuns, L.q, L.reg, border != 0, aff[t]);
+            } catch (...) {
+                ffcuda_vec_destroy(db);
+                throw;
+            }
+            if (all_fe) { // the constant parts (2 + kappa) join the constant terms, assembled first
+                for (size_t t = 0; t < L.qterms.size(); ++t)
+                    if (aff[t].beta != 0.0) {
+                        static const int slot_op[4] = {FFCUDA_OP_ID, FFCUDA_OP_DX, FFCUDA_OP_DY, FFCUDA_OP_DZ};
+                        ffcuda_lterm lt;
+                        lt.vcomp = L.qterms[t].vcomp;
+                        lt.vop = slot_op[L.qterms[t].slot];
+                        lt.coef = negate ? -aff[t].beta : aff[t].beta;
+                        terms.push_back(lt);
+                    }
+            }
             if (!terms.empty() || L.qterms.empty()) {
                 rc = (border ? ffcuda_assemble_linear_boundary : ffcuda_assemble_linear)(
                     db, D.space, (int)terms.size(), terms.data(), (int)L.q.w.size(), L.q.pts.data(), L.q.w.data(),
                     (int)L.reg.labels.size(), L.reg.all ? nullptr : L.reg.labels.data(), first ? 0 : 1);
                 first = false;
             }
-            if (!L.qterms.empty() && !rc) {
+            if (all_fe && !rc) {
+                bool grad = false;
+                for (size_t t = 0; t < L.qterms.size(); ++t) grad = grad || L.qterms[t].slot != 0;
+                const int ns = (grad && !border) ? MeshDim<typename FESpaceT::Mesh>::d + 1 : 1;
+                const size_t per = (size_t)(border ? nbe_of(Vh.Th) : Vh.Th.nt) * L.q.w.size();
+                ffcuda_vec *tab = nullptr;
+                try {
+                    if ((size_t)Vh.N * ns * per > (size_t)INT_MAX) throw Unsupported{"table of FE data larger than 2^31 entries"};
+                    FFC(ffcuda_vec_create(context(), (int)((size_t)Vh.N * ns * per), &tab));
+                    for (size_t t = 0; t < L.qterms.size(); ++t)
+                        for (size_t j = 0; j < aff[t].parts.size(); ++j)
+                            fe_table_add(D, fefuns, aff[t].parts[j].first, border != 0, L.q, L.reg,
+                                         negate ? -aff[t].parts[j].second : aff[t].parts[j].second, tab,
+                                         (int64_t)(((size_t)L.qterms[t].vcomp * ns + (ns > 1 ? L.qterms[t].slot : 0)) * per));
+                } catch (...) {
+                    if (tab) ffcuda_vec_destroy(tab);
+                    ffcuda_vec_destroy(db);
+                    throw;
+                }
+                rc = (border ? ffcuda_assemble_linear_boundary_qvalues : grad ? ffcuda_assemble_linear_qterms : ffcuda_assemble_linear_qvalues)(
+                    db, D.space, (int)L.q.w.size(), L.q.pts.data(), L.q.w.data(), (const double *)ffcuda_vec_ptr(tab), first ? 0 : 1);
+                ffcuda_vec_destroy(tab);
+                first = false;
+                nfe += (int)L.qterms.size();
+            } else if (!L.qterms.empty() && !rc) {
                 std::vector<double> fq;
                 bool grad = false;
                 for (size_t t = 0; t < L.qterms.size(); ++t) grad = grad || L.qterms[t].slot != 0;
@@ -1261,6 +1720,9 @@ void gpu_rhs(Stack stack, const FESpaceT &Vh, DevSpace &D, const Varf &V, double
             }
         }
     if (first && !rc) rc = ffcuda_vec_fill(db, 0.0);
+    if (g_verbose && nfe)
+        cout << "  -- ffcuda: " << nfe << " term(s) whose data are FE functions (" << fefuns.funs.size()
+             << " dof array(s) sent), evaluated at the quadrature nodes on the device" << endl;
     host.resize((size_t)n);
     ffcuda_vec *dx = nullptr;
     if (!rc) {
@@ -1318,6 +1780,7 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
                 const MMesh &Th = Vh.Th;
                 if (!isSameMesh(this->b->largs, &Vh.Th, &Vh.Th, stack)) throw Unsupported{"integrals on different meshes"};
                 Varf V = read_varf(stack, this->b->largs, Th, Vh.N, true, Vh);
+                if (g_explain) explain_varf(stack, Vh, V);
                 check_full_pattern(V, Th);
                 check_qterms_supported(Vh, V);
                 DevSpace &D = device_space(Vh);
@@ -1402,6 +1865,7 @@ struct CudaRhsOp : public OpArraytoLinearForm<double, MMesh, v_fes> {
                 if (this->l->nargs[0]) tgv = GetAny<double>((*this->l->nargs[0])(stack));
                 if (tgv != tgv) throw Unsupported{"tgv is NaN"};
                 Varf V = read_varf(stack, this->l->largs, Vh.Th, Vh.N, false, Vh);
+                if (g_explain) explain_varf(stack, Vh, V);
                 if (V.other_rhs_items) throw Unsupported{"right-hand side with array / matrix-vector items"};
                 DevSpace &D = device_space(Vh);
                 const long n = Vh.NbOfDF;
@@ -2168,6 +2632,12 @@ static void Load_Init()
     g_check = env_on("FFCUDA_CHECK");
     if (const char *e = getenv("FFCUDA_SAMPLE_MIN")) g_sample_min = atoi(e); // (testing knobs of the coefficient grouping)
     if (const char *e = getenv("FFCUDA_SAMPLE_N")) g_sample_n = atoi(e);
+    g_fe_dofs = !env_on("FFCUDA_NO_FE_DOFS");
+    g_explain = env_on("FFCUDA_EXPLAIN");
+    if (g_fe_dofs) {
+        find_fe_node_functions<pfer>(g_fe2, 2);
+        find_fe_node_functions<pf3r>(g_fe3, 3);
+    }
     if (const char *e = getenv("FFCUDA_NGPU")) g_ngpu = std::max(1, std::min(16, atoi(e)));
     if (const char *e = getenv("FFCUDA_NGPU_MIN_N")) g_ngpu_min_n = atol(e);
     if (env_on("FFCUDA_DISABLE")) {

@@ -27,6 +27,9 @@
  *   ffcuda_assemble_bilinear_qcoef <- the same inside Element_Op fflib/problem.cpp:6380-6407
  *   ffcuda_assemble_linear_boundary_qvalues / ffcuda_assemble_bilinear_boundary_qcoef <- the same on border elements
  *                                  fflib/problem.cpp:8551-8570, :6526-6556
+ *   ffcuda_fe_table             <- an FE function used as data of a form, evaluated from its dof array instead of through
+ *                                  the interpreter: pfer2R fflib/lgfem.cpp:2053-2088 -> FElement::operator()(PHat,u,comp,op)
+ *                                  femlib/FESpace.cpp:1078-1099, :1637-1654, femlib/P012_3d.cpp:98-122
  *   ffcuda_bc_* / *_apply_bc    <- AssembleBC fflib/problem.cpp:9881-10034, :10039-10194, HashMatrix::SetBC
  *                                  femlib/HashMatrix.cpp:1195-1238 (penalty and exact elimination)
  *   ffcuda_gmres                <- SolverGMRES femlib/VirtualSolverCG.hpp:196-258, fgmres femlib/CG.cpp:347-517
@@ -206,7 +209,7 @@ int ffcuda_assemble_bilinear(ffcuda_matrix *A, ffcuda_space *s, int nterms, cons
                              int nq, const double *qpts, const double *qw,
                              int nlab, const int32_t *labels, int accumulate);
 /* A (+)= the same with every term multiplied by ONE coefficient that depends on the mesh point (kappa(x,y,z), a P0 / P1
- * FE function, ...), given by the values Element_Op would compute (fflib/problem.cpp:6407): cq[k * nq + q] (HOST array) at
+ * FE function, ...), given by the values Element_Op would compute (fflib/problem.cpp:6407): cq[k * nq + q] (HOST array, or a DEVICE pointer: ffcuda_fe_table) at
  * quadrature node q of element k.  P1: the gradients do not depend on the node, so the element integrals reduce exactly to
  * the moments sum_q w_q c_q, sum_q w_q c_q lambda_a, sum_q w_q c_q lambda_a lambda_b of the coefficient, formed on the
  * device.  P2: the per-pair tensors sum_q c_q w_q d phi_a(q) d phi_b(q) are formed on the fly from the node values.
@@ -226,12 +229,12 @@ int ffcuda_assemble_linear_boundary(ffcuda_vec *b, ffcuda_space *s, int nterms, 
                                     int nlab, const int32_t *labels, int accumulate);
 /* b (+)= volume integral of a linear form whose data depend on the mesh point (f(x,y,z) v, uold v / dt, ...): Element_rhs
  * (fflib/problem.cpp:7839-7985) evaluates the coefficient at every quadrature node of every element, and the caller hands
- * those very values over: fq[(c * nt + k) * nq + q] (HOST array) = coefficient of the value of v_c at node q of element k,
+ * those very values over: fq[(c * nt + k) * nq + q] (HOST array or DEVICE pointer) = coefficient of the value of v_c at node q of element k,
  * summed over the terms, 0 where the element is outside the integral's region.  Value terms only. */
 int ffcuda_assemble_linear_qvalues(ffcuda_vec *b, ffcuda_space *s, int nq, const double *qpts, const double *qw,
                                    const double *fq, int accumulate);
 /* the same with derivatives of the test function (the residual of a Newton step, int(dx(uk) dx(v) + ...)):
- * fq[((c * (dim+1) + s) * nt + k) * nq + q] (HOST) = coefficient of d^s v_c, s = 0 value, 1..dim = dx, dy, dz */
+ * fq[((c * (dim+1) + s) * nt + k) * nq + q] (HOST or DEVICE) = coefficient of d^s v_c, s = 0 value, 1..dim = dx, dy, dz */
 int ffcuda_assemble_linear_qterms(ffcuda_vec *b, ffcuda_space *s, int nq, const double *qpts, const double *qw,
                                   const double *fq, int accumulate);
 /* A (+)= boundary integrals int2d(Th3, labels)(c u v) / int1d(Th, labels)(c u v) of a bilinear form (Robin terms):
@@ -242,14 +245,30 @@ int ffcuda_assemble_bilinear_boundary(ffcuda_matrix *A, ffcuda_space *s, int nte
                                       int nq, const double *qpts, const double *qw,
                                       int nlab, const int32_t *labels, int accumulate);
 /* the two boundary integrals with data that depend on the mesh point, given by the values FreeFEM's evaluator returns at
- * the face quadrature nodes (fflib/problem.cpp:8551-8570, :6526-6556): gq[(c * nbe + ib) * nq + q] (HOST) = coefficient of
- * the value of v_c at node q of boundary element ib, 0 where the integral does not go; cq[ib * nq + q] (HOST) = the ONE
+ * the face quadrature nodes (fflib/problem.cpp:8551-8570, :6526-6556): gq[(c * nbe + ib) * nq + q] (HOST or DEVICE) = coefficient of
+ * the value of v_c at node q of boundary element ib, 0 where the integral does not go; cq[ib * nq + q] (HOST or DEVICE) = the ONE
  * coefficient function multiplying every listed term (labels as above). */
 int ffcuda_assemble_linear_boundary_qvalues(ffcuda_vec *b, ffcuda_space *s, int nq, const double *qpts, const double *qw,
                                             const double *gq, int accumulate);
 int ffcuda_assemble_bilinear_boundary_qcoef(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms,
                                             int nq, const double *qpts, const double *qw, const double *cq,
                                             int nlab, const int32_t *labels, int accumulate);
+
+/* An FE function handed over as its DOF ARRAY (f in int3d(Th)(f v), kappa in int3d(Th)(kappa grad u . grad v), uk in the
+ * residual int3d(Th)(dx(uk) dx(v) + ...) of a Newton step): its values (op = FFCUDA_OP_ID) or derivatives (DX, DY, DZ) at
+ * the quadrature nodes, formed on the device instead of one interpreter call per node (pfer2R, fflib/lgfem.cpp:2053-2088 ->
+ * FElement::operator()(PHat,u,comp,op), femlib/FESpace.cpp:1078-1099, :1637-1654, femlib/P012_3d.cpp:98-122):
+ *   table[offset + u * nq + q] (+)= scale * d^op f(P_q of unit u),   0 where the label of unit u is not listed
+ * border = 0: units = elements, qpts nq x dim reference coordinates, labels = region labels;  border = 1: units = boundary
+ * elements, qpts nq x (dim-1) coordinates of the face rule, P_q = PBord(face, q) in the adjacent element, labels = boundary
+ * labels (NULL: every unit).  f lives on mesh m: order 0 (P0), 1 or 2 (P1 / P2 Lagrange); e2n = its element -> node table
+ * (HOST, nt x nloc, required for P2; NULL: node = element for P0, node = vertex for P1, as FreeFEM numbers them); the dof
+ * of node i is dofs[i * dstride + doff] (component c of a [P1,P1,P1] function: dstride 3, doff c).  dofs and table are
+ * device vectors; the table has the layout of cq / fq / gq of the entries above, which all accept a DEVICE pointer
+ * (ffcuda_vec_ptr(table)) in place of the host array and then use it where it lies. */
+int ffcuda_fe_table(ffcuda_mesh *m, int order, const int32_t *e2n, int dstride, int doff, ffcuda_vec *dofs, int op,
+                    int border, int nq, const double *qpts, double scale, int nlab, const int32_t *labels,
+                    ffcuda_vec *table, int64_t offset, int accumulate);
 
 /* ---- Dirichlet conditions ------------------------------------------------------------------------------
  * tgv >= 0: penalty, A(d,d) = tgv and b[d] = tgv*g(d).  tgv < 0: exact elimination exactly as HashMatrix::SetBC

@@ -238,3 +238,45 @@ def p2_node_partition(conn, e2n, part):
     for e, (p, r) in enumerate([(0, 1), (0, 2), (0, 3), (1, 2), (1, 3), (2, 3)]):
         pn[e2n[:, 4 + e]] = part[np.minimum(conn[:, p], conn[:, r])]
     return pn
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# FE functions as data of a form, shipped as dof arrays (fixtures fe*_data.npz).  An FE datum is
+# (array name in the fixture, component, operator); name -> dict(base = the constant part as in CASES,
+#   qcoef = [(datum, bilinear terms it multiplies)], lin = [(vcomp, vop, datum, scale)],
+#   bbil = [(labels, datum, terms)], blin = [(labels, vcomp, datum, scale)])
+# ---------------------------------------------------------------------------------------------------------------
+FE_CASES = {
+    "fe3d_p1_data": dict(base=(1, 1, [], [], "qfV5", [([1], 1, [0.0])]),
+                         qcoef=[(("kap", 0, ID), LAP3), (("rho", 0, ID), [(0, ID, 0, ID, 1.0)])],
+                         lin=[(0, ID, ("ff", 0, ID), 1.0), (0, DX, ("uk", 0, DX), 1.0), (0, DY, ("uk", 0, DY), 1.0), (0, DZ, ("uk", 0, DZ), 1.0)],
+                         bbil=[([2, 3], ("kap", 0, ID), [(0, ID, 0, ID, 1.0)])], blin=[([2, 3], 0, ("ff", 0, ID), 1.0)]),
+    "fe3d_p2_data": dict(base=(2, 1, [], [], "qfV5", [([1, 2], 1, [0.0])]),
+                         qcoef=[(("kap", 0, ID), LAP3), (("m2", 0, ID), [(0, ID, 0, ID, 1.0)])],
+                         lin=[(0, ID, ("uk", 0, ID), 1.0), (0, DX, ("uk", 0, DX), 1.0), (0, DY, ("uk", 0, DZ), 1.0)],
+                         bbil=[], blin=[([6], 0, ("uk", 0, ID), 1.0)]),
+    "fe2d_p1_data": dict(base=(1, 1, [(0, ID, 0, ID, 1.0)], [], "qf5pT", [([4], 1, [0.0])]),
+                         qcoef=[(("kap", 0, ID), LAP2)],
+                         lin=[(0, ID, ("ff", 0, ID), 1.0), (0, DX, ("uk", 0, DX), 1.0), (0, DY, ("uk", 0, DY), 1.0)],
+                         bbil=[([2, 3], ("ff", 0, ID), [(0, ID, 0, ID, 1.0)])], blin=[([2], 0, ("uk", 0, DY), 1.0)]),
+    "fe3d_lame_data": dict(base=(1, 3, [], [], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
+                           qcoef=[(("ee", 0, ID), lame_terms())],
+                           lin=[(0, ID, ("f1", 0, ID), 1.0), (2, ID, ("f1", 2, ID), 1.0), (1, ID, ("f1", 1, DX), 1.0)],
+                           bbil=[], blin=[]),
+}
+
+
+def fe_function(g, datum):
+    """(order, element -> node table, dstride, doff, whole dof array) of the FE function behind a datum of FE_CASES: the space
+    is recognised from its dofs per element, dof(k, c*nloc + a) = node*ncomp + c as everywhere in FreeFEM's Lagrange spaces"""
+    name, comp, _ = datum
+    dof, vals = g["fe_" + name + "_dof"], g["fe_" + name]
+    dim = int(g["dim"])
+    sizes = {1: (0, 1), dim + 1: (1, 1), (10 if dim == 3 else 6): (2, 1), 3 * (dim + 1): (1, 3), 3 * (10 if dim == 3 else 6): (2, 3)}
+    order, ncomp = sizes[dof.shape[1]]
+    nl = dof.shape[1] // ncomp
+    e2n = np.ascontiguousarray(dof[:, :nl] // ncomp, dtype=np.int32)
+    for c in range(ncomp):
+        assert np.array_equal(dof[:, c * nl:(c + 1) * nl], e2n * ncomp + c)
+    assert 0 <= comp < ncomp
+    return order, e2n, ncomp, comp, vals

@@ -151,6 +151,27 @@ CASES = {
                                bc="on(1,u1=0,u2=0,u3=0)", solve=False),
     "lap3d_p2_bnd_gradq": dict(dim=3, mesh="cube(2,2,2,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", fe="P2", bil=LAP3, lin="1.*v",
                                blin="+int2d(Th,2,3)((1+x*z)*(dx(u)*v+0.5*u*dz(v)))", bc="on(1,u=0)", solve=False),
+    # FE functions as data of the form (f-2: shipped as dof arrays): P0 / P1 / P2 coefficients, right-hand sides and Newton
+    # residuals given by FE functions, Robin / Neumann data given by FE functions, components of a vector function
+    "fe3d_p1_data": dict(dim=3, mesh="cube(3,3,3,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", fe="P1",
+                         fes=[dict(space="W1", fe="P1", decl="W1 kap=1+x*y+z*z, ff=x*y+sin(z), uk=x*x+y*z;", arrays=["kap", "ff", "uk"]),
+                              dict(space="W0", fe="P0", decl="W0 rho=1+x+2*z;", arrays=["rho"])],
+                         bil="kap*(" + LAP3 + ")+rho*u*v", lin="ff*v+dx(uk)*dx(v)+dy(uk)*dy(v)+dz(uk)*dz(v)",
+                         blin="+int2d(Th,2,3)(kap*u*v)+int2d(Th,2,3)(ff*v)", bc="on(1,u=0)"),
+    "fe3d_p2_data": dict(dim=3, mesh="cube(2,2,2,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)])", fe="P2",
+                         fes=[dict(space="W1", fe="P1", decl="W1 kap=1+x*y+z*z;", arrays=["kap"]),
+                              dict(space="W2", fe="P2", decl="W2 uk=x*x+y*z+sin(x*z), m2=2+x*y*z;", arrays=["uk", "m2"])],
+                         bil="kap*(" + LAP3 + ")+m2*u*v", lin="uk*v+dx(uk)*dx(v)+dz(uk)*dy(v)",
+                         blin="+int2d(Th,6)(uk*v)", bc="on(1,2,u=0)"),
+    "fe2d_p1_data": dict(dim=2, mesh="square(5,4,[x+0.2*y*y,y*(1+0.3*x)])", fe="P1",
+                         fes=[dict(space="W2", fe="P2", decl="W2 kap=1+sin(x)*y, uk=x*x*y-y*y;", arrays=["kap", "uk"]),
+                              dict(space="W1", fe="P1", decl="W1 ff=exp(x)*y;", arrays=["ff"])],
+                         bil="kap*(" + LAP2 + ")+u*v", lin="ff*v+dx(uk)*dx(v)+dy(uk)*dy(v)",
+                         blin="+int1d(Th,2,3)(ff*u*v)+int1d(Th,2)(dy(uk)*v)", bc="on(4,u=0)"),
+    "fe3d_lame_data": dict(dim=3, mesh="cube(2,3,2)", fe="[P1,P1,P1]", unk="[u1,u2,u3]", tst="[v1,v2,v3]", pre=LAME_PRE,
+                           fes=[dict(space="Wv", fe="[P1,P1,P1]", decl="Wv [f1,f2,f3]=[x*y,sin(z),-0.05*(1+y)];", arrays=["f1"]),
+                                dict(space="W1", fe="P1", decl="W1 ee=1+x;", arrays=["ee"])],
+                           bil="ee*(" + LAME + ")", lin="f1*v1+f3*v3+dx(f2)*v2", bc="on(1,u1=0,u2=0,u3=0)"),
 }
 
 
@@ -166,6 +187,9 @@ def script(c, out):
     s.append(c.get("pre", ""))
     s.append(f"{mtype} Th = {c['mesh']};")
     s.append(f"fespace Vh(Th,{c['fe']});")
+    for sp in c.get("fes", []):  # FE functions used as data of the form: their spaces, declarations (dumped below)
+        s.append(f"fespace {sp['space']}(Th,{sp['fe']});")
+        s.append(sp["decl"])
     s.append(f"varf va({unk},{tst}) = {integ}(Th{opt})({c['bil']}) + {integ}(Th{opt})({c['lin']}){c.get('blin', '')}{bc};")
     tg = (",tgv=%g" % c["tgv"]) if "tgv" in c else ""
     sy = ",sym=1" if c.get("sym") else ""
@@ -191,6 +215,12 @@ def script(c, out):
     s.append(f'  ofstream f("{out}/A.txt"); f.precision(17); f << A.n << " " << A.m << " " << A.nnz << endl;')
     s.append('  for(int k=0;k<I.n;++k) f << I[k] << " " << J[k] << " " << C[k] << endl; }')
     s.append(f'{{ ofstream f("{out}/b.txt"); f.precision(17); for(int i=0;i<b.n;++i) f << b[i] << endl; }}')
+    for sp in c.get("fes", []):
+        w = sp["space"]
+        s.append(f'{{ ofstream f("{out}/fes_{w}.txt"); f << {w}.ndof << " " << {w}.ndofK << endl;')
+        s.append(f'  for(int k=0;k<Th.nt;++k){{ for(int i=0;i<{w}.ndofK;++i) f << {w}(k,i) << " "; f << endl; }} }}')
+        for a in sp["arrays"]:
+            s.append(f'{{ ofstream f("{out}/fe_{a}.txt"); f.precision(17); for(int i=0;i<{a}[].n;++i) f << {a}[][i] << endl; }}')
     if c.get("solve", True):
         s.append("Vh %s; %s[] = 0; verbosity=1;" % (unk, unk.strip("[]").split(",")[0]))
         u0 = unk.strip("[]").split(",")[0]
@@ -251,6 +281,14 @@ def run_case(name, case=None, save=True):
                    ins_i=ins[:, 0].astype(np.int32), ins_j=ins[:, 1].astype(np.int32),
                    coo_i=a[:, 0].astype(np.int32), coo_j=a[:, 1].astype(np.int32), coo_a=a[:, 2].copy(), b=b,
                    edp=np.array(src))
+        for sp in c.get("fes", []):
+            t = toks(os.path.join(td, f"fes_{sp['space']}.txt"))
+            ndk = int(t[1])
+            tab = np.array(t[2:], dtype=np.int32).reshape(nt, ndk)
+            for a in sp["arrays"]:
+                out["fe_" + a] = np.array(toks(os.path.join(td, f"fe_{a}.txt")), dtype=np.float64)
+                assert out["fe_" + a].shape[0] == int(t[0])
+                out["fe_" + a + "_dof"] = tab
         if c.get("solve", True):
             out["u"] = np.array(toks(os.path.join(td, "u.txt")), dtype=np.float64)
             mm = re.findall(r"fgmres has converged in\s+(\d+)" if c.get("solver") == "GMRES" else r"GC:\s+converge after\s+(\d+)", r.stdout)

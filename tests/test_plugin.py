@@ -270,6 +270,113 @@ def test_plugin_has_no_cpu_fallback():
     assert "no CPU fallback" in out and not re.search(r"^NNZ \d", out, re.M)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# FE functions as data of a form: values / derivatives of P0 / P1 / P2 functions living on the mesh of
+# the form, alone or in affine combinations with mesh-independent factors (uold/dt, -f, 2 + kappa), go to the device as dof
+# arrays; the tables at the quadrature nodes are formed there (ffcuda_fe_table), no interpreter call per node
+# ---------------------------------------------------------------------------------------------------------------
+def fe_script(dim, mesh, fe, decl, bil, lin, bc, extra="", pre="", unk="u", tst="v"):
+    mt, integ = ("mesh", "int2d") if dim == 2 else ("mesh3", "int3d")
+    u0 = unk.strip("[]").split(",")[0]
+    s = f'load "msh3"\nload "ffcuda"\n{pre}\n{mt} Th = {mesh};\nfespace Vh(Th,{fe});\n{decl}\n'
+    s += f"varf va({unk},{tst}) = {integ}(Th)({bil}) + {integ}(Th)({lin}){extra}+{bc};\n"
+    s += "matrix A = va(Vh,Vh,solver=CG,eps=1e-14);\nreal[int] b = va(0,Vh);\n" + DUMP
+    s += f"Vh {unk};\n" + SOLVE.replace("UU", u0)
+    return s
+
+
+WARP3 = "[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)]"
+FE_CASES = {
+    # name: (script, bilinear terms on the dof-array path, linear terms on it, coefficient functions left to the interpreter)
+    "fe3d_p1": (fe_script(3, f"cube(5,4,6,{WARP3})", "P1",
+                          "fespace W1(Th,P1); W1 kap=1+x*y+z*z, ff=x*y+sin(z), uk=x*x+y*z; fespace W0(Th,P0); W0 rho=1+x+2*z; real dt=0.1;",
+                          "kap*(" + LAP3 + ")+rho*u*v/dt+2.*u*v", "ff*v+dx(uk)*dx(v)+dy(uk)*dy(v)+dz(uk)*dz(v)+uk*v/dt", "on(1,u=0)",
+                          extra="+int2d(Th,2,3)(kap*u*v)-int2d(Th,2,3)(ff*v)"), True, True, 0),
+    "fe3d_p2": (fe_script(3, f"cube(3,3,4,{WARP3})", "P2",
+                          "fespace W1(Th,P1); W1 kap=1+x*y+z*z; fespace W2(Th,P2); W2 uk=x*x+y*z+sin(x*z), m2=2+x*y*z;",
+                          "kap*(" + LAP3 + ")+m2*u*v", "uk*v+dx(uk)*dx(v)+dz(uk)*dy(v)", "on(1,2,u=0)", extra="+int2d(Th,6)(uk*v)"),
+                True, True, 0),
+    "fe2d_p1": (fe_script(2, "square(9,7,[x+0.2*y*y,y*(1+0.3*x)])", "P1",
+                          "fespace W2(Th,P2); W2 kap=1+sin(x)*y, uk=x*x*y-y*y; fespace W1(Th,P1); W1 ff=exp(x)*y;",
+                          "kap*(" + LAP2 + ")+u*v", "ff*v+dx(uk)*dx(v)+dy(uk)*dy(v)", "on(4,u=0)",
+                          extra="+int1d(Th,2,3)(ff*u*v)+int1d(Th,2)(dy(uk)*v)"), True, True, 0),
+    "fe3d_lame": (fe_script(3, "cube(3,4,3)", "[P1,P1,P1]",
+                            "fespace Wv(Th,[P1,P1,P1]); Wv [f1,f2,f3]=[x*y,sin(z),-0.05*(1+y)]; fespace W1(Th,P1); W1 ee=1+x;",
+                            "ee*(" + LAME + ")", "f1*v1+f3*v3+dx(f2)*v2", "on(1,u1=0,u2=0,u3=0)", pre=LAME_PRE, unk="[u1,u2,u3]",
+                            tst="[v1,v2,v3]"), True, True, 0),
+    # products of FE functions and factors depending on x are NOT affine in the FE data: those terms stay with the interpreter,
+    # the others of the same statement still go as dof arrays
+    "fe3d_mixed": (fe_script(3, f"cube(4,4,4,{WARP3})", "P1", "fespace W1(Th,P1); W1 kap=1+x*y+z*z, ff=x*y+sin(z);",
+                             "(1+x)*kap*dx(u)*dx(v)+kap*ff*dy(u)*dy(v)+kap*dz(u)*dz(v)+u*v", "ff*ff*v-kap*dx(v)", "on(1,u=0)"),
+                   True, False, 2),
+}
+
+
+@needs_ff
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", sorted(FE_CASES))
+def test_plugin_fe_data_go_as_dof_arrays(name):
+    src, bil_fe, lin_fe, ninterp = FE_CASES[name]
+    _, out, gpu = run_ff(src, {"FFCUDA_STRICT": "1", "FFCUDA_VERBOSE": "1"})
+    assert "assembled on the GPU" in out and "GC (ffcuda)" in out
+    assert ("that are FE functions" in out) == bil_fe and ("whose data are FE functions" in out) == lin_fe
+    m = re.search(r"(\d+) coefficient function\(s\) depending on the mesh point", out)
+    assert (int(m.group(1)) if m else 0) == ninterp
+    _, _, cpu = run_ff(src, {"FFCUDA_DISABLE": "1"})
+    compare(gpu, cpu, tight=True)
+    if name == "fe3d_p1":   # the recognition switched off: the same statement through the interpreter tables, same result
+        _, out2, gpu2 = run_ff(src, {"FFCUDA_STRICT": "1", "FFCUDA_VERBOSE": "1", "FFCUDA_NO_FE_DOFS": "1"})
+        assert "FE functions" not in out2 and "coefficient function(s) depending on the mesh point" in out2
+        compare(gpu2, cpu, tight=True)
+
+
+EXPLAIN = """load "msh3"
+load "ffcuda"
+mesh3 Th = cube(3,3,3,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)]);
+fespace Vh(Th,P1);
+fespace W1(Th,P1); W1 kap=1+x*y+z*z, ff=x*y+sin(z), uk=x*x+y*z;
+fespace W0(Th,P0); W0 rho=1+x+2*z;
+fespace W2(Th,P2); W2 m2=2+x*y*z;
+fespace Wv(Th,[P1,P1,P1]); Wv [f1,f2,f3]=[x*y,sin(z),x*z];
+mesh3 Th2 = cube(2,2,2); fespace Z1(Th2,P1); Z1 other=x;
+real dt = 0.1;
+varf va(u,v) = int3d(Th)(2*u*v + kap*u*v + rho*u*v/dt + (1+x)*kap*dx(u)*dx(v) + kap*ff*dy(u)*dy(v) - m2*dz(u)*dz(v) + other*dx(u)*v)
+   - int3d(Th)(ff*v + f2*v + uk*v/dt - 3*rho*v + 2*v + dz(f3)*dx(v))
+   + int2d(Th,2,3)(kap*u*v/4) - int2d(Th,2,3)(ff*v) + on(1,u=0);
+STATEMENT
+"""
+
+
+@needs_ff
+def test_plugin_recognises_fe_data_without_a_device():
+    """the FreeFEM side of the dof-array path, checked where there is no GPU: FFCUDA_EXPLAIN=1 prints, before any device call,
+    how every term with mesh-dependent data will be treated (fe_affine: sub-expressions listed by E_F0::Optimize, factors
+    fitted on the interpreter's own values and verified at every sampled node)"""
+    rc, out, _ = run_ff(EXPLAIN.replace("STATEMENT", "matrix A = va(Vh,Vh);"), {"FFCUDA_EXPLAIN": "1"}, want_fail=True)
+    ex = dict(re.findall(r"ffcuda explain: (.*? item \d+ term \d+): (.*)", out))
+    assert len(ex) == 6, out[-3000:]
+    # u*v: 2 + kap + rho/dt (LinearComb merged the three coefficients into one sum)
+    t = ex["bilinear item 0 term 0"]
+    assert t.startswith("FE data on the device: 2 + 1 * [function #0 (P1, 1 comp., 64 dofs) comp. 0 op 0] + 10 * [function #1 (P0, 1 comp., 162 dofs)")
+    assert "interpreter" in ex["bilinear item 0 term 1"]          # (1+x)*kap
+    assert "interpreter" in ex["bilinear item 0 term 2"]          # kap*ff
+    assert re.search(r": 0 \+ -1 \* \[function #\d \(P2, 1 comp., 343 dofs, own node table\) comp. 0 op 0\]", ": " + ex["bilinear item 0 term 3"])
+    assert "interpreter" in ex["bilinear item 0 term 4"]          # a function on another mesh
+    assert re.search(r"0 \+ 0.25 \* \[function #0 ", ex["boundary bilinear item 1 term 0"])
+    rc, out, _ = run_ff(EXPLAIN.replace("STATEMENT", "real[int] b = va(0,Vh);"), {"FFCUDA_EXPLAIN": "1"}, want_fail=True)
+    ex = dict(re.findall(r"ffcuda explain: (.*? item \d+ term \d+): (.*)", out))
+    assert len(ex) == 3, out[-3000:]
+    t = ex["linear item 0 term 0"]    # -(ff + f2 + uk/dt - 3 rho + 2)
+    assert t.startswith("FE data on the device: -2 + -1 * [function #0 (P1, 1 comp., 64 dofs) comp. 0 op 0] + -1 * [function #1 (P1, 3 comp., 192 dofs) comp. 1 op 0]")
+    assert " + -10 * [function #2 (P1, 1 comp., 64 dofs) comp. 0 op 0] + 3 * [function #3 (P0, 1 comp., 162 dofs) comp. 0 op 0]" in t
+    assert re.search(r"0 \+ -1 \* \[function #1 \(P1, 3 comp., 192 dofs\) comp. 2 op 6\]", ex["linear item 0 term 1"])   # -dz(f3) dx(v)
+    assert re.search(r"0 \+ -1 \* \[function #0 ", ex["boundary linear item 1 term 0"])
+    # switched off: nothing is recognised
+    rc, out, _ = run_ff(EXPLAIN.replace("STATEMENT", "real[int] b = va(0,Vh);"),
+                        {"FFCUDA_EXPLAIN": "1", "FFCUDA_NO_FE_DOFS": "1"}, want_fail=True)
+    assert out.count("evaluated by the interpreter") == 3 and "FE data on the device" not in out
+
+
 # problem / solve statements (Problem::eval, fflib/problem.cpp:12198-12450): the tutorial shape `solve Poisson(u,v,...) = a - l + on`
 SOLVE_DUMP = '{ ofstream f("u.txt"); f.precision(17); for(int i=0;i<UU[].n;++i) f << UU[][i] << endl; }\n'
 SOLVE_CASES = {
