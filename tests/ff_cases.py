@@ -106,6 +106,19 @@ CASES = {
     "lame3d_p1_bnd_grad": (1, 3, lame_terms(), [(2, ID, -0.05)], "qfV5", [([1], 7, [0.0, 0.0, 0.0])]),
     "lap3d_p2_bnd_gradq": (2, 1, LAP3, [(0, ID, 1.0)], "qfV5", [([1], 1, [0.0])]),
 }
+# the reference's own regression problems (examples/tutorial/regtests.edp, values in ref.edp): Laplace.edp, LaplaceP1.edp (Robin +
+# Neumann on label 1), beam.edp ([P1,P1] elasticity on the mesh buildmesh gives it); tgv = 1e5 as in the scripts
+_E2, _S2 = 21.5, 0.29
+_MU2, _LA2 = _E2 / (2 * (1 + _S2)), _E2 * _S2 / ((1 + _S2) * (1 - 2 * _S2))
+BEAM2 = [(0, DX, 0, DX, _LA2 + 2 * _MU2), (1, DY, 1, DY, _LA2 + 2 * _MU2), (0, DX, 1, DY, _LA2), (1, DY, 0, DX, _LA2),
+         (0, DY, 0, DY, _MU2), (1, DX, 1, DX, _MU2), (0, DY, 1, DX, _MU2), (1, DX, 0, DY, _MU2)]
+# name -> (case tuple as in CASES, tgv, Robin item, Neumann item, what regtests.edp asserts on u'*u: reference value, tolerance)
+TUTORIAL_CASES = {
+    "tutorial_laplace": ((1, 1, LAP2, [(0, ID, 1.0)], "qf5pT", [([1, 2, 3, 4], 1, [0.0])]), 1e5, None, None, (0.167397, 1e-2)),
+    "tutorial_laplace_p1": ((1, 1, LAP2, [(0, ID, 1.0)], "qf5pT", [([2, 3, 4], 1, [0.0])]), 1e5, ([1], [(0, ID, 0, ID, 1.0)]),
+                            ([1], [(0, ID, 1.0)]), (2.34669, 1e-2)),
+    "tutorial_beam": ((1, 2, BEAM2, [(1, ID, -0.05)], "qf5pT", [([1], 3, [0.0, 0.0])]), 1e30, None, None, (2.19089, 5e-2)),
+}
 # boundary integrals of the linear form: name -> (labels, terms)
 CASE_BLIN = {"lap3d_p1_neumann": ([2, 3], [(0, ID, 2.5)]), "lap2d_p2_neumann": ([2], [(0, ID, 1.5)]),
              "lame3d_p1_traction": ([2], [(0, ID, 0.3), (2, ID, -0.2)]), "lap3d_p2_neumann": ([6], [(0, ID, -1.0)])}

@@ -172,6 +172,19 @@ CASES = {
                            fes=[dict(space="Wv", fe="[P1,P1,P1]", decl="Wv [f1,f2,f3]=[x*y,sin(z),-0.05*(1+y)];", arrays=["f1"]),
                                 dict(space="W1", fe="P1", decl="W1 ee=1+x;", arrays=["ee"])],
                            bil="ee*(" + LAME + ")", lin="f1*v1+f3*v3+dx(f2)*v2", bc="on(1,u1=0,u2=0,u3=0)"),
+    # the reference's own regression problems (examples/tutorial/regtests.edp with the values of ref.edp): Laplace.edp
+    # (REFLaplace = 0.167397 +-1%), LaplaceP1.edp (REFLaplaceP1 = 2.34669 +-1%), beam.edp (REFbeam = 2.19089 +-5%, on the mesh
+    # buildmesh gives it), written as varf + matrix + CG so that the fixtures hold A, b and the solution
+    "tutorial_laplace": dict(dim=2, mesh="square(10,10)", fe="P1", bil=LAP2, lin="1.*v", bc="on(1,2,3,4,u=0)", tgv=1e5),
+    "tutorial_laplace_p1": dict(dim=2, mesh="square(10,10)", fe="P1", bil=LAP2, lin="1.*v", blin="+int1d(Th,1)(u*v)+int1d(Th,1)(1.*v)",
+                                bc="on(2,3,4,u=0)", tgv=1e5),
+    "tutorial_beam": dict(dim=2, pre="real E=21.5, sigma=0.29, gravity=-0.05; real mu=E/(2*(1+sigma)); real lambda=E*sigma/((1+sigma)*(1-2*sigma));"
+                          " real sqrt2=sqrt(2.);"
+                          " border ba(t=2,0){x=0;y=t;label=1;} border bb(t=0,10){x=t;y=0;label=2;}"
+                          " border bc(t=0,2){x=10;y=t;label=1;} border bd(t=0,10){x=10-t;y=2;label=3;}",
+                          mesh="buildmesh(bb(20)+bc(5)+bd(20)+ba(5))", fe="[P1,P1]", unk="[uu,vv]", tst="[w,s]",
+                          bil="lambda*(dx(w)+dy(s))*(dx(uu)+dy(vv))+2.*mu*(dx(w)*dx(uu)+dy(s)*dy(vv)+(dy(w)+dx(s))*(dy(uu)+dx(vv))/2.)",
+                          lin="gravity*s", bc="on(1,uu=0,vv=0)"),
 }
 
 

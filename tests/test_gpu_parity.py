@@ -138,6 +138,28 @@ def test_golden_case(ctx, name):
         assert abs(r["iters14"] - int(g["cg_iters14"])) <= 3
 
 
+@pytest.mark.parametrize("name", sorted(fc.TUTORIAL_CASES))
+def test_tutorial_known_answers(ctx, name):
+    """the reference's own regression problems (examples/tutorial/regtests.edp: Laplace.edp, LaplaceP1.edp with Robin and Neumann
+    terms, beam.edp = [P1,P1] elasticity on a buildmesh mesh; tgv = 1e5 where the scripts say so) on the device: matrix,
+    right-hand side and solution against the dumps of the reference, u'*u where regtests.edp asserts it (ref.edp values)"""
+    (order, ncomp, bt, lt, qname, bcs), tgv, bbil, blin, (ref, tol) = fc.TUTORIAL_CASES[name]
+    g = fc.load(name)
+    qp, qw = ol.quadrature(g["dim"], qname)
+    e2n = fc.elem2node(g, order, ncomp)
+    r = _run_case(ctx, g, order, ncomp, bt, lt, qp, qw, bcs, e2n, g["ndof"] // ncomp, TGV=tgv, blin=blin, bbil=bbil)
+    grp, gci, gval = fc.golden_csr(g)
+    assert r["n"] == g["ndof"]
+    assert np.array_equal(r["rowptr"], grp) and np.array_equal(r["colind"], gci)
+    isbc = gval == tgv
+    assert isbc.sum() > 0 and np.array_equal(r["vals"] == tgv, isbc)
+    assert np.max(np.abs(r["vals"] - gval)[~isbc]) <= RTOL * np.abs(gval[~isbc]).max()
+    assert np.max(np.abs(r["b"] - g["b"])) <= RTOL * np.abs(g["b"]).max()
+    assert r["conv"] in (1, 2) and abs(r["iters"] - int(g["cg_iters"])) <= 2
+    assert np.max(np.abs(r["u14"] - g["u14"])) <= 1e-11 * np.abs(g["u14"]).max()      # (tgv = 1e5: cond(A) ~ 1e7)
+    assert abs(float(r["u14"] @ r["u14"]) - ref) <= tol * ref
+
+
 @pytest.mark.parametrize("name", sorted(k for k in fc.CASES if fc.CASES[k][5] and k not in fc.NO_SOLVE_TGV))
 def test_cg_on_reference_matrix(ctx, name):
     """the solver entry the FreeFEM plugin calls (host CSR in, host vectors in/out) fed with the reference's own A, b.

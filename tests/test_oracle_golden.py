@@ -234,3 +234,38 @@ def test_boundary_links_turn_the_minority_between_two_regions():
                                 bconn.ctypes.data_as(C.c_void_p), be.ctypes.data_as(C.c_void_p), bf.ctypes.data_as(C.c_void_p))
     assert np.array_equal(bconn, [[0, 1, 2], [1, 2, 0], [0, 1, 2]])
     assert be[0] == be[1] == be[2] and bf[0] == bf[1] == bf[2] == 3
+
+
+@pytest.mark.parametrize("name", sorted(fc.TUTORIAL_CASES))
+def test_tutorial_known_answers(name):
+    """the reference's own regression problems (examples/tutorial/regtests.edp: Laplace.edp, LaplaceP1.edp, beam.edp with the
+    values of ref.edp): the oracle reproduces the matrix and right-hand side FreeFEM dumped for them, and u'*u lands where
+    regtests.edp asserts it (REFLaplace 0.167397, REFLaplaceP1 2.34669 to 1 %, REFbeam 2.19089 to 5 %)"""
+    (order, ncomp, bt, lt, qname, bcs), tgv, bbil, blin, (ref, tol) = fc.TUTORIAL_CASES[name]
+    g = fc.load(name)
+    m = _mesh(g)
+    dim, n = g["dim"], g["ndof"]
+    e2n = fc.elem2node(g, order, ncomp)
+    qp, qw = ol.quadrature(dim, qname)
+    fq, fw = ol.face_quadrature(dim)
+    ci, cj, ca = ol.assemble_coo(m, order, ncomp, e2n, bt, qp, qw)
+    if bbil:
+        ci, cj, ca = ol.coo_add(n, (ci, cj, ca), ol.assemble_coo_boundary(m, order, ncomp, e2n, bbil[1], fq, fw, bbil[0]))
+    o = np.argsort(ci.astype(np.int64) * n + cj, kind="stable")
+    ci, cj, ca = ci[o], cj[o], ca[o]
+    assert np.array_equal(ci, g["coo_i"]) and np.array_equal(cj, g["coo_j"])
+    dofs, vals = _bc(g, order, ncomp, e2n, bcs)
+    ca = ol.bc_matrix_coo(ci, cj, ca, n, dofs, tgv)
+    isbc = (ci == cj) & np.isin(ci, dofs)
+    assert np.array_equal(ca[isbc], g["coo_a"][isbc]) and np.all(ca[isbc] == tgv)
+    assert np.max(np.abs(ca - g["coo_a"])[~isbc]) <= RTOL * np.abs(g["coo_a"][~isbc]).max()
+    b = ol.assemble_rhs(m, order, ncomp, e2n, n, lt, qp, qw)
+    if blin:
+        b = ol.assemble_rhs_boundary(m, order, ncomp, e2n, b, blin[1], fq, fw, blin[0])
+    b = ol.bc_rhs(b, dofs, vals, tgv)
+    assert np.max(np.abs(b - g["b"])) <= RTOL * np.abs(g["b"]).max()
+    x, it, ret, _ = ol.cg(n, ci, cj, ca, b, np.zeros(n), eps=1e-14, itmax=0, tgv=tgv)
+    assert ret in (1, 2) and abs(it - int(g["cg_iters14"])) <= 3
+    assert np.max(np.abs(x - g["u14"])) <= 1e-11 * np.abs(g["u14"]).max()      # (tgv = 1e5: cond(A) ~ 1e7)
+    assert abs(float(x @ x) - ref) <= tol * ref
+    assert abs(float(g["u14"] @ g["u14"]) - ref) <= tol * ref

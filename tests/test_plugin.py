@@ -61,6 +61,15 @@ CASES = {
     "heat3d_p1": script(3, "cube(5,5,5)", "P1", "u*v/dt+" + LAP3, "1.*v", "on(1,2,3,4,5,6,u=0)", pre="real dt=0.01;"),
     "lame3d_p2": script(3, "cube(2,3,2)", "[P2,P2,P2]", LAME, "-0.05*v3", "on(1,u1=0,u2=0,u3=0)", pre=LAME_PRE,
                         unk="[u1,u2,u3]", tst="[v1,v2,v3]", eps="1e-14"),
+    # two components in 2-D: the elasticity of examples/tutorial/beam.edp on a structured beam, and its P2 version
+    "beam2d_p1_vector": script(2, "square(20,5,[10*x,2*y])", "[P1,P1]",
+                               "lambda*(dx(u1)+dy(u2))*(dx(v1)+dy(v2))+2.*mu*(dx(u1)*dx(v1)+dy(u2)*dy(v2)+0.5*(dy(u1)+dx(u2))*(dy(v1)+dx(v2)))",
+                               "-0.05*v2", "on(2,4,u1=0,u2=0)", pre="real E=21.5, sigma=0.29; real mu=E/(2*(1+sigma)); real lambda=E*sigma/((1+sigma)*(1-2*sigma));",
+                               unk="[u1,u2]", tst="[v1,v2]", eps="1e-14"),
+    "beam2d_p2_vector": script(2, "square(8,3,[10*x,2*y])", "[P2,P2]",
+                               "lambda*(dx(u1)+dy(u2))*(dx(v1)+dy(v2))+2.*mu*(dx(u1)*dx(v1)+dy(u2)*dy(v2)+0.5*(dy(u1)+dx(u2))*(dy(v1)+dx(v2)))",
+                               "-0.05*v2", "on(2,4,u1=0,u2=0)", pre="real E=21.5, sigma=0.29; real mu=E/(2*(1+sigma)); real lambda=E*sigma/((1+sigma)*(1-2*sigma));",
+                               unk="[u1,u2]", tst="[v1,v2]", eps="1e-14"),
     # exact elimination of the Dirichlet rows and columns (tgv = -2, HashMatrix::SetBC)
     "poisson3d_p1_tgvm2": script(3, "cube(5,6,4)", "P1", LAP3, "1.*v", "on(1,2,3,4,5,6,u=0)", tgv=-2),
     "laplace2d_p2_tgvm2": script(2, "square(6,5)", "P2", LAP2, "1.*v", "on(1,2,3,4,u=0)", eps="1e-14", tgv=-2),
