@@ -22,7 +22,10 @@
 #include <sys/mman.h>
 #include <thread>
 #include "AFunction_ext.hpp"
+#include <cstdint>
 #include <cstdlib>
+#include <cstring>
+#include <typeinfo>
 #include <map>
 #include <memory>
 #include <set>
@@ -1152,17 +1155,34 @@ std::vector<std::vector<double>> eval_at_bnodes(Stack stack, const FESpaceT &Vh,
     return out;
 }
 // A coefficient that is an AFFINE combination of FE data with mesh-independent factors — uold/dt, -f (what `- int3d(Th)(f*v)`
-// of a problem turns into: (-1)*f), f1 + 2*f2, 2 + kappa (LinearComb::add merges the coefficients of equal terms into one sum,
-// femlib/DOperator.hpp:127-131) — is taken apart without reading FreeFEM's private operator nodes: E_F0::Optimize (the public
-// pass FieldOfForm itself runs, fflib/AFunction2.cpp:839, AFunction.hpp:2607-2614) lists the sub-expressions, the FE nodes
-// among them are the candidates L_i, and beta, alpha_i of  c = beta + sum alpha_i L_i  are fitted on the values the
-// interpreter gives at the quadrature nodes of a sample of the units (~g_sample_n of them, at least one per label).  The
-// decomposition is accepted only if it reproduces c at EVERY sampled node to 1e-13: (1+x)*f, f*g, f^2, sin(f) are refused
-// and stay on the interpreter path.
+// of a problem turns into: (-1)*f), f1 + 2*f2, 2 + kappa + rho/dt (LinearComb::add merges the coefficients of equal terms into
+// one sum, femlib/DOperator.hpp:127-131) — is taken apart without reading FreeFEM's private operator nodes:
+//  1. E_F0::Optimize (the public pass FieldOfForm itself runs on every coefficient, fflib/AFunction2.cpp:839,
+//     AFunction.hpp:2607-2614) flattens the expression into a program: leaves, then operator nodes that read their operands
+//     from stack slots.  Every entry must be (i) an FE node we can evaluate on the device = a candidate L_i, (ii) a leaf that
+//     does not depend on the mesh point (constants, script variables), or (iii) an operator node (E_F_F0_Opt, E_F_F0F0_Opt,
+//     the nested Opt classes of the operator templates, AFunction.hpp:981,1053,2526,2630,2715).  Anything else — x, y, N.x,
+//     region, a function on another mesh — and the term stays on the interpreter path: c is then more than a function of
+//     the FE data.
+//  2. Otherwise c = F(L_1..L_m) with F the program itself, which we can RUN on a scratch stack with any values in the slots
+//     of the candidates: beta and alpha_i are read off F by central differences about the middle of the box the L_i range in
+//     (dof extrema and the values at the sampled nodes, widened), and F is accepted as affine only if
+//     F(p) = beta + sum alpha_i p_i to 1e-13 at the corners, the face centres and 96 random points of that box — so f*g, f^2,
+//     sin(f), max(f,c), f > c ? a : b are refused wherever they bend inside the range of the data.
+//  3. End-to-end check: the decomposition must reproduce the values the interpreter itself gives for c at the quadrature
+//     nodes of a sample of the units (~g_sample_n evenly spread, one per label, every unit of a boundary integral).
+// FFCUDA_CHECK=1 compares the whole statement with FreeFEM's own result; FFCUDA_NO_FE_DOFS=1 switches all of this off.
 struct FeAffine {
     double beta = 0.0;
     std::vector<std::pair<FeRef, double>> parts;
 };
+inline bool is_operator_node(const E_F0 *e)
+{
+    const char *nm = typeid(*e).name(); // Itanium ABI: nested class ...::Opt ends in "3OptE"; the two free templates by prefix
+    const size_t len = strlen(nm);
+    if (len >= 5 && strcmp(nm + len - 5, "3OptE") == 0) return true;
+    return strncmp(nm, "10E_F_F0_Opt", 12) == 0 || strncmp(nm, "12E_F_F0F0_Opt", 14) == 0;
+}
 template <class FESpaceT>
 bool fe_affine(Stack stack, const C_F0 &c, const FESpaceT &Vh, FeFunctions<FESpaceT> &cache, const Quad &Q, const Region &reg, bool border,
                FeAffine &out)
@@ -1176,29 +1196,52 @@ bool fe_affine(Stack stack, const C_F0 &c, const FESpaceT &Vh, FeFunctions<FESpa
         return true;
     }
     if (!g_fe_dofs || c.left() != atype<double>()) return false;
+    // --- 1. the program
     deque<pair<Expression, int>> ll;
     E_F0::MapOfE_F0 mm;
     size_t top = 64; // (offset 0 means "not found" in E_F0::find)
+    int root = 0;
     try {
-        c.LeftValue()->Optimize(ll, mm, top);
+        root = c.LeftValue()->Optimize(ll, mm, top);
     } catch (...) {
         return false;
     }
+    enum Kind { CAND, LEAF, OPER };
+    std::vector<Kind> kind(ll.size());
+    std::vector<int> cand_of(ll.size(), -1);
     std::vector<C_F0> leaves;
     std::vector<FeRef> refs;
     for (size_t i = 0; i < ll.size(); ++i) {
-        if (!dynamic_cast<const E_F0_Func1 *>(ll[i].first)) continue;
         C_F0 e(Type_Expr(atype<double>(), ll[i].first));
         FeRef rr;
-        if (!fe_reference(stack, e, Vh, cache, rr)) continue;
-        bool seen = false;
-        for (size_t j = 0; j < refs.size(); ++j) seen = seen || refs[j] == rr;
-        if (seen) continue;
-        leaves.push_back(e);
-        refs.push_back(rr);
+        if (dynamic_cast<const E_F0_Func1 *>(ll[i].first) && fe_reference(stack, e, Vh, cache, rr)) {
+            kind[i] = CAND;
+            size_t j = 0;
+            while (j < refs.size() && !(refs[j] == rr)) ++j;
+            if (j == refs.size()) {
+                leaves.push_back(e);
+                refs.push_back(rr);
+            }
+            cand_of[i] = (int)j;
+        } else if (is_operator_node(ll[i].first)) kind[i] = OPER;
+        else if (ll[i].first->MeshIndependent()) kind[i] = LEAF;
+        else return false;
     }
-    if (leaves.empty() || leaves.size() > 8) return false;
-    // the sample: units of the integral's domain, evenly spread, and the first unit of every label
+    const size_t m = refs.size();
+    if (m == 0 || m > 6 || root <= 0 || (size_t)root + sizeof(AnyType) > top) return false;
+    std::vector<char> scratch_mem(top + 2 * sizeof(AnyType) + 64, 0);
+    char *scratch = scratch_mem.data();
+    scratch += (64 - (reinterpret_cast<uintptr_t>(scratch) & 63)) & 63;
+    for (size_t i = 0; i < ll.size(); ++i)
+        if (kind[i] == LEAF) *reinterpret_cast<AnyType *>(scratch + ll[i].second) = (*ll[i].first)(stack); // on the REAL stack
+    auto F = [&](const double *p) -> double {
+        for (size_t i = 0; i < ll.size(); ++i) {
+            if (kind[i] == CAND) *reinterpret_cast<AnyType *>(scratch + ll[i].second) = SetAny<double>(p[cand_of[i]]);
+            else if (kind[i] == OPER) *reinterpret_cast<AnyType *>(scratch + ll[i].second) = (*ll[i].first)((Stack)scratch);
+        }
+        return GetAny<double>(*reinterpret_cast<AnyType *>(scratch + root));
+    };
+    // --- the sample of units (used for the ranges of the data and for the end-to-end check)
     const int nunits = border ? nbe_of(Th) : Th.nt;
     std::set<int> labs(reg.labels.begin(), reg.labels.end()), met;
     std::vector<int> inside, sample;
@@ -1209,74 +1252,90 @@ bool fe_affine(Stack stack, const C_F0 &c, const FESpaceT &Vh, FeFunctions<FESpa
         if (met.insert(lab).second) sample.push_back(k);
     }
     if (inside.empty()) return false;
-    const size_t step = std::max<size_t>(1, inside.size() / (size_t)std::max(1, g_sample_n));
+    const size_t step = (border && inside.size() <= 262144) ? 1 : std::max<size_t>(1, inside.size() / (size_t)std::max(1, g_sample_n));
     for (size_t i = 0; i < inside.size(); i += step) sample.push_back(inside[i]);
     std::sort(sample.begin(), sample.end());
     sample.erase(std::unique(sample.begin(), sample.end()), sample.end());
     std::vector<const C_F0 *> ex(1, &c);
-    for (size_t j = 0; j < leaves.size(); ++j) ex.push_back(&leaves[j]);
+    for (size_t j = 0; j < m; ++j) ex.push_back(&leaves[j]);
     const std::vector<std::vector<double>> v = border ? eval_at_bnodes(stack, Vh, ex, Q, reg, &sample) : eval_at_nodes(stack, Vh, ex, Q, reg, &sample);
-    const size_t rows = v[0].size(), m = leaves.size() + 1;
-    if (rows < 4 * m) return false;
-    // least squares for (beta, alpha_1..): columns scaled to unit maximum, normal equations in long double
-    std::vector<double> sc(m, 1.0);
-    double ymax = 0.0;
-    for (size_t k = 0; k < rows; ++k) ymax = std::max(ymax, std::abs(v[0][k]));
-    for (size_t j = 1; j < m; ++j) {
-        sc[j] = 0.0;
-        for (size_t k = 0; k < rows; ++k) sc[j] = std::max(sc[j], std::abs(v[j][k]));
-        if (sc[j] == 0.0) sc[j] = 1.0; // a function that vanishes on the sample: its column is 0, its alpha comes out 0
-    }
-    std::vector<long double> G(m * (m + 1), 0.0L);
-    for (size_t k = 0; k < rows; ++k) {
-        long double a[9];
-        a[0] = 1.0L;
-        for (size_t j = 1; j < m; ++j) a[j] = (long double)v[j][k] / sc[j];
-        for (size_t i = 0; i < m; ++i) {
-            for (size_t j = 0; j < m; ++j) G[i * (m + 1) + j] += a[i] * a[j];
-            G[i * (m + 1) + m] += a[i] * (long double)v[0][k];
+    const size_t rows = v[0].size();
+    // --- 2. the box the data range in, and F on it
+    std::vector<double> lo(m), hi(m), mid(m), h(m);
+    for (size_t j = 0; j < m; ++j) {
+        lo[j] = hi[j] = rows ? v[j + 1][0] : 0.0;
+        for (size_t k = 0; k < rows; ++k) {
+            lo[j] = std::min(lo[j], v[j + 1][k]);
+            hi[j] = std::max(hi[j], v[j + 1][k]);
         }
-    }
-    std::vector<long double> x(m, 0.0L);
-    std::vector<bool> dead(m, false);
-    for (size_t i = 0; i < m; ++i) { // Gauss-Jordan with partial pivoting; a vanishing column is dropped (alpha = 0)
-        size_t piv = i;
-        for (size_t r = i + 1; r < m; ++r)
-            if (fabsl(G[r * (m + 1) + i]) > fabsl(G[piv * (m + 1) + i])) piv = r;
-        if (fabsl(G[piv * (m + 1) + i]) <= 1e-9L * (long double)rows) {
-            bool zero_col = true;
-            for (size_t k = 0; k < rows && zero_col && i > 0; ++k) zero_col = v[i][k] == 0.0;
-            if (i > 0 && zero_col) {
-                dead[i] = true;
-                continue;
+        if (refs[j].op == FFCUDA_OP_ID) { // values: the dofs bound a P0 / P1 function, nearly a P2 one
+            const typename FeFunctions<FESpaceT>::Fun &Fn = cache.funs[refs[j].fun];
+            const KN<double> &x = *Fn.x;
+            for (long q = refs[j].comp; q < x.N(); q += Fn.ncomp) {
+                lo[j] = std::min(lo[j], x[q]);
+                hi[j] = std::max(hi[j], x[q]);
             }
-            return false; // collinear candidates (or a constant function next to beta): no unique decomposition
         }
-        if (piv != i)
-            for (size_t j = 0; j <= m; ++j) std::swap(G[i * (m + 1) + j], G[piv * (m + 1) + j]);
-        for (size_t r = 0; r < m; ++r) {
-            if (r == i) continue;
-            const long double f = G[r * (m + 1) + i] / G[i * (m + 1) + i];
-            for (size_t j = i; j <= m; ++j) G[r * (m + 1) + j] -= f * G[i * (m + 1) + j];
+        const double w = hi[j] - lo[j], pad = refs[j].op == FFCUDA_OP_ID ? 0.25 * w : w; // (derivatives: seen on the sample only)
+        lo[j] -= pad;
+        hi[j] += pad;
+        mid[j] = 0.5 * (lo[j] + hi[j]);
+        h[j] = 0.5 * (hi[j] - lo[j]);
+        if (!(h[j] > 0.0)) h[j] = std::max(1.0, std::abs(mid[j])); // a constant function: any step will do
+        if (!(std::abs(mid[j]) < 1e300) || !(h[j] < 1e300)) return false;
+    }
+    std::vector<double> p(mid), alpha(m);
+    double beta, fmax;
+    try {
+        const double f0 = F(p.data());
+        fmax = std::abs(f0);
+        for (size_t j = 0; j < m; ++j) {
+            p[j] = mid[j] + h[j];
+            const double fp = F(p.data());
+            p[j] = mid[j] - h[j];
+            const double fm = F(p.data());
+            p[j] = mid[j];
+            alpha[j] = (fp - fm) / (2.0 * h[j]);
+            fmax = std::max(fmax, std::max(std::abs(fp), std::abs(fm)));
         }
+        beta = f0;
+        for (size_t j = 0; j < m; ++j) beta -= alpha[j] * mid[j];
+        double mag = std::abs(beta);
+        for (size_t j = 0; j < m; ++j) mag += std::abs(alpha[j]) * (std::abs(mid[j]) + h[j]);
+        if (!(mag < 1e300)) return false;
+        auto affine_at = [&](const double *q) {
+            double fit = beta;
+            for (size_t j = 0; j < m; ++j) fit += alpha[j] * q[j];
+            const double f = F(q);
+            return std::abs(f - fit) <= 1e-13 * std::max(mag, std::abs(f));
+        };
+        for (unsigned corner = 0; corner < (1u << m); ++corner) { // corners of the box
+            for (size_t j = 0; j < m; ++j) p[j] = (corner >> j & 1) ? hi[j] : lo[j];
+            if (!affine_at(p.data())) return false;
+        }
+        uint64_t rng = 0x9E3779B97F4A7C15ull; // deterministic points of the box (xorshift)
+        for (int t = 0; t < 96; ++t) {
+            for (size_t j = 0; j < m; ++j) {
+                rng ^= rng << 13;
+                rng ^= rng >> 7;
+                rng ^= rng << 17;
+                p[j] = lo[j] + (hi[j] - lo[j]) * ((rng >> 11) * (1.0 / 9007199254740992.0));
+            }
+            if (!affine_at(p.data())) return false;
+        }
+        // --- 3. end to end: the interpreter's own values of c at the sampled nodes
+        for (size_t k = 0; k < rows; ++k) {
+            double fit = beta;
+            for (size_t j = 0; j < m; ++j) fit += alpha[j] * v[j + 1][k];
+            if (std::abs(fit - v[0][k]) > 1e-13 * std::max(mag, std::abs(v[0][k]))) return false;
+        }
+        if (std::abs(beta) <= 1e-14 * mag) beta = 0.0;
+    } catch (...) { // an operator that refuses a value of the box (sqrt of a negative number, ...): not affine for us
+        return false;
     }
-    for (size_t i = 0; i < m; ++i) x[i] = dead[i] ? 0.0L : G[i * (m + 1) + m] / G[i * (m + 1) + i];
-    double beta = (double)x[0], mag = std::abs(beta);
-    std::vector<double> alpha(m, 0.0);
-    for (size_t j = 1; j < m; ++j) {
-        alpha[j] = (double)(x[j] / sc[j]);
-        mag += std::abs(alpha[j]) * sc[j];
-    }
-    if (!(mag < 1e300) || mag > 1e6 * std::max(ymax, 1e-300)) return false; // (cancellation between the parts would cost digits)
-    for (size_t k = 0; k < rows; ++k) {
-        double fit = beta;
-        for (size_t j = 1; j < m; ++j) fit += alpha[j] * v[j][k];
-        if (std::abs(fit - v[0][k]) > 1e-13 * std::max(mag, ymax)) return false; // not affine in the FE data
-    }
-    if (std::abs(beta) <= 1e-13 * std::max(mag, ymax)) beta = 0.0;
     out.beta = beta;
-    for (size_t j = 1; j < m; ++j)
-        if (alpha[j] != 0.0) out.parts.push_back(std::make_pair(refs[j - 1], alpha[j]));
+    for (size_t j = 0; j < m; ++j)
+        if (alpha[j] != 0.0) out.parts.push_back(std::make_pair(refs[j], alpha[j]));
     return true;
 }
 

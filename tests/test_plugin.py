@@ -356,6 +356,21 @@ STATEMENT
 """
 
 
+EXPLAIN_TRICKY = """load "msh3"
+load "ffcuda"
+mesh3 Th = cube(12,12,12);
+fespace Vh(Th,P1);
+Vh ff=x*y+sin(z), zero=0, bump=0;
+bump[][777] = 1.;
+fespace W0(Th,P0); W0 chi = (x>0.9)*(y>0.9)*(z>0.9);
+real dt = 0.1;
+varf va(u,v) = int3d(Th)(max(ff,0.9)*v + sin(ff)*dx(v) + x*ff*dy(v) + 2*bump*dz(v))
+  + int3d(Th,qforder=2)(3*zero*v + abs(ff)*dx(v) + (1+chi)*ff*dy(v) + (ff>1.2 ? 2.:1.)*ff*dz(v))
+  + int3d(Th,qforder=3)(2*chi*v - ff*dx(v)/dt + (ff+bump)*dy(v));
+real[int] b = va(0,Vh);
+"""
+
+
 @needs_ff
 def test_plugin_recognises_fe_data_without_a_device():
     """the FreeFEM side of the dof-array path, checked where there is no GPU: FFCUDA_EXPLAIN=1 prints, before any device call,
@@ -380,6 +395,19 @@ def test_plugin_recognises_fe_data_without_a_device():
     assert " + -10 * [function #2 (P1, 1 comp., 64 dofs) comp. 0 op 0] + 3 * [function #3 (P0, 1 comp., 162 dofs) comp. 0 op 0]" in t
     assert re.search(r"0 \+ -1 \* \[function #1 \(P1, 3 comp., 192 dofs\) comp. 2 op 6\]", ex["linear item 0 term 1"])   # -dz(f3) dx(v)
     assert re.search(r"0 \+ -1 \* \[function #0 ", ex["boundary linear item 1 term 0"])
+    # what is NOT affine in the FE data on the range of the data is refused, however the sample of mesh nodes falls: kinks
+    # (max, abs, ?:), products with an indicator supported on a few elements, functions of functions, factors depending on x;
+    # a hat function that vanishes on almost every element keeps its exact factor, a function that is 0 everywhere too
+    rc, out, _ = run_ff(EXPLAIN_TRICKY, {"FFCUDA_EXPLAIN": "1"}, want_fail=True)
+    ex = [e for _, e in re.findall(r"ffcuda explain: (.*? item \d+ term \d+): (.*)", out)]
+    assert len(ex) == 11, out[-3000:]
+    for t in (0, 1, 2, 5, 6, 7):   # max(ff,0.9), sin(ff), x*ff | abs(ff), (1+chi)*ff, (ff>1.2 ? 2:1)*ff
+        assert "interpreter" in ex[t], (t, ex[t])
+    assert re.search(r": 0 \+ 2 \* \[function #\d \(P1, 1 comp., 2197 dofs\) comp. 0 op 0\]$", ": " + ex[3])      # 2*bump
+    assert re.search(r": 0 \+ 3 \* \[function #\d ", ": " + ex[4])                                                  # 3*zero
+    assert re.search(r": 0 \+ 2 \* \[function #\d \(P0, 1 comp., 10368 dofs\)", ": " + ex[8])                     # 2*chi
+    assert re.search(r": 0 \+ -10 \* \[function #\d ", ": " + ex[9])                                                # -ff/dt
+    assert ex[10].count("* [function") == 2 and " + 1 * [function" in ex[10]                                        # ff + bump
     # switched off: nothing is recognised
     rc, out, _ = run_ff(EXPLAIN.replace("STATEMENT", "real[int] b = va(0,Vh);"),
                         {"FFCUDA_EXPLAIN": "1", "FFCUDA_NO_FE_DOFS": "1"}, want_fail=True)
