@@ -1176,6 +1176,12 @@ struct FeAffine {
     double beta = 0.0;
     std::vector<std::pair<FeRef, double>> parts;
 };
+struct FeProgram {
+    deque<pair<Expression, int>> ll; // (sub-expression, stack offset) in evaluation order
+    size_t top;
+    int root;                        // offset of the value of the whole expression (0: the expression could not be flattened)
+};
+std::map<const E_F0 *, FeProgram> g_fe_programs;
 inline bool is_operator_node(const E_F0 *e)
 {
     const char *nm = typeid(*e).name(); // Itanium ABI: nested class ...::Opt ends in "3OptE"; the two free templates by prefix
@@ -1196,16 +1202,24 @@ bool fe_affine(Stack stack, const C_F0 &c, const FESpaceT &Vh, FeFunctions<FESpa
         return true;
     }
     if (!g_fe_dofs || c.left() != atype<double>()) return false;
-    // --- 1. the program
-    deque<pair<Expression, int>> ll;
-    E_F0::MapOfE_F0 mm;
-    size_t top = 64; // (offset 0 means "not found" in E_F0::find)
-    int root = 0;
-    try {
-        root = c.LeftValue()->Optimize(ll, mm, top);
-    } catch (...) {
-        return false;
+    // --- 1. the program (flattened once per expression: Optimize allocates its operator nodes, and a statement inside a time
+    //        loop comes back thousands of times)
+    std::map<const E_F0 *, FeProgram>::iterator pit = g_fe_programs.find(c.LeftValue());
+    if (pit == g_fe_programs.end()) {
+        FeProgram P;
+        E_F0::MapOfE_F0 mm;
+        P.top = 64; // (offset 0 means "not found" in E_F0::find)
+        try {
+            P.root = c.LeftValue()->Optimize(P.ll, mm, P.top);
+        } catch (...) {
+            P.root = 0;
+        }
+        pit = g_fe_programs.insert(std::make_pair((const E_F0 *)c.LeftValue(), P)).first;
     }
+    const deque<pair<Expression, int>> &ll = pit->second.ll;
+    const size_t top = pit->second.top;
+    const int root = pit->second.root;
+    if (root <= 0) return false;
     enum Kind { CAND, LEAF, OPER };
     std::vector<Kind> kind(ll.size());
     std::vector<int> cand_of(ll.size(), -1);

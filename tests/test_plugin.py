@@ -371,6 +371,20 @@ real[int] b = va(0,Vh);
 """
 
 
+EXPLAIN_LOOP = """load "msh3"
+load "ffcuda"
+mesh3 Th = cube(4,4,4);
+fespace Vh(Th,P1);
+Vh ff=x*y+sin(z), uold=x;
+real dt = 0.1;
+varf va(u,v) = int3d(Th)(ff*v/dt + 2*uold*dx(v));
+for (int it = 0; it < 3; ++it) {
+  dt = 0.1*(it+1);
+  try { real[int] b = va(0,Vh); } catch(...) { cout << "no device" << endl; }
+}
+"""
+
+
 @needs_ff
 def test_plugin_recognises_fe_data_without_a_device():
     """the FreeFEM side of the dof-array path, checked where there is no GPU: FFCUDA_EXPLAIN=1 prints, before any device call,
@@ -408,6 +422,10 @@ def test_plugin_recognises_fe_data_without_a_device():
     assert re.search(r": 0 \+ 2 \* \[function #\d \(P0, 1 comp., 10368 dofs\)", ": " + ex[8])                     # 2*chi
     assert re.search(r": 0 \+ -10 \* \[function #\d ", ": " + ex[9])                                                # -ff/dt
     assert ex[10].count("* [function") == 2 and " + 1 * [function" in ex[10]                                        # ff + bump
+    # a statement that comes back in a loop: the flattened program is kept, the factors follow the script's variables
+    rc, out, _ = run_ff(EXPLAIN_LOOP, {"FFCUDA_EXPLAIN": "1"}, want_fail=True)
+    fac = re.findall(r"term 0: FE data on the device: 0 \+ ([0-9.]+) \* \[function #0 ", out)
+    assert [round(float(f), 4) for f in fac] == [10.0, 5.0, 3.3333] and out.count("term 1: FE data on the device: 0 + 2 * [function #1") == 3
     # switched off: nothing is recognised
     rc, out, _ = run_ff(EXPLAIN.replace("STATEMENT", "real[int] b = va(0,Vh);"),
                         {"FFCUDA_EXPLAIN": "1", "FFCUDA_NO_FE_DOFS": "1"}, want_fail=True)
