@@ -703,6 +703,68 @@ static int64_t assemble_coo_impl(int dim, int nv, const double *xyz, int nt, con
     return nnz;
 }
 
+/* Rectangular matrices, `matrix B = vb(Uh,Vh)` with two different spaces on the same mesh (rows = dofs of the test space Vh,
+ * columns = dofs of the space of the unknown Uh): Element_Op with Ku != Kv (fflib/problem.cpp:6337-6437: `same` false, fu and
+ * fv tabulated separately, n = Kv.NbDoF, m = Ku.NbDoF), every (il, jl) couple of the n x m element matrix added to the
+ * HashMatrix (femlib/HashMatrix.cpp:1295-1332).  Each side: P1 / P2, 1..3 components; e2n_* may be NULL for P1.
+ * coo arrays must hold nt * (nloc_v*ncomp_v) * (nloc_u*ncomp_u) entries.  Returns nnz. */
+int64_t ffo_assemble_coo_rect(int dim, const double *xyz, int nt, const int32_t *conn, const int32_t *elab,
+                              int order_v, int ncomp_v, const int32_t *e2n_v, int order_u, int ncomp_u, const int32_t *e2n_u,
+                              int nterms, const ffo_bterm *terms, int nq, const double *qpts, const double *qw,
+                              int nlab, const int32_t *labels, int32_t *coo_i, int32_t *coo_j, double *coo_a)
+{
+    const int nlv = ffo_nloc(dim, order_v), nlu = ffo_nloc(dim, order_u), ndv = nlv * ncomp_v, ndu = nlu * ncomp_u;
+    const int nvk = dim + 1;
+    uint64_t mask;
+    hent *tab = hnew((uint64_t)nt * (uint64_t)(ndv * ndu < 64 ? 32 : ndv * ndu) + 64, &mask);
+    double *mat = (double *)malloc(sizeof(double) * (size_t)ndv * ndu);
+    int32_t *gv = (int32_t *)malloc(sizeof(int32_t) * (size_t)ndv), *gu = (int32_t *)malloc(sizeof(int32_t) * (size_t)ndu);
+    int64_t nnz = 0;
+    for (int k = 0; k < nt; ++k) {
+        if (!in_labels(elab ? elab[k] : 0, nlab, labels)) continue;
+        const int32_t *K = conn + (size_t)nvk * k;
+        const int32_t *Nv = e2n_v ? e2n_v + (size_t)nlv * k : K, *Nu = e2n_u ? e2n_u + (size_t)nlu * k : K;
+        double X[12], G[4][3], fv[10][4], fu[10][4];
+        elem_coords(dim, xyz, K, X);
+        double mes = geom(dim, X, G);
+        for (int i = 0; i < ndv * ndu; ++i) mat[i] = 0.;
+        for (int q = 0; q < nq; ++q) {
+            double coef = mes * qw[q];
+            basis(dim, order_u, qpts + (size_t)q * dim, G, fu);
+            basis(dim, order_v, qpts + (size_t)q * dim, G, fv);
+            for (int t = 0; t < nterms; ++t) {
+                int so = opslot(terms[t].uop), to = opslot(terms[t].vop);
+                double ccc = terms[t].coef;
+                ccc *= coef;
+                int fi = terms[t].vcomp * nlv, fj = terms[t].ucomp * nlu;
+                for (int a = 0; a < nlv; ++a)
+                    for (int b = 0; b < nlu; ++b) {
+                        double w_i = fv[a][to], w_j = fu[b][so];
+                        mat[(fi + a) * ndu + fj + b] += ccc * w_i * w_j;
+                    }
+            }
+        }
+        for (int c = 0; c < ncomp_v; ++c)
+            for (int a = 0; a < nlv; ++a) gv[c * nlv + a] = Nv[a] * ncomp_v + c;
+        for (int c = 0; c < ncomp_u; ++c)
+            for (int a = 0; a < nlu; ++a) gu[c * nlu + a] = Nu[a] * ncomp_u + c;
+        for (int il = 0; il < ndv; ++il)
+            for (int jl = 0; jl < ndu; ++jl) {
+                uint64_t key = ((uint64_t)(uint32_t)gv[il] << 32) | (uint32_t)gu[jl];
+                int isnew;
+                int32_t *pv = hfind(tab, mask, key, &isnew);
+                if (isnew) {
+                    *pv = (int32_t)nnz;
+                    coo_i[nnz] = gv[il]; coo_j[nnz] = gu[jl]; coo_a[nnz] = 0.;
+                    nnz++;
+                }
+                coo_a[*pv] += mat[il * ndu + jl];
+            }
+    }
+    free(tab); free(mat); free(gv); free(gu);
+    return nnz;
+}
+
 typedef struct { int32_t i, j; int64_t k; } ijk;
 static int cmp_ij(const void *a, const void *b)
 {

@@ -84,6 +84,14 @@ int64_t ffo_assemble_coo(int dim, int nv, const double *xyz, int nt, const int32
                          int nlab, const int32_t *labels,
                          int32_t *coo_i, int32_t *coo_j, double *coo_a);
 
+/* Rectangular matrices `matrix B = vb(Uh,Vh)`: two different spaces on the same mesh, rows = test space (order_v, ncomp_v,
+ * e2n_v), columns = space of the unknown (order_u, ncomp_u, e2n_u); Element_Op with Ku != Kv (fflib/problem.cpp:6337-6437).
+ * coo arrays must hold nt * (nloc_v*ncomp_v) * (nloc_u*ncomp_u) entries.  Returns nnz. */
+int64_t ffo_assemble_coo_rect(int dim, const double *xyz, int nt, const int32_t *conn, const int32_t *elab,
+                              int order_v, int ncomp_v, const int32_t *e2n_v, int order_u, int ncomp_u, const int32_t *e2n_u,
+                              int nterms, const ffo_bterm *terms, int nq, const double *qpts, const double *qw,
+                              int nlab, const int32_t *labels, int32_t *coo_i, int32_t *coo_j, double *coo_a);
+
 /* COO -> CSR sorted by (i,j) (Sortij/Buildp). */
 void ffo_coo_to_csr(int n, int64_t nnz, const int32_t *coo_i, const int32_t *coo_j, const double *coo_a,
                     int32_t *rowptr, int32_t *colind, double *vals);

@@ -222,6 +222,28 @@ def golden_csr(g):
     return np.cumsum(rp).astype(np.int32), g["coo_j"][o].astype(np.int32), g["coo_a"][o]
 
 
+# Rectangular matrices `matrix B = vb(Uh,Vh)` (tests/golden/make_golden_rect.py): rows = test space, columns = space of the
+# unknown.  name -> ((order_v, ncomp_v), (order_u, ncomp_u), terms (ucomp,uop,vcomp,vop,coef), quadrature name)
+RECT_CASES = {
+    "rect3d_div_p2p1": ((1, 1), (2, 3), [(0, DX, 0, ID, -1.0), (1, DY, 0, ID, -1.0), (2, DZ, 0, ID, -1.0), (1, ID, 0, DX, 0.5)], "qfV5"),
+    "rect3d_grad_p1p2": ((2, 3), (1, 1), [(0, ID, 0, DX, -1.0), (0, ID, 1, DY, -1.0), (0, ID, 2, DZ, -1.0), (0, DX, 2, ID, 1.0)], "qfV5"),
+    "rect2d_p1_to_p2": ((2, 1), (1, 1), [(0, ID, 0, ID, 1.0), (0, DX, 0, DY, 0.5)], "qf5pT"),
+    "rect2d_div_p2p1": ((1, 1), (2, 2), [(0, DX, 0, ID, -1.0), (1, DY, 0, ID, -1.0)], "qf5pT"),
+    "rect3d_p1vec_p1": ((1, 1), (1, 3), [(0, DX, 0, ID, 1.0), (2, ID, 0, DZ, 2.0)], "qfV5"),
+    "rect2d_p2vec_p1vec": ((1, 2), (2, 2), [(0, ID, 0, ID, 1.0), (1, ID, 1, ID, 1.0), (0, DY, 1, ID, 0.25)], "qf2pT"),
+}
+
+
+def rect_elem2node(g, which, ncomp):
+    """node table of one space of a rectangular fixture (which = "Uh" | "Vh"), see elem2node"""
+    dof = g["dof_" + which]
+    nl = dof.shape[1] // ncomp
+    e2n = dof[:, :nl] // ncomp
+    for c in range(ncomp):
+        assert np.array_equal(dof[:, c * nl:(c + 1) * nl], e2n * ncomp + c)
+    return np.ascontiguousarray(e2n, dtype=np.int32)
+
+
 def elem2node(g, order, ncomp):
     """node table (nt x nloc) recovered from the reference dof table: dof(k, c*nloc+a) = node*ncomp + c."""
     dof = g["dof"]

@@ -36,6 +36,7 @@ def lib():
         _LIB.ffo_assemble_coo_boundary.restype = C.c_int64
         _LIB.ffo_assemble_coo_qcoef.restype = C.c_int64
         _LIB.ffo_assemble_coo_boundary_qcoef.restype = C.c_int64
+        _LIB.ffo_assemble_coo_rect.restype = C.c_int64
     return _LIB
 
 
@@ -168,6 +169,25 @@ def assemble_coo_qcoef(mesh, order, ncomp, elem2node, terms, qpts, qw, cq):
     nnz = lib().ffo_assemble_coo_qcoef(dim, xyz.shape[0], _p(xyz, C.c_double), nt, _p(conn, C.c_int32), _p(elab, C.c_int32),
                                        order, ncomp, _p(e2n, C.c_int32), len(terms), bt, len(qw), _p(qpts, C.c_double),
                                        _p(qw, C.c_double), _p(cq, C.c_double), _p(ci, C.c_int32), _p(cj, C.c_int32), _p(ca, C.c_double))
+    return ci[:nnz].copy(), cj[:nnz].copy(), ca[:nnz].copy()
+
+
+def assemble_coo_rect(mesh, order_v, ncomp_v, e2n_v, order_u, ncomp_u, e2n_u, terms, qpts, qw, labels=None):
+    """COO (HashMatrix insertion order) of a rectangular matrix: rows = dofs of the test space, columns = dofs of the space
+    of the unknown, both on the same mesh"""
+    dim = mesh["dim"]
+    xyz, conn, elab = _f64(mesh["xyz"]), _i32(mesh["conn"]), _i32(mesh["elab"])
+    nt = conn.shape[0]
+    cap = nt * nloc(dim, order_v) * ncomp_v * nloc(dim, order_u) * ncomp_u
+    ci, cj, ca = np.zeros(cap, np.int32), np.zeros(cap, np.int32), np.zeros(cap)
+    ev, eu, lab = _i32(e2n_v), _i32(e2n_u), _i32(labels)
+    bt = bterms(terms)
+    qpts, qw = _f64(qpts), _f64(qw)
+    nnz = lib().ffo_assemble_coo_rect(dim, _p(xyz, C.c_double), nt, _p(conn, C.c_int32), _p(elab, C.c_int32),
+                                      order_v, ncomp_v, _p(ev, C.c_int32), order_u, ncomp_u, _p(eu, C.c_int32),
+                                      len(terms), bt, len(qw), _p(qpts, C.c_double), _p(qw, C.c_double),
+                                      0 if lab is None else len(lab), _p(lab, C.c_int32),
+                                      _p(ci, C.c_int32), _p(cj, C.c_int32), _p(ca, C.c_double))
     return ci[:nnz].copy(), cj[:nnz].copy(), ca[:nnz].copy()
 
 

@@ -1,0 +1,42 @@
+"""CPU tests: the oracle's restatement of the rectangular assembly (`matrix B = vb(Uh,Vh)`, Element_Op with Ku != Kv,
+fflib/problem.cpp:6337-6437) pinned on fixtures dumped from the unmodified reference (tests/golden/make_golden_rect.py):
+HashMatrix insertion order and sorted pattern bit-exact, values 1e-12 of the largest entry."""
+import numpy as np
+import pytest
+
+import ff_cases as fc
+import oracle_lib as ol
+
+RTOL = 1e-12
+
+
+def oracle_rect(name):
+    (ov, cv), (ou, cu), terms, qname = fc.RECT_CASES[name]
+    g = fc.load(name)
+    mesh = {k: g[k] for k in ("dim", "xyz", "conn", "elab")}
+    ev, eu = fc.rect_elem2node(g, "Vh", cv), fc.rect_elem2node(g, "Uh", cu)
+    qp, qw = ol.quadrature(g["dim"], qname)
+    return g, ol.assemble_coo_rect(mesh, ov, cv, ev, ou, cu, eu, terms, qp, qw)
+
+
+@pytest.mark.parametrize("name", sorted(fc.RECT_CASES))
+def test_rectangular_matrix_against_the_reference(name):
+    g, (ci, cj, ca) = oracle_rect(name)
+    n, m = int(g["n"]), int(g["m"])
+    assert ci.max() < n and cj.max() < m
+    assert np.array_equal(ci, g["ins_i"]) and np.array_equal(cj, g["ins_j"])
+    o = np.argsort(ci.astype(np.int64) * m + cj, kind="stable")
+    assert np.array_equal(ci[o], g["coo_i"]) and np.array_equal(cj[o], g["coo_j"])
+    assert np.max(np.abs(ca[o] - g["coo_a"])) <= RTOL * np.abs(g["coo_a"]).max()
+
+
+def test_rectangular_with_equal_spaces_is_the_square_assembly():
+    """Uh = Vh: the rectangular restatement gives what ffo_assemble_coo gives, bit for bit"""
+    g = fc.load("lame3d_p2_cube2")
+    order, ncomp, bt, _, qname, _ = fc.CASES["lame3d_p2_cube2"]
+    mesh = {k: g[k] for k in ("dim", "xyz", "conn", "elab")}
+    e2n = fc.elem2node(g, order, ncomp)
+    qp, qw = ol.quadrature(3, qname)
+    a = ol.assemble_coo(mesh, order, ncomp, e2n, bt, qp, qw)
+    b = ol.assemble_coo_rect(mesh, order, ncomp, e2n, order, ncomp, e2n, bt, qp, qw)
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
