@@ -2484,3 +2484,145 @@ extern "C" int ffcuda_fe_table(ffcuda_mesh *m, int order, const int32_t *e2n, in
     FF_CUDA(cudaStreamSynchronize(st)); // Bq and e2n are host memory of this call / of the caller
     FF_API_END(m ? m->ctx : nullptr)
 }
+
+// ----------------------------------------------------------------------------------------------------
+// RECTANGULAR matrices: `matrix B = vb(Uh,Vh)` with two different spaces on one mesh (the blocks of a Stokes / mixed
+// problem assembled one by one, interpolation and projection matrices between P1 and P2).  Rows = dofs of the test space,
+// columns = dofs of the space of the unknown (Element_Op with Ku != Kv, fflib/problem.cpp:6337-6437, 2-D :6063-6160; the
+// operator takes the two spaces, fflib/problem.hpp:1628-1631).  Symbolic phase: ff_rect_node_pattern (symbolic.cu);
+// numeric phase: one thread per row node runs rect_row (rect_row.cuh) over the incidence lists of the test space.  The
+// result is a matrix without a pattern object (like ffcuda_matrix_from_csr): products and hand-off formats apply, the
+// solvers and Dirichlet entries do not.  O(nt nq nloc_v nloc_u) on a general kernel: clarity over speed, this is not the
+// square hot path.
+// ----------------------------------------------------------------------------------------------------
+#include "rect_row.cuh"
+
+struct RecView { // e-th record of row `row` in either incidence layout
+    IncView V;
+    int row;
+    __device__ __forceinline__ uint32_t operator()(int e) const { return V.inc[V.idx(row, e)]; }
+};
+
+template <int DIM>
+__global__ void __launch_bounds__(128) k_asm_rect(int nrows, const IncView V, const int32_t *__restrict__ conn, const int32_t *__restrict__ elab,
+                                                  const double *__restrict__ xyz, int vstride, const int32_t *__restrict__ e2n_u,
+                                                  const RectParams *__restrict__ Pp, const int32_t *__restrict__ nrowptr,
+                                                  const int32_t *__restrict__ ncol, double *__restrict__ vals)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrows) return;
+    const int rb = nrowptr[i], L = nrowptr[i + 1] - rb;
+    if (L == 0) return;
+    rect_row<DIM>(V.cnt[i], RecView{V, i}, conn, elab, xyz, vstride, e2n_u, *Pp, ncol, rb, L,
+                  vals + (size_t)Pp->ncv * Pp->ncu * rb);
+}
+
+// node-level CSR -> dof-level CSR of the component-block layout: row (i, cv) holds, for every column node p of row node i
+// in order, the ncu components: rowptr[i*ncv + cv] = ncu * (ncv * nrowptr[i] + cv * L), colind = ncol[p] * ncu + cu
+__global__ void k_rect_expand(int nrows, int ncv, int ncu, const int32_t *__restrict__ nrowptr, const int32_t *__restrict__ ncol,
+                              int32_t *__restrict__ rowptr, int32_t *__restrict__ colind)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > nrows) return;
+    if (i == nrows) {
+        rowptr[(size_t)nrows * ncv] = ncu * ncv * nrowptr[nrows];
+        return;
+    }
+    const int b = nrowptr[i], L = nrowptr[i + 1] - b;
+    for (int cv = 0; cv < ncv; ++cv) {
+        const int r = ncu * (ncv * b + cv * L);
+        rowptr[(size_t)i * ncv + cv] = r;
+        for (int p = 0; p < L; ++p)
+            for (int cu = 0; cu < ncu; ++cu) colind[(size_t)r + (size_t)p * ncu + cu] = ncol[b + p] * ncu + cu;
+    }
+}
+
+extern "C" int ffcuda_assemble_bilinear_rect(ffcuda_space *sv, ffcuda_space *su, int nterms, const ffcuda_bterm *terms, int nq,
+                                             const double *qpts, const double *qw, int nlab, const int32_t *labels, ffcuda_matrix **out)
+{
+    ffcuda_matrix *A = nullptr;
+    FF_API_BEGIN
+    FF_REQUIRE(sv && su && out && terms && qpts && qw, "ffcuda_assemble_bilinear_rect: null argument");
+    FF_REQUIRE(sv->mesh == su->mesh, "ffcuda_assemble_bilinear_rect: the two spaces must live on the same device mesh");
+    ffcuda_ctx *ctx = sv->ctx;
+    ffcuda_mesh *m = sv->mesh;
+    FF_REQUIRE(!m->distributed, "rectangular matrices on distributed meshes are not on the ffcuda path");
+    FF_REQUIRE(nterms >= 1 && nterms <= RECT_MAXT, "rectangular forms: 1 to 64 terms");
+    FF_REQUIRE(nq >= 1 && nq <= RECT_MAXQ, "rectangular forms: at most 32 quadrature points");
+    FF_REQUIRE(!labels || (nlab >= 0 && nlab <= RECT_MAXLAB), "at most 16 region labels per integral");
+    ff_enter(ctx);
+    cudaStream_t st = ctx->stream;
+    const int dim = m->dim, ncv = sv->ncomp, ncu = su->ncomp;
+    FF_REQUIRE(dim == 2 || dim == 3, "bad dimension");
+    FF_REQUIRE(ncv >= 1 && ncv <= 3 && ncu >= 1 && ncu <= 3, "1 to 3 components per space");
+    std::unique_ptr<RectParams> P(new RectParams());
+    memset(P.get(), 0, sizeof(RectParams));
+    P->nq = nq;
+    P->nterms = nterms;
+    P->nlab = labels ? nlab : -1;
+    for (int i = 0; labels && i < nlab; ++i) P->labels[i] = labels[i];
+    P->order_v = sv->order;
+    P->order_u = su->order;
+    P->ncv = ncv;
+    P->ncu = ncu;
+    P->nloc_u = su->nloc;
+    for (int q = 0; q < nq; ++q) {
+        P->w[q] = qw[q];
+        double l0 = 1.0;
+        for (int d = 0; d < dim; ++d) {
+            P->lam[q][d + 1] = qpts[(size_t)q * dim + d];
+            l0 -= qpts[(size_t)q * dim + d];
+        }
+        P->lam[q][0] = l0;
+    }
+    for (int t = 0; t < nterms; ++t) {
+        const ffcuda_bterm &T = terms[t];
+        FF_REQUIRE(T.ucomp >= 0 && T.ucomp < ncu && T.vcomp >= 0 && T.vcomp < ncv, "term component out of range");
+        P->t[t] = RectTerm{T.coef, T.vcomp, T.ucomp, op_slot(T.vop), op_slot(T.uop)};
+        FF_REQUIRE(dim == 3 || (P->t[t].uslot < 3 && P->t[t].vslot < 3), "dz on a 2-D mesh");
+    }
+    // --- symbolic phase
+    DBuf<int32_t> nrowptr, ncol;
+    int64_t nnzn = 0;
+    int maxrow_node = 0;
+    ff_rect_node_pattern(sv, su, nrowptr, ncol, &nnzn, &maxrow_node);
+    const int nrows = sv->nnodes_owned;
+    const int64_t nnz = nnzn * ncv * ncu;
+    FF_REQUIRE(nnz > 0, "rectangular form on a mesh without elements");
+    FF_REQUIRE(nnz < ((int64_t)1 << 31), "matrix exceeds 2^31 nonzeros (int32 CSR, like MatriceMorse)");
+    A = new ffcuda_matrix();
+    A->ctx = ctx;
+    A->ref.set(ctx);
+    A->rect = true;
+    A->n = nrows * ncv;
+    A->ncols = su->nnodes * ncu;
+    A->nnz = nnz;
+    A->maxrow = maxrow_node * ncu;
+    A->rowptr_own.alloc((size_t)A->n + 1);
+    A->colind_own.alloc((size_t)std::max<int64_t>(nnz, 1));
+    A->vals.alloc((size_t)std::max<int64_t>(nnz, 1));
+    A->rowptr = A->rowptr_own.p;
+    A->colind = A->colind_own.p;
+    A->diagpos = nullptr;
+    FF_CUDA(cudaMemsetAsync(A->vals.p, 0, A->vals.bytes(), st));
+    ff_launch(ctx, "rect_expand", [&] {
+        k_rect_expand<<<ff_blocks((size_t)nrows + 1, 128), 128, 0, st>>>(nrows, ncv, ncu, nrowptr.p, ncol.p, A->rowptr_own.p, A->colind_own.p);
+    });
+    // --- numeric phase
+    DBuf<RectParams> dP;
+    dP.alloc(1);
+    FF_CUDA(cudaMemcpyAsync(dP.p, P.get(), sizeof(RectParams), cudaMemcpyHostToDevice, st));
+    const IncView V = ff_view(sv->incidence);
+    ff_launch(ctx, "asm_rect", [&] {
+        if (dim == 3)
+            k_asm_rect<3><<<ff_blocks(nrows, 128), 128, 0, st>>>(nrows, V, m->conn.p, m->elab.p, m->xyz.p, m->vstride, su->e2n, dP.p, nrowptr.p,
+                                                                 ncol.p, A->vals.p);
+        else
+            k_asm_rect<2><<<ff_blocks(nrows, 128), 128, 0, st>>>(nrows, V, m->conn.p, m->elab.p, m->xyz.p, m->vstride, su->e2n, dP.p, nrowptr.p,
+                                                                 ncol.p, A->vals.p);
+    });
+    FF_CUDA(cudaStreamSynchronize(st)); // P (host) and the node-level pattern go out of scope
+    *out = A;
+    A = nullptr;
+    FF_API_END((delete A, sv ? sv->ctx : nullptr))
+}

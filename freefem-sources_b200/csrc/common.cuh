@@ -428,6 +428,7 @@ struct ffcuda_matrix {
     const int32_t *rowptr = nullptr, *colind = nullptr, *diagpos = nullptr;
     DBuf<double> vals;
     bool vals_stale = false;  // allocated but not yet zeroed/written (ffcuda_matrix_create defers the memset)
+    bool rect = false;        // rectangular (ffcuda_assemble_bilinear_rect): n rows, ncols columns, no diagonal; products and hand-off only
     int maxrow = 0;           // longest dof row
     // CSR-stream SpMV set-up (lazily built, once per matrix): row-block table
     int stream_state = 0;     // 0 not prepared, 1 ready, -1 not applicable
@@ -469,6 +470,9 @@ struct ffcuda_bc {
     DBuf<double> vals;
 };
 
+// symbolic.cu: node-level pattern (rows = nodes of sv, columns = nodes of su) of a rectangular matrix
+void ff_rect_node_pattern(ffcuda_space *sv, ffcuda_space *su, DBuf<int32_t> &nrowptr, DBuf<int32_t> &ncol, int64_t *nnz_node,
+                          int *maxrow_node);
 void ff_pattern_ensure_colind(ffcuda_pattern *P); // symbolic.cu: dof-level column indices of a vector-space pattern, on demand
 void ff_pattern_ensure_pos(ffcuda_pattern *P); // symbolic.cu: per-record positions of a P1 pattern, on demand
 void ff_matrix_touch(ffcuda_matrix *A); // matrix.cu: zero the values if nothing has written them yet

@@ -291,6 +291,32 @@ extern "C" int ffcuda_matrix_info(ffcuda_matrix *A, int *n, int64_t *nnz)
     FF_API_END(A ? A->ctx : nullptr)
 }
 
+extern "C" int ffcuda_matrix_shape(ffcuda_matrix *A, int *n, int *ncols, int64_t *nnz)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A, "null matrix");
+    if (n) *n = A->n;
+    if (ncols) *ncols = A->ncols;
+    if (nnz) *nnz = A->nnz;
+    FF_API_END(A ? A->ctx : nullptr)
+}
+
+// CSR arrays of a matrix that has no pattern object (ffcuda_matrix_from_csr*, ffcuda_assemble_bilinear_rect) -> host
+extern "C" int ffcuda_matrix_download_csr(ffcuda_matrix *A, int32_t *rowptr, int32_t *colind, double *vals)
+{
+    FF_API_BEGIN
+    FF_REQUIRE(A && rowptr && colind, "null argument");
+    ffcuda_ctx *ctx = A->ctx;
+    ff_enter(ctx);
+    ff_matrix_touch(A);
+    const int32_t *ci = ff_matrix_colind(A);
+    FF_CUDA(cudaMemcpyAsync(rowptr, A->rowptr, ((size_t)A->n + 1) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (A->nnz > 0) FF_CUDA(cudaMemcpyAsync(colind, ci, (size_t)A->nnz * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (vals && A->nnz > 0) FF_CUDA(cudaMemcpyAsync(vals, A->vals.p, (size_t)A->nnz * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    FF_CUDA(cudaStreamSynchronize(ctx->stream));
+    FF_API_END(A ? A->ctx : nullptr)
+}
+
 extern "C" int ffcuda_matrix_download(ffcuda_matrix *A, double *vals)
 {
     FF_API_BEGIN
@@ -654,6 +680,7 @@ extern "C" int ffcuda_matrix_apply_bc(ffcuda_matrix *A, ffcuda_bc *bc, double tg
     FF_API_BEGIN
     FF_REQUIRE(A && bc, "null argument");
     FF_REQUIRE(tgv == tgv, "tgv is NaN");
+    FF_REQUIRE(!A->rect, "ffcuda_matrix_apply_bc is for square matrices (this one is rectangular: products and hand-off only)");
     ffcuda_ctx *ctx = A->ctx;
     ff_enter(ctx);
     ff_matrix_touch(A);

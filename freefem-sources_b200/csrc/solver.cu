@@ -1098,6 +1098,7 @@ extern "C" int ffcuda_cg(ffcuda_matrix *A, ffcuda_vec *b, ffcuda_vec *x, double 
 {
     FF_API_BEGIN
     FF_REQUIRE(A && b && x, "ffcuda_cg: null argument");
+    FF_REQUIRE(!A->rect, "ffcuda_cg is for square matrices (this one is rectangular: products and hand-off only)");
     FF_REQUIRE(b->n >= A->n && x->n >= A->n, "ffcuda_cg: vectors shorter than the matrix");
     ff_enter(A->ctx);
     cg_device(A, b->d.p, x->d.p, eps, itmax, tgv, iters, converged, gcg);
@@ -1109,6 +1110,7 @@ extern "C" int ffcuda_cg_host(ffcuda_matrix *A, const double *b, double *x, doub
 {
     FF_API_BEGIN
     FF_REQUIRE(A && b && x, "ffcuda_cg_host: null argument");
+    FF_REQUIRE(!A->rect, "ffcuda_cg_host is for square matrices (this one is rectangular: products and hand-off only)");
     ffcuda_ctx *ctx = A->ctx;
     ff_enter(ctx);
     DBuf<double> db, dx;
@@ -1652,6 +1654,7 @@ extern "C" int ffcuda_gmres(ffcuda_matrix *A, ffcuda_vec *b, ffcuda_vec *x, doub
 {
     FF_API_BEGIN
     FF_REQUIRE(A && b && x, "ffcuda_gmres: null argument");
+    FF_REQUIRE(!A->rect, "ffcuda_gmres is for square matrices (this one is rectangular: products and hand-off only)");
     FF_REQUIRE(b->n >= A->n && x->n >= A->n, "ffcuda_gmres: vectors shorter than the matrix");
     ff_enter(A->ctx);
     gmres_device(A, b->d.p, x->d.p, eps, itmax, restart, tgv, iters, converged, relres);
@@ -1663,6 +1666,7 @@ extern "C" int ffcuda_gmres_host(ffcuda_matrix *A, const double *b, double *x, d
 {
     FF_API_BEGIN
     FF_REQUIRE(A && b && x, "ffcuda_gmres_host: null argument");
+    FF_REQUIRE(!A->rect, "ffcuda_gmres_host is for square matrices (this one is rectangular: products and hand-off only)");
     ffcuda_ctx *ctx = A->ctx;
     ff_enter(ctx);
     DBuf<double> db, dx;

@@ -879,8 +879,8 @@ __global__ void __launch_bounds__(256) k_row_pattern(const int32_t *__restrict__
                 ncol[(size_t)rb + x] = v;
                 if (v == row) diagnode[row] = x;
             }
-            // positions of the nodes of every incident element inside this row
-            for (int x = lane; x < ncand; x += 32) {
+            // positions of the nodes of every incident element inside this row (not asked for by rectangular patterns)
+            for (int x = lane; pos != nullptr && x < ncand; x += 32) {
                 const int v = cand[x];
                 int lo = 0, hi = nu - 1;
                 while (lo < hi) {
@@ -1170,6 +1170,56 @@ extern "C" int ffcuda_symbolic(ffcuda_space *s, ffcuda_pattern **out)
     *out = P;
     P = nullptr;
     FF_API_END((delete P, s ? s->ctx : nullptr))
+}
+
+// Node-level pattern of a RECTANGULAR matrix (`matrix B = vb(Uh,Vh)`, assemble.cu: ffcuda_assemble_bilinear_rect): row
+// node i of the test space sv is coupled with every node of the space of the unknown su carried by an element around i.
+// The two passes of k_row_pattern with the incidence lists of sv and the element -> node table of su.
+void ff_rect_node_pattern(ffcuda_space *sv, ffcuda_space *su, DBuf<int32_t> &nrowptr, DBuf<int32_t> &ncol, int64_t *nnz_node,
+                          int *maxrow_node)
+{
+    ffcuda_ctx *ctx = sv->ctx;
+    cudaStream_t st = ctx->stream;
+    ff_build_incidence(sv);
+    const Incidence &I = sv->incidence;
+    const IncView V = ff_view(I);
+    const int nrows = sv->nnodes_owned, nloc = su->nloc;
+    DBuf<int32_t> rowlen, diagnode, d_max;
+    rowlen.alloc((size_t)nrows + 1);
+    diagnode.alloc((size_t)nrows); // written where a column node has the number of the row node; not used
+    d_max.alloc(1);
+    FF_CUDA(cudaMemsetAsync(rowlen.p, 0, rowlen.bytes(), st));
+    FF_CUDA(cudaMemsetAsync(d_max.p, 0, sizeof(int32_t), st));
+    nrowptr.alloc((size_t)nrows + 1);
+    int TS = 64, LOG = 6;
+    while (TS < 2 * std::max(I.maxinc, 1) * nloc) {
+        TS <<= 1;
+        ++LOG;
+    }
+    const size_t per_warp = ((size_t)TS + TS / 2) * 4;
+    FF_REQUIRE(per_warp <= 200 * 1024, "a node has too many incident elements for the shared-memory hash table");
+    int warps = 8;
+    while (warps > 1 && (size_t)warps * per_warp > 96 * 1024) warps >>= 1;
+    const size_t shmem = (size_t)warps * per_warp;
+    const int blocks = std::max(1, min(ff_blocks((size_t)nrows, warps), ctx->sm_count * 16));
+    FF_CUDA(cudaFuncSetAttribute(k_row_pattern<0, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    ff_launch(ctx, "sym_rect_count", [&] {
+        k_row_pattern<0, uint8_t><<<blocks, warps * 32, shmem, st>>>(su->e2n, nloc, nloc, nrows, TS, LOG, V, rowlen.p, nullptr, nullptr, nullptr,
+                                                                     nullptr, d_max.p);
+    });
+    int32_t h_max = 0;
+    int64_t nnzn = 0;
+    FF_CUDA(cudaMemcpyAsync(&h_max, d_max.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    ff_exclusive_scan_i32(ctx, rowlen.p, nrowptr.p, (size_t)nrows + 1, &nnzn); // synchronises the stream
+    ncol.alloc((size_t)std::max<int64_t>(nnzn, 1));
+    FF_CUDA(cudaFuncSetAttribute(k_row_pattern<1, uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shmem));
+    ff_launch(ctx, "sym_rect_fill", [&] {
+        k_row_pattern<1, uint8_t><<<blocks, warps * 32, shmem, st>>>(su->e2n, nloc, nloc, nrows, TS, LOG, V, nullptr, nrowptr.p, ncol.p, nullptr,
+                                                                     diagnode.p, nullptr);
+    });
+    FF_CUDA(cudaStreamSynchronize(st)); // rowlen / diagnode / d_max go out of scope
+    *nnz_node = nnzn;
+    *maxrow_node = h_max;
 }
 
 // dof-level column indices of a vector-space pattern, expanded from the node-level ones on first use

@@ -24,7 +24,8 @@ ffcuda_vec_upload ffcuda_vec_download ffcuda_vec_fill ffcuda_vec_ptr ffcuda_vec_
 ffcuda_assemble_linear ffcuda_assemble_linear_qvalues ffcuda_assemble_linear_qterms ffcuda_assemble_linear_boundary ffcuda_assemble_bilinear_boundary ffcuda_assemble_linear_boundary_qvalues ffcuda_assemble_bilinear_boundary_qcoef ffcuda_bc_from_pairs ffcuda_bc_from_labels ffcuda_bc_count ffcuda_matrix_apply_bc ffcuda_vec_apply_bc
 ffcuda_vec_set_bc_values ffcuda_bc_destroy ffcuda_spmv ffcuda_cg ffcuda_cg_host ffcuda_gmres ffcuda_gmres_host ffcuda_comm_unique_id ffcuda_comm_init
 ffcuda_comm_finalize ffcuda_mesh_cube_distributed ffcuda_mesh_local_to_global ffcuda_quadrature ffcuda_partition_cube
-ffcuda_partition_rcb ffcuda_partition_local ffcuda_matrix_export_device ffcuda_matrix_download_coo ffcuda_matrix_write_morse ffcuda_mesh_adjacency ffcuda_mesh_upload_distributed ffcuda_cg_stop_threshold ffcuda_fe_table""".split()
+ffcuda_partition_rcb ffcuda_partition_local ffcuda_matrix_export_device ffcuda_matrix_download_coo ffcuda_matrix_write_morse ffcuda_mesh_adjacency ffcuda_mesh_upload_distributed ffcuda_cg_stop_threshold ffcuda_fe_table
+ffcuda_assemble_bilinear_rect ffcuda_matrix_shape ffcuda_matrix_download_csr""".split()
 
 
 class FfcudaError(RuntimeError):
@@ -397,6 +398,17 @@ class Space(_Handle):
         _ck(lib().ffcuda_symbolic(_h(self), C.byref(out)), self.ctx.h)
         return Pattern(out.value, self.ctx, self)
 
+    def assemble_rect(self, unknown_space, terms, qpts, qw, labels=None):
+        """`matrix B = vb(Uh,Vh)`: self = the test space Vh (rows), unknown_space = Uh (columns), both on the same device mesh"""
+        arr = (BTerm * max(len(terms), 1))()
+        for k, (uc, uo, vc, vo, c) in enumerate(terms):
+            arr[k] = BTerm(uc, uo, vc, vo, c)
+        qpts, qw, lab = _f64(qpts), _f64(qw), _i32(labels)
+        out = C.c_void_p()
+        _ck(lib().ffcuda_assemble_bilinear_rect(_h(self), _h(unknown_space), len(terms), arr, len(qw), _p(qpts), _p(qw),
+                                                0 if lab is None else len(lab), _p(lab), C.byref(out)), self.ctx.h)
+        return Matrix(out.value, self.ctx, None)
+
     def bc_from_labels(self, labels, compmask, values):
         labels, values = _i32(labels), _f64(values)
         out = C.c_void_p()
@@ -501,6 +513,18 @@ class Matrix(_Handle):
         v = np.zeros(nnz) if out is None else out
         _ck(lib().ffcuda_matrix_download(_h(self), _p(v)), self.ctx.h)
         return v
+
+    def shape(self):
+        n, m, nnz = C.c_int(), C.c_int(), C.c_int64()
+        _ck(lib().ffcuda_matrix_shape(_h(self), C.byref(n), C.byref(m), C.byref(nnz)), self.ctx.h)
+        return n.value, m.value, nnz.value
+
+    def download_csr(self):
+        """(rowptr, colind, vals) of a matrix without a pattern object"""
+        n, _, nnz = self.shape()
+        rp, ci, v = np.zeros(n + 1, np.int32), np.zeros(nnz, np.int32), np.zeros(nnz)
+        _ck(lib().ffcuda_matrix_download_csr(_h(self), _p(rp), _p(ci), _p(v)), self.ctx.h)
+        return rp, ci, v
 
     def download_lower(self):
         nl = C.c_int64()

@@ -905,6 +905,7 @@ struct FeNodeFunctions {
 };
 FeNodeFunctions g_fe2 = {{0, 0, 0, 0}}, g_fe3 = {{0, 0, 0, 0}};
 bool g_fe_dofs = true, g_explain = false;
+bool g_rect = false; // FFCUDA_RECT=1: `matrix B = vb(Uh,Vh)` with two different spaces goes to the device as well (see rect_form)
 template <class PF>
 void find_fe_node_functions(FeNodeFunctions &F, int dim)
 {
@@ -1826,6 +1827,99 @@ void gpu_rhs(Stack stack, const FESpaceT &Vh, DevSpace &D, const Varf &V, double
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// 0. matrix B = vb(Uh,Vh) with two DIFFERENT spaces on one mesh (FFCUDA_RECT=1): the blocks of a Stokes / mixed problem
+//    assembled one by one, projection matrices between P1 and P2.  The built-in operator takes the two spaces
+//    (fflib/problem.hpp:1628-1631, creationBlockOfMatrixToBilinearForm :1664-1700: a MatriceMorse with Vh.NbOfDF rows and
+//    Uh.NbOfDF columns, "lines corresponding to test functions").  Claimed here: volume integrals with constant coefficients,
+//    one quadrature rule and one set of regions for the whole form, no on(...), no sym=1.  Everything else goes to FreeFEM.
+//    Off by default: the library entry behind it (ffcuda_assemble_bilinear_rect) is pinned against the reference on the host
+//    only (tests/test_rect_row_host.py) until a GPU run is on record.
+// ------------------------------------------------------------------------------------------------------------
+struct RectForm {
+    std::vector<ffcuda_bterm> terms;
+    Quad q;
+    Region reg;
+    bool have = false;
+};
+template <class MeshT>
+RectForm read_rect_form(Stack stack, const list<C_F0> &largs, const MeshT &Th, int ncomp_u, int ncomp_v)
+{
+    const int dim = MeshDim<MeshT>::d;
+    RectForm F;
+    for (list<C_F0>::const_iterator ii = largs.begin(); ii != largs.end(); ++ii) {
+        Expression e = ii->LeftValue();
+        aType r = ii->left();
+        if (r == atype<const FormLinear *>()) continue; // ignored when a matrix is assembled
+        if (r == atype<const BC_set *>()) throw Unsupported{"on(...) in a form with two different spaces"};
+        if (r != atype<const FormBilinear *>()) throw Unsupported{"varf item other than integrals"};
+        const FormBilinear *bf = dynamic_cast<const FormBilinear *>(e);
+        if (bf->VF()) throw Unsupported{"discontinuous-Galerkin operators"};
+        if (check_domain(stack, *bf->di, Th)) throw Unsupported{"boundary integral in a form with two different spaces"};
+        Quad q = volume_rule(stack, *bf->di, &Th);
+        Region reg = region_of(stack, *bf->di, 16);
+        if (!F.have) {
+            F.q = q;
+            F.reg = reg;
+            F.have = true;
+        } else if (q.pts != F.q.pts || q.w != F.q.w || reg.all != F.reg.all || reg.labels != F.reg.labels)
+            throw Unsupported{"integrals with different quadrature rules or regions in a form with two different spaces"};
+        const Foperator &op = *bf->b;
+        for (size_t k = 0; k < op.v.size(); ++k) {
+            const pair<MGauche, MDroit> &id = op.v[k].first; // (unknown, test)
+            ffcuda_bterm t;
+            t.ucomp = id.first.first;
+            t.uop = check_op(id.first.second, dim);
+            t.vcomp = id.second.first;
+            t.vop = check_op(id.second.second, dim);
+            if (t.ucomp < 0 || t.ucomp >= ncomp_u || t.vcomp < 0 || t.vcomp >= ncomp_v) throw Unsupported{"component out of range"};
+            t.coef = constant_coef(stack, op.v[k].second); // (mesh-dependent coefficients: left to FreeFEM here)
+            F.terms.push_back(t);
+        }
+    }
+    if (!F.have || F.terms.empty()) throw Unsupported{"no bilinear term"};
+    if (F.terms.size() > 64) throw Unsupported{"more than 64 terms"};
+    if (F.q.w.size() > 32) throw Unsupported{"more than 32 quadrature points"};
+    return F;
+}
+
+// the device part: B as host CSR triple (rows = dofs of Vh, columns = dofs of Uh)
+template <class FESpaceT>
+void gpu_rect_matrix(const FESpaceT &Uh, const FESpaceT &Vh, const RectForm &F, std::vector<int> &I, std::vector<int> &J,
+                     std::vector<double> &C)
+{
+    typedef typename FESpaceT::FElement FElementT;
+    typedef typename FESpaceT::Mesh MeshT;
+    const int dim = MeshDim<MeshT>::d;
+    int order_u, ncomp_u, nloc_u;
+    classify_space(Uh, dim, order_u, ncomp_u, nloc_u);
+    DevSpace &DV = device_space(Vh); // the test space and its copy of the mesh; the space of the unknown is put on the same mesh
+    const int nt = Uh.NbOfElements;
+    std::vector<int32_t> e2n((size_t)nt * nloc_u);
+    for (int k = 0; k < nt; ++k) {
+        const FElementT K(Uh[k]);
+        for (int a = 0; a < nloc_u; ++a) e2n[(size_t)k * nloc_u + a] = K(a) / ncomp_u;
+    }
+    ffcuda_space *su = nullptr;
+    FFC(ffcuda_space_create(DV.mesh, order_u, ncomp_u, e2n.data(), Uh.NbOfNodes, &su));
+    ffcuda_matrix *dB = nullptr;
+    int rc = ffcuda_assemble_bilinear_rect(DV.space, su, (int)F.terms.size(), F.terms.data(), (int)F.q.w.size(), F.q.pts.data(), F.q.w.data(),
+                                           (int)F.reg.labels.size(), F.reg.all ? nullptr : F.reg.labels.data(), &dB);
+    int n = 0, m = 0;
+    int64_t nnz = 0;
+    if (!rc) rc = ffcuda_matrix_shape(dB, &n, &m, &nnz);
+    if (!rc && (n != Vh.NbOfDF || m != Uh.NbOfDF)) rc = -1;
+    if (!rc) {
+        I.resize((size_t)nnz);
+        J.resize((size_t)nnz);
+        C.resize((size_t)nnz);
+        rc = ffcuda_matrix_download_coo(dB, I.data(), J.data(), C.data(), 0);
+    }
+    if (dB) ffcuda_matrix_destroy(dB);
+    ffcuda_space_destroy(su);
+    if (rc) fail("assembling the rectangular matrix");
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // 1. matrix A = va(Vh,Vh,...)
 // ------------------------------------------------------------------------------------------------------------
 template <class MMesh, class v_fes>
@@ -1833,6 +1927,64 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
     typedef OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes> Base;
     struct Op : public Base::Op {
         Op(Expression aa, Expression bb, int initt) : Base::Op(aa, bb, initt) {}
+        // matrix B = vb(Uh,Vh), two different spaces (section 0 above); throws Unsupported for what it does not claim
+        AnyType rectangular(Stack stack, const typename v_fes::FESpace &Uh, const typename v_fes::FESpace &Vh) const
+        {
+            if ((const void *)&Uh.Th != (const void *)&Vh.Th) throw Unsupported{"the two spaces live on different meshes"};
+            Data_Sparse_Solver ds;
+            ds.factorize = 0;
+            ds.initmat = true;
+            int np = OpCall_FormBilinear_np::n_name_param - NB_NAME_PARM_HMAT;
+            SetEnd_Data_Sparse_Solver<double>(stack, ds, this->b->nargs, np);
+            if (ds.sym) throw Unsupported{"sym=1 with two different spaces"};
+            const MMesh &Th = Vh.Th;
+            if (!isSameMesh(this->b->largs, &Uh.Th, &Vh.Th, stack)) throw Unsupported{"integrals on different meshes"};
+            if (Uh.N < 1 || Uh.N > 3 || Vh.N < 1 || Vh.N > 3) throw Unsupported{"more than 3 components"};
+            const RectForm F = read_rect_form(stack, this->b->largs, Th, Uh.N, Vh.N);
+            if (g_explain)
+                cout << "  -- ffcuda explain: rectangular matrix " << Vh.NbOfDF << " x " << Uh.NbOfDF << ": " << F.terms.size() << " term(s), "
+                     << F.q.w.size() << " quadrature point(s), " << (F.reg.all ? std::string("all regions") : std::to_string(F.reg.labels.size()) + " region label(s)")
+                     << endl;
+            std::vector<int> I, J;
+            std::vector<double> C;
+            gpu_rect_matrix(Uh, Vh, F, I, J, C);
+            const int n = Vh.NbOfDF, m = Uh.NbOfDF;
+            MatriceMorse<double> *M = new MatriceMorse<double>(n, m, 0, 0);
+            M->set(n, m, 0, I.size(), I.data(), J.data(), C.data(), 0, 0); // COO triple sorted by (i, j): HashMatrix::set copies it
+            if (g_check) { // FFCUDA_CHECK=1: FreeFEM's own operator runs as well, the two matrices are compared, FreeFEM's is kept
+                delete M;
+                AnyType r = Base::Op::operator()(stack);
+                Matrice_Creuse<double> &Af(*GetAny<Matrice_Creuse<double> *>((*this->a)(stack)));
+                HashMatrix<int, double> *H = Af.pHM();
+                if (!H) ExecError("ffcuda check: FreeFEM's operator did not produce a sparse matrix");
+                H->CSR();
+                bool same = H->n == n && H->m == m && (size_t)H->nnz == J.size();
+                for (int r = 0; same && r < n; ++r)
+                    for (int k = H->p[r]; same && k < H->p[r + 1]; ++k) same = I[k] == r && H->j[k] == J[k];
+                if (!same) ExecError("ffcuda check: the sparsity pattern of the rectangular matrix differs from FreeFEM's");
+                double amax = 0, dmax = 0;
+                for (size_t k = 0; k < C.size(); ++k) {
+                    amax = std::max(amax, std::abs(H->aij[k]));
+                    dmax = std::max(dmax, std::abs(H->aij[k] - C[k]));
+                }
+                cout << "  -- ffcuda check: rectangular matrix " << n << " x " << m << ", nnz " << J.size()
+                     << ": pattern identical, max |dB| / max |B| = " << (amax > 0 ? dmax / amax : dmax) << endl;
+                if (dmax > 1e-12 * amax) ExecError("ffcuda check: values of the rectangular matrix differ from FreeFEM's by more than 1e-12");
+                return r;
+            }
+            // --- hand-over as the built-in operator does it (problem.hpp:1640-1660)
+            WhereStackOfPtr2Free(stack) = new StackOfPtr2Free(stack);
+            Matrice_Creuse<double> &A(*GetAny<Matrice_Creuse<double> *>((*this->a)(stack)));
+            if (this->init) A.init();
+            A.A = 0;
+            A.Uh = Uh;
+            A.Vh = Vh;
+            A.A.master(M);
+            A.pHM()->half = 0;
+            if (Uh.NbOfDF == Vh.NbOfDF) SetSolver(stack, false, *A.A, ds); // (square by its sizes: the built-in operator sets the solver then)
+            if (g_verbose) cout << "  -- ffcuda: rectangular matrix " << n << " x " << m << ", nnz " << J.size() << " assembled on the GPU" << endl;
+            return SetAny<Matrice_Creuse<double> *>(&A);
+        }
         AnyType operator()(Stack stack) const
         {
             typedef typename v_fes::pfes pfes;
@@ -1842,7 +1994,10 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
             const FESpaceT *PUh = (FESpaceT *)**pUh, *PVh = (FESpaceT *)**pVh;
             try {
                 if (!PUh || !PVh) throw Unsupported{"null fespace"};
-                if (PUh != PVh) throw Unsupported{"test and unknown spaces differ"};
+                if (PUh != PVh) {
+                    if (!g_rect) throw Unsupported{"test and unknown spaces differ (FFCUDA_RECT=1 takes such forms to the device)"};
+                    return rectangular(stack, *PUh, *PVh);
+                }
                 Data_Sparse_Solver ds;
                 ds.factorize = 0;
                 ds.initmat = true;
@@ -2707,6 +2862,7 @@ static void Load_Init()
     if (const char *e = getenv("FFCUDA_SAMPLE_N")) g_sample_n = atoi(e);
     g_fe_dofs = !env_on("FFCUDA_NO_FE_DOFS");
     g_explain = env_on("FFCUDA_EXPLAIN");
+    g_rect = env_on("FFCUDA_RECT");
     if (g_fe_dofs) {
         find_fe_node_functions<pfer>(g_fe2, 2);
         find_fe_node_functions<pf3r>(g_fe3, 3);

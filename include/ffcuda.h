@@ -27,6 +27,8 @@
  *   ffcuda_assemble_bilinear_qcoef <- the same inside Element_Op fflib/problem.cpp:6380-6407
  *   ffcuda_assemble_linear_boundary_qvalues / ffcuda_assemble_bilinear_boundary_qcoef <- the same on border elements
  *                                  fflib/problem.cpp:8551-8570, :6526-6556
+ *   ffcuda_assemble_bilinear_rect <- `matrix B = vb(Uh,Vh)` with two different spaces: the operator takes both
+ *                                  fflib/problem.hpp:1628-1631, Element_Op with Ku != Kv fflib/problem.cpp:6337-6437, :6063-6160
  *   ffcuda_fe_table             <- an FE function used as data of a form, evaluated from its dof array instead of through
  *                                  the interpreter: pfer2R fflib/lgfem.cpp:2053-2088 -> FElement::operator()(PHat,u,comp,op)
  *                                  femlib/FESpace.cpp:1078-1099, :1637-1654, femlib/P012_3d.cpp:98-122
@@ -168,6 +170,10 @@ int ffcuda_matrix_from_csr(ffcuda_ctx *ctx, int n, int64_t nnz, const int32_t *r
 int ffcuda_matrix_from_csr_lower(ffcuda_ctx *ctx, int n, int64_t nnz_lower, const int32_t *rowptr, const int32_t *colind,
                                  const double *vals, ffcuda_matrix **out);
 int ffcuda_matrix_info(ffcuda_matrix *A, int *n, int64_t *nnz);
+int ffcuda_matrix_shape(ffcuda_matrix *A, int *n, int *ncols, int64_t *nnz); /* rows, columns (rectangular / distributed matrices), nnz */
+/* CSR arrays of a matrix that has no pattern object (ffcuda_matrix_from_csr*, ffcuda_assemble_bilinear_rect) -> host;
+ * vals may be NULL */
+int ffcuda_matrix_download_csr(ffcuda_matrix *A, int32_t *rowptr /* n+1 */, int32_t *colind /* nnz */, double *vals /* nnz */);
 int ffcuda_matrix_download(ffcuda_matrix *A, double *vals /* nnz, CSR order */);
 int ffcuda_matrix_download_lower(ffcuda_matrix *A, double *vals); /* values of the lower triangle, see ffcuda_pattern_lower_nnz */
 int ffcuda_matrix_upload(ffcuda_matrix *A, const double *vals);
@@ -216,6 +222,18 @@ int ffcuda_assemble_bilinear(ffcuda_matrix *A, ffcuda_space *s, int nterms, cons
  * Forms with several coefficient functions: one call per function. */
 int ffcuda_assemble_bilinear_qcoef(ffcuda_matrix *A, ffcuda_space *s, int nterms, const ffcuda_bterm *terms,
                                    int nq, const double *qpts, const double *qw, const double *cq, int accumulate);
+/* RECTANGULAR matrices, `matrix B = vb(Uh,Vh)` with two different spaces on the SAME device mesh (blocks of a Stokes / mixed
+ * problem assembled one by one, projection matrices between P1 and P2): *out = a new matrix with the dofs of the test
+ * space sv as rows and the dofs of the space of the unknown su as columns (Element_Op with Ku != Kv,
+ * fflib/problem.cpp:6337-6437), every couple of the element matrices in the pattern (HashMatrix::operator+=), sorted CSR.
+ * Terms: ucomp < ncomp(su), vcomp < ncomp(sv), constant coefficients; labels: regions that contribute (NULL = all; the
+ * pattern keeps every couple).  Each space P1 / P2 with 1..3 components.  The result has no pattern object: ffcuda_spmv
+ * (x of size columns, y of size rows), ffcuda_matrix_shape / _download_csr / _download_coo / _export_device /
+ * _write_morse apply; the solvers and ffcuda_matrix_apply_bc refuse it.  General kernel (one thread per row node,
+ * quadrature loop per couple): not the square hot path. */
+int ffcuda_assemble_bilinear_rect(ffcuda_space *sv, ffcuda_space *su, int nterms, const ffcuda_bterm *terms,
+                                  int nq, const double *qpts, const double *qw,
+                                  int nlab, const int32_t *labels, ffcuda_matrix **out);
 int ffcuda_assemble_linear(ffcuda_vec *b, ffcuda_space *s, int nterms, const ffcuda_lterm *terms,
                            int nq, const double *qpts, const double *qw,
                            int nlab, const int32_t *labels, int accumulate);

@@ -268,6 +268,48 @@ def test_plugin_loads_and_leaves_out_of_scope_forms_to_freefem():
     assert rc != 0 and "FFCUDA_STRICT" in out
 
 
+RECT_FORMS = """load "msh3"
+load "ffcuda"
+mesh3 Th = cube(3,3,3);
+fespace Uh(Th,[P2,P2,P2]);
+fespace Ph(Th,P1);
+varf vb([u1,u2,u3],[q]) = int3d(Th)(-(dx(u1)+dy(u2)+dz(u3))*q) + int3d(Th)(0.5*u2*dx(q));
+fespace Wh(Th,P2);
+varf von(u,q) = int3d(Th)(dx(u)*q) + on(1,u=0);
+varf vx([u1,u2,u3],[q]) = int3d(Th)(x*dx(u1)*q);
+varf vbd([u1,u2,u3],[q]) = int3d(Th)(dx(u1)*q) + int2d(Th,2)(u1*q);
+varf vq([u1,u2,u3],[q]) = int3d(Th)(dx(u1)*q) + int3d(Th,qfV=qfV1)(u2*q);
+try { matrix B = vb(Uh,Ph); cout << "B " << B.n << " " << B.m << " " << B.nnz << endl; } catch(...) { cout << "B: no device" << endl; }
+matrix Bon = von(Wh,Ph);
+matrix Bx = vx(Uh,Ph);
+matrix Bbd = vbd(Uh,Ph);
+matrix Bq = vq(Uh,Ph);
+cout << "NNZ " << Bon.nnz << " " << Bx.nnz << " " << Bbd.nnz << " " << Bq.nnz << endl;
+"""
+
+
+@needs_ff
+def test_plugin_rectangular_forms_are_recognised_without_a_device():
+    """`matrix B = vb(Uh,Vh)` with two different spaces: left to FreeFEM unless FFCUDA_RECT=1; with it, volume integrals with
+    constant coefficients and one rule are claimed (FFCUDA_EXPLAIN prints what was read before any device call), forms with
+    on(...), mesh-dependent coefficients, boundary integrals or two rules are left to FreeFEM.  Checked where there is no GPU
+    (the claimed statement then fails loudly: no CPU fallback); on a GPU box tests/test_zz_gpu_rect.py runs the statement."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    rc, out, _ = run_ff(RECT_FORMS, {}, want_fail=True)
+    assert rc == 0 and re.search(r"^B 64 1029 ", out, re.M) and out.count("FFCUDA_RECT=1 takes such forms to the device") == 5
+    rc, out, _ = run_ff(RECT_FORMS, {"FFCUDA_RECT": "1", "FFCUDA_EXPLAIN": "1"}, want_fail=True)
+    assert rc == 0, out[-2000:]
+    assert "rectangular matrix 64 x 1029: 4 term(s), 14 quadrature point(s), all regions" in out
+    assert "B: no device" in out and not re.search(r"^B 64", out, re.M)
+    for why in ("on(...) in a form with two different spaces", "coefficient depends on the mesh point",
+                "boundary integral in a form with two different spaces", "different quadrature rules or regions"):
+        assert why in out, why
+    assert re.search(r"^NNZ \d+ \d+ \d+ \d+", out, re.M)
+
+
 @needs_ff
 def test_plugin_has_no_cpu_fallback():
     import torch

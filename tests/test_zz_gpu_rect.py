@@ -1,0 +1,174 @@
+"""GPU tests of RECTANGULAR matrices (`matrix B = vb(Uh,Vh)`, ffcuda_assemble_bilinear_rect) through the C ABI, against the 6
+fixtures dumped from the unmodified reference (tests/golden/make_golden_rect.py) and against the oracle on a larger mesh.
+Bars: pattern bit-exact, values 1e-12 of the largest entry.
+
+STATUS: this path was written after the round's GPU minutes were spent.  Its arithmetic (csrc/rect_row.cuh) is pinned on
+the host against the same fixtures (tests/test_rect_row_host.py) and its symbolic phase reuses the kernel of the P2 patterns,
+but the launch plumbing has NOT run on hardware yet.  Until a run is on record every test of this file (and of nothing
+else) is marked xfail(strict=False): a pass is reported as XPASS, a failure as xfail, and neither hides or stops the
+verified tests, which is why the file sorts last."""
+import os
+import re
+import shutil
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import ff_cases as fc
+import oracle_lib as ol
+from ffcuda_lib import ffcuda
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600),
+              pytest.mark.xfail(strict=False, reason="rectangular path: host-verified arithmetic, not yet run on a GPU (see module docstring)")]
+
+RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    c = ffcuda.Context(0)
+    yield c
+    try:
+        c.close()
+    except Exception:  # (a failed kernel leaves the context unusable: not a second failure)
+        pass
+
+
+def _fixture_spaces(ctx, name):
+    (ov, cv), (ou, cu), terms, qname = fc.RECT_CASES[name]
+    g = fc.load(name)
+    mesh = ctx.mesh_upload(g["dim"], g["xyz"], g["conn"], g["elab"])
+    ev, eu = fc.rect_elem2node(g, "Vh", cv), fc.rect_elem2node(g, "Uh", cu)
+    sv = mesh.space(ov, cv, ev, int(g["n"]) // cv)
+    su = mesh.space(ou, cu, eu, int(g["m"]) // cu)
+    qp, qw = ol.quadrature(g["dim"], qname)
+    return g, mesh, sv, su, terms, qp, qw
+
+
+@pytest.mark.parametrize("name", sorted(fc.RECT_CASES))
+def test_rect_fixture(ctx, name):
+    g, mesh, sv, su, terms, qp, qw = _fixture_spaces(ctx, name)
+    B = sv.assemble_rect(su, terms, qp, qw)
+    n, m, nnz = B.shape()
+    assert (n, m, nnz) == (int(g["n"]), int(g["m"]), len(g["coo_a"]))
+    rp, ci, val = B.download_csr()
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    assert np.array_equal(rows, g["coo_i"]) and np.array_equal(ci, g["coo_j"])  # the fixture's [I,J,C] is sorted by (i, j)
+    assert np.max(np.abs(val - g["coo_a"])) <= RTOL * np.abs(g["coo_a"]).max()
+    # the triple of `[I,J,C] = B` and the product B x
+    I, J, C = B.download_coo()  # noqa: E741
+    assert np.array_equal(I, rows) and np.array_equal(J, ci) and np.array_equal(C, val)
+    x = np.cos(np.arange(m) * 0.7) + 0.1
+    dx, dy = ctx.vec_from(x), ctx.vec(n)
+    B.spmv(dx, dy)
+    ref = np.zeros(n)
+    np.add.at(ref, g["coo_i"], g["coo_a"] * x[g["coo_j"]])
+    assert np.max(np.abs(dy.download() - ref)) <= 1e-12 * max(np.abs(ref).max(), 1e-300)
+
+
+def test_rect_against_the_oracle_on_a_generated_cube(ctx):
+    """Stokes divergence block on cube(8,7,9): velocity [P2,P2,P2] numbered by the device, pressure P1; regions filtered"""
+    nx, ny, nz = 8, 7, 9
+    mesh = ctx.mesh_cube(nx, ny, nz)
+    su, sv = mesh.space(2, 3), mesh.space(1, 1)
+    eu = np.ascontiguousarray(su.dofs()[:, :10] // 3)
+    m = ol.cube(nx, ny, nz)
+    terms = fc.RECT_CASES["rect3d_div_p2p1"][2]
+    qp, qw = ol.quadrature(3, "qfV5")
+    for labels in (None, [0]):
+        B = sv.assemble_rect(su, terms, qp, qw, labels=labels)
+        n, ncol, nnz = B.shape()
+        rp, ci, val = B.download_csr()
+        oi, oj, oa = ol.assemble_coo_rect(m, 1, 1, None, 2, 3, eu, terms, qp, qw)  # every couple, as the pattern keeps them
+        assert (n, ncol, nnz) == ((nx + 1) * (ny + 1) * (nz + 1), su.info()[0], len(oa))
+        o = np.argsort(oi.astype(np.int64) * ncol + oj, kind="stable")
+        assert np.array_equal(np.repeat(np.arange(n), np.diff(rp)), oi[o]) and np.array_equal(ci, oj[o])
+        if labels is not None:  # cube() labels every tetrahedron 0: the filter keeps them all
+            oi, oj, oa = ol.assemble_coo_rect(m, 1, 1, None, 2, 3, eu, terms, qp, qw, labels=labels)
+        assert np.max(np.abs(val - oa[o])) <= RTOL * np.abs(oa).max()
+    B = sv.assemble_rect(su, terms, qp, qw, labels=[7])  # no such region: the pattern stays, the values are zero
+    assert B.shape()[2] == len(oa) and not B.download_csr()[2].any()
+
+
+def test_rect_with_equal_spaces_gives_the_square_matrix(ctx):
+    name = "lame3d_p2_cube2"
+    order, ncomp, bt, _, qname, _ = fc.CASES[name]
+    g = fc.load(name)
+    mesh = ctx.mesh_upload(g["dim"], g["xyz"], g["conn"], g["elab"])
+    e2n = fc.elem2node(g, order, ncomp)
+    sp = mesh.space(order, ncomp, e2n, g["ndof"] // ncomp)
+    qp, qw = ol.quadrature(3, qname)
+    pat = sp.symbolic()
+    A = pat.matrix()
+    A.assemble(bt, qp, qw)
+    rp, ci = pat.download()
+    B = sp.assemble_rect(sp, bt, qp, qw)
+    brp, bci, bval = B.download_csr()
+    assert np.array_equal(brp, rp) and np.array_equal(bci, ci)
+    aval = A.download()
+    assert np.max(np.abs(bval - aval)) <= RTOL * np.abs(aval).max()
+
+
+def test_rect_matrices_are_refused_by_solvers_and_dirichlet_entries(ctx):
+    g, mesh, sv, su, terms, qp, qw = _fixture_spaces(ctx, "rect2d_div_p2p1")
+    B = sv.assemble_rect(su, terms, qp, qw)
+    n, m, _ = B.shape()
+    with pytest.raises(ffcuda.FfcudaError, match="rectangular"):
+        B.cg(ctx.vec(max(n, m)), ctx.vec(max(n, m)))
+    with pytest.raises(ffcuda.FfcudaError, match="rectangular"):
+        B.apply_bc(sv.bc_from_pairs([0], [0.0]))
+    other = ctx.mesh_upload(g["dim"], g["xyz"], g["conn"], g["elab"])
+    with pytest.raises(ffcuda.FfcudaError, match="same device mesh"):
+        sv.assemble_rect(other.space(1, 1), [(0, fc.ID, 0, fc.ID, 1.0)], qp, qw)
+
+
+# ---- through the plugin: `matrix B = vb(Uh,Vh)` in the unmodified FreeFem++ with FFCUDA_RECT=1 ----
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+FF = os.path.join(ROOT, "oracle", "_ref", "FreeFem++-nw")
+PLUGIN_DIR = os.path.join(ROOT, "freefem-sources_b200", "lib")
+
+STOKES_BLOCKS = """load "msh3"
+LOADFFCUDA
+mesh3 Th = cube(5,4,6,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)]);
+fespace Uh(Th,[P2,P2,P2]);
+fespace Ph(Th,P1);
+varf vb([u1,u2,u3],[q]) = int3d(Th)(-(dx(u1)+dy(u2)+dz(u3))*q + 0.5*u2*dx(q));
+varf vbt([p],[v1,v2,v3]) = int3d(Th)(-p*(dx(v1)+dy(v2)+dz(v3)));
+matrix B = vb(Uh,Ph);
+matrix Bt = vbt(Ph,Uh);
+Uh [w1,w2,w3] = [x*y, sin(z), x+z*z];
+Ph pp = 1+x-y*z;
+real[int] r = B*w1[];
+real[int] s = Bt*pp[];
+cout.precision(15);
+cout << "SHAPE " << B.n << " " << B.m << " " << B.nnz << " " << Bt.n << " " << Bt.m << " " << Bt.nnz << endl;
+cout << "NORMS " << r.l2 << " " << s.l2 << " " << r.sum << " " << s.sum << endl;
+"""
+
+
+def _run_ff(src, env_extra):
+    td = tempfile.mkdtemp(prefix="ffrect_")
+    try:
+        with open(os.path.join(td, "c.edp"), "w") as f:
+            f.write(src)
+        env = dict(os.environ)
+        env.update(env_extra)
+        env["FF_LOADPATH"] = PLUGIN_DIR
+        r = subprocess.run([FF, "-nw", "-v", "0", "c.edp"], cwd=td, env=env, capture_output=True, text=True, timeout=300)
+        return r.returncode, r.stdout + r.stderr
+    finally:
+        shutil.rmtree(td, ignore_errors=True)
+
+
+@pytest.mark.skipif(not (os.path.exists(FF) and os.path.exists(os.path.join(PLUGIN_DIR, "ffcuda.so"))), reason="reference binary / plugin not built")
+def test_plugin_rectangular_blocks_with_FFCUDA_RECT():  # noqa: N802
+    rc0, ref = _run_ff(STOKES_BLOCKS.replace("LOADFFCUDA", ""), {})
+    rc1, out = _run_ff(STOKES_BLOCKS.replace("LOADFFCUDA", 'load "ffcuda"'), {"FFCUDA_RECT": "1", "FFCUDA_VERBOSE": "1"})
+    assert rc0 == 0 and rc1 == 0, out[-3000:]
+    assert out.count("rectangular matrix") == 2 and "assembled on the GPU" in out
+    assert re.search(r"SHAPE .*", ref).group(0) == re.search(r"SHAPE .*", out).group(0)
+    a = np.array(re.search(r"NORMS (.*)", ref).group(1).split(), dtype=float)
+    b = np.array(re.search(r"NORMS (.*)", out).group(1).split(), dtype=float)
+    assert np.max(np.abs(a - b)) <= 1e-11 * np.abs(a).max()
