@@ -351,7 +351,9 @@ extern "C" int ffcuda_comm_finalize(ffcuda_ctx *ctx)
 
 static ffcuda_mesh *dist_mesh(ffcuda_matrix *A)
 {
-    if (!A->pattern || !A->pattern->space) return nullptr;
+    // (the space of a pattern on an ordinary mesh may be gone by now - the FreeFEM plugin keeps a matrix and its pattern with
+    //  the solver while its cache of fespaces moves on - so it is only looked at when the pattern says the mesh is distributed)
+    if (!A->pattern || !A->pattern->dist || !A->pattern->space) return nullptr;
     ffcuda_mesh *m = A->pattern->space->mesh;
     return (m && m->distributed) ? m : nullptr;
 }

@@ -416,6 +416,8 @@ struct ffcuda_pattern {
     DBuf<int32_t> lower_rowptr; // row pointers of the lower triangle (sym=1 hand-off), built on first use
     int64_t lower_nnz = 0;
     bool copy_pending = false; // an asynchronous download of rowptr / colind may still be in flight on ctx->copy_stream
+    bool dist = false;         // created on a distributed mesh (then, and only then, the space and its mesh must outlive the pattern:
+                               // solves read their halo lists; otherwise a matrix and its pattern may be used after the space is gone)
 };
 
 struct ffcuda_matrix {

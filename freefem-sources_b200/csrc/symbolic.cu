@@ -976,6 +976,7 @@ extern "C" int ffcuda_symbolic(ffcuda_space *s, ffcuda_pattern **out)
     const IncView V = ff_view(I);
     P = new ffcuda_pattern();
     P->space = s;
+    P->dist = s->mesh && s->mesh->distributed;
     P->ctx = ctx;
     P->ref.set(ctx);
     P->nrows_node = nrows;

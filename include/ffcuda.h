@@ -145,7 +145,10 @@ void ffcuda_space_destroy(ffcuda_space *s);
 /* ---- symbolic sparsity (kernel 1) ----------------------------------------------------------------- */
 /* CSR pattern of the (Vh,Vh) matrix exactly as MatriceMorse would hold it after CSR(): one entry per couple
  * of dofs sharing an element (structural zeros and uncoupled components included), rows and columns sorted
- * ascending, int32, 0-based.  Also builds the node->element incidence used by the row-owner assembly. */
+ * ascending, int32, 0-based.  Also builds the node->element incidence used by the row-owner assembly.
+ * Lifetimes: the space must be alive whenever a matrix of this pattern is ASSEMBLED (the assembly entries take both).  A
+ * matrix and its pattern on an ordinary (non-distributed) mesh may be solved with, multiplied and downloaded after the space
+ * and its mesh are destroyed; on a distributed mesh the space and the mesh must outlive them (solves read the halo lists). */
 int ffcuda_symbolic(ffcuda_space *s, ffcuda_pattern **out);
 int ffcuda_pattern_info(ffcuda_pattern *p, int *n, int64_t *nnz);
 int ffcuda_pattern_download(ffcuda_pattern *p, int32_t *rowptr /* n+1 */, int32_t *colind /* nnz */);
