@@ -144,10 +144,8 @@ void on_ranks(int n, F f)
     auto run = [&](int r) {
         try {
             f(r);
-        } catch (const std::exception &e) {
+        } catch (const std::exception &e) { // (FreeFEM's ErrorExec is one)
             err[r] = e.what();
-        } catch (const ErrorExec &e) {
-            err[r] = "error in rank thread";
         } catch (...) {
             err[r] = "unknown error in rank thread";
         }
