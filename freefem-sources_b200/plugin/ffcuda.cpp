@@ -1840,15 +1840,20 @@ struct RectForm {
     bool have = false;
 };
 template <class MeshT>
-RectForm read_rect_form(Stack stack, const list<C_F0> &largs, const MeshT &Th, int ncomp_u, int ncomp_v)
+RectForm read_rect_form(Stack stack, const list<C_F0> &largs, const MeshT &Th, int ncomp_u, int ncomp_v, bool *has_bc = nullptr)
 {
     const int dim = MeshDim<MeshT>::d;
     RectForm F;
+    if (has_bc) *has_bc = false;
     for (list<C_F0>::const_iterator ii = largs.begin(); ii != largs.end(); ++ii) {
         Expression e = ii->LeftValue();
         aType r = ii->left();
         if (r == atype<const FormLinear *>()) continue; // ignored when a matrix is assembled
-        if (r == atype<const BC_set *>()) throw Unsupported{"on(...) in a form with two different spaces"};
+        if (r == atype<const BC_set *>()) {
+            if (!has_bc) throw Unsupported{"on(...) in a form with two different spaces"};
+            *has_bc = true; // (one space: the caller runs FreeFEM's own AssembleBC on the assembled matrix)
+            continue;
+        }
         if (r != atype<const FormBilinear *>()) throw Unsupported{"varf item other than integrals"};
         const FormBilinear *bf = dynamic_cast<const FormBilinear *>(e);
         if (bf->VF()) throw Unsupported{"discontinuous-Galerkin operators"};
@@ -1918,6 +1923,140 @@ void gpu_rect_matrix(const FESpaceT &Uh, const FESpaceT &Vh, const RectForm &F, 
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// 0b. matrix A = va(Xh,Xh) on a MIXED-ORDER product space in one fespace (FFCUDA_RECT=1): Taylor-Hood `[P2,P2,P1]`,
+//     `[P2,P2,P2,P1]`.  The local dofs of such an element are component-major (begin_dfcomp / end_dfcomp,
+//     femlib/FESpacen.hpp:454-455, FESpace.hpp:516-517: what Element_Op loops over, fflib/problem.cpp:6414-6417), the global
+//     numbering is whatever FreeFEM made it.  Every couple of components (cv, cu) is one scalar block: the rectangular
+//     entry is called with two scalar spaces whose "nodes" are the GLOBAL dofs of the component, so each block comes back
+//     in the numbering of the whole space and the matrix is their union (the blocks are disjoint; a couple of components
+//     without a term still contributes its structural zeros, as HashMatrix::operator+= keeps them).  on(...) items: FreeFEM's
+//     own AssembleBC runs on the assembled matrix (O(boundary) work).  Same status and guard as section 0.
+// ------------------------------------------------------------------------------------------------------------
+struct MixedSpace {
+    int ncomp = 0, nd = 0;
+    int order[4], begin[5];
+};
+// is Vh a product of P1 / P2 Lagrange components that are NOT all of the same order ?  (throws nothing; false = not ours)
+template <class FESpaceT>
+bool classify_mixed(const FESpaceT &Vh, MixedSpace &X)
+{
+    typedef typename FESpaceT::FElement FElementT;
+    typedef typename FESpaceT::Mesh MeshT;
+    const int dim = MeshDim<MeshT>::d, nv = dim + 1, n2 = dim == 3 ? 10 : 6;
+    X.ncomp = Vh.N;
+    if (X.ncomp < 2 || X.ncomp > 4 || Vh.NbOfElements <= 0) return false;
+    const FElementT K0(Vh[0]);
+    X.nd = K0.NbDoF();
+    bool differ = false;
+    int at = 0;
+    for (int c = 0; c < X.ncomp; ++c) {
+        if (K0.dfcbegin(c) != at) return false; // component-major, no gaps
+        const int nl = K0.dfcend(c) - K0.dfcbegin(c);
+        X.begin[c] = at;
+        if (nl == nv) X.order[c] = 1;
+        else if (nl == n2) X.order[c] = 2;
+        else return false;
+        at += nl;
+        differ = differ || X.order[c] != X.order[0];
+    }
+    X.begin[X.ncomp] = at;
+    if (at != X.nd || !differ) return false;
+    // basis fingerprint: component c of local dof begin[c] + a is the Lagrange function a of that order, the others vanish
+    double l[4] = {0.1, 0.2, 0.3, 0.4};
+    if (dim == 2) l[0] = 0.2, l[1] = 0.3, l[2] = 0.5;
+    KNMK<double> val(X.nd, X.ncomp, (int)last_operatortype);
+    val = 0.;
+    basis_values(K0, hat_point((const MeshT *)0, l), val);
+    for (int c = 0; c < X.ncomp; ++c) {
+        double phi[10];
+        lagrange_values(dim, X.order[c], l, phi);
+        for (int a = 0; a < X.begin[c + 1] - X.begin[c]; ++a)
+            for (int c2 = 0; c2 < X.ncomp; ++c2)
+                if (fabs(val(X.begin[c] + a, c2, (int)op_id) - (c == c2 ? phi[a] : 0.0)) > 1e-12) return false;
+    }
+    const int nt = Vh.NbOfElements, step = std::max(1, nt / 64);
+    for (int k = 0; k < nt; k += step)
+        if (FElementT(Vh[k]).NbDoF() != X.nd) return false;
+    return true;
+}
+
+// the mesh of a space on the device, for this statement only (no fespace of ours is attached to it: see device_space for
+// the cached path of the square operator)
+template <class MeshT>
+ffcuda_mesh *upload_mesh_plain(const MeshT &Th)
+{
+    const int dim = MeshDim<MeshT>::d, nv = Th.nv, nt = Th.nt, nvk = dim + 1;
+    std::vector<double> xyz((size_t)nv * dim);
+    for (int i = 0; i < nv; ++i) coords(Th, i, &xyz[(size_t)i * dim]);
+    std::vector<int32_t> conn((size_t)nt * nvk), elab(nt);
+    for (int k = 0; k < nt; ++k) {
+        for (int j = 0; j < nvk; ++j) conn[(size_t)k * nvk + j] = Th(k, j);
+        elab[k] = elabel(Th, k);
+    }
+    ffcuda_mesh *m = nullptr;
+    FFC(ffcuda_mesh_upload(context(), dim, nv, xyz.data(), nt, conn.data(), elab.data(), 0, nullptr, nullptr, nullptr, nullptr, &m));
+    return m;
+}
+
+// the device part: the union of the ncomp^2 scalar blocks as a COO triple in the numbering of Vh
+template <class FESpaceT>
+void gpu_mixed_matrix(const FESpaceT &Vh, const MixedSpace &X, const RectForm &F, std::vector<int> &I, std::vector<int> &J,
+                      std::vector<double> &C)
+{
+    typedef typename FESpaceT::FElement FElementT;
+    const int nt = Vh.NbOfElements, nc = X.ncomp, ndof = Vh.NbOfDF;
+    ffcuda_mesh *mesh = upload_mesh_plain(Vh.Th);
+    std::vector<ffcuda_space *> sp((size_t)nc, nullptr);
+    ffcuda_matrix *dB = nullptr;
+    int rc = 0;
+    for (int c = 0; c < nc && !rc; ++c) { // scalar space of component c: its nodes are the global dofs of the component
+        const int nl = X.begin[c + 1] - X.begin[c];
+        std::vector<int32_t> tab((size_t)nt * nl);
+        for (int k = 0; k < nt; ++k) {
+            const FElementT K(Vh[k]);
+            for (int a = 0; a < nl; ++a) tab[(size_t)k * nl + a] = K(X.begin[c] + a);
+        }
+        rc = ffcuda_space_create(mesh, X.order[c], 1, tab.data(), ndof, &sp[c]);
+    }
+    for (int cv = 0; cv < nc && !rc; ++cv)
+        for (int cu = 0; cu < nc && !rc; ++cu) {
+            std::vector<ffcuda_bterm> bt;
+            for (size_t t = 0; t < F.terms.size(); ++t)
+                if (F.terms[t].vcomp == cv && F.terms[t].ucomp == cu) {
+                    ffcuda_bterm b = F.terms[t];
+                    b.vcomp = b.ucomp = 0;
+                    bt.push_back(b);
+                }
+            if (bt.empty()) { // no term couples these components: their couples are in the matrix all the same, with zeros
+                ffcuda_bterm z;
+                z.ucomp = z.vcomp = 0;
+                z.uop = z.vop = FFCUDA_OP_ID;
+                z.coef = 0.0;
+                bt.push_back(z);
+            }
+            rc = ffcuda_assemble_bilinear_rect(sp[cv], sp[cu], (int)bt.size(), bt.data(), (int)F.q.w.size(), F.q.pts.data(), F.q.w.data(),
+                                               (int)F.reg.labels.size(), F.reg.all ? nullptr : F.reg.labels.data(), &dB);
+            int n = 0, m = 0;
+            int64_t nnz = 0;
+            if (!rc) rc = ffcuda_matrix_shape(dB, &n, &m, &nnz);
+            if (!rc && (n != ndof || m != ndof)) rc = -1;
+            if (!rc) {
+                const size_t at = I.size();
+                I.resize(at + (size_t)nnz);
+                J.resize(at + (size_t)nnz);
+                C.resize(at + (size_t)nnz);
+                rc = ffcuda_matrix_download_coo(dB, I.data() + at, J.data() + at, C.data() + at, 0);
+            }
+            if (dB) ffcuda_matrix_destroy(dB);
+            dB = nullptr;
+        }
+    for (int c = 0; c < nc; ++c)
+        if (sp[c]) ffcuda_space_destroy(sp[c]);
+    ffcuda_mesh_destroy(mesh);
+    if (rc) fail("assembling the blocks of the mixed-order matrix");
+}
+
+// ------------------------------------------------------------------------------------------------------------
 // 1. matrix A = va(Vh,Vh,...)
 // ------------------------------------------------------------------------------------------------------------
 template <class MMesh, class v_fes>
@@ -1983,6 +2122,75 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
             if (g_verbose) cout << "  -- ffcuda: rectangular matrix " << n << " x " << m << ", nnz " << J.size() << " assembled on the GPU" << endl;
             return SetAny<Matrice_Creuse<double> *>(&A);
         }
+        // matrix A = va(Xh,Xh) on a mixed-order product space (section 0b above); throws Unsupported for what it does not claim
+        AnyType mixed(Stack stack, const typename v_fes::FESpace &Vh, const MixedSpace &X) const
+        {
+            typedef typename v_fes::FESpace FESpaceT;
+            Data_Sparse_Solver ds;
+            ds.factorize = 0;
+            ds.initmat = true;
+            int np = OpCall_FormBilinear_np::n_name_param - NB_NAME_PARM_HMAT;
+            SetEnd_Data_Sparse_Solver<double>(stack, ds, this->b->nargs, np);
+            if (ds.sym) throw Unsupported{"sym=1 on a mixed-order space"};
+            if (ds.tgv != ds.tgv) throw Unsupported{"tgv is NaN"};
+            const MMesh &Th = Vh.Th;
+            if (!isSameMesh(this->b->largs, &Vh.Th, &Vh.Th, stack)) throw Unsupported{"integrals on different meshes"};
+            bool has_bc = false;
+            const RectForm F = read_rect_form(stack, this->b->largs, Th, X.ncomp, X.ncomp, &has_bc);
+            if (g_explain) {
+                cout << "  -- ffcuda explain: mixed-order space [";
+                for (int c = 0; c < X.ncomp; ++c) cout << (c ? ",P" : "P") << X.order[c];
+                cout << "], " << Vh.NbOfDF << " dofs: " << X.ncomp * X.ncomp << " scalar blocks, " << F.terms.size() << " term(s), " << F.q.w.size()
+                     << " quadrature point(s)" << (has_bc ? ", on(...) by FreeFEM's AssembleBC" : "") << endl;
+            }
+            std::vector<int> I, J;
+            std::vector<double> C;
+            gpu_mixed_matrix(Vh, X, F, I, J, C);
+            const int n = Vh.NbOfDF;
+            MatriceMorse<double> *M = new MatriceMorse<double>(n, n, 0, 0);
+            M->set(n, n, 0, I.size(), I.data(), J.data(), C.data(), 0, 0); // COO, block after block: HashMatrix::set copies it
+            if (has_bc) AssembleBC<double, MMesh, FESpaceT, FESpaceT>(stack, Th, Vh, Vh, false, M, 0, 0, this->b->largs, ds.tgv);
+            if (g_check) { // FFCUDA_CHECK=1: FreeFEM's own operator runs as well, the two matrices are compared, FreeFEM's is kept
+                M->CSR();
+                const std::vector<int> p0(M->p, M->p + n + 1), j0(M->j, M->j + M->nnz);
+                const std::vector<double> a0(M->aij, M->aij + M->nnz);
+                delete M;
+                AnyType r = Base::Op::operator()(stack);
+                Matrice_Creuse<double> &Af(*GetAny<Matrice_Creuse<double> *>((*this->a)(stack)));
+                HashMatrix<int, double> *H = Af.pHM();
+                if (!H) ExecError("ffcuda check: FreeFEM's operator did not produce a sparse matrix");
+                H->CSR();
+                bool same = H->n == n && H->m == n && (size_t)H->nnz == j0.size();
+                for (int i = 0; same && i <= n; ++i) same = H->p[i] == p0[i];
+                for (size_t k = 0; same && k < j0.size(); ++k) same = H->j[k] == j0[k];
+                if (!same) ExecError("ffcuda check: the sparsity pattern of the mixed-order matrix differs from FreeFEM's");
+                double amax = 0, dmax = 0;
+                for (size_t k = 0; k < a0.size(); ++k) {
+                    const double a = H->aij[k];
+                    if (std::abs(a) > 1e29 || std::abs(a0[k]) > 1e29) {
+                        if (a != a0[k]) dmax = 1e300;
+                        continue;
+                    }
+                    amax = std::max(amax, std::abs(a));
+                    dmax = std::max(dmax, std::abs(a - a0[k]));
+                }
+                cout << "  -- ffcuda check: mixed-order matrix " << n << " x " << n << ", nnz " << j0.size()
+                     << ": pattern identical, max |dA| / max |A| = " << (amax > 0 ? dmax / amax : dmax) << endl;
+                if (dmax > 1e-12 * amax) ExecError("ffcuda check: values of the mixed-order matrix differ from FreeFEM's by more than 1e-12");
+                return r;
+            }
+            WhereStackOfPtr2Free(stack) = new StackOfPtr2Free(stack);
+            Matrice_Creuse<double> &A(*GetAny<Matrice_Creuse<double> *>((*this->a)(stack)));
+            if (this->init) A.init();
+            A.A = 0;
+            A.Uh = Vh;
+            A.Vh = Vh;
+            A.A.master(M);
+            A.pHM()->half = 0;
+            SetSolver(stack, false, *A.A, ds);
+            if (g_verbose) cout << "  -- ffcuda: mixed-order matrix " << n << " x " << n << ", nnz " << I.size() << " assembled on the GPU" << endl;
+            return SetAny<Matrice_Creuse<double> *>(&A);
+        }
         AnyType operator()(Stack stack) const
         {
             typedef typename v_fes::pfes pfes;
@@ -1995,6 +2203,10 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
                 if (PUh != PVh) {
                     if (!g_rect) throw Unsupported{"test and unknown spaces differ (FFCUDA_RECT=1 takes such forms to the device)"};
                     return rectangular(stack, *PUh, *PVh);
+                }
+                if (g_rect) { // one mixed-order product space ([P2,P2,P1] ...): scalar blocks through the rectangular entry
+                    MixedSpace X;
+                    if (classify_mixed(*PVh, X)) return mixed(stack, *PVh, X);
                 }
                 Data_Sparse_Solver ds;
                 ds.factorize = 0;

@@ -234,6 +234,40 @@ RECT_CASES = {
 }
 
 
+# Mixed-order product spaces in one fespace (Taylor-Hood): name -> (orders of the components, terms, quadrature name).  The
+# local dofs of an element are component-major (begin_dfcomp / end_dfcomp, femlib/FESpacen.hpp:454-455); the plugin assembles
+# one scalar block per couple of components, with the GLOBAL dofs of the component as its "nodes" (mixed_blocks below)
+def _stokes(dim):
+    d = [DX, DY, DZ][:dim]
+    t = [(c, o, c, o, 1.0) for c in range(dim) for o in d]                    # grad u_c . grad v_c
+    t += [(dim, ID, c, d[c], -1.0) for c in range(dim)]                      # - p div v
+    t += [(c, d[c], dim, ID, -1.0) for c in range(dim)]                      # - div u q
+    return t + [(dim, ID, dim, ID, -1e-10)]
+
+
+MIXED_CASES = {
+    "mixed2d_stokes": ([2, 2, 1], _stokes(2), "qf5pT"),
+    "mixed3d_stokes": ([2, 2, 2, 1], _stokes(3), "qfV5"),
+}
+
+
+def mixed_blocks(g, orders, terms):
+    """[(order_v, table_v, order_u, table_u, terms of the block re-indexed to component 0)] for every couple of components;
+    table_c[k, a] = global dof of local node a of component c in element k"""
+    dim = int(g["dim"])
+    nl = [(dim + 1) if o == 1 else (6 if dim == 2 else 10) for o in orders]
+    beg = np.concatenate([[0], np.cumsum(nl)])
+    dof = g["dof_Vh"]
+    assert dof.shape[1] == beg[-1] and np.array_equal(dof, g["dof_Uh"])
+    tab = [np.ascontiguousarray(dof[:, beg[c]:beg[c + 1]], dtype=np.int32) for c in range(len(orders))]
+    out = []
+    for cv in range(len(orders)):
+        for cu in range(len(orders)):
+            bt = [(0, uo, 0, vo, co) for (uc, uo, vc, vo, co) in terms if uc == cu and vc == cv]
+            out.append((orders[cv], tab[cv], orders[cu], tab[cu], bt or [(0, ID, 0, ID, 0.0)]))  # no term: the couples, with zeros
+    return out
+
+
 def rect_elem2node(g, which, ncomp):
     """node table of one space of a rectangular fixture (which = "Uh" | "Vh"), see elem2node"""
     dof = g["dof_" + which]

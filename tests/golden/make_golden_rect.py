@@ -30,6 +30,13 @@ CASES = {
     # two components against two components of another order, region-restricted rule left at its default, lumped quadrature
     "rect2d_p2vec_p1vec": dict(dim=2, mesh="square(3,3)", ufe="[P2,P2]", unk="[u1,u2]", vfe="[P1,P1]", tst="[v1,v2]",
                                bil="u1*v1+u2*v2+0.25*dy(u1)*v2", intopt=",qft=qf2pT"),
+    # mixed-order product spaces (Taylor-Hood Stokes matrices) in ONE fespace: assembled by the plugin as scalar blocks in the
+    # global dof numbering of the space (tests/ff_cases.py MIXED_CASES); Uh and Vh are two objects of the same type here
+    "mixed2d_stokes": dict(dim=2, mesh=f"square(3,3,{W2})", ufe="[P2,P2,P1]", unk="[u1,u2,p]", vfe="[P2,P2,P1]", tst="[v1,v2,q]",
+                           bil="dx(u1)*dx(v1)+dy(u1)*dy(v1)+dx(u2)*dx(v2)+dy(u2)*dy(v2)-p*dx(v1)-p*dy(v2)-dx(u1)*q-dy(u2)*q-1e-10*p*q"),
+    "mixed3d_stokes": dict(dim=3, mesh=f"cube(2,2,2,{W3})", ufe="[P2,P2,P2,P1]", unk="[u1,u2,u3,p]", vfe="[P2,P2,P2,P1]", tst="[v1,v2,v3,q]",
+                           bil="dx(u1)*dx(v1)+dy(u1)*dy(v1)+dz(u1)*dz(v1)+dx(u2)*dx(v2)+dy(u2)*dy(v2)+dz(u2)*dz(v2)"
+                               "+dx(u3)*dx(v3)+dy(u3)*dy(v3)+dz(u3)*dz(v3)-p*(dx(v1)+dy(v2)+dz(v3))-(dx(u1)+dy(u2)+dz(u3))*q-1e-10*p*q"),
 }
 
 

@@ -40,3 +40,24 @@ def test_rectangular_with_equal_spaces_is_the_square_assembly():
     a = ol.assemble_coo(mesh, order, ncomp, e2n, bt, qp, qw)
     b = ol.assemble_coo_rect(mesh, order, ncomp, e2n, order, ncomp, e2n, bt, qp, qw)
     assert all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+@pytest.mark.parametrize("name", sorted(fc.MIXED_CASES))
+def test_mixed_order_space_as_scalar_blocks(name):
+    """[P2,P2,P1] / [P2,P2,P2,P1] in one fespace: the sum of the scalar blocks, each assembled with the global dofs of its
+    components as node numbers, is the matrix the reference assembles (sorted pattern bit-exact, values 1e-12)"""
+    orders, terms, qname = fc.MIXED_CASES[name]
+    g = fc.load(name)
+    n = int(g["n"])
+    mesh = {k: g[k] for k in ("dim", "xyz", "conn", "elab")}
+    qp, qw = ol.quadrature(g["dim"], qname)
+    I, J, A = [], [], []  # noqa: E741
+    for ov, tv, ou, tu, bt in fc.mixed_blocks(g, orders, terms):
+        ci, cj, ca = ol.assemble_coo_rect(mesh, ov, 1, tv, ou, 1, tu, bt, qp, qw)
+        I.append(ci), J.append(cj), A.append(ca)
+    I, J, A = np.concatenate(I), np.concatenate(J), np.concatenate(A)  # noqa: E741
+    key = I.astype(np.int64) * n + J
+    assert len(np.unique(key)) == len(key)  # the blocks are disjoint
+    o = np.argsort(key, kind="stable")
+    assert np.array_equal(I[o], g["coo_i"]) and np.array_equal(J[o], g["coo_j"])
+    assert np.max(np.abs(A[o] - g["coo_a"])) <= RTOL * np.abs(g["coo_a"]).max()

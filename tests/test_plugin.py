@@ -285,6 +285,10 @@ matrix Bx = vx(Uh,Ph);
 matrix Bbd = vbd(Uh,Ph);
 matrix Bq = vq(Uh,Ph);
 cout << "NNZ " << Bon.nnz << " " << Bx.nnz << " " << Bbd.nnz << " " << Bq.nnz << endl;
+fespace Xh(Th,[P2,P2,P2,P1]);
+varf vs([u1,u2,u3,p],[v1,v2,v3,q]) = int3d(Th)(dx(u1)*dx(v1)+dy(u2)*dy(v2)+dz(u3)*dz(v3)-p*(dx(v1)+dy(v2)+dz(v3))-(dx(u1)+dy(u2)+dz(u3))*q)
+   + on(1,2,u1=0,u2=0,u3=0);
+try { matrix S = vs(Xh,Xh); cout << "S " << S.n << " " << S.nnz << endl; } catch(...) { cout << "S: no device" << endl; }
 """
 
 
@@ -300,6 +304,7 @@ def test_plugin_rectangular_forms_are_recognised_without_a_device():
         pytest.skip("a CUDA device is present")
     rc, out, _ = run_ff(RECT_FORMS, {}, want_fail=True)
     assert rc == 0 and re.search(r"^B 64 1029 ", out, re.M) and out.count("FFCUDA_RECT=1 takes such forms to the device") == 5
+    assert re.search(r"^S 1093 \d+", out, re.M) and "boundary condition on some components only" in out  # (left to FreeFEM)
     rc, out, _ = run_ff(RECT_FORMS, {"FFCUDA_RECT": "1", "FFCUDA_EXPLAIN": "1"}, want_fail=True)
     assert rc == 0, out[-2000:]
     assert "rectangular matrix 64 x 1029: 4 term(s), 14 quadrature point(s), all regions" in out
@@ -308,6 +313,9 @@ def test_plugin_rectangular_forms_are_recognised_without_a_device():
                 "boundary integral in a form with two different spaces", "different quadrature rules or regions"):
         assert why in out, why
     assert re.search(r"^NNZ \d+ \d+ \d+ \d+", out, re.M)
+    # a mixed-order product space in one fespace: claimed as scalar blocks, on(...) left to FreeFEM's AssembleBC
+    assert "mixed-order space [P2,P2,P2,P1], 1093 dofs: 16 scalar blocks, 9 term(s), 14 quadrature point(s), on(...) by FreeFEM's AssembleBC" in out
+    assert "S: no device" in out and not re.search(r"^S 1093", out, re.M)
 
 
 @needs_ff

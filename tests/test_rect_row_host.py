@@ -43,7 +43,7 @@ def node_pattern(incptr, inc, e2n_u):
     rows = []
     for i in range(len(incptr) - 1):
         els = inc[incptr[i]:incptr[i + 1]] >> np.uint32(4)
-        rows.append(np.unique(e2n_u[els].ravel()))
+        rows.append(np.unique(e2n_u[els].ravel()) if len(els) else np.zeros(0, np.int32))
     nrowptr = np.zeros(len(rows) + 1, np.int32)
     nrowptr[1:] = np.cumsum([len(r) for r in rows])
     return nrowptr, np.ascontiguousarray(np.concatenate(rows), dtype=np.int32)
@@ -56,10 +56,10 @@ def bary(dim, qp):
     return lam
 
 
-def host_assemble(g, ov, cv, ev, ou, cu, eu, terms, qp, qw, labels=None):
+def host_assemble(g, ov, cv, ev, ou, cu, eu, terms, qp, qw, labels=None, nnodes_v=None):
     """(rowptr, colind, vals) dof-level CSR as the device entry lays it out"""
     dim = int(g["dim"])
-    nnv = int(ev.max()) + 1
+    nnv = int(ev.max()) + 1 if nnodes_v is None else int(nnodes_v)
     incptr, inc = node_incidence(ev, nnv)
     nrowptr, ncol = node_pattern(incptr, inc, eu)
     vals = np.zeros(cv * cu * len(ncol))
@@ -116,3 +116,22 @@ def test_row_routine_region_filter_and_params_size():
     ref = np.zeros((n, m))
     ref[ci, cj] = ca
     assert np.max(np.abs(dense - ref)) <= 1e-12 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("name", sorted(fc.MIXED_CASES))
+def test_row_routine_on_the_blocks_of_a_mixed_order_space(name):
+    """what the plugin does for [P2,P2,P1] / [P2,P2,P2,P1] spaces: one call of the rectangular entry per couple of components,
+    scalar spaces whose node numbers are the global dofs of the component (most rows of a block have no element at all),
+    blocks merged as COO"""
+    orders, terms, qname = fc.MIXED_CASES[name]
+    g = fc.load(name)
+    n = int(g["n"])
+    qp, qw = ol.quadrature(g["dim"], qname)
+    I, J, A = [], [], []  # noqa: E741
+    for ov, tv, ou, tu, bt in fc.mixed_blocks(g, orders, terms):
+        rp, col, val = host_assemble(g, ov, 1, tv, ou, 1, tu, bt, qp, qw, nnodes_v=n)
+        I.append(np.repeat(np.arange(n), np.diff(rp))), J.append(col), A.append(val)
+    I, J, A = np.concatenate(I), np.concatenate(J), np.concatenate(A)  # noqa: E741
+    o = np.argsort(I.astype(np.int64) * n + J, kind="stable")
+    assert np.array_equal(I[o], g["coo_i"]) and np.array_equal(J[o], g["coo_j"])
+    assert np.max(np.abs(A[o] - g["coo_a"])) <= 1e-12 * np.abs(g["coo_a"]).max()

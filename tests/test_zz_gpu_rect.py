@@ -124,6 +124,32 @@ def test_rect_matrices_are_refused_by_solvers_and_dirichlet_entries(ctx):
         sv.assemble_rect(other.space(1, 1), [(0, fc.ID, 0, fc.ID, 1.0)], qp, qw)
 
 
+@pytest.mark.parametrize("name", sorted(fc.MIXED_CASES))
+def test_mixed_order_space_as_scalar_blocks_on_the_device(ctx, name):
+    """what the plugin does for `[P2,P2,P1]` / `[P2,P2,P2,P1]` in one fespace: one call of the rectangular entry per couple of
+    components, scalar spaces whose node numbers are the GLOBAL dofs of the component (most rows of a block are empty), the
+    blocks merged as COO = the matrix the reference assembles (tests/test_oracle_rect.py pins the same on the oracle)"""
+    orders, terms, qname = fc.MIXED_CASES[name]
+    g = fc.load(name)
+    n = int(g["n"])
+    mesh = ctx.mesh_upload(g["dim"], g["xyz"], g["conn"], g["elab"])
+    qp, qw = ol.quadrature(g["dim"], qname)
+    spaces = {}
+    I, J, A = [], [], []  # noqa: E741
+    for ov, tv, ou, tu, bt in fc.mixed_blocks(g, orders, terms):
+        for o, t in ((ov, tv), (ou, tu)):
+            if id(t) not in spaces:
+                spaces[id(t)] = mesh.space(o, 1, t, n)
+        B = spaces[id(tv)].assemble_rect(spaces[id(tu)], bt, qp, qw)
+        assert B.shape()[:2] == (n, n)
+        bi, bj, ba = B.download_coo()
+        I.append(bi), J.append(bj), A.append(ba)
+    I, J, A = np.concatenate(I), np.concatenate(J), np.concatenate(A)  # noqa: E741
+    o = np.argsort(I.astype(np.int64) * n + J, kind="stable")
+    assert np.array_equal(I[o], g["coo_i"]) and np.array_equal(J[o], g["coo_j"])
+    assert np.max(np.abs(A[o] - g["coo_a"])) <= RTOL * np.abs(g["coo_a"]).max()
+
+
 # ---- through the plugin: `matrix B = vb(Uh,Vh)` in the unmodified FreeFem++ with FFCUDA_RECT=1 ----
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FF = os.path.join(ROOT, "oracle", "_ref", "FreeFem++-nw")
@@ -172,3 +198,37 @@ def test_plugin_rectangular_blocks_with_FFCUDA_RECT():  # noqa: N802
     a = np.array(re.search(r"NORMS (.*)", ref).group(1).split(), dtype=float)
     b = np.array(re.search(r"NORMS (.*)", out).group(1).split(), dtype=float)
     assert np.max(np.abs(a - b)) <= 1e-11 * np.abs(a).max()
+
+
+STOKES_ONE_SPACE = """load "msh3"
+LOADFFCUDA
+mesh Th = square(6,5,[x+0.2*y*y,y*(1+0.3*x)]);
+fespace Xh(Th,[P2,P2,P1]);
+varf vs([u1,u2,p],[v1,v2,q]) = int2d(Th)(dx(u1)*dx(v1)+dy(u1)*dy(v1)+dx(u2)*dx(v2)+dy(u2)*dy(v2)-p*dx(v1)-p*dy(v2)-dx(u1)*q-dy(u2)*q-1e-10*p*q)
+   + on(1,2,3,4,u1=0,u2=0);
+matrix S = vs(Xh,Xh,tgv=1);
+Xh [w1,w2,wp] = [x*y, sin(y), 1+x];
+real[int] r = S*w1[];
+mesh3 Th3 = cube(3,2,3,[x+0.1*y*y,y+0.05*z,z*(1+0.2*x)]);
+fespace Yh(Th3,[P2,P2,P2,P1]);
+varf vs3([u1,u2,u3,p],[v1,v2,v3,q]) = int3d(Th3)(dx(u1)*dx(v1)+dy(u1)*dy(v1)+dz(u1)*dz(v1)+dx(u2)*dx(v2)+dy(u2)*dy(v2)+dz(u2)*dz(v2)
+   +dx(u3)*dx(v3)+dy(u3)*dy(v3)+dz(u3)*dz(v3)-p*(dx(v1)+dy(v2)+dz(v3))-(dx(u1)+dy(u2)+dz(u3))*q) + on(1,6,u1=0,u2=0,u3=0);
+matrix S3 = vs3(Yh,Yh,tgv=1);
+Yh [z1,z2,z3,zp] = [x*y, sin(z), x+z*z, 1-y];
+real[int] r3 = S3*z1[];
+cout.precision(15);
+cout << "SHAPE " << S.n << " " << S.nnz << " " << S3.n << " " << S3.nnz << endl;
+cout << "NORMS " << r.l2 << " " << r.sum << " " << r3.l2 << " " << r3.sum << endl;
+"""
+
+
+@pytest.mark.skipif(not (os.path.exists(FF) and os.path.exists(os.path.join(PLUGIN_DIR, "ffcuda.so"))), reason="reference binary / plugin not built")
+def test_plugin_stokes_matrix_on_one_mixed_order_space_with_FFCUDA_RECT():  # noqa: N802
+    rc0, ref = _run_ff(STOKES_ONE_SPACE.replace("LOADFFCUDA", ""), {})
+    rc1, out = _run_ff(STOKES_ONE_SPACE.replace("LOADFFCUDA", 'load "ffcuda"'), {"FFCUDA_RECT": "1", "FFCUDA_VERBOSE": "1"})
+    assert rc0 == 0 and rc1 == 0, out[-3000:]
+    assert out.count("mixed-order matrix") == 2 and "assembled on the GPU" in out
+    assert re.search(r"SHAPE .*", ref).group(0) == re.search(r"SHAPE .*", out).group(0)
+    a = np.array(re.search(r"NORMS (.*)", ref).group(1).split(), dtype=float)
+    b = np.array(re.search(r"NORMS (.*)", out).group(1).split(), dtype=float)
+    assert np.max(np.abs(a - b) / np.abs(a)) <= 1e-11
