@@ -1880,6 +1880,13 @@ RectForm read_rect_form(Stack stack, const list<C_F0> &largs, const MeshT &Th, i
         }
     }
     if (!F.have || F.terms.empty()) throw Unsupported{"no bilinear term"};
+    // the device pattern holds the couples of EVERY element; FreeFEM's only those of the elements the integral visits
+    // (HashMatrix creates them as it goes): the same thing only when the regions cover the mesh (cf. check_full_pattern)
+    if (!F.reg.all) {
+        const std::set<int> labs(F.reg.labels.begin(), F.reg.labels.end());
+        for (int k = 0; k < Th.nt; ++k)
+            if (!labs.count(Th[k].lab)) throw Unsupported{"the volume integrals do not visit every element (sub-pattern)"};
+    }
     if (F.terms.size() > 64) throw Unsupported{"more than 64 terms"};
     if (F.q.w.size() > 32) throw Unsupported{"more than 32 quadrature points"};
     return F;

@@ -279,11 +279,15 @@ varf von(u,q) = int3d(Th)(dx(u)*q) + on(1,u=0);
 varf vx([u1,u2,u3],[q]) = int3d(Th)(x*dx(u1)*q);
 varf vbd([u1,u2,u3],[q]) = int3d(Th)(dx(u1)*q) + int2d(Th,2)(u1*q);
 varf vq([u1,u2,u3],[q]) = int3d(Th)(dx(u1)*q) + int3d(Th,qfV=qfV1)(u2*q);
+varf vr([u1,u2,u3],[q]) = int3d(Th,7)(dx(u1)*q);
+varf vr0([u1,u2,u3],[q]) = int3d(Th,0)(dx(u1)*q);
 try { matrix B = vb(Uh,Ph); cout << "B " << B.n << " " << B.m << " " << B.nnz << endl; } catch(...) { cout << "B: no device" << endl; }
 matrix Bon = von(Wh,Ph);
 matrix Bx = vx(Uh,Ph);
 matrix Bbd = vbd(Uh,Ph);
 matrix Bq = vq(Uh,Ph);
+matrix Br = vr(Uh,Ph);
+try { matrix Br0 = vr0(Uh,Ph); cout << "Br0 " << Br0.nnz << endl; } catch(...) { cout << "Br0: no device" << endl; }
 cout << "NNZ " << Bon.nnz << " " << Bx.nnz << " " << Bbd.nnz << " " << Bq.nnz << endl;
 fespace Xh(Th,[P2,P2,P2,P1]);
 varf vs([u1,u2,u3,p],[v1,v2,v3,q]) = int3d(Th)(dx(u1)*dx(v1)+dy(u2)*dy(v2)+dz(u3)*dz(v3)-p*(dx(v1)+dy(v2)+dz(v3))-(dx(u1)+dy(u2)+dz(u3))*q)
@@ -303,14 +307,16 @@ def test_plugin_rectangular_forms_are_recognised_without_a_device():
     if torch.cuda.is_available():
         pytest.skip("a CUDA device is present")
     rc, out, _ = run_ff(RECT_FORMS, {}, want_fail=True)
-    assert rc == 0 and re.search(r"^B 64 1029 ", out, re.M) and out.count("FFCUDA_RECT=1 takes such forms to the device") == 5
+    assert rc == 0 and re.search(r"^B 64 1029 ", out, re.M) and out.count("FFCUDA_RECT=1 takes such forms to the device") == 7
     assert re.search(r"^S 1093 \d+", out, re.M) and "boundary condition on some components only" in out  # (left to FreeFEM)
     rc, out, _ = run_ff(RECT_FORMS, {"FFCUDA_RECT": "1", "FFCUDA_EXPLAIN": "1"}, want_fail=True)
     assert rc == 0, out[-2000:]
     assert "rectangular matrix 64 x 1029: 4 term(s), 14 quadrature point(s), all regions" in out
     assert "B: no device" in out and not re.search(r"^B 64", out, re.M)
+    assert "1 region label(s)" in out and "Br0: no device" in out  # (region 0 is the whole cube: claimed)
     for why in ("on(...) in a form with two different spaces", "coefficient depends on the mesh point",
-                "boundary integral in a form with two different spaces", "different quadrature rules or regions"):
+                "boundary integral in a form with two different spaces", "different quadrature rules or regions",
+                "do not visit every element (sub-pattern)"):
         assert why in out, why
     assert re.search(r"^NNZ \d+ \d+ \d+ \d+", out, re.M)
     # a mixed-order product space in one fespace: claimed as scalar blocks, on(...) left to FreeFEM's AssembleBC
