@@ -30,6 +30,9 @@ CASES = {
     # two components against two components of another order, region-restricted rule left at its default, lumped quadrature
     "rect2d_p2vec_p1vec": dict(dim=2, mesh="square(3,3)", ufe="[P2,P2]", unk="[u1,u2]", vfe="[P1,P1]", tst="[v1,v2]",
                                bil="u1*v1+u2*v2+0.25*dy(u1)*v2", intopt=",qft=qf2pT"),
+    # an integral restricted to one of two regions: only the visited elements put their couples into the matrix
+    "rect3d_region": dict(dim=3, mesh="change(cube(3,2,3),fregion=(x<0.5)?1:2)", ufe="P2", unk="[u]", vfe="P1", tst="[q]", bil="dx(u)*q+u*q",
+                          region=",2"),
     # mixed-order product spaces (Taylor-Hood Stokes matrices) in ONE fespace: assembled by the plugin as scalar blocks in the
     # global dof numbering of the space (tests/ff_cases.py MIXED_CASES); Uh and Vh are two objects of the same type here
     "mixed2d_stokes": dict(dim=2, mesh=f"square(3,3,{W2})", ufe="[P2,P2,P1]", unk="[u1,u2,p]", vfe="[P2,P2,P1]", tst="[v1,v2,q]",
@@ -45,7 +48,7 @@ def script(c, out):
     mtype, integ = ("mesh", "int2d") if dim == 2 else ("mesh3", "int3d")
     nvk = dim + 1
     s = ['load "msh3"', f"{mtype} Th = {c['mesh']};", f"fespace Uh(Th,{c['ufe']});", f"fespace Vh(Th,{c['vfe']});",
-         f"varf vb({c['unk']},{c['tst']}) = {integ}(Th{c.get('intopt', '')})({c['bil']});", "matrix B = vb(Uh,Vh);"]
+         f"varf vb({c['unk']},{c['tst']}) = {integ}(Th{c.get('region', '')}{c.get('intopt', '')})({c['bil']});", "matrix B = vb(Uh,Vh);"]
     s.append(f'{{ ofstream f("{out}/mesh.txt"); f.precision(17);')
     s.append('  f << Th.nv << " " << Th.nt << " " << Th.nbe << endl;')
     if dim == 2:

@@ -61,3 +61,22 @@ def test_mixed_order_space_as_scalar_blocks(name):
     o = np.argsort(key, kind="stable")
     assert np.array_equal(I[o], g["coo_i"]) and np.array_equal(J[o], g["coo_j"])
     assert np.max(np.abs(A[o] - g["coo_a"])) <= RTOL * np.abs(g["coo_a"]).max()
+
+
+def test_region_restricted_rectangular_form_has_the_sub_pattern():
+    """int3d(Th,2)(...) on a mesh with two regions: HashMatrix only holds the couples of the visited elements - the oracle
+    follows; the device entry documents that ITS pattern keeps every couple (the plugin therefore leaves such forms to
+    FreeFEM unless the regions cover the mesh), its values on the sub-pattern are what the row routine's filter gives"""
+    g = fc.load("rect3d_region")
+    mesh = {k: g[k] for k in ("dim", "xyz", "conn", "elab")}
+    ev, eu = fc.rect_elem2node(g, "Vh", 1), fc.rect_elem2node(g, "Uh", 1)
+    terms = [(0, fc.DX, 0, fc.ID, 1.0), (0, fc.ID, 0, fc.ID, 1.0)]
+    qp, qw = ol.quadrature(3, "qfV5")
+    ci, cj, ca = ol.assemble_coo_rect(mesh, 1, 1, ev, 2, 1, eu, terms, qp, qw, labels=[2])
+    assert np.array_equal(ci, g["ins_i"]) and np.array_equal(cj, g["ins_j"])
+    m = int(g["m"])
+    o = np.argsort(ci.astype(np.int64) * m + cj, kind="stable")
+    assert np.array_equal(ci[o], g["coo_i"]) and np.array_equal(cj[o], g["coo_j"])
+    assert np.max(np.abs(ca[o] - g["coo_a"])) <= RTOL * np.abs(g["coo_a"]).max()
+    fi, fj, _ = ol.assemble_coo_rect(mesh, 1, 1, ev, 2, 1, eu, terms, qp, qw)
+    assert len(fi) > len(ci)  # the full pattern is strictly larger

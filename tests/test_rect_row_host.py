@@ -135,3 +135,18 @@ def test_row_routine_on_the_blocks_of_a_mixed_order_space(name):
     o = np.argsort(I.astype(np.int64) * n + J, kind="stable")
     assert np.array_equal(I[o], g["coo_i"]) and np.array_equal(J[o], g["coo_j"])
     assert np.max(np.abs(A[o] - g["coo_a"])) <= 1e-12 * np.abs(g["coo_a"]).max()
+
+
+def test_row_routine_region_filter_against_the_reference():
+    """the fixture of a region-restricted form: the row routine's values on the reference's (sub-)pattern, zeros elsewhere"""
+    g = fc.load("rect3d_region")
+    ev, eu = fc.rect_elem2node(g, "Vh", 1), fc.rect_elem2node(g, "Uh", 1)
+    terms = [(0, fc.DX, 0, fc.ID, 1.0), (0, fc.ID, 0, fc.ID, 1.0)]
+    qp, qw = ol.quadrature(3, "qfV5")
+    rp, col, val = host_assemble(g, 1, 1, ev, 2, 1, eu, terms, qp, qw, labels=[2])
+    n, m = int(g["n"]), int(g["m"])
+    dense = np.zeros((n, m))
+    dense[np.repeat(np.arange(n), np.diff(rp)), col] = val
+    ref = np.zeros((n, m))
+    ref[g["coo_i"], g["coo_j"]] = g["coo_a"]
+    assert np.max(np.abs(dense - ref)) <= 1e-12 * np.abs(ref).max()
