@@ -232,3 +232,27 @@ def test_plugin_stokes_matrix_on_one_mixed_order_space_with_FFCUDA_RECT():  # no
     a = np.array(re.search(r"NORMS (.*)", ref).group(1).split(), dtype=float)
     b = np.array(re.search(r"NORMS (.*)", out).group(1).split(), dtype=float)
     assert np.max(np.abs(a - b) / np.abs(a)) <= 1e-11
+
+
+CHECK_BOTH = """load "msh3"
+load "ffcuda"
+mesh3 Th = cube(6,5,7);
+fespace Uh(Th,[P2,P2,P2]); fespace Ph(Th,P1); fespace Xh(Th,[P2,P2,P2,P1]);
+varf vb([u1,u2,u3],[q]) = int3d(Th)(-(dx(u1)+dy(u2)+dz(u3))*q);
+varf vs([u1,u2,u3,p],[v1,v2,v3,q]) = int3d(Th)(dx(u1)*dx(v1)+dy(u2)*dy(v2)+dz(u3)*dz(v3)-p*(dx(v1)+dy(v2)+dz(v3))-(dx(u1)+dy(u2)+dz(u3))*q)
+  + on(1,2,u1=0,u2=0,u3=0);
+matrix B = vb(Uh,Ph);
+matrix S = vs(Xh,Xh);
+cout << "DONE " << B.nnz << " " << S.nnz << endl;
+"""
+
+
+@pytest.mark.skipif(not (os.path.exists(FF) and os.path.exists(os.path.join(PLUGIN_DIR, "ffcuda.so"))), reason="reference binary / plugin not built")
+def test_plugin_check_mode_on_rectangular_and_mixed_order_statements():
+    """FFCUDA_CHECK=1: both statements also run FreeFEM's own operator inside the same process and are compared there (pattern
+    identical, values within 1e-12; Dirichlet rows of the mixed-order matrix equal)"""
+    rc, out = _run_ff(CHECK_BOTH, {"FFCUDA_RECT": "1", "FFCUDA_CHECK": "1"})
+    assert rc == 0, out[-3000:]
+    m1 = re.search(r"ffcuda check: rectangular matrix .*pattern identical, max \|dB\| / max \|B\| = (\S+)", out)
+    m2 = re.search(r"ffcuda check: mixed-order matrix .*pattern identical, max \|dA\| / max \|A\| = (\S+)", out)
+    assert m1 and m2 and float(m1.group(1)) <= 1e-12 and float(m2.group(1)) <= 1e-12 and "DONE" in out
