@@ -2093,10 +2093,10 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
             std::vector<double> C;
             gpu_rect_matrix(Uh, Vh, F, I, J, C);
             const int n = Vh.NbOfDF, m = Uh.NbOfDF;
-            MatriceMorse<double> *M = new MatriceMorse<double>(n, m, 0, 0);
-            M->set(n, m, 0, I.size(), I.data(), J.data(), C.data(), 0, 0); // COO triple sorted by (i, j): HashMatrix::set copies it
+            std::unique_ptr<MatriceMorse<double>> guard(new MatriceMorse<double>(n, m, 0, 0));
+            guard->set(n, m, 0, I.size(), I.data(), J.data(), C.data(), 0, 0); // COO triple sorted by (i, j): HashMatrix::set copies it
             if (g_check) { // FFCUDA_CHECK=1: FreeFEM's own operator runs as well, the two matrices are compared, FreeFEM's is kept
-                delete M;
+                guard.reset();
                 AnyType r = Base::Op::operator()(stack);
                 Matrice_Creuse<double> &Af(*GetAny<Matrice_Creuse<double> *>((*this->a)(stack)));
                 HashMatrix<int, double> *H = Af.pHM();
@@ -2123,7 +2123,7 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
             A.A = 0;
             A.Uh = Uh;
             A.Vh = Vh;
-            A.A.master(M);
+            A.A.master(guard.release());
             A.pHM()->half = 0;
             if (Uh.NbOfDF == Vh.NbOfDF) SetSolver(stack, false, *A.A, ds); // (square by its sizes: the built-in operator sets the solver then)
             if (g_verbose) cout << "  -- ffcuda: rectangular matrix " << n << " x " << m << ", nnz " << J.size() << " assembled on the GPU" << endl;
@@ -2154,14 +2154,15 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
             std::vector<double> C;
             gpu_mixed_matrix(Vh, X, F, I, J, C);
             const int n = Vh.NbOfDF;
-            MatriceMorse<double> *M = new MatriceMorse<double>(n, n, 0, 0);
+            std::unique_ptr<MatriceMorse<double>> guard(new MatriceMorse<double>(n, n, 0, 0)); // (AssembleBC may raise an ExecError)
+            MatriceMorse<double> *M = guard.get();
             M->set(n, n, 0, I.size(), I.data(), J.data(), C.data(), 0, 0); // COO, block after block: HashMatrix::set copies it
             if (has_bc) AssembleBC<double, MMesh, FESpaceT, FESpaceT>(stack, Th, Vh, Vh, false, M, 0, 0, this->b->largs, ds.tgv);
             if (g_check) { // FFCUDA_CHECK=1: FreeFEM's own operator runs as well, the two matrices are compared, FreeFEM's is kept
                 M->CSR();
                 const std::vector<int> p0(M->p, M->p + n + 1), j0(M->j, M->j + M->nnz);
                 const std::vector<double> a0(M->aij, M->aij + M->nnz);
-                delete M;
+                guard.reset();
                 AnyType r = Base::Op::operator()(stack);
                 Matrice_Creuse<double> &Af(*GetAny<Matrice_Creuse<double> *>((*this->a)(stack)));
                 HashMatrix<int, double> *H = Af.pHM();
@@ -2192,7 +2193,7 @@ struct CudaMatrixOp : public OpMatrixtoBilinearForm<double, MMesh, v_fes, v_fes>
             A.A = 0;
             A.Uh = Vh;
             A.Vh = Vh;
-            A.A.master(M);
+            A.A.master(guard.release());
             A.pHM()->half = 0;
             SetSolver(stack, false, *A.A, ds);
             if (g_verbose) cout << "  -- ffcuda: mixed-order matrix " << n << " x " << n << ", nnz " << I.size() << " assembled on the GPU" << endl;
