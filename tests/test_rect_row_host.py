@@ -4,6 +4,7 @@ incidence lists and node-level pattern are formed here with numpy.  Pattern bit-
 (The launch plumbing and the device symbolic phase around it are what tests/test_zz_gpu_rect.py checks on the GPU.)"""
 import ctypes as C
 import os
+import shutil
 import subprocess
 import tempfile
 
@@ -14,6 +15,7 @@ import ff_cases as fc
 import oracle_lib as ol
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+pytestmark = pytest.mark.skipif(shutil.which("g++") is None, reason="no g++ to build the host harness")
 _LIB = None
 SLOT = {fc.ID: 0, fc.DX: 1, fc.DY: 2, fc.DZ: 3}
 
